@@ -1,0 +1,103 @@
+// oracle/backend.hpp -- TEST INFRASTRUCTURE ONLY (never linked by the product).
+//
+// Selects what the serial driver restatement (driver.hpp) calls for the
+// Charm++-free parts of the path:
+//   default      : the plain C++ restatement in physics_port.hpp
+//   -DORACLE_REF : the reference's own, unmodified translation units compiled in
+//                  place from /root/reference/src (oracle/Makefile target `ref`,
+//                  output oracle/_ref/liboracle_ref.so). Hash containers are then
+//                  the reference's tk::UnsMesh types as well.
+#pragma once
+#include "siphash.hpp"
+#include "physics_port.hpp"
+
+#ifdef ORACLE_REF
+  #include "Fields.hpp"
+  #include "UnsMesh.hpp"
+  #include "DerivedData.hpp"
+  #include "Riemann.hpp"
+  #include "BC.hpp"
+  #include "Problems.hpp"
+  #include "InciterConfig.hpp"
+  namespace inciter { extern ctr::Config g_cfg; }
+#endif
+
+namespace orc {
+namespace be {
+
+using Coords = std::array< std::vector< real >, 3 >;
+
+#ifdef ORACLE_REF
+
+using Fields = tk::Fields;
+template< std::size_t N > using Hash = tk::UnsMesh::Hash< N >;
+template< std::size_t N > using Eq = tk::UnsMesh::Eq< N >;
+inline const char* name() { return "reference"; }
+
+void set_cfg( const Cfg& c );   // ref_backend.cpp: fills inciter::g_cfg
+
+inline void grad( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                  const std::array< std::vector< real >, 3 >& dsupint,
+                  const Coords& coord, const std::vector< std::size_t >& triinpoel,
+                  const Fields& U, Fields& G )
+{ riemann::grad( dsupedge, dsupint, coord, triinpoel, U, G ); }
+
+inline void rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                 const std::array< std::vector< real >, 3 >& dsupint,
+                 const Coords& coord, const std::vector< std::size_t >& triinpoel,
+                 const std::vector< std::uint8_t >& besym, const Fields& G, const Fields& U,
+                 const std::vector< real >& v, real t, const std::vector< real >& tp, Fields& R )
+{ riemann::rhs( dsupedge, dsupint, coord, triinpoel, besym, G, U, v, t, tp, R ); }
+
+inline void initialize( const Coords& coord, Fields& U, real t )
+{ problems::initialize( coord, U, t, 0, {} ); }
+
+inline void dirbc( Fields& U, real t, const Coords& coord, const std::vector< std::size_t >& m )
+{ physics::dirbc( 0, U, t, coord, {}, m ); }
+inline void symbc( Fields& U, const std::vector< std::size_t >& n, const std::vector< real >& nn,
+                   std::size_t pos ) { physics::symbc( U, n, nn, pos ); }
+inline void farbc( Fields& U, const std::vector< std::size_t >& n, const std::vector< real >& nn )
+{ physics::farbc( U, n, nn ); }
+inline void prebc( Fields& U, const std::vector< std::size_t >& n, const std::vector< real >& v )
+{ physics::prebc( U, n, v ); }
+
+inline port::ICFn SOL() {
+  auto s = problems::SOL();
+  if (!s) return {};
+  return [s]( real x, real y, real z, real t ){ return s( x, y, z, t, 0 ); };
+}
+real eos_pressure( real re );
+real eos_soundspeed( real r, real p );
+
+using LinkedList = std::pair< std::vector< std::size_t >, std::vector< std::size_t > >;
+inline LinkedList genEsup( const std::vector< std::size_t >& inpoel, std::size_t nnpe )
+{ return tk::genEsup( inpoel, nnpe ); }
+inline LinkedList genPsup( const std::vector< std::size_t >& inpoel, std::size_t nnpe,
+                           const LinkedList& esup ) { return tk::genPsup( inpoel, nnpe, esup ); }
+
+#else
+
+using Fields = PFields;
+template< std::size_t N > using Hash = IdHash< N >;
+template< std::size_t N > using Eq = IdEq< N >;
+inline const char* name() { return "port"; }
+
+inline void set_cfg( const Cfg& c ) { port::set_cfg( c ); }
+using port::grad;
+using port::rhs;
+using port::initialize;
+using port::dirbc;
+using port::symbc;
+using port::farbc;
+using port::prebc;
+using port::SOL;
+inline real eos_pressure( real re ) { return port::eos_pressure( re ); }
+inline real eos_soundspeed( real r, real p ) { return port::eos_soundspeed( r, p ); }
+using port::LinkedList;
+using port::genEsup;
+using port::genPsup;
+
+#endif
+
+} // be::
+} // orc::

@@ -1,0 +1,197 @@
+// oracle/capi.cpp -- TEST INFRASTRUCTURE ONLY (never linked by the product).
+// C entry points (ctypes) around the serial oracle driver; see oracle/oracle.h.
+#include <cstring>
+#include <string>
+#include "driver.hpp"
+#include "oracle.h"
+
+using namespace orc;
+
+namespace {
+thread_local std::string g_err;
+
+struct Handle { MeshInput in; std::unique_ptr< Run > run; };
+
+Cfg to_cfg( const orc_cfg* c ) {
+  Cfg k;
+  k.problem = c->problem; k.flux = c->flux; k.ncomp = static_cast< std::size_t >( c->ncomp );
+  k.gamma = c->gamma; k.p0 = c->p0; k.cfl = c->cfl; k.dt = c->dt; k.t0 = c->t0; k.term = c->term;
+  k.nstep = c->nstep; k.stab2 = c->stab2 != 0; k.stab2coef = c->stab2coef; k.steady = c->steady != 0;
+  k.diag_iter = c->diag_iter ? c->diag_iter : 1;
+  for (int i=0; i<c->nsym; ++i) k.bc_sym.push_back( c->sym[i] );
+  for (int i=0; i<c->ndir; ++i) {
+    std::vector< int > m( k.ncomp+1 );
+    for (std::size_t j=0; j<k.ncomp+1; ++j) m[j] = c->dir[i][j];
+    k.bc_dir.push_back( m );
+  }
+  for (int i=0; i<c->nfar; ++i) k.bc_far.push_back( c->far_sets[i] );
+  k.far_density = c->far_density; k.far_pressure = c->far_pressure;
+  k.far_velocity = {{ c->far_velocity[0], c->far_velocity[1], c->far_velocity[2] }};
+  for (int i=0; i<c->npre; ++i) {
+    k.bc_pre.push_back( { c->pre_sets[i] } );
+    k.pre_density.push_back( c->pre_density[i] );
+    k.pre_pressure.push_back( c->pre_pressure[i] );
+  }
+  for (int i=0; i<c->nfieldout; ++i) k.fieldout_sets.push_back( c->fieldout_sets[i] );
+  return k;
+}
+
+template< class T >
+std::size_t put( const std::vector< T >& v, void* out, std::size_t cap ) {
+  auto bytes = v.size()*sizeof(T);
+  if (out && cap >= bytes && bytes) std::memcpy( out, v.data(), bytes );
+  return bytes;
+}
+std::size_t putf( const be::Fields& f, void* out, std::size_t cap ) {
+  std::vector< real > v( f.nunk()*f.nprop() );
+  for (std::size_t i=0; i<f.nunk(); ++i) for (std::size_t c=0; c<f.nprop(); ++c) v[i*f.nprop()+c] = f(i,c);
+  return put( v, out, cap );
+}
+}
+
+extern "C" {
+
+const char* orc_backend() { return be::name(); }
+const char* orc_last_error() { return g_err.c_str(); }
+
+void* orc_create( std::size_t npoin, const double* x, const double* y, const double* z,
+                  std::size_t ntet, const std::uint64_t* tets,
+                  std::size_t ntri, const std::uint64_t* tris,
+                  int nblocks, const int* block_type, const std::uint64_t* block_n,
+                  int nsets, const int* set_id, const std::uint64_t* set_off,
+                  const std::uint64_t* set_elem, const std::uint64_t* set_side,
+                  const orc_cfg* cfg, int nchare, const std::uint64_t* target )
+{
+  try {
+    auto h = std::make_unique< Handle >();
+    auto& in = h->in;
+    in.coord[0].assign( x, x+npoin ); in.coord[1].assign( y, y+npoin ); in.coord[2].assign( z, z+npoin );
+    in.tets.assign( tets, tets+ntet*4 );
+    if (ntri) in.tris.assign( tris, tris+ntri*3 );
+    for (int b=0; b<nblocks; ++b) in.blocks.emplace_back( block_type[b], block_n[b] );
+    for (int s=0; s<nsets; ++s) {
+      in.ss_elem[ set_id[s] ].assign( set_elem+set_off[s], set_elem+set_off[s+1] );
+      in.ss_side[ set_id[s] ].assign( set_side+set_off[s], set_side+set_off[s+1] );
+    }
+    std::vector< std::size_t > tg( ntet, 0 );
+    if (target) for (std::size_t e=0; e<ntet; ++e) tg[e] = target[e];
+    h->run.reset( new Run( in, to_cfg(cfg), tg, nchare ) );
+    return h.release();
+  } catch (std::exception& e) { g_err = e.what(); return nullptr; }
+}
+
+void orc_destroy( void* h ) { delete static_cast< Handle* >( h ); }
+
+int orc_step( void* hv, int nsteps )
+{
+  auto h = static_cast< Handle* >( hv );
+  try {
+    be::set_cfg( h->run->cfg );
+    int n = 0;
+    while (n < nsteps && !h->run->finished) { h->run->step(); ++n; }
+    return n;
+  } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+std::size_t orc_ndiag( void* hv ) { return static_cast< Handle* >( hv )->run->diagrows.size(); }
+
+std::size_t orc_diagrow( void* hv, std::size_t i, double* out, std::size_t cap )
+{
+  const auto& r = static_cast< Handle* >( hv )->run->diagrows.at( i );
+  if (out && cap >= r.size()) std::memcpy( out, r.data(), r.size()*sizeof(double) );
+  return r.size();
+}
+
+double orc_scalar( void* hv, const char* name )
+{
+  auto& r = *static_cast< Handle* >( hv )->run;
+  std::string n( name );
+  if (n == "t") return r.t;
+  if (n == "dt") return r.dt;
+  if (n == "it") return static_cast< double >( r.it );
+  if (n == "meshvol") return r.meshvol;
+  if (n == "nchare") return static_cast< double >( r.ch.size() );
+  if (n == "finished") return r.finished ? 1.0 : 0.0;
+  return std::nan("");
+}
+
+std::size_t orc_get( void* hv, int chare, const char* name, void* out, std::size_t cap )
+{
+  auto& c = *static_cast< Handle* >( hv )->run->ch.at( static_cast< std::size_t >( chare ) );
+  std::string n( name );
+  if (n == "gid") return put( c.gid, out, cap );
+  if (n == "inpoel") return put( c.inpoel, out, cap );
+  if (n == "x") return put( c.coord[0], out, cap );
+  if (n == "y") return put( c.coord[1], out, cap );
+  if (n == "z") return put( c.coord[2], out, cap );
+  if (n == "vol") return put( c.vol, out, cap );
+  if (n == "v") return put( c.v, out, cap );
+  if (n == "triinpoel") return put( c.triinpoel, out, cap );
+  if (n == "besym") return put( c.besym, out, cap );
+  if (n == "dsupedge0") return put( c.dsupedge[0], out, cap );
+  if (n == "dsupedge1") return put( c.dsupedge[1], out, cap );
+  if (n == "dsupedge2") return put( c.dsupedge[2], out, cap );
+  if (n == "dsupint0") return put( c.dsupint[0], out, cap );
+  if (n == "dsupint1") return put( c.dsupint[1], out, cap );
+  if (n == "dsupint2") return put( c.dsupint[2], out, cap );
+  if (n == "dirbcmasks") return put( c.dirbcmasks, out, cap );
+  if (n == "symbcnodes") return put( c.symbcnodes, out, cap );
+  if (n == "symbcnorms") return put( c.symbcnorms, out, cap );
+  if (n == "farbcnodes") return put( c.farbcnodes, out, cap );
+  if (n == "farbcnorms") return put( c.farbcnorms, out, cap );
+  if (n == "prebcnodes") return put( c.prebcnodes, out, cap );
+  if (n == "prebcvals") return put( c.prebcvals, out, cap );
+  if (n == "u") return putf( c.u, out, cap );
+  if (n == "un") return putf( c.un, out, cap );
+  if (n == "rhs") return putf( c.rhs, out, cap );
+  if (n == "grad") return putf( c.grad, out, cap );
+  if (n == "bface") {       // flattened: setid, nfaces, face ids ...
+    std::vector< std::uint64_t > f;
+    for (const auto& [s,ids] : c.bface) { f.push_back( static_cast<std::uint64_t>(s) ); f.push_back( ids.size() ); for (auto i : ids) f.push_back( i ); }
+    return put( f, out, cap );
+  }
+  if (n == "commmap") {     // flattened: neighbour, n, gids (sorted) ...
+    std::vector< std::uint64_t > f;
+    for (const auto& [b,g] : c.nodeCommMap) {
+      f.push_back( static_cast<std::uint64_t>(b) ); f.push_back( g.size() );
+      std::vector< std::size_t > s( g.begin(), g.end() ); std::sort( s.begin(), s.end() );
+      for (auto i : s) f.push_back( i );
+    }
+    return put( f, out, cap );
+  }
+  g_err = "orc_get: unknown array " + n;
+  return static_cast< std::size_t >( -1 );
+}
+
+int orc_set_u( void* hv, int chare, const double* u )
+{
+  auto& c = *static_cast< Handle* >( hv )->run->ch.at( static_cast< std::size_t >( chare ) );
+  for (std::size_t i=0; i<c.u.nunk(); ++i) for (std::size_t k=0; k<c.u.nprop(); ++k) c.u(i,k) = u[i*c.u.nprop()+k];
+  return 0;
+}
+
+int orc_kernel( void* hv, int chare, const char* what, int stage, double t, double dt )
+{
+  auto h = static_cast< Handle* >( hv );
+  auto& c = *h->run->ch.at( static_cast< std::size_t >( chare ) );
+  try {
+    be::set_cfg( h->run->cfg );
+    std::string w( what );
+    if (w == "grad") c.grad_own();
+    else if (w == "rhs") c.rhs_own( stage, t );
+    else if (w == "solve") c.solve( stage, t, dt );
+    else if (w == "bc") c.BC( t );
+    else if (w == "mindt") { h->run->dt = c.mindt(); }
+    else { g_err = "orc_kernel: unknown " + w; return -1; }
+    return 0;
+  } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+std::uint64_t orc_siphash_ids( const std::uint64_t* ids, int n )
+{
+  if (n == 2) return IdHash<2>()( {{ ids[0], ids[1] }} );
+  if (n == 3) return IdHash<3>()( {{ ids[0], ids[1], ids[2] }} );
+  return 0;
+}
+
+} // extern "C"

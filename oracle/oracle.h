@@ -1,0 +1,57 @@
+/* oracle/oracle.h -- TEST INFRASTRUCTURE ONLY.
+ * C interface of the CPU oracle (serial restatement of the reference's RieCG
+ * path, oracle/driver.hpp). Only tests/, __graft_entry__.smoke() and bench.py's
+ * CPU-baseline legs may load this library; the product never does. */
+#ifndef XYST_ORACLE_H
+#define XYST_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_cfg {
+  char problem[32];
+  char flux[16];
+  int32_t ncomp;
+  int32_t stab2;
+  int32_t steady;
+  int32_t nsym;
+  int32_t sym[16];
+  int32_t ndir;
+  int32_t dir[16][12];        /* { setid, mask_0 .. mask_{ncomp-1} } */
+  int32_t nfar;
+  int32_t far_sets[16];
+  int32_t npre;
+  int32_t pre_sets[16];
+  int32_t nfieldout;
+  int32_t fieldout_sets[16];
+  uint64_t nstep;
+  uint64_t diag_iter;
+  double gamma, p0, cfl, dt, t0, term, stab2coef;
+  double far_density, far_pressure, far_velocity[3];
+  double pre_density[16], pre_pressure[16];
+} orc_cfg;
+
+const char* orc_backend(void);      /* "port" or "reference" */
+const char* orc_last_error(void);
+void* orc_create( size_t npoin, const double* x, const double* y, const double* z,
+                  size_t ntet, const uint64_t* tets, size_t ntri, const uint64_t* tris,
+                  int nblocks, const int* block_type, const uint64_t* block_n,
+                  int nsets, const int* set_id, const uint64_t* set_off,
+                  const uint64_t* set_elem, const uint64_t* set_side,
+                  const orc_cfg* cfg, int nchare, const uint64_t* target );
+void orc_destroy( void* h );
+int orc_step( void* h, int nsteps );
+size_t orc_ndiag( void* h );
+size_t orc_diagrow( void* h, size_t i, double* out, size_t cap );
+double orc_scalar( void* h, const char* name );
+size_t orc_get( void* h, int chare, const char* name, void* out, size_t cap_bytes );
+int orc_set_u( void* h, int chare, const double* u );
+int orc_kernel( void* h, int chare, const char* what, int stage, double t, double dt );
+uint64_t orc_siphash_ids( const uint64_t* ids, int n );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

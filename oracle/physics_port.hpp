@@ -1,0 +1,649 @@
+// oracle/physics_port.hpp -- TEST INFRASTRUCTURE ONLY (never linked by the product).
+//
+// Plain serial C++ restatement of the arithmetic of the reference's RieCG hot
+// path, written to be bit-identical to the reference when compiled without FMA
+// contraction (the reference's GNU Release build has none, SURVEY.md 8a'-14):
+//   nodal gradients            src/Physics/Riemann.cpp:229-367
+//   MUSCL + van Leer           src/Physics/Riemann.cpp:34-143 (flow), :145-209 (scalars)
+//   Rusanov / HLLC edge flux   src/Physics/Riemann.cpp:369-478 / :480-650
+//   domain/boundary/source rhs src/Physics/Riemann.cpp:652-946
+//   ideal gas EOS              src/Physics/EOS.hpp:29-56
+//   nodal BCs                  src/Physics/BC.cpp:29-241
+//   problem ICs / sources      src/Physics/Problems.cpp:337-440,1071-1330
+// It is pinned against the reference's own objects (oracle/_ref, built from
+// /root/reference in place) by tests/test_oracle_ref.py and against the
+// reference's regression goldens by tests/test_oracle_golden.py.
+#pragma once
+#include <vector>
+#include <array>
+#include <string>
+#include <cmath>
+#include <cstring>
+#include <cstdint>
+#include <stdexcept>
+#include <functional>
+#include <unordered_set>
+#include <algorithm>
+
+namespace orc {
+
+using real = double;
+
+//! Run configuration: the subset of the reference's g_cfg read on this path
+//! (src/Control/InciterConfig.hpp:161-413; defaults InciterConfig.cpp:1707-1757)
+struct Cfg {
+  std::string problem = "userdef";
+  std::string flux = "rusanov";
+  std::size_t ncomp = 5;
+  real gamma = 1.4;             // mat_spec_heat_ratio
+  real p0 = 0.0;                // problem_p0 (sedov)
+  real cfl = 0.0;
+  real dt = 0.0;                // constant dt if |dt|>eps
+  real t0 = 0.0;
+  real term = 1.0e+300;
+  std::uint64_t nstep = ~0ULL;
+  bool stab2 = false;
+  real stab2coef = 0.2;
+  bool steady = false;
+  std::vector< int > bc_sym;
+  std::vector< std::vector< int > > bc_dir;   // { setid, mask_0 .. mask_{ncomp-1} }
+  std::vector< int > bc_far;
+  real far_density = 0.0, far_pressure = 0.0;
+  std::array< real, 3 > far_velocity{{0,0,0}};
+  std::vector< std::vector< int > > bc_pre;   // side set groups
+  std::vector< real > pre_density, pre_pressure;
+  std::vector< int > fieldout_sets, integout_sets;
+  std::uint64_t diag_iter = 1;
+};
+
+//! Nodal field container with the reference's default layout [node][component]
+//! (src/Base/Data.hpp:420-426 with FIELD_DATA_LAYOUT_AS_FIELD_MAJOR)
+class PFields {
+  public:
+    PFields() : m_n(0), m_p(0) {}
+    PFields( std::size_t n, std::size_t p ) : m_v( n*p, 0.0 ), m_n(n), m_p(p) {}
+    real& operator()( std::size_t i, std::size_t c ) { return m_v[ i*m_p + c ]; }
+    const real& operator()( std::size_t i, std::size_t c ) const { return m_v[ i*m_p + c ]; }
+    std::vector< real > operator[]( std::size_t i ) const {
+      return std::vector< real >( m_v.begin()+static_cast<long>(i*m_p),
+                                  m_v.begin()+static_cast<long>((i+1)*m_p) ); }
+    std::size_t nunk() const { return m_n; }
+    std::size_t nprop() const { return m_p; }
+    void fill( real a ) { std::fill( m_v.begin(), m_v.end(), a ); }
+    std::vector< real >& vec() { return m_v; }
+    const std::vector< real >& vec() const { return m_v; }
+  private:
+    std::vector< real > m_v;
+    std::size_t m_n, m_p;
+};
+
+namespace port {
+
+using Fields = PFields;
+using Coords = std::array< std::vector< real >, 3 >;
+
+inline Cfg& cfg() { static Cfg c; return c; }
+inline void set_cfg( const Cfg& c ) { cfg() = c; }
+
+// ---- EOS (EOS.hpp:29-56) ----------------------------------------------------
+inline real eos_pressure( real re ) { auto g = cfg().gamma; return re * (g-1.0); }
+inline real eos_soundspeed( real r, real p ) { auto g = cfg().gamma; return std::sqrt( g * p / r ); }
+inline real eos_totalenergy( real r, real u, real v, real w, real p ) {
+  auto g = cfg().gamma; return p / (g-1.0) + 0.5 * r * (u*u + v*v + w*w); }
+
+// ---- problems (Problems.cpp) -------------------------------------------------
+using ICFn = std::function< std::vector< real >( real, real, real, real ) >;
+
+inline std::vector< real > ic_sedov( real x, real y, real z, real ) {      // :337-367
+  auto eps = std::numeric_limits< real >::epsilon();
+  real p;
+  if (std::abs(x) < eps && std::abs(y) < eps && std::abs(z) < eps) p = cfg().p0;
+  else p = 0.67e-4;
+  real r = 1.0, u = 0.0, v = 0.0, w = 0.0;
+  real rE = eos_totalenergy( r, u, v, w, p );
+  return { r, r*u, r*v, r*w, rE };
+}
+inline std::vector< real > ic_sod( real x, real, real, real ) {            // :373-404
+  real r, p;
+  if (x < 0.5) { r = 1.0; p = 1.0; } else { r = 0.125; p = 0.1; }
+  real u = 0.0, v = 0.0, w = 0.0;
+  real rE = eos_totalenergy( r, u, v, w, p );
+  return { r, r*u, r*v, r*w, rE };
+}
+inline std::vector< real > ic_taylor_green( real x, real y, real, real ) { // :410-431
+  real r = 1.0;
+  real p = 10.0 + r/4.0*(std::cos(2.0*M_PI*x) + std::cos(2.0*M_PI*y));
+  real u =  std::sin(M_PI*x) * std::cos(M_PI*y);
+  real v = -std::cos(M_PI*x) * std::sin(M_PI*y);
+  real w = 0.0;
+  auto rE = eos_totalenergy( r, u, v, w, p );
+  return { r, r*u, r*v, r*w, rE };
+}
+inline std::vector< real > src_taylor_green( real x, real y, real, real ) { // :433-452
+  std::vector< real > s( 5, 0.0 );
+  s[4] = 3.0*M_PI/8.0*( std::cos(3.0*M_PI*x)*std::cos(M_PI*y)
+                      - std::cos(3.0*M_PI*y)*std::cos(M_PI*x) );
+  return s;
+}
+
+inline ICFn IC() {                                                          // :1071-1108
+  const auto& p = cfg().problem;
+  if (p == "sedov") return ic_sedov;
+  if (p == "sod") return ic_sod;
+  if (p == "taylor_green") return ic_taylor_green;
+  throw std::runtime_error( "oracle port: problem type ic not hooked up: " + p );
+}
+inline ICFn SOL() {                                                         // :1114-1131
+  const auto& p = cfg().problem;
+  if (p == "userdef" || p == "sod" || p == "sedov" || p == "point_src") return {};
+  return IC();
+}
+inline ICFn SRC() {                                                         // :1299-1325
+  const auto& p = cfg().problem;
+  if (p == "taylor_green") return src_taylor_green;
+  return {};
+}
+
+inline void initialize( const Coords& coord, Fields& U, real t ) {          // :1134-1167
+  auto ic = IC();
+  for (std::size_t i=0; i<coord[0].size(); ++i) {
+    auto s = ic( coord[0][i], coord[1][i], coord[2][i], t );
+    for (std::size_t c=0; c<s.size(); ++c) U(i,c) = s[c];
+  }
+}
+
+// ---- BCs (BC.cpp) --------------------------------------------------------------
+inline void dirbc( Fields& U, real t, const Coords& coord,
+                   const std::vector< std::size_t >& dirbcmask )            // :29-72
+{
+  auto ncomp = U.nprop();
+  auto nmask = ncomp + 1;
+  if (dirbcmask.empty()) return;
+  auto ic = IC();
+  for (std::size_t i=0; i<dirbcmask.size()/nmask; ++i) {
+    auto p = dirbcmask[i*nmask+0];
+    auto u = ic( coord[0][p], coord[1][p], coord[2][p], t );
+    for (std::size_t c=0; c<ncomp; ++c) {
+      auto mask = dirbcmask[i*nmask+1+c];
+      if (mask == 1) U(p,c) = u[c];
+    }
+  }
+}
+
+inline void symbc( Fields& U, const std::vector< std::size_t >& nodes,
+                   const std::vector< real >& norms, std::size_t pos )       // :110-136
+{
+  for (std::size_t i=0; i<nodes.size(); ++i) {
+    auto p = nodes[i];
+    auto n = norms.data() + i*3;
+    auto& u = U(p,pos+0);
+    auto& v = U(p,pos+1);
+    auto& w = U(p,pos+2);
+    auto vn = u*n[0] + v*n[1] + w*n[2];
+    u -= vn * n[0];
+    v -= vn * n[1];
+    w -= vn * n[2];
+  }
+}
+
+inline void farbc( Fields& U, const std::vector< std::size_t >& nodes,
+                   const std::vector< real >& norms )                        // :152-220
+{
+  if (cfg().bc_far.empty()) return;
+  real fr = cfg().far_density;
+  real fu = cfg().far_velocity[0], fv = cfg().far_velocity[1], fw = cfg().far_velocity[2];
+  real fp = cfg().far_pressure;
+  for (std::size_t i=0; i<nodes.size(); ++i) {
+    auto p = nodes[i];
+    auto nx = norms[i*3+0], ny = norms[i*3+1], nz = norms[i*3+2];
+    auto& r = U(p,0); auto& ru = U(p,1); auto& rv = U(p,2); auto& rw = U(p,3); auto& re = U(p,4);
+    auto vn = fu*nx + fv*ny + fw*nz;
+    auto a = eos_soundspeed( fr, fp );
+    auto M = vn / a;
+    if (M <= -1.0) {
+      r = fr; ru = fr*fu; rv = fr*fv; rw = fr*fw;
+      re = eos_totalenergy( fr, fu, fv, fw, fp );
+    } else if (M > -1.0 && M < 0.0) {
+      auto pr = eos_pressure( re - 0.5*(ru*ru + rv*rv + rw*rw)/r );
+      r = fr; ru = fr*fu; rv = fr*fv; rw = fr*fw;
+      re = eos_totalenergy( fr, fu, fv, fw, pr );
+    } else if (M >= 0.0 && M < 1.0) {
+      re = eos_totalenergy( r, ru/r, rv/r, rw/r, fp );
+    }
+  }
+}
+
+inline void prebc( Fields& U, const std::vector< std::size_t >& nodes,
+                   const std::vector< real >& vals )                         // :222-241
+{
+  for (std::size_t i=0; i<nodes.size(); ++i) {
+    auto p = nodes[i];
+    U(p,0) = vals[i*2+0];
+    U(p,4) = eos_totalenergy( U(p,0), U(p,1)/U(p,0), U(p,2)/U(p,0),
+                              U(p,3)/U(p,0), vals[i*2+1] );
+  }
+}
+
+// ---- Riemann.cpp -----------------------------------------------------------------
+static const real muscl_eps = 1.0e-9;
+static const real muscl_const = 1.0/3.0;
+
+inline void primitive( std::size_t ncomp, std::size_t i, const Fields& U, real u[] ) // :211-227
+{
+  u[0] = U(i,0);
+  u[1] = U(i,1) / u[0];
+  u[2] = U(i,2) / u[0];
+  u[3] = U(i,3) / u[0];
+  u[4] = U(i,4) / u[0] - 0.5*(u[1]*u[1] + u[2]*u[2] + u[3]*u[3]);
+  for (std::size_t c=5; c<ncomp; ++c) u[c] = U(i,c);
+}
+
+//! van Leer-limited MUSCL reconstruction of component range [c0,c1)      // :34-143,:145-209
+inline void muscl_range( std::size_t p, std::size_t q, const Coords& coord, const Fields& G,
+                         std::size_t c0, std::size_t c1, real l[], real r[],
+                         real d1[], real d3[] )
+{
+  real vw[3] = { coord[0][q]-coord[0][p], coord[1][q]-coord[1][p], coord[2][q]-coord[2][p] };
+  for (std::size_t c=c0; c<c1; ++c) {
+    auto g1 = G(p,c*3+0)*vw[0] + G(p,c*3+1)*vw[1] + G(p,c*3+2)*vw[2];
+    auto g2 = G(q,c*3+0)*vw[0] + G(q,c*3+1)*vw[1] + G(q,c*3+2)*vw[2];
+    real delta2 = r[c] - l[c];
+    real delta1 = 2.0 * g1 - delta2;
+    real delta3 = 2.0 * g2 - delta2;
+    auto rcL = (delta2 + muscl_eps) / (delta1 + muscl_eps);
+    auto rcR = (delta2 + muscl_eps) / (delta3 + muscl_eps);
+    auto rLinv = (delta1 + muscl_eps) / (delta2 + muscl_eps);
+    auto rRinv = (delta3 + muscl_eps) / (delta2 + muscl_eps);
+    auto phiL = (std::abs(rcL) + rcL) / (std::abs(rcL) + 1.0);
+    auto phiR = (std::abs(rcR) + rcR) / (std::abs(rcR) + 1.0);
+    auto phi_L_inv = (std::abs(rLinv) + rLinv) / (std::abs(rLinv) + 1.0);
+    auto phi_R_inv = (std::abs(rRinv) + rRinv) / (std::abs(rRinv) + 1.0);
+    l[c] += 0.25*(delta1*(1.0-muscl_const)*phiL + delta2*(1.0+muscl_const)*phi_L_inv);
+    r[c] -= 0.25*(delta3*(1.0-muscl_const)*phiR + delta2*(1.0+muscl_const)*phi_R_inv);
+    d1[c] = delta1; d3[c] = delta3;
+  }
+}
+
+//! MUSCL for the five flow variables incl. first-order fallback            // :34-143
+inline void muscl_flow( std::size_t p, std::size_t q, const Coords& coord, const Fields& G,
+                        real l[], real r[] )
+{
+  real ls[5], rs[5], d1[5], d3[5];
+  std::memcpy( ls, l, sizeof ls );
+  std::memcpy( rs, r, sizeof rs );
+  muscl_range( p, q, coord, G, 0, 5, l, r, d1, d3 );
+  if (ls[0] < d1[0] || ls[4] < d1[4]) std::memcpy( l, ls, sizeof ls );
+  if (rs[0] < -d3[0] || rs[4] < -d3[4]) std::memcpy( r, rs, sizeof rs );
+}
+
+using FluxFn = void(*)( const Coords&, const Fields&, const real[], std::size_t, std::size_t,
+                        const real[], const real[], real[] );
+
+inline void rusanov( const Coords& coord, const Fields& G, const real dsupint[],
+                     std::size_t p, std::size_t q, const real L[], const real R[], real f[] ) // :369-478
+{
+  auto ncomp = G.nprop() / 3;
+  std::vector< real > lv( L, L+ncomp ), rv( R, R+ncomp );
+  real* l = lv.data(); real* r = rv.data();
+  muscl_flow( p, q, coord, G, l, r );
+  auto pL = eos_pressure( l[0]*l[4] );
+  auto pR = eos_pressure( r[0]*r[4] );
+  auto nx = dsupint[0], ny = dsupint[1], nz = dsupint[2];
+  auto vnL = l[1]*nx + l[2]*ny + l[3]*nz;       // symL = symR = 0 always (:707-753)
+  auto vnR = r[1]*nx + r[2]*ny + r[3]*nz;
+  l[4] = (l[4] + 0.5*(l[1]*l[1] + l[2]*l[2] + l[3]*l[3])) * l[0];
+  l[1] *= l[0]; l[2] *= l[0]; l[3] *= l[0];
+  r[4] = (r[4] + 0.5*(r[1]*r[1] + r[2]*r[2] + r[3]*r[3])) * r[0];
+  r[1] *= r[0]; r[2] *= r[0]; r[3] *= r[0];
+  auto len = std::sqrt( nx*nx + ny*ny + nz*nz );
+  auto sl = std::abs(vnL) + eos_soundspeed(l[0],pL)*len;
+  auto sr = std::abs(vnR) + eos_soundspeed(r[0],pR)*len;
+  auto fw = std::max( sl, sr );
+  f[0] = l[0]*vnL + r[0]*vnR + fw*(r[0] - l[0]);
+  f[1] = l[1]*vnL + r[1]*vnR + (pL + pR)*nx + fw*(r[1] - l[1]);
+  f[2] = l[2]*vnL + r[2]*vnR + (pL + pR)*ny + fw*(r[2] - l[2]);
+  f[3] = l[3]*vnL + r[3]*vnR + (pL + pR)*nz + fw*(r[3] - l[3]);
+  f[4] = (l[4] + pL)*vnL + (r[4] + pR)*vnR + fw*(r[4] - l[4]);
+  if (cfg().stab2) {
+    auto fws = cfg().stab2coef * fw;
+    f[0] -= fws*(l[0] - r[0]);
+    f[1] -= fws*(l[1] - r[1]);
+    f[2] -= fws*(l[2] - r[2]);
+    f[3] -= fws*(l[3] - r[3]);
+    f[4] -= fws*(l[4] - r[4]);
+  }
+  if (ncomp == 5) return;
+  std::vector< real > d1( ncomp ), d3( ncomp );
+  muscl_range( p, q, coord, G, 5, ncomp, l, r, d1.data(), d3.data() );
+  auto sw = std::max( std::abs(vnL), std::abs(vnR) );
+  for (std::size_t c=5; c<ncomp; ++c) f[c] = l[c]*vnL + r[c]*vnR + sw*(r[c] - l[c]);
+}
+
+inline void hllc( const Coords& coord, const Fields& G, const real dsupint[],
+                  std::size_t p, std::size_t q, const real L[], const real R[], real f[] )   // :480-650
+{
+  auto ncomp = G.nprop() / 3;
+  std::vector< real > lv( L, L+ncomp ), rv( R, R+ncomp );
+  real* l = lv.data(); real* r = rv.data();
+  muscl_flow( p, q, coord, G, l, r );
+  auto nx = -dsupint[0], ny = -dsupint[1], nz = -dsupint[2];
+  auto len = std::sqrt( nx*nx + ny*ny + nz*nz );
+  nx /= len; ny /= len; nz /= len;
+  auto qL = l[1]*nx + l[2]*ny + l[3]*nz;
+  auto qR = r[1]*nx + r[2]*ny + r[3]*nz;
+  auto pL = eos_pressure( l[0]*l[4] );
+  auto pR = eos_pressure( r[0]*r[4] );
+  l[4] = (l[4] + 0.5*(l[1]*l[1] + l[2]*l[2] + l[3]*l[3])) * l[0];
+  l[1] *= l[0]; l[2] *= l[0]; l[3] *= l[0];
+  r[4] = (r[4] + 0.5*(r[1]*r[1] + r[2]*r[2] + r[3]*r[3])) * r[0];
+  r[1] *= r[0]; r[2] *= r[0]; r[3] *= r[0];
+  auto cL = eos_soundspeed(l[0],pL);
+  auto cR = eos_soundspeed(r[0],pR);
+  auto sL = std::fmin( qL - cL, qR - cR );
+  auto sR = std::fmax( qL + cL, qR + cR );
+  auto tL = sL - qL;
+  auto tR = sR - qR;
+  auto sM = (r[0]*qR*tR - l[0]*qL*tL + pL - pR) / (r[0]*tR - l[0]*tL);
+  auto pS = pL - l[0]*tL*(qL - sM);
+  real uL[5], uR[5];
+  auto s = sL - sM;
+  uL[0] = tL*l[0]/s;
+  uL[1] = (tL*l[1] + (pS-pL)*nx)/s;
+  uL[2] = (tL*l[2] + (pS-pL)*ny)/s;
+  uL[3] = (tL*l[3] + (pS-pL)*nz)/s;
+  uL[4] = (tL*l[4] - pL*qL + pS*sM)/s;
+  s = sR - sM;
+  uR[0] = tR*r[0]/s;
+  uR[1] = (tR*r[1] + (pS-pR)*nx)/s;
+  uR[2] = (tR*r[2] + (pS-pR)*ny)/s;
+  uR[3] = (tR*r[3] + (pS-pR)*nz)/s;
+  uR[4] = (tR*r[4] - pR*qR + pS*sM)/s;
+  auto L2 = -2.0*len;
+  nx *= L2; ny *= L2; nz *= L2;
+  if (sL > 0.0) {
+    auto qL2 = qL * L2;
+    f[0] = l[0]*qL2;
+    f[1] = l[1]*qL2 + pL*nx;
+    f[2] = l[2]*qL2 + pL*ny;
+    f[3] = l[3]*qL2 + pL*nz;
+    f[4] = (l[4] + pL)*qL2;
+  } else if (sL <= 0.0 && sM > 0.0) {
+    auto qL2 = qL * L2;
+    auto sL2 = sL * L2;
+    f[0] = l[0]*qL2 + sL2*(uL[0] - l[0]);
+    f[1] = l[1]*qL2 + pL*nx + sL2*(uL[1] - l[1]);
+    f[2] = l[2]*qL2 + pL*ny + sL2*(uL[2] - l[2]);
+    f[3] = l[3]*qL2 + pL*nz + sL2*(uL[3] - l[3]);
+    f[4] = (l[4] + pL)*qL2 + sL2*(uL[4] - l[4]);
+  } else if (sM <= 0.0 && sR >= 0.0) {
+    auto qR2 = qR * L2;
+    auto sR2 = sR * L2;
+    f[0] = r[0]*qR2 + sR2*(uR[0] - r[0]);
+    f[1] = r[1]*qR2 + pR*nx + sR2*(uR[1] - r[1]);
+    f[2] = r[2]*qR2 + pR*ny + sR2*(uR[2] - r[2]);
+    f[3] = r[3]*qR2 + pR*nz + sR2*(uR[3] - r[3]);
+    f[4] = (r[4] + pR)*qR2 + sR2*(uR[4] - r[4]);
+  } else {
+    auto qR2 = qR * L2;
+    f[0] = r[0]*qR2;
+    f[1] = r[1]*qR2 + pR*nx;
+    f[2] = r[2]*qR2 + pR*ny;
+    f[3] = r[3]*qR2 + pR*nz;
+    f[4] = (r[4] + pR)*qR2;
+  }
+  if (cfg().stab2) {
+    auto sl = std::abs(qL) + cL;
+    auto sr = std::abs(qR) + cR;
+    auto fws = cfg().stab2coef * std::max(sl,sr) * len;
+    f[0] -= fws * (l[0] - r[0]);
+    f[1] -= fws * (l[1] - r[1]);
+    f[2] -= fws * (l[2] - r[2]);
+    f[3] -= fws * (l[3] - r[3]);
+    f[4] -= fws * (l[4] - r[4]);
+  }
+  if (ncomp == 5) return;
+  std::vector< real > d1( ncomp ), d3( ncomp );
+  muscl_range( p, q, coord, G, 5, ncomp, l, r, d1.data(), d3.data() );
+  auto sw = std::max( std::abs(qL), std::abs(qR) ) * len;
+  for (std::size_t c=5; c<ncomp; ++c) f[c] = (l[c]*qL + r[c]*qR)*len + sw*(r[c] - l[c]);
+}
+
+//! Nodal gradients of primitive variables, weak (un-normalised) form       // :229-367
+inline void grad( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                  const std::array< std::vector< real >, 3 >& dsupint,
+                  const Coords& coord,
+                  const std::vector< std::size_t >& triinpoel,
+                  const Fields& U, Fields& G )
+{
+  auto ncomp = U.nprop();
+  G.fill( 0.0 );
+  std::vector< real > ub( 4*ncomp );
+  real* u[4] = { ub.data(), ub.data()+ncomp, ub.data()+2*ncomp, ub.data()+3*ncomp };
+
+  for (std::size_t e=0; e<dsupedge[0].size()/4; ++e) {                      // tets :266-289
+    const auto N = dsupedge[0].data() + e*4;
+    for (int k=0; k<4; ++k) primitive( ncomp, N[k], U, u[k] );
+    const auto d = dsupint[0].data();
+    for (std::size_t c=0; c<ncomp; ++c)
+      for (std::size_t j=0; j<3; ++j) {
+        real f[6];
+        f[0] = d[(e*6+0)*3+j] * (u[1][c] + u[0][c]);
+        f[1] = d[(e*6+1)*3+j] * (u[2][c] + u[1][c]);
+        f[2] = d[(e*6+2)*3+j] * (u[0][c] + u[2][c]);
+        f[3] = d[(e*6+3)*3+j] * (u[3][c] + u[0][c]);
+        f[4] = d[(e*6+4)*3+j] * (u[3][c] + u[1][c]);
+        f[5] = d[(e*6+5)*3+j] * (u[3][c] + u[2][c]);
+        G(N[0],c*3+j) = G(N[0],c*3+j) - f[0] + f[2] - f[3];
+        G(N[1],c*3+j) = G(N[1],c*3+j) + f[0] - f[1] - f[4];
+        G(N[2],c*3+j) = G(N[2],c*3+j) + f[1] - f[2] - f[5];
+        G(N[3],c*3+j) = G(N[3],c*3+j) + f[3] + f[4] + f[5];
+      }
+  }
+  for (std::size_t e=0; e<dsupedge[1].size()/3; ++e) {                      // triangles :291-310
+    const auto N = dsupedge[1].data() + e*3;
+    for (int k=0; k<3; ++k) primitive( ncomp, N[k], U, u[k] );
+    const auto d = dsupint[1].data();
+    for (std::size_t c=0; c<ncomp; ++c)
+      for (std::size_t j=0; j<3; ++j) {
+        real f[3];
+        f[0] = d[(e*3+0)*3+j] * (u[1][c] + u[0][c]);
+        f[1] = d[(e*3+1)*3+j] * (u[2][c] + u[1][c]);
+        f[2] = d[(e*3+2)*3+j] * (u[0][c] + u[2][c]);
+        G(N[0],c*3+j) = G(N[0],c*3+j) - f[0] + f[2];
+        G(N[1],c*3+j) = G(N[1],c*3+j) + f[0] - f[1];
+        G(N[2],c*3+j) = G(N[2],c*3+j) + f[1] - f[2];
+      }
+  }
+  for (std::size_t e=0; e<dsupedge[2].size()/2; ++e) {                      // edges :312-326
+    const auto N = dsupedge[2].data() + e*2;
+    for (int k=0; k<2; ++k) primitive( ncomp, N[k], U, u[k] );
+    const auto d = dsupint[2].data() + e*3;
+    for (std::size_t c=0; c<ncomp; ++c)
+      for (std::size_t j=0; j<3; ++j) {
+        real f = d[j] * (u[1][c] + u[0][c]);
+        G(N[0],c*3+j) -= f;
+        G(N[1],c*3+j) += f;
+      }
+  }
+  const auto& x = coord[0]; const auto& y = coord[1]; const auto& z = coord[2];
+  for (std::size_t e=0; e<triinpoel.size()/3; ++e) {                        // boundary :334-360
+    const auto N = triinpoel.data() + e*3;
+    for (int k=0; k<3; ++k) primitive( ncomp, N[k], U, u[k] );
+    real ba[3] = { x[N[1]]-x[N[0]], y[N[1]]-y[N[0]], z[N[1]]-z[N[0]] },
+         ca[3] = { x[N[2]]-x[N[0]], y[N[2]]-y[N[0]], z[N[2]]-z[N[0]] };
+    real n[3] = { ba[1]*ca[2] - ca[1]*ba[2], ba[2]*ca[0] - ca[2]*ba[0], ba[0]*ca[1] - ca[0]*ba[1] };
+    n[0] /= 12.0; n[1] /= 12.0; n[2] /= 12.0;
+    for (std::size_t c=0; c<ncomp; ++c) {
+      auto uab = (u[0][c] + u[1][c])/4.0;
+      auto ubc = (u[1][c] + u[2][c])/4.0;
+      auto uca = (u[2][c] + u[0][c])/4.0;
+      real g[] = { uab + uca + u[0][c], uab + ubc + u[1][c], ubc + uca + u[2][c] };
+      for (std::size_t j=0; j<3; ++j) {      // g indexed by direction j: reference quirk :351-357
+        G(N[0],c*3+j) += g[j] * n[j];
+        G(N[1],c*3+j) += g[j] * n[j];
+        G(N[2],c*3+j) += g[j] * n[j];
+      }
+    }
+  }
+}
+
+inline void advdom( const Coords& coord,
+                    const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                    const std::array< std::vector< real >, 3 >& dsupint,
+                    const Fields& G, const Fields& U, Fields& R )             // :652-766
+{
+  auto ncomp = U.nprop();
+  FluxFn flux;
+  if (cfg().flux == "rusanov") flux = rusanov;
+  else if (cfg().flux == "hllc") flux = hllc;
+  else throw std::runtime_error( "oracle port: Flux not configured" );
+  std::vector< real > ub( 4*ncomp ), fb( 6*ncomp );
+  real* u[4] = { ub.data(), ub.data()+ncomp, ub.data()+2*ncomp, ub.data()+3*ncomp };
+  real* f[6]; for (int k=0; k<6; ++k) f[k] = fb.data() + static_cast<std::size_t>(k)*ncomp;
+
+  for (std::size_t e=0; e<dsupedge[0].size()/4; ++e) {
+    const auto N = dsupedge[0].data() + e*4;
+    for (int k=0; k<4; ++k) primitive( ncomp, N[k], U, u[k] );
+    const auto d = dsupint[0].data();
+    flux( coord, G, d+(e*6+0)*3, N[0], N[1], u[0], u[1], f[0] );
+    flux( coord, G, d+(e*6+1)*3, N[1], N[2], u[1], u[2], f[1] );
+    flux( coord, G, d+(e*6+2)*3, N[2], N[0], u[2], u[0], f[2] );
+    flux( coord, G, d+(e*6+3)*3, N[0], N[3], u[0], u[3], f[3] );
+    flux( coord, G, d+(e*6+4)*3, N[1], N[3], u[1], u[3], f[4] );
+    flux( coord, G, d+(e*6+5)*3, N[2], N[3], u[2], u[3], f[5] );
+    for (std::size_t c=0; c<ncomp; ++c) {
+      R(N[0],c) = R(N[0],c) - f[0][c] + f[2][c] - f[3][c];
+      R(N[1],c) = R(N[1],c) + f[0][c] - f[1][c] - f[4][c];
+      R(N[2],c) = R(N[2],c) + f[1][c] - f[2][c] - f[5][c];
+      R(N[3],c) = R(N[3],c) + f[3][c] + f[4][c] + f[5][c];
+    }
+  }
+  for (std::size_t e=0; e<dsupedge[1].size()/3; ++e) {
+    const auto N = dsupedge[1].data() + e*3;
+    for (int k=0; k<3; ++k) primitive( ncomp, N[k], U, u[k] );
+    const auto d = dsupint[1].data();
+    flux( coord, G, d+(e*3+0)*3, N[0], N[1], u[0], u[1], f[0] );
+    flux( coord, G, d+(e*3+1)*3, N[1], N[2], u[1], u[2], f[1] );
+    flux( coord, G, d+(e*3+2)*3, N[2], N[0], u[2], u[0], f[2] );
+    for (std::size_t c=0; c<ncomp; ++c) {
+      R(N[0],c) = R(N[0],c) - f[0][c] + f[2][c];
+      R(N[1],c) = R(N[1],c) + f[0][c] - f[1][c];
+      R(N[2],c) = R(N[2],c) + f[1][c] - f[2][c];
+    }
+  }
+  for (std::size_t e=0; e<dsupedge[2].size()/2; ++e) {
+    const auto N = dsupedge[2].data() + e*2;
+    for (int k=0; k<2; ++k) primitive( ncomp, N[k], U, u[k] );
+    const auto d = dsupint[2].data();
+    flux( coord, G, d+e*3, N[0], N[1], u[0], u[1], f[0] );
+    for (std::size_t c=0; c<ncomp; ++c) {
+      R(N[0],c) -= f[0][c];
+      R(N[1],c) += f[0][c];
+    }
+  }
+}
+
+inline void advbnd( const std::vector< std::size_t >& triinpoel, const Coords& coord,
+                    const std::vector< std::uint8_t >& besym, const Fields& U, Fields& R ) // :768-878
+{
+  auto ncomp = U.nprop();
+  const auto& x = coord[0]; const auto& y = coord[1]; const auto& z = coord[2];
+  std::vector< real > fb( ncomp*3 );
+  auto f = [&]( std::size_t c, std::size_t k ) -> real& { return fb[c*3+k]; };
+  for (std::size_t e=0; e<triinpoel.size()/3; ++e) {
+    const auto N = triinpoel.data() + e*3;
+    real ba[3] = { x[N[1]]-x[N[0]], y[N[1]]-y[N[0]], z[N[1]]-z[N[0]] },
+         ca[3] = { x[N[2]]-x[N[0]], y[N[2]]-y[N[0]], z[N[2]]-z[N[0]] };
+    real nx = ba[1]*ca[2] - ca[1]*ba[2], ny = ba[2]*ca[0] - ca[2]*ba[0], nz = ba[0]*ca[1] - ca[0]*ba[1];
+    nx /= 12.0; ny /= 12.0; nz /= 12.0;
+    const auto sym = besym.data() + e*3;
+    for (std::size_t k=0; k<3; ++k) {
+      auto r = U(N[k],0), ru = U(N[k],1), rv = U(N[k],2), rw = U(N[k],3), re = U(N[k],4);
+      real p = eos_pressure( re - 0.5*(ru*ru + rv*rv + rw*rw)/r );
+      real vn = sym[k] ? 0.0 : (nx*ru + ny*rv + nz*rw)/r;
+      f(0,k) = r*vn;
+      f(1,k) = ru*vn + p*nx;
+      f(2,k) = rv*vn + p*ny;
+      f(3,k) = rw*vn + p*nz;
+      f(4,k) = (re + p)*vn;
+      for (std::size_t c=5; c<ncomp; ++c) f(c,k) = U(N[k],c)*vn;
+    }
+    for (std::size_t c=0; c<ncomp; ++c) {
+      auto fab = (f(c,0) + f(c,1))/4.0;
+      auto fbc = (f(c,1) + f(c,2))/4.0;
+      auto fca = (f(c,2) + f(c,0))/4.0;
+      R(N[0],c) += fab + fca + f(c,0);
+      R(N[1],c) += fab + fbc + f(c,1);
+      R(N[2],c) += fbc + fca + f(c,2);
+    }
+  }
+}
+
+inline void src( const Coords& coord, const std::vector< real >& v, real t,
+                 const std::vector< real >& tp, Fields& R )                    // :880-907
+{
+  auto s_ = SRC();
+  if (!s_) return;
+  for (std::size_t p=0; p<R.nunk(); ++p) {
+    if (cfg().steady) t = tp[p];
+    auto s = s_( coord[0][p], coord[1][p], coord[2][p], t );
+    for (std::size_t c=0; c<s.size(); ++c) R(p,c) -= s[c] * v[p];
+  }
+}
+
+inline void rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                 const std::array< std::vector< real >, 3 >& dsupint,
+                 const Coords& coord,
+                 const std::vector< std::size_t >& triinpoel,
+                 const std::vector< std::uint8_t >& besym,
+                 const Fields& G, const Fields& U, const std::vector< real >& v,
+                 real t, const std::vector< real >& tp, Fields& R )            // :909-946
+{
+  R.fill( 0.0 );
+  advdom( coord, dsupedge, dsupint, G, U, R );
+  advbnd( triinpoel, coord, besym, U, R );
+  src( coord, v, t, tp, R );
+}
+
+// ---- Mesh/DerivedData.cpp ----------------------------------------------------------
+using LinkedList = std::pair< std::vector< std::size_t >, std::vector< std::size_t > >;
+
+inline LinkedList genEsup( const std::vector< std::size_t >& inpoel, std::size_t nnpe ) // :49-130
+{
+  auto npoin = *std::max_element( inpoel.begin(), inpoel.end() ) + 1;
+  std::vector< std::size_t > esup2( npoin+1, 0 );
+  for (auto n : inpoel) ++esup2[ n+1 ];
+  for (std::size_t i=1; i<npoin+1; ++i) esup2[i] += esup2[i-1];
+  std::vector< std::size_t > esup1( esup2[npoin]+1 );
+  std::size_t e = 0;
+  for (auto n : inpoel) { auto j = esup2[n]+1; esup2[n] = j; esup1[j] = e/nnpe; ++e; }
+  for (auto i=npoin; i>0; --i) esup2[i] = esup2[i-1];
+  esup2[0] = 0;
+  return { std::move(esup1), std::move(esup2) };
+}
+
+inline LinkedList genPsup( const std::vector< std::size_t >& inpoel, std::size_t nnpe,
+                           const LinkedList& esup )                            // :132-215
+{
+  auto npoin = *std::max_element( inpoel.begin(), inpoel.end() ) + 1;
+  const auto& esup1 = esup.first; const auto& esup2 = esup.second;
+  std::vector< std::size_t > psup2( npoin+1 ), psup1( 1, 0 );
+  std::vector< std::size_t > lpoin( npoin, 0 );
+  psup2[0] = 0;
+  std::size_t j = 0;
+  for (std::size_t p=0; p<npoin; ++p) {
+    for (std::size_t i=esup2[p]+1; i<=esup2[p+1]; ++i)
+      for (std::size_t n=0; n<nnpe; ++n) {
+        auto q = inpoel[ esup1[i]*nnpe + n ];
+        if (q != p && lpoin[q] != p+1) { ++j; psup1.push_back( q ); lpoin[q] = p+1; }
+      }
+    psup2[p+1] = j;
+  }
+  for (std::size_t p=0; p<npoin; ++p)          // neighbour ids ascending per point :216-220
+    std::sort( psup1.begin() + static_cast<std::ptrdiff_t>(psup2[p]+1),
+               psup1.begin() + static_cast<std::ptrdiff_t>(psup2[p+1]+1) );
+  return { std::move(psup1), std::move(psup2) };
+}
+
+} // port::
+} // orc::

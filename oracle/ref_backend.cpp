@@ -1,0 +1,48 @@
+// oracle/ref_backend.cpp -- TEST INFRASTRUCTURE ONLY; compiled only into
+// oracle/_ref/liboracle_ref.so together with the reference's own sources.
+// Defines the reference's global configuration object (normally filled by its
+// Lua parser, src/Control/InciterConfig.cpp) and fills the fields the hot path
+// reads from the oracle's plain Cfg struct.
+#include "backend.hpp"
+#include "EOS.hpp"
+
+namespace inciter { ctr::Config g_cfg; }
+
+namespace orc { namespace be {
+
+void set_cfg( const Cfg& c )
+{
+  auto& g = inciter::g_cfg;
+  g = inciter::ctr::Config();
+  g.get< tag::problem >() = c.problem;
+  g.get< tag::flux >() = c.flux;
+  g.get< tag::solver >() = "riecg";
+  g.get< tag::problem_ncomp >() = c.ncomp;
+  g.get< tag::mat_spec_heat_ratio >() = c.gamma;
+  g.get< tag::problem_p0 >() = c.p0;
+  g.get< tag::cfl >() = c.cfl;
+  g.get< tag::dt >() = c.dt;
+  g.get< tag::t0 >() = c.t0;
+  g.get< tag::term >() = c.term;
+  g.get< tag::nstep >() = c.nstep;
+  g.get< tag::stab2 >() = c.stab2;
+  g.get< tag::stab2coef >() = c.stab2coef;
+  g.get< tag::steady >() = c.steady;
+  g.get< tag::bc_sym >() = c.bc_sym;
+  g.get< tag::bc_dir >() = c.bc_dir;
+  g.get< tag::bc_far, tag::sidesets >() = c.bc_far;
+  g.get< tag::bc_far, tag::density >() = c.far_density;
+  g.get< tag::bc_far, tag::pressure >() = c.far_pressure;
+  g.get< tag::bc_far, tag::velocity >() =
+    std::vector< double >{ c.far_velocity[0], c.far_velocity[1], c.far_velocity[2] };
+  g.get< tag::bc_pre, tag::sidesets >() = c.bc_pre;
+  g.get< tag::bc_pre, tag::density >() = c.pre_density;
+  g.get< tag::bc_pre, tag::pressure >() = c.pre_pressure;
+  g.get< tag::diag_iter >() = c.diag_iter;
+  port::set_cfg( c );
+}
+
+real eos_pressure( real re ) { return eos::pressure( re ); }
+real eos_soundspeed( real r, real p ) { return eos::soundspeed( r, p ); }
+
+}} // orc::be::

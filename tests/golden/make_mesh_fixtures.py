@@ -1,0 +1,69 @@
+#!/usr/bin/env python3
+"""Generate the committed golden fixtures from the reference's regression tests.
+
+Run in the build container (needs /root/reference, scipy):
+    python tests/golden/make_mesh_fixtures.py
+
+For each regression case of the hot path it writes
+  tests/golden/<case>.mesh.npz : the ExodusII (classic NetCDF CDF-2) mesh flattened to
+       arrays -- coords, tet/tri connectivity (0-based, file order), element-block
+       order, side sets (file-internal element ids + side ids, 0-based)
+  tests/golden/<case>.diag.std : the reference's golden diagnostics file, verbatim
+       (tests/regression/inciter/RieCG/<Case>/diag.std)
+The .exo files cannot travel to the GPU box; these fixtures can.
+"""
+import os, shutil, sys
+import numpy as np
+from scipy.io import netcdf_file
+
+REF = "/root/reference/tests/regression/inciter"
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = {
+    "riecg_sod": ("RieCG/Sod/rectangle_01_1.5k.exo", "RieCG/Sod/diag.std"),
+    "riecg_sedov": ("RieCG/Sedov/sedov_coarse.exo", "RieCG/Sedov/diag.std"),
+    "riecg_taylor_green": ("RieCG/TaylorGreen/unitcube_1k.exo", "RieCG/TaylorGreen/diag.std"),
+}
+
+
+def flatten(exo):
+    f = netcdf_file(exo, "r", mmap=False)
+    v = f.variables
+    coord = np.stack([v["coordx"][:], v["coordy"][:], v["coordz"][:]]).astype(np.float64)
+    nblk = f.dimensions["num_el_blk"]
+    tets, tris, btype, bn = [], [], [], []
+    for b in range(1, nblk + 1):
+        c = v[f"connect{b}"]
+        et = c.elem_type.decode().upper()
+        conn = np.asarray(c[:], dtype=np.int64) - 1
+        if et.startswith("TET"):
+            tets.append(conn); btype.append(1)
+        elif et.startswith("TRI"):
+            tris.append(conn); btype.append(0)
+        else:
+            raise RuntimeError("unsupported element type " + et)
+        bn.append(conn.shape[0])
+    tets = np.concatenate(tets) if tets else np.zeros((0, 4), np.int64)
+    tris = np.concatenate(tris) if tris else np.zeros((0, 3), np.int64)
+    ids = np.asarray(v["ss_prop1"][:], dtype=np.int32)
+    off, elem, side = [0], [], []
+    for s in range(1, len(ids) + 1):
+        e = np.asarray(v[f"elem_ss{s}"][:], dtype=np.int64) - 1
+        sd = np.asarray(v[f"side_ss{s}"][:], dtype=np.int64) - 1
+        elem.append(e); side.append(sd); off.append(off[-1] + len(e))
+    return dict(coord=coord, tets=tets.astype(np.uint64), tris=tris.astype(np.uint64),
+                block_type=np.asarray(btype, np.int32), block_n=np.asarray(bn, np.uint64),
+                set_id=ids, set_off=np.asarray(off, np.uint64),
+                set_elem=np.concatenate(elem).astype(np.uint64),
+                set_side=np.concatenate(side).astype(np.uint64))
+
+
+def main():
+    for name, (exo, diag) in CASES.items():
+        m = flatten(os.path.join(REF, exo))
+        np.savez_compressed(os.path.join(HERE, name + ".mesh.npz"), **m)
+        shutil.copyfile(os.path.join(REF, diag), os.path.join(HERE, name + ".diag.std"))
+        print(name, m["coord"].shape[1], "nodes", len(m["tets"]), "tets", len(m["tris"]), "tris")
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,213 @@
+"""ctypes front end of the CPU oracle (oracle/): TEST INFRASTRUCTURE ONLY.
+
+Loads oracle/_build/liboracle.so (the self-contained restatement, "port") or
+oracle/_ref/liboracle_ref.so (the same serial driver running the reference's own
+unmodified Physics/Mesh objects, "reference"). Builds them on demand with
+oracle/Makefile; the "reference" flavour can only be (re)built where
+/root/reference exists, elsewhere the prebuilt file is used if present.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORC = os.path.join(ROOT, "oracle")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+class Cfg(C.Structure):
+    _fields_ = [
+        ("problem", C.c_char * 32), ("flux", C.c_char * 16),
+        ("ncomp", C.c_int32), ("stab2", C.c_int32), ("steady", C.c_int32),
+        ("nsym", C.c_int32), ("sym", C.c_int32 * 16),
+        ("ndir", C.c_int32), ("dir", (C.c_int32 * 12) * 16),
+        ("nfar", C.c_int32), ("far_sets", C.c_int32 * 16),
+        ("npre", C.c_int32), ("pre_sets", C.c_int32 * 16),
+        ("nfieldout", C.c_int32), ("fieldout_sets", C.c_int32 * 16),
+        ("nstep", C.c_uint64), ("diag_iter", C.c_uint64),
+        ("gamma", C.c_double), ("p0", C.c_double), ("cfl", C.c_double), ("dt", C.c_double),
+        ("t0", C.c_double), ("term", C.c_double), ("stab2coef", C.c_double),
+        ("far_density", C.c_double), ("far_pressure", C.c_double), ("far_velocity", C.c_double * 3),
+        ("pre_density", C.c_double * 16), ("pre_pressure", C.c_double * 16),
+    ]
+
+
+def make_cfg(problem, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0, term=1e300,
+             nstep=2**63, sym=(), dir_=(), stab2=False, stab2coef=0.2, diag_iter=1, ncomp=5,
+             fieldout=(), cls=Cfg):
+    """Control-file equivalent; defaults are the reference's (InciterConfig.cpp:1707-1757)."""
+    c = cls()
+    c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
+    c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term
+    c.nstep = nstep; c.stab2 = int(stab2); c.stab2coef = stab2coef; c.steady = 0
+    c.diag_iter = diag_iter
+    c.nsym = len(sym)
+    for i, s in enumerate(sym):
+        c.sym[i] = s
+    c.nfieldout = len(fieldout)
+    for i, s in enumerate(fieldout):
+        c.fieldout_sets[i] = s
+    c.ndir = len(dir_)
+    for i, m in enumerate(dir_):
+        for j, v in enumerate(m):
+            c.dir[i][j] = v
+    return c
+
+
+# The three RieCG regression cases pinned by golden diag.std files (control files:
+# tests/regression/inciter/RieCG/{Sod/sod.q,Sedov/sedov.q,TaylorGreen/taylor_green.q})
+CASES = {
+    "riecg_sod": dict(problem="sod", gamma=1.4, cfl=0.5, nstep=10, term=0.2, sym=(2, 4, 5, 6)),
+    "riecg_sedov": dict(problem="sedov", gamma=5.0 / 3.0, p0=4.86e3, cfl=0.5, nstep=10, term=1.0,
+                        sym=(1, 2, 3)),
+    "riecg_taylor_green": dict(problem="taylor_green", gamma=5.0 / 3.0, cfl=0.8, term=1.0,
+                               diag_iter=2, dir_=tuple((s, 1, 1, 1, 1, 1) for s in range(1, 7))),
+}
+
+
+def load_mesh(name):
+    m = np.load(os.path.join(GOLDEN, name + ".mesh.npz"))
+    return {k: m[k] for k in m.files}
+
+
+def load_golden_diag(name):
+    rows = []
+    with open(os.path.join(GOLDEN, name + ".diag.std")) as f:
+        for line in f:
+            if line.startswith("#") or not line.strip():
+                continue
+            rows.append([float(x) for x in line.split()])
+    return np.asarray(rows)
+
+
+def build(flavour):
+    target = {"port": "port", "reference": "ref"}[flavour]
+    so = os.path.join(ORC, "_build", "liboracle.so") if flavour == "port" else \
+        os.path.join(ORC, "_ref", "liboracle_ref.so")
+    if flavour == "reference" and not os.path.isdir("/root/reference/src"):
+        return so if os.path.exists(so) else None
+    subprocess.run(["make", "-s", "-C", ORC, target], check=True)
+    return so
+
+
+_libs = {}
+
+
+def lib(flavour="port"):
+    if flavour in _libs:
+        return _libs[flavour]
+    so = build(flavour)
+    if so is None or not os.path.exists(so):
+        _libs[flavour] = None
+        return None
+    L = C.CDLL(so)
+    L.orc_backend.restype = C.c_char_p
+    L.orc_last_error.restype = C.c_char_p
+    L.orc_create.restype = C.c_void_p
+    L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_step.argtypes = [C.c_void_p, C.c_int]
+    L.orc_ndiag.argtypes = [C.c_void_p]; L.orc_ndiag.restype = C.c_size_t
+    L.orc_diagrow.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    L.orc_diagrow.restype = C.c_size_t
+    L.orc_scalar.argtypes = [C.c_void_p, C.c_char_p]; L.orc_scalar.restype = C.c_double
+    L.orc_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_size_t]
+    L.orc_get.restype = C.c_size_t
+    L.orc_set_u.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_kernel.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_double, C.c_double]
+    L.orc_siphash_ids.argtypes = [C.c_void_p, C.c_int]; L.orc_siphash_ids.restype = C.c_uint64
+    _libs[flavour] = L
+    return L
+
+
+_DT = {"gid": np.uint64, "inpoel": np.uint64, "triinpoel": np.uint64, "besym": np.uint8,
+       "dsupedge0": np.uint64, "dsupedge1": np.uint64, "dsupedge2": np.uint64,
+       "dirbcmasks": np.uint64, "symbcnodes": np.uint64, "farbcnodes": np.uint64,
+       "prebcnodes": np.uint64, "bface": np.uint64, "commmap": np.uint64}
+
+
+class Oracle:
+    """One oracle run (mesh + configuration), `nchare` partitions stepped serially."""
+
+    def __init__(self, mesh, cfg, flavour="port", nchare=1, target=None):
+        self.L = lib(flavour)
+        if self.L is None:
+            raise RuntimeError("oracle flavour %s unavailable" % flavour)
+        self.cfg = cfg
+        co = np.ascontiguousarray(mesh["coord"], dtype=np.float64)
+        tets = np.ascontiguousarray(mesh["tets"], dtype=np.uint64)
+        tris = np.ascontiguousarray(mesh["tris"], dtype=np.uint64)
+        bt = np.ascontiguousarray(mesh["block_type"], dtype=np.int32)
+        bn = np.ascontiguousarray(mesh["block_n"], dtype=np.uint64)
+        sid = np.ascontiguousarray(mesh["set_id"], dtype=np.int32)
+        soff = np.ascontiguousarray(mesh["set_off"], dtype=np.uint64)
+        sel = np.ascontiguousarray(mesh["set_elem"], dtype=np.uint64)
+        ssd = np.ascontiguousarray(mesh["set_side"], dtype=np.uint64)
+        tg = None if target is None else np.ascontiguousarray(target, dtype=np.uint64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.L.orc_create.argtypes = [C.c_size_t] + [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p,
+                                      C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_void_p]
+        self.h = self.L.orc_create(co.shape[1], p(co[0]), p(co[1]), p(co[2]), len(tets), p(tets),
+                                   len(tris), p(tris) if len(tris) else None, len(bt), p(bt), p(bn),
+                                   len(sid), p(sid), p(soff), p(sel), p(ssd), C.byref(cfg), nchare,
+                                   None if tg is None else p(tg))
+        if not self.h:
+            raise RuntimeError("oracle: " + self.L.orc_last_error().decode())
+        self.nchare = nchare
+        self.ncomp = cfg.ncomp
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_destroy(self.h)
+            self.h = None
+
+    def step(self, n=1):
+        r = self.L.orc_step(self.h, n)
+        if r < 0:
+            raise RuntimeError("oracle: " + self.L.orc_last_error().decode())
+        return r
+
+    def scalar(self, name):
+        return self.L.orc_scalar(self.h, name.encode())
+
+    def diag(self):
+        rows = []
+        for i in range(self.L.orc_ndiag(self.h)):
+            n = self.L.orc_diagrow(self.h, i, None, 0)
+            a = np.zeros(n)
+            self.L.orc_diagrow(self.h, i, a.ctypes.data_as(C.c_void_p), n)
+            rows.append(a)
+        return np.asarray(rows)
+
+    def get(self, name, chare=0):
+        nb = self.L.orc_get(self.h, chare, name.encode(), None, 0)
+        if nb == C.c_size_t(-1).value:
+            raise KeyError(name)
+        dt = _DT.get(name, np.float64)
+        a = np.zeros(nb // np.dtype(dt).itemsize, dtype=dt)
+        if nb:
+            self.L.orc_get(self.h, chare, name.encode(), a.ctypes.data_as(C.c_void_p), nb)
+        if name in ("u", "un", "rhs"):
+            a = a.reshape(-1, self.ncomp)
+        elif name == "grad":
+            a = a.reshape(-1, 3 * self.ncomp)
+        return a
+
+    def set_u(self, u, chare=0):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        self.L.orc_set_u(self.h, chare, u.ctypes.data_as(C.c_void_p))
+
+    def kernel(self, what, stage=0, t=0.0, dt=0.0, chare=0):
+        if self.L.orc_kernel(self.h, chare, what.encode(), stage, t, dt) != 0:
+            raise RuntimeError("oracle: " + self.L.orc_last_error().decode())
+
+
+def numdiff_ok(res, gold, abs_tol, rel_tol):
+    """numdiff's 'any' constraint: pass if abs OR rel error is within tolerance
+    (tests/regression/inciter/RieCG/Sod/diag.ndiff.cfg)."""
+    res = np.asarray(res); gold = np.asarray(gold)
+    ae = np.abs(res - gold)
+    re = ae / np.maximum(np.minimum(np.abs(res), np.abs(gold)), 1e-300)
+    return (ae <= abs_tol) | (re <= rel_tol)

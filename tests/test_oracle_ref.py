@@ -1,0 +1,56 @@
+"""Pin the oracle restatement against the reference's OWN objects (no GPU).
+
+oracle/_ref/liboracle_ref.so is the same serial driver but running the reference's
+unmodified Physics/{Riemann,BC,Problems}.cpp and Mesh/{DerivedData,Reorder}.cpp
+compiled in place from /root/reference (oracle/Makefile target `ref`), and the
+reference's own SipHash-keyed containers. The self-contained restatement must be
+BIT-identical to it: connectivity, superedges, integrals, and every nodal value
+after the full regression run. Skipped where neither /root/reference nor a prebuilt
+oracle/_ref exists.
+"""
+import numpy as np
+import pytest
+import oraclelib as O
+
+ARRAYS = ["gid", "inpoel", "x", "y", "z", "vol", "v", "triinpoel", "besym", "bface",
+          "dsupedge0", "dsupedge1", "dsupedge2", "dsupint0", "dsupint1", "dsupint2",
+          "symbcnodes", "symbcnorms", "dirbcmasks", "u"]
+
+needs_ref = pytest.mark.skipif(O.lib("reference") is None, reason="oracle/_ref not available")
+
+
+@needs_ref
+@pytest.mark.parametrize("case", list(O.CASES))
+def test_port_is_bit_identical_to_reference_objects(case):
+    mesh = O.load_mesh(case)
+    gold = O.load_golden_diag(case)
+    a = O.Oracle(mesh, O.make_cfg(**O.CASES[case]), "port")
+    b = O.Oracle(mesh, O.make_cfg(**O.CASES[case]), "reference")
+    assert O.lib("reference").orc_backend() == b"reference"
+    for n in ARRAYS:
+        assert np.array_equal(a.get(n), b.get(n)), n
+    # one gradient + rhs evaluation, then the whole run
+    for o in (a, b):
+        o.kernel("grad")
+    assert np.array_equal(a.get("grad"), b.get("grad"))
+    for o in (a, b):
+        o.kernel("rhs", 0, 0.0)
+    assert np.array_equal(a.get("rhs"), b.get("rhs"))
+    n = int(gold[-1, 0])
+    a.step(n); b.step(n)
+    assert np.array_equal(a.diag(), b.diag())
+    assert np.array_equal(a.get("u"), b.get("u"))
+
+
+@needs_ref
+@pytest.mark.parametrize("flux", ["rusanov", "hllc"])
+@pytest.mark.parametrize("stab2", [False, True])
+def test_flux_variants_bit_identical(flux, stab2):
+    case = "riecg_sod"
+    mesh = O.load_mesh(case)
+    kw = dict(O.CASES[case], flux=flux, stab2=stab2)
+    a = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    b = O.Oracle(mesh, O.make_cfg(**kw), "reference")
+    a.step(5); b.step(5)
+    assert np.array_equal(a.get("u"), b.get("u"))
+    assert np.isfinite(a.get("u")).all()

@@ -1,0 +1,147 @@
+/* xyst_b200.h -- C ABI of the B200-native (sm_100a) RieCG hot path.
+ *
+ * The reference (jbakosi/xyst) has no plugin/FFI layer; its solver chares call
+ * free functions in namespaces with caller-owned std::vector / tk::Fields
+ * arguments and a hidden global configuration. This header is the
+ * replacement seam: an opaque per-GPU context owns device-resident connectivity
+ * and nodal state, and each entry point replaces one reference call site. Array
+ * arguments use the reference's own host layouts (tk::Fields = row-major
+ * [node][component] doubles, std::size_t ids) so a maintainer can bind them with
+ * .data() pointers; see INTEGRATION.md for the stubs.
+ *
+ * All functions return 0 on success and a non-zero code on failure;
+ * xyst_last_error() returns the message of the last failure on this thread (the
+ * reference throws tk::Exception instead, src/Base/Exception.hpp:40-52). There is
+ * no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef XYST_B200_H
+#define XYST_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xyst_ctx xyst_ctx;
+
+/* Replaces the reads of inciter::g_cfg made inside the kernels
+ * (src/Physics/Riemann.cpp:449,621,675; src/Physics/EOS.hpp:31,41,55). */
+typedef struct xyst_params {
+  int32_t ncomp;       /* scalar components per node; 5 = Euler system           */
+  int32_t flux;        /* 0 = "rusanov" (Riemann.cpp:369), 1 = "hllc" (:480)      */
+  int32_t stab2;       /* tag::stab2                                             */
+  int32_t exact_muscl; /* 1: van Leer limiter with the reference's 8 divisions per
+                          component (Riemann.cpp:92-99); 0: algebraically equal
+                          form with 2 reciprocals per component                   */
+  double gamma;        /* tag::mat_spec_heat_ratio                               */
+  double stab2coef;    /* tag::stab2coef                                         */
+} xyst_params;
+
+const char* xyst_last_error(void);
+int xyst_device_count(void);
+
+/* Context: one per GPU / mesh partition (one reference chare). */
+int xyst_ctx_create(int device, const xyst_params* params, xyst_ctx** out);
+/* Launch on a caller-owned stream (a cudaStream_t), e.g. torch's current stream. */
+int xyst_ctx_set_stream(xyst_ctx* ctx, void* cuda_stream);
+int xyst_ctx_destroy(xyst_ctx* ctx);
+int xyst_sync(xyst_ctx* ctx);
+
+/* Device-resident mesh data of one partition. Arguments are the members the
+ * reference's RieCG chare passes to riemann::grad/rhs (src/Inciter/RieCG.cpp:879,948):
+ *   coord            Discretization::Coord()            3 arrays of npoin
+ *   dsupedge[3]      RieCG::m_dsupedge  (RieCG.cpp:620-736): 4/3/2 node ids per tet/tri/edge
+ *   dsupint[3]       RieCG::m_dsupint : 6x3 / 3x3 / 3 doubles per superedge
+ *   triinpoel,besym  RieCG::m_triinpoel, m_besym (RieCG.cpp:534-538)
+ *   vol, v           Discretization::Vol() (with neighbour contributions), V() (without)
+ * nsup[k] is the number of superedges in group k. Superedges may come in any
+ * order; the library re-sorts edges for locality and builds its own node
+ * incidence structure (results do not depend on the grouping). */
+int xyst_mesh_upload(xyst_ctx* ctx, size_t npoin,
+                     const double* x, const double* y, const double* z,
+                     const size_t nsup[3], const size_t* const dsupedge[3],
+                     const double* const dsupint[3],
+                     size_t ntri, const size_t* triinpoel, const uint8_t* besym,
+                     const double* vol, const double* v);
+
+/* Boundary-condition node lists of RieCG::BC (RieCG.cpp:764-785 -> BC.cpp:29-241):
+ *   dirbcmasks  m_dirbcmasks: ndir x (1+ncomp) {node, mask_c...}; dirvals: ndir x ncomp
+ *               values of problems::IC() at the node (evaluated by the host, which
+ *               re-uploads them with xyst_dirbc_values() if the IC depends on time)
+ *   symbcnodes/norms  m_symbcnodes, m_symbcnorms (a node may repeat, applied in order)
+ *   farbcnodes/norms  m_farbcnodes, m_farbcnorms + far-field state
+ *   prebcnodes/vals   m_prebcnodes, m_prebcvals {density, pressure} */
+int xyst_bc_upload(xyst_ctx* ctx,
+                   size_t ndir, const size_t* dirbcmasks, const double* dirvals,
+                   size_t nsym, const size_t* symbcnodes, const double* symbcnorms,
+                   size_t nfar, const size_t* farbcnodes, const double* farbcnorms,
+                   double far_density, double far_pressure, const double far_velocity[3],
+                   size_t npre, const size_t* prebcnodes, const double* prebcvals);
+int xyst_dirbc_values(xyst_ctx* ctx, const double* dirvals);
+
+/* Source term of riemann::src (Riemann.cpp:880-907): S = problems::SRC()(x,y,z,t)
+ * per node, npoin x ncomp, NULL for none. R(p,c) -= S(p,c) * v[p]. */
+int xyst_src_upload(xyst_ctx* ctx, const double* S);
+
+/* Nodal unknowns, tk::Fields layout npoin x ncomp (RieCG::m_u). */
+int xyst_state_set(xyst_ctx* ctx, const double* U);
+int xyst_state_get(xyst_ctx* ctx, double* U);
+
+/* riemann::grad (Riemann.cpp:229-367) followed by the nodal normalisation of
+ * RieCG::rhs (RieCG.cpp:936-939): G = (weak gradient sums) / vol.
+ * xyst_grad_get returns G as npoin x 3*ncomp. */
+int xyst_riecg_grad(xyst_ctx* ctx);
+int xyst_grad_get(xyst_ctx* ctx, double* G);
+
+/* riemann::rhs (Riemann.cpp:909-946): advdom + advbnd + src using the gradients
+ * of the last xyst_riecg_grad. xyst_rhs_get returns R as npoin x ncomp. */
+int xyst_riecg_rhs(xyst_ctx* ctx);
+int xyst_rhs_get(xyst_ctx* ctx, double* R);
+
+/* RieCG::solve update (RieCG.cpp:1011-1021): stage 0 saves un=u; u = un - rk*dt*R/vol,
+ * with R from the last xyst_riecg_rhs. */
+int xyst_rk_update(xyst_ctx* ctx, int stage, double dt);
+
+/* RieCG::BC (RieCG.cpp:764-785). */
+int xyst_apply_bc(xyst_ctx* ctx);
+
+/* RieCG::dt (RieCG.cpp:827-839): cfl * min_p cbrt(vol_p)/max(|v|+c,1e-8), this partition. */
+int xyst_dt_min(xyst_ctx* ctx, double cfl, double* dt);
+
+/* One RK stage without materialising R: grad, edge fluxes, nodal gather fused with
+ * the update, BCs. Equivalent to grad+rhs+rk_update+apply_bc. */
+int xyst_riecg_stage(xyst_ctx* ctx, int stage, double dt);
+/* Three stages (rkcoef = 1/3, 1/2, 1; RieCG.cpp:41). */
+int xyst_riecg_step(xyst_ctx* ctx, double dt);
+
+/* NodeDiagnostics::rhocompute sums (NodeDiagnostics.cpp:85-118) over this
+ * partition: out[0..nc) = sum u^2 v, out[nc..2nc) = sum (u-un)^2 v, out[2nc] = sum u_4 v,
+ * and, if `an` (npoin x ncomp analytic PRIMITIVE solution) is given,
+ * out[2nc+1..3nc+1) = sum (prim-an)^2 v, out[3nc+1..4nc+1) = sum |prim-an| v.
+ * `out` must hold 4*ncomp+1 doubles. */
+int xyst_diag(xyst_ctx* ctx, const double* an, double* out);
+
+/* Shared-node ("chare-boundary") partial-sum exchange, replacing comgrad/comrhs
+ * (RieCG.cpp:881-916,955-990). neigh_rank[i] shares the nodes
+ * shared[neigh_off[i]..neigh_off[i+1]) (local ids, SAME ORDER on both sides, i.e.
+ * ordered by global id). xyst_comm_unique_id + xyst_comm_init create the NCCL
+ * communicator (id bytes are broadcast by the caller, e.g. torch.distributed). */
+int xyst_comm_unique_id(void* id128);
+int xyst_comm_init(xyst_ctx* ctx, int nranks, int rank, const void* id128);
+int xyst_halo_upload(xyst_ctx* ctx, int nneigh, const int* neigh_rank,
+                     const size_t* neigh_off, const size_t* shared);
+/* NCCL all-reduce helpers for dt (min) and diagnostics (sum) over the communicator. */
+int xyst_allreduce_min(xyst_ctx* ctx, double* v, int n);
+int xyst_allreduce_sum(xyst_ctx* ctx, double* v, int n);
+
+/* Counters: kernels launched by this context so far; edges held. */
+uint64_t xyst_launch_count(const xyst_ctx* ctx);
+uint64_t xyst_nedge(const xyst_ctx* ctx);
+/* CUDA-event time (ms) accumulated inside flux-kernel launches, and their count,
+ * since the last call with reset != 0 (bench.py's roofline figure). */
+int xyst_kernel_time(xyst_ctx* ctx, const char* kernel, int reset, double* ms, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

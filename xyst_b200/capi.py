@@ -1,0 +1,211 @@
+"""ctypes bindings of include/xyst_b200.h (the device-side C ABI)."""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libxyst_b200.so")
+
+
+class XystError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("ncomp", C.c_int32), ("flux", C.c_int32), ("stab2", C.c_int32),
+                ("exact_muscl", C.c_int32), ("gamma", C.c_double), ("stab2coef", C.c_double)]
+
+
+FLUX = {"rusanov": 0, "hllc": 1}
+_lib = None
+
+SYMBOLS = [
+    "xyst_last_error", "xyst_device_count", "xyst_ctx_create", "xyst_ctx_set_stream",
+    "xyst_ctx_destroy", "xyst_sync", "xyst_mesh_upload", "xyst_bc_upload", "xyst_dirbc_values",
+    "xyst_src_upload", "xyst_state_set", "xyst_state_get", "xyst_riecg_grad", "xyst_grad_get",
+    "xyst_riecg_rhs", "xyst_rhs_get", "xyst_rk_update", "xyst_apply_bc", "xyst_dt_min",
+    "xyst_riecg_stage", "xyst_riecg_step", "xyst_diag", "xyst_comm_unique_id", "xyst_comm_init",
+    "xyst_halo_upload", "xyst_allreduce_min", "xyst_allreduce_sum", "xyst_launch_count",
+    "xyst_nedge", "xyst_kernel_time",
+]
+
+
+def lib():
+    """Load libxyst_b200.so; raise if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise XystError("libxyst_b200.so is missing: run `python -m xyst_b200.build` "
+                        "(the CUDA path has no CPU fallback)")
+    L = C.CDLL(SO, mode=C.RTLD_GLOBAL)
+    L.xyst_last_error.restype = C.c_char_p
+    L.xyst_ctx_create.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]
+    L.xyst_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_ctx_destroy.argtypes = [C.c_void_p]
+    L.xyst_sync.argtypes = [C.c_void_p]
+    L.xyst_mesh_upload.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 3 + \
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.xyst_bc_upload.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                 C.c_size_t, C.c_void_p, C.c_void_p,
+                                 C.c_size_t, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                 C.c_size_t, C.c_void_p, C.c_void_p]
+    L.xyst_dirbc_values.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_src_upload.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_state_set.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_state_get.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_riecg_grad.argtypes = [C.c_void_p]
+    L.xyst_grad_get.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_riecg_rhs.argtypes = [C.c_void_p]
+    L.xyst_rhs_get.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_rk_update.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.xyst_apply_bc.argtypes = [C.c_void_p]
+    L.xyst_dt_min.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+    L.xyst_riecg_stage.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.xyst_riecg_step.argtypes = [C.c_void_p, C.c_double]
+    L.xyst_diag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.xyst_comm_unique_id.argtypes = [C.c_void_p]
+    L.xyst_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.xyst_halo_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.xyst_allreduce_min.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.xyst_allreduce_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.xyst_launch_count.argtypes = [C.c_void_p]; L.xyst_launch_count.restype = C.c_uint64
+    L.xyst_nedge.argtypes = [C.c_void_p]; L.xyst_nedge.restype = C.c_uint64
+    L.xyst_kernel_time.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_double),
+                                   C.POINTER(C.c_uint64)]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """One device context = one mesh partition on one GPU (thin wrapper, no logic)."""
+
+    def __init__(self, device=0, flux="rusanov", gamma=1.4, stab2=False, stab2coef=0.2,
+                 exact_muscl=False, ncomp=5):
+        self.L = lib()
+        self.ncomp = ncomp
+        prm = Params(ncomp, FLUX[flux], int(stab2), int(exact_muscl), gamma, stab2coef)
+        h = C.c_void_p()
+        self._ck(self.L.xyst_ctx_create(device, C.byref(prm), C.byref(h)))
+        self.h = h
+        self.npoin = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise XystError(self.L.xyst_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.xyst_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.xyst_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        self._ck(self.L.xyst_sync(self.h))
+
+    def mesh_upload(self, x, y, z, dsupedge, dsupint, triinpoel, besym, vol, v):
+        x, y, z, vol, v = map(_f64, (x, y, z, vol, v))
+        se = [_u64(a) for a in dsupedge]
+        si = [_f64(a) for a in dsupint]
+        nsup = (C.c_size_t * 3)(len(se[0]) // 4, len(se[1]) // 3, len(se[2]) // 2)
+        pe = (C.c_void_p * 3)(*[a.ctypes.data for a in se])
+        pi = (C.c_void_p * 3)(*[a.ctypes.data for a in si])
+        tri = _u64(triinpoel)
+        bs = np.ascontiguousarray(besym, dtype=np.uint8)
+        self.npoin = len(x)
+        self._keep = (x, y, z, vol, v, se, si, tri, bs)
+        self._ck(self.L.xyst_mesh_upload(self.h, len(x), _p(x), _p(y), _p(z), nsup, pe, pi,
+                                         len(tri) // 3, _p(tri), _p(bs), _p(vol), _p(v)))
+
+    def bc_upload(self, dirbcmasks=(), dirvals=None, symbcnodes=(), symbcnorms=(), farbcnodes=(),
+                  farbcnorms=(), far=(0.0, 0.0, (0.0, 0.0, 0.0)), prebcnodes=(), prebcvals=()):
+        dm = _u64(dirbcmasks); ndir = len(dm) // (self.ncomp + 1)
+        dv = _f64(dirvals) if dirvals is not None and ndir else None
+        sn = _u64(symbcnodes); snn = _f64(symbcnorms)
+        fn = _u64(farbcnodes); fnn = _f64(farbcnorms)
+        pn = _u64(prebcnodes); pv = _f64(prebcvals)
+        fu = (C.c_double * 3)(*far[2])
+        self._ck(self.L.xyst_bc_upload(self.h, ndir, _p(dm), _p(dv), len(sn), _p(sn), _p(snn),
+                                       len(fn), _p(fn), _p(fnn), far[0], far[1], fu,
+                                       len(pn), _p(pn), _p(pv)))
+
+    def src_upload(self, S):
+        S = None if S is None else _f64(S)
+        self._ck(self.L.xyst_src_upload(self.h, _p(S)))
+
+    def state_set(self, U):
+        U = _f64(U)
+        assert U.size == self.npoin * self.ncomp
+        self._ck(self.L.xyst_state_set(self.h, _p(U)))
+
+    def state_get(self):
+        U = np.empty((self.npoin, self.ncomp))
+        self._ck(self.L.xyst_state_get(self.h, _p(U)))
+        return U
+
+    def grad(self):
+        self._ck(self.L.xyst_riecg_grad(self.h))
+
+    def grad_get(self):
+        G = np.empty((self.npoin, 3 * self.ncomp))
+        self._ck(self.L.xyst_grad_get(self.h, _p(G)))
+        return G
+
+    def rhs(self):
+        self._ck(self.L.xyst_riecg_rhs(self.h))
+
+    def rhs_get(self):
+        R = np.empty((self.npoin, self.ncomp))
+        self._ck(self.L.xyst_rhs_get(self.h, _p(R)))
+        return R
+
+    def rk_update(self, stage, dt):
+        self._ck(self.L.xyst_rk_update(self.h, stage, dt))
+
+    def apply_bc(self):
+        self._ck(self.L.xyst_apply_bc(self.h))
+
+    def dt_min(self, cfl):
+        dt = C.c_double()
+        self._ck(self.L.xyst_dt_min(self.h, cfl, C.byref(dt)))
+        return dt.value
+
+    def stage(self, stage, dt):
+        self._ck(self.L.xyst_riecg_stage(self.h, stage, dt))
+
+    def step(self, dt):
+        self._ck(self.L.xyst_riecg_step(self.h, dt))
+
+    def diag(self, an=None):
+        out = np.zeros(4 * self.ncomp + 1)
+        an = None if an is None else _f64(an)
+        self._ck(self.L.xyst_diag(self.h, _p(an), _p(out)))
+        return out
+
+    def launch_count(self):
+        return int(self.L.xyst_launch_count(self.h))
+
+    def nedge(self):
+        return int(self.L.xyst_nedge(self.h))
+
+    def kernel_time(self, name, reset=False):
+        ms = C.c_double(); n = C.c_uint64()
+        self._ck(self.L.xyst_kernel_time(self.h, name.encode(), int(reset), C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)

@@ -130,6 +130,10 @@ int xyst_comm_unique_id(void* id128);
 int xyst_comm_init(xyst_ctx* ctx, int nranks, int rank, const void* id128);
 int xyst_halo_upload(xyst_ctx* ctx, int nneigh, const int* neigh_rank,
                      const size_t* neigh_off, const size_t* shared);
+/* Setup-time helper: sum w (<= 15) doubles per UNIQUE shared node (ascending local id)
+ * over all partitions sharing it, in place on a host array -- replaces comvol/comnorm
+ * (src/Inciter/Discretization.cpp:663-702, src/Inciter/RieCG.cpp:264-277,384-407). */
+int xyst_halo_sum(xyst_ctx* ctx, int w, double* vals);
 /* NCCL all-reduce helpers for dt (min) and diagnostics (sum) over the communicator. */
 int xyst_allreduce_min(xyst_ctx* ctx, double* v, int n);
 int xyst_allreduce_sum(xyst_ctx* ctx, double* v, int n);

@@ -1,0 +1,86 @@
+/* xyst_host.h -- C interface of the C++ host mirror (xyst_b200/host): the restated
+ * Discretization + RieCG solver classes of the reference (src/Inciter/RieCG.cpp,
+ * Discretization.cpp) driving the device C ABI of xyst_b200.h. Used by tests and
+ * bench.py through ctypes; a C++ application links the classes directly.
+ * Returns 0 on success; xyst_host_last_error() has the message otherwise. */
+#ifndef XYST_HOST_H
+#define XYST_HOST_H
+#include <stddef.h>
+#include <stdint.h>
+#include "xyst_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Control-file equivalent (the tags the RieCG path reads; src/Control/InciterConfig.hpp) */
+typedef struct xyst_host_cfg {
+  char problem[32];           /* "sod" | "sedov" | "taylor_green" | "userdef" */
+  char flux[16];              /* "rusanov" | "hllc" */
+  int32_t ncomp;
+  int32_t stab2;
+  int32_t exact_muscl;
+  int32_t nsym;  int32_t sym[16];
+  int32_t ndir;  int32_t dir[16][12];      /* { setid, mask_0 .. mask_{ncomp-1} } */
+  int32_t nfar;  int32_t far_sets[16];
+  int32_t npre;  int32_t pre_sets[16];
+  uint64_t nstep;
+  uint64_t diag_iter;
+  double gamma, p0, cfl, dt, t0, term, stab2coef;
+  double far_density, far_pressure, far_velocity[3];
+  double pre_density[16], pre_pressure[16];
+} xyst_host_cfg;
+
+typedef struct xyst_solver xyst_solver;
+/* Communication hooks for the setup/control path (default: NCCL through the device
+ * context): op 0 = sum over the partitions sharing each unique shared node (n = number of
+ * shared nodes, w values each), op 1 = all-reduce sum, op 2 = all-reduce min (n*w values) */
+typedef void (*xyst_comm_fn)( void* user, int op, int w, size_t n, double* vals );
+
+const char* xyst_host_last_error(void);
+
+/* Partition `part` of `nparts` (1,2,4,8; coordinate bisection) of the structured box
+ * [0,L]^3 of nx*ny*nz hexahedra split into 6 tets each; side sets 1..6 = x-,x+,y-,y+,z-,z+ */
+int xyst_solver_create_box(const xyst_host_cfg* cfg, size_t nx, size_t ny, size_t nz,
+                           double Lx, double Ly, double Lz, int nparts, int part,
+                           xyst_solver** out);
+/* Partition `part` of a general tet mesh given in full (global node ids): tetpart[e] is the
+ * partition of tet e (NULL: recursive coordinate bisection into nparts). Side set s has the
+ * boundary triangles set_tri[3*set_off[s] .. 3*set_off[s+1]). */
+int xyst_solver_create_mesh(const xyst_host_cfg* cfg, size_t npoin, const double* x,
+                            const double* y, const double* z, size_t ntet, const uint64_t* tets,
+                            int nsets, const int* set_id, const uint64_t* set_off,
+                            const uint64_t* set_tri, int nparts, int part, const int32_t* tetpart,
+                            xyst_solver** out);
+int xyst_solver_destroy(xyst_solver* s);
+
+int xyst_solver_prepare(xyst_solver* s);     /* host only: renumber, volumes, edge integrals, superedges */
+int xyst_solver_attach(xyst_solver* s, int device, int nranks, int rank, const void* ncclid128);
+int xyst_solver_set_comm(xyst_solver* s, xyst_comm_fn fn, void* user, int nranks, int rank);
+int xyst_solver_set_u0(xyst_solver* s, const double* u0);   /* user-defined IC, npoin x ncomp, local order */
+int xyst_solver_host_setup(xyst_solver* s);  /* exchanges (volumes, normals), BC lists, ICs: no device */
+int xyst_solver_setup(xyst_solver* s);       /* host_setup if needed + device upload + BCs */
+/* Advance up to nsteps time steps; diagnostics rows (ncols doubles each, layout of the
+ * reference's diag file: it t dt L2(U)x5 L2(dU)x5 mE [L2err x5 L1err x5]) are appended to
+ * rows (capacity cap doubles); *nrows, *ncols report what was written. */
+int xyst_solver_step(xyst_solver* s, int nsteps, double* rows, size_t cap, size_t* nrows, size_t* ncols);
+/* Unfused stepping through the reference-shaped members dt/advance/grad/rhs/solve. */
+int xyst_solver_step_unfused(xyst_solver* s, int nsteps);
+
+double xyst_solver_scalar(xyst_solver* s, const char* name); /* npoin ntet nedge t dt it meshvol finished nshared */
+/* copy out an array by name (same names as the oracle's): returns bytes needed */
+size_t xyst_solver_get(xyst_solver* s, const char* name, void* out, size_t cap_bytes);
+xyst_ctx* xyst_solver_ctx(xyst_solver* s);
+
+/* Stand-alone mesh helpers (tests): full box mesh and RCB */
+int xyst_box_counts(size_t nx, size_t ny, size_t nz, size_t* npoin, size_t* ntet, size_t* ntri);
+int xyst_box_mesh(size_t nx, size_t ny, size_t nz, double Lx, double Ly, double Lz,
+                  double* x, double* y, double* z, uint64_t* tets,
+                  int32_t set_id[6], uint64_t set_off[7], uint64_t* set_tri);
+int xyst_rcb(size_t npoin, const double* x, const double* y, const double* z, size_t ntet,
+             const uint64_t* tets, int nparts, int32_t* part);
+int xyst_box_part_range(size_t nx, size_t ny, size_t nz, int nparts, int part, uint64_t range[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,102 @@
+"""GPU tests of the full drop-in path: the C++ host mirror of the reference's RieCG solver
+class (setup pipeline + time loop) driving the CUDA kernels through the C ABI, compared
+with the oracle, with the reference's golden diagnostics, and -- at BASELINE.json's full
+size -- through size-independent properties."""
+import numpy as np
+import pytest
+import oraclelib as O
+from xyst_b200 import hostapi as H
+from host_common import fixture_to_host_mesh, host_mesh_to_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1.0e-12            # north_star: norms/diagnostics within 1e-12 relative, fp64
+
+
+def solver_for(case, **over):
+    kw = dict(O.CASES[case], **over)
+    hm = fixture_to_host_mesh(O.load_mesh(case))
+    s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"], hm["set_tri"])
+    s.prepare(); s.attach(0); s.setup()
+    return s, kw
+
+
+@pytest.mark.parametrize("case", list(O.CASES))
+def test_diag_rows_match_oracle_and_golden(case):
+    gold = O.load_golden_diag(case)
+    nsteps = int(gold[-1, 0])
+    s, kw = solver_for(case)
+    rows = s.step(nsteps)
+    o = O.Oracle(O.load_mesh(case), O.make_cfg(**kw), "port")
+    o.step(nsteps)
+    d = o.diag()
+    assert rows.shape == d.shape == gold.shape
+    assert np.array_equal(rows[:, 0], d[:, 0])
+    # t, dt, L2 norms of the conserved variables, total energy: the parity metric
+    for c in list(range(1, 8)) + [13]:
+        assert np.abs(rows[:, c] - d[:, c]).max() <= TOL * np.abs(d[:, c]).max(), c
+    # L2 norms of the increments (differences of nearly equal numbers): 1e-9
+    for c in range(8, 13):
+        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-9 * np.abs(d[:, c]).max(), c
+    if gold.shape[1] > 14:           # L2/L1 errors vs the analytic solution
+        for c in range(14, gold.shape[1]):
+            assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-10 * np.abs(d[:, c]).max(), c
+    # and the reference's own acceptance test against its golden file
+    assert O.numdiff_ok(rows[:, 1:8], gold[:, 1:8], 2.0e-4, 1.0e-5).all()
+    assert O.numdiff_ok(rows[:, 8:13], gold[:, 8:13], 3.0e-4, 1.0e-7).all()
+    assert (np.abs(rows - gold) / np.maximum(np.abs(gold), 1e-300)).max() < 1e-7
+
+
+@pytest.mark.parametrize("case", ["riecg_sod", "riecg_taylor_green"])
+def test_reference_shaped_members_equal_fused_step(case):
+    """dt/advance/grad/rhs/solve (materialised R, RieCG.cpp:871-1057) == fused stage kernels."""
+    a, _ = solver_for(case); b, _ = solver_for(case)
+    a.step(4, want_diag=False); b.step_unfused(4)
+    assert np.array_equal(a.get("u"), b.get("u"))
+    assert a.scalar("t") == b.scalar("t")
+
+
+def test_exact_and_fast_limiter_agree():
+    a, _ = solver_for("riecg_sedov", exact_muscl=True); b, _ = solver_for("riecg_sedov", exact_muscl=False)
+    ra = a.step(10); rb = b.step(10)
+    assert np.abs(ra[:, 3:8] - rb[:, 3:8]).max() <= TOL * np.abs(ra[:, 3:8]).max()
+
+
+def test_box_vs_oracle_small():
+    n = 8
+    kw = dict(O.CASES["riecg_sedov"], sym=(1, 3, 5), p0=4.13e-2 / ((1.2 / n) ** 3 / 4))
+    m = H.box_mesh(n, n, n, 1.2, 1.2, 1.2)
+    o = O.Oracle(host_mesh_to_oracle(m), O.make_cfg(**kw), "port")
+    s = H.Solver.box(H.make_cfg(**kw), n, n, n, 1.2, 1.2, 1.2)
+    s.prepare(); s.attach(0); s.setup()
+    rows = s.step(10); o.step(10); d = o.diag()
+    for c in list(range(1, 8)) + [13]:
+        assert np.abs(rows[:, c] - d[:, c]).max() <= TOL * np.abs(d[:, c]).max(), c
+    U, Uo = s.get("u"), o.get("u")
+    assert np.abs(U - Uo).max() <= 1e-11 * np.abs(Uo).max()
+
+
+def test_full_size_box_properties():
+    """BASELINE.json configs[1]: 20.25M-tet box (n=150). Properties that need no oracle:
+    conservation of total energy and mass with closed (symmetry) boundaries, the axis
+    symmetry of the problem on the Kuhn mesh, finiteness, run-to-run bit-reproducibility."""
+    import bench
+    n = 150; h = 1.2 / n
+    cfg = bench.sedov_cfg(H.make_cfg, h)
+    cfg.diag_iter = 1
+    res = []
+    for rep in range(2):
+        s = H.Solver.box(cfg, n, n, n, 1.2, 1.2, 1.2)
+        s.prepare(); s.attach(0); s.setup()
+        assert s.scalar("nedge") == 23827950 and s.scalar("npoin") == 3442951
+        rows = s.step(5 if rep == 0 else 2)
+        res.append(rows)
+        if rep == 0:
+            assert np.isfinite(rows).all()
+            mE = rows[:, 13]
+            assert np.abs(mE - mE[0]).max() <= 1e-12 * abs(mE[0])          # energy conserved
+            # x/y/z momentum norms equal: the mesh and the problem are invariant under
+            # permutations of the axes
+            assert np.abs(rows[:, 4] - rows[:, 5]).max() <= 1e-9 * rows[:, 4].max()
+            assert np.abs(rows[:, 4] - rows[:, 6]).max() <= 1e-9 * rows[:, 4].max()
+            assert (rows[:, 2] > 0).all()
+    assert np.array_equal(res[0][:2], res[1][:2])                          # deterministic

@@ -25,7 +25,7 @@ SYMBOLS = [
     "xyst_src_upload", "xyst_state_set", "xyst_state_get", "xyst_riecg_grad", "xyst_grad_get",
     "xyst_riecg_rhs", "xyst_rhs_get", "xyst_rk_update", "xyst_apply_bc", "xyst_dt_min",
     "xyst_riecg_stage", "xyst_riecg_step", "xyst_diag", "xyst_comm_unique_id", "xyst_comm_init",
-    "xyst_halo_upload", "xyst_allreduce_min", "xyst_allreduce_sum", "xyst_launch_count",
+    "xyst_halo_upload", "xyst_halo_sum", "xyst_allreduce_min", "xyst_allreduce_sum", "xyst_launch_count",
     "xyst_nedge", "xyst_kernel_time",
 ]
 
@@ -67,6 +67,7 @@ def lib():
     L.xyst_comm_unique_id.argtypes = [C.c_void_p]
     L.xyst_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.xyst_halo_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.xyst_halo_sum.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.xyst_allreduce_min.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.xyst_allreduce_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.xyst_launch_count.argtypes = [C.c_void_p]; L.xyst_launch_count.restype = C.c_uint64

@@ -1392,12 +1392,13 @@ int xyst_halo_upload( xyst_ctx* c, int nneigh, const int* neigh_rank, const size
 {
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
-  need_mesh( c );
   c->neigh.assign( neigh_rank, neigh_rank + nneigh );
   c->neigh_off.assign( neigh_off, neigh_off + nneigh + 1 );
   size_t nsend = nneigh ? neigh_off[nneigh] : 0;
   std::vector< int > uniq;
-  for (size_t i=0; i<nsend; ++i) { if (shared[i] >= c->npoin) throw std::runtime_error( "shared node id out of range" ); uniq.push_back( (int)shared[i] ); }
+  for (size_t i=0; i<nsend; ++i) {   // may be called before the mesh upload (volume exchange)
+    if (c->npoin && shared[i] >= c->npoin) throw std::runtime_error( "shared node id out of range" );
+    uniq.push_back( (int)shared[i] ); }
   std::sort( uniq.begin(), uniq.end() );
   uniq.erase( std::unique( uniq.begin(), uniq.end() ), uniq.end() );
   std::vector< int > send( nsend ), roff( uniq.size()+1, 0 ), ridx( nsend );
@@ -1412,6 +1413,34 @@ int xyst_halo_upload( xyst_ctx* c, int nneigh, const int* neigh_rank, const size
   c->nsh = uniq.size(); c->nsend = nsend;
   c->sh_node.upload( uniq, s ); c->sh_send.upload( send, s ); c->sh_roff.upload( roff, s ); c->sh_ridx.upload( ridx, s );
   c->sh_part.alloc( uniq.size()*15 ); c->sh_sendbuf.alloc( nsend*15 ); c->sh_recvbuf.alloc( nsend*15 );
+  API_END
+}
+
+__global__ void k_halo_add( int nsh, int w, const int* __restrict__ roff, const int* __restrict__ ridx,
+                            const double* __restrict__ recvbuf, double* __restrict__ part )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  for (int j=0; j<w; ++j) {
+    double a = part[(size_t)i*w+j];
+    for (int r=roff[i]; r<roff[i+1]; ++r) a += recvbuf[(size_t)ridx[r]*w+j];
+    part[(size_t)i*w+j] = a;
+  }
+}
+
+int xyst_halo_sum( xyst_ctx* c, int w, double* vals )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  if (!c->nsh || !c->comm) return 0;
+  if (w < 1 || w > 15) throw std::runtime_error( "halo_sum: width must be 1..15" );
+  CK( cudaMemcpyAsync( c->sh_part.p, vals, c->nsh*(size_t)w*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+  exchange( c, w );
+  exchange_wait( c );
+  k_halo_add<<< nblk( c->nsh, 128 ), 128, 0, c->stream >>>( (int)c->nsh, w, c->sh_roff.p, c->sh_ridx.p,
+    c->sh_recvbuf.p, c->sh_part.p ); ++c->launches;
+  CK( cudaMemcpyAsync( vals, c->sh_part.p, c->nsh*(size_t)w*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+  CK( cudaStreamSynchronize( c->stream ) );
   API_END
 }
 

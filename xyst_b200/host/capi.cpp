@@ -1,0 +1,293 @@
+// xyst_b200/host/capi.cpp -- C entry points of include/xyst_host.h
+#include <cstring>
+#include <memory>
+#include <string>
+#include <algorithm>
+#include <stdexcept>
+#include <cmath>
+#include "riecg.hpp"
+#include "xyst_host.h"
+
+using namespace xyst;
+
+struct xyst_solver {
+  Config cfg;
+  TetMesh chunk;
+  std::unique_ptr< Discretization > disc;
+  std::unique_ptr< RieCG > riecg;
+};
+
+namespace {
+thread_local std::string g_err;
+int fail( const std::string& m ) { g_err = m; return 1; }
+#define API_BEGIN try {
+#define API_END } catch (std::exception& e) { return fail( e.what() ); } return 0;
+
+Config to_cfg( const xyst_host_cfg* c ) {
+  Config k;
+  k.problem = c->problem; k.flux = c->flux; k.ncomp = static_cast< std::size_t >( c->ncomp );
+  k.gamma = c->gamma; k.p0 = c->p0; k.cfl = c->cfl; k.dt = c->dt; k.t0 = c->t0; k.term = c->term;
+  k.nstep = c->nstep; k.diag_iter = c->diag_iter ? c->diag_iter : 1;
+  k.stab2 = c->stab2 != 0; k.stab2coef = c->stab2coef; k.exact_muscl = c->exact_muscl != 0;
+  for (int i=0; i<c->nsym; ++i) k.bc_sym.push_back( c->sym[i] );
+  for (int i=0; i<c->ndir; ++i) {
+    std::vector< int > m( k.ncomp+1 );
+    for (std::size_t j=0; j<k.ncomp+1; ++j) m[j] = c->dir[i][j];
+    k.bc_dir.push_back( m );
+  }
+  for (int i=0; i<c->nfar; ++i) k.bc_far.push_back( c->far_sets[i] );
+  k.far_density = c->far_density; k.far_pressure = c->far_pressure;
+  k.far_velocity = {{ c->far_velocity[0], c->far_velocity[1], c->far_velocity[2] }};
+  for (int i=0; i<c->npre; ++i) {
+    k.bc_pre.push_back( c->pre_sets[i] );
+    k.pre_density.push_back( c->pre_density[i] ); k.pre_pressure.push_back( c->pre_pressure[i] );
+  }
+  return k;
+}
+
+template< class T >
+std::size_t put( const std::vector< T >& v, void* out, std::size_t cap ) {
+  auto bytes = v.size()*sizeof(T);
+  if (out && cap >= bytes && bytes) std::memcpy( out, v.data(), bytes );
+  return bytes;
+}
+
+void finish( xyst_solver* s ) {
+  s->disc.reset( new Discretization( s->chunk, s->cfg ) );
+  s->riecg.reset( new RieCG( *s->disc, s->chunk, s->cfg ) );
+}
+}
+
+extern "C" {
+
+const char* xyst_host_last_error(void) { return g_err.c_str(); }
+
+int xyst_solver_create_box( const xyst_host_cfg* cfg, size_t nx, size_t ny, size_t nz,
+                            double Lx, double Ly, double Lz, int nparts, int part, xyst_solver** out )
+{
+  API_BEGIN
+  auto s = std::make_unique< xyst_solver >();
+  s->cfg = to_cfg( cfg );
+  auto r = boxPartRange( nx, ny, nz, nparts, part );
+  s->chunk = boxMesh( nx, ny, nz, Lx, Ly, Lz, r[0], r[1], r[2], r[3], r[4], r[5] );
+  finish( s.get() );
+  // shared nodes with every other partition: intersection of the node boxes, ascending gid
+  const std::size_t px = nx+1, py = ny+1;
+  for (int q=0; q<nparts; ++q) {
+    if (q == part) continue;
+    auto o = boxPartRange( nx, ny, nz, nparts, q );
+    std::size_t lo[3], hi[3]; bool empty = false;
+    for (int d=0; d<3; ++d) { lo[d] = std::max( r[2*d], o[2*d] ); hi[d] = std::min( r[2*d+1], o[2*d+1] ); if (lo[d] > hi[d]) empty = true; }
+    if (empty) continue;
+    auto& g = s->disc->NodeCommMap()[q];
+    for (std::size_t k=lo[2]; k<=hi[2]; ++k) for (std::size_t j=lo[1]; j<=hi[1]; ++j) for (std::size_t i=lo[0]; i<=hi[0]; ++i)
+      g.push_back( (k*py + j)*px + i );
+  }
+  *out = s.release();
+  API_END
+}
+
+int xyst_solver_create_mesh( const xyst_host_cfg* cfg, size_t npoin, const double* x, const double* y,
+                             const double* z, size_t ntet, const uint64_t* tets, int nsets,
+                             const int* set_id, const uint64_t* set_off, const uint64_t* set_tri,
+                             int nparts, int part, const int32_t* tetpart, xyst_solver** out )
+{
+  API_BEGIN
+  auto s = std::make_unique< xyst_solver >();
+  s->cfg = to_cfg( cfg );
+  Coords co;
+  co[0].assign( x, x+npoin ); co[1].assign( y, y+npoin ); co[2].assign( z, z+npoin );
+  std::vector< std::size_t > g( tets, tets+ntet*4 );
+  std::vector< int > tp;
+  if (nparts > 1) { if (tetpart) tp.assign( tetpart, tetpart+ntet ); else tp = rcb( co, g, nparts ); }
+  else tp.assign( ntet, 0 );
+  // node -> partitions touching it (bit mask, nparts <= 64)
+  if (nparts > 64) throw std::runtime_error( "at most 64 partitions" );
+  std::vector< std::uint64_t > nodeparts( npoin, 0 );
+  for (std::size_t e=0; e<ntet; ++e) for (int k=0; k<4; ++k) nodeparts[ g[e*4+static_cast<std::size_t>(k)] ] |= 1ULL << tp[e];
+  auto& ch = s->chunk;
+  ch.coord = co;                       // indexed by global id (gid left empty)
+  for (std::size_t e=0; e<ntet; ++e) if (tp[e] == part) for (int k=0; k<4; ++k) ch.ginpoel.push_back( g[e*4+static_cast<std::size_t>(k)] );
+  const std::uint64_t me = 1ULL << part;
+  for (int i=0; i<nsets; ++i) {
+    auto& t = ch.sidetri[ set_id[i] ];
+    for (auto f=set_off[i]; f<set_off[i+1]; ++f) {
+      bool mine = true;
+      for (int k=0; k<3; ++k) if (!(nodeparts[ set_tri[f*3+static_cast<std::uint64_t>(k)] ] & me)) mine = false;
+      if (mine) for (int k=0; k<3; ++k) t.push_back( set_tri[f*3+static_cast<std::uint64_t>(k)] );
+    }
+  }
+  finish( s.get() );
+  for (std::size_t p=0; p<npoin; ++p) {
+    auto m = nodeparts[p];
+    if (!(m & me) || m == me) continue;
+    for (int q=0; q<nparts; ++q) if (q != part && (m & (1ULL << q))) s->disc->NodeCommMap()[q].push_back( p );
+  }
+  *out = s.release();
+  API_END
+}
+
+int xyst_solver_destroy( xyst_solver* s ) { delete s; return 0; }
+
+int xyst_solver_prepare( xyst_solver* s ) { API_BEGIN s->riecg->prepare(); API_END }
+
+int xyst_solver_attach( xyst_solver* s, int device, int nranks, int rank, const void* id )
+{ API_BEGIN s->riecg->attach( device, nranks, rank, id ); API_END }
+
+int xyst_solver_set_comm( xyst_solver* s, xyst_comm_fn fn, void* user, int nranks, int rank )
+{
+  API_BEGIN
+  s->riecg->setRanks( nranks, rank );
+  s->riecg->setComm(
+    [fn,user]( int w, std::vector< real >& v ){ fn( user, 0, w, v.size()/static_cast<std::size_t>(w), v.data() ); },
+    [fn,user]( int op, std::vector< real >& v ){ fn( user, op == 0 ? 1 : 2, 1, v.size(), v.data() ); } );
+  API_END
+}
+
+int xyst_solver_host_setup( xyst_solver* s ) { API_BEGIN s->riecg->hostSetup(); API_END }
+
+int xyst_solver_set_u0( xyst_solver* s, const double* u0 )
+{ API_BEGIN s->riecg->m_u0.assign( u0, u0 + s->disc->Gid().size()*s->cfg.ncomp ); API_END }
+
+int xyst_solver_setup( xyst_solver* s ) { API_BEGIN s->riecg->setup(); API_END }
+
+int xyst_solver_step( xyst_solver* s, int nsteps, double* rows, size_t cap, size_t* nrows, size_t* ncols )
+{
+  API_BEGIN
+  size_t nr = 0, nc = 0, used = 0;
+  std::vector< real > row;
+  for (int i=0; i<nsteps; ++i) {
+    if (s->riecg->m_finished) break;
+    s->riecg->step( rows ? &row : nullptr );
+    if (rows && !row.empty()) {
+      nc = row.size();
+      if (used + nc <= cap) { std::memcpy( rows+used, row.data(), nc*sizeof(double) ); used += nc; ++nr; }
+    }
+  }
+  if (nrows) *nrows = nr;
+  if (ncols) *ncols = nc;
+  API_END
+}
+
+int xyst_solver_step_unfused( xyst_solver* s, int nsteps )
+{
+  API_BEGIN
+  auto& r = *s->riecg;
+  for (int i=0; i<nsteps; ++i) {
+    if (r.m_finished) break;
+    r.advance( r.dt() );
+    for (int st=0; st<3; ++st) { r.grad(); r.rhs(); r.solve(); }
+    r.Disc().next();
+    if (r.Disc().finished()) r.m_finished = true;
+  }
+  API_END
+}
+
+double xyst_solver_scalar( xyst_solver* s, const char* name )
+{
+  std::string n( name );
+  auto& d = *s->disc;
+  if (n == "npoin") return static_cast< double >( d.Gid().size() );
+  if (n == "ntet") return static_cast< double >( d.Inpoel().size()/4 );
+  if (n == "nedge") return static_cast< double >( s->riecg->m_dsupedge[0].size()/4*6 + s->riecg->m_dsupedge[1].size() + s->riecg->m_dsupedge[2].size()/2 );
+  if (n == "ntri") return static_cast< double >( s->riecg->m_triinpoel.size()/3 );
+  if (n == "t") return d.T();
+  if (n == "dt") return d.Dt();
+  if (n == "it") return static_cast< double >( d.It() );
+  if (n == "meshvol") return d.MeshVol();
+  if (n == "finished") return s->riecg->m_finished ? 1.0 : 0.0;
+  if (n == "nshared") return static_cast< double >( d.sharedNodes().size() );
+  if (n.rfind( "timing", 0 ) == 0) { auto i = static_cast< std::size_t >( std::stoi( n.substr(6) ) ); return i < s->riecg->timings.size() ? s->riecg->timings[i] : -1.0; }
+  return std::nan( "" );
+}
+
+size_t xyst_solver_get( xyst_solver* s, const char* name, void* out, size_t cap )
+{
+  try {
+    std::string n( name );
+    auto& d = *s->disc; auto& r = *s->riecg;
+    if (n == "gid") return put( d.Gid(), out, cap );
+    if (n == "inpoel") return put( d.Inpoel(), out, cap );
+    if (n == "x") return put( d.Coord()[0], out, cap );
+    if (n == "y") return put( d.Coord()[1], out, cap );
+    if (n == "z") return put( d.Coord()[2], out, cap );
+    if (n == "vol") return put( d.Vol(), out, cap );
+    if (n == "v") return put( d.V(), out, cap );
+    if (n == "triinpoel") return put( r.m_triinpoel, out, cap );
+    if (n == "besym") return put( r.m_besym, out, cap );
+    if (n == "dsupedge0") return put( r.m_dsupedge[0], out, cap );
+    if (n == "dsupedge1") return put( r.m_dsupedge[1], out, cap );
+    if (n == "dsupedge2") return put( r.m_dsupedge[2], out, cap );
+    if (n == "dsupint0") return put( r.m_dsupint[0], out, cap );
+    if (n == "dsupint1") return put( r.m_dsupint[1], out, cap );
+    if (n == "dsupint2") return put( r.m_dsupint[2], out, cap );
+    if (n == "dirbcmasks") return put( r.m_dirbcmasks, out, cap );
+    if (n == "symbcnodes") return put( r.m_symbcnodes, out, cap );
+    if (n == "symbcnorms") return put( r.m_symbcnorms, out, cap );
+    if (n == "u0") return put( r.m_u0, out, cap );
+    if (n == "u") return put( r.solution(), out, cap );
+    if (n == "shared") return put( d.sharedNodes(), out, cap );
+    if (n == "bface") {
+      std::vector< std::uint64_t > f;
+      for (const auto& [st,ids] : r.m_bface) { f.push_back( static_cast<std::uint64_t>(st) ); f.push_back( ids.size() ); for (auto i : ids) f.push_back( i ); }
+      return put( f, out, cap );
+    }
+    if (n == "commmap") {
+      std::vector< std::uint64_t > f;
+      for (const auto& [b,g] : d.NodeCommMap()) { f.push_back( static_cast<std::uint64_t>(b) ); f.push_back( g.size() ); for (auto i : g) f.push_back( i ); }
+      return put( f, out, cap );
+    }
+    g_err = "xyst_solver_get: unknown array " + n;
+  } catch (std::exception& e) { g_err = e.what(); }
+  return static_cast< size_t >( -1 );
+}
+
+xyst_ctx* xyst_solver_ctx( xyst_solver* s ) { return s->riecg->ctx(); }
+
+int xyst_box_counts( size_t nx, size_t ny, size_t nz, size_t* npoin, size_t* ntet, size_t* ntri )
+{
+  *npoin = (nx+1)*(ny+1)*(nz+1); *ntet = 6*nx*ny*nz; *ntri = 4*(nx*ny + ny*nz + nx*nz);
+  return 0;
+}
+
+int xyst_box_mesh( size_t nx, size_t ny, size_t nz, double Lx, double Ly, double Lz,
+                   double* x, double* y, double* z, uint64_t* tets,
+                   int32_t set_id[6], uint64_t set_off[7], uint64_t* set_tri )
+{
+  API_BEGIN
+  auto m = boxMesh( nx, ny, nz, Lx, Ly, Lz, 0, nx, 0, ny, 0, nz );
+  std::copy( m.coord[0].begin(), m.coord[0].end(), x );
+  std::copy( m.coord[1].begin(), m.coord[1].end(), y );
+  std::copy( m.coord[2].begin(), m.coord[2].end(), z );
+  std::copy( m.ginpoel.begin(), m.ginpoel.end(), tets );
+  int i = 0; set_off[0] = 0; size_t k = 0;
+  for (const auto& [s,t] : m.sidetri) {
+    set_id[i] = s;
+    for (auto n : t) set_tri[k++] = n;
+    set_off[i+1] = set_off[i] + t.size()/3;
+    ++i;
+  }
+  API_END
+}
+
+int xyst_rcb( size_t npoin, const double* x, const double* y, const double* z, size_t ntet,
+              const uint64_t* tets, int nparts, int32_t* part )
+{
+  API_BEGIN
+  Coords co;
+  co[0].assign( x, x+npoin ); co[1].assign( y, y+npoin ); co[2].assign( z, z+npoin );
+  std::vector< std::size_t > g( tets, tets+ntet*4 );
+  auto p = rcb( co, g, nparts );
+  std::copy( p.begin(), p.end(), part );
+  API_END
+}
+
+int xyst_box_part_range( size_t nx, size_t ny, size_t nz, int nparts, int part, uint64_t range[6] )
+{
+  API_BEGIN
+  auto r = boxPartRange( nx, ny, nz, nparts, part );
+  for (int i=0; i<6; ++i) range[i] = r[static_cast<std::size_t>(i)];
+  API_END
+}
+
+} // extern "C"

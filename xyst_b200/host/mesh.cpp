@@ -1,0 +1,215 @@
+// xyst_b200/host/mesh.cpp -- see mesh.hpp
+#include "mesh.hpp"
+#include <algorithm>
+#include <numeric>
+#include <stdexcept>
+#include <cmath>
+
+namespace xyst {
+
+namespace {
+// local edges of a tetrahedron, tk::lpoed (src/Mesh/DerivedData.hpp:40-41)
+const int lpoed[6][2] = { {0,1}, {1,2}, {2,0}, {0,3}, {1,3}, {2,3} };
+
+// The six Kuhn tetrahedra of the unit hex as corner offsets (dx,dy,dz), each a monotone
+// path from corner 000 to corner 111; node order chosen so that the Jacobian
+// triple(b-a, c-a, d-a) is positive (the reference requires J>0,
+// src/Inciter/Discretization.cpp:100-101,:629).
+struct Kuhn {
+  int c[6][4][3];
+  Kuhn() {
+    const int perm[6][3] = { {0,1,2}, {0,2,1}, {1,0,2}, {1,2,0}, {2,0,1}, {2,1,0} };
+    for (int t=0; t<6; ++t) {
+      int v[4][3] = { {0,0,0}, {0,0,0}, {0,0,0}, {1,1,1} };
+      v[1][perm[t][0]] = 1;
+      v[2][perm[t][0]] = 1; v[2][perm[t][1]] = 1;
+      double ba[3], ca[3], da[3];
+      for (int d=0; d<3; ++d) { ba[d] = v[1][d]-v[0][d]; ca[d] = v[2][d]-v[0][d]; da[d] = v[3][d]-v[0][d]; }
+      double J = ba[0]*(ca[1]*da[2]-da[1]*ca[2]) + ba[1]*(ca[2]*da[0]-da[2]*ca[0]) + ba[2]*(ca[0]*da[1]-da[0]*ca[1]);
+      if (J < 0) for (int d=0; d<3; ++d) std::swap( v[1][d], v[2][d] );
+      for (int k=0; k<4; ++k) for (int d=0; d<3; ++d) c[t][k][d] = v[k][d];
+    }
+  }
+};
+const Kuhn kuhn;
+}
+
+TetMesh boxMesh( std::size_t nx, std::size_t ny, std::size_t nz, real Lx, real Ly, real Lz,
+                 std::size_t i0, std::size_t i1, std::size_t j0, std::size_t j1,
+                 std::size_t k0, std::size_t k1 )
+{
+  if (i1 > nx || j1 > ny || k1 > nz || i0 >= i1 || j0 >= j1 || k0 >= k1)
+    throw std::runtime_error( "boxMesh: invalid hex range" );
+  TetMesh m;
+  const std::size_t px = nx+1, py = ny+1;
+  auto id = [&]( std::size_t i, std::size_t j, std::size_t k ){ return (k*py + j)*px + i; };
+  const bool full = i0 == 0 && j0 == 0 && k0 == 0 && i1 == nx && j1 == ny && k1 == nz;
+  // nodes of this range; coordinates are those of the full box (i*Lx/nx, ...)
+  const std::size_t mx = i1-i0+1, my = j1-j0+1, mz = k1-k0+1;
+  for (auto& c : m.coord) c.resize( mx*my*mz );
+  if (!full) m.gid.resize( mx*my*mz );
+  #pragma omp parallel for schedule(static)
+  for (std::size_t k=k0; k<=k1; ++k)
+    for (std::size_t j=j0; j<=j1; ++j)
+      for (std::size_t i=i0; i<=i1; ++i) {
+        std::size_t l = ((k-k0)*my + (j-j0))*mx + (i-i0);
+        m.coord[0][l] = Lx * static_cast< real >( i ) / static_cast< real >( nx );
+        m.coord[1][l] = Ly * static_cast< real >( j ) / static_cast< real >( ny );
+        m.coord[2][l] = Lz * static_cast< real >( k ) / static_cast< real >( nz );
+        if (!full) m.gid[l] = id( i, j, k );      // ascending in l since ranges are boxes
+      }
+  // tetrahedra
+  const std::size_t nhex = (i1-i0)*(j1-j0)*(k1-k0);
+  m.ginpoel.resize( nhex*24 );
+  #pragma omp parallel for schedule(static)
+  for (std::size_t k=k0; k<k1; ++k)
+    for (std::size_t j=j0; j<j1; ++j)
+      for (std::size_t i=i0; i<i1; ++i) {
+        std::size_t h = ((k-k0)*(j1-j0) + (j-j0))*(i1-i0) + (i-i0);
+        for (int t=0; t<6; ++t)
+          for (int v=0; v<4; ++v)
+            m.ginpoel[h*24 + static_cast<std::size_t>(t)*4 + static_cast<std::size_t>(v)] =
+              id( i+static_cast<std::size_t>(kuhn.c[t][v][0]), j+static_cast<std::size_t>(kuhn.c[t][v][1]),
+                  k+static_cast<std::size_t>(kuhn.c[t][v][2]) );
+      }
+  // side sets: tet faces lying on a face of the FULL box, outward orientation as the
+  // reference derives it from the tet (src/Inciter/Partitioner.cpp:575-577)
+  const int tf[4][3] = { {0,2,1}, {0,1,3}, {0,3,2}, {1,2,3} };
+  auto addfaces = [&]( int set, int dim, int side, std::size_t a0, std::size_t a1, std::size_t b0, std::size_t b1,
+                       std::size_t fixed ) {
+    auto& out = m.sidetri[set];
+    for (std::size_t b=b0; b<b1; ++b)
+      for (std::size_t a=a0; a<a1; ++a) {
+        std::size_t i, j, k;
+        if (dim == 0) { i = fixed; j = a; k = b; } else if (dim == 1) { i = a; j = fixed; k = b; } else { i = a; j = b; k = fixed; }
+        for (int t=0; t<6; ++t)
+          for (int f=0; f<4; ++f) {
+            bool on = true;
+            for (int v=0; v<3; ++v) if (kuhn.c[t][tf[f][v]][dim] != side) on = false;
+            if (!on) continue;
+            for (int v=0; v<3; ++v) {
+              const int* c = kuhn.c[t][tf[f][v]];
+              out.push_back( id( i+static_cast<std::size_t>(c[0]), j+static_cast<std::size_t>(c[1]), k+static_cast<std::size_t>(c[2]) ) );
+            }
+          }
+      }
+    if (out.empty()) m.sidetri.erase( set );
+  };
+  if (i0 == 0)  addfaces( 1, 0, 0, j0, j1, k0, k1, 0 );
+  if (i1 == nx) addfaces( 2, 0, 1, j0, j1, k0, k1, nx-1 );
+  if (j0 == 0)  addfaces( 3, 1, 0, i0, i1, k0, k1, 0 );
+  if (j1 == ny) addfaces( 4, 1, 1, i0, i1, k0, k1, ny-1 );
+  if (k0 == 0)  addfaces( 5, 2, 0, i0, i1, j0, j1, 0 );
+  if (k1 == nz) addfaces( 6, 2, 1, i0, i1, j0, j1, nz-1 );
+  return m;
+}
+
+std::vector< int > rcb( const Coords& coord, const std::vector< std::size_t >& ginpoel, int nparts )
+{
+  if (nparts < 1 || (nparts & (nparts-1))) throw std::runtime_error( "rcb: nparts must be a power of two" );
+  std::size_t nel = ginpoel.size()/4;
+  std::vector< std::array< real, 3 > > cen( nel );
+  for (std::size_t e=0; e<nel; ++e)
+    for (std::size_t d=0; d<3; ++d) {
+      const auto N = ginpoel.data() + e*4;
+      cen[e][d] = (coord[d][N[0]] + coord[d][N[1]] + coord[d][N[2]] + coord[d][N[3]]) / 4.0;
+    }
+  std::vector< int > part( nel, 0 );
+  std::vector< std::size_t > idx( nel );
+  std::iota( idx.begin(), idx.end(), 0 );
+  // recursive bisection on index ranges of idx
+  struct Job { std::size_t b, e; int p0, np; };
+  std::vector< Job > jobs{ { 0, nel, 0, nparts } };
+  while (!jobs.empty()) {
+    auto jb = jobs.back(); jobs.pop_back();
+    if (jb.np == 1) { for (std::size_t i=jb.b; i<jb.e; ++i) part[idx[i]] = jb.p0; continue; }
+    real lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+    for (std::size_t i=jb.b; i<jb.e; ++i) for (int d=0; d<3; ++d) {
+      lo[d] = std::min( lo[d], cen[idx[i]][static_cast<std::size_t>(d)] ); hi[d] = std::max( hi[d], cen[idx[i]][static_cast<std::size_t>(d)] ); }
+    int dim = 0;
+    for (int d=1; d<3; ++d) if (hi[d]-lo[d] > (hi[dim]-lo[dim])*(1.0+1e-12)) dim = d;
+    std::size_t mid = jb.b + (jb.e-jb.b)/2;
+    auto D = static_cast< std::size_t >( dim );
+    std::nth_element( idx.begin()+static_cast<std::ptrdiff_t>(jb.b), idx.begin()+static_cast<std::ptrdiff_t>(mid),
+                      idx.begin()+static_cast<std::ptrdiff_t>(jb.e),
+      [&]( std::size_t a, std::size_t b ){ return cen[a][D] < cen[b][D] || (cen[a][D] == cen[b][D] && a < b); } );
+    jobs.push_back( { jb.b, mid, jb.p0, jb.np/2 } );
+    jobs.push_back( { mid, jb.e, jb.p0 + jb.np/2, jb.np/2 } );
+  }
+  return part;
+}
+
+std::array< std::size_t, 6 > boxPartRange( std::size_t nx, std::size_t ny, std::size_t nz, int nparts, int part )
+{
+  std::size_t lo[3] = { 0, 0, 0 }, hi[3] = { nx, ny, nz };
+  int np = nparts, p = part;
+  while (np > 1) {
+    int dim = 0;
+    for (int d=1; d<3; ++d) if (hi[d]-lo[d] > hi[dim]-lo[dim]) dim = d;
+    std::size_t ext = hi[dim]-lo[dim];
+    if (ext % 2) throw std::runtime_error( "boxPartRange: extent not divisible by 2" );
+    std::size_t mid = lo[dim] + ext/2;
+    if (p < np/2) hi[dim] = mid; else { lo[dim] = mid; p -= np/2; }
+    np /= 2;
+  }
+  return {{ lo[0], hi[0], lo[1], hi[1], lo[2], hi[2] }};
+}
+
+EdgeCSR uniqueEdges( const std::vector< std::size_t >& inpoel, std::size_t npoin )
+{
+  const std::size_t nel = inpoel.size()/4;
+  std::vector< std::size_t > cnt( npoin+1, 0 );
+  for (std::size_t e=0; e<nel; ++e) {
+    const auto N = inpoel.data() + e*4;
+    for (const auto& pq : lpoed) ++cnt[ std::min( N[pq[0]], N[pq[1]] ) + 1 ];
+  }
+  for (std::size_t p=0; p<npoin; ++p) cnt[p+1] += cnt[p];
+  std::vector< std::uint32_t > tmp( cnt[npoin] );
+  {
+    std::vector< std::size_t > fill( cnt.begin(), cnt.end()-1 );
+    for (std::size_t e=0; e<nel; ++e) {
+      const auto N = inpoel.data() + e*4;
+      for (const auto& pq : lpoed) {
+        auto a = N[pq[0]], b = N[pq[1]];
+        tmp[ fill[ std::min(a,b) ]++ ] = static_cast< std::uint32_t >( std::max(a,b) );
+      }
+    }
+  }
+  EdgeCSR out;
+  out.off.assign( npoin+1, 0 );
+  #pragma omp parallel for schedule(dynamic,4096)
+  for (std::size_t p=0; p<npoin; ++p) {
+    auto b = tmp.begin()+static_cast<std::ptrdiff_t>(cnt[p]), e = tmp.begin()+static_cast<std::ptrdiff_t>(cnt[p+1]);
+    std::sort( b, e );
+    out.off[p+1] = static_cast< std::size_t >( std::unique( b, e ) - b );
+  }
+  for (std::size_t p=0; p<npoin; ++p) out.off[p+1] += out.off[p];
+  out.hi.resize( out.off[npoin] );
+  #pragma omp parallel for schedule(dynamic,4096)
+  for (std::size_t p=0; p<npoin; ++p)
+    std::copy( tmp.begin()+static_cast<std::ptrdiff_t>(cnt[p]),
+               tmp.begin()+static_cast<std::ptrdiff_t>(cnt[p] + (out.off[p+1]-out.off[p])),
+               out.hi.begin()+static_cast<std::ptrdiff_t>(out.off[p]) );
+  return out;
+}
+
+void psupFromEdges( const EdgeCSR& e, std::size_t npoin,
+                    std::vector< std::size_t >& off, std::vector< std::uint32_t >& nbr )
+{
+  off.assign( npoin+1, 0 );
+  for (std::size_t p=0; p<npoin; ++p) {
+    off[p+1] += e.off[p+1]-e.off[p];
+    for (auto i=e.off[p]; i<e.off[p+1]; ++i) ++off[ e.hi[i]+1 ];
+  }
+  for (std::size_t p=0; p<npoin; ++p) off[p+1] += off[p];
+  nbr.resize( off[npoin] );
+  std::vector< std::size_t > fill( off.begin(), off.end()-1 );
+  // lower neighbours arrive in ascending p, then the node's own higher neighbours
+  // (ascending): every list ends up sorted ascending without a sort
+  for (std::size_t p=0; p<npoin; ++p)
+    for (auto i=e.off[p]; i<e.off[p+1]; ++i) nbr[ fill[ e.hi[i] ]++ ] = static_cast< std::uint32_t >( p );
+  for (std::size_t p=0; p<npoin; ++p)
+    for (auto i=e.off[p]; i<e.off[p+1]; ++i) nbr[ fill[p]++ ] = e.hi[i];
+}
+
+} // xyst::

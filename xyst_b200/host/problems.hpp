@@ -1,0 +1,68 @@
+// xyst_b200/host/problems.hpp -- host-side problem definitions used by the RieCG mirror:
+// initial conditions, analytic solutions and source terms of the configured problem
+// (cf. src/Physics/Problems.cpp: sedov::ic :337, sod::ic :373, taylor_green::ic/src
+// :410/:433, dispatch IC() :1071, SOL() :1114, SRC() :1299) and the ideal-gas EOS
+// (src/Physics/EOS.hpp:29-56). Evaluated once on the host; the device receives arrays.
+#pragma once
+#include <array>
+#include <cmath>
+#include <functional>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include "riecg.hpp"
+
+namespace xyst {
+namespace problems {
+
+using Fn = std::function< std::array< real, 5 >( real, real, real, real ) >;
+
+inline real totalenergy( real g, real r, real u, real v, real w, real p ) {
+  return p / (g-1.0) + 0.5 * r * (u*u + v*v + w*w);
+}
+
+inline Fn IC( const Config& cfg ) {
+  const real g = cfg.gamma;
+  if (cfg.problem == "sedov") {
+    const real p0 = cfg.p0;
+    return [g,p0]( real x, real y, real z, real ) -> std::array< real, 5 > {
+      auto eps = std::numeric_limits< real >::epsilon();
+      real p = (std::abs(x) < eps && std::abs(y) < eps && std::abs(z) < eps) ? p0 : 0.67e-4;
+      real r = 1.0, u = 0.0, v = 0.0, w = 0.0;
+      return {{ r, r*u, r*v, r*w, totalenergy( g, r, u, v, w, p ) }}; };
+  }
+  if (cfg.problem == "sod")
+    return [g]( real x, real, real, real ) -> std::array< real, 5 > {
+      real r, p;
+      if (x < 0.5) { r = 1.0; p = 1.0; } else { r = 0.125; p = 0.1; }
+      real u = 0.0, v = 0.0, w = 0.0;
+      return {{ r, r*u, r*v, r*w, totalenergy( g, r, u, v, w, p ) }}; };
+  if (cfg.problem == "taylor_green")
+    return [g]( real x, real y, real, real ) -> std::array< real, 5 > {
+      real r = 1.0;
+      real p = 10.0 + r/4.0*(std::cos(2.0*M_PI*x) + std::cos(2.0*M_PI*y));
+      real u =  std::sin(M_PI*x) * std::cos(M_PI*y);
+      real v = -std::cos(M_PI*x) * std::sin(M_PI*y);
+      real w = 0.0;
+      return {{ r, r*u, r*v, r*w, totalenergy( g, r, u, v, w, p ) }}; };
+  throw std::runtime_error( "problem type ic not hooked up: " + cfg.problem );
+}
+
+inline Fn SOL( const Config& cfg ) {
+  const auto& p = cfg.problem;
+  if (p == "userdef" || p == "sod" || p == "sedov" || p == "point_src") return {};
+  return IC( cfg );
+}
+
+inline Fn SRC( const Config& cfg ) {
+  if (cfg.problem == "taylor_green")
+    return []( real x, real y, real, real ) -> std::array< real, 5 > {
+      std::array< real, 5 > s{{ 0, 0, 0, 0, 0 }};
+      s[4] = 3.0*M_PI/8.0*( std::cos(3.0*M_PI*x)*std::cos(M_PI*y)
+                          - std::cos(3.0*M_PI*y)*std::cos(M_PI*x) );
+      return s; };
+  return {};
+}
+
+} // problems::
+} // xyst::

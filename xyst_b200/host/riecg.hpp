@@ -1,0 +1,143 @@
+// xyst_b200/host/riecg.hpp -- C++ host mirror of the reference's solver-side interface for
+// the RieCG path: the same class and member names as src/Inciter/Discretization.{hpp,cpp}
+// and src/Inciter/RieCG.{hpp,cpp}, minus Charm++. The members that hold the hot path
+// (grad, rhs, solve, BC, dt, diagnostics) call the device C ABI (include/xyst_b200.h);
+// the setup members build what the reference builds, with sort/CSR algorithms that scale
+// to 10^8 tetrahedra instead of hash maps.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+#include "mesh.hpp"
+#include "xyst_b200.h"
+
+namespace xyst {
+
+//! The fields of the reference's global inciter::g_cfg that this path reads
+//! (src/Control/InciterConfig.hpp:161-413; defaults InciterConfig.cpp:1707-1757)
+struct Config {
+  std::string problem = "userdef";
+  std::string flux = "rusanov";
+  std::size_t ncomp = 5;
+  real gamma = 1.4, p0 = 0.0, cfl = 0.0, dt = 0.0, t0 = 0.0, term = 1.0e+300;
+  std::uint64_t nstep = ~0ULL, diag_iter = 1;
+  bool stab2 = false;
+  real stab2coef = 0.2;
+  bool exact_muscl = false;                 //!< device option, see xyst_params
+  std::vector< int > bc_sym;
+  std::vector< std::vector< int > > bc_dir; //!< { setid, mask_0 .. mask_{ncomp-1} }
+  std::vector< int > bc_far;
+  real far_density = 0.0, far_pressure = 0.0;
+  std::array< real, 3 > far_velocity{{ 0, 0, 0 }};
+  std::vector< int > bc_pre;
+  std::vector< real > pre_density, pre_pressure;
+};
+
+//! Sum, over all partitions sharing them, `w` doubles per unique shared node (ascending
+//! local id); in place. Default: NCCL through the device context.
+using HaloSum = std::function< void( int w, std::vector< real >& vals ) >;
+//! All-reduce (op 0 = sum, 1 = min) over all partitions, in place. Default: NCCL.
+using AllReduce = std::function< void( int op, std::vector< real >& vals ) >;
+
+//! Mesh partition owner, cf. inciter::Discretization
+class Discretization {
+  public:
+    explicit Discretization( const TetMesh& chunk, const Config& cfg );
+    const std::vector< std::size_t >& Inpoel() const { return m_inpoel; }
+    const std::vector< std::size_t >& Gid() const { return m_gid; }
+    const Coords& Coord() const { return m_coord; }
+    const std::vector< real >& Vol() const { return m_vol; }   //!< with neighbour contributions
+    const std::vector< real >& V() const { return m_v; }       //!< own elements only
+    std::map< int, std::vector< std::size_t > >& NodeCommMap() { return m_nodeCommMap; }
+    std::size_t lid( std::size_t g ) const;
+    real T() const { return m_t; }
+    real Dt() const { return m_dt; }
+    std::uint64_t It() const { return m_it; }
+    real& MeshVol() { return m_meshvol; }
+    void vol();                                          //!< Discretization.cpp:618-676 (own part)
+    void remap( const std::vector< std::size_t >& newid );   //!< :560-606
+    void setdt( real newdt );                            //!< :926-938
+    void next();                                         //!< :941-983
+    bool finished() const;                               //!< :1251-1262
+    std::vector< std::size_t > sharedNodes() const;      //!< unique shared local ids, ascending
+    std::vector< real > m_vol, m_v;
+  private:
+    const Config& m_cfg;
+    std::vector< std::size_t > m_inpoel, m_gid;
+    std::vector< std::uint32_t > m_g2l;                  //!< dense global->local (+1), 0 = absent
+    std::size_t m_gmin = 0;
+    Coords m_coord;
+    std::map< int, std::vector< std::size_t > > m_nodeCommMap;  //!< neighbour -> shared GLOBAL ids, ascending
+    real m_t, m_dt, m_dtn, m_meshvol = 0.0;
+    std::uint64_t m_it = 0;
+};
+
+//! cf. inciter::RieCG
+class RieCG {
+  public:
+    RieCG( Discretization& disc, const TetMesh& chunk, const Config& cfg );
+    ~RieCG();
+    //! create the device context and, for nranks>1, the NCCL communicator
+    void attach( int device, int nranks, int rank, const void* ncclid );
+    void setComm( HaloSum h, AllReduce a ) { m_halosum = std::move(h); m_allreduce = std::move(a); }
+    void setRanks( int nranks, int rank ) { m_nranks = nranks; m_rank = rank; }
+    //! host-only part of RieCG::RieCG + feop(): renumber, volumes, edge integrals, superedges
+    void prepare();
+    //! host part of setup: exchanges (volumes, boundary normals), BC lists, ICs
+    void hostSetup();
+    //! hostSetup() if not done + device upload + BC(t0)
+    void setup();
+    real dt();                       //!< RieCG.cpp:787-852 incl. the global min reduction
+    void advance( real newdt );      //!< :854-869
+    void grad();                     //!< :871-893 (+ comgrad, normalisation)
+    void rhs();                      //!< :918-966 (+ comrhs)
+    void solve();                    //!< :992-1057 update + BC for the current stage
+    void BC();                       //!< :764-785
+    //! one full time step through the fused device path; returns false when finished
+    bool step( std::vector< real >* diagrow );
+    //! NodeDiagnostics::rhocompute + Transporter::rhodiagnostics
+    std::vector< real > diagnostics();
+    std::vector< real > solution();  //!< m_u, npoin x ncomp
+    void setSolution( const std::vector< real >& u );
+    xyst_ctx* ctx() { return m_ctx; }
+    Discretization& Disc() { return m_disc; }
+
+    // streamable data, same names/meaning as the reference's members
+    std::map< int, std::vector< std::size_t > > m_bface;
+    std::vector< std::size_t > m_triinpoel;
+    std::array< std::vector< std::size_t >, 3 > m_dsupedge;
+    std::array< std::vector< real >, 3 > m_dsupint;
+    std::vector< std::uint8_t > m_besym;
+    std::vector< std::size_t > m_dirbcmasks, m_symbcnodes, m_farbcnodes, m_prebcnodes;
+    std::vector< real > m_symbcnorms, m_farbcnorms, m_prebcvals;
+    std::vector< real > m_u0;        //!< initial condition (npoin x ncomp)
+    std::vector< double > timings;   //!< seconds spent in the setup phases (for reporting)
+    bool m_finished = false;
+  private:
+    void renumber();                 //!< RieCG.cpp:82-100
+    void boundaryFaces( const TetMesh& chunk );    //!< Partitioner.cpp:539-626 per partition
+    void domint( const EdgeCSR& edges, std::vector< real >& d ) const;   //!< :339-382
+    void domsuped( const EdgeCSR& edges, const std::vector< real >& d ); //!< :620-736
+    void bndint();                   //!< :281-337
+    void setupBC();                  //!< :109-245 (after normals are known)
+    void uploadHalo();
+    bool m_haloup = false;
+    Discretization& m_disc;
+    const Config& m_cfg;
+    std::map< int, std::vector< std::size_t > > m_sidetri;  //!< chunk side sets (global ids)
+    std::map< int, std::map< std::size_t, std::array< real, 4 > > > m_bnorm;  //!< set -> local node -> normal
+    std::set< std::size_t > m_symbcnodeset, m_farbcnodeset;
+    xyst_ctx* m_ctx = nullptr;
+    int m_nranks = 1, m_rank = 0;
+    int m_stage = 0;
+    HaloSum m_halosum;
+    AllReduce m_allreduce;
+    bool m_hostready = false;
+    real m_ownvol = 0.0;
+    std::vector< real > m_dirvals, m_src;
+};
+
+} // xyst::

@@ -19,6 +19,7 @@ typedef struct xyst_host_cfg {
   int32_t ncomp;
   int32_t stab2;
   int32_t exact_muscl;
+  int32_t reforder;           /* triangle superedge walk: 1 reference hash order, 0 element order, -1 auto */
   int32_t nsym;  int32_t sym[16];
   int32_t ndir;  int32_t dir[16][12];      /* { setid, mask_0 .. mask_{ncomp-1} } */
   int32_t nfar;  int32_t far_sets[16];
@@ -58,6 +59,7 @@ int xyst_solver_attach(xyst_solver* s, int device, int nranks, int rank, const v
 int xyst_solver_set_comm(xyst_solver* s, xyst_comm_fn fn, void* user, int nranks, int rank);
 int xyst_solver_set_u0(xyst_solver* s, const double* u0);   /* user-defined IC, npoin x ncomp, local order */
 int xyst_solver_host_setup(xyst_solver* s);  /* exchanges (volumes, normals), BC lists, ICs: no device */
+int xyst_solver_set_u(xyst_solver* s, const double* u);    /* overwrite the device state (after setup) */
 int xyst_solver_setup(xyst_solver* s);       /* host_setup if needed + device upload + BCs */
 /* Advance up to nsteps time steps; diagnostics rows (ncols doubles each, layout of the
  * reference's diag file: it t dt L2(U)x5 L2(dU)x5 mE [L2err x5 L1err x5]) are appended to
@@ -78,6 +80,8 @@ int xyst_box_mesh(size_t nx, size_t ny, size_t nz, double Lx, double Ly, double 
                   int32_t set_id[6], uint64_t set_off[7], uint64_t* set_tri);
 int xyst_rcb(size_t npoin, const double* x, const double* y, const double* z, size_t ntet,
              const uint64_t* tets, int nparts, int32_t* part);
+int xyst_test_faceset_order(size_t nface, const uint64_t* faces, size_t nerase, const uint64_t* erase,
+                            uint64_t* out_std, uint64_t* out_emu, size_t* nout);
 int xyst_box_part_range(size_t nx, size_t ny, size_t nz, int nparts, int part, uint64_t range[6]);
 
 #ifdef __cplusplus

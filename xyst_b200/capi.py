@@ -35,10 +35,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(SO):
+    so = os.environ.get("XYST_B200_LIB", SO)      # alternative CUDA builds (e.g. -fmad=false)
+    if not os.path.exists(so):
         raise XystError("libxyst_b200.so is missing: run `python -m xyst_b200.build` "
                         "(the CUDA path has no CPU fallback)")
-    L = C.CDLL(SO, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(so, mode=C.RTLD_GLOBAL)
     L.xyst_last_error.restype = C.c_char_p
     L.xyst_ctx_create.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]
     L.xyst_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]

@@ -6,6 +6,7 @@
 #include <stdexcept>
 #include <cmath>
 #include "riecg.hpp"
+#include "refhashset.hpp"
 #include "xyst_host.h"
 
 using namespace xyst;
@@ -28,7 +29,7 @@ Config to_cfg( const xyst_host_cfg* c ) {
   k.problem = c->problem; k.flux = c->flux; k.ncomp = static_cast< std::size_t >( c->ncomp );
   k.gamma = c->gamma; k.p0 = c->p0; k.cfl = c->cfl; k.dt = c->dt; k.t0 = c->t0; k.term = c->term;
   k.nstep = c->nstep; k.diag_iter = c->diag_iter ? c->diag_iter : 1;
-  k.stab2 = c->stab2 != 0; k.stab2coef = c->stab2coef; k.exact_muscl = c->exact_muscl != 0;
+  k.stab2 = c->stab2 != 0; k.stab2coef = c->stab2coef; k.exact_muscl = c->exact_muscl != 0; k.reforder = c->reforder;
   for (int i=0; i<c->nsym; ++i) k.bc_sym.push_back( c->sym[i] );
   for (int i=0; i<c->ndir; ++i) {
     std::vector< int > m( k.ncomp+1 );
@@ -150,6 +151,13 @@ int xyst_solver_set_u0( xyst_solver* s, const double* u0 )
 { API_BEGIN s->riecg->m_u0.assign( u0, u0 + s->disc->Gid().size()*s->cfg.ncomp ); API_END }
 
 int xyst_solver_setup( xyst_solver* s ) { API_BEGIN s->riecg->setup(); API_END }
+
+int xyst_solver_set_u( xyst_solver* s, const double* u )
+{
+  API_BEGIN
+  s->riecg->setSolution( std::vector< real >( u, u + s->disc->Gid().size()*s->cfg.ncomp ) );
+  API_END
+}
 
 int xyst_solver_step( xyst_solver* s, int nsteps, double* rows, size_t cap, size_t* nrows, size_t* ncols )
 {
@@ -279,6 +287,26 @@ int xyst_rcb( size_t npoin, const double* x, const double* y, const double* z, s
   std::vector< std::size_t > g( tets, tets+ntet*4 );
   auto p = rcb( co, g, nparts );
   std::copy( p.begin(), p.end(), part );
+  API_END
+}
+
+// test hook: iteration order of the real std::unordered_set vs RefOrderFaceSet after
+// inserting nface faces and erasing nerase of them; writes surviving faces (3 ids each)
+int xyst_test_faceset_order( size_t nface, const uint64_t* faces, size_t nerase, const uint64_t* erase,
+                             uint64_t* out_std, uint64_t* out_emu, size_t* nout )
+{
+  API_BEGIN
+  using Face = std::array< std::size_t, 3 >;
+  std::unordered_set< Face, IdHash<3>, IdEq<3> > a;
+  RefOrderFaceSet b;
+  for (size_t i=0; i<nface; ++i) { Face f{{ faces[i*3], faces[i*3+1], faces[i*3+2] }}; a.insert( f ); b.insert( f ); }
+  for (size_t i=0; i<nerase; ++i) { Face f{{ erase[i*3], erase[i*3+1], erase[i*3+2] }}; a.erase( f ); b.erase( f ); }
+  size_t k = 0;
+  for (const auto& f : a) { for (auto n : f) out_std[k++] = n; }
+  size_t m = 0;
+  b.forEach( [&]( const Face& f ){ for (auto n : f) out_emu[m++] = n; } );
+  if (k != m) throw std::runtime_error( "faceset size mismatch" );
+  *nout = k/3;
   API_END
 }
 

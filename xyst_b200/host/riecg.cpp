@@ -1,6 +1,8 @@
 // xyst_b200/host/riecg.cpp -- see riecg.hpp
 #include "riecg.hpp"
 #include "problems.hpp"
+#include "siphash.hpp"
+#include "refhashset.hpp"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -258,11 +260,13 @@ void RieCG::domint( const EdgeCSR& edges, std::vector< real >& d ) const
   }
 }
 
-//! Superedge groups, RieCG.cpp:620-736. Tetrahedra: the reference's greedy pass in element
-//! order (identical result). Triangles and leftover edges: the reference takes them in
-//! hash-iteration order; here faces are visited in element order and edges in edge-id
-//! order -- the groups cover the same edges with the same integrals, only the grouping of
-//! the non-tet remainder (and the summation order it implied on the CPU) differs.
+//! Superedge groups, RieCG.cpp:620-736. Tetrahedra: greedy pass in element order.
+//! Triangles: the reference walks an unordered set of the faces not covered by a
+//! tetrahedron superedge in hash-iteration order; because edge orientation inside a
+//! triangle differs from that of a single edge and the limiter is orientation dependent at
+//! 1e-9 (see siphash.hpp), the same container type, hash and insert/erase sequence are
+//! used here so that the same triangles come out with the same node order. Leftover edges:
+//! low -> high global id as in the reference (their order does not matter to the device).
 void RieCG::domsuped( const EdgeCSR& edges, const std::vector< real >& d )
 {
   const auto& inpoel = m_disc.Inpoel(); const auto& gid = m_disc.Gid();
@@ -270,33 +274,53 @@ void RieCG::domsuped( const EdgeCSR& edges, const std::vector< real >& d )
   for (auto& a : m_dsupint) a.clear();
   std::vector< std::uint8_t > claimed( edges.nedge(), 0 );
   auto ntet = inpoel.size()/4;
+  const bool reforder = m_cfg.reforder == 1 || (m_cfg.reforder < 0 && ntet <= 4000000);
+  // hashes of all tet faces in parallel, then the (inherently sequential) set operations
+  std::vector< std::uint64_t > fh( reforder ? ntet*4 : 0 );
+  if (reforder) {
+  #pragma omp parallel for schedule(static)
+  for (std::size_t e=0; e<ntet; ++e) {
+    const auto N = inpoel.data() + e*4;
+    for (std::size_t k=0; k<4; ++k) fh[e*4+k] = IdHash<3>()( {{ N[lpofa[k][0]], N[lpofa[k][1]], N[lpofa[k][2]] }} );
+  }
+  }
+  RefOrderFaceSet untri( reforder ? ntet*2 + ntet/8 : 0 );
+  if (reforder)
+  for (std::size_t e=0; e<ntet; ++e) {
+    const auto N = inpoel.data() + e*4;
+    for (std::size_t k=0; k<4; ++k) untri.insert( {{ N[lpofa[k][0]], N[lpofa[k][1]], N[lpofa[k][2]] }}, fh[e*4+k] );
+  }
+  std::vector< std::uint64_t >().swap( fh );
   for (std::size_t e=0; e<ntet; ++e) {
     const auto N = inpoel.data() + e*4;
     std::size_t id[6]; bool all = true;
     for (int k=0; k<6; ++k) { id[k] = edges.find( N[lpoed[k][0]], N[lpoed[k][1]] ); if (claimed[id[k]]) { all = false; break; } }
     if (!all) continue;
     for (int k=0; k<4; ++k) m_dsupedge[0].push_back( N[k] );
+    if (reforder) for (const auto& f : lpofa) untri.erase( {{ N[f[0]], N[f[1]], N[f[2]] }} );
     for (int k=0; k<6; ++k) {
       real sig = gid[N[lpoed[k][0]]] < gid[N[lpoed[k][1]]] ? 1.0 : -1.0;
       for (int j=0; j<3; ++j) m_dsupint[0].push_back( sig * d[id[k]*3+static_cast<std::size_t>(j)] );
       claimed[id[k]] = 1;
     }
   }
-  for (std::size_t e=0; e<ntet; ++e) {
-    const auto N = inpoel.data() + e*4;
-    for (const auto& f : lpofa) {
-      std::size_t T[3] = { N[f[0]], N[f[1]], N[f[2]] };
-      std::size_t id[3]; bool all = true;
-      for (int k=0; k<3; ++k) { id[k] = edges.find( T[lpoet[k][0]], T[lpoet[k][1]] ); if (claimed[id[k]]) { all = false; break; } }
-      if (!all) continue;
-      for (int k=0; k<3; ++k) m_dsupedge[1].push_back( T[k] );
-      for (int k=0; k<3; ++k) {
-        real sig = gid[T[lpoet[k][0]]] < gid[T[lpoet[k][1]]] ? 1.0 : -1.0;
-        for (int j=0; j<3; ++j) m_dsupint[1].push_back( sig * d[id[k]*3+static_cast<std::size_t>(j)] );
-        claimed[id[k]] = 1;
-      }
+  auto tryface = [&]( const RefOrderFaceSet::Face& T ) {
+    std::size_t id[3]; bool all = true;
+    for (int k=0; k<3; ++k) { id[k] = edges.find( T[static_cast<std::size_t>(lpoet[k][0])], T[static_cast<std::size_t>(lpoet[k][1])] ); if (claimed[id[k]]) { all = false; break; } }
+    if (!all) return;
+    for (std::size_t k=0; k<3; ++k) m_dsupedge[1].push_back( T[k] );
+    for (int k=0; k<3; ++k) {
+      real sig = gid[T[static_cast<std::size_t>(lpoet[k][0])]] < gid[T[static_cast<std::size_t>(lpoet[k][1])]] ? 1.0 : -1.0;
+      for (int j=0; j<3; ++j) m_dsupint[1].push_back( sig * d[id[k]*3+static_cast<std::size_t>(j)] );
+      claimed[id[k]] = 1;
     }
-  }
+  };
+  if (reforder) untri.forEach( tryface );
+  else
+    for (std::size_t e=0; e<ntet; ++e) {        // element order: a face is met first at its first tet
+      const auto N = inpoel.data() + e*4;
+      for (const auto& f : lpofa) tryface( {{ N[f[0]], N[f[1]], N[f[2]] }} );
+    }
   for (std::size_t p=0; p+1<edges.off.size(); ++p)
     for (auto i=edges.off[p]; i<edges.off[p+1]; ++i) {
       if (claimed[i]) continue;

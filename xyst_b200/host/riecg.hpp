@@ -27,6 +27,10 @@ struct Config {
   bool stab2 = false;
   real stab2coef = 0.2;
   bool exact_muscl = false;                 //!< device option, see xyst_params
+  //! Triangle superedges: 1 = walk the leftover faces in the reference's hash-set order
+  //! (identical triangles, needed for parity beyond 1e-9, ~2 us per tet), 0 = walk them in
+  //! element order (same edges and integrals, other triangles), -1 = 1 up to 4M tets
+  int reforder = -1;
   std::vector< int > bc_sym;
   std::vector< std::vector< int > > bc_dir; //!< { setid, mask_0 .. mask_{ncomp-1} }
   std::vector< int > bc_far;

@@ -11,7 +11,7 @@ SO = os.path.join(HERE, "libxyst_host.so")
 class HostCfg(C.Structure):
     _fields_ = [
         ("problem", C.c_char * 32), ("flux", C.c_char * 16),
-        ("ncomp", C.c_int32), ("stab2", C.c_int32), ("exact_muscl", C.c_int32),
+        ("ncomp", C.c_int32), ("stab2", C.c_int32), ("exact_muscl", C.c_int32), ("reforder", C.c_int32),
         ("nsym", C.c_int32), ("sym", C.c_int32 * 16),
         ("ndir", C.c_int32), ("dir", (C.c_int32 * 12) * 16),
         ("nfar", C.c_int32), ("far_sets", C.c_int32 * 16),
@@ -29,12 +29,12 @@ COMM_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(
 
 def make_cfg(problem, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0, term=1e300,
              nstep=2**63, sym=(), dir_=(), stab2=False, stab2coef=0.2, diag_iter=1, ncomp=5,
-             exact_muscl=False, **_ignored):
+             exact_muscl=False, reforder=-1, **_ignored):
     c = HostCfg()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term
     c.nstep = nstep; c.stab2 = int(stab2); c.stab2coef = stab2coef
-    c.exact_muscl = int(exact_muscl); c.diag_iter = diag_iter
+    c.exact_muscl = int(exact_muscl); c.diag_iter = diag_iter; c.reforder = reforder
     c.nsym = len(sym)
     for i, s in enumerate(sym):
         c.sym[i] = s
@@ -68,6 +68,7 @@ def lib():
     L.xyst_solver_attach.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.xyst_solver_set_comm.argtypes = [vp, COMM_FN, vp, C.c_int, C.c_int]
     L.xyst_solver_set_u0.argtypes = [vp, vp]
+    L.xyst_solver_set_u.argtypes = [vp, vp]
     L.xyst_solver_step.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t),
                                    C.POINTER(C.c_size_t)]
     L.xyst_solver_step_unfused.argtypes = [vp, C.c_int]
@@ -171,6 +172,10 @@ class Solver:
     def set_u0(self, u0):
         u0 = np.ascontiguousarray(u0, np.float64)
         _ck(self.L.xyst_solver_set_u0(self.h, _p(u0)))
+
+    def set_u(self, u):
+        u = np.ascontiguousarray(u, np.float64)
+        _ck(self.L.xyst_solver_set_u(self.h, _p(u)))
 
     def host_setup(self):
         _ck(self.L.xyst_solver_host_setup(self.h))

@@ -14,7 +14,8 @@ ROOT = os.path.dirname(HERE)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CUDA_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include")]
+              "-Xcompiler", "-fPIC", "-shared", "-Xlinker", "-soname=libxyst_b200.so",
+              "-I" + os.path.join(ROOT, "include")]
 
 
 def _stale(target, sources):
@@ -24,13 +25,14 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build_device(force=False, verbose=False):
+def build_device(force=False, verbose=False, out=None, defines=()):
     """libxyst_b200.so: CUDA kernels + the C ABI of include/xyst_b200.h."""
     src = [os.path.join(HERE, "csrc", "xyst_b200.cu")]
     dep = src + [os.path.join(ROOT, "include", "xyst_b200.h")]
-    out = os.path.join(HERE, "libxyst_b200.so")
+    out = out or os.path.join(HERE, "libxyst_b200.so")
     if force or _stale(out, dep):
-        cmd = [NVCC] + CUDA_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + src + ["-ldl"]
+        cmd = [NVCC] + CUDA_FLAGS + ["-D" + d for d in defines] + \
+            (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + src + ["-ldl"]
         subprocess.run(cmd, check=True)
     return out
 

@@ -8,16 +8,22 @@
 //    edges, each node owns a sliced-ELL (32 nodes per slice = one warp) incidence
 //    list, and one thread sums its node's contributions in a fixed order. No atomics,
 //    no zero-fill, bit-reproducible from run to run.
-//  * Gradients: one gather kernel reads neighbour primitives and the signed edge
-//    normals, adds the boundary-face part, divides by the nodal volume and writes a
-//    128-byte row per node (fuses riemann::grad + RieCG::rhs :936-939).
-//  * Fluxes: one thread per edge does MUSCL + Rusanov/HLLC once and stores 5 doubles;
-//    a second gather kernel sums them per node, adds boundary and source terms and
-//    applies the Runge-Kutta update in the same pass (fuses advdom/advbnd/src +
-//    RieCG::solve :1011-1021), also refreshing the packed primitive+coordinate record
-//    the next stage reads.
-//  * Nodal records are packed for 128-bit loads: WX = {rho,u,v,w,e,x,y,z} (64 B),
-//    G = 15 gradients + pad (128 B).
+//  * Everything nodal is structure-of-arrays (U, primitives W, coordinates X,
+//    gradients G: one array per component, stride NP), and EDGES live in slots ordered
+//    like their owner nodes: the j-th edge owned by node p (its lower endpoint) sits at
+//    slice_base(p/32) + j*32 + p%32. A warp of the flux kernel therefore works on 32
+//    consecutive owner nodes, and the k-th neighbour of consecutive nodes is, on a
+//    locality-ordered mesh, a run of consecutive nodes too -- endpoint loads, normal
+//    loads and flux stores coalesce into a few 128-byte lines per request instead of
+//    one line per lane (the first, array-of-structures version of these kernels was
+//    bound by L1 wavefronts, see profiles/).
+//  * Gradients: one gather kernel reads neighbour primitives and the edge normals,
+//    adds the boundary-face part and divides by the nodal volume (fuses riemann::grad
+//    + RieCG::rhs :936-939).
+//  * Fluxes: one thread per edge slot does MUSCL + Rusanov/HLLC once and stores 5
+//    doubles; a second gather kernel sums them per node, adds boundary and source terms
+//    and applies the Runge-Kutta update in the same pass (fuses advdom/advbnd/src +
+//    RieCG::solve :1011-1021), also refreshing the primitive variables.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <cstdio>
@@ -44,9 +50,28 @@ int fail( const std::string& m ) { g_err = m; return 1; }
 #define API_BEGIN try {
 #define API_END } catch (std::exception& e) { return fail( e.what() ); } return 0;
 
+// tuning knobs (compile-time; defaults chosen from the ncu measurements under profiles/)
+#ifndef FLUX_THREADS
+#define FLUX_THREADS 128
+#endif
+#ifndef FLUX_MINB
+#define FLUX_MINB 6
+#endif
+#ifndef NODE_THREADS
+#define NODE_THREADS 256
+#endif
+#ifndef GRAD_MINB
+#define GRAD_MINB 4
+#endif
+#ifndef RHS_MINB
+#define RHS_MINB 4
+#endif
+#ifndef NODE_UNROLL
+#define NODE_UNROLL 4
+#endif
+
+constexpr int kNodeUnroll = NODE_UNROLL;
 constexpr int NC = 5;          // flow components handled by the kernels
-constexpr int WXS = 8;         // doubles per packed primitive+coordinate record
-constexpr int GS = 16;         // doubles per gradient record (15 + pad)
 
 // ---------------------------------------------------------------------------------
 // NCCL through dlopen: the process normally has torch's libnccl.so.2 loaded already
@@ -110,19 +135,18 @@ struct xyst_ctx {
   cudaStream_t stream = nullptr, comm_stream = nullptr;
   bool own_stream = false;
   xyst_params prm{};
-  size_t npoin = 0, nedge = 0, ntri = 0, nslice = 0;
+  size_t npoin = 0, NP = 0, nedge = 0, nslot = 0, ntri = 0, nslice = 0, nent = 0;
   uint64_t launches = 0;
-  // nodal state
-  DevBuf< double > U, Un, WX, G, F, R, vol, v, S;
+  // nodal state, structure of arrays with stride NP (npoin rounded up to 32)
+  DevBuf< double > U, Un, W, X, G, vol, v;   // [5][NP] [5][NP] [5][NP] [3][NP] [15][NP]
+  DevBuf< double > R, stage, S;              // reference layout [npoin][5]: rhs out, copy staging, source
   int src_mask = 0;
-  // edges (sorted by lower node, then higher node)
+  // edge slots (owner-slice order): endpoints (-1 = padding), normals [3][nslot], fluxes [5][nslot]
   DevBuf< int > ep, eq;
-  DevBuf< double > ed;                   // [3][nedge]
-  // sliced-ELL node incidence
+  DevBuf< double > D, F;
+  // sliced-ELL node incidence: signed (slot+1) and neighbour node
   DevBuf< long long > sl_base;           // [nslice+1] entry offsets
-  DevBuf< int > inc_e, inc_q;            // signed (edge+1), neighbour
-  DevBuf< double > inc_d;                // [3][nent] signed normals
-  size_t nent = 0;
+  DevBuf< int > inc_e, inc_q;
   // boundary faces
   DevBuf< int > tri;                     // [ntri][3]
   DevBuf< unsigned char > besym;         // [ntri][3]
@@ -158,30 +182,35 @@ namespace {
 // ---------------------------------------------------------------------------------
 struct DParams { double gamma, stab2coef; int flux, stab2, exact; };
 
-__device__ __forceinline__ double2 ldg2( const double* p ) {
-  return __ldg( reinterpret_cast< const double2* >( p ) );
-}
-
 // Primitive variables from conserved ones, Riemann.cpp:211-227
-__device__ __forceinline__ void primitive( const double* __restrict__ U, double w[NC] ) {
-  w[0] = U[0];
-  w[1] = U[1] / w[0];
-  w[2] = U[2] / w[0];
-  w[3] = U[3] / w[0];
-  w[4] = U[4] / w[0] - 0.5*(w[1]*w[1] + w[2]*w[2] + w[3]*w[3]);
+__device__ __forceinline__ void primitive( const double u[NC], double w[NC] ) {
+  w[0] = u[0];
+  w[1] = u[1] / w[0];
+  w[2] = u[2] / w[0];
+  w[3] = u[3] / w[0];
+  w[4] = u[4] / w[0] - 0.5*(w[1]*w[1] + w[2]*w[2] + w[3]*w[3]);
 }
 
-__global__ void k_pack_wx( size_t n, const double* __restrict__ U, const double* __restrict__ x,
-                           const double* __restrict__ y, const double* __restrict__ z,
-                           double* __restrict__ WX, int coords )
+// reference layout [node][comp] -> SoA state + primitives
+__global__ void k_set_state( size_t n, size_t NP, const double* __restrict__ A,
+                             double* __restrict__ U, double* __restrict__ W )
 {
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= n) return;
-  double w[NC];
-  primitive( U + p*NC, w );
-  double* o = WX + p*WXS;
-  o[0] = w[0]; o[1] = w[1]; o[2] = w[2]; o[3] = w[3]; o[4] = w[4];
-  if (coords) { o[5] = x[p]; o[6] = y[p]; o[7] = z[p]; }
+  double u[NC], w[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) u[c] = A[p*NC+c];
+  primitive( u, w );
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { U[c*NP+p] = u[c]; W[c*NP+p] = w[c]; }
+}
+
+__global__ void k_get_state( size_t n, size_t NP, const double* __restrict__ U, double* __restrict__ A )
+{
+  size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  #pragma unroll
+  for (int c=0; c<NC; ++c) A[p*NC+c] = U[c*NP+p];
 }
 
 // ---------------------------------------------------------------------------------
@@ -189,19 +218,19 @@ __global__ void k_pack_wx( size_t n, const double* __restrict__ U, const double*
 //   gradient part: Riemann.cpp:334-360 (incl. the direction-indexed g[j]*n[j] form)
 //   flux part    : Riemann.cpp:798-871
 // ---------------------------------------------------------------------------------
-__device__ __forceinline__ void face_normal( const double* __restrict__ WX, const int N[3], double n[3] ) {
-  const double* a = WX + (size_t)N[0]*WXS + 5;
-  const double* b = WX + (size_t)N[1]*WXS + 5;
-  const double* c = WX + (size_t)N[2]*WXS + 5;
+__device__ __forceinline__ void face_normal( const double* __restrict__ X, size_t NP, const int N[3], double n[3] ) {
+  double a[3], b[3], c[3];
+  #pragma unroll
+  for (int j=0; j<3; ++j) { a[j] = X[j*NP+N[0]]; b[j] = X[j*NP+N[1]]; c[j] = X[j*NP+N[2]]; }
   double ba[3] = { b[0]-a[0], b[1]-a[1], b[2]-a[2] }, ca[3] = { c[0]-a[0], c[1]-a[1], c[2]-a[2] };
   n[0] = (ba[1]*ca[2] - ca[1]*ba[2]) / 12.0;
   n[1] = (ba[2]*ca[0] - ca[2]*ba[0]) / 12.0;
   n[2] = (ba[0]*ca[1] - ca[0]*ba[1]) / 12.0;
 }
 
-__global__ void k_bnd_grad( int nbn, const int* __restrict__ bn_off, const int* __restrict__ bn_face,
-                            const int* __restrict__ tri, const double* __restrict__ WX,
-                            double* __restrict__ Gb )
+__global__ void k_bnd_grad( int nbn, size_t NP, const int* __restrict__ bn_off, const int* __restrict__ bn_face,
+                            const int* __restrict__ tri, const double* __restrict__ X,
+                            const double* __restrict__ W, double* __restrict__ Gb )
 {
   int b = blockIdx.x*blockDim.x + threadIdx.x;
   if (b >= nbn) return;
@@ -212,15 +241,14 @@ __global__ void k_bnd_grad( int nbn, const int* __restrict__ bn_off, const int* 
     int f = bn_face[i] >> 2;
     int N[3] = { tri[f*3+0], tri[f*3+1], tri[f*3+2] };
     double n[3];
-    face_normal( WX, N, n );
-    const double* u0 = WX + (size_t)N[0]*WXS; const double* u1 = WX + (size_t)N[1]*WXS;
-    const double* u2 = WX + (size_t)N[2]*WXS;
+    face_normal( X, NP, N, n );
     #pragma unroll
     for (int c=0; c<NC; ++c) {
-      double uab = (u0[c] + u1[c])/4.0;
-      double ubc = (u1[c] + u2[c])/4.0;
-      double uca = (u2[c] + u0[c])/4.0;
-      double g[3] = { uab + uca + u0[c], uab + ubc + u1[c], ubc + uca + u2[c] };
+      double u0 = W[c*NP+N[0]], u1 = W[c*NP+N[1]], u2 = W[c*NP+N[2]];
+      double uab = (u0 + u1)/4.0;
+      double ubc = (u1 + u2)/4.0;
+      double uca = (u2 + u0)/4.0;
+      double g[3] = { uab + uca + u0, uab + ubc + u1, ubc + uca + u2 };
       #pragma unroll
       for (int j=0; j<3; ++j) acc[c*3+j] += g[j] * n[j];
     }
@@ -229,9 +257,9 @@ __global__ void k_bnd_grad( int nbn, const int* __restrict__ bn_off, const int* 
   for (int i=0; i<15; ++i) Gb[(size_t)b*15+i] = acc[i];
 }
 
-__global__ void k_bnd_rhs( int nbn, const int* __restrict__ bn_off, const int* __restrict__ bn_face,
+__global__ void k_bnd_rhs( int nbn, size_t NP, const int* __restrict__ bn_off, const int* __restrict__ bn_face,
                            const int* __restrict__ tri, const unsigned char* __restrict__ besym,
-                           const double* __restrict__ WX, const double* __restrict__ U,
+                           const double* __restrict__ X, const double* __restrict__ U,
                            double* __restrict__ Rb, double gamma )
 {
   int b = blockIdx.x*blockDim.x + threadIdx.x;
@@ -241,12 +269,11 @@ __global__ void k_bnd_rhs( int nbn, const int* __restrict__ bn_off, const int* _
     int f = bn_face[i] >> 2, k = bn_face[i] & 3;
     int N[3] = { tri[f*3+0], tri[f*3+1], tri[f*3+2] };
     double n[3];
-    face_normal( WX, N, n );
+    face_normal( X, NP, N, n );
     double fl[NC][3];
     #pragma unroll
     for (int m=0; m<3; ++m) {
-      const double* u = U + (size_t)N[m]*NC;
-      double r = u[0], ru = u[1], rv = u[2], rw = u[3], re = u[4];
+      double r = U[N[m]], ru = U[NP+N[m]], rv = U[2*NP+N[m]], rw = U[3*NP+N[m]], re = U[4*NP+N[m]];
       double p = (re - 0.5*(ru*ru + rv*rv + rw*rw)/r) * (gamma-1.0);
       double vn = besym[f*3+m] ? 0.0 : (n[0]*ru + n[1]*rv + n[2]*rw)/r;
       fl[0][m] = r*vn;
@@ -271,37 +298,40 @@ __global__ void k_bnd_rhs( int nbn, const int* __restrict__ bn_off, const int* _
 // ---------------------------------------------------------------------------------
 // gradient gather: one warp per 32-node slice, one thread per node
 //   G(p) = [ sum_edges -/+ d*(w_q + w_p)  +  boundary part ] / vol(p)
+// entry = signed edge slot: +(slot+1) if p is the edge's second node (receives +f),
+// -(slot+1) if it is the first (receives -f), 0 = padding (multiplier 0 on slot 0)
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void grad_sum( size_t p, int lane, long long base, int kmax,
-    const int* __restrict__ inc_q, const double* __restrict__ inc_d, size_t nent,
-    const double* __restrict__ WX, double acc[15] )
+    const int* __restrict__ inc_e, const int* __restrict__ inc_q, const double* __restrict__ D,
+    size_t nslot, const double* __restrict__ W, size_t NP, double acc[15] )
 {
   double wp[NC];
-  { double2 a = ldg2( WX + p*WXS ), b = ldg2( WX + p*WXS + 2 );
-    wp[0] = a.x; wp[1] = a.y; wp[2] = b.x; wp[3] = b.y; wp[4] = __ldg( WX + p*WXS + 4 ); }
+  #pragma unroll
+  for (int c=0; c<NC; ++c) wp[c] = __ldg( W + c*NP + p );
   #pragma unroll
   for (int i=0; i<15; ++i) acc[i] = 0.0;
+  #pragma unroll kNodeUnroll
   for (int k=0; k<kmax; ++k) {
     long long i = base + (long long)k*32 + lane;
+    int se = __ldg( inc_e + i );
     int q = __ldg( inc_q + i );
-    if (q < 0) continue;
-    double d0 = __ldg( inc_d + i ), d1 = __ldg( inc_d + nent + i ), d2 = __ldg( inc_d + 2*nent + i );
-    const double* wq = WX + (size_t)q*WXS;
-    double2 a = ldg2( wq ), b = ldg2( wq + 2 ); double e = __ldg( wq + 4 );
-    double s[NC] = { a.x + wp[0], a.y + wp[1], b.x + wp[2], b.y + wp[3], e + wp[4] };
+    double sg = se > 0 ? 1.0 : (se < 0 ? -1.0 : 0.0);
+    size_t sl = se == 0 ? 0 : (size_t)(abs(se)-1);
+    double d0 = sg * __ldg( D + sl ), d1 = sg * __ldg( D + nslot + sl ), d2 = sg * __ldg( D + 2*nslot + sl );
     #pragma unroll
     for (int c=0; c<NC; ++c) {
-      acc[c*3+0] += d0 * s[c];
-      acc[c*3+1] += d1 * s[c];
-      acc[c*3+2] += d2 * s[c];
+      double s = __ldg( W + c*NP + q ) + wp[c];
+      acc[c*3+0] += d0 * s;
+      acc[c*3+1] += d1 * s;
+      acc[c*3+2] += d2 * s;
     }
   }
 }
 
-__global__ void __launch_bounds__(256)
-k_grad_node( size_t npoin, const long long* __restrict__ sl_base, const int* __restrict__ inc_q,
-             const double* __restrict__ inc_d, size_t nent, const double* __restrict__ WX,
-             const int* __restrict__ bslot, const double* __restrict__ Gb,
+__global__ void __launch_bounds__(NODE_THREADS, GRAD_MINB)
+k_grad_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
+             const int* __restrict__ inc_q, const double* __restrict__ D, size_t nslot,
+             const double* __restrict__ W, const int* __restrict__ bslot, const double* __restrict__ Gb,
              const double* __restrict__ vol, double* __restrict__ G )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
@@ -311,27 +341,23 @@ k_grad_node( size_t npoin, const long long* __restrict__ sl_base, const int* __r
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
   double acc[15];
-  grad_sum( p, lane, base, kmax, inc_q, inc_d, nent, WX, acc );
+  grad_sum( p, lane, base, kmax, inc_e, inc_q, D, nslot, W, NP, acc );
   int b = bslot[p];
   if (b >= 0) {
     #pragma unroll
     for (int i=0; i<15; ++i) acc[i] += Gb[(size_t)b*15+i];
   }
   double vp = vol[p];
-  double* g = G + p*GS;
   #pragma unroll
-  for (int i=0; i<14; i+=2) {
-    double2 o = make_double2( acc[i]/vp, acc[i+1]/vp );
-    *reinterpret_cast< double2* >( g + i ) = o;
-  }
-  *reinterpret_cast< double2* >( g + 14 ) = make_double2( acc[14]/vp, 0.0 );
+  for (int i=0; i<15; ++i) G[i*NP+p] = acc[i]/vp;
 }
 
 // partial (un-normalised) gradient sums of the shared nodes, for the halo exchange
-__global__ void k_grad_shared( int nsh, const int* __restrict__ sh_node,
-             const long long* __restrict__ sl_base, const int* __restrict__ inc_q,
-             const double* __restrict__ inc_d, size_t nent, const double* __restrict__ WX,
-             const int* __restrict__ bslot, const double* __restrict__ Gb, double* __restrict__ part )
+__global__ void k_grad_shared( int nsh, size_t NP, const int* __restrict__ sh_node,
+             const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
+             const int* __restrict__ inc_q, const double* __restrict__ D, size_t nslot,
+             const double* __restrict__ W, const int* __restrict__ bslot,
+             const double* __restrict__ Gb, double* __restrict__ part )
 {
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= nsh) return;
@@ -340,7 +366,7 @@ __global__ void k_grad_shared( int nsh, const int* __restrict__ sh_node,
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
   double acc[15];
-  grad_sum( p, lane, base, kmax, inc_q, inc_d, nent, WX, acc );
+  grad_sum( p, lane, base, kmax, inc_e, inc_q, D, nslot, W, NP, acc );
   int b = bslot[p];
   if (b >= 0) for (int j=0; j<15; ++j) acc[j] += Gb[(size_t)b*15+j];
   for (int j=0; j<15; ++j) part[(size_t)i*15+j] = acc[j];
@@ -355,7 +381,7 @@ __global__ void k_pack( int nsend, int w, const int* __restrict__ sh_send,
   sendbuf[i] = part[(size_t)sh_send[s]*w + c];
 }
 
-__global__ void k_grad_finish( int nsh, const int* __restrict__ sh_node, const int* __restrict__ roff,
+__global__ void k_grad_finish( int nsh, size_t NP, const int* __restrict__ sh_node, const int* __restrict__ roff,
              const int* __restrict__ ridx, const double* __restrict__ part,
              const double* __restrict__ recvbuf, const double* __restrict__ vol, double* __restrict__ G )
 {
@@ -366,7 +392,7 @@ __global__ void k_grad_finish( int nsh, const int* __restrict__ sh_node, const i
   for (int j=0; j<15; ++j) {
     double a = part[(size_t)i*15+j];
     for (int r=roff[i]; r<roff[i+1]; ++r) a += recvbuf[(size_t)ridx[r]*15+j];
-    G[p*GS+j] = a / vp;
+    G[j*NP+p] = a / vp;
   }
 }
 
@@ -380,6 +406,20 @@ __global__ void k_grad_finish( int nsh, const int* __restrict__ sh_node, const i
 // exact: the reference's expression tree (8 divisions). fast: with a = d2+eps, b = d1+eps
 // the two limiter values are phi(a/b) = 2a/(a+b) and phi(b/a) = 2b/(a+b) when a and b
 // have the same sign and 0 otherwise, i.e. one reciprocal per side.
+// 1/x to ~1 ulp without the IEEE division's slow path: hardware seed (MUFU.RCP64H, ~20
+// bits) + two Newton steps. Only used by the non-"exact" limiter form; x is a sum of two
+// same-signed numbers of magnitude >= 1e-9 whenever the result is used.
+__device__ __forceinline__ double fast_rcp( double x )
+{
+  double y;
+  asm( "rcp.approx.ftz.f64 %0, %1;" : "=d"( y ) : "d"( x ) );
+  double e = fma( -x, y, 1.0 );
+  y = fma( y, e, y );
+  e = fma( -x, y, 1.0 );
+  y = fma( y, e, y );
+  return y;
+}
+
 template< bool EXACT >
 __device__ __forceinline__ void vanleer( double d1, double d2, double d3, double& incL, double& incR )
 {
@@ -398,7 +438,7 @@ __device__ __forceinline__ void vanleer( double d1, double d2, double d3, double
     double a = d2 + MUSCL_EPS, bL = d1 + MUSCL_EPS, bR = d3 + MUSCL_EPS;
     bool sL = (a > 0.0 && bL > 0.0) || (a < 0.0 && bL < 0.0);
     bool sR = (a > 0.0 && bR > 0.0) || (a < 0.0 && bR < 0.0);
-    double iL = 2.0 / (a + bL), iR = 2.0 / (a + bR);
+    double iL = 2.0 * fast_rcp( a + bL ), iR = 2.0 * fast_rcp( a + bR );
     double phiL = sL ? a*iL : 0.0, phi_L_inv = sL ? bL*iL : 0.0;
     double phiR = sR ? a*iR : 0.0, phi_R_inv = sR ? bR*iR : 0.0;
     incL = 0.25*(d1*(1.0-MUSCL_K)*phiL + d2*(1.0+MUSCL_K)*phi_L_inv);
@@ -406,22 +446,17 @@ __device__ __forceinline__ void vanleer( double d1, double d2, double d3, double
   }
 }
 
+// gp/gq: the 15 gradient components of the two end nodes, element i at gp[i*gs]
 template< bool EXACT >
-__device__ __forceinline__ void muscl( const double* __restrict__ Gp, const double* __restrict__ Gq,
+__device__ __forceinline__ void muscl( const double* gp, const double* gq, int gs,
                                        const double vw[3], double l[NC], double r[NC] )
 {
   double ls[NC], rs[NC], d1[NC], d3[NC];
-  double gp[GS], gq[GS];
-  #pragma unroll
-  for (int i=0; i<GS; i+=2) {
-    double2 a = ldg2( Gp + i ), b = ldg2( Gq + i );
-    gp[i] = a.x; gp[i+1] = a.y; gq[i] = b.x; gq[i+1] = b.y;
-  }
   #pragma unroll
   for (int c=0; c<NC; ++c) {
     ls[c] = l[c]; rs[c] = r[c];
-    double g1 = gp[c*3+0]*vw[0] + gp[c*3+1]*vw[1] + gp[c*3+2]*vw[2];
-    double g2 = gq[c*3+0]*vw[0] + gq[c*3+1]*vw[1] + gq[c*3+2]*vw[2];
+    double g1 = gp[(c*3+0)*gs]*vw[0] + gp[(c*3+1)*gs]*vw[1] + gp[(c*3+2)*gs]*vw[2];
+    double g2 = gq[(c*3+0)*gs]*vw[0] + gq[(c*3+1)*gs]*vw[1] + gq[(c*3+2)*gs]*vw[2];
     double delta2 = r[c] - l[c];
     d1[c] = 2.0 * g1 - delta2;
     d3[c] = 2.0 * g2 - delta2;
@@ -545,54 +580,67 @@ __device__ __forceinline__ void hllc( double l[NC], double r[NC], const double n
   }
 }
 
+// one thread per edge slot; a warp covers the j-th owned edge of 32 consecutive nodes.
+// The 30 gradient values of the two end nodes are fetched with cp.async straight into a
+// per-thread column of shared memory: the copies need no registers while in flight, so
+// every thread has its whole working set (46 doubles) outstanding at once and the kernel
+// still fits enough warps per SM to cover the latency; the limiter then reads its
+// operands from shared memory as it goes.
+__device__ __forceinline__ void cp_async8( double* smem_dst, const double* gsrc )
+{
+  unsigned d = (unsigned)__cvta_generic_to_shared( smem_dst );
+  asm volatile( "cp.async.ca.shared.global [%0], [%1], 8;" :: "r"( d ), "l"( gsrc ) : "memory" );
+}
+
 template< bool EXACT, int FLUX >
-__global__ void __launch_bounds__(256)
-k_flux_edge( size_t nedge, const int* __restrict__ ep, const int* __restrict__ eq,
-             const double* __restrict__ ed, const double* __restrict__ WX,
+__global__ void __launch_bounds__(FLUX_THREADS, FLUX_MINB)
+k_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __restrict__ eq,
+             const double* __restrict__ D, const double* __restrict__ W, const double* __restrict__ X,
              const double* __restrict__ G, double* __restrict__ F, DParams P )
 {
+  __shared__ double sg[30*FLUX_THREADS];
   size_t e = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
-  if (e >= nedge) return;
-  size_t p = ep[e], q = eq[e];
-  double n[3] = { ed[e], ed[nedge+e], ed[2*nedge+e] };
-  const double* wp = WX + p*WXS; const double* wq = WX + q*WXS;
+  if (e >= nslot) return;
+  int pi = ep[e];
+  if (pi < 0) return;                      // padding slot
+  size_t p = pi, q = eq[e];
+  double* gp = sg + threadIdx.x;
+  double* gq = gp + 15*FLUX_THREADS;
+  #pragma unroll
+  for (int i=0; i<15; ++i) { cp_async8( gp + i*FLUX_THREADS, G + i*NP + p ); cp_async8( gq + i*FLUX_THREADS, G + i*NP + q ); }
+  asm volatile( "cp.async.commit_group;" ::: "memory" );
+  double n[3] = { D[e], D[nslot+e], D[2*nslot+e] };
   double l[NC], r[NC], vw[3];
-  {
-    double2 a0 = ldg2( wp ), a1 = ldg2( wp+2 ), a2 = ldg2( wp+4 ), a3 = ldg2( wp+6 );
-    double2 b0 = ldg2( wq ), b1 = ldg2( wq+2 ), b2 = ldg2( wq+4 ), b3 = ldg2( wq+6 );
-    l[0] = a0.x; l[1] = a0.y; l[2] = a1.x; l[3] = a1.y; l[4] = a2.x;
-    r[0] = b0.x; r[1] = b0.y; r[2] = b1.x; r[3] = b1.y; r[4] = b2.x;
-    vw[0] = b2.y - a2.y; vw[1] = b3.x - a3.x; vw[2] = b3.y - a3.y;
-  }
-  muscl< EXACT >( G + p*GS, G + q*GS, vw, l, r );
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { l[c] = __ldg( W + c*NP + p ); r[c] = __ldg( W + c*NP + q ); }
+  #pragma unroll
+  for (int j=0; j<3; ++j) vw[j] = __ldg( X + j*NP + q ) - __ldg( X + j*NP + p );
+  asm volatile( "cp.async.wait_group 0;" ::: "memory" );
+  muscl< EXACT >( gp, gq, FLUX_THREADS, vw, l, r );
   double f[NC];
   if (FLUX == 0) rusanov( l, r, n, P, f ); else hllc( l, r, n, P, f );
-  double* o = F + e*NC;
   #pragma unroll
-  for (int c=0; c<NC; ++c) o[c] = f[c];
+  for (int c=0; c<NC; ++c) F[c*nslot+e] = f[c];
 }
 
 // ---------------------------------------------------------------------------------
 // flux gather per node (+ boundary + source) and, fused, the RK stage update
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void rhs_sum( size_t p, int lane, long long base, int kmax,
-    const int* __restrict__ inc_e, const double* __restrict__ F, const int* __restrict__ bslot,
-    const double* __restrict__ Rb, const double* __restrict__ S, int src_mask,
-    const double* __restrict__ v, double acc[NC] )
+    const int* __restrict__ inc_e, const double* __restrict__ F, size_t nslot,
+    const int* __restrict__ bslot, const double* __restrict__ Rb, const double* __restrict__ S,
+    int src_mask, const double* __restrict__ v, double acc[NC] )
 {
   #pragma unroll
   for (int c=0; c<NC; ++c) acc[c] = 0.0;
+  // sg*f is exact, so this equals the add/subtract of the reference's scatter
+  #pragma unroll kNodeUnroll
   for (int k=0; k<kmax; ++k) {
     int se = __ldg( inc_e + base + (long long)k*32 + lane );
-    if (se == 0) continue;
-    const double* f = F + (size_t)(abs(se)-1)*NC;
-    if (se > 0) {
-      #pragma unroll
-      for (int c=0; c<NC; ++c) acc[c] += __ldg( f + c );
-    } else {
-      #pragma unroll
-      for (int c=0; c<NC; ++c) acc[c] -= __ldg( f + c );
-    }
+    double sg = se > 0 ? 1.0 : (se < 0 ? -1.0 : 0.0);
+    size_t sl = se == 0 ? 0 : (size_t)(abs(se)-1);
+    #pragma unroll
+    for (int c=0; c<NC; ++c) acc[c] = fma( sg, __ldg( F + c*nslot + sl ), acc[c] );
   }
   int b = bslot[p];
   if (b >= 0) {
@@ -607,12 +655,12 @@ __device__ __forceinline__ void rhs_sum( size_t p, int lane, long long base, int
 }
 
 template< bool FUSED >
-__global__ void __launch_bounds__(256)
-k_rhs_node( size_t npoin, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
-            const double* __restrict__ F, const int* __restrict__ bslot, const double* __restrict__ Rb,
-            const double* __restrict__ S, int src_mask, const double* __restrict__ v,
-            const double* __restrict__ vol, const double* __restrict__ Un, double rkdt,
-            double* __restrict__ U, double* __restrict__ WX, double* __restrict__ R )
+__global__ void __launch_bounds__(NODE_THREADS, RHS_MINB)
+k_rhs_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
+            const double* __restrict__ F, size_t nslot, const int* __restrict__ bslot,
+            const double* __restrict__ Rb, const double* __restrict__ S, int src_mask,
+            const double* __restrict__ v, const double* __restrict__ vol, const double* __restrict__ Un,
+            double rkdt, double* __restrict__ U, double* __restrict__ W, double* __restrict__ R )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -621,17 +669,15 @@ k_rhs_node( size_t npoin, const long long* __restrict__ sl_base, const int* __re
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
   double acc[NC];
-  rhs_sum( p, lane, base, kmax, inc_e, F, bslot, Rb, S, src_mask, v, acc );
+  rhs_sum( p, lane, base, kmax, inc_e, F, nslot, bslot, Rb, S, src_mask, v, acc );
   if (FUSED) {
     double vp = vol[p];
     double u[NC], w[NC];
     #pragma unroll
-    for (int c=0; c<NC; ++c) { u[c] = Un[p*NC+c] - rkdt * acc[c] / vp; U[p*NC+c] = u[c]; }
+    for (int c=0; c<NC; ++c) { u[c] = Un[c*NP+p] - rkdt * acc[c] / vp; U[c*NP+p] = u[c]; }
     primitive( u, w );
-    double* o = WX + p*WXS;
-    *reinterpret_cast< double2* >( o ) = make_double2( w[0], w[1] );
-    *reinterpret_cast< double2* >( o+2 ) = make_double2( w[2], w[3] );
-    o[4] = w[4];
+    #pragma unroll
+    for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
   } else {
     #pragma unroll
     for (int c=0; c<NC; ++c) R[p*NC+c] = acc[c];
@@ -640,9 +686,9 @@ k_rhs_node( size_t npoin, const long long* __restrict__ sl_base, const int* __re
 
 __global__ void k_rhs_shared( int nsh, const int* __restrict__ sh_node,
             const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
-            const double* __restrict__ F, const int* __restrict__ bslot, const double* __restrict__ Rb,
-            const double* __restrict__ S, int src_mask, const double* __restrict__ v,
-            double* __restrict__ part )
+            const double* __restrict__ F, size_t nslot, const int* __restrict__ bslot,
+            const double* __restrict__ Rb, const double* __restrict__ S, int src_mask,
+            const double* __restrict__ v, double* __restrict__ part )
 {
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= nsh) return;
@@ -651,16 +697,16 @@ __global__ void k_rhs_shared( int nsh, const int* __restrict__ sh_node,
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
   double acc[NC];
-  rhs_sum( p, lane, base, kmax, inc_e, F, bslot, Rb, S, src_mask, v, acc );
+  rhs_sum( p, lane, base, kmax, inc_e, F, nslot, bslot, Rb, S, src_mask, v, acc );
   for (int c=0; c<NC; ++c) part[(size_t)i*NC+c] = acc[c];
 }
 
 template< bool FUSED >
-__global__ void k_rhs_finish( int nsh, const int* __restrict__ sh_node, const int* __restrict__ roff,
+__global__ void k_rhs_finish( int nsh, size_t NP, const int* __restrict__ sh_node, const int* __restrict__ roff,
             const int* __restrict__ ridx, const double* __restrict__ part,
             const double* __restrict__ recvbuf, const double* __restrict__ vol,
             const double* __restrict__ Un, double rkdt, double* __restrict__ U,
-            double* __restrict__ WX, double* __restrict__ R )
+            double* __restrict__ W, double* __restrict__ R )
 {
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= nsh) return;
@@ -673,47 +719,47 @@ __global__ void k_rhs_finish( int nsh, const int* __restrict__ sh_node, const in
   }
   if (FUSED) {
     double vp = vol[p], u[NC], w[NC];
-    for (int c=0; c<NC; ++c) { u[c] = Un[p*NC+c] - rkdt * acc[c] / vp; U[p*NC+c] = u[c]; }
+    for (int c=0; c<NC; ++c) { u[c] = Un[c*NP+p] - rkdt * acc[c] / vp; U[c*NP+p] = u[c]; }
     primitive( u, w );
-    for (int c=0; c<NC; ++c) WX[p*WXS+c] = w[c];
+    for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
   } else {
     for (int c=0; c<NC; ++c) R[p*NC+c] = acc[c];
   }
 }
 
 // unfused RK update from a materialised R (drop-in for RieCG::solve :1016-1021)
-__global__ void k_update( size_t npoin, const double* __restrict__ R, const double* __restrict__ vol,
+__global__ void k_update( size_t npoin, size_t NP, const double* __restrict__ R, const double* __restrict__ vol,
                           const double* __restrict__ Un, double rkdt, double* __restrict__ U,
-                          double* __restrict__ WX )
+                          double* __restrict__ W )
 {
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= npoin) return;
   double vp = vol[p], u[NC], w[NC];
   #pragma unroll
-  for (int c=0; c<NC; ++c) { u[c] = Un[p*NC+c] - rkdt * R[p*NC+c] / vp; U[p*NC+c] = u[c]; }
+  for (int c=0; c<NC; ++c) { u[c] = Un[c*NP+p] - rkdt * R[p*NC+c] / vp; U[c*NP+p] = u[c]; }
   primitive( u, w );
   #pragma unroll
-  for (int c=0; c<NC; ++c) WX[p*WXS+c] = w[c];
+  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
 }
 
 // ---------------------------------------------------------------------------------
 // boundary conditions, BC.cpp:29-241, one thread per BC node applying dirbc, symbc,
-// farbc, prebc in the reference's order, then refreshing the primitive record
+// farbc, prebc in the reference's order, then refreshing the primitive variables
 // ---------------------------------------------------------------------------------
 struct FarState { double r, p, u, v, w; };
 
-__global__ void k_bc( int nbc, const int* __restrict__ node, const int* __restrict__ dir,
+__global__ void k_bc( int nbc, size_t NP, const int* __restrict__ node, const int* __restrict__ dir,
                       const int* __restrict__ dir_mask, const double* __restrict__ dir_val,
                       const int* __restrict__ symoff, const double* __restrict__ sym_n,
                       const int* __restrict__ faroff, const double* __restrict__ far_n, FarState fs,
                       const int* __restrict__ pre, const double* __restrict__ pre_val,
-                      double gamma, double* __restrict__ U, double* __restrict__ WX )
+                      double gamma, double* __restrict__ U, double* __restrict__ W )
 {
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= nbc) return;
   size_t p = node[i];
   double u[NC];
-  for (int c=0; c<NC; ++c) u[c] = U[p*NC+c];
+  for (int c=0; c<NC; ++c) u[c] = U[c*NP+p];
   int d = dir[i];
   if (d >= 0) for (int c=0; c<NC; ++c) if (dir_mask[d*NC+c] == 1) u[c] = dir_val[d*NC+c];
   for (int s=symoff[i]; s<symoff[i+1]; ++s) {                 // symbc, BC.cpp:110-136
@@ -747,9 +793,9 @@ __global__ void k_bc( int nbc, const int* __restrict__ node, const int* __restri
     u[4] = pre_val[pb*2+1]/(gamma-1.0) + 0.5*u[0]*(uu*uu + vv*vv + ww*ww);
   }
   double w[NC];
-  for (int c=0; c<NC; ++c) U[p*NC+c] = u[c];
+  for (int c=0; c<NC; ++c) U[c*NP+p] = u[c];
   primitive( u, w );
-  for (int c=0; c<NC; ++c) WX[p*WXS+c] = w[c];
+  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
 }
 
 // ---------------------------------------------------------------------------------
@@ -784,14 +830,13 @@ __device__ __forceinline__ void block_reduce( double v[NV], double* __restrict__
 }
 
 __global__ void __launch_bounds__(RED_THREADS)
-k_dt( size_t npoin, const double* __restrict__ U, const double* __restrict__ vol, double gamma,
+k_dt( size_t npoin, size_t NP, const double* __restrict__ U, const double* __restrict__ vol, double gamma,
       double* __restrict__ part )
 {
   double m[1] = { 1.7976931348623157e308 };
   for (size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x; p < npoin; p += (size_t)gridDim.x*blockDim.x) {
-    const double* u_ = U + p*NC;
-    double r = u_[0], u = u_[1]/r, v = u_[2]/r, w = u_[3]/r;
-    double pr = (u_[4] - 0.5*r*(u*u + v*v + w*w)) * (gamma-1.0);
+    double r = U[p], u = U[NP+p]/r, v = U[2*NP+p]/r, w = U[3*NP+p]/r;
+    double pr = (U[4*NP+p] - 0.5*r*(u*u + v*v + w*w)) * (gamma-1.0);
     double c = sqrt( gamma * fmax(pr,0.0) / r );
     double L = cbrt( vol[p] );
     double vel = sqrt( u*u + v*v + w*w );
@@ -816,7 +861,7 @@ k_reduce_final( int nblocks, const double* __restrict__ part, double* __restrict
 
 constexpr int NDIAG = 4*NC+1;
 __global__ void __launch_bounds__(RED_THREADS)
-k_diag( size_t npoin, const double* __restrict__ U, const double* __restrict__ Un,
+k_diag( size_t npoin, size_t NP, const double* __restrict__ U, const double* __restrict__ Un,
         const double* __restrict__ v, const double* __restrict__ an, double* __restrict__ part )
 {
   double a[NDIAG];
@@ -826,8 +871,8 @@ k_diag( size_t npoin, const double* __restrict__ U, const double* __restrict__ U
     double vp = v[p], u[NC];
     #pragma unroll
     for (int c=0; c<NC; ++c) {
-      u[c] = U[p*NC+c];
-      double d = u[c] - Un[p*NC+c];
+      u[c] = U[c*NP+p];
+      double d = u[c] - Un[c*NP+p];
       a[c] += u[c]*u[c]*vp;
       a[NC+c] += d*d*vp;
     }
@@ -897,22 +942,22 @@ void do_grad( xyst_ctx* c )
 {
   need_mesh( c );
   auto s = c->stream;
-  if (c->nbn) { k_bnd_grad<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->bn_off.p, c->bn_face.p,
-                  c->tri.p, c->WX.p, c->Gb.p ); ++c->launches; }
+  if (c->nbn) { k_bnd_grad<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
+                  c->tri.p, c->X.p, c->W.p, c->Gb.p ); ++c->launches; }
   bool halo = c->nsh > 0 && c->comm;
   if (halo) {
-    k_grad_shared<<< nblk( c->nsh, 128 ), 128, 0, s >>>( (int)c->nsh, c->sh_node.p, c->sl_base.p,
-      c->inc_q.p, c->inc_d.p, c->nent, c->WX.p, c->bslot.p, c->Gb.p, c->sh_part.p ); ++c->launches;
+    k_grad_shared<<< nblk( c->nsh, 128 ), 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sl_base.p,
+      c->inc_e.p, c->inc_q.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->sh_part.p ); ++c->launches;
     exchange( c, 15 );
   }
   {
     ProfScope ps( c, "grad" );
-    k_grad_node<<< nblk( c->nslice*32, 256 ), 256, 0, s >>>( c->npoin, c->sl_base.p, c->inc_q.p,
-      c->inc_d.p, c->nent, c->WX.p, c->bslot.p, c->Gb.p, c->vol.p, c->G.p ); ++c->launches;
+    k_grad_node<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p,
+      c->inc_e.p, c->inc_q.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->vol.p, c->G.p ); ++c->launches;
   }
   if (halo) {
     exchange_wait( c );
-    k_grad_finish<<< nblk( c->nsh, 128 ), 128, 0, s >>>( (int)c->nsh, c->sh_node.p, c->sh_roff.p,
+    k_grad_finish<<< nblk( c->nsh, 128 ), 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p,
       c->sh_ridx.p, c->sh_part.p, c->sh_recvbuf.p, c->vol.p, c->G.p ); ++c->launches;
   }
   CK( cudaGetLastError() );
@@ -923,10 +968,10 @@ void do_flux( xyst_ctx* c )
   auto s = c->stream;
   auto P = dparams( c );
   ProfScope ps( c, "flux" );
-  unsigned g = nblk( c->nedge, 256 );
+  unsigned g = nblk( c->nslot, FLUX_THREADS );
   if (!g) return;
-  #define LAUNCH_FLUX( EX, FL ) k_flux_edge< EX, FL ><<< g, 256, 0, s >>>( c->nedge, c->ep.p, c->eq.p, \
-      c->ed.p, c->WX.p, c->G.p, c->F.p, P )
+  #define LAUNCH_FLUX( EX, FL ) k_flux_edge< EX, FL ><<< g, FLUX_THREADS, 0, s >>>( c->nslot, c->NP, c->ep.p, \
+      c->eq.p, c->D.p, c->W.p, c->X.p, c->G.p, c->F.p, P )
   if (P.exact) { if (P.flux == 0) LAUNCH_FLUX( true, 0 ); else LAUNCH_FLUX( true, 1 ); }
   else         { if (P.flux == 0) LAUNCH_FLUX( false, 0 ); else LAUNCH_FLUX( false, 1 ); }
   #undef LAUNCH_FLUX
@@ -939,34 +984,34 @@ void do_flux( xyst_ctx* c )
 void do_rhs_nodes( xyst_ctx* c, bool fused, double rkdt, const double* Uin, const double* Un, double* Uout )
 {
   auto s = c->stream;
-  if (c->nbn) { k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->bn_off.p, c->bn_face.p,
-                  c->tri.p, c->besym.p, c->WX.p, Uin, c->Rb.p, c->prm.gamma ); ++c->launches; }
+  if (c->nbn) { k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
+                  c->tri.p, c->besym.p, c->X.p, Uin, c->Rb.p, c->prm.gamma ); ++c->launches; }
   bool halo = c->nsh > 0 && c->comm;
   if (halo) {
     k_rhs_shared<<< nblk( c->nsh, 128 ), 128, 0, s >>>( (int)c->nsh, c->sh_node.p, c->sl_base.p,
-      c->inc_e.p, c->F.p, c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->sh_part.p ); ++c->launches;
+      c->inc_e.p, c->F.p, c->nslot, c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->sh_part.p ); ++c->launches;
     exchange( c, NC );
   }
   {
     ProfScope ps( c, fused ? "update" : "rhsnode" );
-    unsigned g = nblk( c->nslice*32, 256 );
+    unsigned g = nblk( c->nslice*32, NODE_THREADS );
     if (fused)
-      k_rhs_node< true ><<< g, 256, 0, s >>>( c->npoin, c->sl_base.p, c->inc_e.p, c->F.p, c->bslot.p,
-        c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, rkdt, Uout, c->WX.p, c->R.p );
+      k_rhs_node< true ><<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
+        c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, rkdt, Uout, c->W.p, c->R.p );
     else
-      k_rhs_node< false ><<< g, 256, 0, s >>>( c->npoin, c->sl_base.p, c->inc_e.p, c->F.p, c->bslot.p,
-        c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, rkdt, Uout, c->WX.p, c->R.p );
+      k_rhs_node< false ><<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
+        c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, rkdt, Uout, c->W.p, c->R.p );
     ++c->launches;
   }
   if (halo) {
     exchange_wait( c );
     unsigned g = nblk( c->nsh, 128 );
     if (fused)
-      k_rhs_finish< true ><<< g, 128, 0, s >>>( (int)c->nsh, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
-        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, rkdt, Uout, c->WX.p, c->R.p );
+      k_rhs_finish< true ><<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
+        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, rkdt, Uout, c->W.p, c->R.p );
     else
-      k_rhs_finish< false ><<< g, 128, 0, s >>>( (int)c->nsh, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
-        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, rkdt, Uout, c->WX.p, c->R.p );
+      k_rhs_finish< false ><<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
+        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, rkdt, Uout, c->W.p, c->R.p );
     ++c->launches;
   }
   CK( cudaGetLastError() );
@@ -976,16 +1021,16 @@ void do_bc( xyst_ctx* c )
 {
   if (!c->nbc) return;
   FarState fs{ c->far_r, c->far_p, c->far_u[0], c->far_u[1], c->far_u[2] };
-  k_bc<<< nblk( c->nbc, 128 ), 128, 0, c->stream >>>( (int)c->nbc, c->bc_node.p, c->bc_dir.p,
+  k_bc<<< nblk( c->nbc, 128 ), 128, 0, c->stream >>>( (int)c->nbc, c->NP, c->bc_node.p, c->bc_dir.p,
     c->dir_mask.p, c->dir_val.p, c->bc_symoff.p, c->sym_n.p, c->bc_faroff.p, c->far_n.p, fs,
-    c->bc_pre.p, c->pre_val.p, c->prm.gamma, c->U.p, c->WX.p ); ++c->launches;
+    c->bc_pre.p, c->pre_val.p, c->prm.gamma, c->U.p, c->W.p ); ++c->launches;
   CK( cudaGetLastError() );
 }
 
 static const double rkcoef[3] = { 1.0/3.0, 1.0/2.0, 1.0 };   // RieCG.cpp:41
 
 void save_un( xyst_ctx* c ) {           // RieCG.cpp:1011  m_un = m_u
-  CK( cudaMemcpyAsync( c->Un.p, c->U.p, c->npoin*NC*sizeof(double), cudaMemcpyDeviceToDevice, c->stream ) );
+  CK( cudaMemcpyAsync( c->Un.p, c->U.p, c->NP*NC*sizeof(double), cudaMemcpyDeviceToDevice, c->stream ) );
 }
 
 } // namespace
@@ -1084,7 +1129,9 @@ int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* 
     for (int j=0; j<3; ++j) ed.d[j] = dsupint[2][e*3+j];
     edges.push_back( ed );
   }
-  // locality order: by lower node id, then higher node id (stable, deterministic)
+  // --- edge slots in owner order ----------------------------------------------------
+  // owner = lower endpoint; its edges sorted by the other endpoint. The j-th edge owned
+  // by node o lives in slot ebase[o/32] + j*32 + o%32 (padding slots have ep = -1).
   std::vector< int > perm( ne );
   std::iota( perm.begin(), perm.end(), 0 );
   std::sort( perm.begin(), perm.end(), [&]( int a, int b ){
@@ -1093,18 +1140,34 @@ int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* 
     int ha = std::max( edges[a].p, edges[a].q ), hb = std::max( edges[b].p, edges[b].q );
     if (ha != hb) return ha < hb;
     return a < b; } );
-  std::vector< int > ep( ne ), eq( ne );
-  std::vector< double > ed( 3*ne );
-  for (size_t i=0; i<ne; ++i) {
-    const auto& e = edges[perm[i]];
-    ep[i] = e.p; eq[i] = e.q;
-    for (int j=0; j<3; ++j) ed[j*ne+i] = e.d[j];
-  }
-  // --- sliced-ELL incidence: node -> (signed edge, neighbour, signed normal) ----------
-  // reference scatter: G(p) -= f, G(q) += f with f = d*(u_q+u_p)  (Riemann.cpp:321-323)
-  std::vector< int > deg( npoin, 0 );
-  for (size_t i=0; i<ne; ++i) { ++deg[ep[i]]; ++deg[eq[i]]; }
   size_t nslice = (npoin + 31) / 32;
+  std::vector< int > udeg( npoin, 0 );
+  for (size_t i=0; i<ne; ++i) ++udeg[ std::min( edges[i].p, edges[i].q ) ];
+  std::vector< long long > ebase( nslice+1, 0 );
+  for (size_t s=0; s<nslice; ++s) {
+    int km = 0;
+    for (size_t p=s*32; p<std::min( npoin, s*32+32 ); ++p) km = std::max( km, udeg[p] );
+    ebase[s+1] = ebase[s] + (long long)km*32;
+  }
+  size_t nslot = (size_t)ebase[nslice];
+  if (nslot > 0x7ffffff0ULL) throw std::runtime_error( "too many edge slots for 32-bit ids" );
+  std::vector< int > ep( nslot, -1 ), eq( nslot, -1 ), slot_of( ne );
+  std::vector< double > ed( 3*nslot, 0.0 );
+  { std::vector< int > fillu( npoin, 0 );
+    for (size_t i=0; i<ne; ++i) {
+      const auto& e = edges[perm[i]];
+      int o = std::min( e.p, e.q );
+      size_t sl = (size_t)ebase[o/32] + (size_t)fillu[o]*32 + (size_t)(o%32);
+      ++fillu[o];
+      ep[sl] = e.p; eq[sl] = e.q; slot_of[i] = (int)sl;
+      for (int j=0; j<3; ++j) ed[j*nslot+sl] = e.d[j];
+    } }
+  // --- sliced-ELL incidence: node -> (signed slot, neighbour) -------------------------
+  // reference scatter: G(p) -= f, G(q) += f with f = d*(u_q+u_p)  (Riemann.cpp:321-323).
+  // Per node: its owned edges first (ascending other endpoint), then the edges owned by
+  // lower neighbours (ascending neighbour) -- the fixed summation order of the gathers.
+  std::vector< int > deg( npoin, 0 );
+  for (size_t i=0; i<ne; ++i) { ++deg[edges[i].p]; ++deg[edges[i].q]; }
   std::vector< long long > base( nslice+1, 0 );
   for (size_t s=0; s<nslice; ++s) {
     int km = 0;
@@ -1112,18 +1175,23 @@ int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* 
     base[s+1] = base[s] + (long long)km*32;
   }
   size_t nent = (size_t)base[nslice];
-  std::vector< int > inc_e( nent, 0 ), inc_q( nent, -1 ), fill( npoin, 0 );
-  std::vector< double > inc_d( 3*nent, 0.0 );
-  for (size_t i=0; i<ne; ++i) {
-    for (int side=0; side<2; ++side) {
-      int node = side ? eq[i] : ep[i], other = side ? ep[i] : eq[i];
-      double sg = side ? 1.0 : -1.0;
-      size_t slot = (size_t)base[node/32] + (size_t)fill[node]*32 + (size_t)(node%32);
-      ++fill[node];
-      inc_e[slot] = side ? (int)(i+1) : -(int)(i+1);
-      inc_q[slot] = other;
-      for (int j=0; j<3; ++j) inc_d[j*nent+slot] = sg * ed[j*ne+i];
-    }
+  std::vector< int > inc_e( nent, 0 ), inc_q( nent, 0 ), fill( npoin, 0 );
+  for (size_t sl=0; sl<nslice; ++sl)            // padding: the node itself (last node for the tail slice)
+    for (size_t j=(size_t)base[sl]; j<(size_t)base[sl+1]; ++j) inc_q[j] = (int)std::min( npoin-1, sl*32 + (j - (size_t)base[sl])%32 );
+  auto addinc = [&]( int node, int other, int signedslot ) {
+    size_t slot = (size_t)base[node/32] + (size_t)fill[node]*32 + (size_t)(node%32);
+    ++fill[node];
+    inc_e[slot] = signedslot; inc_q[slot] = other;
+  };
+  for (size_t i=0; i<ne; ++i) {                 // owned edges (sorted by owner, other)
+    const auto& e = edges[perm[i]];
+    int o = std::min( e.p, e.q ), h = std::max( e.p, e.q );
+    addinc( o, h, o == e.q ? slot_of[i]+1 : -(slot_of[i]+1) );
+  }
+  for (size_t i=0; i<ne; ++i) {                 // edges owned by lower neighbours: arrive ascending in owner
+    const auto& e = edges[perm[i]];
+    int o = std::min( e.p, e.q ), h = std::max( e.p, e.q );
+    addinc( h, o, h == e.q ? slot_of[i]+1 : -(slot_of[i]+1) );
   }
   // --- boundary faces: node -> (face, local index) CSR -------------------------------
   std::vector< int > tri( ntri*3 );
@@ -1139,26 +1207,25 @@ int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* 
     for (size_t t=0; t<ntri; ++t) for (int k=0; k<3; ++k) bn_face[ f[ bslot[tri[t*3+k]] ]++ ] = (int)(t*4) + k; }
   // --- upload ------------------------------------------------------------------------
   auto s = c->stream;
-  c->npoin = npoin; c->nedge = ne; c->ntri = ntri; c->nslice = nslice; c->nent = nent; c->nbn = nbn;
-  c->ep.upload( ep, s ); c->eq.upload( eq, s ); c->ed.upload( ed, s );
+  size_t NP = nslice*32;
+  c->npoin = npoin; c->NP = NP; c->nedge = ne; c->nslot = nslot; c->ntri = ntri; c->nslice = nslice;
+  c->nent = nent; c->nbn = nbn;
+  c->ep.upload( ep, s ); c->eq.upload( eq, s ); c->D.upload( ed, s );
   c->sl_base.upload( base, s ); c->inc_e.upload( inc_e, s ); c->inc_q.upload( inc_q, s );
-  c->inc_d.upload( inc_d, s );
   c->tri.upload( tri, s );
   c->besym.upload( std::vector< unsigned char >( besym, besym + ntri*3 ), s );
   c->bslot.upload( bslot, s ); c->bn_node.upload( bn_node, s ); c->bn_off.upload( bn_off, s );
   c->bn_face.upload( bn_face, s );
   c->Gb.alloc( nbn*15 ); c->Rb.alloc( nbn*NC );
-  c->vol.upload( std::vector< double >( vol, vol+npoin ), s );
-  c->v.upload( std::vector< double >( v, v+npoin ), s );
-  c->U.alloc( npoin*NC ); c->Un.alloc( npoin*NC ); c->R.alloc( npoin*NC );
-  c->WX.alloc( npoin*WXS ); c->G.alloc( npoin*GS ); c->F.alloc( ne*NC );
-  CK( cudaMemsetAsync( c->U.p, 0, npoin*NC*sizeof(double), s ) );
-  CK( cudaMemsetAsync( c->Un.p, 0, npoin*NC*sizeof(double), s ) );
-  CK( cudaMemsetAsync( c->G.p, 0, npoin*GS*sizeof(double), s ) );
-  // coordinates into the packed record
-  { std::vector< double > wx( npoin*WXS, 1.0 );
-    for (size_t p=0; p<npoin; ++p) { wx[p*WXS+5] = x[p]; wx[p*WXS+6] = y[p]; wx[p*WXS+7] = z[p]; }
-    c->WX.upload( wx, s ); }
+  { std::vector< double > pv( NP, 1.0 ), pw( NP, 1.0 ), px( 3*NP, 0.0 );
+    for (size_t p=0; p<npoin; ++p) { pv[p] = vol[p]; pw[p] = v[p]; px[p] = x[p]; px[NP+p] = y[p]; px[2*NP+p] = z[p]; }
+    c->vol.upload( pv, s ); c->v.upload( pw, s ); c->X.upload( px, s ); }
+  c->U.alloc( NP*NC ); c->Un.alloc( NP*NC ); c->W.alloc( NP*NC ); c->G.alloc( NP*15 );
+  c->R.alloc( npoin*NC ); c->stage.alloc( npoin*NC ); c->F.alloc( std::max< size_t >( nslot, 1 )*NC );
+  { std::vector< double > one( NP*NC, 1.0 );    // a harmless state until xyst_state_set
+    c->U.upload( one, s ); c->Un.upload( one, s ); c->W.upload( one, s ); }
+  CK( cudaMemsetAsync( c->G.p, 0, NP*15*sizeof(double), s ) );
+  CK( cudaMemsetAsync( c->F.p, 0, std::max< size_t >( nslot, 1 )*NC*sizeof(double), s ) );
   c->S.release(); c->src_mask = 0;
   CK( cudaStreamSynchronize( s ) );
   API_END
@@ -1241,8 +1308,8 @@ int xyst_state_set( xyst_ctx* c, const double* U )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  CK( cudaMemcpyAsync( c->U.p, U, c->npoin*NC*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
-  k_pack_wx<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->U.p, nullptr, nullptr, nullptr, c->WX.p, 0 );
+  CK( cudaMemcpyAsync( c->stage.p, U, c->npoin*NC*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+  k_set_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->stage.p, c->U.p, c->W.p );
   ++c->launches;
   CK( cudaGetLastError() );
   CK( cudaStreamSynchronize( c->stream ) );
@@ -1254,7 +1321,10 @@ int xyst_state_get( xyst_ctx* c, double* U )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  CK( cudaMemcpyAsync( U, c->U.p, c->npoin*NC*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+  k_get_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->stage.p );
+  ++c->launches;
+  CK( cudaGetLastError() );
+  CK( cudaMemcpyAsync( U, c->stage.p, c->npoin*NC*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
   CK( cudaStreamSynchronize( c->stream ) );
   API_END
 }
@@ -1266,10 +1336,10 @@ int xyst_grad_get( xyst_ctx* c, double* G )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  std::vector< double > h( c->npoin*GS );
+  std::vector< double > h( c->NP*15 );
   CK( cudaMemcpyAsync( h.data(), c->G.p, h.size()*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
   CK( cudaStreamSynchronize( c->stream ) );
-  for (size_t p=0; p<c->npoin; ++p) for (int i=0; i<15; ++i) G[p*15+i] = h[p*GS+i];
+  for (size_t p=0; p<c->npoin; ++p) for (size_t i=0; i<15; ++i) G[p*15+i] = h[i*c->NP+p];
   API_END
 }
 
@@ -1300,8 +1370,8 @@ int xyst_rk_update( xyst_ctx* c, int stage, double dt )
   need_mesh( c );
   if (stage < 0 || stage > 2) throw std::runtime_error( "stage must be 0, 1 or 2" );
   if (stage == 0) save_un( c );
-  k_update<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->R.p, c->vol.p, c->Un.p,
-    rkcoef[stage]*dt, c->U.p, c->WX.p ); ++c->launches;
+  k_update<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->Un.p,
+    rkcoef[stage]*dt, c->U.p, c->W.p ); ++c->launches;
   CK( cudaGetLastError() );
   API_END
 }
@@ -1314,7 +1384,7 @@ int xyst_dt_min( xyst_ctx* c, double cfl, double* dt )
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
   int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( c->npoin, RED_THREADS ) );
-  k_dt<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->U.p, c->vol.p, c->prm.gamma, c->red.p );
+  k_dt<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->vol.p, c->prm.gamma, c->red.p );
   k_reduce_final< 1, true ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, c->red.p + (size_t)RED_BLOCKS*NDIAG );
   c->launches += 2;
   CK( cudaMemcpyAsync( c->red_host, c->red.p + (size_t)RED_BLOCKS*NDIAG, sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
@@ -1355,7 +1425,7 @@ int xyst_diag( xyst_ctx* c, const double* an, double* out )
   DevBuf< double > dan;
   if (an) dan.upload( std::vector< double >( an, an + c->npoin*NC ), c->stream );
   int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( c->npoin, RED_THREADS ) );
-  k_diag<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->U.p, c->Un.p, c->v.p, dan.p, c->red.p );
+  k_diag<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->Un.p, c->v.p, dan.p, c->red.p );
   k_reduce_final< NDIAG, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, c->red.p + (size_t)RED_BLOCKS*NDIAG );
   c->launches += 2;
   CK( cudaMemcpyAsync( c->red_host, c->red.p + (size_t)RED_BLOCKS*NDIAG, NDIAG*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );

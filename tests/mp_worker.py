@@ -1,0 +1,108 @@
+"""Multi-process worker for the partitioned-path tests (launched by torch.distributed.run).
+
+  mode=host : gloo, CPU only -- partition, comm maps, volume / boundary-normal exchange
+              through the host mirror's communication hooks, compared with the oracle's
+              multi-chare serial run (same element->partition map)
+  mode=gpu  : nccl, one GPU per rank -- the full RieCG time loop with device-side packing +
+              NCCL send/recv halo sums and all-reduces, compared with the same oracle run
+"""
+import os
+import sys
+import json
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+import oraclelib as O                                     # noqa: E402
+from xyst_b200 import hostapi as H, capi                 # noqa: E402
+from host_common import fixture_to_host_mesh             # noqa: E402
+
+
+def gloo_comm(solver, rank, world):
+    """Communication hooks on torch.distributed (any backend with all_gather_object)."""
+    commmap = solver.get("commmap"); gid = solver.get("gid")
+    shared = solver.get("shared")
+    sh_gid = gid[shared.astype(np.int64)]
+
+    def fn(op, w, n, a):
+        if op == 0:
+            vals = a.reshape(n, w).copy()
+            out = [None] * world
+            dist.all_gather_object(out, (sh_gid.tolist(), vals.tolist()))
+            tot = vals.copy()
+            # fixed order: ascending rank of the contributing partition
+            for r in range(world):
+                if r == rank:
+                    continue
+                g, v = out[r]
+                pos = {x: i for i, x in enumerate(g)}
+                for i, x in enumerate(sh_gid.tolist()):
+                    j = pos.get(x)
+                    if j is not None and _shares(commmap, r, x):
+                        tot[i] += np.asarray(v[j])
+            a[:] = tot.reshape(-1)
+        else:
+            t = torch.from_numpy(a.copy())
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 1 else dist.ReduceOp.MIN)
+            a[:] = t.numpy()
+    return fn
+
+
+def _shares(commmap, r, g):
+    i = 0
+    f = commmap.astype(np.int64)
+    while i < len(f):
+        b, n = int(f[i]), int(f[i + 1])
+        if b == r:
+            return g in set(f[i + 2:i + 2 + n].tolist())
+        i += 2 + n
+    return False
+
+
+def main():
+    mode, case, nsteps, out = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    kw = O.CASES[case]
+    mesh = O.load_mesh(case)
+    hm = fixture_to_host_mesh(mesh)
+    part = H.rcb(hm["coord"], hm["tets"], world)
+    if mode == "gpu":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
+    s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"],
+                      hm["set_tri"], nparts=world, part=rank, tetpart=part)
+    s.prepare()
+    res = {"rank": rank}
+    if mode == "host":
+        s.set_comm(gloo_comm(s, rank, world), world, rank)
+        s.host_setup()
+    else:
+        idb = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            import ctypes as C
+            buf = (C.c_char * 128)()
+            assert capi.lib().xyst_comm_unique_id(buf) == 0
+            idb = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(idb, 0)
+        s.attach(local, world, rank, bytes(idb.cpu().numpy().tobytes()))
+        s.setup()
+        rows = s.step(nsteps)
+        res["rows"] = rows.tolist()
+        res["u"] = s.get("u").tolist()
+        res["launches"] = s.ctx().launch_count()
+    for n in ("gid", "vol", "v", "symbcnodes", "symbcnorms", "dsupint0", "dsupedge0"):
+        res[n] = s.get(n).tolist()
+    res["meshvol"] = s.scalar("meshvol")
+    res["part"] = part.tolist() if rank == 0 else None
+    json.dump(res, open("%s.%d.json" % (out, rank), "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <string>
 #include "driver.hpp"
+#include "cg_port.hpp"
 #include "oracle.h"
 
 using namespace orc;
@@ -185,6 +186,95 @@ int orc_kernel( void* hv, int chare, const char* what, int stage, double t, doub
     else { g_err = "orc_kernel: unknown " + w; return -1; }
     return 0;
   } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// ---- linear solver (cg_port.hpp) --------------------------------------------------------
+void* orc_cg_create( const char* pc ) {
+  auto s = new cg::Solver; s->pc = pc; return s;
+}
+void orc_cg_destroy( void* h ) { delete static_cast< cg::Solver* >( h ); }
+const char* orc_cg_backend() { return cg::matrix_backend(); }
+
+int orc_cg_add( void* h, std::size_t npoin, std::size_t ncomp, std::size_t npsup1, const std::uint64_t* psup1,
+                const std::uint64_t* psup2, const std::uint64_t* gid, int ncomm, const int* comm_rank,
+                const std::uint64_t* comm_off, const std::uint64_t* comm_gid )
+{
+  try {
+    cg::Psup ps;
+    ps.first.assign( psup1, psup1+npsup1 ); ps.second.assign( psup2, psup2+npoin+1 );
+    std::vector< std::size_t > g( gid, gid+npoin );
+    cg::CommMap cm;
+    for (int i=0; i<ncomm; ++i) cm[comm_rank[i]].insert( comm_gid+comm_off[i], comm_gid+comm_off[i+1] );
+    return static_cast< int >( static_cast< cg::Solver* >( h )->add( ncomp, ps, g, cm ) );
+  } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+int orc_cg_laplacian( void* h, int part, std::size_t ntet, const std::uint64_t* inpoel,
+                      const double* x, const double* y, const double* z )
+{
+  try {
+    auto& P = *static_cast< cg::Solver* >( h )->parts.at( static_cast< std::size_t >( part ) );
+    std::vector< std::size_t > inp( inpoel, inpoel+ntet*4 );
+    auto np = P.gid.size();
+    cg::laplacian( P.A, inp, std::vector< double >( x, x+np ), std::vector< double >( y, y+np ), std::vector< double >( z, z+np ) );
+    return 0;
+  } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+int orc_cg_dirichlet( void* h, int part, std::size_t node, double val, std::size_t pos )
+{
+  try {
+    auto& P = *static_cast< cg::Solver* >( h )->parts.at( static_cast< std::size_t >( part ) );
+    P.A.dirichlet( node, val, P.b, P.gid, P.nodeCommMap, pos );
+    return 0;
+  } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
+
+int orc_cg_set( void* h, int part, const double* x, const double* b )
+{
+  auto& P = *static_cast< cg::Solver* >( h )->parts.at( static_cast< std::size_t >( part ) );
+  if (x) P.x.assign( x, x+P.x.size() );
+  if (b) P.b.assign( b, b+P.b.size() );
+  return 0;
+}
+
+//! name: x b r p q z d (doubles), ia ja (uint64, 1-based), a (doubles, CSR order)
+std::size_t orc_cg_get( void* h, int part, const char* name, void* out, std::size_t cap )
+{
+  auto& P = *static_cast< cg::Solver* >( h )->parts.at( static_cast< std::size_t >( part ) );
+  std::string n( name );
+  if (n == "x") return put( P.x, out, cap );
+  if (n == "b") return put( P.b, out, cap );
+  if (n == "r") return put( P.r, out, cap );
+  if (n == "q") return put( P.q, out, cap );
+  if (n == "d") return put( P.d, out, cap );
+  if (n == "ia") return put( P.S.IA(), out, cap );
+  if (n == "ja") return put( P.S.JA(), out, cap );
+  if (n == "a") {
+    const auto& ia = P.S.IA(); const auto& ja = P.S.JA(); auto nc = P.S.Ncomp();
+    std::vector< double > a( ja.size() );
+    for (std::size_t r=0; r+1<ia.size(); ++r)
+      for (std::size_t j=ia[r]-1; j<ia[r+1]-1; ++j) a[j] = P.A( r/nc, (ja[j]-1)/nc, r%nc );
+    return put( a, out, cap );
+  }
+  g_err = "orc_cg_get: unknown " + n; return static_cast< std::size_t >( -1 );
+}
+
+int orc_cg_mult( void* h, int part, const double* x, double* r )
+{
+  auto& P = *static_cast< cg::Solver* >( h )->parts.at( static_cast< std::size_t >( part ) );
+  std::vector< double > xv( x, x+P.x.size() ), rv( P.x.size() );
+  P.A.mult( xv, rv );
+  std::copy( rv.begin(), rv.end(), r );
+  return 0;
+}
+
+double orc_cg_setup( void* h ) {
+  try { return static_cast< cg::Solver* >( h )->setup(); } catch (std::exception& e) { g_err = e.what(); return std::nan(""); }
+}
+double orc_cg_solve( void* h, std::size_t maxit, double tol, std::uint64_t* it ) {
+  try { auto s = static_cast< cg::Solver* >( h ); auto r = s->solve( maxit, tol ); if (it) *it = s->it; return r; }
+  catch (std::exception& e) { g_err = e.what(); return std::nan(""); }
 }
 
 std::uint64_t orc_siphash_ids( const std::uint64_t* ids, int n )

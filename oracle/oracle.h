@@ -51,6 +51,22 @@ int orc_set_u( void* h, int chare, const double* u );
 int orc_kernel( void* h, int chare, const char* what, int stage, double t, double dt );
 uint64_t orc_siphash_ids( const uint64_t* ids, int n );
 
+/* linear solver: tk::CSR + ConjugateGradients restatement (cg_port.hpp) */
+void* orc_cg_create( const char* pc );
+void orc_cg_destroy( void* h );
+const char* orc_cg_backend(void);
+int orc_cg_add( void* h, size_t npoin, size_t ncomp, size_t npsup1, const uint64_t* psup1,
+                const uint64_t* psup2, const uint64_t* gid, int ncomm, const int* comm_rank,
+                const uint64_t* comm_off, const uint64_t* comm_gid );
+int orc_cg_laplacian( void* h, int part, size_t ntet, const uint64_t* inpoel,
+                      const double* x, const double* y, const double* z );
+int orc_cg_dirichlet( void* h, int part, size_t node, double val, size_t pos );
+int orc_cg_set( void* h, int part, const double* x, const double* b );
+size_t orc_cg_get( void* h, int part, const char* name, void* out, size_t cap );
+int orc_cg_mult( void* h, int part, const double* x, double* r );
+double orc_cg_setup( void* h );
+double orc_cg_solve( void* h, size_t maxit, double tol, uint64_t* it );
+
 #ifdef __cplusplus
 }
 #endif

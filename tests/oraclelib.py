@@ -211,3 +211,96 @@ def numdiff_ok(res, gold, abs_tol, rel_tol):
     ae = np.abs(res - gold)
     re = ae / np.maximum(np.minimum(np.abs(res), np.abs(gold)), 1e-300)
     return (ae <= abs_tol) | (re <= rel_tol)
+
+
+# ---- linear solver oracle (oracle/cg_port.hpp) ------------------------------------------------
+def psup_of(inpoel, npoin):
+    """Points surrounding points in the reference's linked-list form (psup1 with a leading 0,
+    psup2 offsets), neighbour ids ascending per point (tk::genPsup)."""
+    nb = [set() for _ in range(npoin)]
+    for t in np.asarray(inpoel, dtype=np.int64).reshape(-1, 4):
+        for a in t:
+            for b in t:
+                if a != b:
+                    nb[a].add(int(b))
+    p1 = [0]; p2 = [0]
+    for s in nb:
+        p1.extend(sorted(s)); p2.append(len(p1) - 1)
+    return np.asarray(p1, np.uint64), np.asarray(p2, np.uint64)
+
+
+class CGOracle:
+    """Serial multi-partition conjugate gradients (restatement of ConjugateGradients.cpp)."""
+
+    def __init__(self, flavour="port", pc="none"):
+        self.L = lib(flavour)
+        L = self.L
+        L.orc_cg_create.restype = C.c_void_p; L.orc_cg_create.argtypes = [C.c_char_p]
+        L.orc_cg_destroy.argtypes = [C.c_void_p]
+        L.orc_cg_backend.restype = C.c_char_p
+        L.orc_cg_add.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t] + [C.c_void_p] * 3 + \
+            [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_cg_laplacian.argtypes = [C.c_void_p, C.c_int, C.c_size_t] + [C.c_void_p] * 4
+        L.orc_cg_dirichlet.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_double, C.c_size_t]
+        L.orc_cg_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_cg_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_size_t]
+        L.orc_cg_get.restype = C.c_size_t
+        L.orc_cg_mult.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_cg_setup.argtypes = [C.c_void_p]; L.orc_cg_setup.restype = C.c_double
+        L.orc_cg_solve.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.POINTER(C.c_uint64)]
+        L.orc_cg_solve.restype = C.c_double
+        self.h = L.orc_cg_create(pc.encode())
+        self.ncomp = []; self.np = []
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_cg_destroy(self.h); self.h = None
+
+    def add(self, inpoel, npoin, ncomp=1, gid=None, comm=None):
+        p1, p2 = psup_of(inpoel, npoin)
+        gid = np.arange(npoin, dtype=np.uint64) if gid is None else np.ascontiguousarray(gid, np.uint64)
+        comm = comm or {}
+        ranks = np.asarray(sorted(comm), np.int32)
+        off = [0]; g = []
+        for r in ranks:
+            g.extend(comm[int(r)]); off.append(len(g))
+        off = np.asarray(off, np.uint64); g = np.asarray(g, np.uint64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        k = self.L.orc_cg_add(self.h, npoin, ncomp, len(p1), p(p1), p(p2), p(gid), len(ranks),
+                              p(ranks) if len(ranks) else None, p(off), p(g) if len(g) else None)
+        assert k >= 0, self.L.orc_last_error()
+        self.ncomp.append(ncomp); self.np.append(npoin)
+        return k
+
+    def laplacian(self, part, inpoel, coord):
+        t = np.ascontiguousarray(inpoel, np.uint64); co = np.ascontiguousarray(coord, np.float64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        assert self.L.orc_cg_laplacian(self.h, part, len(t), p(t), p(co[0]), p(co[1]), p(co[2])) == 0
+
+    def dirichlet(self, part, node, val=0.0, pos=0):
+        assert self.L.orc_cg_dirichlet(self.h, part, node, val, pos) == 0
+
+    def set(self, part, x=None, b=None):
+        x = None if x is None else np.ascontiguousarray(x, np.float64)
+        b = None if b is None else np.ascontiguousarray(b, np.float64)
+        self.L.orc_cg_set(self.h, part, None if x is None else x.ctypes.data, None if b is None else b.ctypes.data)
+
+    def get(self, part, name):
+        nb = self.L.orc_cg_get(self.h, part, name.encode(), None, 0)
+        dt = np.uint64 if name in ("ia", "ja") else np.float64
+        a = np.zeros(nb // 8, dt)
+        self.L.orc_cg_get(self.h, part, name.encode(), a.ctypes.data, nb)
+        return a
+
+    def mult(self, part, x):
+        x = np.ascontiguousarray(x, np.float64); r = np.zeros_like(x)
+        self.L.orc_cg_mult(self.h, part, x.ctypes.data, r.ctypes.data)
+        return r
+
+    def setup(self):
+        return self.L.orc_cg_setup(self.h)
+
+    def solve(self, maxit, tol):
+        it = C.c_uint64()
+        r = self.L.orc_cg_solve(self.h, maxit, tol, C.byref(it))
+        return r, int(it.value)

@@ -138,6 +138,25 @@ int xyst_halo_sum(xyst_ctx* ctx, int w, double* vals);
 int xyst_allreduce_min(xyst_ctx* ctx, double* v, int n);
 int xyst_allreduce_sum(xyst_ctx* ctx, double* v, int n);
 
+/* ---- linear solver of the pressure projection (ChoCG/LohCG) -----------------------------
+ * tk::CSR (src/LinearSolver/CSR.hpp:30-107): block CSR exactly as the reference stores it,
+ * nrow = npoin*ncomp scalar rows, 1-based ia[nrow+1] / ja[nnz], values a[nnz] (after
+ * CSR::dirichlet etc. were applied by the caller). */
+int xyst_csr_upload(xyst_ctx* ctx, size_t nrow, size_t ncomp, const size_t* ia, const size_t* ja,
+                    const double* a);
+/* CSR::mult (CSR.cpp:154-172): r = A x, this partition's own contribution; host vectors. */
+int xyst_csr_mult(xyst_ctx* ctx, const double* x, double* r);
+/* ConjugateGradients::setup (ConjugateGradients.cpp:105-126 -> residual, pc, initres, normb,
+ * rho): x = initial guess, b = right-hand side (complete on every partition); pc 0 = "none",
+ * 1 = "jacobi"; slave[i] != 0 marks nodes counted by a lower partition (tk::slave, skipped in
+ * dot products), count[i] = tk::count (1 + number of sharers); both NULL in serial.
+ * Shared rows are summed/averaged over the lists of xyst_halo_upload. Returns ||b||. */
+int xyst_cg_setup(xyst_ctx* ctx, const double* x, const double* b, int pc,
+                  const uint8_t* slave, const double* count, double* normb);
+/* ConjugateGradients::solve (:558-823): iterate until ||r|| < tol*max(||b||,->1) or maxit. */
+int xyst_cg_solve(xyst_ctx* ctx, size_t maxit, double tol, size_t* it, double* normr);
+int xyst_cg_get_x(xyst_ctx* ctx, double* x);
+
 /* Counters: kernels launched by this context so far; edges held. */
 uint64_t xyst_launch_count(const xyst_ctx* ctx);
 uint64_t xyst_nedge(const xyst_ctx* ctx);

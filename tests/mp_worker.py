@@ -61,10 +61,57 @@ def _shares(commmap, r, g):
     return False
 
 
+def cg_main(out, rank, world, local):
+    """2-partition CG of the reference's unit test (TestConjugateGradients.cpp:236-355) on 2 GPUs."""
+    import ctypes as C
+    import xyst_b200
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import cg_cube as K
+    ncomp = int(sys.argv[2])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P = K.PART[rank]
+    o = O.CGOracle("port")
+    o.add(P["inpoel"], len(P["gid"]), ncomp, P["gid"], P["comm"])
+    o.laplacian(0, P["inpoel"], P["coord"])
+    npn = len(P["gid"])
+    o.set(0, x=np.zeros(npn * ncomp), b=np.ones(npn * ncomp))
+    for c in range(ncomp):
+        o.dirichlet(0, int(np.where(P["gid"] == 0)[0][0]), 0.0, c)       # CSR::dirichlet with 1/count diagonal
+    ctx = xyst_b200.Context(device=local)
+    idb = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf = (C.c_char * 128)()
+        assert capi.lib().xyst_comm_unique_id(buf) == 0
+        idb = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+    dist.broadcast(idb, 0)
+    L = capi.lib()
+    assert L.xyst_comm_init(ctx.h, world, rank, bytes(idb.cpu().numpy().tobytes())) == 0
+    other = 1 - rank
+    sh_g = np.asarray(P["comm"][other], np.uint64)                       # ascending global ids
+    lid = {int(g): i for i, g in enumerate(P["gid"])}
+    sh = np.asarray([lid[int(g)] for g in sh_g], np.uint64)
+    nr = np.asarray([other], np.int32); off = np.asarray([0, len(sh)], np.uint64)
+    assert L.xyst_halo_upload(ctx.h, 1, nr.ctypes.data, off.ctypes.data, sh.ctypes.data) == 0
+    ctx.csr_upload(o.get(0, "ia"), o.get(0, "ja"), o.get(0, "a"), ncomp)
+    shared = set(int(g) for g in sh_g)
+    slave = np.asarray([1 if (int(g) in shared and other < rank) else 0 for g in P["gid"]], np.uint8)
+    count = np.asarray([2.0 if int(g) in shared else 1.0 for g in P["gid"]])
+    k = K.KAT[ncomp]
+    normb = ctx.cg_setup(np.zeros(npn * ncomp), o.get(0, "b"), "none", slave, count)
+    res, it = ctx.cg_solve(k["maxit"], k["tol"])
+    json.dump({"rank": rank, "normb": normb, "res": res, "it": it, "x": ctx.cg_x().tolist(),
+               "gid": P["gid"].tolist()}, open("%s.%d.json" % (out, rank), "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     mode, case, nsteps, out = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    if mode == "cg":
+        return cg_main(out, rank, world, local)
     kw = O.CASES[case]
     mesh = O.load_mesh(case)
     hm = fixture_to_host_mesh(mesh)

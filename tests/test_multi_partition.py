@@ -76,3 +76,31 @@ def test_two_gpus_match_oracle_two_chares(case, tmp_path):
         U = np.asarray(res[k]["u"]); Uo = o.get("u", k)
         assert np.abs(U - Uo).max() <= 1e-12 * np.abs(Uo).max()
         assert res[k]["launches"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ncomp", [1, 3])
+def test_two_gpus_cg_known_answer(ncomp, tmp_path):
+    """TestConjugateGradients.cpp tests 2 and 4 (2 PEs, 1 and 3 DOFs) with the SpMV halo sum,
+    masked dots and shared-row averaging done on two GPUs over NCCL."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import cg_cube as K
+    res = launch("cg", str(ncomp), 0, tmp_path)
+    k = K.KAT[ncomp]
+    # serial oracle solution for comparison
+    o = O.CGOracle("port")
+    o.add(K.INPOEL, 14, ncomp); o.laplacian(0, K.INPOEL, K.COORD)
+    o.set(0, x=np.zeros(14 * ncomp), b=np.ones(14 * ncomp))
+    for c in range(ncomp):
+        o.dirichlet(0, 0, 0.0, c)
+    o.setup(); o.solve(k["maxit"], k["tol"])
+    xs = o.get(0, "x").reshape(14, ncomp)
+    for r in res:
+        assert abs(r["normb"] - k["normb"]) < 1e-12
+        assert abs(r["res"] - k["normres"]) < 1e-12
+        x = np.asarray(r["x"]).reshape(-1, ncomp)
+        assert np.abs(x - xs[np.asarray(r["gid"], np.int64)]).max() < 1e-12
+    assert res[0]["it"] == res[1]["it"]

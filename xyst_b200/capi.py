@@ -26,7 +26,8 @@ SYMBOLS = [
     "xyst_riecg_rhs", "xyst_rhs_get", "xyst_rk_update", "xyst_apply_bc", "xyst_dt_min",
     "xyst_riecg_stage", "xyst_riecg_step", "xyst_diag", "xyst_comm_unique_id", "xyst_comm_init",
     "xyst_halo_upload", "xyst_halo_sum", "xyst_allreduce_min", "xyst_allreduce_sum", "xyst_launch_count",
-    "xyst_nedge", "xyst_kernel_time",
+    "xyst_nedge", "xyst_kernel_time", "xyst_csr_upload", "xyst_csr_mult", "xyst_cg_setup",
+    "xyst_cg_solve", "xyst_cg_get_x",
 ]
 
 
@@ -75,6 +76,13 @@ def lib():
     L.xyst_nedge.argtypes = [C.c_void_p]; L.xyst_nedge.restype = C.c_uint64
     L.xyst_kernel_time.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_double),
                                    C.POINTER(C.c_uint64)]
+    L.xyst_csr_upload.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.xyst_csr_mult.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.xyst_cg_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                C.POINTER(C.c_double)]
+    L.xyst_cg_solve.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.POINTER(C.c_size_t),
+                                C.POINTER(C.c_double)]
+    L.xyst_cg_get_x.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -200,6 +208,36 @@ class Context:
         an = None if an is None else _f64(an)
         self._ck(self.L.xyst_diag(self.h, _p(an), _p(out)))
         return out
+
+    # ---- linear solver (tk::CSR + ConjugateGradients) ----
+    def csr_upload(self, ia, ja, a, ncomp=1):
+        ia = _u64(ia); ja = _u64(ja); a = _f64(a)
+        self.cg_nrow = len(ia) - 1
+        self._ck(self.L.xyst_csr_upload(self.h, self.cg_nrow, ncomp, _p(ia), _p(ja), _p(a)))
+
+    def csr_mult(self, x):
+        x = _f64(x); r = np.empty_like(x)
+        self._ck(self.L.xyst_csr_mult(self.h, _p(x), _p(r)))
+        return r
+
+    def cg_setup(self, x, b, pc="none", slave=None, count=None):
+        x = _f64(x); b = _f64(b)
+        sl = None if slave is None else np.ascontiguousarray(slave, np.uint8)
+        ct = None if count is None else _f64(count)
+        nb = C.c_double()
+        self._ck(self.L.xyst_cg_setup(self.h, _p(x), _p(b), {"none": 0, "jacobi": 1}[pc], _p(sl), _p(ct),
+                                      C.byref(nb)))
+        return nb.value
+
+    def cg_solve(self, maxit, tol):
+        it = C.c_size_t(); nr = C.c_double()
+        self._ck(self.L.xyst_cg_solve(self.h, maxit, tol, C.byref(it), C.byref(nr)))
+        return nr.value, int(it.value)
+
+    def cg_x(self):
+        x = np.empty(self.cg_nrow)
+        self._ck(self.L.xyst_cg_get_x(self.h, _p(x)))
+        return x
 
     def launch_count(self):
         return int(self.L.xyst_launch_count(self.h))

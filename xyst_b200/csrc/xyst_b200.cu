@@ -170,6 +170,11 @@ struct xyst_ctx {
   DevBuf< double > sh_part, sh_sendbuf, sh_recvbuf;
   size_t nsh = 0, nsend = 0;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  // linear solver: sliced-ELL matrix over scalar rows + CG vectors
+  size_t cg_nrow = 0, cg_ncomp = 1, cg_nslice = 0, cg_nent = 0;
+  DevBuf< long long > cg_base; DevBuf< int > cg_col; DevBuf< double > cg_val, cg_diag;
+  DevBuf< double > cg_x, cg_b, cg_r, cg_p, cg_q, cg_z, cg_d, cg_mask, cg_cnt, cg_scal;
+  double cg_normb = 0.0; bool cg_converged = false, cg_finished = false;
   // profiling
   bool prof_on = false;
   std::map< std::string, Prof > prof;
@@ -892,6 +897,124 @@ k_diag( size_t npoin, size_t NP, const double* __restrict__ U, const double* __r
 }
 
 // ---------------------------------------------------------------------------------
+// linear solver: CSR::mult (CSR.cpp:154-172) and the vector operations of
+// ConjugateGradients.cpp:584-823. Matrix in sliced ELL over scalar rows (one warp per 32
+// rows, entry k of lane l at base + 32k + l: coalesced), dots by fixed two-pass trees.
+// device scalars: [0] rho [1] rho0 [2] alpha [3] beta [4] normr2 [5] finished
+//                 [8..] partial sums handed to the all-reduce
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_spmv( size_t nrow, const long long* __restrict__ base, const int* __restrict__ col,
+        const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t r = slice*32 + lane;
+  if (r >= nrow) return;
+  long long b = base[slice];
+  int kmax = (int)((base[slice+1] - b) >> 5);
+  double acc = 0.0;
+  #pragma unroll 4
+  for (int k=0; k<kmax; ++k) {
+    long long i = b + (long long)k*32 + lane;
+    acc += __ldg( val + i ) * __ldg( x + __ldg( col + i ) );
+  }
+  y[r] = acc;
+}
+
+// p = z + beta p    (ConjugateGradients::next :584-599)
+__global__ void k_cg_p( size_t n, const double* __restrict__ scal, const double* __restrict__ z, double* __restrict__ p )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  p[i] = z[i] + scal[3] * p[i];
+}
+
+// partial masked dot products (ConjugateGradients::dot :128-151): NV pairs at once
+template< int NV >
+__global__ void __launch_bounds__(RED_THREADS)
+k_cg_dot( size_t n, const double* __restrict__ mask, const double* __restrict__ a0, const double* __restrict__ b0,
+          const double* __restrict__ a1, const double* __restrict__ b1, double* __restrict__ part )
+{
+  double s[NV];
+  #pragma unroll
+  for (int k=0; k<NV; ++k) s[k] = 0.0;
+  for (size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x*blockDim.x) {
+    double m = mask[i];
+    s[0] += m * (a0[i] * b0[i]);
+    if (NV > 1) s[1] += m * (a1[i] * b1[i]);
+  }
+  block_reduce< NV, false >( s, part );
+}
+
+// r -= alpha q ; z = r/d ; x += alpha p ; partial (r,z) and (r,r)   (pq :671-704, rz :717-727)
+__global__ void __launch_bounds__(RED_THREADS)
+k_cg_update( size_t n, const double* __restrict__ scal, const double* __restrict__ mask,
+             const double* __restrict__ q, const double* __restrict__ d, const double* __restrict__ p,
+             double* __restrict__ r, double* __restrict__ z, double* __restrict__ x, double* __restrict__ part )
+{
+  double s[2] = { 0.0, 0.0 };
+  double alpha = scal[2];
+  for (size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x*blockDim.x) {
+    double ri = r[i] - alpha * q[i];
+    double zi = ri / d[i];
+    r[i] = ri; z[i] = zi;
+    x[i] += alpha * p[i];
+    double m = mask[i];
+    s[0] += m * (ri * zi);
+    s[1] += m * (ri * ri);
+  }
+  block_reduce< 2, false >( s, part );
+}
+
+// scalar bookkeeping after a reduction; mode 0: alpha = rho/(p,q) (pq :671-690);
+// mode 1: rho0 = rho, rho = (r,z), beta = rho/rho0, normr2 = (r,r)  (next :586-588, rz :719)
+__global__ void k_cg_scalars( int mode, double* __restrict__ scal )
+{
+  if (threadIdx.x || blockIdx.x) return;
+  if (mode == 0) {
+    double d = scal[8];
+    if (fabs(d) < 2.220446049250313e-16) { scal[5] = 1.0; scal[2] = 0.0; } else scal[2] = scal[0] / d;
+  } else {
+    scal[1] = scal[0];
+    scal[0] = scal[8];
+    scal[3] = scal[0] / scal[1];
+    scal[4] = scal[9];
+  }
+}
+
+// shared rows: sum of the sharers (halo) then optionally divide by the count (x :772-785)
+__global__ void k_cg_shared_get( int nsh, int w, const int* __restrict__ sh_node, const double* __restrict__ v, double* __restrict__ part )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)nsh*w) return;
+  part[i] = v[(size_t)sh_node[i/w]*w + i%w];
+}
+__global__ void k_cg_shared_put( int nsh, int w, const int* __restrict__ sh_node, const int* __restrict__ roff,
+                                 const int* __restrict__ ridx, const double* __restrict__ part,
+                                 const double* __restrict__ recvbuf, const double* __restrict__ cnt, int average,
+                                 double* __restrict__ v )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)nsh*w) return;
+  size_t s = i / w, c = i % w;
+  double a = part[i];
+  for (int r=roff[s]; r<roff[s+1]; ++r) a += recvbuf[(size_t)ridx[r]*w + c];
+  size_t row = (size_t)sh_node[s]*w + c;
+  v[row] = average ? a / cnt[row] : a;
+}
+__global__ void k_cg_div( size_t n, const double* __restrict__ r, const double* __restrict__ d, double* __restrict__ z )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i < n) z[i] = r[i] / d[i];
+}
+__global__ void k_cg_resid( size_t n, const double* __restrict__ b, double* __restrict__ r, double* __restrict__ p )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i < n) { double v = r[i] * -1.0 + b[i]; r[i] = v; p[i] = v; }     // initres :293-298
+}
+
+// ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
 inline unsigned nblk( size_t n, int t ) { return (unsigned)((n + (size_t)t - 1) / (size_t)t); }
@@ -1530,6 +1653,176 @@ static int allreduce( xyst_ctx* c, double* v, int n, int op )
 }
 int xyst_allreduce_min( xyst_ctx* c, double* v, int n ) { return allreduce( c, v, n, NCCL_MIN ); }
 int xyst_allreduce_sum( xyst_ctx* c, double* v, int n ) { return allreduce( c, v, n, NCCL_SUM ); }
+
+// ---- linear solver ------------------------------------------------------------------
+static void cg_halo( xyst_ctx* c, double* v, int average )
+{
+  if (!(c->nsh > 0 && c->comm)) return;
+  int w = (int)c->cg_ncomp;
+  size_t n = c->nsh*(size_t)w;
+  k_cg_shared_get<<< nblk( n, 256 ), 256, 0, c->stream >>>( (int)c->nsh, w, c->sh_node.p, v, c->sh_part.p ); ++c->launches;
+  exchange( c, w );
+  exchange_wait( c );
+  k_cg_shared_put<<< nblk( n, 256 ), 256, 0, c->stream >>>( (int)c->nsh, w, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
+    c->sh_part.p, c->sh_recvbuf.p, c->cg_cnt.p, average, v ); ++c->launches;
+}
+
+// local partial sums -> scal[8..8+nv), all-reduced over the communicator
+static void cg_reduce( xyst_ctx* c, int nv, int nb )
+{
+  double* out = c->cg_scal.p + 8;
+  if (nv == 1) k_reduce_final< 1, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, out );
+  else         k_reduce_final< 2, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, out );
+  ++c->launches;
+  if (c->comm) NK( g_nccl.AllReduce( out, out, (size_t)nv, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream ) );
+}
+
+int xyst_csr_upload( xyst_ctx* c, size_t nrow, size_t ncomp, const size_t* ia, const size_t* ja, const double* a )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  if (!nrow || !ncomp || nrow % ncomp) throw std::runtime_error( "csr_upload: bad sizes" );
+  if (nrow > 0x7fffffffULL) throw std::runtime_error( "csr_upload: too many rows" );
+  size_t nslice = (nrow + 31) / 32;
+  std::vector< long long > base( nslice+1, 0 );
+  for (size_t s=0; s<nslice; ++s) {
+    size_t km = 0;
+    for (size_t r=s*32; r<std::min( nrow, s*32+32 ); ++r) km = std::max( km, ia[r+1]-ia[r] );
+    base[s+1] = base[s] + (long long)km*32;
+  }
+  size_t nent = (size_t)base[nslice];
+  std::vector< int > col( nent ); std::vector< double > val( nent, 0.0 ), diag( nrow, 0.0 );
+  for (size_t s=0; s<nslice; ++s)
+    for (size_t j=(size_t)base[s]; j<(size_t)base[s+1]; ++j) col[j] = (int)std::min( nrow-1, s*32 + (j-(size_t)base[s])%32 );
+  for (size_t r=0; r<nrow; ++r)
+    for (size_t j=ia[r]-1, k=0; j<ia[r+1]-1; ++j, ++k) {
+      if (ja[j] < 1 || ja[j] > nrow) throw std::runtime_error( "csr_upload: column out of range" );
+      size_t slot = (size_t)base[r/32] + k*32 + r%32;
+      col[slot] = (int)(ja[j]-1); val[slot] = a[j];
+      if (ja[j]-1 == r) diag[r] = a[j];
+    }
+  auto s = c->stream;
+  c->cg_nrow = nrow; c->cg_ncomp = ncomp; c->cg_nslice = nslice; c->cg_nent = nent;
+  c->cg_base.upload( base, s ); c->cg_col.upload( col, s ); c->cg_val.upload( val, s ); c->cg_diag.upload( diag, s );
+  for (auto* v : { &c->cg_x, &c->cg_b, &c->cg_r, &c->cg_p, &c->cg_q, &c->cg_z, &c->cg_d, &c->cg_mask, &c->cg_cnt }) v->alloc( nrow );
+  c->cg_scal.alloc( 16 );
+  if (c->nsh) {           // halo buffers wide enough for ncomp values per shared node
+    size_t w = std::max< size_t >( 15, ncomp );
+    c->sh_part.alloc( c->nsh*w ); c->sh_sendbuf.alloc( c->nsend*w ); c->sh_recvbuf.alloc( c->nsend*w );
+  }
+  API_END
+}
+
+int xyst_csr_mult( xyst_ctx* c, const double* x, double* r )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  if (!c->cg_nrow) throw std::runtime_error( "no matrix uploaded" );
+  size_t n = c->cg_nrow;
+  CK( cudaMemcpyAsync( c->cg_p.p, x, n*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+  k_spmv<<< nblk( c->cg_nslice*32, 256 ), 256, 0, c->stream >>>( n, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_p.p, c->cg_q.p ); ++c->launches;
+  CK( cudaGetLastError() );
+  CK( cudaMemcpyAsync( r, c->cg_q.p, n*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+  CK( cudaStreamSynchronize( c->stream ) );
+  API_END
+}
+
+int xyst_cg_setup( xyst_ctx* c, const double* x, const double* b, int pc, const uint8_t* slave,
+                   const double* count, double* normb )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  if (!c->cg_nrow) throw std::runtime_error( "no matrix uploaded" );
+  size_t n = c->cg_nrow, nc = c->cg_ncomp, np = n/nc;
+  auto s = c->stream;
+  std::vector< double > mask( n, 1.0 ), cnt( n, 1.0 );
+  for (size_t i=0; i<np; ++i) for (size_t k=0; k<nc; ++k) {
+    if (slave && slave[i]) mask[i*nc+k] = 0.0;
+    if (count) cnt[i*nc+k] = count[i];
+  }
+  c->cg_mask.upload( mask, s ); c->cg_cnt.upload( cnt, s );
+  CK( cudaMemcpyAsync( c->cg_x.p, x, n*sizeof(double), cudaMemcpyHostToDevice, s ) );
+  CK( cudaMemcpyAsync( c->cg_b.p, b, n*sizeof(double), cudaMemcpyHostToDevice, s ) );
+  CK( cudaMemsetAsync( c->cg_scal.p, 0, 16*sizeof(double), s ) );
+  c->cg_converged = false; c->cg_finished = false;
+  // residual(): r = A x (own) summed over sharers; pc(): q = 1/count or diag(A), summed
+  k_spmv<<< nblk( c->cg_nslice*32, 256 ), 256, 0, s >>>( n, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_x.p, c->cg_r.p ); ++c->launches;
+  { std::vector< double > q( n );
+    if (pc == 0) for (size_t i=0; i<n; ++i) q[i] = 1.0 / cnt[i];
+    else if (pc == 1) { CK( cudaMemcpyAsync( q.data(), c->cg_diag.p, n*sizeof(double), cudaMemcpyDeviceToHost, s ) ); CK( cudaStreamSynchronize( s ) ); }
+    else throw std::runtime_error( "unknown preconditioner" );
+    CK( cudaMemcpyAsync( c->cg_d.p, q.data(), n*sizeof(double), cudaMemcpyHostToDevice, s ) );
+    CK( cudaStreamSynchronize( s ) ); }
+  cg_halo( c, c->cg_r.p, 0 );
+  cg_halo( c, c->cg_d.p, 0 );
+  int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( n, RED_THREADS ) );
+  // normb = sqrt((b,b))
+  k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_b.p, c->cg_b.p, nullptr, nullptr, c->red.p ); ++c->launches;
+  cg_reduce( c, 1, nb );
+  CK( cudaMemcpyAsync( c->red_host, c->cg_scal.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s ) );
+  CK( cudaStreamSynchronize( s ) );
+  c->cg_normb = std::sqrt( c->red_host[0] );
+  // initres(): r = b - r, p = r, z = r/d, rho = (r,z)
+  k_cg_resid<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_b.p, c->cg_r.p, c->cg_p.p ); ++c->launches;
+  k_cg_div<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_r.p, c->cg_d.p, c->cg_z.p ); ++c->launches;
+  k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_r.p, c->cg_z.p, nullptr, nullptr, c->red.p ); ++c->launches;
+  cg_reduce( c, 1, nb );
+  CK( cudaMemcpyAsync( c->cg_scal.p, c->cg_scal.p + 8, sizeof(double), cudaMemcpyDeviceToDevice, s ) );   // rho
+  CK( cudaGetLastError() );
+  CK( cudaStreamSynchronize( s ) );
+  if (normb) *normb = c->cg_normb;
+  API_END
+}
+
+int xyst_cg_solve( xyst_ctx* c, size_t maxit, double tol, size_t* it_out, double* normr_out )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  if (!c->cg_nrow) throw std::runtime_error( "no matrix uploaded" );
+  size_t n = c->cg_nrow, it = 0;
+  auto s = c->stream;
+  int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( n, RED_THREADS ) );
+  double normr = 0.0;
+  if (!c->cg_converged) {
+    // beta = 0 on the first pass (next :586)
+    CK( cudaMemsetAsync( c->cg_scal.p + 3, 0, sizeof(double), s ) );
+    for (;;) {
+      k_cg_p<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_scal.p, c->cg_z.p, c->cg_p.p ); ++c->launches;
+      { ProfScope ps( c, "spmv" );
+        k_spmv<<< nblk( c->cg_nslice*32, 256 ), 256, 0, s >>>( n, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_p.p, c->cg_q.p ); ++c->launches; }
+      cg_halo( c, c->cg_q.p, 0 );
+      k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_p.p, c->cg_q.p, nullptr, nullptr, c->red.p ); ++c->launches;
+      cg_reduce( c, 1, nb );
+      k_cg_scalars<<< 1, 32, 0, s >>>( 0, c->cg_scal.p ); ++c->launches;
+      k_cg_update<<< nb, RED_THREADS, 0, s >>>( n, c->cg_scal.p, c->cg_mask.p, c->cg_q.p, c->cg_d.p, c->cg_p.p,
+        c->cg_r.p, c->cg_z.p, c->cg_x.p, c->red.p ); ++c->launches;
+      cg_reduce( c, 2, nb );
+      k_cg_scalars<<< 1, 32, 0, s >>>( 1, c->cg_scal.p ); ++c->launches;
+      cg_halo( c, c->cg_x.p, 1 );
+      CK( cudaMemcpyAsync( c->red_host, c->cg_scal.p + 4, 2*sizeof(double), cudaMemcpyDeviceToHost, s ) );
+      CK( cudaStreamSynchronize( s ) );
+      ++it;
+      double nbn = c->cg_normb > 1.0e-14 ? c->cg_normb : 1.0;
+      normr = std::sqrt( c->red_host[0] );
+      bool finished = c->red_host[1] != 0.0;
+      if (finished || normr < tol*nbn || it >= maxit) { c->cg_converged = !(normr > tol*nbn); break; }
+    }
+    CK( cudaGetLastError() );
+  }
+  if (it_out) *it_out = it;
+  if (normr_out) *normr_out = normr;
+  API_END
+}
+
+int xyst_cg_get_x( xyst_ctx* c, double* x )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  if (!c->cg_nrow) throw std::runtime_error( "no matrix uploaded" );
+  CK( cudaMemcpyAsync( x, c->cg_x.p, c->cg_nrow*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+  CK( cudaStreamSynchronize( c->stream ) );
+  API_END
+}
 
 uint64_t xyst_launch_count( const xyst_ctx* c ) { return c ? c->launches : 0; }
 uint64_t xyst_nedge( const xyst_ctx* c ) { return c ? c->nedge : 0; }

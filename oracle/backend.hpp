@@ -16,6 +16,7 @@
   #include "UnsMesh.hpp"
   #include "DerivedData.hpp"
   #include "Riemann.hpp"
+  #include "Zalesak.hpp"
   #include "BC.hpp"
   #include "Problems.hpp"
   #include "InciterConfig.hpp"
@@ -48,6 +49,13 @@ inline void rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
                  const std::vector< std::uint8_t >& besym, const Fields& G, const Fields& U,
                  const std::vector< real >& v, real t, const std::vector< real >& tp, Fields& R )
 { riemann::rhs( dsupedge, dsupint, coord, triinpoel, besym, G, U, v, t, tp, R ); }
+
+inline void zal_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                     const std::array< std::vector< real >, 3 >& dsupint,
+                     const Coords& coord, const std::vector< std::size_t >& triinpoel,
+                     const std::vector< std::uint8_t >& besym, real t, real dt, const Fields& U, Fields& R )
+{ std::vector< real > tp, dtp;
+  zalesak::rhs( dsupedge, dsupint, coord, triinpoel, besym, t, dt, tp, dtp, U, R ); }
 
 inline void initialize( const Coords& coord, Fields& U, real t )
 { problems::initialize( coord, U, t, 0, {} ); }
@@ -85,6 +93,7 @@ inline const char* name() { return "port"; }
 inline void set_cfg( const Cfg& c ) { port::set_cfg( c ); }
 using port::grad;
 using port::rhs;
+using port::zal_rhs;
 using port::initialize;
 using port::dirbc;
 using port::symbc;

@@ -34,6 +34,9 @@ Cfg to_cfg( const orc_cfg* c ) {
     k.pre_pressure.push_back( c->pre_pressure[i] );
   }
   for (int i=0; i<c->nfieldout; ++i) k.fieldout_sets.push_back( c->fieldout_sets[i] );
+  if (c->solver[0]) k.solver = c->solver;
+  k.fct = c->fct != 0; k.fctclip = c->fctclip != 0; k.fctdif = c->fctdif;
+  for (int i=0; i<c->nfctsys; ++i) k.fctsys.push_back( static_cast< std::uint64_t >( c->fctsys[i] ) );
   return k;
 }
 
@@ -146,6 +149,9 @@ std::size_t orc_get( void* hv, int chare, const char* name, void* out, std::size
   if (n == "un") return putf( c.un, out, cap );
   if (n == "rhs") return putf( c.rhs, out, cap );
   if (n == "grad") return putf( c.grad, out, cap );
+  if (n == "p") return putf( c.p, out, cap );
+  if (n == "q") return putf( c.q, out, cap );
+  if (n == "a") return putf( c.a, out, cap );
   if (n == "bface") {       // flattened: setid, nfaces, face ids ...
     std::vector< std::uint64_t > f;
     for (const auto& [s,ids] : c.bface) { f.push_back( static_cast<std::uint64_t>(s) ); f.push_back( ids.size() ); for (auto i : ids) f.push_back( i ); }
@@ -183,6 +189,11 @@ int orc_kernel( void* hv, int chare, const char* what, int stage, double t, doub
     else if (w == "solve") c.solve( stage, t, dt );
     else if (w == "bc") c.BC( t );
     else if (w == "mindt") { h->run->dt = c.mindt(); }
+    else if (w == "zrhs") c.zrhs_own( t, dt );
+    else if (w == "aec") c.aec_own();
+    else if (w == "alw") c.alw_own( dt );
+    else if (w == "lim") c.lim_own();
+    else if (w == "zsolve") c.zsolve( t, dt );
     else { g_err = "orc_kernel: unknown " + w; return -1; }
     return 0;
   } catch (std::exception& e) { g_err = e.what(); return -1; }

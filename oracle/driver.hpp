@@ -16,6 +16,7 @@
 //   RieCG ctor renumber             src/Inciter/RieCG.cpp:82-100
 //   setupBC/bndint/domint/bnorm/streamable/domsuped   src/Inciter/RieCG.cpp:109-736
 //   BC / dt / grad / rhs / solve    src/Inciter/RieCG.cpp:764-1057
+//   ZalCG: domint (stride 4), rhs, aec, alw, lim, solve   src/Inciter/ZalCG.cpp:354-400,:990-1607
 //   diagnostics                     src/Inciter/NodeDiagnostics.cpp:46-145,
 //                                   src/Inciter/Transporter.cpp:1472-1505
 #pragma once
@@ -256,7 +257,12 @@ class Chare {
     std::vector< std::size_t > triinpoel;
     Fields u, un, rhs, grad;
     std::unordered_map< int, std::unordered_map< std::size_t, std::array< real, 4 > > > bnorm, bnormc;
-    std::unordered_map< Edge, std::array< real, 3 >, be::Hash<2>, be::Eq<2> > domedgeint;
+    std::unordered_map< Edge, std::array< real, 4 >, be::Hash<2>, be::Eq<2> > domedgeint;
+    bool zal = false;                     // ZalCG: stride-4 integrals, no renumbering, FCT members
+    std::size_t stride = 3;
+    Fields p, q, a;                       // ZalCG::m_p, m_q, m_a
+    std::vector< real > mvol;             // ZalCG::m_vol (copy taken at construction)
+    std::unordered_map< std::size_t, std::vector< real > > pc, qc, ac;
     std::array< std::vector< std::size_t >, 3 > dsupedge;
     std::array< std::vector< real >, 3 > dsupint;
     std::vector< std::size_t > dirbcmasks, symbcnodes, farbcnodes, prebcnodes;
@@ -271,6 +277,7 @@ class Chare {
     Chare( const ChareMesh& cm, const std::array< std::vector< real >, 3 >& gcoord, const Cfg& c )
       : bnode( cm.bnode ), bface( cm.bface ), cfg( c )
     {
+      zal = cfg.solver == "zalcg"; stride = zal ? 4 : 3;
       // global2local, Reorder.cpp:279-306
       gid = cm.ginpoel;
       std::sort( gid.begin(), gid.end() );
@@ -309,6 +316,7 @@ class Chare {
 
     //! RieCG ctor :82-100 + Discretization::remap :560-606
     void renumber() {
+      if (zal) return;                    // ZalCG keeps the global2local order (ZalCG.cpp:82-92)
       std::unordered_map< std::size_t, std::size_t > map;
       std::size_t n = 0;
       auto psup = be::genPsup( inpoel, 4, be::genEsup( inpoel, 4 ) );
@@ -331,6 +339,7 @@ class Chare {
       auto n = gid.size();
       u = Fields( n, cfg.ncomp ); un = Fields( n, cfg.ncomp ); rhs = Fields( n, cfg.ncomp );
       grad = Fields( n, cfg.ncomp*3 );
+      if (zal) { p = Fields( n, cfg.ncomp*2 ); q = Fields( n, cfg.ncomp*2 ); a = Fields( n, cfg.ncomp ); mvol = vol; }
       dtp.assign( n, 0.0 ); tp.assign( n, cfg.t0 );
     }
 
@@ -439,6 +448,8 @@ class Chare {
           r[0] = a[1]*b[2] - b[1]*a[2]; r[1] = a[2]*b[0] - b[2]*a[0]; r[2] = a[0]*b[1] - b[0]*a[1]; };
         cross( ca, da, g[1] ); cross( da, ba, g[2] ); cross( ba, ca, g[3] );
         for (std::size_t i=0; i<3; ++i) g[0][i] = -g[1][i]-g[2][i]-g[3][i];
+        real cx = ca[1]*da[2] - da[1]*ca[2], cy = ca[2]*da[0] - da[2]*ca[0], cz = ca[0]*da[1] - da[0]*ca[1];
+        auto J120 = (ba[0]*cx + ba[1]*cy + ba[2]*cz) / 120.0;          // ZalCG.cpp:375,386
         for (const auto& pq : lpoed) {
           auto p = pq[0], q = pq[1];
           Edge ed{{ gid[N[p]], gid[N[q]] }};
@@ -448,6 +459,7 @@ class Chare {
           n[0] += sig * (g[p][0] - g[q][0]) / 48.0;
           n[1] += sig * (g[p][1] - g[q][1]) / 48.0;
           n[2] += sig * (g[p][2] - g[q][2]) / 48.0;
+          if (zal) n[3] += J120;
         }
       }
     }
@@ -492,6 +504,7 @@ class Chare {
             dsupint[0].push_back( sig[ed] * d[ed]->second[0] );
             dsupint[0].push_back( sig[ed] * d[ed]->second[1] );
             dsupint[0].push_back( sig[ed] * d[ed]->second[2] );
+            if (zal) dsupint[0].push_back( d[ed]->second[3] );
             domedgeint.erase( d[ed] );
           }
         }
@@ -512,17 +525,18 @@ class Chare {
             dsupint[1].push_back( sig[ed] * d[ed]->second[0] );
             dsupint[1].push_back( sig[ed] * d[ed]->second[1] );
             dsupint[1].push_back( sig[ed] * d[ed]->second[2] );
+            if (zal) dsupint[1].push_back( d[ed]->second[3] );
             domedgeint.erase( d[ed] );
           }
         }
       }
       dsupedge[2].resize( domedgeint.size()*2 );
-      dsupint[2].resize( domedgeint.size()*3 );
+      dsupint[2].resize( domedgeint.size()*stride );
       std::size_t k = 0;
       for (const auto& [ed,d] : domedgeint) {
         dsupedge[2][k*2+0] = lid.at( ed[0] );
         dsupedge[2][k*2+1] = lid.at( ed[1] );
-        dsupint[2][k*3+0] = d[0]; dsupint[2][k*3+1] = d[1]; dsupint[2][k*3+2] = d[2];
+        for (std::size_t j=0; j<stride; ++j) dsupint[2][k*stride+j] = d[j];
         ++k;
       }
     }
@@ -619,6 +633,123 @@ class Chare {
       }
       BC( t + rkcoef[s] * dt );
     }
+
+    // ---- ZalCG (flux-corrected transport) ----------------------------------------------
+    //! ZalCG::rhs :990-1012 (own part)
+    void zrhs_own( real t, real dt ) { be::zal_rhs( dsupedge, dsupint, coord, triinpoel, besym, t, dt, u, rhs ); }
+
+    //! visit every edge of the superedge groups: fn( first node, second node, integrals )
+    template< class F > void foredge( F fn ) const {
+      for (std::size_t e=0; e<dsupedge[0].size()/4; ++e) { const auto N = dsupedge[0].data() + e*4; std::size_t i = 0;
+        for (const auto& pq : lpoed) { fn( N[pq[0]], N[pq[1]], dsupint[0].data() + (e*6+i)*4 ); ++i; } }
+      for (std::size_t e=0; e<dsupedge[1].size()/3; ++e) { const auto N = dsupedge[1].data() + e*3; std::size_t i = 0;
+        for (const auto& pq : lpoet) { fn( N[pq[0]], N[pq[1]], dsupint[1].data() + (e*3+i)*4 ); ++i; } }
+      for (std::size_t e=0; e<dsupedge[2].size()/2; ++e) { const auto N = dsupedge[2].data() + e*2;
+        fn( N[0], N[1], dsupint[2].data() + e*4 ); }
+    }
+
+    //! ZalCG::fct :1036-1054 (merge rhs) + aec :1056-1150 (own antidiffusive contributions P+/-)
+    void aec_own() {
+      for (const auto& [g,r] : rhsc) { auto i = lid.at(g); for (std::size_t c=0; c<r.size(); ++c) rhs(i,c) += r[c]; }
+      rhsc.clear();
+      const auto ncomp = u.nprop();
+      auto ctau = cfg.fctdif;
+      p.fill( 0.0 );
+      foredge( [&]( std::size_t P, std::size_t Q, const real* D ){
+        auto dif = D[3];
+        for (std::size_t c=0; c<ncomp; ++c) {
+          auto aec = -dif * ctau * (u(P,c) - u(Q,c));
+          auto A = c*2; auto B = A+1;
+          if (aec > 0.0) std::swap(A,B);
+          p(P,A) -= aec;
+          p(Q,B) += aec;
+        } } );
+      for (std::size_t i=0; i<symbcnodes.size(); ++i) {       // symmetry BCs on AEC :1117-1133
+        auto P = symbcnodes[i];
+        auto nx = symbcnorms[i*3+0], ny = symbcnorms[i*3+1], nz = symbcnorms[i*3+2];
+        auto rvnp = p(P,2)*nx + p(P,4)*ny + p(P,6)*nz;
+        auto rvnn = p(P,3)*nx + p(P,5)*ny + p(P,7)*nz;
+        p(P,2) -= rvnp * nx; p(P,3) -= rvnn * nx;
+        p(P,4) -= rvnp * ny; p(P,5) -= rvnn * ny;
+        p(P,6) -= rvnp * nz; p(P,7) -= rvnn * nz;
+      }
+    }
+
+    //! ZalCG::alw :1173-1330: merge P, low-order solution (overwrites rhs), allowed limits Q+/-
+    void alw_own( real dt ) {
+      const auto npoin = u.nunk(); const auto ncomp = u.nprop();
+      for (const auto& [g,pp] : pc) { auto i = lid.at(g); for (std::size_t c=0; c<pp.size(); ++c) p(i,c) += pp[c]; }
+      pc.clear();
+      for (std::size_t i=0; i<npoin; ++i)
+        for (std::size_t c=0; c<ncomp; ++c) {
+          auto A = c*2; auto B = A+1;
+          p(i,A) /= mvol[i];
+          p(i,B) /= mvol[i];
+          rhs(i,c) = u(i,c) - dt*rhs(i,c)/mvol[i] - p(i,A) - p(i,B);
+        }
+      using std::max; using std::min;
+      auto large = std::numeric_limits< real >::max();
+      for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) { q(i,c*2+0) = -large; q(i,c*2+1) = +large; }
+      foredge( [&]( std::size_t P, std::size_t Q, const real* ){
+        for (std::size_t c=0; c<ncomp; ++c) {
+          auto A = c*2; auto B = A+1;
+          real alwp, alwn;
+          if (cfg.fctclip) { alwp = max( rhs(P,c), rhs(Q,c) ); alwn = min( rhs(P,c), rhs(Q,c) ); }
+          else { alwp = max( max(rhs(P,c), u(P,c)), max(rhs(Q,c), u(Q,c)) );
+                 alwn = min( min(rhs(P,c), u(P,c)), min(rhs(Q,c), u(Q,c)) ); }
+          q(P,A) = max(q(P,A), alwp); q(P,B) = min(q(P,B), alwn);
+          q(Q,A) = max(q(Q,A), alwp); q(Q,B) = min(q(Q,B), alwn);
+        } } );
+    }
+
+    //! ZalCG::lim :1335-1520: merge Q (max/min), limit coefficients, limited AEC
+    void lim_own() {
+      const auto npoin = u.nunk(); const auto ncomp = u.nprop();
+      using std::max; using std::min;
+      for (const auto& [g,alw] : qc) {
+        auto i = lid.at(g);
+        for (std::size_t c=0; c<alw.size()/2; ++c) { auto A = c*2; auto B = A+1; q(i,A) = max( q(i,A), alw[A] ); q(i,B) = min( q(i,B), alw[B] ); }
+      }
+      qc.clear();
+      for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) { q(i,c*2) -= rhs(i,c); q(i,c*2+1) -= rhs(i,c); }
+      for (std::size_t i=0; i<npoin; ++i)
+        for (std::size_t c=0; c<ncomp; ++c) {
+          auto A = c*2; auto B = A+1;
+          auto eps = std::numeric_limits< real >::epsilon();
+          q(i,A) = p(i,A) <  eps ? 0.0 : min(1.0, q(i,A)/p(i,A));
+          q(i,B) = p(i,B) > -eps ? 0.0 : min(1.0, q(i,B)/p(i,B));
+        }
+      auto ctau = cfg.fctdif;
+      a.fill( 0.0 );
+      auto fctsys = cfg.fctsys;
+      for (auto& c : fctsys) --c;
+      std::vector< real > aec( ncomp ), coef( ncomp );
+      foredge( [&]( std::size_t P, std::size_t Q, const real* D ){
+        auto dif = D[3];
+        for (std::size_t c=0; c<ncomp; ++c) {
+          aec[c] = -dif * ctau * (u(P,c) - u(Q,c));
+          auto A = c*2; auto B = A+1;
+          coef[c] = min( aec[c] < 0.0 ? q(P,A) : q(P,B), aec[c] > 0.0 ? q(Q,A) : q(Q,B) );
+        }
+        real cs = 1.0;
+        for (auto c : fctsys) cs = min( cs, coef[c] );
+        for (auto c : fctsys) coef[c] = cs;
+        for (std::size_t c=0; c<ncomp; ++c) { aec[c] *= coef[c]; a(P,c) -= aec[c]; a(Q,c) += aec[c]; }
+      } );
+    }
+
+    //! ZalCG::solve :1524-1607: merge A, apply to the low-order solution, BCs; un/u for diagnostics
+    void zsolve( real t, real dt ) {
+      const auto npoin = u.nunk(); const auto ncomp = u.nprop();
+      for (const auto& [g,aa] : ac) { auto i = lid.at(g); for (std::size_t c=0; c<aa.size(); ++c) a(i,c) += aa[c]; }
+      ac.clear();
+      if (cfg.fct) { for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) a(i,c) = rhs(i,c) + a(i,c)/mvol[i]; }
+      else { for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) a(i,c) = u(i,c) - dt*rhs(i,c)/mvol[i]; }
+      un = u;                               // rhocompute( m_a, m_u ) sees new and old
+      u = a;
+      BC( t + dt );                         // BC( m_a, T+Dt )
+      a.fill( 0.0 );
+    }
 };
 
 // -----------------------------------------------------------------------------
@@ -688,6 +819,20 @@ class Run {
         }
     }
 
+    //! comalw :1297-1333: allowed limits combine with max (even entries) / min (odd entries)
+    void exchange_maxmin() {
+      for (std::size_t a=0; a<ch.size(); ++a)
+        for (const auto& [b,n] : ch[a]->nodeCommMap) {
+          auto& dst = ch[static_cast<std::size_t>(b)]->qc;
+          for (auto g : n) {
+            auto r = ch[a]->q[ ch[a]->lid.at(g) ];
+            auto& acc = dst[g];
+            if (acc.empty()) acc = r;
+            else for (std::size_t c=0; c<r.size()/2; ++c) { acc[c*2] = std::max( acc[c*2], r[c*2] ); acc[c*2+1] = std::min( acc[c*2+1], r[c*2+1] ); }
+          }
+        }
+    }
+
     //! one full time step: dt, 3 x (grad, rhs, solve), diagnostics, next
     bool step() {
       if (finished) return false;
@@ -697,6 +842,25 @@ class Run {
       if (mindt < eps) finished = true;                       // RieCG::advance :862-863
       dtn = dt; dt = mindt;                                    // setdt :926-938
       if (t + dt > cfg.term) dt = cfg.term - t;
+      if (cfg.solver == "zalcg") {                             // ZalCG.cpp:973-1607, one stage
+        for (auto& c_ : ch) c_->zrhs_own( t, dt );
+        exchange( []( Chare& c_ ) -> be::Fields& { return c_.rhs; }, []( Chare& c_ ) -> auto& { return c_.rhsc; } );
+        if (cfg.fct) {
+          for (auto& c_ : ch) c_->aec_own();
+          exchange( []( Chare& c_ ) -> be::Fields& { return c_.p; }, []( Chare& c_ ) -> auto& { return c_.pc; } );
+          for (auto& c_ : ch) c_->alw_own( dt );
+          exchange_maxmin();
+          for (auto& c_ : ch) c_->lim_own();
+          exchange( []( Chare& c_ ) -> be::Fields& { return c_.a; }, []( Chare& c_ ) -> auto& { return c_.ac; } );
+        } else {
+          for (auto& c_ : ch) { for (const auto& [g,r] : c_->rhsc) { auto i = c_->lid.at(g); for (std::size_t c=0; c<r.size(); ++c) c_->rhs(i,c) += r[c]; } c_->rhsc.clear(); }
+        }
+        for (auto& c_ : ch) c_->zsolve( t, dt );
+        diagnostics();
+        ++it; t += dt;
+        if (done()) finished = true;
+        return !finished;
+      }
       for (int stage=0; stage<3; ++stage) {
         for (auto& c_ : ch) c_->grad_own();
         exchange( []( Chare& c_ ) -> be::Fields& { return c_.grad; },

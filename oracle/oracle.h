@@ -26,6 +26,10 @@ typedef struct orc_cfg {
   int32_t pre_sets[16];
   int32_t nfieldout;
   int32_t fieldout_sets[16];
+  char solver[16];            /* "riecg" | "zalcg" */
+  int32_t fct, fctclip, nfctsys;
+  int32_t fctsys[8];
+  double fctdif;
   uint64_t nstep;
   uint64_t diag_iter;
   double gamma, p0, cfl, dt, t0, term, stab2coef;

@@ -54,6 +54,12 @@ struct Cfg {
   std::vector< real > pre_density, pre_pressure;
   std::vector< int > fieldout_sets, integout_sets;
   std::uint64_t diag_iter = 1;
+  // ZalCG (flux-corrected transport), defaults InciterConfig.cpp:1751-1757
+  std::string solver = "riecg";
+  bool fct = true;
+  real fctdif = 1.0;
+  bool fctclip = false;
+  std::vector< std::uint64_t > fctsys;       // 1-based component ids limited as a system
 };
 
 //! Nodal field container with the reference's default layout [node][component]
@@ -603,6 +609,132 @@ inline void rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
   advdom( coord, dsupedge, dsupint, G, U, R );
   advbnd( triinpoel, coord, besym, U, R );
   src( coord, v, t, tp, R );
+}
+
+// ---- Zalesak.cpp: Taylor-Galerkin two-step edge flux for ZalCG --------------------------
+//! edge flux, Zalesak.cpp:31-200 (problems without source term; the f[ncomp..2ncomp) source
+//! half is only produced when problems::SRC() is set)
+inline void zal_advedge( const real supint[], const Fields& U, const Coords& coord, real t, real dt,
+                         std::size_t p, std::size_t q, real f[], const ICFn& src )
+{
+  const auto ncomp = U.nprop();
+  const auto& x = coord[0]; const auto& y = coord[1]; const auto& z = coord[2];
+  auto dx = x[p] - x[q], dy = y[p] - y[q], dz = z[p] - z[q];
+  auto dl = dx*dx + dy*dy + dz*dz;
+  dx /= dl; dy /= dl; dz /= dl;
+  auto rL = U(p,0), ruL = U(p,1), rvL = U(p,2), rwL = U(p,3), reL = U(p,4);
+  auto pL = eos_pressure( reL - 0.5*(ruL*ruL + rvL*rvL + rwL*rwL)/rL );
+  auto dnL = (ruL*dx + rvL*dy + rwL*dz)/rL;
+  auto rR = U(q,0), ruR = U(q,1), rvR = U(q,2), rwR = U(q,3), reR = U(q,4);
+  auto pR = eos_pressure( reR - 0.5*(ruR*ruR + rvR*rvR + rwR*rwR)/rR );
+  auto dnR = (ruR*dx + rvR*dy + rwR*dz)/rR;
+  auto nx = supint[0], ny = supint[1], nz = supint[2];
+  std::vector< real > ue( ncomp );
+  auto dp = pL - pR;
+  ue[0] = 0.5*(rL + rR - dt*(rL*dnL - rR*dnR));
+  ue[1] = 0.5*(ruL + ruR - dt*(ruL*dnL - ruR*dnR + dp*dx));
+  ue[2] = 0.5*(rvL + rvR - dt*(rvL*dnL - rvR*dnR + dp*dy));
+  ue[3] = 0.5*(rwL + rwR - dt*(rwL*dnL - rwR*dnR + dp*dz));
+  ue[4] = 0.5*(reL + reR - dt*((reL+pL)*dnL - (reR+pR)*dnR));
+  for (std::size_t c=5; c<ncomp; ++c) ue[c] = 0.5*(U(p,c) + U(q,c) - dt*(U(p,c)*dnL - U(q,c)*dnR));
+  if (src) {
+    auto coef = dt/4.0;
+    auto sL = src( x[p], y[p], z[p], t );
+    auto sR = src( x[q], y[q], z[q], t );
+    for (std::size_t c=0; c<ncomp; ++c) ue[c] += coef*(sL[c] + sR[c]);
+  }
+  auto rh = ue[0], ruh = ue[1], rvh = ue[2], rwh = ue[3], reh = ue[4];
+  auto ph = eos_pressure( reh - 0.5*(ruh*ruh + rvh*rvh + rwh*rwh)/rh );
+  auto vn = (ruh*nx + rvh*ny + rwh*nz)/rh;
+  f[0] = 2.0*rh*vn;
+  f[1] = 2.0*(ruh*vn + ph*nx);
+  f[2] = 2.0*(rvh*vn + ph*ny);
+  f[3] = 2.0*(rwh*vn + ph*nz);
+  f[4] = 2.0*(reh + ph)*vn;
+  for (std::size_t c=5; c<ncomp; ++c) f[c] = 2.0*ue[c]*vn;
+  if (src) {
+    auto coef = -5.0/3.0*supint[3];
+    auto se = src( (x[p] + x[q])/2.0, (y[p] + y[q])/2.0, (z[p] + z[q])/2.0, t+dt/2.0 );
+    for (std::size_t c=0; c<ncomp; ++c) f[ncomp+c] = coef*se[c];
+  }
+  if (!cfg().stab2) return;
+  auto stab2coef = cfg().stab2coef;
+  auto vnL = (ruL*nx + rvL*ny + rwL*nz)/rL;
+  auto vnR = (ruR*nx + rvR*ny + rwR*nz)/rR;
+  auto len = std::sqrt( nx*nx + ny*ny + nz*nz );
+  auto cL = eos_soundspeed( std::max(rL,1.0e-8), std::max(pL,0.0) );
+  auto cR = eos_soundspeed( std::max(rR,1.0e-8), std::max(pR,0.0) );
+  auto sl = std::abs(vnL) + cL*len;
+  auto sr = std::abs(vnR) + cR*len;
+  auto fw = stab2coef * std::max( sl, sr );
+  f[0] -= fw*(rL - rR); f[1] -= fw*(ruL - ruR); f[2] -= fw*(rvL - rvR);
+  f[3] -= fw*(rwL - rwR); f[4] -= fw*(reL - reR);
+  for (std::size_t c=5; c<ncomp; ++c) f[c] -= fw*(U(p,c) - U(q,c));
+}
+
+//! zalesak::rhs, Zalesak.cpp:202-457 (superedge integrals have stride 4)
+inline void zal_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                     const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                     const std::vector< std::size_t >& triinpoel, const std::vector< std::uint8_t >& besym,
+                     real t, real dt, const Fields& U, Fields& R )
+{
+  auto ncomp = U.nprop();
+  auto src = SRC();
+  R.fill( 0.0 );
+  std::vector< real > fb( 6*ncomp*2 );
+  real* f[6]; for (int k=0; k<6; ++k) f[k] = fb.data() + static_cast<std::size_t>(k)*ncomp*2;
+  for (std::size_t e=0; e<dsupedge[0].size()/4; ++e) {
+    const auto N = dsupedge[0].data() + e*4;
+    const auto d = dsupint[0].data();
+    zal_advedge( d+(e*6+0)*4, U, coord, t, dt, N[0], N[1], f[0], src );
+    zal_advedge( d+(e*6+1)*4, U, coord, t, dt, N[1], N[2], f[1], src );
+    zal_advedge( d+(e*6+2)*4, U, coord, t, dt, N[2], N[0], f[2], src );
+    zal_advedge( d+(e*6+3)*4, U, coord, t, dt, N[0], N[3], f[3], src );
+    zal_advedge( d+(e*6+4)*4, U, coord, t, dt, N[1], N[3], f[4], src );
+    zal_advedge( d+(e*6+5)*4, U, coord, t, dt, N[2], N[3], f[5], src );
+    for (std::size_t c=0; c<ncomp; ++c) {
+      R(N[0],c) = R(N[0],c) - f[0][c] + f[2][c] - f[3][c];
+      R(N[1],c) = R(N[1],c) + f[0][c] - f[1][c] - f[4][c];
+      R(N[2],c) = R(N[2],c) + f[1][c] - f[2][c] - f[5][c];
+      R(N[3],c) = R(N[3],c) + f[3][c] + f[4][c] + f[5][c];
+      if (src) {
+        auto nc = ncomp + c;
+        R(N[0],c) += f[0][nc] + f[2][nc] + f[3][nc];
+        R(N[1],c) += f[0][nc] + f[1][nc] + f[4][nc];
+        R(N[2],c) += f[1][nc] + f[2][nc] + f[5][nc];
+        R(N[3],c) += f[3][nc] + f[4][nc] + f[5][nc];
+      }
+    }
+  }
+  for (std::size_t e=0; e<dsupedge[1].size()/3; ++e) {
+    const auto N = dsupedge[1].data() + e*3;
+    const auto d = dsupint[1].data();
+    zal_advedge( d+(e*3+0)*4, U, coord, t, dt, N[0], N[1], f[0], src );
+    zal_advedge( d+(e*3+1)*4, U, coord, t, dt, N[1], N[2], f[1], src );
+    zal_advedge( d+(e*3+2)*4, U, coord, t, dt, N[2], N[0], f[2], src );
+    for (std::size_t c=0; c<ncomp; ++c) {
+      R(N[0],c) = R(N[0],c) - f[0][c] + f[2][c];
+      R(N[1],c) = R(N[1],c) + f[0][c] - f[1][c];
+      R(N[2],c) = R(N[2],c) + f[1][c] - f[2][c];
+      if (src) {
+        auto nc = ncomp + c;
+        R(N[0],c) += f[0][nc] + f[2][nc];
+        R(N[1],c) += f[0][nc] + f[1][nc];
+        R(N[2],c) += f[1][nc] + f[2][nc];
+      }
+    }
+  }
+  for (std::size_t e=0; e<dsupedge[2].size()/2; ++e) {
+    const auto N = dsupedge[2].data() + e*2;
+    const auto d = dsupint[2].data();
+    zal_advedge( d+e*4, U, coord, t, dt, N[0], N[1], f[0], src );
+    for (std::size_t c=0; c<ncomp; ++c) {
+      R(N[0],c) -= f[0][c];
+      R(N[1],c) += f[0][c];
+      if (src) { auto nc = ncomp + c; R(N[0],c) += f[0][nc]; R(N[1],c) += f[0][nc]; }
+    }
+  }
+  advbnd( triinpoel, coord, besym, U, R );      // Zalesak.cpp:309-419, same form as Riemann.cpp:768-878
 }
 
 // ---- Mesh/DerivedData.cpp ----------------------------------------------------------

@@ -16,7 +16,11 @@ void set_cfg( const Cfg& c )
   g = inciter::ctr::Config();
   g.get< tag::problem >() = c.problem;
   g.get< tag::flux >() = c.flux;
-  g.get< tag::solver >() = "riecg";
+  g.get< tag::solver >() = c.solver;
+  g.get< tag::fct >() = c.fct;
+  g.get< tag::fctdif >() = c.fctdif;
+  g.get< tag::fctclip >() = c.fctclip;
+  g.get< tag::fctsys >() = c.fctsys;
   g.get< tag::problem_ncomp >() = c.ncomp;
   g.get< tag::mat_spec_heat_ratio >() = c.gamma;
   g.get< tag::problem_p0 >() = c.p0;

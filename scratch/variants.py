@@ -3,13 +3,10 @@ import os, sys, subprocess, json
 sys.path.insert(0, '.')
 from xyst_b200 import build as B
 VAR = {
- "f128x4": ["FLUX_THREADS=128", "FLUX_MINB=4"],
- "f128x5": ["FLUX_THREADS=128", "FLUX_MINB=5"],
- "f128x6": ["FLUX_THREADS=128", "FLUX_MINB=6"],
- "f128x7": ["FLUX_THREADS=128", "FLUX_MINB=7"],
- "f64x10": ["FLUX_THREADS=64", "FLUX_MINB=10"],
- "f64x12": ["FLUX_THREADS=64", "FLUX_MINB=12"],
- "f256x3": ["FLUX_THREADS=256", "FLUX_MINB=3"],
+ "edge": ["FLUX_SLICE=0"],
+ "slice2": ["FLUX_SLICE=1", "FSLICE_MINB=2"],
+ "slice3": ["FLUX_SLICE=1", "FSLICE_MINB=3"],
+ "slice4": ["FLUX_SLICE=1", "FSLICE_MINB=4"],
 }
 if sys.argv[1] == "build":
     for k, d in VAR.items():

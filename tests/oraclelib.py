@@ -25,6 +25,8 @@ class Cfg(C.Structure):
         ("nfar", C.c_int32), ("far_sets", C.c_int32 * 16),
         ("npre", C.c_int32), ("pre_sets", C.c_int32 * 16),
         ("nfieldout", C.c_int32), ("fieldout_sets", C.c_int32 * 16),
+        ("solver", C.c_char * 16), ("fct", C.c_int32), ("fctclip", C.c_int32), ("nfctsys", C.c_int32),
+        ("fctsys", C.c_int32 * 8), ("fctdif", C.c_double),
         ("nstep", C.c_uint64), ("diag_iter", C.c_uint64),
         ("gamma", C.c_double), ("p0", C.c_double), ("cfl", C.c_double), ("dt", C.c_double),
         ("t0", C.c_double), ("term", C.c_double), ("stab2coef", C.c_double),
@@ -33,15 +35,19 @@ class Cfg(C.Structure):
     ]
 
 
-def make_cfg(problem, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0, term=1e300,
+def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0, term=1e300,
              nstep=2**63, sym=(), dir_=(), stab2=False, stab2coef=0.2, diag_iter=1, ncomp=5,
-             fieldout=(), cls=Cfg):
+             fieldout=(), solver="riecg", fct=True, fctclip=False, fctsys=(), fctdif=1.0, cls=Cfg):
     """Control-file equivalent; defaults are the reference's (InciterConfig.cpp:1707-1757)."""
     c = cls()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term
     c.nstep = nstep; c.stab2 = int(stab2); c.stab2coef = stab2coef; c.steady = 0
     c.diag_iter = diag_iter
+    c.solver = solver.encode(); c.fct = int(fct); c.fctclip = int(fctclip); c.fctdif = fctdif
+    c.nfctsys = len(fctsys)
+    for i, s_ in enumerate(fctsys):
+        c.fctsys[i] = s_
     c.nsym = len(sym)
     for i, s in enumerate(sym):
         c.sym[i] = s
@@ -57,6 +63,15 @@ def make_cfg(problem, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0
 
 # The three RieCG regression cases pinned by golden diag.std files (control files:
 # tests/regression/inciter/RieCG/{Sod/sod.q,Sedov/sedov.q,TaylorGreen/taylor_green.q})
+# ZalCG regression cases (tests/regression/inciter/ZalCG/{Sod/sod.q,Sedov/sedov.q})
+ZCASES = {
+    "zalcg_sod": dict(solver="zalcg", problem="sod", gamma=1.4, cfl=0.5, nstep=10, term=0.2,
+                      sym=(2, 4, 5, 6), dir_=((1, 1, 1, 1, 1, 1), (3, 1, 1, 1, 1, 1)),
+                      fctclip=True, fctsys=(1, 2, 5), mesh="riecg_sod"),
+    "zalcg_sedov": dict(solver="zalcg", problem="sedov", gamma=5.0 / 3.0, p0=4.86e3, cfl=0.5, nstep=20,
+                        term=1.0, sym=(1, 2, 3), fctsys=(1, 2, 3, 4, 5), mesh="riecg_sedov"),
+}
+
 CASES = {
     "riecg_sod": dict(problem="sod", gamma=1.4, cfl=0.5, nstep=10, term=0.2, sym=(2, 4, 5, 6)),
     "riecg_sedov": dict(problem="sedov", gamma=5.0 / 3.0, p0=4.86e3, cfl=0.5, nstep=10, term=1.0,
@@ -189,10 +204,12 @@ class Oracle:
         a = np.zeros(nb // np.dtype(dt).itemsize, dtype=dt)
         if nb:
             self.L.orc_get(self.h, chare, name.encode(), a.ctypes.data_as(C.c_void_p), nb)
-        if name in ("u", "un", "rhs"):
+        if name in ("u", "un", "rhs", "a"):
             a = a.reshape(-1, self.ncomp)
         elif name == "grad":
             a = a.reshape(-1, 3 * self.ncomp)
+        elif name in ("p", "q"):
+            a = a.reshape(-1, 2 * self.ncomp)
         return a
 
     def set_u(self, u, chare=0):

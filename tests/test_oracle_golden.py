@@ -66,3 +66,18 @@ def test_siphash_known_answers():
     # 0x0f0e0d0c0b0a0908), already sorted ascending
     v = np.array([0x0706050403020100, 0x0F0E0D0C0B0A0908], dtype=np.uint64)
     assert L.orc_siphash_ids(v.ctypes.data, 2) == 0x3F2ACC7F57C29BDB
+
+
+@pytest.mark.parametrize("case", list(O.ZCASES))
+def test_zalcg_oracle_reproduces_reference_golden_diag(case):
+    """ZalCG (Taylor-Galerkin + flux-corrected transport): tests/regression/inciter/ZalCG/
+    {Sod,Sedov}/diag.std; reference tolerance (diag.ndiff.cfg) abs 1e-8 | rel 1e-7."""
+    kw = O.ZCASES[case]
+    gold = O.load_golden_diag(case)
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(int(gold[-1, 0]))
+    d = o.diag()
+    assert d.shape == gold.shape
+    assert numdiff(d[:, 1:8], gold[:, 1:8], 1.0e-8, 1.0e-7)
+    assert numdiff(d[:, 8:13], gold[:, 8:13], 0.0, 1.0e-7)
+    assert (np.abs(d - gold) / np.maximum(np.abs(gold), 1e-300)).max() < 6e-9

@@ -132,7 +132,7 @@ struct Prof {
 
 struct xyst_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaStream_t stream = nullptr, comm_stream = nullptr, aux_stream = nullptr;
   bool own_stream = false;
   xyst_params prm{};
   size_t npoin = 0, NP = 0, nedge = 0, nslot = 0, ntri = 0, nslice = 0, nent = 0;
@@ -153,6 +153,7 @@ struct xyst_ctx {
   DevBuf< int > bslot;                   // [npoin] boundary-node slot or -1
   DevBuf< int > bn_node, bn_off, bn_face;// boundary nodes, CSR of (face*4+k)
   DevBuf< double > Gb, Rb;               // [nbn][15], [nbn][5]
+  DevBuf< double > fn;                   // [ntri][3] face normals cross(ba,ca)/12 (constant)
   size_t nbn = 0;
   // BCs: union node list with per-node records
   DevBuf< int > bc_node, bc_dir, bc_symoff, bc_faroff, bc_pre;
@@ -169,7 +170,8 @@ struct xyst_ctx {
   DevBuf< int > sh_roff, sh_ridx;        // CSR unique node -> positions in recv buffer
   DevBuf< double > sh_part, sh_sendbuf, sh_recvbuf;
   size_t nsh = 0, nsend = 0;
-  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  bool rb_pending = false;              // Rb of the current state already in flight on aux_stream
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
   // linear solver: sliced-ELL matrix over scalar rows + CG vectors
   size_t cg_nrow = 0, cg_ncomp = 1, cg_nslice = 0, cg_nent = 0;
   DevBuf< long long > cg_base; DevBuf< int > cg_col; DevBuf< double > cg_val, cg_diag;
@@ -233,8 +235,20 @@ __device__ __forceinline__ void face_normal( const double* __restrict__ X, size_
   n[2] = (ba[0]*ca[1] - ca[0]*ba[1]) / 12.0;
 }
 
+// the normals depend on coordinates only: computed once at upload with this arithmetic
+__global__ void k_face_normals( int ntri, size_t NP, const int* __restrict__ tri, const double* __restrict__ X,
+                                double* __restrict__ fn )
+{
+  int f = blockIdx.x*blockDim.x + threadIdx.x;
+  if (f >= ntri) return;
+  int N[3] = { tri[f*3+0], tri[f*3+1], tri[f*3+2] };
+  double n[3];
+  face_normal( X, NP, N, n );
+  fn[(size_t)f*3+0] = n[0]; fn[(size_t)f*3+1] = n[1]; fn[(size_t)f*3+2] = n[2];
+}
+
 __global__ void k_bnd_grad( int nbn, size_t NP, const int* __restrict__ bn_off, const int* __restrict__ bn_face,
-                            const int* __restrict__ tri, const double* __restrict__ X,
+                            const int* __restrict__ tri, const double* __restrict__ fn,
                             const double* __restrict__ W, double* __restrict__ Gb )
 {
   int b = blockIdx.x*blockDim.x + threadIdx.x;
@@ -245,8 +259,7 @@ __global__ void k_bnd_grad( int nbn, size_t NP, const int* __restrict__ bn_off, 
   for (int i=bn_off[b]; i<bn_off[b+1]; ++i) {
     int f = bn_face[i] >> 2;
     int N[3] = { tri[f*3+0], tri[f*3+1], tri[f*3+2] };
-    double n[3];
-    face_normal( X, NP, N, n );
+    double n[3] = { fn[(size_t)f*3+0], fn[(size_t)f*3+1], fn[(size_t)f*3+2] };
     #pragma unroll
     for (int c=0; c<NC; ++c) {
       double u0 = W[c*NP+N[0]], u1 = W[c*NP+N[1]], u2 = W[c*NP+N[2]];
@@ -264,7 +277,7 @@ __global__ void k_bnd_grad( int nbn, size_t NP, const int* __restrict__ bn_off, 
 
 __global__ void k_bnd_rhs( int nbn, size_t NP, const int* __restrict__ bn_off, const int* __restrict__ bn_face,
                            const int* __restrict__ tri, const unsigned char* __restrict__ besym,
-                           const double* __restrict__ X, const double* __restrict__ U,
+                           const double* __restrict__ fn, const double* __restrict__ U,
                            double* __restrict__ Rb, double gamma )
 {
   int b = blockIdx.x*blockDim.x + threadIdx.x;
@@ -273,8 +286,7 @@ __global__ void k_bnd_rhs( int nbn, size_t NP, const int* __restrict__ bn_off, c
   for (int i=bn_off[b]; i<bn_off[b+1]; ++i) {
     int f = bn_face[i] >> 2, k = bn_face[i] & 3;
     int N[3] = { tri[f*3+0], tri[f*3+1], tri[f*3+2] };
-    double n[3];
-    face_normal( X, NP, N, n );
+    double n[3] = { fn[(size_t)f*3+0], fn[(size_t)f*3+1], fn[(size_t)f*3+2] };
     double fl[NC][3];
     #pragma unroll
     for (int m=0; m<3; ++m) {
@@ -337,7 +349,7 @@ __global__ void __launch_bounds__(NODE_THREADS, GRAD_MINB)
 k_grad_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
              const int* __restrict__ inc_q, const double* __restrict__ D, size_t nslot,
              const double* __restrict__ W, const int* __restrict__ bslot, const double* __restrict__ Gb,
-             const double* __restrict__ vol, double* __restrict__ G )
+             const double* __restrict__ vol, double* __restrict__ G, int defer_bnd )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -349,12 +361,28 @@ k_grad_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
   grad_sum( p, lane, base, kmax, inc_e, inc_q, D, nslot, W, NP, acc );
   int b = bslot[p];
   if (b >= 0) {
+    if (defer_bnd) {          // boundary part and division follow in k_grad_bfix (same operation order)
+      #pragma unroll
+      for (int i=0; i<15; ++i) G[i*NP+p] = acc[i];
+      return;
+    }
     #pragma unroll
     for (int i=0; i<15; ++i) acc[i] += Gb[(size_t)b*15+i];
   }
   double vp = vol[p];
   #pragma unroll
   for (int i=0; i<15; ++i) G[i*NP+p] = acc[i]/vp;
+}
+
+// boundary nodes: G = (domain sum + boundary sum) / vol, once both are known
+__global__ void k_grad_bfix( int nbn, size_t NP, const int* __restrict__ bn_node, const double* __restrict__ Gb,
+                             const double* __restrict__ vol, double* __restrict__ G )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)nbn*15) return;
+  size_t b = i / 15, k = i % 15;
+  size_t p = bn_node[b];
+  G[k*NP+p] = (G[k*NP+p] + Gb[b*15+k]) / vol[p];
 }
 
 // partial (un-normalised) gradient sums of the shared nodes, for the halo exchange
@@ -451,17 +479,17 @@ __device__ __forceinline__ void vanleer( double d1, double d2, double d3, double
   }
 }
 
-// gp/gq: the 15 gradient components of the two end nodes, element i at gp[i*gs]
+// gp/gq: the 15 gradient components of the two end nodes, element i at gp[i*gsp], gq[i*gsq]
 template< bool EXACT >
-__device__ __forceinline__ void muscl( const double* gp, const double* gq, int gs,
+__device__ __forceinline__ void muscl( const double* gp, int gsp, const double* gq, int gsq,
                                        const double vw[3], double l[NC], double r[NC] )
 {
   double ls[NC], rs[NC], d1[NC], d3[NC];
   #pragma unroll
   for (int c=0; c<NC; ++c) {
     ls[c] = l[c]; rs[c] = r[c];
-    double g1 = gp[(c*3+0)*gs]*vw[0] + gp[(c*3+1)*gs]*vw[1] + gp[(c*3+2)*gs]*vw[2];
-    double g2 = gq[(c*3+0)*gs]*vw[0] + gq[(c*3+1)*gs]*vw[1] + gq[(c*3+2)*gs]*vw[2];
+    double g1 = gp[(c*3+0)*gsp]*vw[0] + gp[(c*3+1)*gsp]*vw[1] + gp[(c*3+2)*gsp]*vw[2];
+    double g2 = gq[(c*3+0)*gsq]*vw[0] + gq[(c*3+1)*gsq]*vw[1] + gq[(c*3+2)*gsq]*vw[2];
     double delta2 = r[c] - l[c];
     d1[c] = 2.0 * g1 - delta2;
     d3[c] = 2.0 * g2 - delta2;
@@ -621,7 +649,7 @@ k_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __r
   #pragma unroll
   for (int j=0; j<3; ++j) vw[j] = __ldg( X + j*NP + q ) - __ldg( X + j*NP + p );
   asm volatile( "cp.async.wait_group 0;" ::: "memory" );
-  muscl< EXACT >( gp, gq, FLUX_THREADS, vw, l, r );
+  muscl< EXACT >( gp, FLUX_THREADS, gq, FLUX_THREADS, vw, l, r );
   double f[NC];
   if (FLUX == 0) rusanov( l, r, n, P, f ); else hllc( l, r, n, P, f );
   #pragma unroll
@@ -1065,9 +1093,24 @@ void do_grad( xyst_ctx* c )
 {
   need_mesh( c );
   auto s = c->stream;
-  if (c->nbn) { k_bnd_grad<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
-                  c->tri.p, c->X.p, c->W.p, c->Gb.p ); ++c->launches; }
   bool halo = c->nsh > 0 && c->comm;
+  // Single partition: both boundary kernels depend only on the state at stage start, so they
+  // run on a side stream under the gradient gather; boundary nodes are finished afterwards.
+  bool overlap = c->nbn && !halo;
+  if (overlap) {
+    CK( cudaEventRecord( c->ev_c, s ) );
+    CK( cudaStreamWaitEvent( c->aux_stream, c->ev_c, 0 ) );
+    k_bnd_grad<<< nblk( c->nbn, 128 ), 128, 0, c->aux_stream >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
+      c->tri.p, c->fn.p, c->W.p, c->Gb.p ); ++c->launches;
+    CK( cudaEventRecord( c->ev_d, c->aux_stream ) );
+    k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, c->aux_stream >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
+      c->tri.p, c->besym.p, c->fn.p, c->U.p, c->Rb.p, c->prm.gamma ); ++c->launches;
+    CK( cudaEventRecord( c->ev_e, c->aux_stream ) );
+    c->rb_pending = true;
+  } else if (c->nbn) {
+    k_bnd_grad<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
+      c->tri.p, c->fn.p, c->W.p, c->Gb.p ); ++c->launches;
+  }
   if (halo) {
     k_grad_shared<<< nblk( c->nsh, 128 ), 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sl_base.p,
       c->inc_e.p, c->inc_q.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->sh_part.p ); ++c->launches;
@@ -1076,7 +1119,11 @@ void do_grad( xyst_ctx* c )
   {
     ProfScope ps( c, "grad" );
     k_grad_node<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p,
-      c->inc_e.p, c->inc_q.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->vol.p, c->G.p ); ++c->launches;
+      c->inc_e.p, c->inc_q.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->vol.p, c->G.p, overlap ? 1 : 0 ); ++c->launches;
+  }
+  if (overlap) {
+    CK( cudaStreamWaitEvent( s, c->ev_d, 0 ) );
+    k_grad_bfix<<< nblk( c->nbn*15, 256 ), 256, 0, s >>>( (int)c->nbn, c->NP, c->bn_node.p, c->Gb.p, c->vol.p, c->G.p ); ++c->launches;
   }
   if (halo) {
     exchange_wait( c );
@@ -1107,8 +1154,13 @@ void do_flux( xyst_ctx* c )
 void do_rhs_nodes( xyst_ctx* c, bool fused, double rkdt, const double* Uin, const double* Un, double* Uout )
 {
   auto s = c->stream;
-  if (c->nbn) { k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
-                  c->tri.p, c->besym.p, c->X.p, Uin, c->Rb.p, c->prm.gamma ); ++c->launches; }
+  if (c->rb_pending) {                   // computed on the side stream during this stage's do_grad
+    CK( cudaStreamWaitEvent( s, c->ev_e, 0 ) );
+    c->rb_pending = false;
+  } else if (c->nbn) {
+    k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
+      c->tri.p, c->besym.p, c->fn.p, Uin, c->Rb.p, c->prm.gamma ); ++c->launches;
+  }
   bool halo = c->nsh > 0 && c->comm;
   if (halo) {
     k_rhs_shared<<< nblk( c->nsh, 128 ), 128, 0, s >>>( (int)c->nsh, c->sh_node.p, c->sl_base.p,
@@ -1182,6 +1234,10 @@ int xyst_ctx_create( int device, const xyst_params* params, xyst_ctx** out )
   c->device = device; c->prm = *params;
   CK( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ); c->own_stream = true;
   CK( cudaStreamCreateWithFlags( &c->comm_stream, cudaStreamNonBlocking ) );
+  CK( cudaStreamCreateWithFlags( &c->aux_stream, cudaStreamNonBlocking ) );
+  CK( cudaEventCreateWithFlags( &c->ev_c, cudaEventDisableTiming ) );
+  CK( cudaEventCreateWithFlags( &c->ev_d, cudaEventDisableTiming ) );
+  CK( cudaEventCreateWithFlags( &c->ev_e, cudaEventDisableTiming ) );
   CK( cudaEventCreateWithFlags( &c->ev_a, cudaEventDisableTiming ) );
   CK( cudaEventCreateWithFlags( &c->ev_b, cudaEventDisableTiming ) );
   c->red.alloc( (size_t)RED_BLOCKS*NDIAG + NDIAG );
@@ -1209,6 +1265,8 @@ int xyst_ctx_destroy( xyst_ctx* c )
   for (auto& [k,p] : c->prof) for (auto& e : p.ev) { cudaEventDestroy( e.first ); cudaEventDestroy( e.second ); }
   if (c->own_stream && c->stream) cudaStreamDestroy( c->stream );
   if (c->comm_stream) cudaStreamDestroy( c->comm_stream );
+  if (c->aux_stream) cudaStreamDestroy( c->aux_stream );
+  for (auto e : { c->ev_c, c->ev_d, c->ev_e }) if (e) cudaEventDestroy( e );
   if (c->ev_a) cudaEventDestroy( c->ev_a );
   if (c->ev_b) cudaEventDestroy( c->ev_b );
   if (c->red_host) cudaFreeHost( c->red_host );
@@ -1343,6 +1401,8 @@ int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* 
   { std::vector< double > pv( NP, 1.0 ), pw( NP, 1.0 ), px( 3*NP, 0.0 );
     for (size_t p=0; p<npoin; ++p) { pv[p] = vol[p]; pw[p] = v[p]; px[p] = x[p]; px[NP+p] = y[p]; px[2*NP+p] = z[p]; }
     c->vol.upload( pv, s ); c->v.upload( pw, s ); c->X.upload( px, s ); }
+  c->fn.alloc( std::max< size_t >( ntri, 1 )*3 );
+  if (ntri) { k_face_normals<<< nblk( ntri, 128 ), 128, 0, s >>>( (int)ntri, NP, c->tri.p, c->X.p, c->fn.p ); ++c->launches; CK( cudaGetLastError() ); }
   c->U.alloc( NP*NC ); c->Un.alloc( NP*NC ); c->W.alloc( NP*NC ); c->G.alloc( NP*15 );
   c->R.alloc( npoin*NC ); c->stage.alloc( npoin*NC ); c->F.alloc( std::max< size_t >( nslot, 1 )*NC );
   { std::vector< double > one( NP*NC, 1.0 );    // a harmless state until xyst_state_set
@@ -1431,6 +1491,7 @@ int xyst_state_set( xyst_ctx* c, const double* U )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
+  if (c->rb_pending) { CK( cudaStreamSynchronize( c->aux_stream ) ); c->rb_pending = false; }
   CK( cudaMemcpyAsync( c->stage.p, U, c->npoin*NC*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
   k_set_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->stage.p, c->U.p, c->W.p );
   ++c->launches;

@@ -138,6 +138,30 @@ int xyst_halo_sum(xyst_ctx* ctx, int w, double* vals);
 int xyst_allreduce_min(xyst_ctx* ctx, double* v, int n);
 int xyst_allreduce_sum(xyst_ctx* ctx, double* v, int n);
 
+/* ---- ZalCG: Taylor-Galerkin edge flux + flux-corrected transport ------------------------
+ * (src/Physics/Zalesak.cpp, src/Inciter/ZalCG.cpp:990-1607). Same context, state, BC and
+ * dt/diagnostics entry points as RieCG; the superedge integrals have stride 4
+ * (ZalCG::m_dsupint: normal + J/120, ZalCG.cpp:354-400). */
+typedef struct xyst_zalcg_params {
+  int32_t fct;          /* tag::fct (default true)                                  */
+  int32_t fctclip;      /* tag::fctclip                                             */
+  int32_t fctsys_mask;  /* bit c set <=> component c+1 listed in tag::fctsys         */
+  int32_t pad_;
+  double fctdif;        /* tag::fctdif                                              */
+} xyst_zalcg_params;
+int xyst_zalcg_config(xyst_ctx* ctx, const xyst_zalcg_params* p);
+int xyst_zalcg_mesh_upload(xyst_ctx* ctx, size_t npoin,
+                           const double* x, const double* y, const double* z,
+                           const size_t nsup[3], const size_t* const dsupedge[3],
+                           const double* const dsupint[3],
+                           size_t ntri, const size_t* triinpoel, const uint8_t* besym,
+                           const double* vol, const double* v);
+/* zalesak::rhs (Zalesak.cpp:421-457) for problems without source term -> R (xyst_rhs_get) */
+int xyst_zalcg_rhs(xyst_ctx* ctx, double dt);
+/* one ZalCG time step: rhs, aec (P+/-), alw (low-order solution, Q+/-), lim (C+/-, limited
+ * antidiffusive contributions), solve, BC (ZalCG.cpp:990-1607); un keeps the old state */
+int xyst_zalcg_step(xyst_ctx* ctx, double dt);
+
 /* ---- linear solver of the pressure projection (ChoCG/LohCG) -----------------------------
  * tk::CSR (src/LinearSolver/CSR.hpp:30-107): block CSR exactly as the reference stores it,
  * nrow = npoin*ncomp scalar rows, 1-based ia[nrow+1] / ja[nnz], values a[nnz] (after

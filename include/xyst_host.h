@@ -29,6 +29,10 @@ typedef struct xyst_host_cfg {
   double gamma, p0, cfl, dt, t0, term, stab2coef;
   double far_density, far_pressure, far_velocity[3];
   double pre_density[16], pre_pressure[16];
+  char solver[16];            /* "riecg" (default when empty) | "zalcg" */
+  int32_t fct, fctclip, nfctsys;
+  int32_t fctsys[8];
+  double fctdif;
 } xyst_host_cfg;
 
 typedef struct xyst_solver xyst_solver;

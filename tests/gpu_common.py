@@ -28,9 +28,12 @@ def context_from_oracle(o, kw, chare=0, exact_muscl=False, device=0):
                             exact_muscl=exact_muscl)
     g = lambda n: o.get(n, chare)
     x, y, z = g("x"), g("y"), g("z")
+    zal = kw.get("solver") == "zalcg"
     ctx.mesh_upload(x, y, z, [g("dsupedge0"), g("dsupedge1"), g("dsupedge2")],
                     [g("dsupint0"), g("dsupint1"), g("dsupint2")], g("triinpoel"), g("besym"),
-                    g("vol"), g("v"))
+                    g("vol"), g("v"), stride=4 if zal else 3)
+    if zal:
+        ctx.zalcg_config(kw.get("fct", True), kw.get("fctclip", False), kw.get("fctsys", ()), kw.get("fctdif", 1.0))
     U0 = g("u")
     dm = g("dirbcmasks")
     dv = U0[dm.reshape(-1, 6)[:, 0].astype(np.int64)] if len(dm) else None
@@ -61,7 +64,9 @@ def drive_steps(ctxs, kw, nsteps, t0=0.0, fused=True, allreduce_min=None):
         if t + dt > kw.get("term", 1e300):
             dt = kw["term"] - t
         for c in ctxs:
-            if fused:
+            if kw.get("solver") == "zalcg":
+                c.zalcg_step(dt)
+            elif fused:
                 c.step(dt)
             else:
                 for s in range(3):

@@ -106,3 +106,18 @@ def test_face_set_iteration_order_equals_libstdcxx_unordered_set():
                                          a.ctypes.data, b.ctypes.data, C.byref(k)) == 0
         assert k.value > 0
         assert np.array_equal(a[:k.value], b[:k.value]), (n, maxid)
+
+
+@pytest.mark.parametrize("case", list(O.ZCASES))
+def test_zalcg_setup_matches_oracle(case):
+    """ZalCG variant of the setup: no renumbering, 4 integrals per edge (normal + J/120)."""
+    kw = O.ZCASES[case]
+    mesh = O.load_mesh(kw["mesh"])
+    o = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    hm = fixture_to_host_mesh(mesh)
+    s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"], hm["set_tri"])
+    s.prepare(); s.host_setup()
+    for n in ["gid", "inpoel", "x", "vol", "dsupedge0", "dsupint0", "dsupedge1", "dsupint1", "symbcnodes", "symbcnorms"]:
+        assert np.array_equal(o.get(n), s.get(n)), n
+    assert np.array_equal(np.sort(o.get("dsupint2").reshape(-1, 4), axis=0), np.sort(s.get("dsupint2").reshape(-1, 4), axis=0))
+    assert np.array_equal(o.get("gid"), np.arange(len(o.get("gid")), dtype=np.uint64))      # not renumbered

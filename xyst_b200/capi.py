@@ -11,6 +11,11 @@ class XystError(RuntimeError):
     pass
 
 
+class ZalParams(C.Structure):
+    _fields_ = [("fct", C.c_int32), ("fctclip", C.c_int32), ("fctsys_mask", C.c_int32), ("pad_", C.c_int32),
+                ("fctdif", C.c_double)]
+
+
 class Params(C.Structure):
     _fields_ = [("ncomp", C.c_int32), ("flux", C.c_int32), ("stab2", C.c_int32),
                 ("exact_muscl", C.c_int32), ("gamma", C.c_double), ("stab2coef", C.c_double)]
@@ -27,7 +32,8 @@ SYMBOLS = [
     "xyst_riecg_stage", "xyst_riecg_step", "xyst_diag", "xyst_comm_unique_id", "xyst_comm_init",
     "xyst_halo_upload", "xyst_halo_sum", "xyst_allreduce_min", "xyst_allreduce_sum", "xyst_launch_count",
     "xyst_nedge", "xyst_kernel_time", "xyst_csr_upload", "xyst_csr_mult", "xyst_cg_setup",
-    "xyst_cg_solve", "xyst_cg_get_x",
+    "xyst_cg_solve", "xyst_cg_get_x", "xyst_zalcg_config", "xyst_zalcg_mesh_upload", "xyst_zalcg_rhs",
+    "xyst_zalcg_step",
 ]
 
 
@@ -76,6 +82,10 @@ def lib():
     L.xyst_nedge.argtypes = [C.c_void_p]; L.xyst_nedge.restype = C.c_uint64
     L.xyst_kernel_time.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_double),
                                    C.POINTER(C.c_uint64)]
+    L.xyst_zalcg_config.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_zalcg_mesh_upload.argtypes = L.xyst_mesh_upload.argtypes
+    L.xyst_zalcg_rhs.argtypes = [C.c_void_p, C.c_double]
+    L.xyst_zalcg_step.argtypes = [C.c_void_p, C.c_double]
     L.xyst_csr_upload.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     L.xyst_csr_mult.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.xyst_cg_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
@@ -130,7 +140,20 @@ class Context:
     def sync(self):
         self._ck(self.L.xyst_sync(self.h))
 
-    def mesh_upload(self, x, y, z, dsupedge, dsupint, triinpoel, besym, vol, v):
+    def zalcg_config(self, fct=True, fctclip=False, fctsys=(), fctdif=1.0):
+        mask = 0
+        for c_ in fctsys:
+            mask |= 1 << (c_ - 1)
+        zp = ZalParams(int(fct), int(fctclip), mask, 0, fctdif)
+        self._ck(self.L.xyst_zalcg_config(self.h, C.byref(zp)))
+
+    def zalcg_rhs(self, dt):
+        self._ck(self.L.xyst_zalcg_rhs(self.h, dt))
+
+    def zalcg_step(self, dt):
+        self._ck(self.L.xyst_zalcg_step(self.h, dt))
+
+    def mesh_upload(self, x, y, z, dsupedge, dsupint, triinpoel, besym, vol, v, stride=3):
         x, y, z, vol, v = map(_f64, (x, y, z, vol, v))
         se = [_u64(a) for a in dsupedge]
         si = [_f64(a) for a in dsupint]
@@ -141,8 +164,9 @@ class Context:
         bs = np.ascontiguousarray(besym, dtype=np.uint8)
         self.npoin = len(x)
         self._keep = (x, y, z, vol, v, se, si, tri, bs)
-        self._ck(self.L.xyst_mesh_upload(self.h, len(x), _p(x), _p(y), _p(z), nsup, pe, pi,
-                                         len(tri) // 3, _p(tri), _p(bs), _p(vol), _p(v)))
+        fn = self.L.xyst_mesh_upload if stride == 3 else self.L.xyst_zalcg_mesh_upload
+        self._ck(fn(self.h, len(x), _p(x), _p(y), _p(z), nsup, pe, pi,
+                    len(tri) // 3, _p(tri), _p(bs), _p(vol), _p(v)))
 
     def bc_upload(self, dirbcmasks=(), dirvals=None, symbcnodes=(), symbcnorms=(), farbcnodes=(),
                   farbcnorms=(), far=(0.0, 0.0, (0.0, 0.0, 0.0)), prebcnodes=(), prebcvals=()):

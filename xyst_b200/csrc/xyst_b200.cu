@@ -172,6 +172,11 @@ struct xyst_ctx {
   size_t nsh = 0, nsend = 0;
   bool rb_pending = false;              // Rb of the current state already in flight on aux_stream
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
+  // ZalCG: integrals stride, FCT parameters, P/Q (C) and low-order solution
+  int dstride = 3;
+  xyst_zalcg_params zal{ 1, 0, 0, 0, 1.0 };
+  DevBuf< double > zP, zQ, zUL;          // [10][NP] [10][NP] [5][NP]
+  DevBuf< int > bcof;                    // [npoin] slot in the BC node list or -1
   // linear solver: sliced-ELL matrix over scalar rows + CG vectors
   size_t cg_nrow = 0, cg_ncomp = 1, cg_nslice = 0, cg_nent = 0;
   DevBuf< long long > cg_base; DevBuf< int > cg_col; DevBuf< double > cg_val, cg_diag;
@@ -925,6 +930,244 @@ k_diag( size_t npoin, size_t NP, const double* __restrict__ U, const double* __r
 }
 
 // ---------------------------------------------------------------------------------
+// ZalCG: Taylor-Galerkin two-step edge flux (Zalesak.cpp:31-200, no source term) and the
+// flux-corrected-transport passes of ZalCG.cpp:1056-1607 as node gathers
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_zal_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __restrict__ eq,
+                 const double* __restrict__ D, const double* __restrict__ U, const double* __restrict__ X,
+                 double dt, DParams P, double* __restrict__ F )
+{
+  size_t e = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (e >= nslot) return;
+  int pi = ep[e];
+  if (pi < 0) return;
+  size_t p = pi, q = eq[e];
+  double g = P.gamma;
+  double dx = X[p] - X[q], dy = X[NP+p] - X[NP+q], dz = X[2*NP+p] - X[2*NP+q];
+  double dl = dx*dx + dy*dy + dz*dz;
+  dx /= dl; dy /= dl; dz /= dl;
+  double rL = U[p], ruL = U[NP+p], rvL = U[2*NP+p], rwL = U[3*NP+p], reL = U[4*NP+p];
+  double pL = (reL - 0.5*(ruL*ruL + rvL*rvL + rwL*rwL)/rL) * (g-1.0);
+  double dnL = (ruL*dx + rvL*dy + rwL*dz)/rL;
+  double rR = U[q], ruR = U[NP+q], rvR = U[2*NP+q], rwR = U[3*NP+q], reR = U[4*NP+q];
+  double pR = (reR - 0.5*(ruR*ruR + rvR*rvR + rwR*rwR)/rR) * (g-1.0);
+  double dnR = (ruR*dx + rvR*dy + rwR*dz)/rR;
+  double nx = D[e], ny = D[nslot+e], nz = D[2*nslot+e];
+  double dp = pL - pR;
+  double rh  = 0.5*(rL + rR - dt*(rL*dnL - rR*dnR));
+  double ruh = 0.5*(ruL + ruR - dt*(ruL*dnL - ruR*dnR + dp*dx));
+  double rvh = 0.5*(rvL + rvR - dt*(rvL*dnL - rvR*dnR + dp*dy));
+  double rwh = 0.5*(rwL + rwR - dt*(rwL*dnL - rwR*dnR + dp*dz));
+  double reh = 0.5*(reL + reR - dt*((reL+pL)*dnL - (reR+pR)*dnR));
+  double ph = (reh - 0.5*(ruh*ruh + rvh*rvh + rwh*rwh)/rh) * (g-1.0);
+  double vn = (ruh*nx + rvh*ny + rwh*nz)/rh;
+  double f[NC];
+  f[0] = 2.0*rh*vn;
+  f[1] = 2.0*(ruh*vn + ph*nx);
+  f[2] = 2.0*(rvh*vn + ph*ny);
+  f[3] = 2.0*(rwh*vn + ph*nz);
+  f[4] = 2.0*(reh + ph)*vn;
+  if (P.stab2) {
+    double vnL = (ruL*nx + rvL*ny + rwL*nz)/rL;
+    double vnR = (ruR*nx + rvR*ny + rwR*nz)/rR;
+    double len = sqrt( nx*nx + ny*ny + nz*nz );
+    double cL = sqrt( g * fmax(pL,0.0) / fmax(rL,1.0e-8) );
+    double cR = sqrt( g * fmax(pR,0.0) / fmax(rR,1.0e-8) );
+    double fw = P.stab2coef * fmax( fabs(vnL) + cL*len, fabs(vnR) + cR*len );
+    f[0] -= fw*(rL - rR); f[1] -= fw*(ruL - ruR); f[2] -= fw*(rvL - rvR);
+    f[3] -= fw*(rwL - rwR); f[4] -= fw*(reL - reR);
+  }
+  #pragma unroll
+  for (int c=0; c<NC; ++c) F[c*nslot+e] = f[c];
+}
+
+// pass 1 (aec + first half of alw): R = sum +-F + boundary; P+/- from the antidiffusive edge
+// contributions aec = -dif*ctau*(u_first - u_second) (ZalCG.cpp:1071-1115), symmetry BC on P
+// (:1117-1133), then P /= vol and the low-order solution ul = u - dt R/vol - P+ - P- (:1195-1204)
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
+             const int* __restrict__ inc_q, const double* __restrict__ D, size_t nslot,
+             const double* __restrict__ F, const double* __restrict__ U, const int* __restrict__ bslot,
+             const double* __restrict__ Rb, const int* __restrict__ bcof, const int* __restrict__ symoff,
+             const double* __restrict__ sym_n, const double* __restrict__ vol, double dt, double ctau, int fct,
+             double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = sl_base[slice];
+  int kmax = (int)((sl_base[slice+1] - base) >> 5);
+  double up[NC], r[NC], pp[NC], pn[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { up[c] = U[c*NP+p]; r[c] = 0.0; pp[c] = 0.0; pn[c] = 0.0; }
+  for (int k=0; k<kmax; ++k) {
+    long long i = base + (long long)k*32 + lane;
+    int se = __ldg( inc_e + i );
+    if (se == 0) continue;
+    size_t q = __ldg( inc_q + i );
+    size_t sl = (size_t)(abs(se)-1);
+    double dif = __ldg( D + 3*nslot + sl );
+    #pragma unroll
+    for (int c=0; c<NC; ++c) {
+      double f = __ldg( F + c*nslot + sl );
+      double uq = __ldg( U + c*NP + q );
+      if (se < 0) {                       // this node is the edge's first node
+        r[c] -= f;
+        double aec = -dif * ctau * (up[c] - uq);
+        if (aec > 0.0) pn[c] -= aec; else pp[c] -= aec;
+      } else {                            // second node
+        r[c] += f;
+        double aec = -dif * ctau * (uq - up[c]);
+        if (aec > 0.0) pp[c] += aec; else pn[c] += aec;
+      }
+    }
+  }
+  int b = bslot[p];
+  if (b >= 0) {
+    #pragma unroll
+    for (int c=0; c<NC; ++c) r[c] += Rb[(size_t)b*NC+c];
+  }
+  if (!fct) {
+    #pragma unroll
+    for (int c=0; c<NC; ++c) R[p*NC+c] = r[c];
+    return;
+  }
+  int bc = bcof[p];
+  if (bc >= 0)
+    for (int s=symoff[bc]; s<symoff[bc+1]; ++s) {
+      const double* n = sym_n + (size_t)s*3;
+      double rvnp = pp[1]*n[0] + pp[2]*n[1] + pp[3]*n[2];
+      double rvnn = pn[1]*n[0] + pn[2]*n[1] + pn[3]*n[2];
+      pp[1] -= rvnp * n[0]; pn[1] -= rvnn * n[0];
+      pp[2] -= rvnp * n[1]; pn[2] -= rvnn * n[1];
+      pp[3] -= rvnp * n[2]; pn[3] -= rvnn * n[2];
+    }
+  double vp = vol[p];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) {
+    pp[c] /= vp; pn[c] /= vp;
+    P[(2*c)*NP+p] = pp[c]; P[(2*c+1)*NP+p] = pn[c];
+    UL[c*NP+p] = up[c] - dt*r[c]/vp - pp[c] - pn[c];
+    R[p*NC+c] = r[c];
+  }
+}
+
+// pass 2 (second half of alw + first half of lim): allowed bounds Q+/- over the edge
+// neighbours (:1206-1290), Q -= ul, limit coefficients C+/- (:1361-1380) -> Q
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_zal_node2( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
+             const int* __restrict__ inc_q, const double* __restrict__ U, const double* __restrict__ UL,
+             const double* __restrict__ P, int clip, double* __restrict__ Q )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = sl_base[slice];
+  int kmax = (int)((sl_base[slice+1] - base) >> 5);
+  double hp[NC], lp[NC], qa[NC], qb[NC], ulp[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) {
+    ulp[c] = UL[c*NP+p]; double u = U[c*NP+p];
+    hp[c] = clip ? ulp[c] : fmax( ulp[c], u );
+    lp[c] = clip ? ulp[c] : fmin( ulp[c], u );
+    qa[c] = -1.7976931348623157e308; qb[c] = 1.7976931348623157e308;
+  }
+  for (int k=0; k<kmax; ++k) {
+    long long i = base + (long long)k*32 + lane;
+    if (__ldg( inc_e + i ) == 0) continue;
+    size_t q = __ldg( inc_q + i );
+    #pragma unroll
+    for (int c=0; c<NC; ++c) {
+      double ulq = __ldg( UL + c*NP + q );
+      double hq = ulq, lq = ulq;
+      if (!clip) { double uq = __ldg( U + c*NP + q ); hq = fmax( ulq, uq ); lq = fmin( ulq, uq ); }
+      qa[c] = fmax( qa[c], fmax( hp[c], hq ) );
+      qb[c] = fmin( qb[c], fmin( lp[c], lq ) );
+    }
+  }
+  const double eps = 2.220446049250313e-16;
+  #pragma unroll
+  for (int c=0; c<NC; ++c) {
+    double a = qa[c] - ulp[c], b = qb[c] - ulp[c];
+    double pa = P[(2*c)*NP+p], pb = P[(2*c+1)*NP+p];
+    Q[(2*c)*NP+p]   = pa <  eps ? 0.0 : fmin( 1.0, a/pa );
+    Q[(2*c+1)*NP+p] = pb > -eps ? 0.0 : fmin( 1.0, b/pb );
+  }
+}
+
+// pass 3 (second half of lim + solve): limited antidiffusive contributions (:1382-1481) and
+// u = ul + a/vol (:1552-1557)
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_zal_node3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
+             const int* __restrict__ inc_q, const double* __restrict__ D, size_t nslot,
+             const double* __restrict__ U, const double* __restrict__ UL, const double* __restrict__ Q,
+             const double* __restrict__ vol, double ctau, int sysmask, double* __restrict__ Unew,
+             double* __restrict__ W )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = sl_base[slice];
+  int kmax = (int)((sl_base[slice+1] - base) >> 5);
+  double up[NC], cpa[NC], cpb[NC], a[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { up[c] = U[c*NP+p]; cpa[c] = Q[(2*c)*NP+p]; cpb[c] = Q[(2*c+1)*NP+p]; a[c] = 0.0; }
+  for (int k=0; k<kmax; ++k) {
+    long long i = base + (long long)k*32 + lane;
+    int se = __ldg( inc_e + i );
+    if (se == 0) continue;
+    size_t q = __ldg( inc_q + i );
+    double dif = __ldg( D + 3*nslot + (size_t)(abs(se)-1) );
+    double aec[NC], coef[NC];
+    #pragma unroll
+    for (int c=0; c<NC; ++c) {
+      double uq = __ldg( U + c*NP + q );
+      double cqa = __ldg( Q + (2*c)*NP + q ), cqb = __ldg( Q + (2*c+1)*NP + q );
+      if (se < 0) {      // first = this node, second = q
+        aec[c] = -dif * ctau * (up[c] - uq);
+        coef[c] = fmin( aec[c] < 0.0 ? cpa[c] : cpb[c], aec[c] > 0.0 ? cqa : cqb );
+      } else {           // first = q, second = this node
+        aec[c] = -dif * ctau * (uq - up[c]);
+        coef[c] = fmin( aec[c] < 0.0 ? cqa : cqb, aec[c] > 0.0 ? cpa[c] : cpb[c] );
+      }
+    }
+    double cs = 1.0;
+    #pragma unroll
+    for (int c=0; c<NC; ++c) if (sysmask & (1<<c)) cs = fmin( cs, coef[c] );
+    #pragma unroll
+    for (int c=0; c<NC; ++c) {
+      if (sysmask & (1<<c)) coef[c] = cs;
+      double v = aec[c] * coef[c];
+      if (se < 0) a[c] -= v; else a[c] += v;
+    }
+  }
+  double vp = vol[p], u[NC], w[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { u[c] = UL[c*NP+p] + a[c]/vp; Unew[c*NP+p] = u[c]; }
+  primitive( u, w );
+  #pragma unroll
+  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+}
+
+// fct = false: u = u - dt R/vol (ZalCG.cpp:1560-1567)
+__global__ void k_zal_nofct( size_t npoin, size_t NP, const double* __restrict__ R, const double* __restrict__ vol,
+                             const double* __restrict__ U, double dt, double* __restrict__ Unew, double* __restrict__ W )
+{
+  size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (p >= npoin) return;
+  double vp = vol[p], u[NC], w[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { u[c] = U[c*NP+p] - dt*R[p*NC+c]/vp; Unew[c*NP+p] = u[c]; }
+  primitive( u, w );
+  #pragma unroll
+  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+}
+
+// ---------------------------------------------------------------------------------
 // linear solver: CSR::mult (CSR.cpp:154-172) and the vector operations of
 // ConjugateGradients.cpp:584-823. Matrix in sliced ELL over scalar rows (one warp per 32
 // rows, entry k of lane l at base + 32k + l: coalesced), dots by fixed two-pass trees.
@@ -1276,12 +1519,13 @@ int xyst_ctx_destroy( xyst_ctx* c )
 
 int xyst_sync( xyst_ctx* c ) { API_BEGIN CK( cudaSetDevice( c->device ) ); CK( cudaStreamSynchronize( c->stream ) ); API_END }
 
-int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* y, const double* z,
+static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const double* y, const double* z,
                       const size_t nsup[3], const size_t* const dsupedge[3],
                       const double* const dsupint[3], size_t ntri, const size_t* triinpoel,
-                      const uint8_t* besym, const double* vol, const double* v )
+                      const uint8_t* besym, const double* vol, const double* v, size_t stride )
 {
   API_BEGIN
+  c->dstride = (int)stride;
   CK( cudaSetDevice( c->device ) );
   if (npoin == 0 || npoin > 0x7fffffffULL) throw std::runtime_error( "npoin out of range" );
   // --- flatten superedges to edges (orientation and normals as given) ---------------
@@ -1290,24 +1534,24 @@ int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* 
   static const int lpoet[3][2] = { {0,1}, {1,2}, {2,0} };
   size_t ne = nsup[0]*6 + nsup[1]*3 + nsup[2];
   if (ne > 0x7ffffff0ULL) throw std::runtime_error( "too many edges for 32-bit edge ids" );
-  struct E { int p, q; double d[3]; };
+  struct E { int p, q; double d[4]; };
   std::vector< E > edges; edges.reserve( ne );
   auto chk = [&]( size_t id ){ if (id >= npoin) throw std::runtime_error( "node id out of range in superedge" ); return (int)id; };
   for (size_t e=0; e<nsup[0]; ++e)
     for (int k=0; k<6; ++k) {
       E ed; ed.p = chk( dsupedge[0][e*4+lpoed[k][0]] ); ed.q = chk( dsupedge[0][e*4+lpoed[k][1]] );
-      for (int j=0; j<3; ++j) ed.d[j] = dsupint[0][(e*6+k)*3+j];
+      ed.d[3] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[0][(e*6+k)*stride+j];
       edges.push_back( ed );
     }
   for (size_t e=0; e<nsup[1]; ++e)
     for (int k=0; k<3; ++k) {
       E ed; ed.p = chk( dsupedge[1][e*3+lpoet[k][0]] ); ed.q = chk( dsupedge[1][e*3+lpoet[k][1]] );
-      for (int j=0; j<3; ++j) ed.d[j] = dsupint[1][(e*3+k)*3+j];
+      ed.d[3] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[1][(e*3+k)*stride+j];
       edges.push_back( ed );
     }
   for (size_t e=0; e<nsup[2]; ++e) {
     E ed; ed.p = chk( dsupedge[2][e*2+0] ); ed.q = chk( dsupedge[2][e*2+1] );
-    for (int j=0; j<3; ++j) ed.d[j] = dsupint[2][e*3+j];
+    ed.d[3] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[2][e*stride+j];
     edges.push_back( ed );
   }
   // --- edge slots in owner order ----------------------------------------------------
@@ -1333,7 +1577,7 @@ int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* 
   size_t nslot = (size_t)ebase[nslice];
   if (nslot > 0x7ffffff0ULL) throw std::runtime_error( "too many edge slots for 32-bit ids" );
   std::vector< int > ep( nslot, -1 ), eq( nslot, -1 ), slot_of( ne );
-  std::vector< double > ed( 3*nslot, 0.0 );
+  std::vector< double > ed( 4*nslot, 0.0 );
   { std::vector< int > fillu( npoin, 0 );
     for (size_t i=0; i<ne; ++i) {
       const auto& e = edges[perm[i]];
@@ -1341,7 +1585,7 @@ int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* 
       size_t sl = (size_t)ebase[o/32] + (size_t)fillu[o]*32 + (size_t)(o%32);
       ++fillu[o];
       ep[sl] = e.p; eq[sl] = e.q; slot_of[i] = (int)sl;
-      for (int j=0; j<3; ++j) ed[j*nslot+sl] = e.d[j];
+      for (int j=0; j<4; ++j) ed[j*nslot+sl] = e.d[j];
     } }
   // --- sliced-ELL incidence: node -> (signed slot, neighbour) -------------------------
   // reference scatter: G(p) -= f, G(q) += f with f = d*(u_q+u_p)  (Riemann.cpp:321-323).
@@ -1398,6 +1642,8 @@ int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* 
   c->bslot.upload( bslot, s ); c->bn_node.upload( bn_node, s ); c->bn_off.upload( bn_off, s );
   c->bn_face.upload( bn_face, s );
   c->Gb.alloc( nbn*15 ); c->Rb.alloc( nbn*NC );
+  c->bcof.upload( std::vector< int >( npoin, -1 ), s );
+  c->zP.release(); c->zQ.release(); c->zUL.release();
   { std::vector< double > pv( NP, 1.0 ), pw( NP, 1.0 ), px( 3*NP, 0.0 );
     for (size_t p=0; p<npoin; ++p) { pv[p] = vol[p]; pw[p] = v[p]; px[p] = x[p]; px[NP+p] = y[p]; px[2*NP+p] = z[p]; }
     c->vol.upload( pv, s ); c->v.upload( pw, s ); c->X.upload( px, s ); }
@@ -1411,6 +1657,86 @@ int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* 
   CK( cudaMemsetAsync( c->F.p, 0, std::max< size_t >( nslot, 1 )*NC*sizeof(double), s ) );
   c->S.release(); c->src_mask = 0;
   CK( cudaStreamSynchronize( s ) );
+  API_END
+}
+
+int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* y, const double* z,
+                      const size_t nsup[3], const size_t* const dsupedge[3],
+                      const double* const dsupint[3], size_t ntri, const size_t* triinpoel,
+                      const uint8_t* besym, const double* vol, const double* v )
+{ return mesh_upload_impl( c, npoin, x, y, z, nsup, dsupedge, dsupint, ntri, triinpoel, besym, vol, v, 3 ); }
+
+int xyst_zalcg_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* y, const double* z,
+                            const size_t nsup[3], const size_t* const dsupedge[3],
+                            const double* const dsupint[3], size_t ntri, const size_t* triinpoel,
+                            const uint8_t* besym, const double* vol, const double* v )
+{ return mesh_upload_impl( c, npoin, x, y, z, nsup, dsupedge, dsupint, ntri, triinpoel, besym, vol, v, 4 ); }
+
+int xyst_zalcg_config( xyst_ctx* c, const xyst_zalcg_params* p )
+{
+  API_BEGIN
+  if (!p) throw std::runtime_error( "null argument" );
+  c->zal = *p;
+  API_END
+}
+
+namespace {
+void zal_need( xyst_ctx* c ) {
+  need_mesh( c );
+  if (c->dstride != 4) throw std::runtime_error( "ZalCG needs stride-4 superedge integrals: use xyst_zalcg_mesh_upload" );
+  if (c->nsh > 0 && c->comm) throw std::runtime_error( "ZalCG on several partitions is not implemented yet" );
+  if (!c->zP.p) { c->zP.alloc( c->NP*10 ); c->zQ.alloc( c->NP*10 ); c->zUL.alloc( c->NP*NC ); }
+}
+void zal_flux_and_bnd( xyst_ctx* c, double dt )
+{
+  auto s = c->stream;
+  if (c->nbn) { k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
+                  c->tri.p, c->besym.p, c->fn.p, c->U.p, c->Rb.p, c->prm.gamma ); ++c->launches; }
+  { ProfScope ps( c, "zalflux" );
+    k_zal_flux_edge<<< nblk( c->nslot, 128 ), 128, 0, s >>>( c->nslot, c->NP, c->ep.p, c->eq.p, c->D.p, c->U.p, c->X.p,
+      dt, dparams( c ), c->F.p ); ++c->launches; }
+}
+void zal_node1( xyst_ctx* c, double dt, int fct )
+{
+  k_zal_node1<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p,
+    c->inc_e.p, c->inc_q.p, c->D.p, c->nslot, c->F.p, c->U.p, c->bslot.p, c->Rb.p, c->bcof.p, c->bc_symoff.p,
+    c->sym_n.p, c->vol.p, dt, c->zal.fctdif, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
+}
+}
+
+int xyst_zalcg_rhs( xyst_ctx* c, double dt )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  zal_need( c );
+  zal_flux_and_bnd( c, dt );
+  zal_node1( c, dt, 0 );
+  CK( cudaGetLastError() );
+  API_END
+}
+
+int xyst_zalcg_step( xyst_ctx* c, double dt )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  zal_need( c );
+  auto s = c->stream;
+  unsigned g = nblk( c->nslice*32, NODE_THREADS );
+  zal_flux_and_bnd( c, dt );
+  if (c->zal.fct) {
+    zal_node1( c, dt, 1 );
+    k_zal_node2<<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->U.p, c->zUL.p,
+      c->zP.p, c->zal.fctclip, c->zQ.p ); ++c->launches;
+    // new state into the other buffer, then swap: Un keeps the old state for the diagnostics
+    k_zal_node3<<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p, c->nslot,
+      c->U.p, c->zUL.p, c->zQ.p, c->vol.p, c->zal.fctdif, c->zal.fctsys_mask, c->Un.p, c->W.p ); ++c->launches;
+  } else {
+    zal_node1( c, dt, 0 );
+    k_zal_nofct<<< nblk( c->npoin, 256 ), 256, 0, s >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->U.p, dt, c->Un.p, c->W.p ); ++c->launches;
+  }
+  std::swap( c->U.p, c->Un.p );
+  do_bc( c );
+  CK( cudaGetLastError() );
   API_END
 }
 
@@ -1455,6 +1781,7 @@ int xyst_bc_upload( xyst_ctx* c, size_t ndir, const size_t* dirbcmasks, const do
   for (size_t i=0; i<npre; ++i) { pre[ slot[(int)prebcnodes[i]] ] = (int)i; preval[i*2] = prebcvals[i*2]; preval[i*2+1] = prebcvals[i*2+1]; }
   auto s = c->stream;
   c->nbc = nbc; c->ndir = ndir;
+  { std::vector< int > bcof( c->npoin, -1 ); for (size_t i=0; i<nbc; ++i) bcof[nodes[i]] = (int)i; c->bcof.upload( bcof, s ); }
   c->bc_node.upload( nodes, s ); c->bc_dir.upload( dir, s ); c->bc_pre.upload( pre, s );
   c->bc_symoff.upload( symoff, s ); c->bc_faroff.upload( faroff, s );
   c->dir_mask.upload( dmask, s ); c->dir_val.upload( dval, s );

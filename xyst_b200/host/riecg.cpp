@@ -125,6 +125,8 @@ RieCG::RieCG( Discretization& disc, const TetMesh& chunk, const Config& cfg )
   : m_disc( disc ), m_cfg( cfg ), m_sidetri( chunk.sidetri )
 {
   if (cfg.ncomp != 5) throw std::runtime_error( "only ncomp = 5 is supported" );
+  if (cfg.solver != "riecg" && cfg.solver != "zalcg") throw std::runtime_error( "Unknown solver: " + cfg.solver );
+  m_zal = cfg.solver == "zalcg"; m_stride = m_zal ? 4 : 3;
   // Transporter::matchsets as the reference executes it (Transporter.cpp:125-187 with the
   // short-circuit at :347-348): with at least one side set named in the configuration the
   // faces of ALL side sets of the mesh keep their boundary integrals; with none, no face does.
@@ -240,7 +242,8 @@ void RieCG::domint( const EdgeCSR& edges, std::vector< real >& d ) const
 {
   const auto& inpoel = m_disc.Inpoel(); const auto& gid = m_disc.Gid();
   const auto& x = m_disc.Coord()[0]; const auto& y = m_disc.Coord()[1]; const auto& z = m_disc.Coord()[2];
-  d.assign( edges.nedge()*3, 0.0 );
+  const auto st = m_stride;
+  d.assign( edges.nedge()*st, 0.0 );
   for (std::size_t e=0; e<inpoel.size()/4; ++e) {
     const auto N = inpoel.data() + e*4;
     real ba[3] = { x[N[1]]-x[N[0]], y[N[1]]-y[N[0]], z[N[1]]-z[N[0]] },
@@ -249,13 +252,16 @@ void RieCG::domint( const EdgeCSR& edges, std::vector< real >& d ) const
     real g[4][3];
     cross( ca, da, g[1] ); cross( da, ba, g[2] ); cross( ba, ca, g[3] );
     for (std::size_t i=0; i<3; ++i) g[0][i] = -g[1][i]-g[2][i]-g[3][i];
+    real cx[3]; cross( ca, da, cx );
+    const auto J120 = (ba[0]*cx[0] + ba[1]*cx[1] + ba[2]*cx[2]) / 120.0;     // ZalCG.cpp:375,386
     for (const auto& pq : lpoed) {
       auto p = pq[0], q = pq[1];
       real sig = gid[N[p]] > gid[N[q]] ? -1.0 : 1.0;
-      auto n = d.data() + edges.find( N[p], N[q] )*3;
+      auto n = d.data() + edges.find( N[p], N[q] )*st;
       n[0] += sig * (g[p][0] - g[q][0]) / 48.0;
       n[1] += sig * (g[p][1] - g[q][1]) / 48.0;
       n[2] += sig * (g[p][2] - g[q][2]) / 48.0;
+      if (st == 4) n[3] += J120;
     }
   }
 }
@@ -300,7 +306,8 @@ void RieCG::domsuped( const EdgeCSR& edges, const std::vector< real >& d )
     if (reforder) for (const auto& f : lpofa) untri.erase( {{ N[f[0]], N[f[1]], N[f[2]] }} );
     for (int k=0; k<6; ++k) {
       real sig = gid[N[lpoed[k][0]]] < gid[N[lpoed[k][1]]] ? 1.0 : -1.0;
-      for (int j=0; j<3; ++j) m_dsupint[0].push_back( sig * d[id[k]*3+static_cast<std::size_t>(j)] );
+      for (std::size_t j=0; j<3; ++j) m_dsupint[0].push_back( sig * d[id[k]*m_stride+j] );
+      if (m_zal) m_dsupint[0].push_back( d[id[k]*m_stride+3] );
       claimed[id[k]] = 1;
     }
   }
@@ -311,7 +318,8 @@ void RieCG::domsuped( const EdgeCSR& edges, const std::vector< real >& d )
     for (std::size_t k=0; k<3; ++k) m_dsupedge[1].push_back( T[k] );
     for (int k=0; k<3; ++k) {
       real sig = gid[T[static_cast<std::size_t>(lpoet[k][0])]] < gid[T[static_cast<std::size_t>(lpoet[k][1])]] ? 1.0 : -1.0;
-      for (int j=0; j<3; ++j) m_dsupint[1].push_back( sig * d[id[k]*3+static_cast<std::size_t>(j)] );
+      for (std::size_t j=0; j<3; ++j) m_dsupint[1].push_back( sig * d[id[k]*m_stride+j] );
+      if (m_zal) m_dsupint[1].push_back( d[id[k]*m_stride+3] );
       claimed[id[k]] = 1;
     }
   };
@@ -327,7 +335,7 @@ void RieCG::domsuped( const EdgeCSR& edges, const std::vector< real >& d )
       std::size_t a = p, b = edges.hi[i];
       if (gid[a] > gid[b]) std::swap( a, b );           // low gid -> high gid (:706-714)
       m_dsupedge[2].push_back( a ); m_dsupedge[2].push_back( b );
-      for (int j=0; j<3; ++j) m_dsupint[2].push_back( d[i*3+static_cast<std::size_t>(j)] );
+      for (std::size_t j=0; j<m_stride; ++j) m_dsupint[2].push_back( d[i*m_stride+j] );
     }
 }
 
@@ -421,7 +429,7 @@ void RieCG::prepare()
   m_ownvol = 0.0;                    // ... and sums the mesh volume then (Discretization.cpp:719-721)
   for (auto v : m_disc.V()) m_ownvol += v;
   timings.push_back( now()-t0 ); t0 = now();
-  renumber();
+  if (!m_zal) renumber();            // ZalCG keeps the global2local order (ZalCG.cpp:82-92)
   timings.push_back( now()-t0 ); t0 = now();
   auto np = m_disc.Gid().size();
   auto edges = uniqueEdges( m_disc.Inpoel(), np );
@@ -524,9 +532,15 @@ void RieCG::setup()
   std::size_t nsup[3] = { m_dsupedge[0].size()/4, m_dsupedge[1].size()/3, m_dsupedge[2].size()/2 };
   const std::size_t* se[3] = { m_dsupedge[0].data(), m_dsupedge[1].data(), m_dsupedge[2].data() };
   const real* si[3] = { m_dsupint[0].data(), m_dsupint[1].data(), m_dsupint[2].data() };
-  ck( xyst_mesh_upload( m_ctx, np, co[0].data(), co[1].data(), co[2].data(), nsup, se, si,
-                        m_triinpoel.size()/3, m_triinpoel.data(), m_besym.data(),
+  ck( (m_zal ? xyst_zalcg_mesh_upload : xyst_mesh_upload)( m_ctx, np, co[0].data(), co[1].data(), co[2].data(),
+                        nsup, se, si, m_triinpoel.size()/3, m_triinpoel.data(), m_besym.data(),
                         m_disc.Vol().data(), m_disc.V().data() ) );
+  if (m_zal) {
+    xyst_zalcg_params zp{};
+    zp.fct = m_cfg.fct; zp.fctclip = m_cfg.fctclip; zp.fctdif = m_cfg.fctdif;
+    for (auto c : m_cfg.fctsys) zp.fctsys_mask |= 1 << (c-1);
+    ck( xyst_zalcg_config( m_ctx, &zp ) );
+  }
   timings.push_back( now()-t0 ); t0 = now();
   ck( xyst_bc_upload( m_ctx, m_dirbcmasks.size()/(ncomp+1), m_dirbcmasks.data(), m_dirvals.data(),
                       m_symbcnodes.size(), m_symbcnodes.data(), m_symbcnorms.data(),
@@ -571,7 +585,8 @@ bool RieCG::step( std::vector< real >* diagrow )
 {
   if (m_finished) return false;
   advance( dt() );
-  ck( xyst_riecg_step( m_ctx, m_disc.Dt() ) );
+  if (m_zal) ck( xyst_zalcg_step( m_ctx, m_disc.Dt() ) );      // ZalCG.cpp:973-1607
+  else ck( xyst_riecg_step( m_ctx, m_disc.Dt() ) );
   if (diagrow && (m_disc.It()+1) % m_cfg.diag_iter == 0) *diagrow = diagnostics();
   else if (diagrow) diagrow->clear();
   m_disc.next();

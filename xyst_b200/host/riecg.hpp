@@ -31,6 +31,13 @@ struct Config {
   //! (identical triangles, needed for parity beyond 1e-9, ~2 us per tet), 0 = walk them in
   //! element order (same edges and integrals, other triangles), -1 = 1 up to 4M tets
   int reforder = -1;
+  //! "riecg" or "zalcg": the ZalCG variant (src/Inciter/ZalCG.cpp) shares the setup pipeline
+  //! but keeps the global2local node order, carries 4 integrals per edge (normal + J/120)
+  //! and advances with one Taylor-Galerkin + flux-corrected-transport stage per step
+  std::string solver = "riecg";
+  bool fct = true, fctclip = false;
+  real fctdif = 1.0;
+  std::vector< int > fctsys;                //!< 1-based components limited as a system
   std::vector< int > bc_sym;
   std::vector< std::vector< int > > bc_dir; //!< { setid, mask_0 .. mask_{ncomp-1} }
   std::vector< int > bc_far;
@@ -123,7 +130,7 @@ class RieCG {
   private:
     void renumber();                 //!< RieCG.cpp:82-100
     void boundaryFaces( const TetMesh& chunk );    //!< Partitioner.cpp:539-626 per partition
-    void domint( const EdgeCSR& edges, std::vector< real >& d ) const;   //!< :339-382
+    void domint( const EdgeCSR& edges, std::vector< real >& d ) const;   //!< :339-382, ZalCG.cpp:354-400
     void domsuped( const EdgeCSR& edges, const std::vector< real >& d ); //!< :620-736
     void bndint();                   //!< :281-337
     void setupBC();                  //!< :109-245 (after normals are known)
@@ -140,6 +147,8 @@ class RieCG {
     HaloSum m_halosum;
     AllReduce m_allreduce;
     bool m_hostready = false;
+    bool m_zal = false;
+    std::size_t m_stride = 3;
     real m_ownvol = 0.0;
     std::vector< real > m_dirvals, m_src;
 };

@@ -21,6 +21,8 @@ class HostCfg(C.Structure):
         ("t0", C.c_double), ("term", C.c_double), ("stab2coef", C.c_double),
         ("far_density", C.c_double), ("far_pressure", C.c_double), ("far_velocity", C.c_double * 3),
         ("pre_density", C.c_double * 16), ("pre_pressure", C.c_double * 16),
+        ("solver", C.c_char * 16), ("fct", C.c_int32), ("fctclip", C.c_int32), ("nfctsys", C.c_int32),
+        ("fctsys", C.c_int32 * 8), ("fctdif", C.c_double),
     ]
 
 
@@ -29,12 +31,17 @@ COMM_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(
 
 def make_cfg(problem, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0, term=1e300,
              nstep=2**63, sym=(), dir_=(), stab2=False, stab2coef=0.2, diag_iter=1, ncomp=5,
-             exact_muscl=False, reforder=-1, **_ignored):
+             exact_muscl=False, reforder=-1, solver="riecg", fct=True, fctclip=False, fctsys=(),
+             fctdif=1.0, **_ignored):
     c = HostCfg()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term
     c.nstep = nstep; c.stab2 = int(stab2); c.stab2coef = stab2coef
     c.exact_muscl = int(exact_muscl); c.diag_iter = diag_iter; c.reforder = reforder
+    c.solver = solver.encode(); c.fct = int(fct); c.fctclip = int(fctclip); c.fctdif = fctdif
+    c.nfctsys = len(fctsys)
+    for i, s_ in enumerate(fctsys):
+        c.fctsys[i] = s_
     c.nsym = len(sym)
     for i, s in enumerate(sym):
         c.sym[i] = s

@@ -174,6 +174,7 @@ struct xyst_ctx {
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
   // ZalCG: integrals stride, FCT parameters, P/Q (C) and low-order solution
   int dstride = 3;
+  int maxdeg = 0;                        // largest number of edges at a node
   xyst_zalcg_params zal{ 1, 0, 0, 0, 1.0 };
   DevBuf< double > zP, zQ, zUL;          // [10][NP] [10][NP] [5][NP]
   DevBuf< int > bcof;                    // [npoin] slot in the BC node list or -1
@@ -202,6 +203,15 @@ __device__ __forceinline__ void primitive( const double u[NC], double w[NC] ) {
   w[3] = u[3] / w[0];
   w[4] = u[4] / w[0] - 0.5*(w[1]*w[1] + w[2]*w[2] + w[3]*w[3]);
 }
+
+// 8-byte asynchronous global->shared copy (LDGSTS): in flight without holding a register
+__device__ __forceinline__ void cp_async8( double* smem_dst, const double* gsrc )
+{
+  unsigned d = (unsigned)__cvta_generic_to_shared( smem_dst );
+  asm volatile( "cp.async.ca.shared.global [%0], [%1], 8;" :: "r"( d ), "l"( gsrc ) : "memory" );
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile( "cp.async.commit_group;" ::: "memory" ); }
+template< int N > __device__ __forceinline__ void cp_async_wait() { asm volatile( "cp.async.wait_group %0;" :: "n"( N ) : "memory" ); }
 
 // reference layout [node][comp] -> SoA state + primitives
 __global__ void k_set_state( size_t n, size_t NP, const double* __restrict__ A,
@@ -624,12 +634,6 @@ __device__ __forceinline__ void hllc( double l[NC], double r[NC], const double n
 // every thread has its whole working set (46 doubles) outstanding at once and the kernel
 // still fits enough warps per SM to cover the latency; the limiter then reads its
 // operands from shared memory as it goes.
-__device__ __forceinline__ void cp_async8( double* smem_dst, const double* gsrc )
-{
-  unsigned d = (unsigned)__cvta_generic_to_shared( smem_dst );
-  asm volatile( "cp.async.ca.shared.global [%0], [%1], 8;" :: "r"( d ), "l"( gsrc ) : "memory" );
-}
-
 template< bool EXACT, int FLUX >
 __global__ void __launch_bounds__(FLUX_THREADS, FLUX_MINB)
 k_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __restrict__ eq,
@@ -872,13 +876,25 @@ k_dt( size_t npoin, size_t NP, const double* __restrict__ U, const double* __res
       double* __restrict__ part )
 {
   double m[1] = { 1.7976931348623157e308 };
-  for (size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x; p < npoin; p += (size_t)gridDim.x*blockDim.x) {
-    double r = U[p], u = U[NP+p]/r, v = U[2*NP+p]/r, w = U[3*NP+p]/r;
-    double pr = (U[4*NP+p] - 0.5*r*(u*u + v*v + w*w)) * (gamma-1.0);
-    double c = sqrt( gamma * fmax(pr,0.0) / r );
-    double L = cbrt( vol[p] );
-    double vel = sqrt( u*u + v*v + w*w );
-    m[0] = fmin( m[0], L / fmax( vel+c, 1.0e-8 ) );
+  const size_t stride = (size_t)gridDim.x*blockDim.x;
+  for (size_t p0 = blockIdx.x*(size_t)blockDim.x + threadIdx.x; p0 < npoin; p0 += 4*stride) {
+    double a[4][6];
+    #pragma unroll
+    for (int k=0; k<4; ++k) {               // 24 independent loads in flight per thread
+      size_t p = min( p0 + k*stride, npoin-1 );
+      #pragma unroll
+      for (int c=0; c<NC; ++c) a[k][c] = U[c*NP+p];
+      a[k][5] = vol[p];
+    }
+    #pragma unroll
+    for (int k=0; k<4; ++k) {
+      double r = a[k][0], u = a[k][1]/r, v = a[k][2]/r, w = a[k][3]/r;
+      double pr = (a[k][4] - 0.5*r*(u*u + v*v + w*w)) * (gamma-1.0);
+      double c = sqrt( gamma * fmax(pr,0.0) / r );
+      double L = cbrt( a[k][5] );
+      double vel = sqrt( u*u + v*v + w*w );
+      m[0] = fmin( m[0], L / fmax( vel+c, 1.0e-8 ) );
+    }
   }
   block_reduce< 1, true >( m, part );
 }
@@ -1362,7 +1378,8 @@ void do_grad( xyst_ctx* c )
   {
     ProfScope ps( c, "grad" );
     k_grad_node<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p,
-      c->inc_e.p, c->inc_q.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->vol.p, c->G.p, overlap ? 1 : 0 ); ++c->launches;
+      c->inc_e.p, c->inc_q.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->vol.p, c->G.p, overlap ? 1 : 0 );
+    ++c->launches;
   }
   if (overlap) {
     CK( cudaStreamWaitEvent( s, c->ev_d, 0 ) );
@@ -1600,6 +1617,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
     base[s+1] = base[s] + (long long)km*32;
   }
   size_t nent = (size_t)base[nslice];
+  c->maxdeg = 0; for (size_t p=0; p<npoin; ++p) c->maxdeg = std::max( c->maxdeg, deg[p] );
   std::vector< int > inc_e( nent, 0 ), inc_q( nent, 0 ), fill( npoin, 0 );
   for (size_t sl=0; sl<nslice; ++sl)            // padding: the node itself (last node for the tail slice)
     for (size_t j=(size_t)base[sl]; j<(size_t)base[sl+1]; ++j) inc_q[j] = (int)std::min( npoin-1, sl*32 + (j - (size_t)base[sl])%32 );

@@ -17,6 +17,7 @@
   #include "DerivedData.hpp"
   #include "Riemann.hpp"
   #include "Zalesak.hpp"
+  #include "Kozak.hpp"
   #include "BC.hpp"
   #include "Problems.hpp"
   #include "InciterConfig.hpp"
@@ -57,6 +58,10 @@ inline void zal_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge
 { std::vector< real > tp, dtp;
   zalesak::rhs( dsupedge, dsupint, coord, triinpoel, besym, t, dt, tp, dtp, U, R ); }
 
+inline void koz_rhs( const std::vector< std::size_t >& inpoel, const Coords& coord, real t, real dt,
+                     const Fields& U, Fields& R )
+{ std::vector< real > tp, dtp; kozak::rhs( inpoel, coord, t, dt, tp, dtp, U, R ); }
+
 inline void initialize( const Coords& coord, Fields& U, real t )
 { problems::initialize( coord, U, t, 0, {} ); }
 
@@ -94,6 +99,7 @@ inline void set_cfg( const Cfg& c ) { port::set_cfg( c ); }
 using port::grad;
 using port::rhs;
 using port::zal_rhs;
+using port::koz_rhs;
 using port::initialize;
 using port::dirbc;
 using port::symbc;

@@ -190,6 +190,7 @@ int orc_kernel( void* hv, int chare, const char* what, int stage, double t, doub
     else if (w == "bc") c.BC( t );
     else if (w == "mindt") { h->run->dt = c.mindt(); }
     else if (w == "zrhs") c.zrhs_own( t, dt );
+    else if (w == "krhs") c.krhs_own( t, dt );
     else if (w == "aec") c.aec_own();
     else if (w == "alw") c.alw_own( dt );
     else if (w == "lim") c.lim_own();

@@ -259,6 +259,7 @@ class Chare {
     std::unordered_map< int, std::unordered_map< std::size_t, std::array< real, 4 > > > bnorm, bnormc;
     std::unordered_map< Edge, std::array< real, 4 >, be::Hash<2>, be::Eq<2> > domedgeint;
     bool zal = false;                     // ZalCG: stride-4 integrals, no renumbering, FCT members
+    bool koz = false;                     // KozCG: element-based, no edge integrals at all
     std::size_t stride = 3;
     Fields p, q, a;                       // ZalCG::m_p, m_q, m_a
     std::vector< real > mvol;             // ZalCG::m_vol (copy taken at construction)
@@ -277,7 +278,7 @@ class Chare {
     Chare( const ChareMesh& cm, const std::array< std::vector< real >, 3 >& gcoord, const Cfg& c )
       : bnode( cm.bnode ), bface( cm.bface ), cfg( c )
     {
-      zal = cfg.solver == "zalcg"; stride = zal ? 4 : 3;
+      zal = cfg.solver == "zalcg"; stride = zal ? 4 : 3; koz = cfg.solver == "kozcg";
       // global2local, Reorder.cpp:279-306
       gid = cm.ginpoel;
       std::sort( gid.begin(), gid.end() );
@@ -316,7 +317,7 @@ class Chare {
 
     //! RieCG ctor :82-100 + Discretization::remap :560-606
     void renumber() {
-      if (zal) return;                    // ZalCG keeps the global2local order (ZalCG.cpp:82-92)
+      if (zal || koz) return;             // ZalCG/KozCG keep the global2local order (ZalCG.cpp:82-92)
       std::unordered_map< std::size_t, std::size_t > map;
       std::size_t n = 0;
       auto psup = be::genPsup( inpoel, 4, be::genEsup( inpoel, 4 ) );
@@ -339,7 +340,7 @@ class Chare {
       auto n = gid.size();
       u = Fields( n, cfg.ncomp ); un = Fields( n, cfg.ncomp ); rhs = Fields( n, cfg.ncomp );
       grad = Fields( n, cfg.ncomp*3 );
-      if (zal) { p = Fields( n, cfg.ncomp*2 ); q = Fields( n, cfg.ncomp*2 ); a = Fields( n, cfg.ncomp ); mvol = vol; }
+      if (zal || koz) { p = Fields( n, cfg.ncomp*2 ); q = Fields( n, cfg.ncomp*2 ); a = Fields( n, cfg.ncomp ); mvol = vol; }
       dtp.assign( n, 0.0 ); tp.assign( n, cfg.t0 );
     }
 
@@ -436,6 +437,7 @@ class Chare {
 
     //! RieCG::domint :339-382
     void domint() {
+      if (koz) return;                    // KozCG::feop :246-276 has no domain edge integrals
       const auto& x = coord[0]; const auto& y = coord[1]; const auto& z = coord[2];
       domedgeint.clear();
       for (std::size_t e=0; e<inpoel.size()/4; ++e) {
@@ -546,7 +548,7 @@ class Chare {
       besym.resize( triinpoel.size() );
       std::size_t i = 0;
       for (auto p : triinpoel) besym[i++] = static_cast< std::uint8_t >( symbcnodeset.count(p) );
-      domsuped();
+      if (!koz) domsuped();
       domedgeint.clear();
       symbcnodes.clear(); symbcnorms.clear();
       for (auto p : symbcnodeset)
@@ -750,6 +752,128 @@ class Chare {
       BC( t + dt );                         // BC( m_a, T+Dt )
       a.fill( 0.0 );
     }
+
+    // ---- KozCG (element-based Taylor-Galerkin + FCT), KozCG.cpp:709-1197 --------------------
+    void krhs_own( real t, real dt ) { be::koz_rhs( inpoel, coord, t, dt, u, rhs ); }
+
+    real tetJ( const std::size_t* N ) const {
+      const auto& x = coord[0]; const auto& y = coord[1]; const auto& z = coord[2];
+      real ba[3] = { x[N[1]]-x[N[0]], y[N[1]]-y[N[0]], z[N[1]]-z[N[0]] },
+           ca[3] = { x[N[2]]-x[N[0]], y[N[2]]-y[N[0]], z[N[2]]-z[N[0]] },
+           da[3] = { x[N[3]]-x[N[0]], y[N[3]]-y[N[0]], z[N[3]]-z[N[0]] };
+      real cx = ca[1]*da[2] - da[1]*ca[2], cy = ca[2]*da[0] - da[2]*ca[0], cz = ca[0]*da[1] - da[0]*ca[1];
+      return ba[0]*cx + ba[1]*cy + ba[2]*cz;
+    }
+
+    //! KozCG::fct :754-772 (merge rhs) + aec :774-844
+    void kaec_own() {
+      for (const auto& [g,r] : rhsc) { auto i = lid.at(g); for (std::size_t c=0; c<r.size(); ++c) rhs(i,c) += r[c]; }
+      rhsc.clear();
+      const auto ncomp = u.nprop();
+      auto ctau = cfg.fctdif;
+      p.fill( 0.0 );
+      for (std::size_t e=0; e<inpoel.size()/4; ++e) {
+        const auto N = inpoel.data() + e*4;
+        const auto J = tetJ( N );
+        for (std::size_t c=0; c<ncomp; ++c) {
+          auto P = c*2; auto Nn = P+1;
+          real aec[4] = { 0.0, 0.0, 0.0, 0.0 };
+          for (std::size_t a=0; a<4; ++a) {
+            for (std::size_t b=0; b<4; ++b) { auto m = J/120.0 * ((a == b) ? 3.0 : -1.0); aec[a] += m * ctau * u(N[b],c); }
+            p(N[a],P) += std::max(0.0,aec[a]);
+            p(N[a],Nn) += std::min(0.0,aec[a]);
+          }
+        }
+      }
+      for (std::size_t i=0; i<symbcnodes.size(); ++i) {
+        auto P = symbcnodes[i];
+        auto nx = symbcnorms[i*3+0], ny = symbcnorms[i*3+1], nz = symbcnorms[i*3+2];
+        auto rvnp = p(P,2)*nx + p(P,4)*ny + p(P,6)*nz;
+        auto rvnn = p(P,3)*nx + p(P,5)*ny + p(P,7)*nz;
+        p(P,2) -= rvnp * nx; p(P,3) -= rvnn * nx;
+        p(P,4) -= rvnp * ny; p(P,5) -= rvnn * ny;
+        p(P,6) -= rvnp * nz; p(P,7) -= rvnn * nz;
+      }
+    }
+
+    //! KozCG::alw :866-949 (note the sign: u + dt rhs/vol, :897)
+    void kalw_own( real dt ) {
+      const auto npoin = u.nunk(); const auto ncomp = u.nprop();
+      for (const auto& [g,pp] : pc) { auto i = lid.at(g); for (std::size_t c=0; c<pp.size(); ++c) p(i,c) += pp[c]; }
+      pc.clear();
+      for (std::size_t i=0; i<npoin; ++i)
+        for (std::size_t c=0; c<ncomp; ++c) {
+          auto P = c*2; auto Nn = P+1;
+          p(i,P) /= vol[i]; p(i,Nn) /= vol[i];
+          rhs(i,c) = u(i,c) + dt*rhs(i,c)/vol[i] - p(i,P) - p(i,Nn);
+        }
+      using std::max; using std::min;
+      auto large = std::numeric_limits< real >::max();
+      for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) { q(i,c*2+0) = -large; q(i,c*2+1) = +large; }
+      for (std::size_t e=0; e<inpoel.size()/4; ++e) {
+        const auto N = inpoel.data() + e*4;
+        for (std::size_t c=0; c<ncomp; ++c) {
+          auto alwp = -large; auto alwn = +large;
+          for (std::size_t a=0; a<4; ++a) {
+            if (cfg.fctclip) { alwp = max( alwp, rhs(N[a],c) ); alwn = min( alwn, rhs(N[a],c) ); }
+            else { alwp = max( alwp, max(rhs(N[a],c), u(N[a],c)) ); alwn = min( alwn, min(rhs(N[a],c), u(N[a],c)) ); }
+          }
+          auto P = c*2; auto Nn = P+1;
+          for (std::size_t a=0; a<4; ++a) { q(N[a],P) = max(q(N[a],P), alwp); q(N[a],Nn) = min(q(N[a],Nn), alwn); }
+        }
+      }
+    }
+
+    //! KozCG::lim :979-1098
+    void klim_own() {
+      const auto npoin = u.nunk(); const auto ncomp = u.nprop();
+      using std::max; using std::min;
+      for (const auto& [g,alw] : qc) { auto i = lid.at(g);
+        for (std::size_t c=0; c<alw.size()/2; ++c) { auto P = c*2; auto Nn = P+1; q(i,P) = max( q(i,P), alw[P] ); q(i,Nn) = min( q(i,Nn), alw[Nn] ); } }
+      qc.clear();
+      for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) { q(i,c*2) -= rhs(i,c); q(i,c*2+1) -= rhs(i,c); }
+      for (std::size_t i=0; i<npoin; ++i)
+        for (std::size_t c=0; c<ncomp; ++c) {
+          auto P = c*2; auto Nn = P+1;
+          auto eps = std::numeric_limits< real >::epsilon();
+          q(i,P) = p(i,P) <  eps ? 0.0 : min(1.0, q(i,P)/p(i,P));
+          q(i,Nn) = p(i,Nn) > -eps ? 0.0 : min(1.0, q(i,Nn)/p(i,Nn));
+        }
+      auto ctau = cfg.fctdif;
+      a.fill( 0.0 );
+      auto fctsys = cfg.fctsys;
+      for (auto& c : fctsys) --c;
+      std::vector< real > coef( ncomp ), aec( ncomp*4 );
+      for (std::size_t e=0; e<inpoel.size()/4; ++e) {
+        const auto N = inpoel.data() + e*4;
+        const auto J = tetJ( N );
+        for (std::size_t c=0; c<ncomp; ++c) {
+          auto P = c*2; auto Nn = P+1;
+          coef[c] = 1.0;
+          for (std::size_t aa=0; aa<4; ++aa) {
+            aec[c*4+aa] = 0.0;
+            for (std::size_t b=0; b<4; ++b) { auto m = J/120.0 * ((aa == b) ? 3.0 : -1.0); aec[c*4+aa] += m * ctau * u(N[b],c); }
+            coef[c] = min(coef[c], aec[c*4+aa] > 0.0 ? q(N[aa],P) : q(N[aa],Nn));
+          }
+        }
+        real cs = 1.0;
+        for (auto c : fctsys) cs = min( cs, coef[c] );
+        for (auto c : fctsys) coef[c] = cs;
+        for (std::size_t c=0; c<ncomp; ++c) for (std::size_t aa=0; aa<4; ++aa) a(N[aa],c) += coef[c] * aec[c*4+aa];
+      }
+    }
+
+    //! KozCG::solve :1120-1197
+    void ksolve( real t, real dt ) {
+      const auto npoin = u.nunk(); const auto ncomp = u.nprop();
+      for (const auto& [g,aa] : ac) { auto i = lid.at(g); for (std::size_t c=0; c<aa.size(); ++c) a(i,c) += aa[c]; }
+      ac.clear();
+      if (cfg.fct) { for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) a(i,c) = rhs(i,c) + a(i,c)/vol[i]; }
+      else { for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) a(i,c) = u(i,c) + dt*rhs(i,c)/vol[i]; }
+      un = u; u = a;
+      BC( t + dt );
+      a.fill( 0.0 );
+    }
 };
 
 // -----------------------------------------------------------------------------
@@ -842,6 +966,25 @@ class Run {
       if (mindt < eps) finished = true;                       // RieCG::advance :862-863
       dtn = dt; dt = mindt;                                    // setdt :926-938
       if (t + dt > cfg.term) dt = cfg.term - t;
+      if (cfg.solver == "kozcg") {                             // KozCG.cpp:691-1197, one stage
+        for (auto& c_ : ch) c_->krhs_own( t, dt );
+        exchange( []( Chare& c_ ) -> be::Fields& { return c_.rhs; }, []( Chare& c_ ) -> auto& { return c_.rhsc; } );
+        if (cfg.fct) {
+          for (auto& c_ : ch) c_->kaec_own();
+          exchange( []( Chare& c_ ) -> be::Fields& { return c_.p; }, []( Chare& c_ ) -> auto& { return c_.pc; } );
+          for (auto& c_ : ch) c_->kalw_own( dt );
+          exchange_maxmin();
+          for (auto& c_ : ch) c_->klim_own();
+          exchange( []( Chare& c_ ) -> be::Fields& { return c_.a; }, []( Chare& c_ ) -> auto& { return c_.ac; } );
+        } else {
+          for (auto& c_ : ch) { for (const auto& [g,r] : c_->rhsc) { auto i = c_->lid.at(g); for (std::size_t c=0; c<r.size(); ++c) c_->rhs(i,c) += r[c]; } c_->rhsc.clear(); }
+        }
+        for (auto& c_ : ch) c_->ksolve( t, dt );
+        diagnostics();
+        ++it; t += dt;
+        if (done()) finished = true;
+        return !finished;
+      }
       if (cfg.solver == "zalcg") {                             // ZalCG.cpp:973-1607, one stage
         for (auto& c_ : ch) c_->zrhs_own( t, dt );
         exchange( []( Chare& c_ ) -> be::Fields& { return c_.rhs; }, []( Chare& c_ ) -> auto& { return c_.rhsc; } );

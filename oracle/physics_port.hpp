@@ -737,6 +737,78 @@ inline void zal_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge
   advbnd( triinpoel, coord, besym, U, R );      // Zalesak.cpp:309-419, same form as Riemann.cpp:768-878
 }
 
+// ---- Kozak.cpp: element-based Taylor-Galerkin rhs for KozCG --------------------------------
+inline void koz_rhs( const std::vector< std::size_t >& inpoel, const Coords& coord, real t, real dt,
+                     const Fields& U, Fields& R )                               // Kozak.cpp:29-180
+{
+  R.fill( 0.0 );
+  const auto ncomp = U.nprop();
+  const auto& x = coord[0]; const auto& y = coord[1]; const auto& z = coord[2];
+  auto src = SRC();
+  std::vector< real > ue( ncomp );
+  for (std::size_t e=0; e<inpoel.size()/4; ++e) {
+    const auto N = inpoel.data() + e*4;
+    real ba[3] = { x[N[1]]-x[N[0]], y[N[1]]-y[N[0]], z[N[1]]-z[N[0]] },
+         ca[3] = { x[N[2]]-x[N[0]], y[N[2]]-y[N[0]], z[N[2]]-z[N[0]] },
+         da[3] = { x[N[3]]-x[N[0]], y[N[3]]-y[N[0]], z[N[3]]-z[N[0]] };
+    auto cross = []( const real a[3], const real b[3], real r[3] ){
+      r[0] = a[1]*b[2] - b[1]*a[2]; r[1] = a[2]*b[0] - b[2]*a[0]; r[2] = a[0]*b[1] - b[0]*a[1]; };
+    real grad[4][3], cx[3];
+    cross( ca, da, cx );
+    const auto J = ba[0]*cx[0] + ba[1]*cx[1] + ba[2]*cx[2];
+    cross( ca, da, grad[1] ); cross( da, ba, grad[2] ); cross( ba, ca, grad[3] );
+    for (std::size_t i=0; i<3; ++i) grad[0][i] = -grad[1][i]-grad[2][i]-grad[3][i];
+    real p[4];
+    for (std::size_t a=0; a<4; ++a) {
+      auto r = U(N[a],0), ru = U(N[a],1), rv = U(N[a],2), rw = U(N[a],3);
+      p[a] = eos_pressure( U(N[a],4) - 0.5*(ru*ru + rv*rv + rw*rw)/r );
+    }
+    for (std::size_t c=0; c<ncomp; ++c) ue[c] = (U(N[0],c) + U(N[1],c) + U(N[2],c) + U(N[3],c))/4.0;
+    auto coef = dt/J/2.0;
+    for (std::size_t j=0; j<3; ++j)
+      for (std::size_t a=0; a<4; ++a) {
+        auto cg = coef * grad[a][j];
+        auto uj = U(N[a],j+1) / U(N[a],0);
+        ue[0] -= cg * U(N[a],j+1);
+        ue[1] -= cg * U(N[a],1) * uj;
+        ue[2] -= cg * U(N[a],2) * uj;
+        ue[3] -= cg * U(N[a],3) * uj;
+        ue[j+1] -= cg * p[a];
+        ue[4] -= cg * (U(N[a],4) + p[a]) * uj;
+        for (std::size_t c=5; c<ncomp; ++c) ue[c] -= cg * U(N[a],c) * uj;
+      }
+    if (src) {
+      coef = dt/8.0;
+      for (std::size_t a=0; a<4; ++a) {
+        auto s = src( x[N[a]], y[N[a]], z[N[a]], t );
+        for (std::size_t c=0; c<ncomp; ++c) ue[c] += coef * s[c];
+      }
+    }
+    auto r = ue[0], ru = ue[1], rv = ue[2], rw = ue[3];
+    auto pr = eos_pressure( ue[4] - 0.5*(ru*ru + rv*rv + rw*rw)/r );
+    coef = 1.0/6.0;
+    for (std::size_t j=0; j<3; ++j) {
+      auto uj = ue[j+1] / ue[0];
+      for (std::size_t a=0; a<4; ++a) {
+        auto cg = coef * grad[a][j];
+        R(N[a],0) += cg * ue[j+1];
+        R(N[a],1) += cg * ue[1] * uj;
+        R(N[a],2) += cg * ue[2] * uj;
+        R(N[a],3) += cg * ue[3] * uj;
+        R(N[a],j+1) += cg * pr;
+        R(N[a],4) += cg * (ue[4] + pr) * uj;
+        for (std::size_t c=5; c<ncomp; ++c) R(N[a],c) += cg * ue[c] * uj;
+      }
+    }
+    if (src) {
+      auto se = src( (x[N[0]] + x[N[1]] + x[N[2]] + x[N[3]])/4.0, (y[N[0]] + y[N[1]] + y[N[2]] + y[N[3]])/4.0,
+                     (z[N[0]] + z[N[1]] + z[N[2]] + z[N[3]])/4.0, t+dt/2.0 );
+      coef = J/24.0;
+      for (std::size_t a=0; a<4; ++a) for (std::size_t c=0; c<ncomp; ++c) R(N[a],c) += coef * se[c];
+    }
+  }
+}
+
 // ---- Mesh/DerivedData.cpp ----------------------------------------------------------
 using LinkedList = std::pair< std::vector< std::size_t >, std::vector< std::size_t > >;
 

@@ -61,8 +61,16 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
     return c
 
 
-# The three RieCG regression cases pinned by golden diag.std files (control files:
-# tests/regression/inciter/RieCG/{Sod/sod.q,Sedov/sedov.q,TaylorGreen/taylor_green.q})
+# KozCG regression cases (tests/regression/inciter/KozCG/{Sod/sod.q,TaylorGreen/taylor_green.q})
+KCASES = {
+    "kozcg_sod": dict(solver="kozcg", problem="sod", gamma=1.4, cfl=0.5, nstep=10,
+                      sym=(2, 4, 5, 6), dir_=((1, 1, 1, 1, 1, 1), (3, 1, 1, 1, 1, 1)),
+                      fctclip=True, fctsys=(1, 2, 5), mesh="riecg_sod"),
+    "kozcg_taylor_green": dict(solver="kozcg", problem="taylor_green", gamma=5.0 / 3.0, cfl=0.8, term=1.0,
+                               fct=False, diag_iter=2, dir_=tuple((s, 1, 1, 1, 1, 1) for s in range(1, 7)),
+                               mesh="riecg_taylor_green"),
+}
+
 # ZalCG regression cases (tests/regression/inciter/ZalCG/{Sod/sod.q,Sedov/sedov.q})
 ZCASES = {
     "zalcg_sod": dict(solver="zalcg", problem="sod", gamma=1.4, cfl=0.5, nstep=10, term=0.2,
@@ -72,6 +80,8 @@ ZCASES = {
                         term=1.0, sym=(1, 2, 3), fctsys=(1, 2, 3, 4, 5), mesh="riecg_sedov"),
 }
 
+# The three RieCG regression cases pinned by golden diag.std files (control files:
+# tests/regression/inciter/RieCG/{Sod/sod.q,Sedov/sedov.q,TaylorGreen/taylor_green.q})
 CASES = {
     "riecg_sod": dict(problem="sod", gamma=1.4, cfl=0.5, nstep=10, term=0.2, sym=(2, 4, 5, 6)),
     "riecg_sedov": dict(problem="sedov", gamma=5.0 / 3.0, p0=4.86e3, cfl=0.5, nstep=10, term=1.0,

@@ -81,3 +81,16 @@ def test_zalcg_oracle_reproduces_reference_golden_diag(case):
     assert numdiff(d[:, 1:8], gold[:, 1:8], 1.0e-8, 1.0e-7)
     assert numdiff(d[:, 8:13], gold[:, 8:13], 0.0, 1.0e-7)
     assert (np.abs(d - gold) / np.maximum(np.abs(gold), 1e-300)).max() < 6e-9
+
+
+@pytest.mark.parametrize("case", list(O.KCASES))
+def test_kozcg_oracle_reproduces_reference_golden_diag(case):
+    """KozCG (element-based Taylor-Galerkin + FCT): tests/regression/inciter/KozCG/
+    {Sod,TaylorGreen}/diag.std (the latter without FCT and with the source term)."""
+    kw = O.KCASES[case]
+    gold = O.load_golden_diag(case)
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(int(gold[-1, 0]))
+    d = o.diag()
+    assert d.shape == gold.shape
+    assert (np.abs(d - gold) / np.maximum(np.abs(gold), 1e-300)).max() < 6e-9

@@ -76,3 +76,21 @@ def test_zalcg_port_is_bit_identical_to_reference_objects(case):
     a.step(n); b.step(n)
     assert np.array_equal(a.diag(), b.diag())
     assert np.array_equal(a.get("u"), b.get("u"))
+
+
+@needs_ref
+@pytest.mark.parametrize("case", list(O.KCASES))
+def test_kozcg_port_is_bit_identical_to_reference_objects(case):
+    """kozak::rhs from the reference's own Kozak.cpp vs the restatement under the same driver."""
+    kw = O.KCASES[case]
+    gold = O.load_golden_diag(case)
+    mesh = O.load_mesh(kw["mesh"])
+    a = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    b = O.Oracle(mesh, O.make_cfg(**kw), "reference")
+    for o in (a, b):
+        o.kernel("krhs", 0, 0.0, 1.0e-3)
+    assert np.array_equal(a.get("rhs"), b.get("rhs"))
+    n = int(gold[-1, 0])
+    a.step(n); b.step(n)
+    assert np.array_equal(a.diag(), b.diag())
+    assert np.array_equal(a.get("u"), b.get("u"))

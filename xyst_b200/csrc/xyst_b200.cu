@@ -650,14 +650,14 @@ k_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __r
   double* gq = gp + 15*FLUX_THREADS;
   #pragma unroll
   for (int i=0; i<15; ++i) { cp_async8( gp + i*FLUX_THREADS, G + i*NP + p ); cp_async8( gq + i*FLUX_THREADS, G + i*NP + q ); }
-  asm volatile( "cp.async.commit_group;" ::: "memory" );
+  cp_async_commit();
   double n[3] = { D[e], D[nslot+e], D[2*nslot+e] };
   double l[NC], r[NC], vw[3];
   #pragma unroll
   for (int c=0; c<NC; ++c) { l[c] = __ldg( W + c*NP + p ); r[c] = __ldg( W + c*NP + q ); }
   #pragma unroll
   for (int j=0; j<3; ++j) vw[j] = __ldg( X + j*NP + q ) - __ldg( X + j*NP + p );
-  asm volatile( "cp.async.wait_group 0;" ::: "memory" );
+  cp_async_wait< 0 >();
   muscl< EXACT >( gp, FLUX_THREADS, gq, FLUX_THREADS, vw, l, r );
   double f[NC];
   if (FLUX == 0) rusanov( l, r, n, P, f ); else hllc( l, r, n, P, f );

@@ -162,6 +162,20 @@ int xyst_zalcg_rhs(xyst_ctx* ctx, double dt);
  * antidiffusive contributions), solve, BC (ZalCG.cpp:990-1607); un keeps the old state */
 int xyst_zalcg_step(xyst_ctx* ctx, double dt);
 
+/* ---- KozCG: element-based Taylor-Galerkin + flux-corrected transport ---------------------
+ * (src/Physics/Kozak.cpp:29-180, src/Inciter/KozCG.cpp:709-1197). Works on the tetrahedra
+ * themselves: inpoel = Discretization::Inpoel(), 4 local node ids per tet. FCT parameters
+ * through xyst_zalcg_config; state/BC/dt/diagnostics entry points as for RieCG.
+ * Ssrc_nodes (npoin x ncomp) and Ssrc_cent (ntet x ncomp) are problems::SRC() evaluated at
+ * the nodes and at the tet centroids (time-independent sources), or NULL. */
+int xyst_kozcg_mesh_upload(xyst_ctx* ctx, size_t npoin, const double* x, const double* y, const double* z,
+                           size_t ntet, const size_t* inpoel, const double* vol, const double* v,
+                           const double* Ssrc_nodes, const double* Ssrc_cent);
+/* kozak::rhs -> R (xyst_rhs_get) */
+int xyst_kozcg_rhs(xyst_ctx* ctx, double dt);
+/* one KozCG time step: rhs, aec, alw, lim, solve, BC; un keeps the old state */
+int xyst_kozcg_step(xyst_ctx* ctx, double dt);
+
 /* ---- linear solver of the pressure projection (ChoCG/LohCG) -----------------------------
  * tk::CSR (src/LinearSolver/CSR.hpp:30-107): block CSR exactly as the reference stores it,
  * nrow = npoin*ncomp scalar rows, 1-based ia[nrow+1] / ja[nnz], values a[nnz] (after

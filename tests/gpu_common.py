@@ -29,6 +29,8 @@ def context_from_oracle(o, kw, chare=0, exact_muscl=False, device=0):
     g = lambda n: o.get(n, chare)
     x, y, z = g("x"), g("y"), g("z")
     zal = kw.get("solver") == "zalcg"
+    if kw.get("solver") == "kozcg":
+        return _kozcg_context(ctx, o, kw, chare)
     ctx.mesh_upload(x, y, z, [g("dsupedge0"), g("dsupedge1"), g("dsupedge2")],
                     [g("dsupint0"), g("dsupint1"), g("dsupint2")], g("triinpoel"), g("besym"),
                     g("vol"), g("v"), stride=4 if zal else 3)
@@ -40,6 +42,24 @@ def context_from_oracle(o, kw, chare=0, exact_muscl=False, device=0):
     ctx.bc_upload(dirbcmasks=dm, dirvals=dv, symbcnodes=g("symbcnodes"), symbcnorms=g("symbcnorms"))
     if kw["problem"] == "taylor_green":
         ctx.src_upload(tg_source(x, y))
+    ctx.state_set(U0)
+    return ctx
+
+
+def _kozcg_context(ctx, o, kw, chare):
+    g = lambda n: o.get(n, chare)
+    x, y, z = g("x"), g("y"), g("z")
+    inpoel = g("inpoel").reshape(-1, 4).astype(np.int64)
+    Sn = Sc = None
+    if kw["problem"] == "taylor_green":
+        Sn = tg_source(x, y)
+        Sc = tg_source(x[inpoel].sum(axis=1) / 4.0, y[inpoel].sum(axis=1) / 4.0)
+    ctx.kozcg_mesh_upload(x, y, z, inpoel, g("vol"), g("v"), Sn, Sc)
+    ctx.zalcg_config(kw.get("fct", True), kw.get("fctclip", False), kw.get("fctsys", ()), kw.get("fctdif", 1.0))
+    U0 = g("u")
+    dm = g("dirbcmasks")
+    dv = U0[dm.reshape(-1, 6)[:, 0].astype(np.int64)] if len(dm) else None
+    ctx.bc_upload(dirbcmasks=dm, dirvals=dv, symbcnodes=g("symbcnodes"), symbcnorms=g("symbcnorms"))
     ctx.state_set(U0)
     return ctx
 
@@ -66,6 +86,8 @@ def drive_steps(ctxs, kw, nsteps, t0=0.0, fused=True, allreduce_min=None):
         for c in ctxs:
             if kw.get("solver") == "zalcg":
                 c.zalcg_step(dt)
+            elif kw.get("solver") == "kozcg":
+                c.kozcg_step(dt)
             elif fused:
                 c.step(dt)
             else:

@@ -33,7 +33,7 @@ SYMBOLS = [
     "xyst_halo_upload", "xyst_halo_sum", "xyst_allreduce_min", "xyst_allreduce_sum", "xyst_launch_count",
     "xyst_nedge", "xyst_kernel_time", "xyst_csr_upload", "xyst_csr_mult", "xyst_cg_setup",
     "xyst_cg_solve", "xyst_cg_get_x", "xyst_zalcg_config", "xyst_zalcg_mesh_upload", "xyst_zalcg_rhs",
-    "xyst_zalcg_step",
+    "xyst_zalcg_step", "xyst_kozcg_mesh_upload", "xyst_kozcg_rhs", "xyst_kozcg_step",
 ]
 
 
@@ -86,6 +86,9 @@ def lib():
     L.xyst_zalcg_mesh_upload.argtypes = L.xyst_mesh_upload.argtypes
     L.xyst_zalcg_rhs.argtypes = [C.c_void_p, C.c_double]
     L.xyst_zalcg_step.argtypes = [C.c_void_p, C.c_double]
+    L.xyst_kozcg_mesh_upload.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 3 + [C.c_size_t] + [C.c_void_p] * 5
+    L.xyst_kozcg_rhs.argtypes = [C.c_void_p, C.c_double]
+    L.xyst_kozcg_step.argtypes = [C.c_void_p, C.c_double]
     L.xyst_csr_upload.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     L.xyst_csr_mult.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.xyst_cg_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
@@ -146,6 +149,20 @@ class Context:
             mask |= 1 << (c_ - 1)
         zp = ZalParams(int(fct), int(fctclip), mask, 0, fctdif)
         self._ck(self.L.xyst_zalcg_config(self.h, C.byref(zp)))
+
+    def kozcg_mesh_upload(self, x, y, z, inpoel, vol, v, Sn=None, Sc=None):
+        x, y, z, vol, v = map(_f64, (x, y, z, vol, v))
+        t = _u64(inpoel)
+        Sn = None if Sn is None else _f64(Sn); Sc = None if Sc is None else _f64(Sc)
+        self.npoin = len(x)
+        self._ck(self.L.xyst_kozcg_mesh_upload(self.h, len(x), _p(x), _p(y), _p(z), t.size // 4, _p(t),
+                                               _p(vol), _p(v), _p(Sn), _p(Sc)))
+
+    def kozcg_rhs(self, dt):
+        self._ck(self.L.xyst_kozcg_rhs(self.h, dt))
+
+    def kozcg_step(self, dt):
+        self._ck(self.L.xyst_kozcg_step(self.h, dt))
 
     def zalcg_rhs(self, dt):
         self._ck(self.L.xyst_zalcg_rhs(self.h, dt))

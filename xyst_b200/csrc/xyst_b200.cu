@@ -178,6 +178,13 @@ struct xyst_ctx {
   xyst_zalcg_params zal{ 1, 0, 0, 0, 1.0 };
   DevBuf< double > zP, zQ, zUL;          // [10][NP] [10][NP] [5][NP]
   DevBuf< int > bcof;                    // [npoin] slot in the BC node list or -1
+  // KozCG: tetrahedra (sorted by lowest node), node -> (tet, local index) sliced ELL, per-tet buffers
+  size_t ntet = 0, knent = 0;
+  DevBuf< int > ktet;                    // [4][ntet]
+  DevBuf< long long > kbase;             // [nslice+1]
+  DevBuf< int > kinc;                    // tet*4+a, -1 = padding
+  DevBuf< double > kT, kSc;              // [40][ntet] per-tet contributions; [ntet][5] centroid source
+  bool ksrc = false;
   // linear solver: sliced-ELL matrix over scalar rows + CG vectors
   size_t cg_nrow = 0, cg_ncomp = 1, cg_nslice = 0, cg_nent = 0;
   DevBuf< long long > cg_base; DevBuf< int > cg_col; DevBuf< double > cg_val, cg_diag;
@@ -1184,6 +1191,301 @@ __global__ void k_zal_nofct( size_t npoin, size_t NP, const double* __restrict__
 }
 
 // ---------------------------------------------------------------------------------
+// KozCG: element-based Taylor-Galerkin (Kozak.cpp:29-180) and FCT (KozCG.cpp:774-1197).
+// Each pass = one kernel over tetrahedra writing per-tet, per-local-node values, and one
+// node gather over the incident tetrahedra (fixed order, no atomics).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double koz_geom( const double* __restrict__ X, size_t NP, const int N[4], double grad[4][3] )
+{
+  double x[4][3];
+  #pragma unroll
+  for (int a=0; a<4; ++a) { x[a][0] = X[N[a]]; x[a][1] = X[NP+N[a]]; x[a][2] = X[2*NP+N[a]]; }
+  double ba[3] = { x[1][0]-x[0][0], x[1][1]-x[0][1], x[1][2]-x[0][2] },
+         ca[3] = { x[2][0]-x[0][0], x[2][1]-x[0][1], x[2][2]-x[0][2] },
+         da[3] = { x[3][0]-x[0][0], x[3][1]-x[0][1], x[3][2]-x[0][2] };
+  grad[1][0] = ca[1]*da[2] - da[1]*ca[2]; grad[1][1] = ca[2]*da[0] - da[2]*ca[0]; grad[1][2] = ca[0]*da[1] - da[0]*ca[1];
+  grad[2][0] = da[1]*ba[2] - ba[1]*da[2]; grad[2][1] = da[2]*ba[0] - ba[2]*da[0]; grad[2][2] = da[0]*ba[1] - ba[0]*da[1];
+  grad[3][0] = ba[1]*ca[2] - ca[1]*ba[2]; grad[3][1] = ba[2]*ca[0] - ca[2]*ba[0]; grad[3][2] = ba[0]*ca[1] - ca[0]*ba[1];
+  #pragma unroll
+  for (int i=0; i<3; ++i) grad[0][i] = -grad[1][i]-grad[2][i]-grad[3][i];
+  return ba[0]*grad[1][0] + ba[1]*grad[1][1] + ba[2]*grad[1][2];          // triple(ba,ca,da)
+}
+
+// pass 1: rhs contributions T[a*5+c] and antidiffusive element contributions T[20+c*4+a]
+__global__ void __launch_bounds__(128)
+k_koz_elem1( size_t ntet, size_t NP, const int* __restrict__ tet, const double* __restrict__ U,
+             const double* __restrict__ X, const double* __restrict__ S, const double* __restrict__ Sc,
+             double dt, double gamma, double ctau, int fct, double* __restrict__ T )
+{
+  size_t e = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (e >= ntet) return;
+  int N[4] = { tet[e], tet[ntet+e], tet[2*ntet+e], tet[3*ntet+e] };
+  double grad[4][3];
+  double J = koz_geom( X, NP, N, grad );
+  double u[4][NC], p[4];
+  #pragma unroll
+  for (int a=0; a<4; ++a) {
+    #pragma unroll
+    for (int c=0; c<NC; ++c) u[a][c] = U[c*NP+N[a]];
+    p[a] = (u[a][4] - 0.5*(u[a][1]*u[a][1] + u[a][2]*u[a][2] + u[a][3]*u[a][3])/u[a][0]) * (gamma-1.0);
+  }
+  double ue[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) ue[c] = (u[0][c] + u[1][c] + u[2][c] + u[3][c])/4.0;
+  double coef = dt/J/2.0;
+  #pragma unroll
+  for (int j=0; j<3; ++j)
+    #pragma unroll
+    for (int a=0; a<4; ++a) {
+      double cg = coef * grad[a][j];
+      double uj = u[a][j+1] / u[a][0];
+      ue[0] -= cg * u[a][j+1];
+      ue[1] -= cg * u[a][1] * uj;
+      ue[2] -= cg * u[a][2] * uj;
+      ue[3] -= cg * u[a][3] * uj;
+      ue[j+1] -= cg * p[a];
+      ue[4] -= cg * (u[a][4] + p[a]) * uj;
+    }
+  if (S) {
+    coef = dt/8.0;
+    #pragma unroll
+    for (int a=0; a<4; ++a)
+      #pragma unroll
+      for (int c=0; c<NC; ++c) ue[c] += coef * S[(size_t)N[a]*NC+c];
+  }
+  double pr = (ue[4] - 0.5*(ue[1]*ue[1] + ue[2]*ue[2] + ue[3]*ue[3])/ue[0]) * (gamma-1.0);
+  double R[4][NC];
+  #pragma unroll
+  for (int a=0; a<4; ++a)
+    #pragma unroll
+    for (int c=0; c<NC; ++c) R[a][c] = 0.0;
+  coef = 1.0/6.0;
+  #pragma unroll
+  for (int j=0; j<3; ++j) {
+    double uj = ue[j+1] / ue[0];
+    #pragma unroll
+    for (int a=0; a<4; ++a) {
+      double cg = coef * grad[a][j];
+      R[a][0] += cg * ue[j+1];
+      R[a][1] += cg * ue[1] * uj;
+      R[a][2] += cg * ue[2] * uj;
+      R[a][3] += cg * ue[3] * uj;
+      R[a][j+1] += cg * pr;
+      R[a][4] += cg * (ue[4] + pr) * uj;
+    }
+  }
+  if (S) {
+    coef = J/24.0;
+    #pragma unroll
+    for (int a=0; a<4; ++a)
+      #pragma unroll
+      for (int c=0; c<NC; ++c) R[a][c] += coef * Sc[e*NC+c];
+  }
+  #pragma unroll
+  for (int a=0; a<4; ++a)
+    #pragma unroll
+    for (int c=0; c<NC; ++c) T[(size_t)(a*NC+c)*ntet+e] = R[a][c];
+  if (fct) {
+    #pragma unroll
+    for (int c=0; c<NC; ++c)
+      #pragma unroll
+      for (int a=0; a<4; ++a) {
+        double aec = 0.0;
+        #pragma unroll
+        for (int b=0; b<4; ++b) { double m = J/120.0 * ((a == b) ? 3.0 : -1.0); aec += m * ctau * u[b][c]; }
+        T[(size_t)(20+c*4+a)*ntet+e] = aec;
+      }
+  }
+}
+
+// node pass 1: R, P+/-, symmetry BC on P, low-order solution ul = u + dt R/vol - P+ - P-
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_koz_node1( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__ kbase, const int* __restrict__ kinc,
+             const double* __restrict__ T, const double* __restrict__ U, const int* __restrict__ bcof,
+             const int* __restrict__ symoff, const double* __restrict__ sym_n, const double* __restrict__ vol,
+             double dt, int fct, double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = kbase[slice];
+  int kmax = (int)((kbase[slice+1] - base) >> 5);
+  double r[NC], pp[NC], pn[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { r[c] = 0.0; pp[c] = 0.0; pn[c] = 0.0; }
+  for (int k=0; k<kmax; ++k) {
+    int ta = __ldg( kinc + base + (long long)k*32 + lane );
+    if (ta < 0) continue;
+    size_t e = (size_t)(ta >> 2); int a = ta & 3;
+    #pragma unroll
+    for (int c=0; c<NC; ++c) {
+      r[c] += __ldg( T + (size_t)(a*NC+c)*ntet + e );
+      if (fct) { double aec = __ldg( T + (size_t)(20+c*4+a)*ntet + e ); pp[c] += fmax( 0.0, aec ); pn[c] += fmin( 0.0, aec ); }
+    }
+  }
+  #pragma unroll
+  for (int c=0; c<NC; ++c) R[p*NC+c] = r[c];
+  if (!fct) return;
+  int bc = bcof[p];
+  if (bc >= 0)
+    for (int s=symoff[bc]; s<symoff[bc+1]; ++s) {
+      const double* n = sym_n + (size_t)s*3;
+      double rvnp = pp[1]*n[0] + pp[2]*n[1] + pp[3]*n[2];
+      double rvnn = pn[1]*n[0] + pn[2]*n[1] + pn[3]*n[2];
+      pp[1] -= rvnp * n[0]; pn[1] -= rvnn * n[0];
+      pp[2] -= rvnp * n[1]; pn[2] -= rvnn * n[1];
+      pp[3] -= rvnp * n[2]; pn[3] -= rvnn * n[2];
+    }
+  double vp = vol[p];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) {
+    pp[c] /= vp; pn[c] /= vp;
+    P[(2*c)*NP+p] = pp[c]; P[(2*c+1)*NP+p] = pn[c];
+    UL[c*NP+p] = U[c*NP+p] + dt*r[c]/vp - pp[c] - pn[c];
+  }
+}
+
+// pass 2: per-tet allowed bounds over its 4 nodes -> T[c*2], T[c*2+1]
+__global__ void __launch_bounds__(128)
+k_koz_elem2( size_t ntet, size_t NP, const int* __restrict__ tet, const double* __restrict__ U,
+             const double* __restrict__ UL, int clip, double* __restrict__ T )
+{
+  size_t e = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (e >= ntet) return;
+  int N[4] = { tet[e], tet[ntet+e], tet[2*ntet+e], tet[3*ntet+e] };
+  #pragma unroll
+  for (int c=0; c<NC; ++c) {
+    double alwp = -1.7976931348623157e308, alwn = 1.7976931348623157e308;
+    #pragma unroll
+    for (int a=0; a<4; ++a) {
+      double ul = UL[c*NP+N[a]];
+      if (clip) { alwp = fmax( alwp, ul ); alwn = fmin( alwn, ul ); }
+      else { double u = U[c*NP+N[a]]; alwp = fmax( alwp, fmax( ul, u ) ); alwn = fmin( alwn, fmin( ul, u ) ); }
+    }
+    T[(size_t)(2*c)*ntet+e] = alwp; T[(size_t)(2*c+1)*ntet+e] = alwn;
+  }
+}
+
+// node pass 2: Q+/- = max/min over incident tets, minus ul, limit coefficients C+/-
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_koz_node2( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__ kbase, const int* __restrict__ kinc,
+             const double* __restrict__ T, const double* __restrict__ UL, const double* __restrict__ P,
+             double* __restrict__ Q )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = kbase[slice];
+  int kmax = (int)((kbase[slice+1] - base) >> 5);
+  double qa[NC], qb[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { qa[c] = -1.7976931348623157e308; qb[c] = 1.7976931348623157e308; }
+  for (int k=0; k<kmax; ++k) {
+    int ta = __ldg( kinc + base + (long long)k*32 + lane );
+    if (ta < 0) continue;
+    size_t e = (size_t)(ta >> 2);
+    #pragma unroll
+    for (int c=0; c<NC; ++c) {
+      qa[c] = fmax( qa[c], __ldg( T + (size_t)(2*c)*ntet + e ) );
+      qb[c] = fmin( qb[c], __ldg( T + (size_t)(2*c+1)*ntet + e ) );
+    }
+  }
+  const double eps = 2.220446049250313e-16;
+  #pragma unroll
+  for (int c=0; c<NC; ++c) {
+    double ul = UL[c*NP+p];
+    double a = qa[c] - ul, b = qb[c] - ul;
+    double pa = P[(2*c)*NP+p], pb = P[(2*c+1)*NP+p];
+    Q[(2*c)*NP+p]   = pa <  eps ? 0.0 : fmin( 1.0, a/pa );
+    Q[(2*c+1)*NP+p] = pb > -eps ? 0.0 : fmin( 1.0, b/pb );
+  }
+}
+
+// pass 3: limited antidiffusive element contributions coef[c]*aec[c][a] -> T[a*5+c]
+__global__ void __launch_bounds__(128)
+k_koz_elem3( size_t ntet, size_t NP, const int* __restrict__ tet, const double* __restrict__ U,
+             const double* __restrict__ X, const double* __restrict__ Q, double ctau, int sysmask,
+             double* __restrict__ T )
+{
+  size_t e = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (e >= ntet) return;
+  int N[4] = { tet[e], tet[ntet+e], tet[2*ntet+e], tet[3*ntet+e] };
+  double grad[4][3];
+  double J = koz_geom( X, NP, N, grad );
+  double coef[NC], aec[NC][4];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) {
+    double u[4];
+    #pragma unroll
+    for (int a=0; a<4; ++a) u[a] = U[c*NP+N[a]];
+    coef[c] = 1.0;
+    #pragma unroll
+    for (int a=0; a<4; ++a) {
+      double v = 0.0;
+      #pragma unroll
+      for (int b=0; b<4; ++b) { double m = J/120.0 * ((a == b) ? 3.0 : -1.0); v += m * ctau * u[b]; }
+      aec[c][a] = v;
+      coef[c] = fmin( coef[c], v > 0.0 ? Q[(2*c)*NP+N[a]] : Q[(2*c+1)*NP+N[a]] );
+    }
+  }
+  double cs = 1.0;
+  #pragma unroll
+  for (int c=0; c<NC; ++c) if (sysmask & (1<<c)) cs = fmin( cs, coef[c] );
+  #pragma unroll
+  for (int c=0; c<NC; ++c) {
+    if (sysmask & (1<<c)) coef[c] = cs;
+    #pragma unroll
+    for (int a=0; a<4; ++a) T[(size_t)(a*NC+c)*ntet+e] = coef[c] * aec[c][a];
+  }
+}
+
+// node pass 3: a = sum of limited contributions, u = ul + a/vol (KozCG.cpp:1140-1146)
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_koz_node3( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__ kbase, const int* __restrict__ kinc,
+             const double* __restrict__ T, const double* __restrict__ UL, const double* __restrict__ vol,
+             double* __restrict__ Unew, double* __restrict__ W )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = kbase[slice];
+  int kmax = (int)((kbase[slice+1] - base) >> 5);
+  double a_[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) a_[c] = 0.0;
+  for (int k=0; k<kmax; ++k) {
+    int ta = __ldg( kinc + base + (long long)k*32 + lane );
+    if (ta < 0) continue;
+    size_t e = (size_t)(ta >> 2); int a = ta & 3;
+    #pragma unroll
+    for (int c=0; c<NC; ++c) a_[c] += __ldg( T + (size_t)(a*NC+c)*ntet + e );
+  }
+  double vp = vol[p], u[NC], w[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { u[c] = UL[c*NP+p] + a_[c]/vp; Unew[c*NP+p] = u[c]; }
+  primitive( u, w );
+  #pragma unroll
+  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+}
+
+// fct = false: u = u + dt R/vol (KozCG.cpp:1150-1157)
+__global__ void k_koz_nofct( size_t npoin, size_t NP, const double* __restrict__ R, const double* __restrict__ vol,
+                             const double* __restrict__ U, double dt, double* __restrict__ Unew, double* __restrict__ W )
+{
+  size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (p >= npoin) return;
+  double vp = vol[p], u[NC], w[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { u[c] = U[c*NP+p] + dt*R[p*NC+c]/vp; Unew[c*NP+p] = u[c]; }
+  primitive( u, w );
+  #pragma unroll
+  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+}
+
+// ---------------------------------------------------------------------------------
 // linear solver: CSR::mult (CSR.cpp:154-172) and the vector operations of
 // ConjugateGradients.cpp:584-823. Matrix in sliced ELL over scalar rows (one warp per 32
 // rows, entry k of lane l at base + 32k + l: coalesced), dots by fixed two-pass trees.
@@ -1656,7 +1958,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   c->ep.upload( ep, s ); c->eq.upload( eq, s ); c->D.upload( ed, s );
   c->sl_base.upload( base, s ); c->inc_e.upload( inc_e, s ); c->inc_q.upload( inc_q, s );
   c->tri.upload( tri, s );
-  c->besym.upload( std::vector< unsigned char >( besym, besym + ntri*3 ), s );
+  c->besym.upload( ntri ? std::vector< unsigned char >( besym, besym + ntri*3 ) : std::vector< unsigned char >(), s );
   c->bslot.upload( bslot, s ); c->bn_node.upload( bn_node, s ); c->bn_off.upload( bn_off, s );
   c->bn_face.upload( bn_face, s );
   c->Gb.alloc( nbn*15 ); c->Rb.alloc( nbn*NC );
@@ -2059,6 +2361,108 @@ static int allreduce( xyst_ctx* c, double* v, int n, int op )
 }
 int xyst_allreduce_min( xyst_ctx* c, double* v, int n ) { return allreduce( c, v, n, NCCL_MIN ); }
 int xyst_allreduce_sum( xyst_ctx* c, double* v, int n ) { return allreduce( c, v, n, NCCL_SUM ); }
+
+// ---- KozCG -----------------------------------------------------------------------------
+int xyst_kozcg_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* y, const double* z,
+                            size_t ntet, const size_t* inpoel, const double* vol, const double* v,
+                            const double* Sn, const double* Sc )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  if (npoin == 0 || npoin > 0x7fffffffULL || ntet == 0 || ntet > 0x1fffffffULL) throw std::runtime_error( "size out of range" );
+  // nodal part exactly as for the edge-based solvers, with no superedges and no boundary faces
+  const size_t nsup[3] = { 0, 0, 0 }; const size_t* se[3] = { nullptr, nullptr, nullptr }; const double* si[3] = { nullptr, nullptr, nullptr };
+  if (int r = mesh_upload_impl( c, npoin, x, y, z, nsup, se, si, 0, nullptr, nullptr, vol, v, 3 )) return r;
+  // tetrahedra sorted by their lowest node (locality); the order only fixes summation order
+  std::vector< int > perm( ntet );
+  std::iota( perm.begin(), perm.end(), 0 );
+  auto lo = [&]( int e ){ const auto N = inpoel + (size_t)e*4; return std::min( std::min( N[0], N[1] ), std::min( N[2], N[3] ) ); };
+  std::stable_sort( perm.begin(), perm.end(), [&]( int a, int b ){ return lo(a) < lo(b); } );
+  std::vector< int > tet( 4*ntet ), deg( npoin, 0 );
+  for (size_t i=0; i<ntet; ++i)
+    for (size_t a=0; a<4; ++a) {
+      size_t n = inpoel[(size_t)perm[i]*4+a];
+      if (n >= npoin) throw std::runtime_error( "node id out of range in inpoel" );
+      tet[a*ntet+i] = (int)n; ++deg[n];
+    }
+  size_t nslice = c->nslice;
+  std::vector< long long > base( nslice+1, 0 );
+  for (size_t s=0; s<nslice; ++s) {
+    int km = 0;
+    for (size_t p=s*32; p<std::min( npoin, s*32+32 ); ++p) km = std::max( km, deg[p] );
+    base[s+1] = base[s] + (long long)km*32;
+  }
+  std::vector< int > inc( (size_t)base[nslice], -1 ), fill( npoin, 0 );
+  for (size_t i=0; i<ntet; ++i)
+    for (size_t a=0; a<4; ++a) {
+      int n = tet[a*ntet+i];
+      inc[ (size_t)base[n/32] + (size_t)fill[n]*32 + (size_t)(n%32) ] = (int)(i*4+a);
+      ++fill[n];
+    }
+  auto s = c->stream;
+  c->ntet = ntet; c->knent = inc.size();
+  c->ktet.upload( tet, s ); c->kbase.upload( base, s ); c->kinc.upload( inc, s );
+  c->kT.alloc( 40*ntet );
+  c->ksrc = Sn && Sc;
+  if (c->ksrc) {
+    c->S.upload( std::vector< double >( Sn, Sn + npoin*NC ), s );
+    std::vector< double > sc( ntet*NC );
+    for (size_t i=0; i<ntet; ++i) for (size_t k=0; k<NC; ++k) sc[i*NC+k] = Sc[(size_t)perm[i]*NC+k];
+    c->kSc.upload( sc, s );
+  }
+  c->zP.alloc( c->NP*10 ); c->zQ.alloc( c->NP*10 ); c->zUL.alloc( c->NP*NC );
+  API_END
+}
+
+namespace {
+void koz_need( xyst_ctx* c ) {
+  need_mesh( c );
+  if (!c->ntet) throw std::runtime_error( "KozCG needs xyst_kozcg_mesh_upload" );
+  if (c->nsh > 0 && c->comm) throw std::runtime_error( "KozCG on several partitions is not implemented yet" );
+}
+void koz_pass1( xyst_ctx* c, double dt, int fct )
+{
+  auto s = c->stream;
+  { ProfScope ps( c, "kozelem" );
+    k_koz_elem1<<< nblk( c->ntet, 128 ), 128, 0, s >>>( c->ntet, c->NP, c->ktet.p, c->U.p, c->X.p,
+      c->ksrc ? c->S.p : nullptr, c->kSc.p, dt, c->prm.gamma, c->zal.fctdif, fct, c->kT.p ); ++c->launches; }
+  k_koz_node1<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->ntet, c->kbase.p, c->kinc.p,
+    c->kT.p, c->U.p, c->bcof.p, c->bc_symoff.p, c->sym_n.p, c->vol.p, dt, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
+}
+}
+
+int xyst_kozcg_rhs( xyst_ctx* c, double dt )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  koz_need( c );
+  koz_pass1( c, dt, 0 );
+  CK( cudaGetLastError() );
+  API_END
+}
+
+int xyst_kozcg_step( xyst_ctx* c, double dt )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  koz_need( c );
+  auto s = c->stream;
+  unsigned gn = nblk( c->nslice*32, NODE_THREADS ), ge = nblk( c->ntet, 128 );
+  if (c->zal.fct) {
+    koz_pass1( c, dt, 1 );
+    k_koz_elem2<<< ge, 128, 0, s >>>( c->ntet, c->NP, c->ktet.p, c->U.p, c->zUL.p, c->zal.fctclip, c->kT.p ); ++c->launches;
+    k_koz_node2<<< gn, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->ntet, c->kbase.p, c->kinc.p, c->kT.p, c->zUL.p, c->zP.p, c->zQ.p ); ++c->launches;
+    k_koz_elem3<<< ge, 128, 0, s >>>( c->ntet, c->NP, c->ktet.p, c->U.p, c->X.p, c->zQ.p, c->zal.fctdif, c->zal.fctsys_mask, c->kT.p ); ++c->launches;
+    k_koz_node3<<< gn, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->ntet, c->kbase.p, c->kinc.p, c->kT.p, c->zUL.p, c->vol.p, c->Un.p, c->W.p ); ++c->launches;
+  } else {
+    koz_pass1( c, dt, 0 );
+    k_koz_nofct<<< nblk( c->npoin, 256 ), 256, 0, s >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->U.p, dt, c->Un.p, c->W.p ); ++c->launches;
+  }
+  std::swap( c->U.p, c->Un.p );
+  do_bc( c );
+  CK( cudaGetLastError() );
+  API_END
+}
 
 // ---- linear solver ------------------------------------------------------------------
 static void cg_halo( xyst_ctx* c, double* v, int average )

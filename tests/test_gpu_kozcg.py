@@ -54,3 +54,24 @@ def test_kozcg_fct_variants():
         drive_steps([ctx], kw, 5)
         o.step(5)
         assert relerr(ctx.state_get(), o.get("u")) < 1e-11
+
+
+@pytest.mark.parametrize("case", list(O.KCASES))
+def test_kozcg_host_mirror_diag_rows(case):
+    """Full drop-in path (C++ host mirror of KozCG's setup + time loop) vs oracle and golden."""
+    from xyst_b200 import hostapi as H
+    from host_common import fixture_to_host_mesh
+    kw = O.KCASES[case]
+    gold = O.load_golden_diag(case)
+    nsteps = int(gold[-1, 0])
+    hm = fixture_to_host_mesh(O.load_mesh(kw["mesh"]))
+    s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"], hm["set_tri"])
+    s.prepare(); s.attach(0); s.setup()
+    rows = s.step(nsteps)
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(nsteps); d = o.diag()
+    assert rows.shape == d.shape == gold.shape
+    for c in range(1, 8):
+        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-11 * np.abs(d[:, c]).max(), c
+    assert O.numdiff_ok(rows[:, 1:8], gold[:, 1:8], 1.0e-8, 1.0e-7).all()     # reference's own tolerance
+    assert O.numdiff_ok(rows[:, 8:13], gold[:, 8:13], 1.0e-8, 1.0e-6).all()

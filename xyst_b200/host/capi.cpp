@@ -44,7 +44,7 @@ Config to_cfg( const xyst_host_cfg* c ) {
     k.pre_density.push_back( c->pre_density[i] ); k.pre_pressure.push_back( c->pre_pressure[i] );
   }
   if (c->solver[0]) k.solver = c->solver;
-  if (k.solver == "zalcg") { k.fct = c->fct != 0; k.fctclip = c->fctclip != 0; k.fctdif = c->fctdif;
+  if (k.solver == "zalcg" || k.solver == "kozcg") { k.fct = c->fct != 0; k.fctclip = c->fctclip != 0; k.fctdif = c->fctdif;
     for (int i=0; i<c->nfctsys; ++i) k.fctsys.push_back( c->fctsys[i] ); }
   return k;
 }

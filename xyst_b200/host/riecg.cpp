@@ -125,8 +125,9 @@ RieCG::RieCG( Discretization& disc, const TetMesh& chunk, const Config& cfg )
   : m_disc( disc ), m_cfg( cfg ), m_sidetri( chunk.sidetri )
 {
   if (cfg.ncomp != 5) throw std::runtime_error( "only ncomp = 5 is supported" );
-  if (cfg.solver != "riecg" && cfg.solver != "zalcg") throw std::runtime_error( "Unknown solver: " + cfg.solver );
-  m_zal = cfg.solver == "zalcg"; m_stride = m_zal ? 4 : 3;
+  if (cfg.solver != "riecg" && cfg.solver != "zalcg" && cfg.solver != "kozcg")
+    throw std::runtime_error( "Unknown solver: " + cfg.solver );
+  m_zal = cfg.solver == "zalcg"; m_stride = m_zal ? 4 : 3; m_koz = cfg.solver == "kozcg";
   // Transporter::matchsets as the reference executes it (Transporter.cpp:125-187 with the
   // short-circuit at :347-348): with at least one side set named in the configuration the
   // faces of ALL side sets of the mesh keep their boundary integrals; with none, no face does.
@@ -429,8 +430,14 @@ void RieCG::prepare()
   m_ownvol = 0.0;                    // ... and sums the mesh volume then (Discretization.cpp:719-721)
   for (auto v : m_disc.V()) m_ownvol += v;
   timings.push_back( now()-t0 ); t0 = now();
-  if (!m_zal) renumber();            // ZalCG keeps the global2local order (ZalCG.cpp:82-92)
+  if (!m_zal && !m_koz) renumber();  // ZalCG/KozCG keep the global2local order (ZalCG.cpp:82-92)
   timings.push_back( now()-t0 ); t0 = now();
+  if (m_koz) {                       // KozCG::feop (KozCG.cpp:246-276): boundary integrals only
+    timings.push_back( 0.0 ); timings.push_back( 0.0 );
+    bndint();
+    timings.push_back( now()-t0 );
+    return;
+  }
   auto np = m_disc.Gid().size();
   auto edges = uniqueEdges( m_disc.Inpoel(), np );
   std::vector< real > d;
@@ -532,10 +539,30 @@ void RieCG::setup()
   std::size_t nsup[3] = { m_dsupedge[0].size()/4, m_dsupedge[1].size()/3, m_dsupedge[2].size()/2 };
   const std::size_t* se[3] = { m_dsupedge[0].data(), m_dsupedge[1].data(), m_dsupedge[2].data() };
   const real* si[3] = { m_dsupint[0].data(), m_dsupint[1].data(), m_dsupint[2].data() };
+  if (m_koz) {
+    // kozak::rhs source terms (Kozak.cpp:97-108,160-171): nodes and tet centroids
+    std::vector< real > sc;
+    const auto& inpoel = m_disc.Inpoel();
+    if (auto src = problems::SRC( m_cfg )) {
+      sc.resize( inpoel.size()/4*ncomp );
+      #pragma omp parallel for schedule(static)
+      for (std::size_t e=0; e<inpoel.size()/4; ++e) {
+        const auto N = inpoel.data() + e*4;
+        auto xe = (co[0][N[0]] + co[0][N[1]] + co[0][N[2]] + co[0][N[3]]) / 4.0;
+        auto ye = (co[1][N[0]] + co[1][N[1]] + co[1][N[2]] + co[1][N[3]]) / 4.0;
+        auto ze = (co[2][N[0]] + co[2][N[1]] + co[2][N[2]] + co[2][N[3]]) / 4.0;
+        auto v = src( xe, ye, ze, m_disc.T() );
+        for (std::size_t c=0; c<ncomp; ++c) sc[e*ncomp+c] = v[c];
+      }
+    }
+    ck( xyst_kozcg_mesh_upload( m_ctx, np, co[0].data(), co[1].data(), co[2].data(), inpoel.size()/4, inpoel.data(),
+                                m_disc.Vol().data(), m_disc.V().data(),
+                                sc.empty() ? nullptr : m_src.data(), sc.empty() ? nullptr : sc.data() ) );
+  } else
   ck( (m_zal ? xyst_zalcg_mesh_upload : xyst_mesh_upload)( m_ctx, np, co[0].data(), co[1].data(), co[2].data(),
                         nsup, se, si, m_triinpoel.size()/3, m_triinpoel.data(), m_besym.data(),
                         m_disc.Vol().data(), m_disc.V().data() ) );
-  if (m_zal) {
+  if (m_zal || m_koz) {
     xyst_zalcg_params zp{};
     zp.fct = m_cfg.fct; zp.fctclip = m_cfg.fctclip; zp.fctdif = m_cfg.fctdif;
     for (auto c : m_cfg.fctsys) zp.fctsys_mask |= 1 << (c-1);
@@ -547,7 +574,7 @@ void RieCG::setup()
                       m_farbcnodes.size(), m_farbcnodes.data(), m_farbcnorms.data(),
                       m_cfg.far_density, m_cfg.far_pressure, m_cfg.far_velocity.data(),
                       m_prebcnodes.size(), m_prebcnodes.data(), m_prebcvals.data() ) );
-  if (!m_src.empty()) ck( xyst_src_upload( m_ctx, m_src.data() ) );
+  if (!m_src.empty() && !m_koz) ck( xyst_src_upload( m_ctx, m_src.data() ) );
   ck( xyst_state_set( m_ctx, m_u0.data() ) );
   BC();                                            // RieCG::merge :754
   ck( xyst_sync( m_ctx ) );
@@ -586,6 +613,7 @@ bool RieCG::step( std::vector< real >* diagrow )
   if (m_finished) return false;
   advance( dt() );
   if (m_zal) ck( xyst_zalcg_step( m_ctx, m_disc.Dt() ) );      // ZalCG.cpp:973-1607
+  else if (m_koz) ck( xyst_kozcg_step( m_ctx, m_disc.Dt() ) ); // KozCG.cpp:691-1197
   else ck( xyst_riecg_step( m_ctx, m_disc.Dt() ) );
   if (diagrow && (m_disc.It()+1) % m_cfg.diag_iter == 0) *diagrow = diagnostics();
   else if (diagrow) diagrow->clear();

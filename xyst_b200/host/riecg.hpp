@@ -148,6 +148,7 @@ class RieCG {
     AllReduce m_allreduce;
     bool m_hostready = false;
     bool m_zal = false;
+    bool m_koz = false;                    //!< KozCG: element-based, no edge integrals
     std::size_t m_stride = 3;
     real m_ownvol = 0.0;
     std::vector< real > m_dirvals, m_src;

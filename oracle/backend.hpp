@@ -18,6 +18,7 @@
   #include "Riemann.hpp"
   #include "Zalesak.hpp"
   #include "Kozak.hpp"
+  #include "Lax.hpp"
   #include "BC.hpp"
   #include "Problems.hpp"
   #include "InciterConfig.hpp"
@@ -62,6 +63,21 @@ inline void koz_rhs( const std::vector< std::size_t >& inpoel, const Coords& coo
                      const Fields& U, Fields& R )
 { std::vector< real > tp, dtp; kozak::rhs( inpoel, coord, t, dt, tp, dtp, U, R ); }
 
+inline void lax_grad( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                      const std::array< std::vector< real >, 3 >& dsupint,
+                      const Coords& coord, const std::vector< std::size_t >& triinpoel,
+                      const Fields& U, Fields& G )
+{ lax::grad( dsupedge, dsupint, coord, triinpoel, U, G ); }
+
+inline void lax_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                     const std::array< std::vector< real >, 3 >& dsupint,
+                     const Coords& coord, const std::vector< std::size_t >& triinpoel,
+                     const std::vector< std::uint8_t >& besym, const Fields& G, const Fields& U,
+                     const std::vector< real >& v, real t, const std::vector< real >& tp, Fields& R )
+{ lax::rhs( dsupedge, dsupint, coord, triinpoel, besym, G, U, v, t, tp, R ); }
+
+inline real lax_refvel( real r, real p, real v ) { return lax::refvel( r, p, v ); }
+
 inline void initialize( const Coords& coord, Fields& U, real t )
 { problems::initialize( coord, U, t, 0, {} ); }
 
@@ -100,6 +116,9 @@ using port::grad;
 using port::rhs;
 using port::zal_rhs;
 using port::koz_rhs;
+using port::lax_grad;
+using port::lax_rhs;
+using port::lax_refvel;
 using port::initialize;
 using port::dirbc;
 using port::symbc;

@@ -37,6 +37,11 @@ Cfg to_cfg( const orc_cfg* c ) {
   if (c->solver[0]) k.solver = c->solver;
   k.fct = c->fct != 0; k.fctclip = c->fctclip != 0; k.fctdif = c->fctdif;
   for (int i=0; i<c->nfctsys; ++i) k.fctsys.push_back( static_cast< std::uint64_t >( c->fctsys[i] ) );
+  if (c->rgas != 0.0) k.rgas = c->rgas;
+  k.turkel = c->turkel; k.velinf = {{ c->velinf[0], c->velinf[1], c->velinf[2] }};
+  k.residual = c->residual; k.rescomp = c->rescomp ? c->rescomp : 1;
+  k.ic_density = c->ic_density; k.ic_pressure = c->ic_pressure;
+  k.ic_velocity = {{ c->ic_velocity[0], c->ic_velocity[1], c->ic_velocity[2] }};
   return k;
 }
 
@@ -191,6 +196,9 @@ int orc_kernel( void* hv, int chare, const char* what, int stage, double t, doub
     else if (w == "mindt") { h->run->dt = c.mindt(); }
     else if (w == "zrhs") c.zrhs_own( t, dt );
     else if (w == "krhs") c.krhs_own( t, dt );
+    else if (w == "lgrad") c.lgrad_own();
+    else if (w == "lrhs") c.lrhs_own( stage, t );
+    else if (w == "lsolve") c.lsolve( stage, t, dt );
     else if (w == "aec") c.aec_own();
     else if (w == "alw") c.alw_own( dt );
     else if (w == "lim") c.lim_own();

@@ -260,6 +260,7 @@ class Chare {
     std::unordered_map< Edge, std::array< real, 4 >, be::Hash<2>, be::Eq<2> > domedgeint;
     bool zal = false;                     // ZalCG: stride-4 integrals, no renumbering, FCT members
     bool koz = false;                     // KozCG: element-based, no edge integrals at all
+    bool lax = false;                     // LaxCG: (p,u,v,w,T) unknowns inside a stage, preconditioned update
     std::size_t stride = 3;
     Fields p, q, a;                       // ZalCG::m_p, m_q, m_a
     std::vector< real > mvol;             // ZalCG::m_vol (copy taken at construction)
@@ -278,7 +279,7 @@ class Chare {
     Chare( const ChareMesh& cm, const std::array< std::vector< real >, 3 >& gcoord, const Cfg& c )
       : bnode( cm.bnode ), bface( cm.bface ), cfg( c )
     {
-      zal = cfg.solver == "zalcg"; stride = zal ? 4 : 3; koz = cfg.solver == "kozcg";
+      zal = cfg.solver == "zalcg"; stride = zal ? 4 : 3; koz = cfg.solver == "kozcg"; lax = cfg.solver == "laxcg";
       // global2local, Reorder.cpp:279-306
       gid = cm.ginpoel;
       std::sort( gid.begin(), gid.end() );
@@ -592,6 +593,16 @@ class Chare {
       real mindt = std::numeric_limits< real >::max();
       auto eps = std::numeric_limits< real >::epsilon();
       if (std::abs( cfg.dt ) > eps) return cfg.dt;
+      if (lax) {                                               // LaxCG::dt :940-993
+        for (std::size_t i=0; i<u.nunk(); ++i) {
+          auto vch = lcharvel( i );
+          auto L = std::cbrt( vol[i] );
+          auto euler_dt = L / std::max( vch, 1.0e-8 );
+          if (cfg.steady) { dtp[i] = euler_dt * cfg.cfl; mindt = std::min( mindt, dtp[i] ); }
+          else mindt = std::min( mindt, euler_dt );
+        }
+        return cfg.steady ? mindt : mindt * cfg.cfl;
+      }
       for (std::size_t p=0; p<u.nunk(); ++p) {
         auto r = u(p,0);
         auto uu = u(p,1)/r, vv = u(p,2)/r, ww = u(p,3)/r;
@@ -634,6 +645,103 @@ class Chare {
           u(i,c) = un(i,c) - rkcoef[s] * ldt * rhs(i,c) / vol[i];
       }
       BC( t + rkcoef[s] * dt );
+    }
+
+    // ---- LaxCG (time-derivative preconditioning) ---------------------------------------
+    //! LaxCG::primitive :115-137
+    void lprimitive( Fields& U ) const {
+      auto rgas = cfg.rgas;
+      for (std::size_t i=0; i<U.nunk(); ++i) {
+        auto r = U(i,0);
+        auto uu = U(i,1)/r, vv = U(i,2)/r, ww = U(i,3)/r;
+        auto p_ = be::eos_pressure( U(i,4) - 0.5*r*(uu*uu + vv*vv + ww*ww) );
+        U(i,0) = p_; U(i,1) = uu; U(i,2) = vv; U(i,3) = ww; U(i,4) = p_/r/rgas;
+      }
+    }
+    //! LaxCG::conservative :139-164
+    void lconservative( Fields& U ) const {
+      auto g = cfg.gamma, rgas = cfg.rgas;
+      for (std::size_t i=0; i<U.nunk(); ++i) {
+        auto p_ = U(i,0), uu = U(i,1), vv = U(i,2), ww = U(i,3), T = U(i,4);
+        auto r = p_/T/rgas;
+        U(i,0) = r; U(i,1) = r*uu; U(i,2) = r*vv; U(i,3) = r*ww;
+        U(i,4) = p_/(g-1.0) + 0.5*r*(uu*uu + vv*vv + ww*ww);
+      }
+    }
+    //! LaxCG::precond :166-226: inverse of the time-derivative preconditioning matrix
+    std::array< real, 25 > lprecond( const Fields& U, std::size_t i ) const {
+      auto g = cfg.gamma, rgas = cfg.rgas;
+      auto p_ = U(i,0), uu = U(i,1), vv = U(i,2), ww = U(i,3), T = U(i,4);
+      auto r = p_/T/rgas;
+      auto cp = g*rgas/(g-1.0);
+      auto k = uu*uu + vv*vv + ww*ww;
+      auto vr = be::lax_refvel( r, p_, std::sqrt(k) );
+      auto vr2 = vr*vr;
+      auto rt = -r/T;
+      auto H = cp*T + k/2.0;
+      auto theta = 1.0/vr2 - rt/r/cp;
+      auto coef = r*cp*theta + rt;
+      return {{ (rt*(H - k) + r*cp)/coef, rt*uu/coef, rt*vv/coef, rt*ww/coef, -rt/coef,
+                -uu/r, 1.0/r, 0.0, 0.0, 0.0,
+                -vv/r, 0.0, 1.0/r, 0.0, 0.0,
+                -ww/r, 0.0, 0.0, 1.0/r, 0.0,
+                -(theta*(H - k) - 1.0)/coef, -theta*uu/coef, -theta*vv/coef, -theta*ww/coef, theta/coef }};
+    }
+    //! LaxCG::charvel :228-259
+    real lcharvel( std::size_t i ) const {
+      auto g = cfg.gamma, rgas = cfg.rgas;
+      auto cp = g*rgas/(g-1.0);
+      auto r = u(i,0);
+      auto uu = u(i,1)/r, vv = u(i,2)/r, ww = u(i,3)/r;
+      auto k = uu*uu + vv*vv + ww*ww;
+      auto e = u(i,4)/r - k/2.0;
+      auto p_ = be::eos_pressure( r*e );
+      auto T = p_/r/rgas;
+      auto rp = r/p_;
+      auto rt = -r/T;
+      auto vel = std::sqrt( k );
+      auto vr = be::lax_refvel( r, p_, vel );
+      auto vr2 = vr*vr;
+      auto beta = rp + rt/r/cp;
+      auto alpha = 0.5*(1.0 - beta*vr2);
+      auto vpri = vel*(1.0 - alpha);
+      auto cpri = std::sqrt( alpha*alpha*k + vr2 );
+      return std::abs(vpri) + cpri;
+    }
+    //! LaxCG::grad :1011-1036 (own contribution); u becomes (p,u,v,w,T)
+    void lgrad_own() { lprimitive( u ); be::lax_grad( dsupedge, dsupint, coord, triinpoel, u, grad ); }
+    //! LaxCG::rhs :1061-1109
+    void lrhs_own( int stage, real t ) {
+      for (const auto& [g,r] : gradc) { auto i = lid.at(g); for (std::size_t c=0; c<r.size(); ++c) grad(i,c) += r[c]; }
+      gradc.clear();
+      for (std::size_t p=0; p<grad.nunk(); ++p)
+        for (std::size_t c=0; c<grad.nprop(); ++c) grad(p,c) /= vol[p];
+      auto prev_rkcoef = stage == 0 ? 0.0 : rkcoef[ static_cast<std::size_t>(stage-1) ];
+      if (cfg.steady) for (std::size_t p=0; p<tp.size(); ++p) tp[p] += prev_rkcoef * dtp[p];
+      be::lax_rhs( dsupedge, dsupint, coord, triinpoel, besym, grad, u, v, t, tp, rhs );
+      if (cfg.steady) for (std::size_t p=0; p<tp.size(); ++p) tp[p] -= prev_rkcoef * dtp[p];
+    }
+    //! LaxCG::solve :1136-1214
+    void lsolve( int stage, real t, real dt ) {
+      for (const auto& [g,r] : rhsc) { auto i = lid.at(g); for (std::size_t c=0; c<r.size(); ++c) rhs(i,c) += r[c]; }
+      rhsc.clear();
+      if (stage == 0) un = u;
+      auto s = static_cast< std::size_t >( stage );
+      auto ldt = dt;
+      auto ncomp = u.nprop();
+      for (std::size_t i=0; i<u.nunk(); ++i) {
+        if (cfg.steady) ldt = dtp[i];
+        auto R = -rkcoef[s] * ldt / vol[i];
+        auto P = lprecond( u, i );
+        real r[] = { R*rhs(i,0), R*rhs(i,1), R*rhs(i,2), R*rhs(i,3), R*rhs(i,4) };
+        auto pp = P.data();
+        for (std::size_t c=0; c<5; ++c, pp+=5)
+          u(i,c) = un(i,c) + pp[0]*r[0] + pp[1]*r[1] + pp[2]*r[2] + pp[3]*r[3] + pp[4]*r[4];
+        for (std::size_t c=5; c<ncomp; ++c) u(i,c) = un(i,c) + R*rhs(i,c);
+      }
+      lconservative( u );
+      BC( t + rkcoef[s] * dt );
+      if (stage == 2) lconservative( un );
     }
 
     // ---- ZalCG (flux-corrected transport) ----------------------------------------------
@@ -885,6 +993,7 @@ class Run {
     real t = 0.0, dt = 0.0, dtn = 0.0, meshvol = 0.0;
     std::uint64_t it = 0;
     bool finished = false;
+    real res = 0.0;                       // Discretization::m_res (residual of steady-state runs)
     std::vector< std::vector< real > > diagrows;
 
     Run( const MeshInput& in, const Cfg& c, const std::vector< std::size_t >& target, int nchare )
@@ -926,7 +1035,7 @@ class Run {
     //! Discretization::finished :1251-1262
     bool done() const {
       auto eps = std::numeric_limits< real >::epsilon();
-      return std::abs( t - cfg.term ) < eps || it >= cfg.nstep;
+      return std::abs( t - cfg.term ) < eps || it >= cfg.nstep || (res > 0.0 && res < cfg.residual);
     }
 
     //! sum partial nodal results over chare boundaries (comgrad/comrhs)
@@ -1004,17 +1113,20 @@ class Run {
         if (done()) finished = true;
         return !finished;
       }
+      const bool lax = cfg.solver == "laxcg";                  // LaxCG.cpp:1011-1214, same stage structure
       for (int stage=0; stage<3; ++stage) {
-        for (auto& c_ : ch) c_->grad_own();
+        for (auto& c_ : ch) { if (lax) c_->lgrad_own(); else c_->grad_own(); }
         exchange( []( Chare& c_ ) -> be::Fields& { return c_.grad; },
                   []( Chare& c_ ) -> auto& { return c_.gradc; } );
-        for (auto& c_ : ch) c_->rhs_own( stage, t );
+        for (auto& c_ : ch) { if (lax) c_->lrhs_own( stage, t ); else c_->rhs_own( stage, t ); }
         exchange( []( Chare& c_ ) -> be::Fields& { return c_.rhs; },
                   []( Chare& c_ ) -> auto& { return c_.rhsc; } );
-        for (auto& c_ : ch) c_->solve( stage, t, dt );
+        for (auto& c_ : ch) { if (lax) c_->lsolve( stage, t, dt ); else c_->solve( stage, t, dt ); }
       }
       diagnostics();
       ++it; t += dt;                                           // next :941-983
+      if (cfg.steady)                                          // RieCG.cpp:1050-1053, LaxCG.cpp:1204-1207
+        for (auto& c_ : ch) for (std::size_t p=0; p<c_->tp.size(); ++p) c_->tp[p] += c_->dtp[p];
       if (done()) finished = true;
       return !finished;
     }
@@ -1055,6 +1167,7 @@ class Run {
       for (std::size_t i=0; i<ncomp; ++i) row.push_back( std::sqrt( d[0][i] / meshvol ) );
       for (std::size_t i=0; i<ncomp; ++i) row.push_back( std::sqrt( d[1][i] / meshvol ) );
       row.push_back( d[2][0] );
+      if (cfg.steady) res = std::sqrt( d[1][cfg.rescomp-1] / meshvol );   // evalres: RieCG.cpp:1062-1075, Discretization.cpp:1267-1283
       if (sol) {
         for (std::size_t i=0; i<ncomp; ++i) row.push_back( std::sqrt( d[3][i] / meshvol ) );
         for (std::size_t i=0; i<ncomp; ++i) row.push_back( d[4][i] / meshvol );

@@ -26,7 +26,7 @@ typedef struct orc_cfg {
   int32_t pre_sets[16];
   int32_t nfieldout;
   int32_t fieldout_sets[16];
-  char solver[16];            /* "riecg" | "zalcg" */
+  char solver[16];            /* "riecg" | "zalcg" | "kozcg" | "laxcg" */
   int32_t fct, fctclip, nfctsys;
   int32_t fctsys[8];
   double fctdif;
@@ -35,6 +35,10 @@ typedef struct orc_cfg {
   double gamma, p0, cfl, dt, t0, term, stab2coef;
   double far_density, far_pressure, far_velocity[3];
   double pre_density[16], pre_pressure[16];
+  /* LaxCG + steady state + user-defined initial conditions */
+  double rgas, turkel, velinf[3], residual;
+  uint64_t rescomp;
+  double ic_density, ic_pressure, ic_velocity[3];
 } orc_cfg;
 
 const char* orc_backend(void);      /* "port" or "reference" */

@@ -60,6 +60,15 @@ struct Cfg {
   real fctdif = 1.0;
   bool fctclip = false;
   std::vector< std::uint64_t > fctsys;       // 1-based component ids limited as a system
+  // LaxCG (time-derivative preconditioning), defaults InciterConfig.cpp:1409,1731-1739
+  real rgas = 287.052874;                    // mat_spec_gas_const
+  real turkel = 0.5;
+  std::array< real, 3 > velinf{{1.0,1.0,1.0}};
+  real residual = 0.0;
+  std::uint64_t rescomp = 1;
+  // ic block of user-defined problems (Problems.cpp:28-115)
+  real ic_density = 0.0, ic_pressure = 0.0;
+  std::array< real, 3 > ic_velocity{{0,0,0}};
 };
 
 //! Nodal field container with the reference's default layout [node][component]
@@ -132,8 +141,19 @@ inline std::vector< real > src_taylor_green( real x, real y, real, real ) { // :
   return s;
 }
 
+inline std::vector< real > ic_userdef( real, real, real, real ) {           // :28-115 (pressure given)
+  std::vector< real > u( cfg().ncomp, 0.0 );
+  u[0] = cfg().ic_density;
+  u[1] = u[0] * cfg().ic_velocity[0];
+  u[2] = u[0] * cfg().ic_velocity[1];
+  u[3] = u[0] * cfg().ic_velocity[2];
+  u[4] = eos_totalenergy( u[0], u[1]/u[0], u[2]/u[0], u[3]/u[0], cfg().ic_pressure );
+  return u;
+}
+
 inline ICFn IC() {                                                          // :1071-1108
   const auto& p = cfg().problem;
+  if (p == "userdef") return ic_userdef;
   if (p == "sedov") return ic_sedov;
   if (p == "sod") return ic_sod;
   if (p == "taylor_green") return ic_taylor_green;
@@ -415,11 +435,16 @@ inline void hllc( const Coords& coord, const Fields& G, const real dsupint[],
 }
 
 //! Nodal gradients of primitive variables, weak (un-normalised) form       // :229-367
-inline void grad( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+//! loader of the nodal variables the edge loops work on
+struct LoadPrimitive { void operator()( std::size_t ncomp, std::size_t i, const Fields& U, real u[] ) const { primitive( ncomp, i, U, u ); } };
+struct LoadAsIs { void operator()( std::size_t ncomp, std::size_t i, const Fields& U, real u[] ) const { for (std::size_t c=0; c<ncomp; ++c) u[c] = U(i,c); } };
+
+template< class Load >
+inline void grad_impl( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
                   const std::array< std::vector< real >, 3 >& dsupint,
                   const Coords& coord,
                   const std::vector< std::size_t >& triinpoel,
-                  const Fields& U, Fields& G )
+                  const Fields& U, Fields& G, Load primitive )
 {
   auto ncomp = U.nprop();
   G.fill( 0.0 );
@@ -493,16 +518,21 @@ inline void grad( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
   }
 }
 
-inline void advdom( const Coords& coord,
+//! riemann::grad, Riemann.cpp:229-367
+inline void grad( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                  const std::array< std::vector< real >, 3 >& dsupint,
+                  const Coords& coord,
+                  const std::vector< std::size_t >& triinpoel,
+                  const Fields& U, Fields& G )
+{ grad_impl( dsupedge, dsupint, coord, triinpoel, U, G, LoadPrimitive() ); }
+
+template< class Load >
+inline void advdom_impl( const Coords& coord,
                     const std::array< std::vector< std::size_t >, 3 >& dsupedge,
                     const std::array< std::vector< real >, 3 >& dsupint,
-                    const Fields& G, const Fields& U, Fields& R )             // :652-766
+                    const Fields& G, const Fields& U, Fields& R, FluxFn flux, Load primitive )
 {
   auto ncomp = U.nprop();
-  FluxFn flux;
-  if (cfg().flux == "rusanov") flux = rusanov;
-  else if (cfg().flux == "hllc") flux = hllc;
-  else throw std::runtime_error( "oracle port: Flux not configured" );
   std::vector< real > ub( 4*ncomp ), fb( 6*ncomp );
   real* u[4] = { ub.data(), ub.data()+ncomp, ub.data()+2*ncomp, ub.data()+3*ncomp };
   real* f[6]; for (int k=0; k<6; ++k) f[k] = fb.data() + static_cast<std::size_t>(k)*ncomp;
@@ -547,6 +577,18 @@ inline void advdom( const Coords& coord,
       R(N[1],c) += f[0][c];
     }
   }
+}
+
+inline void advdom( const Coords& coord,
+                    const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                    const std::array< std::vector< real >, 3 >& dsupint,
+                    const Fields& G, const Fields& U, Fields& R )             // :652-766
+{
+  FluxFn flux;
+  if (cfg().flux == "rusanov") flux = rusanov;
+  else if (cfg().flux == "hllc") flux = hllc;
+  else throw std::runtime_error( "oracle port: Flux not configured" );
+  advdom_impl( coord, dsupedge, dsupint, G, U, R, flux, LoadPrimitive() );
 }
 
 inline void advbnd( const std::vector< std::size_t >& triinpoel, const Coords& coord,
@@ -608,6 +650,221 @@ inline void rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
   R.fill( 0.0 );
   advdom( coord, dsupedge, dsupint, G, U, R );
   advbnd( triinpoel, coord, besym, U, R );
+  src( coord, v, t, tp, R );
+}
+
+// ---- Lax.cpp: time-derivative preconditioned edge fluxes for LaxCG ------------------------
+// nodal unknowns are (p,u,v,w,T) throughout (LaxCG::primitive, LaxCG.cpp:115-137)
+
+//! lax::grad, Lax.cpp:216-343: same edge/boundary formulas, applied to the unknowns as they are
+inline void lax_grad( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                      const std::array< std::vector< real >, 3 >& dsupint,
+                      const Coords& coord, const std::vector< std::size_t >& triinpoel,
+                      const Fields& U, Fields& G )
+{ grad_impl( dsupedge, dsupint, coord, triinpoel, U, G, LoadAsIs() ); }
+
+inline real lax_refvel( real r, real p, real v ) {                          // :344-360
+  const auto& vi = cfg().velinf;
+  auto vinf = std::sqrt( vi[0]*vi[0] + vi[1]*vi[1] + vi[2]*vi[2] );
+  return std::min( eos_soundspeed( r, p ), std::max( v, cfg().turkel*vinf ) );
+}
+
+inline void lax_sigvel( real p, real T, real v, real vn, real& vpri, real& cpri ) {  // :362-388
+  auto g = cfg().gamma, rgas = cfg().rgas;
+  auto cp = g*rgas/(g-1.0);
+  auto r = p/T/rgas;
+  auto rp = r/p;
+  auto rt = -r/T;
+  auto vr = lax_refvel( r, p, v );
+  auto vr2 = vr*vr;
+  auto beta = rp + rt/r/cp;
+  auto alpha = 0.5*(1.0 - beta*vr2);
+  vpri = vn*(1.0 - alpha);
+  cpri = std::sqrt( alpha*alpha*vn*vn + vr2 );
+}
+
+inline real length3( real a, real b, real c ) { return std::sqrt( a*a + b*b + c*c ); }
+
+//! (p,u,v,w,T) -> (r,ru,rv,rw,rE) of an edge-end state, :438-451
+inline void lax_conserved( real l[], real pL ) {
+  auto g = cfg().gamma, rgas = cfg().rgas;
+  l[0] = pL/l[4]/rgas;
+  l[1] *= l[0]; l[2] *= l[0]; l[3] *= l[0];
+  l[4] = pL/(g-1.0) + 0.5*(l[1]*l[1] + l[2]*l[2] + l[3]*l[3])/l[0];
+}
+
+inline void lax_rusanov( const Coords& coord, const Fields& G, const real dsupint[],
+                         std::size_t p, std::size_t q, const real L[], const real R[], real f[] ) // :390-511
+{
+  auto ncomp = G.nprop() / 3;
+  std::vector< real > lv( L, L+ncomp ), rv( R, R+ncomp );
+  real* l = lv.data(); real* r = rv.data();
+  muscl_flow( p, q, coord, G, l, r );        // same limiter, fallback tests pressure and temperature
+  auto nx = dsupint[0], ny = dsupint[1], nz = dsupint[2];
+  auto vnL = l[1]*nx + l[2]*ny + l[3]*nz;
+  auto vnR = r[1]*nx + r[2]*ny + r[3]*nz;
+  auto pL = l[0], pR = r[0];
+  auto len = length3( nx, ny, nz );
+  real vpL, cpL, vpR, cpR;
+  lax_sigvel( l[0], l[4], length3(l[1],l[2],l[3]), vnL, vpL, cpL );
+  lax_sigvel( r[0], r[4], length3(r[1],r[2],r[3]), vnR, vpR, cpR );
+  lax_conserved( l, pL );
+  lax_conserved( r, pR );
+  using std::abs; using std::max;
+  auto sp = max(abs(vpL-cpL),max(abs(vpR-cpR),max(abs(vpL+cpL),abs(vpR+cpR))));
+  auto sL = -sp, sR = +sp;
+  auto fw = std::max( sL, sR ) * len;
+  f[0] = l[0]*vnL + r[0]*vnR + fw*(r[0] - l[0]);
+  f[1] = l[1]*vnL + r[1]*vnR + (pL + pR)*nx + fw*(r[1] - l[1]);
+  f[2] = l[2]*vnL + r[2]*vnR + (pL + pR)*ny + fw*(r[2] - l[2]);
+  f[3] = l[3]*vnL + r[3]*vnR + (pL + pR)*nz + fw*(r[3] - l[3]);
+  f[4] = (l[4] + pL)*vnL + (r[4] + pR)*vnR + fw*(r[4] - l[4]);
+  if (cfg().stab2) {
+    auto fws = cfg().stab2coef * fw;
+    for (int c=0; c<5; ++c) f[c] -= fws*(l[c] - r[c]);
+  }
+  if (ncomp == 5) return;
+  std::vector< real > d1( ncomp ), d3( ncomp );
+  muscl_range( p, q, coord, G, 5, ncomp, l, r, d1.data(), d3.data() );
+  auto sw = std::max( std::abs(vnL), std::abs(vnR) );
+  for (std::size_t c=5; c<ncomp; ++c) f[c] = l[c]*vnL + r[c]*vnR + sw*(r[c] - l[c]);
+}
+
+inline void lax_hllc( const Coords& coord, const Fields& G, const real dsupint[],
+                      std::size_t p, std::size_t q, const real L[], const real R[], real f[] )   // :513-723
+{
+  auto ncomp = G.nprop() / 3;
+  std::vector< real > lv( L, L+ncomp ), rv( R, R+ncomp );
+  real* l = lv.data(); real* r = rv.data();
+  muscl_flow( p, q, coord, G, l, r );
+  auto nx = -dsupint[0], ny = -dsupint[1], nz = -dsupint[2];
+  auto len = length3( nx, ny, nz );
+  nx /= len; ny /= len; nz /= len;
+  auto qL = l[1]*nx + l[2]*ny + l[3]*nz;
+  auto qR = r[1]*nx + r[2]*ny + r[3]*nz;
+  auto pL = l[0], pR = r[0];
+  real vpL, cpL, vpR, cpR;
+  lax_sigvel( l[0], l[4], length3(l[1],l[2],l[3]), qL*len, vpL, cpL );
+  lax_sigvel( r[0], r[4], length3(r[1],r[2],r[3]), qR*len, vpR, cpR );
+  lax_conserved( l, pL );
+  lax_conserved( r, pR );
+  using std::abs; using std::max;
+  auto sp = max(abs(vpL-cpL),max(abs(vpR-cpR),max(abs(vpL+cpL),abs(vpR+cpR))));
+  auto sL = -sp, sR = +sp;
+  auto tL = sL - qL;
+  auto tR = sR - qR;
+  auto sM = (r[0]*qR*tR - l[0]*qL*tL + pL - pR) / (r[0]*tR - l[0]*tL);
+  auto pS = pL - l[0]*tL*(qL - sM);
+  real uL[5], uR[5];
+  auto s = sL - sM;
+  uL[0] = tL*l[0]/s;
+  uL[1] = (tL*l[1] + (pS-pL)*nx)/s;
+  uL[2] = (tL*l[2] + (pS-pL)*ny)/s;
+  uL[3] = (tL*l[3] + (pS-pL)*nz)/s;
+  uL[4] = (tL*l[4] - pL*qL + pS*sM)/s;
+  s = sR - sM;
+  uR[0] = tR*r[0]/s;
+  uR[1] = (tR*r[1] + (pS-pR)*nx)/s;
+  uR[2] = (tR*r[2] + (pS-pR)*ny)/s;
+  uR[3] = (tR*r[3] + (pS-pR)*nz)/s;
+  uR[4] = (tR*r[4] - pR*qR + pS*sM)/s;
+  auto L2 = -2.0*len;
+  nx *= L2; ny *= L2; nz *= L2;
+  if (sL > 0.0) {
+    auto qL2 = qL * L2;
+    f[0] = l[0]*qL2;
+    f[1] = l[1]*qL2 + pL*nx;
+    f[2] = l[2]*qL2 + pL*ny;
+    f[3] = l[3]*qL2 + pL*nz;
+    f[4] = (l[4] + pL)*qL2;
+  }
+  else if (sL <= 0.0 && sM > 0.0) {
+    auto qL2 = qL * L2;
+    auto sL2 = sL * L2;
+    f[0] = l[0]*qL2 + sL2*(uL[0] - l[0]);
+    f[1] = l[1]*qL2 + pL*nx + sL2*(uL[1] - l[1]);
+    f[2] = l[2]*qL2 + pL*ny + sL2*(uL[2] - l[2]);
+    f[3] = l[3]*qL2 + pL*nz + sL2*(uL[3] - l[3]);
+    f[4] = (l[4] + pL)*qL2 + sL2*(uL[4] - l[4]);
+  }
+  else if (sM <= 0.0 && sR >= 0.0) {
+    auto qR2 = qR * L2;
+    auto sR2 = sR * L2;
+    f[0] = r[0]*qR2 + sR2*(uR[0] - r[0]);
+    f[1] = r[1]*qR2 + pR*nx + sR2*(uR[1] - r[1]);
+    f[2] = r[2]*qR2 + pR*ny + sR2*(uR[2] - r[2]);
+    f[3] = r[3]*qR2 + pR*nz + sR2*(uR[3] - r[3]);
+    f[4] = (r[4] + pR)*qR2 + sR2*(uR[4] - r[4]);
+  }
+  else {
+    auto qR2 = qR * L2;
+    f[0] = r[0]*qR2;
+    f[1] = r[1]*qR2 + pR*nx;
+    f[2] = r[2]*qR2 + pR*ny;
+    f[3] = r[3]*qR2 + pR*nz;
+    f[4] = (r[4] + pR)*qR2;
+  }
+  if (ncomp == 5) return;
+  // the reference reconstructs the scalars but leaves their hllc fluxes unset (:707-717)
+  std::vector< real > d1( ncomp ), d3( ncomp );
+  muscl_range( p, q, coord, G, 5, ncomp, l, r, d1.data(), d3.data() );
+}
+
+inline void lax_advbnd( const std::vector< std::size_t >& triinpoel, const Coords& coord,
+                        const std::vector< std::uint8_t >& besym, const Fields& U, Fields& R ) // :840-950
+{
+  auto ncomp = U.nprop();
+  auto g = cfg().gamma, rgas = cfg().rgas;
+  const auto& x = coord[0]; const auto& y = coord[1]; const auto& z = coord[2];
+  std::vector< real > fb( ncomp*3 );
+  auto f = [&]( std::size_t c, std::size_t k ) -> real& { return fb[c*3+k]; };
+  for (std::size_t e=0; e<triinpoel.size()/3; ++e) {
+    const auto N = triinpoel.data() + e*3;
+    real ba[3] = { x[N[1]]-x[N[0]], y[N[1]]-y[N[0]], z[N[1]]-z[N[0]] },
+         ca[3] = { x[N[2]]-x[N[0]], y[N[2]]-y[N[0]], z[N[2]]-z[N[0]] };
+    real nx = ba[1]*ca[2] - ca[1]*ba[2], ny = ba[2]*ca[0] - ca[2]*ba[0], nz = ba[0]*ca[1] - ca[0]*ba[1];
+    nx /= 12.0; ny /= 12.0; nz /= 12.0;
+    const auto sym = besym.data() + e*3;
+    for (std::size_t k=0; k<3; ++k) {
+      auto rA  = U(N[k],0)/U(N[k],4)/rgas;
+      auto ruA = U(N[k],1) * rA;
+      auto rvA = U(N[k],2) * rA;
+      auto rwA = U(N[k],3) * rA;
+      auto reA = U(N[k],0)/(g-1.0) + 0.5*(ruA*ruA + rvA*rvA + rwA*rwA)/rA;
+      real vn = sym[k] ? 0.0 : (nx*U(N[k],1) + ny*U(N[k],2) + nz*U(N[k],3));
+      f(0,k) = rA*vn;
+      f(1,k) = ruA*vn + U(N[k],0)*nx;
+      f(2,k) = rvA*vn + U(N[k],0)*ny;
+      f(3,k) = rwA*vn + U(N[k],0)*nz;
+      f(4,k) = (reA + U(N[k],0))*vn;
+      for (std::size_t c=5; c<ncomp; ++c) f(c,k) = U(N[k],c)*vn;
+    }
+    for (std::size_t c=0; c<ncomp; ++c) {
+      auto fab = (f(c,0) + f(c,1))/4.0;
+      auto fbc = (f(c,1) + f(c,2))/4.0;
+      auto fca = (f(c,2) + f(c,0))/4.0;
+      R(N[0],c) += fab + fca + f(c,0);
+      R(N[1],c) += fab + fbc + f(c,1);
+      R(N[2],c) += fbc + fca + f(c,2);
+    }
+  }
+}
+
+//! lax::rhs, Lax.cpp:981-1018
+inline void lax_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                     const std::array< std::vector< real >, 3 >& dsupint,
+                     const Coords& coord, const std::vector< std::size_t >& triinpoel,
+                     const std::vector< std::uint8_t >& besym,
+                     const Fields& G, const Fields& U, const std::vector< real >& v,
+                     real t, const std::vector< real >& tp, Fields& R )
+{
+  R.fill( 0.0 );
+  FluxFn flux;
+  if (cfg().flux == "rusanov") flux = lax_rusanov;
+  else if (cfg().flux == "hllc") flux = lax_hllc;
+  else throw std::runtime_error( "oracle port: Flux not configured" );
+  advdom_impl( coord, dsupedge, dsupint, G, U, R, flux, LoadAsIs() );
+  lax_advbnd( triinpoel, coord, besym, U, R );
   src( coord, v, t, tp, R );
 }
 

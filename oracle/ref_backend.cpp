@@ -43,6 +43,16 @@ void set_cfg( const Cfg& c )
   g.get< tag::bc_pre, tag::density >() = c.pre_density;
   g.get< tag::bc_pre, tag::pressure >() = c.pre_pressure;
   g.get< tag::diag_iter >() = c.diag_iter;
+  g.get< tag::mat_spec_gas_const >() = c.rgas;
+  g.get< tag::turkel >() = c.turkel;
+  g.get< tag::velinf >() = std::vector< double >{ c.velinf[0], c.velinf[1], c.velinf[2] };
+  g.get< tag::residual >() = c.residual;
+  g.get< tag::rescomp >() = c.rescomp;
+  if (c.problem == "userdef") {
+    g.get< tag::ic, tag::density >() = c.ic_density;
+    g.get< tag::ic, tag::pressure >() = c.ic_pressure;
+    g.get< tag::ic, tag::velocity >() = std::vector< double >{ c.ic_velocity[0], c.ic_velocity[1], c.ic_velocity[2] };
+  }
   port::set_cfg( c );
 }
 

@@ -22,7 +22,9 @@ CASES = {
     "riecg_sod": ("RieCG/Sod/rectangle_01_1.5k.exo", "RieCG/Sod/diag.std"),
     "riecg_sedov": ("RieCG/Sedov/sedov_coarse.exo", "RieCG/Sedov/diag.std"),
     "riecg_taylor_green": ("RieCG/TaylorGreen/unitcube_1k.exo", "RieCG/TaylorGreen/diag.std"),
+    "laxcg_bump": ("LaxCG/Bump/bump.exo", "LaxCG/Bump/diag.std"),
 }
+EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std"}
 
 
 def flatten(exo):
@@ -62,7 +64,11 @@ def main():
         m = flatten(os.path.join(REF, exo))
         np.savez_compressed(os.path.join(HERE, name + ".mesh.npz"), **m)
         shutil.copyfile(os.path.join(REF, diag), os.path.join(HERE, name + ".diag.std"))
+        os.chmod(os.path.join(HERE, name + ".diag.std"), 0o644)
         print(name, m["coord"].shape[1], "nodes", len(m["tets"]), "tets", len(m["tris"]), "tris")
+    for name, diag in EXTRA_DIAG.items():
+        shutil.copyfile(os.path.join(REF, diag), os.path.join(HERE, name + ".diag.std"))
+        os.chmod(os.path.join(HERE, name + ".diag.std"), 0o644)
 
 
 if __name__ == "__main__":

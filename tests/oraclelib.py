@@ -32,18 +32,31 @@ class Cfg(C.Structure):
         ("t0", C.c_double), ("term", C.c_double), ("stab2coef", C.c_double),
         ("far_density", C.c_double), ("far_pressure", C.c_double), ("far_velocity", C.c_double * 3),
         ("pre_density", C.c_double * 16), ("pre_pressure", C.c_double * 16),
+        ("rgas", C.c_double), ("turkel", C.c_double), ("velinf", C.c_double * 3), ("residual", C.c_double),
+        ("rescomp", C.c_uint64),
+        ("ic_density", C.c_double), ("ic_pressure", C.c_double), ("ic_velocity", C.c_double * 3),
     ]
 
 
 def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0, term=1e300,
              nstep=2**63, sym=(), dir_=(), stab2=False, stab2coef=0.2, diag_iter=1, ncomp=5,
-             fieldout=(), solver="riecg", fct=True, fctclip=False, fctsys=(), fctdif=1.0, cls=Cfg):
+             fieldout=(), solver="riecg", fct=True, fctclip=False, fctsys=(), fctdif=1.0,
+             steady=False, residual=0.0, rescomp=1, rgas=287.052874, turkel=0.5, velinf=(1.0, 1.0, 1.0),
+             far=(), far_density=0.0, far_pressure=0.0, far_velocity=(0.0, 0.0, 0.0),
+             ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0), cls=Cfg):
     """Control-file equivalent; defaults are the reference's (InciterConfig.cpp:1707-1757)."""
     c = cls()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term
-    c.nstep = nstep; c.stab2 = int(stab2); c.stab2coef = stab2coef; c.steady = 0
+    c.nstep = nstep; c.stab2 = int(stab2); c.stab2coef = stab2coef; c.steady = int(steady)
     c.diag_iter = diag_iter
+    c.residual = residual; c.rescomp = rescomp; c.rgas = rgas; c.turkel = turkel
+    c.nfar = len(far); c.far_density = far_density; c.far_pressure = far_pressure
+    for i, s_ in enumerate(far):
+        c.far_sets[i] = s_
+    c.ic_density = ic_density; c.ic_pressure = ic_pressure
+    for i in range(3):
+        c.velinf[i] = velinf[i]; c.far_velocity[i] = far_velocity[i]; c.ic_velocity[i] = ic_velocity[i]
     c.solver = solver.encode(); c.fct = int(fct); c.fctclip = int(fctclip); c.fctdif = fctdif
     c.nfctsys = len(fctsys)
     for i, s_ in enumerate(fctsys):
@@ -60,6 +73,18 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
             c.dir[i][j] = v
     return c
 
+
+# LaxCG regression case (tests/regression/inciter/LaxCG/Bump/{bump.q,bump_hllc.q}): steady-state
+# local time stepping, free stream rho=1.225, p=101325, Mach 0.675
+_C_INF = (1.4 * 101325.0 / 1.225) ** 0.5
+_BUMP = dict(solver="laxcg", problem="userdef", gamma=1.4, cfl=0.7, nstep=20, steady=True, residual=1.0e-14,
+             rescomp=1, sym=(3,), far=(4,), far_density=1.225, far_pressure=101325.0,
+             far_velocity=(_C_INF * 0.675, 0.0, 0.0), ic_density=1.225, ic_pressure=101325.0,
+             ic_velocity=(_C_INF * 0.675, 0.0, 0.0), velinf=(_C_INF * 0.675, 0.0, 0.0), mesh="laxcg_bump")
+LCASES = {
+    "laxcg_bump": dict(_BUMP),
+    "laxcg_bump_hllc": dict(_BUMP, flux="hllc"),
+}
 
 # KozCG regression cases (tests/regression/inciter/KozCG/{Sod/sod.q,TaylorGreen/taylor_green.q})
 KCASES = {

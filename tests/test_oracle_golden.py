@@ -94,3 +94,32 @@ def test_kozcg_oracle_reproduces_reference_golden_diag(case):
     d = o.diag()
     assert d.shape == gold.shape
     assert (np.abs(d - gold) / np.maximum(np.abs(gold), 1e-300)).max() < 6e-9
+
+
+def test_laxcg_oracle_reproduces_reference_golden_diag():
+    """LaxCG (time-derivative preconditioning, steady-state local time stepping, far-field BC):
+    tests/regression/inciter/LaxCG/Bump/diag.std, serial run with the Rusanov flux, to the printed
+    12 significant digits."""
+    kw = O.LCASES["laxcg_bump"]
+    gold = O.load_golden_diag("laxcg_bump")
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(int(gold[-1, 0]))
+    d = o.diag()
+    assert d.shape == gold.shape
+    assert (np.abs(d - gold) / np.maximum(np.abs(gold), 1e-300)).max() < 2e-12
+
+
+def test_laxcg_hllc_oracle_within_reference_tolerance_of_parallel_golden():
+    """diag_hllc.std was produced on 4 PEs: the partition changes which edges end up in which
+    superedge and with that their orientation, which MUSCL's +eps sees (SURVEY 8a' item 5), so a
+    serial run can only match it to the reference's parallel tolerance (diag.par.ndiff.cfg). The
+    first time steps sizes still agree to printed precision."""
+    kw = O.LCASES["laxcg_bump_hllc"]
+    gold = O.load_golden_diag("laxcg_bump_hllc")
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(int(gold[-1, 0]))
+    d = o.diag()
+    assert d.shape == gold.shape
+    assert (np.abs(d[:3, 1:3] - gold[:3, 1:3]) / gold[:3, 1:3]).max() < 1e-11     # first steps: same dt
+    assert O.numdiff_ok(d[:, 1:13], gold[:, 1:13], 1.0e-3, 3.0e-3).all()
+    assert (np.abs(d[:, 3:8] - gold[:, 3:8]) / gold[:, 3:8]).max() < 2e-4

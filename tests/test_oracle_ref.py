@@ -94,3 +94,22 @@ def test_kozcg_port_is_bit_identical_to_reference_objects(case):
     a.step(n); b.step(n)
     assert np.array_equal(a.diag(), b.diag())
     assert np.array_equal(a.get("u"), b.get("u"))
+
+
+@needs_ref
+@pytest.mark.parametrize("case", list(O.LCASES))
+def test_laxcg_port_is_bit_identical_to_reference_objects(case):
+    """lax::grad/rhs/refvel from the reference's own Lax.cpp vs the restatement under the same driver."""
+    kw = O.LCASES[case]
+    mesh = O.load_mesh(kw["mesh"])
+    a = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    b = O.Oracle(mesh, O.make_cfg(**kw), "reference")
+    for o in (a, b):
+        o.kernel("mindt")
+        o.kernel("lgrad")
+        o.kernel("lrhs", 0, 0.0)
+    assert np.array_equal(a.get("grad"), b.get("grad"))
+    assert np.array_equal(a.get("rhs"), b.get("rhs"))
+    a.step(5); b.step(5)
+    assert np.array_equal(a.diag(), b.diag())
+    assert np.array_equal(a.get("u"), b.get("u"))

@@ -162,6 +162,25 @@ int xyst_zalcg_rhs(xyst_ctx* ctx, double dt);
  * antidiffusive contributions), solve, BC (ZalCG.cpp:990-1607); un keeps the old state */
 int xyst_zalcg_step(xyst_ctx* ctx, double dt);
 
+/* ---- LaxCG: time-derivative preconditioning for all Mach numbers ------------------------
+ * (src/Physics/Lax.cpp:216-1018, src/Inciter/LaxCG.cpp:115-259,940-1214). Same superedge data
+ * and entry points as RieCG: after xyst_laxcg_config the context keeps (p,u,v,w,T) next to the
+ * conserved state and xyst_riecg_grad = lax::grad, xyst_riecg_rhs = lax::rhs, xyst_rk_update /
+ * xyst_riecg_stage / xyst_riecg_step = LaxCG::solve (update preconditioned by LaxCG::precond),
+ * xyst_dt_min = LaxCG::dt with LaxCG::charvel. Call after the mesh upload and before
+ * xyst_state_set. rgas = mat_spec_gas_const, turkel and velinf as in the control file. */
+typedef struct xyst_laxcg_params {
+  double rgas;
+  double turkel;
+  double velinf[3];
+} xyst_laxcg_params;
+int xyst_laxcg_config(xyst_ctx* ctx, const xyst_laxcg_params* p);
+
+/* steady = true (RieCG.cpp:812-825,1013, LaxCG.cpp:962-969,1153): local time stepping. xyst_dt_min
+ * then also stores the nodal time steps dtp = cfl L/v, and the stage updates use them instead of
+ * the dt argument. Sources are evaluated at the nodes once (time-independent). */
+int xyst_steady(xyst_ctx* ctx, int on);
+
 /* ---- KozCG: element-based Taylor-Galerkin + flux-corrected transport ---------------------
  * (src/Physics/Kozak.cpp:29-180, src/Inciter/KozCG.cpp:709-1197). Works on the tetrahedra
  * themselves: inpoel = Discretization::Inpoel(), 4 local node ids per tet. FCT parameters

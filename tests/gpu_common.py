@@ -36,10 +36,16 @@ def context_from_oracle(o, kw, chare=0, exact_muscl=False, device=0):
                     g("vol"), g("v"), stride=4 if zal else 3)
     if zal:
         ctx.zalcg_config(kw.get("fct", True), kw.get("fctclip", False), kw.get("fctsys", ()), kw.get("fctdif", 1.0))
+    if kw.get("solver") == "laxcg":
+        ctx.laxcg_config(kw.get("rgas", 287.052874), kw.get("turkel", 0.5), kw.get("velinf", (1.0, 1.0, 1.0)))
+    if kw.get("steady"):
+        ctx.steady(True)
     U0 = g("u")
     dm = g("dirbcmasks")
     dv = U0[dm.reshape(-1, 6)[:, 0].astype(np.int64)] if len(dm) else None
-    ctx.bc_upload(dirbcmasks=dm, dirvals=dv, symbcnodes=g("symbcnodes"), symbcnorms=g("symbcnorms"))
+    ctx.bc_upload(dirbcmasks=dm, dirvals=dv, symbcnodes=g("symbcnodes"), symbcnorms=g("symbcnorms"),
+                  farbcnodes=g("farbcnodes"), farbcnorms=g("farbcnorms"),
+                  far=(kw.get("far_density", 0.0), kw.get("far_pressure", 0.0), kw.get("far_velocity", (0.0, 0.0, 0.0))))
     if kw["problem"] == "taylor_green":
         ctx.src_upload(tg_source(x, y))
     ctx.state_set(U0)

@@ -11,6 +11,10 @@ class XystError(RuntimeError):
     pass
 
 
+class LaxParams(C.Structure):
+    _fields_ = [("rgas", C.c_double), ("turkel", C.c_double), ("velinf", C.c_double * 3)]
+
+
 class ZalParams(C.Structure):
     _fields_ = [("fct", C.c_int32), ("fctclip", C.c_int32), ("fctsys_mask", C.c_int32), ("pad_", C.c_int32),
                 ("fctdif", C.c_double)]
@@ -33,7 +37,7 @@ SYMBOLS = [
     "xyst_halo_upload", "xyst_halo_sum", "xyst_allreduce_min", "xyst_allreduce_sum", "xyst_launch_count",
     "xyst_nedge", "xyst_kernel_time", "xyst_csr_upload", "xyst_csr_mult", "xyst_cg_setup",
     "xyst_cg_solve", "xyst_cg_get_x", "xyst_zalcg_config", "xyst_zalcg_mesh_upload", "xyst_zalcg_rhs",
-    "xyst_zalcg_step", "xyst_kozcg_mesh_upload", "xyst_kozcg_rhs", "xyst_kozcg_step",
+    "xyst_zalcg_step", "xyst_laxcg_config", "xyst_steady", "xyst_kozcg_mesh_upload", "xyst_kozcg_rhs", "xyst_kozcg_step",
 ]
 
 
@@ -86,6 +90,8 @@ def lib():
     L.xyst_zalcg_mesh_upload.argtypes = L.xyst_mesh_upload.argtypes
     L.xyst_zalcg_rhs.argtypes = [C.c_void_p, C.c_double]
     L.xyst_zalcg_step.argtypes = [C.c_void_p, C.c_double]
+    L.xyst_laxcg_config.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_steady.argtypes = [C.c_void_p, C.c_int]
     L.xyst_kozcg_mesh_upload.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 3 + [C.c_size_t] + [C.c_void_p] * 5
     L.xyst_kozcg_rhs.argtypes = [C.c_void_p, C.c_double]
     L.xyst_kozcg_step.argtypes = [C.c_void_p, C.c_double]
@@ -149,6 +155,13 @@ class Context:
             mask |= 1 << (c_ - 1)
         zp = ZalParams(int(fct), int(fctclip), mask, 0, fctdif)
         self._ck(self.L.xyst_zalcg_config(self.h, C.byref(zp)))
+
+    def laxcg_config(self, rgas=287.052874, turkel=0.5, velinf=(1.0, 1.0, 1.0)):
+        p = LaxParams(rgas, turkel, (C.c_double * 3)(*velinf))
+        self._ck(self.L.xyst_laxcg_config(self.h, C.byref(p)))
+
+    def steady(self, on=True):
+        self._ck(self.L.xyst_steady(self.h, int(on)))
 
     def kozcg_mesh_upload(self, x, y, z, inpoel, vol, v, Sn=None, Sc=None):
         x, y, z, vol, v = map(_f64, (x, y, z, vol, v))

@@ -171,6 +171,10 @@ struct xyst_ctx {
   DevBuf< double > sh_part, sh_sendbuf, sh_recvbuf;
   size_t nsh = 0, nsend = 0;
   bool rb_pending = false;              // Rb of the current state already in flight on aux_stream
+  // LaxCG: W holds (p,u,v,w,T); Wn = these at time level n. Steady state: local time steps.
+  bool lax = false, steady = false;
+  double rgas = 0.0, kvinf = 0.0;
+  DevBuf< double > Wn, dtp;              // [5][NP], [NP]
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
   // ZalCG: integrals stride, FCT parameters, P/Q (C) and low-order solution
   int dstride = 3;
@@ -200,7 +204,9 @@ namespace {
 // ---------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------
-struct DParams { double gamma, stab2coef; int flux, stab2, exact; };
+struct DParams { double gamma, stab2coef; int flux, stab2, exact; double rgas, kvinf; };
+// what the node kernels need to convert between variable sets; rgas > 0 selects LaxCG
+struct Mode { double gamma, rgas, kvinf; };
 
 // Primitive variables from conserved ones, Riemann.cpp:211-227
 __device__ __forceinline__ void primitive( const double u[NC], double w[NC] ) {
@@ -209,6 +215,28 @@ __device__ __forceinline__ void primitive( const double u[NC], double w[NC] ) {
   w[2] = u[2] / w[0];
   w[3] = u[3] / w[0];
   w[4] = u[4] / w[0] - 0.5*(w[1]*w[1] + w[2]*w[2] + w[3]*w[3]);
+}
+
+// LaxCG::primitive, LaxCG.cpp:115-137: (r,ru,rv,rw,rE) -> (p,u,v,w,T)
+__device__ __forceinline__ void lax_primitive( const double u[NC], double w[NC], double gamma, double rgas ) {
+  double r = u[0];
+  double uu = u[1]/r, vv = u[2]/r, ww = u[3]/r;
+  double p = (u[4] - 0.5*r*(uu*uu + vv*vv + ww*ww)) * (gamma-1.0);
+  w[0] = p; w[1] = uu; w[2] = vv; w[3] = ww; w[4] = p/r/rgas;
+}
+// LaxCG::conservative, LaxCG.cpp:139-164
+__device__ __forceinline__ void lax_conservative( const double w[NC], double u[NC], double gamma, double rgas ) {
+  double p = w[0], uu = w[1], vv = w[2], ww = w[3], T = w[4];
+  double r = p/T/rgas;
+  u[0] = r; u[1] = r*uu; u[2] = r*vv; u[3] = r*ww;
+  u[4] = p/(gamma-1.0) + 0.5*r*(uu*uu + vv*vv + ww*ww);
+}
+__device__ __forceinline__ void primitive_of( const double u[NC], double w[NC], const Mode& M ) {
+  if (M.rgas > 0.0) lax_primitive( u, w, M.gamma, M.rgas ); else primitive( u, w );
+}
+// lax::refvel, Lax.cpp:344-360
+__device__ __forceinline__ double lax_refvel( double r, double p, double v, double gamma, double kvinf ) {
+  return fmin( sqrt( gamma * p / r ), fmax( v, kvinf ) );
 }
 
 // 8-byte asynchronous global->shared copy (LDGSTS): in flight without holding a register
@@ -222,14 +250,14 @@ template< int N > __device__ __forceinline__ void cp_async_wait() { asm volatile
 
 // reference layout [node][comp] -> SoA state + primitives
 __global__ void k_set_state( size_t n, size_t NP, const double* __restrict__ A,
-                             double* __restrict__ U, double* __restrict__ W )
+                             double* __restrict__ U, double* __restrict__ W, Mode M )
 {
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= n) return;
   double u[NC], w[NC];
   #pragma unroll
   for (int c=0; c<NC; ++c) u[c] = A[p*NC+c];
-  primitive( u, w );
+  primitive_of( u, w, M );
   #pragma unroll
   for (int c=0; c<NC; ++c) { U[c*NP+p] = u[c]; W[c*NP+p] = w[c]; }
 }
@@ -300,10 +328,43 @@ __global__ void k_bnd_grad( int nbn, size_t NP, const int* __restrict__ bn_off, 
 __global__ void k_bnd_rhs( int nbn, size_t NP, const int* __restrict__ bn_off, const int* __restrict__ bn_face,
                            const int* __restrict__ tri, const unsigned char* __restrict__ besym,
                            const double* __restrict__ fn, const double* __restrict__ U,
-                           double* __restrict__ Rb, double gamma )
+                           double* __restrict__ Rb, double gamma, const double* __restrict__ W, double rgas )
 {
   int b = blockIdx.x*blockDim.x + threadIdx.x;
   if (b >= nbn) return;
+  if (rgas > 0.0) {                       // lax::advbnd, Lax.cpp:840-950, on (p,u,v,w,T)
+    double acc[NC] = { 0, 0, 0, 0, 0 };
+    for (int i=bn_off[b]; i<bn_off[b+1]; ++i) {
+      int f = bn_face[i] >> 2, k = bn_face[i] & 3;
+      int N[3] = { tri[f*3+0], tri[f*3+1], tri[f*3+2] };
+      double n[3] = { fn[(size_t)f*3+0], fn[(size_t)f*3+1], fn[(size_t)f*3+2] };
+      double fl[NC][3];
+      #pragma unroll
+      for (int m=0; m<3; ++m) {
+        double pr = W[N[m]], uu = W[NP+N[m]], vv = W[2*NP+N[m]], ww = W[3*NP+N[m]], T = W[4*NP+N[m]];
+        double rA = pr/T/rgas;
+        double ruA = uu * rA, rvA = vv * rA, rwA = ww * rA;
+        double reA = pr/(gamma-1.0) + 0.5*(ruA*ruA + rvA*rvA + rwA*rwA)/rA;
+        double vn = besym[f*3+m] ? 0.0 : (n[0]*uu + n[1]*vv + n[2]*ww);
+        fl[0][m] = rA*vn;
+        fl[1][m] = ruA*vn + pr*n[0];
+        fl[2][m] = rvA*vn + pr*n[1];
+        fl[3][m] = rwA*vn + pr*n[2];
+        fl[4][m] = (reA + pr)*vn;
+      }
+      #pragma unroll
+      for (int c=0; c<NC; ++c) {
+        double fab = (fl[c][0] + fl[c][1])/4.0;
+        double fbc = (fl[c][1] + fl[c][2])/4.0;
+        double fca = (fl[c][2] + fl[c][0])/4.0;
+        double add = k == 0 ? fab + fca + fl[c][0] : (k == 1 ? fab + fbc + fl[c][1] : fbc + fca + fl[c][2]);
+        acc[c] += add;
+      }
+    }
+    #pragma unroll
+    for (int c=0; c<NC; ++c) Rb[(size_t)b*NC+c] = acc[c];
+    return;
+  }
   double acc[NC] = { 0, 0, 0, 0, 0 };
   for (int i=bn_off[b]; i<bn_off[b+1]; ++i) {
     int f = bn_face[i] >> 2, k = bn_face[i] & 3;
@@ -635,6 +696,125 @@ __device__ __forceinline__ void hllc( double l[NC], double r[NC], const double n
   }
 }
 
+// lax::sigvel, Lax.cpp:362-388: signal velocities of the preconditioned system
+__device__ __forceinline__ void lax_sigvel( double p, double T, double v, double vn, const DParams& P,
+                                            double& vpri, double& cpri )
+{
+  double g = P.gamma, rgas = P.rgas;
+  double cp = g*rgas/(g-1.0);
+  double r = p/T/rgas;
+  double rp = r/p;
+  double rt = -r/T;
+  double vr = lax_refvel( r, p, v, g, P.kvinf );
+  double vr2 = vr*vr;
+  double beta = rp + rt/r/cp;
+  double alpha = 0.5*(1.0 - beta*vr2);
+  vpri = vn*(1.0 - alpha);
+  cpri = sqrt( alpha*alpha*vn*vn + vr2 );
+}
+
+// edge-end state (p,u,v,w,T) -> conserved, Lax.cpp:438-451
+__device__ __forceinline__ void lax_edge_conserved( double l[NC], double pL, const DParams& P ) {
+  l[0] = pL/l[4]/P.rgas;
+  l[1] *= l[0]; l[2] *= l[0]; l[3] *= l[0];
+  l[4] = pL/(P.gamma-1.0) + 0.5*(l[1]*l[1] + l[2]*l[2] + l[3]*l[3])/l[0];
+}
+
+// lax::rusanov, Lax.cpp:390-511
+__device__ __forceinline__ void lax_rusanov( double l[NC], double r[NC], const double n[3],
+                                             const DParams& P, double f[NC] )
+{
+  double nx = n[0], ny = n[1], nz = n[2];
+  double vnL = l[1]*nx + l[2]*ny + l[3]*nz;
+  double vnR = r[1]*nx + r[2]*ny + r[3]*nz;
+  double pL = l[0], pR = r[0];
+  double len = sqrt( nx*nx + ny*ny + nz*nz );
+  double vpL, cpL, vpR, cpR;
+  lax_sigvel( l[0], l[4], sqrt( l[1]*l[1] + l[2]*l[2] + l[3]*l[3] ), vnL, P, vpL, cpL );
+  lax_sigvel( r[0], r[4], sqrt( r[1]*r[1] + r[2]*r[2] + r[3]*r[3] ), vnR, P, vpR, cpR );
+  lax_edge_conserved( l, pL, P );
+  lax_edge_conserved( r, pR, P );
+  double sp = fmax( fabs(vpL-cpL), fmax( fabs(vpR-cpR), fmax( fabs(vpL+cpL), fabs(vpR+cpR) ) ) );
+  double fw = fmax( -sp, sp ) * len;
+  f[0] = l[0]*vnL + r[0]*vnR + fw*(r[0] - l[0]);
+  f[1] = l[1]*vnL + r[1]*vnR + (pL + pR)*nx + fw*(r[1] - l[1]);
+  f[2] = l[2]*vnL + r[2]*vnR + (pL + pR)*ny + fw*(r[2] - l[2]);
+  f[3] = l[3]*vnL + r[3]*vnR + (pL + pR)*nz + fw*(r[3] - l[3]);
+  f[4] = (l[4] + pL)*vnL + (r[4] + pR)*vnR + fw*(r[4] - l[4]);
+  if (P.stab2) {
+    double fws = P.stab2coef * fw;
+    #pragma unroll
+    for (int c=0; c<NC; ++c) f[c] -= fws*(l[c] - r[c]);
+  }
+}
+
+// lax::hllc, Lax.cpp:513-723 (wave speed option 3: symmetric +-sp; no artificial viscosity)
+__device__ __forceinline__ void lax_hllc( double l[NC], double r[NC], const double n[3],
+                                          const DParams& P, double f[NC] )
+{
+  double nx = -n[0], ny = -n[1], nz = -n[2];
+  double len = sqrt( nx*nx + ny*ny + nz*nz );
+  nx /= len; ny /= len; nz /= len;
+  double qL = l[1]*nx + l[2]*ny + l[3]*nz;
+  double qR = r[1]*nx + r[2]*ny + r[3]*nz;
+  double pL = l[0], pR = r[0];
+  double vpL, cpL, vpR, cpR;
+  lax_sigvel( l[0], l[4], sqrt( l[1]*l[1] + l[2]*l[2] + l[3]*l[3] ), qL*len, P, vpL, cpL );
+  lax_sigvel( r[0], r[4], sqrt( r[1]*r[1] + r[2]*r[2] + r[3]*r[3] ), qR*len, P, vpR, cpR );
+  lax_edge_conserved( l, pL, P );
+  lax_edge_conserved( r, pR, P );
+  double sp = fmax( fabs(vpL-cpL), fmax( fabs(vpR-cpR), fmax( fabs(vpL+cpL), fabs(vpR+cpR) ) ) );
+  double sL = -sp, sR = +sp;
+  double tL = sL - qL;
+  double tR = sR - qR;
+  double sM = (r[0]*qR*tR - l[0]*qL*tL + pL - pR) / (r[0]*tR - l[0]*tL);
+  double pS = pL - l[0]*tL*(qL - sM);
+  double uL[NC], uR[NC];
+  double s = sL - sM;
+  uL[0] = tL*l[0]/s;
+  uL[1] = (tL*l[1] + (pS-pL)*nx)/s;
+  uL[2] = (tL*l[2] + (pS-pL)*ny)/s;
+  uL[3] = (tL*l[3] + (pS-pL)*nz)/s;
+  uL[4] = (tL*l[4] - pL*qL + pS*sM)/s;
+  s = sR - sM;
+  uR[0] = tR*r[0]/s;
+  uR[1] = (tR*r[1] + (pS-pR)*nx)/s;
+  uR[2] = (tR*r[2] + (pS-pR)*ny)/s;
+  uR[3] = (tR*r[3] + (pS-pR)*nz)/s;
+  uR[4] = (tR*r[4] - pR*qR + pS*sM)/s;
+  double L2 = -2.0*len;
+  nx *= L2; ny *= L2; nz *= L2;
+  if (sL > 0.0) {
+    double qL2 = qL * L2;
+    f[0] = l[0]*qL2;
+    f[1] = l[1]*qL2 + pL*nx;
+    f[2] = l[2]*qL2 + pL*ny;
+    f[3] = l[3]*qL2 + pL*nz;
+    f[4] = (l[4] + pL)*qL2;
+  } else if (sL <= 0.0 && sM > 0.0) {
+    double qL2 = qL * L2, sL2 = sL * L2;
+    f[0] = l[0]*qL2 + sL2*(uL[0] - l[0]);
+    f[1] = l[1]*qL2 + pL*nx + sL2*(uL[1] - l[1]);
+    f[2] = l[2]*qL2 + pL*ny + sL2*(uL[2] - l[2]);
+    f[3] = l[3]*qL2 + pL*nz + sL2*(uL[3] - l[3]);
+    f[4] = (l[4] + pL)*qL2 + sL2*(uL[4] - l[4]);
+  } else if (sM <= 0.0 && sR >= 0.0) {
+    double qR2 = qR * L2, sR2 = sR * L2;
+    f[0] = r[0]*qR2 + sR2*(uR[0] - r[0]);
+    f[1] = r[1]*qR2 + pR*nx + sR2*(uR[1] - r[1]);
+    f[2] = r[2]*qR2 + pR*ny + sR2*(uR[2] - r[2]);
+    f[3] = r[3]*qR2 + pR*nz + sR2*(uR[3] - r[3]);
+    f[4] = (r[4] + pR)*qR2 + sR2*(uR[4] - r[4]);
+  } else {
+    double qR2 = qR * L2;
+    f[0] = r[0]*qR2;
+    f[1] = r[1]*qR2 + pR*nx;
+    f[2] = r[2]*qR2 + pR*ny;
+    f[3] = r[3]*qR2 + pR*nz;
+    f[4] = (r[4] + pR)*qR2;
+  }
+}
+
 // one thread per edge slot; a warp covers the j-th owned edge of 32 consecutive nodes.
 // The 30 gradient values of the two end nodes are fetched with cp.async straight into a
 // per-thread column of shared memory: the copies need no registers while in flight, so
@@ -667,7 +847,8 @@ k_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __r
   cp_async_wait< 0 >();
   muscl< EXACT >( gp, FLUX_THREADS, gq, FLUX_THREADS, vw, l, r );
   double f[NC];
-  if (FLUX == 0) rusanov( l, r, n, P, f ); else hllc( l, r, n, P, f );
+  if (FLUX == 0) rusanov( l, r, n, P, f ); else if (FLUX == 1) hllc( l, r, n, P, f );
+  else if (FLUX == 2) lax_rusanov( l, r, n, P, f ); else lax_hllc( l, r, n, P, f );
   #pragma unroll
   for (int c=0; c<NC; ++c) F[c*nslot+e] = f[c];
 }
@@ -703,13 +884,79 @@ __device__ __forceinline__ void rhs_sum( size_t p, int lane, long long base, int
   }
 }
 
-template< bool FUSED >
+// RK stage update of one node from its summed rhs.
+//   RieCG::solve, RieCG.cpp:1011-1021:  u = un - rk dt rhs / vol   (dt = local dtp if steady)
+//   LaxCG::solve, LaxCG.cpp:1150-1176:  (p,u,v,w,T) = (..)_n + P^-1 (-rk dt rhs / vol), then
+//   back to conserved variables; W keeps what LaxCG::primitive gives for the next stage.
+struct StageArgs { double rk, dt; const double* dtp; int stage; Mode M; };
+
+template< bool LAX >
+__device__ __forceinline__ void node_update( size_t p, size_t NP, const double acc[NC], double vp,
+    const double* __restrict__ Un, double* __restrict__ U, double* __restrict__ W,
+    double* __restrict__ Wn, double* __restrict__ UnOut, const StageArgs& A )
+{
+  double dtl = A.dtp ? A.dtp[p] : A.dt;
+  double u[NC], w[NC];
+  if (LAX) {
+    double g = A.M.gamma, rgas = A.M.rgas;
+    double wn[NC];
+    #pragma unroll
+    for (int c=0; c<NC; ++c) w[c] = W[c*NP+p];
+    if (A.stage == 0) {
+      #pragma unroll
+      for (int c=0; c<NC; ++c) { wn[c] = w[c]; Wn[c*NP+p] = w[c]; }
+    } else {
+      #pragma unroll
+      for (int c=0; c<NC; ++c) wn[c] = Wn[c*NP+p];
+    }
+    double R = -A.rk * dtl / vp;
+    // inverse of the time-derivative preconditioning matrix, LaxCG::precond :166-226
+    double pr = w[0], uu = w[1], vv = w[2], ww = w[3], T = w[4];
+    double r = pr/T/rgas;
+    double cp = g*rgas/(g-1.0);
+    double k = uu*uu + vv*vv + ww*ww;
+    double vr = lax_refvel( r, pr, sqrt(k), g, A.M.kvinf );
+    double vr2 = vr*vr;
+    double rt = -r/T;
+    double H = cp*T + k/2.0;
+    double theta = 1.0/vr2 - rt/r/cp;
+    double coef = r*cp*theta + rt;
+    double q[NC] = { R*acc[0], R*acc[1], R*acc[2], R*acc[3], R*acc[4] };
+    double wnew[NC];
+    wnew[0] = wn[0] + (rt*(H - k) + r*cp)/coef*q[0] + rt*uu/coef*q[1] + rt*vv/coef*q[2] + rt*ww/coef*q[3] + (-rt/coef)*q[4];
+    wnew[1] = wn[1] + (-uu/r)*q[0] + 1.0/r*q[1] + 0.0*q[2] + 0.0*q[3] + 0.0*q[4];
+    wnew[2] = wn[2] + (-vv/r)*q[0] + 0.0*q[1] + 1.0/r*q[2] + 0.0*q[3] + 0.0*q[4];
+    wnew[3] = wn[3] + (-ww/r)*q[0] + 0.0*q[1] + 0.0*q[2] + 1.0/r*q[3] + 0.0*q[4];
+    wnew[4] = wn[4] + (-(theta*(H - k) - 1.0)/coef)*q[0] + (-theta*uu/coef)*q[1] + (-theta*vv/coef)*q[2]
+                    + (-theta*ww/coef)*q[3] + theta/coef*q[4];
+    lax_conservative( wnew, u, g, rgas );
+    lax_primitive( u, w, g, rgas );
+    #pragma unroll
+    for (int c=0; c<NC; ++c) { U[c*NP+p] = u[c]; W[c*NP+p] = w[c]; }
+    if (A.stage == 2) {                   // conservative( m_un ) for the diagnostics, :1196
+      double un[NC];
+      lax_conservative( wn, un, g, rgas );
+      #pragma unroll
+      for (int c=0; c<NC; ++c) UnOut[c*NP+p] = un[c];
+    }
+  } else {
+    double rkdt = A.rk * dtl;
+    #pragma unroll
+    for (int c=0; c<NC; ++c) { u[c] = Un[c*NP+p] - rkdt * acc[c] / vp; U[c*NP+p] = u[c]; }
+    primitive( u, w );
+    #pragma unroll
+    for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+  }
+}
+
+template< bool FUSED, bool LAX >
 __global__ void __launch_bounds__(NODE_THREADS, RHS_MINB)
 k_rhs_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
             const double* __restrict__ F, size_t nslot, const int* __restrict__ bslot,
             const double* __restrict__ Rb, const double* __restrict__ S, int src_mask,
             const double* __restrict__ v, const double* __restrict__ vol, const double* __restrict__ Un,
-            double rkdt, double* __restrict__ U, double* __restrict__ W, double* __restrict__ R )
+            StageArgs A, double* __restrict__ U, double* __restrict__ W, double* __restrict__ R,
+            double* __restrict__ Wn, double* __restrict__ UnOut )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -720,13 +967,7 @@ k_rhs_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, cons
   double acc[NC];
   rhs_sum( p, lane, base, kmax, inc_e, F, nslot, bslot, Rb, S, src_mask, v, acc );
   if (FUSED) {
-    double vp = vol[p];
-    double u[NC], w[NC];
-    #pragma unroll
-    for (int c=0; c<NC; ++c) { u[c] = Un[c*NP+p] - rkdt * acc[c] / vp; U[c*NP+p] = u[c]; }
-    primitive( u, w );
-    #pragma unroll
-    for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+    node_update< LAX >( p, NP, acc, vol[p], Un, U, W, Wn, UnOut, A );
   } else {
     #pragma unroll
     for (int c=0; c<NC; ++c) R[p*NC+c] = acc[c];
@@ -754,8 +995,8 @@ template< bool FUSED >
 __global__ void k_rhs_finish( int nsh, size_t NP, const int* __restrict__ sh_node, const int* __restrict__ roff,
             const int* __restrict__ ridx, const double* __restrict__ part,
             const double* __restrict__ recvbuf, const double* __restrict__ vol,
-            const double* __restrict__ Un, double rkdt, double* __restrict__ U,
-            double* __restrict__ W, double* __restrict__ R )
+            const double* __restrict__ Un, StageArgs A, double* __restrict__ U,
+            double* __restrict__ W, double* __restrict__ R, double* __restrict__ Wn, double* __restrict__ UnOut )
 {
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= nsh) return;
@@ -767,10 +1008,8 @@ __global__ void k_rhs_finish( int nsh, size_t NP, const int* __restrict__ sh_nod
     acc[c] = a;
   }
   if (FUSED) {
-    double vp = vol[p], u[NC], w[NC];
-    for (int c=0; c<NC; ++c) { u[c] = Un[c*NP+p] - rkdt * acc[c] / vp; U[c*NP+p] = u[c]; }
-    primitive( u, w );
-    for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+    if (A.M.rgas > 0.0) node_update< true >( p, NP, acc, vol[p], Un, U, W, Wn, UnOut, A );
+    else node_update< false >( p, NP, acc, vol[p], Un, U, W, Wn, UnOut, A );
   } else {
     for (int c=0; c<NC; ++c) R[p*NC+c] = acc[c];
   }
@@ -778,17 +1017,16 @@ __global__ void k_rhs_finish( int nsh, size_t NP, const int* __restrict__ sh_nod
 
 // unfused RK update from a materialised R (drop-in for RieCG::solve :1016-1021)
 __global__ void k_update( size_t npoin, size_t NP, const double* __restrict__ R, const double* __restrict__ vol,
-                          const double* __restrict__ Un, double rkdt, double* __restrict__ U,
-                          double* __restrict__ W )
+                          const double* __restrict__ Un, StageArgs A, double* __restrict__ U,
+                          double* __restrict__ W, double* __restrict__ Wn, double* __restrict__ UnOut )
 {
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= npoin) return;
-  double vp = vol[p], u[NC], w[NC];
+  double acc[NC];
   #pragma unroll
-  for (int c=0; c<NC; ++c) { u[c] = Un[c*NP+p] - rkdt * R[p*NC+c] / vp; U[c*NP+p] = u[c]; }
-  primitive( u, w );
-  #pragma unroll
-  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+  for (int c=0; c<NC; ++c) acc[c] = R[p*NC+c];
+  if (A.M.rgas > 0.0) node_update< true >( p, NP, acc, vol[p], Un, U, W, Wn, UnOut, A );
+  else node_update< false >( p, NP, acc, vol[p], Un, U, W, Wn, UnOut, A );
 }
 
 // ---------------------------------------------------------------------------------
@@ -802,7 +1040,7 @@ __global__ void k_bc( int nbc, size_t NP, const int* __restrict__ node, const in
                       const int* __restrict__ symoff, const double* __restrict__ sym_n,
                       const int* __restrict__ faroff, const double* __restrict__ far_n, FarState fs,
                       const int* __restrict__ pre, const double* __restrict__ pre_val,
-                      double gamma, double* __restrict__ U, double* __restrict__ W )
+                      double gamma, double* __restrict__ U, double* __restrict__ W, Mode M )
 {
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= nbc) return;
@@ -843,7 +1081,7 @@ __global__ void k_bc( int nbc, size_t NP, const int* __restrict__ node, const in
   }
   double w[NC];
   for (int c=0; c<NC; ++c) U[c*NP+p] = u[c];
-  primitive( u, w );
+  primitive_of( u, w, M );
   for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
 }
 
@@ -880,7 +1118,7 @@ __device__ __forceinline__ void block_reduce( double v[NV], double* __restrict__
 
 __global__ void __launch_bounds__(RED_THREADS)
 k_dt( size_t npoin, size_t NP, const double* __restrict__ U, const double* __restrict__ vol, double gamma,
-      double* __restrict__ part )
+      double* __restrict__ part, Mode M, double cfl, double* __restrict__ dtp )
 {
   double m[1] = { 1.7976931348623157e308 };
   const size_t stride = (size_t)gridDim.x*blockDim.x;
@@ -896,11 +1134,32 @@ k_dt( size_t npoin, size_t NP, const double* __restrict__ U, const double* __res
     #pragma unroll
     for (int k=0; k<4; ++k) {
       double r = a[k][0], u = a[k][1]/r, v = a[k][2]/r, w = a[k][3]/r;
-      double pr = (a[k][4] - 0.5*r*(u*u + v*v + w*w)) * (gamma-1.0);
-      double c = sqrt( gamma * fmax(pr,0.0) / r );
       double L = cbrt( a[k][5] );
-      double vel = sqrt( u*u + v*v + w*w );
-      m[0] = fmin( m[0], L / fmax( vel+c, 1.0e-8 ) );
+      double e;
+      if (M.rgas > 0.0) {                  // LaxCG::charvel, LaxCG.cpp:228-259
+        double cp = gamma*M.rgas/(gamma-1.0);
+        double kk = u*u + v*v + w*w;
+        double ei = a[k][4]/r - kk/2.0;
+        double pr = (r*ei) * (gamma-1.0);
+        double T = pr/r/M.rgas;
+        double rp = r/pr;
+        double rt = -r/T;
+        double vel = sqrt( kk );
+        double vr = lax_refvel( r, pr, vel, gamma, M.kvinf );
+        double vr2 = vr*vr;
+        double beta = rp + rt/r/cp;
+        double alpha = 0.5*(1.0 - beta*vr2);
+        double vpri = vel*(1.0 - alpha);
+        double cpri = sqrt( alpha*alpha*kk + vr2 );
+        e = L / fmax( fabs(vpri) + cpri, 1.0e-8 );
+      } else {
+        double pr = (a[k][4] - 0.5*r*(u*u + v*v + w*w)) * (gamma-1.0);
+        double c = sqrt( gamma * fmax(pr,0.0) / r );
+        double vel = sqrt( u*u + v*v + w*w );
+        e = L / fmax( vel+c, 1.0e-8 );
+      }
+      if (dtp && p0 + k*stride < npoin) dtp[p0 + k*stride] = e * cfl;   // local time step (steady)
+      m[0] = fmin( m[0], e );
     }
   }
   block_reduce< 1, true >( m, part );
@@ -1624,8 +1883,9 @@ struct ProfScope {
 };
 
 DParams dparams( const xyst_ctx* c ) {
-  return DParams{ c->prm.gamma, c->prm.stab2coef, c->prm.flux, c->prm.stab2, c->prm.exact_muscl };
+  return DParams{ c->prm.gamma, c->prm.stab2coef, c->prm.flux, c->prm.stab2, c->prm.exact_muscl, c->rgas, c->kvinf };
 }
+Mode mode( const xyst_ctx* c ) { return Mode{ c->prm.gamma, c->lax ? c->rgas : 0.0, c->kvinf }; }
 
 void need_mesh( xyst_ctx* c ) { if (!c->npoin) throw std::runtime_error( "no mesh uploaded" ); }
 
@@ -1665,7 +1925,7 @@ void do_grad( xyst_ctx* c )
       c->tri.p, c->fn.p, c->W.p, c->Gb.p ); ++c->launches;
     CK( cudaEventRecord( c->ev_d, c->aux_stream ) );
     k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, c->aux_stream >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
-      c->tri.p, c->besym.p, c->fn.p, c->U.p, c->Rb.p, c->prm.gamma ); ++c->launches;
+      c->tri.p, c->besym.p, c->fn.p, c->U.p, c->Rb.p, c->prm.gamma, c->W.p, c->rgas ); ++c->launches;
     CK( cudaEventRecord( c->ev_e, c->aux_stream ) );
     c->rb_pending = true;
   } else if (c->nbn) {
@@ -1704,16 +1964,21 @@ void do_flux( xyst_ctx* c )
   if (!g) return;
   #define LAUNCH_FLUX( EX, FL ) k_flux_edge< EX, FL ><<< g, FLUX_THREADS, 0, s >>>( c->nslot, c->NP, c->ep.p, \
       c->eq.p, c->D.p, c->W.p, c->X.p, c->G.p, c->F.p, P )
-  if (P.exact) { if (P.flux == 0) LAUNCH_FLUX( true, 0 ); else LAUNCH_FLUX( true, 1 ); }
-  else         { if (P.flux == 0) LAUNCH_FLUX( false, 0 ); else LAUNCH_FLUX( false, 1 ); }
+  int fl = P.flux + (c->lax ? 2 : 0);
+  if (P.exact) { if (fl == 0) LAUNCH_FLUX( true, 0 ); else if (fl == 1) LAUNCH_FLUX( true, 1 );
+                 else if (fl == 2) LAUNCH_FLUX( true, 2 ); else LAUNCH_FLUX( true, 3 ); }
+  else         { if (fl == 0) LAUNCH_FLUX( false, 0 ); else if (fl == 1) LAUNCH_FLUX( false, 1 );
+                 else if (fl == 2) LAUNCH_FLUX( false, 2 ); else LAUNCH_FLUX( false, 3 ); }
   #undef LAUNCH_FLUX
   ++c->launches;
 }
 
+static const double rkcoef[3] = { 1.0/3.0, 1.0/2.0, 1.0 };   // RieCG.cpp:41
+
 // nodal gather of the rhs; fused = apply the RK update in the same pass
 // Uin: conserved state the fluxes were computed from; Un: state at time level n;
 // Uout: where the updated state goes (may alias Uin)
-void do_rhs_nodes( xyst_ctx* c, bool fused, double rkdt, const double* Uin, const double* Un, double* Uout )
+void do_rhs_nodes( xyst_ctx* c, bool fused, int stage, double dt, const double* Uin, const double* Un, double* Uout )
 {
   auto s = c->stream;
   if (c->rb_pending) {                   // computed on the side stream during this stage's do_grad
@@ -1721,8 +1986,9 @@ void do_rhs_nodes( xyst_ctx* c, bool fused, double rkdt, const double* Uin, cons
     c->rb_pending = false;
   } else if (c->nbn) {
     k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
-      c->tri.p, c->besym.p, c->fn.p, Uin, c->Rb.p, c->prm.gamma ); ++c->launches;
+      c->tri.p, c->besym.p, c->fn.p, Uin, c->Rb.p, c->prm.gamma, c->W.p, c->rgas ); ++c->launches;
   }
+  StageArgs A{ rkcoef[stage], dt, c->steady ? c->dtp.p : nullptr, stage, mode( c ) };
   bool halo = c->nsh > 0 && c->comm;
   if (halo) {
     k_rhs_shared<<< nblk( c->nsh, 128 ), 128, 0, s >>>( (int)c->nsh, c->sh_node.p, c->sl_base.p,
@@ -1732,12 +1998,15 @@ void do_rhs_nodes( xyst_ctx* c, bool fused, double rkdt, const double* Uin, cons
   {
     ProfScope ps( c, fused ? "update" : "rhsnode" );
     unsigned g = nblk( c->nslice*32, NODE_THREADS );
-    if (fused)
-      k_rhs_node< true ><<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
-        c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, rkdt, Uout, c->W.p, c->R.p );
+    if (fused && c->lax)
+      k_rhs_node< true, true ><<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
+        c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p );
+    else if (fused)
+      k_rhs_node< true, false ><<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
+        c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p );
     else
-      k_rhs_node< false ><<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
-        c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, rkdt, Uout, c->W.p, c->R.p );
+      k_rhs_node< false, false ><<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
+        c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p );
     ++c->launches;
   }
   if (halo) {
@@ -1745,10 +2014,10 @@ void do_rhs_nodes( xyst_ctx* c, bool fused, double rkdt, const double* Uin, cons
     unsigned g = nblk( c->nsh, 128 );
     if (fused)
       k_rhs_finish< true ><<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
-        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, rkdt, Uout, c->W.p, c->R.p );
+        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p );
     else
       k_rhs_finish< false ><<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
-        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, rkdt, Uout, c->W.p, c->R.p );
+        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p );
     ++c->launches;
   }
   CK( cudaGetLastError() );
@@ -1760,11 +2029,10 @@ void do_bc( xyst_ctx* c )
   FarState fs{ c->far_r, c->far_p, c->far_u[0], c->far_u[1], c->far_u[2] };
   k_bc<<< nblk( c->nbc, 128 ), 128, 0, c->stream >>>( (int)c->nbc, c->NP, c->bc_node.p, c->bc_dir.p,
     c->dir_mask.p, c->dir_val.p, c->bc_symoff.p, c->sym_n.p, c->bc_faroff.p, c->far_n.p, fs,
-    c->bc_pre.p, c->pre_val.p, c->prm.gamma, c->U.p, c->W.p ); ++c->launches;
+    c->bc_pre.p, c->pre_val.p, c->prm.gamma, c->U.p, c->W.p, mode( c ) ); ++c->launches;
   CK( cudaGetLastError() );
 }
 
-static const double rkcoef[3] = { 1.0/3.0, 1.0/2.0, 1.0 };   // RieCG.cpp:41
 
 void save_un( xyst_ctx* c ) {           // RieCG.cpp:1011  m_un = m_u
   CK( cudaMemcpyAsync( c->Un.p, c->U.p, c->NP*NC*sizeof(double), cudaMemcpyDeviceToDevice, c->stream ) );
@@ -2011,7 +2279,7 @@ void zal_flux_and_bnd( xyst_ctx* c, double dt )
 {
   auto s = c->stream;
   if (c->nbn) { k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
-                  c->tri.p, c->besym.p, c->fn.p, c->U.p, c->Rb.p, c->prm.gamma ); ++c->launches; }
+                  c->tri.p, c->besym.p, c->fn.p, c->U.p, c->Rb.p, c->prm.gamma, c->W.p, c->rgas ); ++c->launches; }
   { ProfScope ps( c, "zalflux" );
     k_zal_flux_edge<<< nblk( c->nslot, 128 ), 128, 0, s >>>( c->nslot, c->NP, c->ep.p, c->eq.p, c->D.p, c->U.p, c->X.p,
       dt, dparams( c ), c->F.p ); ++c->launches; }
@@ -2140,7 +2408,7 @@ int xyst_state_set( xyst_ctx* c, const double* U )
   need_mesh( c );
   if (c->rb_pending) { CK( cudaStreamSynchronize( c->aux_stream ) ); c->rb_pending = false; }
   CK( cudaMemcpyAsync( c->stage.p, U, c->npoin*NC*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
-  k_set_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->stage.p, c->U.p, c->W.p );
+  k_set_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->stage.p, c->U.p, c->W.p, mode( c ) );
   ++c->launches;
   CK( cudaGetLastError() );
   CK( cudaStreamSynchronize( c->stream ) );
@@ -2180,7 +2448,7 @@ int xyst_riecg_rhs( xyst_ctx* c )
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
   do_flux( c );
-  do_rhs_nodes( c, false, 0.0, c->U.p, c->Un.p, c->U.p );
+  do_rhs_nodes( c, false, 0, 0.0, c->U.p, c->Un.p, c->U.p );
   API_END
 }
 
@@ -2200,9 +2468,10 @@ int xyst_rk_update( xyst_ctx* c, int stage, double dt )
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
   if (stage < 0 || stage > 2) throw std::runtime_error( "stage must be 0, 1 or 2" );
-  if (stage == 0) save_un( c );
+  if (stage == 0 && !c->lax) save_un( c );
+  StageArgs A{ rkcoef[stage], dt, c->steady ? c->dtp.p : nullptr, stage, mode( c ) };
   k_update<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->Un.p,
-    rkcoef[stage]*dt, c->U.p, c->W.p ); ++c->launches;
+    A, c->U.p, c->W.p, c->Wn.p, c->Un.p ); ++c->launches;
   CK( cudaGetLastError() );
   API_END
 }
@@ -2215,7 +2484,8 @@ int xyst_dt_min( xyst_ctx* c, double cfl, double* dt )
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
   int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( c->npoin, RED_THREADS ) );
-  k_dt<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->vol.p, c->prm.gamma, c->red.p );
+  k_dt<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->vol.p, c->prm.gamma, c->red.p, mode( c ), cfl,
+    c->steady ? c->dtp.p : nullptr );
   k_reduce_final< 1, true ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, c->red.p + (size_t)RED_BLOCKS*NDIAG );
   c->launches += 2;
   CK( cudaMemcpyAsync( c->red_host, c->red.p + (size_t)RED_BLOCKS*NDIAG, sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
@@ -2232,12 +2502,14 @@ int xyst_riecg_stage( xyst_ctx* c, int stage, double dt )
   if (stage < 0 || stage > 2) throw std::runtime_error( "stage must be 0, 1 or 2" );
   do_grad( c );
   do_flux( c );
-  if (stage == 0) {     // un = u (RieCG.cpp:1011) without a copy: write the new state into the
+  if (c->lax)           // time level n is kept in (p,u,v,w,T) form (Wn); Un is refreshed at stage 2
+    do_rhs_nodes( c, true, stage, dt, c->U.p, c->Un.p, c->U.p );
+  else if (stage == 0) { // un = u (RieCG.cpp:1011) without a copy: write the new state into the
                         // other buffer and swap the roles of the two
-    do_rhs_nodes( c, true, rkcoef[stage]*dt, c->U.p, c->U.p, c->Un.p );
+    do_rhs_nodes( c, true, stage, dt, c->U.p, c->U.p, c->Un.p );
     std::swap( c->U.p, c->Un.p );
   } else
-    do_rhs_nodes( c, true, rkcoef[stage]*dt, c->U.p, c->Un.p, c->U.p );
+    do_rhs_nodes( c, true, stage, dt, c->U.p, c->Un.p, c->U.p );
   do_bc( c );
   API_END
 }
@@ -2361,6 +2633,31 @@ static int allreduce( xyst_ctx* c, double* v, int n, int op )
 }
 int xyst_allreduce_min( xyst_ctx* c, double* v, int n ) { return allreduce( c, v, n, NCCL_MIN ); }
 int xyst_allreduce_sum( xyst_ctx* c, double* v, int n ) { return allreduce( c, v, n, NCCL_SUM ); }
+
+// ---- LaxCG / steady state ---------------------------------------------------------------
+int xyst_laxcg_config( xyst_ctx* c, const xyst_laxcg_params* p )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  need_mesh( c );
+  if (!p) throw std::runtime_error( "null argument" );
+  if (!(p->rgas > 0.0)) throw std::runtime_error( "spec_gas_const must be positive" );
+  c->lax = true; c->rgas = p->rgas;
+  c->kvinf = p->turkel * std::sqrt( p->velinf[0]*p->velinf[0] + p->velinf[1]*p->velinf[1] + p->velinf[2]*p->velinf[2] );
+  c->Wn.alloc( c->NP*NC );
+  CK( cudaMemsetAsync( c->Wn.p, 0, c->NP*NC*sizeof(double), c->stream ) );
+  API_END
+}
+
+int xyst_steady( xyst_ctx* c, int on )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  need_mesh( c );
+  c->steady = on != 0;
+  if (c->steady) { c->dtp.alloc( c->NP ); CK( cudaMemsetAsync( c->dtp.p, 0, c->NP*sizeof(double), c->stream ) ); }
+  API_END
+}
 
 // ---- KozCG -----------------------------------------------------------------------------
 int xyst_kozcg_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* y, const double* z,

@@ -29,10 +29,16 @@ typedef struct xyst_host_cfg {
   double gamma, p0, cfl, dt, t0, term, stab2coef;
   double far_density, far_pressure, far_velocity[3];
   double pre_density[16], pre_pressure[16];
-  char solver[16];            /* "riecg" (default when empty) | "zalcg" */
+  char solver[16];            /* "riecg" (default when empty) | "zalcg" | "kozcg" | "laxcg" */
   int32_t fct, fctclip, nfctsys;
   int32_t fctsys[8];
   double fctdif;
+  /* steady-state local time stepping, LaxCG preconditioning, user-defined initial conditions */
+  int32_t steady;
+  uint64_t rescomp;
+  double residual;
+  double rgas, turkel, velinf[3];      /* rgas = 0: reference default 287.052874 */
+  double ic_density, ic_pressure, ic_velocity[3];
 } xyst_host_cfg;
 
 typedef struct xyst_solver xyst_solver;

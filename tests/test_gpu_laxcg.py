@@ -64,3 +64,28 @@ def test_riecg_steady_local_time_stepping_matches_oracle():
     drive_steps([ctx], kw, 5)
     o.step(5)
     assert relerr(ctx.state_get(), o.get("u")) < 1e-11
+
+
+@pytest.mark.parametrize("case", list(O.LCASES))
+def test_laxcg_host_mirror_diag_rows(case):
+    """Full drop-in path (C++ host mirror of LaxCG's setup + time loop, exact limiter divisions)
+    vs oracle and, for the serial Rusanov case, the reference's golden file."""
+    from xyst_b200 import hostapi as H
+    from host_common import fixture_to_host_mesh
+    kw = O.LCASES[case]
+    gold = O.load_golden_diag(case)
+    nsteps = int(gold[-1, 0])
+    hm = fixture_to_host_mesh(O.load_mesh(kw["mesh"]))
+    s = H.Solver.mesh(H.make_cfg(exact_muscl=True, **kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"], hm["set_tri"])
+    s.prepare(); s.attach(0); s.setup()
+    rows = s.step(nsteps)
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(nsteps); d = o.diag()
+    assert rows.shape == d.shape == gold.shape
+    for c in range(1, 8):
+        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-10 * np.abs(d[:, c]).max(), c
+    for c in range(8, 13):
+        assert (np.abs(rows[:, c] - d[:, c]) <= 1e-8 * np.abs(d[:, c])).all(), c
+    if case == "laxcg_bump":
+        assert O.numdiff_ok(rows[:, 1:13], gold[:, 1:13], 1.0e-5, 1.0e-5).all()      # diag.ndiff.cfg
+        assert (np.abs(rows[:, 3:8] - gold[:, 3:8]) <= 1e-9 * np.abs(gold[:, 3:8])).all()

@@ -46,6 +46,11 @@ Config to_cfg( const xyst_host_cfg* c ) {
   if (c->solver[0]) k.solver = c->solver;
   if (k.solver == "zalcg" || k.solver == "kozcg") { k.fct = c->fct != 0; k.fctclip = c->fctclip != 0; k.fctdif = c->fctdif;
     for (int i=0; i<c->nfctsys; ++i) k.fctsys.push_back( c->fctsys[i] ); }
+  k.steady = c->steady != 0; k.residual = c->residual; k.rescomp = c->rescomp ? c->rescomp : 1;
+  if (c->rgas != 0.0) k.rgas = c->rgas;
+  k.turkel = c->turkel; k.velinf = {{ c->velinf[0], c->velinf[1], c->velinf[2] }};
+  k.ic_density = c->ic_density; k.ic_pressure = c->ic_pressure;
+  k.ic_velocity = {{ c->ic_velocity[0], c->ic_velocity[1], c->ic_velocity[2] }};
   return k;
 }
 

@@ -45,6 +45,13 @@ inline Fn IC( const Config& cfg ) {
       real v = -std::cos(M_PI*x) * std::sin(M_PI*y);
       real w = 0.0;
       return {{ r, r*u, r*v, r*w, totalenergy( g, r, u, v, w, p ) }}; };
+  if (cfg.problem == "userdef") {               // userdef::ic :28-115, density + velocity + pressure
+    const real r = cfg.ic_density, p = cfg.ic_pressure;
+    const auto vel = cfg.ic_velocity;
+    return [g,r,p,vel]( real, real, real, real ) -> std::array< real, 5 > {
+      real ru = r*vel[0], rv = r*vel[1], rw = r*vel[2];
+      return {{ r, ru, rv, rw, totalenergy( g, r, ru/r, rv/r, rw/r, p ) }}; };
+  }
   throw std::runtime_error( "problem type ic not hooked up: " + cfg.problem );
 }
 

@@ -107,7 +107,7 @@ void Discretization::setdt( real newdt ) {
 void Discretization::next() { ++m_it; m_t += m_dt; }
 bool Discretization::finished() const {
   auto eps = std::numeric_limits< real >::epsilon();
-  return std::abs( m_t - m_cfg.term ) < eps || m_it >= m_cfg.nstep;
+  return std::abs( m_t - m_cfg.term ) < eps || m_it >= m_cfg.nstep || (m_res > 0.0 && m_res < m_cfg.residual);
 }
 
 std::vector< std::size_t > Discretization::sharedNodes() const {
@@ -125,9 +125,9 @@ RieCG::RieCG( Discretization& disc, const TetMesh& chunk, const Config& cfg )
   : m_disc( disc ), m_cfg( cfg ), m_sidetri( chunk.sidetri )
 {
   if (cfg.ncomp != 5) throw std::runtime_error( "only ncomp = 5 is supported" );
-  if (cfg.solver != "riecg" && cfg.solver != "zalcg" && cfg.solver != "kozcg")
+  if (cfg.solver != "riecg" && cfg.solver != "zalcg" && cfg.solver != "kozcg" && cfg.solver != "laxcg")
     throw std::runtime_error( "Unknown solver: " + cfg.solver );
-  m_zal = cfg.solver == "zalcg"; m_stride = m_zal ? 4 : 3; m_koz = cfg.solver == "kozcg";
+  m_zal = cfg.solver == "zalcg"; m_stride = m_zal ? 4 : 3; m_koz = cfg.solver == "kozcg"; m_lax = cfg.solver == "laxcg";
   // Transporter::matchsets as the reference executes it (Transporter.cpp:125-187 with the
   // short-circuit at :347-348): with at least one side set named in the configuration the
   // faces of ALL side sets of the mesh keep their boundary integrals; with none, no face does.
@@ -562,6 +562,14 @@ void RieCG::setup()
   ck( (m_zal ? xyst_zalcg_mesh_upload : xyst_mesh_upload)( m_ctx, np, co[0].data(), co[1].data(), co[2].data(),
                         nsup, se, si, m_triinpoel.size()/3, m_triinpoel.data(), m_besym.data(),
                         m_disc.Vol().data(), m_disc.V().data() ) );
+  if (m_lax) {                                     // LaxCG.cpp:115-259
+    xyst_laxcg_params lp{ m_cfg.rgas, m_cfg.turkel, { m_cfg.velinf[0], m_cfg.velinf[1], m_cfg.velinf[2] } };
+    ck( xyst_laxcg_config( m_ctx, &lp ) );
+  }
+  if (m_cfg.steady) {
+    if (m_zal || m_koz) throw std::runtime_error( "steady state is a RieCG/LaxCG option" );
+    ck( xyst_steady( m_ctx, 1 ) );
+  }
   if (m_zal || m_koz) {
     xyst_zalcg_params zp{};
     zp.fct = m_cfg.fct; zp.fctclip = m_cfg.fctclip; zp.fctdif = m_cfg.fctdif;
@@ -616,7 +624,10 @@ bool RieCG::step( std::vector< real >* diagrow )
   else if (m_koz) ck( xyst_kozcg_step( m_ctx, m_disc.Dt() ) ); // KozCG.cpp:691-1197
   else ck( xyst_riecg_step( m_ctx, m_disc.Dt() ) );
   if (diagrow && (m_disc.It()+1) % m_cfg.diag_iter == 0) *diagrow = diagnostics();
-  else if (diagrow) diagrow->clear();
+  else {
+    if (diagrow) diagrow->clear();
+    if (m_cfg.steady) m_disc.residual( 1.0 );      // no diagnostics this step: evalres( 1.0 ), RieCG.cpp:1055
+  }
   m_disc.next();
   if (m_disc.finished()) m_finished = true;
   return !m_finished;
@@ -646,6 +657,7 @@ std::vector< real > RieCG::diagnostics()
   for (std::size_t i=0; i<ncomp; ++i) row.push_back( std::sqrt( d[i] / mv ) );
   for (std::size_t i=0; i<ncomp; ++i) row.push_back( std::sqrt( d[ncomp+i] / mv ) );
   row.push_back( d[2*ncomp] );
+  if (m_cfg.steady) m_disc.residual( row[ 3 + ncomp + m_cfg.rescomp - 1 ] );   // evalres, RieCG.cpp:1062-1075
   if (sol) {
     for (std::size_t i=0; i<ncomp; ++i) row.push_back( std::sqrt( d[2*ncomp+1+i] / mv ) );
     for (std::size_t i=0; i<ncomp; ++i) row.push_back( d[3*ncomp+1+i] / mv );

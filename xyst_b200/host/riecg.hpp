@@ -38,6 +38,17 @@ struct Config {
   bool fct = true, fctclip = false;
   real fctdif = 1.0;
   std::vector< int > fctsys;                //!< 1-based components limited as a system
+  //! steady = true: local time stepping towards a steady state, stop when the L2 residual of
+  //! component rescomp falls below residual (Discretization.cpp:1251-1283)
+  bool steady = false;
+  real residual = 0.0;
+  std::uint64_t rescomp = 1;
+  //! LaxCG (solver = "laxcg"): gas constant, Turkel parameter, free-stream velocity
+  real rgas = 287.052874, turkel = 0.5;
+  std::array< real, 3 > velinf{{ 1.0, 1.0, 1.0 }};
+  //! ic block of user-defined problems (density, pressure, velocity)
+  real ic_density = 0.0, ic_pressure = 0.0;
+  std::array< real, 3 > ic_velocity{{ 0, 0, 0 }};
   std::vector< int > bc_sym;
   std::vector< std::vector< int > > bc_dir; //!< { setid, mask_0 .. mask_{ncomp-1} }
   std::vector< int > bc_far;
@@ -73,6 +84,8 @@ class Discretization {
     void setdt( real newdt );                            //!< :926-938
     void next();                                         //!< :941-983
     bool finished() const;                               //!< :1251-1262
+    void residual( real r ) { m_res = r; }               //!< :1267-1283
+    real m_res = 0.0;
     std::vector< std::size_t > sharedNodes() const;      //!< unique shared local ids, ascending
     std::vector< real > m_vol, m_v;
   private:
@@ -148,6 +161,7 @@ class RieCG {
     AllReduce m_allreduce;
     bool m_hostready = false;
     bool m_zal = false;
+    bool m_lax = false;                    //!< LaxCG: same setup as RieCG, preconditioned update
     bool m_koz = false;                    //!< KozCG: element-based, no edge integrals
     std::size_t m_stride = 3;
     real m_ownvol = 0.0;

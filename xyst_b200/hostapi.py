@@ -23,6 +23,9 @@ class HostCfg(C.Structure):
         ("pre_density", C.c_double * 16), ("pre_pressure", C.c_double * 16),
         ("solver", C.c_char * 16), ("fct", C.c_int32), ("fctclip", C.c_int32), ("nfctsys", C.c_int32),
         ("fctsys", C.c_int32 * 8), ("fctdif", C.c_double),
+        ("steady", C.c_int32), ("rescomp", C.c_uint64), ("residual", C.c_double),
+        ("rgas", C.c_double), ("turkel", C.c_double), ("velinf", C.c_double * 3),
+        ("ic_density", C.c_double), ("ic_pressure", C.c_double), ("ic_velocity", C.c_double * 3),
     ]
 
 
@@ -32,7 +35,9 @@ COMM_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(
 def make_cfg(problem, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0, term=1e300,
              nstep=2**63, sym=(), dir_=(), stab2=False, stab2coef=0.2, diag_iter=1, ncomp=5,
              exact_muscl=False, reforder=-1, solver="riecg", fct=True, fctclip=False, fctsys=(),
-             fctdif=1.0, **_ignored):
+             fctdif=1.0, steady=False, residual=0.0, rescomp=1, rgas=287.052874, turkel=0.5,
+             velinf=(1.0, 1.0, 1.0), far=(), far_density=0.0, far_pressure=0.0, far_velocity=(0.0, 0.0, 0.0),
+             ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0), **_ignored):
     c = HostCfg()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term
@@ -42,6 +47,13 @@ def make_cfg(problem, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0
     c.nfctsys = len(fctsys)
     for i, s_ in enumerate(fctsys):
         c.fctsys[i] = s_
+    c.steady = int(steady); c.residual = residual; c.rescomp = rescomp; c.rgas = rgas; c.turkel = turkel
+    c.nfar = len(far); c.far_density = far_density; c.far_pressure = far_pressure
+    for i, s_ in enumerate(far):
+        c.far_sets[i] = s_
+    c.ic_density = ic_density; c.ic_pressure = ic_pressure
+    for i in range(3):
+        c.velinf[i] = velinf[i]; c.far_velocity[i] = far_velocity[i]; c.ic_velocity[i] = ic_velocity[i]
     c.nsym = len(sym)
     for i, s in enumerate(sym):
         c.sym[i] = s

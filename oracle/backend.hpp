@@ -19,6 +19,7 @@
   #include "Zalesak.hpp"
   #include "Kozak.hpp"
   #include "Lax.hpp"
+  #include "Chorin.hpp"
   #include "BC.hpp"
   #include "Problems.hpp"
   #include "InciterConfig.hpp"
@@ -81,8 +82,30 @@ inline real lax_refvel( real r, real p, real v ) { return lax::refvel( r, p, v )
 inline void initialize( const Coords& coord, Fields& U, real t )
 { problems::initialize( coord, U, t, 0, {} ); }
 
-inline void dirbc( Fields& U, real t, const Coords& coord, const std::vector< std::size_t >& m )
-{ physics::dirbc( 0, U, t, coord, {}, m ); }
+inline void dirbc( Fields& U, real t, const Coords& coord, const std::vector< std::size_t >& m,
+                   const std::vector< double >& val = {} )
+{ physics::dirbc( 0, U, t, coord, {}, m, val ); }
+inline void noslipbc( Fields& U, const std::vector< std::size_t >& n, std::size_t pos ) { physics::noslipbc( U, n, pos ); }
+
+using SupEdge = std::array< std::vector< std::size_t >, 3 >;
+using SupInt = std::array< std::vector< real >, 3 >;
+inline void chorin_div( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
+                        real dt, const std::vector< real >& P, const Fields& G, const Fields& U,
+                        std::vector< real >& D, bool stab ) { chorin::div( e, d, coord, tri, dt, P, G, U, D, stab ); }
+inline void chorin_vgrad( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
+                          const Fields& U, Fields& G ) { chorin::vgrad( e, d, coord, tri, U, G ); }
+inline void chorin_grad( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
+                         const std::vector< real >& U, Fields& G ) { chorin::grad( e, d, coord, tri, U, G ); }
+inline void chorin_flux( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
+                         const Fields& U, const Fields& G, Fields& F ) { chorin::flux( e, d, coord, tri, U, G, F ); }
+inline void chorin_rhs( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
+                        const std::vector< real >& v, real t, const std::vector< real >& P, const Fields& U,
+                        const Fields& G, Fields& R ) { chorin::rhs( e, d, coord, tri, v, t, P, U, G, R ); }
+inline port::PFn PRESSURE_RHS() { return problems::PRESSURE_RHS(); }
+inline port::PFn PRESSURE_IC() { auto f = problems::PRESSURE_IC(); return [f]( real x, real y, real z ){ return f( x, y, z, 0 ); }; }
+inline port::PFn PRESSURE_SOL() { auto f = problems::PRESSURE_SOL(); if (!f) return {};
+  return [f]( real x, real y, real z ){ return f( x, y, z, 0 ); }; }
+inline std::function< std::array< real, 3 >( real, real, real ) > PRESSURE_GRAD() { return problems::PRESSURE_GRAD(); }
 inline void symbc( Fields& U, const std::vector< std::size_t >& n, const std::vector< real >& nn,
                    std::size_t pos ) { physics::symbc( U, n, nn, pos ); }
 inline void farbc( Fields& U, const std::vector< std::size_t >& n, const std::vector< real >& nn )
@@ -121,6 +144,16 @@ using port::lax_rhs;
 using port::lax_refvel;
 using port::initialize;
 using port::dirbc;
+using port::noslipbc;
+using port::chorin_div;
+using port::chorin_vgrad;
+using port::chorin_grad;
+using port::chorin_flux;
+using port::chorin_rhs;
+using port::PRESSURE_RHS;
+using port::PRESSURE_IC;
+using port::PRESSURE_SOL;
+using port::PRESSURE_GRAD;
 using port::symbc;
 using port::farbc;
 using port::prebc;

@@ -4,6 +4,7 @@
 #include <string>
 #include "driver.hpp"
 #include "cg_port.hpp"
+#include "chocg_port.hpp"
 #include "oracle.h"
 
 using namespace orc;
@@ -42,6 +43,14 @@ Cfg to_cfg( const orc_cfg* c ) {
   k.residual = c->residual; k.rescomp = c->rescomp ? c->rescomp : 1;
   k.ic_density = c->ic_density; k.ic_pressure = c->ic_pressure;
   k.ic_velocity = {{ c->ic_velocity[0], c->ic_velocity[1], c->ic_velocity[2] }};
+  k.mu = c->mu; k.dif = c->dif; k.stab = c->stab != 0; k.rk = c->rk ? c->rk : 1;
+  for (int i=0; i<c->nnoslip; ++i) k.bc_noslip.push_back( c->noslip[i] );
+  for (int i=0; i<c->ndirval; ++i) { std::vector< real > v( k.ncomp+1 ); for (std::size_t j=0; j<k.ncomp+1; ++j) v[j] = c->dirval[i][j]; k.bc_dirval.push_back( v ); }
+  k.p_iter = c->p_iter ? c->p_iter : 10; k.p_tol = c->p_tol; if (c->p_pc[0]) k.p_pc = c->p_pc;
+  for (int i=0; i<c->np_dir; ++i) k.p_bc_dir.push_back( { c->p_dir[i][0], c->p_dir[i][1] } );
+  for (int i=0; i<c->np_dirval; ++i) k.p_bc_dirval.push_back( { c->p_dirval[i][0], c->p_dirval[i][1] } );
+  for (int i=0; i<c->np_sym; ++i) k.p_bc_sym.push_back( c->p_sym[i] );
+  k.p_hydrostat = c->p_hydrostat_set ? c->p_hydrostat : ~0ULL;
   return k;
 }
 
@@ -84,7 +93,9 @@ void* orc_create( std::size_t npoin, const double* x, const double* y, const dou
     }
     std::vector< std::size_t > tg( ntet, 0 );
     if (target) for (std::size_t e=0; e<ntet; ++e) tg[e] = target[e];
-    h->run.reset( new Run( in, to_cfg(cfg), tg, nchare ) );
+    auto k = to_cfg( cfg );
+    if (k.solver == "chocg") h->run.reset( new ChoRun( in, k, tg, nchare ) );
+    else h->run.reset( new Run( in, k, tg, nchare ) );
     return h.release();
   } catch (std::exception& e) { g_err = e.what(); return nullptr; }
 }
@@ -121,15 +132,29 @@ double orc_scalar( void* hv, const char* name )
   if (n == "meshvol") return r.meshvol;
   if (n == "nchare") return static_cast< double >( r.ch.size() );
   if (n == "finished") return r.finished ? 1.0 : 0.0;
+  if (n == "pit") { if (auto c = dynamic_cast< ChoRun* >( &r )) return static_cast< double >( c->pit ); }
   return std::nan("");
 }
 
 std::size_t orc_get( void* hv, int chare, const char* name, void* out, std::size_t cap )
 {
-  auto& c = *static_cast< Handle* >( hv )->run->ch.at( static_cast< std::size_t >( chare ) );
+  auto h = static_cast< Handle* >( hv );
+  auto& c = *h->run->ch.at( static_cast< std::size_t >( chare ) );
   std::string n( name );
   if (n == "gid") return put( c.gid, out, cap );
   if (n == "inpoel") return put( c.inpoel, out, cap );
+  if (n == "pr") return put( c.pr, out, cap );
+  if (n == "div") return put( c.div, out, cap );
+  if (n == "sgrad") return putf( c.sgrad, out, cap );
+  if (n == "pgrad") return putf( c.pgrad, out, cap );
+  if (n == "mflux") return putf( c.mflux, out, cap );
+  if (n == "dirbcmaskp") return put( c.dirbcmaskp, out, cap );
+  if (n == "dirbcval") return put( c.dirbcval, out, cap );
+  if (n == "dirbcvalp") return put( c.dirbcvalp, out, cap );
+  if (n == "noslipbcnodes") return put( c.noslipbcnodes, out, cap );
+  if (n == "dp") { if (auto cr = dynamic_cast< ChoRun* >( h->run.get() )) return put( cr->cgpre.parts[static_cast<std::size_t>(chare)]->x, out, cap ); }
+  if (n == "plhs_ia") { if (auto cr = dynamic_cast< ChoRun* >( h->run.get() )) return put( cr->cgpre.parts[static_cast<std::size_t>(chare)]->S.IA(), out, cap ); }
+  if (n == "plhs_ja") { if (auto cr = dynamic_cast< ChoRun* >( h->run.get() )) return put( cr->cgpre.parts[static_cast<std::size_t>(chare)]->S.JA(), out, cap ); }
   if (n == "x") return put( c.coord[0], out, cap );
   if (n == "y") return put( c.coord[1], out, cap );
   if (n == "z") return put( c.coord[2], out, cap );

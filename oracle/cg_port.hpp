@@ -130,6 +130,15 @@ struct Part {
   std::unordered_map< std::size_t, std::size_t > lid;
   CommMap nodeCommMap;
   int index = 0;
+  // boundary conditions of the current solve (ConjugateGradients::m_dirbc, m_An)
+  std::map< std::size_t, std::vector< std::pair< int, real > > > dirbc;
+  Matrix An;
+};
+
+//! Dirichlet (local node -> {set?, value} per component) and Neumann data of one partition
+struct BCs {
+  std::unordered_map< std::size_t, std::vector< std::pair< int, real > > > dirbc;
+  std::vector< real > neubc;
 };
 
 class Solver {
@@ -182,6 +191,57 @@ class Solver {
         auto& P = *parts[c]; auto ncomp = P.A.Ncomp();
         for (const auto& [g,val] : recv[c]) { auto i = P.lid.at( g ); for (std::size_t k=0; k<ncomp; ++k) (P.*v)[i*ncomp+k] += val[k]; }
       }
+    }
+
+    bool applied = false;                  // m_apply: matrix is restored after the solve
+
+    //! init :336-428, combc :430-448, apply :451-505, comr/r :508-556
+    //! b: complete right hand sides per partition (empty: keep)
+    void init( const std::vector< std::vector< real > >& b, const std::vector< BCs >& bcs, bool apply, const std::string& pc_ ) {
+      pc = pc_;
+      for (std::size_t k=0; k<parts.size(); ++k) if (k < b.size() && !b[k].empty()) parts[k]->b = b[k];
+      applied = apply;
+      if (!apply) { setup(); return; }
+      for (std::size_t k=0; k<parts.size(); ++k) {
+        auto& P = *parts[k];
+        P.An = P.A;
+        if (!bcs[k].neubc.empty()) P.q = bcs[k].neubc; else std::fill( P.q.begin(), P.q.end(), 0.0 );
+        P.dirbc.clear();
+        for (const auto& [i,bc] : bcs[k].dirbc) P.dirbc[i] = bc;
+      }
+      // combc: Dirichlet BCs and Neumann contributions at shared nodes go to the sharers
+      std::vector< std::map< std::size_t, std::vector< std::pair< int, real > > > > dirbcc( parts.size() );
+      std::vector< std::unordered_map< std::size_t, std::vector< real > > > qc( parts.size() );
+      for (auto& pp : parts) {
+        auto& P = *pp; auto ncomp = P.A.Ncomp();
+        for (const auto& [c,n] : P.nodeCommMap)
+          for (auto g : n) {
+            auto i = P.lid.at( g );
+            auto j = P.dirbc.find( i );
+            if (j != P.dirbc.end()) dirbcc[static_cast<std::size_t>(c)][g] = j->second;
+            auto& acc = qc[static_cast<std::size_t>(c)][g];
+            if (acc.empty()) acc.assign( ncomp, 0.0 );
+            for (std::size_t d=0; d<ncomp; ++d) acc[d] += P.q[i*ncomp+d];
+          }
+      }
+      for (std::size_t k=0; k<parts.size(); ++k) {
+        auto& P = *parts[k]; auto ncomp = P.A.Ncomp();
+        for (const auto& [g,bc] : dirbcc[k]) P.dirbc[ P.lid.at(g) ] = bc;
+        for (const auto& [g,q] : qc[k]) { auto i = P.lid.at( g ); for (std::size_t c=0; c<ncomp; ++c) P.q[i*ncomp+c] += q[c]; }
+        for (std::size_t i=0; i<P.b.size(); ++i) P.b[i] += P.q[i];
+        std::fill( P.r.begin(), P.r.end(), 0.0 );
+        for (auto bi = P.dirbc.rbegin(); bi != P.dirbc.rend(); ++bi)
+          for (std::size_t j=0; j<ncomp; ++j)
+            if (bi->second[j].first) P.A.dirichlet( bi->first, bi->second[j].second, P.r, P.gid, P.nodeCommMap, j );
+      }
+      halosum( &Part::r );                                               // comr
+      for (auto& pp : parts) {
+        auto& P = *pp; auto ncomp = P.A.Ncomp();
+        for (std::size_t i=0; i<P.b.size(); ++i) P.b[i] -= P.r[i];
+        for (const auto& [i,bc] : P.dirbc)
+          for (std::size_t j=0; j<ncomp; ++j) if (bc[j].first) P.b[i*ncomp+j] = bc[j].second;
+      }
+      setup();
     }
 
     //! setup :105-126, residual :164-190, pc :213-259, initres :280-319
@@ -248,7 +308,11 @@ class Solver {
         ++it;
         auto nb = normb > 1.0e-14 ? normb : 1.0;
         nr = std::sqrt( normr );
-        if (finished || nr < tol*nb || it >= maxit) { converged = !(nr > tol*nb); return nr; }
+        if (finished || nr < tol*nb || it >= maxit) {
+          converged = !(nr > tol*nb);
+          if (applied) for (auto& pp : parts) pp->A = pp->An;          // restore, :809
+          return nr;
+        }
       }
     }
 };

@@ -102,6 +102,8 @@ prepare( const MeshInput& in, const Cfg& cfg, const std::vector< std::size_t >& 
   for (auto s : cfg.bc_sym) usersets.insert( s );
   for (auto s : cfg.bc_far) usersets.insert( s );
   for (const auto& s : cfg.bc_pre) if (!s.empty()) usersets.insert( s[0] );
+  for (const auto& s : cfg.p_bc_dir) if (!s.empty()) usersets.insert( s[0] );
+  for (auto s : cfg.p_bc_sym) usersets.insert( s );
   for (auto s : cfg.fieldout_sets) usersets.insert( s );
   for (auto s : cfg.integout_sets) usersets.insert( s );
   auto match = [&]( std::map< int, std::vector< std::size_t > >& bnd ) {
@@ -257,9 +259,10 @@ class Chare {
     std::vector< std::size_t > triinpoel;
     Fields u, un, rhs, grad;
     std::unordered_map< int, std::unordered_map< std::size_t, std::array< real, 4 > > > bnorm, bnormc;
-    std::unordered_map< Edge, std::array< real, 4 >, be::Hash<2>, be::Eq<2> > domedgeint;
+    std::unordered_map< Edge, std::array< real, 5 >, be::Hash<2>, be::Eq<2> > domedgeint;
     bool zal = false;                     // ZalCG: stride-4 integrals, no renumbering, FCT members
     bool koz = false;                     // KozCG: element-based, no edge integrals at all
+    bool cho = false;                     // ChoCG: stride-5 integrals, velocity unknowns, pressure projection
     bool lax = false;                     // LaxCG: (p,u,v,w,T) unknowns inside a stage, preconditioned update
     std::size_t stride = 3;
     Fields p, q, a;                       // ZalCG::m_p, m_q, m_a
@@ -272,6 +275,11 @@ class Chare {
     std::set< std::size_t > symbcnodeset, farbcnodeset;
     std::vector< std::uint8_t > besym;
     std::vector< real > dtp, tp;
+    // ChoCG members
+    std::vector< real > pr, div;
+    Fields sgrad, pgrad, mflux;
+    std::vector< std::size_t > dirbcmaskp, noslipbcnodes;
+    std::vector< double > dirbcval, dirbcvalp;
     std::unordered_map< std::size_t, std::vector< real > > gradc, rhsc;
     std::unordered_map< std::size_t, real > volc;
     const Cfg& cfg;
@@ -280,6 +288,7 @@ class Chare {
       : bnode( cm.bnode ), bface( cm.bface ), cfg( c )
     {
       zal = cfg.solver == "zalcg"; stride = zal ? 4 : 3; koz = cfg.solver == "kozcg"; lax = cfg.solver == "laxcg";
+      cho = cfg.solver == "chocg"; if (cho) stride = 5;
       // global2local, Reorder.cpp:279-306
       gid = cm.ginpoel;
       std::sort( gid.begin(), gid.end() );
@@ -343,10 +352,77 @@ class Chare {
       grad = Fields( n, cfg.ncomp*3 );
       if (zal || koz) { p = Fields( n, cfg.ncomp*2 ); q = Fields( n, cfg.ncomp*2 ); a = Fields( n, cfg.ncomp ); mvol = vol; }
       dtp.assign( n, 0.0 ); tp.assign( n, cfg.t0 );
+      if (cho) { pr.assign( n, 0.0 ); div.assign( n, 0.0 ); sgrad = Fields( n, 3 ); pgrad = Fields( n, 3 ); mflux = Fields( n, 3 ); }
+    }
+
+    //! ChoCG::setupDirBC, ChoCG.cpp:210-300
+    void setupDirBC( const std::vector< std::vector< int > >& cfgmask, const std::vector< std::vector< real > >& cfgval,
+                     std::size_t ncomp, std::vector< std::size_t >& mask, std::vector< double >& val ) {
+      std::unordered_map< int, std::unordered_set< std::size_t > > dir;
+      for (const auto& s : cfgmask) {
+        auto k = bface.find( s[0] );
+        if (k != bface.end()) { auto& n = dir[ k->first ];
+          for (auto f : k->second) { n.insert( triinpoel[f*3+0] ); n.insert( triinpoel[f*3+1] ); n.insert( triinpoel[f*3+2] ); } }
+      }
+      for (const auto& s : cfgmask) {
+        auto k = bnode.find( s[0] );
+        if (k != bnode.end()) { auto& n = dir[ k->first ]; for (auto g : k->second) n.insert( lid.at(g) ); }
+      }
+      std::unordered_map< int, std::vector< double > > dirval;
+      for (const auto& s : cfgval) {
+        auto k = dir.find( static_cast<int>(s[0]) );
+        if (k != dir.end()) { auto& v_ = dirval[ k->first ]; v_.resize( s.size()-1 ); for (std::size_t i=1; i<s.size(); ++i) v_[i-1] = s[i]; }
+      }
+      auto nmask = ncomp + 1;
+      std::unordered_map< std::size_t, std::pair< std::vector< int >, std::vector< double > > > dirbcset;
+      for (const auto& vec : cfgmask) {
+        if (vec.size() != nmask) throw std::runtime_error( "Incorrect Dirichlet BC mask ncomp" );
+        auto n = dir.find( vec[0] );
+        if (n != dir.end()) {
+          std::vector< double > v_( ncomp, 0.0 );
+          auto m = dirval.find( vec[0] );
+          if (m != dirval.end()) { if (m->second.size() != ncomp) throw std::runtime_error( "Incorrect Dirichlet BC val ncomp" ); v_ = m->second; }
+          for (auto p_ : n->second) {
+            auto& mv = dirbcset[p_];
+            mv.second = v_;
+            auto& mval = mv.first;
+            if (mval.empty()) mval.resize( ncomp, 0 );
+            for (std::size_t c=0; c<ncomp; ++c) if (!mval[c]) mval[c] = vec[c+1];
+          }
+        }
+      }
+      mask.clear();                        // (the reference clears only the mask list, :286)
+      for (const auto& [p_,mv] : dirbcset) {
+        mask.push_back( p_ );
+        for (auto m : mv.first) mask.push_back( static_cast< std::size_t >( m ) );
+        val.push_back( static_cast< double >( p_ ) );
+        val.insert( val.end(), mv.second.begin(), mv.second.end() );
+      }
     }
 
     //! RieCG::setupBC :109-245
     void setupBC() {
+      if (cho) {                          // ChoCG::feop :310-315; symmetry sets as below
+        dirbcval.clear(); dirbcvalp.clear();
+        setupDirBC( cfg.bc_dir, cfg.bc_dirval, cfg.ncomp, dirbcmasks, dirbcval );
+        setupDirBC( cfg.p_bc_dir, cfg.p_bc_dirval, 1, dirbcmaskp, dirbcvalp );
+        std::unordered_map< int, std::unordered_set< std::size_t > > sym;
+        for (auto s : cfg.bc_sym) {
+          auto k = bface.find( s );
+          if (k != bface.end()) { auto& n = sym[ k->first ];
+            for (auto f : k->second) { n.insert( triinpoel[f*3+0] ); n.insert( triinpoel[f*3+1] ); n.insert( triinpoel[f*3+2] ); } }
+        }
+        symbcnodeset.clear(); farbcnodeset.clear();
+        for (const auto& [s,n] : sym) symbcnodeset.insert( n.begin(), n.end() );
+        // noslip nodes, ChoCG::streamable :655-682
+        std::set< std::size_t > ns;
+        for (auto s : cfg.bc_noslip) {
+          auto k = bface.find( s );
+          if (k != bface.end()) for (auto f : k->second) { ns.insert( triinpoel[f*3+0] ); ns.insert( triinpoel[f*3+1] ); ns.insert( triinpoel[f*3+2] ); }
+        }
+        noslipbcnodes.assign( ns.begin(), ns.end() );
+        return;
+      }
       std::unordered_map< int, std::unordered_set< std::size_t > > dir;
       for (const auto& s : cfg.bc_dir) {
         auto k = bface.find( s[0] );
@@ -463,6 +539,11 @@ class Chare {
           n[1] += sig * (g[p][1] - g[q][1]) / 48.0;
           n[2] += sig * (g[p][2] - g[q][2]) / 48.0;
           if (zal) n[3] += J120;
+          if (cho) {                                               // ChoCG.cpp:441-442
+            auto J = ba[0]*cx + ba[1]*cy + ba[2]*cz;
+            n[3] += J / 120.0;
+            n[4] += (g[p][0]*g[q][0] + g[p][1]*g[q][1] + g[p][2]*g[q][2]) / J / 6.0;
+          }
         }
       }
     }
@@ -507,7 +588,7 @@ class Chare {
             dsupint[0].push_back( sig[ed] * d[ed]->second[0] );
             dsupint[0].push_back( sig[ed] * d[ed]->second[1] );
             dsupint[0].push_back( sig[ed] * d[ed]->second[2] );
-            if (zal) dsupint[0].push_back( d[ed]->second[3] );
+            for (std::size_t k=3; k<stride; ++k) dsupint[0].push_back( d[ed]->second[k] );
             domedgeint.erase( d[ed] );
           }
         }
@@ -528,7 +609,7 @@ class Chare {
             dsupint[1].push_back( sig[ed] * d[ed]->second[0] );
             dsupint[1].push_back( sig[ed] * d[ed]->second[1] );
             dsupint[1].push_back( sig[ed] * d[ed]->second[2] );
-            if (zal) dsupint[1].push_back( d[ed]->second[3] );
+            for (std::size_t k=3; k<stride; ++k) dsupint[1].push_back( d[ed]->second[k] );
             domedgeint.erase( d[ed] );
           }
         }
@@ -582,6 +663,12 @@ class Chare {
 
     //! RieCG::BC :764-785
     void BC( real t ) {
+      if (cho) {                          // ChoCG::BC :1340-1353
+        be::dirbc( u, t, coord, dirbcmasks, dirbcval );
+        be::symbc( u, symbcnodes, symbcnorms, 0 );
+        be::noslipbc( u, noslipbcnodes, 0 );
+        return;
+      }
       be::dirbc( u, t, coord, dirbcmasks );
       be::symbc( u, symbcnodes, symbcnorms, 1 );
       be::farbc( u, farbcnodes, farbcnorms );
@@ -1067,7 +1154,8 @@ class Run {
     }
 
     //! one full time step: dt, 3 x (grad, rhs, solve), diagnostics, next
-    bool step() {
+    virtual ~Run() = default;
+    virtual bool step() {
       if (finished) return false;
       real mindt = std::numeric_limits< real >::max();
       for (auto& c_ : ch) mindt = std::min( mindt, c_->mindt() );

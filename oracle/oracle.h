@@ -39,6 +39,18 @@ typedef struct orc_cfg {
   double rgas, turkel, velinf[3], residual;
   uint64_t rescomp;
   double ic_density, ic_pressure, ic_velocity[3];
+  /* ChoCG: viscosity/diffusivity, stabilisation, RK stages, noslip + valued Dirichlet BCs,
+   * pressure solve (iterations, tolerance, preconditioner, BCs, hydrostat node) */
+  double mu, dif;
+  int32_t stab;
+  uint64_t rk;
+  int32_t nnoslip; int32_t noslip[16];
+  int32_t ndirval; double dirval[16][12];
+  uint64_t p_iter; double p_tol; char p_pc[16];
+  int32_t np_dir; int32_t p_dir[16][2];
+  int32_t np_dirval; double p_dirval[16][2];
+  int32_t np_sym; int32_t p_sym[16];
+  int32_t p_hydrostat_set; uint64_t p_hydrostat;
 } orc_cfg;
 
 const char* orc_backend(void);      /* "port" or "reference" */

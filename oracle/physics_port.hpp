@@ -69,6 +69,19 @@ struct Cfg {
   // ic block of user-defined problems (Problems.cpp:28-115)
   real ic_density = 0.0, ic_pressure = 0.0;
   std::array< real, 3 > ic_velocity{{0,0,0}};
+  // ChoCG (projection method), defaults InciterConfig.cpp:1411-1412,1558-1564,1728-1748
+  real mu = 0.0, dif = 0.0;                  // mat_dyn_viscosity, mat_dyn_diffusivity
+  bool stab = true;
+  std::uint64_t rk = 1;
+  std::vector< int > bc_noslip;
+  std::vector< std::vector< real > > bc_dirval;      // { setid, val_0 .. }
+  std::uint64_t p_iter = 10;
+  real p_tol = 1.0e-3;
+  std::string p_pc = "none";
+  std::vector< std::vector< int > > p_bc_dir;        // { setid, mask }
+  std::vector< std::vector< real > > p_bc_dirval;    // { setid, val }
+  std::vector< int > p_bc_sym;
+  std::uint64_t p_hydrostat = ~0ULL;
 };
 
 //! Nodal field container with the reference's default layout [node][component]
@@ -151,8 +164,20 @@ inline std::vector< real > ic_userdef( real, real, real, real ) {           // :
   return u;
 }
 
+inline std::vector< real > ic_poiseuille( real, real y, real, real ) {      // :999-1026 (chocg)
+  auto dpdx = -0.12;
+  auto u = -dpdx * y * (1.0 - y) / 2.0 / cfg().mu;
+  return { u, 0.0, 0.0 };
+}
+
 inline ICFn IC() {                                                          // :1071-1108
   const auto& p = cfg().problem;
+  if (cfg().solver == "chocg") {             // velocity unknowns only
+    if (p == "userdef") return []( real, real, real, real ){                // :44-52
+      return std::vector< real >{ cfg().ic_velocity[0], cfg().ic_velocity[1], cfg().ic_velocity[2] }; };
+    if (p.find("poisson") != std::string::npos) return []( real, real, real, real ){ return std::vector< real >{ 0, 0, 0 }; };
+    if (p == "poiseuille") return ic_poiseuille;
+  }
   if (p == "userdef") return ic_userdef;
   if (p == "sedov") return ic_sedov;
   if (p == "sod") return ic_sod;
@@ -163,6 +188,39 @@ inline ICFn SOL() {                                                         // :
   const auto& p = cfg().problem;
   if (p == "userdef" || p == "sod" || p == "sedov" || p == "point_src") return {};
   return IC();
+}
+
+// pressure problems of the projection solvers, Problems.cpp:841-997,1172-1262
+using PFn = std::function< real( real, real, real ) >;
+inline PFn PRESSURE_RHS() {
+  const auto& p = cfg().problem;
+  if (p == "poisson_const") return []( real, real, real ){ return 6.0; };
+  if (p == "poisson_sine") return []( real x, real y, real z ){ return -M_PI * M_PI * x * y * std::sin( M_PI * z ); };
+  if (p == "poisson_sine3") return []( real x, real y, real z ){ using std::sin;
+    return -3.0 * M_PI * M_PI * sin(M_PI*x) * sin(M_PI*y) * sin(M_PI*z); };
+  if (p == "poisson_neumann") return []( real x, real y, real ){ return -3.0 * std::cos(2.0*x) * std::exp(y); };
+  return {};
+}
+inline PFn PRESSURE_IC() {
+  const auto& p = cfg().problem;
+  if (p == "userdef" || p == "slot_cyl" || p == "sheardiff" || p == "poiseuille" || p == "point_src")
+    return []( real, real, real ){ return 0.0; };
+  if (p == "poisson_const") return []( real x, real y, real z ){ return x*x + y*y + z*z; };
+  if (p == "poisson_sine") return []( real x, real y, real z ){ return x * y * std::sin( M_PI * z ); };
+  if (p == "poisson_sine3") return []( real x, real y, real z ){ using std::sin; return sin(M_PI*x) * sin(M_PI*y) * sin(M_PI*z); };
+  if (p == "poisson_neumann") return []( real x, real y, real ){ return std::cos(2.0*x) * std::exp(y); };
+  throw std::runtime_error( "oracle port: pressure ic not hooked up: " + p );
+}
+inline PFn PRESSURE_SOL() {
+  const auto& p = cfg().problem;
+  if (p == "userdef" || p == "slot_cyl" || p == "poiseuille" || p == "point_src" || p == "sheardiff") return {};
+  return PRESSURE_IC();
+}
+inline std::function< std::array< real, 3 >( real, real, real ) > PRESSURE_GRAD() {
+  if (cfg().problem == "poisson_neumann")
+    return []( real x, real y, real ) -> std::array< real, 3 > {
+      return {{ -2.0 * std::sin( 2.0 * x ) * std::exp( y ), std::cos(2.0*x) * std::exp(y), 0.0 }}; };
+  return {};
 }
 inline ICFn SRC() {                                                         // :1299-1325
   const auto& p = cfg().problem;
@@ -180,7 +238,8 @@ inline void initialize( const Coords& coord, Fields& U, real t ) {          // :
 
 // ---- BCs (BC.cpp) --------------------------------------------------------------
 inline void dirbc( Fields& U, real t, const Coords& coord,
-                   const std::vector< std::size_t >& dirbcmask )            // :29-72
+                   const std::vector< std::size_t >& dirbcmask,
+                   const std::vector< double >& dirbcval = {} )             // :29-72
 {
   auto ncomp = U.nprop();
   auto nmask = ncomp + 1;
@@ -192,8 +251,13 @@ inline void dirbc( Fields& U, real t, const Coords& coord,
     for (std::size_t c=0; c<ncomp; ++c) {
       auto mask = dirbcmask[i*nmask+1+c];
       if (mask == 1) U(p,c) = u[c];
+      else if (mask == 2 && !dirbcval.empty()) U(p,c) = dirbcval[i*nmask+1+c];
     }
   }
+}
+
+inline void noslipbc( Fields& U, const std::vector< std::size_t >& nodes, std::size_t pos ) {  // :138-150
+  for (auto p : nodes) U(p,pos+0) = U(p,pos+1) = U(p,pos+2) = 0.0;
 }
 
 inline void symbc( Fields& U, const std::vector< std::size_t >& nodes,
@@ -866,6 +930,379 @@ inline void lax_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge
   advdom_impl( coord, dsupedge, dsupint, G, U, R, flux, LoadAsIs() );
   lax_advbnd( triinpoel, coord, besym, U, R );
   src( coord, v, t, tp, R );
+}
+
+// ---- Chorin.cpp: edge operators of the projection solver ChoCG --------------------------
+// superedge integrals have stride 5: normal(3), J/120, grad_p.grad_q/(6J) (ChoCG.cpp:399-446)
+
+//! visit all domain edges of the superedge groups in the reference's order and scatter
+//! pattern: fn( p, q, integrals ) returns nothing, add( node, sign ) applies +-f
+template< class EdgeFn >
+inline void chorin_foredge( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                            const std::array< std::vector< real >, 3 >& dsupint, EdgeFn fn )
+{
+  for (std::size_t e=0; e<dsupedge[0].size()/4; ++e) {
+    const auto N = dsupedge[0].data() + e*4;
+    const auto d = dsupint[0].data();
+    fn( 0, e, N, d );
+  }
+  for (std::size_t e=0; e<dsupedge[1].size()/3; ++e) {
+    const auto N = dsupedge[1].data() + e*3;
+    const auto d = dsupint[1].data();
+    fn( 1, e, N, d );
+  }
+  for (std::size_t e=0; e<dsupedge[2].size()/2; ++e) {
+    const auto N = dsupedge[2].data() + e*2;
+    const auto d = dsupint[2].data();
+    fn( 2, e, N, d );
+  }
+}
+
+inline void crossdiv6( const Coords& coord, const std::size_t N[3], real n[3] ) {
+  const auto& x = coord[0]; const auto& y = coord[1]; const auto& z = coord[2];
+  real a[3] = { x[N[1]]-x[N[0]], y[N[1]]-y[N[0]], z[N[1]]-z[N[0]] },
+       b[3] = { x[N[2]]-x[N[0]], y[N[2]]-y[N[0]], z[N[2]]-z[N[0]] };
+  n[0] = (a[1]*b[2] - a[2]*b[1]) / 6.0;      // tk::crossdiv, Vector.hpp
+  n[1] = (a[2]*b[0] - a[0]*b[2]) / 6.0;
+  n[2] = (a[0]*b[1] - a[1]*b[0]) / 6.0;
+}
+
+//! edge divergence with optional pressure stabilisation, Chorin.cpp:34-83
+inline real chorin_div_edge( const Coords& coord, const real d[], real dt, const std::vector< real >& P,
+                             const Fields& G, const Fields& U, std::size_t p, std::size_t q, bool stab )
+{
+  real div = d[0] * (U(p,0) + U(q,0)) + d[1] * (U(p,1) + U(q,1)) + d[2] * (U(p,2) + U(q,2));
+  if (!stab) return div;
+  auto dx = coord[0][p] - coord[0][q];
+  auto dy = coord[1][p] - coord[1][q];
+  auto dz = coord[2][p] - coord[2][q];
+  auto dl = std::sqrt( dx*dx + dy*dy + dz*dz );
+  auto p2 = P[q] - P[p];
+  auto D = std::sqrt( d[0]*d[0] + d[1]*d[1] + d[2]*d[2] );
+  auto dpx = G(p,0) + G(q,0);
+  auto dpy = G(p,1) + G(q,1);
+  auto dpz = G(p,2) + G(q,2);
+  auto p4 = 0.5 * (dx*dpx + dy*dpy + dz*dpz);
+  div += D*dt/dl*(p2 + p4);
+  return div;
+}
+
+//! chorin::div, Chorin.cpp:85-209 (accumulates into D)
+inline void chorin_div( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                        const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                        const std::vector< std::size_t >& triinpoel, real dt, const std::vector< real >& P,
+                        const Fields& G, const Fields& U, std::vector< real >& D, bool stab )
+{
+  auto ed = [&]( const real* d, std::size_t p, std::size_t q ){ return chorin_div_edge( coord, d, dt, P, G, U, p, q, stab ); };
+  chorin_foredge( dsupedge, dsupint, [&]( int kind, std::size_t e, const std::size_t* N, const real* d ){
+    if (kind == 0) {
+      real f[] = { ed( d+(e*6+0)*5, N[0], N[1] ), ed( d+(e*6+1)*5, N[1], N[2] ), ed( d+(e*6+2)*5, N[2], N[0] ),
+                   ed( d+(e*6+3)*5, N[0], N[3] ), ed( d+(e*6+4)*5, N[1], N[3] ), ed( d+(e*6+5)*5, N[2], N[3] ) };
+      D[N[0]] = D[N[0]] - f[0] + f[2] - f[3];
+      D[N[1]] = D[N[1]] + f[0] - f[1] - f[4];
+      D[N[2]] = D[N[2]] + f[1] - f[2] - f[5];
+      D[N[3]] = D[N[3]] + f[3] + f[4] + f[5];
+    } else if (kind == 1) {
+      real f[] = { ed( d+(e*3+0)*5, N[0], N[1] ), ed( d+(e*3+1)*5, N[1], N[2] ), ed( d+(e*3+2)*5, N[2], N[0] ) };
+      D[N[0]] = D[N[0]] - f[0] + f[2];
+      D[N[1]] = D[N[1]] + f[0] - f[1];
+      D[N[2]] = D[N[2]] + f[1] - f[2];
+    } else {
+      real f = ed( d+e*5, N[0], N[1] );
+      D[N[0]] -= f;
+      D[N[1]] += f;
+    }
+  } );
+  for (std::size_t e=0; e<triinpoel.size()/3; ++e) {
+    const auto N = triinpoel.data() + e*3;
+    real n[3]; crossdiv6( coord, N, n );
+    auto uxA = U(N[0],0), uyA = U(N[0],1), uzA = U(N[0],2);
+    auto uxB = U(N[1],0), uyB = U(N[1],1), uzB = U(N[1],2);
+    auto uxC = U(N[2],0), uyC = U(N[2],1), uzC = U(N[2],2);
+    auto ux = (6.0*uxA + uxB + uxC)/8.0;
+    auto uy = (6.0*uyA + uyB + uyC)/8.0;
+    auto uz = (6.0*uzA + uzB + uzC)/8.0;
+    D[N[0]] += ux*n[0] + uy*n[1] + uz*n[2];
+    ux = (uxA + 6.0*uxB + uxC)/8.0;
+    uy = (uyA + 6.0*uyB + uyC)/8.0;
+    uz = (uzA + 6.0*uzB + uzC)/8.0;
+    D[N[1]] += ux*n[0] + uy*n[1] + uz*n[2];
+    ux = (uxA + uxB + 6.0*uxC)/8.0;
+    uy = (uyA + uyB + 6.0*uyC)/8.0;
+    uz = (uzA + uzB + 6.0*uzC)/8.0;
+    D[N[2]] += ux*n[0] + uy*n[1] + uz*n[2];
+  }
+}
+
+//! gradient of ncomp nodal scalars get(node,i) into G(node,i*3+j): common body of
+//! chorin::vgrad (:211-334) and chorin::grad (:336-449); accumulates
+template< class Get >
+inline void chorin_grad_impl( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                              const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                              const std::vector< std::size_t >& triinpoel, std::size_t ncomp, Get U, Fields& G )
+{
+  chorin_foredge( dsupedge, dsupint, [&]( int kind, std::size_t e, const std::size_t* N, const real* d ){
+    for (std::size_t i=0; i<ncomp; ++i) {
+      auto i3 = i*3;
+      if (kind == 0) {
+        real u[] = { U(N[0],i), U(N[1],i), U(N[2],i), U(N[3],i) };
+        for (std::size_t j=0; j<3; ++j) {
+          real f[] = { d[(e*6+0)*5+j] * (u[1] + u[0]), d[(e*6+1)*5+j] * (u[2] + u[1]), d[(e*6+2)*5+j] * (u[0] + u[2]),
+                       d[(e*6+3)*5+j] * (u[3] + u[0]), d[(e*6+4)*5+j] * (u[3] + u[1]), d[(e*6+5)*5+j] * (u[3] + u[2]) };
+          G(N[0],i3+j) = G(N[0],i3+j) - f[0] + f[2] - f[3];
+          G(N[1],i3+j) = G(N[1],i3+j) + f[0] - f[1] - f[4];
+          G(N[2],i3+j) = G(N[2],i3+j) + f[1] - f[2] - f[5];
+          G(N[3],i3+j) = G(N[3],i3+j) + f[3] + f[4] + f[5];
+        }
+      } else if (kind == 1) {
+        real u[] = { U(N[0],i), U(N[1],i), U(N[2],i) };
+        for (std::size_t j=0; j<3; ++j) {
+          real f[] = { d[(e*3+0)*5+j] * (u[1] + u[0]), d[(e*3+1)*5+j] * (u[2] + u[1]), d[(e*3+2)*5+j] * (u[0] + u[2]) };
+          G(N[0],i3+j) = G(N[0],i3+j) - f[0] + f[2];
+          G(N[1],i3+j) = G(N[1],i3+j) + f[0] - f[1];
+          G(N[2],i3+j) = G(N[2],i3+j) + f[1] - f[2];
+        }
+      } else {
+        real u[] = { U(N[0],i), U(N[1],i) };
+        for (std::size_t j=0; j<3; ++j) {
+          real f = d[e*5+j] * (u[1] + u[0]);
+          G(N[0],i3+j) -= f;
+          G(N[1],i3+j) += f;
+        }
+      }
+    }
+  } );
+  for (std::size_t e=0; e<triinpoel.size()/3; ++e) {
+    const auto N = triinpoel.data() + e*3;
+    real n[3]; crossdiv6( coord, N, n );
+    for (std::size_t i=0; i<ncomp; ++i) {
+      real u[] = { U(N[0],i), U(N[1],i), U(N[2],i) };
+      auto i3 = i*3;
+      auto f = (6.0*u[0] + u[1] + u[2])/8.0;
+      G(N[0],i3+0) += f * n[0]; G(N[0],i3+1) += f * n[1]; G(N[0],i3+2) += f * n[2];
+      f = (u[0] + 6.0*u[1] + u[2])/8.0;
+      G(N[1],i3+0) += f * n[0]; G(N[1],i3+1) += f * n[1]; G(N[1],i3+2) += f * n[2];
+      f = (u[0] + u[1] + 6.0*u[2])/8.0;
+      G(N[2],i3+0) += f * n[0]; G(N[2],i3+1) += f * n[1]; G(N[2],i3+2) += f * n[2];
+    }
+  }
+}
+
+inline void chorin_vgrad( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                          const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                          const std::vector< std::size_t >& triinpoel, const Fields& U, Fields& G )
+{ chorin_grad_impl( dsupedge, dsupint, coord, triinpoel, U.nprop(),
+                    [&]( std::size_t p, std::size_t i ){ return U(p,i); }, G ); }
+
+inline void chorin_grad( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                         const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                         const std::vector< std::size_t >& triinpoel, const std::vector< real >& U, Fields& G )
+{ chorin_grad_impl( dsupedge, dsupint, coord, triinpoel, 1,
+                    [&]( std::size_t p, std::size_t ){ return U[p]; }, G ); }
+
+//! momentum flux of an edge (:451-480) and of a point (:482-509)
+inline real chorin_flux2( const Fields& U, const Fields& G, std::size_t i, std::size_t j, std::size_t p, std::size_t q ) {
+  auto inv = U(p,i)*U(p,j) + U(q,i)*U(q,j);
+  auto eps = std::numeric_limits< real >::epsilon();
+  auto mu = cfg().mu;
+  if (mu < eps) return -inv;
+  auto vis = G(p,i*3+j) + G(p,j*3+i) + G(q,i*3+j) + G(q,j*3+i);
+  if (i == j) vis -= 2.0/3.0 * ( G(p,0) + G(p,4) + G(p,8) + G(q,0) + G(q,4) + G(q,8) );
+  return mu*vis - inv;
+}
+inline real chorin_flux1( const Fields& U, const Fields& G, std::size_t i, std::size_t j, std::size_t p ) {
+  auto inv = U(p,i)*U(p,j);
+  auto eps = std::numeric_limits< real >::epsilon();
+  auto mu = cfg().mu;
+  if (mu < eps) return -inv;
+  auto vis = G(p,i*3+j) + G(p,j*3+i);
+  if (i == j) vis -= 2.0/3.0 * ( G(p,0) + G(p,4) + G(p,8) );
+  return mu*vis - inv;
+}
+
+//! chorin::flux, Chorin.cpp:511-638 (accumulates into F)
+inline void chorin_flux( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                         const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                         const std::vector< std::size_t >& triinpoel, const Fields& U, const Fields& G, Fields& F )
+{
+  chorin_foredge( dsupedge, dsupint, [&]( int kind, std::size_t e, const std::size_t* N, const real* d ){
+    for (std::size_t i=0; i<3; ++i)
+      for (std::size_t j=0; j<3; ++j) {
+        if (kind == 0) {
+          real f[] = { d[(e*6+0)*5+j] * chorin_flux2(U,G,i,j,N[1],N[0]), d[(e*6+1)*5+j] * chorin_flux2(U,G,i,j,N[2],N[1]),
+                       d[(e*6+2)*5+j] * chorin_flux2(U,G,i,j,N[0],N[2]), d[(e*6+3)*5+j] * chorin_flux2(U,G,i,j,N[3],N[0]),
+                       d[(e*6+4)*5+j] * chorin_flux2(U,G,i,j,N[3],N[1]), d[(e*6+5)*5+j] * chorin_flux2(U,G,i,j,N[3],N[2]) };
+          F(N[0],i) = F(N[0],i) - f[0] + f[2] - f[3];
+          F(N[1],i) = F(N[1],i) + f[0] - f[1] - f[4];
+          F(N[2],i) = F(N[2],i) + f[1] - f[2] - f[5];
+          F(N[3],i) = F(N[3],i) + f[3] + f[4] + f[5];
+        } else if (kind == 1) {
+          real f[] = { d[(e*3+0)*5+j] * chorin_flux2(U,G,i,j,N[1],N[0]), d[(e*3+1)*5+j] * chorin_flux2(U,G,i,j,N[2],N[1]),
+                       d[(e*3+2)*5+j] * chorin_flux2(U,G,i,j,N[0],N[2]) };
+          F(N[0],i) = F(N[0],i) - f[0] + f[2];
+          F(N[1],i) = F(N[1],i) + f[0] - f[1];
+          F(N[2],i) = F(N[2],i) + f[1] - f[2];
+        } else {
+          real f = d[e*5+j] * chorin_flux2(U,G,i,j,N[1],N[0]);
+          F(N[0],i) -= f;
+          F(N[1],i) += f;
+        }
+      }
+  } );
+  for (std::size_t e=0; e<triinpoel.size()/3; ++e) {
+    const auto N = triinpoel.data() + e*3;
+    real n[3]; crossdiv6( coord, N, n );
+    for (std::size_t i=0; i<3; ++i) {
+      auto fxA = chorin_flux1(U,G,i,0,N[0]), fyA = chorin_flux1(U,G,i,1,N[0]), fzA = chorin_flux1(U,G,i,2,N[0]);
+      auto fxB = chorin_flux1(U,G,i,0,N[1]), fyB = chorin_flux1(U,G,i,1,N[1]), fzB = chorin_flux1(U,G,i,2,N[1]);
+      auto fxC = chorin_flux1(U,G,i,0,N[2]), fyC = chorin_flux1(U,G,i,1,N[2]), fzC = chorin_flux1(U,G,i,2,N[2]);
+      auto fx = (6.0*fxA + fxB + fxC)/8.0;
+      auto fy = (6.0*fyA + fyB + fyC)/8.0;
+      auto fz = (6.0*fzA + fzB + fzC)/8.0;
+      F(N[0],i) += fx*n[0] + fy*n[1] + fz*n[2];
+      fx = (fxA + 6.0*fxB + fxC)/8.0;
+      fy = (fyA + 6.0*fyB + fyC)/8.0;
+      fz = (fzA + 6.0*fzB + fzC)/8.0;
+      F(N[1],i) += fx*n[0] + fy*n[1] + fz*n[2];
+      fx = (fxA + fxB + 6.0*fxC)/8.0;
+      fy = (fyA + fyB + 6.0*fyC)/8.0;
+      fz = (fzA + fzB + 6.0*fzC)/8.0;
+      F(N[2],i) += fx*n[0] + fy*n[1] + fz*n[2];
+    }
+  }
+}
+
+//! advection edge flux with second-order damping, Chorin.cpp:640-709 (velocity components)
+inline void chorin_adv_damp2( const real supint[], const Fields& U, const Fields&, const std::vector< real >& P,
+                              const Coords&, std::size_t p, std::size_t q, real f[] )
+{
+  auto nx = supint[0], ny = supint[1], nz = supint[2];
+  auto uL = U(p,0), vL = U(p,1), wL = U(p,2);
+  auto vnL = uL*nx + vL*ny + wL*nz;
+  auto uR = U(q,0), vR = U(q,1), wR = U(q,2);
+  auto vnR = uR*nx + vR*ny + wR*nz;
+  real aw = 0.0;
+  if (cfg().stab) aw = std::abs( vnL + vnR ) / 2.0;
+  if (cfg().stab2) aw += cfg().stab2coef * std::max( std::abs(vnL), std::abs(vnR) );
+  auto v = supint[4] * cfg().mu;
+  auto pf = P[p] + P[q];
+  f[0] = uL*vnL + uR*vnR + pf*nx + (aw-v)*(uR-uL);
+  f[1] = vL*vnL + vR*vnR + pf*ny + (aw-v)*(vR-vL);
+  f[2] = wL*vnL + wR*vnR + pf*nz + (aw-v)*(wR-wL);
+  auto ncomp = U.nprop();
+  if (ncomp == 3) return;
+  auto d = supint[4] * cfg().dif;
+  for (std::size_t c=3; c<ncomp; ++c) f[c] = U(p,c)*vnL + U(q,c)*vnR + (aw-d)*(U(q,c)-U(p,c));
+}
+
+//! advection edge flux with fourth-order damping (limited reconstruction), Chorin.cpp:711-829
+inline void chorin_adv_damp4( const real supint[], const Fields& U, const Fields& G, const std::vector< real >& P,
+                              const Coords& coord, std::size_t p, std::size_t q, real f[] )
+{
+  auto dx = coord[0][q] - coord[0][p];
+  auto dy = coord[1][q] - coord[1][p];
+  auto dz = coord[2][q] - coord[2][p];
+  auto ncomp = U.nprop();
+  std::vector< real > uL( ncomp ), uR( ncomp );
+  for (std::size_t i=0; i<ncomp; ++i) { uL[i] = U(p,i); uR[i] = U(q,i); }
+  for (std::size_t c=0; c<ncomp; ++c) {
+    auto g1 = G(p,c*3+0)*dx + G(p,c*3+1)*dy + G(p,c*3+2)*dz;
+    auto g2 = G(q,c*3+0)*dx + G(q,c*3+1)*dy + G(q,c*3+2)*dz;
+    auto delta2 = uR[c] - uL[c];
+    auto delta1 = 2.0 * g1 - delta2;
+    auto delta3 = 2.0 * g2 - delta2;
+    auto rL = (delta2 + muscl_eps) / (delta1 + muscl_eps);
+    auto rR = (delta2 + muscl_eps) / (delta3 + muscl_eps);
+    auto rLinv = (delta1 + muscl_eps) / (delta2 + muscl_eps);
+    auto rRinv = (delta3 + muscl_eps) / (delta2 + muscl_eps);
+    auto phiL = (std::abs(rL) + rL) / (std::abs(rL) + 1.0);
+    auto phiR = (std::abs(rR) + rR) / (std::abs(rR) + 1.0);
+    auto phi_L_inv = (std::abs(rLinv) + rLinv) / (std::abs(rLinv) + 1.0);
+    auto phi_R_inv = (std::abs(rRinv) + rRinv) / (std::abs(rRinv) + 1.0);
+    uL[c] += 0.25*(delta1*(1.0-muscl_const)*phiL + delta2*(1.0+muscl_const)*phi_L_inv);
+    uR[c] -= 0.25*(delta3*(1.0-muscl_const)*phiR + delta2*(1.0+muscl_const)*phi_R_inv);
+  }
+  auto nx = supint[0], ny = supint[1], nz = supint[2];
+  auto vnL = uL[0]*nx + uL[1]*ny + uL[2]*nz;
+  auto vnR = uR[0]*nx + uR[1]*ny + uR[2]*nz;
+  real aw = 0.0;
+  if (cfg().stab) aw = std::abs( vnL + vnR ) / 2.0;
+  if (cfg().stab2) aw += cfg().stab2coef * std::max( std::abs(vnL), std::abs(vnR) );
+  auto v = supint[4] * cfg().mu;
+  auto pf = P[p] + P[q];
+  f[0] = uL[0]*vnL + uR[0]*vnR + pf*nx + aw*(uR[0]-uL[0]) - v*(U(q,0)-U(p,0));
+  f[1] = uL[1]*vnL + uR[1]*vnR + pf*ny + aw*(uR[1]-uL[1]) - v*(U(q,1)-U(p,1));
+  f[2] = uL[2]*vnL + uR[2]*vnR + pf*nz + aw*(uR[2]-uL[2]) - v*(U(q,2)-U(p,2));
+  if (ncomp == 3) return;
+  auto d = supint[4] * cfg().dif;
+  for (std::size_t c=3; c<ncomp; ++c) f[c] = uL[c]*vnL + uR[c]*vnR + aw*(uR[c]-uL[c]) - d*(U(q,c)-U(p,c));
+}
+
+//! chorin::rhs = adv (:831-982) + src (:984-1007), Chorin.cpp:1010-1044
+inline void chorin_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                        const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                        const std::vector< std::size_t >& triinpoel, const std::vector< real >& v, real t,
+                        const std::vector< real >& P, const Fields& U, const Fields& G, Fields& R )
+{
+  R.fill( 0.0 );
+  auto ncomp = U.nprop();
+  auto adv = cfg().flux == "damp2" ? chorin_adv_damp2 : chorin_adv_damp4;
+  if (cfg().flux != "damp2" && cfg().flux != "damp4") throw std::runtime_error( "oracle port: Flux not correctly configured" );
+  std::vector< real > fb( 6*ncomp );
+  real* f[6]; for (int k=0; k<6; ++k) f[k] = fb.data() + static_cast<std::size_t>(k)*ncomp;
+  chorin_foredge( dsupedge, dsupint, [&]( int kind, std::size_t e, const std::size_t* N, const real* d ){
+    if (kind == 0) {
+      adv( d+(e*6+0)*5, U, G, P, coord, N[0], N[1], f[0] );
+      adv( d+(e*6+1)*5, U, G, P, coord, N[1], N[2], f[1] );
+      adv( d+(e*6+2)*5, U, G, P, coord, N[2], N[0], f[2] );
+      adv( d+(e*6+3)*5, U, G, P, coord, N[0], N[3], f[3] );
+      adv( d+(e*6+4)*5, U, G, P, coord, N[1], N[3], f[4] );
+      adv( d+(e*6+5)*5, U, G, P, coord, N[2], N[3], f[5] );
+      for (std::size_t c=0; c<ncomp; ++c) {
+        R(N[0],c) = R(N[0],c) - f[0][c] + f[2][c] - f[3][c];
+        R(N[1],c) = R(N[1],c) + f[0][c] - f[1][c] - f[4][c];
+        R(N[2],c) = R(N[2],c) + f[1][c] - f[2][c] - f[5][c];
+        R(N[3],c) = R(N[3],c) + f[3][c] + f[4][c] + f[5][c];
+      }
+    } else if (kind == 1) {
+      adv( d+(e*3+0)*5, U, G, P, coord, N[0], N[1], f[0] );
+      adv( d+(e*3+1)*5, U, G, P, coord, N[1], N[2], f[1] );
+      adv( d+(e*3+2)*5, U, G, P, coord, N[2], N[0], f[2] );
+      for (std::size_t c=0; c<ncomp; ++c) {
+        R(N[0],c) = R(N[0],c) - f[0][c] + f[2][c];
+        R(N[1],c) = R(N[1],c) + f[0][c] - f[1][c];
+        R(N[2],c) = R(N[2],c) + f[1][c] - f[2][c];
+      }
+    } else {
+      adv( d+e*5, U, G, P, coord, N[0], N[1], f[0] );
+      for (std::size_t c=0; c<ncomp; ++c) { R(N[0],c) -= f[0][c]; R(N[1],c) += f[0][c]; }
+    }
+  } );
+  std::vector< real > fl( ncomp*3 );
+  auto F = [&]( std::size_t c, std::size_t k ) -> real& { return fl[c*3+k]; };
+  for (std::size_t e=0; e<triinpoel.size()/3; ++e) {
+    const auto N = triinpoel.data() + e*3;
+    real n[3]; crossdiv6( coord, N, n );
+    for (std::size_t k=0; k<3; ++k) {
+      auto u = U(N[k],0), vv = U(N[k],1), w = U(N[k],2);
+      auto p = P[N[k]];
+      auto vn = n[0]*u + n[1]*vv + n[2]*w;
+      F(0,k) = u*vn + p*n[0];
+      F(1,k) = vv*vn + p*n[1];
+      F(2,k) = w*vn + p*n[2];
+      for (std::size_t c=3; c<ncomp; ++c) F(c,k) = U(N[k],c)*vn;
+    }
+    for (std::size_t c=0; c<ncomp; ++c) {
+      R(N[0],c) += (6.0*F(c,0) + F(c,1) + F(c,2))/8.0;
+      R(N[1],c) += (F(c,0) + 6.0*F(c,1) + F(c,2))/8.0;
+      R(N[2],c) += (F(c,0) + F(c,1) + 6.0*F(c,2))/8.0;
+    }
+  }
+  if (auto s_ = SRC())
+    for (std::size_t p=0; p<R.nunk(); ++p) {
+      auto s = s_( coord[0][p], coord[1][p], coord[2][p], t );
+      for (std::size_t c=0; c<s.size(); ++c) R(p,c) -= s[c] * v[p];
+    }
 }
 
 // ---- Zalesak.cpp: Taylor-Galerkin two-step edge flux for ZalCG --------------------------

@@ -46,9 +46,15 @@ void set_cfg( const Cfg& c )
   g.get< tag::mat_spec_gas_const >() = c.rgas;
   g.get< tag::turkel >() = c.turkel;
   g.get< tag::velinf >() = std::vector< double >{ c.velinf[0], c.velinf[1], c.velinf[2] };
+  g.get< tag::mat_dyn_viscosity >() = c.mu;
+  g.get< tag::mat_dyn_diffusivity >() = c.dif;
+  g.get< tag::stab >() = c.stab;
+  g.get< tag::rk >() = c.rk;
   g.get< tag::residual >() = c.residual;
   g.get< tag::rescomp >() = c.rescomp;
-  if (c.problem == "userdef") {
+  if (c.solver == "chocg")
+    g.get< tag::ic, tag::velocity >() = std::vector< double >{ c.ic_velocity[0], c.ic_velocity[1], c.ic_velocity[2] };
+  else if (c.problem == "userdef") {
     g.get< tag::ic, tag::density >() = c.ic_density;
     g.get< tag::ic, tag::pressure >() = c.ic_pressure;
     g.get< tag::ic, tag::velocity >() = std::vector< double >{ c.ic_velocity[0], c.ic_velocity[1], c.ic_velocity[2] };

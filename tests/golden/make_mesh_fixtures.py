@@ -23,8 +23,21 @@ CASES = {
     "riecg_sedov": ("RieCG/Sedov/sedov_coarse.exo", "RieCG/Sedov/diag.std"),
     "riecg_taylor_green": ("RieCG/TaylorGreen/unitcube_1k.exo", "RieCG/TaylorGreen/diag.std"),
     "laxcg_bump": ("LaxCG/Bump/bump.exo", "LaxCG/Bump/diag.std"),
+    "chocg_unitcube": ("ChoCG/Poisson/unitcube_01_1k.exo", None),
+    "chocg_pidiv4": ("ChoCG/Poisson/unitcube_0pidiv4_1k.exo", None),
+    "chocg_poiseuille": ("ChoCG/Poiseuille/poiseuille1tetz.exo", None),
 }
-EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std"}
+EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
+              "chocg_poisson_const": "ChoCG/Poisson/diag_poisson_const.std",
+              "chocg_poisson_sine": "ChoCG/Poisson/diag_poisson_sine.std",
+              "chocg_poisson_sine3": "ChoCG/Poisson/diag_poisson_sine3.std",
+              "chocg_poisson_neumann": "ChoCG/Poisson/diag_poisson_neumann.std",
+              "chocg_poiseuille_damp2": "ChoCG/Poiseuille/diag_poiseuille_damp2.std",
+              "chocg_poiseuille_damp4": "ChoCG/Poiseuille/diag_poiseuille_damp4.std",
+              "chocg_poiseuille_rk2": "ChoCG/Poiseuille/diag_poiseuille_rk2.std",
+              "chocg_poiseuille_rk3": "ChoCG/Poiseuille/diag_poiseuille_rk3.std",
+              "chocg_poiseuille_rk4": "ChoCG/Poiseuille/diag_poiseuille_rk4.std",
+              "chocg_ldc": "ChoCG/Lid/diag_ldc.std"}
 
 
 def flatten(exo):
@@ -63,8 +76,9 @@ def main():
     for name, (exo, diag) in CASES.items():
         m = flatten(os.path.join(REF, exo))
         np.savez_compressed(os.path.join(HERE, name + ".mesh.npz"), **m)
-        shutil.copyfile(os.path.join(REF, diag), os.path.join(HERE, name + ".diag.std"))
-        os.chmod(os.path.join(HERE, name + ".diag.std"), 0o644)
+        if diag:
+            shutil.copyfile(os.path.join(REF, diag), os.path.join(HERE, name + ".diag.std"))
+            os.chmod(os.path.join(HERE, name + ".diag.std"), 0o644)
         print(name, m["coord"].shape[1], "nodes", len(m["tets"]), "tets", len(m["tris"]), "tris")
     for name, diag in EXTRA_DIAG.items():
         shutil.copyfile(os.path.join(REF, diag), os.path.join(HERE, name + ".diag.std"))

@@ -35,6 +35,14 @@ class Cfg(C.Structure):
         ("rgas", C.c_double), ("turkel", C.c_double), ("velinf", C.c_double * 3), ("residual", C.c_double),
         ("rescomp", C.c_uint64),
         ("ic_density", C.c_double), ("ic_pressure", C.c_double), ("ic_velocity", C.c_double * 3),
+        ("mu", C.c_double), ("dif", C.c_double), ("stab", C.c_int32), ("rk", C.c_uint64),
+        ("nnoslip", C.c_int32), ("noslip", C.c_int32 * 16),
+        ("ndirval", C.c_int32), ("dirval", (C.c_double * 12) * 16),
+        ("p_iter", C.c_uint64), ("p_tol", C.c_double), ("p_pc", C.c_char * 16),
+        ("np_dir", C.c_int32), ("p_dir", (C.c_int32 * 2) * 16),
+        ("np_dirval", C.c_int32), ("p_dirval", (C.c_double * 2) * 16),
+        ("np_sym", C.c_int32), ("p_sym", C.c_int32 * 16),
+        ("p_hydrostat_set", C.c_int32), ("p_hydrostat", C.c_uint64),
     ]
 
 
@@ -43,7 +51,9 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
              fieldout=(), solver="riecg", fct=True, fctclip=False, fctsys=(), fctdif=1.0,
              steady=False, residual=0.0, rescomp=1, rgas=287.052874, turkel=0.5, velinf=(1.0, 1.0, 1.0),
              far=(), far_density=0.0, far_pressure=0.0, far_velocity=(0.0, 0.0, 0.0),
-             ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0), cls=Cfg):
+             ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0),
+             mu=0.0, dif=0.0, stab=True, rk=1, noslip=(), dirval=(), p_iter=10, p_tol=1.0e-3, p_pc="none",
+             p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, cls=Cfg):
     """Control-file equivalent; defaults are the reference's (InciterConfig.cpp:1707-1757)."""
     c = cls()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
@@ -55,6 +65,25 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
     for i, s_ in enumerate(far):
         c.far_sets[i] = s_
     c.ic_density = ic_density; c.ic_pressure = ic_pressure
+    c.mu = mu; c.dif = dif; c.stab = int(stab); c.rk = rk
+    c.nnoslip = len(noslip)
+    for i, s_ in enumerate(noslip):
+        c.noslip[i] = s_
+    c.ndirval = len(dirval)
+    for i, m in enumerate(dirval):
+        for j, v in enumerate(m):
+            c.dirval[i][j] = v
+    c.p_iter = p_iter; c.p_tol = p_tol; c.p_pc = p_pc.encode()
+    c.np_dir = len(p_dir)
+    for i, m in enumerate(p_dir):
+        c.p_dir[i][0], c.p_dir[i][1] = m
+    c.np_dirval = len(p_dirval)
+    for i, m in enumerate(p_dirval):
+        c.p_dirval[i][0], c.p_dirval[i][1] = m
+    c.np_sym = len(p_sym)
+    for i, s_ in enumerate(p_sym):
+        c.p_sym[i] = s_
+    c.p_hydrostat_set = int(p_hydrostat is not None); c.p_hydrostat = p_hydrostat or 0
     for i in range(3):
         c.velinf[i] = velinf[i]; c.far_velocity[i] = far_velocity[i]; c.ic_velocity[i] = ic_velocity[i]
     c.solver = solver.encode(); c.fct = int(fct); c.fctclip = int(fctclip); c.fctdif = fctdif
@@ -84,6 +113,31 @@ _BUMP = dict(solver="laxcg", problem="userdef", gamma=1.4, cfl=0.7, nstep=20, st
 LCASES = {
     "laxcg_bump": dict(_BUMP),
     "laxcg_bump_hllc": dict(_BUMP, flux="hllc"),
+}
+
+# ChoCG regression cases (tests/regression/inciter/ChoCG/{Poisson,Poiseuille,Lid}/*.q)
+_PDIR6 = tuple((s, 1) for s in range(1, 7))
+_POIS = dict(solver="chocg", ncomp=3, cfl=0.5, nstep=20, mu=0.01, p_iter=500, p_tol=1.0e-3, p_pc="jacobi",
+             p_dir=((1, 2), (2, 2)), p_dirval=((1, 2.4), (2, 0.0)), problem="userdef", noslip=(3, 4),
+             dir_=((1, 0, 1, 1), (5, 0, 1, 1)), mesh="chocg_poiseuille")
+CCASES = {
+    "chocg_poisson_const": dict(solver="chocg", ncomp=3, nstep=1, dt=0.5, problem="poisson_const", p_iter=100,
+                                p_tol=1.0e-6, p_dir=_PDIR6, mesh="chocg_unitcube"),
+    "chocg_poisson_sine": dict(solver="chocg", ncomp=3, nstep=1, dt=0.5, problem="poisson_sine", p_iter=100,
+                               p_tol=1.0e-6, p_dir=_PDIR6, mesh="chocg_unitcube"),
+    "chocg_poisson_sine3": dict(solver="chocg", ncomp=3, nstep=1, dt=0.5, problem="poisson_sine3", p_iter=100,
+                                p_tol=1.0e-6, p_dir=_PDIR6, mesh="chocg_unitcube"),
+    "chocg_poisson_neumann": dict(solver="chocg", ncomp=3, nstep=1, dt=0.5, problem="poisson_neumann", p_iter=100,
+                                  p_tol=1.0e-6, p_dir=((1, 1), (2, 1), (3, 1)), p_sym=(4, 5, 6),
+                                  mesh="chocg_pidiv4"),
+    "chocg_poiseuille_damp2": dict(_POIS, flux="damp2", cfl=0.05),
+    "chocg_poiseuille_damp4": dict(_POIS, flux="damp4", cfl=0.05),
+    "chocg_poiseuille_rk2": dict(_POIS, flux="damp2", rk=2),
+    "chocg_poiseuille_rk3": dict(_POIS, flux="damp2", rk=3),
+    "chocg_poiseuille_rk4": dict(_POIS, flux="damp4", rk=4, cfl=1.0),
+    "chocg_ldc": dict(solver="chocg", ncomp=3, nstep=10, cfl=0.9, flux="damp4", mu=0.01, p_iter=500, p_tol=1.0e-3,
+                      p_pc="jacobi", p_hydrostat=0, problem="userdef", noslip=(1, 2, 3, 5, 6),
+                      dir_=((4, 2, 2, 2),), dirval=((4, 1.0, 0.0, 0.0),), mesh="riecg_taylor_green"),
 }
 
 # KozCG regression cases (tests/regression/inciter/KozCG/{Sod/sod.q,TaylorGreen/taylor_green.q})

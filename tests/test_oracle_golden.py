@@ -123,3 +123,22 @@ def test_laxcg_hllc_oracle_within_reference_tolerance_of_parallel_golden():
     assert (np.abs(d[:3, 1:3] - gold[:3, 1:3]) / gold[:3, 1:3]).max() < 1e-11     # first steps: same dt
     assert O.numdiff_ok(d[:, 1:13], gold[:, 1:13], 1.0e-3, 3.0e-3).all()
     assert (np.abs(d[:, 3:8] - gold[:, 3:8]) / gold[:, 3:8]).max() < 2e-4
+
+
+@pytest.mark.parametrize("case", list(O.CCASES))
+def test_chocg_oracle_reproduces_reference_golden_diag(case):
+    """ChoCG (projection method: Chorin edge operators + pressure Poisson solve by conjugate
+    gradients): tests/regression/inciter/ChoCG/{Poisson,Poiseuille,Lid}/diag*.std -- four Poisson
+    problems (Dirichlet, Neumann BCs), Poiseuille flow with damp2/damp4 fluxes and 1-4 RK stages,
+    lid-driven cavity with a hydrostat node. The Neumann case was recorded on 2 PEs (CG stops
+    at its tolerance at a slightly different iterate)."""
+    kw = O.CCASES[case]
+    gold = O.load_golden_diag(case)
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(int(gold[-1, 0]))
+    d = o.diag()
+    assert d.shape == gold.shape
+    tol = 2e-7 if case == "chocg_poisson_neumann" else 2e-10
+    assert (np.abs(d - gold) <= tol * np.abs(gold)).all()
+    if case != "chocg_poisson_neumann":
+        assert (np.abs(d[:, :6] - gold[:, :6]) <= 2e-12 * np.abs(gold[:, :6])).all()

@@ -117,3 +117,19 @@ def test_laxcg_port_is_bit_identical_to_reference_objects(case):
     assert np.isfinite(a.diag()).all()
     assert np.array_equal(a.diag(), b.diag())
     assert np.array_equal(a.get("u"), b.get("u"))
+
+
+@needs_ref
+@pytest.mark.parametrize("case", ["chocg_poisson_neumann", "chocg_poiseuille_rk3", "chocg_poiseuille_damp4", "chocg_ldc"])
+def test_chocg_port_is_bit_identical_to_reference_objects(case):
+    """chorin::div/grad/vgrad/flux/rhs, tk::CSR and the problem functions from the reference's own
+    translation units vs the restatement under the same ChoCG driver."""
+    kw = O.CCASES[case]
+    mesh = O.load_mesh(kw["mesh"])
+    a = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    b = O.Oracle(mesh, O.make_cfg(**kw), "reference")
+    n = min(kw["nstep"], 5)
+    a.step(n); b.step(n)
+    assert np.array_equal(a.diag(), b.diag())
+    for name in ("u", "pr", "pgrad", "grad", "div"):
+        assert np.array_equal(a.get(name), b.get(name)), name

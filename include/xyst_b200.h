@@ -195,6 +195,66 @@ int xyst_kozcg_rhs(xyst_ctx* ctx, double dt);
 /* one KozCG time step: rhs, aec, alw, lim, solve, BC; un keeps the old state */
 int xyst_kozcg_step(xyst_ctx* ctx, double dt);
 
+/* ---- ChoCG: projection method for constant-density flow -----------------------------------
+ * Edge operators chorin::div/grad/vgrad/flux/rhs (src/Physics/Chorin.cpp:85-1044) on superedge
+ * integrals of stride 5 (normal, J/120, grad_p.grad_q/(6J); ChoCG::domint, ChoCG.cpp:399-446) and
+ * the solver steps of src/Inciter/ChoCG.cpp that call them. The state (velocity u, pressure, their
+ * gradients, divergence) stays on the device; the pressure Poisson matrix (ChoCG::prelhs :146-188)
+ * is given with xyst_csr_upload and solved with the xyst_cg_* entries below. One partition per
+ * context for now (no halo exchange on this path yet). */
+typedef struct xyst_chocg_params {
+  int flux;          /* 0 = damp2, 1 = damp4 (Chorin.cpp:640-829) */
+  int stab;          /* tag::stab */
+  int stab2;         /* tag::stab2 */
+  double stab2coef;
+  double mu;         /* mat_dyn_viscosity */
+} xyst_chocg_params;
+int xyst_chocg_mesh_upload(xyst_ctx* ctx, size_t npoin, const double* x, const double* y, const double* z,
+                           const size_t nsup[3], const size_t* const dsupedge[3],
+                           const double* const dsupint[3], size_t ntri, const size_t* triinpoel,
+                           const double* vol, const double* v, const xyst_chocg_params* prm);
+/* ChoCG::BC (:1340-1353): physics::dirbc with values (dirmask/dirval: npoin-independent lists of
+ * ndir entries { node, mask_0..2 } / { value_0..2 } with mask 1 or 2 = set to value), symbc in the
+ * given order (a node may appear once per side set), noslipbc */
+int xyst_chocg_bc_upload(xyst_ctx* ctx, size_t ndir, const size_t* dirnodes, const int* dirmask,
+                         const double* dirval, size_t nsym, const size_t* symbcnodes,
+                         const double* symbcnorms, size_t nnoslip, const size_t* noslipbcnodes);
+int xyst_chocg_set_u(xyst_ctx* ctx, const double* u /* [npoin][3] */);
+int xyst_chocg_get_u(xyst_ctx* ctx, double* u);
+int xyst_chocg_set_p(xyst_ctx* ctx, const double* p /* [npoin] */);
+int xyst_chocg_get(xyst_ctx* ctx, const char* what, double* out);   /* "pr","div" [npoin]; "sgrad","pgrad","flux","rhs" [npoin][3]; "vgrad" [npoin][9]; "un" [npoin][3] */
+int xyst_chocg_apply_bc(xyst_ctx* ctx);
+/* chorin::div of the velocity (which = 0) or the momentum flux (1: ChoCG::div finishes the flux
+ * first: /vol and symbc, :879-882); stab adds the pressure stabilisation (:58-80) */
+int xyst_chocg_div(xyst_ctx* ctx, int which, double dt, int stab);
+/* chorin::vgrad + ChoCG::fingrad (/vol); chorin::flux (weak, un-normalised as in ChoCG::flux) */
+int xyst_chocg_vgrad(xyst_ctx* ctx);
+int xyst_chocg_flux(xyst_ctx* ctx);
+/* chorin::grad of the CG solution (which = 0 -> sgrad) or of the pressure (1 -> pgrad), /vol */
+int xyst_chocg_grad(xyst_ctx* ctx, int which);
+/* chorin::rhs -> rhs (xyst_chocg_get "rhs"); source term values at the nodes with xyst_chocg_src */
+int xyst_chocg_src(xyst_ctx* ctx, const double* S /* [npoin][3] or NULL */);
+int xyst_chocg_rhs(xyst_ctx* ctx);
+/* one RK stage of ChoCG::solve + pred (:1529-1668): rhs, u = un - rk dt rhs/vol, BC, and for the
+ * damp4 flux the velocity gradient of the new state */
+int xyst_chocg_stage(xyst_ctx* ctx, int stage, double rkcoef, double dt);
+/* pressure solve set-up, ChoCG::pinit (:1025-1125) + ConjugateGradients::init/apply (:336-556):
+ * rhs = div / divisor (:1044; 1.0 = as is), or rhs0 if given (PRESSURE_RHS * vol, :1117-1122);
+ * Dirichlet nodes/values and the Neumann vector are applied to the rhs and, on the fly, to the
+ * matrix of xyst_csr_upload (which is left untouched, cf. the restore at :809); the initial guess
+ * is the previous solution (:363). Continue with xyst_cg_solve. */
+int xyst_chocg_pinit(xyst_ctx* ctx, double divisor, size_t nbc, const size_t* bcnodes,
+                     const double* bcvals, const double* neubc, const double* rhs0, int pc);
+/* u -= pdt * sgrad, then BC (ChoCG::psolved :1204-1217); pr = x or pr += x (:1241,1249) */
+int xyst_chocg_project(xyst_ctx* ctx, double pdt);
+int xyst_chocg_pressure_update(xyst_ctx* ctx, int increment);
+/* ChoCG::dt (:1356-1411): min over nodes of L/|u| and L^2/max(mu,dif), times cfl */
+int xyst_chocg_dt_min(xyst_ctx* ctx, double cfl, double dif, double* dt);
+/* NodeDiagnostics::precompute sums (NodeDiagnostics.cpp:223-252), out[16]: [0..3] = sum v p^2,
+ * v u_c^2; [4..7] = sum v dp^2, v (u-un)_c^2; with an_p (analytic pressure [npoin], or NULL):
+ * [8] L2, [9] L1 sums; with an_u (analytic velocity [npoin][3], or NULL): [10..12] L2, [13..15] L1 */
+int xyst_chocg_diag(xyst_ctx* ctx, const double* an_p, const double* an_u, double* out);
+
 /* ---- linear solver of the pressure projection (ChoCG/LohCG) -----------------------------
  * tk::CSR (src/LinearSolver/CSR.hpp:30-107): block CSR exactly as the reference stores it,
  * nrow = npoin*ncomp scalar rows, 1-based ia[nrow+1] / ja[nnz], values a[nnz] (after

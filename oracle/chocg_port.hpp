@@ -53,10 +53,47 @@ class ChoRun : public Run {
               A( N[a], N[b] ) -= (grad[a][0]*grad[b][0] + grad[a][1]*grad[b][1] + grad[a][2]*grad[b][2]) / J;
         }
       }
+      for (auto& cp : ch) u0.push_back( cp->u );
       // ChoCG::merge :816-837 onwards: make the initial velocity divergence free, initial pressure
       div_u();
       pinit(); psolve();
       sgrad(); psolved();
+    }
+
+    std::vector< be::Fields > u0;         // initial velocity, before the first projection
+
+    //! nodal values of the problem functions and the assembled pressure matrix of one chare, for
+    //! the parity tests of the device path (the host solver class evaluates these itself)
+    std::vector< real > exported( std::size_t k, const std::string& n ) {
+      auto& c_ = *ch.at( k );
+      const auto& x = c_.coord[0]; const auto& y = c_.coord[1]; const auto& z = c_.coord[2];
+      std::vector< real > r;
+      if (n == "u0") { const auto& f = u0.at( k ); for (std::size_t i=0; i<f.nunk(); ++i) for (std::size_t c=0; c<f.nprop(); ++c) r.push_back( f(i,c) ); }
+      else if (n == "p_ic") { auto ic = be::PRESSURE_IC(); for (std::size_t i=0; i<x.size(); ++i) r.push_back( ic( x[i], y[i], z[i] ) ); }
+      else if (n == "p_sol") { if (auto f = be::PRESSURE_SOL()) for (std::size_t i=0; i<x.size(); ++i) r.push_back( f( x[i], y[i], z[i] ) ); }
+      else if (n == "p_rhs") { if (auto f = be::PRESSURE_RHS()) for (std::size_t i=0; i<x.size(); ++i) r.push_back( f( x[i], y[i], z[i] ) * c_.vol[i] ); }
+      else if (n == "u_sol") { if (auto f = be::SOL()) for (std::size_t i=0; i<x.size(); ++i) { auto s = f( x[i], y[i], z[i], t+dt ); r.insert( r.end(), s.begin(), s.end() ); } }
+      else if (n == "neubc") {
+        if (auto pg = be::PRESSURE_GRAD()) {
+          std::vector< std::uint8_t > besym( c_.triinpoel.size(), 0 );
+          for (auto s : cfg.p_bc_sym) { auto kk = c_.bface.find( s ); if (kk != c_.bface.end()) for (auto f : kk->second) besym[f] = 1; }
+          r.assign( x.size(), 0.0 );
+          for (std::size_t e=0; e<c_.triinpoel.size()/3; ++e)
+            if (besym[e]) {
+              const auto N = c_.triinpoel.data() + e*3;
+              real nn[3]; port::crossdiv6( c_.coord, N, nn );
+              for (std::size_t a=0; a<3; ++a) { auto g = pg( x[N[a]], y[N[a]], z[N[a]] ); r[ N[a] ] -= nn[0]*g[0] + nn[1]*g[1] + nn[2]*g[2]; }
+            }
+        }
+      }
+      else if (n == "hydrostat") { if (cfg.p_hydrostat != ~0ULL) { auto pi = c_.lid.find( cfg.p_hydrostat ); if (pi != c_.lid.end()) r.push_back( static_cast< real >( pi->second ) ); } }
+      else if (n == "plhs_a") {
+        auto& P = *cgpre.parts.at( k );
+        const auto& ia = P.S.IA(); const auto& ja = P.S.JA();
+        for (std::size_t row=0; row+1<ia.size(); ++row) for (std::size_t j=ia[row]-1; j<ia[row+1]-1; ++j) r.push_back( P.A( row, ja[j]-1 ) );
+      }
+      else throw std::runtime_error( "oracle ChoCG: unknown export " + n );
+      return r;
     }
 
     //! sum a nodal field over the chares sharing each node (com* entry methods)

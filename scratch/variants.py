@@ -3,19 +3,26 @@ import os, sys, subprocess, json
 sys.path.insert(0, '.')
 from xyst_b200 import build as B
 VAR = {
- "edge": ["FLUX_SLICE=0"],
- "slice2": ["FLUX_SLICE=1", "FSLICE_MINB=2"],
- "slice3": ["FLUX_SLICE=1", "FSLICE_MINB=3"],
- "slice4": ["FLUX_SLICE=1", "FSLICE_MINB=4"],
+ "base": [],
+ "v2off": ["MUSCL_V2=0"],
+ "g3u4": ["GRAD_MINB=3", "RHS_MINB=3"],
+ "g3u8": ["GRAD_MINB=3", "RHS_MINB=3", "NODE_UNROLL=8"],
+ "g2u8": ["GRAD_MINB=2", "RHS_MINB=2", "NODE_UNROLL=8"],
+ "g4u2": ["NODE_UNROLL=2"],
+ "f7": ["FLUX_MINB=7"],
+ "f5": ["FLUX_MINB=5"],
+ "ft64": ["FLUX_THREADS=64", "FLUX_MINB=12"],
 }
+if len(sys.argv) > 3:
+    VAR = {k: v for k, v in VAR.items() if k in sys.argv[3].split(",")}
 if sys.argv[1] == "build":
     for k, d in VAR.items():
-        B.build_device(force=True, out="scratch/lib_%s.so" % k, defines=d, verbose=True)
+        B.build_device(force=True, out="scratch/lib_%s.so" % k, defines=d, verbose=False)
         print("built", k)
 else:
     for k in VAR:
         env = dict(os.environ, XYST_B200_LIB="scratch/lib_%s.so" % k)
-        r = subprocess.run([sys.executable, "bench.py", "--steps", "5", "--warmup", "2", "--no-cpu-baseline", "--no-e2e", "--n", sys.argv[2] if len(sys.argv) > 2 else "150"],
+        r = subprocess.run([sys.executable, "bench.py", "--steps", "8", "--warmup", "3", "--no-cpu-baseline", "--no-e2e", "--n", sys.argv[2] if len(sys.argv) > 2 else "150"],
                            env=env, capture_output=True, text=True)
         try:
             j = json.loads(r.stdout.strip().splitlines()[-1])

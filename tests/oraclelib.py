@@ -227,7 +227,8 @@ def lib(flavour="port"):
 _DT = {"gid": np.uint64, "inpoel": np.uint64, "triinpoel": np.uint64, "besym": np.uint8,
        "dsupedge0": np.uint64, "dsupedge1": np.uint64, "dsupedge2": np.uint64,
        "dirbcmasks": np.uint64, "symbcnodes": np.uint64, "farbcnodes": np.uint64,
-       "prebcnodes": np.uint64, "bface": np.uint64, "commmap": np.uint64}
+       "prebcnodes": np.uint64, "bface": np.uint64, "commmap": np.uint64,
+       "plhs_ia": np.uint64, "plhs_ja": np.uint64, "dirbcmaskp": np.uint64, "noslipbcnodes": np.uint64}
 
 
 class Oracle:

@@ -28,7 +28,9 @@ def _stale(target, sources):
 def build_device(force=False, verbose=False, out=None, defines=()):
     """libxyst_b200.so: CUDA kernels + the C ABI of include/xyst_b200.h."""
     src = [os.path.join(HERE, "csrc", "xyst_b200.cu")]
-    dep = src + [os.path.join(ROOT, "include", "xyst_b200.h")]
+    cdir = os.path.join(HERE, "csrc")
+    dep = src + [os.path.join(cdir, f) for f in os.listdir(cdir) if f.endswith(".cuh")] + \
+        [os.path.join(ROOT, "include", "xyst_b200.h")]
     out = out or os.path.join(HERE, "libxyst_b200.so")
     if force or _stale(out, dep):
         cmd = [NVCC] + CUDA_FLAGS + ["-D" + d for d in defines] + \

@@ -20,6 +20,11 @@ class ZalParams(C.Structure):
                 ("fctdif", C.c_double)]
 
 
+class ChoParams(C.Structure):
+    _fields_ = [("flux", C.c_int32), ("stab", C.c_int32), ("stab2", C.c_int32), ("pad_", C.c_int32),
+                ("stab2coef", C.c_double), ("mu", C.c_double)]
+
+
 class Params(C.Structure):
     _fields_ = [("ncomp", C.c_int32), ("flux", C.c_int32), ("stab2", C.c_int32),
                 ("exact_muscl", C.c_int32), ("gamma", C.c_double), ("stab2coef", C.c_double)]
@@ -38,6 +43,10 @@ SYMBOLS = [
     "xyst_nedge", "xyst_kernel_time", "xyst_csr_upload", "xyst_csr_mult", "xyst_cg_setup",
     "xyst_cg_solve", "xyst_cg_get_x", "xyst_zalcg_config", "xyst_zalcg_mesh_upload", "xyst_zalcg_rhs",
     "xyst_zalcg_step", "xyst_laxcg_config", "xyst_steady", "xyst_kozcg_mesh_upload", "xyst_kozcg_rhs", "xyst_kozcg_step",
+    "xyst_chocg_mesh_upload", "xyst_chocg_bc_upload", "xyst_chocg_set_u", "xyst_chocg_get_u", "xyst_chocg_set_p",
+    "xyst_chocg_get", "xyst_chocg_apply_bc", "xyst_chocg_div", "xyst_chocg_vgrad", "xyst_chocg_flux",
+    "xyst_chocg_grad", "xyst_chocg_src", "xyst_chocg_rhs", "xyst_chocg_stage", "xyst_chocg_pinit",
+    "xyst_chocg_project", "xyst_chocg_pressure_update", "xyst_chocg_dt_min", "xyst_chocg_diag",
 ]
 
 
@@ -102,6 +111,24 @@ def lib():
     L.xyst_cg_solve.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.POINTER(C.c_size_t),
                                 C.POINTER(C.c_double)]
     L.xyst_cg_get_x.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_chocg_mesh_upload.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 3 + \
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.xyst_chocg_bc_upload.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    for f in (L.xyst_chocg_set_u, L.xyst_chocg_get_u, L.xyst_chocg_set_p, L.xyst_chocg_src):
+        f.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_chocg_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    for f in (L.xyst_chocg_apply_bc, L.xyst_chocg_vgrad, L.xyst_chocg_flux, L.xyst_chocg_rhs):
+        f.argtypes = [C.c_void_p]
+    L.xyst_chocg_div.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
+    L.xyst_chocg_grad.argtypes = [C.c_void_p, C.c_int]
+    L.xyst_chocg_stage.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+    L.xyst_chocg_pinit.argtypes = [C.c_void_p, C.c_double, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int]
+    L.xyst_chocg_project.argtypes = [C.c_void_p, C.c_double]
+    L.xyst_chocg_pressure_update.argtypes = [C.c_void_p, C.c_int]
+    L.xyst_chocg_dt_min.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_double)]
+    L.xyst_chocg_diag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -292,6 +319,91 @@ class Context:
         x = np.empty(self.cg_nrow)
         self._ck(self.L.xyst_cg_get_x(self.h, _p(x)))
         return x
+
+    # ---- ChoCG (projection method; Chorin edge operators) ----
+    CHO_W = {"pr": 1, "div": 1, "dp": 1, "sgrad": 3, "pgrad": 3, "flux": 3, "rhs": 3, "un": 3, "u": 3, "vgrad": 9}
+
+    def chocg_mesh_upload(self, x, y, z, dsupedge, dsupint, triinpoel, vol, v, flux="damp2", stab=True,
+                          stab2=False, stab2coef=0.1, mu=0.0):
+        x, y, z, vol, v = map(_f64, (x, y, z, vol, v))
+        se = [_u64(a) for a in dsupedge]
+        si = [_f64(a) for a in dsupint]
+        nsup = (C.c_size_t * 3)(len(se[0]) // 4, len(se[1]) // 3, len(se[2]) // 2)
+        pe = (C.c_void_p * 3)(*[a.ctypes.data for a in se])
+        pi = (C.c_void_p * 3)(*[a.ctypes.data for a in si])
+        tri = _u64(triinpoel)
+        self.npoin = len(x)
+        prm = ChoParams({"damp2": 0, "damp4": 1}[flux], int(stab), int(stab2), 0, stab2coef, mu)
+        self._ck(self.L.xyst_chocg_mesh_upload(self.h, len(x), _p(x), _p(y), _p(z), nsup, pe, pi,
+                                               len(tri) // 3, _p(tri), _p(vol), _p(v), C.byref(prm)))
+
+    def chocg_bc_upload(self, dirnodes=(), dirmask=(), dirval=None, symbcnodes=(), symbcnorms=(), noslipbcnodes=()):
+        dn = _u64(dirnodes); dm = np.ascontiguousarray(dirmask, np.int32)
+        dv = None if dirval is None else _f64(dirval)
+        sn = _u64(symbcnodes); snn = _f64(symbcnorms); nn = _u64(noslipbcnodes)
+        self._ck(self.L.xyst_chocg_bc_upload(self.h, len(dn), _p(dn), _p(dm), _p(dv), len(sn), _p(sn), _p(snn),
+                                             len(nn), _p(nn)))
+
+    def chocg_set_u(self, u):
+        u = _f64(u); self._ck(self.L.xyst_chocg_set_u(self.h, _p(u)))
+
+    def chocg_set_p(self, p):
+        p = _f64(p); self._ck(self.L.xyst_chocg_set_p(self.h, _p(p)))
+
+    def chocg_get(self, what):
+        w = self.CHO_W[what]
+        out = np.empty((self.npoin, w)) if w > 1 else np.empty(self.npoin)
+        self._ck(self.L.xyst_chocg_get(self.h, what.encode(), _p(out)))
+        return out
+
+    def chocg_apply_bc(self):
+        self._ck(self.L.xyst_chocg_apply_bc(self.h))
+
+    def chocg_div(self, which=0, dt=0.0, stab=False):
+        self._ck(self.L.xyst_chocg_div(self.h, which, dt, int(stab)))
+
+    def chocg_vgrad(self):
+        self._ck(self.L.xyst_chocg_vgrad(self.h))
+
+    def chocg_flux(self):
+        self._ck(self.L.xyst_chocg_flux(self.h))
+
+    def chocg_grad(self, which):
+        self._ck(self.L.xyst_chocg_grad(self.h, which))
+
+    def chocg_src(self, S):
+        S = None if S is None else _f64(S)
+        self._ck(self.L.xyst_chocg_src(self.h, _p(S)))
+
+    def chocg_rhs(self):
+        self._ck(self.L.xyst_chocg_rhs(self.h))
+
+    def chocg_stage(self, stage, rkcoef, dt):
+        self._ck(self.L.xyst_chocg_stage(self.h, stage, rkcoef, dt))
+
+    def chocg_pinit(self, divisor=1.0, bcnodes=(), bcvals=None, neubc=None, rhs0=None, pc="none"):
+        bn = _u64(bcnodes); bv = None if bcvals is None else _f64(bcvals)
+        ne = None if neubc is None else _f64(neubc); r0 = None if rhs0 is None else _f64(rhs0)
+        self.cg_nrow = self.npoin
+        self._ck(self.L.xyst_chocg_pinit(self.h, divisor, len(bn), _p(bn), _p(bv), _p(ne), _p(r0),
+                                         {"none": 0, "jacobi": 1}[pc]))
+
+    def chocg_project(self, pdt):
+        self._ck(self.L.xyst_chocg_project(self.h, pdt))
+
+    def chocg_pressure_update(self, increment):
+        self._ck(self.L.xyst_chocg_pressure_update(self.h, int(increment)))
+
+    def chocg_dt_min(self, cfl, dif=0.0):
+        dt = C.c_double()
+        self._ck(self.L.xyst_chocg_dt_min(self.h, cfl, dif, C.byref(dt)))
+        return dt.value
+
+    def chocg_diag(self, an_p=None, an_u=None):
+        out = np.zeros(16)
+        ap = None if an_p is None else _f64(an_p); au = None if an_u is None else _f64(an_u)
+        self._ck(self.L.xyst_chocg_diag(self.h, _p(ap), _p(au), _p(out)))
+        return out
 
     def launch_count(self):
         return int(self.L.xyst_launch_count(self.h))

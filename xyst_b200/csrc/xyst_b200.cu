@@ -133,6 +133,7 @@ struct Prof {
 struct xyst_ctx {
   int device = 0;
   cudaStream_t stream = nullptr, comm_stream = nullptr, aux_stream = nullptr;
+  std::vector< long long > h_ebase;      // host copy of the edge-slot offsets per slice
   bool own_stream = false;
   xyst_params prm{};
   size_t npoin = 0, NP = 0, nedge = 0, nslot = 0, ntri = 0, nslice = 0, nent = 0;
@@ -189,6 +190,19 @@ struct xyst_ctx {
   DevBuf< int > kinc;                    // tet*4+a, -1 = padding
   DevBuf< double > kT, kSc;              // [40][ntet] per-tet contributions; [ntet][5] centroid source
   bool ksrc = false;
+  // ChoCG: velocity (3 rotating buffers: time level n, current, next), pressure, divergence,
+  // gradients of the CG solution / pressure / velocity, momentum flux; BC lists
+  bool cho = false;
+  xyst_chocg_params chp{};
+  DevBuf< double > cUa, cUb, cUc, cP, cDiv, cSg, cPg, cVg, cFl, cR, cS;
+  double *cU = nullptr, *cUn = nullptr, *cUx = nullptr;   // current, time level n, scratch (point into cUa/b/c)
+  DevBuf< int > cb_dnode, cb_dmask, cb_snode, cb_soff, cb_nnode;
+  DevBuf< double > cb_dval, cb_snorm;
+  size_t cb_nd = 0, cb_ns = 0, cb_nn = 0;
+  // pressure solve BCs (matrix-free: masked rows/columns), Neumann part, rhs override
+  DevBuf< unsigned char > cg_bc;
+  DevBuf< double > cg_bcval, cg_neu, cg_rhs0;
+  bool cg_hasbc = false, cg_hasneu = false, cg_hasrhs0 = false;
   // linear solver: sliced-ELL matrix over scalar rows + CG vectors
   size_t cg_nrow = 0, cg_ncomp = 1, cg_nslice = 0, cg_nent = 0;
   DevBuf< long long > cg_base; DevBuf< int > cg_col; DevBuf< double > cg_val, cg_diag;
@@ -517,6 +531,9 @@ __global__ void k_grad_finish( int nsh, size_t NP, const int* __restrict__ sh_no
 // ---------------------------------------------------------------------------------
 #define MUSCL_EPS 1.0e-9
 #define MUSCL_K (1.0/3.0)
+#ifndef MUSCL_V2
+#define MUSCL_V2 1        // 0: the first form of the two-reciprocal limiter (A/B timing)
+#endif
 
 // van Leer limited extrapolation increments for one component.
 // exact: the reference's expression tree (8 divisions). fast: with a = d2+eps, b = d1+eps
@@ -529,11 +546,27 @@ __device__ __forceinline__ double fast_rcp( double x )
 {
   double y;
   asm( "rcp.approx.ftz.f64 %0, %1;" : "=d"( y ) : "d"( x ) );
+#if MUSCL_V2
+  // one cubically convergent step: y (1 + e + e^2), e = 1 - x y  (seed error 2^-20 -> 2^-60)
+  double e = fma( -x, y, 1.0 );
+  double t = fma( e, e, e );
+  return fma( y, t, y );
+#else
   double e = fma( -x, y, 1.0 );
   y = fma( y, e, y );
   e = fma( -x, y, 1.0 );
   y = fma( y, e, y );
   return y;
+#endif
+}
+
+// a and b nonzero with the same sign, decided on the integer pipe (the fp64 pipe is the busy one)
+__device__ __forceinline__ bool same_sign_nz( double a, double b )
+{
+  int ha = __double2hiint( a ), hb = __double2hiint( b );
+  bool nza = ((ha & 0x7fffffff) | __double2loint( a )) != 0;
+  bool nzb = ((hb & 0x7fffffff) | __double2loint( b )) != 0;
+  return nza && nzb && ((ha ^ hb) >= 0);
 }
 
 template< bool EXACT >
@@ -551,6 +584,17 @@ __device__ __forceinline__ void vanleer( double d1, double d2, double d3, double
     incL = 0.25*(d1*(1.0-MUSCL_K)*phiL + d2*(1.0+MUSCL_K)*phi_L_inv);
     incR = 0.25*(d3*(1.0-MUSCL_K)*phiR + d2*(1.0+MUSCL_K)*phi_R_inv);
   } else {
+#if MUSCL_V2
+    // phi(a/b) = 2a/(a+b), phi(b/a) = 2b/(a+b) for same-signed a, b (else 0), so that
+    // inc = 0.25 [ d1 (1-k) 2a + d2 (1+k) 2b ] / (a+b): one reciprocal, five multiply-adds per side
+    const double c1 = 0.5*(1.0-MUSCL_K), c2 = 0.5*(1.0+MUSCL_K);
+    double a = d2 + MUSCL_EPS, bL = d1 + MUSCL_EPS, bR = d3 + MUSCL_EPS;
+    double t2 = c2*d2;
+    double vL = fma( c1*d1, a, t2*bL ) * fast_rcp( a + bL );
+    double vR = fma( c1*d3, a, t2*bR ) * fast_rcp( a + bR );
+    incL = same_sign_nz( a, bL ) ? vL : 0.0;
+    incR = same_sign_nz( a, bR ) ? vR : 0.0;
+#else
     double a = d2 + MUSCL_EPS, bL = d1 + MUSCL_EPS, bR = d3 + MUSCL_EPS;
     bool sL = (a > 0.0 && bL > 0.0) || (a < 0.0 && bL < 0.0);
     bool sR = (a > 0.0 && bR > 0.0) || (a < 0.0 && bR < 0.0);
@@ -559,6 +603,7 @@ __device__ __forceinline__ void vanleer( double d1, double d2, double d3, double
     double phiR = sR ? a*iR : 0.0, phi_R_inv = sR ? bR*iR : 0.0;
     incL = 0.25*(d1*(1.0-MUSCL_K)*phiL + d2*(1.0+MUSCL_K)*phi_L_inv);
     incR = 0.25*(d3*(1.0-MUSCL_K)*phiR + d2*(1.0+MUSCL_K)*phi_R_inv);
+#endif
   }
 }
 
@@ -598,6 +643,7 @@ __device__ __forceinline__ void rusanov( double l[NC], double r[NC], const doubl
   double g = P.gamma;
   double pL = (l[0]*l[4]) * (g-1.0);
   double pR = (r[0]*r[4]) * (g-1.0);
+  const double gg1 = g*(g-1.0), eL = l[4], eR = r[4];
   double nx = n[0], ny = n[1], nz = n[2];
   double vnL = l[1]*nx + l[2]*ny + l[3]*nz;
   double vnR = r[1]*nx + r[2]*ny + r[3]*nz;
@@ -606,8 +652,14 @@ __device__ __forceinline__ void rusanov( double l[NC], double r[NC], const doubl
   r[4] = (r[4] + 0.5*(r[1]*r[1] + r[2]*r[2] + r[3]*r[3])) * r[0];
   r[1] *= r[0]; r[2] *= r[0]; r[3] *= r[0];
   double len = sqrt( nx*nx + ny*ny + nz*nz );
+#if MUSCL_V2
+  double sl, sr;
+  if (P.exact) { sl = fabs(vnL) + sqrt( g * pL / l[0] )*len; sr = fabs(vnR) + sqrt( g * pR / r[0] )*len; }
+  else { sl = fabs(vnL) + sqrt( gg1 * eL )*len; sr = fabs(vnR) + sqrt( gg1 * eR )*len; }   // g p / rho = g (g-1) e
+#else
   double sl = fabs(vnL) + sqrt( g * pL / l[0] )*len;
   double sr = fabs(vnR) + sqrt( g * pR / r[0] )*len;
+#endif
   double fw = fmax( sl, sr );
   f[0] = l[0]*vnL + r[0]*vnR + fw*(r[0] - l[0]);
   f[1] = l[1]*vnL + r[1]*vnR + (pL + pR)*nx + fw*(r[1] - l[1]);
@@ -825,11 +877,11 @@ template< bool EXACT, int FLUX >
 __global__ void __launch_bounds__(FLUX_THREADS, FLUX_MINB)
 k_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __restrict__ eq,
              const double* __restrict__ D, const double* __restrict__ W, const double* __restrict__ X,
-             const double* __restrict__ G, double* __restrict__ F, DParams P )
+             const double* __restrict__ G, double* __restrict__ F, DParams P, size_t e0, size_t e1 )
 {
   __shared__ double sg[30*FLUX_THREADS];
-  size_t e = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
-  if (e >= nslot) return;
+  size_t e = e0 + blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (e >= e1) return;
   int pi = ep[e];
   if (pi < 0) return;                      // padding slot
   size_t p = pi, q = eq[e];
@@ -956,12 +1008,12 @@ k_rhs_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, cons
             const double* __restrict__ Rb, const double* __restrict__ S, int src_mask,
             const double* __restrict__ v, const double* __restrict__ vol, const double* __restrict__ Un,
             StageArgs A, double* __restrict__ U, double* __restrict__ W, double* __restrict__ R,
-            double* __restrict__ Wn, double* __restrict__ UnOut )
+            double* __restrict__ Wn, double* __restrict__ UnOut, size_t slice0, size_t slice1 )
 {
-  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  size_t slice = slice0 + ((blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5);
   int lane = threadIdx.x & 31;
   size_t p = slice*32 + lane;
-  if (p >= npoin) return;
+  if (slice >= slice1 || p >= npoin) return;
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
   double acc[NC];
@@ -1770,6 +1822,72 @@ k_spmv( size_t nrow, const long long* __restrict__ base, const int* __restrict__
   y[r] = acc;
 }
 
+// The same product with Dirichlet rows/columns applied on the fly: what tk::CSR::dirichlet
+// (CSR.cpp:106-152) leaves in the matrix -- BC columns zero, BC rows the unit row (diag =
+// 1/count over the sharing partitions) -- without touching (or having to restore,
+// ConjugateGradients.cpp:809) the stored values.
+__global__ void __launch_bounds__(256)
+k_spmv_bc( size_t nrow, const long long* __restrict__ base, const int* __restrict__ col,
+           const double* __restrict__ val, const unsigned char* __restrict__ bc,
+           const double* __restrict__ cnt, const double* __restrict__ x, double* __restrict__ y )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t r = slice*32 + lane;
+  if (r >= nrow) return;
+  if (bc[r]) { y[r] = (1.0 / cnt[r]) * x[r]; return; }
+  long long b = base[slice];
+  int kmax = (int)((base[slice+1] - b) >> 5);
+  double acc = 0.0;
+  #pragma unroll 4
+  for (int k=0; k<kmax; ++k) {
+    long long i = b + (long long)k*32 + lane;
+    int cl = __ldg( col + i );
+    double a = bc[cl] ? 0.0 : __ldg( val + i );
+    acc += a * __ldg( x + cl );
+  }
+  y[r] = acc;
+}
+
+// rhs with BCs (ConjugateGradients::apply/r :451-556): b += neumann; b -= A(:,bc) val; b(bc) = val
+// (own part r of the column sums: shared rows are summed over the partitions by the caller)
+__global__ void __launch_bounds__(256)
+k_cg_bc_colsum( size_t nrow, const long long* __restrict__ base, const int* __restrict__ col,
+                const double* __restrict__ val, const unsigned char* __restrict__ bc,
+                const double* __restrict__ bcval, double* __restrict__ rsum )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t r = slice*32 + lane;
+  if (r >= nrow) return;
+  long long b = base[slice];
+  int kmax = (int)((base[slice+1] - b) >> 5);
+  double acc = 0.0;
+  for (int k=kmax-1; k>=0; --k) {            // descending column id, the order BCs are applied in (:481)
+    long long i = b + (long long)k*32 + lane;
+    int cl = __ldg( col + i );
+    if (bc[cl]) acc += __ldg( val + i ) * bcval[cl];
+  }
+  rsum[r] = acc;
+}
+__global__ void k_cg_bc_rhs( size_t nrow, const unsigned char* __restrict__ bc, const double* __restrict__ bcval,
+                             const double* __restrict__ neu, const double* __restrict__ rsum, double* __restrict__ b )
+{
+  size_t r = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (r >= nrow) return;
+  double v = b[r];
+  if (neu) v += neu[r];
+  v -= rsum[r];
+  b[r] = bc[r] ? bcval[r] : v;
+}
+__global__ void k_cg_bc_diag( size_t nrow, const unsigned char* __restrict__ bc, const double* __restrict__ cnt,
+                              double* __restrict__ d )
+{
+  size_t r = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (r >= nrow) return;
+  if (bc[r]) d[r] = 1.0 / cnt[r];
+}
+
 // p = z + beta p    (ConjugateGradients::next :584-599)
 __global__ void k_cg_p( size_t n, const double* __restrict__ scal, const double* __restrict__ z, double* __restrict__ p )
 {
@@ -1851,6 +1969,11 @@ __global__ void k_cg_shared_put( int nsh, int w, const int* __restrict__ sh_node
   size_t row = (size_t)sh_node[s]*w + c;
   v[row] = average ? a / cnt[row] : a;
 }
+__global__ void k_cg_inv( size_t n, const double* __restrict__ cnt, double* __restrict__ d )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i < n) d[i] = 1.0 / cnt[i];
+}
 __global__ void k_cg_div( size_t n, const double* __restrict__ r, const double* __restrict__ d, double* __restrict__ z )
 {
   size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
@@ -1861,6 +1984,10 @@ __global__ void k_cg_resid( size_t n, const double* __restrict__ b, double* __re
   size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (i < n) { double v = r[i] * -1.0 + b[i]; r[i] = v; p[i] = v; }     // initres :293-298
 }
+
+#define XYST_CHOCG_KERNELS
+#include "chocg.cuh"
+#undef XYST_CHOCG_KERNELS
 
 // ---------------------------------------------------------------------------------
 // host side
@@ -1955,15 +2082,16 @@ void do_grad( xyst_ctx* c )
   CK( cudaGetLastError() );
 }
 
-void do_flux( xyst_ctx* c )
+void do_flux( xyst_ctx* c, size_t e0 = 0, size_t e1 = ~(size_t)0 )
 {
   auto s = c->stream;
   auto P = dparams( c );
   ProfScope ps( c, "flux" );
-  unsigned g = nblk( c->nslot, FLUX_THREADS );
-  if (!g) return;
+  e1 = std::min( e1, c->nslot );
+  if (e1 <= e0) return;
+  unsigned g = nblk( e1 - e0, FLUX_THREADS );
   #define LAUNCH_FLUX( EX, FL ) k_flux_edge< EX, FL ><<< g, FLUX_THREADS, 0, s >>>( c->nslot, c->NP, c->ep.p, \
-      c->eq.p, c->D.p, c->W.p, c->X.p, c->G.p, c->F.p, P )
+      c->eq.p, c->D.p, c->W.p, c->X.p, c->G.p, c->F.p, P, e0, e1 )
   int fl = P.flux + (c->lax ? 2 : 0);
   if (P.exact) { if (fl == 0) LAUNCH_FLUX( true, 0 ); else if (fl == 1) LAUNCH_FLUX( true, 1 );
                  else if (fl == 2) LAUNCH_FLUX( true, 2 ); else LAUNCH_FLUX( true, 3 ); }
@@ -1974,6 +2102,24 @@ void do_flux( xyst_ctx* c )
 }
 
 static const double rkcoef[3] = { 1.0/3.0, 1.0/2.0, 1.0 };   // RieCG.cpp:41
+
+// the node gather over slices [s0,s1) on stream st
+void launch_rhs_node( xyst_ctx* c, bool fused, const StageArgs& A, const double* Un, double* Uout,
+                      size_t s0, size_t s1, cudaStream_t st )
+{
+  if (s1 <= s0) return;
+  unsigned g = nblk( (s1-s0)*32, NODE_THREADS );
+  if (fused && c->lax)
+    k_rhs_node< true, true ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
+      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1 );
+  else if (fused)
+    k_rhs_node< true, false ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
+      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1 );
+  else
+    k_rhs_node< false, false ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
+      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1 );
+  ++c->launches;
+}
 
 // nodal gather of the rhs; fused = apply the RK update in the same pass
 // Uin: conserved state the fluxes were computed from; Un: state at time level n;
@@ -1997,17 +2143,7 @@ void do_rhs_nodes( xyst_ctx* c, bool fused, int stage, double dt, const double* 
   }
   {
     ProfScope ps( c, fused ? "update" : "rhsnode" );
-    unsigned g = nblk( c->nslice*32, NODE_THREADS );
-    if (fused && c->lax)
-      k_rhs_node< true, true ><<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
-        c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p );
-    else if (fused)
-      k_rhs_node< true, false ><<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
-        c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p );
-    else
-      k_rhs_node< false, false ><<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
-        c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p );
-    ++c->launches;
+    launch_rhs_node( c, fused, A, Un, Uout, 0, c->nslice, s );
   }
   if (halo) {
     exchange_wait( c );
@@ -2121,24 +2257,25 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   static const int lpoet[3][2] = { {0,1}, {1,2}, {2,0} };
   size_t ne = nsup[0]*6 + nsup[1]*3 + nsup[2];
   if (ne > 0x7ffffff0ULL) throw std::runtime_error( "too many edges for 32-bit edge ids" );
-  struct E { int p, q; double d[4]; };
+  struct E { int p, q; double d[5]; };
+  const int drows = stride > 4 ? 5 : 4;
   std::vector< E > edges; edges.reserve( ne );
   auto chk = [&]( size_t id ){ if (id >= npoin) throw std::runtime_error( "node id out of range in superedge" ); return (int)id; };
   for (size_t e=0; e<nsup[0]; ++e)
     for (int k=0; k<6; ++k) {
       E ed; ed.p = chk( dsupedge[0][e*4+lpoed[k][0]] ); ed.q = chk( dsupedge[0][e*4+lpoed[k][1]] );
-      ed.d[3] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[0][(e*6+k)*stride+j];
+      ed.d[3] = ed.d[4] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[0][(e*6+k)*stride+j];
       edges.push_back( ed );
     }
   for (size_t e=0; e<nsup[1]; ++e)
     for (int k=0; k<3; ++k) {
       E ed; ed.p = chk( dsupedge[1][e*3+lpoet[k][0]] ); ed.q = chk( dsupedge[1][e*3+lpoet[k][1]] );
-      ed.d[3] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[1][(e*3+k)*stride+j];
+      ed.d[3] = ed.d[4] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[1][(e*3+k)*stride+j];
       edges.push_back( ed );
     }
   for (size_t e=0; e<nsup[2]; ++e) {
     E ed; ed.p = chk( dsupedge[2][e*2+0] ); ed.q = chk( dsupedge[2][e*2+1] );
-    ed.d[3] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[2][e*stride+j];
+    ed.d[3] = ed.d[4] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[2][e*stride+j];
     edges.push_back( ed );
   }
   // --- edge slots in owner order ----------------------------------------------------
@@ -2164,7 +2301,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   size_t nslot = (size_t)ebase[nslice];
   if (nslot > 0x7ffffff0ULL) throw std::runtime_error( "too many edge slots for 32-bit ids" );
   std::vector< int > ep( nslot, -1 ), eq( nslot, -1 ), slot_of( ne );
-  std::vector< double > ed( 4*nslot, 0.0 );
+  std::vector< double > ed( (size_t)drows*nslot, 0.0 );
   { std::vector< int > fillu( npoin, 0 );
     for (size_t i=0; i<ne; ++i) {
       const auto& e = edges[perm[i]];
@@ -2172,7 +2309,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
       size_t sl = (size_t)ebase[o/32] + (size_t)fillu[o]*32 + (size_t)(o%32);
       ++fillu[o];
       ep[sl] = e.p; eq[sl] = e.q; slot_of[i] = (int)sl;
-      for (int j=0; j<4; ++j) ed[j*nslot+sl] = e.d[j];
+      for (int j=0; j<drows; ++j) ed[j*nslot+sl] = e.d[j];
     } }
   // --- sliced-ELL incidence: node -> (signed slot, neighbour) -------------------------
   // reference scatter: G(p) -= f, G(q) += f with f = d*(u_q+u_p)  (Riemann.cpp:321-323).
@@ -2224,6 +2361,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   c->npoin = npoin; c->NP = NP; c->nedge = ne; c->nslot = nslot; c->ntri = ntri; c->nslice = nslice;
   c->nent = nent; c->nbn = nbn;
   c->ep.upload( ep, s ); c->eq.upload( eq, s ); c->D.upload( ed, s );
+  c->h_ebase = ebase;
   c->sl_base.upload( base, s ); c->inc_e.upload( inc_e, s ); c->inc_q.upload( inc_q, s );
   c->tri.upload( tri, s );
   c->besym.upload( ntri ? std::vector< unsigned char >( besym, besym + ntri*3 ) : std::vector< unsigned char >(), s );
@@ -2237,6 +2375,12 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
     c->vol.upload( pv, s ); c->v.upload( pw, s ); c->X.upload( px, s ); }
   c->fn.alloc( std::max< size_t >( ntri, 1 )*3 );
   if (ntri) { k_face_normals<<< nblk( ntri, 128 ), 128, 0, s >>>( (int)ntri, NP, c->tri.p, c->X.p, c->fn.p ); ++c->launches; CK( cudaGetLastError() ); }
+  if (c->cho) {            // the projection solver keeps its own state (chocg.cuh)
+    for (auto* b : { &c->U, &c->Un, &c->W, &c->G, &c->R, &c->stage, &c->F }) b->release();
+    c->S.release(); c->src_mask = 0;
+    CK( cudaStreamSynchronize( s ) );
+    return 0;
+  }
   c->U.alloc( NP*NC ); c->Un.alloc( NP*NC ); c->W.alloc( NP*NC ); c->G.alloc( NP*15 );
   c->R.alloc( npoin*NC ); c->stage.alloc( npoin*NC ); c->F.alloc( std::max< size_t >( nslot, 1 )*NC );
   { std::vector< double > one( NP*NC, 1.0 );    // a harmless state until xyst_state_set
@@ -2784,6 +2928,51 @@ static void cg_reduce( xyst_ctx* c, int nv, int nb )
   if (c->comm) NK( g_nccl.AllReduce( out, out, (size_t)nv, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream ) );
 }
 
+// y = A x with the Dirichlet conditions of the current solve, if any
+static void cg_spmv( xyst_ctx* c, const double* x, double* y )
+{
+  unsigned g = nblk( c->cg_nslice*32, 256 );
+  if (c->cg_hasbc)
+    k_spmv_bc<<< g, 256, 0, c->stream >>>( c->cg_nrow, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_bc.p, c->cg_cnt.p, x, y );
+  else
+    k_spmv<<< g, 256, 0, c->stream >>>( c->cg_nrow, c->cg_base.p, c->cg_col.p, c->cg_val.p, x, y );
+  ++c->launches;
+}
+
+// ConjugateGradients::setup :105-126 with x and b already on the device (cg_x, cg_b)
+static void cg_setup_dev( xyst_ctx* c, int pc )
+{
+  size_t n = c->cg_nrow;
+  auto s = c->stream;
+  CK( cudaMemsetAsync( c->cg_scal.p, 0, 16*sizeof(double), s ) );
+  c->cg_converged = false; c->cg_finished = false;
+  // residual(): r = A x (own) summed over sharers; pc(): q = 1/count or diag(A), summed
+  cg_spmv( c, c->cg_x.p, c->cg_r.p );
+  if (pc == 0) { k_cg_inv<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_cnt.p, c->cg_d.p ); ++c->launches; }
+  else if (pc == 1) {
+    CK( cudaMemcpyAsync( c->cg_d.p, c->cg_diag.p, n*sizeof(double), cudaMemcpyDeviceToDevice, s ) );
+    if (c->cg_hasbc) { k_cg_bc_diag<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_bc.p, c->cg_cnt.p, c->cg_d.p ); ++c->launches; }
+  }
+  else throw std::runtime_error( "unknown preconditioner" );
+  cg_halo( c, c->cg_r.p, 0 );
+  cg_halo( c, c->cg_d.p, 0 );
+  int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( n, RED_THREADS ) );
+  // normb = sqrt((b,b))
+  k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_b.p, c->cg_b.p, nullptr, nullptr, c->red.p ); ++c->launches;
+  cg_reduce( c, 1, nb );
+  CK( cudaMemcpyAsync( c->red_host, c->cg_scal.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s ) );
+  CK( cudaStreamSynchronize( s ) );
+  c->cg_normb = std::sqrt( c->red_host[0] );
+  // initres(): r = b - r, p = r, z = r/d, rho = (r,z)
+  k_cg_resid<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_b.p, c->cg_r.p, c->cg_p.p ); ++c->launches;
+  k_cg_div<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_r.p, c->cg_d.p, c->cg_z.p ); ++c->launches;
+  k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_r.p, c->cg_z.p, nullptr, nullptr, c->red.p ); ++c->launches;
+  cg_reduce( c, 1, nb );
+  CK( cudaMemcpyAsync( c->cg_scal.p, c->cg_scal.p + 8, sizeof(double), cudaMemcpyDeviceToDevice, s ) );   // rho
+  CK( cudaGetLastError() );
+  CK( cudaStreamSynchronize( s ) );
+}
+
 int xyst_csr_upload( xyst_ctx* c, size_t nrow, size_t ncomp, const size_t* ia, const size_t* ja, const double* a )
 {
   API_BEGIN
@@ -2813,6 +3002,10 @@ int xyst_csr_upload( xyst_ctx* c, size_t nrow, size_t ncomp, const size_t* ia, c
   c->cg_base.upload( base, s ); c->cg_col.upload( col, s ); c->cg_val.upload( val, s ); c->cg_diag.upload( diag, s );
   for (auto* v : { &c->cg_x, &c->cg_b, &c->cg_r, &c->cg_p, &c->cg_q, &c->cg_z, &c->cg_d, &c->cg_mask, &c->cg_cnt }) v->alloc( nrow );
   c->cg_scal.alloc( 16 );
+  // one partition until xyst_cg_setup says otherwise: every row counted once; x = 0
+  c->cg_mask.upload( std::vector< double >( nrow, 1.0 ), s ); c->cg_cnt.upload( std::vector< double >( nrow, 1.0 ), s );
+  CK( cudaMemsetAsync( c->cg_x.p, 0, nrow*sizeof(double), s ) );
+  c->cg_hasbc = false;
   if (c->nsh) {           // halo buffers wide enough for ncomp values per shared node
     size_t w = std::max< size_t >( 15, ncomp );
     c->sh_part.alloc( c->nsh*w ); c->sh_sendbuf.alloc( c->nsend*w ); c->sh_recvbuf.alloc( c->nsend*w );
@@ -2850,33 +3043,8 @@ int xyst_cg_setup( xyst_ctx* c, const double* x, const double* b, int pc, const 
   c->cg_mask.upload( mask, s ); c->cg_cnt.upload( cnt, s );
   CK( cudaMemcpyAsync( c->cg_x.p, x, n*sizeof(double), cudaMemcpyHostToDevice, s ) );
   CK( cudaMemcpyAsync( c->cg_b.p, b, n*sizeof(double), cudaMemcpyHostToDevice, s ) );
-  CK( cudaMemsetAsync( c->cg_scal.p, 0, 16*sizeof(double), s ) );
-  c->cg_converged = false; c->cg_finished = false;
-  // residual(): r = A x (own) summed over sharers; pc(): q = 1/count or diag(A), summed
-  k_spmv<<< nblk( c->cg_nslice*32, 256 ), 256, 0, s >>>( n, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_x.p, c->cg_r.p ); ++c->launches;
-  { std::vector< double > q( n );
-    if (pc == 0) for (size_t i=0; i<n; ++i) q[i] = 1.0 / cnt[i];
-    else if (pc == 1) { CK( cudaMemcpyAsync( q.data(), c->cg_diag.p, n*sizeof(double), cudaMemcpyDeviceToHost, s ) ); CK( cudaStreamSynchronize( s ) ); }
-    else throw std::runtime_error( "unknown preconditioner" );
-    CK( cudaMemcpyAsync( c->cg_d.p, q.data(), n*sizeof(double), cudaMemcpyHostToDevice, s ) );
-    CK( cudaStreamSynchronize( s ) ); }
-  cg_halo( c, c->cg_r.p, 0 );
-  cg_halo( c, c->cg_d.p, 0 );
-  int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( n, RED_THREADS ) );
-  // normb = sqrt((b,b))
-  k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_b.p, c->cg_b.p, nullptr, nullptr, c->red.p ); ++c->launches;
-  cg_reduce( c, 1, nb );
-  CK( cudaMemcpyAsync( c->red_host, c->cg_scal.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s ) );
-  CK( cudaStreamSynchronize( s ) );
-  c->cg_normb = std::sqrt( c->red_host[0] );
-  // initres(): r = b - r, p = r, z = r/d, rho = (r,z)
-  k_cg_resid<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_b.p, c->cg_r.p, c->cg_p.p ); ++c->launches;
-  k_cg_div<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_r.p, c->cg_d.p, c->cg_z.p ); ++c->launches;
-  k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_r.p, c->cg_z.p, nullptr, nullptr, c->red.p ); ++c->launches;
-  cg_reduce( c, 1, nb );
-  CK( cudaMemcpyAsync( c->cg_scal.p, c->cg_scal.p + 8, sizeof(double), cudaMemcpyDeviceToDevice, s ) );   // rho
-  CK( cudaGetLastError() );
-  CK( cudaStreamSynchronize( s ) );
+  c->cg_hasbc = false;
+  cg_setup_dev( c, pc );
   if (normb) *normb = c->cg_normb;
   API_END
 }
@@ -2896,7 +3064,7 @@ int xyst_cg_solve( xyst_ctx* c, size_t maxit, double tol, size_t* it_out, double
     for (;;) {
       k_cg_p<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_scal.p, c->cg_z.p, c->cg_p.p ); ++c->launches;
       { ProfScope ps( c, "spmv" );
-        k_spmv<<< nblk( c->cg_nslice*32, 256 ), 256, 0, s >>>( n, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_p.p, c->cg_q.p ); ++c->launches; }
+        cg_spmv( c, c->cg_p.p, c->cg_q.p ); }
       cg_halo( c, c->cg_q.p, 0 );
       k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_p.p, c->cg_q.p, nullptr, nullptr, c->red.p ); ++c->launches;
       cg_reduce( c, 1, nb );
@@ -2930,6 +3098,10 @@ int xyst_cg_get_x( xyst_ctx* c, double* x )
   CK( cudaStreamSynchronize( c->stream ) );
   API_END
 }
+
+#define XYST_CHOCG_API
+#include "chocg.cuh"
+#undef XYST_CHOCG_API
 
 uint64_t xyst_launch_count( const xyst_ctx* c ) { return c ? c->launches : 0; }
 uint64_t xyst_nedge( const xyst_ctx* c ) { return c ? c->nedge : 0; }

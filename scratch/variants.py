@@ -3,15 +3,13 @@ import os, sys, subprocess, json
 sys.path.insert(0, '.')
 from xyst_b200 import build as B
 VAR = {
- "base": [],
- "v2off": ["MUSCL_V2=0"],
- "g3u4": ["GRAD_MINB=3", "RHS_MINB=3"],
- "g3u8": ["GRAD_MINB=3", "RHS_MINB=3", "NODE_UNROLL=8"],
- "g2u8": ["GRAD_MINB=2", "RHS_MINB=2", "NODE_UNROLL=8"],
- "g4u2": ["NODE_UNROLL=2"],
- "f7": ["FLUX_MINB=7"],
- "f5": ["FLUX_MINB=5"],
- "ft64": ["FLUX_THREADS=64", "FLUX_MINB=12"],
+ "g7r7": [],
+ "g14r7": ["GRAD_UNROLL=14"],
+ "g7r14": ["RHS_UNROLL=14"],
+ "g5r7": ["GRAD_UNROLL=5"],
+ "g7r5": ["RHS_UNROLL=5"],
+ "g7r7n128": ["NODE_THREADS=128", "GRAD_MINB=8", "RHS_MINB=8"],
+ "g7r7f7": ["FLUX_MINB=7"],
 }
 if len(sys.argv) > 3:
     VAR = {k: v for k, v in VAR.items() if k in sys.argv[3].split(",")}

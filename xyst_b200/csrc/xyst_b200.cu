@@ -69,8 +69,15 @@ int fail( const std::string& m ) { g_err = m; return 1; }
 #ifndef NODE_UNROLL
 #define NODE_UNROLL 4
 #endif
+#ifndef GRAD_UNROLL
+#define GRAD_UNROLL 14     // interior nodes of a Kuhn-split box have 14 edges: one full batch
+#endif
+#ifndef RHS_UNROLL
+#define RHS_UNROLL 14
+#endif
 
 constexpr int kNodeUnroll = NODE_UNROLL;
+constexpr int kGradUnroll = GRAD_UNROLL, kRhsUnroll = RHS_UNROLL;
 constexpr int NC = 5;          // flow components handled by the kernels
 
 // ---------------------------------------------------------------------------------
@@ -133,7 +140,6 @@ struct Prof {
 struct xyst_ctx {
   int device = 0;
   cudaStream_t stream = nullptr, comm_stream = nullptr, aux_stream = nullptr;
-  std::vector< long long > h_ebase;      // host copy of the edge-slot offsets per slice
   bool own_stream = false;
   xyst_params prm{};
   size_t npoin = 0, NP = 0, nedge = 0, nslot = 0, ntri = 0, nslice = 0, nent = 0;
@@ -145,6 +151,8 @@ struct xyst_ctx {
   // edge slots (owner-slice order): endpoints (-1 = padding), normals [3][nslot], fluxes [5][nslot]
   DevBuf< int > ep, eq;
   DevBuf< double > D, F;
+  DevBuf< double2 > D2;                  // normals' (x,y) as one 16-byte pair per slot (rows 0,1 of D)
+  DevBuf< int2 > inc_eq;                 // (inc_e, inc_q) as one 8-byte pair per entry
   // sliced-ELL node incidence: signed (slot+1) and neighbour node
   DevBuf< long long > sl_base;           // [nslice+1] entry offsets
   DevBuf< int > inc_e, inc_q;
@@ -260,7 +268,46 @@ __device__ __forceinline__ void cp_async8( double* smem_dst, const double* gsrc 
   asm volatile( "cp.async.ca.shared.global [%0], [%1], 8;" :: "r"( d ), "l"( gsrc ) : "memory" );
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile( "cp.async.commit_group;" ::: "memory" ); }
+// flat index of tk::Fields G(p,i), i = c*3+j, in the structure-of-arrays gradient storage
+__host__ __device__ __forceinline__ size_t gidx( int i, size_t p, size_t NP ) { return (size_t)i*NP + p; }
 template< int N > __device__ __forceinline__ void cp_async_wait() { asm volatile( "cp.async.wait_group %0;" :: "n"( N ) : "memory" ); }
+
+// Primitive variables and coordinates of a node as four 16-byte pairs, pair k of node p at
+// WX[k*NP+p]: (w0,w1) (w2,w3) (w4,x) (y,z) -- what both edge sweeps gather from an edge's other
+// end: 3 loads (gradient) or 4 (flux) instead of 5 or 8, still coalesced over consecutive nodes.
+// x,y,z are written once at upload; writers of W leave them alone.
+__device__ __forceinline__ void load_w( const double2* __restrict__ WX, size_t NP, size_t p, double w[NC] ) {
+  double2 a = __ldg( WX + p ), b = __ldg( WX + NP + p ), c = __ldg( WX + 2*NP + p );
+  w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x;
+}
+__device__ __forceinline__ void load_wx( const double2* __restrict__ WX, size_t NP, size_t p, double w[NC], double x[3] ) {
+  double2 a = __ldg( WX + p ), b = __ldg( WX + NP + p ), c = __ldg( WX + 2*NP + p ), d = __ldg( WX + 3*NP + p );
+  w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; x[0] = c.y; x[1] = d.x; x[2] = d.y;
+}
+__device__ __forceinline__ void store_w( double* __restrict__ W, size_t NP, size_t p, const double w[NC] ) {
+  double2* WX = reinterpret_cast< double2* >( W );
+  WX[p] = make_double2( w[0], w[1] );
+  WX[NP+p] = make_double2( w[2], w[3] );
+  W[(2*NP+p)*2] = w[4];
+}
+__device__ __forceinline__ double get_w( const double* __restrict__ W, size_t NP, int c, size_t p ) {
+  return W[((size_t)(c>>1)*NP + p)*2 + (size_t)(c&1)];
+}
+// Edge fluxes as (f0,f1) (f2,f3) pairs and f4: component c of slot e
+__host__ __device__ __forceinline__ size_t fidx( int c, size_t e, size_t nslot ) {
+  return c < 4 ? (size_t)(c>>1)*2*nslot + 2*e + (size_t)(c&1) : 4*nslot + e;
+}
+__device__ __forceinline__ void store_f( double* __restrict__ F, size_t nslot, size_t e, const double f[NC] ) {
+  double2* F2 = reinterpret_cast< double2* >( F );
+  F2[e] = make_double2( f[0], f[1] );
+  F2[nslot+e] = make_double2( f[2], f[3] );
+  F[4*nslot+e] = f[4];
+}
+__device__ __forceinline__ void load_f( const double* __restrict__ F, size_t nslot, size_t e, double f[NC] ) {
+  const double2* F2 = reinterpret_cast< const double2* >( F );
+  double2 a = __ldg( F2 + e ), b = __ldg( F2 + nslot + e );
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = __ldg( F + 4*nslot + e );
+}
 
 // reference layout [node][comp] -> SoA state + primitives
 __global__ void k_set_state( size_t n, size_t NP, const double* __restrict__ A,
@@ -273,7 +320,8 @@ __global__ void k_set_state( size_t n, size_t NP, const double* __restrict__ A,
   for (int c=0; c<NC; ++c) u[c] = A[p*NC+c];
   primitive_of( u, w, M );
   #pragma unroll
-  for (int c=0; c<NC; ++c) { U[c*NP+p] = u[c]; W[c*NP+p] = w[c]; }
+  for (int c=0; c<NC; ++c) U[c*NP+p] = u[c];
+  store_w( W, NP, p, w );
 }
 
 __global__ void k_get_state( size_t n, size_t NP, const double* __restrict__ U, double* __restrict__ A )
@@ -326,7 +374,7 @@ __global__ void k_bnd_grad( int nbn, size_t NP, const int* __restrict__ bn_off, 
     double n[3] = { fn[(size_t)f*3+0], fn[(size_t)f*3+1], fn[(size_t)f*3+2] };
     #pragma unroll
     for (int c=0; c<NC; ++c) {
-      double u0 = W[c*NP+N[0]], u1 = W[c*NP+N[1]], u2 = W[c*NP+N[2]];
+      double u0 = get_w( W, NP, c, N[0] ), u1 = get_w( W, NP, c, N[1] ), u2 = get_w( W, NP, c, N[2] );
       double uab = (u0 + u1)/4.0;
       double ubc = (u1 + u2)/4.0;
       double uca = (u2 + u0)/4.0;
@@ -355,7 +403,7 @@ __global__ void k_bnd_rhs( int nbn, size_t NP, const int* __restrict__ bn_off, c
       double fl[NC][3];
       #pragma unroll
       for (int m=0; m<3; ++m) {
-        double pr = W[N[m]], uu = W[NP+N[m]], vv = W[2*NP+N[m]], ww = W[3*NP+N[m]], T = W[4*NP+N[m]];
+        double pr = get_w( W, NP, 0, N[m] ), uu = get_w( W, NP, 1, N[m] ), vv = get_w( W, NP, 2, N[m] ), ww = get_w( W, NP, 3, N[m] ), T = get_w( W, NP, 4, N[m] );
         double rA = pr/T/rgas;
         double ruA = uu * rA, rvA = vv * rA, rwA = ww * rA;
         double reA = pr/(gamma-1.0) + 0.5*(ruA*ruA + rvA*rvA + rwA*rwA)/rA;
@@ -416,25 +464,28 @@ __global__ void k_bnd_rhs( int nbn, size_t NP, const int* __restrict__ bn_off, c
 // -(slot+1) if it is the first (receives -f), 0 = padding (multiplier 0 on slot 0)
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void grad_sum( size_t p, int lane, long long base, int kmax,
-    const int* __restrict__ inc_e, const int* __restrict__ inc_q, const double* __restrict__ D,
+    const int2* __restrict__ inc_eq, const double2* __restrict__ D2, const double* __restrict__ D,
     size_t nslot, const double* __restrict__ W, size_t NP, double acc[15] )
 {
+  const double2* WX = reinterpret_cast< const double2* >( W );
   double wp[NC];
-  #pragma unroll
-  for (int c=0; c<NC; ++c) wp[c] = __ldg( W + c*NP + p );
+  load_w( WX, NP, p, wp );
   #pragma unroll
   for (int i=0; i<15; ++i) acc[i] = 0.0;
-  #pragma unroll kNodeUnroll
+  #pragma unroll kGradUnroll
   for (int k=0; k<kmax; ++k) {
     long long i = base + (long long)k*32 + lane;
-    int se = __ldg( inc_e + i );
-    int q = __ldg( inc_q + i );
+    int2 eq = __ldg( inc_eq + i );
+    int se = eq.x, q = eq.y;
     double sg = se > 0 ? 1.0 : (se < 0 ? -1.0 : 0.0);
     size_t sl = se == 0 ? 0 : (size_t)(abs(se)-1);
-    double d0 = sg * __ldg( D + sl ), d1 = sg * __ldg( D + nslot + sl ), d2 = sg * __ldg( D + 2*nslot + sl );
+    double2 d01 = __ldg( D2 + sl );
+    double d0 = sg * d01.x, d1 = sg * d01.y, d2 = sg * __ldg( D + 2*nslot + sl );
+    double wq[NC];
+    load_w( WX, NP, (size_t)q, wq );
     #pragma unroll
     for (int c=0; c<NC; ++c) {
-      double s = __ldg( W + c*NP + q ) + wp[c];
+      double s = wq[c] + wp[c];
       acc[c*3+0] += d0 * s;
       acc[c*3+1] += d1 * s;
       acc[c*3+2] += d2 * s;
@@ -443,8 +494,8 @@ __device__ __forceinline__ void grad_sum( size_t p, int lane, long long base, in
 }
 
 __global__ void __launch_bounds__(NODE_THREADS, GRAD_MINB)
-k_grad_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
-             const int* __restrict__ inc_q, const double* __restrict__ D, size_t nslot,
+k_grad_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq,
+             const double2* __restrict__ D2, const double* __restrict__ D, size_t nslot,
              const double* __restrict__ W, const int* __restrict__ bslot, const double* __restrict__ Gb,
              const double* __restrict__ vol, double* __restrict__ G, int defer_bnd )
 {
@@ -455,7 +506,7 @@ k_grad_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
   double acc[15];
-  grad_sum( p, lane, base, kmax, inc_e, inc_q, D, nslot, W, NP, acc );
+  grad_sum( p, lane, base, kmax, inc_eq, D2, D, nslot, W, NP, acc );
   int b = bslot[p];
   if (b >= 0) {
     if (defer_bnd) {          // boundary part and division follow in k_grad_bfix (same operation order)
@@ -479,13 +530,14 @@ __global__ void k_grad_bfix( int nbn, size_t NP, const int* __restrict__ bn_node
   if (i >= (size_t)nbn*15) return;
   size_t b = i / 15, k = i % 15;
   size_t p = bn_node[b];
-  G[k*NP+p] = (G[k*NP+p] + Gb[b*15+k]) / vol[p];
+  size_t g = gidx( (int)k, p, NP );
+  G[g] = (G[g] + Gb[b*15+k]) / vol[p];
 }
 
 // partial (un-normalised) gradient sums of the shared nodes, for the halo exchange
 __global__ void k_grad_shared( int nsh, size_t NP, const int* __restrict__ sh_node,
-             const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
-             const int* __restrict__ inc_q, const double* __restrict__ D, size_t nslot,
+             const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq,
+             const double2* __restrict__ D2, const double* __restrict__ D, size_t nslot,
              const double* __restrict__ W, const int* __restrict__ bslot,
              const double* __restrict__ Gb, double* __restrict__ part )
 {
@@ -496,7 +548,7 @@ __global__ void k_grad_shared( int nsh, size_t NP, const int* __restrict__ sh_no
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
   double acc[15];
-  grad_sum( p, lane, base, kmax, inc_e, inc_q, D, nslot, W, NP, acc );
+  grad_sum( p, lane, base, kmax, inc_eq, D2, D, nslot, W, NP, acc );
   int b = bslot[p];
   if (b >= 0) for (int j=0; j<15; ++j) acc[j] += Gb[(size_t)b*15+j];
   for (int j=0; j<15; ++j) part[(size_t)i*15+j] = acc[j];
@@ -522,7 +574,7 @@ __global__ void k_grad_finish( int nsh, size_t NP, const int* __restrict__ sh_no
   for (int j=0; j<15; ++j) {
     double a = part[(size_t)i*15+j];
     for (int r=roff[i]; r<roff[i+1]; ++r) a += recvbuf[(size_t)ridx[r]*15+j];
-    G[j*NP+p] = a / vp;
+    G[gidx( j, p, NP )] = a / vp;
   }
 }
 
@@ -891,18 +943,18 @@ k_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __r
   for (int i=0; i<15; ++i) { cp_async8( gp + i*FLUX_THREADS, G + i*NP + p ); cp_async8( gq + i*FLUX_THREADS, G + i*NP + q ); }
   cp_async_commit();
   double n[3] = { D[e], D[nslot+e], D[2*nslot+e] };
-  double l[NC], r[NC], vw[3];
+  double l[NC], r[NC], vw[3], xp[3];
+  const double2* WX = reinterpret_cast< const double2* >( W );
+  load_wx( WX, NP, p, l, xp );
+  load_wx( WX, NP, q, r, vw );
   #pragma unroll
-  for (int c=0; c<NC; ++c) { l[c] = __ldg( W + c*NP + p ); r[c] = __ldg( W + c*NP + q ); }
-  #pragma unroll
-  for (int j=0; j<3; ++j) vw[j] = __ldg( X + j*NP + q ) - __ldg( X + j*NP + p );
+  for (int j=0; j<3; ++j) vw[j] -= xp[j];
   cp_async_wait< 0 >();
   muscl< EXACT >( gp, FLUX_THREADS, gq, FLUX_THREADS, vw, l, r );
   double f[NC];
   if (FLUX == 0) rusanov( l, r, n, P, f ); else if (FLUX == 1) hllc( l, r, n, P, f );
   else if (FLUX == 2) lax_rusanov( l, r, n, P, f ); else lax_hllc( l, r, n, P, f );
-  #pragma unroll
-  for (int c=0; c<NC; ++c) F[c*nslot+e] = f[c];
+  store_f( F, nslot, e, f );
 }
 
 // ---------------------------------------------------------------------------------
@@ -916,13 +968,15 @@ __device__ __forceinline__ void rhs_sum( size_t p, int lane, long long base, int
   #pragma unroll
   for (int c=0; c<NC; ++c) acc[c] = 0.0;
   // sg*f is exact, so this equals the add/subtract of the reference's scatter
-  #pragma unroll kNodeUnroll
+  #pragma unroll kRhsUnroll
   for (int k=0; k<kmax; ++k) {
     int se = __ldg( inc_e + base + (long long)k*32 + lane );
     double sg = se > 0 ? 1.0 : (se < 0 ? -1.0 : 0.0);
     size_t sl = se == 0 ? 0 : (size_t)(abs(se)-1);
+    double f[NC];
+    load_f( F, nslot, sl, f );
     #pragma unroll
-    for (int c=0; c<NC; ++c) acc[c] = fma( sg, __ldg( F + c*nslot + sl ), acc[c] );
+    for (int c=0; c<NC; ++c) acc[c] = fma( sg, f[c], acc[c] );
   }
   int b = bslot[p];
   if (b >= 0) {
@@ -953,7 +1007,7 @@ __device__ __forceinline__ void node_update( size_t p, size_t NP, const double a
     double g = A.M.gamma, rgas = A.M.rgas;
     double wn[NC];
     #pragma unroll
-    for (int c=0; c<NC; ++c) w[c] = W[c*NP+p];
+    for (int c=0; c<NC; ++c) w[c] = get_w( W, NP, c, p );
     if (A.stage == 0) {
       #pragma unroll
       for (int c=0; c<NC; ++c) { wn[c] = w[c]; Wn[c*NP+p] = w[c]; }
@@ -984,7 +1038,8 @@ __device__ __forceinline__ void node_update( size_t p, size_t NP, const double a
     lax_conservative( wnew, u, g, rgas );
     lax_primitive( u, w, g, rgas );
     #pragma unroll
-    for (int c=0; c<NC; ++c) { U[c*NP+p] = u[c]; W[c*NP+p] = w[c]; }
+    for (int c=0; c<NC; ++c) U[c*NP+p] = u[c];
+    store_w( W, NP, p, w );
     if (A.stage == 2) {                   // conservative( m_un ) for the diagnostics, :1196
       double un[NC];
       lax_conservative( wn, un, g, rgas );
@@ -996,8 +1051,7 @@ __device__ __forceinline__ void node_update( size_t p, size_t NP, const double a
     #pragma unroll
     for (int c=0; c<NC; ++c) { u[c] = Un[c*NP+p] - rkdt * acc[c] / vp; U[c*NP+p] = u[c]; }
     primitive( u, w );
-    #pragma unroll
-    for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+    store_w( W, NP, p, w );
   }
 }
 
@@ -1134,7 +1188,7 @@ __global__ void k_bc( int nbc, size_t NP, const int* __restrict__ node, const in
   double w[NC];
   for (int c=0; c<NC; ++c) U[c*NP+p] = u[c];
   primitive_of( u, w, M );
-  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+  store_w( W, NP, p, w );
 }
 
 // ---------------------------------------------------------------------------------
@@ -1312,8 +1366,7 @@ k_zal_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int*
     f[0] -= fw*(rL - rR); f[1] -= fw*(ruL - ruR); f[2] -= fw*(rvL - rvR);
     f[3] -= fw*(rwL - rwR); f[4] -= fw*(reL - reR);
   }
-  #pragma unroll
-  for (int c=0; c<NC; ++c) F[c*nslot+e] = f[c];
+  store_f( F, nslot, e, f );
 }
 
 // pass 1 (aec + first half of alw): R = sum +-F + boundary; P+/- from the antidiffusive edge
@@ -1345,7 +1398,7 @@ k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
     double dif = __ldg( D + 3*nslot + sl );
     #pragma unroll
     for (int c=0; c<NC; ++c) {
-      double f = __ldg( F + c*nslot + sl );
+      double f = __ldg( F + fidx( c, sl, nslot ) );
       double uq = __ldg( U + c*NP + q );
       if (se < 0) {                       // this node is the edge's first node
         r[c] -= f;
@@ -1483,8 +1536,7 @@ k_zal_node3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
   #pragma unroll
   for (int c=0; c<NC; ++c) { u[c] = UL[c*NP+p] + a[c]/vp; Unew[c*NP+p] = u[c]; }
   primitive( u, w );
-  #pragma unroll
-  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+  store_w( W, NP, p, w );
 }
 
 // fct = false: u = u - dt R/vol (ZalCG.cpp:1560-1567)
@@ -1497,8 +1549,7 @@ __global__ void k_zal_nofct( size_t npoin, size_t NP, const double* __restrict__
   #pragma unroll
   for (int c=0; c<NC; ++c) { u[c] = U[c*NP+p] - dt*R[p*NC+c]/vp; Unew[c*NP+p] = u[c]; }
   primitive( u, w );
-  #pragma unroll
-  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+  store_w( W, NP, p, w );
 }
 
 // ---------------------------------------------------------------------------------
@@ -1778,8 +1829,7 @@ k_koz_node3( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__
   #pragma unroll
   for (int c=0; c<NC; ++c) { u[c] = UL[c*NP+p] + a_[c]/vp; Unew[c*NP+p] = u[c]; }
   primitive( u, w );
-  #pragma unroll
-  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+  store_w( W, NP, p, w );
 }
 
 // fct = false: u = u + dt R/vol (KozCG.cpp:1150-1157)
@@ -1792,8 +1842,7 @@ __global__ void k_koz_nofct( size_t npoin, size_t NP, const double* __restrict__
   #pragma unroll
   for (int c=0; c<NC; ++c) { u[c] = U[c*NP+p] + dt*R[p*NC+c]/vp; Unew[c*NP+p] = u[c]; }
   primitive( u, w );
-  #pragma unroll
-  for (int c=0; c<NC; ++c) W[c*NP+p] = w[c];
+  store_w( W, NP, p, w );
 }
 
 // ---------------------------------------------------------------------------------
@@ -2061,13 +2110,13 @@ void do_grad( xyst_ctx* c )
   }
   if (halo) {
     k_grad_shared<<< nblk( c->nsh, 128 ), 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sl_base.p,
-      c->inc_e.p, c->inc_q.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->sh_part.p ); ++c->launches;
+      c->inc_eq.p, c->D2.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->sh_part.p ); ++c->launches;
     exchange( c, 15 );
   }
   {
     ProfScope ps( c, "grad" );
     k_grad_node<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p,
-      c->inc_e.p, c->inc_q.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->vol.p, c->G.p, overlap ? 1 : 0 );
+      c->inc_eq.p, c->D2.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->vol.p, c->G.p, overlap ? 1 : 0 );
     ++c->launches;
   }
   if (overlap) {
@@ -2361,7 +2410,12 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   c->npoin = npoin; c->NP = NP; c->nedge = ne; c->nslot = nslot; c->ntri = ntri; c->nslice = nslice;
   c->nent = nent; c->nbn = nbn;
   c->ep.upload( ep, s ); c->eq.upload( eq, s ); c->D.upload( ed, s );
-  c->h_ebase = ebase;
+  { std::vector< double2 > d2( nslot );
+    for (size_t i=0; i<nslot; ++i) d2[i] = make_double2( ed[i], ed[nslot+i] );
+    c->D2.upload( d2, s );
+    std::vector< int2 > iq( nent );
+    for (size_t i=0; i<nent; ++i) iq[i] = make_int2( inc_e[i], inc_q[i] );
+    c->inc_eq.upload( iq, s ); }
   c->sl_base.upload( base, s ); c->inc_e.upload( inc_e, s ); c->inc_q.upload( inc_q, s );
   c->tri.upload( tri, s );
   c->besym.upload( ntri ? std::vector< unsigned char >( besym, besym + ntri*3 ) : std::vector< unsigned char >(), s );
@@ -2381,10 +2435,14 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
     CK( cudaStreamSynchronize( s ) );
     return 0;
   }
-  c->U.alloc( NP*NC ); c->Un.alloc( NP*NC ); c->W.alloc( NP*NC ); c->G.alloc( NP*15 );
+  c->U.alloc( NP*NC ); c->Un.alloc( NP*NC ); c->G.alloc( NP*15 );
   c->R.alloc( npoin*NC ); c->stage.alloc( npoin*NC ); c->F.alloc( std::max< size_t >( nslot, 1 )*NC );
   { std::vector< double > one( NP*NC, 1.0 );    // a harmless state until xyst_state_set
-    c->U.upload( one, s ); c->Un.upload( one, s ); c->W.upload( one, s ); }
+    c->U.upload( one, s ); c->Un.upload( one, s );
+    // primitives + coordinates as pairs (w0,w1) (w2,w3) (w4,x) (y,z), see load_wx
+    std::vector< double > wx( NP*8, 1.0 );
+    for (size_t p=0; p<npoin; ++p) { wx[(2*NP+p)*2+1] = x[p]; wx[(3*NP+p)*2] = y[p]; wx[(3*NP+p)*2+1] = z[p]; }
+    c->W.upload( wx, s ); }
   CK( cudaMemsetAsync( c->G.p, 0, NP*15*sizeof(double), s ) );
   CK( cudaMemsetAsync( c->F.p, 0, std::max< size_t >( nslot, 1 )*NC*sizeof(double), s ) );
   c->S.release(); c->src_mask = 0;
@@ -2582,7 +2640,7 @@ int xyst_grad_get( xyst_ctx* c, double* G )
   std::vector< double > h( c->NP*15 );
   CK( cudaMemcpyAsync( h.data(), c->G.p, h.size()*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
   CK( cudaStreamSynchronize( c->stream ) );
-  for (size_t p=0; p<c->npoin; ++p) for (size_t i=0; i<15; ++i) G[p*15+i] = h[i*c->NP+p];
+  for (size_t p=0; p<c->npoin; ++p) for (int i=0; i<15; ++i) G[p*15+(size_t)i] = h[gidx( i, p, c->NP )];
   API_END
 }
 

@@ -29,7 +29,7 @@ typedef struct xyst_host_cfg {
   double gamma, p0, cfl, dt, t0, term, stab2coef;
   double far_density, far_pressure, far_velocity[3];
   double pre_density[16], pre_pressure[16];
-  char solver[16];            /* "riecg" (default when empty) | "zalcg" | "kozcg" | "laxcg" */
+  char solver[16];            /* "riecg" (default when empty) | "zalcg" | "kozcg" | "laxcg" | "chocg" */
   int32_t fct, fctclip, nfctsys;
   int32_t fctsys[8];
   double fctdif;
@@ -39,6 +39,20 @@ typedef struct xyst_host_cfg {
   double residual;
   double rgas, turkel, velinf[3];      /* rgas = 0: reference default 287.052874 */
   double ic_density, ic_pressure, ic_velocity[3];
+  /* ChoCG (solver "chocg", ncomp 3): flux "damp2" | "damp4", viscosity/diffusivity, stabilisation,
+   * RK stages (1..4, 0 = 1), no-slip sets, Dirichlet values { setid, v_0..v_2 }, pressure solve
+   * (iterations, tolerance, preconditioner "none" | "jacobi", Dirichlet { setid, mask } + values
+   * { setid, value }, Neumann sets, hydrostat node (global id) if p_hydrostat_set) */
+  double mu, dif;
+  int32_t stab;
+  int32_t nnoslip; int32_t noslip[16];
+  uint64_t rk;
+  int32_t ndirval; double dirval[16][12];
+  uint64_t p_iter; double p_tol; char p_pc[16];
+  int32_t np_dir; int32_t p_dir[16][2];
+  int32_t np_dirval; double p_dirval[16][2];
+  int32_t np_sym; int32_t p_sym[16];
+  int32_t p_hydrostat_set; uint64_t p_hydrostat;
 } xyst_host_cfg;
 
 typedef struct xyst_solver xyst_solver;

@@ -84,3 +84,39 @@ def test_time_stepping_matches_oracle_and_golden(case):
     assert relerr(d.ctx.chocg_get("pr"), o.get("pr")) < 1e-8
     assert (np.abs(rows - gold) <= 2e-8 * np.abs(gold) + 1e-12).all()
     print(case, "max rel diag diff vs oracle", (np.abs(rows - ro) / np.maximum(np.abs(ro), 1e-300)).max())
+
+
+def host_solver_for(case):
+    from xyst_b200 import hostapi as H
+    from host_common import fixture_to_host_mesh
+    kw = O.CCASES[case]
+    hm = fixture_to_host_mesh(O.load_mesh(kw["mesh"]))
+    s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"], hm["set_tri"])
+    s.prepare(); s.attach(0); s.setup()
+    return s, kw
+
+
+@pytest.mark.parametrize("case", list(O.CCASES))
+def test_host_mirror_chocg_matches_oracle_and_golden(case):
+    """The drop-in path end to end: the C++ host mirror of ChoCG (setup: stride-5 integrals,
+    BC lists, Poisson matrix; control flow of the projection step) driving the device."""
+    s, kw = host_solver_for(case)
+    gold = O.load_golden_diag(case)
+    n = int(gold[-1, 0])
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    rows = []
+    for _ in range(n):
+        r = s.step(1)
+        o.step(1)
+        if len(r):
+            rows.append(r[0])
+        if kw.get("nstep") != 1:
+            assert int(s.scalar("pit")) == int(o.scalar("pit"))
+    rows = np.asarray(rows); ro = o.diag()
+    assert rows.shape == ro.shape == gold.shape
+    neu = case == "chocg_poisson_neumann"
+    assert (np.abs(rows[:, :3] - ro[:, :3]) <= TOL * np.abs(ro[:, :3])).all()
+    assert (np.abs(rows - ro) <= (2e-6 if neu else 1e-9) * np.abs(ro) + 1e-11 * np.abs(ro[:, 3:4])).all()
+    assert relerr(s.get("u"), o.get("u")) < (2e-6 if neu else 1e-9) or np.abs(o.get("u")).max() < 1e-10
+    assert relerr(s.get("pr"), o.get("pr")) < (2e-7 if neu else 1e-8)
+    assert (np.abs(rows - gold) <= (2e-7 if neu else 2e-8) * np.abs(gold) + 1e-12).all()

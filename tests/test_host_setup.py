@@ -121,3 +121,30 @@ def test_zalcg_setup_matches_oracle(case):
         assert np.array_equal(o.get(n), s.get(n)), n
     assert np.array_equal(np.sort(o.get("dsupint2").reshape(-1, 4), axis=0), np.sort(s.get("dsupint2").reshape(-1, 4), axis=0))
     assert np.array_equal(o.get("gid"), np.arange(len(o.get("gid")), dtype=np.uint64))      # not renumbered
+
+
+@pytest.mark.parametrize("case", ["chocg_poiseuille_damp4", "chocg_ldc", "chocg_poisson_neumann"])
+def test_chocg_setup(case):
+    """ChoCG: stride-5 edge integrals (normal, J/120, Laplacian term; ChoCG.cpp:399-446), Dirichlet
+    masks/values of velocity and pressure (:210-300), no-slip nodes (:655-682), the pressure
+    Poisson matrix in tk::CSR form (:146-188) -- all bitwise equal to the oracle's."""
+    kw = O.CCASES[case]
+    mesh = O.load_mesh(kw["mesh"])
+    o = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    hm = fixture_to_host_mesh(mesh)
+    s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"], hm["set_tri"])
+    s.prepare(); s.host_setup()
+    for n in EXACT + ["plhs_ia", "plhs_ja", "plhs_a", "noslipbcnodes", "symbcnodes", "symbcnorms"]:
+        assert np.array_equal(o.get(n), s.get(n)), n
+    # single edges: same (edge, 5 integrals) set; order is hash order in the reference
+    def singles(g):
+        e = g("dsupedge2").reshape(-1, 2); d = g("dsupint2").reshape(-1, 5)
+        return sorted((tuple(a), tuple(b)) for a, b in zip(e.tolist(), d.tolist()))
+    assert singles(o.get) == singles(s.get)
+    assert face_multiset(o.get("triinpoel"), o.get("bface")) == face_multiset(s.get("triinpoel"), s.get("bface"))
+    for masks, vals, w in (("dirbcmasks", "dirbcval", 4), ("dirbcmaskp", "dirbcvalp", 2)):
+        mo, ms = o.get(masks).reshape(-1, w), s.get(masks).reshape(-1, w)
+        assert np.array_equal(mo[np.argsort(mo[:, 0])], ms[np.argsort(ms[:, 0])]), masks
+        vo, vs = o.get(vals).reshape(-1, w), s.get(vals).reshape(-1, w)
+        assert np.array_equal(vo[np.argsort(vo[:, 0])], vs[np.argsort(vs[:, 0])]), vals
+    assert s.scalar("meshvol") == o.scalar("meshvol")     # (the oracle's u0 already carries BC(t0): compared on the GPU)

@@ -51,6 +51,16 @@ Config to_cfg( const xyst_host_cfg* c ) {
   k.turkel = c->turkel; k.velinf = {{ c->velinf[0], c->velinf[1], c->velinf[2] }};
   k.ic_density = c->ic_density; k.ic_pressure = c->ic_pressure;
   k.ic_velocity = {{ c->ic_velocity[0], c->ic_velocity[1], c->ic_velocity[2] }};
+  if (k.solver == "chocg") {
+    k.mu = c->mu; k.dif = c->dif; k.stab = c->stab != 0; k.rk = c->rk ? c->rk : 1;
+    for (int i=0; i<c->nnoslip; ++i) k.bc_noslip.push_back( c->noslip[i] );
+    for (int i=0; i<c->ndirval; ++i) k.bc_dirval.emplace_back( c->dirval[i], c->dirval[i] + k.ncomp+1 );
+    k.p_iter = c->p_iter; k.p_tol = c->p_tol; if (c->p_pc[0]) k.p_pc = c->p_pc;
+    for (int i=0; i<c->np_dir; ++i) k.p_bc_dir.push_back( { c->p_dir[i][0], c->p_dir[i][1] } );
+    for (int i=0; i<c->np_dirval; ++i) k.p_bc_dirval.push_back( { c->p_dirval[i][0], c->p_dirval[i][1] } );
+    for (int i=0; i<c->np_sym; ++i) k.p_bc_sym.push_back( c->p_sym[i] );
+    if (c->p_hydrostat_set) k.p_hydrostat = c->p_hydrostat;
+  }
   return k;
 }
 
@@ -173,7 +183,7 @@ int xyst_solver_step( xyst_solver* s, int nsteps, double* rows, size_t cap, size
   size_t nr = 0, nc = 0, used = 0;
   std::vector< real > row;
   for (int i=0; i<nsteps; ++i) {
-    if (s->riecg->m_finished) break;
+    if (s->riecg->m_finished && !s->riecg->pendingDiag()) break;
     s->riecg->step( rows ? &row : nullptr );
     if (rows && !row.empty()) {
       nc = row.size();
@@ -212,6 +222,7 @@ double xyst_solver_scalar( xyst_solver* s, const char* name )
   if (n == "it") return static_cast< double >( d.It() );
   if (n == "meshvol") return d.MeshVol();
   if (n == "finished") return s->riecg->m_finished ? 1.0 : 0.0;
+  if (n == "pit") return static_cast< double >( s->riecg->m_pit );
   if (n == "nshared") return static_cast< double >( d.sharedNodes().size() );
   if (n.rfind( "timing", 0 ) == 0) { auto i = static_cast< std::size_t >( std::stoi( n.substr(6) ) ); return i < s->riecg->timings.size() ? s->riecg->timings[i] : -1.0; }
   return std::nan( "" );
@@ -240,6 +251,16 @@ size_t xyst_solver_get( xyst_solver* s, const char* name, void* out, size_t cap 
     if (n == "dirbcmasks") return put( r.m_dirbcmasks, out, cap );
     if (n == "symbcnodes") return put( r.m_symbcnodes, out, cap );
     if (n == "symbcnorms") return put( r.m_symbcnorms, out, cap );
+    if (n == "dirbcval") return put( r.m_dirbcval, out, cap );
+    if (n == "dirbcmaskp") return put( r.m_dirbcmaskp, out, cap );
+    if (n == "dirbcvalp") return put( r.m_dirbcvalp, out, cap );
+    if (n == "noslipbcnodes") return put( r.m_noslipbcnodes, out, cap );
+    if (n == "plhs_ia") return put( r.m_plhs_ia, out, cap );
+    if (n == "plhs_ja") return put( r.m_plhs_ja, out, cap );
+    if (n == "plhs_a") return put( r.m_plhs_a, out, cap );
+    if (n == "pr") return put( r.choGet( "pr", 1 ), out, cap );
+    if (n == "dp") return put( r.choGet( "dp", 1 ), out, cap );
+    if (n == "pgrad") return put( r.choGet( "pgrad", 3 ), out, cap );
     if (n == "u0") return put( r.m_u0, out, cap );
     if (n == "u") return put( r.solution(), out, cap );
     if (n == "shared") return put( d.sharedNodes(), out, cap );

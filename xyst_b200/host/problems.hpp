@@ -23,6 +23,18 @@ inline real totalenergy( real g, real r, real u, real v, real w, real p ) {
 
 inline Fn IC( const Config& cfg ) {
   const real g = cfg.gamma;
+  if (cfg.solver == "chocg") {                  // velocity unknowns only: entries 0..2
+    const auto& p = cfg.problem;
+    if (p == "userdef") { const auto vel = cfg.ic_velocity;                    // userdef::ic :44-52
+      return [vel]( real, real, real, real ) -> std::array< real, 5 > { return {{ vel[0], vel[1], vel[2], 0, 0 }}; }; }
+    if (p.find( "poisson" ) != std::string::npos)
+      return []( real, real, real, real ) -> std::array< real, 5 > { return {{ 0, 0, 0, 0, 0 }}; };
+    if (p == "poiseuille") { const real mu = cfg.mu;                           // poiseuille::ic :999-1026
+      return [mu]( real, real y, real, real ) -> std::array< real, 5 > {
+        auto dpdx = -0.12;
+        return {{ -dpdx * y * (1.0 - y) / 2.0 / mu, 0, 0, 0, 0 }}; }; }
+    throw std::runtime_error( "problem type ic not hooked up: " + p );
+  }
   if (cfg.problem == "sedov") {
     const real p0 = cfg.p0;
     return [g,p0]( real x, real y, real z, real ) -> std::array< real, 5 > {
@@ -68,6 +80,39 @@ inline Fn SRC( const Config& cfg ) {
       s[4] = 3.0*M_PI/8.0*( std::cos(3.0*M_PI*x)*std::cos(M_PI*y)
                           - std::cos(3.0*M_PI*y)*std::cos(M_PI*x) );
       return s; };
+  return {};
+}
+
+// pressure problems of the projection solvers, Problems.cpp:841-997,1172-1262
+using PFn = std::function< real( real, real, real ) >;
+inline PFn PRESSURE_RHS( const Config& cfg ) {
+  const auto& p = cfg.problem;
+  if (p == "poisson_const") return []( real, real, real ){ return 6.0; };
+  if (p == "poisson_sine") return []( real x, real y, real z ){ return -M_PI * M_PI * x * y * std::sin( M_PI * z ); };
+  if (p == "poisson_sine3") return []( real x, real y, real z ){
+    return -3.0 * M_PI * M_PI * std::sin(M_PI*x) * std::sin(M_PI*y) * std::sin(M_PI*z); };
+  if (p == "poisson_neumann") return []( real x, real y, real ){ return -3.0 * std::cos(2.0*x) * std::exp(y); };
+  return {};
+}
+inline PFn PRESSURE_IC( const Config& cfg ) {
+  const auto& p = cfg.problem;
+  if (p == "userdef" || p == "slot_cyl" || p == "sheardiff" || p == "poiseuille" || p == "point_src")
+    return []( real, real, real ){ return 0.0; };
+  if (p == "poisson_const") return []( real x, real y, real z ){ return x*x + y*y + z*z; };
+  if (p == "poisson_sine") return []( real x, real y, real z ){ return x * y * std::sin( M_PI * z ); };
+  if (p == "poisson_sine3") return []( real x, real y, real z ){ return std::sin(M_PI*x) * std::sin(M_PI*y) * std::sin(M_PI*z); };
+  if (p == "poisson_neumann") return []( real x, real y, real ){ return std::cos(2.0*x) * std::exp(y); };
+  throw std::runtime_error( "pressure ic not hooked up: " + p );
+}
+inline PFn PRESSURE_SOL( const Config& cfg ) {
+  const auto& p = cfg.problem;
+  if (p == "userdef" || p == "slot_cyl" || p == "poiseuille" || p == "point_src" || p == "sheardiff") return {};
+  return PRESSURE_IC( cfg );
+}
+inline std::function< std::array< real, 3 >( real, real, real ) > PRESSURE_GRAD( const Config& cfg ) {
+  if (cfg.problem == "poisson_neumann")
+    return []( real x, real y, real ) -> std::array< real, 3 > {
+      return {{ -2.0 * std::sin( 2.0 * x ) * std::exp( y ), std::cos(2.0*x) * std::exp(y), 0.0 }}; };
   return {};
 }
 

@@ -124,15 +124,18 @@ std::vector< std::size_t > Discretization::sharedNodes() const {
 RieCG::RieCG( Discretization& disc, const TetMesh& chunk, const Config& cfg )
   : m_disc( disc ), m_cfg( cfg ), m_sidetri( chunk.sidetri )
 {
-  if (cfg.ncomp != 5) throw std::runtime_error( "only ncomp = 5 is supported" );
-  if (cfg.solver != "riecg" && cfg.solver != "zalcg" && cfg.solver != "kozcg" && cfg.solver != "laxcg")
+  if (cfg.solver != "riecg" && cfg.solver != "zalcg" && cfg.solver != "kozcg" && cfg.solver != "laxcg" && cfg.solver != "chocg")
     throw std::runtime_error( "Unknown solver: " + cfg.solver );
   m_zal = cfg.solver == "zalcg"; m_stride = m_zal ? 4 : 3; m_koz = cfg.solver == "kozcg"; m_lax = cfg.solver == "laxcg";
+  m_cho = cfg.solver == "chocg"; if (m_cho) m_stride = 5;      // ChoCG::domint, ChoCG.cpp:399-446
+  if (cfg.ncomp != (m_cho ? 3u : 5u)) throw std::runtime_error( m_cho ? "ChoCG: only ncomp = 3 (velocity) is supported" : "only ncomp = 5 is supported" );
   // Transporter::matchsets as the reference executes it (Transporter.cpp:125-187 with the
   // short-circuit at :347-348): with at least one side set named in the configuration the
   // faces of ALL side sets of the mesh keep their boundary integrals; with none, no face does.
   bool any = !cfg.bc_sym.empty() || !cfg.bc_far.empty() || !cfg.bc_pre.empty();
   for (const auto& d : cfg.bc_dir) if (!d.empty()) any = true;
+  for (const auto& d : cfg.p_bc_dir) if (!d.empty()) any = true;
+  if (!cfg.p_bc_sym.empty() || !cfg.bc_noslip.empty()) any = true;
   if (!any) m_sidetri.clear();
 }
 
@@ -141,8 +144,8 @@ RieCG::~RieCG() { if (m_ctx) xyst_ctx_destroy( m_ctx ); }
 void RieCG::attach( int device, int nranks, int rank, const void* ncclid )
 {
   xyst_params p{};
-  p.ncomp = static_cast< int >( m_cfg.ncomp );
-  if (m_cfg.flux == "rusanov") p.flux = 0; else if (m_cfg.flux == "hllc") p.flux = 1;
+  p.ncomp = m_cho ? 5 : static_cast< int >( m_cfg.ncomp );      // (the context's Euler kernels stay unused for ChoCG)
+  if (m_cfg.flux == "rusanov" || m_cho) p.flux = 0; else if (m_cfg.flux == "hllc") p.flux = 1;
   else throw std::runtime_error( "Flux not configured" );       // Riemann.cpp:676-681
   p.stab2 = m_cfg.stab2; p.stab2coef = m_cfg.stab2coef; p.gamma = m_cfg.gamma;
   p.exact_muscl = m_cfg.exact_muscl;
@@ -263,6 +266,11 @@ void RieCG::domint( const EdgeCSR& edges, std::vector< real >& d ) const
       n[1] += sig * (g[p][1] - g[q][1]) / 48.0;
       n[2] += sig * (g[p][2] - g[q][2]) / 48.0;
       if (st == 4) n[3] += J120;
+      if (st == 5) {                                                     // ChoCG.cpp:441-442
+        auto J = ba[0]*cx[0] + ba[1]*cx[1] + ba[2]*cx[2];
+        n[3] += J / 120.0;
+        n[4] += (g[p][0]*g[q][0] + g[p][1]*g[q][1] + g[p][2]*g[q][2]) / J / 6.0;
+      }
     }
   }
 }
@@ -308,7 +316,7 @@ void RieCG::domsuped( const EdgeCSR& edges, const std::vector< real >& d )
     for (int k=0; k<6; ++k) {
       real sig = gid[N[lpoed[k][0]]] < gid[N[lpoed[k][1]]] ? 1.0 : -1.0;
       for (std::size_t j=0; j<3; ++j) m_dsupint[0].push_back( sig * d[id[k]*m_stride+j] );
-      if (m_zal) m_dsupint[0].push_back( d[id[k]*m_stride+3] );
+      for (std::size_t j=3; j<m_stride; ++j) m_dsupint[0].push_back( d[id[k]*m_stride+j] );
       claimed[id[k]] = 1;
     }
   }
@@ -320,7 +328,7 @@ void RieCG::domsuped( const EdgeCSR& edges, const std::vector< real >& d )
     for (int k=0; k<3; ++k) {
       real sig = gid[T[static_cast<std::size_t>(lpoet[k][0])]] < gid[T[static_cast<std::size_t>(lpoet[k][1])]] ? 1.0 : -1.0;
       for (std::size_t j=0; j<3; ++j) m_dsupint[1].push_back( sig * d[id[k]*m_stride+j] );
-      if (m_zal) m_dsupint[1].push_back( d[id[k]*m_stride+3] );
+      for (std::size_t j=3; j<m_stride; ++j) m_dsupint[1].push_back( d[id[k]*m_stride+j] );
       claimed[id[k]] = 1;
     }
   };
@@ -375,9 +383,10 @@ void RieCG::setupBC()
     auto k = m_bface.find( s );
     if (k != m_bface.end()) for (auto f : k->second) for (int j=0; j<3; ++j) out.insert( m_triinpoel[f*3+static_cast<std::size_t>(j)] );
   };
+  if (m_cho) choSetupBC();
   // Dirichlet: node -> mask (0 -> 1 overwrite only)
   std::map< std::size_t, std::vector< int > > dirbcset;
-  for (const auto& mask : m_cfg.bc_dir) {
+  if (!m_cho) for (const auto& mask : m_cfg.bc_dir) {
     if (mask.size() != ncomp+1) throw std::runtime_error( "Incorrect Dirichlet BC mask ncomp" );
     std::set< std::size_t > nodes;
     facenodes( mask[0], nodes );
@@ -387,7 +396,7 @@ void RieCG::setupBC()
       for (std::size_t c=0; c<ncomp; ++c) if (!m[c]) m[c] = mask[c+1];
     }
   }
-  m_dirbcmasks.clear();
+  if (!m_cho) m_dirbcmasks.clear();
   for (const auto& [p,mask] : dirbcset) { m_dirbcmasks.push_back( p ); for (auto m : mask) m_dirbcmasks.push_back( static_cast< std::size_t >( m ) ); }
   // pressure BC
   m_prebcnodes.clear(); m_prebcvals.clear();
@@ -522,6 +531,7 @@ void RieCG::hostSetup()
       for (std::size_t c=0; c<ncomp; ++c) m_src[i*ncomp+c] = s[c];
     }
   }
+  if (m_cho) choPrelhs();
   m_hostready = true;
   timings.push_back( now()-t0 );
 }
@@ -531,6 +541,7 @@ void RieCG::setup()
   if (!m_ctx) throw std::runtime_error( "RieCG::setup: attach() a device first" );
   if (!m_hostready) hostSetup();
   auto t0 = now();
+  if (m_cho) { choSetup(); timings.push_back( now()-t0 ); timings.push_back( 0.0 ); return; }
   uploadHalo();
   auto np = m_disc.Gid().size();
   auto ncomp = m_cfg.ncomp;
@@ -618,6 +629,7 @@ void RieCG::solve()
 
 bool RieCG::step( std::vector< real >* diagrow )
 {
+  if (m_cho) return choStep( diagrow );
   if (m_finished) return false;
   advance( dt() );
   if (m_zal) ck( xyst_zalcg_step( m_ctx, m_disc.Dt() ) );      // ZalCG.cpp:973-1607
@@ -667,11 +679,12 @@ std::vector< real > RieCG::diagnostics()
 
 std::vector< real > RieCG::solution()
 {
+  if (m_cho) return choGet( "u", 3 );
   std::vector< real > u( m_disc.Gid().size()*m_cfg.ncomp );
   ck( xyst_state_get( m_ctx, u.data() ) );
   return u;
 }
 
-void RieCG::setSolution( const std::vector< real >& u ) { ck( xyst_state_set( m_ctx, u.data() ) ); }
+void RieCG::setSolution( const std::vector< real >& u ) { ck( m_cho ? xyst_chocg_set_u( m_ctx, u.data() ) : xyst_state_set( m_ctx, u.data() ) ); }
 
 } // xyst::

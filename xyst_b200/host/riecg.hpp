@@ -56,6 +56,22 @@ struct Config {
   std::array< real, 3 > far_velocity{{ 0, 0, 0 }};
   std::vector< int > bc_pre;
   std::vector< real > pre_density, pre_pressure;
+  //! ChoCG (solver = "chocg", ncomp = 3 velocity unknowns): projection method for constant-
+  //! density flow (src/Inciter/ChoCG.cpp). flux = "damp2" | "damp4"; number of RK stages;
+  //! pressure solve: iterations, tolerance, preconditioner ("none" | "jacobi"), Dirichlet sets
+  //! { setid, mask } with values { setid, value }, Neumann (symmetry) sets, hydrostat node (global id)
+  real mu = 0.0, dif = 0.0;
+  bool stab = true;
+  std::uint64_t rk = 1;
+  std::vector< int > bc_noslip;
+  std::vector< std::vector< real > > bc_dirval;   //!< { setid, value_0 .. value_{ncomp-1} }
+  std::uint64_t p_iter = 10;
+  real p_tol = 1.0e-3;
+  std::string p_pc = "none";
+  std::vector< std::vector< int > > p_bc_dir;
+  std::vector< std::vector< real > > p_bc_dirval;
+  std::vector< int > p_bc_sym;
+  std::uint64_t p_hydrostat = ~0ULL;
 };
 
 //! Sum, over all partitions sharing them, `w` doubles per unique shared node (ascending
@@ -137,6 +153,15 @@ class RieCG {
     std::vector< std::uint8_t > m_besym;
     std::vector< std::size_t > m_dirbcmasks, m_symbcnodes, m_farbcnodes, m_prebcnodes;
     std::vector< real > m_symbcnorms, m_farbcnorms, m_prebcvals;
+    // ChoCG: Dirichlet values, pressure Dirichlet masks/values, no-slip nodes (ChoCG.hpp members of
+    // the same names), the pressure Poisson matrix in the reference's CSR form (tk::CSR, 1-based)
+    std::vector< real > m_dirbcval, m_dirbcvalp;
+    std::vector< std::size_t > m_dirbcmaskp, m_noslipbcnodes;
+    std::vector< std::size_t > m_plhs_ia, m_plhs_ja;
+    std::vector< real > m_plhs_a;
+    std::size_t m_pit = 0;           //!< iterations of the last pressure solve
+    std::vector< real > choGet( const char* what, std::size_t width );
+    bool pendingDiag() const { return !m_lastdiag.empty(); }   //!< row of a run that ended during setup (nstep = 1)
     std::vector< real > m_u0;        //!< initial condition (npoin x ncomp)
     std::vector< double > timings;   //!< seconds spent in the setup phases (for reporting)
     bool m_finished = false;
@@ -163,6 +188,19 @@ class RieCG {
     bool m_zal = false;
     bool m_lax = false;                    //!< LaxCG: same setup as RieCG, preconditioned update
     bool m_koz = false;                    //!< KozCG: element-based, no edge integrals
+    bool m_cho = false;                    //!< ChoCG: stride-5 integrals, projection steps (chocg.cpp)
+    int m_np = 0;                          //!< ChoCG::m_np
+    bool m_initial = true;                 //!< Discretization::Initial()
+    std::map< std::size_t, real > m_pbc;   //!< pressure Dirichlet node -> value of the first solves
+    std::vector< real > m_neubc, m_prhs, m_psol, m_lastdiag;
+    void choSetupBC();                     //!< ChoCG::setupDirBC :210-300, streamable :655-682
+    void choPrelhs();                      //!< ChoCG::prelhs :146-188 on tk::CSR( psup )
+    void choSetup();                       //!< device upload + ChoCG::merge :816-837 onwards
+    bool choStep( std::vector< real >* diagrow );
+    void choPinit();                       //!< :1025-1125
+    void choPsolve();                      //!< :1127-1142
+    void choPsolved( std::vector< real >* diagrow );   //!< :1194-1253
+    std::vector< real > choDiag();         //!< NodeDiagnostics::precompute + Transporter::prediagnostics
     std::size_t m_stride = 3;
     real m_ownvol = 0.0;
     std::vector< real > m_dirvals, m_src;

@@ -26,6 +26,14 @@ class HostCfg(C.Structure):
         ("steady", C.c_int32), ("rescomp", C.c_uint64), ("residual", C.c_double),
         ("rgas", C.c_double), ("turkel", C.c_double), ("velinf", C.c_double * 3),
         ("ic_density", C.c_double), ("ic_pressure", C.c_double), ("ic_velocity", C.c_double * 3),
+        ("mu", C.c_double), ("dif", C.c_double), ("stab", C.c_int32),
+        ("nnoslip", C.c_int32), ("noslip", C.c_int32 * 16), ("rk", C.c_uint64),
+        ("ndirval", C.c_int32), ("dirval", (C.c_double * 12) * 16),
+        ("p_iter", C.c_uint64), ("p_tol", C.c_double), ("p_pc", C.c_char * 16),
+        ("np_dir", C.c_int32), ("p_dir", (C.c_int32 * 2) * 16),
+        ("np_dirval", C.c_int32), ("p_dirval", (C.c_double * 2) * 16),
+        ("np_sym", C.c_int32), ("p_sym", C.c_int32 * 16),
+        ("p_hydrostat_set", C.c_int32), ("p_hydrostat", C.c_uint64),
     ]
 
 
@@ -37,7 +45,9 @@ def make_cfg(problem, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0
              exact_muscl=False, reforder=-1, solver="riecg", fct=True, fctclip=False, fctsys=(),
              fctdif=1.0, steady=False, residual=0.0, rescomp=1, rgas=287.052874, turkel=0.5,
              velinf=(1.0, 1.0, 1.0), far=(), far_density=0.0, far_pressure=0.0, far_velocity=(0.0, 0.0, 0.0),
-             ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0), **_ignored):
+             ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0), mu=0.0, dif=0.0, stab=True, rk=1,
+             noslip=(), dirval=(), p_iter=10, p_tol=1.0e-3, p_pc="none", p_dir=(), p_dirval=(), p_sym=(),
+             p_hydrostat=None, **_ignored):
     c = HostCfg()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term
@@ -61,6 +71,25 @@ def make_cfg(problem, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0
     for i, m in enumerate(dir_):
         for j, v in enumerate(m):
             c.dir[i][j] = v
+    c.mu = mu; c.dif = dif; c.stab = int(stab); c.rk = rk
+    c.nnoslip = len(noslip)
+    for i, s_ in enumerate(noslip):
+        c.noslip[i] = s_
+    c.ndirval = len(dirval)
+    for i, m in enumerate(dirval):
+        for j, v in enumerate(m):
+            c.dirval[i][j] = v
+    c.p_iter = p_iter; c.p_tol = p_tol; c.p_pc = p_pc.encode()
+    c.np_dir = len(p_dir)
+    for i, m in enumerate(p_dir):
+        c.p_dir[i][0], c.p_dir[i][1] = m
+    c.np_dirval = len(p_dirval)
+    for i, m in enumerate(p_dirval):
+        c.p_dirval[i][0], c.p_dirval[i][1] = m
+    c.np_sym = len(p_sym)
+    for i, s_ in enumerate(p_sym):
+        c.p_sym[i] = s_
+    c.p_hydrostat_set = int(p_hydrostat is not None); c.p_hydrostat = 0 if p_hydrostat is None else p_hydrostat
     return c
 
 
@@ -114,7 +143,8 @@ def _p(a):
 _DT = {"gid": np.uint64, "inpoel": np.uint64, "triinpoel": np.uint64, "besym": np.uint8,
        "dsupedge0": np.uint64, "dsupedge1": np.uint64, "dsupedge2": np.uint64,
        "dirbcmasks": np.uint64, "symbcnodes": np.uint64, "bface": np.uint64, "commmap": np.uint64,
-       "shared": np.uint64}
+       "shared": np.uint64, "plhs_ia": np.uint64, "plhs_ja": np.uint64, "dirbcmaskp": np.uint64,
+       "noslipbcnodes": np.uint64}
 
 
 def box_mesh(nx, ny, nz, Lx=1.0, Ly=1.0, Lz=1.0):

@@ -123,3 +123,62 @@ def test_full_size_box_properties():
             assert np.abs(rows[:, 3] - 1.0).max() < 1e-6                    # L2(rho) ~ 1
             assert (rows[:, 2] > 0).all()
     assert np.array_equal(res[0][:2], res[1][:2])                          # deterministic
+
+
+@pytest.mark.parametrize("solver", ["zalcg", "kozcg"])
+def test_full_size_fct_box_properties(solver):
+    """BASELINE.json configs[2]: flux-corrected transport on the 50M-tet box (n=203, 50.19M tets,
+    8.49M nodes). Properties that need no oracle: conservation of mass and total energy with
+    closed (symmetry) boundaries -- the FCT anti-diffusive edge/element contributions cancel
+    pairwise -- finiteness, a positive time step, density bounded below by its initial minimum
+    (the limiter's purpose)."""
+    import bench
+    n = 203; h = 1.2 / n
+    cfg = bench.sedov_cfg(H.make_cfg, h, solver=solver, fctsys=(1, 2, 3, 4, 5))
+    cfg.diag_iter = 1
+    s = H.Solver.box(cfg, n, n, n, 1.2, 1.2, 1.2)
+    s.prepare(); s.attach(0); s.setup()
+    assert s.scalar("ntet") == 6 * n ** 3 == 50192562 and s.scalar("npoin") == 8489664
+    rows = s.step(3)
+    assert np.isfinite(rows).all() and (rows[:, 2] > 0).all()
+    mE = rows[:, 13]
+    assert np.abs(mE - mE[0]).max() <= 1e-11 * abs(mE[0])
+    assert np.abs(rows[:, 3] - 1.0).max() < 1e-5                           # L2(rho) ~ 1
+    u = s.get("u")
+    assert u[:, 0].min() > 0.0 and u[:, 4].min() > 0.0
+
+
+def test_full_size_chocg_box_properties():
+    """BASELINE.json configs[3]: ChoCG on the 50M-tet box -- lid-driven cavity set-up of the
+    reference's regression case (tests/regression/inciter/ChoCG/Lid) on the 203^3 Kuhn box,
+    pressure Poisson matrix with 8.49M rows. Properties: the assembled Laplacian has zero row sums
+    (constants are in its null space) and is symmetric, the CG solve reduces the residual to its
+    tolerance or uses all its iterations, the state stays finite, no-slip and lid values hold
+    exactly after every step, and the run is bit-reproducible."""
+    n = 203
+    kw = dict(solver="chocg", ncomp=3, cfl=0.9, flux="damp4", mu=0.01, p_iter=40, p_tol=1.0e-3, p_pc="jacobi",
+              p_hydrostat=0, problem="userdef", noslip=(1, 2, 3, 5, 6), dir_=((4, 2, 2, 2),),
+              dirval=((4, 1.0, 0.0, 0.0),), nstep=2)
+    res = []
+    for rep in range(2):
+        s = H.Solver.box(H.make_cfg(**kw), n, n, n)
+        s.prepare(); s.host_setup()
+        if rep == 0:
+            ia = s.get("plhs_ia").astype(np.int64) - 1; a = s.get("plhs_a")
+            assert len(ia) - 1 == 8489664
+            rs = np.add.reduceat(a, ia[:-1])
+            assert np.abs(rs).max() <= 1e-12 * np.abs(a).max()
+        s.attach(0); s.setup()
+        rows = s.step(2)
+        assert rows.shape[0] == 2 and np.isfinite(rows).all()
+        assert 1 <= int(s.scalar("pit")) <= 40
+        u = s.get("u")
+        x = s.get("x"); y = s.get("y"); z = s.get("z")
+        wall = np.isclose(x, 0) | np.isclose(x, 1) | np.isclose(y, 0) | np.isclose(z, 0) | np.isclose(z, 1)
+        lid = np.isclose(y, 1.0) & ~wall                     # no-slip is applied last: it wins on the lid's rim
+        assert lid.sum() == (n - 1) ** 2
+        assert np.array_equal(u[lid], np.tile([1.0, 0.0, 0.0], (lid.sum(), 1)))
+        assert not u[wall].any()
+        res.append(rows)
+        s.close()
+    assert np.array_equal(res[0], res[1])

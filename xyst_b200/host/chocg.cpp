@@ -85,25 +85,36 @@ void RieCG::choPrelhs()
     }
     if (!self) ja[j++] = i+1;
   }
-  auto at = [&]( std::size_t row, std::size_t col ) -> real& {
-    auto b = ja.begin() + static_cast< std::ptrdiff_t >( ia[row]-1 ), e = ja.begin() + static_cast< std::ptrdiff_t >( ia[row+1]-1 );
-    auto it = std::lower_bound( b, e, col+1 );
-    if (it == e || *it != col+1) throw std::runtime_error( "Sparse matrix index not found" );
-    return a[ static_cast< std::size_t >( it - ja.begin() ) ];
-  };
+  // Row-parallel assembly: every row visits its surrounding tetrahedra in ascending element order,
+  // i.e. each matrix entry receives its contributions in the order of the reference's element loop
+  // (bitwise the same sums), without write conflicts between rows.
+  const auto ntet = inpoel.size()/4;
+  std::vector< std::size_t > eoff( np+1, 0 );
+  for (std::size_t i=0; i<inpoel.size(); ++i) ++eoff[ inpoel[i]+1 ];
+  for (std::size_t i=0; i<np; ++i) eoff[i+1] += eoff[i];
+  std::vector< std::uint64_t > esup( inpoel.size() );           // tet*4 + local node
+  { std::vector< std::size_t > fill( eoff.begin(), eoff.end()-1 );
+    for (std::size_t e=0; e<ntet; ++e) for (std::size_t k=0; k<4; ++k) esup[ fill[ inpoel[e*4+k] ]++ ] = e*4+k; }
   const auto& X = m_disc.Coord()[0]; const auto& Y = m_disc.Coord()[1]; const auto& Z = m_disc.Coord()[2];
-  for (std::size_t e=0; e<inpoel.size()/4; ++e) {
-    const auto N = inpoel.data() + e*4;
-    real ba[3] = { X[N[1]]-X[N[0]], Y[N[1]]-Y[N[0]], Z[N[1]]-Z[N[0]] },
-         ca[3] = { X[N[2]]-X[N[0]], Y[N[2]]-Y[N[0]], Z[N[2]]-Z[N[0]] },
-         da[3] = { X[N[3]]-X[N[0]], Y[N[3]]-Y[N[0]], Z[N[3]]-Z[N[0]] };
-    real grad[4][3];
-    cross( ca, da, grad[1] ); cross( da, ba, grad[2] ); cross( ba, ca, grad[3] );
-    const auto J = (ba[0]*grad[1][0] + ba[1]*grad[1][1] + ba[2]*grad[1][2]) * 6.0;
-    for (std::size_t i=0; i<3; ++i) grad[0][i] = -grad[1][i]-grad[2][i]-grad[3][i];
-    for (std::size_t p=0; p<4; ++p)
-      for (std::size_t q=0; q<4; ++q)
-        at( N[p], N[q] ) -= (grad[p][0]*grad[q][0] + grad[p][1]*grad[q][1] + grad[p][2]*grad[q][2]) / J;
+  #pragma omp parallel for schedule(dynamic,1024)
+  for (std::size_t row=0; row<np; ++row) {
+    auto rb = ja.begin() + static_cast< std::ptrdiff_t >( ia[row]-1 ), re = ja.begin() + static_cast< std::ptrdiff_t >( ia[row+1]-1 );
+    for (auto i=eoff[row]; i<eoff[row+1]; ++i) {
+      const auto e = esup[i] >> 2; const auto p = static_cast< std::size_t >( esup[i] & 3 );
+      const auto N = inpoel.data() + e*4;
+      real ba[3] = { X[N[1]]-X[N[0]], Y[N[1]]-Y[N[0]], Z[N[1]]-Z[N[0]] },
+           ca[3] = { X[N[2]]-X[N[0]], Y[N[2]]-Y[N[0]], Z[N[2]]-Z[N[0]] },
+           da[3] = { X[N[3]]-X[N[0]], Y[N[3]]-Y[N[0]], Z[N[3]]-Z[N[0]] };
+      real grad[4][3];
+      cross( ca, da, grad[1] ); cross( da, ba, grad[2] ); cross( ba, ca, grad[3] );
+      const auto J = (ba[0]*grad[1][0] + ba[1]*grad[1][1] + ba[2]*grad[1][2]) * 6.0;
+      for (std::size_t k=0; k<3; ++k) grad[0][k] = -grad[1][k]-grad[2][k]-grad[3][k];
+      for (std::size_t q=0; q<4; ++q) {
+        auto it = std::lower_bound( rb, re, N[q]+1 );
+        a[ static_cast< std::size_t >( it - ja.begin() ) ] -=
+          (grad[p][0]*grad[q][0] + grad[p][1]*grad[q][1] + grad[p][2]*grad[q][2]) / J;
+      }
+    }
   }
 }
 

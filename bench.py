@@ -209,7 +209,7 @@ def run_ours(a):
     ctx = s.ctx()
     s.setup()
     t_setup = time.perf_counter() - t0
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)   # a non-blocking stream (not the legacy default one)
     ctx.set_stream(stream.cuda_stream)                     # so that torch events see our kernels
     npoin = int(s.scalar("npoin")); nedge_local = ctx.nedge()
     E = box_edges(nx, ny, nz)                              # unique edges of the whole box

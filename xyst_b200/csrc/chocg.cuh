@@ -445,6 +445,12 @@ k_cho_diag( size_t npoin, size_t NP, const double* __restrict__ U, const double*
   block_reduce< NCHODIAG, false >( a, part );
 }
 
+__global__ void k_cg_bc_scatter( int nbc, const int* __restrict__ node, const double* __restrict__ v, double* __restrict__ bcval )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < nbc) bcval[ node[i] ] = v[i];
+}
+
 // reference layout [node][m] <-> structure of arrays with stride NP
 __global__ void k_aos_to_soa( size_t n, size_t NP, int m, const double* __restrict__ A, double* __restrict__ S )
 {
@@ -705,10 +711,24 @@ int xyst_chocg_pinit( xyst_ctx* c, double divisor, size_t nbc, const size_t* bcn
   if (rhs0) CK( cudaMemcpyAsync( c->cg_b.p, rhs0, n*sizeof(double), cudaMemcpyHostToDevice, s ) );
   else { k_cho_prhs<<< nblk( n, 256 ), 256, 0, s >>>( n, divisor, c->cDiv.p, c->cg_b.p ); ++c->launches; }
   // ConjugateGradients::init :336-428 + apply :451-505 + r :508-556 for one partition
-  { std::vector< unsigned char > bc( n, 0 ); std::vector< double > val( n, 0.0 );
-    for (size_t i=0; i<nbc; ++i) { if (bcnodes[i] >= n) throw std::runtime_error( "pressure BC node out of range" );
-      bc[ bcnodes[i] ] = 1; val[ bcnodes[i] ] = bcvals ? bcvals[i] : 0.0; }
-    c->cg_bc.upload( bc, s ); c->cg_bcval.upload( val, s ); }
+  { // the BC node set rarely changes between solves: the row mask is rebuilt only when it does,
+    // the values are scattered from an nbc-long upload
+    std::vector< size_t > nodes( bcnodes, bcnodes + nbc );
+    if (!c->cg_bc.p || c->cg_bc.n != n || nodes != c->cg_bcnodes_h) {
+      std::vector< unsigned char > bc( n, 0 ); std::vector< int > nd( nbc );
+      for (size_t i=0; i<nbc; ++i) { if (bcnodes[i] >= n) throw std::runtime_error( "pressure BC node out of range" );
+        bc[ bcnodes[i] ] = 1; nd[i] = (int)bcnodes[i]; }
+      c->cg_bc.upload( bc, s ); c->cg_bcnode.upload( nd, s ); c->cg_bcnodes_h = nodes;
+      c->cg_bcval.alloc( n ); c->cg_bcsmall.alloc( std::max< size_t >( nbc, 1 ) );
+      CK( cudaMemsetAsync( c->cg_bcval.p, 0, n*sizeof(double), s ) );
+    }
+    if (nbc) {
+      std::vector< double > v( nbc, 0.0 );
+      if (bcvals) std::copy( bcvals, bcvals + nbc, v.begin() );
+      CK( cudaMemcpyAsync( c->cg_bcsmall.p, v.data(), nbc*sizeof(double), cudaMemcpyHostToDevice, s ) );
+      CK( cudaStreamSynchronize( s ) );
+      k_cg_bc_scatter<<< nblk( nbc, 256 ), 256, 0, s >>>( (int)nbc, c->cg_bcnode.p, c->cg_bcsmall.p, c->cg_bcval.p ); ++c->launches;
+    } }
   c->cg_hasbc = true;
   const double* neu = nullptr;
   if (neubc) { c->cg_neu.upload( std::vector< double >( neubc, neubc+n ), s ); neu = c->cg_neu.p; }

@@ -66,9 +66,6 @@ int fail( const std::string& m ) { g_err = m; return 1; }
 #ifndef RHS_MINB
 #define RHS_MINB 4
 #endif
-#ifndef NODE_UNROLL
-#define NODE_UNROLL 4
-#endif
 #ifndef GRAD_UNROLL
 #define GRAD_UNROLL 14     // interior nodes of a Kuhn-split box have 14 edges: one full batch
 #endif
@@ -76,7 +73,6 @@ int fail( const std::string& m ) { g_err = m; return 1; }
 #define RHS_UNROLL 14
 #endif
 
-constexpr int kNodeUnroll = NODE_UNROLL;
 constexpr int kGradUnroll = GRAD_UNROLL, kRhsUnroll = RHS_UNROLL;
 constexpr int NC = 5;          // flow components handled by the kernels
 
@@ -209,7 +205,8 @@ struct xyst_ctx {
   size_t cb_nd = 0, cb_ns = 0, cb_nn = 0;
   // pressure solve BCs (matrix-free: masked rows/columns), Neumann part, rhs override
   DevBuf< unsigned char > cg_bc;
-  DevBuf< double > cg_bcval, cg_neu, cg_rhs0;
+  DevBuf< double > cg_bcval, cg_neu, cg_rhs0, cg_bcsmall;
+  DevBuf< int > cg_bcnode; std::vector< size_t > cg_bcnodes_h;
   bool cg_hasbc = false, cg_hasneu = false, cg_hasrhs0 = false;
   // linear solver: sliced-ELL matrix over scalar rows + CG vectors
   size_t cg_nrow = 0, cg_ncomp = 1, cg_nslice = 0, cg_nent = 0;

@@ -27,8 +27,9 @@ def launch(mode, case, nsteps, tmp_path, world=2):
 
 
 def oracle_for(case, part, world):
-    kw = O.CASES[case]
-    return O.Oracle(O.load_mesh(case), O.make_cfg(**kw), "port", nchare=world, target=np.asarray(part, np.uint64))
+    kw = {**O.CASES, **O.LCASES}[case]
+    return O.Oracle(O.load_mesh(kw.get("mesh", case)), O.make_cfg(**kw), "port", nchare=world,
+                    target=np.asarray(part, np.uint64))
 
 
 def check_setup(res, o, world):
@@ -76,6 +77,27 @@ def test_two_gpus_match_oracle_two_chares(case, tmp_path):
         U = np.asarray(res[k]["u"]); Uo = o.get("u", k)
         assert np.abs(U - Uo).max() <= 1e-12 * np.abs(Uo).max()
         assert res[k]["launches"] > 0
+
+
+@pytest.mark.gpu
+def test_two_gpus_laxcg_match_oracle_two_chares(tmp_path):
+    """LaxCG (preconditioned update reads the primitives of the stage: shared nodes must be
+    updated from the complete sums only) with steady-state local time stepping on 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    case = "laxcg_bump"; nsteps = 10
+    res = launch("gpu", case, nsteps, tmp_path)
+    o = oracle_for(case, res[0]["part"], 2)
+    o.step(nsteps)
+    d = o.diag()
+    rows = np.asarray(res[0]["rows"])
+    assert rows.shape == d.shape
+    for c in range(1, 8):
+        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-11 * np.abs(d[:, c]).max(), c
+    for k in range(2):
+        U = np.asarray(res[k]["u"]); Uo = o.get("u", k)
+        assert np.abs(U - Uo).max() <= 1e-11 * np.abs(Uo).max()
 
 
 @pytest.mark.gpu

@@ -171,6 +171,7 @@ struct xyst_ctx {
   void* comm = nullptr; int nranks = 1, rank = 0;
   std::vector< int > neigh; std::vector< size_t > neigh_off;
   DevBuf< int > sh_node;                 // unique shared nodes
+  std::vector< int > sh_node_h; DevBuf< unsigned char > sh_flag;   // host copy; [npoin] 1 = shared (built on first use)
   DevBuf< int > sh_send;                 // [nsend] index into unique list, per neighbour segment
   DevBuf< int > sh_roff, sh_ridx;        // CSR unique node -> positions in recv buffer
   DevBuf< double > sh_part, sh_sendbuf, sh_recvbuf;
@@ -1059,12 +1060,16 @@ k_rhs_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, cons
             const double* __restrict__ Rb, const double* __restrict__ S, int src_mask,
             const double* __restrict__ v, const double* __restrict__ vol, const double* __restrict__ Un,
             StageArgs A, double* __restrict__ U, double* __restrict__ W, double* __restrict__ R,
-            double* __restrict__ Wn, double* __restrict__ UnOut, size_t slice0, size_t slice1 )
+            double* __restrict__ Wn, double* __restrict__ UnOut, size_t slice0, size_t slice1,
+            const unsigned char* __restrict__ skip )
 {
   size_t slice = slice0 + ((blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5);
   int lane = threadIdx.x & 31;
   size_t p = slice*32 + lane;
   if (slice >= slice1 || p >= npoin) return;
+  // nodes shared with other partitions are updated by k_rhs_finish from the complete sums (and,
+  // for LaxCG, from the still unmodified primitives of this stage)
+  if (FUSED && skip && skip[p]) return;
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
   double acc[NC];
@@ -2063,15 +2068,18 @@ Mode mode( const xyst_ctx* c ) { return Mode{ c->prm.gamma, c->lax ? c->rgas : 0
 void need_mesh( xyst_ctx* c ) { if (!c->npoin) throw std::runtime_error( "no mesh uploaded" ); }
 
 // ---- halo exchange of per-shared-node partial sums (width w doubles) ----------------
-void exchange( xyst_ctx* c, int w )
+// on_comm = false: the partial sums were produced on the compute stream, pack there and hand over
+// to the side stream. on_comm = true: the caller produced them on the side stream itself (the
+// RieCG sweeps: nothing of the exchange sits in front of the full-mesh gather on the compute stream).
+void exchange( xyst_ctx* c, int w, bool on_comm = false )
 {
-  // pack on the compute stream, send/recv on the compute stream as well (NCCL kernels
-  // are ordered with ours; the interior kernel is launched BEFORE the exchange is
-  // waited on by the caller through stream order of the finish kernel)
-  k_pack<<< nblk( c->nsend*(size_t)w, 256 ), 256, 0, c->stream >>>( (int)c->nsend, w, c->sh_send.p,
+  auto ps = on_comm ? c->comm_stream : c->stream;
+  k_pack<<< nblk( c->nsend*(size_t)w, 256 ), 256, 0, ps >>>( (int)c->nsend, w, c->sh_send.p,
     c->sh_part.p, c->sh_sendbuf.p ); ++c->launches;
-  CK( cudaEventRecord( c->ev_a, c->stream ) );
-  CK( cudaStreamWaitEvent( c->comm_stream, c->ev_a, 0 ) );
+  if (!on_comm) {
+    CK( cudaEventRecord( c->ev_a, c->stream ) );
+    CK( cudaStreamWaitEvent( c->comm_stream, c->ev_a, 0 ) );
+  }
   NK( g_nccl.GroupStart() );
   for (size_t i=0; i<c->neigh.size(); ++i) {
     size_t off = c->neigh_off[i]*(size_t)w, cnt = (c->neigh_off[i+1]-c->neigh_off[i])*(size_t)w;
@@ -2088,11 +2096,13 @@ void do_grad( xyst_ctx* c )
   need_mesh( c );
   auto s = c->stream;
   bool halo = c->nsh > 0 && c->comm;
-  // Single partition: both boundary kernels depend only on the state at stage start, so they
-  // run on a side stream under the gradient gather; boundary nodes are finished afterwards.
-  bool overlap = c->nbn && !halo;
+  // Both boundary kernels depend only on the state at stage start, so they run on a side stream
+  // under the gradient gather; boundary nodes are finished afterwards. With several partitions
+  // the partial sums of the shared nodes, their packing and the NCCL send/recv run on the
+  // communication stream as well, so the compute stream goes straight into the full-mesh gather.
+  bool overlap = c->nbn > 0;
+  if (overlap || halo) CK( cudaEventRecord( c->ev_c, s ) );
   if (overlap) {
-    CK( cudaEventRecord( c->ev_c, s ) );
     CK( cudaStreamWaitEvent( c->aux_stream, c->ev_c, 0 ) );
     k_bnd_grad<<< nblk( c->nbn, 128 ), 128, 0, c->aux_stream >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
       c->tri.p, c->fn.p, c->W.p, c->Gb.p ); ++c->launches;
@@ -2101,14 +2111,14 @@ void do_grad( xyst_ctx* c )
       c->tri.p, c->besym.p, c->fn.p, c->U.p, c->Rb.p, c->prm.gamma, c->W.p, c->rgas ); ++c->launches;
     CK( cudaEventRecord( c->ev_e, c->aux_stream ) );
     c->rb_pending = true;
-  } else if (c->nbn) {
-    k_bnd_grad<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
-      c->tri.p, c->fn.p, c->W.p, c->Gb.p ); ++c->launches;
   }
   if (halo) {
-    k_grad_shared<<< nblk( c->nsh, 128 ), 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sl_base.p,
+    auto cs = c->comm_stream;
+    CK( cudaStreamWaitEvent( cs, c->ev_c, 0 ) );
+    if (overlap) CK( cudaStreamWaitEvent( cs, c->ev_d, 0 ) );        // needs the boundary part Gb
+    k_grad_shared<<< nblk( c->nsh, 128 ), 128, 0, cs >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sl_base.p,
       c->inc_eq.p, c->D2.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->sh_part.p ); ++c->launches;
-    exchange( c, 15 );
+    exchange( c, 15, true );
   }
   {
     ProfScope ps( c, "grad" );
@@ -2155,15 +2165,24 @@ void launch_rhs_node( xyst_ctx* c, bool fused, const StageArgs& A, const double*
 {
   if (s1 <= s0) return;
   unsigned g = nblk( (s1-s0)*32, NODE_THREADS );
+  const unsigned char* skip = nullptr;
+  if (c->nsh > 0 && c->comm) {
+    if (c->sh_flag.n != c->npoin) {
+      std::vector< unsigned char > f( c->npoin, 0 );
+      for (auto i : c->sh_node_h) f[(size_t)i] = 1;
+      c->sh_flag.upload( f, st );
+    }
+    skip = c->sh_flag.p;
+  }
   if (fused && c->lax)
     k_rhs_node< true, true ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
-      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1 );
+      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1, skip );
   else if (fused)
     k_rhs_node< true, false ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
-      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1 );
+      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1, skip );
   else
     k_rhs_node< false, false ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
-      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1 );
+      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1, skip );
   ++c->launches;
 }
 
@@ -2173,19 +2192,23 @@ void launch_rhs_node( xyst_ctx* c, bool fused, const StageArgs& A, const double*
 void do_rhs_nodes( xyst_ctx* c, bool fused, int stage, double dt, const double* Uin, const double* Un, double* Uout )
 {
   auto s = c->stream;
+  bool halo = c->nsh > 0 && c->comm;
   if (c->rb_pending) {                   // computed on the side stream during this stage's do_grad
     CK( cudaStreamWaitEvent( s, c->ev_e, 0 ) );
+    if (halo) CK( cudaStreamWaitEvent( c->comm_stream, c->ev_e, 0 ) );
     c->rb_pending = false;
   } else if (c->nbn) {
     k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
       c->tri.p, c->besym.p, c->fn.p, Uin, c->Rb.p, c->prm.gamma, c->W.p, c->rgas ); ++c->launches;
   }
   StageArgs A{ rkcoef[stage], dt, c->steady ? c->dtp.p : nullptr, stage, mode( c ) };
-  bool halo = c->nsh > 0 && c->comm;
-  if (halo) {
-    k_rhs_shared<<< nblk( c->nsh, 128 ), 128, 0, s >>>( (int)c->nsh, c->sh_node.p, c->sl_base.p,
+  if (halo) {                            // fluxes (and Rb) are ready on the compute stream here
+    auto cs = c->comm_stream;
+    CK( cudaEventRecord( c->ev_a, s ) );
+    CK( cudaStreamWaitEvent( cs, c->ev_a, 0 ) );
+    k_rhs_shared<<< nblk( c->nsh, 128 ), 128, 0, cs >>>( (int)c->nsh, c->sh_node.p, c->sl_base.p,
       c->inc_e.p, c->F.p, c->nslot, c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->sh_part.p ); ++c->launches;
-    exchange( c, NC );
+    exchange( c, NC, true );
   }
   {
     ProfScope ps( c, fused ? "update" : "rhsnode" );
@@ -2245,8 +2268,13 @@ int xyst_ctx_create( int device, const xyst_params* params, xyst_ctx** out )
   auto c = new xyst_ctx;
   c->device = device; c->prm = *params;
   CK( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ); c->own_stream = true;
-  CK( cudaStreamCreateWithFlags( &c->comm_stream, cudaStreamNonBlocking ) );
-  CK( cudaStreamCreateWithFlags( &c->aux_stream, cudaStreamNonBlocking ) );
+  // side streams at the highest priority: their small kernels (boundary terms, shared-node sums,
+  // packing, NCCL send/recv) get the thread-block slots the full-mesh gather frees first
+  // instead of queueing behind all of its blocks
+  { int lo = 0, hi = 0;
+    CK( cudaDeviceGetStreamPriorityRange( &lo, &hi ) );
+    CK( cudaStreamCreateWithPriority( &c->comm_stream, cudaStreamNonBlocking, hi ) );
+    CK( cudaStreamCreateWithPriority( &c->aux_stream, cudaStreamNonBlocking, hi ) ); }
   CK( cudaEventCreateWithFlags( &c->ev_c, cudaEventDisableTiming ) );
   CK( cudaEventCreateWithFlags( &c->ev_d, cudaEventDisableTiming ) );
   CK( cudaEventCreateWithFlags( &c->ev_e, cudaEventDisableTiming ) );
@@ -2782,7 +2810,7 @@ int xyst_halo_upload( xyst_ctx* c, int nneigh, const int* neigh_rank, const size
   { std::vector< int > f( roff.begin(), roff.end()-1 );
     for (size_t i=0; i<nsend; ++i) ridx[ f[send[i]]++ ] = (int)i; }   // ascending recv position = fixed neighbour order
   auto s = c->stream;
-  c->nsh = uniq.size(); c->nsend = nsend;
+  c->nsh = uniq.size(); c->nsend = nsend; c->sh_node_h = uniq; c->sh_flag.release();
   c->sh_node.upload( uniq, s ); c->sh_send.upload( send, s ); c->sh_roff.upload( roff, s ); c->sh_ridx.upload( ridx, s );
   c->sh_part.alloc( uniq.size()*15 ); c->sh_sendbuf.alloc( nsend*15 ); c->sh_recvbuf.alloc( nsend*15 );
   API_END

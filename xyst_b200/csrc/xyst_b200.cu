@@ -69,11 +69,14 @@ int fail( const std::string& m ) { g_err = m; return 1; }
 #ifndef GRAD_UNROLL
 #define GRAD_UNROLL 14     // interior nodes of a Kuhn-split box have 14 edges: one full batch
 #endif
+#ifndef ZAL_UNROLL
+#define ZAL_UNROLL 2
+#endif
 #ifndef RHS_UNROLL
 #define RHS_UNROLL 14
 #endif
 
-constexpr int kGradUnroll = GRAD_UNROLL, kRhsUnroll = RHS_UNROLL;
+constexpr int kGradUnroll = GRAD_UNROLL, kRhsUnroll = RHS_UNROLL, kZalUnroll = ZAL_UNROLL;
 constexpr int NC = 5;          // flow components handled by the kernels
 
 // ---------------------------------------------------------------------------------
@@ -291,10 +294,7 @@ __device__ __forceinline__ void store_w( double* __restrict__ W, size_t NP, size
 __device__ __forceinline__ double get_w( const double* __restrict__ W, size_t NP, int c, size_t p ) {
   return W[((size_t)(c>>1)*NP + p)*2 + (size_t)(c&1)];
 }
-// Edge fluxes as (f0,f1) (f2,f3) pairs and f4: component c of slot e
-__host__ __device__ __forceinline__ size_t fidx( int c, size_t e, size_t nslot ) {
-  return c < 4 ? (size_t)(c>>1)*2*nslot + 2*e + (size_t)(c&1) : 4*nslot + e;
-}
+// Edge fluxes as (f0,f1) (f2,f3) pairs and f4 per slot
 __device__ __forceinline__ void store_f( double* __restrict__ F, size_t nslot, size_t e, const double f[NC] ) {
   double2* F2 = reinterpret_cast< double2* >( F );
   F2[e] = make_double2( f[0], f[1] );
@@ -1369,8 +1369,7 @@ k_zal_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int*
 // contributions aec = -dif*ctau*(u_first - u_second) (ZalCG.cpp:1071-1115), symmetry BC on P
 // (:1117-1133), then P /= vol and the low-order solution ul = u - dt R/vol - P+ - P- (:1195-1204)
 __global__ void __launch_bounds__(NODE_THREADS, 3)
-k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
-             const int* __restrict__ inc_q, const double* __restrict__ D, size_t nslot,
+k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot,
              const double* __restrict__ F, const double* __restrict__ U, const int* __restrict__ bslot,
              const double* __restrict__ Rb, const int* __restrict__ bcof, const int* __restrict__ symoff,
              const double* __restrict__ sym_n, const double* __restrict__ vol, double dt, double ctau, int fct,
@@ -1385,16 +1384,20 @@ k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
   double up[NC], r[NC], pp[NC], pn[NC];
   #pragma unroll
   for (int c=0; c<NC; ++c) { up[c] = U[c*NP+p]; r[c] = 0.0; pp[c] = 0.0; pn[c] = 0.0; }
+  // padding entries (se = 0) point at the node itself and at slot 0 with weight 0: no branch
+  #pragma unroll kZalUnroll
   for (int k=0; k<kmax; ++k) {
     long long i = base + (long long)k*32 + lane;
-    int se = __ldg( inc_e + i );
-    if (se == 0) continue;
-    size_t q = __ldg( inc_q + i );
-    size_t sl = (size_t)(abs(se)-1);
-    double dif = __ldg( D + 3*nslot + sl );
+    int2 eq = __ldg( inc_eq + i );
+    const int se = eq.x;
+    size_t q = (size_t)eq.y;
+    size_t sl = se == 0 ? 0 : (size_t)(abs(se)-1);
+    double dif = se == 0 ? 0.0 : __ldg( D + 3*nslot + sl );
+    double fl[NC];
+    load_f( F, nslot, sl, fl );
     #pragma unroll
     for (int c=0; c<NC; ++c) {
-      double f = __ldg( F + fidx( c, sl, nslot ) );
+      double f = se == 0 ? 0.0 : fl[c];
       double uq = __ldg( U + c*NP + q );
       if (se < 0) {                       // this node is the edge's first node
         r[c] -= f;
@@ -1440,8 +1443,7 @@ k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
 // pass 2 (second half of alw + first half of lim): allowed bounds Q+/- over the edge
 // neighbours (:1206-1290), Q -= ul, limit coefficients C+/- (:1361-1380) -> Q
 __global__ void __launch_bounds__(NODE_THREADS, 3)
-k_zal_node2( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
-             const int* __restrict__ inc_q, const double* __restrict__ U, const double* __restrict__ UL,
+k_zal_node2( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ U, const double* __restrict__ UL,
              const double* __restrict__ P, int clip, double* __restrict__ Q )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
@@ -1458,10 +1460,10 @@ k_zal_node2( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
     lp[c] = clip ? ulp[c] : fmin( ulp[c], u );
     qa[c] = -1.7976931348623157e308; qb[c] = 1.7976931348623157e308;
   }
-  for (int k=0; k<kmax; ++k) {
+  #pragma unroll kZalUnroll
+  for (int k=0; k<kmax; ++k) {                 // padding entries point at the node itself: no effect on the bounds
     long long i = base + (long long)k*32 + lane;
-    if (__ldg( inc_e + i ) == 0) continue;
-    size_t q = __ldg( inc_q + i );
+    size_t q = (size_t)__ldg( inc_eq + i ).y;
     #pragma unroll
     for (int c=0; c<NC; ++c) {
       double ulq = __ldg( UL + c*NP + q );
@@ -1484,8 +1486,7 @@ k_zal_node2( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
 // pass 3 (second half of lim + solve): limited antidiffusive contributions (:1382-1481) and
 // u = ul + a/vol (:1552-1557)
 __global__ void __launch_bounds__(NODE_THREADS, 3)
-k_zal_node3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
-             const int* __restrict__ inc_q, const double* __restrict__ D, size_t nslot,
+k_zal_node3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot,
              const double* __restrict__ U, const double* __restrict__ UL, const double* __restrict__ Q,
              const double* __restrict__ vol, double ctau, int sysmask, double* __restrict__ Unew,
              double* __restrict__ W )
@@ -1499,12 +1500,13 @@ k_zal_node3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
   double up[NC], cpa[NC], cpb[NC], a[NC];
   #pragma unroll
   for (int c=0; c<NC; ++c) { up[c] = U[c*NP+p]; cpa[c] = Q[(2*c)*NP+p]; cpb[c] = Q[(2*c+1)*NP+p]; a[c] = 0.0; }
-  for (int k=0; k<kmax; ++k) {
+  #pragma unroll kZalUnroll
+  for (int k=0; k<kmax; ++k) {                 // padding entries: dif = 0, neighbour = the node itself
     long long i = base + (long long)k*32 + lane;
-    int se = __ldg( inc_e + i );
-    if (se == 0) continue;
-    size_t q = __ldg( inc_q + i );
-    double dif = __ldg( D + 3*nslot + (size_t)(abs(se)-1) );
+    int2 eq = __ldg( inc_eq + i );
+    const int se = eq.x;
+    size_t q = (size_t)eq.y;
+    double dif = se == 0 ? 0.0 : __ldg( D + 3*nslot + (size_t)(abs(se)-1) );
     double aec[NC], coef[NC];
     #pragma unroll
     for (int c=0; c<NC; ++c) {
@@ -2508,7 +2510,7 @@ void zal_flux_and_bnd( xyst_ctx* c, double dt )
 void zal_node1( xyst_ctx* c, double dt, int fct )
 {
   k_zal_node1<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p,
-    c->inc_e.p, c->inc_q.p, c->D.p, c->nslot, c->F.p, c->U.p, c->bslot.p, c->Rb.p, c->bcof.p, c->bc_symoff.p,
+    c->inc_eq.p, c->D.p, c->nslot, c->F.p, c->U.p, c->bslot.p, c->Rb.p, c->bcof.p, c->bc_symoff.p,
     c->sym_n.p, c->vol.p, dt, c->zal.fctdif, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
 }
 }
@@ -2534,10 +2536,10 @@ int xyst_zalcg_step( xyst_ctx* c, double dt )
   zal_flux_and_bnd( c, dt );
   if (c->zal.fct) {
     zal_node1( c, dt, 1 );
-    k_zal_node2<<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->U.p, c->zUL.p,
+    k_zal_node2<<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_eq.p, c->U.p, c->zUL.p,
       c->zP.p, c->zal.fctclip, c->zQ.p ); ++c->launches;
     // new state into the other buffer, then swap: Un keeps the old state for the diagnostics
-    k_zal_node3<<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p, c->nslot,
+    k_zal_node3<<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot,
       c->U.p, c->zUL.p, c->zQ.p, c->vol.p, c->zal.fctdif, c->zal.fctsys_mask, c->Un.p, c->W.p ); ++c->launches;
   } else {
     zal_node1( c, dt, 0 );

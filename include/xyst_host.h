@@ -14,7 +14,7 @@ extern "C" {
 
 /* Control-file equivalent (the tags the RieCG path reads; src/Control/InciterConfig.hpp) */
 typedef struct xyst_host_cfg {
-  char problem[32];           /* "sod" | "sedov" | "taylor_green" | "userdef" */
+  char problem[32];           /* "sod" | "sedov" | "taylor_green" | "vortical_flow" | "userdef" | (ChoCG) "poiseuille", "poisson_*" */
   char flux[16];              /* "rusanov" | "hllc" */
   int32_t ncomp;
   int32_t stab2;
@@ -53,6 +53,7 @@ typedef struct xyst_host_cfg {
   int32_t np_dirval; double p_dirval[16][2];
   int32_t np_sym; int32_t p_sym[16];
   int32_t p_hydrostat_set; uint64_t p_hydrostat;
+  double alpha, kappa;        /* problem_alpha, problem_kappa ("vortical_flow") */
 } xyst_host_cfg;
 
 typedef struct xyst_solver xyst_solver;

@@ -51,6 +51,8 @@ typedef struct orc_cfg {
   int32_t np_dirval; double p_dirval[16][2];
   int32_t np_sym; int32_t p_sym[16];
   int32_t p_hydrostat_set; uint64_t p_hydrostat;
+  /* manufactured-solution parameters (problem_alpha, problem_kappa; vortical_flow etc.) */
+  double alpha, kappa;
 } orc_cfg;
 
 const char* orc_backend(void);      /* "port" or "reference" */

@@ -36,7 +36,8 @@ struct Cfg {
   std::string flux = "rusanov";
   std::size_t ncomp = 5;
   real gamma = 1.4;             // mat_spec_heat_ratio
-  real p0 = 0.0;                // problem_p0 (sedov)
+  real p0 = 0.0;                // problem_p0 (sedov, vortical_flow)
+  real alpha = 0.0, kappa = 0.0; // problem_alpha, problem_kappa (manufactured solutions)
   real cfl = 0.0;
   real dt = 0.0;                // constant dt if |dt|>eps
   real t0 = 0.0;
@@ -154,6 +155,23 @@ inline std::vector< real > src_taylor_green( real x, real y, real, real ) { // :
   return s;
 }
 
+inline std::vector< real > ic_vortical_flow( real x, real y, real z, real ) { // :454-478
+  auto a = cfg().alpha, k = cfg().kappa, p0 = cfg().p0, g = cfg().gamma;
+  real ru = a*x - k*y;
+  real rv = k*x + a*y;
+  real rw = -2.0*a*z;
+  real rE = (ru*ru + rv*rv + rw*rw)/2.0 + (p0 - 2.0*a*a*z*z) / (g - 1.0);
+  return { 1.0, ru, rv, rw, rE };
+}
+inline std::vector< real > src_vortical_flow( real x, real y, real z, real ) { // :480-507
+  auto a = cfg().alpha, k = cfg().kappa, g = cfg().gamma;
+  auto u = ic_vortical_flow( x, y, z, 0.0 );
+  std::vector< real > s( 5, 0.0 );
+  s[1] = a*u[1]/u[0] - k*u[2]/u[0];
+  s[2] = k*u[1]/u[0] + a*u[2]/u[0];
+  s[4] = (s[1]*u[1] + s[2]*u[2])/u[0] + 8.0*a*a*a*z*z/(g-1.0);
+  return s;
+}
 inline std::vector< real > ic_userdef( real, real, real, real ) {           // :28-115 (pressure given)
   std::vector< real > u( cfg().ncomp, 0.0 );
   u[0] = cfg().ic_density;
@@ -182,6 +200,7 @@ inline ICFn IC() {                                                          // :
   if (p == "sedov") return ic_sedov;
   if (p == "sod") return ic_sod;
   if (p == "taylor_green") return ic_taylor_green;
+  if (p == "vortical_flow") return ic_vortical_flow;
   throw std::runtime_error( "oracle port: problem type ic not hooked up: " + p );
 }
 inline ICFn SOL() {                                                         // :1114-1131
@@ -225,6 +244,7 @@ inline std::function< std::array< real, 3 >( real, real, real ) > PRESSURE_GRAD(
 inline ICFn SRC() {                                                         // :1299-1325
   const auto& p = cfg().problem;
   if (p == "taylor_green") return src_taylor_green;
+  if (p == "vortical_flow") return src_vortical_flow;
   return {};
 }
 

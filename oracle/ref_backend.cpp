@@ -24,6 +24,8 @@ void set_cfg( const Cfg& c )
   g.get< tag::problem_ncomp >() = c.ncomp;
   g.get< tag::mat_spec_heat_ratio >() = c.gamma;
   g.get< tag::problem_p0 >() = c.p0;
+  g.get< tag::problem_alpha >() = c.alpha;
+  g.get< tag::problem_kappa >() = c.kappa;
   g.get< tag::cfl >() = c.cfl;
   g.get< tag::dt >() = c.dt;
   g.get< tag::t0 >() = c.t0;

@@ -37,7 +37,13 @@ EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "chocg_poiseuille_rk2": "ChoCG/Poiseuille/diag_poiseuille_rk2.std",
               "chocg_poiseuille_rk3": "ChoCG/Poiseuille/diag_poiseuille_rk3.std",
               "chocg_poiseuille_rk4": "ChoCG/Poiseuille/diag_poiseuille_rk4.std",
-              "chocg_ldc": "ChoCG/Lid/diag_ldc.std"}
+              "chocg_ldc": "ChoCG/Lid/diag_ldc.std",
+              # vortical flow runs on the Taylor-Green case's mesh (same unitcube_1k.exo)
+              "riecg_vortical_flow": "RieCG/VorticalFlow/diag.std",
+              "riecg_vortical_flow_hllc": "RieCG/VorticalFlow/diag_hllc.std",
+              "riecg_vortical_flow_stab2": "RieCG/VorticalFlow/diag_stab2.std",
+              "riecg_vortical_flow_hllc_stab2": "RieCG/VorticalFlow/diag_hllc_stab2.std",
+              "riecg_vortical_flow_steady": "RieCG/VorticalFlow/diag_steady.std"}
 
 
 def flatten(exo):

@@ -43,6 +43,7 @@ class Cfg(C.Structure):
         ("np_dirval", C.c_int32), ("p_dirval", (C.c_double * 2) * 16),
         ("np_sym", C.c_int32), ("p_sym", C.c_int32 * 16),
         ("p_hydrostat_set", C.c_int32), ("p_hydrostat", C.c_uint64),
+        ("alpha", C.c_double), ("kappa", C.c_double),
     ]
 
 
@@ -53,11 +54,11 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
              far=(), far_density=0.0, far_pressure=0.0, far_velocity=(0.0, 0.0, 0.0),
              ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0),
              mu=0.0, dif=0.0, stab=True, rk=1, noslip=(), dirval=(), p_iter=10, p_tol=1.0e-3, p_pc="none",
-             p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, cls=Cfg):
+             p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, alpha=0.0, kappa=0.0, cls=Cfg):
     """Control-file equivalent; defaults are the reference's (InciterConfig.cpp:1707-1757)."""
     c = cls()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
-    c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term
+    c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term; c.alpha = alpha; c.kappa = kappa
     c.nstep = nstep; c.stab2 = int(stab2); c.stab2coef = stab2coef; c.steady = int(steady)
     c.diag_iter = diag_iter
     c.residual = residual; c.rescomp = rescomp; c.rgas = rgas; c.turkel = turkel
@@ -167,6 +168,20 @@ CASES = {
                         sym=(1, 2, 3)),
     "riecg_taylor_green": dict(problem="taylor_green", gamma=5.0 / 3.0, cfl=0.8, term=1.0,
                                diag_iter=2, dir_=tuple((s, 1, 1, 1, 1, 1) for s in range(1, 7))),
+}
+
+
+# Vortical flow (tests/regression/inciter/RieCG/VorticalFlow/vortical_flow{,_hllc,_stab2,_hllc_stab2,_steady}.q):
+# a steady manufactured solution with a source term on the unit cube (the mesh of the Taylor-Green case),
+# Dirichlet BCs on all sides -- golden diagnostics for both Riemann solvers, stab2 and the steady-state path
+_VF = dict(problem="vortical_flow", alpha=0.1, kappa=1.0, p0=10.0, gamma=5.0 / 3.0, cfl=0.8, term=1.0,
+           dir_=tuple((s, 1, 1, 1, 1, 1) for s in range(1, 7)), mesh="riecg_taylor_green")
+VCASES = {
+    "riecg_vortical_flow": dict(_VF),
+    "riecg_vortical_flow_hllc": dict(_VF, flux="hllc"),
+    "riecg_vortical_flow_stab2": dict(_VF, stab2=True),
+    "riecg_vortical_flow_hllc_stab2": dict(_VF, flux="hllc", stab2=True),
+    "riecg_vortical_flow_steady": dict(_VF, term=1e300, nstep=10, steady=True, residual=1.0e-8, rescomp=1),
 }
 
 

@@ -142,3 +142,35 @@ def test_chocg_oracle_reproduces_reference_golden_diag(case):
     assert (np.abs(d - gold) <= tol * np.abs(gold)).all()
     if case != "chocg_poisson_neumann":
         assert (np.abs(d[:, :6] - gold[:, :6]) <= 2e-12 * np.abs(gold[:, :6])).all()
+
+
+@pytest.mark.parametrize("case", list(O.VCASES))
+def test_vortical_flow_oracle_reproduces_reference_golden_diag(case):
+    """RieCG vortical flow (tests/regression/inciter/RieCG/VorticalFlow/diag*.std): the goldens that pin
+    the stab2 term, the steady-state (local time step, residual) path and the HLLC flux; 69 steps to
+    t = 1 for the unsteady variants, 10 for the steady one.
+    diag.std, diag_stab2.std, diag_steady.std were recorded serially: reproduced to the 9 printed digits.
+    diag_hllc.std (4 PEs, -u 0.5) and diag_hllc_stab2.std (4 PEs) were recorded on partitioned runs,
+    and the reference's results depend on the partitioning at the 1e-4 level (the Riemann fluxes are
+    nonlinear in the partial edge normals that partitions hold for shared edges): Zoltan's partitions
+    are not reproducible here, so those two are checked with the reference's own acceptance test
+    (diag.ndiff.cfg) on a 4-way coordinate bisection."""
+    kw = O.VCASES[case]
+    gold = O.load_golden_diag(case)
+    mesh = O.load_mesh(kw["mesh"])
+    partitioned = "hllc" in case
+    part = None
+    if partitioned:
+        from xyst_b200 import hostapi as H
+        from host_common import fixture_to_host_mesh
+        hm = fixture_to_host_mesh(mesh)
+        part = H.rcb(hm["coord"], hm["tets"], 4).astype(np.uint64)
+    o = O.Oracle(mesh, O.make_cfg(**kw), "port", nchare=4 if partitioned else 1, target=part)
+    o.step(int(gold[-1, 0]))
+    d = o.diag()
+    assert d.shape == gold.shape
+    assert O.numdiff_ok(d[:, 1:8], gold[:, 1:8], 3.0e-5, 2.0e-5).all()
+    assert O.numdiff_ok(d[:, 8:13], gold[:, 8:13], 1.0e-2, 1.0e-7).all()
+    if not partitioned:
+        assert (np.abs(d[:, 1:8] - gold[:, 1:8]) <= 2e-8 * np.abs(gold[:, 1:8])).all()
+        assert (np.abs(d[:, 13:] - gold[:, 13:]) <= 1e-6 * np.abs(gold[:, 13:]) + 1e-12).all()

@@ -133,3 +133,17 @@ def test_chocg_port_is_bit_identical_to_reference_objects(case):
     assert np.array_equal(a.diag(), b.diag())
     for name in ("u", "pr", "pgrad", "grad", "div"):
         assert np.array_equal(a.get(name), b.get(name)), name
+
+
+@needs_ref
+@pytest.mark.parametrize("case", ["riecg_vortical_flow_hllc_stab2", "riecg_vortical_flow_steady"])
+def test_vortical_flow_port_is_bit_identical_to_reference_objects(case):
+    """problems::vortical_flow ic/src from the reference's Problems.cpp vs the restatement."""
+    kw = O.VCASES[case]
+    mesh = O.load_mesh(kw["mesh"])
+    a = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    b = O.Oracle(mesh, O.make_cfg(**kw), "reference")
+    assert np.array_equal(a.get("u"), b.get("u"))
+    a.step(10); b.step(10)
+    assert np.array_equal(a.diag(), b.diag())
+    assert np.array_equal(a.get("u"), b.get("u"))

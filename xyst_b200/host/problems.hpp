@@ -1,7 +1,7 @@
 // xyst_b200/host/problems.hpp -- host-side problem definitions used by the RieCG mirror:
 // initial conditions, analytic solutions and source terms of the configured problem
 // (cf. src/Physics/Problems.cpp: sedov::ic :337, sod::ic :373, taylor_green::ic/src
-// :410/:433, dispatch IC() :1071, SOL() :1114, SRC() :1299) and the ideal-gas EOS
+// :410/:433, vortical_flow::ic/src :454/:480, dispatch IC() :1071, SOL() :1114, SRC() :1299) and the ideal-gas EOS
 // (src/Physics/EOS.hpp:29-56). Evaluated once on the host; the device receives arrays.
 #pragma once
 #include <array>
@@ -57,6 +57,15 @@ inline Fn IC( const Config& cfg ) {
       real v = -std::cos(M_PI*x) * std::sin(M_PI*y);
       real w = 0.0;
       return {{ r, r*u, r*v, r*w, totalenergy( g, r, u, v, w, p ) }}; };
+  if (cfg.problem == "vortical_flow") {         // vortical_flow::ic :454-478
+    const real a = cfg.alpha, k = cfg.kappa, p0 = cfg.p0;
+    return [g,a,k,p0]( real x, real y, real z, real ) -> std::array< real, 5 > {
+      real ru = a*x - k*y;
+      real rv = k*x + a*y;
+      real rw = -2.0*a*z;
+      real rE = (ru*ru + rv*rv + rw*rw)/2.0 + (p0 - 2.0*a*a*z*z) / (g - 1.0);
+      return {{ 1.0, ru, rv, rw, rE }}; };
+  }
   if (cfg.problem == "userdef") {               // userdef::ic :28-115, density + velocity + pressure
     const real r = cfg.ic_density, p = cfg.ic_pressure;
     const auto vel = cfg.ic_velocity;
@@ -74,6 +83,17 @@ inline Fn SOL( const Config& cfg ) {
 }
 
 inline Fn SRC( const Config& cfg ) {
+  if (cfg.problem == "vortical_flow") {         // vortical_flow::src :480-507
+    const real a = cfg.alpha, k = cfg.kappa, g = cfg.gamma;
+    auto ic = IC( cfg );
+    return [a,k,g,ic]( real x, real y, real z, real ) -> std::array< real, 5 > {
+      auto u = ic( x, y, z, 0.0 );
+      std::array< real, 5 > s{{ 0, 0, 0, 0, 0 }};
+      s[1] = a*u[1]/u[0] - k*u[2]/u[0];
+      s[2] = k*u[1]/u[0] + a*u[2]/u[0];
+      s[4] = (s[1]*u[1] + s[2]*u[2])/u[0] + 8.0*a*a*a*z*z/(g-1.0);
+      return s; };
+  }
   if (cfg.problem == "taylor_green")
     return []( real x, real y, real, real ) -> std::array< real, 5 > {
       std::array< real, 5 > s{{ 0, 0, 0, 0, 0 }};

@@ -23,6 +23,7 @@ struct Config {
   std::string flux = "rusanov";
   std::size_t ncomp = 5;
   real gamma = 1.4, p0 = 0.0, cfl = 0.0, dt = 0.0, t0 = 0.0, term = 1.0e+300;
+  real alpha = 0.0, kappa = 0.0;             //!< problem_alpha, problem_kappa (manufactured solutions)
   std::uint64_t nstep = ~0ULL, diag_iter = 1;
   bool stab2 = false;
   real stab2coef = 0.2;

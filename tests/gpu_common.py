@@ -21,6 +21,21 @@ def tg_source(x, y):
     return s
 
 
+def source(kw, x, y, z):
+    """Nodal values of problems::SRC() for the problems that have one (time-independent ones)."""
+    if kw["problem"] == "taylor_green":
+        return tg_source(x, y)
+    if kw["problem"] == "vortical_flow":                 # Problems.cpp:480-507
+        a, k, g = kw["alpha"], kw["kappa"], kw["gamma"]
+        ru = a * x - k * y; rv = k * x + a * y
+        s = np.zeros((len(x), 5))
+        s[:, 1] = a * ru - k * rv
+        s[:, 2] = k * ru + a * rv
+        s[:, 4] = s[:, 1] * ru + s[:, 2] * rv + 8.0 * a * a * a * z * z / (g - 1.0)
+        return s
+    return None
+
+
 def context_from_oracle(o, kw, chare=0, exact_muscl=False, device=0):
     """Upload one oracle chare's mesh/BC/state arrays into a device context."""
     ctx = xyst_b200.Context(device=device, flux=kw.get("flux", "rusanov"), gamma=kw["gamma"],
@@ -46,8 +61,9 @@ def context_from_oracle(o, kw, chare=0, exact_muscl=False, device=0):
     ctx.bc_upload(dirbcmasks=dm, dirvals=dv, symbcnodes=g("symbcnodes"), symbcnorms=g("symbcnorms"),
                   farbcnodes=g("farbcnodes"), farbcnorms=g("farbcnorms"),
                   far=(kw.get("far_density", 0.0), kw.get("far_pressure", 0.0), kw.get("far_velocity", (0.0, 0.0, 0.0))))
-    if kw["problem"] == "taylor_green":
-        ctx.src_upload(tg_source(x, y))
+    S = source(kw, x, y, z)
+    if S is not None:
+        ctx.src_upload(S)
     ctx.state_set(U0)
     return ctx
 
@@ -56,10 +72,9 @@ def _kozcg_context(ctx, o, kw, chare):
     g = lambda n: o.get(n, chare)
     x, y, z = g("x"), g("y"), g("z")
     inpoel = g("inpoel").reshape(-1, 4).astype(np.int64)
-    Sn = Sc = None
-    if kw["problem"] == "taylor_green":
-        Sn = tg_source(x, y)
-        Sc = tg_source(x[inpoel].sum(axis=1) / 4.0, y[inpoel].sum(axis=1) / 4.0)
+    Sn = source(kw, x, y, z)
+    Sc = None if Sn is None else source(kw, x[inpoel].sum(axis=1) / 4.0, y[inpoel].sum(axis=1) / 4.0,
+                                        z[inpoel].sum(axis=1) / 4.0)
     ctx.kozcg_mesh_upload(x, y, z, inpoel, g("vol"), g("v"), Sn, Sc)
     ctx.zalcg_config(kw.get("fct", True), kw.get("fctclip", False), kw.get("fctsys", ()), kw.get("fctdif", 1.0))
     U0 = g("u")

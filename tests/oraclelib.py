@@ -149,6 +149,10 @@ KCASES = {
     "kozcg_taylor_green": dict(solver="kozcg", problem="taylor_green", gamma=5.0 / 3.0, cfl=0.8, term=1.0,
                                fct=False, diag_iter=2, dir_=tuple((s, 1, 1, 1, 1, 1) for s in range(1, 7)),
                                mesh="riecg_taylor_green"),
+    # KozCG/VorticalFlow/vortical_flow.q: no FCT, manufactured solution with nodal + centroid source terms
+    "kozcg_vortical_flow": dict(solver="kozcg", problem="vortical_flow", alpha=0.1, kappa=1.0, p0=10.0,
+                                gamma=5.0 / 3.0, cfl=0.8, term=1.0, fct=False,
+                                dir_=tuple((s, 1, 1, 1, 1, 1) for s in range(1, 7)), mesh="riecg_taylor_green"),
 }
 
 # ZalCG regression cases (tests/regression/inciter/ZalCG/{Sod/sod.q,Sedov/sedov.q})

@@ -84,3 +84,18 @@ def test_no_device_work_on_empty_context():
     ctx = xyst_b200.Context()
     with pytest.raises(xyst_b200.XystError):
         ctx.grad()
+
+
+@pytest.mark.parametrize("case", ["riecg_vortical_flow", "riecg_vortical_flow_hllc_stab2"])
+def test_vortical_flow_with_source_term(case):
+    """riemann::src (Riemann.cpp:880-907) with a non-trivial momentum + energy source on every node,
+    both Riemann solvers, through the C ABI: 20 steps against the oracle."""
+    kw = O.VCASES[case]
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    ctx = context_from_oracle(o, kw)
+    ctx.grad(); ctx.rhs()
+    o.kernel("grad"); o.kernel("rhs", 0, 0.0)
+    assert relerr(ctx.rhs_get(), o.get("rhs")) < TOL
+    drive_steps([ctx], kw, 20)
+    o.step(20)
+    assert relerr(ctx.state_get(), o.get("u")) < 1e-11

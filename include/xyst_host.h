@@ -14,7 +14,7 @@ extern "C" {
 
 /* Control-file equivalent (the tags the RieCG path reads; src/Control/InciterConfig.hpp) */
 typedef struct xyst_host_cfg {
-  char problem[32];           /* "sod" | "sedov" | "taylor_green" | "vortical_flow" | "userdef" | (ChoCG) "poiseuille", "poisson_*" */
+  char problem[32];           /* "sod" | "sedov" | "taylor_green" | "vortical_flow" | "nonlinear_energy_growth" | "rayleigh_taylor" | "userdef" | (ChoCG) "poiseuille", "poisson_*" */
   char flux[16];              /* "rusanov" | "hllc" */
   int32_t ncomp;
   int32_t stab2;
@@ -54,6 +54,7 @@ typedef struct xyst_host_cfg {
   int32_t np_sym; int32_t p_sym[16];
   int32_t p_hydrostat_set; uint64_t p_hydrostat;
   double alpha, kappa;        /* problem_alpha, problem_kappa ("vortical_flow") */
+  double r0, ce, beta[3];     /* problem_r0, problem_ce, problem_beta ("nonlinear_energy_growth", "rayleigh_taylor") */
 } xyst_host_cfg;
 
 typedef struct xyst_solver xyst_solver;

@@ -17,7 +17,7 @@ struct Handle { MeshInput in; std::unique_ptr< Run > run; };
 Cfg to_cfg( const orc_cfg* c ) {
   Cfg k;
   k.problem = c->problem; k.flux = c->flux; k.ncomp = static_cast< std::size_t >( c->ncomp );
-  k.alpha = c->alpha; k.kappa = c->kappa;
+  k.alpha = c->alpha; k.kappa = c->kappa; k.r0 = c->r0; k.ce = c->ce; k.beta = {{ c->beta[0], c->beta[1], c->beta[2] }};
   k.gamma = c->gamma; k.p0 = c->p0; k.cfl = c->cfl; k.dt = c->dt; k.t0 = c->t0; k.term = c->term;
   k.nstep = c->nstep; k.stab2 = c->stab2 != 0; k.stab2coef = c->stab2coef; k.steady = c->steady != 0;
   k.diag_iter = c->diag_iter ? c->diag_iter : 1;

@@ -53,6 +53,8 @@ typedef struct orc_cfg {
   int32_t p_hydrostat_set; uint64_t p_hydrostat;
   /* manufactured-solution parameters (problem_alpha, problem_kappa; vortical_flow etc.) */
   double alpha, kappa;
+  /* problem_r0, problem_ce, problem_beta (nonlinear_energy_growth, rayleigh_taylor) */
+  double r0, ce, beta[3];
 } orc_cfg;
 
 const char* orc_backend(void);      /* "port" or "reference" */

@@ -26,6 +26,9 @@ void set_cfg( const Cfg& c )
   g.get< tag::problem_p0 >() = c.p0;
   g.get< tag::problem_alpha >() = c.alpha;
   g.get< tag::problem_kappa >() = c.kappa;
+  g.get< tag::problem_r0 >() = c.r0;
+  g.get< tag::problem_ce >() = c.ce;
+  g.get< tag::problem_beta >() = std::vector< double >{ c.beta[0], c.beta[1], c.beta[2] };
   g.get< tag::cfl >() = c.cfl;
   g.get< tag::dt >() = c.dt;
   g.get< tag::t0 >() = c.t0;

@@ -44,7 +44,9 @@ EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "riecg_vortical_flow_stab2": "RieCG/VorticalFlow/diag_stab2.std",
               "riecg_vortical_flow_hllc_stab2": "RieCG/VorticalFlow/diag_hllc_stab2.std",
               "riecg_vortical_flow_steady": "RieCG/VorticalFlow/diag_steady.std",
-              "kozcg_vortical_flow": "KozCG/VorticalFlow/diag.std"}
+              "kozcg_vortical_flow": "KozCG/VorticalFlow/diag.std",
+              "riecg_nleg": "RieCG/NonlinearEnergyGrowth/diag.std",
+              "riecg_rayleigh_taylor": "RieCG/RayleighTaylor/diag.std"}
 
 
 def flatten(exo):

@@ -44,6 +44,7 @@ class Cfg(C.Structure):
         ("np_sym", C.c_int32), ("p_sym", C.c_int32 * 16),
         ("p_hydrostat_set", C.c_int32), ("p_hydrostat", C.c_uint64),
         ("alpha", C.c_double), ("kappa", C.c_double),
+        ("r0", C.c_double), ("ce", C.c_double), ("beta", C.c_double * 3),
     ]
 
 
@@ -54,11 +55,14 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
              far=(), far_density=0.0, far_pressure=0.0, far_velocity=(0.0, 0.0, 0.0),
              ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0),
              mu=0.0, dif=0.0, stab=True, rk=1, noslip=(), dirval=(), p_iter=10, p_tol=1.0e-3, p_pc="none",
-             p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, alpha=0.0, kappa=0.0, cls=Cfg):
+             p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, alpha=0.0, kappa=0.0, r0=0.0, ce=0.0, beta=(0.0, 0.0, 0.0), cls=Cfg):
     """Control-file equivalent; defaults are the reference's (InciterConfig.cpp:1707-1757)."""
     c = cls()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term; c.alpha = alpha; c.kappa = kappa
+    c.r0 = r0; c.ce = ce
+    for i in range(3):
+        c.beta[i] = beta[i]
     c.nstep = nstep; c.stab2 = int(stab2); c.stab2coef = stab2coef; c.steady = int(steady)
     c.diag_iter = diag_iter
     c.residual = residual; c.rescomp = rescomp; c.rgas = rgas; c.turkel = turkel
@@ -180,6 +184,17 @@ CASES = {
 # Dirichlet BCs on all sides -- golden diagnostics for both Riemann solvers, stab2 and the steady-state path
 _VF = dict(problem="vortical_flow", alpha=0.1, kappa=1.0, p0=10.0, gamma=5.0 / 3.0, cfl=0.8, term=1.0,
            dir_=tuple((s, 1, 1, 1, 1, 1) for s in range(1, 7)), mesh="riecg_taylor_green")
+# Time-dependent manufactured solutions on the same mesh: Dirichlet values and source term change in time
+# (RieCG/NonlinearEnergyGrowth/nleg.q, RieCG/RayleighTaylor/rayleigh_taylor.q), goldens recorded serially
+_DIR6 = tuple((s, 1, 1, 1, 1, 1) for s in range(1, 7))
+TCASES = {
+    "riecg_nleg": dict(problem="nonlinear_energy_growth", alpha=0.25, r0=2.0, ce=-1.0, kappa=0.8,
+                       beta=(1.0, 0.75, 0.5), gamma=5.0 / 3.0, cfl=0.8, term=1.0, dir_=_DIR6,
+                       mesh="riecg_taylor_green"),
+    "riecg_rayleigh_taylor": dict(problem="rayleigh_taylor", alpha=1.0, beta=(1.0, 1.0, 1.0), p0=1.0, r0=1.0,
+                                  kappa=1.0, gamma=5.0 / 3.0, cfl=0.5, nstep=50, dir_=_DIR6,
+                                  mesh="riecg_taylor_green"),
+}
 VCASES = {
     "riecg_vortical_flow": dict(_VF),
     "riecg_vortical_flow_hllc": dict(_VF, flux="hllc"),

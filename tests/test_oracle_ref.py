@@ -136,10 +136,12 @@ def test_chocg_port_is_bit_identical_to_reference_objects(case):
 
 
 @needs_ref
-@pytest.mark.parametrize("case", ["riecg_vortical_flow_hllc_stab2", "riecg_vortical_flow_steady"])
-def test_vortical_flow_port_is_bit_identical_to_reference_objects(case):
-    """problems::vortical_flow ic/src from the reference's Problems.cpp vs the restatement."""
-    kw = O.VCASES[case]
+@pytest.mark.parametrize("case", ["riecg_vortical_flow_hllc_stab2", "riecg_vortical_flow_steady", "riecg_nleg",
+                                  "riecg_rayleigh_taylor"])
+def test_manufactured_problems_port_is_bit_identical_to_reference_objects(case):
+    """problems::vortical_flow / nonlinear_energy_growth / rayleigh_taylor ic and src from the
+    reference's Problems.cpp vs the restatement."""
+    kw = {**O.VCASES, **O.TCASES}[case]
     mesh = O.load_mesh(kw["mesh"])
     a = O.Oracle(mesh, O.make_cfg(**kw), "port")
     b = O.Oracle(mesh, O.make_cfg(**kw), "reference")

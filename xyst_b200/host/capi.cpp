@@ -27,7 +27,7 @@ int fail( const std::string& m ) { g_err = m; return 1; }
 Config to_cfg( const xyst_host_cfg* c ) {
   Config k;
   k.problem = c->problem; k.flux = c->flux; k.ncomp = static_cast< std::size_t >( c->ncomp );
-  k.alpha = c->alpha; k.kappa = c->kappa;
+  k.alpha = c->alpha; k.kappa = c->kappa; k.r0 = c->r0; k.ce = c->ce; k.beta = {{ c->beta[0], c->beta[1], c->beta[2] }};
   k.gamma = c->gamma; k.p0 = c->p0; k.cfl = c->cfl; k.dt = c->dt; k.t0 = c->t0; k.term = c->term;
   k.nstep = c->nstep; k.diag_iter = c->diag_iter ? c->diag_iter : 1;
   k.stab2 = c->stab2 != 0; k.stab2coef = c->stab2coef; k.exact_muscl = c->exact_muscl != 0; k.reforder = c->reforder;

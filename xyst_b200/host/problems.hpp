@@ -66,6 +66,25 @@ inline Fn IC( const Config& cfg ) {
       real rE = (ru*ru + rv*rv + rw*rw)/2.0 + (p0 - 2.0*a*a*z*z) / (g - 1.0);
       return {{ 1.0, ru, rv, rw, rE }}; };
   }
+  if (cfg.problem == "nonlinear_energy_growth") {   // nonlinear_energy_growth::ic :126-160
+    const real ce = cfg.ce, r0 = cfg.r0, a = cfg.alpha, k = cfg.kappa; const auto b = cfg.beta;
+    return [ce,r0,a,k,b]( real x, real y, real z, real t ) -> std::array< real, 5 > {
+      auto hx = std::cos(b[0]*M_PI*x) * std::cos(b[1]*M_PI*y) * std::cos(b[2]*M_PI*z);
+      auto r = r0 + std::exp(-a*t) * (1.0 - x*x - y*y - z*z);
+      auto re = r * std::pow( -3.0*(ce + k*hx*hx*t), -1.0/3.0 );
+      return {{ r, 0.0, 0.0, 0.0, re }}; };
+  }
+  if (cfg.problem == "rayleigh_taylor") {       // rayleigh_taylor::ic :225-258
+    const real a = cfg.alpha, p0 = cfg.p0, r0 = cfg.r0, k = cfg.kappa; const auto b = cfg.beta;
+    return [g,a,p0,r0,k,b]( real x, real y, real z, real t ) -> std::array< real, 5 > {
+      real gx = b[0]*x*x + b[1]*y*y + b[2]*z*z;
+      real r = r0 - gx;
+      real ft = std::cos(k*M_PI*t);
+      real u = ft * z * std::sin(M_PI*x);
+      real v = ft * z * std::cos(M_PI*y);
+      real w = ft * ( -0.5*M_PI*z*z*(std::cos(M_PI*x) - std::sin(M_PI*y)) );
+      return {{ r, r*u, r*v, r*w, totalenergy( g, r, u, v, w, p0 + a*gx ) }}; };
+  }
   if (cfg.problem == "userdef") {               // userdef::ic :28-115, density + velocity + pressure
     const real r = cfg.ic_density, p = cfg.ic_pressure;
     const auto vel = cfg.ic_velocity;
@@ -82,7 +101,81 @@ inline Fn SOL( const Config& cfg ) {
   return IC( cfg );
 }
 
+//! IC (= Dirichlet values, analytic solution) or source term change in time
+inline bool timeDependent( const Config& cfg ) {
+  return cfg.problem == "nonlinear_energy_growth" || cfg.problem == "rayleigh_taylor";
+}
+
 inline Fn SRC( const Config& cfg ) {
+  if (cfg.problem == "nonlinear_energy_growth") {   // nonlinear_energy_growth::src :162-219
+    const real a = cfg.alpha, ce = cfg.ce, kappa = cfg.kappa, r0 = cfg.r0, g = cfg.gamma; const auto b = cfg.beta;
+    return [a,ce,kappa,r0,g,b]( real x, real y, real z, real t ) -> std::array< real, 5 > {
+      using std::sin; using std::cos; using std::pow;
+      auto gx = 1.0 - x*x - y*y - z*z;
+      std::array< real, 3 > dg{{ -2.0*x, -2.0*y, -2.0*z }};
+      auto h = cos(b[0]*M_PI*x) * cos(b[1]*M_PI*y) * cos(b[2]*M_PI*z);
+      std::array< real, 3 >
+        dh{{ -b[0]*M_PI*sin(b[0]*M_PI*x)*cos(b[1]*M_PI*y)*cos(b[2]*M_PI*z),
+             -b[1]*M_PI*cos(b[0]*M_PI*x)*sin(b[1]*M_PI*y)*cos(b[2]*M_PI*z),
+             -b[2]*M_PI*cos(b[0]*M_PI*x)*cos(b[1]*M_PI*y)*sin(b[2]*M_PI*z) }};
+      auto ft = std::exp(-a*t);
+      auto dfdt = -a*ft;
+      auto rho = r0 + ft*gx;
+      std::array< real, 3 > drdx{{ ft*dg[0], ft*dg[1], ft*dg[2] }};
+      auto drdt = gx*dfdt;
+      auto ie = pow( -3.0*(ce + kappa*h*h*t), -1.0/3.0 );
+      std::array< real, 3 > dedx{{ 2.0 * pow(ie,4.0) * kappa * h * dh[0] * t,
+                                   2.0 * pow(ie,4.0) * kappa * h * dh[1] * t,
+                                   2.0 * pow(ie,4.0) * kappa * h * dh[2] * t }};
+      const auto dedt = kappa * h * h * pow(ie,4.0);
+      std::array< real, 5 > s{{ 0, 0, 0, 0, 0 }};
+      s[0] = drdt;
+      s[1] = (g-1.0)*(rho*dedx[0] + ie*drdx[0]);
+      s[2] = (g-1.0)*(rho*dedx[1] + ie*drdx[1]);
+      s[3] = (g-1.0)*(rho*dedx[2] + ie*drdx[2]);
+      s[4] = rho*dedt + ie*drdt;
+      return s; };
+  }
+  if (cfg.problem == "rayleigh_taylor") {       // rayleigh_taylor::src :260-332
+    const real a = cfg.alpha, k = cfg.kappa, p0 = cfg.p0, g = cfg.gamma; const auto b = cfg.beta;
+    auto ic = IC( cfg );
+    return [a,k,p0,g,b,ic]( real x, real y, real z, real t ) -> std::array< real, 5 > {
+      using std::sin; using std::cos;
+      auto U = ic( x, y, z, t );
+      auto rho = U[0];
+      auto u = U[1]/U[0];
+      auto v = U[2]/U[0];
+      auto w = U[3]/U[0];
+      auto E = U[4]/U[0];
+      auto p = p0 + a*(b[0]*x*x + b[1]*y*y + b[2]*z*z);
+      std::array< real, 3 > drdx{{ -2.0*b[0]*x, -2.0*b[1]*y, -2.0*b[2]*z }};
+      std::array< real, 3 > dpdx{{ 2.0*a*b[0]*x, 2.0*a*b[1]*y, 2.0*a*b[2]*z }};
+      real ft = cos(k*M_PI*t);
+      std::array< real, 3 > dudx{{ ft*M_PI*z*cos(M_PI*x), 0.0, ft*sin(M_PI*x) }};
+      std::array< real, 3 > dvdx{{ 0.0, -ft*M_PI*z*sin(M_PI*y), ft*cos(M_PI*y) }};
+      std::array< real, 3 > dwdx{{ ft*M_PI*0.5*M_PI*z*z*sin(M_PI*x),
+                                   ft*M_PI*0.5*M_PI*z*z*cos(M_PI*y),
+                                  -ft*M_PI*z*(cos(M_PI*x) - sin(M_PI*y)) }};
+      std::array< real, 3 > dedx{{
+        dpdx[0]/rho/(g-1.0) - p/(g-1.0)/rho/rho*drdx[0]
+        + u*dudx[0] + v*dvdx[0] + w*dwdx[0],
+        dpdx[1]/rho/(g-1.0) - p/(g-1.0)/rho/rho*drdx[1]
+        + u*dudx[1] + v*dvdx[1] + w*dwdx[1],
+        dpdx[2]/rho/(g-1.0) - p/(g-1.0)/rho/rho*drdx[2]
+        + u*dudx[2] + v*dvdx[2] + w*dwdx[2] }};
+      auto dudt = -k*M_PI*sin(k*M_PI*t)*z*sin(M_PI*x);
+      auto dvdt = -k*M_PI*sin(k*M_PI*t)*z*cos(M_PI*y);
+      auto dwdt =  k*M_PI*sin(k*M_PI*t)/2*M_PI*z*z*(cos(M_PI*x) - sin(M_PI*y));
+      auto dedt = u*dudt + v*dvdt + w*dwdt;
+      std::array< real, 5 > s{{ 0, 0, 0, 0, 0 }};
+      s[0] = u*drdx[0] + v*drdx[1] + w*drdx[2];
+      s[1] = rho*dudt+u*s[0]+dpdx[0] + U[1]*dudx[0]+U[2]*dudx[1]+U[3]*dudx[2];
+      s[2] = rho*dvdt+v*s[0]+dpdx[1] + U[1]*dvdx[0]+U[2]*dvdx[1]+U[3]*dvdx[2];
+      s[3] = rho*dwdt+w*s[0]+dpdx[2] + U[1]*dwdx[0]+U[2]*dwdx[1]+U[3]*dwdx[2];
+      s[4] = rho*dedt + E*s[0] + U[1]*dedx[0]+U[2]*dedx[1]+U[3]*dedx[2]
+           + u*dpdx[0]+v*dpdx[1]+w*dpdx[2];
+      return s; };
+  }
   if (cfg.problem == "vortical_flow") {         // vortical_flow::src :480-507
     const real a = cfg.alpha, k = cfg.kappa, g = cfg.gamma;
     auto ic = IC( cfg );

@@ -509,31 +509,47 @@ void RieCG::hostSetup()
       for (std::size_t c=0; c<ncomp; ++c) m_u0[i*ncomp+c] = s[c];
     }
   }
-  // Dirichlet values = IC at the BC nodes (physics::dirbc, BC.cpp:57-66)
-  m_dirvals.clear();
-  if (!m_dirbcmasks.empty()) {
-    auto ic = problems::IC( m_cfg );
-    auto nd = m_dirbcmasks.size()/(ncomp+1);
-    m_dirvals.resize( nd*ncomp );
-    for (std::size_t i=0; i<nd; ++i) {
-      auto p = m_dirbcmasks[i*(ncomp+1)];
-      auto s = ic( co[0][p], co[1][p], co[2][p], m_disc.T() );
-      for (std::size_t c=0; c<ncomp; ++c) m_dirvals[i*ncomp+c] = s[c];
-    }
-  }
-  // source term (riemann::src, Riemann.cpp:880-907), time-independent problems only
-  m_src.clear();
-  if (auto src = problems::SRC( m_cfg )) {
-    m_src.resize( np*ncomp );
-    #pragma omp parallel for schedule(static)
-    for (std::size_t i=0; i<np; ++i) {
-      auto s = src( co[0][i], co[1][i], co[2][i], m_disc.T() );
-      for (std::size_t c=0; c<ncomp; ++c) m_src[i*ncomp+c] = s[c];
-    }
-  }
+  m_timedep = problems::timeDependent( m_cfg );
+  if (m_timedep && (m_zal || m_koz || m_cho || m_lax || m_cfg.steady))
+    throw std::runtime_error( "time-dependent problems are hooked up for RieCG only" );
+  evalDirvals( m_disc.T() );
+  evalSrc( m_disc.T() );
   if (m_cho) choPrelhs();
   m_hostready = true;
   timings.push_back( now()-t0 );
+}
+
+void RieCG::evalDirvals( real t )
+{
+  const auto& co = m_disc.Coord();
+  auto ncomp = m_cfg.ncomp;
+  m_dirvals.clear();
+  if (m_dirbcmasks.empty()) return;
+  auto ic = problems::IC( m_cfg );
+  auto nd = m_dirbcmasks.size()/(ncomp+1);
+  m_dirvals.resize( nd*ncomp );
+  #pragma omp parallel for schedule(static)
+  for (std::size_t i=0; i<nd; ++i) {
+    auto p = m_dirbcmasks[i*(ncomp+1)];
+    auto s = ic( co[0][p], co[1][p], co[2][p], t );
+    for (std::size_t c=0; c<ncomp; ++c) m_dirvals[i*ncomp+c] = s[c];
+  }
+}
+
+void RieCG::evalSrc( real t )
+{
+  const auto& co = m_disc.Coord();
+  auto ncomp = m_cfg.ncomp;
+  auto np = m_disc.Gid().size();
+  m_src.clear();
+  auto src = problems::SRC( m_cfg );
+  if (!src) return;
+  m_src.resize( np*ncomp );
+  #pragma omp parallel for schedule(static)
+  for (std::size_t i=0; i<np; ++i) {
+    auto s = src( co[0][i], co[1][i], co[2][i], t );
+    for (std::size_t c=0; c<ncomp; ++c) m_src[i*ncomp+c] = s[c];
+  }
 }
 
 void RieCG::setup()
@@ -634,6 +650,18 @@ bool RieCG::step( std::vector< real >* diagrow )
   advance( dt() );
   if (m_zal) ck( xyst_zalcg_step( m_ctx, m_disc.Dt() ) );      // ZalCG.cpp:973-1607
   else if (m_koz) ck( xyst_kozcg_step( m_ctx, m_disc.Dt() ) ); // KozCG.cpp:691-1197
+  else if (m_timedep) {
+    // source at the time level of the step for all stages (RieCG.cpp:949), Dirichlet values at the
+    // stage time t + rk dt (:1028): refreshed on the host, three separate stage calls
+    static const real rk[3] = { 1.0/3.0, 1.0/2.0, 1.0 };
+    evalSrc( m_disc.T() );
+    if (!m_src.empty()) ck( xyst_src_upload( m_ctx, m_src.data() ) );
+    for (int s=0; s<3; ++s) {
+      evalDirvals( m_disc.T() + rk[s]*m_disc.Dt() );
+      if (!m_dirvals.empty()) ck( xyst_dirbc_values( m_ctx, m_dirvals.data() ) );
+      ck( xyst_riecg_stage( m_ctx, s, m_disc.Dt() ) );
+    }
+  }
   else ck( xyst_riecg_step( m_ctx, m_disc.Dt() ) );
   if (diagrow && (m_disc.It()+1) % m_cfg.diag_iter == 0) *diagrow = diagnostics();
   else {

@@ -5,6 +5,7 @@
 // the setup members build what the reference builds, with sort/CSR algorithms that scale
 // to 10^8 tetrahedra instead of hash maps.
 #pragma once
+#include <array>
 #include <cstdint>
 #include <functional>
 #include <map>
@@ -24,6 +25,8 @@ struct Config {
   std::size_t ncomp = 5;
   real gamma = 1.4, p0 = 0.0, cfl = 0.0, dt = 0.0, t0 = 0.0, term = 1.0e+300;
   real alpha = 0.0, kappa = 0.0;             //!< problem_alpha, problem_kappa (manufactured solutions)
+  real r0 = 0.0, ce = 0.0;                   //!< problem_r0, problem_ce
+  std::array< real, 3 > beta{{ 0, 0, 0 }};   //!< problem_beta
   std::uint64_t nstep = ~0ULL, diag_iter = 1;
   bool stab2 = false;
   real stab2coef = 0.2;
@@ -174,6 +177,9 @@ class RieCG {
     void bndint();                   //!< :281-337
     void setupBC();                  //!< :109-245 (after normals are known)
     void uploadHalo();
+    void evalDirvals( real t );      //!< physics::dirbc values = IC at the BC nodes at time t (BC.cpp:57-66)
+    void evalSrc( real t );          //!< problems::SRC at the nodes at time t (riemann::src, Riemann.cpp:880-907)
+    bool m_timedep = false;          //!< IC / source depend on time: BC values per stage, source per step
     bool m_haloup = false;
     Discretization& m_disc;
     const Config& m_cfg;

@@ -46,7 +46,8 @@ EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "riecg_vortical_flow_steady": "RieCG/VorticalFlow/diag_steady.std",
               "kozcg_vortical_flow": "KozCG/VorticalFlow/diag.std",
               "riecg_nleg": "RieCG/NonlinearEnergyGrowth/diag.std",
-              "riecg_rayleigh_taylor": "RieCG/RayleighTaylor/diag.std"}
+              "riecg_rayleigh_taylor": "RieCG/RayleighTaylor/diag.std",
+              "riecg_pipe": "RieCG/Pipe/diag.std"}
 
 
 def flatten(exo):

@@ -55,7 +55,7 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
              far=(), far_density=0.0, far_pressure=0.0, far_velocity=(0.0, 0.0, 0.0),
              ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0),
              mu=0.0, dif=0.0, stab=True, rk=1, noslip=(), dirval=(), p_iter=10, p_tol=1.0e-3, p_pc="none",
-             p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, alpha=0.0, kappa=0.0, r0=0.0, ce=0.0, beta=(0.0, 0.0, 0.0), cls=Cfg):
+             p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, alpha=0.0, kappa=0.0, r0=0.0, ce=0.0, beta=(0.0, 0.0, 0.0), pre=(), cls=Cfg):
     """Control-file equivalent; defaults are the reference's (InciterConfig.cpp:1707-1757)."""
     c = cls()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
@@ -63,6 +63,9 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
     c.r0 = r0; c.ce = ce
     for i in range(3):
         c.beta[i] = beta[i]
+    c.npre = len(pre)
+    for i, (sid, dens, pres) in enumerate(pre):          # bc_pre = { name = { sideset = { sid }, density, pressure } }
+        c.pre_sets[i] = sid; c.pre_density[i] = dens; c.pre_pressure[i] = pres
     c.nstep = nstep; c.stab2 = int(stab2); c.stab2coef = stab2coef; c.steady = int(steady)
     c.diag_iter = diag_iter
     c.residual = residual; c.rescomp = rescomp; c.rgas = rgas; c.turkel = turkel
@@ -194,6 +197,13 @@ TCASES = {
     "riecg_rayleigh_taylor": dict(problem="rayleigh_taylor", alpha=1.0, beta=(1.0, 1.0, 1.0), p0=1.0, r0=1.0,
                                   kappa=1.0, gamma=5.0 / 3.0, cfl=0.5, nstep=50, dir_=_DIR6,
                                   mesh="riecg_taylor_green"),
+}
+# RieCG/Pipe/pipe.q: user-defined quiescent IC, symmetry walls, pressure BCs at inlet and outlet
+# (physics::prebc, BC.cpp:222-241); serial golden printed with 12 digits
+PCASES = {
+    "riecg_pipe": dict(problem="userdef", gamma=1.4, cfl=0.5, nstep=20, sym=(2, 4, 5, 6),
+                       pre=((1, 1.0, 100000.0), (3, 1.0, 99900.0)), ic_density=1.0, ic_pressure=99950.0,
+                       ic_velocity=(0.0, 0.0, 0.0), mesh="riecg_sod"),
 }
 VCASES = {
     "riecg_vortical_flow": dict(_VF),

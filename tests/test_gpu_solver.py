@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1.0e-12            # north_star: norms/diagnostics within 1e-12 relative, fp64
 
 
-ALLCASES = {**O.CASES, **O.VCASES, **O.TCASES}
+ALLCASES = {**O.CASES, **O.VCASES, **O.TCASES, **O.PCASES}
 
 
 def solver_for(case, **over):
@@ -122,6 +122,28 @@ def test_time_dependent_problems_match_oracle_and_golden(case):
     U, Uo = s.get("u"), o.get("u")
     assert np.abs(U - Uo).max() <= 1e-11 * np.abs(Uo).max()
     assert (np.abs(rows - gold) <= 1e-8 * np.abs(gold) + 1e-15).all()
+
+
+def test_pipe_with_pressure_bc_matches_oracle_and_golden():
+    """Pipe flow: user-defined IC, symmetry walls, pressure BCs (physics::prebc) at inlet/outlet through
+    the host mirror; 20 steps vs the oracle and the reference's 12-digit golden."""
+    case = "riecg_pipe"
+    gold = O.load_golden_diag(case)
+    s, kw = solver_for(case)
+    rows = s.step(20)
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(20)
+    d = o.diag()
+    assert rows.shape == d.shape == gold.shape
+    for c in (1, 2, 3, 4, 7, 13):
+        assert np.abs(rows[:, c] - d[:, c]).max() <= TOL * np.abs(d[:, c]).max(), c
+    U, Uo = s.get("u"), o.get("u")
+    for c in range(5):       # (momenta are ~1e-2 next to an energy of 2.5e5: same scale rule as the lock-step test)
+        scale = max(np.abs(Uo[:, c]).max(), 1e-3 * np.abs(Uo).max())
+        assert np.abs(U[:, c] - Uo[:, c]).max() <= 1e-11 * scale, c
+    assert np.abs(U[:, 1] - Uo[:, 1]).max() <= 1e-9 * np.abs(Uo[:, 1]).max()
+    for c in (1, 2, 3, 4, 7, 13):
+        assert (np.abs(rows[:, c] - gold[:, c]) <= 5e-12 * np.abs(gold[:, c])).all(), c
 
 
 @pytest.mark.parametrize("case", ["riecg_sod", "riecg_taylor_green"])

@@ -189,3 +189,16 @@ def test_time_dependent_problems_oracle_reproduces_reference_golden_diag(case):
     d = o.diag()
     assert d.shape == gold.shape
     assert (np.abs(d - gold) <= 1e-8 * np.abs(gold) + 1e-15).all()
+
+
+def test_pipe_oracle_reproduces_reference_golden_diag():
+    """RieCG pipe flow (tests/regression/inciter/RieCG/Pipe/diag.std, serial, 12 printed digits):
+    user-defined initial conditions, symmetry walls and the pressure BC physics::prebc."""
+    kw = O.PCASES["riecg_pipe"]
+    gold = O.load_golden_diag("riecg_pipe")
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    assert len(o.get("prebcnodes")) > 0
+    o.step(int(gold[-1, 0]))
+    d = o.diag()
+    assert d.shape == gold.shape
+    assert (np.abs(d[:, 1:] - gold[:, 1:]) <= 2e-12 * np.abs(gold[:, 1:])).all()

@@ -49,13 +49,16 @@ def make_cfg(problem, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0
              velinf=(1.0, 1.0, 1.0), far=(), far_density=0.0, far_pressure=0.0, far_velocity=(0.0, 0.0, 0.0),
              ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0), mu=0.0, dif=0.0, stab=True, rk=1,
              noslip=(), dirval=(), p_iter=10, p_tol=1.0e-3, p_pc="none", p_dir=(), p_dirval=(), p_sym=(),
-             p_hydrostat=None, alpha=0.0, kappa=0.0, r0=0.0, ce=0.0, beta=(0.0, 0.0, 0.0), **_ignored):
+             p_hydrostat=None, alpha=0.0, kappa=0.0, r0=0.0, ce=0.0, beta=(0.0, 0.0, 0.0), pre=(), **_ignored):
     c = HostCfg()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term; c.alpha = alpha; c.kappa = kappa
     c.r0 = r0; c.ce = ce
     for i in range(3):
         c.beta[i] = beta[i]
+    c.npre = len(pre)
+    for i, (sid, dens, pres) in enumerate(pre):
+        c.pre_sets[i] = sid; c.pre_density[i] = dens; c.pre_pressure[i] = pres
     c.nstep = nstep; c.stab2 = int(stab2); c.stab2coef = stab2coef
     c.exact_muscl = int(exact_muscl); c.diag_iter = diag_iter; c.reforder = reforder
     c.solver = solver.encode(); c.fct = int(fct); c.fctclip = int(fctclip); c.fctdif = fctdif

@@ -78,6 +78,18 @@ int xyst_solver_create_mesh(const xyst_host_cfg* cfg, size_t npoin, const double
                             int nsets, const int* set_id, const uint64_t* set_off,
                             const uint64_t* set_tri, int nparts, int part, const int32_t* tetpart,
                             xyst_solver** out);
+/* The same from an ExodusII mesh file (NetCDF classic CDF-1/CDF-2; 4-node tetrahedra, side sets on
+ * tetrahedron faces or triangle-block elements), cf. src/IO/ExodusIIMeshReader.cpp */
+int xyst_solver_create_exo(const xyst_host_cfg* cfg, const char* path, int nparts, int part,
+                           xyst_solver** out);
+/* Read such a file into arrays (call with NULL pointers first for the sizes): coordinates, tets,
+ * side-set ids / offsets (in triangles) / triangles. */
+int xyst_exo_read(const char* path, size_t* npoin, size_t* ntet, int* nsets, size_t* ntri,
+                  double* x, double* y, double* z, uint64_t* tets, int32_t* set_id, uint64_t* set_off,
+                  uint64_t* set_tri);
+/* Write every diagnostics row of the following xyst_solver_step calls to a text file in the format of
+ * the reference's diag file (src/IO/DiagWriter.cpp; scientific, given precision, 0 = 8 as the default) */
+int xyst_solver_diag_file(xyst_solver* s, const char* path, int precision);
 int xyst_solver_destroy(xyst_solver* s);
 
 int xyst_solver_prepare(xyst_solver* s);     /* host only: renumber, volumes, edge integrals, superedges */

@@ -90,6 +90,9 @@ def main():
             shutil.copyfile(os.path.join(REF, diag), os.path.join(HERE, name + ".diag.std"))
             os.chmod(os.path.join(HERE, name + ".diag.std"), 0o644)
         print(name, m["coord"].shape[1], "nodes", len(m["tets"]), "tets", len(m["tris"]), "tris")
+    # one small mesh file verbatim, for the test of the product's own ExodusII reader
+    shutil.copyfile(os.path.join(REF, "RieCG/Sod/rectangle_01_1.5k.exo"), os.path.join(HERE, "riecg_sod.exo"))
+    os.chmod(os.path.join(HERE, "riecg_sod.exo"), 0o644)
     for name, diag in EXTRA_DIAG.items():
         shutil.copyfile(os.path.join(REF, diag), os.path.join(HERE, name + ".diag.std"))
         os.chmod(os.path.join(HERE, name + ".diag.std"), 0o644)

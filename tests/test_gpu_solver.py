@@ -256,3 +256,29 @@ def test_full_size_chocg_box_properties():
         res.append(rows)
         s.close()
     assert np.array_equal(res[0], res[1])
+
+
+def test_mesh_file_to_diag_file_end_to_end(tmp_path):
+    """The reference's own workflow for a regression case, through the product alone: ExodusII mesh
+    file in (tests/golden/riecg_sod.exo = RieCG/Sod/rectangle_01_1.5k.exo), control-file equivalent,
+    10 steps on the GPU, `diag` text file out in the reference's format (src/IO/DiagWriter.cpp) --
+    compared with the golden diag.std by the reference's own acceptance rule (diag.ndiff.cfg) and,
+    tighter, to the digits the default precision prints."""
+    import os
+    kw = O.CASES["riecg_sod"]
+    exo = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "riecg_sod.exo")
+    s = H.Solver.exo(H.make_cfg(**kw), exo)
+    s.prepare(); s.attach(0); s.setup()
+    out = str(tmp_path / "diag")
+    s.diag_file(out)
+    s.step(10)
+    s.close()
+    lines = open(out).read().splitlines()
+    gl = open(os.path.join(os.path.dirname(exo), "riecg_sod.diag.std")).read().splitlines()
+    assert lines[0].split() == gl[0].split()                       # same header: "# 1:it 2:t 3:dt 4:L2(r) ..."
+    rows = np.asarray([[float(x) for x in l.split()] for l in lines[1:]])
+    gold = O.load_golden_diag("riecg_sod")
+    assert rows.shape == gold.shape
+    assert np.array_equal(rows[:, 0], gold[:, 0])
+    assert O.numdiff_ok(rows[:, 1:8], gold[:, 1:8], 2.0e-4, 1.0e-5).all()
+    assert (np.abs(rows[:, 1:] - gold[:, 1:]) <= 2e-8 * np.abs(gold[:, 1:]) + 1e-14).all()

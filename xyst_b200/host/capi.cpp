@@ -7,6 +7,7 @@
 #include <cmath>
 #include "riecg.hpp"
 #include "refhashset.hpp"
+#include "exodus.hpp"
 #include "xyst_host.h"
 
 using namespace xyst;
@@ -16,6 +17,7 @@ struct xyst_solver {
   TetMesh chunk;
   std::unique_ptr< Discretization > disc;
   std::unique_ptr< RieCG > riecg;
+  std::unique_ptr< DiagWriter > diag;
 };
 
 namespace {
@@ -147,6 +149,56 @@ int xyst_solver_create_mesh( const xyst_host_cfg* cfg, size_t npoin, const doubl
   API_END
 }
 
+int xyst_exo_read( const char* path, size_t* npoin, size_t* ntet, int* nsets, size_t* ntri,
+                   double* x, double* y, double* z, uint64_t* tets, int32_t* set_id, uint64_t* set_off,
+                   uint64_t* set_tri )
+{
+  API_BEGIN
+  auto m = readExodus( path );
+  std::size_t nt = 0;
+  for (const auto& [id,t] : m.sidetri) nt += t.size()/3;
+  if (npoin) *npoin = m.coord[0].size();
+  if (ntet) *ntet = m.tets.size()/4;
+  if (nsets) *nsets = static_cast< int >( m.sidetri.size() );
+  if (ntri) *ntri = nt;
+  if (x) std::copy( m.coord[0].begin(), m.coord[0].end(), x );
+  if (y) std::copy( m.coord[1].begin(), m.coord[1].end(), y );
+  if (z) std::copy( m.coord[2].begin(), m.coord[2].end(), z );
+  if (tets) std::copy( m.tets.begin(), m.tets.end(), tets );
+  if (set_id && set_off && set_tri) {
+    std::size_t i = 0, k = 0; set_off[0] = 0;
+    for (const auto& [id,t] : m.sidetri) {
+      set_id[i] = id;
+      for (auto n : t) set_tri[k++] = n;
+      set_off[i+1] = set_off[i] + t.size()/3;
+      ++i;
+    }
+  }
+  API_END
+}
+
+int xyst_solver_create_exo( const xyst_host_cfg* cfg, const char* path, int nparts, int part, xyst_solver** out )
+{
+  std::vector< std::uint64_t > tets, off{ 0 }, tri;
+  std::vector< int > ids;
+  ExoMesh m;
+  try {
+    m = readExodus( path );
+    tets.assign( m.tets.begin(), m.tets.end() );
+    for (const auto& [id,t] : m.sidetri) { ids.push_back( id ); tri.insert( tri.end(), t.begin(), t.end() ); off.push_back( tri.size()/3 ); }
+  } catch (std::exception& e) { return fail( e.what() ); }
+  return xyst_solver_create_mesh( cfg, m.coord[0].size(), m.coord[0].data(), m.coord[1].data(), m.coord[2].data(),
+                                  tets.size()/4, tets.data(), static_cast< int >( ids.size() ), ids.data(), off.data(),
+                                  tri.data(), nparts, part, nullptr, out );
+}
+
+int xyst_solver_diag_file( xyst_solver* s, const char* path, int precision )
+{
+  API_BEGIN
+  s->diag.reset( new DiagWriter( path, precision > 0 ? precision : 8, diagNames( s->cfg ) ) );
+  API_END
+}
+
 int xyst_solver_destroy( xyst_solver* s ) { delete s; return 0; }
 
 int xyst_solver_prepare( xyst_solver* s ) { API_BEGIN s->riecg->prepare(); API_END }
@@ -185,7 +237,8 @@ int xyst_solver_step( xyst_solver* s, int nsteps, double* rows, size_t cap, size
   std::vector< real > row;
   for (int i=0; i<nsteps; ++i) {
     if (s->riecg->m_finished && !s->riecg->pendingDiag()) break;
-    s->riecg->step( rows ? &row : nullptr );
+    s->riecg->step( rows || s->diag ? &row : nullptr );
+    if (s->diag && !row.empty()) s->diag->write( row );
     if (rows && !row.empty()) {
       nc = row.size();
       if (used + nc <= cap) { std::memcpy( rows+used, row.data(), nc*sizeof(double) ); used += nc; ++nr; }

@@ -119,6 +119,10 @@ def lib():
                                          C.POINTER(vp)]
     L.xyst_solver_create_mesh.argtypes = [C.POINTER(HostCfg), C.c_size_t, vp, vp, vp, C.c_size_t, vp,
                                           C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.xyst_solver_create_exo.argtypes = [C.POINTER(HostCfg), C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    L.xyst_exo_read.argtypes = [C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_int),
+                                C.POINTER(C.c_size_t)] + [vp] * 7
+    L.xyst_solver_diag_file.argtypes = [vp, C.c_char_p, C.c_int]
     for f in ("destroy", "prepare", "host_setup", "setup"):
         getattr(L, "xyst_solver_" + f).argtypes = [vp]
     L.xyst_solver_attach.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
@@ -167,6 +171,18 @@ def box_mesh(nx, ny, nz, Lx=1.0, Ly=1.0, Lz=1.0):
     return dict(coord=co, tets=tets, set_id=sid, set_off=soff, set_tri=stri)
 
 
+def exo_read(path):
+    """An ExodusII mesh file as arrays (coord 3xN, tets ntetx4, side-set ids, offsets, triangles)."""
+    L = lib()
+    npn, nt, ns, ntri = C.c_size_t(), C.c_size_t(), C.c_int(), C.c_size_t()
+    _ck(L.xyst_exo_read(path.encode(), C.byref(npn), C.byref(nt), C.byref(ns), C.byref(ntri), *([None] * 7)))
+    co = np.zeros((3, npn.value)); tets = np.zeros((nt.value, 4), np.uint64)
+    sid = np.zeros(ns.value, np.int32); soff = np.zeros(ns.value + 1, np.uint64); stri = np.zeros((ntri.value, 3), np.uint64)
+    _ck(L.xyst_exo_read(path.encode(), None, None, None, None, _p(co[0]), _p(co[1]), _p(co[2]), _p(tets), _p(sid),
+                        _p(soff), _p(stri)))
+    return dict(coord=co, tets=tets, set_id=sid, set_off=soff, set_tri=stri)
+
+
 def rcb(coord, tets, nparts):
     L = lib()
     co = np.ascontiguousarray(coord, np.float64); t = np.ascontiguousarray(tets, np.uint64)
@@ -204,6 +220,15 @@ class Solver:
                                           len(t), _p(t), len(sid), _p(sid), _p(so), _p(st),
                                           nparts, part, _p(tp), C.byref(h)))
         return cls(h, cfg, cfg.ncomp)
+
+    @classmethod
+    def exo(cls, cfg, path, nparts=1, part=0):
+        h = C.c_void_p()
+        _ck(lib().xyst_solver_create_exo(C.byref(cfg), path.encode(), nparts, part, C.byref(h)))
+        return cls(h, cfg, cfg.ncomp)
+
+    def diag_file(self, path, precision=8):
+        _ck(self.L.xyst_solver_diag_file(self.h, path.encode(), precision))
 
     def close(self):
         if getattr(self, "h", None):

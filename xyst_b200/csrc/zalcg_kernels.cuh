@@ -1,0 +1,239 @@
+// xyst_b200/csrc/zalcg_kernels.cuh -- ZalCG device code: Taylor-Galerkin edge flux and the flux-corrected-transport node gathers
+// Part of the single translation unit xyst_b200.cu (included inside its anonymous namespace).
+
+// ---------------------------------------------------------------------------------
+// ZalCG: Taylor-Galerkin two-step edge flux (Zalesak.cpp:31-200, no source term) and the
+// flux-corrected-transport passes of ZalCG.cpp:1056-1607 as node gathers
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_zal_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __restrict__ eq,
+                 const double* __restrict__ D, const double* __restrict__ U, const double* __restrict__ X,
+                 double dt, DParams P, double* __restrict__ F )
+{
+  size_t e = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (e >= nslot) return;
+  int pi = ep[e];
+  if (pi < 0) return;
+  size_t p = pi, q = eq[e];
+  double g = P.gamma;
+  double dx = X[p] - X[q], dy = X[NP+p] - X[NP+q], dz = X[2*NP+p] - X[2*NP+q];
+  double dl = dx*dx + dy*dy + dz*dz;
+  dx /= dl; dy /= dl; dz /= dl;
+  double rL = U[p], ruL = U[NP+p], rvL = U[2*NP+p], rwL = U[3*NP+p], reL = U[4*NP+p];
+  double pL = (reL - 0.5*(ruL*ruL + rvL*rvL + rwL*rwL)/rL) * (g-1.0);
+  double dnL = (ruL*dx + rvL*dy + rwL*dz)/rL;
+  double rR = U[q], ruR = U[NP+q], rvR = U[2*NP+q], rwR = U[3*NP+q], reR = U[4*NP+q];
+  double pR = (reR - 0.5*(ruR*ruR + rvR*rvR + rwR*rwR)/rR) * (g-1.0);
+  double dnR = (ruR*dx + rvR*dy + rwR*dz)/rR;
+  double nx = D[e], ny = D[nslot+e], nz = D[2*nslot+e];
+  double dp = pL - pR;
+  double rh  = 0.5*(rL + rR - dt*(rL*dnL - rR*dnR));
+  double ruh = 0.5*(ruL + ruR - dt*(ruL*dnL - ruR*dnR + dp*dx));
+  double rvh = 0.5*(rvL + rvR - dt*(rvL*dnL - rvR*dnR + dp*dy));
+  double rwh = 0.5*(rwL + rwR - dt*(rwL*dnL - rwR*dnR + dp*dz));
+  double reh = 0.5*(reL + reR - dt*((reL+pL)*dnL - (reR+pR)*dnR));
+  double ph = (reh - 0.5*(ruh*ruh + rvh*rvh + rwh*rwh)/rh) * (g-1.0);
+  double vn = (ruh*nx + rvh*ny + rwh*nz)/rh;
+  double f[NC];
+  f[0] = 2.0*rh*vn;
+  f[1] = 2.0*(ruh*vn + ph*nx);
+  f[2] = 2.0*(rvh*vn + ph*ny);
+  f[3] = 2.0*(rwh*vn + ph*nz);
+  f[4] = 2.0*(reh + ph)*vn;
+  if (P.stab2) {
+    double vnL = (ruL*nx + rvL*ny + rwL*nz)/rL;
+    double vnR = (ruR*nx + rvR*ny + rwR*nz)/rR;
+    double len = sqrt( nx*nx + ny*ny + nz*nz );
+    double cL = sqrt( g * fmax(pL,0.0) / fmax(rL,1.0e-8) );
+    double cR = sqrt( g * fmax(pR,0.0) / fmax(rR,1.0e-8) );
+    double fw = P.stab2coef * fmax( fabs(vnL) + cL*len, fabs(vnR) + cR*len );
+    f[0] -= fw*(rL - rR); f[1] -= fw*(ruL - ruR); f[2] -= fw*(rvL - rvR);
+    f[3] -= fw*(rwL - rwR); f[4] -= fw*(reL - reR);
+  }
+  store_f( F, nslot, e, f );
+}
+
+// pass 1 (aec + first half of alw): R = sum +-F + boundary; P+/- from the antidiffusive edge
+// contributions aec = -dif*ctau*(u_first - u_second) (ZalCG.cpp:1071-1115), symmetry BC on P
+// (:1117-1133), then P /= vol and the low-order solution ul = u - dt R/vol - P+ - P- (:1195-1204)
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot,
+             const double* __restrict__ F, const double* __restrict__ U, const int* __restrict__ bslot,
+             const double* __restrict__ Rb, const int* __restrict__ bcof, const int* __restrict__ symoff,
+             const double* __restrict__ sym_n, const double* __restrict__ vol, double dt, double ctau, int fct,
+             double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = sl_base[slice];
+  int kmax = (int)((sl_base[slice+1] - base) >> 5);
+  double up[NC], r[NC], pp[NC], pn[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { up[c] = U[c*NP+p]; r[c] = 0.0; pp[c] = 0.0; pn[c] = 0.0; }
+  // padding entries (se = 0) point at the node itself and at slot 0 with weight 0: no branch
+  #pragma unroll kZalUnroll
+  for (int k=0; k<kmax; ++k) {
+    long long i = base + (long long)k*32 + lane;
+    int2 eq = __ldg( inc_eq + i );
+    const int se = eq.x;
+    size_t q = (size_t)eq.y;
+    size_t sl = se == 0 ? 0 : (size_t)(abs(se)-1);
+    double dif = se == 0 ? 0.0 : __ldg( D + 3*nslot + sl );
+    double fl[NC];
+    load_f( F, nslot, sl, fl );
+    #pragma unroll
+    for (int c=0; c<NC; ++c) {
+      double f = se == 0 ? 0.0 : fl[c];
+      double uq = __ldg( U + c*NP + q );
+      if (se < 0) {                       // this node is the edge's first node
+        r[c] -= f;
+        double aec = -dif * ctau * (up[c] - uq);
+        if (aec > 0.0) pn[c] -= aec; else pp[c] -= aec;
+      } else {                            // second node
+        r[c] += f;
+        double aec = -dif * ctau * (uq - up[c]);
+        if (aec > 0.0) pp[c] += aec; else pn[c] += aec;
+      }
+    }
+  }
+  int b = bslot[p];
+  if (b >= 0) {
+    #pragma unroll
+    for (int c=0; c<NC; ++c) r[c] += Rb[(size_t)b*NC+c];
+  }
+  if (!fct) {
+    #pragma unroll
+    for (int c=0; c<NC; ++c) R[p*NC+c] = r[c];
+    return;
+  }
+  int bc = bcof[p];
+  if (bc >= 0)
+    for (int s=symoff[bc]; s<symoff[bc+1]; ++s) {
+      const double* n = sym_n + (size_t)s*3;
+      double rvnp = pp[1]*n[0] + pp[2]*n[1] + pp[3]*n[2];
+      double rvnn = pn[1]*n[0] + pn[2]*n[1] + pn[3]*n[2];
+      pp[1] -= rvnp * n[0]; pn[1] -= rvnn * n[0];
+      pp[2] -= rvnp * n[1]; pn[2] -= rvnn * n[1];
+      pp[3] -= rvnp * n[2]; pn[3] -= rvnn * n[2];
+    }
+  double vp = vol[p];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) {
+    pp[c] /= vp; pn[c] /= vp;
+    P[(2*c)*NP+p] = pp[c]; P[(2*c+1)*NP+p] = pn[c];
+    UL[c*NP+p] = up[c] - dt*r[c]/vp - pp[c] - pn[c];
+    R[p*NC+c] = r[c];
+  }
+}
+
+// pass 2 (second half of alw + first half of lim): allowed bounds Q+/- over the edge
+// neighbours (:1206-1290), Q -= ul, limit coefficients C+/- (:1361-1380) -> Q
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_zal_node2( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ U, const double* __restrict__ UL,
+             const double* __restrict__ P, int clip, double* __restrict__ Q )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = sl_base[slice];
+  int kmax = (int)((sl_base[slice+1] - base) >> 5);
+  double hp[NC], lp[NC], qa[NC], qb[NC], ulp[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) {
+    ulp[c] = UL[c*NP+p]; double u = U[c*NP+p];
+    hp[c] = clip ? ulp[c] : fmax( ulp[c], u );
+    lp[c] = clip ? ulp[c] : fmin( ulp[c], u );
+    qa[c] = -1.7976931348623157e308; qb[c] = 1.7976931348623157e308;
+  }
+  #pragma unroll kZalUnroll
+  for (int k=0; k<kmax; ++k) {                 // padding entries point at the node itself: no effect on the bounds
+    long long i = base + (long long)k*32 + lane;
+    size_t q = (size_t)__ldg( inc_eq + i ).y;
+    #pragma unroll
+    for (int c=0; c<NC; ++c) {
+      double ulq = __ldg( UL + c*NP + q );
+      double hq = ulq, lq = ulq;
+      if (!clip) { double uq = __ldg( U + c*NP + q ); hq = fmax( ulq, uq ); lq = fmin( ulq, uq ); }
+      qa[c] = fmax( qa[c], fmax( hp[c], hq ) );
+      qb[c] = fmin( qb[c], fmin( lp[c], lq ) );
+    }
+  }
+  const double eps = 2.220446049250313e-16;
+  #pragma unroll
+  for (int c=0; c<NC; ++c) {
+    double a = qa[c] - ulp[c], b = qb[c] - ulp[c];
+    double pa = P[(2*c)*NP+p], pb = P[(2*c+1)*NP+p];
+    Q[(2*c)*NP+p]   = pa <  eps ? 0.0 : fmin( 1.0, a/pa );
+    Q[(2*c+1)*NP+p] = pb > -eps ? 0.0 : fmin( 1.0, b/pb );
+  }
+}
+
+// pass 3 (second half of lim + solve): limited antidiffusive contributions (:1382-1481) and
+// u = ul + a/vol (:1552-1557)
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_zal_node3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot,
+             const double* __restrict__ U, const double* __restrict__ UL, const double* __restrict__ Q,
+             const double* __restrict__ vol, double ctau, int sysmask, double* __restrict__ Unew,
+             double* __restrict__ W )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = sl_base[slice];
+  int kmax = (int)((sl_base[slice+1] - base) >> 5);
+  double up[NC], cpa[NC], cpb[NC], a[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { up[c] = U[c*NP+p]; cpa[c] = Q[(2*c)*NP+p]; cpb[c] = Q[(2*c+1)*NP+p]; a[c] = 0.0; }
+  #pragma unroll kZalUnroll
+  for (int k=0; k<kmax; ++k) {                 // padding entries: dif = 0, neighbour = the node itself
+    long long i = base + (long long)k*32 + lane;
+    int2 eq = __ldg( inc_eq + i );
+    const int se = eq.x;
+    size_t q = (size_t)eq.y;
+    double dif = se == 0 ? 0.0 : __ldg( D + 3*nslot + (size_t)(abs(se)-1) );
+    double aec[NC], coef[NC];
+    #pragma unroll
+    for (int c=0; c<NC; ++c) {
+      double uq = __ldg( U + c*NP + q );
+      double cqa = __ldg( Q + (2*c)*NP + q ), cqb = __ldg( Q + (2*c+1)*NP + q );
+      if (se < 0) {      // first = this node, second = q
+        aec[c] = -dif * ctau * (up[c] - uq);
+        coef[c] = fmin( aec[c] < 0.0 ? cpa[c] : cpb[c], aec[c] > 0.0 ? cqa : cqb );
+      } else {           // first = q, second = this node
+        aec[c] = -dif * ctau * (uq - up[c]);
+        coef[c] = fmin( aec[c] < 0.0 ? cqa : cqb, aec[c] > 0.0 ? cpa[c] : cpb[c] );
+      }
+    }
+    double cs = 1.0;
+    #pragma unroll
+    for (int c=0; c<NC; ++c) if (sysmask & (1<<c)) cs = fmin( cs, coef[c] );
+    #pragma unroll
+    for (int c=0; c<NC; ++c) {
+      if (sysmask & (1<<c)) coef[c] = cs;
+      double v = aec[c] * coef[c];
+      if (se < 0) a[c] -= v; else a[c] += v;
+    }
+  }
+  double vp = vol[p], u[NC], w[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { u[c] = UL[c*NP+p] + a[c]/vp; Unew[c*NP+p] = u[c]; }
+  primitive( u, w );
+  store_w( W, NP, p, w );
+}
+
+// fct = false: u = u - dt R/vol (ZalCG.cpp:1560-1567)
+__global__ void k_zal_nofct( size_t npoin, size_t NP, const double* __restrict__ R, const double* __restrict__ vol,
+                             const double* __restrict__ U, double dt, double* __restrict__ Unew, double* __restrict__ W )
+{
+  size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (p >= npoin) return;
+  double vp = vol[p], u[NC], w[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) { u[c] = U[c*NP+p] - dt*R[p*NC+c]/vp; Unew[c*NP+p] = u[c]; }
+  primitive( u, w );
+  store_w( W, NP, p, w );
+}

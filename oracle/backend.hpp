@@ -20,6 +20,7 @@
   #include "Kozak.hpp"
   #include "Lax.hpp"
   #include "Chorin.hpp"
+  #include "Lohner.hpp"
   #include "BC.hpp"
   #include "Problems.hpp"
   #include "InciterConfig.hpp"
@@ -101,6 +102,21 @@ inline void chorin_flux( const SupEdge& e, const SupInt& d, const Coords& coord,
 inline void chorin_rhs( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
                         const std::vector< real >& v, real t, const std::vector< real >& P, const Fields& U,
                         const Fields& G, Fields& R ) { chorin::rhs( e, d, coord, tri, v, t, P, U, G, R ); }
+inline void lohner_div( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
+                        const Fields& U, std::vector< real >& D, std::size_t pos ) { lohner::div( e, d, coord, tri, U, D, pos ); }
+inline void lohner_grad( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
+                         const std::vector< real >& U, Fields& G ) { lohner::grad( e, d, coord, tri, U, G ); }
+inline void lohner_vgrad( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
+                          const Fields& U, Fields& G ) { lohner::vgrad( e, d, coord, tri, U, G ); }
+inline void lohner_flux( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
+                         const Fields& U, const Fields& G, Fields& F ) { lohner::flux( e, d, coord, tri, U, G, F ); }
+inline void lohner_gradall( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
+                            const Fields& U, Fields& G ) { lohner::grad( e, d, coord, tri, U, G ); }
+inline void lohner_rhs( const SupEdge& e, const SupInt& d, const Coords& coord, const std::vector< std::size_t >& tri,
+                        const std::vector< real >& v, real t, const Fields& U, const Fields& G, Fields& R )
+{ lohner::rhs( e, d, coord, tri, v, t, U, G, R ); }
+inline void dirbcp( Fields& U, const Coords& coord, const std::vector< std::size_t >& m, const std::vector< double >& v )
+{ physics::dirbcp( 0, U, coord, m, v ); }
 inline port::PFn PRESSURE_RHS() { return problems::PRESSURE_RHS(); }
 inline port::PFn PRESSURE_IC() { auto f = problems::PRESSURE_IC(); return [f]( real x, real y, real z ){ return f( x, y, z, 0 ); }; }
 inline port::PFn PRESSURE_SOL() { auto f = problems::PRESSURE_SOL(); if (!f) return {};
@@ -150,6 +166,13 @@ using port::chorin_vgrad;
 using port::chorin_grad;
 using port::chorin_flux;
 using port::chorin_rhs;
+using port::lohner_div;
+using port::lohner_grad;
+using port::lohner_vgrad;
+using port::lohner_flux;
+using port::lohner_gradall;
+using port::lohner_rhs;
+using port::dirbcp;
 using port::PRESSURE_RHS;
 using port::PRESSURE_IC;
 using port::PRESSURE_SOL;

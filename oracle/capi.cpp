@@ -5,6 +5,7 @@
 #include "driver.hpp"
 #include "cg_port.hpp"
 #include "chocg_port.hpp"
+#include "lohcg_port.hpp"
 #include "oracle.h"
 
 using namespace orc;
@@ -17,6 +18,7 @@ struct Handle { MeshInput in; std::unique_ptr< Run > run; };
 Cfg to_cfg( const orc_cfg* c ) {
   Cfg k;
   k.problem = c->problem; k.flux = c->flux; k.ncomp = static_cast< std::size_t >( c->ncomp );
+  k.soundspeed = c->soundspeed;
   k.alpha = c->alpha; k.kappa = c->kappa; k.r0 = c->r0; k.ce = c->ce; k.beta = {{ c->beta[0], c->beta[1], c->beta[2] }};
   k.gamma = c->gamma; k.p0 = c->p0; k.cfl = c->cfl; k.dt = c->dt; k.t0 = c->t0; k.term = c->term;
   k.nstep = c->nstep; k.stab2 = c->stab2 != 0; k.stab2coef = c->stab2coef; k.steady = c->steady != 0;
@@ -96,6 +98,7 @@ void* orc_create( std::size_t npoin, const double* x, const double* y, const dou
     if (target) for (std::size_t e=0; e<ntet; ++e) tg[e] = target[e];
     auto k = to_cfg( cfg );
     if (k.solver == "chocg") h->run.reset( new ChoRun( in, k, tg, nchare ) );
+    else if (k.solver == "lohcg") h->run.reset( new LohRun( in, k, tg, nchare ) );
     else h->run.reset( new Run( in, k, tg, nchare ) );
     return h.release();
   } catch (std::exception& e) { g_err = e.what(); return nullptr; }
@@ -133,7 +136,8 @@ double orc_scalar( void* hv, const char* name )
   if (n == "meshvol") return r.meshvol;
   if (n == "nchare") return static_cast< double >( r.ch.size() );
   if (n == "finished") return r.finished ? 1.0 : 0.0;
-  if (n == "pit") { if (auto c = dynamic_cast< ChoRun* >( &r )) return static_cast< double >( c->pit ); }
+  if (n == "pit") { if (auto c = dynamic_cast< ChoRun* >( &r )) return static_cast< double >( c->pit );
+                    if (auto c = dynamic_cast< LohRun* >( &r )) return static_cast< double >( c->pit ); }
   return std::nan("");
 }
 

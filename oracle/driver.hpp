@@ -264,6 +264,7 @@ class Chare {
     bool koz = false;                     // KozCG: element-based, no edge integrals at all
     bool cho = false;                     // ChoCG: stride-5 integrals, velocity unknowns, pressure projection
     bool lax = false;                     // LaxCG: (p,u,v,w,T) unknowns inside a stage, preconditioned update
+    bool loh = false;                     // LohCG: stride-4 integrals (normal + Laplacian term), unknowns (p,u,v,w), ChoCG-like BC lists
     std::size_t stride = 3;
     Fields p, q, a;                       // ZalCG::m_p, m_q, m_a
     std::vector< real > mvol;             // ZalCG::m_vol (copy taken at construction)
@@ -277,7 +278,7 @@ class Chare {
     std::vector< real > dtp, tp;
     // ChoCG members
     std::vector< real > pr, div;
-    Fields sgrad, pgrad, mflux;
+    Fields sgrad, pgrad, mflux, vgrad;   // (vgrad: LohCG::m_vgrad)
     std::vector< std::size_t > dirbcmaskp, noslipbcnodes;
     std::vector< double > dirbcval, dirbcvalp;
     std::unordered_map< std::size_t, std::vector< real > > gradc, rhsc;
@@ -289,6 +290,7 @@ class Chare {
     {
       zal = cfg.solver == "zalcg"; stride = zal ? 4 : 3; koz = cfg.solver == "kozcg"; lax = cfg.solver == "laxcg";
       cho = cfg.solver == "chocg"; if (cho) stride = 5;
+      loh = cfg.solver == "lohcg"; if (loh) stride = 4;
       // global2local, Reorder.cpp:279-306
       gid = cm.ginpoel;
       std::sort( gid.begin(), gid.end() );
@@ -352,7 +354,8 @@ class Chare {
       grad = Fields( n, cfg.ncomp*3 );
       if (zal || koz) { p = Fields( n, cfg.ncomp*2 ); q = Fields( n, cfg.ncomp*2 ); a = Fields( n, cfg.ncomp ); mvol = vol; }
       dtp.assign( n, 0.0 ); tp.assign( n, cfg.t0 );
-      if (cho) { pr.assign( n, 0.0 ); div.assign( n, 0.0 ); sgrad = Fields( n, 3 ); pgrad = Fields( n, 3 ); mflux = Fields( n, 3 ); }
+      if (cho || loh) { pr.assign( n, 0.0 ); div.assign( n, 0.0 ); sgrad = Fields( n, 3 ); pgrad = Fields( n, 3 ); mflux = Fields( n, 3 ); }
+      if (loh) vgrad = Fields( n, 9 );
     }
 
     //! ChoCG::setupDirBC, ChoCG.cpp:210-300
@@ -402,7 +405,7 @@ class Chare {
 
     //! RieCG::setupBC :109-245
     void setupBC() {
-      if (cho) {                          // ChoCG::feop :310-315; symmetry sets as below
+      if (cho || loh) {                   // ChoCG::feop :310-315 = LohCG::feop :298-347; symmetry sets as below
         dirbcval.clear(); dirbcvalp.clear();
         setupDirBC( cfg.bc_dir, cfg.bc_dirval, cfg.ncomp, dirbcmasks, dirbcval );
         setupDirBC( cfg.p_bc_dir, cfg.p_bc_dirval, 1, dirbcmaskp, dirbcvalp );
@@ -539,6 +542,10 @@ class Chare {
           n[1] += sig * (g[p][1] - g[q][1]) / 48.0;
           n[2] += sig * (g[p][2] - g[q][2]) / 48.0;
           if (zal) n[3] += J120;
+          if (loh) {                                               // LohCG.cpp:449
+            auto J = ba[0]*cx + ba[1]*cy + ba[2]*cz;
+            n[3] += (g[p][0]*g[q][0] + g[p][1]*g[q][1] + g[p][2]*g[q][2]) / J / 6.0;
+          }
           if (cho) {                                               // ChoCG.cpp:441-442
             auto J = ba[0]*cx + ba[1]*cy + ba[2]*cz;
             n[3] += J / 120.0;
@@ -661,8 +668,22 @@ class Chare {
       bnorm.clear();
     }
 
+    //! LohCG::merge :917-921, psolved :1308-1312: velocity BCs only (no dirbcp)
+    void BCnoP( real t ) {
+      be::dirbc( u, t, coord, dirbcmasks, dirbcval );
+      be::symbc( u, symbcnodes, symbcnorms, 1 );
+      be::noslipbc( u, noslipbcnodes, 1 );
+    }
+
     //! RieCG::BC :764-785
     void BC( real t ) {
+      if (loh) {                          // LohCG::solve/solved :1617-1650
+        be::dirbc( u, t, coord, dirbcmasks, dirbcval );
+        be::dirbcp( u, coord, dirbcmaskp, dirbcvalp );
+        be::symbc( u, symbcnodes, symbcnorms, 1 );
+        be::noslipbc( u, noslipbcnodes, 1 );
+        return;
+      }
       if (cho) {                          // ChoCG::BC :1340-1353
         be::dirbc( u, t, coord, dirbcmasks, dirbcval );
         be::symbc( u, symbcnodes, symbcnorms, 0 );

@@ -55,6 +55,7 @@ typedef struct orc_cfg {
   double alpha, kappa;
   /* problem_r0, problem_ce, problem_beta (nonlinear_energy_growth, rayleigh_taylor) */
   double r0, ce, beta[3];
+  double soundspeed;          /* LohCG artificial speed of sound */
 } orc_cfg;
 
 const char* orc_backend(void);      /* "port" or "reference" */

@@ -39,6 +39,7 @@ struct Cfg {
   real p0 = 0.0;                // problem_p0 (sedov, vortical_flow)
   real alpha = 0.0, kappa = 0.0; // problem_alpha, problem_kappa (manufactured solutions)
   real r0 = 0.0, ce = 0.0;       // problem_r0, problem_ce
+  real soundspeed = 1.0;         // LohCG artificial speed of sound (tag::soundspeed)
   std::array< real, 3 > beta{{0,0,0}};   // problem_beta
   real cfl = 0.0;
   real dt = 0.0;                // constant dt if |dt|>eps
@@ -279,6 +280,12 @@ inline std::vector< real > ic_poiseuille( real, real y, real, real ) {      // :
 
 inline ICFn IC() {                                                          // :1071-1108
   const auto& p = cfg().problem;
+  if (cfg().solver == "lohcg") {             // unknowns (p,u,v,w)
+    if (p == "userdef") return []( real, real, real, real ){                // :53-65
+      return std::vector< real >{ 0.0, cfg().ic_velocity[0], cfg().ic_velocity[1], cfg().ic_velocity[2] }; };
+    if (p == "poiseuille") return []( real, real, real, real ){ return std::vector< real >{ 0, 0, 0, 0 }; };   // :1017-1019
+    throw std::runtime_error( "oracle port: problem type ic not hooked up for lohcg: " + p );
+  }
   if (cfg().solver == "chocg") {             // velocity unknowns only
     if (p == "userdef") return []( real, real, real, real ){                // :44-52
       return std::vector< real >{ cfg().ic_velocity[0], cfg().ic_velocity[1], cfg().ic_velocity[2] }; };
@@ -368,6 +375,10 @@ inline void dirbc( Fields& U, real t, const Coords& coord,
     }
   }
 }
+
+//! pressure Dirichlet BC of LohCG, BC.cpp:74-108 (defined after PRESSURE_IC below)
+inline void dirbcp( Fields& U, const Coords& coord, const std::vector< std::size_t >& dirbcmaskp,
+                    const std::vector< double >& dirbcvalp );
 
 inline void noslipbc( Fields& U, const std::vector< std::size_t >& nodes, std::size_t pos ) {  // :138-150
   for (auto p : nodes) U(p,pos+0) = U(p,pos+1) = U(p,pos+2) = 0.0;
@@ -1082,9 +1093,10 @@ inline void crossdiv6( const Coords& coord, const std::size_t N[3], real n[3] ) 
 
 //! edge divergence with optional pressure stabilisation, Chorin.cpp:34-83
 inline real chorin_div_edge( const Coords& coord, const real d[], real dt, const std::vector< real >& P,
-                             const Fields& G, const Fields& U, std::size_t p, std::size_t q, bool stab )
+                             const Fields& G, const Fields& U, std::size_t p, std::size_t q, bool stab,
+                             std::size_t pos = 0 )
 {
-  real div = d[0] * (U(p,0) + U(q,0)) + d[1] * (U(p,1) + U(q,1)) + d[2] * (U(p,2) + U(q,2));
+  real div = d[0] * (U(p,pos+0) + U(q,pos+0)) + d[1] * (U(p,pos+1) + U(q,pos+1)) + d[2] * (U(p,pos+2) + U(q,pos+2));
   if (!stab) return div;
   auto dx = coord[0][p] - coord[0][q];
   auto dy = coord[1][p] - coord[1][q];
@@ -1100,28 +1112,30 @@ inline real chorin_div_edge( const Coords& coord, const real d[], real dt, const
   return div;
 }
 
-//! chorin::div, Chorin.cpp:85-209 (accumulates into D)
+//! chorin::div, Chorin.cpp:85-209 (accumulates into D); with S = 4 integrals per edge and the velocity
+//! at components pos.. it is lohner::div, Lohner.cpp:35-159
 inline void chorin_div( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
                         const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
                         const std::vector< std::size_t >& triinpoel, real dt, const std::vector< real >& P,
-                        const Fields& G, const Fields& U, std::vector< real >& D, bool stab )
+                        const Fields& G, const Fields& U, std::vector< real >& D, bool stab,
+                        std::size_t S = 5, std::size_t pos = 0 )
 {
-  auto ed = [&]( const real* d, std::size_t p, std::size_t q ){ return chorin_div_edge( coord, d, dt, P, G, U, p, q, stab ); };
+  auto ed = [&]( const real* d, std::size_t p, std::size_t q ){ return chorin_div_edge( coord, d, dt, P, G, U, p, q, stab, pos ); };
   chorin_foredge( dsupedge, dsupint, [&]( int kind, std::size_t e, const std::size_t* N, const real* d ){
     if (kind == 0) {
-      real f[] = { ed( d+(e*6+0)*5, N[0], N[1] ), ed( d+(e*6+1)*5, N[1], N[2] ), ed( d+(e*6+2)*5, N[2], N[0] ),
-                   ed( d+(e*6+3)*5, N[0], N[3] ), ed( d+(e*6+4)*5, N[1], N[3] ), ed( d+(e*6+5)*5, N[2], N[3] ) };
+      real f[] = { ed( d+(e*6+0)*S, N[0], N[1] ), ed( d+(e*6+1)*S, N[1], N[2] ), ed( d+(e*6+2)*S, N[2], N[0] ),
+                   ed( d+(e*6+3)*S, N[0], N[3] ), ed( d+(e*6+4)*S, N[1], N[3] ), ed( d+(e*6+5)*S, N[2], N[3] ) };
       D[N[0]] = D[N[0]] - f[0] + f[2] - f[3];
       D[N[1]] = D[N[1]] + f[0] - f[1] - f[4];
       D[N[2]] = D[N[2]] + f[1] - f[2] - f[5];
       D[N[3]] = D[N[3]] + f[3] + f[4] + f[5];
     } else if (kind == 1) {
-      real f[] = { ed( d+(e*3+0)*5, N[0], N[1] ), ed( d+(e*3+1)*5, N[1], N[2] ), ed( d+(e*3+2)*5, N[2], N[0] ) };
+      real f[] = { ed( d+(e*3+0)*S, N[0], N[1] ), ed( d+(e*3+1)*S, N[1], N[2] ), ed( d+(e*3+2)*S, N[2], N[0] ) };
       D[N[0]] = D[N[0]] - f[0] + f[2];
       D[N[1]] = D[N[1]] + f[0] - f[1];
       D[N[2]] = D[N[2]] + f[1] - f[2];
     } else {
-      real f = ed( d+e*5, N[0], N[1] );
+      real f = ed( d+e*S, N[0], N[1] );
       D[N[0]] -= f;
       D[N[1]] += f;
     }
@@ -1129,9 +1143,9 @@ inline void chorin_div( const std::array< std::vector< std::size_t >, 3 >& dsupe
   for (std::size_t e=0; e<triinpoel.size()/3; ++e) {
     const auto N = triinpoel.data() + e*3;
     real n[3]; crossdiv6( coord, N, n );
-    auto uxA = U(N[0],0), uyA = U(N[0],1), uzA = U(N[0],2);
-    auto uxB = U(N[1],0), uyB = U(N[1],1), uzB = U(N[1],2);
-    auto uxC = U(N[2],0), uyC = U(N[2],1), uzC = U(N[2],2);
+    auto uxA = U(N[0],pos+0), uyA = U(N[0],pos+1), uzA = U(N[0],pos+2);
+    auto uxB = U(N[1],pos+0), uyB = U(N[1],pos+1), uzB = U(N[1],pos+2);
+    auto uxC = U(N[2],pos+0), uyC = U(N[2],pos+1), uzC = U(N[2],pos+2);
     auto ux = (6.0*uxA + uxB + uxC)/8.0;
     auto uy = (6.0*uyA + uyB + uyC)/8.0;
     auto uz = (6.0*uzA + uzB + uzC)/8.0;
@@ -1152,7 +1166,8 @@ inline void chorin_div( const std::array< std::vector< std::size_t >, 3 >& dsupe
 template< class Get >
 inline void chorin_grad_impl( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
                               const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
-                              const std::vector< std::size_t >& triinpoel, std::size_t ncomp, Get U, Fields& G )
+                              const std::vector< std::size_t >& triinpoel, std::size_t ncomp, Get U, Fields& G,
+                              std::size_t S = 5 )
 {
   chorin_foredge( dsupedge, dsupint, [&]( int kind, std::size_t e, const std::size_t* N, const real* d ){
     for (std::size_t i=0; i<ncomp; ++i) {
@@ -1160,8 +1175,8 @@ inline void chorin_grad_impl( const std::array< std::vector< std::size_t >, 3 >&
       if (kind == 0) {
         real u[] = { U(N[0],i), U(N[1],i), U(N[2],i), U(N[3],i) };
         for (std::size_t j=0; j<3; ++j) {
-          real f[] = { d[(e*6+0)*5+j] * (u[1] + u[0]), d[(e*6+1)*5+j] * (u[2] + u[1]), d[(e*6+2)*5+j] * (u[0] + u[2]),
-                       d[(e*6+3)*5+j] * (u[3] + u[0]), d[(e*6+4)*5+j] * (u[3] + u[1]), d[(e*6+5)*5+j] * (u[3] + u[2]) };
+          real f[] = { d[(e*6+0)*S+j] * (u[1] + u[0]), d[(e*6+1)*S+j] * (u[2] + u[1]), d[(e*6+2)*S+j] * (u[0] + u[2]),
+                       d[(e*6+3)*S+j] * (u[3] + u[0]), d[(e*6+4)*S+j] * (u[3] + u[1]), d[(e*6+5)*S+j] * (u[3] + u[2]) };
           G(N[0],i3+j) = G(N[0],i3+j) - f[0] + f[2] - f[3];
           G(N[1],i3+j) = G(N[1],i3+j) + f[0] - f[1] - f[4];
           G(N[2],i3+j) = G(N[2],i3+j) + f[1] - f[2] - f[5];
@@ -1170,7 +1185,7 @@ inline void chorin_grad_impl( const std::array< std::vector< std::size_t >, 3 >&
       } else if (kind == 1) {
         real u[] = { U(N[0],i), U(N[1],i), U(N[2],i) };
         for (std::size_t j=0; j<3; ++j) {
-          real f[] = { d[(e*3+0)*5+j] * (u[1] + u[0]), d[(e*3+1)*5+j] * (u[2] + u[1]), d[(e*3+2)*5+j] * (u[0] + u[2]) };
+          real f[] = { d[(e*3+0)*S+j] * (u[1] + u[0]), d[(e*3+1)*S+j] * (u[2] + u[1]), d[(e*3+2)*S+j] * (u[0] + u[2]) };
           G(N[0],i3+j) = G(N[0],i3+j) - f[0] + f[2];
           G(N[1],i3+j) = G(N[1],i3+j) + f[0] - f[1];
           G(N[2],i3+j) = G(N[2],i3+j) + f[1] - f[2];
@@ -1178,7 +1193,7 @@ inline void chorin_grad_impl( const std::array< std::vector< std::size_t >, 3 >&
       } else {
         real u[] = { U(N[0],i), U(N[1],i) };
         for (std::size_t j=0; j<3; ++j) {
-          real f = d[e*5+j] * (u[1] + u[0]);
+          real f = d[e*S+j] * (u[1] + u[0]);
           G(N[0],i3+j) -= f;
           G(N[1],i3+j) += f;
         }
@@ -1214,8 +1229,9 @@ inline void chorin_grad( const std::array< std::vector< std::size_t >, 3 >& dsup
                     [&]( std::size_t p, std::size_t ){ return U[p]; }, G ); }
 
 //! momentum flux of an edge (:451-480) and of a point (:482-509)
-inline real chorin_flux2( const Fields& U, const Fields& G, std::size_t i, std::size_t j, std::size_t p, std::size_t q ) {
-  auto inv = U(p,i)*U(p,j) + U(q,i)*U(q,j);
+inline real chorin_flux2( const Fields& U, const Fields& G, std::size_t i, std::size_t j, std::size_t p, std::size_t q,
+                          std::size_t pos = 0 ) {
+  auto inv = U(p,i+pos)*U(p,j+pos) + U(q,i+pos)*U(q,j+pos);
   auto eps = std::numeric_limits< real >::epsilon();
   auto mu = cfg().mu;
   if (mu < eps) return -inv;
@@ -1223,8 +1239,9 @@ inline real chorin_flux2( const Fields& U, const Fields& G, std::size_t i, std::
   if (i == j) vis -= 2.0/3.0 * ( G(p,0) + G(p,4) + G(p,8) + G(q,0) + G(q,4) + G(q,8) );
   return mu*vis - inv;
 }
-inline real chorin_flux1( const Fields& U, const Fields& G, std::size_t i, std::size_t j, std::size_t p ) {
-  auto inv = U(p,i)*U(p,j);
+inline real chorin_flux1( const Fields& U, const Fields& G, std::size_t i, std::size_t j, std::size_t p,
+                          std::size_t pos = 0 ) {
+  auto inv = U(p,i+pos)*U(p,j+pos);
   auto eps = std::numeric_limits< real >::epsilon();
   auto mu = cfg().mu;
   if (mu < eps) return -inv;
@@ -1236,27 +1253,28 @@ inline real chorin_flux1( const Fields& U, const Fields& G, std::size_t i, std::
 //! chorin::flux, Chorin.cpp:511-638 (accumulates into F)
 inline void chorin_flux( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
                          const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
-                         const std::vector< std::size_t >& triinpoel, const Fields& U, const Fields& G, Fields& F )
+                         const std::vector< std::size_t >& triinpoel, const Fields& U, const Fields& G, Fields& F,
+                         std::size_t S = 5, std::size_t pos = 0 )
 {
   chorin_foredge( dsupedge, dsupint, [&]( int kind, std::size_t e, const std::size_t* N, const real* d ){
     for (std::size_t i=0; i<3; ++i)
       for (std::size_t j=0; j<3; ++j) {
         if (kind == 0) {
-          real f[] = { d[(e*6+0)*5+j] * chorin_flux2(U,G,i,j,N[1],N[0]), d[(e*6+1)*5+j] * chorin_flux2(U,G,i,j,N[2],N[1]),
-                       d[(e*6+2)*5+j] * chorin_flux2(U,G,i,j,N[0],N[2]), d[(e*6+3)*5+j] * chorin_flux2(U,G,i,j,N[3],N[0]),
-                       d[(e*6+4)*5+j] * chorin_flux2(U,G,i,j,N[3],N[1]), d[(e*6+5)*5+j] * chorin_flux2(U,G,i,j,N[3],N[2]) };
+          real f[] = { d[(e*6+0)*S+j] * chorin_flux2(U,G,i,j,N[1],N[0],pos), d[(e*6+1)*S+j] * chorin_flux2(U,G,i,j,N[2],N[1],pos),
+                       d[(e*6+2)*S+j] * chorin_flux2(U,G,i,j,N[0],N[2],pos), d[(e*6+3)*S+j] * chorin_flux2(U,G,i,j,N[3],N[0],pos),
+                       d[(e*6+4)*S+j] * chorin_flux2(U,G,i,j,N[3],N[1],pos), d[(e*6+5)*S+j] * chorin_flux2(U,G,i,j,N[3],N[2],pos) };
           F(N[0],i) = F(N[0],i) - f[0] + f[2] - f[3];
           F(N[1],i) = F(N[1],i) + f[0] - f[1] - f[4];
           F(N[2],i) = F(N[2],i) + f[1] - f[2] - f[5];
           F(N[3],i) = F(N[3],i) + f[3] + f[4] + f[5];
         } else if (kind == 1) {
-          real f[] = { d[(e*3+0)*5+j] * chorin_flux2(U,G,i,j,N[1],N[0]), d[(e*3+1)*5+j] * chorin_flux2(U,G,i,j,N[2],N[1]),
-                       d[(e*3+2)*5+j] * chorin_flux2(U,G,i,j,N[0],N[2]) };
+          real f[] = { d[(e*3+0)*S+j] * chorin_flux2(U,G,i,j,N[1],N[0],pos), d[(e*3+1)*S+j] * chorin_flux2(U,G,i,j,N[2],N[1],pos),
+                       d[(e*3+2)*S+j] * chorin_flux2(U,G,i,j,N[0],N[2],pos) };
           F(N[0],i) = F(N[0],i) - f[0] + f[2];
           F(N[1],i) = F(N[1],i) + f[0] - f[1];
           F(N[2],i) = F(N[2],i) + f[1] - f[2];
         } else {
-          real f = d[e*5+j] * chorin_flux2(U,G,i,j,N[1],N[0]);
+          real f = d[e*S+j] * chorin_flux2(U,G,i,j,N[1],N[0],pos);
           F(N[0],i) -= f;
           F(N[1],i) += f;
         }
@@ -1266,9 +1284,9 @@ inline void chorin_flux( const std::array< std::vector< std::size_t >, 3 >& dsup
     const auto N = triinpoel.data() + e*3;
     real n[3]; crossdiv6( coord, N, n );
     for (std::size_t i=0; i<3; ++i) {
-      auto fxA = chorin_flux1(U,G,i,0,N[0]), fyA = chorin_flux1(U,G,i,1,N[0]), fzA = chorin_flux1(U,G,i,2,N[0]);
-      auto fxB = chorin_flux1(U,G,i,0,N[1]), fyB = chorin_flux1(U,G,i,1,N[1]), fzB = chorin_flux1(U,G,i,2,N[1]);
-      auto fxC = chorin_flux1(U,G,i,0,N[2]), fyC = chorin_flux1(U,G,i,1,N[2]), fzC = chorin_flux1(U,G,i,2,N[2]);
+      auto fxA = chorin_flux1(U,G,i,0,N[0],pos), fyA = chorin_flux1(U,G,i,1,N[0],pos), fzA = chorin_flux1(U,G,i,2,N[0],pos);
+      auto fxB = chorin_flux1(U,G,i,0,N[1],pos), fyB = chorin_flux1(U,G,i,1,N[1],pos), fzB = chorin_flux1(U,G,i,2,N[1],pos);
+      auto fxC = chorin_flux1(U,G,i,0,N[2],pos), fyC = chorin_flux1(U,G,i,1,N[2],pos), fzC = chorin_flux1(U,G,i,2,N[2],pos);
       auto fx = (6.0*fxA + fxB + fxC)/8.0;
       auto fy = (6.0*fyA + fyB + fyC)/8.0;
       auto fz = (6.0*fzA + fzB + fzC)/8.0;
@@ -1415,6 +1433,197 @@ inline void chorin_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupe
     for (std::size_t p=0; p<R.nunk(); ++p) {
       auto s = s_( coord[0][p], coord[1][p], coord[2][p], t );
       for (std::size_t c=0; c<s.size(); ++c) R(p,c) -= s[c] * v[p];
+    }
+}
+
+inline void dirbcp( Fields& U, const Coords& coord, const std::vector< std::size_t >& dirbcmaskp,
+                    const std::vector< double >& dirbcvalp )
+{
+  auto ic = PRESSURE_IC();
+  for (std::size_t i=0; i<dirbcmaskp.size()/2; ++i) {
+    auto p = dirbcmaskp[i*2+0];
+    auto mask = dirbcmaskp[i*2+1];
+    if (mask == 1) U(p,0) = ic( coord[0][p], coord[1][p], coord[2][p] );
+    else if (mask == 2 && !dirbcvalp.empty()) U(p,0) = dirbcvalp[i*2+1];
+  }
+}
+
+// ---- Lohner.cpp: edge operators of LohCG (artificial compressibility; unknowns p,u,v,w[,c..]) ----
+// superedge integrals have stride 4: normal(3), grad_p.grad_q/(6J) (LohCG.cpp:407-453). div, grad,
+// vgrad and flux are the Chorin operators on these integrals with the velocity at components 1..3.
+inline void lohner_div( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                        const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                        const std::vector< std::size_t >& triinpoel, const Fields& U, std::vector< real >& D,
+                        std::size_t pos )                                   // Lohner.cpp:35-159
+{ static const std::vector< real > nop; static const Fields nof;
+  chorin_div( dsupedge, dsupint, coord, triinpoel, 0.0, nop, nof, U, D, false, 4, pos ); }
+inline void lohner_grad( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                         const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                         const std::vector< std::size_t >& triinpoel, const std::vector< real >& U, Fields& G )
+{ chorin_grad_impl( dsupedge, dsupint, coord, triinpoel, 1,                 // :161-277
+                    [&]( std::size_t p, std::size_t ){ return U[p]; }, G, 4 ); }
+inline void lohner_vgrad( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                          const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                          const std::vector< std::size_t >& triinpoel, const Fields& U, Fields& G )
+{ chorin_grad_impl( dsupedge, dsupint, coord, triinpoel, 3,                 // :279-400
+                    [&]( std::size_t p, std::size_t i ){ return U(p,i+1); }, G, 4 ); }
+inline void lohner_flux( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                         const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                         const std::vector< std::size_t >& triinpoel, const Fields& U, const Fields& G, Fields& F )
+{ chorin_flux( dsupedge, dsupint, coord, triinpoel, U, G, F, 4, 1 ); }      // :402-589
+inline void lohner_gradall( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                            const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                            const std::vector< std::size_t >& triinpoel, const Fields& U, Fields& G )
+{ if (G.nprop() == 0) return;                                               // :591-722
+  chorin_grad_impl( dsupedge, dsupint, coord, triinpoel, U.nprop(),
+                    [&]( std::size_t p, std::size_t i ){ return U(p,i); }, G, 4 ); }
+
+//! pressure + momentum (+ scalar) edge flux with second-order damping, Lohner.cpp:724-795
+inline void lohner_adv_damp2( const real supint[], const Fields& U, const Fields&, const Coords&,
+                              std::size_t p, std::size_t q, real f[] )
+{
+  auto ncomp = U.nprop();
+  auto nx = supint[0], ny = supint[1], nz = supint[2];
+  auto pL = U(p,0), uL = U(p,1), vL = U(p,2), wL = U(p,3);
+  auto vnL = uL*nx + vL*ny + wL*nz;
+  auto pR = U(q,0), uR = U(q,1), vR = U(q,2), wR = U(q,3);
+  auto vnR = uR*nx + vR*ny + wR*nz;
+  auto s = cfg().soundspeed;
+  auto s2 = s*s;
+  auto v = supint[3] * cfg().mu;
+  real aw = 0.0;
+  if (cfg().stab) aw = std::abs( vnL + vnR ) / 2.0;
+  if (cfg().stab2) {
+    auto len = length3( nx, ny, nz );
+    auto sl = std::abs(vnL) + s*len;
+    auto sr = std::abs(vnR) + s*len;
+    aw += cfg().stab2coef * std::max(sl,sr);
+  }
+  auto pf = pL + pR;
+  f[0] = (vnL + vnR + aw*(pR - pL))*s2;
+  f[1] = uL*vnL + uR*vnR + pf*nx + (aw-v)*(uR - uL);
+  f[2] = vL*vnL + vR*vnR + pf*ny + (aw-v)*(vR - vL);
+  f[3] = wL*vnL + wR*vnR + pf*nz + (aw-v)*(wR - wL);
+  auto d = supint[3] * cfg().dif;
+  for (std::size_t c=4; c<ncomp; ++c) f[c] = U(p,c)*vnL + U(q,c)*vnR + (aw-d)*(U(q,c) - U(p,c));
+}
+
+//! the same with fourth-order damping (limited reconstruction of all unknowns), Lohner.cpp:797-914
+inline void lohner_adv_damp4( const real supint[], const Fields& U, const Fields& G, const Coords& coord,
+                              std::size_t p, std::size_t q, real f[] )
+{
+  const auto ncomp = U.nprop();
+  auto dx = coord[0][q] - coord[0][p];
+  auto dy = coord[1][q] - coord[1][p];
+  auto dz = coord[2][q] - coord[2][p];
+  std::vector< real > uL( ncomp ), uR( ncomp );
+  for (std::size_t i=0; i<ncomp; ++i) { uL[i] = U(p,i); uR[i] = U(q,i); }
+  for (std::size_t c=0; c<ncomp; ++c) {
+    auto g1 = G(p,c*3+0)*dx + G(p,c*3+1)*dy + G(p,c*3+2)*dz;
+    auto g2 = G(q,c*3+0)*dx + G(q,c*3+1)*dy + G(q,c*3+2)*dz;
+    auto delta2 = uR[c] - uL[c];
+    auto delta1 = 2.0 * g1 - delta2;
+    auto delta3 = 2.0 * g2 - delta2;
+    auto rL = (delta2 + muscl_eps) / (delta1 + muscl_eps);
+    auto rR = (delta2 + muscl_eps) / (delta3 + muscl_eps);
+    auto rLinv = (delta1 + muscl_eps) / (delta2 + muscl_eps);
+    auto rRinv = (delta3 + muscl_eps) / (delta2 + muscl_eps);
+    auto phiL = (std::abs(rL) + rL) / (std::abs(rL) + 1.0);
+    auto phiR = (std::abs(rR) + rR) / (std::abs(rR) + 1.0);
+    auto phi_L_inv = (std::abs(rLinv) + rLinv) / (std::abs(rLinv) + 1.0);
+    auto phi_R_inv = (std::abs(rRinv) + rRinv) / (std::abs(rRinv) + 1.0);
+    uL[c] += 0.25*(delta1*(1.0-muscl_const)*phiL + delta2*(1.0+muscl_const)*phi_L_inv);
+    uR[c] -= 0.25*(delta3*(1.0-muscl_const)*phiR + delta2*(1.0+muscl_const)*phi_R_inv);
+  }
+  auto nx = supint[0], ny = supint[1], nz = supint[2];
+  auto vnL = uL[1]*nx + uL[2]*ny + uL[3]*nz;
+  auto vnR = uR[1]*nx + uR[2]*ny + uR[3]*nz;
+  auto s = cfg().soundspeed;
+  auto s2 = s*s;
+  auto v = supint[3] * cfg().mu;
+  real aw = 0.0;
+  if (cfg().stab) aw = std::abs( vnL + vnR ) / 2.0;
+  if (cfg().stab2) {
+    auto len = length3( nx, ny, nz );
+    auto sl = std::abs(vnL) + s*len;
+    auto sr = std::abs(vnR) + s*len;
+    aw += cfg().stab2coef * std::max(sl,sr);
+  }
+  auto pf = uL[0] + uR[0];
+  f[0] = (vnL + vnR + aw*(uR[0]-uL[0]))*s2;
+  f[1] = uL[1]*vnL + uR[1]*vnR + pf*nx + aw*(uR[1]-uL[1]) - v*(U(q,1)-U(p,1));
+  f[2] = uL[2]*vnL + uR[2]*vnR + pf*ny + aw*(uR[2]-uL[2]) - v*(U(q,2)-U(p,2));
+  f[3] = uL[3]*vnL + uR[3]*vnR + pf*nz + aw*(uR[3]-uL[3]) - v*(U(q,3)-U(p,3));
+  auto d = supint[3] * cfg().dif;
+  for (std::size_t c=4; c<ncomp; ++c) f[c] = uL[c]*vnL + uR[c]*vnR + aw*(uR[c]-uL[c]) - d*(U(q,c)-U(p,c));
+}
+
+//! lohner::rhs = adv (:916-1071) + src (:1073-1097), Lohner.cpp:1099-1130
+inline void lohner_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
+                        const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
+                        const std::vector< std::size_t >& triinpoel, const std::vector< real >& v, real t,
+                        const Fields& U, const Fields& G, Fields& R )
+{
+  R.fill( 0.0 );
+  auto ncomp = U.nprop();
+  if (cfg().flux != "damp2" && cfg().flux != "damp4") throw std::runtime_error( "oracle port: Flux not correctly configured" );
+  auto adv = cfg().flux == "damp2" ? lohner_adv_damp2 : lohner_adv_damp4;
+  std::vector< real > fb( 6*ncomp );
+  real* f[6]; for (int k=0; k<6; ++k) f[k] = fb.data() + static_cast<std::size_t>(k)*ncomp;
+  chorin_foredge( dsupedge, dsupint, [&]( int kind, std::size_t e, const std::size_t* N, const real* d ){
+    if (kind == 0) {
+      adv( d+(e*6+0)*4, U, G, coord, N[0], N[1], f[0] );
+      adv( d+(e*6+1)*4, U, G, coord, N[1], N[2], f[1] );
+      adv( d+(e*6+2)*4, U, G, coord, N[2], N[0], f[2] );
+      adv( d+(e*6+3)*4, U, G, coord, N[0], N[3], f[3] );
+      adv( d+(e*6+4)*4, U, G, coord, N[1], N[3], f[4] );
+      adv( d+(e*6+5)*4, U, G, coord, N[2], N[3], f[5] );
+      for (std::size_t c=0; c<ncomp; ++c) {
+        R(N[0],c) = R(N[0],c) - f[0][c] + f[2][c] - f[3][c];
+        R(N[1],c) = R(N[1],c) + f[0][c] - f[1][c] - f[4][c];
+        R(N[2],c) = R(N[2],c) + f[1][c] - f[2][c] - f[5][c];
+        R(N[3],c) = R(N[3],c) + f[3][c] + f[4][c] + f[5][c];
+      }
+    } else if (kind == 1) {
+      adv( d+(e*3+0)*4, U, G, coord, N[0], N[1], f[0] );
+      adv( d+(e*3+1)*4, U, G, coord, N[1], N[2], f[1] );
+      adv( d+(e*3+2)*4, U, G, coord, N[2], N[0], f[2] );
+      for (std::size_t c=0; c<ncomp; ++c) {
+        R(N[0],c) = R(N[0],c) - f[0][c] + f[2][c];
+        R(N[1],c) = R(N[1],c) + f[0][c] - f[1][c];
+        R(N[2],c) = R(N[2],c) + f[1][c] - f[2][c];
+      }
+    } else {
+      adv( d+e*4, U, G, coord, N[0], N[1], f[0] );
+      for (std::size_t c=0; c<ncomp; ++c) { R(N[0],c) -= f[0][c]; R(N[1],c) += f[0][c]; }
+    }
+  } );
+  auto s = cfg().soundspeed;
+  auto s2 = s * s;
+  std::vector< real > fl( ncomp*3 );
+  auto F = [&]( std::size_t c, std::size_t k ) -> real& { return fl[c*3+k]; };
+  for (std::size_t e=0; e<triinpoel.size()/3; ++e) {
+    const auto N = triinpoel.data() + e*3;
+    real n[3]; crossdiv6( coord, N, n );
+    for (std::size_t k=0; k<3; ++k) {
+      auto p = U(N[k],0), u = U(N[k],1), vv = U(N[k],2), w = U(N[k],3);
+      auto vn = n[0]*u + n[1]*vv + n[2]*w;
+      F(0,k) = vn * s2;
+      F(1,k) = u*vn + p*n[0];
+      F(2,k) = vv*vn + p*n[1];
+      F(3,k) = w*vn + p*n[2];
+      for (std::size_t c=4; c<ncomp; ++c) F(c,k) = U(N[k],c)*vn;
+    }
+    for (std::size_t c=0; c<ncomp; ++c) {
+      R(N[0],c) += (6.0*F(c,0) + F(c,1) + F(c,2))/8.0;
+      R(N[1],c) += (F(c,0) + 6.0*F(c,1) + F(c,2))/8.0;
+      R(N[2],c) += (F(c,0) + F(c,1) + 6.0*F(c,2))/8.0;
+    }
+  }
+  if (auto s_ = SRC())
+    for (std::size_t p=0; p<R.nunk(); ++p) {
+      auto sv = s_( coord[0][p], coord[1][p], coord[2][p], t );
+      for (std::size_t c=0; c<sv.size(); ++c) R(p,c) -= sv[c] * v[p];
     }
 }
 

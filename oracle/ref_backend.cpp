@@ -26,6 +26,7 @@ void set_cfg( const Cfg& c )
   g.get< tag::problem_p0 >() = c.p0;
   g.get< tag::problem_alpha >() = c.alpha;
   g.get< tag::problem_kappa >() = c.kappa;
+  g.get< tag::soundspeed >() = c.soundspeed;
   g.get< tag::problem_r0 >() = c.r0;
   g.get< tag::problem_ce >() = c.ce;
   g.get< tag::problem_beta >() = std::vector< double >{ c.beta[0], c.beta[1], c.beta[2] };
@@ -57,7 +58,7 @@ void set_cfg( const Cfg& c )
   g.get< tag::rk >() = c.rk;
   g.get< tag::residual >() = c.residual;
   g.get< tag::rescomp >() = c.rescomp;
-  if (c.solver == "chocg")
+  if (c.solver == "chocg" || c.solver == "lohcg")
     g.get< tag::ic, tag::velocity >() = std::vector< double >{ c.ic_velocity[0], c.ic_velocity[1], c.ic_velocity[2] };
   else if (c.problem == "userdef") {
     g.get< tag::ic, tag::density >() = c.ic_density;

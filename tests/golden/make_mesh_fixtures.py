@@ -47,7 +47,10 @@ EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "kozcg_vortical_flow": "KozCG/VorticalFlow/diag.std",
               "riecg_nleg": "RieCG/NonlinearEnergyGrowth/diag.std",
               "riecg_rayleigh_taylor": "RieCG/RayleighTaylor/diag.std",
-              "riecg_pipe": "RieCG/Pipe/diag.std"}
+              "riecg_pipe": "RieCG/Pipe/diag.std",
+              "lohcg_poiseuille_damp2": "LohCG/Poiseuille/diag_poiseuille_damp2.std",
+              "lohcg_poiseuille_damp4": "LohCG/Poiseuille/diag_poiseuille_damp4.std",
+              "lohcg_ldc": "LohCG/Lid/diag_ldc.std"}
 
 
 def flatten(exo):

@@ -202,3 +202,18 @@ def test_pipe_oracle_reproduces_reference_golden_diag():
     d = o.diag()
     assert d.shape == gold.shape
     assert (np.abs(d[:, 1:] - gold[:, 1:]) <= 2e-12 * np.abs(gold[:, 1:])).all()
+
+
+@pytest.mark.parametrize("case", list(O.HCASES))
+def test_lohcg_oracle_reproduces_reference_golden_diag(case):
+    """LohCG (artificial-compressibility solver, unknowns p,u,v,w: Lohner edge operators, RK stages,
+    initial projection through the conjugate-gradient pressure solve): tests/regression/inciter/LohCG/
+    {Poiseuille/diag_poiseuille_damp2.std, diag_poiseuille_damp4.std, Lid/diag_ldc.std}, serial runs,
+    to the 12 printed digits."""
+    kw = O.HCASES[case]
+    gold = O.load_golden_diag(case)
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(int(gold[-1, 0]))
+    d = o.diag()
+    assert d.shape == gold.shape
+    assert (np.abs(d - gold) <= 2e-12 * np.abs(gold)).all()

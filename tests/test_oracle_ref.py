@@ -149,3 +149,19 @@ def test_manufactured_problems_port_is_bit_identical_to_reference_objects(case):
     a.step(10); b.step(10)
     assert np.array_equal(a.diag(), b.diag())
     assert np.array_equal(a.get("u"), b.get("u"))
+
+
+@needs_ref
+@pytest.mark.parametrize("case", list(O.HCASES))
+def test_lohcg_port_is_bit_identical_to_reference_objects(case):
+    """lohner::div/grad/vgrad/flux/rhs and physics::dirbcp from the reference's own translation units
+    vs the restatement under the same LohCG driver."""
+    kw = O.HCASES[case]
+    mesh = O.load_mesh(kw["mesh"])
+    a = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    b = O.Oracle(mesh, O.make_cfg(**kw), "reference")
+    assert np.array_equal(a.get("u"), b.get("u"))
+    assert np.array_equal(a.get("dsupint0"), b.get("dsupint0"))
+    a.step(20); b.step(20)
+    assert np.array_equal(a.diag(), b.diag())
+    assert np.array_equal(a.get("u"), b.get("u"))

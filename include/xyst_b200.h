@@ -255,6 +255,50 @@ int xyst_chocg_dt_min(xyst_ctx* ctx, double cfl, double dif, double* dt);
  * [8] L2, [9] L1 sums; with an_u (analytic velocity [npoin][3], or NULL): [10..12] L2, [13..15] L1 */
 int xyst_chocg_diag(xyst_ctx* ctx, const double* an_p, const double* an_u, double* out);
 
+/* ---- LohCG: artificial-compressibility solver for constant-density flow -------------------
+ * Unknowns (p,u,v,w). Edge operators lohner::div/grad/vgrad/flux/rhs (src/Physics/Lohner.cpp:35-1130)
+ * on superedge integrals of stride 4 (normal, grad_p.grad_q/(6J); LohCG::domint, LohCG.cpp:407-453)
+ * and the solver steps of src/Inciter/LohCG.cpp. div/grad/vgrad/flux are the Chorin operators on the
+ * velocity: after xyst_lohcg_mesh_upload the entries xyst_chocg_div (stab 0), _vgrad, _flux, _grad(0),
+ * _pinit (divisor 1), _get and xyst_cg_* serve this context too; the entries below are LohCG's own.
+ * One partition per context for now. */
+typedef struct xyst_lohcg_params {
+  int flux;          /* 0 = damp2, 1 = damp4 (Lohner.cpp:724-914) */
+  int stab;          /* tag::stab */
+  int stab2;         /* tag::stab2 */
+  double stab2coef;
+  double mu;         /* mat_dyn_viscosity */
+  double soundspeed; /* tag::soundspeed */
+} xyst_lohcg_params;
+int xyst_lohcg_mesh_upload(xyst_ctx* ctx, size_t npoin, const double* x, const double* y, const double* z,
+                           const size_t nsup[3], const size_t* const dsupedge[3],
+                           const double* const dsupint[3], size_t ntri, const size_t* triinpoel,
+                           const double* vol, const double* v, const xyst_lohcg_params* prm);
+/* LohCG::solve BCs (:1617-1622): physics::dirbc on the four unknowns (ndir entries { node },
+ * { mask_0..3 }, { value_0..3 }, mask 1 or 2 = set to value), physics::dirbcp (npdir pressure
+ * Dirichlet nodes with values, BC.cpp:74-108), symbc and noslipbc on the velocity */
+int xyst_lohcg_bc_upload(xyst_ctx* ctx, size_t ndir, const size_t* dirnodes, const int* dirmask,
+                         const double* dirval, size_t npdir, const size_t* pdirnodes, const double* pdirval,
+                         size_t nsym, const size_t* symbcnodes, const double* symbcnorms,
+                         size_t nnoslip, const size_t* noslipbcnodes);
+int xyst_lohcg_set_u(xyst_ctx* ctx, const double* u /* [npoin][4] */);
+int xyst_lohcg_get_u(xyst_ctx* ctx, double* u);
+int xyst_lohcg_get_rhs(xyst_ctx* ctx, double* rhs /* [npoin][4] */);
+/* dirbc, dirbcp (if pressure != 0), symbc, noslipbc; LohCG::merge :917-921 applies them without dirbcp */
+int xyst_lohcg_apply_bc(xyst_ctx* ctx, int pressure);
+/* lohner::rhs (for damp4 preceded by the gradient of all unknowns, LohCG::grad :1485-1508 + fingrad) */
+int xyst_lohcg_rhs(xyst_ctx* ctx);
+/* one RK stage of LohCG::rhs + solve (:1534-1631): rhs, u = un - rk dt rhs/vol, BCs */
+int xyst_lohcg_stage(xyst_ctx* ctx, int stage, double rkcoef, double dt);
+/* u -= sgrad, velocity BCs (LohCG::psolved :1300-1312); p = CG solution (:1332,1355) */
+int xyst_lohcg_project(xyst_ctx* ctx);
+int xyst_lohcg_pressure_set(xyst_ctx* ctx);
+/* LohCG::dt (:1401-1449): min over nodes of L/(|u|+c) and L^2/max(mu,dif), times cfl */
+int xyst_lohcg_dt_min(xyst_ctx* ctx, double cfl, double dif, double* dt);
+/* NodeDiagnostics::accompute sums (NodeDiagnostics.cpp:270-372), out[16]: [0..3] = sum v u_c^2,
+ * [4..7] = sum v (u-un)_c^2; with an (analytic solution [npoin][4], or NULL): [9..11] L2, [13..15] L1 */
+int xyst_lohcg_diag(xyst_ctx* ctx, const double* an, double* out);
+
 /* ---- linear solver of the pressure projection (ChoCG/LohCG) -----------------------------
  * tk::CSR (src/LinearSolver/CSR.hpp:30-107): block CSR exactly as the reference stores it,
  * nrow = npoin*ncomp scalar rows, 1-based ia[nrow+1] / ja[nnz], values a[nnz] (after

@@ -162,6 +162,15 @@ std::size_t orc_get( void* hv, int chare, const char* name, void* out, std::size
     if (auto cr = dynamic_cast< ChoRun* >( h->run.get() )) { be::set_cfg( cr->cfg ); return put( cr->exported( static_cast<std::size_t>(chare), n ), out, cap ); } }
   if (n == "plhs_ia") { if (auto cr = dynamic_cast< ChoRun* >( h->run.get() )) return put( cr->cgpre.parts[static_cast<std::size_t>(chare)]->S.IA(), out, cap ); }
   if (n == "plhs_ja") { if (auto cr = dynamic_cast< ChoRun* >( h->run.get() )) return put( cr->cgpre.parts[static_cast<std::size_t>(chare)]->S.JA(), out, cap ); }
+  if (auto lr = dynamic_cast< LohRun* >( h->run.get() )) {          // LohCG: the assembled pressure matrix
+    auto& P = *lr->cgpre.parts[static_cast<std::size_t>(chare)];
+    if (n == "plhs_ia") return put( P.S.IA(), out, cap );
+    if (n == "plhs_ja") return put( P.S.JA(), out, cap );
+    if (n == "dp") return put( P.x, out, cap );
+    if (n == "plhs_a") { std::vector< real > r; const auto& ia = P.S.IA(); const auto& ja = P.S.JA();
+      for (std::size_t row=0; row+1<ia.size(); ++row) for (std::size_t j=ia[row]-1; j<ia[row+1]-1; ++j) r.push_back( P.A( row, ja[j]-1 ) );
+      return put( r, out, cap ); }
+  }
   if (n == "x") return put( c.coord[0], out, cap );
   if (n == "y") return put( c.coord[1], out, cap );
   if (n == "z") return put( c.coord[2], out, cap );

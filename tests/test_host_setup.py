@@ -123,12 +123,15 @@ def test_zalcg_setup_matches_oracle(case):
     assert np.array_equal(o.get("gid"), np.arange(len(o.get("gid")), dtype=np.uint64))      # not renumbered
 
 
-@pytest.mark.parametrize("case", ["chocg_poiseuille_damp4", "chocg_ldc", "chocg_poisson_neumann"])
+@pytest.mark.parametrize("case", ["chocg_poiseuille_damp4", "chocg_ldc", "chocg_poisson_neumann",
+                                  "lohcg_poiseuille_damp4", "lohcg_ldc"])
 def test_chocg_setup(case):
     """ChoCG: stride-5 edge integrals (normal, J/120, Laplacian term; ChoCG.cpp:399-446), Dirichlet
     masks/values of velocity and pressure (:210-300), no-slip nodes (:655-682), the pressure
-    Poisson matrix in tk::CSR form (:146-188) -- all bitwise equal to the oracle's."""
-    kw = O.CCASES[case]
+    Poisson matrix in tk::CSR form (:146-188) -- all bitwise equal to the oracle's. LohCG: the same
+    with stride-4 integrals (normal, Laplacian term; LohCG.cpp:407-453) and four unknowns."""
+    kw = {**O.CCASES, **O.HCASES}[case]
+    st, nc = (4, 4) if kw["solver"] == "lohcg" else (5, 3)
     mesh = O.load_mesh(kw["mesh"])
     o = O.Oracle(mesh, O.make_cfg(**kw), "port")
     hm = fixture_to_host_mesh(mesh)
@@ -138,11 +141,11 @@ def test_chocg_setup(case):
         assert np.array_equal(o.get(n), s.get(n)), n
     # single edges: same (edge, 5 integrals) set; order is hash order in the reference
     def singles(g):
-        e = g("dsupedge2").reshape(-1, 2); d = g("dsupint2").reshape(-1, 5)
+        e = g("dsupedge2").reshape(-1, 2); d = g("dsupint2").reshape(-1, st)
         return sorted((tuple(a), tuple(b)) for a, b in zip(e.tolist(), d.tolist()))
     assert singles(o.get) == singles(s.get)
     assert face_multiset(o.get("triinpoel"), o.get("bface")) == face_multiset(s.get("triinpoel"), s.get("bface"))
-    for masks, vals, w in (("dirbcmasks", "dirbcval", 4), ("dirbcmaskp", "dirbcvalp", 2)):
+    for masks, vals, w in (("dirbcmasks", "dirbcval", nc + 1), ("dirbcmaskp", "dirbcvalp", 2)):
         mo, ms = o.get(masks).reshape(-1, w), s.get(masks).reshape(-1, w)
         assert np.array_equal(mo[np.argsort(mo[:, 0])], ms[np.argsort(ms[:, 0])]), masks
         vo, vs = o.get(vals).reshape(-1, w), s.get(vals).reshape(-1, w)

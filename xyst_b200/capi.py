@@ -25,6 +25,11 @@ class ChoParams(C.Structure):
                 ("stab2coef", C.c_double), ("mu", C.c_double)]
 
 
+class LohParams(C.Structure):
+    _fields_ = [("flux", C.c_int32), ("stab", C.c_int32), ("stab2", C.c_int32), ("pad_", C.c_int32),
+                ("stab2coef", C.c_double), ("mu", C.c_double), ("soundspeed", C.c_double)]
+
+
 class Params(C.Structure):
     _fields_ = [("ncomp", C.c_int32), ("flux", C.c_int32), ("stab2", C.c_int32),
                 ("exact_muscl", C.c_int32), ("gamma", C.c_double), ("stab2coef", C.c_double)]
@@ -47,6 +52,9 @@ SYMBOLS = [
     "xyst_chocg_get", "xyst_chocg_apply_bc", "xyst_chocg_div", "xyst_chocg_vgrad", "xyst_chocg_flux",
     "xyst_chocg_grad", "xyst_chocg_src", "xyst_chocg_rhs", "xyst_chocg_stage", "xyst_chocg_pinit",
     "xyst_chocg_project", "xyst_chocg_pressure_update", "xyst_chocg_dt_min", "xyst_chocg_diag",
+    "xyst_lohcg_mesh_upload", "xyst_lohcg_bc_upload", "xyst_lohcg_set_u", "xyst_lohcg_get_u", "xyst_lohcg_get_rhs",
+    "xyst_lohcg_apply_bc", "xyst_lohcg_rhs", "xyst_lohcg_stage", "xyst_lohcg_project", "xyst_lohcg_pressure_set",
+    "xyst_lohcg_dt_min", "xyst_lohcg_diag",
 ]
 
 
@@ -129,6 +137,18 @@ def lib():
     L.xyst_chocg_pressure_update.argtypes = [C.c_void_p, C.c_int]
     L.xyst_chocg_dt_min.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_double)]
     L.xyst_chocg_diag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.xyst_lohcg_mesh_upload.argtypes = L.xyst_chocg_mesh_upload.argtypes
+    L.xyst_lohcg_bc_upload.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.c_void_p]
+    for f in (L.xyst_lohcg_set_u, L.xyst_lohcg_get_u, L.xyst_lohcg_get_rhs):
+        f.argtypes = [C.c_void_p, C.c_void_p]
+    L.xyst_lohcg_apply_bc.argtypes = [C.c_void_p, C.c_int]
+    for f in (L.xyst_lohcg_rhs, L.xyst_lohcg_project, L.xyst_lohcg_pressure_set):
+        f.argtypes = [C.c_void_p]
+    L.xyst_lohcg_stage.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+    L.xyst_lohcg_dt_min.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_double)]
+    L.xyst_lohcg_diag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -403,6 +423,66 @@ class Context:
         out = np.zeros(16)
         ap = None if an_p is None else _f64(an_p); au = None if an_u is None else _f64(an_u)
         self._ck(self.L.xyst_chocg_diag(self.h, _p(ap), _p(au), _p(out)))
+        return out
+
+    # ---- LohCG (artificial compressibility; Lohner edge operators). div/vgrad/flux/grad(0)/pinit/get of
+    # the chocg_* methods act on the velocity part of the same context ----
+    def lohcg_mesh_upload(self, x, y, z, dsupedge, dsupint, triinpoel, vol, v, flux="damp2", stab=True,
+                          stab2=False, stab2coef=0.1, mu=0.0, soundspeed=1.0):
+        x, y, z, vol, v = map(_f64, (x, y, z, vol, v))
+        se = [_u64(a) for a in dsupedge]
+        si = [_f64(a) for a in dsupint]
+        nsup = (C.c_size_t * 3)(len(se[0]) // 4, len(se[1]) // 3, len(se[2]) // 2)
+        pe = (C.c_void_p * 3)(*[a.ctypes.data for a in se])
+        pi = (C.c_void_p * 3)(*[a.ctypes.data for a in si])
+        tri = _u64(triinpoel)
+        self.npoin = len(x)
+        prm = LohParams({"damp2": 0, "damp4": 1}[flux], int(stab), int(stab2), 0, stab2coef, mu, soundspeed)
+        self._ck(self.L.xyst_lohcg_mesh_upload(self.h, len(x), _p(x), _p(y), _p(z), nsup, pe, pi,
+                                               len(tri) // 3, _p(tri), _p(vol), _p(v), C.byref(prm)))
+
+    def lohcg_bc_upload(self, dirnodes=(), dirmask=(), dirval=None, pdirnodes=(), pdirval=(), symbcnodes=(),
+                        symbcnorms=(), noslipbcnodes=()):
+        dn = _u64(dirnodes); dm = np.ascontiguousarray(dirmask, np.int32)
+        dv = None if dirval is None else _f64(dirval)
+        pn = _u64(pdirnodes); pv = _f64(pdirval)
+        sn = _u64(symbcnodes); snn = _f64(symbcnorms); nn = _u64(noslipbcnodes)
+        self._ck(self.L.xyst_lohcg_bc_upload(self.h, len(dn), _p(dn), _p(dm), _p(dv), len(pn), _p(pn), _p(pv),
+                                             len(sn), _p(sn), _p(snn), len(nn), _p(nn)))
+
+    def lohcg_set_u(self, u):
+        u = _f64(u); self._ck(self.L.xyst_lohcg_set_u(self.h, _p(u)))
+
+    def lohcg_get_u(self):
+        out = np.empty((self.npoin, 4)); self._ck(self.L.xyst_lohcg_get_u(self.h, _p(out))); return out
+
+    def lohcg_get_rhs(self):
+        out = np.empty((self.npoin, 4)); self._ck(self.L.xyst_lohcg_get_rhs(self.h, _p(out))); return out
+
+    def lohcg_apply_bc(self, pressure=True):
+        self._ck(self.L.xyst_lohcg_apply_bc(self.h, int(pressure)))
+
+    def lohcg_rhs(self):
+        self._ck(self.L.xyst_lohcg_rhs(self.h))
+
+    def lohcg_stage(self, stage, rkcoef, dt):
+        self._ck(self.L.xyst_lohcg_stage(self.h, stage, rkcoef, dt))
+
+    def lohcg_project(self):
+        self._ck(self.L.xyst_lohcg_project(self.h))
+
+    def lohcg_pressure_set(self):
+        self._ck(self.L.xyst_lohcg_pressure_set(self.h))
+
+    def lohcg_dt_min(self, cfl, dif=0.0):
+        dt = C.c_double(0.0)
+        self._ck(self.L.xyst_lohcg_dt_min(self.h, cfl, dif, C.byref(dt)))
+        return dt.value
+
+    def lohcg_diag(self, an=None):
+        out = np.zeros(16)
+        a = None if an is None else _f64(an)
+        self._ck(self.L.xyst_lohcg_diag(self.h, _p(a), _p(out)))
         return out
 
     def launch_count(self):

@@ -514,6 +514,7 @@ void cho_vgrad( xyst_ctx* c ) {
   CK( cudaGetLastError() );
 }
 void cho_rhs( xyst_ctx* c, const double* Un, double sdt, double* Uout, double* R ) {
+  if (c->loh) throw std::runtime_error( "context holds a LohCG mesh: use xyst_lohcg_rhs / xyst_lohcg_stage" );
   ProfScope ps( c, "cho_rhs" );
   auto g = cho_grid( c );
   if (c->chp.flux == 1)

@@ -207,6 +207,13 @@ struct xyst_ctx {
   DevBuf< int > cb_dnode, cb_dmask, cb_snode, cb_soff, cb_nnode;
   DevBuf< double > cb_dval, cb_snorm;
   size_t cb_nd = 0, cb_ns = 0, cb_nn = 0;
+  // LohCG (lohcg.cuh): (p,u,v,w) in cUa/b/c as [4][NP] with cU/cUn/cUx pointing at the velocity rows,
+  // sound speed, gradients of all unknowns, 4-component Dirichlet list, pressure Dirichlet list
+  bool loh = false;
+  double loh_s = 1.0;
+  DevBuf< double > lG, lb_dval, lp_val;
+  DevBuf< int > lb_dnode, lb_dmask, lp_node;
+  size_t lb_nd = 0, lp_n = 0;
   // pressure solve BCs (matrix-free: masked rows/columns), Neumann part, rhs override
   DevBuf< unsigned char > cg_bc;
   DevBuf< double > cg_bcval, cg_neu, cg_rhs0, cg_bcsmall;
@@ -231,6 +238,9 @@ namespace {
 #define XYST_CHOCG_KERNELS
 #include "chocg.cuh"
 #undef XYST_CHOCG_KERNELS
+#define XYST_LOHCG_KERNELS
+#include "lohcg.cuh"
+#undef XYST_LOHCG_KERNELS
 
 // ---------------------------------------------------------------------------------
 // host side
@@ -1377,6 +1387,9 @@ int xyst_cg_get_x( xyst_ctx* c, double* x )
 #define XYST_CHOCG_API
 #include "chocg.cuh"
 #undef XYST_CHOCG_API
+#define XYST_LOHCG_API
+#include "lohcg.cuh"
+#undef XYST_LOHCG_API
 
 uint64_t xyst_launch_count( const xyst_ctx* c ) { return c ? c->launches : 0; }
 uint64_t xyst_nedge( const xyst_ctx* c ) { return c ? c->nedge : 0; }

@@ -54,7 +54,8 @@ Config to_cfg( const xyst_host_cfg* c ) {
   k.turkel = c->turkel; k.velinf = {{ c->velinf[0], c->velinf[1], c->velinf[2] }};
   k.ic_density = c->ic_density; k.ic_pressure = c->ic_pressure;
   k.ic_velocity = {{ c->ic_velocity[0], c->ic_velocity[1], c->ic_velocity[2] }};
-  if (k.solver == "chocg") {
+  if (c->soundspeed != 0.0) k.soundspeed = c->soundspeed;
+  if (k.solver == "chocg" || k.solver == "lohcg") {
     k.mu = c->mu; k.dif = c->dif; k.stab = c->stab != 0; k.rk = c->rk ? c->rk : 1;
     for (int i=0; i<c->nnoslip; ++i) k.bc_noslip.push_back( c->noslip[i] );
     for (int i=0; i<c->ndirval; ++i) k.bc_dirval.emplace_back( c->dirval[i], c->dirval[i] + k.ncomp+1 );

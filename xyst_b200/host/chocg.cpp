@@ -118,6 +118,47 @@ void RieCG::choPrelhs()
   }
 }
 
+//! Pressure BCs and problem functions of ChoCG::pinit :1047-1122 (= LohCG::pinit :1140-1215):
+//! Dirichlet node -> value, Neumann vector, rhs override
+void RieCG::choPressureSetup()
+{
+  auto np = m_disc.Gid().size();
+  const auto& co = m_disc.Coord();
+  const auto& x = co[0]; const auto& y = co[1]; const auto& z = co[2];
+  auto pic = problems::PRESSURE_IC( m_cfg );
+  m_pbc.clear();
+  for (std::size_t i=0; i<m_dirbcmaskp.size()/2; ++i) {
+    auto p = m_dirbcmaskp[i*2]; auto mask = m_dirbcmaskp[i*2+1];
+    if (mask == 1) m_pbc[p] = pic( x[p], y[p], z[p] );
+    else if (mask == 2 && !m_dirbcvalp.empty()) m_pbc[p] = m_dirbcvalp[i*2+1];
+  }
+  if (m_cfg.p_hydrostat != ~0ULL) {
+    const auto& gid = m_disc.Gid();
+    for (std::size_t p=0; p<np; ++p)
+      if (gid[p] == m_cfg.p_hydrostat) { if (!m_pbc.count( p )) m_pbc[p] = pic( x[p], y[p], z[p] ); break; }
+  }
+  m_neubc.clear();
+  if (auto pg = problems::PRESSURE_GRAD( m_cfg )) {
+    std::vector< std::uint8_t > besym( m_triinpoel.size()/3, 0 );
+    for (auto s : m_cfg.p_bc_sym) { auto k = m_bface.find( s ); if (k != m_bface.end()) for (auto f : k->second) besym[f] = 1; }
+    m_neubc.assign( np, 0.0 );
+    for (std::size_t e=0; e<m_triinpoel.size()/3; ++e)
+      if (besym[e]) {
+        const auto N = m_triinpoel.data() + e*3;
+        real a[3] = { x[N[1]]-x[N[0]], y[N[1]]-y[N[0]], z[N[1]]-z[N[0]] },
+             b[3] = { x[N[2]]-x[N[0]], y[N[2]]-y[N[0]], z[N[2]]-z[N[0]] };
+        real n[3] = { (a[1]*b[2] - a[2]*b[1]) / 6.0, (a[2]*b[0] - a[0]*b[2]) / 6.0, (a[0]*b[1] - a[1]*b[0]) / 6.0 };
+        for (std::size_t k=0; k<3; ++k) { auto g = pg( x[N[k]], y[N[k]], z[N[k]] ); m_neubc[ N[k] ] -= n[0]*g[0] + n[1]*g[1] + n[2]*g[2]; }
+      }
+  }
+  m_prhs.clear();
+  if (auto pr = problems::PRESSURE_RHS( m_cfg )) {
+    m_prhs.resize( np );
+    const auto& vol = m_disc.Vol();
+    for (std::size_t i=0; i<np; ++i) m_prhs[i] = pr( x[i], y[i], z[i] ) * vol[i];
+  }
+}
+
 //! Device upload and the start-up sequence of ChoCG::merge :816-837 onwards: make the initial
 //! velocity divergence-free and compute the initial pressure
 void RieCG::choSetup()
@@ -154,39 +195,7 @@ void RieCG::choSetup()
   ck( xyst_chocg_bc_upload( m_ctx, nd, dn.data(), dm.data(), dv.data(), m_symbcnodes.size(), m_symbcnodes.data(),
                             m_symbcnorms.data(), m_noslipbcnodes.size(), m_noslipbcnodes.data() ) );
   ck( xyst_csr_upload( m_ctx, np, 1, m_plhs_ia.data(), m_plhs_ja.data(), m_plhs_a.data() ) );
-  // pressure BCs and problem functions of ChoCG::pinit :1047-1122
-  auto pic = problems::PRESSURE_IC( m_cfg );
-  m_pbc.clear();
-  for (std::size_t i=0; i<m_dirbcmaskp.size()/2; ++i) {
-    auto p = m_dirbcmaskp[i*2]; auto mask = m_dirbcmaskp[i*2+1];
-    if (mask == 1) m_pbc[p] = pic( x[p], y[p], z[p] );
-    else if (mask == 2 && !m_dirbcvalp.empty()) m_pbc[p] = m_dirbcvalp[i*2+1];
-  }
-  if (m_cfg.p_hydrostat != ~0ULL) {
-    const auto& gid = m_disc.Gid();
-    for (std::size_t p=0; p<np; ++p)
-      if (gid[p] == m_cfg.p_hydrostat) { if (!m_pbc.count( p )) m_pbc[p] = pic( x[p], y[p], z[p] ); break; }
-  }
-  m_neubc.clear();
-  if (auto pg = problems::PRESSURE_GRAD( m_cfg )) {
-    std::vector< std::uint8_t > besym( m_triinpoel.size()/3, 0 );
-    for (auto s : m_cfg.p_bc_sym) { auto k = m_bface.find( s ); if (k != m_bface.end()) for (auto f : k->second) besym[f] = 1; }
-    m_neubc.assign( np, 0.0 );
-    for (std::size_t e=0; e<m_triinpoel.size()/3; ++e)
-      if (besym[e]) {
-        const auto N = m_triinpoel.data() + e*3;
-        real a[3] = { x[N[1]]-x[N[0]], y[N[1]]-y[N[0]], z[N[1]]-z[N[0]] },
-             b[3] = { x[N[2]]-x[N[0]], y[N[2]]-y[N[0]], z[N[2]]-z[N[0]] };
-        real n[3] = { (a[1]*b[2] - a[2]*b[1]) / 6.0, (a[2]*b[0] - a[0]*b[2]) / 6.0, (a[0]*b[1] - a[1]*b[0]) / 6.0 };
-        for (std::size_t k=0; k<3; ++k) { auto g = pg( x[N[k]], y[N[k]], z[N[k]] ); m_neubc[ N[k] ] -= n[0]*g[0] + n[1]*g[1] + n[2]*g[2]; }
-      }
-  }
-  m_prhs.clear();
-  if (auto pr = problems::PRESSURE_RHS( m_cfg )) {
-    m_prhs.resize( np );
-    const auto& vol = m_disc.Vol();
-    for (std::size_t i=0; i<np; ++i) m_prhs[i] = pr( x[i], y[i], z[i] ) * vol[i];
-  }
+  choPressureSetup();
   m_psol.clear();
   if (auto ps = problems::PRESSURE_SOL( m_cfg )) { m_psol.resize( np ); for (std::size_t i=0; i<np; ++i) m_psol[i] = ps( x[i], y[i], z[i] ); }
   if (!m_src.empty()) ck( xyst_chocg_src( m_ctx, m_src.data() ) );

@@ -23,6 +23,14 @@ inline real totalenergy( real g, real r, real u, real v, real w, real p ) {
 
 inline Fn IC( const Config& cfg ) {
   const real g = cfg.gamma;
+  if (cfg.solver == "lohcg") {                  // unknowns (p,u,v,w): entries 0..3
+    const auto& p = cfg.problem;
+    if (p == "userdef") { const auto vel = cfg.ic_velocity;                    // userdef::ic :53-65
+      return [vel]( real, real, real, real ) -> std::array< real, 5 > { return {{ 0, vel[0], vel[1], vel[2], 0 }}; }; }
+    if (p == "poiseuille")                                                     // poiseuille::ic :1017-1019
+      return []( real, real, real, real ) -> std::array< real, 5 > { return {{ 0, 0, 0, 0, 0 }}; };
+    throw std::runtime_error( "problem type ic not hooked up: " + p );
+  }
   if (cfg.solver == "chocg") {                  // velocity unknowns only: entries 0..2
     const auto& p = cfg.problem;
     if (p == "userdef") { const auto vel = cfg.ic_velocity;                    // userdef::ic :44-52

@@ -124,11 +124,13 @@ std::vector< std::size_t > Discretization::sharedNodes() const {
 RieCG::RieCG( Discretization& disc, const TetMesh& chunk, const Config& cfg )
   : m_disc( disc ), m_cfg( cfg ), m_sidetri( chunk.sidetri )
 {
-  if (cfg.solver != "riecg" && cfg.solver != "zalcg" && cfg.solver != "kozcg" && cfg.solver != "laxcg" && cfg.solver != "chocg")
+  if (cfg.solver != "riecg" && cfg.solver != "zalcg" && cfg.solver != "kozcg" && cfg.solver != "laxcg" && cfg.solver != "chocg" && cfg.solver != "lohcg")
     throw std::runtime_error( "Unknown solver: " + cfg.solver );
   m_zal = cfg.solver == "zalcg"; m_stride = m_zal ? 4 : 3; m_koz = cfg.solver == "kozcg"; m_lax = cfg.solver == "laxcg";
   m_cho = cfg.solver == "chocg"; if (m_cho) m_stride = 5;      // ChoCG::domint, ChoCG.cpp:399-446
-  if (cfg.ncomp != (m_cho ? 3u : 5u)) throw std::runtime_error( m_cho ? "ChoCG: only ncomp = 3 (velocity) is supported" : "only ncomp = 5 is supported" );
+  m_loh = cfg.solver == "lohcg"; if (m_loh) m_stride = 4;      // LohCG::domint, LohCG.cpp:407-453
+  if (m_loh) { if (cfg.ncomp != 4) throw std::runtime_error( "LohCG: only ncomp = 4 (p,u,v,w) is supported" ); }
+  else if (cfg.ncomp != (m_cho ? 3u : 5u)) throw std::runtime_error( m_cho ? "ChoCG: only ncomp = 3 (velocity) is supported" : "only ncomp = 5 is supported" );
   // Transporter::matchsets as the reference executes it (Transporter.cpp:125-187 with the
   // short-circuit at :347-348): with at least one side set named in the configuration the
   // faces of ALL side sets of the mesh keep their boundary integrals; with none, no face does.
@@ -144,8 +146,8 @@ RieCG::~RieCG() { if (m_ctx) xyst_ctx_destroy( m_ctx ); }
 void RieCG::attach( int device, int nranks, int rank, const void* ncclid )
 {
   xyst_params p{};
-  p.ncomp = m_cho ? 5 : static_cast< int >( m_cfg.ncomp );      // (the context's Euler kernels stay unused for ChoCG)
-  if (m_cfg.flux == "rusanov" || m_cho) p.flux = 0; else if (m_cfg.flux == "hllc") p.flux = 1;
+  p.ncomp = m_cho || m_loh ? 5 : static_cast< int >( m_cfg.ncomp );      // (the context's Euler kernels stay unused for ChoCG)
+  if (m_cfg.flux == "rusanov" || m_cho || m_loh) p.flux = 0; else if (m_cfg.flux == "hllc") p.flux = 1;
   else throw std::runtime_error( "Flux not configured" );       // Riemann.cpp:676-681
   p.stab2 = m_cfg.stab2; p.stab2coef = m_cfg.stab2coef; p.gamma = m_cfg.gamma;
   p.exact_muscl = m_cfg.exact_muscl;
@@ -265,7 +267,11 @@ void RieCG::domint( const EdgeCSR& edges, std::vector< real >& d ) const
       n[0] += sig * (g[p][0] - g[q][0]) / 48.0;
       n[1] += sig * (g[p][1] - g[q][1]) / 48.0;
       n[2] += sig * (g[p][2] - g[q][2]) / 48.0;
-      if (st == 4) n[3] += J120;
+      if (st == 4 && !m_loh) n[3] += J120;
+      if (m_loh) {                                                       // LohCG.cpp:449
+        auto J = ba[0]*cx[0] + ba[1]*cx[1] + ba[2]*cx[2];
+        n[3] += (g[p][0]*g[q][0] + g[p][1]*g[q][1] + g[p][2]*g[q][2]) / J / 6.0;
+      }
       if (st == 5) {                                                     // ChoCG.cpp:441-442
         auto J = ba[0]*cx[0] + ba[1]*cx[1] + ba[2]*cx[2];
         n[3] += J / 120.0;
@@ -383,10 +389,10 @@ void RieCG::setupBC()
     auto k = m_bface.find( s );
     if (k != m_bface.end()) for (auto f : k->second) for (int j=0; j<3; ++j) out.insert( m_triinpoel[f*3+static_cast<std::size_t>(j)] );
   };
-  if (m_cho) choSetupBC();
+  if (m_cho || m_loh) choSetupBC();          // LohCG::setupDirBC :215-296 is ChoCG's
   // Dirichlet: node -> mask (0 -> 1 overwrite only)
   std::map< std::size_t, std::vector< int > > dirbcset;
-  if (!m_cho) for (const auto& mask : m_cfg.bc_dir) {
+  if (!m_cho && !m_loh) for (const auto& mask : m_cfg.bc_dir) {
     if (mask.size() != ncomp+1) throw std::runtime_error( "Incorrect Dirichlet BC mask ncomp" );
     std::set< std::size_t > nodes;
     facenodes( mask[0], nodes );
@@ -396,7 +402,7 @@ void RieCG::setupBC()
       for (std::size_t c=0; c<ncomp; ++c) if (!m[c]) m[c] = mask[c+1];
     }
   }
-  if (!m_cho) m_dirbcmasks.clear();
+  if (!m_cho && !m_loh) m_dirbcmasks.clear();
   for (const auto& [p,mask] : dirbcset) { m_dirbcmasks.push_back( p ); for (auto m : mask) m_dirbcmasks.push_back( static_cast< std::size_t >( m ) ); }
   // pressure BC
   m_prebcnodes.clear(); m_prebcvals.clear();
@@ -510,11 +516,11 @@ void RieCG::hostSetup()
     }
   }
   m_timedep = problems::timeDependent( m_cfg );
-  if (m_timedep && (m_zal || m_koz || m_cho || m_lax || m_cfg.steady))
+  if (m_timedep && (m_zal || m_koz || m_cho || m_loh || m_lax || m_cfg.steady))
     throw std::runtime_error( "time-dependent problems are hooked up for RieCG only" );
   evalDirvals( m_disc.T() );
   evalSrc( m_disc.T() );
-  if (m_cho) choPrelhs();
+  if (m_cho || m_loh) choPrelhs();           // LohCG::prelhs :140-181 is ChoCG's
   m_hostready = true;
   timings.push_back( now()-t0 );
 }
@@ -558,6 +564,7 @@ void RieCG::setup()
   if (!m_hostready) hostSetup();
   auto t0 = now();
   if (m_cho) { choSetup(); timings.push_back( now()-t0 ); timings.push_back( 0.0 ); return; }
+  if (m_loh) { lohSetup(); timings.push_back( now()-t0 ); timings.push_back( 0.0 ); return; }
   uploadHalo();
   auto np = m_disc.Gid().size();
   auto ncomp = m_cfg.ncomp;
@@ -646,6 +653,7 @@ void RieCG::solve()
 bool RieCG::step( std::vector< real >* diagrow )
 {
   if (m_cho) return choStep( diagrow );
+  if (m_loh) return lohStep( diagrow );
   if (m_finished) return false;
   advance( dt() );
   if (m_zal) ck( xyst_zalcg_step( m_ctx, m_disc.Dt() ) );      // ZalCG.cpp:973-1607
@@ -708,11 +716,12 @@ std::vector< real > RieCG::diagnostics()
 std::vector< real > RieCG::solution()
 {
   if (m_cho) return choGet( "u", 3 );
+  if (m_loh) { std::vector< real > r( m_disc.Gid().size()*4 ); ck( xyst_lohcg_get_u( m_ctx, r.data() ) ); return r; }
   std::vector< real > u( m_disc.Gid().size()*m_cfg.ncomp );
   ck( xyst_state_get( m_ctx, u.data() ) );
   return u;
 }
 
-void RieCG::setSolution( const std::vector< real >& u ) { ck( m_cho ? xyst_chocg_set_u( m_ctx, u.data() ) : xyst_state_set( m_ctx, u.data() ) ); }
+void RieCG::setSolution( const std::vector< real >& u ) { ck( m_loh ? xyst_lohcg_set_u( m_ctx, u.data() ) : m_cho ? xyst_chocg_set_u( m_ctx, u.data() ) : xyst_state_set( m_ctx, u.data() ) ); }
 
 } // xyst::

@@ -76,6 +76,9 @@ struct Config {
   std::vector< std::vector< real > > p_bc_dirval;
   std::vector< int > p_bc_sym;
   std::uint64_t p_hydrostat = ~0ULL;
+  //! LohCG (solver = "lohcg", ncomp = 4 unknowns p,u,v,w): artificial compressibility
+  //! (src/Inciter/LohCG.cpp); shares the ChoCG keys above, plus the artificial sound speed
+  real soundspeed = 1.0;
 };
 
 //! Sum, over all partitions sharing them, `w` doubles per unique shared node (ascending
@@ -202,12 +205,19 @@ class RieCG {
     std::vector< real > m_neubc, m_prhs, m_psol, m_lastdiag;
     void choSetupBC();                     //!< ChoCG::setupDirBC :210-300, streamable :655-682
     void choPrelhs();                      //!< ChoCG::prelhs :146-188 on tk::CSR( psup )
+    void choPressureSetup();               //!< pressure BC values, Neumann vector, rhs override of pinit
     void choSetup();                       //!< device upload + ChoCG::merge :816-837 onwards
     bool choStep( std::vector< real >* diagrow );
     void choPinit();                       //!< :1025-1125
     void choPsolve();                      //!< :1127-1142
     void choPsolved( std::vector< real >* diagrow );   //!< :1194-1253
     std::vector< real > choDiag();         //!< NodeDiagnostics::precompute + Transporter::prediagnostics
+    bool m_loh = false;                    //!< LohCG: stride-4 integrals with the Laplacian term (lohcg.cpp)
+    void lohSetup();                       //!< device upload + LohCG::merge :909-931 onwards
+    bool lohStep( std::vector< real >* diagrow );
+    void lohPinit();                       //!< :1127-1219
+    void lohPsolved();                     //!< :1289-1363
+    std::vector< real > lohDiag();         //!< NodeDiagnostics::accompute + Transporter::acdiagnostics
     std::size_t m_stride = 3;
     real m_ownvol = 0.0;
     std::vector< real > m_dirvals, m_src;

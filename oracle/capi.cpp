@@ -19,6 +19,7 @@ Cfg to_cfg( const orc_cfg* c ) {
   Cfg k;
   k.problem = c->problem; k.flux = c->flux; k.ncomp = static_cast< std::size_t >( c->ncomp );
   k.soundspeed = c->soundspeed;
+  k.theta = c->theta; k.mom_iter = c->mom_iter ? c->mom_iter : 10; k.mom_tol = c->mom_tol; if (c->mom_pc[0]) k.mom_pc = c->mom_pc;
   k.alpha = c->alpha; k.kappa = c->kappa; k.r0 = c->r0; k.ce = c->ce; k.beta = {{ c->beta[0], c->beta[1], c->beta[2] }};
   k.gamma = c->gamma; k.p0 = c->p0; k.cfl = c->cfl; k.dt = c->dt; k.t0 = c->t0; k.term = c->term;
   k.nstep = c->nstep; k.stab2 = c->stab2 != 0; k.stab2coef = c->stab2coef; k.steady = c->steady != 0;
@@ -136,6 +137,7 @@ double orc_scalar( void* hv, const char* name )
   if (n == "meshvol") return r.meshvol;
   if (n == "nchare") return static_cast< double >( r.ch.size() );
   if (n == "finished") return r.finished ? 1.0 : 0.0;
+  if (n == "mit") { if (auto c = dynamic_cast< ChoRun* >( &r )) return static_cast< double >( c->mit ); }
   if (n == "pit") { if (auto c = dynamic_cast< ChoRun* >( &r )) return static_cast< double >( c->pit );
                     if (auto c = dynamic_cast< LohRun* >( &r )) return static_cast< double >( c->pit ); }
   return std::nan("");

@@ -76,6 +76,7 @@ class PCSR {
       for (std::size_t i=0; i<rnz.size()*ncomp; ++i)
         for (std::size_t j=ia[i]-1; j<ia[i+1]-1; ++j) r[i] += a[j] * x[ja[j]-1];
     }
+    void zero() { std::fill( a.begin(), a.end(), 0.0 ); }                                // CSR.hpp:63
     std::size_t Ncomp() const { return ncomp; }
     std::size_t rsize() const { return rnz.size()*ncomp; }
     const std::vector< std::size_t >& IA() const { return ia; }
@@ -97,6 +98,7 @@ class RCSR {
     void dirichlet( std::size_t i, real val, std::vector< real >& b, const std::vector< std::size_t >& gid,
                     const CommMap& c, std::size_t pos ) { m.dirichlet( i, val, b, gid, c, pos ); }
     void mult( const std::vector< real >& x, std::vector< real >& r ) const { m.mult( x, r ); }
+    void zero() { m.zero(); }
     std::size_t Ncomp() const { return m.Ncomp(); }
     std::size_t rsize() const { return nrow; }
     //! structure and values through the reference's own writer-free accessors: rebuilt with

@@ -4,7 +4,9 @@
 // constant-density flow, src/Inciter/ChoCG.cpp) on top of the shared setup pipeline of
 // driver.hpp, the Chorin edge operators (physics_port.hpp or, with -DORACLE_REF, the
 // reference's own Chorin.cpp) and the conjugate gradients restatement (cg_port.hpp).
-// Explicit momentum update only (theta = 0), velocity components only (ncomp = 3).
+// Explicit (theta = 0) or semi-implicit (theta > 0: consistent-mass + theta-weighted viscous matrix,
+// block CG on the three velocity components at the last RK stage) momentum update, velocity
+// components only (ncomp = 3).
 // Each member cites the ChoCG.cpp lines it follows; the SDAG control flow
 // (src/Inciter/chocg.ci) is unrolled into plain calls, chares are visited in index order.
 #pragma once
@@ -15,7 +17,8 @@ namespace orc {
 
 class ChoRun : public Run {
   public:
-    cg::Solver cgpre;
+    cg::Solver cgpre, cgmom;              // pressure solve; momentum solve (theta > 0, ChoCG.cpp:134-140)
+    std::size_t mit = 0;                  // iterations of the last momentum solve
     int np = 0;                           // ChoCG::m_np
     bool initial = true;                  // Discretization::Initial()
     std::vector< real > rk;               // m_rkcoef, ChoCG.cpp:43-48
@@ -35,6 +38,7 @@ class ChoRun : public Run {
         cg::CommMap cm;
         for (const auto& [k,n] : c_.nodeCommMap) cm[k] = n;
         auto k = cgpre.add( 1, psup, c_.gid, cm );
+        if (cfg.theta > std::numeric_limits< real >::epsilon()) cgmom.add( cfg.ncomp, psup, c_.gid, cm );   // momlhs :190-208
         auto& A = cgpre.parts[k]->A;
         const auto& X = c_.coord[0]; const auto& Y = c_.coord[1]; const auto& Z = c_.coord[2];
         for (std::size_t e=0; e<c_.inpoel.size()/4; ++e) {
@@ -256,6 +260,67 @@ class ChoRun : public Run {
       }
     }
 
+    //! ChoCG::lhs :1433-1477: consistent mass / dt + theta * viscous Laplacian, the same for every component
+    void lhs() {
+      if (cfg.theta < std::numeric_limits< real >::epsilon()) return;
+      for (std::size_t k=0; k<ch.size(); ++k) {
+        auto& c_ = *ch[k];
+        auto& A = cgmom.parts[k]->A;
+        A.zero();
+        const auto& X = c_.coord[0]; const auto& Y = c_.coord[1]; const auto& Z = c_.coord[2];
+        auto ncomp = c_.u.nprop();
+        for (std::size_t e=0; e<c_.inpoel.size()/4; ++e) {
+          const auto N = c_.inpoel.data() + e*4;
+          real ba[3] = { X[N[1]]-X[N[0]], Y[N[1]]-Y[N[0]], Z[N[1]]-Z[N[0]] },
+               ca[3] = { X[N[2]]-X[N[0]], Y[N[2]]-Y[N[0]], Z[N[2]]-Z[N[0]] },
+               da[3] = { X[N[3]]-X[N[0]], Y[N[3]]-Y[N[0]], Z[N[3]]-Z[N[0]] };
+          auto cross = []( const real a[3], const real b[3], real r[3] ){
+            r[0] = a[1]*b[2] - b[1]*a[2]; r[1] = a[2]*b[0] - b[2]*a[0]; r[2] = a[0]*b[1] - b[0]*a[1]; };
+          real grad[4][3];
+          cross( ca, da, grad[1] ); cross( da, ba, grad[2] ); cross( ba, ca, grad[3] );
+          const auto J = ba[0]*grad[1][0] + ba[1]*grad[1][1] + ba[2]*grad[1][2];      // J = 6V
+          for (std::size_t i=0; i<3; ++i) grad[0][i] = -grad[1][i]-grad[2][i]-grad[3][i];
+          for (std::size_t a=0; a<4; ++a)
+            for (std::size_t b=0; b<4; ++b) {
+              auto v = J/dt/120.0 * ((a == b) ? 2.0 : 1.0);
+              v += cfg.theta * cfg.mu * (grad[a][0]*grad[b][0] + grad[a][1]*grad[b][1] + grad[a][2]*grad[b][2]) / J / 6.0;
+              for (std::size_t c=0; c<ncomp; ++c) A( N[a], N[b], c ) -= v;
+            }
+        }
+      }
+    }
+    //! the semi-implicit branch of ChoCG::solve :1574-1607 + msolve :1610-1623 + msolved :1625-1645
+    void msolve() {
+      std::vector< std::vector< real > > b( ch.size() );
+      std::vector< cg::BCs > bcs( ch.size() );
+      for (std::size_t k=0; k<ch.size(); ++k) {
+        auto& c_ = *ch[k];
+        auto ncomp = c_.u.nprop(), nmask = ncomp + 1;
+        auto& dirbc = bcs[k].dirbc;
+        if (np < 3) {
+          for (std::size_t i=0; i<c_.dirbcmasks.size()/nmask; ++i) {
+            auto& bc = dirbc[ c_.dirbcmasks[i*nmask+0] ];
+            bc.resize( ncomp );
+            for (std::size_t c=0; c<ncomp; ++c) bc[c] = { static_cast< int >( c_.dirbcmasks[i*nmask+1+c] ), 0.0 };
+          }
+          for (auto p : c_.noslipbcnodes) {
+            auto& bc = dirbc[p];
+            bc.resize( ncomp );
+            for (std::size_t c=0; c<ncomp; ++c) bc[c] = { 1, 0.0 };
+          }
+        }
+        b[k] = c_.rhs.vec();
+      }
+      cgmom.init( b, bcs, np < 3, cfg.mom_pc );
+      cgmom.solve( cfg.mom_iter, cfg.mom_tol ); mit = cgmom.it;
+      for (std::size_t k=0; k<ch.size(); ++k) {
+        auto& c_ = *ch[k]; const auto& du = cgmom.parts[k]->x;
+        auto ncomp = c_.u.nprop();
+        for (std::size_t i=0; i<c_.u.nunk(); ++i)
+          for (std::size_t c=0; c<ncomp; ++c) c_.u(i,c) = c_.un(i,c) + du[i*ncomp+c];
+      }
+    }
+
     //! ChoCG::dt :1356-1411 (local minimum)
     real chodt( const Chare& c_ ) const {
       auto eps = std::numeric_limits< real >::epsilon();
@@ -285,16 +350,20 @@ class ChoRun : public Run {
       if (mindt < eps) finished = true;
       dtn = dt; dt = mindt;
       if (t + dt > cfg.term) dt = cfg.term - t;
+      lhs();                                                               // advance :1414-1431
+      const bool implicit = cfg.theta > eps;
       for (std::size_t stage=0; stage<rk.size(); ++stage) {
         for (auto& cp : ch) { auto& c_ = *cp;
           be::chorin_rhs( c_.dsupedge, c_.dsupint, c_.coord, c_.triinpoel, c_.v, t, c_.pr, c_.u, c_.grad, c_.rhs ); }
         sumShared( []( Chare& c_ ) -> be::Fields& { return c_.rhs; } );
-        for (auto& cp : ch) { auto& c_ = *cp;
-          if (stage == 0) c_.un = c_.u;
-          auto sdt = rk[stage] * dt;
-          for (std::size_t i=0; i<c_.u.nunk(); ++i)
-            for (std::size_t c=0; c<c_.u.nprop(); ++c) c_.u(i,c) = c_.un(i,c) - sdt*c_.rhs(i,c)/c_.vol[i];
-          c_.BC( t + rk[stage] * dt ); }                                   // pred :1647-1668
+        for (auto& cp : ch) if (stage == 0) cp->un = cp->u;
+        if (!implicit || stage+1 < rk.size()) {                            // solve :1555-1572
+          for (auto& cp : ch) { auto& c_ = *cp;
+            auto sdt = rk[stage] * dt;
+            for (std::size_t i=0; i<c_.u.nunk(); ++i)
+              for (std::size_t c=0; c<c_.u.nprop(); ++c) c_.u(i,c) = c_.un(i,c) - sdt*c_.rhs(i,c)/c_.vol[i]; }
+        } else msolve();
+        for (auto& cp : ch) cp->BC( t + rk[stage] * dt );                  // pred :1647-1668
         if (cfg.flux == "damp4") { velgrad(); for (auto& cp : ch) fingrad( *cp, cp->grad ); }   // corr :1677
       }
       div_u();

@@ -86,6 +86,11 @@ struct Cfg {
   std::vector< std::vector< real > > p_bc_dirval;    // { setid, val }
   std::vector< int > p_bc_sym;
   std::uint64_t p_hydrostat = ~0ULL;
+  // semi-implicit momentum solve of ChoCG (tag::theta, mom_iter, mom_tol, mom_pc)
+  real theta = 0.0;
+  std::uint64_t mom_iter = 10;
+  real mom_tol = 1.0e-3;
+  std::string mom_pc = "none";
 };
 
 //! Nodal field container with the reference's default layout [node][component]

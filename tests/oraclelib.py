@@ -46,6 +46,7 @@ class Cfg(C.Structure):
         ("alpha", C.c_double), ("kappa", C.c_double),
         ("r0", C.c_double), ("ce", C.c_double), ("beta", C.c_double * 3),
         ("soundspeed", C.c_double),
+        ("theta", C.c_double), ("mom_iter", C.c_uint64), ("mom_tol", C.c_double), ("mom_pc", C.c_char * 16),
     ]
 
 
@@ -56,12 +57,14 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
              far=(), far_density=0.0, far_pressure=0.0, far_velocity=(0.0, 0.0, 0.0),
              ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0),
              mu=0.0, dif=0.0, stab=True, rk=1, noslip=(), dirval=(), p_iter=10, p_tol=1.0e-3, p_pc="none",
-             p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, alpha=0.0, kappa=0.0, r0=0.0, ce=0.0, beta=(0.0, 0.0, 0.0), pre=(), soundspeed=1.0, cls=Cfg):
+             p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, alpha=0.0, kappa=0.0, r0=0.0, ce=0.0, beta=(0.0, 0.0, 0.0), pre=(), soundspeed=1.0,
+             theta=0.0, mom_iter=10, mom_tol=1.0e-3, mom_pc="none", cls=Cfg):
     """Control-file equivalent; defaults are the reference's (InciterConfig.cpp:1707-1757)."""
     c = cls()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term; c.alpha = alpha; c.kappa = kappa
     c.r0 = r0; c.ce = ce; c.soundspeed = soundspeed
+    c.theta = theta; c.mom_iter = mom_iter; c.mom_tol = mom_tol; c.mom_pc = mom_pc.encode()
     for i in range(3):
         c.beta[i] = beta[i]
     c.npre = len(pre)
@@ -147,6 +150,15 @@ CCASES = {
     "chocg_ldc": dict(solver="chocg", ncomp=3, nstep=10, cfl=0.9, flux="damp4", mu=0.01, p_iter=500, p_tol=1.0e-3,
                       p_pc="jacobi", p_hydrostat=0, problem="userdef", noslip=(1, 2, 3, 5, 6),
                       dir_=((4, 2, 2, 2),), dirval=((4, 1.0, 0.0, 0.0),), mesh="riecg_taylor_green"),
+}
+
+# ChoCG with the semi-implicit momentum solve (tests/regression/inciter/ChoCG/Poiseuille/poiseuille_theta.q;
+# golden recorded on 2 PEs)
+ICASES = {
+    "chocg_poiseuille_theta": dict(solver="chocg", ncomp=3, nstep=20, cfl=0.5, flux="damp2", theta=0.5, mu=0.01,
+                                   mom_iter=50, mom_tol=1.0e-3, mom_pc="jacobi", p_iter=500, p_tol=1.0e-3, p_pc="jacobi",
+                                   p_dir=((1, 2), (2, 2)), p_dirval=((1, 2.4), (2, 0.0)), problem="userdef", noslip=(3, 4),
+                                   dir_=((1, 0, 1, 1), (5, 0, 1, 1)), mesh="chocg_poiseuille"),
 }
 
 # LohCG regression cases (tests/regression/inciter/LohCG/{Poiseuille,Lid}/*.q): artificial compressibility,

@@ -204,6 +204,30 @@ def test_pipe_oracle_reproduces_reference_golden_diag():
     assert (np.abs(d[:, 1:] - gold[:, 1:]) <= 2e-12 * np.abs(gold[:, 1:])).all()
 
 
+def test_chocg_semi_implicit_momentum_oracle_reproduces_reference_golden_diag():
+    """ChoCG with theta = 0.5 (ChoCG::lhs :1433-1477: consistent mass / dt + theta * viscous Laplacian in
+    3-component block CSR; momentum CG at the last RK stage, :1574-1645): tests/regression/inciter/ChoCG/
+    Poiseuille/diag_poiseuille_theta.std was recorded on 2 PEs -- a 2-way coordinate bisection reproduces
+    it to the printed digits, the serial run within the reference's own acceptance test (diag.ndiff.cfg)."""
+    case = "chocg_poiseuille_theta"
+    kw = O.ICASES[case]
+    gold = O.load_golden_diag(case)
+    mesh = O.load_mesh(kw["mesh"])
+    from xyst_b200 import hostapi as H
+    from host_common import fixture_to_host_mesh
+    hm = fixture_to_host_mesh(mesh)
+    part = H.rcb(hm["coord"], hm["tets"], 2).astype(np.uint64)
+    o = O.Oracle(mesh, O.make_cfg(**kw), "port", nchare=2, target=part)
+    o.step(int(gold[-1, 0]))
+    d = o.diag()
+    assert d.shape == gold.shape
+    assert (np.abs(d - gold) <= 2e-12 * np.abs(gold) + 1e-14).all()
+    assert int(o.scalar("mit")) > 1
+    s = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    s.step(int(gold[-1, 0]))
+    assert O.numdiff_ok(s.diag()[:, 1:], gold[:, 1:], 1.0e-7, 1.0e-7).all()
+
+
 @pytest.mark.parametrize("case", list(O.HCASES))
 def test_lohcg_oracle_reproduces_reference_golden_diag(case):
     """LohCG (artificial-compressibility solver, unknowns p,u,v,w: Lohner edge operators, RK stages,

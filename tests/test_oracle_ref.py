@@ -120,11 +120,13 @@ def test_laxcg_port_is_bit_identical_to_reference_objects(case):
 
 
 @needs_ref
-@pytest.mark.parametrize("case", ["chocg_poisson_neumann", "chocg_poiseuille_rk3", "chocg_poiseuille_damp4", "chocg_ldc"])
+@pytest.mark.parametrize("case", ["chocg_poisson_neumann", "chocg_poiseuille_rk3", "chocg_poiseuille_damp4", "chocg_ldc",
+                                  "chocg_poiseuille_theta"])
 def test_chocg_port_is_bit_identical_to_reference_objects(case):
-    """chorin::div/grad/vgrad/flux/rhs, tk::CSR and the problem functions from the reference's own
-    translation units vs the restatement under the same ChoCG driver."""
-    kw = O.CCASES[case]
+    """chorin::div/grad/vgrad/flux/rhs, tk::CSR (scalar and, for the semi-implicit momentum solve,
+    3-component block rows) and the problem functions from the reference's own translation units vs
+    the restatement under the same ChoCG driver."""
+    kw = {**O.CCASES, **O.ICASES}[case]
     mesh = O.load_mesh(kw["mesh"])
     a = O.Oracle(mesh, O.make_cfg(**kw), "port")
     b = O.Oracle(mesh, O.make_cfg(**kw), "reference")

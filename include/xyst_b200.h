@@ -245,6 +245,14 @@ int xyst_chocg_stage(xyst_ctx* ctx, int stage, double rkcoef, double dt);
  * is the previous solution (:363). Continue with xyst_cg_solve. */
 int xyst_chocg_pinit(xyst_ctx* ctx, double divisor, size_t nbc, const size_t* bcnodes,
                      const double* bcvals, const double* neubc, const double* rhs0, int pc);
+/* Semi-implicit momentum solve (theta > 0) at the last RK stage, ChoCG::solve :1574-1607 + msolve +
+ * msolved :1610-1645. With the momentum solver selected (xyst_cg_select 1) and its matrix (ChoCG::lhs
+ * :1433-1477, block CSR with 3 scalar rows per node) given by xyst_csr_upload / xyst_csr_update:
+ * minit: b = rhs of the last xyst_chocg_rhs, Dirichlet rows (node*3 + component) with value 0, initial
+ * guess = previous solution; then xyst_cg_solve; mupdate: u = un + du, BC, velocity gradient for damp4
+ * (stage = index of this RK stage: at stage 0 un is the current velocity). */
+int xyst_chocg_minit(xyst_ctx* ctx, size_t nbc, const size_t* bcrows, int pc);
+int xyst_chocg_mupdate(xyst_ctx* ctx, int stage);
 /* u -= pdt * sgrad, then BC (ChoCG::psolved :1204-1217); pr = x or pr += x (:1241,1249) */
 int xyst_chocg_project(xyst_ctx* ctx, double pdt);
 int xyst_chocg_pressure_update(xyst_ctx* ctx, int increment);
@@ -305,6 +313,13 @@ int xyst_lohcg_diag(xyst_ctx* ctx, const double* an, double* out);
  * CSR::dirichlet etc. were applied by the caller). */
 int xyst_csr_upload(xyst_ctx* ctx, size_t nrow, size_t ncomp, const size_t* ia, const size_t* ja,
                     const double* a);
+/* A context holds two linear solvers (ChoCG::m_cgpre and m_cgmom, ChoCG.cpp:126-140): which = 0
+ * (pressure, selected initially) or 1 (momentum). Every xyst_csr_* / xyst_cg_* entry acts on the
+ * selected one; the other keeps its matrix, vectors and BCs. */
+int xyst_cg_select(xyst_ctx* ctx, int which);
+/* New values a[nnz] for the uploaded matrix (same ia/ja, cf. CSR::zero + refill in ChoCG::lhs); the
+ * solution vector (next initial guess) is kept. */
+int xyst_csr_update(xyst_ctx* ctx, const size_t* ia, const double* a);
 /* CSR::mult (CSR.cpp:154-172): r = A x, this partition's own contribution; host vectors. */
 int xyst_csr_mult(xyst_ctx* ctx, const double* x, double* r);
 /* ConjugateGradients::setup (ConjugateGradients.cpp:105-126 -> residual, pc, initres, normb,

@@ -55,6 +55,8 @@ typedef struct xyst_host_cfg {
   int32_t p_hydrostat_set; uint64_t p_hydrostat;
   double alpha, kappa;        /* problem_alpha, problem_kappa ("vortical_flow") */
   double r0, ce, beta[3];     /* problem_r0, problem_ce, problem_beta ("nonlinear_energy_growth", "rayleigh_taylor") */
+  /* ChoCG semi-implicit momentum solve (theta > 0): CG iterations (0 = 10), tolerance, preconditioner */
+  double theta; uint64_t mom_iter; double mom_tol; char mom_pc[16];
   double soundspeed;          /* LohCG (solver "lohcg", ncomp 4: p,u,v,w): artificial sound speed; 0 = reference default 1.0 */
 } xyst_host_cfg;
 

@@ -160,7 +160,7 @@ std::size_t orc_get( void* hv, int chare, const char* name, void* out, std::size
   if (n == "dirbcvalp") return put( c.dirbcvalp, out, cap );
   if (n == "noslipbcnodes") return put( c.noslipbcnodes, out, cap );
   if (n == "dp") { if (auto cr = dynamic_cast< ChoRun* >( h->run.get() )) return put( cr->cgpre.parts[static_cast<std::size_t>(chare)]->x, out, cap ); }
-  if (n == "u0" || n == "p_ic" || n == "p_sol" || n == "p_rhs" || n == "u_sol" || n == "neubc" || n == "hydrostat" || n == "plhs_a") {
+  if (n == "u0" || n == "p_ic" || n == "p_sol" || n == "p_rhs" || n == "u_sol" || n == "neubc" || n == "hydrostat" || n == "plhs_a" || n == "mlhs_a") {
     if (auto cr = dynamic_cast< ChoRun* >( h->run.get() )) { be::set_cfg( cr->cfg ); return put( cr->exported( static_cast<std::size_t>(chare), n ), out, cap ); } }
   if (n == "plhs_ia") { if (auto cr = dynamic_cast< ChoRun* >( h->run.get() )) return put( cr->cgpre.parts[static_cast<std::size_t>(chare)]->S.IA(), out, cap ); }
   if (n == "plhs_ja") { if (auto cr = dynamic_cast< ChoRun* >( h->run.get() )) return put( cr->cgpre.parts[static_cast<std::size_t>(chare)]->S.JA(), out, cap ); }

@@ -96,6 +96,14 @@ class ChoRun : public Run {
         const auto& ia = P.S.IA(); const auto& ja = P.S.JA();
         for (std::size_t row=0; row+1<ia.size(); ++row) for (std::size_t j=ia[row]-1; j<ia[row+1]-1; ++j) r.push_back( P.A( row, ja[j]-1 ) );
       }
+      else if (n == "mlhs_a") {            // momentum matrix of the last step (restored after the solve)
+        if (cgmom.parts.empty()) return r;
+        auto& P = *cgmom.parts.at( k );
+        const auto& ia = P.S.IA(); const auto& ja = P.S.JA();
+        auto nc = P.A.Ncomp();
+        for (std::size_t row=0; row+1<ia.size(); ++row) for (std::size_t j=ia[row]-1; j<ia[row+1]-1; ++j)
+          r.push_back( P.A( row/nc, (ja[j]-1)/nc, row%nc ) );
+      }
       else throw std::runtime_error( "oracle ChoCG: unknown export " + n );
       return r;
     }

@@ -120,3 +120,47 @@ def test_host_mirror_chocg_matches_oracle_and_golden(case):
     assert relerr(s.get("u"), o.get("u")) < (2e-6 if neu else 1e-9) or np.abs(o.get("u")).max() < 1e-10
     assert relerr(s.get("pr"), o.get("pr")) < (2e-7 if neu else 1e-8)
     assert (np.abs(rows - gold) <= (2e-7 if neu else 2e-8) * np.abs(gold) + 1e-12).all()
+
+
+def test_host_mirror_chocg_semi_implicit_momentum_matches_oracle_and_golden():
+    """theta = 0.5 (poiseuille_theta.q): the momentum matrix of ChoCG::lhs assembled by the host mirror
+    (bitwise the oracle's), the second linear solver of the context (3 scalar rows per node, Dirichlet
+    rows with value 0, initial guess = previous increment), u = un + du, then the usual projection."""
+    from xyst_b200 import hostapi as H
+    from host_common import fixture_to_host_mesh
+    case = "chocg_poiseuille_theta"
+    kw = O.ICASES[case]
+    hm = fixture_to_host_mesh(O.load_mesh(kw["mesh"]))
+    s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"], hm["set_tri"])
+    s.prepare(); s.attach(0); s.setup()
+    gold = O.load_golden_diag(case)
+    n = int(gold[-1, 0])
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    rows = []
+    for it in range(n):
+        r = s.step(1)
+        o.step(1)
+        rows.append(r[0])
+        assert int(s.scalar("mit")) == int(o.scalar("mit")) > 1
+        assert int(s.scalar("pit")) == int(o.scalar("pit"))
+        if it < 2:
+            # same dt to the last bit -> the same matrix to the last bit
+            if s.scalar("dt") == o.scalar("dt"):
+                assert np.array_equal(s.get("mlhs_a"), o.get("mlhs_a"))
+            else:
+                assert relerr(s.get("mlhs_a"), o.get("mlhs_a")) < 1e-13
+    rows = np.asarray(rows); ro = o.diag()
+    assert rows.shape == ro.shape == gold.shape
+    assert (np.abs(rows[:, :3] - ro[:, :3]) <= TOL * np.abs(ro[:, :3])).all()
+    assert (np.abs(rows - ro) <= 1e-9 * np.abs(ro) + 1e-11 * np.abs(ro[:, 3:4])).all()
+    assert relerr(s.get("u"), o.get("u")) < 1e-9
+    assert relerr(s.get("pr"), o.get("pr")) < 1e-8
+    # the golden was recorded on 2 PEs: the reference's own acceptance test (diag.ndiff.cfg)
+    assert O.numdiff_ok(rows[:, 1:], gold[:, 1:], 1.0e-7, 1.0e-7).all()
+    # the pressure entries refuse to act while the momentum solver is selected
+    ctx = s.ctx()
+    ctx.cg_select(1)
+    from xyst_b200 import capi
+    with pytest.raises(capi.XystError, match="pressure Poisson matrix"):
+        ctx.chocg_pressure_update(0)
+    ctx.cg_select(0)

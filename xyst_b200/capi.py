@@ -52,6 +52,7 @@ SYMBOLS = [
     "xyst_chocg_get", "xyst_chocg_apply_bc", "xyst_chocg_div", "xyst_chocg_vgrad", "xyst_chocg_flux",
     "xyst_chocg_grad", "xyst_chocg_src", "xyst_chocg_rhs", "xyst_chocg_stage", "xyst_chocg_pinit",
     "xyst_chocg_project", "xyst_chocg_pressure_update", "xyst_chocg_dt_min", "xyst_chocg_diag",
+    "xyst_chocg_minit", "xyst_chocg_mupdate", "xyst_cg_select", "xyst_csr_update",
     "xyst_lohcg_mesh_upload", "xyst_lohcg_bc_upload", "xyst_lohcg_set_u", "xyst_lohcg_get_u", "xyst_lohcg_get_rhs",
     "xyst_lohcg_apply_bc", "xyst_lohcg_rhs", "xyst_lohcg_stage", "xyst_lohcg_project", "xyst_lohcg_pressure_set",
     "xyst_lohcg_dt_min", "xyst_lohcg_diag",
@@ -137,6 +138,10 @@ def lib():
     L.xyst_chocg_pressure_update.argtypes = [C.c_void_p, C.c_int]
     L.xyst_chocg_dt_min.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_double)]
     L.xyst_chocg_diag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.xyst_chocg_minit.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    L.xyst_chocg_mupdate.argtypes = [C.c_void_p, C.c_int]
+    L.xyst_cg_select.argtypes = [C.c_void_p, C.c_int]
+    L.xyst_csr_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.xyst_lohcg_mesh_upload.argtypes = L.xyst_chocg_mesh_upload.argtypes
     L.xyst_lohcg_bc_upload.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
@@ -424,6 +429,20 @@ class Context:
         ap = None if an_p is None else _f64(an_p); au = None if an_u is None else _f64(an_u)
         self._ck(self.L.xyst_chocg_diag(self.h, _p(ap), _p(au), _p(out)))
         return out
+
+    def chocg_minit(self, bcrows=(), pc="none"):
+        br = _u64(bcrows)
+        self._ck(self.L.xyst_chocg_minit(self.h, len(br), _p(br), {"none": 0, "jacobi": 1}[pc]))
+
+    def chocg_mupdate(self, stage):
+        self._ck(self.L.xyst_chocg_mupdate(self.h, stage))
+
+    def cg_select(self, which):
+        self._ck(self.L.xyst_cg_select(self.h, which))
+
+    def csr_update(self, ia, a):
+        ia = _u64(ia); a = _f64(a)
+        self._ck(self.L.xyst_csr_update(self.h, _p(ia), _p(a)))
 
     # ---- LohCG (artificial compressibility; Lohner edge operators). div/vgrad/flux/grad(0)/pinit/get of
     # the chocg_* methods act on the velocity part of the same context ----

@@ -75,6 +75,23 @@ k_cg_bc_colsum( size_t nrow, const long long* __restrict__ base, const int* __re
   }
   rsum[r] = acc;
 }
+// diagonal of the sliced-ELL matrix
+__global__ void k_cg_getdiag( size_t nrow, const long long* __restrict__ base, const int* __restrict__ col,
+                              const double* __restrict__ val, double* __restrict__ diag )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t r = slice*32 + lane;
+  if (r >= nrow) return;
+  long long b = base[slice];
+  int kmax = (int)((base[slice+1] - b) >> 5);
+  double d = 0.0;
+  for (int k=0; k<kmax; ++k) {
+    long long i = b + (long long)k*32 + lane;
+    if ((size_t)col[i] == r && val[i] != 0.0) d = val[i];
+  }
+  diag[r] = d;
+}
 __global__ void k_cg_bc_rhs( size_t nrow, const unsigned char* __restrict__ bc, const double* __restrict__ bcval,
                              const double* __restrict__ neu, const double* __restrict__ rsum, double* __restrict__ b )
 {

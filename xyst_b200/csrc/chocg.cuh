@@ -445,6 +445,23 @@ k_cho_diag( size_t npoin, size_t NP, const double* __restrict__ U, const double*
   block_reduce< NCHODIAG, false >( a, part );
 }
 
+// right-hand side of the momentum solve: b[i*3+c] = R[c][i] (ChoCG::solve :1603, m_rhs.vec())
+__global__ void k_cho_mrhs( size_t npoin, size_t NP, const double* __restrict__ R, double* __restrict__ b )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i >= npoin*3) return;
+  size_t p = i / 3; int cc = (int)(i % 3);
+  b[i] = R[cc*NP+p];
+}
+// u = un + du (ChoCG::msolved :1636-1641)
+__global__ void k_cho_mupdate( size_t npoin, size_t NP, const double* __restrict__ Un, const double* __restrict__ du,
+                               double* __restrict__ U )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i >= npoin*3) return;
+  size_t p = i / 3; int cc = (int)(i % 3);
+  U[cc*NP+p] = Un[cc*NP+p] + du[i];
+}
 __global__ void k_cg_bc_scatter( int nbc, const int* __restrict__ node, const double* __restrict__ v, double* __restrict__ bcval )
 {
   int i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -526,6 +543,38 @@ void cho_rhs( xyst_ctx* c, const double* Un, double sdt, double* Uout, double* R
       c->nslot, c->cU, c->cP.p, c->cVg.p, c->X.p, chop( c ), c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p,
       c->cS.p, c->v.p, c->vol.p, Un, sdt, Uout, R );
   ++c->launches;
+  CK( cudaGetLastError() );
+}
+// ConjugateGradients::init :336-428 + apply :451-505 + r :508-556 for one partition: Dirichlet rows
+// (scalar row ids of the selected solver) with values, optional Neumann vector, applied to cg_b and,
+// on the fly, to the matrix
+void cho_cg_bc( xyst_ctx* c, size_t nbc, const size_t* bcnodes, const double* bcvals, const double* neubc ) {
+  auto s = c->stream;
+  size_t n = c->cg_nrow;
+  { // the BC node set rarely changes between solves: the row mask is rebuilt only when it does,
+    // the values are scattered from an nbc-long upload
+    std::vector< size_t > nodes( bcnodes, bcnodes + nbc );
+    if (!c->cg_bc.p || c->cg_bc.n != n || nodes != c->cg_bcnodes_h) {
+      std::vector< unsigned char > bc( n, 0 ); std::vector< int > nd( nbc );
+      for (size_t i=0; i<nbc; ++i) { if (bcnodes[i] >= n) throw std::runtime_error( "pressure BC node out of range" );
+        bc[ bcnodes[i] ] = 1; nd[i] = (int)bcnodes[i]; }
+      c->cg_bc.upload( bc, s ); c->cg_bcnode.upload( nd, s ); c->cg_bcnodes_h = nodes;
+      c->cg_bcval.alloc( n ); c->cg_bcsmall.alloc( std::max< size_t >( nbc, 1 ) );
+      CK( cudaMemsetAsync( c->cg_bcval.p, 0, n*sizeof(double), s ) );
+    }
+    if (nbc) {
+      std::vector< double > v( nbc, 0.0 );
+      if (bcvals) std::copy( bcvals, bcvals + nbc, v.begin() );
+      CK( cudaMemcpyAsync( c->cg_bcsmall.p, v.data(), nbc*sizeof(double), cudaMemcpyHostToDevice, s ) );
+      CK( cudaStreamSynchronize( s ) );
+      k_cg_bc_scatter<<< nblk( nbc, 256 ), 256, 0, s >>>( (int)nbc, c->cg_bcnode.p, c->cg_bcsmall.p, c->cg_bcval.p ); ++c->launches;
+    } }
+  c->cg_hasbc = true;
+  const double* neu = nullptr;
+  if (neubc) { c->cg_neu.upload( std::vector< double >( neubc, neubc+n ), s ); neu = c->cg_neu.p; }
+  k_cg_bc_colsum<<< nblk( c->cg_nslice*32, 256 ), 256, 0, s >>>( n, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_bc.p,
+    c->cg_bcval.p, c->cg_q.p ); ++c->launches;
+  k_cg_bc_rhs<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_bc.p, c->cg_bcval.p, neu, c->cg_q.p, c->cg_b.p ); ++c->launches;
   CK( cudaGetLastError() );
 }
 } // namespace
@@ -711,33 +760,45 @@ int xyst_chocg_pinit( xyst_ctx* c, double divisor, size_t nbc, const size_t* bcn
   size_t n = c->npoin;
   if (rhs0) CK( cudaMemcpyAsync( c->cg_b.p, rhs0, n*sizeof(double), cudaMemcpyHostToDevice, s ) );
   else { k_cho_prhs<<< nblk( n, 256 ), 256, 0, s >>>( n, divisor, c->cDiv.p, c->cg_b.p ); ++c->launches; }
-  // ConjugateGradients::init :336-428 + apply :451-505 + r :508-556 for one partition
-  { // the BC node set rarely changes between solves: the row mask is rebuilt only when it does,
-    // the values are scattered from an nbc-long upload
-    std::vector< size_t > nodes( bcnodes, bcnodes + nbc );
-    if (!c->cg_bc.p || c->cg_bc.n != n || nodes != c->cg_bcnodes_h) {
-      std::vector< unsigned char > bc( n, 0 ); std::vector< int > nd( nbc );
-      for (size_t i=0; i<nbc; ++i) { if (bcnodes[i] >= n) throw std::runtime_error( "pressure BC node out of range" );
-        bc[ bcnodes[i] ] = 1; nd[i] = (int)bcnodes[i]; }
-      c->cg_bc.upload( bc, s ); c->cg_bcnode.upload( nd, s ); c->cg_bcnodes_h = nodes;
-      c->cg_bcval.alloc( n ); c->cg_bcsmall.alloc( std::max< size_t >( nbc, 1 ) );
-      CK( cudaMemsetAsync( c->cg_bcval.p, 0, n*sizeof(double), s ) );
-    }
-    if (nbc) {
-      std::vector< double > v( nbc, 0.0 );
-      if (bcvals) std::copy( bcvals, bcvals + nbc, v.begin() );
-      CK( cudaMemcpyAsync( c->cg_bcsmall.p, v.data(), nbc*sizeof(double), cudaMemcpyHostToDevice, s ) );
-      CK( cudaStreamSynchronize( s ) );
-      k_cg_bc_scatter<<< nblk( nbc, 256 ), 256, 0, s >>>( (int)nbc, c->cg_bcnode.p, c->cg_bcsmall.p, c->cg_bcval.p ); ++c->launches;
-    } }
-  c->cg_hasbc = true;
-  const double* neu = nullptr;
-  if (neubc) { c->cg_neu.upload( std::vector< double >( neubc, neubc+n ), s ); neu = c->cg_neu.p; }
-  k_cg_bc_colsum<<< nblk( c->cg_nslice*32, 256 ), 256, 0, s >>>( n, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_bc.p,
-    c->cg_bcval.p, c->cg_q.p ); ++c->launches;
-  k_cg_bc_rhs<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_bc.p, c->cg_bcval.p, neu, c->cg_q.p, c->cg_b.p ); ++c->launches;
-  CK( cudaGetLastError() );
+  cho_cg_bc( c, nbc, bcnodes, bcvals, neubc );
   cg_setup_dev( c, pc );
+  API_END
+}
+
+// semi-implicit momentum solve (theta > 0) at the last RK stage, ChoCG::solve :1574-1607: with the
+// momentum matrix selected (xyst_cg_select 1; block CSR with 3 scalar rows per node, ChoCG::lhs
+// :1433-1477), b = rhs of the last xyst_chocg_rhs, Dirichlet rows (node*3+component) with value 0,
+// initial guess = previous solution. Continue with xyst_cg_solve and xyst_chocg_mupdate.
+int xyst_chocg_minit( xyst_ctx* c, size_t nbc, const size_t* bcrows, int pc )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  cho_need( c );
+  if (c->loh) throw std::runtime_error( "context holds a LohCG mesh" );
+  if (c->cg_nrow != c->npoin*3 || c->cg_ncomp != 3)
+    throw std::runtime_error( "ChoCG: select the momentum matrix (3 scalar rows per node) with xyst_cg_select / xyst_csr_upload first" );
+  k_cho_mrhs<<< nblk( c->npoin*3, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->cR.p, c->cg_b.p ); ++c->launches;
+  cho_cg_bc( c, nbc, bcrows, nullptr, nullptr );
+  cg_setup_dev( c, pc );
+  API_END
+}
+
+// u = un + du, BC, and for the damp4 flux the velocity gradient (ChoCG::msolved :1625-1645 + pred);
+// stage = index of this (the last) RK stage: at stage 0 un is the current velocity
+int xyst_chocg_mupdate( xyst_ctx* c, int stage )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  cho_need( c );
+  if (c->cg_nrow != c->npoin*3) throw std::runtime_error( "ChoCG: the momentum solver is not selected" );
+  if (stage < 0) throw std::runtime_error( "stage must be >= 0" );
+  unsigned g = nblk( c->npoin*3, 256 );
+  if (stage == 0) { double* old_un = c->cUn; c->cUn = c->cU;
+    k_cho_mupdate<<< g, 256, 0, c->stream >>>( c->npoin, c->NP, c->cUn, c->cg_x.p, c->cUx ); c->cU = c->cUx; c->cUx = old_un; }
+  else { k_cho_mupdate<<< g, 256, 0, c->stream >>>( c->npoin, c->NP, c->cUn, c->cg_x.p, c->cUx ); std::swap( c->cU, c->cUx ); }
+  ++c->launches;
+  cho_bc( c, c->cU, true, true );
+  if (c->chp.flux == 1) cho_vgrad( c );
   API_END
 }
 

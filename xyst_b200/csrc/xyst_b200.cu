@@ -119,6 +119,11 @@ constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3;   // nccl.h enums (s
 
 template< class T > struct DevBuf {
   T* p = nullptr; size_t n = 0;
+  DevBuf() = default;
+  DevBuf( const DevBuf& ) = delete;
+  DevBuf& operator=( const DevBuf& ) = delete;
+  DevBuf( DevBuf&& o ) noexcept : p( o.p ), n( o.n ) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=( DevBuf&& o ) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
   void alloc( size_t m ) { release(); n = m; if (m) CK( cudaMalloc( &p, m*sizeof(T) ) ); }
   void upload( const std::vector< T >& h, cudaStream_t s ) {
     alloc( h.size() );
@@ -136,7 +141,21 @@ struct Prof {
 
 } // namespace
 
-struct xyst_ctx {
+// One linear solver (the selected one is the base of the context, so that c->cg_* names it)
+struct CgState {
+  // solve BCs (matrix-free: masked rows/columns), Neumann part, rhs override
+  DevBuf< unsigned char > cg_bc;
+  DevBuf< double > cg_bcval, cg_neu, cg_rhs0, cg_bcsmall;
+  DevBuf< int > cg_bcnode; std::vector< size_t > cg_bcnodes_h;
+  bool cg_hasbc = false, cg_hasneu = false, cg_hasrhs0 = false;
+  // sliced-ELL matrix over scalar rows + CG vectors
+  size_t cg_nrow = 0, cg_ncomp = 1, cg_nslice = 0, cg_nent = 0;
+  DevBuf< long long > cg_base; DevBuf< int > cg_col; DevBuf< double > cg_val, cg_diag;
+  DevBuf< double > cg_x, cg_b, cg_r, cg_p, cg_q, cg_z, cg_d, cg_mask, cg_cnt, cg_scal;
+  double cg_normb = 0.0; bool cg_converged = false, cg_finished = false;
+};
+
+struct xyst_ctx : CgState {
   int device = 0;
   cudaStream_t stream = nullptr, comm_stream = nullptr, aux_stream = nullptr;
   bool own_stream = false;
@@ -214,16 +233,8 @@ struct xyst_ctx {
   DevBuf< double > lG, lb_dval, lp_val;
   DevBuf< int > lb_dnode, lb_dmask, lp_node;
   size_t lb_nd = 0, lp_n = 0;
-  // pressure solve BCs (matrix-free: masked rows/columns), Neumann part, rhs override
-  DevBuf< unsigned char > cg_bc;
-  DevBuf< double > cg_bcval, cg_neu, cg_rhs0, cg_bcsmall;
-  DevBuf< int > cg_bcnode; std::vector< size_t > cg_bcnodes_h;
-  bool cg_hasbc = false, cg_hasneu = false, cg_hasrhs0 = false;
-  // linear solver: sliced-ELL matrix over scalar rows + CG vectors
-  size_t cg_nrow = 0, cg_ncomp = 1, cg_nslice = 0, cg_nent = 0;
-  DevBuf< long long > cg_base; DevBuf< int > cg_col; DevBuf< double > cg_val, cg_diag;
-  DevBuf< double > cg_x, cg_b, cg_r, cg_p, cg_q, cg_z, cg_d, cg_mask, cg_cnt, cg_scal;
-  double cg_normb = 0.0; bool cg_converged = false, cg_finished = false;
+  // the linear solvers not selected at the moment (xyst_cg_select): [0] pressure, [1] momentum
+  CgState cg_other[2]; int cg_sel = 0;
   // profiling
   bool prof_on = false;
   std::map< std::string, Prof > prof;
@@ -1295,6 +1306,46 @@ int xyst_csr_upload( xyst_ctx* c, size_t nrow, size_t ncomp, const size_t* ia, c
     size_t w = std::max< size_t >( 15, ncomp );
     c->sh_part.alloc( c->nsh*w ); c->sh_sendbuf.alloc( c->nsend*w ); c->sh_recvbuf.alloc( c->nsend*w );
   }
+  API_END
+}
+
+// the context holds two linear solvers (ChoCG with theta > 0: ChoCG::m_cgpre and m_cgmom,
+// ChoCG.cpp:126-140); all xyst_csr_* / xyst_cg_* entries act on the selected one
+int xyst_cg_select( xyst_ctx* c, int which )
+{
+  API_BEGIN
+  if (which < 0 || which > 1) throw std::runtime_error( "xyst_cg_select: which must be 0 (pressure) or 1 (momentum)" );
+  if (which != c->cg_sel) {
+    CgState& cur = *c;
+    c->cg_other[c->cg_sel] = std::move( cur );
+    cur = std::move( c->cg_other[which] );
+    c->cg_sel = which;
+  }
+  API_END
+}
+
+// new values for the matrix of xyst_csr_upload (same ia/ja); the solution vector is kept
+int xyst_csr_update( xyst_ctx* c, const size_t* ia, const double* a )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  if (!c->cg_nrow) throw std::runtime_error( "no matrix uploaded" );
+  size_t nrow = c->cg_nrow, nslice = c->cg_nslice;
+  std::vector< long long > base( nslice+1, 0 );
+  for (size_t s=0; s<nslice; ++s) {
+    size_t km = 0;
+    for (size_t r=s*32; r<std::min( nrow, s*32+32 ); ++r) km = std::max( km, ia[r+1]-ia[r] );
+    base[s+1] = base[s] + (long long)km*32;
+  }
+  if ((size_t)base[nslice] != c->cg_nent) throw std::runtime_error( "csr_update: structure differs from the uploaded one" );
+  std::vector< double > val( c->cg_nent, 0.0 ), diag( nrow, 0.0 );
+  #pragma omp parallel for schedule(static)
+  for (size_t r=0; r<nrow; ++r)
+    for (size_t j=ia[r]-1, k=0; j<ia[r+1]-1; ++j, ++k) val[ (size_t)base[r/32] + k*32 + r%32 ] = a[j];
+  CK( cudaMemcpyAsync( c->cg_val.p, val.data(), val.size()*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+  k_cg_getdiag<<< nblk( c->cg_nslice*32, 256 ), 256, 0, c->stream >>>( nrow, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_diag.p ); ++c->launches;
+  CK( cudaGetLastError() );
+  CK( cudaStreamSynchronize( c->stream ) );
   API_END
 }
 

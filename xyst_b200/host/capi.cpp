@@ -64,6 +64,7 @@ Config to_cfg( const xyst_host_cfg* c ) {
     for (int i=0; i<c->np_dirval; ++i) k.p_bc_dirval.push_back( { c->p_dirval[i][0], c->p_dirval[i][1] } );
     for (int i=0; i<c->np_sym; ++i) k.p_bc_sym.push_back( c->p_sym[i] );
     if (c->p_hydrostat_set) k.p_hydrostat = c->p_hydrostat;
+    k.theta = c->theta; k.mom_iter = c->mom_iter ? c->mom_iter : 10; k.mom_tol = c->mom_tol; if (c->mom_pc[0]) k.mom_pc = c->mom_pc;
   }
   return k;
 }
@@ -278,6 +279,7 @@ double xyst_solver_scalar( xyst_solver* s, const char* name )
   if (n == "meshvol") return d.MeshVol();
   if (n == "finished") return s->riecg->m_finished ? 1.0 : 0.0;
   if (n == "pit") return static_cast< double >( s->riecg->m_pit );
+  if (n == "mit") return static_cast< double >( s->riecg->m_mit );
   if (n == "nshared") return static_cast< double >( d.sharedNodes().size() );
   if (n.rfind( "timing", 0 ) == 0) { auto i = static_cast< std::size_t >( std::stoi( n.substr(6) ) ); return i < s->riecg->timings.size() ? s->riecg->timings[i] : -1.0; }
   return std::nan( "" );
@@ -313,6 +315,7 @@ size_t xyst_solver_get( xyst_solver* s, const char* name, void* out, size_t cap 
     if (n == "plhs_ia") return put( r.m_plhs_ia, out, cap );
     if (n == "plhs_ja") return put( r.m_plhs_ja, out, cap );
     if (n == "plhs_a") return put( r.m_plhs_a, out, cap );
+    if (n == "mlhs_a") return put( r.m_mlhs_a, out, cap );
     if (n == "pr") return put( r.choGet( "pr", 1 ), out, cap );
     if (n == "dp") return put( r.choGet( "dp", 1 ), out, cap );
     if (n == "pgrad") return put( r.choGet( "pgrad", 3 ), out, cap );

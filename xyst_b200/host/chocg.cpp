@@ -159,6 +159,75 @@ void RieCG::choPressureSetup()
   }
 }
 
+//! Momentum matrix of the semi-implicit solve, ChoCG::lhs :1433-1477: per tetrahedron
+//! A(a,b,c) -= J/dt/120 (2 if a == b else 1) + theta mu grad N_a . grad N_b / (6J), the same for the
+//! three components, in tk::CSR( ncomp, psup ) block form (momlhs :190-208): scalar row i*3+c holds
+//! the entries of node row i at columns j*3+c. Row-parallel assembly in the reference's element order
+//! (bitwise the same sums); new values go to the device's momentum solver every step (dt changes).
+void RieCG::choLhs()
+{
+  const auto& inpoel = m_disc.Inpoel();
+  auto np = m_disc.Gid().size();
+  const auto& ia = m_plhs_ia; const auto& ja = m_plhs_ja;       // scalar structure = the pressure matrix's
+  if (m_eoff.empty()) {
+    const auto ntet = inpoel.size()/4;
+    m_eoff.assign( np+1, 0 );
+    for (std::size_t i=0; i<inpoel.size(); ++i) ++m_eoff[ inpoel[i]+1 ];
+    for (std::size_t i=0; i<np; ++i) m_eoff[i+1] += m_eoff[i];
+    m_esup.resize( inpoel.size() );
+    std::vector< std::size_t > fill( m_eoff.begin(), m_eoff.end()-1 );
+    for (std::size_t e=0; e<ntet; ++e) for (std::size_t k=0; k<4; ++k) m_esup[ fill[ inpoel[e*4+k] ]++ ] = e*4+k;
+    m_mlhs_ia.assign( np*3+1, 1 );
+    for (std::size_t i=0; i<np; ++i) for (std::size_t c=0; c<3; ++c) m_mlhs_ia[i*3+c+1] = m_mlhs_ia[i*3+c] + (ia[i+1]-ia[i]);
+    // momentum BC rows (ChoCG::solve :1580-1599): masked Dirichlet components and no-slip nodes, value 0
+    std::set< std::size_t > rows;
+    for (std::size_t i=0; i<m_dirbcmasks.size()/4; ++i)
+      for (std::size_t c=0; c<3; ++c) if (m_dirbcmasks[i*4+1+c]) rows.insert( m_dirbcmasks[i*4]*3+c );
+    for (auto p : m_noslipbcnodes) for (std::size_t c=0; c<3; ++c) rows.insert( p*3+c );
+    m_mbcrows.assign( rows.begin(), rows.end() );
+  }
+  const auto& X = m_disc.Coord()[0]; const auto& Y = m_disc.Coord()[1]; const auto& Z = m_disc.Coord()[2];
+  const auto dt = m_disc.Dt(); const auto theta = m_cfg.theta, mu = m_cfg.mu;
+  auto& a = m_mlhs_a;
+  a.assign( m_mlhs_ia[np*3]-1, 0.0 );
+  #pragma omp parallel for schedule(dynamic,1024)
+  for (std::size_t row=0; row<np; ++row) {
+    auto rb = ja.begin() + static_cast< std::ptrdiff_t >( ia[row]-1 ), re = ja.begin() + static_cast< std::ptrdiff_t >( ia[row+1]-1 );
+    const auto rnz = ia[row+1]-ia[row];
+    auto out = a.data() + (m_mlhs_ia[row*3]-1);                   // component 0 of this node row
+    for (auto i=m_eoff[row]; i<m_eoff[row+1]; ++i) {
+      const auto e = m_esup[i] >> 2; const auto p = static_cast< std::size_t >( m_esup[i] & 3 );
+      const auto N = inpoel.data() + e*4;
+      real ba[3] = { X[N[1]]-X[N[0]], Y[N[1]]-Y[N[0]], Z[N[1]]-Z[N[0]] },
+           ca[3] = { X[N[2]]-X[N[0]], Y[N[2]]-Y[N[0]], Z[N[2]]-Z[N[0]] },
+           da[3] = { X[N[3]]-X[N[0]], Y[N[3]]-Y[N[0]], Z[N[3]]-Z[N[0]] };
+      real grad[4][3];
+      cross( ca, da, grad[1] ); cross( da, ba, grad[2] ); cross( ba, ca, grad[3] );
+      const auto J = ba[0]*grad[1][0] + ba[1]*grad[1][1] + ba[2]*grad[1][2];        // J = 6V
+      for (std::size_t k=0; k<3; ++k) grad[0][k] = -grad[1][k]-grad[2][k]-grad[3][k];
+      for (std::size_t q=0; q<4; ++q) {
+        auto v = J/dt/120.0 * ((p == q) ? 2.0 : 1.0);
+        v += theta * mu * (grad[p][0]*grad[q][0] + grad[p][1]*grad[q][1] + grad[p][2]*grad[q][2]) / J / 6.0;
+        auto it = std::lower_bound( rb, re, N[q]+1 );
+        out[ it - rb ] -= v;
+      }
+    }
+    for (std::size_t c=1; c<3; ++c) std::copy( out, out + rnz, out + c*rnz );
+  }
+  ck( xyst_cg_select( m_ctx, 1 ) );
+  if (!m_mlhsup) {
+    std::vector< std::size_t > jab( a.size() );
+    for (std::size_t i=0; i<np; ++i) for (std::size_t c=0; c<3; ++c) {
+      auto o = m_mlhs_ia[i*3+c]-1;
+      for (auto j=ia[i]-1; j<ia[i+1]-1; ++j) jab[ o + (j-(ia[i]-1)) ] = (ja[j]-1)*3 + c + 1;
+    }
+    ck( xyst_csr_upload( m_ctx, np*3, 3, m_mlhs_ia.data(), jab.data(), a.data() ) );
+    m_mlhsup = true;
+  } else
+    ck( xyst_csr_update( m_ctx, m_mlhs_ia.data(), a.data() ) );
+  ck( xyst_cg_select( m_ctx, 0 ) );
+}
+
 //! Device upload and the start-up sequence of ChoCG::merge :816-837 onwards: make the initial
 //! velocity divergence-free and compute the initial pressure
 void RieCG::choSetup()
@@ -265,8 +334,20 @@ bool RieCG::choStep( std::vector< real >* diagrow )
   else ck( xyst_chocg_dt_min( m_ctx, m_cfg.cfl, m_cfg.dif, &mindt ) );
   if (mindt < eps) m_finished = true;
   m_disc.setdt( mindt );
+  const bool implicit = m_cfg.theta > eps;
+  if (implicit) choLhs();                    // advance :1414-1431
   for (std::uint64_t s=0; s<m_cfg.rk; ++s)
-    ck( xyst_chocg_stage( m_ctx, static_cast< int >( s ), rkcoef[m_cfg.rk-1][s], m_disc.Dt() ) );
+    if (!implicit || s+1 < m_cfg.rk)         // solve :1555-1572
+      ck( xyst_chocg_stage( m_ctx, static_cast< int >( s ), rkcoef[m_cfg.rk-1][s], m_disc.Dt() ) );
+    else {                                   // semi-implicit momentum solve at the last stage, :1574-1645
+      ck( xyst_chocg_rhs( m_ctx ) );
+      ck( xyst_cg_select( m_ctx, 1 ) );
+      ck( xyst_chocg_minit( m_ctx, m_mbcrows.size(), m_mbcrows.data(), m_cfg.mom_pc == "jacobi" ? 1 : 0 ) );
+      real normr = 0.0;
+      ck( xyst_cg_solve( m_ctx, m_cfg.mom_iter, m_cfg.mom_tol, &m_mit, &normr ) );
+      ck( xyst_chocg_mupdate( m_ctx, static_cast< int >( s ) ) );
+      ck( xyst_cg_select( m_ctx, 0 ) );
+    }
   ck( xyst_chocg_div( m_ctx, 0, m_disc.Dt(), m_np > 1 ) );
   choPinit(); choPsolve();
   ck( xyst_chocg_grad( m_ctx, 0 ) );

@@ -76,6 +76,11 @@ struct Config {
   std::vector< std::vector< real > > p_bc_dirval;
   std::vector< int > p_bc_sym;
   std::uint64_t p_hydrostat = ~0ULL;
+  //! ChoCG semi-implicit momentum solve (tag::theta > 0; momentum = { iter, tol, pc })
+  real theta = 0.0;
+  std::uint64_t mom_iter = 10;
+  real mom_tol = 1.0e-3;
+  std::string mom_pc = "none";
   //! LohCG (solver = "lohcg", ncomp = 4 unknowns p,u,v,w): artificial compressibility
   //! (src/Inciter/LohCG.cpp); shares the ChoCG keys above, plus the artificial sound speed
   real soundspeed = 1.0;
@@ -166,7 +171,9 @@ class RieCG {
     std::vector< std::size_t > m_dirbcmaskp, m_noslipbcnodes;
     std::vector< std::size_t > m_plhs_ia, m_plhs_ja;
     std::vector< real > m_plhs_a;
+    std::vector< real > m_mlhs_a;    //!< momentum matrix values of the last step (theta > 0), block CSR
     std::size_t m_pit = 0;           //!< iterations of the last pressure solve
+    std::size_t m_mit = 0;           //!< iterations of the last momentum solve (theta > 0)
     std::vector< real > choGet( const char* what, std::size_t width );
     bool pendingDiag() const { return !m_lastdiag.empty(); }   //!< row of a run that ended during setup (nstep = 1)
     std::vector< real > m_u0;        //!< initial condition (npoin x ncomp)
@@ -205,6 +212,10 @@ class RieCG {
     std::vector< real > m_neubc, m_prhs, m_psol, m_lastdiag;
     void choSetupBC();                     //!< ChoCG::setupDirBC :210-300, streamable :655-682
     void choPrelhs();                      //!< ChoCG::prelhs :146-188 on tk::CSR( psup )
+    void choLhs();                         //!< ChoCG::lhs :1433-1477 -> momentum matrix on the device
+    std::vector< std::size_t > m_mlhs_ia, m_eoff, m_mbcrows;   //!< block-CSR row offsets; elements surrounding points; momentum BC rows
+    std::vector< std::uint64_t > m_esup;
+    bool m_mlhsup = false;
     void choPressureSetup();               //!< pressure BC values, Neumann vector, rhs override of pinit
     void choSetup();                       //!< device upload + ChoCG::merge :816-837 onwards
     bool choStep( std::vector< real >* diagrow );

@@ -6,12 +6,18 @@
 // ConjugateGradients.cpp:584-823. Matrix in sliced ELL over scalar rows (one warp per 32
 // rows, entry k of lane l at base + 32k + l: coalesced), dots by fixed two-pass trees.
 // device scalars: [0] rho [1] rho0 [2] alpha [3] beta [4] normr2 [5] finished
-//                 [8..] partial sums handed to the all-reduce
+//                 [6] done (stop test of ConjugateGradients::x :787-823 evaluated on the device)
+//                 [7] iterations done   [8..] partial sums handed to the all-reduce
+// The kernels of the iteration take `done` (= scal + 6, or NULL outside the iteration) and return
+// at once when it is set: the host may enqueue several iterations per read-back of the stop test
+// and still stops exactly where the reference does.
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_spmv( size_t nrow, const long long* __restrict__ base, const int* __restrict__ col,
-        const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y )
+        const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+        const double* __restrict__ done )
 {
+  if (done && *done != 0.0) return;
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   size_t r = slice*32 + lane;
@@ -34,8 +40,10 @@ k_spmv( size_t nrow, const long long* __restrict__ base, const int* __restrict__
 __global__ void __launch_bounds__(256)
 k_spmv_bc( size_t nrow, const long long* __restrict__ base, const int* __restrict__ col,
            const double* __restrict__ val, const unsigned char* __restrict__ bc,
-           const double* __restrict__ cnt, const double* __restrict__ x, double* __restrict__ y )
+           const double* __restrict__ cnt, const double* __restrict__ x, double* __restrict__ y,
+           const double* __restrict__ done )
 {
+  if (done && *done != 0.0) return;
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   size_t r = slice*32 + lane;
@@ -113,6 +121,7 @@ __global__ void k_cg_bc_diag( size_t nrow, const unsigned char* __restrict__ bc,
 // p = z + beta p    (ConjugateGradients::next :584-599)
 __global__ void k_cg_p( size_t n, const double* __restrict__ scal, const double* __restrict__ z, double* __restrict__ p )
 {
+  if (scal[6] != 0.0) return;
   size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   p[i] = z[i] + scal[3] * p[i];
@@ -122,8 +131,10 @@ __global__ void k_cg_p( size_t n, const double* __restrict__ scal, const double*
 template< int NV >
 __global__ void __launch_bounds__(RED_THREADS)
 k_cg_dot( size_t n, const double* __restrict__ mask, const double* __restrict__ a0, const double* __restrict__ b0,
-          const double* __restrict__ a1, const double* __restrict__ b1, double* __restrict__ part )
+          const double* __restrict__ a1, const double* __restrict__ b1, double* __restrict__ part,
+          const double* __restrict__ done )
 {
+  if (done && *done != 0.0) return;
   double s[NV];
   #pragma unroll
   for (int k=0; k<NV; ++k) s[k] = 0.0;
@@ -141,6 +152,7 @@ k_cg_update( size_t n, const double* __restrict__ scal, const double* __restrict
              const double* __restrict__ q, const double* __restrict__ d, const double* __restrict__ p,
              double* __restrict__ r, double* __restrict__ z, double* __restrict__ x, double* __restrict__ part )
 {
+  if (scal[6] != 0.0) return;
   double s[2] = { 0.0, 0.0 };
   double alpha = scal[2];
   for (size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x*blockDim.x) {
@@ -157,9 +169,11 @@ k_cg_update( size_t n, const double* __restrict__ scal, const double* __restrict
 
 // scalar bookkeeping after a reduction; mode 0: alpha = rho/(p,q) (pq :671-690);
 // mode 1: rho0 = rho, rho = (r,z), beta = rho/rho0, normr2 = (r,r)  (next :586-588, rz :719)
-__global__ void k_cg_scalars( int mode, double* __restrict__ scal )
+// and the stop test: finished, or ||r|| < thr (= tol * max-ed ||b||), or maxit iterations
+__global__ void k_cg_scalars( int mode, double* __restrict__ scal, double thr, double maxit )
 {
   if (threadIdx.x || blockIdx.x) return;
+  if (scal[6] != 0.0) return;
   if (mode == 0) {
     double d = scal[8];
     if (fabs(d) < 2.220446049250313e-16) { scal[5] = 1.0; scal[2] = 0.0; } else scal[2] = scal[0] / d;
@@ -168,6 +182,8 @@ __global__ void k_cg_scalars( int mode, double* __restrict__ scal )
     scal[0] = scal[8];
     scal[3] = scal[0] / scal[1];
     scal[4] = scal[9];
+    scal[7] += 1.0;
+    if (scal[5] != 0.0 || sqrt( scal[4] ) < thr || scal[7] >= maxit) scal[6] = 1.0;
   }
 }
 

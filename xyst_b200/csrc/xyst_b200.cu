@@ -1217,6 +1217,7 @@ static void cg_halo( xyst_ctx* c, double* v, int average )
 // local partial sums -> scal[8..8+nv), all-reduced over the communicator
 static void cg_reduce( xyst_ctx* c, int nv, int nb )
 {
+  // (after the device-side stop flag is set the partial sums are stale: k_cg_scalars ignores them)
   double* out = c->cg_scal.p + 8;
   if (nv == 1) k_reduce_final< 1, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, out );
   else         k_reduce_final< 2, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, out );
@@ -1225,13 +1226,13 @@ static void cg_reduce( xyst_ctx* c, int nv, int nb )
 }
 
 // y = A x with the Dirichlet conditions of the current solve, if any
-static void cg_spmv( xyst_ctx* c, const double* x, double* y )
+static void cg_spmv( xyst_ctx* c, const double* x, double* y, const double* done = nullptr )
 {
   unsigned g = nblk( c->cg_nslice*32, 256 );
   if (c->cg_hasbc)
-    k_spmv_bc<<< g, 256, 0, c->stream >>>( c->cg_nrow, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_bc.p, c->cg_cnt.p, x, y );
+    k_spmv_bc<<< g, 256, 0, c->stream >>>( c->cg_nrow, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_bc.p, c->cg_cnt.p, x, y, done );
   else
-    k_spmv<<< g, 256, 0, c->stream >>>( c->cg_nrow, c->cg_base.p, c->cg_col.p, c->cg_val.p, x, y );
+    k_spmv<<< g, 256, 0, c->stream >>>( c->cg_nrow, c->cg_base.p, c->cg_col.p, c->cg_val.p, x, y, done );
   ++c->launches;
 }
 
@@ -1254,7 +1255,7 @@ static void cg_setup_dev( xyst_ctx* c, int pc )
   cg_halo( c, c->cg_d.p, 0 );
   int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( n, RED_THREADS ) );
   // normb = sqrt((b,b))
-  k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_b.p, c->cg_b.p, nullptr, nullptr, c->red.p ); ++c->launches;
+  k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_b.p, c->cg_b.p, nullptr, nullptr, c->red.p, nullptr ); ++c->launches;
   cg_reduce( c, 1, nb );
   CK( cudaMemcpyAsync( c->red_host, c->cg_scal.p + 8, sizeof(double), cudaMemcpyDeviceToHost, s ) );
   CK( cudaStreamSynchronize( s ) );
@@ -1262,7 +1263,7 @@ static void cg_setup_dev( xyst_ctx* c, int pc )
   // initres(): r = b - r, p = r, z = r/d, rho = (r,z)
   k_cg_resid<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_b.p, c->cg_r.p, c->cg_p.p ); ++c->launches;
   k_cg_div<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_r.p, c->cg_d.p, c->cg_z.p ); ++c->launches;
-  k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_r.p, c->cg_z.p, nullptr, nullptr, c->red.p ); ++c->launches;
+  k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_r.p, c->cg_z.p, nullptr, nullptr, c->red.p, nullptr ); ++c->launches;
   cg_reduce( c, 1, nb );
   CK( cudaMemcpyAsync( c->cg_scal.p, c->cg_scal.p + 8, sizeof(double), cudaMemcpyDeviceToDevice, s ) );   // rho
   CK( cudaGetLastError() );
@@ -1356,7 +1357,7 @@ int xyst_csr_mult( xyst_ctx* c, const double* x, double* r )
   if (!c->cg_nrow) throw std::runtime_error( "no matrix uploaded" );
   size_t n = c->cg_nrow;
   CK( cudaMemcpyAsync( c->cg_p.p, x, n*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
-  k_spmv<<< nblk( c->cg_nslice*32, 256 ), 256, 0, c->stream >>>( n, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_p.p, c->cg_q.p ); ++c->launches;
+  k_spmv<<< nblk( c->cg_nslice*32, 256 ), 256, 0, c->stream >>>( n, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_p.p, c->cg_q.p, nullptr ); ++c->launches;
   CK( cudaGetLastError() );
   CK( cudaMemcpyAsync( r, c->cg_q.p, n*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
   CK( cudaStreamSynchronize( c->stream ) );
@@ -1395,28 +1396,36 @@ int xyst_cg_solve( xyst_ctx* c, size_t maxit, double tol, size_t* it_out, double
   int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( n, RED_THREADS ) );
   double normr = 0.0;
   if (!c->cg_converged) {
-    // beta = 0 on the first pass (next :586)
+    // beta = 0 on the first pass (next :586); done flag and iteration counter
     CK( cudaMemsetAsync( c->cg_scal.p + 3, 0, sizeof(double), s ) );
-    for (;;) {
-      k_cg_p<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_scal.p, c->cg_z.p, c->cg_p.p ); ++c->launches;
-      { ProfScope ps( c, "spmv" );
-        cg_spmv( c, c->cg_p.p, c->cg_q.p ); }
-      cg_halo( c, c->cg_q.p, 0 );
-      k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_p.p, c->cg_q.p, nullptr, nullptr, c->red.p ); ++c->launches;
-      cg_reduce( c, 1, nb );
-      k_cg_scalars<<< 1, 32, 0, s >>>( 0, c->cg_scal.p ); ++c->launches;
-      k_cg_update<<< nb, RED_THREADS, 0, s >>>( n, c->cg_scal.p, c->cg_mask.p, c->cg_q.p, c->cg_d.p, c->cg_p.p,
-        c->cg_r.p, c->cg_z.p, c->cg_x.p, c->red.p ); ++c->launches;
-      cg_reduce( c, 2, nb );
-      k_cg_scalars<<< 1, 32, 0, s >>>( 1, c->cg_scal.p ); ++c->launches;
-      cg_halo( c, c->cg_x.p, 1 );
-      CK( cudaMemcpyAsync( c->red_host, c->cg_scal.p + 4, 2*sizeof(double), cudaMemcpyDeviceToHost, s ) );
+    CK( cudaMemsetAsync( c->cg_scal.p + 6, 0, 2*sizeof(double), s ) );
+    const double nbn = c->cg_normb > 1.0e-14 ? c->cg_normb : 1.0;
+    const double* done = c->cg_scal.p + 6;
+    // The stop test of ConjugateGradients::x (:787-823) runs on the device (k_cg_scalars) and turns the
+    // kernels of later iterations into no-ops, so one partition reads it back only every few
+    // iterations; with a communicator every iteration is read (the collectives cannot be skipped).
+    const size_t batch = c->comm ? 1 : 8;
+    for (bool stop=false; !stop; ) {
+      for (size_t b=0; b<batch && it+b<std::max< size_t >( maxit, 1 ); ++b) {
+        k_cg_p<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_scal.p, c->cg_z.p, c->cg_p.p ); ++c->launches;
+        { ProfScope ps( c, "spmv" );
+          cg_spmv( c, c->cg_p.p, c->cg_q.p, done ); }
+        cg_halo( c, c->cg_q.p, 0 );
+        k_cg_dot< 1 ><<< nb, RED_THREADS, 0, s >>>( n, c->cg_mask.p, c->cg_p.p, c->cg_q.p, nullptr, nullptr, c->red.p, done ); ++c->launches;
+        cg_reduce( c, 1, nb );
+        k_cg_scalars<<< 1, 32, 0, s >>>( 0, c->cg_scal.p, 0.0, 0.0 ); ++c->launches;
+        k_cg_update<<< nb, RED_THREADS, 0, s >>>( n, c->cg_scal.p, c->cg_mask.p, c->cg_q.p, c->cg_d.p, c->cg_p.p,
+          c->cg_r.p, c->cg_z.p, c->cg_x.p, c->red.p ); ++c->launches;
+        cg_reduce( c, 2, nb );
+        k_cg_scalars<<< 1, 32, 0, s >>>( 1, c->cg_scal.p, tol*nbn, (double)maxit ); ++c->launches;
+        cg_halo( c, c->cg_x.p, 1 );
+      }
+      CK( cudaMemcpyAsync( c->red_host, c->cg_scal.p + 4, 4*sizeof(double), cudaMemcpyDeviceToHost, s ) );
       CK( cudaStreamSynchronize( s ) );
-      ++it;
-      double nbn = c->cg_normb > 1.0e-14 ? c->cg_normb : 1.0;
+      it = (size_t)c->red_host[3];
       normr = std::sqrt( c->red_host[0] );
-      bool finished = c->red_host[1] != 0.0;
-      if (finished || normr < tol*nbn || it >= maxit) { c->cg_converged = !(normr > tol*nbn); break; }
+      stop = c->red_host[2] != 0.0 || it >= maxit;
+      if (stop) c->cg_converged = !(normr > tol*nbn);
     }
     CK( cudaGetLastError() );
   }

@@ -6,6 +6,7 @@ larger than L2. One JSON line per workload; results are kept under profiles/.
 
   ZalCG / KozCG : edge-updates/s (one stage per step) against the 223 B/edge-update model
   ChoCG         : step time, CG iterations/s, SpMV GB/s against 12 nnz + 20 N bytes per product
+  LohCG         : step time, edge-updates/s (--only lohcg,lohcg_damp4)
 
     python bench_secondary.py [--n 203] [--steps 20]
 """
@@ -92,6 +93,33 @@ def chocg(n, steps):
             "finite": bool(np.isfinite(s.get("u")).all())}
 
 
+def lohcg(n, steps, flux):
+    import torch
+    import bench
+    from xyst_b200 import hostapi as H
+    rk = 2
+    kw = dict(solver="lohcg", ncomp=4, cfl=0.3, flux=flux, rk=rk, mu=0.01, soundspeed=10.0, p_iter=40, p_tol=1.0e-3,
+              p_pc="jacobi", p_hydrostat=0, problem="userdef", sym=(1, 2, 3, 4, 5, 6), nstep=10 ** 9)
+    s = H.Solver.box(H.make_cfg(**kw), n, n, n)
+    s.prepare(); s.host_setup()
+    x, y = s.get("x"), s.get("y")
+    u0 = np.stack([np.zeros_like(x), np.sin(np.pi * x) * np.cos(np.pi * y), -np.cos(np.pi * x) * np.sin(np.pi * y),
+                   np.zeros_like(x)], 1)
+    s.set_u0(u0)
+    s.attach(0); ctx = s.ctx(); s.setup()
+    stream = torch.cuda.Stream(); ctx.set_stream(stream.cuda_stream)
+    s.step(2, want_diag=False)
+    ctx.kernel_time("loh_rhs", reset=True)
+    ms = timed(stream, lambda: s.step(1, want_diag=False), steps)
+    r_ms, r_n = ctx.kernel_time("loh_rhs")
+    E = bench.box_edges(n, n, n)
+    return {"workload": "LohCG, %d^3-cell box = %d tets, %d edges; Taylor-Green-like velocity, symmetry on all sides, "
+                        "%s, rk %d, soundspeed 10, mu 0.01" % (n, 6 * n ** 3, E, flux, rk),
+            "metric": "edge-updates/sec (rk stages per step)", "value": E * rk / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
+            "rhs_kernel_avg_ms": r_ms / max(r_n, 1), "rhs_launches": r_n,
+            "finite": bool(np.isfinite(s.get("u")).all())}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=203)
@@ -102,5 +130,10 @@ if __name__ == "__main__":
     if not torch.cuda.is_available():
         raise SystemExit("bench_secondary.py: no CUDA device (the B200 path has no CPU fallback)")
     for w in a.only.split(","):
-        r = chocg(a.n, max(2, a.steps // 4)) if w == "chocg" else fct(w, a.n, a.steps)
+        if w == "chocg":
+            r = chocg(a.n, max(2, a.steps // 4))
+        elif w.startswith("lohcg"):
+            r = lohcg(a.n, a.steps, "damp4" if w.endswith("damp4") else "damp2")
+        else:
+            r = fct(w, a.n, a.steps)
         print(json.dumps(r), flush=True)

@@ -31,16 +31,13 @@ __device__ __forceinline__ void loh_adv( const double d[3], double lap, const do
       double delta2 = uR[c] - uL[c];
       double delta1 = 2.0 * g1 - delta2;
       double delta3 = 2.0 * g2 - delta2;
-      double rL = (delta2 + MUSCL_EPS) / (delta1 + MUSCL_EPS);
-      double rR = (delta2 + MUSCL_EPS) / (delta3 + MUSCL_EPS);
-      double rLinv = (delta1 + MUSCL_EPS) / (delta2 + MUSCL_EPS);
-      double rRinv = (delta3 + MUSCL_EPS) / (delta2 + MUSCL_EPS);
-      double phiL = (fabs(rL) + rL) / (fabs(rL) + 1.0);
-      double phiR = (fabs(rR) + rR) / (fabs(rR) + 1.0);
-      double phi_L_inv = (fabs(rLinv) + rLinv) / (fabs(rLinv) + 1.0);
-      double phi_R_inv = (fabs(rRinv) + rRinv) / (fabs(rRinv) + 1.0);
-      uL[c] += 0.25*(delta1*(1.0-MUSCL_K)*phiL + delta2*(1.0+MUSCL_K)*phi_L_inv);
-      uR[c] -= 0.25*(delta3*(1.0-MUSCL_K)*phiR + delta2*(1.0+MUSCL_K)*phi_R_inv);
+      // van Leer limited increments in the one-reciprocal-per-side form of the RieCG kernels
+      // (riecg_kernels.cuh, vanleer<false>: algebraically the reference's eight quotients, rounding
+      // differs at 1e-16)
+      double incL, incR;
+      vanleer< false >( delta1, delta2, delta3, incL, incR );
+      uL[c] += incL;
+      uR[c] -= incR;
     }
   }
   double vnL = uL[1]*d[0] + uL[2]*d[1] + uL[3]*d[2];
@@ -105,13 +102,27 @@ k_loh_rhs( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const
     #pragma unroll
     for (int i=0; i<12; ++i) go[i] = DAMP4 ? __ldg( G + i*NP + nb ) : 0.0;
     double f[4];
-    if (se < 0) {                          // this node is the edge's first node
-      double dx[3] = { xo[0]-xm[0], xo[1]-xm[1], xo[2]-xm[2] };
+    const bool first = se < 0;             // this node is the edge's first node
+    if (DAMP4) {
+      // one evaluation for both orientations: the end states are ordered by selects, so that lanes
+      // with different edge orientations do not diverge around the (expensive) limited reconstruction
+      double ua[4], ub[4], ga[12], gb[12], dx[3];
+      #pragma unroll
+      for (int i=0; i<4; ++i) { ua[i] = first ? um[i] : uo[i]; ub[i] = first ? uo[i] : um[i]; }
+      #pragma unroll
+      for (int i=0; i<12; ++i) { ga[i] = first ? gm[i] : go[i]; gb[i] = first ? go[i] : gm[i]; }
+      #pragma unroll
+      for (int i=0; i<3; ++i) dx[i] = first ? xo[i]-xm[i] : xm[i]-xo[i];
+      loh_adv< DAMP4 >( d, lap, ua, ub, ga, gb, dx, C, f );
+      #pragma unroll
+      for (int c=0; c<4; ++c) acc[c] = first ? acc[c] - f[c] : acc[c] + f[c];
+    } else if (first) {
+      double dx[3] = { 0.0, 0.0, 0.0 };
       loh_adv< DAMP4 >( d, lap, um, uo, gm, go, dx, C, f );
       #pragma unroll
       for (int c=0; c<4; ++c) acc[c] -= f[c];
     } else {
-      double dx[3] = { xm[0]-xo[0], xm[1]-xo[1], xm[2]-xo[2] };
+      double dx[3] = { 0.0, 0.0, 0.0 };
       loh_adv< DAMP4 >( d, lap, uo, um, go, gm, dx, C, f );
       #pragma unroll
       for (int c=0; c<4; ++c) acc[c] += f[c];

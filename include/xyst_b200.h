@@ -190,6 +190,8 @@ int xyst_steady(xyst_ctx* ctx, int on);
 int xyst_kozcg_mesh_upload(xyst_ctx* ctx, size_t npoin, const double* x, const double* y, const double* z,
                            size_t ntet, const size_t* inpoel, const double* vol, const double* v,
                            const double* Ssrc_nodes, const double* Ssrc_cent);
+/* new source values for time-dependent problems: nodes at t, centroids at t + dt/2 (Kozak.cpp:97-108,160-171) */
+int xyst_kozcg_src(xyst_ctx* ctx, const double* Ssrc_nodes, const double* Ssrc_cent);
 /* kozak::rhs -> R (xyst_rhs_get) */
 int xyst_kozcg_rhs(xyst_ctx* ctx, double dt);
 /* one KozCG time step: rhs, aec, alw, lim, solve, BC; un keeps the old state */

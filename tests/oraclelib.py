@@ -225,6 +225,12 @@ TCASES = {
                                   kappa=1.0, gamma=5.0 / 3.0, cfl=0.5, nstep=50, dir_=_DIR6,
                                   mesh="riecg_taylor_green"),
 }
+# KozCG/{NonlinearEnergyGrowth/nleg.q,RayleighTaylor/rayleigh_taylor.q}: the time-dependent manufactured
+# solutions through the element-based solver (no FCT): nodal sources at t, centroid sources at t + dt/2
+KTCASES = {
+    "kozcg_nleg": dict(TCASES["riecg_nleg"], solver="kozcg", fct=False),
+    "kozcg_rayleigh_taylor": dict(TCASES["riecg_rayleigh_taylor"], solver="kozcg", fct=False),
+}
 # RieCG/Pipe/pipe.q: user-defined quiescent IC, symmetry walls, pressure BCs at inlet and outlet
 # (physics::prebc, BC.cpp:222-241); serial golden printed with 12 digits
 PCASES = {

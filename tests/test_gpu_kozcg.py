@@ -56,12 +56,14 @@ def test_kozcg_fct_variants():
         assert relerr(ctx.state_get(), o.get("u")) < 1e-11
 
 
-@pytest.mark.parametrize("case", list(O.KCASES))
+@pytest.mark.parametrize("case", list(O.KCASES) + list(O.KTCASES))
 def test_kozcg_host_mirror_diag_rows(case):
-    """Full drop-in path (C++ host mirror of KozCG's setup + time loop) vs oracle and golden."""
+    """Full drop-in path (C++ host mirror of KozCG's setup + time loop) vs oracle and golden; the
+    time-dependent problems refresh nodal sources (t), centroid sources (t + dt/2) and Dirichlet
+    values (t + dt) every step."""
     from xyst_b200 import hostapi as H
     from host_common import fixture_to_host_mesh
-    kw = O.KCASES[case]
+    kw = {**O.KCASES, **O.KTCASES}[case]
     gold = O.load_golden_diag(case)
     nsteps = int(gold[-1, 0])
     hm = fixture_to_host_mesh(O.load_mesh(kw["mesh"]))
@@ -75,3 +77,5 @@ def test_kozcg_host_mirror_diag_rows(case):
         assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-11 * np.abs(d[:, c]).max(), c
     assert O.numdiff_ok(rows[:, 1:8], gold[:, 1:8], 1.0e-8, 1.0e-7).all()     # reference's own tolerance
     assert O.numdiff_ok(rows[:, 8:13], gold[:, 8:13], 1.0e-8, 1.0e-6).all()
+    if rows.shape[1] > 14:      # L2 and L1 errors against the analytic solution (manufactured problems)
+        assert (np.abs(rows[:, 14:] - d[:, 14:]) <= 1e-9 * np.abs(d[:, 14:]) + 1e-14).all()

@@ -83,11 +83,12 @@ def test_zalcg_oracle_reproduces_reference_golden_diag(case):
     assert (np.abs(d - gold) / np.maximum(np.abs(gold), 1e-300)).max() < 6e-9
 
 
-@pytest.mark.parametrize("case", list(O.KCASES))
+@pytest.mark.parametrize("case", list(O.KCASES) + list(O.KTCASES))
 def test_kozcg_oracle_reproduces_reference_golden_diag(case):
     """KozCG (element-based Taylor-Galerkin + FCT): tests/regression/inciter/KozCG/
-    {Sod,TaylorGreen}/diag.std (the latter without FCT and with the source term)."""
-    kw = O.KCASES[case]
+    {Sod,TaylorGreen,VorticalFlow,NonlinearEnergyGrowth,RayleighTaylor}/diag.std (all but Sod without
+    FCT and with source terms; the last two with time-dependent sources and Dirichlet values)."""
+    kw = {**O.KCASES, **O.KTCASES}[case]
     gold = O.load_golden_diag(case)
     o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
     o.step(int(gold[-1, 0]))

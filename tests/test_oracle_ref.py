@@ -79,10 +79,10 @@ def test_zalcg_port_is_bit_identical_to_reference_objects(case):
 
 
 @needs_ref
-@pytest.mark.parametrize("case", list(O.KCASES))
+@pytest.mark.parametrize("case", list(O.KCASES) + list(O.KTCASES))
 def test_kozcg_port_is_bit_identical_to_reference_objects(case):
     """kozak::rhs from the reference's own Kozak.cpp vs the restatement under the same driver."""
-    kw = O.KCASES[case]
+    kw = {**O.KCASES, **O.KTCASES}[case]
     gold = O.load_golden_diag(case)
     mesh = O.load_mesh(kw["mesh"])
     a = O.Oracle(mesh, O.make_cfg(**kw), "port")

@@ -52,7 +52,7 @@ SYMBOLS = [
     "xyst_chocg_get", "xyst_chocg_apply_bc", "xyst_chocg_div", "xyst_chocg_vgrad", "xyst_chocg_flux",
     "xyst_chocg_grad", "xyst_chocg_src", "xyst_chocg_rhs", "xyst_chocg_stage", "xyst_chocg_pinit",
     "xyst_chocg_project", "xyst_chocg_pressure_update", "xyst_chocg_dt_min", "xyst_chocg_diag",
-    "xyst_chocg_minit", "xyst_chocg_mupdate", "xyst_cg_select", "xyst_csr_update",
+    "xyst_kozcg_src", "xyst_chocg_minit", "xyst_chocg_mupdate", "xyst_cg_select", "xyst_csr_update",
     "xyst_lohcg_mesh_upload", "xyst_lohcg_bc_upload", "xyst_lohcg_set_u", "xyst_lohcg_get_u", "xyst_lohcg_get_rhs",
     "xyst_lohcg_apply_bc", "xyst_lohcg_rhs", "xyst_lohcg_stage", "xyst_lohcg_project", "xyst_lohcg_pressure_set",
     "xyst_lohcg_dt_min", "xyst_lohcg_diag",
@@ -138,6 +138,7 @@ def lib():
     L.xyst_chocg_pressure_update.argtypes = [C.c_void_p, C.c_int]
     L.xyst_chocg_dt_min.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_double)]
     L.xyst_chocg_diag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.xyst_kozcg_src.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.xyst_chocg_minit.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
     L.xyst_chocg_mupdate.argtypes = [C.c_void_p, C.c_int]
     L.xyst_cg_select.argtypes = [C.c_void_p, C.c_int]

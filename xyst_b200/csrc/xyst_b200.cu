@@ -217,6 +217,7 @@ struct xyst_ctx : CgState {
   DevBuf< int > kinc;                    // tet*4+a, -1 = padding
   DevBuf< double > kT, kSc;              // [40][ntet] per-tet contributions; [ntet][5] centroid source
   bool ksrc = false;
+  std::vector< int > kperm;              // device tet order -> caller's tet index
   // ChoCG: velocity (3 rotating buffers: time level n, current, next), pressure, divergence,
   // gradients of the CG solution / pressure / velocity, momentum flux; BC lists
   bool cho = false;
@@ -1140,6 +1141,7 @@ int xyst_kozcg_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const do
   c->ntet = ntet; c->knent = inc.size();
   c->ktet.upload( tet, s ); c->kbase.upload( base, s ); c->kinc.upload( inc, s );
   c->kT.alloc( 40*ntet );
+  c->kperm = perm;
   c->ksrc = Sn && Sc;
   if (c->ksrc) {
     c->S.upload( std::vector< double >( Sn, Sn + npoin*NC ), s );
@@ -1148,6 +1150,27 @@ int xyst_kozcg_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const do
     c->kSc.upload( sc, s );
   }
   c->zP.alloc( c->NP*10 ); c->zQ.alloc( c->NP*10 ); c->zUL.alloc( c->NP*NC );
+  API_END
+}
+
+// new source term values (time-dependent problems: nodes at t, centroids at t + dt/2,
+// Kozak.cpp:97-108,160-171)
+int xyst_kozcg_src( xyst_ctx* c, const double* Sn, const double* Sc )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  if (!c->ntet || c->kperm.size() != c->ntet) throw std::runtime_error( "no KozCG mesh uploaded" );
+  if (!Sn || !Sc) throw std::runtime_error( "xyst_kozcg_src: null argument" );
+  auto s = c->stream;
+  size_t ntet = c->ntet;
+  if (c->S.n != c->npoin*NC) c->S.alloc( c->npoin*NC );
+  if (c->kSc.n != ntet*NC) c->kSc.alloc( ntet*NC );
+  std::vector< double > sc( ntet*NC );
+  for (size_t i=0; i<ntet; ++i) for (size_t k=0; k<NC; ++k) sc[i*NC+k] = Sc[(size_t)c->kperm[i]*NC+k];
+  CK( cudaMemcpyAsync( c->S.p, Sn, c->npoin*NC*sizeof(double), cudaMemcpyHostToDevice, s ) );
+  CK( cudaMemcpyAsync( c->kSc.p, sc.data(), ntet*NC*sizeof(double), cudaMemcpyHostToDevice, s ) );
+  CK( cudaStreamSynchronize( s ) );
+  c->ksrc = true;
   API_END
 }
 

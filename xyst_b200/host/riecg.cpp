@@ -516,8 +516,8 @@ void RieCG::hostSetup()
     }
   }
   m_timedep = problems::timeDependent( m_cfg );
-  if (m_timedep && (m_zal || m_koz || m_cho || m_loh || m_lax || m_cfg.steady))
-    throw std::runtime_error( "time-dependent problems are hooked up for RieCG only" );
+  if (m_timedep && (m_zal || m_cho || m_loh || m_lax || m_cfg.steady))
+    throw std::runtime_error( "time-dependent problems are hooked up for RieCG and KozCG only" );
   evalDirvals( m_disc.T() );
   evalSrc( m_disc.T() );
   if (m_cho || m_loh) choPrelhs();           // LohCG::prelhs :140-181 is ChoCG's
@@ -558,6 +558,27 @@ void RieCG::evalSrc( real t )
   }
 }
 
+//! problems::SRC at the tet centroids at time t (kozak::rhs, Kozak.cpp:160-171)
+void RieCG::evalSrcCentroids( real t, std::vector< real >& sc )
+{
+  const auto& co = m_disc.Coord();
+  const auto& inpoel = m_disc.Inpoel();
+  auto ncomp = m_cfg.ncomp;
+  sc.clear();
+  auto src = problems::SRC( m_cfg );
+  if (!src) return;
+  sc.resize( inpoel.size()/4*ncomp );
+  #pragma omp parallel for schedule(static)
+  for (std::size_t e=0; e<inpoel.size()/4; ++e) {
+    const auto N = inpoel.data() + e*4;
+    auto xe = (co[0][N[0]] + co[0][N[1]] + co[0][N[2]] + co[0][N[3]]) / 4.0;
+    auto ye = (co[1][N[0]] + co[1][N[1]] + co[1][N[2]] + co[1][N[3]]) / 4.0;
+    auto ze = (co[2][N[0]] + co[2][N[1]] + co[2][N[2]] + co[2][N[3]]) / 4.0;
+    auto v = src( xe, ye, ze, t );
+    for (std::size_t c=0; c<ncomp; ++c) sc[e*ncomp+c] = v[c];
+  }
+}
+
 void RieCG::setup()
 {
   if (!m_ctx) throw std::runtime_error( "RieCG::setup: attach() a device first" );
@@ -577,18 +598,7 @@ void RieCG::setup()
     // kozak::rhs source terms (Kozak.cpp:97-108,160-171): nodes and tet centroids
     std::vector< real > sc;
     const auto& inpoel = m_disc.Inpoel();
-    if (auto src = problems::SRC( m_cfg )) {
-      sc.resize( inpoel.size()/4*ncomp );
-      #pragma omp parallel for schedule(static)
-      for (std::size_t e=0; e<inpoel.size()/4; ++e) {
-        const auto N = inpoel.data() + e*4;
-        auto xe = (co[0][N[0]] + co[0][N[1]] + co[0][N[2]] + co[0][N[3]]) / 4.0;
-        auto ye = (co[1][N[0]] + co[1][N[1]] + co[1][N[2]] + co[1][N[3]]) / 4.0;
-        auto ze = (co[2][N[0]] + co[2][N[1]] + co[2][N[2]] + co[2][N[3]]) / 4.0;
-        auto v = src( xe, ye, ze, m_disc.T() );
-        for (std::size_t c=0; c<ncomp; ++c) sc[e*ncomp+c] = v[c];
-      }
-    }
+    evalSrcCentroids( m_disc.T(), sc );
     ck( xyst_kozcg_mesh_upload( m_ctx, np, co[0].data(), co[1].data(), co[2].data(), inpoel.size()/4, inpoel.data(),
                                 m_disc.Vol().data(), m_disc.V().data(),
                                 sc.empty() ? nullptr : m_src.data(), sc.empty() ? nullptr : sc.data() ) );
@@ -657,7 +667,19 @@ bool RieCG::step( std::vector< real >* diagrow )
   if (m_finished) return false;
   advance( dt() );
   if (m_zal) ck( xyst_zalcg_step( m_ctx, m_disc.Dt() ) );      // ZalCG.cpp:973-1607
-  else if (m_koz) ck( xyst_kozcg_step( m_ctx, m_disc.Dt() ) ); // KozCG.cpp:691-1197
+  else if (m_koz) {                                            // KozCG.cpp:691-1197
+    if (m_timedep) {
+      // sources at the nodes at t and at the centroids at t + dt/2 (Kozak.cpp:104,163), Dirichlet
+      // values at t + dt (KozCG::solve -> BC)
+      std::vector< real > sc;
+      evalSrc( m_disc.T() );
+      evalSrcCentroids( m_disc.T() + m_disc.Dt()/2.0, sc );
+      if (!m_src.empty()) ck( xyst_kozcg_src( m_ctx, m_src.data(), sc.data() ) );
+      evalDirvals( m_disc.T() + m_disc.Dt() );
+      if (!m_dirvals.empty()) ck( xyst_dirbc_values( m_ctx, m_dirvals.data() ) );
+    }
+    ck( xyst_kozcg_step( m_ctx, m_disc.Dt() ) );
+  }
   else if (m_timedep) {
     // source at the time level of the step for all stages (RieCG.cpp:949), Dirichlet values at the
     // stage time t + rk dt (:1028): refreshed on the host, three separate stage calls

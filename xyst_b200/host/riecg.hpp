@@ -188,6 +188,7 @@ class RieCG {
     void setupBC();                  //!< :109-245 (after normals are known)
     void uploadHalo();
     void evalDirvals( real t );      //!< physics::dirbc values = IC at the BC nodes at time t (BC.cpp:57-66)
+    void evalSrcCentroids( real t, std::vector< real >& sc );   //!< problems::SRC at the tet centroids (kozak::rhs)
     void evalSrc( real t );          //!< problems::SRC at the nodes at time t (riemann::src, Riemann.cpp:880-907)
     bool m_timedep = false;          //!< IC / source depend on time: BC values per stage, source per step
     bool m_haloup = false;

@@ -57,9 +57,9 @@ inline void rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
 inline void zal_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
                      const std::array< std::vector< real >, 3 >& dsupint,
                      const Coords& coord, const std::vector< std::size_t >& triinpoel,
-                     const std::vector< std::uint8_t >& besym, real t, real dt, const Fields& U, Fields& R )
-{ std::vector< real > tp, dtp;
-  zalesak::rhs( dsupedge, dsupint, coord, triinpoel, besym, t, dt, tp, dtp, U, R ); }
+                     const std::vector< std::uint8_t >& besym, real t, real dt,
+                     const std::vector< real >& tp, const std::vector< real >& dtp, const Fields& U, Fields& R )
+{ zalesak::rhs( dsupedge, dsupint, coord, triinpoel, besym, t, dt, tp, dtp, U, R ); }
 
 inline void koz_rhs( const std::vector< std::size_t >& inpoel, const Coords& coord, real t, real dt,
                      const Fields& U, Fields& R )

@@ -854,7 +854,7 @@ class Chare {
 
     // ---- ZalCG (flux-corrected transport) ----------------------------------------------
     //! ZalCG::rhs :990-1012 (own part)
-    void zrhs_own( real t, real dt ) { be::zal_rhs( dsupedge, dsupint, coord, triinpoel, besym, t, dt, u, rhs ); }
+    void zrhs_own( real t, real dt ) { be::zal_rhs( dsupedge, dsupint, coord, triinpoel, besym, t, dt, tp, dtp, u, rhs ); }
 
     //! visit every edge of the superedge groups: fn( first node, second node, integrals )
     template< class F > void foredge( F fn ) const {
@@ -898,13 +898,15 @@ class Chare {
       const auto npoin = u.nunk(); const auto ncomp = u.nprop();
       for (const auto& [g,pp] : pc) { auto i = lid.at(g); for (std::size_t c=0; c<pp.size(); ++c) p(i,c) += pp[c]; }
       pc.clear();
-      for (std::size_t i=0; i<npoin; ++i)
+      for (std::size_t i=0; i<npoin; ++i) {
+        if (cfg.steady) dt = dtp[i];                                       // :1195
         for (std::size_t c=0; c<ncomp; ++c) {
           auto A = c*2; auto B = A+1;
           p(i,A) /= mvol[i];
           p(i,B) /= mvol[i];
           rhs(i,c) = u(i,c) - dt*rhs(i,c)/mvol[i] - p(i,A) - p(i,B);
         }
+      }
       using std::max; using std::min;
       auto large = std::numeric_limits< real >::max();
       for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) { q(i,c*2+0) = -large; q(i,c*2+1) = +large; }
@@ -962,11 +964,14 @@ class Chare {
       for (const auto& [g,aa] : ac) { auto i = lid.at(g); for (std::size_t c=0; c<aa.size(); ++c) a(i,c) += aa[c]; }
       ac.clear();
       if (cfg.fct) { for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) a(i,c) = rhs(i,c) + a(i,c)/mvol[i]; }
-      else { for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) a(i,c) = u(i,c) - dt*rhs(i,c)/mvol[i]; }
+      else { auto ldt = dt;
+        for (std::size_t i=0; i<npoin; ++i) { if (cfg.steady) ldt = dtp[i];                 // :1563
+          for (std::size_t c=0; c<ncomp; ++c) a(i,c) = u(i,c) - ldt*rhs(i,c)/mvol[i]; } }
       un = u;                               // rhocompute( m_a, m_u ) sees new and old
       u = a;
       BC( t + dt );                         // BC( m_a, T+Dt )
       a.fill( 0.0 );
+      if (cfg.steady) for (std::size_t i=0; i<tp.size(); ++i) tp[i] += dtp[i];              // :1600-1603
     }
 
     // ---- KozCG (element-based Taylor-Galerkin + FCT), KozCG.cpp:709-1197 --------------------

@@ -1636,8 +1636,10 @@ inline void lohner_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupe
 //! edge flux, Zalesak.cpp:31-200 (problems without source term; the f[ncomp..2ncomp) source
 //! half is only produced when problems::SRC() is set)
 inline void zal_advedge( const real supint[], const Fields& U, const Coords& coord, real t, real dt,
+                         const std::vector< real >& tp, const std::vector< real >& dtp,
                          std::size_t p, std::size_t q, real f[], const ICFn& src )
 {
+  const auto steady = cfg().steady;
   const auto ncomp = U.nprop();
   const auto& x = coord[0]; const auto& y = coord[1]; const auto& z = coord[2];
   auto dx = x[p] - x[q], dy = y[p] - y[q], dz = z[p] - z[q];
@@ -1651,6 +1653,7 @@ inline void zal_advedge( const real supint[], const Fields& U, const Coords& coo
   auto dnR = (ruR*dx + rvR*dy + rwR*dz)/rR;
   auto nx = supint[0], ny = supint[1], nz = supint[2];
   std::vector< real > ue( ncomp );
+  if (steady) dt = (dtp[p] + dtp[q])/2.0;                                   // Zalesak.cpp:107
   auto dp = pL - pR;
   ue[0] = 0.5*(rL + rR - dt*(rL*dnL - rR*dnR));
   ue[1] = 0.5*(ruL + ruR - dt*(ruL*dnL - ruR*dnR + dp*dx));
@@ -1659,6 +1662,7 @@ inline void zal_advedge( const real supint[], const Fields& U, const Coords& coo
   ue[4] = 0.5*(reL + reR - dt*((reL+pL)*dnL - (reR+pR)*dnR));
   for (std::size_t c=5; c<ncomp; ++c) ue[c] = 0.5*(U(p,c) + U(q,c) - dt*(U(p,c)*dnL - U(q,c)*dnR));
   if (src) {
+    if (steady) t = (tp[p] + tp[q])/2.0;                                    // :125
     auto coef = dt/4.0;
     auto sL = src( x[p], y[p], z[p], t );
     auto sR = src( x[q], y[q], z[q], t );
@@ -1697,7 +1701,8 @@ inline void zal_advedge( const real supint[], const Fields& U, const Coords& coo
 inline void zal_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge,
                      const std::array< std::vector< real >, 3 >& dsupint, const Coords& coord,
                      const std::vector< std::size_t >& triinpoel, const std::vector< std::uint8_t >& besym,
-                     real t, real dt, const Fields& U, Fields& R )
+                     real t, real dt, const std::vector< real >& tp, const std::vector< real >& dtp,
+                     const Fields& U, Fields& R )
 {
   auto ncomp = U.nprop();
   auto src = SRC();
@@ -1707,12 +1712,12 @@ inline void zal_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge
   for (std::size_t e=0; e<dsupedge[0].size()/4; ++e) {
     const auto N = dsupedge[0].data() + e*4;
     const auto d = dsupint[0].data();
-    zal_advedge( d+(e*6+0)*4, U, coord, t, dt, N[0], N[1], f[0], src );
-    zal_advedge( d+(e*6+1)*4, U, coord, t, dt, N[1], N[2], f[1], src );
-    zal_advedge( d+(e*6+2)*4, U, coord, t, dt, N[2], N[0], f[2], src );
-    zal_advedge( d+(e*6+3)*4, U, coord, t, dt, N[0], N[3], f[3], src );
-    zal_advedge( d+(e*6+4)*4, U, coord, t, dt, N[1], N[3], f[4], src );
-    zal_advedge( d+(e*6+5)*4, U, coord, t, dt, N[2], N[3], f[5], src );
+    zal_advedge( d+(e*6+0)*4, U, coord, t, dt, tp, dtp, N[0], N[1], f[0], src );
+    zal_advedge( d+(e*6+1)*4, U, coord, t, dt, tp, dtp, N[1], N[2], f[1], src );
+    zal_advedge( d+(e*6+2)*4, U, coord, t, dt, tp, dtp, N[2], N[0], f[2], src );
+    zal_advedge( d+(e*6+3)*4, U, coord, t, dt, tp, dtp, N[0], N[3], f[3], src );
+    zal_advedge( d+(e*6+4)*4, U, coord, t, dt, tp, dtp, N[1], N[3], f[4], src );
+    zal_advedge( d+(e*6+5)*4, U, coord, t, dt, tp, dtp, N[2], N[3], f[5], src );
     for (std::size_t c=0; c<ncomp; ++c) {
       R(N[0],c) = R(N[0],c) - f[0][c] + f[2][c] - f[3][c];
       R(N[1],c) = R(N[1],c) + f[0][c] - f[1][c] - f[4][c];
@@ -1730,9 +1735,9 @@ inline void zal_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge
   for (std::size_t e=0; e<dsupedge[1].size()/3; ++e) {
     const auto N = dsupedge[1].data() + e*3;
     const auto d = dsupint[1].data();
-    zal_advedge( d+(e*3+0)*4, U, coord, t, dt, N[0], N[1], f[0], src );
-    zal_advedge( d+(e*3+1)*4, U, coord, t, dt, N[1], N[2], f[1], src );
-    zal_advedge( d+(e*3+2)*4, U, coord, t, dt, N[2], N[0], f[2], src );
+    zal_advedge( d+(e*3+0)*4, U, coord, t, dt, tp, dtp, N[0], N[1], f[0], src );
+    zal_advedge( d+(e*3+1)*4, U, coord, t, dt, tp, dtp, N[1], N[2], f[1], src );
+    zal_advedge( d+(e*3+2)*4, U, coord, t, dt, tp, dtp, N[2], N[0], f[2], src );
     for (std::size_t c=0; c<ncomp; ++c) {
       R(N[0],c) = R(N[0],c) - f[0][c] + f[2][c];
       R(N[1],c) = R(N[1],c) + f[0][c] - f[1][c];
@@ -1748,7 +1753,7 @@ inline void zal_rhs( const std::array< std::vector< std::size_t >, 3 >& dsupedge
   for (std::size_t e=0; e<dsupedge[2].size()/2; ++e) {
     const auto N = dsupedge[2].data() + e*2;
     const auto d = dsupint[2].data();
-    zal_advedge( d+e*4, U, coord, t, dt, N[0], N[1], f[0], src );
+    zal_advedge( d+e*4, U, coord, t, dt, tp, dtp, N[0], N[1], f[0], src );
     for (std::size_t c=0; c<ncomp; ++c) {
       R(N[0],c) -= f[0][c];
       R(N[1],c) += f[0][c];

@@ -225,6 +225,14 @@ TCASES = {
                                   kappa=1.0, gamma=5.0 / 3.0, cfl=0.5, nstep=50, dir_=_DIR6,
                                   mesh="riecg_taylor_green"),
 }
+# ZalCG/Bump/bump.q: steady-state local time stepping (edge dt = mean of the end nodes' dt), stab2,
+# far-field BC, FCT with defaults; serial golden printed with 12 digits
+ZSCASES = {
+    "zalcg_bump": dict(solver="zalcg", problem="userdef", gamma=1.4, cfl=0.7, nstep=20, steady=True, residual=1.0e-9,
+                       rescomp=1, stab2=True, stab2coef=0.05, sym=(3,), far=(4,), far_density=1.0, far_pressure=1.0,
+                       far_velocity=(0.7987, 0.0, 0.0), ic_density=1.0, ic_pressure=1.0,
+                       ic_velocity=(0.7987, 0.0, 0.0), mesh="laxcg_bump"),
+}
 # KozCG/{NonlinearEnergyGrowth/nleg.q,RayleighTaylor/rayleigh_taylor.q}: the time-dependent manufactured
 # solutions through the element-based solver (no FCT): nodal sources at t, centroid sources at t + dt/2
 KTCASES = {

@@ -55,12 +55,14 @@ def test_zalcg_without_fct_and_with_stab2():
     assert relerr(ctx.state_get(), o.get("u")) < 1e-11
 
 
-@pytest.mark.parametrize("case", list(O.ZCASES))
+@pytest.mark.parametrize("case", list(O.ZCASES) + list(O.ZSCASES))
 def test_zalcg_host_mirror_diag_rows(case):
-    """Full drop-in path (C++ host mirror of ZalCG's setup + time loop) vs oracle and golden."""
+    """Full drop-in path (C++ host mirror of ZalCG's setup + time loop) vs oracle and golden; the Bump
+    case runs towards a steady state with local time steps (per-node dt in the low-order update,
+    per-edge mean in the Taylor-Galerkin half step), stab2 and the far-field BC."""
     from xyst_b200 import hostapi as H
     from host_common import fixture_to_host_mesh
-    kw = O.ZCASES[case]
+    kw = {**O.ZCASES, **O.ZSCASES}[case]
     gold = O.load_golden_diag(case)
     nsteps = int(gold[-1, 0])
     hm = fixture_to_host_mesh(O.load_mesh(kw["mesh"]))

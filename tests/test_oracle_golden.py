@@ -83,6 +83,19 @@ def test_zalcg_oracle_reproduces_reference_golden_diag(case):
     assert (np.abs(d - gold) / np.maximum(np.abs(gold), 1e-300)).max() < 6e-9
 
 
+def test_zalcg_steady_oracle_reproduces_reference_golden_diag():
+    """ZalCG towards a steady state with local time stepping (ZalCG::dt :915-928, zalesak::advedge :107,
+    alw :1195, solve :1563), stab2 and the far-field BC: tests/regression/inciter/ZalCG/Bump/diag.std,
+    serial run, to the 12 printed digits."""
+    kw = O.ZSCASES["zalcg_bump"]
+    gold = O.load_golden_diag("zalcg_bump")
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(int(gold[-1, 0]))
+    d = o.diag()
+    assert d.shape == gold.shape
+    assert (np.abs(d - gold) <= 2e-12 * np.abs(gold)).all()
+
+
 @pytest.mark.parametrize("case", list(O.KCASES) + list(O.KTCASES))
 def test_kozcg_oracle_reproduces_reference_golden_diag(case):
     """KozCG (element-based Taylor-Galerkin + FCT): tests/regression/inciter/KozCG/

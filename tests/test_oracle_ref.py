@@ -57,11 +57,11 @@ def test_flux_variants_bit_identical(flux, stab2):
 
 
 @needs_ref
-@pytest.mark.parametrize("case", list(O.ZCASES))
+@pytest.mark.parametrize("case", list(O.ZCASES) + list(O.ZSCASES))
 def test_zalcg_port_is_bit_identical_to_reference_objects(case):
     """zalesak::rhs from the reference's own Zalesak.cpp vs the restatement, under the same
     serial FCT driver: bitwise equal states after the full regression runs."""
-    kw = O.ZCASES[case]
+    kw = {**O.ZCASES, **O.ZSCASES}[case]
     gold = O.load_golden_diag(case)
     mesh = O.load_mesh(kw["mesh"])
     a = O.Oracle(mesh, O.make_cfg(**kw), "port")

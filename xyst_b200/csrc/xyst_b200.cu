@@ -723,13 +723,13 @@ void zal_flux_and_bnd( xyst_ctx* c, double dt )
                   c->tri.p, c->besym.p, c->fn.p, c->U.p, c->Rb.p, c->prm.gamma, c->W.p, c->rgas ); ++c->launches; }
   { ProfScope ps( c, "zalflux" );
     k_zal_flux_edge<<< nblk( c->nslot, 128 ), 128, 0, s >>>( c->nslot, c->NP, c->ep.p, c->eq.p, c->D.p, c->U.p, c->X.p,
-      dt, dparams( c ), c->F.p ); ++c->launches; }
+      dt, c->steady ? c->dtp.p : nullptr, dparams( c ), c->F.p ); ++c->launches; }
 }
 void zal_node1( xyst_ctx* c, double dt, int fct )
 {
   k_zal_node1<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p,
     c->inc_eq.p, c->D.p, c->nslot, c->F.p, c->U.p, c->bslot.p, c->Rb.p, c->bcof.p, c->bc_symoff.p,
-    c->sym_n.p, c->vol.p, dt, c->zal.fctdif, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
+    c->sym_n.p, c->vol.p, dt, c->steady ? c->dtp.p : nullptr, c->zal.fctdif, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
 }
 }
 
@@ -761,7 +761,7 @@ int xyst_zalcg_step( xyst_ctx* c, double dt )
       c->U.p, c->zUL.p, c->zQ.p, c->vol.p, c->zal.fctdif, c->zal.fctsys_mask, c->Un.p, c->W.p ); ++c->launches;
   } else {
     zal_node1( c, dt, 0 );
-    k_zal_nofct<<< nblk( c->npoin, 256 ), 256, 0, s >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->U.p, dt, c->Un.p, c->W.p ); ++c->launches;
+    k_zal_nofct<<< nblk( c->npoin, 256 ), 256, 0, s >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->U.p, dt, c->steady ? c->dtp.p : nullptr, c->Un.p, c->W.p ); ++c->launches;
   }
   std::swap( c->U.p, c->Un.p );
   do_bc( c );

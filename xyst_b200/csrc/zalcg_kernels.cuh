@@ -8,13 +8,14 @@
 __global__ void __launch_bounds__(128)
 k_zal_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __restrict__ eq,
                  const double* __restrict__ D, const double* __restrict__ U, const double* __restrict__ X,
-                 double dt, DParams P, double* __restrict__ F )
+                 double dt, const double* __restrict__ dtp, DParams P, double* __restrict__ F )
 {
   size_t e = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (e >= nslot) return;
   int pi = ep[e];
   if (pi < 0) return;
   size_t p = pi, q = eq[e];
+  if (dtp) dt = (dtp[p] + dtp[q])/2.0;      // steady state: local time step of the edge (Zalesak.cpp:107)
   double g = P.gamma;
   double dx = X[p] - X[q], dy = X[NP+p] - X[NP+q], dz = X[2*NP+p] - X[2*NP+q];
   double dl = dx*dx + dy*dy + dz*dz;
@@ -60,13 +61,14 @@ __global__ void __launch_bounds__(NODE_THREADS, 3)
 k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot,
              const double* __restrict__ F, const double* __restrict__ U, const int* __restrict__ bslot,
              const double* __restrict__ Rb, const int* __restrict__ bcof, const int* __restrict__ symoff,
-             const double* __restrict__ sym_n, const double* __restrict__ vol, double dt, double ctau, int fct,
-             double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
+             const double* __restrict__ sym_n, const double* __restrict__ vol, double dt, const double* __restrict__ dtp,
+             double ctau, int fct, double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   size_t p = slice*32 + lane;
   if (p >= npoin) return;
+  if (dtp) dt = dtp[p];                     // steady state (ZalCG.cpp:1195)
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
   double up[NC], r[NC], pp[NC], pn[NC];
@@ -227,10 +229,12 @@ k_zal_node3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
 
 // fct = false: u = u - dt R/vol (ZalCG.cpp:1560-1567)
 __global__ void k_zal_nofct( size_t npoin, size_t NP, const double* __restrict__ R, const double* __restrict__ vol,
-                             const double* __restrict__ U, double dt, double* __restrict__ Unew, double* __restrict__ W )
+                             const double* __restrict__ U, double dt, const double* __restrict__ dtp,
+                             double* __restrict__ Unew, double* __restrict__ W )
 {
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= npoin) return;
+  if (dtp) dt = dtp[p];                     // steady state (:1563)
   double vp = vol[p], u[NC], w[NC];
   #pragma unroll
   for (int c=0; c<NC; ++c) { u[c] = U[c*NP+p] - dt*R[p*NC+c]/vp; Unew[c*NP+p] = u[c]; }

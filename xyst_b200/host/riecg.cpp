@@ -611,7 +611,7 @@ void RieCG::setup()
     ck( xyst_laxcg_config( m_ctx, &lp ) );
   }
   if (m_cfg.steady) {
-    if (m_zal || m_koz) throw std::runtime_error( "steady state is a RieCG/LaxCG option" );
+    if (m_koz) throw std::runtime_error( "steady state is a RieCG/LaxCG/ZalCG option" );
     ck( xyst_steady( m_ctx, 1 ) );
   }
   if (m_zal || m_koz) {

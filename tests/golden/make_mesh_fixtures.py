@@ -26,6 +26,7 @@ CASES = {
     "chocg_unitcube": ("ChoCG/Poisson/unitcube_01_1k.exo", None),
     "chocg_pidiv4": ("ChoCG/Poisson/unitcube_0pidiv4_1k.exo", None),
     "chocg_poiseuille": ("ChoCG/Poiseuille/poiseuille1tetz.exo", None),
+    "sphere2_5k": ("ChoCG/Sphere/sphere2_5K.exo", None),
 }
 EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "chocg_poisson_const": "ChoCG/Poisson/diag_poisson_const.std",
@@ -50,7 +51,13 @@ EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "riecg_pipe": "RieCG/Pipe/diag.std",
               "lohcg_poiseuille_damp2": "LohCG/Poiseuille/diag_poiseuille_damp2.std",
               "lohcg_poiseuille_damp4": "LohCG/Poiseuille/diag_poiseuille_damp4.std",
-              "lohcg_ldc": "LohCG/Lid/diag_ldc.std"}
+              "lohcg_ldc": "LohCG/Lid/diag_ldc.std",
+              "chocg_poiseuille_theta": "ChoCG/Poiseuille/diag_poiseuille_theta.std",
+              "kozcg_nleg": "KozCG/NonlinearEnergyGrowth/diag.std",
+              "kozcg_rayleigh_taylor": "KozCG/RayleighTaylor/diag.std",
+              "zalcg_bump": "ZalCG/Bump/diag.std",
+              "chocg_inviscid_sphere": "ChoCG/Sphere/diag_inviscid_sphere.std",
+              "lohcg_viscous_sphere": "LohCG/Sphere/diag_sphere_lohcg_viscous_test.std"}
 
 
 def flatten(exo):

@@ -147,6 +147,11 @@ CCASES = {
     "chocg_poiseuille_rk2": dict(_POIS, flux="damp2", rk=2),
     "chocg_poiseuille_rk3": dict(_POIS, flux="damp2", rk=3),
     "chocg_poiseuille_rk4": dict(_POIS, flux="damp4", rk=4, cfl=1.0),
+    # ChoCG/Sphere/inviscid_sphere.q: potential flow around a sphere, symmetry + inflow Dirichlet, pressure
+    # Dirichlet at the outflow from the pressure IC
+    "chocg_inviscid_sphere": dict(solver="chocg", ncomp=3, nstep=10, cfl=0.5, flux="damp2", p_iter=300, p_tol=1.0e-3,
+                                  p_pc="jacobi", p_dir=((3, 1),), problem="userdef", ic_velocity=(1.0, 0.0, 0.0),
+                                  dir_=((2, 1, 0, 0),), sym=(1, 4), mesh="sphere2_5k"),
     "chocg_ldc": dict(solver="chocg", ncomp=3, nstep=10, cfl=0.9, flux="damp4", mu=0.01, p_iter=500, p_tol=1.0e-3,
                       p_pc="jacobi", p_hydrostat=0, problem="userdef", noslip=(1, 2, 3, 5, 6),
                       dir_=((4, 2, 2, 2),), dirval=((4, 1.0, 0.0, 0.0),), mesh="riecg_taylor_green"),
@@ -169,6 +174,13 @@ _LPOIS = dict(solver="lohcg", ncomp=4, nstep=20, soundspeed=10.0, mu=0.01, p_ite
 HCASES = {
     "lohcg_poiseuille_damp2": dict(_LPOIS, flux="damp2", cfl=0.5, rk=3),
     "lohcg_poiseuille_damp4": dict(_LPOIS, flux="damp4", cfl=0.3, rk=4),
+    # LohCG/Sphere/sphere_lohcg_viscous_test.q: viscous flow around a sphere, Re = 100, damp4 + stab2, rk 4,
+    # no-slip sphere, diagnostics every 10th step
+    "lohcg_viscous_sphere": dict(solver="lohcg", ncomp=4, nstep=20, cfl=0.1, flux="damp4", stab2=True, stab2coef=0.05,
+                                 soundspeed=10.0, rk=4, p_iter=300, p_tol=1.0e-3, p_pc="jacobi", p_dir=((3, 1),),
+                                 mu=1.0 / 100.0, problem="userdef", ic_velocity=(1.0, 0.0, 0.0),
+                                 dir_=((2, 0, 1, 1, 1), (3, 1, 0, 0, 0), (4, 0, 1, 0, 0)), noslip=(1,), diag_iter=10,
+                                 mesh="sphere2_5k"),
     "lohcg_ldc": dict(solver="lohcg", ncomp=4, nstep=20, cfl=0.1, flux="damp2", soundspeed=10.0, rk=2, mu=0.01,
                       p_iter=500, p_tol=1.0e-3, p_pc="jacobi", p_hydrostat=0, problem="userdef",
                       noslip=(1, 2, 3, 5, 6), dir_=((4, 0, 2, 2, 2),), dirval=((4, 0.0, 1.0, 0.0, 0.0),),

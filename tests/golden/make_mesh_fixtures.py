@@ -57,6 +57,7 @@ EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "kozcg_rayleigh_taylor": "KozCG/RayleighTaylor/diag.std",
               "zalcg_bump": "ZalCG/Bump/diag.std",
               "chocg_inviscid_sphere": "ChoCG/Sphere/diag_inviscid_sphere.std",
+              "chocg_viscous_sphere": "ChoCG/Sphere/diag_sphere_chocg_viscous_test.std",
               "lohcg_viscous_sphere": "LohCG/Sphere/diag_sphere_lohcg_viscous_test.std"}
 
 

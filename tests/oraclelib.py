@@ -152,6 +152,11 @@ CCASES = {
     "chocg_inviscid_sphere": dict(solver="chocg", ncomp=3, nstep=10, cfl=0.5, flux="damp2", p_iter=300, p_tol=1.0e-3,
                                   p_pc="jacobi", p_dir=((3, 1),), problem="userdef", ic_velocity=(1.0, 0.0, 0.0),
                                   dir_=((2, 1, 0, 0),), sym=(1, 4), mesh="sphere2_5k"),
+    # ChoCG/Sphere/sphere_chocg_viscous_test.q: Re = 40, damp4, rk 4, no-slip sphere
+    "chocg_viscous_sphere": dict(solver="chocg", ncomp=3, nstep=20, cfl=0.3, flux="damp4", rk=4, p_iter=300, p_tol=1.0e-3,
+                                 p_pc="jacobi", p_dir=((3, 1),), mu=1.0 / 40.0, problem="userdef",
+                                 ic_velocity=(1.0, 0.0, 0.0), dir_=((2, 1, 0, 0), (4, 1, 1, 1)), noslip=(1,),
+                                 mesh="sphere2_5k"),
     "chocg_ldc": dict(solver="chocg", ncomp=3, nstep=10, cfl=0.9, flux="damp4", mu=0.01, p_iter=500, p_tol=1.0e-3,
                       p_pc="jacobi", p_hydrostat=0, problem="userdef", noslip=(1, 2, 3, 5, 6),
                       dir_=((4, 2, 2, 2),), dirval=((4, 1.0, 0.0, 0.0),), mesh="riecg_taylor_green"),

@@ -27,7 +27,7 @@ class ChoRun : public Run {
     ChoRun( const MeshInput& in, const Cfg& c, const std::vector< std::size_t >& target, int nchare )
       : Run( in, c, target, nchare )
     {
-      if (cfg.ncomp != 3) throw std::runtime_error( "oracle ChoCG: velocity components only (ncomp = 3)" );
+      if (cfg.ncomp < 3) throw std::runtime_error( "oracle ChoCG: three velocity components (+ transported scalars)" );
       static const std::vector< std::vector< real > > rkcoef{ { 1.0 }, { 1.0/2.0, 1.0 }, { 1.0/3.0, 1.0/2.0, 1.0 },
                                                                { 1.0/4.0, 1.0/3.0, 1.0/2.0, 1.0 } };
       rk = rkcoef.at( cfg.rk - 1 );

@@ -959,7 +959,7 @@ class Chare {
     }
 
     //! ZalCG::solve :1524-1607: merge A, apply to the low-order solution, BCs; un/u for diagnostics
-    void zsolve( real t, real dt ) {
+    void zsolve( real t, real dt, real freezeflow = 1.0 ) {
       const auto npoin = u.nunk(); const auto ncomp = u.nprop();
       for (const auto& [g,aa] : ac) { auto i = lid.at(g); for (std::size_t c=0; c<aa.size(); ++c) a(i,c) += aa[c]; }
       ac.clear();
@@ -970,6 +970,8 @@ class Chare {
       un = u;                               // rhocompute( m_a, m_u ) sees new and old
       u = a;
       BC( t + dt );                         // BC( m_a, T+Dt )
+      if (freezeflow > 1.0)                 // frozen flow: only the scalars advance (:1549,1577-1584)
+        for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<5; ++c) u(i,c) = un(i,c);
       a.fill( 0.0 );
       if (cfg.steady) for (std::size_t i=0; i<tp.size(); ++i) tp[i] += dtp[i];              // :1600-1603
     }
@@ -1085,7 +1087,7 @@ class Chare {
     }
 
     //! KozCG::solve :1120-1197
-    void ksolve( real t, real dt ) {
+    void ksolve( real t, real dt, real freezeflow = 1.0 ) {
       const auto npoin = u.nunk(); const auto ncomp = u.nprop();
       for (const auto& [g,aa] : ac) { auto i = lid.at(g); for (std::size_t c=0; c<aa.size(); ++c) a(i,c) += aa[c]; }
       ac.clear();
@@ -1093,6 +1095,8 @@ class Chare {
       else { for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) a(i,c) = u(i,c) + dt*rhs(i,c)/vol[i]; }
       un = u; u = a;
       BC( t + dt );
+      if (freezeflow > 1.0)                 // frozen flow: only the scalars advance (KozCG.cpp:1141,1169-1176)
+        for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<5; ++c) u(i,c) = un(i,c);
       a.fill( 0.0 );
     }
 };
@@ -1106,6 +1110,7 @@ class Run {
     real t = 0.0, dt = 0.0, dtn = 0.0, meshvol = 0.0;
     std::uint64_t it = 0;
     bool finished = false;
+    real freezeflow = 1.0;                // ZalCG/KozCG::m_freezeflow
     real res = 0.0;                       // Discretization::m_res (residual of steady-state runs)
     std::vector< std::vector< real > > diagrows;
 
@@ -1186,6 +1191,10 @@ class Run {
       real mindt = std::numeric_limits< real >::max();
       for (auto& c_ : ch) mindt = std::min( mindt, c_->mindt() );
       auto eps = std::numeric_limits< real >::epsilon();
+      if ((cfg.solver == "zalcg" || cfg.solver == "kozcg") && !(std::abs( cfg.dt ) > eps)) {
+        if (t > cfg.freezetime) freezeflow = cfg.freezeflow;   // ZalCG::dt :948-952, KozCG::dt :669-674
+        mindt *= freezeflow;
+      }
       if (mindt < eps) finished = true;                       // RieCG::advance :862-863
       dtn = dt; dt = mindt;                                    // setdt :926-938
       if (t + dt > cfg.term) dt = cfg.term - t;
@@ -1202,7 +1211,7 @@ class Run {
         } else {
           for (auto& c_ : ch) { for (const auto& [g,r] : c_->rhsc) { auto i = c_->lid.at(g); for (std::size_t c=0; c<r.size(); ++c) c_->rhs(i,c) += r[c]; } c_->rhsc.clear(); }
         }
-        for (auto& c_ : ch) c_->ksolve( t, dt );
+        for (auto& c_ : ch) c_->ksolve( t, dt, freezeflow );
         diagnostics();
         ++it; t += dt;
         if (done()) finished = true;
@@ -1221,7 +1230,7 @@ class Run {
         } else {
           for (auto& c_ : ch) { for (const auto& [g,r] : c_->rhsc) { auto i = c_->lid.at(g); for (std::size_t c=0; c<r.size(); ++c) c_->rhs(i,c) += r[c]; } c_->rhsc.clear(); }
         }
-        for (auto& c_ : ch) c_->zsolve( t, dt );
+        for (auto& c_ : ch) c_->zsolve( t, dt, freezeflow );
         diagnostics();
         ++it; t += dt;
         if (done()) finished = true;

@@ -22,7 +22,7 @@ class LohRun : public Run {
     LohRun( const MeshInput& in, const Cfg& c, const std::vector< std::size_t >& target, int nchare )
       : Run( in, c, target, nchare )
     {
-      if (cfg.ncomp != 4) throw std::runtime_error( "oracle LohCG: unknowns (p,u,v,w) only (ncomp = 4)" );
+      if (cfg.ncomp < 4) throw std::runtime_error( "oracle LohCG: unknowns (p,u,v,w) (+ transported scalars)" );
       static const std::vector< std::vector< real > > rkcoef{ { 1.0 }, { 1.0/2.0, 1.0 }, { 1.0/3.0, 1.0/2.0, 1.0 },
                                                                { 1.0/4.0, 1.0/3.0, 1.0/2.0, 1.0 } };
       rk = rkcoef.at( cfg.rk - 1 );

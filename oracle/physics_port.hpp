@@ -86,6 +86,8 @@ struct Cfg {
   std::vector< std::vector< real > > p_bc_dirval;    // { setid, val }
   std::vector< int > p_bc_sym;
   std::uint64_t p_hydrostat = ~0ULL;
+  // ZalCG/KozCG: freeze the flow after freezetime and advance the scalars with freezeflow x dt
+  real freezeflow = 1.0, freezetime = 0.0;
   // semi-implicit momentum solve of ChoCG (tag::theta, mom_iter, mom_tol, mom_pc)
   real theta = 0.0;
   std::uint64_t mom_iter = 10;
@@ -277,6 +279,59 @@ inline std::vector< real > ic_userdef( real, real, real, real ) {           // :
   return u;
 }
 
+//! slot_cyl: solid-body rotation about (0.5,0.5) in the x-y plane carrying a cone, a cosine hump and a
+//! slotted cylinder in the first scalar, Problems.cpp:511-672. The bodies start a quarter turn apart
+//! at distance 0.25 from the axis and have radius 0.15; unknowns depend on the solver (6 for the
+//! compressible solvers, 3 velocities + scalar for chocg, p + velocities + scalar for lohcg).
+inline std::vector< real > ic_slot_cyl( real x, real y, real, real t ) {    // :513-634
+  using std::sin; using std::cos; using std::sqrt;
+  const auto& solver = cfg().solver;
+  const bool cho = solver == "chocg", loh = solver == "lohcg";
+  std::vector< real > u( cho ? 4 : loh ? 5 : 6, 0.0 );
+  std::size_t sc = cho ? 3 : loh ? 4 : 5;
+  if (cho) { u[0] = 0.5 - y; u[1] = x - 0.5; }
+  else if (loh) { u[1] = 0.5 - y; u[2] = x - 0.5; }
+  else {
+    const real p0 = 1.0;
+    u[0] = 1.0; u[1] = u[0] * (0.5 - y); u[2] = u[0] * (x - 0.5); u[3] = 0.0;
+    u[4] = eos_totalenergy( u[0], u[1]/u[0], u[2]/u[0], u[3]/u[0], p0 );
+  }
+  const real R0 = 0.15;
+  // distance of a body's initial centre (x0,y0) from the rotation axis
+  auto axdist = []( real x0, real y0 ){ return sqrt( (x0-0.5)*(x0-0.5) + (y0-0.5)*(y0-0.5) ); };
+  real r = axdist( 0.5, 0.25 );                    // cone
+  real kx = 0.5 + r*sin( t ), ky = 0.5 - r*cos( t );
+  r = axdist( 0.25, 0.5 );                         // hump
+  real hx = 0.5 + r*sin( t-M_PI/2.0 ), hy = 0.5 - r*cos( t-M_PI/2.0 );
+  r = axdist( 0.5, 0.75 );                         // slotted cylinder
+  real cx = 0.5 + r*sin( t+M_PI ), cy = 0.5 - r*cos( t+M_PI );
+  // corner points of the slot, rotated with the flow
+  real ax = 0.525, ay = cy - r*cos( std::asin( 0.025/r ) ), bx = 0.525, by = 0.8, gx = 0.475, gy = 0.8;
+  auto rotx = [t]( real px, real py ){ return 0.5 + cos(t)*(px-0.5) - sin(t)*(py-0.5); };
+  auto roty = [t]( real px, real py ){ return 0.5 + sin(t)*(px-0.5) + cos(t)*(py-0.5); };
+  real rax = rotx( ax, ay ), ray = roty( ax, ay ), rbx = rotx( bx, by ), rby = roty( bx, by ),
+       rgx = rotx( gx, gy ), rgy = roty( gx, gy );
+  real v1x = rbx-rax, v1y = rby-ray, v2x = rgx-rbx, v2y = rgy-rby;
+  real v1 = sqrt( v1x*v1x + v1y*v1y ), v2 = sqrt( v2x*v2x + v2y*v2y );
+  r = sqrt( (x-kx)*(x-kx) + (y-ky)*(y-ky) ) / R0;
+  if (r < 1.0) u[sc] = 0.6*(1.0-r);
+  r = sqrt( (x-hx)*(x-hx) + (y-hy)*(y-hy) ) / R0;
+  if (r < 1.0) u[sc] = 0.2*(1.0 + cos( M_PI*std::min( r, 1.0 ) ));
+  r = sqrt( (x-cx)*(x-cx) + (y-cy)*(y-cy) ) / R0;
+  // signed distances from the two slot sides
+  real d1 = (v1x*(y-ray) - (x-rax)*v1y) / v1;
+  real d2 = (v2x*(y-rby) - (x-rbx)*v2y) / v2;
+  if (r < 1.0 && (d1 > 0.05 || d1 < 0.0 || d2 < 0.0)) u[sc] = 0.6;
+  return u;
+}
+inline std::vector< real > src_slot_cyl( real x, real y, real z, real t ) { // :636-670: centripetal momentum source
+  auto u = ic_slot_cyl( x, y, z, t );
+  std::vector< real > s( u.size(), 0.0 );
+  if (cfg().solver == "chocg") { s[0] = -u[1]; s[1] = u[0]; }
+  else { s[1] = -u[2]; s[2] = u[1]; }
+  return s;
+}
+
 inline std::vector< real > ic_poiseuille( real, real y, real, real ) {      // :999-1026 (chocg)
   auto dpdx = -0.12;
   auto u = -dpdx * y * (1.0 - y) / 2.0 / cfg().mu;
@@ -289,6 +344,7 @@ inline ICFn IC() {                                                          // :
     if (p == "userdef") return []( real, real, real, real ){                // :53-65
       return std::vector< real >{ 0.0, cfg().ic_velocity[0], cfg().ic_velocity[1], cfg().ic_velocity[2] }; };
     if (p == "poiseuille") return []( real, real, real, real ){ return std::vector< real >{ 0, 0, 0, 0 }; };   // :1017-1019
+    if (p == "slot_cyl") return ic_slot_cyl;
     throw std::runtime_error( "oracle port: problem type ic not hooked up for lohcg: " + p );
   }
   if (cfg().solver == "chocg") {             // velocity unknowns only
@@ -301,6 +357,7 @@ inline ICFn IC() {                                                          // :
   if (p == "sedov") return ic_sedov;
   if (p == "sod") return ic_sod;
   if (p == "taylor_green") return ic_taylor_green;
+  if (p == "slot_cyl") return ic_slot_cyl;
   if (p == "vortical_flow") return ic_vortical_flow;
   if (p == "nonlinear_energy_growth") return ic_nleg;
   if (p == "rayleigh_taylor") return ic_rayleigh_taylor;
@@ -347,6 +404,7 @@ inline std::function< std::array< real, 3 >( real, real, real ) > PRESSURE_GRAD(
 inline ICFn SRC() {                                                         // :1299-1325
   const auto& p = cfg().problem;
   if (p == "taylor_green") return src_taylor_green;
+  if (p == "slot_cyl") return src_slot_cyl;
   if (p == "vortical_flow") return src_vortical_flow;
   if (p == "nonlinear_energy_growth") return src_nleg;
   if (p == "rayleigh_taylor") return src_rayleigh_taylor;

@@ -27,6 +27,7 @@ CASES = {
     "chocg_pidiv4": ("ChoCG/Poisson/unitcube_0pidiv4_1k.exo", None),
     "chocg_poiseuille": ("ChoCG/Poiseuille/poiseuille1tetz.exo", None),
     "sphere2_5k": ("ChoCG/Sphere/sphere2_5K.exo", None),
+    "unitsquare_3_6k": ("ZalCG/SlotCyl/unitsquare_01_3.6k.exo", None),
 }
 EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "chocg_poisson_const": "ChoCG/Poisson/diag_poisson_const.std",
@@ -58,7 +59,14 @@ EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "zalcg_bump": "ZalCG/Bump/diag.std",
               "chocg_inviscid_sphere": "ChoCG/Sphere/diag_inviscid_sphere.std",
               "chocg_viscous_sphere": "ChoCG/Sphere/diag_sphere_chocg_viscous_test.std",
-              "lohcg_viscous_sphere": "LohCG/Sphere/diag_sphere_lohcg_viscous_test.std"}
+              "lohcg_viscous_sphere": "LohCG/Sphere/diag_sphere_lohcg_viscous_test.std",
+              "riecg_slot_cyl": "RieCG/SlotCyl/diag.std",
+              "zalcg_slot_cyl": "ZalCG/SlotCyl/diag.std",
+              "kozcg_slot_cyl": "KozCG/SlotCyl/diag.std",
+              "chocg_slot_cyl": "ChoCG/SlotCyl/diag.std",
+              "chocg_slot_cyl_damp4": "ChoCG/SlotCyl/diag_damp4.std",
+              "lohcg_slot_cyl": "LohCG/SlotCyl/diag.std",
+              "lohcg_slot_cyl_damp4": "LohCG/SlotCyl/diag_damp4.std"}
 
 
 def flatten(exo):

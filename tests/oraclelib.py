@@ -46,6 +46,7 @@ class Cfg(C.Structure):
         ("alpha", C.c_double), ("kappa", C.c_double),
         ("r0", C.c_double), ("ce", C.c_double), ("beta", C.c_double * 3),
         ("soundspeed", C.c_double),
+        ("freezeflow", C.c_double), ("freezetime", C.c_double),
         ("theta", C.c_double), ("mom_iter", C.c_uint64), ("mom_tol", C.c_double), ("mom_pc", C.c_char * 16),
     ]
 
@@ -58,12 +59,13 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
              ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0),
              mu=0.0, dif=0.0, stab=True, rk=1, noslip=(), dirval=(), p_iter=10, p_tol=1.0e-3, p_pc="none",
              p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, alpha=0.0, kappa=0.0, r0=0.0, ce=0.0, beta=(0.0, 0.0, 0.0), pre=(), soundspeed=1.0,
-             theta=0.0, mom_iter=10, mom_tol=1.0e-3, mom_pc="none", cls=Cfg):
+             theta=0.0, mom_iter=10, mom_tol=1.0e-3, mom_pc="none", freezeflow=1.0, freezetime=0.0, cls=Cfg):
     """Control-file equivalent; defaults are the reference's (InciterConfig.cpp:1707-1757)."""
     c = cls()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term; c.alpha = alpha; c.kappa = kappa
     c.r0 = r0; c.ce = ce; c.soundspeed = soundspeed
+    c.freezeflow = freezeflow; c.freezetime = freezetime
     c.theta = theta; c.mom_iter = mom_iter; c.mom_tol = mom_tol; c.mom_pc = mom_pc.encode()
     for i in range(3):
         c.beta[i] = beta[i]
@@ -241,6 +243,28 @@ TCASES = {
     "riecg_rayleigh_taylor": dict(problem="rayleigh_taylor", alpha=1.0, beta=(1.0, 1.0, 1.0), p0=1.0, r0=1.0,
                                   kappa=1.0, gamma=5.0 / 3.0, cfl=0.5, nstep=50, dir_=_DIR6,
                                   mesh="riecg_taylor_green"),
+}
+# Scalar transport (slotted cylinder, cone and hump in a rotating flow, problems::slot_cyl): one transported
+# scalar next to the flow variables -- {RieCG,ZalCG,KozCG,ChoCG,LohCG}/SlotCyl/*.q on unitsquare_01_3.6k.exo.
+# The device path carries the flow variables only so far: these cases pin the ORACLE (port and reference
+# objects) for the scalar rows of SURVEY section 8 (a5).
+_SC6 = dict(problem="slot_cyl", ncomp=6, gamma=5.0 / 3.0, nstep=20, dir_=((1, 1, 1, 1, 1, 1, 1), (2, 1, 1, 1, 1, 1, 0)),
+            mesh="unitsquare_3_6k")
+_SCCHO = dict(solver="chocg", problem="slot_cyl", ncomp=4, gamma=5.0 / 3.0, cfl=0.9, nstep=20, flux="damp2", rk=3,
+              p_iter=300, p_tol=1.0e-2, p_pc="jacobi", p_hydrostat=0, dir_=((1, 1, 1, 1, 1), (2, 1, 1, 1, 0)),
+              mesh="unitsquare_3_6k")
+_SCLOH = dict(solver="lohcg", problem="slot_cyl", ncomp=5, gamma=5.0 / 3.0, cfl=0.9, nstep=20, flux="damp2", rk=3,
+              stab2=True, stab2coef=0.1, p_iter=300, p_tol=1.0e-2, p_pc="jacobi", p_hydrostat=0,
+              dir_=((1, 0, 1, 1, 1, 1), (2, 0, 1, 1, 1, 0)), mesh="unitsquare_3_6k")
+SCASES = {
+    "riecg_slot_cyl": dict(_SC6, cfl=0.9),
+    "riecg_slot_cyl_hllc": dict(_SC6, cfl=0.9, flux="hllc"),      # (no golden of its own: port vs reference objects only)
+    "zalcg_slot_cyl": dict(_SC6, solver="zalcg", cfl=0.5, freezeflow=3.0, freezetime=0.0),
+    "kozcg_slot_cyl": dict(_SC6, solver="kozcg", cfl=0.5, freezeflow=3.0, freezetime=0.0),
+    "chocg_slot_cyl": dict(_SCCHO),
+    "chocg_slot_cyl_damp4": dict(_SCCHO, flux="damp4", rk=4),
+    "lohcg_slot_cyl": dict(_SCLOH),
+    "lohcg_slot_cyl_damp4": dict(_SCLOH, flux="damp4", rk=4),
 }
 # ZalCG/Bump/bump.q: steady-state local time stepping (edge dt = mean of the end nodes' dt), stab2,
 # far-field BC, FCT with defaults; serial golden printed with 12 digits

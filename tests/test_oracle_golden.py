@@ -242,6 +242,29 @@ def test_chocg_semi_implicit_momentum_oracle_reproduces_reference_golden_diag():
     assert O.numdiff_ok(s.diag()[:, 1:], gold[:, 1:], 1.0e-7, 1.0e-7).all()
 
 
+@pytest.mark.parametrize("case", [c for c in O.SCASES if c != "riecg_slot_cyl_hllc"])
+def test_scalar_transport_oracle_reproduces_reference_golden_diag(case):
+    """One transported scalar next to the flow variables (problems::slot_cyl; MUSCL and Riemann fluxes of
+    scalars Riemann.cpp:145-209, TG/FCT of scalars with the flow frozen after the first step in
+    ZalCG/KozCG, scalar fluxes of chorin::rhs / lohner::rhs): {RieCG,ZalCG,KozCG,ChoCG,LohCG}/SlotCyl
+    goldens, serial runs, to the 12 printed digits. ChoCG/SlotCyl/diag.std (damp2) is held to the
+    reference's own acceptance test instead (diag.ndiff.cfg: rel 2e-3 | abs 1e-5 for the norms, abs 3e-3
+    for the residuals): the restatement is bit-identical to the reference's objects on this case (see
+    test_oracle_ref.py) yet the committed golden differs from both in the scalar columns at 4e-4."""
+    kw = O.SCASES[case]
+    gold = O.load_golden_diag(case)
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(int(gold[-1, 0]))
+    d = o.diag()
+    assert d.shape == gold.shape
+    if case == "chocg_slot_cyl":
+        assert O.numdiff_ok(d[:, 1:8], gold[:, 1:8], 1.0e-5, 2.0e-3).all()
+        assert O.numdiff_ok(d[:, 8:13], gold[:, 8:13], 3.0e-3, 1.0e-6).all()
+        assert (np.abs(d[:, 1:7] - gold[:, 1:7]) <= 2e-12 * np.abs(gold[:, 1:7])).all()      # t, dt, p, velocity
+    else:
+        assert (np.abs(d - gold) <= 2e-12 * np.abs(gold) + 1e-300).all()
+
+
 @pytest.mark.parametrize("case", list(O.HCASES))
 def test_lohcg_oracle_reproduces_reference_golden_diag(case):
     """LohCG (artificial-compressibility solver, unknowns p,u,v,w: Lohner edge operators, RK stages,

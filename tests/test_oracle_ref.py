@@ -57,6 +57,21 @@ def test_flux_variants_bit_identical(flux, stab2):
 
 
 @needs_ref
+@pytest.mark.parametrize("case", list(O.SCASES))
+def test_scalar_transport_port_is_bit_identical_to_reference_objects(case):
+    """problems::slot_cyl and the scalar parts of the Riemann/Zalesak/Kozak/Chorin/Lohner operators from the
+    reference's own translation units vs the restatement, under the same drivers."""
+    kw = O.SCASES[case]
+    mesh = O.load_mesh(kw["mesh"])
+    a = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    b = O.Oracle(mesh, O.make_cfg(**kw), "reference")
+    assert np.array_equal(a.get("u"), b.get("u"))
+    a.step(10); b.step(10)
+    assert np.array_equal(a.diag(), b.diag())
+    assert np.array_equal(a.get("u"), b.get("u"))
+
+
+@needs_ref
 @pytest.mark.parametrize("case", list(O.ZCASES) + list(O.ZSCASES))
 def test_zalcg_port_is_bit_identical_to_reference_objects(case):
     """zalesak::rhs from the reference's own Zalesak.cpp vs the restatement, under the same

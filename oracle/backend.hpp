@@ -87,6 +87,7 @@ inline void dirbc( Fields& U, real t, const Coords& coord, const std::vector< st
                    const std::vector< double >& val = {} )
 { physics::dirbc( 0, U, t, coord, {}, m, val ); }
 inline void noslipbc( Fields& U, const std::vector< std::size_t >& n, std::size_t pos ) { physics::noslipbc( U, n, pos ); }
+inline void phys_src( const Coords& coord, real t, Fields& U ) { if (auto s = problems::PHYS_SRC()) s( coord, t, U ); }
 
 using SupEdge = std::array< std::vector< std::size_t >, 3 >;
 using SupInt = std::array< std::vector< real >, 3 >;
@@ -161,6 +162,7 @@ using port::lax_refvel;
 using port::initialize;
 using port::dirbc;
 using port::noslipbc;
+using port::phys_src;
 using port::chorin_div;
 using port::chorin_vgrad;
 using port::chorin_grad;

@@ -19,6 +19,8 @@ Cfg to_cfg( const orc_cfg* c ) {
   Cfg k;
   k.problem = c->problem; k.flux = c->flux; k.ncomp = static_cast< std::size_t >( c->ncomp );
   k.soundspeed = c->soundspeed;
+  if (c->src_radius > 0.0) { k.src_location = {{ c->src_location[0], c->src_location[1], c->src_location[2] }};
+    k.src_radius = c->src_radius; k.src_release_time = c->src_release_time; }
   if (c->freezeflow != 0.0) k.freezeflow = c->freezeflow;
   k.freezetime = c->freezetime;
   k.theta = c->theta; k.mom_iter = c->mom_iter ? c->mom_iter : 10; k.mom_tol = c->mom_tol; if (c->mom_pc[0]) k.mom_pc = c->mom_pc;

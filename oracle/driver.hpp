@@ -752,6 +752,7 @@ class Chare {
         for (std::size_t c=0; c<u.nprop(); ++c)
           u(i,c) = un(i,c) - rkcoef[s] * ldt * rhs(i,c) / vol[i];
       }
+      be::phys_src( coord, t, u );                                         // RieCG.cpp:1023-1025
       BC( t + rkcoef[s] * dt );
     }
 
@@ -969,6 +970,7 @@ class Chare {
           for (std::size_t c=0; c<ncomp; ++c) a(i,c) = u(i,c) - ldt*rhs(i,c)/mvol[i]; } }
       un = u;                               // rhocompute( m_a, m_u ) sees new and old
       u = a;
+      be::phys_src( coord, t, u );          // ZalCG.cpp:1570-1572
       BC( t + dt );                         // BC( m_a, T+Dt )
       if (freezeflow > 1.0)                 // frozen flow: only the scalars advance (:1549,1577-1584)
         for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<5; ++c) u(i,c) = un(i,c);
@@ -1094,6 +1096,7 @@ class Chare {
       if (cfg.fct) { for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) a(i,c) = rhs(i,c) + a(i,c)/vol[i]; }
       else { for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<ncomp; ++c) a(i,c) = u(i,c) + dt*rhs(i,c)/vol[i]; }
       un = u; u = a;
+      be::phys_src( coord, t, u );          // KozCG.cpp:1162-1164
       BC( t + dt );
       if (freezeflow > 1.0)                 // frozen flow: only the scalars advance (KozCG.cpp:1141,1169-1176)
         for (std::size_t i=0; i<npoin; ++i) for (std::size_t c=0; c<5; ++c) u(i,c) = un(i,c);

@@ -56,6 +56,7 @@ typedef struct orc_cfg {
   /* problem_r0, problem_ce, problem_beta (nonlinear_energy_growth, rayleigh_taylor) */
   double r0, ce, beta[3];
   double soundspeed;          /* LohCG artificial speed of sound */
+  double src_location[3], src_radius, src_release_time;   /* problems::point_src; radius 0 = not configured */
   double freezeflow, freezetime;   /* ZalCG/KozCG scalar transport in a frozen flow; freezeflow 0 = 1.0 */
   /* ChoCG semi-implicit momentum solve: theta > 0 turns it on; iterations (0 = 10), tolerance, preconditioner */
   double theta; uint64_t mom_iter; double mom_tol; char mom_pc[16];

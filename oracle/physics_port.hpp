@@ -86,6 +86,9 @@ struct Cfg {
   std::vector< std::vector< real > > p_bc_dirval;    // { setid, val }
   std::vector< int > p_bc_sym;
   std::uint64_t p_hydrostat = ~0ULL;
+  // problems::point_src (problem = { src = { location, radius, release_time } }); radius < 0 = not configured
+  std::array< real, 3 > src_location{{ 0, 0, 0 }};
+  real src_radius = -1.0, src_release_time = 0.0;
   // ZalCG/KozCG: freeze the flow after freezetime and advance the scalars with freezeflow x dt
   real freezeflow = 1.0, freezetime = 0.0;
   // semi-implicit momentum solve of ChoCG (tag::theta, mom_iter, mom_tol, mom_pc)
@@ -353,7 +356,7 @@ inline ICFn IC() {                                                          // :
     if (p.find("poisson") != std::string::npos) return []( real, real, real, real ){ return std::vector< real >{ 0, 0, 0 }; };
     if (p == "poiseuille") return ic_poiseuille;
   }
-  if (p == "userdef") return ic_userdef;
+  if (p == "userdef" || p == "point_src") return ic_userdef;                // :1078-1079
   if (p == "sedov") return ic_sedov;
   if (p == "sod") return ic_sod;
   if (p == "taylor_green") return ic_taylor_green;
@@ -409,6 +412,21 @@ inline ICFn SRC() {                                                         // :
   if (p == "nonlinear_energy_growth") return src_nleg;
   if (p == "rayleigh_taylor") return src_rayleigh_taylor;
   return {};
+}
+
+//! problems::PHYS_SRC() -> point_src::src, Problems.cpp:764-823: a source that sets the first scalar to 1
+//! inside a sphere from the release time on, applied directly to the solution (not a rhs term)
+inline void phys_src( const Coords& coord, real t, Fields& U ) {
+  if (cfg().problem != "point_src") return;
+  if (U.nprop() == 5) return;
+  if (cfg().src_radius < 0.0) return;
+  if (t < cfg().src_release_time) return;
+  std::size_t sc = cfg().solver == "chocg" ? 3 : cfg().solver == "lohcg" ? 4 : 5;
+  const auto& s = cfg().src_location; auto sr = cfg().src_radius;
+  for (std::size_t i=0; i<U.nunk(); ++i) {
+    auto rx = s[0] - coord[0][i], ry = s[1] - coord[1][i], rz = s[2] - coord[2][i];
+    if (rx*rx + ry*ry + rz*rz < sr*sr) U(i,sc) = 1.0;
+  }
 }
 
 inline void initialize( const Coords& coord, Fields& U, real t ) {          // :1134-1167

@@ -60,10 +60,16 @@ void set_cfg( const Cfg& c )
   g.get< tag::rescomp >() = c.rescomp;
   if (c.solver == "chocg" || c.solver == "lohcg")
     g.get< tag::ic, tag::velocity >() = std::vector< double >{ c.ic_velocity[0], c.ic_velocity[1], c.ic_velocity[2] };
-  else if (c.problem == "userdef") {
+  else if (c.problem == "userdef" || c.problem == "point_src") {
     g.get< tag::ic, tag::density >() = c.ic_density;
     g.get< tag::ic, tag::pressure >() = c.ic_pressure;
     g.get< tag::ic, tag::velocity >() = std::vector< double >{ c.ic_velocity[0], c.ic_velocity[1], c.ic_velocity[2] };
+  }
+  if (c.src_radius >= 0.0) {
+    auto& s = g.get< tag::problem_src >();
+    s.get< tag::location >() = std::vector< double >{ c.src_location[0], c.src_location[1], c.src_location[2] };
+    s.get< tag::radius >() = c.src_radius;
+    s.get< tag::release_time >() = c.src_release_time;
   }
   port::set_cfg( c );
 }

@@ -28,6 +28,7 @@ CASES = {
     "chocg_poiseuille": ("ChoCG/Poiseuille/poiseuille1tetz.exo", None),
     "sphere2_5k": ("ChoCG/Sphere/sphere2_5K.exo", None),
     "unitsquare_3_6k": ("ZalCG/SlotCyl/unitsquare_01_3.6k.exo", None),
+    "riecg_canyon": ("RieCG/Canyon/canyon.exo", "RieCG/Canyon/diag.std"),
 }
 EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "chocg_poisson_const": "ChoCG/Poisson/diag_poisson_const.std",

@@ -46,6 +46,7 @@ class Cfg(C.Structure):
         ("alpha", C.c_double), ("kappa", C.c_double),
         ("r0", C.c_double), ("ce", C.c_double), ("beta", C.c_double * 3),
         ("soundspeed", C.c_double),
+        ("src_location", C.c_double * 3), ("src_radius", C.c_double), ("src_release_time", C.c_double),
         ("freezeflow", C.c_double), ("freezetime", C.c_double),
         ("theta", C.c_double), ("mom_iter", C.c_uint64), ("mom_tol", C.c_double), ("mom_pc", C.c_char * 16),
     ]
@@ -59,13 +60,17 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
              ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0),
              mu=0.0, dif=0.0, stab=True, rk=1, noslip=(), dirval=(), p_iter=10, p_tol=1.0e-3, p_pc="none",
              p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, alpha=0.0, kappa=0.0, r0=0.0, ce=0.0, beta=(0.0, 0.0, 0.0), pre=(), soundspeed=1.0,
-             theta=0.0, mom_iter=10, mom_tol=1.0e-3, mom_pc="none", freezeflow=1.0, freezetime=0.0, cls=Cfg):
+             theta=0.0, mom_iter=10, mom_tol=1.0e-3, mom_pc="none", freezeflow=1.0, freezetime=0.0,
+             src_location=(0.0, 0.0, 0.0), src_radius=0.0, src_release_time=0.0, cls=Cfg):
     """Control-file equivalent; defaults are the reference's (InciterConfig.cpp:1707-1757)."""
     c = cls()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term; c.alpha = alpha; c.kappa = kappa
     c.r0 = r0; c.ce = ce; c.soundspeed = soundspeed
     c.freezeflow = freezeflow; c.freezetime = freezetime
+    c.src_radius = src_radius; c.src_release_time = src_release_time
+    for i in range(3):
+        c.src_location[i] = src_location[i]
     c.theta = theta; c.mom_iter = mom_iter; c.mom_tol = mom_tol; c.mom_pc = mom_pc.encode()
     for i in range(3):
         c.beta[i] = beta[i]
@@ -256,6 +261,12 @@ _SCCHO = dict(solver="chocg", problem="slot_cyl", ncomp=4, gamma=5.0 / 3.0, cfl=
 _SCLOH = dict(solver="lohcg", problem="slot_cyl", ncomp=5, gamma=5.0 / 3.0, cfl=0.9, nstep=20, flux="damp2", rk=3,
               stab2=True, stab2coef=0.1, p_iter=300, p_tol=1.0e-2, p_pc="jacobi", p_hydrostat=0,
               dir_=((1, 0, 1, 1, 1, 1), (2, 0, 1, 1, 1, 0)), mesh="unitsquare_3_6k")
+# RieCG/Canyon/canyon.q: dispersion from a point source in a street canyon (problems::point_src: the scalar is
+# set to 1 inside a sphere every stage), pressure BCs at inlet/outlet, symmetry walls; golden printed with 6 digits
+CANYON = dict(problem="point_src", ncomp=6, gamma=1.4, cfl=0.5, nstep=50, sym=(1, 2, 3, 4, 5),
+              pre=((6, 1.225, 1.0e5), (7, 1.225, 0.9e5)), ic_density=1.225, ic_pressure=1.0e5,
+              ic_velocity=(0.0, 0.0, 0.0), src_location=(3.0, 0.01, 0.0), src_radius=0.2, src_release_time=0.0,
+              diag_iter=10, mesh="riecg_canyon")
 SCASES = {
     "riecg_slot_cyl": dict(_SC6, cfl=0.9),
     "riecg_slot_cyl_hllc": dict(_SC6, cfl=0.9, flux="hllc"),      # (no golden of its own: port vs reference objects only)

@@ -57,6 +57,19 @@ def test_flux_variants_bit_identical(flux, stab2):
 
 
 @needs_ref
+def test_point_source_port_is_bit_identical_to_reference_objects():
+    """problems::PHYS_SRC (point_src::src) from the reference's Problems.cpp vs the restatement."""
+    kw = O.CANYON
+    mesh = O.load_mesh(kw["mesh"])
+    a = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    b = O.Oracle(mesh, O.make_cfg(**kw), "reference")
+    a.step(20); b.step(20)
+    assert np.array_equal(a.diag(), b.diag())
+    assert np.array_equal(a.get("u"), b.get("u"))
+    assert a.get("u").reshape(-1, 6)[:, 5].max() == 1.0          # the source has been applied
+
+
+@needs_ref
 @pytest.mark.parametrize("case", list(O.SCASES))
 def test_scalar_transport_port_is_bit_identical_to_reference_objects(case):
     """problems::slot_cyl and the scalar parts of the Riemann/Zalesak/Kozak/Chorin/Lohner operators from the

@@ -371,7 +371,8 @@ class ChoRun : public Run {
             for (std::size_t i=0; i<c_.u.nunk(); ++i)
               for (std::size_t c=0; c<c_.u.nprop(); ++c) c_.u(i,c) = c_.un(i,c) - sdt*c_.rhs(i,c)/c_.vol[i]; }
         } else msolve();
-        for (auto& cp : ch) cp->BC( t + rk[stage] * dt );                  // pred :1647-1668
+        for (auto& cp : ch) { be::phys_src( cp->coord, t, cp->u );         // pred :1647-1668
+          cp->BC( t + rk[stage] * dt ); }
         if (cfg.flux == "damp4") { velgrad(); for (auto& cp : ch) fingrad( *cp, cp->grad ); }   // corr :1677
       }
       div_u();

@@ -235,6 +235,7 @@ class LohRun : public Run {
           auto sdt = rk[stage] * dt;
           for (std::size_t i=0; i<c_.u.nunk(); ++i)
             for (std::size_t c=0; c<c_.u.nprop(); ++c) c_.u(i,c) = c_.un(i,c) - sdt*c_.rhs(i,c)/c_.vol[i];
+          be::phys_src( c_.coord, t, c_.u );                              // :1615-1617
           c_.BC( t + rk[stage] * dt ); }
       }
       lohdiag();

@@ -344,15 +344,19 @@ inline std::vector< real > ic_poiseuille( real, real y, real, real ) {      // :
 inline ICFn IC() {                                                          // :1071-1108
   const auto& p = cfg().problem;
   if (cfg().solver == "lohcg") {             // unknowns (p,u,v,w)
-    if (p == "userdef") return []( real, real, real, real ){                // :53-65
-      return std::vector< real >{ 0.0, cfg().ic_velocity[0], cfg().ic_velocity[1], cfg().ic_velocity[2] }; };
+    if (p == "userdef" || p == "point_src") return []( real, real, real, real ){      // :53-65
+      std::vector< real > u( cfg().ncomp, 0.0 );
+      u[1] = cfg().ic_velocity[0]; u[2] = cfg().ic_velocity[1]; u[3] = cfg().ic_velocity[2];
+      return u; };
     if (p == "poiseuille") return []( real, real, real, real ){ return std::vector< real >{ 0, 0, 0, 0 }; };   // :1017-1019
     if (p == "slot_cyl") return ic_slot_cyl;
     throw std::runtime_error( "oracle port: problem type ic not hooked up for lohcg: " + p );
   }
   if (cfg().solver == "chocg") {             // velocity unknowns only
-    if (p == "userdef") return []( real, real, real, real ){                // :44-52
-      return std::vector< real >{ cfg().ic_velocity[0], cfg().ic_velocity[1], cfg().ic_velocity[2] }; };
+    if (p == "userdef" || p == "point_src") return []( real, real, real, real ){      // :44-52
+      std::vector< real > u( cfg().ncomp, 0.0 );
+      u[0] = cfg().ic_velocity[0]; u[1] = cfg().ic_velocity[1]; u[2] = cfg().ic_velocity[2];
+      return u; };
     if (p.find("poisson") != std::string::npos) return []( real, real, real, real ){ return std::vector< real >{ 0, 0, 0 }; };
     if (p == "poiseuille") return ic_poiseuille;
   }

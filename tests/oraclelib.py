@@ -267,6 +267,10 @@ CANYON = dict(problem="point_src", ncomp=6, gamma=1.4, cfl=0.5, nstep=50, sym=(1
               pre=((6, 1.225, 1.0e5), (7, 1.225, 0.9e5)), ic_density=1.225, ic_pressure=1.0e5,
               ic_velocity=(0.0, 0.0, 0.0), src_location=(3.0, 0.01, 0.0), src_radius=0.2, src_release_time=0.0,
               diag_iter=10, mesh="riecg_canyon")
+# ChoCG/Sphere/sphere_point_src.q: the same point source in the projection solver (3 velocities + scalar)
+SPHERE_SRC = dict(solver="chocg", problem="point_src", ncomp=4, nstep=20, cfl=0.5, flux="damp2", p_iter=300, p_tol=1.0e-3,
+                  p_pc="jacobi", p_dir=((3, 1),), ic_velocity=(1.0, 0.0, 0.0), dir_=((2, 1, 0, 0, 0),), sym=(1, 4),
+                  src_location=(-4.95, 0.0, 0.0), src_radius=2.0, src_release_time=0.0, diag_iter=5, mesh="sphere2_5k")
 SCASES = {
     "riecg_slot_cyl": dict(_SC6, cfl=0.9),
     "riecg_slot_cyl_hllc": dict(_SC6, cfl=0.9, flux="hllc"),      # (no golden of its own: port vs reference objects only)

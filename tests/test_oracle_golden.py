@@ -282,6 +282,18 @@ def test_point_source_oracle_reproduces_reference_golden_diag():
     assert np.abs(d[:, 14]).max() < 1e-12 and np.abs(gold[:, 14]).max() < 1e-12
 
 
+def test_chocg_point_source_oracle_reproduces_reference_golden_diag():
+    """ChoCG with a transported scalar from a point source upstream of a sphere (ChoCG::pred :1655-1657):
+    tests/regression/inciter/ChoCG/Sphere/diag_sphere_point_src.std, every 5th step, 12 printed digits."""
+    kw = O.SPHERE_SRC
+    gold = O.load_golden_diag("chocg_sphere_point_src")
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(int(gold[-1, 0]) + 1)
+    d = o.diag()
+    assert d.shape == gold.shape
+    assert (np.abs(d - gold) <= 2e-12 * np.abs(gold)).all()
+
+
 @pytest.mark.parametrize("case", list(O.HCASES))
 def test_lohcg_oracle_reproduces_reference_golden_diag(case):
     """LohCG (artificial-compressibility solver, unknowns p,u,v,w: Lohner edge operators, RK stages,

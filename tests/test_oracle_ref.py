@@ -67,6 +67,13 @@ def test_point_source_port_is_bit_identical_to_reference_objects():
     assert np.array_equal(a.diag(), b.diag())
     assert np.array_equal(a.get("u"), b.get("u"))
     assert a.get("u").reshape(-1, 6)[:, 5].max() == 1.0          # the source has been applied
+    kw = O.SPHERE_SRC
+    mesh = O.load_mesh(kw["mesh"])
+    a = O.Oracle(mesh, O.make_cfg(**kw), "port")
+    b = O.Oracle(mesh, O.make_cfg(**kw), "reference")
+    a.step(10); b.step(10)
+    assert np.array_equal(a.diag(), b.diag())
+    assert np.array_equal(a.get("u"), b.get("u"))
 
 
 @needs_ref

@@ -19,7 +19,10 @@ FILES = {"riecg_sod": os.path.join(GOLDEN, "riecg_sod.exo"),
          "riecg_taylor_green": REF + "/RieCG/TaylorGreen/unitcube_1k.exo",
          "laxcg_bump": REF + "/LaxCG/Bump/bump.exo",
          "chocg_poiseuille": REF + "/ChoCG/Poiseuille/poiseuille1tetz.exo",
-         "chocg_pidiv4": REF + "/ChoCG/Poisson/unitcube_0pidiv4_1k.exo"}
+         "chocg_pidiv4": REF + "/ChoCG/Poisson/unitcube_0pidiv4_1k.exo",
+         "sphere2_5k": REF + "/ChoCG/Sphere/sphere2_5K.exo",
+         "unitsquare_3_6k": REF + "/ZalCG/SlotCyl/unitsquare_01_3.6k.exo",
+         "riecg_canyon": REF + "/RieCG/Canyon/canyon.exo"}
 
 
 def sets_of(m):

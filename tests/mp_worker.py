@@ -112,7 +112,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     if mode == "cg":
         return cg_main(out, rank, world, local)
-    kw = {**O.CASES, **O.LCASES}[case]
+    kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.HCASES}[case]
     mesh = O.load_mesh(kw.get("mesh", case))
     hm = fixture_to_host_mesh(mesh)
     part = H.rcb(hm["coord"], hm["tets"], world)
@@ -144,6 +144,10 @@ def main():
         res["launches"] = s.ctx().launch_count()
     for n in ("gid", "vol", "v", "symbcnodes", "symbcnorms", "dsupint0", "dsupedge0"):
         res[n] = s.get(n).tolist()
+    if kw.get("solver") in ("chocg", "lohcg"):        # partition-level pieces of the projection solvers
+        for n in ("dsupint2", "dsupedge2", "dirbcmasks", "dirbcval", "dirbcmaskp", "dirbcvalp", "noslipbcnodes",
+                  "plhs_ia", "plhs_ja", "plhs_a"):
+            res[n] = s.get(n).tolist()
     res["meshvol"] = s.scalar("meshvol")
     res["part"] = part.tolist() if rank == 0 else None
     json.dump(res, open("%s.%d.json" % (out, rank), "w"))

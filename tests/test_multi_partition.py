@@ -27,7 +27,7 @@ def launch(mode, case, nsteps, tmp_path, world=2):
 
 
 def oracle_for(case, part, world):
-    kw = {**O.CASES, **O.LCASES}[case]
+    kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.HCASES}[case]
     return O.Oracle(O.load_mesh(kw.get("mesh", case)), O.make_cfg(**kw), "port", nchare=world,
                     target=np.asarray(part, np.uint64))
 
@@ -54,6 +54,34 @@ def test_two_partitions_host_logic_gloo(case, tmp_path):
     assert o.scalar("nchare") == 2
     assert len(o.get("commmap", 0)) > 2           # the partitions do share nodes
     check_setup(res, o, 2)
+
+
+@pytest.mark.parametrize("case", ["chocg_poiseuille_damp2", "chocg_ldc", "lohcg_poiseuille_damp4"])
+def test_two_partitions_projection_solver_setup_gloo(case, tmp_path):
+    """The partition-level setup of the projection solvers (groundwork for their multi-GPU path; the device
+    time loop of ChoCG/LohCG is single-partition so far): per-partition stride-5 / stride-4 edge integrals
+    incl. the Laplacian term (partial sums on shared edges), Dirichlet masks and values of velocity and
+    pressure, no-slip nodes and the partition's part of the pressure Poisson matrix -- bitwise equal to the
+    oracle's chares on the same element partition."""
+    res = launch("host", case, 0, tmp_path)
+    o = oracle_for(case, res[0]["part"], 2)
+    assert o.scalar("nchare") == 2 and len(o.get("commmap", 0)) > 2
+    check_setup(res, o, 2)
+    st = 4 if case.startswith("lohcg") else 5
+    for k in range(2):
+        r = res[k]
+        def singles(e, d):
+            e = np.asarray(e).reshape(-1, 2); d = np.asarray(d).reshape(-1, st)
+            return sorted((tuple(a), tuple(b)) for a, b in zip(e.tolist(), d.tolist()))
+        assert singles(r["dsupedge2"], r["dsupint2"]) == singles(o.get("dsupedge2", k), o.get("dsupint2", k))
+        for n in ("plhs_ia", "plhs_ja", "noslipbcnodes"):
+            assert np.array_equal(np.asarray(r[n], np.uint64), o.get(n, k)), n
+        assert np.array_equal(np.asarray(r["plhs_a"]), o.get("plhs_a", k))
+        for masks, vals, w in (("dirbcmasks", "dirbcval", (3 if st == 5 else 4) + 1), ("dirbcmaskp", "dirbcvalp", 2)):
+            mo, ms = o.get(masks, k).reshape(-1, w), np.asarray(r[masks], np.uint64).reshape(-1, w)
+            assert np.array_equal(mo[np.argsort(mo[:, 0])], ms[np.argsort(ms[:, 0])]), masks
+            vo, vs = o.get(vals, k).reshape(-1, w), np.asarray(r[vals]).reshape(-1, w)
+            assert np.array_equal(vo[np.argsort(vo[:, 0])], vs[np.argsort(vs[:, 0])]), vals
 
 
 @pytest.mark.gpu

@@ -62,6 +62,9 @@ EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "chocg_viscous_sphere": "ChoCG/Sphere/diag_sphere_chocg_viscous_test.std",
               "lohcg_viscous_sphere": "LohCG/Sphere/diag_sphere_lohcg_viscous_test.std",
               "chocg_sphere_point_src": "ChoCG/Sphere/diag_sphere_point_src.std",
+              "riecg_rayleigh_taylor_st": "RieCG/RayleighTaylor/diag_st.std",
+              "kozcg_rayleigh_taylor_st": "KozCG/RayleighTaylor/diag_st.std",
+              "riecg_canyon_farfield": "RieCG/Canyon/diag_farfield.std",
               "riecg_slot_cyl": "RieCG/SlotCyl/diag.std",
               "zalcg_slot_cyl": "ZalCG/SlotCyl/diag.std",
               "kozcg_slot_cyl": "KozCG/SlotCyl/diag.std",

@@ -282,6 +282,25 @@ def test_point_source_oracle_reproduces_reference_golden_diag():
     assert np.abs(d[:, 14]).max() < 1e-12 and np.abs(gold[:, 14]).max() < 1e-12
 
 
+@pytest.mark.parametrize("case", list(O.OCASES))
+def test_further_goldens_on_the_oracle(case):
+    """Stationary Rayleigh-Taylor (kappa = 0; RieCG/RayleighTaylor/diag_st.std, KozCG/RayleighTaylor/
+    diag_st.std, printed with 9 digits) and Canyon with far-field BCs (RieCG/Canyon/diag_farfield.std,
+    6 digits, every 10th step; the scalar's increment norm is rounding noise and only bounded)."""
+    kw = O.OCASES[case]
+    gold = O.load_golden_diag(case)
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    o.step(int(gold[-1, 0]) + (1 if "canyon" in case else 0))
+    d = o.diag()
+    assert d.shape == gold.shape
+    if "canyon" in case:
+        cols = [c for c in range(gold.shape[1]) if c != 14]
+        assert (np.abs(d[:, cols] - gold[:, cols]) <= 6e-7 * np.abs(gold[:, cols])).all()
+        assert np.abs(d[:, 14]).max() < 1e-12
+    else:
+        assert (np.abs(d - gold) <= 6e-9 * np.abs(gold) + 1e-300).all()
+
+
 def test_chocg_point_source_oracle_reproduces_reference_golden_diag():
     """ChoCG with a transported scalar from a point source upstream of a sphere (ChoCG::pred :1655-1657):
     tests/regression/inciter/ChoCG/Sphere/diag_sphere_point_src.std, every 5th step, 12 printed digits."""

@@ -271,14 +271,6 @@ CANYON = dict(problem="point_src", ncomp=6, gamma=1.4, cfl=0.5, nstep=50, sym=(1
 SPHERE_SRC = dict(solver="chocg", problem="point_src", ncomp=4, nstep=20, cfl=0.5, flux="damp2", p_iter=300, p_tol=1.0e-3,
                   p_pc="jacobi", p_dir=((3, 1),), ic_velocity=(1.0, 0.0, 0.0), dir_=((2, 1, 0, 0, 0),), sym=(1, 4),
                   src_location=(-4.95, 0.0, 0.0), src_radius=2.0, src_release_time=0.0, diag_iter=5, mesh="sphere2_5k")
-# further goldens pinned on the oracle only (same code paths as cases above; not in the GPU lists yet):
-# stationary Rayleigh-Taylor (kappa = 0) through RieCG and KozCG, Canyon with far-field instead of pressure BCs
-OCASES = {
-    "riecg_rayleigh_taylor_st": dict(TCASES["riecg_rayleigh_taylor"], kappa=0.0, nstep=10),
-    "kozcg_rayleigh_taylor_st": dict(KTCASES["kozcg_rayleigh_taylor"], kappa=0.0, nstep=10),
-    "riecg_canyon_farfield": dict({k: v for k, v in CANYON.items() if k != "pre"}, far=(6, 7), far_density=1.225,
-                                  far_pressure=1.0e5, far_velocity=(10.0, 0.0, 0.0)),
-}
 SCASES = {
     "riecg_slot_cyl": dict(_SC6, cfl=0.9),
     "riecg_slot_cyl_hllc": dict(_SC6, cfl=0.9, flux="hllc"),      # (no golden of its own: port vs reference objects only)
@@ -302,6 +294,14 @@ ZSCASES = {
 KTCASES = {
     "kozcg_nleg": dict(TCASES["riecg_nleg"], solver="kozcg", fct=False),
     "kozcg_rayleigh_taylor": dict(TCASES["riecg_rayleigh_taylor"], solver="kozcg", fct=False),
+}
+# further goldens pinned on the oracle only (same code paths as cases above; not in the GPU lists yet):
+# stationary Rayleigh-Taylor (kappa = 0) through RieCG and KozCG, Canyon with far-field instead of pressure BCs
+OCASES = {
+    "riecg_rayleigh_taylor_st": dict(TCASES["riecg_rayleigh_taylor"], kappa=0.0, nstep=10),
+    "kozcg_rayleigh_taylor_st": dict(KTCASES["kozcg_rayleigh_taylor"], kappa=0.0, nstep=10),
+    "riecg_canyon_farfield": dict({k: v for k, v in CANYON.items() if k != "pre"}, far=(6, 7), far_density=1.225,
+                                  far_pressure=1.0e5, far_velocity=(10.0, 0.0, 0.0)),
 }
 # RieCG/Pipe/pipe.q: user-defined quiescent IC, symmetry walls, pressure BCs at inlet and outlet
 # (physics::prebc, BC.cpp:222-241); serial golden printed with 12 digits

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CUDA_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+CUDA_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fopenmp",
               "-Xcompiler", "-fPIC", "-shared", "-Xlinker", "-soname=libxyst_b200.so",
               "-I" + os.path.join(ROOT, "include")]
 

@@ -47,7 +47,16 @@ __device__ __forceinline__ void cp_async8( double* smem_dst, const double* gsrc 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile( "cp.async.commit_group;" ::: "memory" ); }
 // flat index of tk::Fields G(p,i), i = c*3+j, in the structure-of-arrays gradient storage
-__host__ __device__ __forceinline__ size_t gidx( int i, size_t p, size_t NP ) { return (size_t)i*NP + p; }
+// Gradients are stored as eight 16-byte pairs per node, pair k of node p at G2[k*NP+p]:
+// (g0,g1) ... (g12,g13) (g14,-) -- an edge's other end is gathered with 8 LDG.128.
+constexpr int NGP = 8;
+__host__ __device__ __forceinline__ size_t gidx( int i, size_t p, size_t NP ) { return ((size_t)(i>>1)*NP + p)*2 + (size_t)(i&1); }
+__device__ __forceinline__ void store_g( double* __restrict__ G, size_t NP, size_t p, const double g[15] ) {
+  double2* G2 = reinterpret_cast< double2* >( G );
+  #pragma unroll
+  for (int k=0; k<7; ++k) G2[(size_t)k*NP+p] = make_double2( g[2*k], g[2*k+1] );
+  G[gidx( 14, p, NP )] = g[14];
+}
 template< int N > __device__ __forceinline__ void cp_async_wait() { asm volatile( "cp.async.wait_group %0;" :: "n"( N ) : "memory" ); }
 
 // Primitive variables and coordinates of a node as four 16-byte pairs, pair k of node p at
@@ -85,26 +94,30 @@ __device__ __forceinline__ void load_f( const double* __restrict__ F, size_t nsl
 }
 
 // reference layout [node][comp] -> SoA state + primitives
-__global__ void k_set_state( size_t n, size_t NP, const double* __restrict__ A,
+// (n2o: internal node id -> the caller's, or null if the two orders are the same)
+__global__ void k_set_state( size_t n, size_t NP, const double* __restrict__ A, const int* __restrict__ n2o,
                              double* __restrict__ U, double* __restrict__ W, Mode M )
 {
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= n) return;
   double u[NC], w[NC];
+  size_t o = n2o ? (size_t)n2o[p] : p;
   #pragma unroll
-  for (int c=0; c<NC; ++c) u[c] = A[p*NC+c];
+  for (int c=0; c<NC; ++c) u[c] = A[o*NC+c];
   primitive_of( u, w, M );
   #pragma unroll
   for (int c=0; c<NC; ++c) U[c*NP+p] = u[c];
   store_w( W, NP, p, w );
 }
 
-__global__ void k_get_state( size_t n, size_t NP, const double* __restrict__ U, double* __restrict__ A )
+__global__ void k_get_state( size_t n, size_t NP, const double* __restrict__ U, const int* __restrict__ n2o,
+                             double* __restrict__ A )
 {
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= n) return;
+  size_t o = n2o ? (size_t)n2o[p] : p;
   #pragma unroll
-  for (int c=0; c<NC; ++c) A[p*NC+c] = U[c*NP+p];
+  for (int c=0; c<NC; ++c) A[o*NC+c] = U[c*NP+p];
 }
 
 // ---------------------------------------------------------------------------------
@@ -285,8 +298,7 @@ k_grad_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
   int b = bslot[p];
   if (b >= 0) {
     if (defer_bnd) {          // boundary part and division follow in k_grad_bfix (same operation order)
-      #pragma unroll
-      for (int i=0; i<15; ++i) G[i*NP+p] = acc[i];
+      store_g( G, NP, p, acc );
       return;
     }
     #pragma unroll
@@ -294,7 +306,8 @@ k_grad_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
   }
   double vp = vol[p];
   #pragma unroll
-  for (int i=0; i<15; ++i) G[i*NP+p] = acc[i]/vp;
+  for (int i=0; i<15; ++i) acc[i] /= vp;
+  store_g( G, NP, p, acc );
 }
 
 // boundary nodes: G = (domain sum + boundary sum) / vol, once both are known
@@ -388,13 +401,14 @@ __device__ __forceinline__ double fast_rcp( double x )
 }
 
 template< bool EXACT >
-__device__ __forceinline__ void vanleer( double d1, double d2, double d3, double& incL, double& incR )
+__device__ __forceinline__ void vanleer( double d1, double d2, double d3, double& incL, double& incR,
+                                         const double MUSCL_EPS_ = MUSCL_EPS )
 {
   if (EXACT) {
-    double rcL = (d2 + MUSCL_EPS) / (d1 + MUSCL_EPS);
-    double rcR = (d2 + MUSCL_EPS) / (d3 + MUSCL_EPS);
-    double rLinv = (d1 + MUSCL_EPS) / (d2 + MUSCL_EPS);
-    double rRinv = (d3 + MUSCL_EPS) / (d2 + MUSCL_EPS);
+    double rcL = (d2 + MUSCL_EPS_) / (d1 + MUSCL_EPS_);
+    double rcR = (d2 + MUSCL_EPS_) / (d3 + MUSCL_EPS_);
+    double rLinv = (d1 + MUSCL_EPS_) / (d2 + MUSCL_EPS_);
+    double rRinv = (d3 + MUSCL_EPS_) / (d2 + MUSCL_EPS_);
     double phiL = (fabs(rcL) + rcL) / (fabs(rcL) + 1.0);
     double phiR = (fabs(rcR) + rcR) / (fabs(rcR) + 1.0);
     double phi_L_inv = (fabs(rLinv) + rLinv) / (fabs(rLinv) + 1.0);
@@ -406,7 +420,7 @@ __device__ __forceinline__ void vanleer( double d1, double d2, double d3, double
     // phi(a/b) = 2a/(a+b), phi(b/a) = 2b/(a+b) for same-signed a, b (else 0), so that
     // inc = 0.25 [ d1 (1-k) 2a + d2 (1+k) 2b ] / (a+b): one reciprocal, five multiply-adds per side
     const double c1 = 0.5*(1.0-MUSCL_K), c2 = 0.5*(1.0+MUSCL_K);
-    double a = d2 + MUSCL_EPS, bL = d1 + MUSCL_EPS, bR = d3 + MUSCL_EPS;
+    double a = d2 + MUSCL_EPS_, bL = d1 + MUSCL_EPS_, bR = d3 + MUSCL_EPS_;
     double t2 = c2*d2;
     double vL = fma( c1*d1, a, t2*bL ) * fast_rcp( a + bL );
     double vR = fma( c1*d3, a, t2*bR ) * fast_rcp( a + bR );
@@ -416,7 +430,7 @@ __device__ __forceinline__ void vanleer( double d1, double d2, double d3, double
     incL = a*bL > 0.0 ? vL : 0.0;
     incR = a*bR > 0.0 ? vR : 0.0;
 #else
-    double a = d2 + MUSCL_EPS, bL = d1 + MUSCL_EPS, bR = d3 + MUSCL_EPS;
+    double a = d2 + MUSCL_EPS_, bL = d1 + MUSCL_EPS_, bR = d3 + MUSCL_EPS_;
     bool sL = (a > 0.0 && bL > 0.0) || (a < 0.0 && bL < 0.0);
     bool sR = (a > 0.0 && bR > 0.0) || (a < 0.0 && bR < 0.0);
     double iL = 2.0 * fast_rcp( a + bL ), iR = 2.0 * fast_rcp( a + bR );
@@ -431,7 +445,8 @@ __device__ __forceinline__ void vanleer( double d1, double d2, double d3, double
 // gp/gq: the 15 gradient components of the two end nodes, element i at gp[i*gsp], gq[i*gsq]
 template< bool EXACT >
 __device__ __forceinline__ void muscl( const double* gp, int gsp, const double* gq, int gsq,
-                                       const double vw[3], double l[NC], double r[NC] )
+                                       const double vw[3], double l[NC], double r[NC],
+                                       const double eps = MUSCL_EPS )
 {
   double ls[NC], rs[NC], d1[NC], d3[NC];
   #pragma unroll
@@ -443,7 +458,7 @@ __device__ __forceinline__ void muscl( const double* gp, int gsp, const double* 
     d1[c] = 2.0 * g1 - delta2;
     d3[c] = 2.0 * g2 - delta2;
     double incL, incR;
-    vanleer< EXACT >( d1[c], delta2, d3[c], incL, incR );
+    vanleer< EXACT >( d1[c], delta2, d3[c], incL, incR, eps );
     l[c] += incL;
     r[c] -= incR;
   }
@@ -709,7 +724,7 @@ k_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __r
   double* gp = sg + threadIdx.x;
   double* gq = gp + 15*FLUX_THREADS;
   #pragma unroll
-  for (int i=0; i<15; ++i) { cp_async8( gp + i*FLUX_THREADS, G + i*NP + p ); cp_async8( gq + i*FLUX_THREADS, G + i*NP + q ); }
+  for (int i=0; i<15; ++i) { cp_async8( gp + i*FLUX_THREADS, G + gidx( i, p, NP ) ); cp_async8( gq + i*FLUX_THREADS, G + gidx( i, q, NP ) ); }
   cp_async_commit();
   double n[3] = { D[e], D[nslot+e], D[2*nslot+e] };
   double l[NC], r[NC], vw[3], xp[3];
@@ -767,16 +782,18 @@ struct StageArgs { double rk, dt; const double* dtp; int stage; Mode M; };
 
 template< bool LAX >
 __device__ __forceinline__ void node_update( size_t p, size_t NP, const double acc[NC], double vp,
-    const double* __restrict__ Un, double* __restrict__ U, double* __restrict__ W,
+    const double* __restrict__ Un, double* __restrict__ U, const double* Win, double* W,
     double* __restrict__ Wn, double* __restrict__ UnOut, const StageArgs& A )
 {
+  // Win: primitives of this stage; W: where the new ones go (the same array, or the other one of
+  // two buffers when threads of other blocks may still read this node's old values)
   double dtl = A.dtp ? A.dtp[p] : A.dt;
   double u[NC], w[NC];
   if (LAX) {
     double g = A.M.gamma, rgas = A.M.rgas;
     double wn[NC];
     #pragma unroll
-    for (int c=0; c<NC; ++c) w[c] = get_w( W, NP, c, p );
+    for (int c=0; c<NC; ++c) w[c] = get_w( Win, NP, c, p );
     if (A.stage == 0) {
       #pragma unroll
       for (int c=0; c<NC; ++c) { wn[c] = w[c]; Wn[c*NP+p] = w[c]; }
@@ -846,7 +863,7 @@ k_rhs_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, cons
   double acc[NC];
   rhs_sum( p, lane, base, kmax, inc_e, F, nslot, bslot, Rb, S, src_mask, v, acc );
   if (FUSED) {
-    node_update< LAX >( p, NP, acc, vol[p], Un, U, W, Wn, UnOut, A );
+    node_update< LAX >( p, NP, acc, vol[p], Un, U, W, W, Wn, UnOut, A );
   } else {
     #pragma unroll
     for (int c=0; c<NC; ++c) R[p*NC+c] = acc[c];
@@ -874,8 +891,8 @@ template< bool FUSED >
 __global__ void k_rhs_finish( int nsh, size_t NP, const int* __restrict__ sh_node, const int* __restrict__ roff,
             const int* __restrict__ ridx, const double* __restrict__ part,
             const double* __restrict__ recvbuf, const double* __restrict__ vol,
-            const double* __restrict__ Un, StageArgs A, double* __restrict__ U,
-            double* __restrict__ W, double* __restrict__ R, double* __restrict__ Wn, double* __restrict__ UnOut )
+            const double* __restrict__ Un, StageArgs A, double* __restrict__ U, const double* Win,
+            double* W, double* __restrict__ R, double* __restrict__ Wn, double* __restrict__ UnOut )
 {
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= nsh) return;
@@ -887,8 +904,8 @@ __global__ void k_rhs_finish( int nsh, size_t NP, const int* __restrict__ sh_nod
     acc[c] = a;
   }
   if (FUSED) {
-    if (A.M.rgas > 0.0) node_update< true >( p, NP, acc, vol[p], Un, U, W, Wn, UnOut, A );
-    else node_update< false >( p, NP, acc, vol[p], Un, U, W, Wn, UnOut, A );
+    if (A.M.rgas > 0.0) node_update< true >( p, NP, acc, vol[p], Un, U, Win, W, Wn, UnOut, A );
+    else node_update< false >( p, NP, acc, vol[p], Un, U, Win, W, Wn, UnOut, A );
   } else {
     for (int c=0; c<NC; ++c) R[p*NC+c] = acc[c];
   }
@@ -904,8 +921,8 @@ __global__ void k_update( size_t npoin, size_t NP, const double* __restrict__ R,
   double acc[NC];
   #pragma unroll
   for (int c=0; c<NC; ++c) acc[c] = R[p*NC+c];
-  if (A.M.rgas > 0.0) node_update< true >( p, NP, acc, vol[p], Un, U, W, Wn, UnOut, A );
-  else node_update< false >( p, NP, acc, vol[p], Un, U, W, Wn, UnOut, A );
+  if (A.M.rgas > 0.0) node_update< true >( p, NP, acc, vol[p], Un, U, W, W, Wn, UnOut, A );
+  else node_update< false >( p, NP, acc, vol[p], Un, U, W, W, Wn, UnOut, A );
 }
 
 // ---------------------------------------------------------------------------------

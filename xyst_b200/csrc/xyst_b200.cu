@@ -37,6 +37,7 @@
 #include <numeric>
 #include <stdexcept>
 #include "xyst_b200.h"
+#include "layout.hpp"
 
 namespace {
 
@@ -193,7 +194,8 @@ struct xyst_ctx : CgState {
   void* comm = nullptr; int nranks = 1, rank = 0;
   std::vector< int > neigh; std::vector< size_t > neigh_off;
   DevBuf< int > sh_node;                 // unique shared nodes
-  std::vector< int > sh_node_h; DevBuf< unsigned char > sh_flag;   // host copy; [npoin] 1 = shared (built on first use)
+  std::vector< int > sh_old_h;           // the unique shared nodes in the caller's numbering (ascending)
+  std::vector< int > sh_node_h; DevBuf< unsigned char > sh_flag;   // host copy (library numbering); [npoin] 1 = shared (built on first use)
   DevBuf< int > sh_send;                 // [nsend] index into unique list, per neighbour segment
   DevBuf< int > sh_roff, sh_ridx;        // CSR unique node -> positions in recv buffer
   DevBuf< double > sh_part, sh_sendbuf, sh_recvbuf;
@@ -236,6 +238,22 @@ struct xyst_ctx : CgState {
   size_t lb_nd = 0, lp_n = 0;
   // the linear solvers not selected at the moment (xyst_cg_select): [0] pressure, [1] momentum
   CgState cg_other[2]; int cg_sel = 0;
+  // internal node order (locality.hpp): empty = the caller's order
+  std::vector< int > new2old_h, old2new_h; DevBuf< int > new2old;
+  int tile_nodes = 256;
+  // owner-slot view of the edges for the thread-per-owner kernels: slot base per slice, and per slot
+  // the edge's other end | orientation bit (31: the owner is the edge's SECOND node), -1 = padding
+  DevBuf< long long > ebase; DevBuf< int > eo;
+  // tiles of the fused stage kernel (riecg_tile.cuh): slices per tile, foreign-edge lists, per owned slot
+  // the shared-memory position of its flux (0xffff: receiver in another tile), incoming-edge counts,
+  // second buffer of the primitives, tiles with / without nodes shared with other partitions
+  size_t ntile = 0, nbt = 0, nit = 0; int fstride = 0;
+  std::vector< int > tile_sl_h;
+  DevBuf< int > tile_sl, foff, fa, fsl, btiles, itiles, shidx;
+  DevBuf< unsigned short > fdst, els; DevBuf< unsigned char > indeg;
+  DevBuf< double > W2;
+  int flux_mode = 2;                     // 0: k_flux_edge + gather, 1: k_flux_own + gather, 2: k_stage_tile
+  unsigned tile_attr = 0;                // kernel instances whose shared-memory limit has been raised
   // profiling
   bool prof_on = false;
   std::map< std::string, Prof > prof;
@@ -244,6 +262,7 @@ struct xyst_ctx : CgState {
 namespace {
 
 #include "riecg_kernels.cuh"
+#include "riecg_tile.cuh"
 #include "zalcg_kernels.cuh"
 #include "kozcg_kernels.cuh"
 #include "cg_kernels.cuh"
@@ -278,6 +297,38 @@ DParams dparams( const xyst_ctx* c ) {
   return DParams{ c->prm.gamma, c->prm.stab2coef, c->prm.flux, c->prm.stab2, c->prm.exact_muscl, c->rgas, c->kvinf };
 }
 Mode mode( const xyst_ctx* c ) { return Mode{ c->prm.gamma, c->lax ? c->rgas : 0.0, c->kvinf }; }
+
+// caller's node id -> internal id (identity unless the mesh upload re-ordered the nodes)
+inline bool reordered( const xyst_ctx* c ) { return !c->old2new_h.empty(); }
+inline size_t to_new( const xyst_ctx* c, size_t old, const char* what ) {
+  if (old >= c->npoin) throw std::runtime_error( std::string( what ) + " out of range" );
+  return reordered( c ) ? (size_t)c->old2new_h[old] : old;
+}
+// nodal array [npoin][w] in the caller's order -> internal order
+inline std::vector< double > rows_to_new( const xyst_ctx* c, const double* a, size_t w ) {
+  std::vector< double > r( c->npoin*w );
+  if (!reordered( c )) { std::copy( a, a + c->npoin*w, r.begin() ); return r; }
+  for (size_t i=0; i<c->npoin; ++i) { const double* src = a + (size_t)c->new2old_h[i]*w; for (size_t k=0; k<w; ++k) r[i*w+k] = src[k]; }
+  return r;
+}
+
+// device list of the shared nodes in the library's numbering (the mesh may arrive after the halo)
+void refresh_shared( xyst_ctx* c ) {
+  c->sh_node_h = c->sh_old_h;
+  if (reordered( c )) for (auto& i : c->sh_node_h) i = (int)to_new( c, (size_t)i, "shared node id" );
+  c->sh_flag.release();
+  c->sh_node.upload( c->sh_node_h, c->stream );
+  c->nbt = c->nit = 0;
+  if (c->ntile && c->npoin) {             // fused stage kernel: tiles holding shared nodes run first
+    std::vector< int > shidx( c->npoin, -1 ), tile_of( c->nslice ), bt, it;
+    for (size_t t=0; t<c->ntile; ++t) for (int sl=c->tile_sl_h[t]; sl<c->tile_sl_h[t+1]; ++sl) tile_of[(size_t)sl] = (int)t;
+    std::vector< char > isb( c->ntile, 0 );
+    for (size_t i=0; i<c->sh_node_h.size(); ++i) { size_t p = (size_t)c->sh_node_h[i]; shidx[p] = (int)i; isb[(size_t)tile_of[p/32]] = 1; }
+    for (size_t t=0; t<c->ntile; ++t) (isb[t] ? bt : it).push_back( (int)t );
+    c->nbt = bt.size(); c->nit = it.size();
+    c->shidx.upload( shidx, c->stream ); c->btiles.upload( bt, c->stream ); c->itiles.upload( it, c->stream );
+  }
+}
 
 void need_mesh( xyst_ctx* c ) { if (!c->npoin) throw std::runtime_error( "no mesh uploaded" ); }
 
@@ -433,12 +484,108 @@ void do_rhs_nodes( xyst_ctx* c, bool fused, int stage, double dt, const double* 
     unsigned g = nblk( c->nsh, 128 );
     if (fused)
       k_rhs_finish< true ><<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
-        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p );
+        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, A, Uout, c->W.p, c->W.p, c->R.p, c->Wn.p, c->Un.p );
     else
       k_rhs_finish< false ><<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
-        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p );
+        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, A, Uout, c->W.p, c->W.p, c->R.p, c->Wn.p, c->Un.p );
     ++c->launches;
   }
+  CK( cudaGetLastError() );
+}
+
+// thread-per-owner flux kernel writing the per-edge fluxes (drop-in for do_flux)
+void do_flux_own( xyst_ctx* c )
+{
+  auto s = c->stream;
+  auto P = dparams( c );
+  ProfScope ps( c, "flux" );
+  unsigned g = nblk( c->nslice*32, OWN_THREADS );
+  #define LAUNCH_OWN( EX, FL ) k_flux_own< EX, FL ><<< g, OWN_THREADS, 0, s >>>( c->nslice, c->NP, c->nslot, \
+      c->ebase.p, c->eo.p, c->D.p, c->W.p, c->G.p, c->F.p, P )
+  int fl = P.flux + (c->lax ? 2 : 0);
+  if (P.exact) { if (fl == 0) LAUNCH_OWN( true, 0 ); else if (fl == 1) LAUNCH_OWN( true, 1 );
+                 else if (fl == 2) LAUNCH_OWN( true, 2 ); else LAUNCH_OWN( true, 3 ); }
+  else         { if (fl == 0) LAUNCH_OWN( false, 0 ); else if (fl == 1) LAUNCH_OWN( false, 1 );
+                 else if (fl == 2) LAUNCH_OWN( false, 2 ); else LAUNCH_OWN( false, 3 ); }
+  #undef LAUNCH_OWN
+  ++c->launches;
+}
+
+template< bool EX, int FL, bool FUSED, bool LAX >
+void launch_tile( xyst_ctx* c, const TileArgs& T, unsigned ntile, cudaStream_t st )
+{
+  if (!ntile) return;
+  size_t smem = (size_t)NC*(size_t)c->fstride*sizeof(double);
+  unsigned bit = 1u << ((EX ? 16 : 0) + FL*4 + (FUSED ? 2 : 0) + (LAX ? 1 : 0));
+  if (!(c->tile_attr & bit)) {
+    CK( cudaFuncSetAttribute( k_stage_tile< EX, FL, FUSED, LAX >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
+    c->tile_attr |= bit;
+  }
+  k_stage_tile< EX, FL, FUSED, LAX ><<< ntile, 256, smem, st >>>( T );
+  ++c->launches;
+}
+
+void launch_tile_any( xyst_ctx* c, bool fused, const TileArgs& T, unsigned ntile, cudaStream_t st )
+{
+  int fl = c->prm.flux + (c->lax ? 2 : 0);
+  bool ex = c->prm.exact_muscl != 0;
+  #define TL( EX, FL, LX ) do { if (fused) launch_tile< EX, FL, true, LX >( c, T, ntile, st ); \
+                               else launch_tile< EX, FL, false, LX >( c, T, ntile, st ); } while (0)
+  if (ex) { if (fl == 0) TL( true, 0, false ); else if (fl == 1) TL( true, 1, false );
+            else if (fl == 2) TL( true, 2, true ); else TL( true, 3, true ); }
+  else    { if (fl == 0) TL( false, 0, false ); else if (fl == 1) TL( false, 1, false );
+            else if (fl == 2) TL( false, 2, true ); else TL( false, 3, true ); }
+  #undef TL
+}
+
+// Edge fluxes + nodal sums (+ the RK update if fused) of one stage in the tile kernel. With several
+// partitions the tiles holding shared nodes run first; their partial sums travel (pack + NCCL on
+// the side stream) while the other tiles are computed, then k_rhs_finish completes the shared nodes.
+void do_stage_tile( xyst_ctx* c, bool fused, int stage, double dt, const double* Un, double* Uout )
+{
+  auto s = c->stream;
+  bool halo = c->nsh > 0 && c->comm;
+  if (c->rb_pending) { CK( cudaStreamWaitEvent( s, c->ev_e, 0 ) ); c->rb_pending = false; }
+  else if (c->nbn) {
+    k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
+      c->tri.p, c->besym.p, c->fn.p, c->U.p, c->Rb.p, c->prm.gamma, c->W.p, c->rgas ); ++c->launches;
+  }
+  StageArgs A{ rkcoef[stage], dt, c->steady ? c->dtp.p : nullptr, stage, mode( c ) };
+  TileArgs T{};
+  T.npoin = c->npoin; T.NP = c->NP; T.nslot = c->nslot;
+  T.tile_list = nullptr; T.tile_sl = c->tile_sl.p; T.foff = c->foff.p; T.fa = c->fa.p; T.fsl = c->fsl.p; T.fdst = c->fdst.p;
+  T.ebase = c->ebase.p; T.eo = c->eo.p; T.els = c->els.p; T.indeg = c->indeg.p; T.D = c->D.p;
+  T.W = c->W.p; T.G = c->G.p; T.fstride = c->fstride;
+  T.bslot = c->bslot.p; T.Rb = c->Rb.p; T.S = c->S.p; T.src_mask = c->src_mask; T.v = c->v.p; T.vol = c->vol.p;
+  T.Un = Un; T.U = Uout; T.Wout = c->W2.p; T.R = c->R.p; T.Wn = c->Wn.p; T.UnOut = c->Un.p;
+  T.shidx = halo ? c->shidx.p : nullptr; T.part = c->sh_part.p;
+  T.A = A; T.P = dparams( c );
+  {
+    ProfScope ps( c, "flux" );
+    if (halo) {
+      auto cs = c->comm_stream;
+      T.tile_list = c->btiles.p;
+      launch_tile_any( c, fused, T, (unsigned)c->nbt, s );
+      CK( cudaEventRecord( c->ev_a, s ) );
+      CK( cudaStreamWaitEvent( cs, c->ev_a, 0 ) );
+      exchange( c, NC, true );
+      T.tile_list = c->itiles.p;
+      launch_tile_any( c, fused, T, (unsigned)c->nit, s );
+    } else
+      launch_tile_any( c, fused, T, (unsigned)c->ntile, s );
+  }
+  if (halo) {
+    exchange_wait( c );
+    unsigned g = nblk( c->nsh, 128 );
+    if (fused)
+      k_rhs_finish< true ><<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
+        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, A, Uout, c->W.p, c->W2.p, c->R.p, c->Wn.p, c->Un.p );
+    else
+      k_rhs_finish< false ><<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
+        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, A, Uout, c->W.p, c->W2.p, c->R.p, c->Wn.p, c->Un.p );
+    ++c->launches;
+  }
+  if (fused) std::swap( c->W.p, c->W2.p );      // the new primitives are the current ones from here on
   CK( cudaGetLastError() );
 }
 
@@ -533,107 +680,42 @@ int xyst_sync( xyst_ctx* c ) { API_BEGIN CK( cudaSetDevice( c->device ) ); CK( c
 static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const double* y, const double* z,
                       const size_t nsup[3], const size_t* const dsupedge[3],
                       const double* const dsupint[3], size_t ntri, const size_t* triinpoel,
-                      const uint8_t* besym, const double* vol, const double* v, size_t stride )
+                      const uint8_t* besym, const double* vol, const double* v, size_t stride,
+                      bool allow_reorder = false )
 {
   API_BEGIN
   c->dstride = (int)stride;
   CK( cudaSetDevice( c->device ) );
   if (npoin == 0 || npoin > 0x7fffffffULL) throw std::runtime_error( "npoin out of range" );
-  // --- flatten superedges to edges (orientation and normals as given) ---------------
-  // tk::lpoed / tk::lpoet, src/Mesh/DerivedData.hpp:40-44
-  static const int lpoed[6][2] = { {0,1}, {1,2}, {2,0}, {0,3}, {1,3}, {2,3} };
-  static const int lpoet[3][2] = { {0,1}, {1,2}, {2,0} };
-  size_t ne = nsup[0]*6 + nsup[1]*3 + nsup[2];
-  if (ne > 0x7ffffff0ULL) throw std::runtime_error( "too many edges for 32-bit edge ids" );
-  struct E { int p, q; double d[5]; };
-  const int drows = stride > 4 ? 5 : 4;
-  std::vector< E > edges; edges.reserve( ne );
-  auto chk = [&]( size_t id ){ if (id >= npoin) throw std::runtime_error( "node id out of range in superedge" ); return (int)id; };
-  for (size_t e=0; e<nsup[0]; ++e)
-    for (int k=0; k<6; ++k) {
-      E ed; ed.p = chk( dsupedge[0][e*4+lpoed[k][0]] ); ed.q = chk( dsupedge[0][e*4+lpoed[k][1]] );
-      ed.d[3] = ed.d[4] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[0][(e*6+k)*stride+j];
-      edges.push_back( ed );
-    }
-  for (size_t e=0; e<nsup[1]; ++e)
-    for (int k=0; k<3; ++k) {
-      E ed; ed.p = chk( dsupedge[1][e*3+lpoet[k][0]] ); ed.q = chk( dsupedge[1][e*3+lpoet[k][1]] );
-      ed.d[3] = ed.d[4] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[1][(e*3+k)*stride+j];
-      edges.push_back( ed );
-    }
-  for (size_t e=0; e<nsup[2]; ++e) {
-    E ed; ed.p = chk( dsupedge[2][e*2+0] ); ed.q = chk( dsupedge[2][e*2+1] );
-    ed.d[3] = ed.d[4] = 0.0; for (size_t j=0; j<stride; ++j) ed.d[j] = dsupint[2][e*stride+j];
-    edges.push_back( ed );
+  // --- layout (layout.hpp): internal node order, edge slots, incidence, tiles ---------------
+  // Everything below works in the library's own numbering; ids and nodal arrays crossing the
+  // ABI are mapped at the entry points (to_new / rows_to_new). XYST_REORDER=0 keeps the caller's.
+  layout::Options opt;
+  opt.reorder = allow_reorder; opt.tiles = stride == 3 && !c->cho;
+  { const char* e = getenv( "XYST_REORDER" ); if (e && e[0] == '0') opt.reorder = false;
+    e = getenv( "XYST_TILE" ); if (e && atoi( e ) >= 32) c->tile_nodes = std::min( 256, atoi( e ) / 32 * 32 );
+    e = getenv( "XYST_TILE_CAP" ); if (e && atoi( e ) > 0) opt.cap = (size_t)atoi( e );
+    e = getenv( "XYST_FLUX_MODE" ); if (e) c->flux_mode = atoi( e ); }
+  opt.tile_nodes = (size_t)c->tile_nodes;
+  for (size_t i=0; i<ntri*3; ++i) if (triinpoel[i] >= npoin) throw std::runtime_error( "node id out of range in superedge" );
+  layout::Mesh M = layout::build( npoin, x, y, z, nsup, dsupedge, dsupint, stride, opt );
+  c->new2old_h = M.new2old; c->old2new_h = M.old2new; c->new2old.release();
+  std::vector< double > px, py, pz, pvol, pvv;
+  if (!M.new2old.empty()) {
+    const auto& n2o = M.new2old;
+    px.resize( npoin ); py.resize( npoin ); pz.resize( npoin ); pvol.resize( npoin ); pvv.resize( npoin );
+    for (size_t i=0; i<npoin; ++i) { size_t o = (size_t)n2o[i]; px[i] = x[o]; py[i] = y[o]; pz[i] = z[o]; pvol[i] = vol[o]; pvv[i] = v[o]; }
+    x = px.data(); y = py.data(); z = pz.data(); vol = pvol.data(); v = pvv.data();
+    c->new2old.upload( c->new2old_h, c->stream );
   }
-  // --- edge slots in owner order ----------------------------------------------------
-  // owner = lower endpoint; its edges sorted by the other endpoint. The j-th edge owned
-  // by node o lives in slot ebase[o/32] + j*32 + o%32 (padding slots have ep = -1).
-  std::vector< int > perm( ne );
-  std::iota( perm.begin(), perm.end(), 0 );
-  std::sort( perm.begin(), perm.end(), [&]( int a, int b ){
-    int la = std::min( edges[a].p, edges[a].q ), lb = std::min( edges[b].p, edges[b].q );
-    if (la != lb) return la < lb;
-    int ha = std::max( edges[a].p, edges[a].q ), hb = std::max( edges[b].p, edges[b].q );
-    if (ha != hb) return ha < hb;
-    return a < b; } );
-  size_t nslice = (npoin + 31) / 32;
-  std::vector< int > udeg( npoin, 0 );
-  for (size_t i=0; i<ne; ++i) ++udeg[ std::min( edges[i].p, edges[i].q ) ];
-  std::vector< long long > ebase( nslice+1, 0 );
-  for (size_t s=0; s<nslice; ++s) {
-    int km = 0;
-    for (size_t p=s*32; p<std::min( npoin, s*32+32 ); ++p) km = std::max( km, udeg[p] );
-    ebase[s+1] = ebase[s] + (long long)km*32;
-  }
-  size_t nslot = (size_t)ebase[nslice];
-  if (nslot > 0x7ffffff0ULL) throw std::runtime_error( "too many edge slots for 32-bit ids" );
-  std::vector< int > ep( nslot, -1 ), eq( nslot, -1 ), slot_of( ne );
-  std::vector< double > ed( (size_t)drows*nslot, 0.0 );
-  { std::vector< int > fillu( npoin, 0 );
-    for (size_t i=0; i<ne; ++i) {
-      const auto& e = edges[perm[i]];
-      int o = std::min( e.p, e.q );
-      size_t sl = (size_t)ebase[o/32] + (size_t)fillu[o]*32 + (size_t)(o%32);
-      ++fillu[o];
-      ep[sl] = e.p; eq[sl] = e.q; slot_of[i] = (int)sl;
-      for (int j=0; j<drows; ++j) ed[j*nslot+sl] = e.d[j];
-    } }
-  // --- sliced-ELL incidence: node -> (signed slot, neighbour) -------------------------
-  // reference scatter: G(p) -= f, G(q) += f with f = d*(u_q+u_p)  (Riemann.cpp:321-323).
-  // Per node: its owned edges first (ascending other endpoint), then the edges owned by
-  // lower neighbours (ascending neighbour) -- the fixed summation order of the gathers.
-  std::vector< int > deg( npoin, 0 );
-  for (size_t i=0; i<ne; ++i) { ++deg[edges[i].p]; ++deg[edges[i].q]; }
-  std::vector< long long > base( nslice+1, 0 );
-  for (size_t s=0; s<nslice; ++s) {
-    int km = 0;
-    for (size_t p=s*32; p<std::min( npoin, s*32+32 ); ++p) km = std::max( km, deg[p] );
-    base[s+1] = base[s] + (long long)km*32;
-  }
-  size_t nent = (size_t)base[nslice];
-  c->maxdeg = 0; for (size_t p=0; p<npoin; ++p) c->maxdeg = std::max( c->maxdeg, deg[p] );
-  std::vector< int > inc_e( nent, 0 ), inc_q( nent, 0 ), fill( npoin, 0 );
-  for (size_t sl=0; sl<nslice; ++sl)            // padding: the node itself (last node for the tail slice)
-    for (size_t j=(size_t)base[sl]; j<(size_t)base[sl+1]; ++j) inc_q[j] = (int)std::min( npoin-1, sl*32 + (j - (size_t)base[sl])%32 );
-  auto addinc = [&]( int node, int other, int signedslot ) {
-    size_t slot = (size_t)base[node/32] + (size_t)fill[node]*32 + (size_t)(node%32);
-    ++fill[node];
-    inc_e[slot] = signedslot; inc_q[slot] = other;
-  };
-  for (size_t i=0; i<ne; ++i) {                 // owned edges (sorted by owner, other)
-    const auto& e = edges[perm[i]];
-    int o = std::min( e.p, e.q ), h = std::max( e.p, e.q );
-    addinc( o, h, o == e.q ? slot_of[i]+1 : -(slot_of[i]+1) );
-  }
-  for (size_t i=0; i<ne; ++i) {                 // edges owned by lower neighbours: arrive ascending in owner
-    const auto& e = edges[perm[i]];
-    int o = std::min( e.p, e.q ), h = std::max( e.p, e.q );
-    addinc( h, o, h == e.q ? slot_of[i]+1 : -(slot_of[i]+1) );
-  }
+  const size_t ne = M.ne, nslice = M.nslice, nslot = M.nslot, nent = M.nent;
+  const auto &ep = M.ep, &eq = M.eq; const auto& ed = M.ed; const auto &ebase = M.ebase, &base = M.base;
+  const auto &inc_e = M.inc_e, &inc_q = M.inc_q;
+  c->maxdeg = M.maxdeg; c->ntile = M.ntile; c->tile_sl_h = M.tile_sl; c->fstride = M.fstride;
+  const bool tiles = opt.tiles;
   // --- boundary faces: node -> (face, local index) CSR -------------------------------
   std::vector< int > tri( ntri*3 );
-  for (size_t i=0; i<ntri*3; ++i) tri[i] = chk( triinpoel[i] );
+  for (size_t i=0; i<ntri*3; ++i) tri[i] = (int)M.to_new( triinpoel[i] );
   std::vector< int > bslot( npoin, -1 ), bn_node;
   for (size_t i=0; i<ntri*3; ++i) if (bslot[tri[i]] < 0) { bslot[tri[i]] = 0; }
   for (size_t p=0; p<npoin; ++p) if (bslot[p] == 0) { bslot[p] = (int)bn_node.size(); bn_node.push_back( (int)p ); }
@@ -649,6 +731,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   c->npoin = npoin; c->NP = NP; c->nedge = ne; c->nslot = nslot; c->ntri = ntri; c->nslice = nslice;
   c->nent = nent; c->nbn = nbn;
   c->ep.upload( ep, s ); c->eq.upload( eq, s ); c->D.upload( ed, s );
+  c->eo.upload( M.eo, s ); c->ebase.upload( ebase, s );
   { std::vector< double2 > d2( nslot );
     for (size_t i=0; i<nslot; ++i) d2[i] = make_double2( ed[i], ed[nslot+i] );
     c->D2.upload( d2, s );
@@ -668,21 +751,27 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
     c->vol.upload( pv, s ); c->v.upload( pw, s ); c->X.upload( px, s ); }
   c->fn.alloc( std::max< size_t >( ntri, 1 )*3 );
   if (ntri) { k_face_normals<<< nblk( ntri, 128 ), 128, 0, s >>>( (int)ntri, NP, c->tri.p, c->X.p, c->fn.p ); ++c->launches; CK( cudaGetLastError() ); }
+  if (c->nsh) refresh_shared( c );
   if (c->cho) {            // the projection solver keeps its own state (chocg.cuh)
     for (auto* b : { &c->U, &c->Un, &c->W, &c->G, &c->R, &c->stage, &c->F }) b->release();
     c->S.release(); c->src_mask = 0;
     CK( cudaStreamSynchronize( s ) );
     return 0;
   }
-  c->U.alloc( NP*NC ); c->Un.alloc( NP*NC ); c->G.alloc( NP*15 );
+  c->U.alloc( NP*NC ); c->Un.alloc( NP*NC ); c->G.alloc( NP*2*NGP );
   c->R.alloc( npoin*NC ); c->stage.alloc( npoin*NC ); c->F.alloc( std::max< size_t >( nslot, 1 )*NC );
   { std::vector< double > one( NP*NC, 1.0 );    // a harmless state until xyst_state_set
     c->U.upload( one, s ); c->Un.upload( one, s );
     // primitives + coordinates as pairs (w0,w1) (w2,w3) (w4,x) (y,z), see load_wx
     std::vector< double > wx( NP*8, 1.0 );
     for (size_t p=0; p<npoin; ++p) { wx[(2*NP+p)*2+1] = x[p]; wx[(3*NP+p)*2] = y[p]; wx[(3*NP+p)*2+1] = z[p]; }
-    c->W.upload( wx, s ); }
-  CK( cudaMemsetAsync( c->G.p, 0, NP*15*sizeof(double), s ) );
+    c->W.upload( wx, s ); c->W2.release();
+    if (tiles) c->W2.upload( wx, s ); }
+  if (tiles) {
+    c->tile_sl.upload( M.tile_sl, s ); c->foff.upload( M.foff, s ); c->fa.upload( M.fa, s ); c->fsl.upload( M.fsl, s );
+    c->fdst.upload( M.fdst, s ); c->els.upload( M.els, s ); c->indeg.upload( M.indeg, s );
+  }
+  CK( cudaMemsetAsync( c->G.p, 0, NP*2*NGP*sizeof(double), s ) );
   CK( cudaMemsetAsync( c->F.p, 0, std::max< size_t >( nslot, 1 )*NC*sizeof(double), s ) );
   c->S.release(); c->src_mask = 0;
   CK( cudaStreamSynchronize( s ) );
@@ -693,13 +782,13 @@ int xyst_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* 
                       const size_t nsup[3], const size_t* const dsupedge[3],
                       const double* const dsupint[3], size_t ntri, const size_t* triinpoel,
                       const uint8_t* besym, const double* vol, const double* v )
-{ return mesh_upload_impl( c, npoin, x, y, z, nsup, dsupedge, dsupint, ntri, triinpoel, besym, vol, v, 3 ); }
+{ return mesh_upload_impl( c, npoin, x, y, z, nsup, dsupedge, dsupint, ntri, triinpoel, besym, vol, v, 3, !c->cho ); }
 
 int xyst_zalcg_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* y, const double* z,
                             const size_t nsup[3], const size_t* const dsupedge[3],
                             const double* const dsupint[3], size_t ntri, const size_t* triinpoel,
                             const uint8_t* besym, const double* vol, const double* v )
-{ return mesh_upload_impl( c, npoin, x, y, z, nsup, dsupedge, dsupint, ntri, triinpoel, besym, vol, v, 4 ); }
+{ return mesh_upload_impl( c, npoin, x, y, z, nsup, dsupedge, dsupint, ntri, triinpoel, besym, vol, v, 4, !c->cho ); }
 
 int xyst_zalcg_config( xyst_ctx* c, const xyst_zalcg_params* p )
 {
@@ -783,6 +872,15 @@ int xyst_bc_upload( xyst_ctx* c, size_t ndir, const size_t* dirbcmasks, const do
   // per side set it has a normal in, RieCG.cpp:583-596)
   std::map< int, int > slot;
   std::vector< int > nodes;
+  std::vector< size_t > mdir, msym, mfar, mpre;
+  if (reordered( c )) {            // the lists as the library numbers the nodes
+    mdir.assign( dirbcmasks, dirbcmasks + ndir*(NC+1) );
+    for (size_t i=0; i<ndir; ++i) mdir[i*(NC+1)] = to_new( c, dirbcmasks[i*(NC+1)], "BC node id" );
+    msym.resize( nsym ); for (size_t i=0; i<nsym; ++i) msym[i] = to_new( c, symbcnodes[i], "BC node id" );
+    mfar.resize( nfar ); for (size_t i=0; i<nfar; ++i) mfar[i] = to_new( c, farbcnodes[i], "BC node id" );
+    mpre.resize( npre ); for (size_t i=0; i<npre; ++i) mpre[i] = to_new( c, prebcnodes[i], "BC node id" );
+    dirbcmasks = mdir.data(); symbcnodes = msym.data(); farbcnodes = mfar.data(); prebcnodes = mpre.data();
+  }
   auto add = [&]( size_t p ){ if (p >= c->npoin) throw std::runtime_error( "BC node id out of range" );
     auto it = slot.find( (int)p ); if (it == slot.end()) { slot[(int)p] = (int)nodes.size(); nodes.push_back( (int)p ); } };
   for (size_t i=0; i<ndir; ++i) add( dirbcmasks[i*(NC+1)] );
@@ -837,7 +935,7 @@ int xyst_src_upload( xyst_ctx* c, const double* S )
   if (!S) { c->S.release(); c->src_mask = 0; return 0; }
   int mask = 0;
   for (size_t p=0; p<c->npoin; ++p) for (int k=0; k<NC; ++k) if (S[p*NC+k] != 0.0) mask |= 1<<k;
-  c->S.upload( std::vector< double >( S, S + c->npoin*NC ), c->stream );
+  c->S.upload( rows_to_new( c, S, NC ), c->stream );
   c->src_mask = mask;
   API_END
 }
@@ -849,7 +947,7 @@ int xyst_state_set( xyst_ctx* c, const double* U )
   need_mesh( c );
   if (c->rb_pending) { CK( cudaStreamSynchronize( c->aux_stream ) ); c->rb_pending = false; }
   CK( cudaMemcpyAsync( c->stage.p, U, c->npoin*NC*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
-  k_set_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->stage.p, c->U.p, c->W.p, mode( c ) );
+  k_set_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->stage.p, c->new2old.p, c->U.p, c->W.p, mode( c ) );
   ++c->launches;
   CK( cudaGetLastError() );
   CK( cudaStreamSynchronize( c->stream ) );
@@ -861,7 +959,7 @@ int xyst_state_get( xyst_ctx* c, double* U )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  k_get_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->stage.p );
+  k_get_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->new2old.p, c->stage.p );
   ++c->launches;
   CK( cudaGetLastError() );
   CK( cudaMemcpyAsync( U, c->stage.p, c->npoin*NC*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
@@ -876,10 +974,13 @@ int xyst_grad_get( xyst_ctx* c, double* G )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  std::vector< double > h( c->NP*15 );
+  std::vector< double > h( c->NP*2*NGP );
   CK( cudaMemcpyAsync( h.data(), c->G.p, h.size()*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
   CK( cudaStreamSynchronize( c->stream ) );
-  for (size_t p=0; p<c->npoin; ++p) for (int i=0; i<15; ++i) G[p*15+(size_t)i] = h[gidx( i, p, c->NP )];
+  for (size_t p=0; p<c->npoin; ++p) {
+    size_t o = reordered( c ) ? (size_t)c->new2old_h[p] : p;
+    for (int i=0; i<15; ++i) G[o*15+(size_t)i] = h[gidx( i, p, c->NP )];
+  }
   API_END
 }
 
@@ -888,8 +989,11 @@ int xyst_riecg_rhs( xyst_ctx* c )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  do_flux( c );
-  do_rhs_nodes( c, false, 0, 0.0, c->U.p, c->Un.p, c->U.p );
+  if (c->flux_mode == 2 && c->ntile) do_stage_tile( c, false, 0, 0.0, c->Un.p, c->U.p );
+  else {
+    if (c->flux_mode == 1) do_flux_own( c ); else do_flux( c );
+    do_rhs_nodes( c, false, 0, 0.0, c->U.p, c->Un.p, c->U.p );
+  }
   API_END
 }
 
@@ -898,8 +1002,15 @@ int xyst_rhs_get( xyst_ctx* c, double* R )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  CK( cudaMemcpyAsync( R, c->R.p, c->npoin*NC*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
-  CK( cudaStreamSynchronize( c->stream ) );
+  if (!reordered( c )) {
+    CK( cudaMemcpyAsync( R, c->R.p, c->npoin*NC*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+    CK( cudaStreamSynchronize( c->stream ) );
+  } else {
+    std::vector< double > h( c->npoin*NC );
+    CK( cudaMemcpyAsync( h.data(), c->R.p, h.size()*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+    CK( cudaStreamSynchronize( c->stream ) );
+    for (size_t p=0; p<c->npoin; ++p) for (int k=0; k<NC; ++k) R[(size_t)c->new2old_h[p]*NC+k] = h[p*NC+k];
+  }
   API_END
 }
 
@@ -942,15 +1053,20 @@ int xyst_riecg_stage( xyst_ctx* c, int stage, double dt )
   need_mesh( c );
   if (stage < 0 || stage > 2) throw std::runtime_error( "stage must be 0, 1 or 2" );
   do_grad( c );
-  do_flux( c );
+  const bool tile = c->flux_mode == 2 && c->ntile;
+  if (!tile) { if (c->flux_mode == 1) do_flux_own( c ); else do_flux( c ); }
+  auto nodes = [&]( const double* Un, double* Uout ) {
+    if (tile) do_stage_tile( c, true, stage, dt, Un, Uout );
+    else do_rhs_nodes( c, true, stage, dt, c->U.p, Un, Uout );
+  };
   if (c->lax)           // time level n is kept in (p,u,v,w,T) form (Wn); Un is refreshed at stage 2
-    do_rhs_nodes( c, true, stage, dt, c->U.p, c->Un.p, c->U.p );
+    nodes( c->Un.p, c->U.p );
   else if (stage == 0) { // un = u (RieCG.cpp:1011) without a copy: write the new state into the
                         // other buffer and swap the roles of the two
-    do_rhs_nodes( c, true, stage, dt, c->U.p, c->U.p, c->Un.p );
+    nodes( c->U.p, c->Un.p );
     std::swap( c->U.p, c->Un.p );
   } else
-    do_rhs_nodes( c, true, stage, dt, c->U.p, c->Un.p, c->U.p );
+    nodes( c->Un.p, c->U.p );
   do_bc( c );
   API_END
 }
@@ -967,7 +1083,7 @@ int xyst_diag( xyst_ctx* c, const double* an, double* out )
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
   DevBuf< double > dan;
-  if (an) dan.upload( std::vector< double >( an, an + c->npoin*NC ), c->stream );
+  if (an) dan.upload( rows_to_new( c, an, NC ), c->stream );
   int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( c->npoin, RED_THREADS ) );
   k_diag<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->Un.p, c->v.p, dan.p, c->red.p );
   k_reduce_final< NDIAG, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, c->red.p + (size_t)RED_BLOCKS*NDIAG );
@@ -1024,8 +1140,9 @@ int xyst_halo_upload( xyst_ctx* c, int nneigh, const int* neigh_rank, const size
   { std::vector< int > f( roff.begin(), roff.end()-1 );
     for (size_t i=0; i<nsend; ++i) ridx[ f[send[i]]++ ] = (int)i; }   // ascending recv position = fixed neighbour order
   auto s = c->stream;
-  c->nsh = uniq.size(); c->nsend = nsend; c->sh_node_h = uniq; c->sh_flag.release();
-  c->sh_node.upload( uniq, s ); c->sh_send.upload( send, s ); c->sh_roff.upload( roff, s ); c->sh_ridx.upload( ridx, s );
+  c->nsh = uniq.size(); c->nsend = nsend; c->sh_old_h = uniq;
+  refresh_shared( c );
+  c->sh_send.upload( send, s ); c->sh_roff.upload( roff, s ); c->sh_ridx.upload( ridx, s );
   c->sh_part.alloc( uniq.size()*15 ); c->sh_sendbuf.alloc( nsend*15 ); c->sh_recvbuf.alloc( nsend*15 );
   API_END
 }

@@ -15,17 +15,20 @@ from xyst_b200 import build as B
 LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib")
 # name -> (defines, environment)
 VAR = {
-    "r1_edge_noreorder": ([], {"XYST_FLUX_MODE": "0", "XYST_REORDER": "0"}),
-    "edge_reorder": ([], {"XYST_FLUX_MODE": "0"}),
     "own_reorder": ([], {"XYST_FLUX_MODE": "1"}),
     "tile": ([], {}),
-    "tile_noreorder": ([], {"XYST_REORDER": "0"}),
+    "tile_lb": ([], {"XYST_LOOKBACK": "1"}),
+    "tile224_lb": ([], {"XYST_TILE": "224", "XYST_LOOKBACK": "1"}),
+    "tile_lb_sint": (["MUSCL_SIGN_INT=1"], {"XYST_LOOKBACK": "1"}),
+    "tile224": ([], {"XYST_TILE": "224"}),
+    "tile192": ([], {"XYST_TILE": "192"}),
     "tile128": ([], {"XYST_TILE": "128"}),
+    "tile_sint": (["MUSCL_SIGN_INT=1"], {}),
     "tile_u2": (["OWN_UNROLL=2"], {}),
-    "tile_minb3": (["TILE_MINB=3"], {}),
-    "tile_g3": (["GRAD_MINB=3"], {}),
-    "tile_g2": (["GRAD_MINB=2"], {}),
     "tile_g128": (["NODE_THREADS=128", "GRAD_MINB=4", "RHS_MINB=4"], {}),
+    "tile_g128u7": (["NODE_THREADS=128", "GRAD_MINB=4", "RHS_MINB=4", "GRAD_UNROLL=7"], {}),
+    "tile_g128u4": (["NODE_THREADS=128", "GRAD_MINB=4", "RHS_MINB=4", "GRAD_UNROLL=4"], {}),
+    "tile_g128u2m6": (["NODE_THREADS=128", "GRAD_MINB=6", "RHS_MINB=4", "GRAD_UNROLL=2"], {}),
 }
 
 

@@ -20,6 +20,7 @@
 #include <stdexcept>
 #include <cstddef>
 #include <cstdint>
+#include <cmath>
 #include "locality.hpp"
 
 namespace layout {
@@ -40,6 +41,7 @@ struct Mesh {
   std::vector< double > ed;                        // [drows][nslot] edge integrals (normal, + extra terms)
   std::vector< int > inc_e, inc_q;                 // [nent] signed slot+1 (0 = padding), neighbour
   std::vector< int > tile_sl, foff, fa, fsl;       // tiles: [ntile+1], [ntile+1], foreign owner, foreign slot
+  std::vector< int > tile_of;                      // [nslice] tile of each slice
   std::vector< unsigned short > fdst, els;         // foreign / owned-slot shared-memory positions
   std::vector< unsigned char > indeg;              // [nslice*32] incoming edges per node
   size_t to_new( size_t old ) const { return old2new.empty() ? old : (size_t)old2new[old]; }
@@ -126,6 +128,9 @@ inline Mesh build( size_t npoin, const double* x, const double* y, const double*
       M.eo[sl] = P[e] < Q[e] ? Q[e] : (int)( (unsigned)P[e] | 0x80000000u );
       const double* d = integ( e );
       for (size_t j=0; j<stride; ++j) M.ed[j*nslot+sl] = d[j];
+      // RieCG/LaxCG (3 integrals per edge): the free 4th row holds the normal's length, which the
+      // Riemann solvers would otherwise recompute per edge and stage (Riemann.cpp:412)
+      if (stride == 3) M.ed[3*nslot+sl] = std::sqrt( d[0]*d[0] + d[1]*d[1] + d[2]*d[2] );
     } }
   // --- sliced-ELL incidence: node -> (signed slot, neighbour) -------------------------------
   // reference scatter: G(p) -= f, G(q) += f with f = d*(u_q+u_p)  (Riemann.cpp:321-323): the
@@ -175,7 +180,8 @@ inline Mesh build( size_t npoin, const double* x, const double* y, const double*
     for (size_t a=0; a<nslice; a+=ts) add( add, a, std::min( nslice, a+ts ) );
     size_t ntile = M.tile_sl.size()-1;
     M.ntile = ntile;
-    std::vector< int > tile_of( nslice );
+    M.tile_of.assign( nslice, 0 );
+    auto& tile_of = M.tile_of;
     for (size_t t=0; t<ntile; ++t) for (int sl=M.tile_sl[t]; sl<M.tile_sl[t+1]; ++sl) tile_of[(size_t)sl] = (int)t;
     M.els.assign( nslot, (unsigned short)0xffff );
     M.foff.assign( ntile+1, 0 );

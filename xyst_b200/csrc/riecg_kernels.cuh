@@ -9,12 +9,15 @@ struct DParams { double gamma, stab2coef; int flux, stab2, exact; double rgas, k
 struct Mode { double gamma, rgas, kvinf; };
 
 // Primitive variables from conserved ones, Riemann.cpp:211-227
+// (one reciprocal of the density instead of the reference's four quotients: the same values up to
+// one rounding each)
 __device__ __forceinline__ void primitive( const double u[NC], double w[NC] ) {
   w[0] = u[0];
-  w[1] = u[1] / w[0];
-  w[2] = u[2] / w[0];
-  w[3] = u[3] / w[0];
-  w[4] = u[4] / w[0] - 0.5*(w[1]*w[1] + w[2]*w[2] + w[3]*w[3]);
+  double ir = 1.0 / w[0];
+  w[1] = u[1] * ir;
+  w[2] = u[2] * ir;
+  w[3] = u[3] * ir;
+  w[4] = u[4] * ir - 0.5*(w[1]*w[1] + w[2]*w[2] + w[3]*w[3]);
 }
 
 // LaxCG::primitive, LaxCG.cpp:115-137: (r,ru,rv,rw,rE) -> (p,u,v,w,T)
@@ -371,6 +374,9 @@ __global__ void k_grad_finish( int nsh, size_t NP, const int* __restrict__ sh_no
 // ---------------------------------------------------------------------------------
 #define MUSCL_EPS 1.0e-9
 #define MUSCL_K (1.0/3.0)
+#ifndef MUSCL_SIGN_INT
+#define MUSCL_SIGN_INT 0
+#endif
 #ifndef MUSCL_V2
 #define MUSCL_V2 1        // 0: the first form of the two-reciprocal limiter (A/B timing)
 #endif
@@ -427,8 +433,16 @@ __device__ __forceinline__ void vanleer( double d1, double d2, double d3, double
     // same strict sign <=> positive product (|a|, |b| are >= ~1e-9 unless a difference hits -1e-9
     // to the last bit, so the product cannot underflow in practice); integer sign-bit tests cost
     // 5 % more kernel time, the kernel being limited by instruction issue
+#if MUSCL_SIGN_INT
+    // the same test on the sign bits (integer pipe; differs only if a or b is exactly zero, where the
+    // reference's quotients are 0/0 or x/0 anyway)
+    int ha = __double2hiint( a );
+    incL = (ha ^ __double2hiint( bL )) >= 0 ? vL : 0.0;
+    incR = (ha ^ __double2hiint( bR )) >= 0 ? vR : 0.0;
+#else
     incL = a*bL > 0.0 ? vL : 0.0;
     incR = a*bR > 0.0 ? vR : 0.0;
+#endif
 #else
     double a = d2 + MUSCL_EPS_, bL = d1 + MUSCL_EPS_, bR = d3 + MUSCL_EPS_;
     bool sL = (a > 0.0 && bL > 0.0) || (a < 0.0 && bL < 0.0);
@@ -833,9 +847,9 @@ __device__ __forceinline__ void node_update( size_t p, size_t NP, const double a
       for (int c=0; c<NC; ++c) UnOut[c*NP+p] = un[c];
     }
   } else {
-    double rkdt = A.rk * dtl;
+    double rkdtv = A.rk * dtl / vp;      // rk dt R / vol with one quotient per node
     #pragma unroll
-    for (int c=0; c<NC; ++c) { u[c] = Un[c*NP+p] - rkdt * acc[c] / vp; U[c*NP+p] = u[c]; }
+    for (int c=0; c<NC; ++c) { u[c] = Un[c*NP+p] - rkdtv * acc[c]; U[c*NP+p] = u[c]; }
     primitive( u, w );
     store_w( W, NP, p, w );
   }

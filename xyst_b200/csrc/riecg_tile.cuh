@@ -44,11 +44,59 @@ __device__ __forceinline__ void load_g( const double2* __restrict__ G2, size_t N
   g[14] = a[7].x;
 }
 
+// sqrt(x) for x >= 0 without the IEEE routine's special-case branches (which split the edge loop
+// into many basic blocks): hardware seed (MUFU.RSQ64H, ~20 bits), two coupled Goldschmidt steps on
+// (sqrt x, 1/(2 sqrt x)) -> ~1 ulp. x < 0 gives NaN like sqrt().
+__device__ __forceinline__ double fast_sqrt( double x )
+{
+  double y;
+  asm( "rsqrt.approx.ftz.f64 %0, %1;" : "=d"( y ) : "d"( x ) );
+  double g = x*y, h = 0.5*y;
+  double r = fma( -g, h, 0.5 );
+  g = fma( g, r, g ); h = fma( h, r, h );
+  r = fma( -g, g, x );
+  g = fma( r, h, g );
+  return x == 0.0 ? 0.0 : g;
+}
+
+// rusanov (riecg_kernels.cuh; src/Physics/Riemann.cpp:369-478) with the edge normal's length given
+// (a per-edge constant kept next to the normal) and the limiter form as a template argument
+template< bool EXACT >
+__device__ __forceinline__ void rusanov_len( double l[NC], double r[NC], const double n[3], double len,
+                                             const DParams& P, double f[NC] )
+{
+  double g = P.gamma;
+  double pL = (l[0]*l[4]) * (g-1.0);
+  double pR = (r[0]*r[4]) * (g-1.0);
+  const double gg1 = g*(g-1.0), eL = l[4], eR = r[4];
+  double nx = n[0], ny = n[1], nz = n[2];
+  double vnL = l[1]*nx + l[2]*ny + l[3]*nz;
+  double vnR = r[1]*nx + r[2]*ny + r[3]*nz;
+  l[4] = (l[4] + 0.5*(l[1]*l[1] + l[2]*l[2] + l[3]*l[3])) * l[0];
+  l[1] *= l[0]; l[2] *= l[0]; l[3] *= l[0];
+  r[4] = (r[4] + 0.5*(r[1]*r[1] + r[2]*r[2] + r[3]*r[3])) * r[0];
+  r[1] *= r[0]; r[2] *= r[0]; r[3] *= r[0];
+  double sl, sr;
+  if (EXACT) { sl = fabs(vnL) + sqrt( g * pL / l[0] )*len; sr = fabs(vnR) + sqrt( g * pR / r[0] )*len; }
+  else { sl = fabs(vnL) + fast_sqrt( gg1 * eL )*len; sr = fabs(vnR) + fast_sqrt( gg1 * eR )*len; }   // g p / rho = g (g-1) e
+  double fw = fmax( sl, sr );
+  f[0] = l[0]*vnL + r[0]*vnR + fw*(r[0] - l[0]);
+  f[1] = l[1]*vnL + r[1]*vnR + (pL + pR)*nx + fw*(r[1] - l[1]);
+  f[2] = l[2]*vnL + r[2]*vnR + (pL + pR)*ny + fw*(r[2] - l[2]);
+  f[3] = l[3]*vnL + r[3]*vnR + (pL + pR)*nz + fw*(r[3] - l[3]);
+  f[4] = (l[4] + pL)*vnL + (r[4] + pR)*vnR + fw*(r[4] - l[4]);
+  if (P.stab2) {
+    double fws = P.stab2coef * fw;
+    #pragma unroll
+    for (int c=0; c<NC; ++c) f[c] -= fws*(l[c] - r[c]);
+  }
+}
+
 // flux f' of the edge (owner -> other), owner-first. s = +1: the owner is the reference's first
 // node, -1: its second. n = the stored (reference-oriented) normal.
 template< bool EXACT, int FLUX >
 __device__ __forceinline__ void edge_flux_owner( const double wo[NC], const double xo[3], const double go[15],
-    const double wq[NC], const double xq[3], const double gq[15], double s, const double nref[3],
+    const double wq[NC], const double xq[3], const double gq[15], double s, const double nref[4],
     const DParams& P, double f[NC] )
 {
   double l[NC], r[NC], vw[3], n[3];
@@ -57,7 +105,7 @@ __device__ __forceinline__ void edge_flux_owner( const double wo[NC], const doub
   #pragma unroll
   for (int j=0; j<3; ++j) { vw[j] = xq[j] - xo[j]; n[j] = s * nref[j]; }
   muscl< EXACT >( go, 1, gq, 1, vw, l, r, s * MUSCL_EPS );
-  if (FLUX == 0) rusanov( l, r, n, P, f ); else if (FLUX == 1) hllc( l, r, n, P, f );
+  if (FLUX == 0) rusanov_len< EXACT >( l, r, n, nref[3], P, f ); else if (FLUX == 1) hllc( l, r, n, P, f );
   else if (FLUX == 2) lax_rusanov( l, r, n, P, f ); else lax_hllc( l, r, n, P, f );
 }
 
@@ -87,7 +135,7 @@ k_flux_own( size_t nslice, size_t NP, size_t nslot, const long long* __restrict_
     bool valid = e != -1;
     double s = e < 0 ? -1.0 : 1.0;
     size_t q = valid ? (size_t)(e & 0x7fffffff) : p;
-    double n[3] = { __ldg( D + sl ), __ldg( D + nslot + sl ), __ldg( D + 2*nslot + sl ) };
+    double n[4] = { __ldg( D + sl ), __ldg( D + nslot + sl ), __ldg( D + 2*nslot + sl ), __ldg( D + 3*nslot + sl ) };
     double wq[NC], xq[3], gq[15];
     load_wx( WX, NP, q, wq, xq );
     load_g( G2, NP, q, gq );
@@ -108,8 +156,15 @@ struct TileArgs {
   size_t npoin, NP, nslot;
   const int* tile_list;            // tiles this launch works on (blockIdx.x -> tile), or null = identity
   const int* tile_sl;              // [ntile+1] first slice of each tile
+  const int* tile_of_slice;        // [nslice] tile of each slice of 32 nodes
   const int* foff;                 // [ntile+1] offsets into the foreign-edge lists
   const int* fa; const int* fsl; const unsigned short* fdst;   // foreign edges: owner, global slot, F_s index
+  // look-back: instead of evaluating a foreign edge again, wait until its owner's tile has published
+  // its fluxes (tflag[tile] == epoch) and read the value it left in F. Tiles are claimed in
+  // processing order from a counter, so a tile only ever waits for tiles already running; a foreign
+  // edge whose owner tile is processed LATER (tpos) is evaluated here as before.
+  int lookback; int epoch; int* tflag; const int* tpos; double* F;
+  unsigned long long* counter; unsigned long long cbase;
   const long long* ebase; const int* eo; const unsigned short* els;   // owned slots: other end|orientation, F_s index or 0xffff
   const unsigned char* indeg;      // [NP] number of incoming (not owned) edges
   const double* D;                 // [3][nslot] reference-oriented normals
@@ -127,7 +182,14 @@ __global__ void __launch_bounds__(256, TILE_MINB)
 k_stage_tile( TileArgs T )
 {
   extern __shared__ double Fs[];
-  const int tile = T.tile_list ? T.tile_list[blockIdx.x] : (int)blockIdx.x;
+  __shared__ int s_claim;
+  int claim = (int)blockIdx.x;
+  if (T.lookback) {                 // claim work in launch order: whoever is waited for is already running
+    if (threadIdx.x == 0) s_claim = (int)( atomicAdd( T.counter, 1ULL ) - T.cbase );
+    __syncthreads();
+    claim = s_claim;
+  }
+  const int tile = T.tile_list ? T.tile_list[claim] : claim;
   const int s0 = T.tile_sl[tile], s1 = T.tile_sl[tile+1];
   const int tn = (s1 - s0)*32;                       // nodes of this tile
   const int tid = threadIdx.x, lane = tid & 31;
@@ -147,18 +209,31 @@ k_stage_tile( TileArgs T )
     double wo[NC], xo[3], go[15];
     load_wx( WX, NP, p, wo, xo );
     load_g( G2, NP, p, go );
+    // the next edge's indices and normal are fetched one iteration ahead, so that its operand
+    // gathers can leave as soon as the iteration starts
+    size_t sl = (size_t)b0 + lane;
+    int e_nx = -1; unsigned dst_nx = 0xffffu; double n_nx[4] = { 0.0, 0.0, 0.0, 0.0 };
+    if (kmax > 0) {
+      e_nx = __ldg( T.eo + sl ); dst_nx = __ldg( T.els + sl );
+      #pragma unroll
+      for (int i=0; i<4; ++i) n_nx[i] = __ldg( T.D + (size_t)i*nslot + sl );
+    }
     #pragma unroll kOwnUnroll
     for (int j=0; j<kmax; ++j) {
-      size_t sl = (size_t)b0 + (size_t)j*32 + lane;
-      int e = __ldg( T.eo + sl );
-      unsigned dst = __ldg( T.els + sl );
+      int e = e_nx; unsigned dst = dst_nx;
+      double n[4] = { n_nx[0], n_nx[1], n_nx[2], n_nx[3] };
       bool valid = e != -1;
       double s = e < 0 ? -1.0 : 1.0;
       size_t q = valid ? (size_t)(e & 0x7fffffff) : p;
-      double n[3] = { __ldg( T.D + sl ), __ldg( T.D + nslot + sl ), __ldg( T.D + 2*nslot + sl ) };
       double wq[NC], xq[3], gq[15];
       load_wx( WX, NP, q, wq, xq );
       load_g( G2, NP, q, gq );
+      sl += 32;
+      if (j+1 < kmax) {
+        e_nx = __ldg( T.eo + sl ); dst_nx = __ldg( T.els + sl );
+        #pragma unroll
+        for (int i=0; i<4; ++i) n_nx[i] = __ldg( T.D + (size_t)i*nslot + sl );
+      }
       double f[NC];
       edge_flux_owner< EXACT, FLUX >( wo, xo, go, wq, xq, gq, s, n, T.P, f );
       if (valid) {
@@ -167,18 +242,44 @@ k_stage_tile( TileArgs T )
         if (dst != 0xffffu) {
           #pragma unroll
           for (int c=0; c<NC; ++c) Fs[c*T.fstride + dst] = f[c];
-        }
+        } else if (T.lookback) store_f( T.F, nslot, sl - 32, f );    // for the receiver's tile
       }
     }
+  }
+  if (T.lookback) {                 // publish: this tile's fluxes are in F
+    __syncthreads();
+    if (tid == 0) { __threadfence(); atomicExch( T.tflag + tile, T.epoch ); }
   }
   // ---- foreign edges: owned by a node of another tile, received here ----
   for (int i = T.foff[tile] + tid; i < T.foff[tile+1]; i += blockDim.x) {
     size_t a = (size_t)__ldg( T.fa + i ), sl = (size_t)__ldg( T.fsl + i );
     unsigned dst = __ldg( T.fdst + i );
+    if (T.lookback) {
+      int ot = __ldg( T.tile_of_slice + (a >> 5) );
+      bool ready = false;
+      if (!T.tpos || T.tpos[ot] < T.tpos[tile]) {
+        const int* fl = T.tflag + ot;
+        for (int it=0; it<(1<<22); ++it) {            // bounded: falls back to evaluating the edge
+          int v;
+          asm volatile( "ld.acquire.gpu.global.s32 %0, [%1];" : "=r"( v ) : "l"( fl ) : "memory" );
+          if (v == T.epoch) { ready = true; break; }
+          __nanosleep( 100 );
+        }
+      }
+      if (ready) {
+        const double* Fg = T.F;
+        double2 a01 = __ldcg( reinterpret_cast< const double2* >( Fg ) + sl );
+        double2 a23 = __ldcg( reinterpret_cast< const double2* >( Fg ) + nslot + sl );
+        double a4 = __ldcg( Fg + 4*nslot + sl );
+        Fs[dst] = a01.x; Fs[T.fstride + dst] = a01.y; Fs[2*T.fstride + dst] = a23.x; Fs[3*T.fstride + dst] = a23.y;
+        Fs[4*T.fstride + dst] = a4;
+        continue;
+      }
+    }
     int e = __ldg( T.eo + sl );
     double s = e < 0 ? -1.0 : 1.0;
     size_t q = (size_t)(e & 0x7fffffff);
-    double n[3] = { __ldg( T.D + sl ), __ldg( T.D + nslot + sl ), __ldg( T.D + 2*nslot + sl ) };
+    double n[4] = { __ldg( T.D + sl ), __ldg( T.D + nslot + sl ), __ldg( T.D + 2*nslot + sl ), __ldg( T.D + 3*nslot + sl ) };
     double wo[NC], xo[3], go[15], wq[NC], xq[3], gq[15];
     load_wx( WX, NP, a, wo, xo );
     load_g( G2, NP, a, go );

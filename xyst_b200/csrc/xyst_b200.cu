@@ -252,6 +252,9 @@ struct xyst_ctx : CgState {
   DevBuf< int > tile_sl, foff, fa, fsl, btiles, itiles, shidx;
   DevBuf< unsigned short > fdst, els; DevBuf< unsigned char > indeg;
   DevBuf< double > W2;
+  // look-back between tiles: per-tile "fluxes published" flags, claim counter, processing position
+  DevBuf< int > tile_of, tflag, tpos; DevBuf< unsigned long long > tcounter;
+  unsigned long long tile_count_h = 0; int tile_epoch = 0, lookback = 0;
   int flux_mode = 2;                     // 0: k_flux_edge + gather, 1: k_flux_own + gather, 2: k_stage_tile
   unsigned tile_attr = 0;                // kernel instances whose shared-memory limit has been raised
   // profiling
@@ -327,6 +330,10 @@ void refresh_shared( xyst_ctx* c ) {
     for (size_t t=0; t<c->ntile; ++t) (isb[t] ? bt : it).push_back( (int)t );
     c->nbt = bt.size(); c->nit = it.size();
     c->shidx.upload( shidx, c->stream ); c->btiles.upload( bt, c->stream ); c->itiles.upload( it, c->stream );
+    std::vector< int > tpos( c->ntile );
+    for (size_t i=0; i<bt.size(); ++i) tpos[(size_t)bt[i]] = (int)i;
+    for (size_t i=0; i<it.size(); ++i) tpos[(size_t)it[i]] = (int)( bt.size() + i );
+    c->tpos.upload( tpos, c->stream );
   }
 }
 
@@ -512,16 +519,17 @@ void do_flux_own( xyst_ctx* c )
 }
 
 template< bool EX, int FL, bool FUSED, bool LAX >
-void launch_tile( xyst_ctx* c, const TileArgs& T, unsigned ntile, cudaStream_t st )
+void launch_tile( xyst_ctx* c, TileArgs T, unsigned ntile, cudaStream_t st )
 {
   if (!ntile) return;
+  T.cbase = c->tile_count_h; c->tile_count_h += ntile;
   size_t smem = (size_t)NC*(size_t)c->fstride*sizeof(double);
   unsigned bit = 1u << ((EX ? 16 : 0) + FL*4 + (FUSED ? 2 : 0) + (LAX ? 1 : 0));
   if (!(c->tile_attr & bit)) {
     CK( cudaFuncSetAttribute( k_stage_tile< EX, FL, FUSED, LAX >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
     c->tile_attr |= bit;
   }
-  k_stage_tile< EX, FL, FUSED, LAX ><<< ntile, 256, smem, st >>>( T );
+  k_stage_tile< EX, FL, FUSED, LAX ><<< ntile, (unsigned)c->tile_nodes, smem, st >>>( T );
   ++c->launches;
 }
 
@@ -559,6 +567,8 @@ void do_stage_tile( xyst_ctx* c, bool fused, int stage, double dt, const double*
   T.bslot = c->bslot.p; T.Rb = c->Rb.p; T.S = c->S.p; T.src_mask = c->src_mask; T.v = c->v.p; T.vol = c->vol.p;
   T.Un = Un; T.U = Uout; T.Wout = c->W2.p; T.R = c->R.p; T.Wn = c->Wn.p; T.UnOut = c->Un.p;
   T.shidx = halo ? c->shidx.p : nullptr; T.part = c->sh_part.p;
+  T.tile_of_slice = c->tile_of.p; T.lookback = c->lookback; T.epoch = ++c->tile_epoch; T.tflag = c->tflag.p;
+  T.tpos = halo ? c->tpos.p : nullptr; T.F = c->F.p; T.counter = c->tcounter.p;
   T.A = A; T.P = dparams( c );
   {
     ProfScope ps( c, "flux" );
@@ -695,7 +705,8 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   { const char* e = getenv( "XYST_REORDER" ); if (e && e[0] == '0') opt.reorder = false;
     e = getenv( "XYST_TILE" ); if (e && atoi( e ) >= 32) c->tile_nodes = std::min( 256, atoi( e ) / 32 * 32 );
     e = getenv( "XYST_TILE_CAP" ); if (e && atoi( e ) > 0) opt.cap = (size_t)atoi( e );
-    e = getenv( "XYST_FLUX_MODE" ); if (e) c->flux_mode = atoi( e ); }
+    e = getenv( "XYST_FLUX_MODE" ); if (e) c->flux_mode = atoi( e );
+    e = getenv( "XYST_LOOKBACK" ); if (e) c->lookback = atoi( e ); }
   opt.tile_nodes = (size_t)c->tile_nodes;
   for (size_t i=0; i<ntri*3; ++i) if (triinpoel[i] >= npoin) throw std::runtime_error( "node id out of range in superedge" );
   layout::Mesh M = layout::build( npoin, x, y, z, nsup, dsupedge, dsupint, stride, opt );
@@ -770,6 +781,10 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   if (tiles) {
     c->tile_sl.upload( M.tile_sl, s ); c->foff.upload( M.foff, s ); c->fa.upload( M.fa, s ); c->fsl.upload( M.fsl, s );
     c->fdst.upload( M.fdst, s ); c->els.upload( M.els, s ); c->indeg.upload( M.indeg, s );
+    c->tile_of.upload( M.tile_of, s );
+    c->tflag.upload( std::vector< int >( M.ntile, 0 ), s );
+    c->tcounter.upload( std::vector< unsigned long long >( 1, 0ULL ), s );
+    c->tile_count_h = 0; c->tile_epoch = 0; c->tpos.release();
   }
   CK( cudaMemsetAsync( c->G.p, 0, NP*2*NGP*sizeof(double), s ) );
   CK( cudaMemsetAsync( c->F.p, 0, std::max< size_t >( nslot, 1 )*NC*sizeof(double), s ) );

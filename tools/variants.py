@@ -16,19 +16,17 @@ LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib")
 # name -> (defines, environment)
 VAR = {
     "own_reorder": ([], {"XYST_FLUX_MODE": "1"}),
-    "tile": ([], {}),
-    "tile_lb": ([], {"XYST_LOOKBACK": "1"}),
-    "tile224_lb": ([], {"XYST_TILE": "224", "XYST_LOOKBACK": "1"}),
-    "tile_lb_sint": (["MUSCL_SIGN_INT=1"], {"XYST_LOOKBACK": "1"}),
-    "tile224": ([], {"XYST_TILE": "224"}),
-    "tile192": ([], {"XYST_TILE": "192"}),
-    "tile128": ([], {"XYST_TILE": "128"}),
-    "tile_sint": (["MUSCL_SIGN_INT=1"], {}),
-    "tile_u2": (["OWN_UNROLL=2"], {}),
-    "tile_g128": (["NODE_THREADS=128", "GRAD_MINB=4", "RHS_MINB=4"], {}),
-    "tile_g128u7": (["NODE_THREADS=128", "GRAD_MINB=4", "RHS_MINB=4", "GRAD_UNROLL=7"], {}),
-    "tile_g128u4": (["NODE_THREADS=128", "GRAD_MINB=4", "RHS_MINB=4", "GRAD_UNROLL=4"], {}),
-    "tile_g128u2m6": (["NODE_THREADS=128", "GRAD_MINB=6", "RHS_MINB=4", "GRAD_UNROLL=2"], {}),
+    "own2": ([], {"XYST_FLUX_MODE": "3"}),
+    "own2_noreorder": ([], {"XYST_FLUX_MODE": "3", "XYST_REORDER": "0"}),
+    "own2_sint": (["MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
+    "own2_m3": (["OWN_MINB=3"], {"XYST_FLUX_MODE": "3"}),
+    "own2_m3_sint": (["OWN_MINB=3", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
+    "own2_m5_sint": (["OWN_MINB=5", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
+    "own2_t256m2": (["OWN_THREADS=256", "OWN_MINB=2", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
+    "own2_t64m8": (["OWN_THREADS=64", "OWN_MINB=8", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
+    "own2_r128": (["NODE_THREADS=128", "RHS_MINB=8", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
+    "own2_g256m2": (["GRAD_THREADS=256", "GRAD_MINB=2", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
+    "own2_g64m8": (["GRAD_THREADS=64", "GRAD_MINB=8", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
 }
 
 

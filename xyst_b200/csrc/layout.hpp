@@ -40,6 +40,8 @@ struct Mesh {
   std::vector< int > ep, eq, eo;                   // [nslot]
   std::vector< double > ed;                        // [drows][nslot] edge integrals (normal, + extra terms)
   std::vector< int > inc_e, inc_q;                 // [nent] signed slot+1 (0 = padding), neighbour
+  std::vector< long long > in_base;                // [nslice+1] offsets of the INCOMING-edge lists
+  std::vector< int > in_e;                         // signed slot+1 of the edges owned by lower neighbours
   std::vector< int > tile_sl, foff, fa, fsl;       // tiles: [ntile+1], [ntile+1], foreign owner, foreign slot
   std::vector< int > tile_of;                      // [nslice] tile of each slice
   std::vector< unsigned short > fdst, els;         // foreign / owned-slot shared-memory positions
@@ -157,6 +159,22 @@ inline Mesh build( size_t npoin, const double* x, const double* y, const double*
       size_t e = (size_t)perm[i].i;
       int o = std::min( P[e], Q[e] ), h = std::max( P[e], Q[e] );
       addinc( h, o, h == Q[e] ? slot_of[i]+1 : -(slot_of[i]+1) );
+    } }
+  // --- incoming edges only (k_update_in): sliced ELL, ascending owner ---------------------------
+  { M.in_base.assign( nslice+1, 0 );
+    for (size_t s=0; s<nslice; ++s) {
+      int km = 0;
+      for (size_t p=s*32; p<std::min( npoin, s*32+32 ); ++p) km = std::max( km, deg[p] - udeg[p] );
+      M.in_base[s+1] = M.in_base[s] + (long long)km*32;
+    }
+    M.in_e.assign( (size_t)M.in_base[nslice], 0 );
+    std::vector< int > fill( npoin, 0 );
+    for (size_t i=0; i<ne; ++i) {
+      size_t e = (size_t)perm[i].i;
+      int h = std::max( P[e], Q[e] );
+      size_t pos = (size_t)M.in_base[(size_t)h/32] + (size_t)fill[h]*32 + (size_t)(h%32);
+      ++fill[h];
+      M.in_e[pos] = h == Q[e] ? slot_of[i]+1 : -(slot_of[i]+1);
     } }
   // --- tiles of the fused stage kernel --------------------------------------------------------
   if (opt.tiles) {

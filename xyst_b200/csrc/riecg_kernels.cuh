@@ -284,7 +284,7 @@ __device__ __forceinline__ void grad_sum( size_t p, int lane, long long base, in
   }
 }
 
-__global__ void __launch_bounds__(NODE_THREADS, GRAD_MINB)
+__global__ void __launch_bounds__(GRAD_THREADS, GRAD_MINB)
 k_grad_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq,
              const double2* __restrict__ D2, const double* __restrict__ D, size_t nslot,
              const double* __restrict__ W, const int* __restrict__ bslot, const double* __restrict__ Gb,

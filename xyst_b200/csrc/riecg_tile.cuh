@@ -149,6 +149,136 @@ k_flux_own( size_t nslice, size_t NP, size_t nslot, const long long* __restrict_
   }
 }
 
+// 16-byte asynchronous global->shared copy (LDGSTS.128), cached in L1 as well: a node is the other end
+// of ~7 owners, most of them in the same or a neighbouring thread block
+__device__ __forceinline__ void cp_async16( double2* smem_dst, const double2* gsrc )
+{
+  unsigned d = (unsigned)__cvta_generic_to_shared( smem_dst );
+  asm volatile( "cp.async.ca.shared.global [%0], [%1], 16;" :: "r"( d ), "l"( gsrc ) : "memory" );
+}
+
+// k_flux_own2: as k_flux_own, with the other end's 12 pairs staged through shared memory one edge
+// AHEAD (cp.async into the thread's own column of a double buffer: in flight without registers, so
+// the gather latency of edge j+1 hides behind the ~450 instructions of edge j), and with the owner's
+// own share of the nodal sum kept in registers: Racc(p) = - sum over owned edges f'. The receiver's
+// share is gathered from F by k_update_in.
+constexpr int NQP = 12;            // pairs per node: 4 of WX, 8 of G
+template< bool EXACT, int FLUX >
+__global__ void __launch_bounds__(OWN_THREADS, OWN_MINB)
+k_flux_own2( size_t nslice, size_t NP, size_t nslot, const long long* __restrict__ ebase, const int* __restrict__ eo,
+             const double* __restrict__ D, const double* __restrict__ W, const double* __restrict__ G,
+             double* __restrict__ F, double* __restrict__ Racc, DParams P )
+{
+  extern __shared__ double2 qb[];                    // [2][NQP][OWN_THREADS]
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, tid = threadIdx.x;
+  if (slice >= nslice) return;
+  size_t p = slice*32 + lane;
+  const double2* WX = reinterpret_cast< const double2* >( W );
+  const double2* G2 = reinterpret_cast< const double2* >( G );
+  long long b0 = ebase[slice];
+  int kmax = (int)((ebase[slice+1] - b0) >> 5);
+  double acc[NC] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+  auto stage = [&]( int buf, size_t q ) {
+    double2* dst = qb + (size_t)buf*NQP*OWN_THREADS + tid;
+    #pragma unroll
+    for (int k=0; k<4; ++k) cp_async16( dst + k*OWN_THREADS, WX + (size_t)k*NP + q );
+    #pragma unroll
+    for (int k=0; k<NGP; ++k) cp_async16( dst + (4+k)*OWN_THREADS, G2 + (size_t)k*NP + q );
+    cp_async_commit();
+  };
+  if (kmax > 0) {
+    size_t sl = (size_t)b0 + lane;
+    int e_cur = __ldg( eo + sl );
+    int e_nx = kmax > 1 ? __ldg( eo + sl + 32 ) : -1;
+    stage( 0, e_cur != -1 ? (size_t)(e_cur & 0x7fffffff) : p );
+    double wo[NC], xo[3], go[15];
+    load_wx( WX, NP, p, wo, xo );
+    load_g( G2, NP, p, go );
+    for (int j=0; j<kmax; ++j) {
+      const int e = e_cur, buf = j & 1;
+      double n[4] = { __ldg( D + sl ), __ldg( D + nslot + sl ), __ldg( D + 2*nslot + sl ), __ldg( D + 3*nslot + sl ) };
+      if (j+1 < kmax) {                              // next edge's operands leave now
+        stage( buf ^ 1, e_nx != -1 ? (size_t)(e_nx & 0x7fffffff) : p );
+        e_cur = e_nx;
+        e_nx = j+2 < kmax ? __ldg( eo + sl + 64 ) : -1;
+        cp_async_wait< 1 >();
+      } else
+        cp_async_wait< 0 >();
+      const double2* src = qb + (size_t)buf*NQP*OWN_THREADS + tid;
+      double2 a[NQP];
+      #pragma unroll
+      for (int k=0; k<NQP; ++k) a[k] = src[k*OWN_THREADS];
+      double wq[NC] = { a[0].x, a[0].y, a[1].x, a[1].y, a[2].x }, xq[3] = { a[2].y, a[3].x, a[3].y }, gq[15];
+      #pragma unroll
+      for (int k=0; k<7; ++k) { gq[2*k] = a[4+k].x; gq[2*k+1] = a[4+k].y; }
+      gq[14] = a[11].x;
+      const bool valid = e != -1;
+      const double s = e < 0 ? -1.0 : 1.0;
+      double f[NC];
+      edge_flux_owner< EXACT, FLUX >( wo, xo, go, wq, xq, gq, s, n, P, f );
+      if (valid) {
+        #pragma unroll
+        for (int c=0; c<NC; ++c) { acc[c] -= f[c]; f[c] *= s; }     // F holds the reference-oriented flux
+        store_f( F, nslot, sl, f );
+      }
+      sl += 32;
+    }
+  }
+  #pragma unroll
+  for (int c=0; c<NC; ++c) Racc[c*NP+p] = acc[c];
+}
+
+// Receiver side of k_flux_own2 fused with the RK update: Racc + the node's INCOMING edges (owned by
+// lower neighbours, ascending; entries as in the incidence lists: +(slot+1) if the node is the edge's
+// second node, -(slot+1) if its first, 0 = padding) + boundary + source, then node_update.
+template< bool FUSED, bool LAX >
+__global__ void __launch_bounds__(NODE_THREADS, RHS_MINB)
+k_update_in( size_t npoin, size_t NP, const long long* __restrict__ in_base, const int* __restrict__ in_e,
+             const double* __restrict__ Racc, const double* __restrict__ F, size_t nslot,
+             const int* __restrict__ bslot, const double* __restrict__ Rb, const double* __restrict__ S, int src_mask,
+             const double* __restrict__ v, const double* __restrict__ vol, const double* __restrict__ Un,
+             StageArgs A, double* __restrict__ U, double* __restrict__ W, double* __restrict__ R,
+             double* __restrict__ Wn, double* __restrict__ UnOut, const unsigned char* __restrict__ skip )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  if (FUSED && skip && skip[p]) return;
+  long long base = in_base[slice];
+  int kmax = (int)((in_base[slice+1] - base) >> 5);
+  double acc[NC];
+  #pragma unroll
+  for (int c=0; c<NC; ++c) acc[c] = Racc[c*NP+p];
+  #pragma unroll 7
+  for (int k=0; k<kmax; ++k) {
+    int se = __ldg( in_e + base + (long long)k*32 + lane );
+    double sg = se > 0 ? 1.0 : (se < 0 ? -1.0 : 0.0);
+    size_t sl = se == 0 ? 0 : (size_t)(abs(se)-1);
+    double f[NC];
+    load_f( F, nslot, sl, f );
+    #pragma unroll
+    for (int c=0; c<NC; ++c) acc[c] = fma( sg, f[c], acc[c] );
+  }
+  int b = bslot[p];
+  if (b >= 0) {
+    #pragma unroll
+    for (int c=0; c<NC; ++c) acc[c] += Rb[(size_t)b*NC+c];
+  }
+  if (src_mask) {
+    double vp = v[p];
+    #pragma unroll
+    for (int c=0; c<NC; ++c) if (src_mask & (1<<c)) acc[c] -= S[p*NC+c] * vp;
+  }
+  if (FUSED) {
+    node_update< LAX >( p, NP, acc, vol[p], Un, U, W, W, Wn, UnOut, A );
+  } else {
+    #pragma unroll
+    for (int c=0; c<NC; ++c) R[p*NC+c] = acc[c];
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // fused stage kernel
 // ---------------------------------------------------------------------------------

@@ -61,6 +61,9 @@ int fail( const std::string& m ) { g_err = m; return 1; }
 #ifndef NODE_THREADS
 #define NODE_THREADS 256
 #endif
+#ifndef GRAD_THREADS
+#define GRAD_THREADS 128   // 128 registers per thread: the fully unrolled incidence loop without spills
+#endif
 #ifndef GRAD_MINB
 #define GRAD_MINB 4
 #endif
@@ -244,6 +247,9 @@ struct xyst_ctx : CgState {
   // owner-slot view of the edges for the thread-per-owner kernels: slot base per slice, and per slot
   // the edge's other end | orientation bit (31: the owner is the edge's SECOND node), -1 = padding
   DevBuf< long long > ebase; DevBuf< int > eo;
+  // owner's share of the nodal flux sums (k_flux_own2) and the incoming-edge lists of k_update_in
+  DevBuf< double > Racc; DevBuf< long long > in_base; DevBuf< int > in_e;
+  bool own2_attr = false;
   // tiles of the fused stage kernel (riecg_tile.cuh): slices per tile, foreign-edge lists, per owned slot
   // the shared-memory position of its flux (0xffff: receiver in another tile), incoming-edge counts,
   // second buffer of the primitives, tiles with / without nodes shared with other partitions
@@ -394,7 +400,7 @@ void do_grad( xyst_ctx* c )
   }
   {
     ProfScope ps( c, "grad" );
-    k_grad_node<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p,
+    k_grad_node<<< nblk( c->nslice*32, GRAD_THREADS ), GRAD_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p,
       c->inc_eq.p, c->D2.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->vol.p, c->G.p, overlap ? 1 : 0 );
     ++c->launches;
   }
@@ -445,6 +451,15 @@ void launch_rhs_node( xyst_ctx* c, bool fused, const StageArgs& A, const double*
       c->sh_flag.upload( f, st );
     }
     skip = c->sh_flag.p;
+  }
+  if (c->flux_mode == 3) {        // own share already summed by k_flux_own2
+    #define UPD_IN( FU, LX ) k_update_in< FU, LX ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->in_base.p, c->in_e.p, \
+        c->Racc.p, c->F.p, c->nslot, c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, \
+        c->Wn.p, c->Un.p, skip )
+    if (fused && c->lax) UPD_IN( true, true ); else if (fused) UPD_IN( true, false ); else UPD_IN( false, false );
+    #undef UPD_IN
+    ++c->launches;
+    return;
   }
   if (fused && c->lax)
     k_rhs_node< true, true ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
@@ -515,6 +530,28 @@ void do_flux_own( xyst_ctx* c )
   else         { if (fl == 0) LAUNCH_OWN( false, 0 ); else if (fl == 1) LAUNCH_OWN( false, 1 );
                  else if (fl == 2) LAUNCH_OWN( false, 2 ); else LAUNCH_OWN( false, 3 ); }
   #undef LAUNCH_OWN
+  ++c->launches;
+}
+
+// k_flux_own2: other end staged through shared memory one edge ahead, own share kept (Racc)
+void do_flux_own2( xyst_ctx* c )
+{
+  auto s = c->stream;
+  auto P = dparams( c );
+  ProfScope ps( c, "flux" );
+  unsigned g = nblk( c->nslice*32, OWN_THREADS );
+  size_t smem = (size_t)2*NQP*OWN_THREADS*sizeof(double2);
+  #define LAUNCH_OWN2( EX, FL ) do { \
+      if (!c->own2_attr) CK( cudaFuncSetAttribute( k_flux_own2< EX, FL >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) ); \
+      k_flux_own2< EX, FL ><<< g, OWN_THREADS, smem, s >>>( c->nslice, c->NP, c->nslot, \
+        c->ebase.p, c->eo.p, c->D.p, c->W.p, c->G.p, c->F.p, c->Racc.p, P ); } while (0)
+  int fl = P.flux + (c->lax ? 2 : 0);
+  if (P.exact) { if (fl == 0) LAUNCH_OWN2( true, 0 ); else if (fl == 1) LAUNCH_OWN2( true, 1 );
+                 else if (fl == 2) LAUNCH_OWN2( true, 2 ); else LAUNCH_OWN2( true, 3 ); }
+  else         { if (fl == 0) LAUNCH_OWN2( false, 0 ); else if (fl == 1) LAUNCH_OWN2( false, 1 );
+                 else if (fl == 2) LAUNCH_OWN2( false, 2 ); else LAUNCH_OWN2( false, 3 ); }
+  #undef LAUNCH_OWN2
+  c->own2_attr = true;      // (flux and limiter form are fixed per context)
   ++c->launches;
 }
 
@@ -743,6 +780,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   c->nent = nent; c->nbn = nbn;
   c->ep.upload( ep, s ); c->eq.upload( eq, s ); c->D.upload( ed, s );
   c->eo.upload( M.eo, s ); c->ebase.upload( ebase, s );
+  c->in_base.upload( M.in_base, s ); c->in_e.upload( M.in_e, s );
   { std::vector< double2 > d2( nslot );
     for (size_t i=0; i<nslot; ++i) d2[i] = make_double2( ed[i], ed[nslot+i] );
     c->D2.upload( d2, s );
@@ -769,7 +807,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
     CK( cudaStreamSynchronize( s ) );
     return 0;
   }
-  c->U.alloc( NP*NC ); c->Un.alloc( NP*NC ); c->G.alloc( NP*2*NGP );
+  c->U.alloc( NP*NC ); c->Un.alloc( NP*NC ); c->G.alloc( NP*2*NGP ); c->Racc.alloc( NP*NC );
   c->R.alloc( npoin*NC ); c->stage.alloc( npoin*NC ); c->F.alloc( std::max< size_t >( nslot, 1 )*NC );
   { std::vector< double > one( NP*NC, 1.0 );    // a harmless state until xyst_state_set
     c->U.upload( one, s ); c->Un.upload( one, s );
@@ -1006,7 +1044,7 @@ int xyst_riecg_rhs( xyst_ctx* c )
   need_mesh( c );
   if (c->flux_mode == 2 && c->ntile) do_stage_tile( c, false, 0, 0.0, c->Un.p, c->U.p );
   else {
-    if (c->flux_mode == 1) do_flux_own( c ); else do_flux( c );
+    if (c->flux_mode == 3) do_flux_own2( c ); else if (c->flux_mode == 1) do_flux_own( c ); else do_flux( c );
     do_rhs_nodes( c, false, 0, 0.0, c->U.p, c->Un.p, c->U.p );
   }
   API_END
@@ -1069,7 +1107,7 @@ int xyst_riecg_stage( xyst_ctx* c, int stage, double dt )
   if (stage < 0 || stage > 2) throw std::runtime_error( "stage must be 0, 1 or 2" );
   do_grad( c );
   const bool tile = c->flux_mode == 2 && c->ntile;
-  if (!tile) { if (c->flux_mode == 1) do_flux_own( c ); else do_flux( c ); }
+  if (!tile) { if (c->flux_mode == 3) do_flux_own2( c ); else if (c->flux_mode == 1) do_flux_own( c ); else do_flux( c ); }
   auto nodes = [&]( const double* Un, double* Uout ) {
     if (tile) do_stage_tile( c, true, stage, dt, Un, Uout );
     else do_rhs_nodes( c, true, stage, dt, c->U.p, Un, Uout );

@@ -12,7 +12,7 @@
 extern "C" int layout_check( size_t npoin, const double* x, const double* y, const double* z,
                              const size_t nsup[3], const size_t* const dsupedge[3], const double* const dsupint[3],
                              size_t stride, int reorder, size_t tile_nodes, size_t cap,
-                             size_t* stats /* [8] */, char* msg, size_t msglen )
+                             size_t* stats /* [10] */, char* msg, size_t msglen )
 {
   auto fail = [&]( const std::string& m ){ std::snprintf( msg, msglen, "%s", m.c_str() ); return 1; };
   try {
@@ -114,6 +114,23 @@ extern "C" int layout_check( size_t npoin, const double* x, const double* y, con
         if (got != ref) return fail( "tile sums differ from the incidence list (edges or order)" );
       }
     }
+    // coalescing of the owner kernels' gathers: 32-byte sectors and 128-byte lines one warp-wide 16-byte
+    // load of the other ends touches (ideal: 16 and 4), averaged over all (slice, j) with >= 1 valid lane
+    { double sec = 0, lin = 0, cnt = 0;
+      for (size_t sl=0; sl<M.nslice; ++sl) {
+        int kmax = (int)((M.ebase[sl+1]-M.ebase[sl]) >> 5);
+        for (int j=0; j<kmax; ++j) {
+          std::set< long long > S, L; int nv = 0;
+          for (int lane=0; lane<32; ++lane) {
+            int e = M.eo[(size_t)M.ebase[sl] + (size_t)j*32 + (size_t)lane];
+            if (e == -1) continue;
+            long long q = e & 0x7fffffff; ++nv;
+            S.insert( q/2 ); L.insert( q/8 );
+          }
+          if (nv) { sec += (double)S.size()*32.0/nv; lin += (double)L.size()*32.0/nv; cnt += 1; }
+        }
+      }
+      stats[8] = (size_t)(1000.0*sec/cnt); stats[9] = (size_t)(1000.0*lin/cnt); }
     stats[0] = M.ne; stats[1] = M.nslot; stats[2] = M.ntile; stats[3] = nforeign; stats[4] = (size_t)M.fstride;
     stats[5] = maxtn; stats[6] = M.nent; stats[7] = (size_t)M.maxdeg;
   } catch (std::exception& e) { return fail( e.what() ); }

@@ -15,18 +15,16 @@ from xyst_b200 import build as B
 LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib")
 # name -> (defines, environment)
 VAR = {
-    "own_reorder": ([], {"XYST_FLUX_MODE": "1"}),
-    "own2": ([], {"XYST_FLUX_MODE": "3"}),
-    "own2_noreorder": ([], {"XYST_FLUX_MODE": "3", "XYST_REORDER": "0"}),
-    "own2_sint": (["MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
-    "own2_m3": (["OWN_MINB=3"], {"XYST_FLUX_MODE": "3"}),
-    "own2_m3_sint": (["OWN_MINB=3", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
-    "own2_m5_sint": (["OWN_MINB=5", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
-    "own2_t256m2": (["OWN_THREADS=256", "OWN_MINB=2", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
-    "own2_t64m8": (["OWN_THREADS=64", "OWN_MINB=8", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
-    "own2_r128": (["NODE_THREADS=128", "RHS_MINB=8", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
-    "own2_g256m2": (["GRAD_THREADS=256", "GRAD_MINB=2", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
-    "own2_g64m8": (["GRAD_THREADS=64", "GRAD_MINB=8", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "3"}),
+    "own_noreorder": ([], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
+    "own_reorder": ([], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "1"}),
+    "own_wx125": ([], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "1", "XYST_TILE_WX": "0.125"}),
+    "own_wx03": ([], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "1", "XYST_TILE_WX": "0.03"}),
+    "own_nr_sint": (["MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
+    "own_nr_m3": (["OWN_MINB=3"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
+    "own_nr_m3_sint": (["OWN_MINB=3", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
+    "own_nr_t256m2_sint": (["OWN_THREADS=256", "OWN_MINB=2", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
+    "own_nr_t64m8_sint": (["OWN_THREADS=64", "OWN_MINB=8", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
+    "own_nr_u2_sint": (["OWN_UNROLL=2", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
 }
 
 

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 
 namespace locality {
 
@@ -59,7 +60,8 @@ inline std::vector< int > tile_order( size_t npoin, const double* x, const doubl
   for (size_t i=0; i<npoin; ++i) idx[i] = (int)i;
   Coords X{ x, y, z };
   // x runs fastest inside a tile: prefer tiles about twice as long in x as in y and z
-  const double w[3] = { 0.5, 1.0, 1.0 };
+  double w[3] = { 0.5, 1.0, 1.0 };
+  if (const char* e = getenv( "XYST_TILE_WX" )) w[0] = atof( e );
   bisect( X, idx.data(), npoin, tile, w );
   return idx;
 }

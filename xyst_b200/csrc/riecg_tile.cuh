@@ -113,7 +113,7 @@ template< bool EXACT, int FLUX >
 __global__ void __launch_bounds__(OWN_THREADS, OWN_MINB)
 k_flux_own( size_t nslice, size_t NP, size_t nslot, const long long* __restrict__ ebase, const int* __restrict__ eo,
             const double* __restrict__ D, const double* __restrict__ W, const double* __restrict__ G,
-            double* __restrict__ F, DParams P )
+            double* __restrict__ F, double* __restrict__ Racc, DParams P )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -121,32 +121,42 @@ k_flux_own( size_t nslice, size_t NP, size_t nslot, const long long* __restrict_
   size_t p = slice*32 + lane;
   const double2* WX = reinterpret_cast< const double2* >( W );
   const double2* G2 = reinterpret_cast< const double2* >( G );
-  const double2* D2 = reinterpret_cast< const double2* >( D );   // rows 0,1 are NOT interleaved: use D directly
-  (void)D2;
   long long b0 = ebase[slice];
   int kmax = (int)((ebase[slice+1] - b0) >> 5);
-  double wo[NC], xo[3], go[15];
-  load_wx( WX, NP, p, wo, xo );
-  load_g( G2, NP, p, go );
-  #pragma unroll kOwnUnroll
-  for (int j=0; j<kmax; ++j) {
-    size_t sl = (size_t)b0 + (size_t)j*32 + lane;
-    int e = __ldg( eo + sl );
-    bool valid = e != -1;
-    double s = e < 0 ? -1.0 : 1.0;
-    size_t q = valid ? (size_t)(e & 0x7fffffff) : p;
-    double n[4] = { __ldg( D + sl ), __ldg( D + nslot + sl ), __ldg( D + 2*nslot + sl ), __ldg( D + 3*nslot + sl ) };
-    double wq[NC], xq[3], gq[15];
-    load_wx( WX, NP, q, wq, xq );
-    load_g( G2, NP, q, gq );
-    double f[NC];
-    edge_flux_owner< EXACT, FLUX >( wo, xo, go, wq, xq, gq, s, n, P, f );
-    if (valid) {
-      #pragma unroll
-      for (int c=0; c<NC; ++c) f[c] *= s;       // F holds the reference-oriented flux for k_rhs_node
-      store_f( F, nslot, sl, f );
+  double acc[NC] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+  if (kmax > 0) {
+    double wo[NC], xo[3], go[15];
+    load_wx( WX, NP, p, wo, xo );
+    load_g( G2, NP, p, go );
+    // the next edge's other end and normal are fetched one iteration ahead, so that its operand
+    // gathers can leave as soon as the iteration starts
+    size_t sl = (size_t)b0 + lane;
+    int e_nx = __ldg( eo + sl );
+    #pragma unroll kOwnUnroll
+    for (int j=0; j<kmax; ++j) {
+      const int e = e_nx;
+      // (the normal is needed last, by the Riemann solver: its load hides behind the limiter)
+      const double n[4] = { __ldg( D + sl ), __ldg( D + nslot + sl ), __ldg( D + 2*nslot + sl ), __ldg( D + 3*nslot + sl ) };
+      const bool valid = e != -1;
+      const double s = e < 0 ? -1.0 : 1.0;
+      const size_t q = valid ? (size_t)(e & 0x7fffffff) : p;
+      double wq[NC], xq[3], gq[15];
+      load_wx( WX, NP, q, wq, xq );
+      load_g( G2, NP, q, gq );
+      if (j+1 < kmax) e_nx = __ldg( eo + sl + 32 );
+      double f[NC];
+      edge_flux_owner< EXACT, FLUX >( wo, xo, go, wq, xq, gq, s, n, P, f );
+      if (valid) {
+        #pragma unroll
+        for (int c=0; c<NC; ++c) { acc[c] -= f[c]; f[c] *= s; }     // F holds the reference-oriented flux
+        store_f( F, nslot, sl, f );
+      }
+      sl += 32;
     }
   }
+  // the owner's own share of its nodal sum; the receivers' shares are gathered by k_update_in
+  #pragma unroll
+  for (int c=0; c<NC; ++c) Racc[c*NP+p] = acc[c];
 }
 
 // 16-byte asynchronous global->shared copy (LDGSTS.128), cached in L1 as well: a node is the other end

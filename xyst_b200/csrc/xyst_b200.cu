@@ -452,7 +452,7 @@ void launch_rhs_node( xyst_ctx* c, bool fused, const StageArgs& A, const double*
     }
     skip = c->sh_flag.p;
   }
-  if (c->flux_mode == 3) {        // own share already summed by k_flux_own2
+  if (c->flux_mode == 3 || c->flux_mode == 1) {        // own share already summed by the flux kernel
     #define UPD_IN( FU, LX ) k_update_in< FU, LX ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->in_base.p, c->in_e.p, \
         c->Racc.p, c->F.p, c->nslot, c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, \
         c->Wn.p, c->Un.p, skip )
@@ -523,7 +523,7 @@ void do_flux_own( xyst_ctx* c )
   ProfScope ps( c, "flux" );
   unsigned g = nblk( c->nslice*32, OWN_THREADS );
   #define LAUNCH_OWN( EX, FL ) k_flux_own< EX, FL ><<< g, OWN_THREADS, 0, s >>>( c->nslice, c->NP, c->nslot, \
-      c->ebase.p, c->eo.p, c->D.p, c->W.p, c->G.p, c->F.p, P )
+      c->ebase.p, c->eo.p, c->D.p, c->W.p, c->G.p, c->F.p, c->Racc.p, P )
   int fl = P.flux + (c->lax ? 2 : 0);
   if (P.exact) { if (fl == 0) LAUNCH_OWN( true, 0 ); else if (fl == 1) LAUNCH_OWN( true, 1 );
                  else if (fl == 2) LAUNCH_OWN( true, 2 ); else LAUNCH_OWN( true, 3 ); }

@@ -15,16 +15,14 @@ from xyst_b200 import build as B
 LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib")
 # name -> (defines, environment)
 VAR = {
-    "own_noreorder": ([], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
-    "own_reorder": ([], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "1"}),
-    "own_wx125": ([], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "1", "XYST_TILE_WX": "0.125"}),
-    "own_wx03": ([], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "1", "XYST_TILE_WX": "0.03"}),
-    "own_nr_sint": (["MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
-    "own_nr_m3": (["OWN_MINB=3"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
-    "own_nr_m3_sint": (["OWN_MINB=3", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
-    "own_nr_t256m2_sint": (["OWN_THREADS=256", "OWN_MINB=2", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
-    "own_nr_t64m8_sint": (["OWN_THREADS=64", "OWN_MINB=8", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
-    "own_nr_u2_sint": (["OWN_UNROLL=2", "MUSCL_SIGN_INT=1"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
+    "m3": (["OWN_MINB=3"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
+    "gsm4": (["OWN_GSMEM=1", "OWN_MINB=4"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
+    "gsm5": (["OWN_GSMEM=1", "OWN_MINB=5"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
+    "gsm4_t256": (["OWN_GSMEM=1", "OWN_MINB=2", "OWN_THREADS=256"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
+    "gsm4_gp": (["OWN_GSMEM=1", "OWN_MINB=4"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0", "XYST_GRAD_MODE": "1"}),
+    "gsm4_gp_w4": (["OWN_GSMEM=1", "OWN_MINB=4"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0", "XYST_GRAD_MODE": "1", "XYST_GRAD_WAVES": "4"}),
+    "gsm4_gp_m3": (["OWN_GSMEM=1", "OWN_MINB=4", "GRAD_MINB=3"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0", "XYST_GRAD_MODE": "1"}),
+    "gsm4_gp_reorder": (["OWN_GSMEM=1", "OWN_MINB=4"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "1", "XYST_TILE_WX": "0.03", "XYST_GRAD_MODE": "1"}),
 }
 
 

@@ -313,6 +313,81 @@ k_grad_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
   store_g( G, NP, p, acc );
 }
 
+// The same gather as a persistent kernel: every warp walks over slices s, s+S, s+2S, ... and fetches
+// the NEXT slice's incidence entries into its own piece of shared memory (cp.async, 8 bytes per entry
+// and lane) while it works on the current one -- the dependent chain incidence entry -> normal and
+// neighbour state then costs one trip to memory per slice instead of two.
+// Shared memory: [2][kcap][blockDim.x] int2.
+__global__ void __launch_bounds__(GRAD_THREADS, GRAD_MINB)
+k_grad_node_p( size_t npoin, size_t NP, size_t nslice, int kcap, const long long* __restrict__ sl_base,
+               const int2* __restrict__ inc_eq, const double2* __restrict__ D2, const double* __restrict__ D,
+               size_t nslot, const double* __restrict__ W, const int* __restrict__ bslot,
+               const double* __restrict__ Gb, const double* __restrict__ vol, double* __restrict__ G, int defer_bnd )
+{
+  extern __shared__ int2 sinc[];
+  const int lane = threadIdx.x & 31, nt = blockDim.x;
+  const size_t wstride = (size_t)gridDim.x*(nt >> 5);
+  size_t slice = (size_t)blockIdx.x*(nt >> 5) + (threadIdx.x >> 5);
+  const double2* WX = reinterpret_cast< const double2* >( W );
+  auto fetch = [&]( int buf, size_t s, long long& base, int& kmax ) {
+    base = sl_base[s];
+    kmax = (int)((sl_base[s+1] - base) >> 5);
+    int2* dst = sinc + (size_t)buf*kcap*nt + threadIdx.x;
+    for (int k=0; k<kmax; ++k) {
+      unsigned d = (unsigned)__cvta_generic_to_shared( dst + (size_t)k*nt );
+      asm volatile( "cp.async.ca.shared.global [%0], [%1], 8;" :: "r"( d ), "l"( inc_eq + base + (long long)k*32 + lane ) : "memory" );
+    }
+    cp_async_commit();
+  };
+  if (slice >= nslice) return;
+  long long base, base_nx = 0; int kmax, kmax_nx = 0, buf = 0;
+  fetch( 0, slice, base, kmax );
+  for (; slice < nslice; slice += wstride, buf ^= 1) {
+    const size_t nxt = slice + wstride;
+    if (nxt < nslice) { fetch( buf ^ 1, nxt, base_nx, kmax_nx ); cp_async_wait< 1 >(); }
+    else cp_async_wait< 0 >();
+    const size_t p = slice*32 + lane;
+    const int2* src = sinc + (size_t)buf*kcap*nt + threadIdx.x;
+    double wp[NC], acc[15];
+    load_w( WX, NP, p < npoin ? p : npoin-1, wp );
+    #pragma unroll
+    for (int i=0; i<15; ++i) acc[i] = 0.0;
+    #pragma unroll kGradUnroll
+    for (int k=0; k<kmax; ++k) {
+      int2 eq = src[(size_t)k*nt];
+      int se = eq.x, q = eq.y;
+      double sg = se > 0 ? 1.0 : (se < 0 ? -1.0 : 0.0);
+      size_t sl = se == 0 ? 0 : (size_t)(abs(se)-1);
+      double2 d01 = __ldg( D2 + sl );
+      double d0 = sg * d01.x, d1 = sg * d01.y, d2 = sg * __ldg( D + 2*nslot + sl );
+      double wq[NC];
+      load_w( WX, NP, (size_t)q, wq );
+      #pragma unroll
+      for (int c=0; c<NC; ++c) {
+        double s = wq[c] + wp[c];
+        acc[c*3+0] += d0 * s;
+        acc[c*3+1] += d1 * s;
+        acc[c*3+2] += d2 * s;
+      }
+    }
+    if (p < npoin) {
+      int b = bslot[p];
+      if (b >= 0 && defer_bnd) store_g( G, NP, p, acc );     // finished by k_grad_bfix
+      else {
+        if (b >= 0) {
+          #pragma unroll
+          for (int i=0; i<15; ++i) acc[i] += Gb[(size_t)b*15+i];
+        }
+        double vp = vol[p];
+        #pragma unroll
+        for (int i=0; i<15; ++i) acc[i] /= vp;
+        store_g( G, NP, p, acc );
+      }
+    }
+    base = base_nx; kmax = kmax_nx;
+  }
+}
+
 // boundary nodes: G = (domain sum + boundary sum) / vol, once both are known
 __global__ void k_grad_bfix( int nbn, size_t NP, const int* __restrict__ bn_node, const double* __restrict__ Gb,
                              const double* __restrict__ vol, double* __restrict__ G )

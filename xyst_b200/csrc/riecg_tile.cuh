@@ -33,6 +33,9 @@
 #ifndef TILE_MINB
 #define TILE_MINB 2
 #endif
+#ifndef OWN_GSMEM
+#define OWN_GSMEM 0        // 1: the owner's 15 gradient components live in shared memory, not in registers
+#endif
 constexpr int kOwnUnroll = OWN_UNROLL;
 
 __device__ __forceinline__ void load_g( const double2* __restrict__ G2, size_t NP, size_t p, double g[15] ) {
@@ -124,16 +127,30 @@ k_flux_own( size_t nslice, size_t NP, size_t nslot, const long long* __restrict_
   long long b0 = ebase[slice];
   int kmax = (int)((ebase[slice+1] - b0) >> 5);
   double acc[NC] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+#if OWN_GSMEM
+  __shared__ double2 sgo[NGP*OWN_THREADS];          // the thread's own column: no conflicts, no barrier
+#endif
   if (kmax > 0) {
     double wo[NC], xo[3], go[15];
     load_wx( WX, NP, p, wo, xo );
+#if OWN_GSMEM
+    #pragma unroll
+    for (int k=0; k<NGP; ++k) sgo[k*OWN_THREADS + threadIdx.x] = __ldg( G2 + (size_t)k*NP + p );
+#else
     load_g( G2, NP, p, go );
+#endif
     // the next edge's other end and normal are fetched one iteration ahead, so that its operand
     // gathers can leave as soon as the iteration starts
     size_t sl = (size_t)b0 + lane;
     int e_nx = __ldg( eo + sl );
     #pragma unroll kOwnUnroll
     for (int j=0; j<kmax; ++j) {
+#if OWN_GSMEM
+      { const volatile double2* src = sgo + threadIdx.x;
+        #pragma unroll
+        for (int k=0; k<7; ++k) { go[2*k] = src[k*OWN_THREADS].x; go[2*k+1] = src[k*OWN_THREADS].y; }
+        go[14] = src[7*OWN_THREADS].x; }
+#endif
       const int e = e_nx;
       // (the normal is needed last, by the Riemann solver: its load hides behind the limiter)
       const double n[4] = { __ldg( D + sl ), __ldg( D + nslot + sl ), __ldg( D + 2*nslot + sl ), __ldg( D + 3*nslot + sl ) };

@@ -249,7 +249,8 @@ struct xyst_ctx : CgState {
   DevBuf< long long > ebase; DevBuf< int > eo;
   // owner's share of the nodal flux sums (k_flux_own2) and the incoming-edge lists of k_update_in
   DevBuf< double > Racc; DevBuf< long long > in_base; DevBuf< int > in_e;
-  bool own2_attr = false;
+  bool own2_attr = false, gradp_attr = false;
+  int grad_mode = 0, grad_waves = 1;     // 1: persistent gradient kernel with incidence prefetch
   // tiles of the fused stage kernel (riecg_tile.cuh): slices per tile, foreign-edge lists, per owned slot
   // the shared-memory position of its flux (0xffff: receiver in another tile), incoming-edge counts,
   // second buffer of the primitives, tiles with / without nodes shared with other partitions
@@ -400,6 +401,14 @@ void do_grad( xyst_ctx* c )
   }
   {
     ProfScope ps( c, "grad" );
+    size_t smem = (size_t)2*(size_t)c->maxdeg*GRAD_THREADS*sizeof(int2);
+    if (c->grad_mode == 1 && c->maxdeg > 0 && smem <= 96*1024) {    // persistent form with the incidence prefetch
+      if (!c->gradp_attr) { CK( cudaFuncSetAttribute( k_grad_node_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) ); c->gradp_attr = true; }
+      int nsm = 148; cudaDeviceGetAttribute( &nsm, cudaDevAttrMultiProcessorCount, c->device );
+      unsigned g = (unsigned)std::min< size_t >( nblk( c->nslice*32, GRAD_THREADS ), (size_t)nsm*GRAD_MINB*c->grad_waves );
+      k_grad_node_p<<< g, GRAD_THREADS, smem, s >>>( c->npoin, c->NP, c->nslice, c->maxdeg, c->sl_base.p,
+        c->inc_eq.p, c->D2.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->vol.p, c->G.p, overlap ? 1 : 0 );
+    } else
     k_grad_node<<< nblk( c->nslice*32, GRAD_THREADS ), GRAD_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p,
       c->inc_eq.p, c->D2.p, c->D.p, c->nslot, c->W.p, c->bslot.p, c->Gb.p, c->vol.p, c->G.p, overlap ? 1 : 0 );
     ++c->launches;
@@ -743,7 +752,9 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
     e = getenv( "XYST_TILE" ); if (e && atoi( e ) >= 32) c->tile_nodes = std::min( 256, atoi( e ) / 32 * 32 );
     e = getenv( "XYST_TILE_CAP" ); if (e && atoi( e ) > 0) opt.cap = (size_t)atoi( e );
     e = getenv( "XYST_FLUX_MODE" ); if (e) c->flux_mode = atoi( e );
-    e = getenv( "XYST_LOOKBACK" ); if (e) c->lookback = atoi( e ); }
+    e = getenv( "XYST_LOOKBACK" ); if (e) c->lookback = atoi( e );
+    e = getenv( "XYST_GRAD_MODE" ); if (e) c->grad_mode = atoi( e );
+    e = getenv( "XYST_GRAD_WAVES" ); if (e && atoi( e ) > 0) c->grad_waves = atoi( e ); }
   opt.tile_nodes = (size_t)c->tile_nodes;
   for (size_t i=0; i<ntri*3; ++i) if (triinpoel[i] >= npoin) throw std::runtime_error( "node id out of range in superedge" );
   layout::Mesh M = layout::build( npoin, x, y, z, nsup, dsupedge, dsupint, stride, opt );

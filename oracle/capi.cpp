@@ -229,6 +229,19 @@ int orc_set_u( void* hv, int chare, const double* u )
   return 0;
 }
 
+// Replace one superedge group of a chare (ids + integrals as RieCG::m_dsupedge/m_dsupint hold them):
+// lets a test run the reference's kernels on superedges built elsewhere, e.g. by the product's host
+// mirror with its element-order triangle walk -- same edges and integrals, other grouping/orientation.
+int orc_set_supedge( void* hv, int chare, int k, std::size_t nid, const std::uint64_t* ids,
+                     std::size_t nint, const double* ints )
+{
+  if (k < 0 || k > 2) { g_err = "orc_set_supedge: group must be 0, 1 or 2"; return -1; }
+  auto& c = *static_cast< Handle* >( hv )->run->ch.at( static_cast< std::size_t >( chare ) );
+  c.dsupedge[static_cast<std::size_t>(k)].assign( ids, ids + nid );
+  c.dsupint[static_cast<std::size_t>(k)].assign( ints, ints + nint );
+  return 0;
+}
+
 int orc_kernel( void* hv, int chare, const char* what, int stage, double t, double dt )
 {
   auto h = static_cast< Handle* >( hv );

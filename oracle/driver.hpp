@@ -1106,6 +1106,14 @@ class Chare {
 
 // -----------------------------------------------------------------------------
 //! Transporter + all chares: the serial time-stepping loop
+// The chares of a run are independent between exchanges (one chare per PE in the reference): their
+// own-work loops may run on several host threads (OMP_NUM_THREADS; bench.py's CPU arm). Results do
+// not depend on the thread count: every chare's work is serial and the exchanges stay serial.
+template< class F > inline void forChares( std::size_t n, F fn ) {
+  #pragma omp parallel for schedule(dynamic,1)
+  for (std::size_t i=0; i<n; ++i) fn( i );
+}
+
 class Run {
   public:
     Cfg cfg;
@@ -1132,7 +1140,7 @@ class Run {
           if (!shared.empty()) { ch[a]->nodeCommMap[static_cast<int>(b)] = shared; ch[b]->nodeCommMap[static_cast<int>(a)] = shared; }
         }
       // Discretization::vol, comvol, totalvol :618-725
-      for (auto& c_ : ch) c_->volumes();
+      forChares( ch.size(), [&]( std::size_t i ){ ch[i]->volumes(); } );
       for (std::size_t a=0; a<ch.size(); ++a)
         for (const auto& [b,n] : ch[a]->nodeCommMap)
           for (auto g : n) ch[static_cast<std::size_t>(b)]->volc[g] += ch[a]->v[ ch[a]->lid.at(g) ];
@@ -1140,8 +1148,8 @@ class Run {
       meshvol = 0.0;
       for (auto& c_ : ch) { real tv = 0.0; for (auto vv : c_->v) tv += vv; meshvol += tv; }
       // RieCG ctor, setup, feop
-      for (auto& c_ : ch) { c_->renumber(); c_->allocate(); be::initialize( c_->coord, c_->u, t ); }
-      for (auto& c_ : ch) { c_->setupBC(); c_->bndint(); c_->domint(); }
+      forChares( ch.size(), [&]( std::size_t i ){ auto& c_ = ch[i]; c_->renumber(); c_->allocate(); be::initialize( c_->coord, c_->u, t ); } );
+      forChares( ch.size(), [&]( std::size_t i ){ auto& c_ = ch[i]; c_->setupBC(); c_->bndint(); c_->domint(); } );
       for (std::size_t a=0; a<ch.size(); ++a)          // comnorm :264-277,:384-407
         for (const auto& [b,nodes] : ch[a]->nodeCommMap)
           for (auto i : nodes)
@@ -1150,7 +1158,7 @@ class Run {
               if (k != bn.end()) { auto& norm = ch[static_cast<std::size_t>(b)]->bnormc[s][i];
                 for (std::size_t q=0; q<4; ++q) norm[q] += k->second[q]; }
             }
-      for (auto& c_ : ch) { c_->finish_bnorm(); c_->streamable(); c_->BC( t ); }
+      forChares( ch.size(), [&]( std::size_t i ){ auto& c_ = ch[i]; c_->finish_bnorm(); c_->streamable(); c_->BC( t ); } );
     }
 
     //! Discretization::finished :1251-1262
@@ -1162,15 +1170,19 @@ class Run {
     //! sum partial nodal results over chare boundaries (comgrad/comrhs)
     template< class Get, class Buf >
     void exchange( Get get, Buf buf ) {
-      for (std::size_t a=0; a<ch.size(); ++a)
-        for (const auto& [b,n] : ch[a]->nodeCommMap) {
-          auto& dst = buf( *ch[static_cast<std::size_t>(b)] );
+      // per receiving chare b (its buffer is touched by one thread only), senders a in ascending
+      // order -- the order in which a serial loop over senders would deliver; the maps are symmetric
+      forChares( ch.size(), [&]( std::size_t b ) {
+        auto& dst = buf( *ch[b] );
+        for (const auto& [a,n] : ch[b]->nodeCommMap) {
+          auto& src = *ch[static_cast<std::size_t>(a)];
           for (auto g : n) {
-            auto r = get( *ch[a] )[ ch[a]->lid.at(g) ];
+            auto r = get( src )[ src.lid.at(g) ];
             auto& acc = dst[g];
             if (acc.empty()) acc = r; else for (std::size_t c=0; c<r.size(); ++c) acc[c] += r[c];
           }
         }
+      } );
     }
 
     //! comalw :1297-1333: allowed limits combine with max (even entries) / min (odd entries)
@@ -1241,13 +1253,13 @@ class Run {
       }
       const bool lax = cfg.solver == "laxcg";                  // LaxCG.cpp:1011-1214, same stage structure
       for (int stage=0; stage<3; ++stage) {
-        for (auto& c_ : ch) { if (lax) c_->lgrad_own(); else c_->grad_own(); }
+        forChares( ch.size(), [&]( std::size_t i ){ if (lax) ch[i]->lgrad_own(); else ch[i]->grad_own(); } );
         exchange( []( Chare& c_ ) -> be::Fields& { return c_.grad; },
                   []( Chare& c_ ) -> auto& { return c_.gradc; } );
-        for (auto& c_ : ch) { if (lax) c_->lrhs_own( stage, t ); else c_->rhs_own( stage, t ); }
+        forChares( ch.size(), [&]( std::size_t i ){ if (lax) ch[i]->lrhs_own( stage, t ); else ch[i]->rhs_own( stage, t ); } );
         exchange( []( Chare& c_ ) -> be::Fields& { return c_.rhs; },
                   []( Chare& c_ ) -> auto& { return c_.rhsc; } );
-        for (auto& c_ : ch) { if (lax) c_->lsolve( stage, t, dt ); else c_->solve( stage, t, dt ); }
+        forChares( ch.size(), [&]( std::size_t i ){ if (lax) ch[i]->lsolve( stage, t, dt ); else ch[i]->solve( stage, t, dt ); } );
       }
       diagnostics();
       ++it; t += dt;                                           // next :941-983

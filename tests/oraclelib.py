@@ -368,6 +368,7 @@ def lib(flavour="port"):
     L.orc_get.restype = C.c_size_t
     L.orc_set_u.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.orc_kernel.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_double, C.c_double]
+    L.orc_set_supedge.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
     L.orc_siphash_ids.argtypes = [C.c_void_p, C.c_int]; L.orc_siphash_ids.restype = C.c_uint64
     _libs[flavour] = L
     return L
@@ -454,6 +455,15 @@ class Oracle:
     def set_u(self, u, chare=0):
         u = np.ascontiguousarray(u, dtype=np.float64)
         self.L.orc_set_u(self.h, chare, u.ctypes.data_as(C.c_void_p))
+
+    def set_supedges(self, get, chare=0):
+        """Take the three superedge groups from `get(name)` (e.g. a host-mirror Solver.get)."""
+        for k in range(3):
+            ids = np.ascontiguousarray(get("dsupedge%d" % k), np.uint64)
+            ints = np.ascontiguousarray(get("dsupint%d" % k), np.float64)
+            if self.L.orc_set_supedge(self.h, chare, k, len(ids), ids.ctypes.data_as(C.c_void_p), len(ints),
+                                      ints.ctypes.data_as(C.c_void_p)) != 0:
+                raise RuntimeError(self.L.orc_last_error().decode())
 
     def kernel(self, what, stage=0, t=0.0, dt=0.0, chare=0):
         if self.L.orc_kernel(self.h, chare, what.encode(), stage, t, dt) != 0:

@@ -175,6 +175,88 @@ def test_box_vs_oracle_small():
     assert np.abs(U - Uo).max() <= 1e-11 * np.abs(Uo).max()
 
 
+def _box_pair(n, reforder):
+    import bench
+    L = 1.2 * n / 150.0; h = L / n
+    kw = dict(problem="sedov", gamma=bench.GAMMA, p0=4.13e-2 / (h ** 3 / 4.0), cfl=0.5, sym=(1, 3, 5))
+    m = H.box_mesh(n, n, n, L, L, L)
+    o = O.Oracle(host_mesh_to_oracle(m), O.make_cfg(**kw), "port")
+    s = H.Solver.box(H.make_cfg(reforder=reforder, **kw), n, n, n, L, L, L)
+    s.prepare(); s.attach(0); s.setup()
+    return s, o
+
+
+def _same_supedges(s, o):
+    """The mirror reproduces the reference's grouping bitwise (single edges: as a set, their order is immaterial)."""
+    for k in range(2):
+        assert np.array_equal(s.get("dsupedge%d" % k), o.get("dsupedge%d" % k)), k
+    e2 = lambda g: np.unique(np.asarray(g("dsupedge2")).reshape(-1, 2), axis=0)
+    assert np.array_equal(e2(s.get), e2(o.get))
+
+
+def _steps_match(s, o, steps):
+    """Nodal state pointwise and all diagnostics columns at 1e-12. The reference accumulates its
+    diagnostics sums serially over the nodes (NodeDiagnostics.cpp:85-118); beyond ~10^5 nodes that
+    sum's own rounding reaches 1e-12 relative (3.6e-12 at 10^6 nodes, the same at every step), so
+    the L2 columns of the LAST row are checked against the exactly summed (math.fsum) oracle state,
+    and every row against the oracle's own serial sums at a tolerance that grows with the node count."""
+    import math
+    rows = s.step(steps); o.step(steps); d = o.diag()
+    U, Uo = s.get("u"), o.get("u")
+    for c in range(5):
+        assert np.abs(U[:, c] - Uo[:, c]).max() <= TOL * np.abs(Uo[:, c]).max(), c
+    v = o.get("v"); meshvol = o.scalar("meshvol")
+    for c in range(5):
+        exact = math.sqrt(math.fsum(Uo[:, c] ** 2 * v) / meshvol)
+        assert abs(rows[-1, 3 + c] - exact) <= TOL * exact, c
+    exact = math.fsum(Uo[:, 4] * v)
+    assert abs(rows[-1, 13] - exact) <= TOL * abs(exact)
+    tol_serial = max(TOL, 8.0e-18 * len(v))
+    for c in list(range(1, 8)) + [13]:
+        assert np.abs(rows[:, c] - d[:, c]).max() <= tol_serial * np.abs(d[:, c]).max(), c
+
+
+@pytest.mark.parametrize("reforder", [1, 0])
+def test_box_vs_oracle_n40(reforder):
+    """The benchmark's code path against the oracle on a 40^3 box (384k tets), 10 steps, all diag
+    columns 1e-12, U pointwise. reforder=1: triangle superedges in the reference's hash order,
+    oracle untouched. reforder=0: the host mirror's element-order walk; the oracle then runs the
+    reference's kernels on THESE superedges (orc_set_supedge): kernel against kernel, same inputs."""
+    s, o = _box_pair(40, reforder)
+    if reforder:
+        _same_supedges(s, o)
+    else:
+        o.set_supedges(s.get)
+    _steps_match(s, o, 10)
+
+
+def test_box_vs_oracle_above_4m_tets():
+    """n = 90: 4.37M tets, above the size at which round 1 silently switched the triangle walk.
+    Reference order: same superedges as the oracle, 3 steps at 1e-12. Then the element-order
+    superedges of a second solver are given to the SAME oracle and one gradient + right-hand side
+    evaluation on the stepped state is compared (the oracle's set-up dominates the run time)."""
+    n = 90
+    s, o = _box_pair(n, 1)
+    _same_supedges(s, o)
+    _steps_match(s, o, 3)
+    Uo = o.get("u")
+    s.close()
+    import bench
+    L = 1.2 * n / 150.0
+    kw = dict(problem="sedov", gamma=bench.GAMMA, p0=4.13e-2 / ((L / n) ** 3 / 4.0), cfl=0.5, sym=(1, 3, 5))
+    s0 = H.Solver.box(H.make_cfg(reforder=0, **kw), n, n, n, L, L, L)
+    s0.prepare(); s0.attach(0); s0.setup()
+    o.set_supedges(s0.get)
+    ctx = s0.ctx()
+    ctx.state_set(Uo)
+    ctx.grad(); ctx.rhs()
+    o.kernel("grad"); o.kernel("rhs", 0, o.scalar("t"))
+    G, R = ctx.grad_get(), ctx.rhs_get()
+    Go, Ro = o.get("grad"), o.get("rhs")
+    assert np.abs(G - Go).max() <= TOL * np.abs(Go).max()
+    assert np.abs(R - Ro).max() <= TOL * np.abs(Ro).max()
+
+
 def test_full_size_box_properties():
     """BASELINE.json configs[1]: 20.25M-tet box (n=150). Properties that need no oracle:
     conservation of total energy with closed (symmetry) boundaries, finiteness, positivity

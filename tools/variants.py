@@ -1,5 +1,5 @@
 """Build tuning variants of the device library (compile-time knobs) and time them with bench.py
-on the GPU box; runtime knobs go through the environment (XYST_FLUX_MODE, XYST_REORDER, XYST_TILE).
+on the GPU box; runtime knobs go through the environment (XYST_REORDER, XYST_TILE_WX, XYST_GRAD_MODE).
 
     python tools/variants.py build [-] [names]   # here (nvcc cross-compiles), writes tools/_lib/*.so
     python tools/variants.py run [n] [names]     # on the GPU box
@@ -15,14 +15,12 @@ from xyst_b200 import build as B
 LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib")
 # name -> (defines, environment)
 VAR = {
-    "m3": (["OWN_MINB=3"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
-    "gsm4": (["OWN_GSMEM=1", "OWN_MINB=4"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
-    "gsm5": (["OWN_GSMEM=1", "OWN_MINB=5"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
-    "gsm4_t256": (["OWN_GSMEM=1", "OWN_MINB=2", "OWN_THREADS=256"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0"}),
-    "gsm4_gp": (["OWN_GSMEM=1", "OWN_MINB=4"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0", "XYST_GRAD_MODE": "1"}),
-    "gsm4_gp_w4": (["OWN_GSMEM=1", "OWN_MINB=4"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0", "XYST_GRAD_MODE": "1", "XYST_GRAD_WAVES": "4"}),
-    "gsm4_gp_m3": (["OWN_GSMEM=1", "OWN_MINB=4", "GRAD_MINB=3"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "0", "XYST_GRAD_MODE": "1"}),
-    "gsm4_gp_reorder": (["OWN_GSMEM=1", "OWN_MINB=4"], {"XYST_FLUX_MODE": "1", "XYST_REORDER": "1", "XYST_TILE_WX": "0.03", "XYST_GRAD_MODE": "1"}),
+    "default": ([], {}),
+    "grad_oneshot": ([], {"XYST_GRAD_MODE": "0"}),
+    "tile_order": ([], {"XYST_REORDER": "1"}),
+    "tile_order_rows": ([], {"XYST_REORDER": "1", "XYST_TILE_WX": "0.03"}),
+    "own_regs": (["OWN_GSMEM=0", "OWN_MINB=3"], {}),
+    "own_sint": (["MUSCL_SIGN_INT=1"], {}),
 }
 
 

@@ -504,6 +504,9 @@ namespace {
 void cho_need( xyst_ctx* c ) {
   need_mesh( c );
   if (!c->cho) throw std::runtime_error( "ChoCG needs stride-5 superedge integrals: use xyst_chocg_mesh_upload" );
+  // the node gathers and the rhs column sums of the pressure solve have no halo sums yet: partial results
+  // would be silently wrong on a partitioned mesh
+  if (c->nsh > 0 && c->comm) throw std::runtime_error( "ChoCG/LohCG on several partitions is not implemented yet" );
 }
 void cho_need_cg( xyst_ctx* c ) {
   cho_need( c );

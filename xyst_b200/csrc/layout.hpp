@@ -8,10 +8,8 @@
 //    eo = other end | bit 31 if the owner is the edge's second node);
 //  * the sliced-ELL node incidence of the gather kernels: per node its owned edges (ascending other
 //    end), then the edges owned by lower neighbours (ascending owner) -- the fixed summation order;
-//  * the tiles of the fused stage kernel (riecg_tile.cuh): consecutive slices of 32 nodes per tile,
-//    per owned slot the position of its flux in the tile's shared memory (k-th incoming edge of local
-//    node t at k*tn + t, 0xffff if the receiver is in another tile), and per tile the list of FOREIGN
-//    edges (owner in another tile, receiver here) it evaluates a second time.
+//  * the INCOMING-edge lists (edges owned by lower neighbours) of k_update_in, which completes the
+//    nodal sums the owner-thread flux kernel starts.
 #pragma once
 #include <vector>
 #include <array>
@@ -27,14 +25,12 @@ namespace layout {
 
 struct Options {
   bool reorder = false;        // re-order the nodes into tiles (locality.hpp)
-  bool tiles = false;          // build the tile structures
-  size_t tile_nodes = 256;     // nodes per tile (multiple of 32, at most 256)
-  size_t cap = 2048;           // flux entries (5 doubles each) a tile may keep in shared memory
+  size_t tile_nodes = 256;     // nodes per tile of the library's order (multiple of 32)
 };
 
 struct Mesh {
-  size_t npoin = 0, ne = 0, nslice = 0, nslot = 0, nent = 0, ntile = 0;
-  int drows = 4, maxdeg = 0, fstride = 0;
+  size_t npoin = 0, ne = 0, nslice = 0, nslot = 0, nent = 0;
+  int drows = 4, maxdeg = 0;
   std::vector< int > new2old, old2new;             // empty: the caller's order is kept
   std::vector< long long > ebase, base;            // [nslice+1] slot / incidence-entry offsets
   std::vector< int > ep, eq, eo;                   // [nslot]
@@ -42,10 +38,6 @@ struct Mesh {
   std::vector< int > inc_e, inc_q;                 // [nent] signed slot+1 (0 = padding), neighbour
   std::vector< long long > in_base;                // [nslice+1] offsets of the INCOMING-edge lists
   std::vector< int > in_e;                         // signed slot+1 of the edges owned by lower neighbours
-  std::vector< int > tile_sl, foff, fa, fsl;       // tiles: [ntile+1], [ntile+1], foreign owner, foreign slot
-  std::vector< int > tile_of;                      // [nslice] tile of each slice
-  std::vector< unsigned short > fdst, els;         // foreign / owned-slot shared-memory positions
-  std::vector< unsigned char > indeg;              // [nslice*32] incoming edges per node
   size_t to_new( size_t old ) const { return old2new.empty() ? old : (size_t)old2new[old]; }
 };
 
@@ -176,51 +168,6 @@ inline Mesh build( size_t npoin, const double* x, const double* y, const double*
       ++fill[h];
       M.in_e[pos] = h == Q[e] ? slot_of[i]+1 : -(slot_of[i]+1);
     } }
-  // --- tiles of the fused stage kernel --------------------------------------------------------
-  if (opt.tiles) {
-    M.indeg.assign( nslice*32, 0 );
-    for (size_t p=0; p<npoin; ++p) {
-      int d = deg[p] - udeg[p];
-      if (d > 255) throw std::runtime_error( "more than 255 incoming edges at a node" );
-      M.indeg[p] = (unsigned char)d;
-    }
-    // a tile = tile_nodes/32 consecutive slices, halved until its incoming fluxes fit
-    M.tile_sl.assign( 1, 0 );
-    auto add = [&]( auto&& self, size_t a, size_t b ) -> void {
-      int kin = 0;
-      for (size_t p=a*32; p<std::min( npoin, b*32 ); ++p) kin = std::max( kin, (int)M.indeg[p] );
-      size_t ent = (size_t)kin*(b-a)*32;
-      if (b-a > 1 && ent > opt.cap) { size_t m = (a+b)/2; self( self, a, m ); self( self, m, b ); return; }
-      if (ent > 0xfffe) throw std::runtime_error( "too many incoming edges in one slice of nodes" );
-      M.tile_sl.push_back( (int)b ); M.fstride = std::max( M.fstride, (int)ent );
-    };
-    size_t ts = std::max< size_t >( 1, std::min< size_t >( 8, opt.tile_nodes/32 ) );
-    for (size_t a=0; a<nslice; a+=ts) add( add, a, std::min( nslice, a+ts ) );
-    size_t ntile = M.tile_sl.size()-1;
-    M.ntile = ntile;
-    M.tile_of.assign( nslice, 0 );
-    auto& tile_of = M.tile_of;
-    for (size_t t=0; t<ntile; ++t) for (int sl=M.tile_sl[t]; sl<M.tile_sl[t+1]; ++sl) tile_of[(size_t)sl] = (int)t;
-    M.els.assign( nslot, (unsigned short)0xffff );
-    M.foff.assign( ntile+1, 0 );
-    std::vector< int > fin( npoin, 0 );
-    struct FE { int t, a, sl; unsigned short dst; };
-    std::vector< FE > fe;
-    for (size_t i=0; i<ne; ++i) {               // ascending owner: the k-th arrival at h is its k-th incoming edge
-      size_t e = (size_t)perm[i].i;
-      int o = std::min( P[e], Q[e] ), h = std::max( P[e], Q[e] );
-      int th = tile_of[(size_t)h/32], to = tile_of[(size_t)o/32];
-      int tn = (M.tile_sl[(size_t)th+1] - M.tile_sl[(size_t)th])*32;
-      unsigned short dst = (unsigned short)( fin[h]*tn + (h - M.tile_sl[(size_t)th]*32) );
-      ++fin[h];
-      if (th == to) M.els[(size_t)slot_of[i]] = dst;
-      else { fe.push_back( FE{ th, o, slot_of[i], dst } ); ++M.foff[(size_t)th+1]; }
-    }
-    for (size_t t=0; t<ntile; ++t) M.foff[t+1] += M.foff[t];
-    M.fa.resize( fe.size() ); M.fsl.resize( fe.size() ); M.fdst.resize( fe.size() );
-    std::vector< int > f( M.foff.begin(), M.foff.end()-1 );
-    for (const auto& x : fe) { int k = f[(size_t)x.t]++; M.fa[(size_t)k] = x.a; M.fsl[(size_t)k] = x.sl; M.fdst[(size_t)k] = x.dst; }
-  }
   return M;
 }
 

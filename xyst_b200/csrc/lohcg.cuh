@@ -222,6 +222,7 @@ namespace {
 void loh_need( xyst_ctx* c ) {
   need_mesh( c );
   if (!c->loh) throw std::runtime_error( "LohCG needs stride-4 superedge integrals with the Laplacian term: use xyst_lohcg_mesh_upload" );
+  if (c->nsh > 0 && c->comm) throw std::runtime_error( "ChoCG/LohCG on several partitions is not implemented yet" );
 }
 LohP lohp( const xyst_ctx* c ) { return LohP{ c->chp.stab, c->chp.stab2, c->chp.stab2coef, c->chp.mu, c->loh_s }; }
 // [4][NP] state behind the velocity pointer of the ChoCG machinery

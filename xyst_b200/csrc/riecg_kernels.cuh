@@ -42,12 +42,6 @@ __device__ __forceinline__ double lax_refvel( double r, double p, double v, doub
   return fmin( sqrt( gamma * p / r ), fmax( v, kvinf ) );
 }
 
-// 8-byte asynchronous global->shared copy (LDGSTS): in flight without holding a register
-__device__ __forceinline__ void cp_async8( double* smem_dst, const double* gsrc )
-{
-  unsigned d = (unsigned)__cvta_generic_to_shared( smem_dst );
-  asm volatile( "cp.async.ca.shared.global [%0], [%1], 8;" :: "r"( d ), "l"( gsrc ) : "memory" );
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile( "cp.async.commit_group;" ::: "memory" ); }
 // flat index of tk::Fields G(p,i), i = c*3+j, in the structure-of-arrays gradient storage
 // Gradients are stored as eight 16-byte pairs per node, pair k of node p at G2[k*NP+p]:
@@ -272,6 +266,7 @@ __device__ __forceinline__ void grad_sum( size_t p, int lane, long long base, in
     size_t sl = se == 0 ? 0 : (size_t)(abs(se)-1);
     double2 d01 = __ldg( D2 + sl );
     double d0 = sg * d01.x, d1 = sg * d01.y, d2 = sg * __ldg( D + 2*nslot + sl );
+    if (se == 0) d0 = d1 = d2 = 0.0;      // padding: the neighbour is the node itself, the normal must not be slot 0's
     double wq[NC];
     load_w( WX, NP, (size_t)q, wq );
     #pragma unroll
@@ -792,44 +787,6 @@ __device__ __forceinline__ void lax_hllc( double l[NC], double r[NC], const doub
   }
 }
 
-// one thread per edge slot; a warp covers the j-th owned edge of 32 consecutive nodes.
-// The 30 gradient values of the two end nodes are fetched with cp.async straight into a
-// per-thread column of shared memory: the copies need no registers while in flight, so
-// every thread has its whole working set (46 doubles) outstanding at once and the kernel
-// still fits enough warps per SM to cover the latency; the limiter then reads its
-// operands from shared memory as it goes.
-template< bool EXACT, int FLUX >
-__global__ void __launch_bounds__(FLUX_THREADS, FLUX_MINB)
-k_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __restrict__ eq,
-             const double* __restrict__ D, const double* __restrict__ W, const double* __restrict__ X,
-             const double* __restrict__ G, double* __restrict__ F, DParams P, size_t e0, size_t e1 )
-{
-  __shared__ double sg[30*FLUX_THREADS];
-  size_t e = e0 + blockIdx.x*(size_t)blockDim.x + threadIdx.x;
-  if (e >= e1) return;
-  int pi = ep[e];
-  if (pi < 0) return;                      // padding slot
-  size_t p = pi, q = eq[e];
-  double* gp = sg + threadIdx.x;
-  double* gq = gp + 15*FLUX_THREADS;
-  #pragma unroll
-  for (int i=0; i<15; ++i) { cp_async8( gp + i*FLUX_THREADS, G + gidx( i, p, NP ) ); cp_async8( gq + i*FLUX_THREADS, G + gidx( i, q, NP ) ); }
-  cp_async_commit();
-  double n[3] = { D[e], D[nslot+e], D[2*nslot+e] };
-  double l[NC], r[NC], vw[3], xp[3];
-  const double2* WX = reinterpret_cast< const double2* >( W );
-  load_wx( WX, NP, p, l, xp );
-  load_wx( WX, NP, q, r, vw );
-  #pragma unroll
-  for (int j=0; j<3; ++j) vw[j] -= xp[j];
-  cp_async_wait< 0 >();
-  muscl< EXACT >( gp, FLUX_THREADS, gq, FLUX_THREADS, vw, l, r );
-  double f[NC];
-  if (FLUX == 0) rusanov( l, r, n, P, f ); else if (FLUX == 1) hllc( l, r, n, P, f );
-  else if (FLUX == 2) lax_rusanov( l, r, n, P, f ); else lax_hllc( l, r, n, P, f );
-  store_f( F, nslot, e, f );
-}
-
 // ---------------------------------------------------------------------------------
 // flux gather per node (+ boundary + source) and, fused, the RK stage update
 // ---------------------------------------------------------------------------------
@@ -849,7 +806,7 @@ __device__ __forceinline__ void rhs_sum( size_t p, int lane, long long base, int
     double f[NC];
     load_f( F, nslot, sl, f );
     #pragma unroll
-    for (int c=0; c<NC; ++c) acc[c] = fma( sg, f[c], acc[c] );
+    for (int c=0; c<NC; ++c) acc[c] = fma( sg, se == 0 ? 0.0 : f[c], acc[c] );   // (a padding entry must not pass on a NaN of slot 0)
   }
   int b = bslot[p];
   if (b >= 0) {
@@ -927,35 +884,6 @@ __device__ __forceinline__ void node_update( size_t p, size_t NP, const double a
     for (int c=0; c<NC; ++c) { u[c] = Un[c*NP+p] - rkdtv * acc[c]; U[c*NP+p] = u[c]; }
     primitive( u, w );
     store_w( W, NP, p, w );
-  }
-}
-
-template< bool FUSED, bool LAX >
-__global__ void __launch_bounds__(NODE_THREADS, RHS_MINB)
-k_rhs_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
-            const double* __restrict__ F, size_t nslot, const int* __restrict__ bslot,
-            const double* __restrict__ Rb, const double* __restrict__ S, int src_mask,
-            const double* __restrict__ v, const double* __restrict__ vol, const double* __restrict__ Un,
-            StageArgs A, double* __restrict__ U, double* __restrict__ W, double* __restrict__ R,
-            double* __restrict__ Wn, double* __restrict__ UnOut, size_t slice0, size_t slice1,
-            const unsigned char* __restrict__ skip )
-{
-  size_t slice = slice0 + ((blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5);
-  int lane = threadIdx.x & 31;
-  size_t p = slice*32 + lane;
-  if (slice >= slice1 || p >= npoin) return;
-  // nodes shared with other partitions are updated by k_rhs_finish from the complete sums (and,
-  // for LaxCG, from the still unmodified primitives of this stage)
-  if (FUSED && skip && skip[p]) return;
-  long long base = sl_base[slice];
-  int kmax = (int)((sl_base[slice+1] - base) >> 5);
-  double acc[NC];
-  rhs_sum( p, lane, base, kmax, inc_e, F, nslot, bslot, Rb, S, src_mask, v, acc );
-  if (FUSED) {
-    node_update< LAX >( p, NP, acc, vol[p], Un, U, W, W, Wn, UnOut, A );
-  } else {
-    #pragma unroll
-    for (int c=0; c<NC; ++c) R[p*NC+c] = acc[c];
   }
 }
 

@@ -52,12 +52,6 @@ int fail( const std::string& m ) { g_err = m; return 1; }
 #define API_END } catch (std::exception& e) { return fail( e.what() ); } return 0;
 
 // tuning knobs (compile-time; defaults chosen from the ncu measurements under profiles/)
-#ifndef FLUX_THREADS
-#define FLUX_THREADS 128
-#endif
-#ifndef FLUX_MINB
-#define FLUX_MINB 6
-#endif
 #ifndef NODE_THREADS
 #define NODE_THREADS 256
 #endif
@@ -138,9 +132,13 @@ template< class T > struct DevBuf {
   ~DevBuf() { release(); }
 };
 
+// per-kernel timing on request (xyst_kernel_time): events come from a pool created when a name is
+// first asked for, so a timed loop does not create events; names nobody asked for record nothing
 struct Prof {
-  std::vector< std::pair< cudaEvent_t, cudaEvent_t > > ev;
+  std::vector< std::pair< cudaEvent_t, cudaEvent_t > > ev;   // pool
+  size_t used = 0;
   double ms = 0.0; uint64_t n = 0;
+  bool on = false;
 };
 
 } // namespace
@@ -247,23 +245,10 @@ struct xyst_ctx : CgState {
   // owner-slot view of the edges for the thread-per-owner kernels: slot base per slice, and per slot
   // the edge's other end | orientation bit (31: the owner is the edge's SECOND node), -1 = padding
   DevBuf< long long > ebase; DevBuf< int > eo;
-  // owner's share of the nodal flux sums (k_flux_own2) and the incoming-edge lists of k_update_in
+  // owner's share of the nodal flux sums (k_flux_own) and the incoming-edge lists of k_update_in
   DevBuf< double > Racc; DevBuf< long long > in_base; DevBuf< int > in_e;
-  bool own2_attr = false, gradp_attr = false;
-  int grad_mode = 0, grad_waves = 1;     // 1: persistent gradient kernel with incidence prefetch
-  // tiles of the fused stage kernel (riecg_tile.cuh): slices per tile, foreign-edge lists, per owned slot
-  // the shared-memory position of its flux (0xffff: receiver in another tile), incoming-edge counts,
-  // second buffer of the primitives, tiles with / without nodes shared with other partitions
-  size_t ntile = 0, nbt = 0, nit = 0; int fstride = 0;
-  std::vector< int > tile_sl_h;
-  DevBuf< int > tile_sl, foff, fa, fsl, btiles, itiles, shidx;
-  DevBuf< unsigned short > fdst, els; DevBuf< unsigned char > indeg;
-  DevBuf< double > W2;
-  // look-back between tiles: per-tile "fluxes published" flags, claim counter, processing position
-  DevBuf< int > tile_of, tflag, tpos; DevBuf< unsigned long long > tcounter;
-  unsigned long long tile_count_h = 0; int tile_epoch = 0, lookback = 0;
-  int flux_mode = 2;                     // 0: k_flux_edge + gather, 1: k_flux_own + gather, 2: k_stage_tile
-  unsigned tile_attr = 0;                // kernel instances whose shared-memory limit has been raised
+  bool gradp_attr = false;
+  int grad_mode = 1, grad_waves = 1;     // 1: persistent gradient kernel with incidence prefetch, 0: one warp per slice
   // profiling
   bool prof_on = false;
   std::map< std::string, Prof > prof;
@@ -272,7 +257,7 @@ struct xyst_ctx : CgState {
 namespace {
 
 #include "riecg_kernels.cuh"
-#include "riecg_tile.cuh"
+#include "riecg_own.cuh"
 #include "zalcg_kernels.cuh"
 #include "kozcg_kernels.cuh"
 #include "cg_kernels.cuh"
@@ -292,14 +277,20 @@ struct ProfScope {
   xyst_ctx* c; Prof* pr = nullptr; cudaEvent_t a = nullptr, b = nullptr;
   ProfScope( xyst_ctx* ctx, const char* name ) : c( ctx ) {
     if (!c->prof_on) return;
-    pr = &c->prof[name];
-    CK( cudaEventCreate( &a ) ); CK( cudaEventCreate( &b ) );
+    auto it = c->prof.find( name );
+    if (it == c->prof.end() || !it->second.on) return;
+    pr = &it->second;
+    if (pr->used == pr->ev.size()) {          // pool exhausted between two queries: grow (rare)
+      cudaEvent_t x, y; CK( cudaEventCreate( &x ) ); CK( cudaEventCreate( &y ) );
+      pr->ev.emplace_back( x, y );
+    }
+    a = pr->ev[pr->used].first; b = pr->ev[pr->used].second;
     CK( cudaEventRecord( a, c->stream ) );
   }
   ~ProfScope() {
     if (!pr) return;
     cudaEventRecord( b, c->stream );
-    pr->ev.emplace_back( a, b );
+    ++pr->used;
   }
 };
 
@@ -328,20 +319,6 @@ void refresh_shared( xyst_ctx* c ) {
   if (reordered( c )) for (auto& i : c->sh_node_h) i = (int)to_new( c, (size_t)i, "shared node id" );
   c->sh_flag.release();
   c->sh_node.upload( c->sh_node_h, c->stream );
-  c->nbt = c->nit = 0;
-  if (c->ntile && c->npoin) {             // fused stage kernel: tiles holding shared nodes run first
-    std::vector< int > shidx( c->npoin, -1 ), tile_of( c->nslice ), bt, it;
-    for (size_t t=0; t<c->ntile; ++t) for (int sl=c->tile_sl_h[t]; sl<c->tile_sl_h[t+1]; ++sl) tile_of[(size_t)sl] = (int)t;
-    std::vector< char > isb( c->ntile, 0 );
-    for (size_t i=0; i<c->sh_node_h.size(); ++i) { size_t p = (size_t)c->sh_node_h[i]; shidx[p] = (int)i; isb[(size_t)tile_of[p/32]] = 1; }
-    for (size_t t=0; t<c->ntile; ++t) (isb[t] ? bt : it).push_back( (int)t );
-    c->nbt = bt.size(); c->nit = it.size();
-    c->shidx.upload( shidx, c->stream ); c->btiles.upload( bt, c->stream ); c->itiles.upload( it, c->stream );
-    std::vector< int > tpos( c->ntile );
-    for (size_t i=0; i<bt.size(); ++i) tpos[(size_t)bt[i]] = (int)i;
-    for (size_t i=0; i<it.size(); ++i) tpos[(size_t)it[i]] = (int)( bt.size() + i );
-    c->tpos.upload( tpos, c->stream );
-  }
 }
 
 void need_mesh( xyst_ctx* c ) { if (!c->npoin) throw std::runtime_error( "no mesh uploaded" ); }
@@ -425,25 +402,6 @@ void do_grad( xyst_ctx* c )
   CK( cudaGetLastError() );
 }
 
-void do_flux( xyst_ctx* c, size_t e0 = 0, size_t e1 = ~(size_t)0 )
-{
-  auto s = c->stream;
-  auto P = dparams( c );
-  ProfScope ps( c, "flux" );
-  e1 = std::min( e1, c->nslot );
-  if (e1 <= e0) return;
-  unsigned g = nblk( e1 - e0, FLUX_THREADS );
-  #define LAUNCH_FLUX( EX, FL ) k_flux_edge< EX, FL ><<< g, FLUX_THREADS, 0, s >>>( c->nslot, c->NP, c->ep.p, \
-      c->eq.p, c->D.p, c->W.p, c->X.p, c->G.p, c->F.p, P, e0, e1 )
-  int fl = P.flux + (c->lax ? 2 : 0);
-  if (P.exact) { if (fl == 0) LAUNCH_FLUX( true, 0 ); else if (fl == 1) LAUNCH_FLUX( true, 1 );
-                 else if (fl == 2) LAUNCH_FLUX( true, 2 ); else LAUNCH_FLUX( true, 3 ); }
-  else         { if (fl == 0) LAUNCH_FLUX( false, 0 ); else if (fl == 1) LAUNCH_FLUX( false, 1 );
-                 else if (fl == 2) LAUNCH_FLUX( false, 2 ); else LAUNCH_FLUX( false, 3 ); }
-  #undef LAUNCH_FLUX
-  ++c->launches;
-}
-
 static const double rkcoef[3] = { 1.0/3.0, 1.0/2.0, 1.0 };   // RieCG.cpp:41
 
 // the node gather over slices [s0,s1) on stream st
@@ -461,24 +419,12 @@ void launch_rhs_node( xyst_ctx* c, bool fused, const StageArgs& A, const double*
     }
     skip = c->sh_flag.p;
   }
-  if (c->flux_mode == 3 || c->flux_mode == 1) {        // own share already summed by the flux kernel
-    #define UPD_IN( FU, LX ) k_update_in< FU, LX ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->in_base.p, c->in_e.p, \
-        c->Racc.p, c->F.p, c->nslot, c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, \
-        c->Wn.p, c->Un.p, skip )
-    if (fused && c->lax) UPD_IN( true, true ); else if (fused) UPD_IN( true, false ); else UPD_IN( false, false );
-    #undef UPD_IN
-    ++c->launches;
-    return;
-  }
-  if (fused && c->lax)
-    k_rhs_node< true, true ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
-      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1, skip );
-  else if (fused)
-    k_rhs_node< true, false ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
-      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1, skip );
-  else
-    k_rhs_node< false, false ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->F.p, c->nslot,
-      c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, c->Wn.p, c->Un.p, s0, s1, skip );
+  // the owner's own share was summed by the flux kernel: gather the incoming edges only
+  #define UPD_IN( FU, LX ) k_update_in< FU, LX ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->in_base.p, c->in_e.p, \
+      c->Racc.p, c->F.p, c->nslot, c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, \
+      c->Wn.p, c->Un.p, skip )
+  if (fused && c->lax) UPD_IN( true, true ); else if (fused) UPD_IN( true, false ); else UPD_IN( false, false );
+  #undef UPD_IN
   ++c->launches;
 }
 
@@ -524,8 +470,8 @@ void do_rhs_nodes( xyst_ctx* c, bool fused, int stage, double dt, const double* 
   CK( cudaGetLastError() );
 }
 
-// thread-per-owner flux kernel writing the per-edge fluxes (drop-in for do_flux)
-void do_flux_own( xyst_ctx* c )
+// thread-per-owner flux kernel: per-edge fluxes F and the owners' own shares Racc
+void do_flux( xyst_ctx* c )
 {
   auto s = c->stream;
   auto P = dparams( c );
@@ -540,109 +486,6 @@ void do_flux_own( xyst_ctx* c )
                  else if (fl == 2) LAUNCH_OWN( false, 2 ); else LAUNCH_OWN( false, 3 ); }
   #undef LAUNCH_OWN
   ++c->launches;
-}
-
-// k_flux_own2: other end staged through shared memory one edge ahead, own share kept (Racc)
-void do_flux_own2( xyst_ctx* c )
-{
-  auto s = c->stream;
-  auto P = dparams( c );
-  ProfScope ps( c, "flux" );
-  unsigned g = nblk( c->nslice*32, OWN_THREADS );
-  size_t smem = (size_t)2*NQP*OWN_THREADS*sizeof(double2);
-  #define LAUNCH_OWN2( EX, FL ) do { \
-      if (!c->own2_attr) CK( cudaFuncSetAttribute( k_flux_own2< EX, FL >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) ); \
-      k_flux_own2< EX, FL ><<< g, OWN_THREADS, smem, s >>>( c->nslice, c->NP, c->nslot, \
-        c->ebase.p, c->eo.p, c->D.p, c->W.p, c->G.p, c->F.p, c->Racc.p, P ); } while (0)
-  int fl = P.flux + (c->lax ? 2 : 0);
-  if (P.exact) { if (fl == 0) LAUNCH_OWN2( true, 0 ); else if (fl == 1) LAUNCH_OWN2( true, 1 );
-                 else if (fl == 2) LAUNCH_OWN2( true, 2 ); else LAUNCH_OWN2( true, 3 ); }
-  else         { if (fl == 0) LAUNCH_OWN2( false, 0 ); else if (fl == 1) LAUNCH_OWN2( false, 1 );
-                 else if (fl == 2) LAUNCH_OWN2( false, 2 ); else LAUNCH_OWN2( false, 3 ); }
-  #undef LAUNCH_OWN2
-  c->own2_attr = true;      // (flux and limiter form are fixed per context)
-  ++c->launches;
-}
-
-template< bool EX, int FL, bool FUSED, bool LAX >
-void launch_tile( xyst_ctx* c, TileArgs T, unsigned ntile, cudaStream_t st )
-{
-  if (!ntile) return;
-  T.cbase = c->tile_count_h; c->tile_count_h += ntile;
-  size_t smem = (size_t)NC*(size_t)c->fstride*sizeof(double);
-  unsigned bit = 1u << ((EX ? 16 : 0) + FL*4 + (FUSED ? 2 : 0) + (LAX ? 1 : 0));
-  if (!(c->tile_attr & bit)) {
-    CK( cudaFuncSetAttribute( k_stage_tile< EX, FL, FUSED, LAX >, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
-    c->tile_attr |= bit;
-  }
-  k_stage_tile< EX, FL, FUSED, LAX ><<< ntile, (unsigned)c->tile_nodes, smem, st >>>( T );
-  ++c->launches;
-}
-
-void launch_tile_any( xyst_ctx* c, bool fused, const TileArgs& T, unsigned ntile, cudaStream_t st )
-{
-  int fl = c->prm.flux + (c->lax ? 2 : 0);
-  bool ex = c->prm.exact_muscl != 0;
-  #define TL( EX, FL, LX ) do { if (fused) launch_tile< EX, FL, true, LX >( c, T, ntile, st ); \
-                               else launch_tile< EX, FL, false, LX >( c, T, ntile, st ); } while (0)
-  if (ex) { if (fl == 0) TL( true, 0, false ); else if (fl == 1) TL( true, 1, false );
-            else if (fl == 2) TL( true, 2, true ); else TL( true, 3, true ); }
-  else    { if (fl == 0) TL( false, 0, false ); else if (fl == 1) TL( false, 1, false );
-            else if (fl == 2) TL( false, 2, true ); else TL( false, 3, true ); }
-  #undef TL
-}
-
-// Edge fluxes + nodal sums (+ the RK update if fused) of one stage in the tile kernel. With several
-// partitions the tiles holding shared nodes run first; their partial sums travel (pack + NCCL on
-// the side stream) while the other tiles are computed, then k_rhs_finish completes the shared nodes.
-void do_stage_tile( xyst_ctx* c, bool fused, int stage, double dt, const double* Un, double* Uout )
-{
-  auto s = c->stream;
-  bool halo = c->nsh > 0 && c->comm;
-  if (c->rb_pending) { CK( cudaStreamWaitEvent( s, c->ev_e, 0 ) ); c->rb_pending = false; }
-  else if (c->nbn) {
-    k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
-      c->tri.p, c->besym.p, c->fn.p, c->U.p, c->Rb.p, c->prm.gamma, c->W.p, c->rgas ); ++c->launches;
-  }
-  StageArgs A{ rkcoef[stage], dt, c->steady ? c->dtp.p : nullptr, stage, mode( c ) };
-  TileArgs T{};
-  T.npoin = c->npoin; T.NP = c->NP; T.nslot = c->nslot;
-  T.tile_list = nullptr; T.tile_sl = c->tile_sl.p; T.foff = c->foff.p; T.fa = c->fa.p; T.fsl = c->fsl.p; T.fdst = c->fdst.p;
-  T.ebase = c->ebase.p; T.eo = c->eo.p; T.els = c->els.p; T.indeg = c->indeg.p; T.D = c->D.p;
-  T.W = c->W.p; T.G = c->G.p; T.fstride = c->fstride;
-  T.bslot = c->bslot.p; T.Rb = c->Rb.p; T.S = c->S.p; T.src_mask = c->src_mask; T.v = c->v.p; T.vol = c->vol.p;
-  T.Un = Un; T.U = Uout; T.Wout = c->W2.p; T.R = c->R.p; T.Wn = c->Wn.p; T.UnOut = c->Un.p;
-  T.shidx = halo ? c->shidx.p : nullptr; T.part = c->sh_part.p;
-  T.tile_of_slice = c->tile_of.p; T.lookback = c->lookback; T.epoch = ++c->tile_epoch; T.tflag = c->tflag.p;
-  T.tpos = halo ? c->tpos.p : nullptr; T.F = c->F.p; T.counter = c->tcounter.p;
-  T.A = A; T.P = dparams( c );
-  {
-    ProfScope ps( c, "flux" );
-    if (halo) {
-      auto cs = c->comm_stream;
-      T.tile_list = c->btiles.p;
-      launch_tile_any( c, fused, T, (unsigned)c->nbt, s );
-      CK( cudaEventRecord( c->ev_a, s ) );
-      CK( cudaStreamWaitEvent( cs, c->ev_a, 0 ) );
-      exchange( c, NC, true );
-      T.tile_list = c->itiles.p;
-      launch_tile_any( c, fused, T, (unsigned)c->nit, s );
-    } else
-      launch_tile_any( c, fused, T, (unsigned)c->ntile, s );
-  }
-  if (halo) {
-    exchange_wait( c );
-    unsigned g = nblk( c->nsh, 128 );
-    if (fused)
-      k_rhs_finish< true ><<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
-        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, A, Uout, c->W.p, c->W2.p, c->R.p, c->Wn.p, c->Un.p );
-    else
-      k_rhs_finish< false ><<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
-        c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, A, Uout, c->W.p, c->W2.p, c->R.p, c->Wn.p, c->Un.p );
-    ++c->launches;
-  }
-  if (fused) std::swap( c->W.p, c->W2.p );      // the new primitives are the current ones from here on
-  CK( cudaGetLastError() );
 }
 
 void do_bc( xyst_ctx* c )
@@ -747,12 +590,12 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   // Everything below works in the library's own numbering; ids and nodal arrays crossing the
   // ABI are mapped at the entry points (to_new / rows_to_new). XYST_REORDER=0 keeps the caller's.
   layout::Options opt;
-  opt.reorder = allow_reorder; opt.tiles = stride == 3 && !c->cho;
-  { const char* e = getenv( "XYST_REORDER" ); if (e && e[0] == '0') opt.reorder = false;
+  // The caller's order (the reference's own locality renumbering, RieCG.cpp:82-100) is kept unless
+  // XYST_REORDER=1 asks for the library's tile order (locality.hpp): on the benchmark boxes the
+  // reference order coalesces the neighbour gathers better.
+  opt.reorder = false;
+  { const char* e = getenv( "XYST_REORDER" ); if (e && e[0] == '1') opt.reorder = allow_reorder;
     e = getenv( "XYST_TILE" ); if (e && atoi( e ) >= 32) c->tile_nodes = std::min( 256, atoi( e ) / 32 * 32 );
-    e = getenv( "XYST_TILE_CAP" ); if (e && atoi( e ) > 0) opt.cap = (size_t)atoi( e );
-    e = getenv( "XYST_FLUX_MODE" ); if (e) c->flux_mode = atoi( e );
-    e = getenv( "XYST_LOOKBACK" ); if (e) c->lookback = atoi( e );
     e = getenv( "XYST_GRAD_MODE" ); if (e) c->grad_mode = atoi( e );
     e = getenv( "XYST_GRAD_WAVES" ); if (e && atoi( e ) > 0) c->grad_waves = atoi( e ); }
   opt.tile_nodes = (size_t)c->tile_nodes;
@@ -770,8 +613,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   const size_t ne = M.ne, nslice = M.nslice, nslot = M.nslot, nent = M.nent;
   const auto &ep = M.ep, &eq = M.eq; const auto& ed = M.ed; const auto &ebase = M.ebase, &base = M.base;
   const auto &inc_e = M.inc_e, &inc_q = M.inc_q;
-  c->maxdeg = M.maxdeg; c->ntile = M.ntile; c->tile_sl_h = M.tile_sl; c->fstride = M.fstride;
-  const bool tiles = opt.tiles;
+  c->maxdeg = M.maxdeg;
   // --- boundary faces: node -> (face, local index) CSR -------------------------------
   std::vector< int > tri( ntri*3 );
   for (size_t i=0; i<ntri*3; ++i) tri[i] = (int)M.to_new( triinpoel[i] );
@@ -825,16 +667,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
     // primitives + coordinates as pairs (w0,w1) (w2,w3) (w4,x) (y,z), see load_wx
     std::vector< double > wx( NP*8, 1.0 );
     for (size_t p=0; p<npoin; ++p) { wx[(2*NP+p)*2+1] = x[p]; wx[(3*NP+p)*2] = y[p]; wx[(3*NP+p)*2+1] = z[p]; }
-    c->W.upload( wx, s ); c->W2.release();
-    if (tiles) c->W2.upload( wx, s ); }
-  if (tiles) {
-    c->tile_sl.upload( M.tile_sl, s ); c->foff.upload( M.foff, s ); c->fa.upload( M.fa, s ); c->fsl.upload( M.fsl, s );
-    c->fdst.upload( M.fdst, s ); c->els.upload( M.els, s ); c->indeg.upload( M.indeg, s );
-    c->tile_of.upload( M.tile_of, s );
-    c->tflag.upload( std::vector< int >( M.ntile, 0 ), s );
-    c->tcounter.upload( std::vector< unsigned long long >( 1, 0ULL ), s );
-    c->tile_count_h = 0; c->tile_epoch = 0; c->tpos.release();
-  }
+    c->W.upload( wx, s ); }
   CK( cudaMemsetAsync( c->G.p, 0, NP*2*NGP*sizeof(double), s ) );
   CK( cudaMemsetAsync( c->F.p, 0, std::max< size_t >( nslot, 1 )*NC*sizeof(double), s ) );
   c->S.release(); c->src_mask = 0;
@@ -934,6 +767,9 @@ int xyst_bc_upload( xyst_ctx* c, size_t ndir, const size_t* dirbcmasks, const do
   // union of BC nodes; per node: dirichlet slot, symmetry entries, farfield entries,
   // pressure slot -- entries keep the list order of the reference (a node repeats once
   // per side set it has a normal in, RieCG.cpp:583-596)
+  if (!dirvals)                      // a mask of 1 without a value would impose density 0
+    for (size_t i=0; i<ndir; ++i) for (int k=0; k<NC; ++k)
+      if (dirbcmasks[i*(NC+1)+1+(size_t)k] == 1) throw std::runtime_error( "xyst_bc_upload: Dirichlet masks set but no values given" );
   std::map< int, int > slot;
   std::vector< int > nodes;
   std::vector< size_t > mdir, msym, mfar, mpre;
@@ -986,6 +822,7 @@ int xyst_dirbc_values( xyst_ctx* c, const double* dirvals )
 {
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
+  if (c->ndir && !dirvals) throw std::runtime_error( "xyst_dirbc_values: null values with Dirichlet nodes present" );
   if (c->ndir) { CK( cudaMemcpyAsync( c->dir_val.p, dirvals, c->ndir*NC*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
                  CK( cudaStreamSynchronize( c->stream ) ); }
   API_END
@@ -1053,11 +890,8 @@ int xyst_riecg_rhs( xyst_ctx* c )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  if (c->flux_mode == 2 && c->ntile) do_stage_tile( c, false, 0, 0.0, c->Un.p, c->U.p );
-  else {
-    if (c->flux_mode == 3) do_flux_own2( c ); else if (c->flux_mode == 1) do_flux_own( c ); else do_flux( c );
-    do_rhs_nodes( c, false, 0, 0.0, c->U.p, c->Un.p, c->U.p );
-  }
+  do_flux( c );
+  do_rhs_nodes( c, false, 0, 0.0, c->U.p, c->Un.p, c->U.p );
   API_END
 }
 
@@ -1117,12 +951,8 @@ int xyst_riecg_stage( xyst_ctx* c, int stage, double dt )
   need_mesh( c );
   if (stage < 0 || stage > 2) throw std::runtime_error( "stage must be 0, 1 or 2" );
   do_grad( c );
-  const bool tile = c->flux_mode == 2 && c->ntile;
-  if (!tile) { if (c->flux_mode == 3) do_flux_own2( c ); else if (c->flux_mode == 1) do_flux_own( c ); else do_flux( c ); }
-  auto nodes = [&]( const double* Un, double* Uout ) {
-    if (tile) do_stage_tile( c, true, stage, dt, Un, Uout );
-    else do_rhs_nodes( c, true, stage, dt, c->U.p, Un, Uout );
-  };
+  do_flux( c );
+  auto nodes = [&]( const double* Un, double* Uout ) { do_rhs_nodes( c, true, stage, dt, c->U.p, Un, Uout ); };
   if (c->lax)           // time level n is kept in (p,u,v,w,T) form (Wn); Un is refreshed at stage 2
     nodes( c->Un.p, c->U.p );
   else if (stage == 0) { // un = u (RieCG.cpp:1011) without a copy: write the new state into the
@@ -1664,13 +1494,16 @@ int xyst_kernel_time( xyst_ctx* c, const char* kernel, int reset, double* ms, ui
   CK( cudaSetDevice( c->device ) );
   c->prof_on = true;
   auto& p = c->prof[ kernel ];
-  CK( cudaStreamSynchronize( c->stream ) );
-  for (auto& e : p.ev) {
-    float t = 0; CK( cudaEventElapsedTime( &t, e.first, e.second ) );
-    p.ms += t; ++p.n;
-    cudaEventDestroy( e.first ); cudaEventDestroy( e.second );
+  if (!p.on) {                                  // first request for this name: switch it on, fill its pool
+    p.on = true;
+    for (int i=0; i<512; ++i) { cudaEvent_t x, y; CK( cudaEventCreate( &x ) ); CK( cudaEventCreate( &y ) ); p.ev.emplace_back( x, y ); }
   }
-  p.ev.clear();
+  CK( cudaStreamSynchronize( c->stream ) );
+  for (size_t i=0; i<p.used; ++i) {
+    float t = 0; CK( cudaEventElapsedTime( &t, p.ev[i].first, p.ev[i].second ) );
+    p.ms += t; ++p.n;
+  }
+  p.used = 0;
   if (ms) *ms = p.ms;
   if (launches) *launches = p.n;
   if (reset) { p.ms = 0.0; p.n = 0; }

@@ -27,6 +27,18 @@ int fail( const std::string& m ) { g_err = m; return 1; }
 #define API_END } catch (std::exception& e) { return fail( e.what() ); } return 0;
 
 Config to_cfg( const xyst_host_cfg* c ) {
+  if (!c) throw std::runtime_error( "null configuration" );
+  // counts against the fixed extents of xyst_host_cfg's arrays, strings against their buffers
+  auto cnt = [&]( int n, int cap, const char* what ) {
+    if (n < 0 || n > cap) throw std::runtime_error( std::string( "xyst_host_cfg: " ) + what + " out of range" ); };
+  cnt( c->nsym, 16, "nsym" ); cnt( c->ndir, 16, "ndir" ); cnt( c->nfar, 16, "nfar" ); cnt( c->npre, 16, "npre" );
+  cnt( c->nnoslip, 16, "nnoslip" ); cnt( c->ndirval, 16, "ndirval" ); cnt( c->nfctsys, 8, "nfctsys" );
+  cnt( c->np_dir, 16, "np_dir" ); cnt( c->np_dirval, 16, "np_dirval" ); cnt( c->np_sym, 16, "np_sym" );
+  if (c->ncomp < 1 || c->ncomp + 1 > 12) throw std::runtime_error( "xyst_host_cfg: ncomp out of range (1..11)" );
+  auto str = [&]( const char* s, std::size_t cap, const char* what ) {
+    if (strnlen( s, cap ) == cap) throw std::runtime_error( std::string( "xyst_host_cfg: " ) + what + " is not NUL-terminated" ); };
+  str( c->problem, sizeof c->problem, "problem" ); str( c->flux, sizeof c->flux, "flux" ); str( c->solver, sizeof c->solver, "solver" );
+  str( c->p_pc, sizeof c->p_pc, "p_pc" ); str( c->mom_pc, sizeof c->mom_pc, "mom_pc" );
   Config k;
   k.problem = c->problem; k.flux = c->flux; k.ncomp = static_cast< std::size_t >( c->ncomp );
   k.alpha = c->alpha; k.kappa = c->kappa; k.r0 = c->r0; k.ce = c->ce; k.beta = {{ c->beta[0], c->beta[1], c->beta[2] }};

@@ -295,7 +295,9 @@ void RieCG::domsuped( const EdgeCSR& edges, const std::vector< real >& d )
   for (auto& a : m_dsupint) a.clear();
   std::vector< std::uint8_t > claimed( edges.nedge(), 0 );
   auto ntet = inpoel.size()/4;
-  const bool reforder = m_cfg.reforder == 1 || (m_cfg.reforder < 0 && ntet <= 4000000);
+  // reforder: 0 = walk the faces in element order (same edges and integrals, other triangles;
+  // ~10x faster at 10^8 tets), anything else = the reference's hash order. No size-dependent default.
+  const bool reforder = m_cfg.reforder != 0;
   // hashes of all tet faces in parallel, then the (inherently sequential) set operations
   std::vector< std::uint64_t > fh( reforder ? ntet*4 : 0 );
   if (reforder) {

@@ -421,7 +421,7 @@ def parity_check(rig, a):
     Uo = o.get("u", rig.rank)
     rel_u = max(float(np.abs(U[:, c] - Uo[:, c]).max() / np.abs(Uo[:, c]).max()) for c in range(5)) if ok_gid else float("inf")
     # diagnostics (all-reduced over the ranks) against the exactly summed oracle state -- the reference's
-    # own serial sums carry ~4e-18 x nodes of rounding, which they are held to as well
+    # own serial sums carry up to ~3e-17 x nodes of rounding, which they are held to as well
     import math
     Ua = np.concatenate([o.get("u", k) for k in range(world)]); va = np.concatenate([o.get("v", k) for k in range(world)])
     meshvol = o.scalar("meshvol")
@@ -430,7 +430,7 @@ def parity_check(rig, a):
         exact = math.sqrt(math.fsum(Ua[:, c] ** 2 * va) / meshvol)
         rel_rows = max(rel_rows, abs(rows[-1, 3 + c] - exact) / exact)
     rel_serial = max(float(np.abs(rows[:, c] - d[:, c]).max() / np.abs(d[:, c]).max()) for c in list(range(1, 8)) + [13])
-    if rel_serial > max(1.0e-12, 8.0e-18 * len(va)):
+    if rel_serial > max(1.0e-12, 3.0e-17 * len(va)):
         rel_rows = max(rel_rows, rel_serial)
     res = rig.gather({"rank": rig.rank, "rows": rel_rows, "u": rel_u, "gid": ok_gid,
                       "launches": int(s.ctx().launch_count())})

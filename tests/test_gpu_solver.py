@@ -211,7 +211,7 @@ def _steps_match(s, o, steps):
         assert abs(rows[-1, 3 + c] - exact) <= TOL * exact, c
     exact = math.fsum(Uo[:, 4] * v)
     assert abs(rows[-1, 13] - exact) <= TOL * abs(exact)
-    tol_serial = max(TOL, 8.0e-18 * len(v))
+    tol_serial = max(TOL, 3.0e-17 * len(v))
     for c in list(range(1, 8)) + [13]:
         assert np.abs(rows[:, c] - d[:, c]).max() <= tol_serial * np.abs(d[:, c]).max(), c
 

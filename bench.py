@@ -419,7 +419,8 @@ def parity_check(rig, a):
     ok_gid = bool(np.array_equal(gid.astype(np.uint64), o.get("gid", rig.rank)))
     # nodal state of this rank's partition, pointwise per component
     Uo = o.get("u", rig.rank)
-    rel_u = max(float(np.abs(U[:, c] - Uo[:, c]).max() / np.abs(Uo[:, c]).max()) for c in range(5)) if ok_gid else float("inf")
+    scale = [max(float(np.abs(o.get("u", k)[:, c]).max()) for k in range(world)) for c in range(5)]   # of the whole mesh
+    rel_u = max(float(np.abs(U[:, c] - Uo[:, c]).max() / scale[c]) for c in range(5)) if ok_gid else float("inf")
     # diagnostics (all-reduced over the ranks) against the exactly summed oracle state -- the reference's
     # own serial sums carry up to ~3e-17 x nodes of rounding, which they are held to as well
     import math

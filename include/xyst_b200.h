@@ -107,6 +107,9 @@ int xyst_apply_bc(xyst_ctx* ctx);
 
 /* RieCG::dt (RieCG.cpp:827-839): cfl * min_p cbrt(vol_p)/max(|v|+c,1e-8), this partition. */
 int xyst_dt_min(xyst_ctx* ctx, double cfl, double* dt);
+/* The same followed by the minimum over all partitions of the communicator (the reference's
+ * contribute(min_double) to the host, RieCG.cpp:850), reduced on the device with NCCL: one wait per step. */
+int xyst_dt_min_all(xyst_ctx* ctx, double cfl, double* dt);
 
 /* One RK stage without materialising R: grad, edge fluxes, nodal gather fused with
  * the update, BCs. Equivalent to grad+rhs+rk_update+apply_bc. */

@@ -928,7 +928,7 @@ int xyst_rk_update( xyst_ctx* c, int stage, double dt )
 
 int xyst_apply_bc( xyst_ctx* c ) { API_BEGIN CK( cudaSetDevice( c->device ) ); need_mesh( c ); do_bc( c ); API_END }
 
-int xyst_dt_min( xyst_ctx* c, double cfl, double* dt )
+static int dt_min_impl( xyst_ctx* c, double cfl, double* dt, bool all )
 {
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
@@ -936,13 +936,18 @@ int xyst_dt_min( xyst_ctx* c, double cfl, double* dt )
   int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( c->npoin, RED_THREADS ) );
   k_dt<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->vol.p, c->prm.gamma, c->red.p, mode( c ), cfl,
     c->steady ? c->dtp.p : nullptr );
-  k_reduce_final< 1, true ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, c->red.p + (size_t)RED_BLOCKS*NDIAG );
+  double* d = c->red.p + (size_t)RED_BLOCKS*NDIAG;
+  k_reduce_final< 1, true ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, d );
   c->launches += 2;
-  CK( cudaMemcpyAsync( c->red_host, c->red.p + (size_t)RED_BLOCKS*NDIAG, sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+  // over all partitions: the all-reduce works on the device value, one copy back and one wait per step
+  if (all && c->comm) NK( g_nccl.AllReduce( d, d, 1, NCCL_FLOAT64, NCCL_MIN, c->comm, c->stream ) );
+  CK( cudaMemcpyAsync( c->red_host, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
   CK( cudaStreamSynchronize( c->stream ) );
   *dt = c->red_host[0] * cfl;
   API_END
 }
+int xyst_dt_min( xyst_ctx* c, double cfl, double* dt ) { return dt_min_impl( c, cfl, dt, false ); }
+int xyst_dt_min_all( xyst_ctx* c, double cfl, double* dt ) { return dt_min_impl( c, cfl, dt, true ); }
 
 int xyst_riecg_stage( xyst_ctx* c, int stage, double dt )
 {

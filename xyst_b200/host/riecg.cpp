@@ -158,6 +158,7 @@ void RieCG::attach( int device, int nranks, int rank, const void* ncclid )
     m_halosum = [this]( int w, std::vector< real >& vals ){
       uploadHalo();
       ck( xyst_halo_sum( m_ctx, w, vals.data() ) ); };
+  if (!m_allreduce) m_nccl_reduce = true;       // the library's own NCCL reductions (no caller-supplied hooks)
   if (!m_allreduce)
     m_allreduce = [this]( int op, std::vector< real >& v ){
       ck( op == 0 ? xyst_allreduce_sum( m_ctx, v.data(), static_cast< int >( v.size() ) )
@@ -640,8 +641,9 @@ real RieCG::dt()
   real mindt;
   auto eps = std::numeric_limits< real >::epsilon();
   if (std::abs( m_cfg.dt ) > eps) mindt = m_cfg.dt;
+  else if (m_nranks > 1 && m_nccl_reduce) { ck( xyst_dt_min_all( m_ctx, m_cfg.cfl, &mindt ) ); return mindt; }   // contribute(min_double) :850
   else ck( xyst_dt_min( m_ctx, m_cfg.cfl, &mindt ) );
-  if (m_nranks > 1) { std::vector< real > t{ mindt }; m_allreduce( 1, t ); mindt = t[0]; }   // contribute(min_double) :850
+  if (m_nranks > 1) { std::vector< real > t{ mindt }; m_allreduce( 1, t ); mindt = t[0]; }
   return mindt;
 }
 

@@ -202,6 +202,7 @@ class RieCG {
     int m_stage = 0;
     HaloSum m_halosum;
     AllReduce m_allreduce;
+    bool m_nccl_reduce = false;          // reductions by the device library itself (NCCL), not by caller-supplied hooks
     bool m_hostready = false;
     bool m_zal = false;
     bool m_lax = false;                    //!< LaxCG: same setup as RieCG, preconditioned update

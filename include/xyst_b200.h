@@ -97,6 +97,12 @@ int xyst_grad_get(xyst_ctx* ctx, double* G);
  * of the last xyst_riecg_grad. xyst_rhs_get returns R as npoin x ncomp. */
 int xyst_riecg_rhs(xyst_ctx* ctx);
 int xyst_rhs_get(xyst_ctx* ctx, double* R);
+/* For callers that keep the reference's call structure (include/xyst_shim.hpp): gradients G as
+ * riemann::rhs receives them (npoin x 3*ncomp, already divided by vol, RieCG.cpp:936-939), and
+ * m_besym / V() of an uploaded mesh, which the reference passes to riemann::rhs only. */
+int xyst_grad_set(xyst_ctx* ctx, const double* G);
+int xyst_besym_upload(xyst_ctx* ctx, const uint8_t* besym);
+int xyst_v_upload(xyst_ctx* ctx, const double* v);
 
 /* RieCG::solve update (RieCG.cpp:1011-1021): stage 0 saves un=u; u = un - rk*dt*R/vol,
  * with R from the last xyst_riecg_rhs. */

@@ -75,6 +75,10 @@ std::size_t putf( const be::Fields& f, void* out, std::size_t cap ) {
 }
 }
 
+#ifdef ORACLE_SHIM
+#include "xyst_shim.hpp"
+#endif
+
 extern "C" {
 
 const char* orc_backend() { return be::name(); }
@@ -263,6 +267,14 @@ int orc_kernel( void* hv, int chare, const char* what, int stage, double t, doub
     else if (w == "alw") c.alw_own( dt );
     else if (w == "lim") c.lim_own();
     else if (w == "zsolve") c.zsolve( t, dt );
+#ifdef ORACLE_SHIM
+    // the product's reference-signature wrappers (include/xyst_shim.hpp), called with the chare's own
+    // containers next to the reference functions above: the compiled drop-in binding under test
+    else if (w == "shim_grad") xyst_shim::riemann::grad( c.dsupedge, c.dsupint, c.coord, c.triinpoel, c.u, c.grad );
+    else if (w == "shim_rhs") xyst_shim::riemann::rhs( c.dsupedge, c.dsupint, c.coord, c.triinpoel, c.besym, c.grad, c.u, c.v, t, c.tp, c.rhs );
+    else if (w == "shim_zrhs") xyst_shim::zalesak::rhs( c.dsupedge, c.dsupint, c.coord, c.triinpoel, c.besym, t, dt, c.tp, c.dtp, c.u, c.rhs );
+    else if (w == "shim_release") xyst_shim::release( c.dsupedge );
+#endif
     else { g_err = "orc_kernel: unknown " + w; return -1; }
     return 0;
   } catch (std::exception& e) { g_err = e.what(); return -1; }

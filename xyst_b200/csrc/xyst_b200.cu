@@ -885,6 +885,50 @@ int xyst_grad_get( xyst_ctx* c, double* G )
   API_END
 }
 
+// Gradients given by the caller (already divided by the nodal volumes), npoin x 15: the reference's
+// riemann::rhs takes G as an argument
+int xyst_grad_set( xyst_ctx* c, const double* G )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  need_mesh( c );
+  if (!G) throw std::runtime_error( "null argument" );
+  std::vector< double > h( c->NP*2*NGP, 0.0 );
+  for (size_t p=0; p<c->npoin; ++p) {
+    size_t o = reordered( c ) ? (size_t)c->new2old_h[p] : p;
+    for (int i=0; i<15; ++i) h[gidx( i, p, c->NP )] = G[o*15+(size_t)i];
+  }
+  CK( cudaMemcpyAsync( c->G.p, h.data(), h.size()*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+  CK( cudaStreamSynchronize( c->stream ) );
+  API_END
+}
+
+// New boundary symmetry flags (RieCG::m_besym) / own nodal volumes V() for an uploaded mesh
+int xyst_besym_upload( xyst_ctx* c, const uint8_t* besym )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  need_mesh( c );
+  if (c->ntri && !besym) throw std::runtime_error( "null argument" );
+  if (c->rb_pending) { CK( cudaStreamSynchronize( c->aux_stream ) ); c->rb_pending = false; }   // boundary fluxes of the old flags
+  if (c->ntri) { CK( cudaMemcpyAsync( c->besym.p, besym, c->ntri*3, cudaMemcpyHostToDevice, c->stream ) );
+                 CK( cudaStreamSynchronize( c->stream ) ); }
+  API_END
+}
+
+int xyst_v_upload( xyst_ctx* c, const double* v )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  need_mesh( c );
+  if (!v) throw std::runtime_error( "null argument" );
+  std::vector< double > h( c->NP, 1.0 );
+  for (size_t p=0; p<c->npoin; ++p) h[p] = v[ reordered( c ) ? (size_t)c->new2old_h[p] : p ];
+  CK( cudaMemcpyAsync( c->v.p, h.data(), h.size()*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+  CK( cudaStreamSynchronize( c->stream ) );
+  API_END
+}
+
 int xyst_riecg_rhs( xyst_ctx* c )
 {
   API_BEGIN

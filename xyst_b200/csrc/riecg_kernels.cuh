@@ -302,9 +302,11 @@ k_grad_node( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
     #pragma unroll
     for (int i=0; i<15; ++i) acc[i] += Gb[(size_t)b*15+i];
   }
-  double vp = vol[p];
+  // one quotient per node, then 15 products (the reference divides each component, RieCG.cpp:936-939:
+  // the same values up to one rounding)
+  double ivp = 1.0 / vol[p];
   #pragma unroll
-  for (int i=0; i<15; ++i) acc[i] /= vp;
+  for (int i=0; i<15; ++i) acc[i] *= ivp;
   store_g( G, NP, p, acc );
 }
 
@@ -373,9 +375,9 @@ k_grad_node_p( size_t npoin, size_t NP, size_t nslice, int kcap, const long long
           #pragma unroll
           for (int i=0; i<15; ++i) acc[i] += Gb[(size_t)b*15+i];
         }
-        double vp = vol[p];
+        double ivp = 1.0 / vol[p];
         #pragma unroll
-        for (int i=0; i<15; ++i) acc[i] /= vp;
+        for (int i=0; i<15; ++i) acc[i] *= ivp;
         store_g( G, NP, p, acc );
       }
     }
@@ -392,7 +394,7 @@ __global__ void k_grad_bfix( int nbn, size_t NP, const int* __restrict__ bn_node
   size_t b = i / 15, k = i % 15;
   size_t p = bn_node[b];
   size_t g = gidx( (int)k, p, NP );
-  G[g] = (G[g] + Gb[b*15+k]) / vol[p];
+  G[g] = (G[g] + Gb[b*15+k]) * (1.0 / vol[p]);      // as k_grad_node: quotient first, then product
 }
 
 // partial (un-normalised) gradient sums of the shared nodes, for the halo exchange
@@ -431,11 +433,11 @@ __global__ void k_grad_finish( int nsh, size_t NP, const int* __restrict__ sh_no
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= nsh) return;
   size_t p = sh_node[i];
-  double vp = vol[p];
+  double ivp = 1.0 / vol[p];
   for (int j=0; j<15; ++j) {
     double a = part[(size_t)i*15+j];
     for (int r=roff[i]; r<roff[i+1]; ++r) a += recvbuf[(size_t)ridx[r]*15+j];
-    G[gidx( j, p, NP )] = a / vp;
+    G[gidx( j, p, NP )] = a * ivp;
   }
 }
 
@@ -1029,6 +1031,14 @@ __device__ __forceinline__ void block_reduce( double v[NV], double* __restrict__
   }
 }
 
+// characteristic length cbrt(vol) of RieCG::dt (RieCG.cpp:834): a constant of the mesh, computed once
+__global__ void k_cbrt( size_t n, const double* __restrict__ vol, double* __restrict__ out )
+{
+  size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (p < n) out[p] = cbrt( vol[p] );
+}
+
+// (vol: the nodes' cbrt(vol) from k_cbrt)
 __global__ void __launch_bounds__(RED_THREADS)
 k_dt( size_t npoin, size_t NP, const double* __restrict__ U, const double* __restrict__ vol, double gamma,
       double* __restrict__ part, Mode M, double cfl, double* __restrict__ dtp )
@@ -1047,7 +1057,7 @@ k_dt( size_t npoin, size_t NP, const double* __restrict__ U, const double* __res
     #pragma unroll
     for (int k=0; k<4; ++k) {
       double r = a[k][0], u = a[k][1]/r, v = a[k][2]/r, w = a[k][3]/r;
-      double L = cbrt( a[k][5] );
+      double L = a[k][5];
       double e;
       if (M.rgas > 0.0) {                  // LaxCG::charvel, LaxCG.cpp:228-259
         double cp = gamma*M.rgas/(gamma-1.0);

@@ -166,6 +166,7 @@ struct xyst_ctx : CgState {
   uint64_t launches = 0;
   // nodal state, structure of arrays with stride NP (npoin rounded up to 32)
   DevBuf< double > U, Un, W, X, G, vol, v;   // [5][NP] [5][NP] [5][NP] [3][NP] [15][NP]
+  DevBuf< double > cvol;                     // cbrt(vol), the length scale of the time step
   DevBuf< double > R, stage, S;              // reference layout [npoin][5]: rhs out, copy staging, source
   int src_mask = 0;
   // edge slots (owner-slice order): endpoints (-1 = padding), normals [3][nslot], fluxes [5][nslot]
@@ -650,7 +651,9 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   c->zP.release(); c->zQ.release(); c->zUL.release();
   { std::vector< double > pv( NP, 1.0 ), pw( NP, 1.0 ), px( 3*NP, 0.0 );
     for (size_t p=0; p<npoin; ++p) { pv[p] = vol[p]; pw[p] = v[p]; px[p] = x[p]; px[NP+p] = y[p]; px[2*NP+p] = z[p]; }
-    c->vol.upload( pv, s ); c->v.upload( pw, s ); c->X.upload( px, s ); }
+    c->vol.upload( pv, s ); c->v.upload( pw, s ); c->X.upload( px, s );
+    c->cvol.alloc( NP );
+    k_cbrt<<< nblk( NP, 256 ), 256, 0, s >>>( NP, c->vol.p, c->cvol.p ); ++c->launches; CK( cudaGetLastError() ); }
   c->fn.alloc( std::max< size_t >( ntri, 1 )*3 );
   if (ntri) { k_face_normals<<< nblk( ntri, 128 ), 128, 0, s >>>( (int)ntri, NP, c->tri.p, c->X.p, c->fn.p ); ++c->launches; CK( cudaGetLastError() ); }
   if (c->nsh) refresh_shared( c );
@@ -978,7 +981,7 @@ static int dt_min_impl( xyst_ctx* c, double cfl, double* dt, bool all )
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
   int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( c->npoin, RED_THREADS ) );
-  k_dt<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->vol.p, c->prm.gamma, c->red.p, mode( c ), cfl,
+  k_dt<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->cvol.p, c->prm.gamma, c->red.p, mode( c ), cfl,
     c->steady ? c->dtp.p : nullptr );
   double* d = c->red.p + (size_t)RED_BLOCKS*NDIAG;
   k_reduce_final< 1, true ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, d );

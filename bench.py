@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--no-weak", action="store_true", help="N>1: skip the extra weak-scaling Sedov line")
     ap.add_argument("--parity-n", type=int, default=32, help="cells per side per rank of the multi-GPU parity box")
     ap.add_argument("--exact-muscl", action="store_true")
+    ap.add_argument("--no-strong-base", action="store_true", help="N=1: skip the extra run of the 200M-tet "
+                    "strong-scaling box on one GPU (key strong_scaling_base)")
     return ap.parse_args()
 
 
@@ -523,6 +525,28 @@ def timed_run(rig, a, wl, n, dims, want_e2e):
     return out
 
 
+def strong_base(a):
+    """The N>1 workload (200M-tet Taylor-Green box) on ONE GPU, so that the scaling run has its own
+    base: run in a child process (a host that cannot hold the 200M-tet mesh must not take the main line
+    down with it); the device of this process is idle meanwhile."""
+    try:
+        avail = 0
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                avail = int(ln.split()[1]) / 1e6
+        if avail and avail < 100.0:
+            return {"skipped": "%.0f GB of host memory available, the 200M-tet host mesh needs ~80 GB" % avail}
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "tg_strong", "--steps", "10",
+                            "--warmup", str(a.warmup), "--no-cpu-baseline", "--no-e2e"],
+                           capture_output=True, text=True, timeout=900)
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"workload": j["config"]["workload"], "n_gpus": 1, "value": j["value"], "ms_per_step": j["ms_per_step"],
+                "steps": j["steps"], "roofline_stage_frac": j["roofline_stage"]["frac_of_peak"],
+                "setup_s": j["setup_s"], "finite": j["finite"], "superedge_order": j["config"]["superedge_order"]}
+    except Exception as e:
+        return {"failed": str(e)[:200]}
+
+
 def run_ours(a):
     rig = Rig(a)
     world = rig.world
@@ -600,6 +624,8 @@ def run_ours(a):
     if world == 1 and not a.no_cpu_baseline:
         cores, _, _ = host_cores(a.cpu_cores)
         line["cpu_baseline"] = cpu_arm(a.cpu_n, a.cpu_steps, cores)
+    if world == 1 and wl == "sedov" and a.workload == "auto" and not a.no_strong_base:
+        line["strong_scaling_base"] = strong_base(a)
     print(json.dumps(line), flush=True)
     if world > 1:
         rig.dist.destroy_process_group()

@@ -92,15 +92,17 @@ __device__ __forceinline__ void load_f( const double* __restrict__ F, size_t nsl
 
 // reference layout [node][comp] -> SoA state + primitives
 // (n2o: internal node id -> the caller's, or null if the two orders are the same)
+// (ncomp = 5 + ns: the ns transported scalars of a node follow its flow variables in A and go to sU)
 __global__ void k_set_state( size_t n, size_t NP, const double* __restrict__ A, const int* __restrict__ n2o,
-                             double* __restrict__ U, double* __restrict__ W, Mode M )
+                             double* __restrict__ U, double* __restrict__ W, Mode M, int ncomp, double* __restrict__ sU )
 {
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= n) return;
   double u[NC], w[NC];
   size_t o = n2o ? (size_t)n2o[p] : p;
   #pragma unroll
-  for (int c=0; c<NC; ++c) u[c] = A[o*NC+c];
+  for (int c=0; c<NC; ++c) u[c] = A[o*ncomp+c];
+  for (int c=NC; c<ncomp; ++c) sU[(size_t)(c-NC)*NP+p] = A[o*ncomp+c];
   primitive_of( u, w, M );
   #pragma unroll
   for (int c=0; c<NC; ++c) U[c*NP+p] = u[c];
@@ -108,13 +110,14 @@ __global__ void k_set_state( size_t n, size_t NP, const double* __restrict__ A, 
 }
 
 __global__ void k_get_state( size_t n, size_t NP, const double* __restrict__ U, const int* __restrict__ n2o,
-                             double* __restrict__ A )
+                             double* __restrict__ A, int ncomp, const double* __restrict__ sU )
 {
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= n) return;
   size_t o = n2o ? (size_t)n2o[p] : p;
   #pragma unroll
-  for (int c=0; c<NC; ++c) A[o*NC+c] = U[c*NP+p];
+  for (int c=0; c<NC; ++c) A[o*ncomp+c] = U[c*NP+p];
+  for (int c=NC; c<ncomp; ++c) A[o*ncomp+c] = sU[(size_t)(c-NC)*NP+p];
 }
 
 // ---------------------------------------------------------------------------------
@@ -595,8 +598,9 @@ __device__ __forceinline__ void rusanov( double l[NC], double r[NC], const doubl
   }
 }
 
+// ev (optional): what the scalar flux of the same edge needs (riecg_scalar.cuh), Riemann.cpp:636-643
 __device__ __forceinline__ void hllc( double l[NC], double r[NC], const double n[3],
-                                      const DParams& P, double f[NC] )
+                                      const DParams& P, double f[NC], double* ev = nullptr )
 {
   double g = P.gamma;
   double nx = -n[0], ny = -n[1], nz = -n[2];
@@ -604,6 +608,7 @@ __device__ __forceinline__ void hllc( double l[NC], double r[NC], const double n
   nx /= len; ny /= len; nz /= len;
   double qL = l[1]*nx + l[2]*ny + l[3]*nz;
   double qR = r[1]*nx + r[2]*ny + r[3]*nz;
+  if (ev) { ev[0] = qL*len; ev[1] = qR*len; ev[2] = fmax( fabs(qL), fabs(qR) ) * len; }
   double pL = (l[0]*l[4]) * (g-1.0);
   double pR = (r[0]*r[4]) * (g-1.0);
   l[4] = (l[4] + 0.5*(l[1]*l[1] + l[2]*l[2] + l[3]*l[3])) * l[0];
@@ -933,13 +938,13 @@ __global__ void k_rhs_finish( int nsh, size_t NP, const int* __restrict__ sh_nod
 // unfused RK update from a materialised R (drop-in for RieCG::solve :1016-1021)
 __global__ void k_update( size_t npoin, size_t NP, const double* __restrict__ R, const double* __restrict__ vol,
                           const double* __restrict__ Un, StageArgs A, double* __restrict__ U,
-                          double* __restrict__ W, double* __restrict__ Wn, double* __restrict__ UnOut )
+                          double* __restrict__ W, double* __restrict__ Wn, double* __restrict__ UnOut, int rstride )
 {
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= npoin) return;
   double acc[NC];
   #pragma unroll
-  for (int c=0; c<NC; ++c) acc[c] = R[p*NC+c];
+  for (int c=0; c<NC; ++c) acc[c] = R[p*(size_t)rstride+c];
   if (A.M.rgas > 0.0) node_update< true >( p, NP, acc, vol[p], Un, U, W, W, Wn, UnOut, A );
   else node_update< false >( p, NP, acc, vol[p], Un, U, W, W, Wn, UnOut, A );
 }

@@ -61,7 +61,7 @@ __device__ __forceinline__ double fast_sqrt( double x )
 // (a per-edge constant kept next to the normal) and the limiter form as a template argument
 template< bool EXACT >
 __device__ __forceinline__ void rusanov_len( double l[NC], double r[NC], const double n[3], double len,
-                                             const DParams& P, double f[NC] )
+                                             const DParams& P, double f[NC], double* ev = nullptr )
 {
   double g = P.gamma;
   double pL = (l[0]*l[4]) * (g-1.0);
@@ -70,6 +70,7 @@ __device__ __forceinline__ void rusanov_len( double l[NC], double r[NC], const d
   double nx = n[0], ny = n[1], nz = n[2];
   double vnL = l[1]*nx + l[2]*ny + l[3]*nz;
   double vnR = r[1]*nx + r[2]*ny + r[3]*nz;
+  if (ev) { ev[0] = vnL; ev[1] = vnR; ev[2] = fmax( fabs(vnL), fabs(vnR) ); }   // for the scalar flux, Riemann.cpp:462-470
   l[4] = (l[4] + 0.5*(l[1]*l[1] + l[2]*l[2] + l[3]*l[3])) * l[0];
   l[1] *= l[0]; l[2] *= l[0]; l[3] *= l[0];
   r[4] = (r[4] + 0.5*(r[1]*r[1] + r[2]*r[2] + r[3]*r[3])) * r[0];
@@ -95,7 +96,7 @@ __device__ __forceinline__ void rusanov_len( double l[NC], double r[NC], const d
 template< bool EXACT, int FLUX >
 __device__ __forceinline__ void edge_flux_owner( const double wo[NC], const double xo[3], const double go[15],
     const double wq[NC], const double xq[3], const double gq[15], double s, const double nref[4],
-    const DParams& P, double f[NC] )
+    const DParams& P, double f[NC], double* ev = nullptr )
 {
   double l[NC], r[NC], vw[3], n[3];
   #pragma unroll
@@ -103,7 +104,7 @@ __device__ __forceinline__ void edge_flux_owner( const double wo[NC], const doub
   #pragma unroll
   for (int j=0; j<3; ++j) { vw[j] = xq[j] - xo[j]; n[j] = s * nref[j]; }
   muscl< EXACT >( go, 1, gq, 1, vw, l, r, s * MUSCL_EPS );
-  if (FLUX == 0) rusanov_len< EXACT >( l, r, n, nref[3], P, f ); else if (FLUX == 1) hllc( l, r, n, P, f );
+  if (FLUX == 0) rusanov_len< EXACT >( l, r, n, nref[3], P, f, ev ); else if (FLUX == 1) hllc( l, r, n, P, f, ev );
   else if (FLUX == 2) lax_rusanov( l, r, n, P, f ); else lax_hllc( l, r, n, P, f );
 }
 
@@ -111,8 +112,10 @@ template< bool EXACT, int FLUX >
 __global__ void __launch_bounds__(OWN_THREADS, OWN_MINB)
 k_flux_own( size_t nslice, size_t NP, size_t nslot, const long long* __restrict__ ebase, const int* __restrict__ eo,
             const double* __restrict__ D, const double* __restrict__ W, const double* __restrict__ G,
-            double* __restrict__ F, double* __restrict__ Racc, DParams P )
+            double* __restrict__ F, double* __restrict__ Racc, DParams P, double* __restrict__ EV )
 {
+  // EV (null without transported scalars): per edge, reference-oriented, the normal velocities of the
+  // reconstructed states and the scalar dissipation speed (riecg_scalar.cuh)
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (slice >= nslice) return;
@@ -156,12 +159,15 @@ k_flux_own( size_t nslice, size_t NP, size_t nslot, const long long* __restrict_
       load_wx( WX, NP, q, wq, xq );
       load_g( G2, NP, q, gq );
       if (j+1 < kmax) e_nx = __ldg( eo + sl + 32 );
-      double f[NC];
-      edge_flux_owner< EXACT, FLUX >( wo, xo, go, wq, xq, gq, s, n, P, f );
+      double f[NC], ev[3];
+      edge_flux_owner< EXACT, FLUX >( wo, xo, go, wq, xq, gq, s, n, P, f, EV ? ev : nullptr );
       if (valid) {
         #pragma unroll
         for (int c=0; c<NC; ++c) { acc[c] -= f[c]; f[c] *= s; }     // F holds the reference-oriented flux
         store_f( F, nslot, sl, f );
+        if (EV) {                    // owner-first (a,b) -> reference orientation: (a,b) or (-b,-a)
+          EV[sl] = e < 0 ? -ev[1] : ev[0]; EV[nslot+sl] = e < 0 ? -ev[0] : ev[1]; EV[2*nslot+sl] = ev[2];
+        }
       }
       sl += 32;
     }
@@ -181,7 +187,7 @@ k_update_in( size_t npoin, size_t NP, const long long* __restrict__ in_base, con
              const int* __restrict__ bslot, const double* __restrict__ Rb, const double* __restrict__ S, int src_mask,
              const double* __restrict__ v, const double* __restrict__ vol, const double* __restrict__ Un,
              StageArgs A, double* __restrict__ U, double* __restrict__ W, double* __restrict__ R,
-             double* __restrict__ Wn, double* __restrict__ UnOut, const unsigned char* __restrict__ skip )
+             double* __restrict__ Wn, double* __restrict__ UnOut, const unsigned char* __restrict__ skip, int rstride )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -217,7 +223,7 @@ k_update_in( size_t npoin, size_t NP, const long long* __restrict__ in_base, con
     node_update< LAX >( p, NP, acc, vol[p], Un, U, W, W, Wn, UnOut, A );
   } else {
     #pragma unroll
-    for (int c=0; c<NC; ++c) R[p*NC+c] = acc[c];
+    for (int c=0; c<NC; ++c) R[p*(size_t)rstride+c] = acc[c];      // row stride = all components (5 + scalars)
   }
 }
 

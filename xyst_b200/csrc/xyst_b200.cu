@@ -246,6 +246,11 @@ struct xyst_ctx : CgState {
   // owner-slot view of the edges for the thread-per-owner kernels: slot base per slice, and per slot
   // the edge's other end | orientation bit (31: the owner is the edge's SECOND node), -1 = padding
   DevBuf< long long > ebase; DevBuf< int > eo;
+  // transported scalars (riecg_scalar.cuh): ncomp = 5 + ns
+  int ncomp = NC, ns = 0;
+  DevBuf< double > sU, sUn, sG, sF, EV, sGb, sRb, sS, sdir_val;   // [ns][NP] x2, [3ns][NP], [ns][nslot], [3][nslot], ...
+  DevBuf< int > sdir_mask;
+  bool s_src = false;
   // owner's share of the nodal flux sums (k_flux_own) and the incoming-edge lists of k_update_in
   DevBuf< double > Racc; DevBuf< long long > in_base; DevBuf< int > in_e;
   bool gradp_attr = false;
@@ -259,6 +264,7 @@ namespace {
 
 #include "riecg_kernels.cuh"
 #include "riecg_own.cuh"
+#include "riecg_scalar.cuh"
 #include "zalcg_kernels.cuh"
 #include "kozcg_kernels.cuh"
 #include "cg_kernels.cuh"
@@ -423,7 +429,7 @@ void launch_rhs_node( xyst_ctx* c, bool fused, const StageArgs& A, const double*
   // the owner's own share was summed by the flux kernel: gather the incoming edges only
   #define UPD_IN( FU, LX ) k_update_in< FU, LX ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->in_base.p, c->in_e.p, \
       c->Racc.p, c->F.p, c->nslot, c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, \
-      c->Wn.p, c->Un.p, skip )
+      c->Wn.p, c->Un.p, skip, c->ncomp )
   if (fused && c->lax) UPD_IN( true, true ); else if (fused) UPD_IN( true, false ); else UPD_IN( false, false );
   #undef UPD_IN
   ++c->launches;
@@ -479,7 +485,7 @@ void do_flux( xyst_ctx* c )
   ProfScope ps( c, "flux" );
   unsigned g = nblk( c->nslice*32, OWN_THREADS );
   #define LAUNCH_OWN( EX, FL ) k_flux_own< EX, FL ><<< g, OWN_THREADS, 0, s >>>( c->nslice, c->NP, c->nslot, \
-      c->ebase.p, c->eo.p, c->D.p, c->W.p, c->G.p, c->F.p, c->Racc.p, P )
+      c->ebase.p, c->eo.p, c->D.p, c->W.p, c->G.p, c->F.p, c->Racc.p, P, c->ns ? c->EV.p : nullptr )
   int fl = P.flux + (c->lax ? 2 : 0);
   if (P.exact) { if (fl == 0) LAUNCH_OWN( true, 0 ); else if (fl == 1) LAUNCH_OWN( true, 1 );
                  else if (fl == 2) LAUNCH_OWN( true, 2 ); else LAUNCH_OWN( true, 3 ); }
@@ -489,8 +495,51 @@ void do_flux( xyst_ctx* c )
   ++c->launches;
 }
 
+// ---- transported scalars (riecg_scalar.cuh) -------------------------------------------
+void scal_need( xyst_ctx* c ) {
+  if (c->lax) throw std::runtime_error( "transported scalars are not implemented for LaxCG" );
+  if (c->nsh > 0 && c->comm) throw std::runtime_error( "transported scalars on several partitions are not implemented yet" );
+}
+// boundary parts + gradients of the scalars; needs the state at stage start
+void scal_grad( xyst_ctx* c )
+{
+  scal_need( c );
+  auto s = c->stream;
+  if (c->nbn) { k_scal_bnd<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->ns, c->NP, c->bn_off.p, c->bn_face.p, c->tri.p,
+                  c->besym.p, c->fn.p, c->U.p, c->sU.p, c->sGb.p, c->sRb.p ); ++c->launches; }
+  k_scal_grad<<< nblk( c->nslice*32, 128 ), 128, 0, s >>>( c->npoin, c->ns, c->NP, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot,
+    c->sU.p, c->bslot.p, c->sGb.p, c->vol.p, c->sG.p ); ++c->launches;
+  CK( cudaGetLastError() );
+}
+// scalar edge fluxes (after the flow's k_flux_own, which leaves EV) and nodal sums / update
+void scal_flux_nodes( xyst_ctx* c, bool fused, int stage, double dt )
+{
+  auto s = c->stream;
+  if (c->prm.exact_muscl) k_scal_flux< true ><<< nblk( c->nslot, 128 ), 128, 0, s >>>( c->nslot, c->ns, c->NP, c->ep.p, c->eq.p, c->X.p, c->EV.p, c->sU.p, c->sG.p, c->sF.p );
+  else k_scal_flux< false ><<< nblk( c->nslot, 128 ), 128, 0, s >>>( c->nslot, c->ns, c->NP, c->ep.p, c->eq.p, c->X.p, c->EV.p, c->sU.p, c->sG.p, c->sF.p );
+  ++c->launches;
+  unsigned g = nblk( c->nslice*32, 128 );
+  const double* S = c->s_src ? c->sS.p : nullptr;
+  if (fused) {
+    // stage 0: un = u without a copy, as for the flow variables
+    const double* un = stage == 0 ? c->sU.p : c->sUn.p;
+    double* out = stage == 0 ? c->sUn.p : c->sU.p;
+    k_scal_node< true ><<< g, 128, 0, s >>>( c->npoin, c->ns, c->NP, c->sl_base.p, c->inc_e.p, c->sF.p, c->nslot, c->bslot.p,
+      c->sRb.p, S, c->v.p, c->vol.p, un, rkcoef[stage]*dt, c->steady ? c->dtp.p : nullptr, rkcoef[stage], out, c->R.p, c->ncomp );
+    if (stage == 0) std::swap( c->sU.p, c->sUn.p );
+  } else
+    k_scal_node< false ><<< g, 128, 0, s >>>( c->npoin, c->ns, c->NP, c->sl_base.p, c->inc_e.p, c->sF.p, c->nslot, c->bslot.p,
+      c->sRb.p, S, c->v.p, c->vol.p, c->sUn.p, 0.0, nullptr, 0.0, c->sU.p, c->R.p, c->ncomp );
+  ++c->launches;
+  CK( cudaGetLastError() );
+}
+
 void do_bc( xyst_ctx* c )
 {
+  if (c->ns && c->nbc && c->ndir) {
+    k_scal_bc<<< nblk( c->nbc, 128 ), 128, 0, c->stream >>>( (int)c->nbc, c->ns, c->NP, c->bc_node.p, c->bc_dir.p,
+      c->sdir_mask.p, c->sdir_val.p, c->sU.p ); ++c->launches;
+  }
   if (!c->nbc) return;
   FarState fs{ c->far_r, c->far_p, c->far_u[0], c->far_u[1], c->far_u[2] };
   k_bc<<< nblk( c->nbc, 128 ), 128, 0, c->stream >>>( (int)c->nbc, c->NP, c->bc_node.p, c->bc_dir.p,
@@ -519,7 +568,7 @@ int xyst_ctx_create( int device, const xyst_params* params, xyst_ctx** out )
 {
   API_BEGIN
   if (!params || !out) throw std::runtime_error( "null argument" );
-  if (params->ncomp != NC) throw std::runtime_error( "only ncomp = 5 (Euler system) is supported" );
+  if (params->ncomp < NC || params->ncomp > NC+8) throw std::runtime_error( "ncomp must be 5 (Euler system) + at most 8 transported scalars" );
   if (params->flux != 0 && params->flux != 1) throw std::runtime_error( "Flux not configured" );
   int n = 0;
   if (cudaGetDeviceCount( &n ) != cudaSuccess || n == 0)
@@ -527,7 +576,7 @@ int xyst_ctx_create( int device, const xyst_params* params, xyst_ctx** out )
   if (device < 0 || device >= n) throw std::runtime_error( "invalid device ordinal" );
   CK( cudaSetDevice( device ) );
   auto c = new xyst_ctx;
-  c->device = device; c->prm = *params;
+  c->device = device; c->prm = *params; c->ncomp = params->ncomp; c->ns = params->ncomp - NC;
   CK( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) ); c->own_stream = true;
   // side streams at the highest priority: their small kernels (boundary terms, shared-node sums,
   // packing, NCCL send/recv) get the thread-block slots the full-mesh gather frees first
@@ -664,7 +713,16 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
     return 0;
   }
   c->U.alloc( NP*NC ); c->Un.alloc( NP*NC ); c->G.alloc( NP*2*NGP ); c->Racc.alloc( NP*NC );
-  c->R.alloc( npoin*NC ); c->stage.alloc( npoin*NC ); c->F.alloc( std::max< size_t >( nslot, 1 )*NC );
+  c->R.alloc( npoin*(size_t)c->ncomp ); c->stage.alloc( npoin*(size_t)c->ncomp ); c->F.alloc( std::max< size_t >( nslot, 1 )*NC );
+  if (c->ns) {
+    if (stride != 3) throw std::runtime_error( "transported scalars are implemented for RieCG only" );
+    size_t ns = (size_t)c->ns;
+    c->sU.upload( std::vector< double >( ns*NP, 0.0 ), s ); c->sUn.upload( std::vector< double >( ns*NP, 0.0 ), s );
+    c->sG.upload( std::vector< double >( 3*ns*NP, 0.0 ), s );
+    c->sF.alloc( ns*std::max< size_t >( nslot, 1 ) ); c->EV.alloc( 3*std::max< size_t >( nslot, 1 ) );
+    c->sGb.alloc( std::max< size_t >( nbn, 1 )*3*ns ); c->sRb.alloc( std::max< size_t >( nbn, 1 )*ns );
+    c->sS.release(); c->s_src = false;
+  }
   { std::vector< double > one( NP*NC, 1.0 );    // a harmless state until xyst_state_set
     c->U.upload( one, s ); c->Un.upload( one, s );
     // primitives + coordinates as pairs (w0,w1) (w2,w3) (w4,x) (y,z), see load_wx
@@ -767,18 +825,19 @@ int xyst_bc_upload( xyst_ctx* c, size_t ndir, const size_t* dirbcmasks, const do
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
+  const size_t NCA = (size_t)c->ncomp, NSC = (size_t)c->ns;      // all components, transported scalars
   // union of BC nodes; per node: dirichlet slot, symmetry entries, farfield entries,
   // pressure slot -- entries keep the list order of the reference (a node repeats once
   // per side set it has a normal in, RieCG.cpp:583-596)
   if (!dirvals)                      // a mask of 1 without a value would impose density 0
-    for (size_t i=0; i<ndir; ++i) for (int k=0; k<NC; ++k)
-      if (dirbcmasks[i*(NC+1)+1+(size_t)k] == 1) throw std::runtime_error( "xyst_bc_upload: Dirichlet masks set but no values given" );
+    for (size_t i=0; i<ndir; ++i) for (size_t k=0; k<NCA; ++k)
+      if (dirbcmasks[i*(NCA+1)+1+k] == 1) throw std::runtime_error( "xyst_bc_upload: Dirichlet masks set but no values given" );
   std::map< int, int > slot;
   std::vector< int > nodes;
   std::vector< size_t > mdir, msym, mfar, mpre;
   if (reordered( c )) {            // the lists as the library numbers the nodes
-    mdir.assign( dirbcmasks, dirbcmasks + ndir*(NC+1) );
-    for (size_t i=0; i<ndir; ++i) mdir[i*(NC+1)] = to_new( c, dirbcmasks[i*(NC+1)], "BC node id" );
+    mdir.assign( dirbcmasks, dirbcmasks + ndir*(NCA+1) );
+    for (size_t i=0; i<ndir; ++i) mdir[i*(NCA+1)] = to_new( c, dirbcmasks[i*(NCA+1)], "BC node id" );
     msym.resize( nsym ); for (size_t i=0; i<nsym; ++i) msym[i] = to_new( c, symbcnodes[i], "BC node id" );
     mfar.resize( nfar ); for (size_t i=0; i<nfar; ++i) mfar[i] = to_new( c, farbcnodes[i], "BC node id" );
     mpre.resize( npre ); for (size_t i=0; i<npre; ++i) mpre[i] = to_new( c, prebcnodes[i], "BC node id" );
@@ -786,7 +845,7 @@ int xyst_bc_upload( xyst_ctx* c, size_t ndir, const size_t* dirbcmasks, const do
   }
   auto add = [&]( size_t p ){ if (p >= c->npoin) throw std::runtime_error( "BC node id out of range" );
     auto it = slot.find( (int)p ); if (it == slot.end()) { slot[(int)p] = (int)nodes.size(); nodes.push_back( (int)p ); } };
-  for (size_t i=0; i<ndir; ++i) add( dirbcmasks[i*(NC+1)] );
+  for (size_t i=0; i<ndir; ++i) add( dirbcmasks[i*(NCA+1)] );
   for (size_t i=0; i<nsym; ++i) add( symbcnodes[i] );
   for (size_t i=0; i<nfar; ++i) add( farbcnodes[i] );
   for (size_t i=0; i<npre; ++i) add( prebcnodes[i] );
@@ -795,11 +854,13 @@ int xyst_bc_upload( xyst_ctx* c, size_t ndir, const size_t* dirbcmasks, const do
   for (size_t i=0; i<nodes.size(); ++i) slot[nodes[i]] = (int)i;
   size_t nbc = nodes.size();
   std::vector< int > dir( nbc, -1 ), pre( nbc, -1 ), symoff( nbc+1, 0 ), faroff( nbc+1, 0 );
-  std::vector< int > dmask( ndir*NC );
+  std::vector< int > dmask( ndir*NC ), smask( ndir*NSC );
+  std::vector< double > sval( ndir*NSC, 0.0 );
   std::vector< double > dval( ndir*NC, 0.0 ), symn( nsym*3 ), farn( nfar*3 ), preval( npre*2 );
   for (size_t i=0; i<ndir; ++i) {
-    dir[ slot[(int)dirbcmasks[i*(NC+1)]] ] = (int)i;
-    for (int k=0; k<NC; ++k) { dmask[i*NC+k] = (int)dirbcmasks[i*(NC+1)+1+k]; if (dirvals) dval[i*NC+k] = dirvals[i*NC+k]; }
+    dir[ slot[(int)dirbcmasks[i*(NCA+1)]] ] = (int)i;
+    for (int k=0; k<NC; ++k) { dmask[i*NC+k] = (int)dirbcmasks[i*(NCA+1)+1+(size_t)k]; if (dirvals) dval[i*NC+k] = dirvals[i*NCA+(size_t)k]; }
+    for (size_t k=0; k<NSC; ++k) { smask[i*NSC+k] = (int)dirbcmasks[i*(NCA+1)+1+NC+k]; if (dirvals) sval[i*NSC+k] = dirvals[i*NCA+NC+k]; }
   }
   for (size_t i=0; i<nsym; ++i) ++symoff[ slot[(int)symbcnodes[i]]+1 ];
   for (size_t i=0; i<nfar; ++i) ++faroff[ slot[(int)farbcnodes[i]]+1 ];
@@ -815,6 +876,7 @@ int xyst_bc_upload( xyst_ctx* c, size_t ndir, const size_t* dirbcmasks, const do
   c->bc_node.upload( nodes, s ); c->bc_dir.upload( dir, s ); c->bc_pre.upload( pre, s );
   c->bc_symoff.upload( symoff, s ); c->bc_faroff.upload( faroff, s );
   c->dir_mask.upload( dmask, s ); c->dir_val.upload( dval, s );
+  if (NSC) { c->sdir_mask.upload( smask, s ); c->sdir_val.upload( sval, s ); }
   c->sym_n.upload( symn, s ); c->far_n.upload( farn, s ); c->pre_val.upload( preval, s );
   c->far_r = far_density; c->far_p = far_pressure;
   if (far_velocity) for (int j=0; j<3; ++j) c->far_u[j] = far_velocity[j];
@@ -826,8 +888,16 @@ int xyst_dirbc_values( xyst_ctx* c, const double* dirvals )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   if (c->ndir && !dirvals) throw std::runtime_error( "xyst_dirbc_values: null values with Dirichlet nodes present" );
-  if (c->ndir) { CK( cudaMemcpyAsync( c->dir_val.p, dirvals, c->ndir*NC*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+  if (c->ndir && !c->ns) { CK( cudaMemcpyAsync( c->dir_val.p, dirvals, c->ndir*NC*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
                  CK( cudaStreamSynchronize( c->stream ) ); }
+  else if (c->ndir) {               // rows of 5 + ns values: flow and scalar parts go to their own arrays
+    const size_t w = (size_t)c->ncomp, ns = (size_t)c->ns;
+    std::vector< double > f( c->ndir*NC ), sc( c->ndir*ns );
+    for (size_t i=0; i<c->ndir; ++i) { for (int k=0; k<NC; ++k) f[i*NC+k] = dirvals[i*w+(size_t)k]; for (size_t k=0; k<ns; ++k) sc[i*ns+k] = dirvals[i*w+NC+k]; }
+    CK( cudaMemcpyAsync( c->dir_val.p, f.data(), f.size()*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+    CK( cudaMemcpyAsync( c->sdir_val.p, sc.data(), sc.size()*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+    CK( cudaStreamSynchronize( c->stream ) );
+  }
   API_END
 }
 
@@ -836,11 +906,19 @@ int xyst_src_upload( xyst_ctx* c, const double* S )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  if (!S) { c->S.release(); c->src_mask = 0; return 0; }
-  int mask = 0;
-  for (size_t p=0; p<c->npoin; ++p) for (int k=0; k<NC; ++k) if (S[p*NC+k] != 0.0) mask |= 1<<k;
-  c->S.upload( rows_to_new( c, S, NC ), c->stream );
+  if (!S) { c->S.release(); c->src_mask = 0; c->sS.release(); c->s_src = false; return 0; }
+  const size_t w = (size_t)c->ncomp, ns = (size_t)c->ns;
+  auto rows = rows_to_new( c, S, w );
+  // flow components [npoin][5] and transported scalars [npoin][ns] separately
+  std::vector< double > f( c->npoin*NC ), sc( c->npoin*ns );
+  int mask = 0; bool any = false;
+  for (size_t p=0; p<c->npoin; ++p) {
+    for (int k=0; k<NC; ++k) { f[p*NC+k] = rows[p*w+(size_t)k]; if (f[p*NC+k] != 0.0) mask |= 1<<k; }
+    for (size_t k=0; k<ns; ++k) { sc[p*ns+k] = rows[p*w+NC+k]; if (sc[p*ns+k] != 0.0) any = true; }
+  }
+  c->S.upload( f, c->stream );
   c->src_mask = mask;
+  if (ns) { c->sS.upload( sc, c->stream ); c->s_src = any; }
   API_END
 }
 
@@ -850,8 +928,9 @@ int xyst_state_set( xyst_ctx* c, const double* U )
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
   if (c->rb_pending) { CK( cudaStreamSynchronize( c->aux_stream ) ); c->rb_pending = false; }
-  CK( cudaMemcpyAsync( c->stage.p, U, c->npoin*NC*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
-  k_set_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->stage.p, c->new2old.p, c->U.p, c->W.p, mode( c ) );
+  CK( cudaMemcpyAsync( c->stage.p, U, c->npoin*(size_t)c->ncomp*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+  k_set_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->stage.p, c->new2old.p, c->U.p, c->W.p, mode( c ),
+    c->ncomp, c->sU.p );
   ++c->launches;
   CK( cudaGetLastError() );
   CK( cudaStreamSynchronize( c->stream ) );
@@ -863,27 +942,30 @@ int xyst_state_get( xyst_ctx* c, double* U )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  k_get_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->new2old.p, c->stage.p );
+  k_get_state<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->new2old.p, c->stage.p, c->ncomp, c->sU.p );
   ++c->launches;
   CK( cudaGetLastError() );
-  CK( cudaMemcpyAsync( U, c->stage.p, c->npoin*NC*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+  CK( cudaMemcpyAsync( U, c->stage.p, c->npoin*(size_t)c->ncomp*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
   CK( cudaStreamSynchronize( c->stream ) );
   API_END
 }
 
-int xyst_riecg_grad( xyst_ctx* c ) { API_BEGIN CK( cudaSetDevice( c->device ) ); do_grad( c ); API_END }
+int xyst_riecg_grad( xyst_ctx* c ) { API_BEGIN CK( cudaSetDevice( c->device ) ); do_grad( c ); if (c->ns) scal_grad( c ); API_END }
 
 int xyst_grad_get( xyst_ctx* c, double* G )
 {
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  std::vector< double > h( c->NP*2*NGP );
+  std::vector< double > h( c->NP*2*NGP ), hs( c->NP*3*(size_t)c->ns );
   CK( cudaMemcpyAsync( h.data(), c->G.p, h.size()*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+  if (c->ns) CK( cudaMemcpyAsync( hs.data(), c->sG.p, hs.size()*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
   CK( cudaStreamSynchronize( c->stream ) );
+  const size_t w = 3*(size_t)c->ncomp;
   for (size_t p=0; p<c->npoin; ++p) {
     size_t o = reordered( c ) ? (size_t)c->new2old_h[p] : p;
-    for (int i=0; i<15; ++i) G[o*15+(size_t)i] = h[gidx( i, p, c->NP )];
+    for (int i=0; i<15; ++i) G[o*w+(size_t)i] = h[gidx( i, p, c->NP )];
+    for (size_t i=0; i<3*(size_t)c->ns; ++i) G[o*w+15+i] = hs[i*c->NP+p];
   }
   API_END
 }
@@ -896,6 +978,7 @@ int xyst_grad_set( xyst_ctx* c, const double* G )
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
   if (!G) throw std::runtime_error( "null argument" );
+  if (c->ns) throw std::runtime_error( "xyst_grad_set: transported scalars are not supported here" );
   std::vector< double > h( c->NP*2*NGP, 0.0 );
   for (size_t p=0; p<c->npoin; ++p) {
     size_t o = reordered( c ) ? (size_t)c->new2old_h[p] : p;
@@ -938,6 +1021,7 @@ int xyst_riecg_rhs( xyst_ctx* c )
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
   do_flux( c );
+  if (c->ns) scal_flux_nodes( c, false, 0, 0.0 );
   do_rhs_nodes( c, false, 0, 0.0, c->U.p, c->Un.p, c->U.p );
   API_END
 }
@@ -947,14 +1031,15 @@ int xyst_rhs_get( xyst_ctx* c, double* R )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
+  const size_t w = (size_t)c->ncomp;
   if (!reordered( c )) {
-    CK( cudaMemcpyAsync( R, c->R.p, c->npoin*NC*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+    CK( cudaMemcpyAsync( R, c->R.p, c->npoin*w*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
     CK( cudaStreamSynchronize( c->stream ) );
   } else {
-    std::vector< double > h( c->npoin*NC );
+    std::vector< double > h( c->npoin*w );
     CK( cudaMemcpyAsync( h.data(), c->R.p, h.size()*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
     CK( cudaStreamSynchronize( c->stream ) );
-    for (size_t p=0; p<c->npoin; ++p) for (int k=0; k<NC; ++k) R[(size_t)c->new2old_h[p]*NC+k] = h[p*NC+k];
+    for (size_t p=0; p<c->npoin; ++p) for (size_t k=0; k<w; ++k) R[(size_t)c->new2old_h[p]*w+k] = h[p*w+k];
   }
   API_END
 }
@@ -968,7 +1053,12 @@ int xyst_rk_update( xyst_ctx* c, int stage, double dt )
   if (stage == 0 && !c->lax) save_un( c );
   StageArgs A{ rkcoef[stage], dt, c->steady ? c->dtp.p : nullptr, stage, mode( c ) };
   k_update<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->Un.p,
-    A, c->U.p, c->W.p, c->Wn.p, c->Un.p ); ++c->launches;
+    A, c->U.p, c->W.p, c->Wn.p, c->Un.p, c->ncomp ); ++c->launches;
+  if (c->ns) {
+    if (stage == 0) CK( cudaMemcpyAsync( c->sUn.p, c->sU.p, c->NP*(size_t)c->ns*sizeof(double), cudaMemcpyDeviceToDevice, c->stream ) );
+    k_scal_update<<< nblk( c->npoin, 256 ), 256, 0, c->stream >>>( c->npoin, c->ns, c->NP, c->R.p, c->ncomp, c->vol.p,
+      c->sUn.p, rkcoef[stage]*dt, c->steady ? c->dtp.p : nullptr, rkcoef[stage], c->sU.p ); ++c->launches;
+  }
   CK( cudaGetLastError() );
   API_END
 }
@@ -1003,7 +1093,9 @@ int xyst_riecg_stage( xyst_ctx* c, int stage, double dt )
   need_mesh( c );
   if (stage < 0 || stage > 2) throw std::runtime_error( "stage must be 0, 1 or 2" );
   do_grad( c );
+  if (c->ns) scal_grad( c );
   do_flux( c );
+  if (c->ns) scal_flux_nodes( c, true, stage, dt );
   auto nodes = [&]( const double* Un, double* Uout ) { do_rhs_nodes( c, true, stage, dt, c->U.p, Un, Uout ); };
   if (c->lax)           // time level n is kept in (p,u,v,w,T) form (Wn); Un is refreshed at stage 2
     nodes( c->Un.p, c->U.p );
@@ -1028,15 +1120,39 @@ int xyst_diag( xyst_ctx* c, const double* an, double* out )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   need_mesh( c );
-  DevBuf< double > dan;
-  if (an) dan.upload( rows_to_new( c, an, NC ), c->stream );
+  const size_t w = (size_t)c->ncomp, ns = (size_t)c->ns;
+  DevBuf< double > dan, dans;
+  if (an) {
+    auto rows = rows_to_new( c, an, w );
+    if (!ns) dan.upload( rows, c->stream );
+    else {
+      std::vector< double > f( c->npoin*NC ), sc( c->npoin*ns );
+      for (size_t p=0; p<c->npoin; ++p) { for (int k=0; k<NC; ++k) f[p*NC+k] = rows[p*w+(size_t)k]; for (size_t k=0; k<ns; ++k) sc[p*ns+k] = rows[p*w+NC+k]; }
+      dan.upload( f, c->stream ); dans.upload( sc, c->stream );
+    }
+  }
   int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( c->npoin, RED_THREADS ) );
+  double* res = c->red.p + (size_t)RED_BLOCKS*NDIAG;
   k_diag<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->U.p, c->Un.p, c->v.p, dan.p, c->red.p );
-  k_reduce_final< NDIAG, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, c->red.p + (size_t)RED_BLOCKS*NDIAG );
+  k_reduce_final< NDIAG, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, res );
   c->launches += 2;
-  CK( cudaMemcpyAsync( c->red_host, c->red.p + (size_t)RED_BLOCKS*NDIAG, NDIAG*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+  CK( cudaMemcpyAsync( c->red_host, res, NDIAG*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
   CK( cudaStreamSynchronize( c->stream ) );
-  for (int i=0; i<NDIAG; ++i) out[i] = c->red_host[i];
+  // layout of out: [0,w) sum u^2 v, [w,2w) sum (u-un)^2 v, [2w] sum u_4 v, [2w+1,3w+1) L2 error sums, [3w+1,4w+1) L1
+  for (size_t i=0; i<4*w+1; ++i) out[i] = 0.0;
+  for (int k=0; k<NC; ++k) {
+    out[(size_t)k] = c->red_host[k]; out[w+(size_t)k] = c->red_host[NC+k];
+    out[2*w+1+(size_t)k] = c->red_host[2*NC+1+k]; out[3*w+1+(size_t)k] = c->red_host[3*NC+1+k];
+  }
+  out[2*w] = c->red_host[2*NC];
+  for (size_t k=0; k<ns; ++k) {
+    k_scal_diag<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, (int)k, (int)ns, c->NP, c->sU.p, c->sUn.p, c->v.p, dans.p, c->red.p );
+    k_reduce_final< 4, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, res );
+    c->launches += 2;
+    CK( cudaMemcpyAsync( c->red_host, res, 4*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+    CK( cudaStreamSynchronize( c->stream ) );
+    out[NC+k] = c->red_host[0]; out[w+NC+k] = c->red_host[1]; out[2*w+1+NC+k] = c->red_host[2]; out[3*w+1+NC+k] = c->red_host[3];
+  }
   API_END
 }
 

@@ -15,7 +15,9 @@
 namespace xyst {
 namespace problems {
 
-using Fn = std::function< std::array< real, 5 >( real, real, real, real ) >;
+// values of all unknowns of a node: 5 flow variables + up to 8 transported scalars (unused entries 0)
+using State = std::array< real, 13 >;
+using Fn = std::function< State( real, real, real, real ) >;
 
 inline real totalenergy( real g, real r, real u, real v, real w, real p ) {
   return p / (g-1.0) + 0.5 * r * (u*u + v*v + w*w);
@@ -26,39 +28,71 @@ inline Fn IC( const Config& cfg ) {
   if (cfg.solver == "lohcg") {                  // unknowns (p,u,v,w): entries 0..3
     const auto& p = cfg.problem;
     if (p == "userdef") { const auto vel = cfg.ic_velocity;                    // userdef::ic :53-65
-      return [vel]( real, real, real, real ) -> std::array< real, 5 > { return {{ 0, vel[0], vel[1], vel[2], 0 }}; }; }
+      return [vel]( real, real, real, real ) -> State { return {{ 0, vel[0], vel[1], vel[2], 0 }}; }; }
     if (p == "poiseuille")                                                     // poiseuille::ic :1017-1019
-      return []( real, real, real, real ) -> std::array< real, 5 > { return {{ 0, 0, 0, 0, 0 }}; };
+      return []( real, real, real, real ) -> State { return {{ 0, 0, 0, 0, 0 }}; };
     throw std::runtime_error( "problem type ic not hooked up: " + p );
   }
   if (cfg.solver == "chocg") {                  // velocity unknowns only: entries 0..2
     const auto& p = cfg.problem;
     if (p == "userdef") { const auto vel = cfg.ic_velocity;                    // userdef::ic :44-52
-      return [vel]( real, real, real, real ) -> std::array< real, 5 > { return {{ vel[0], vel[1], vel[2], 0, 0 }}; }; }
+      return [vel]( real, real, real, real ) -> State { return {{ vel[0], vel[1], vel[2], 0, 0 }}; }; }
     if (p.find( "poisson" ) != std::string::npos)
-      return []( real, real, real, real ) -> std::array< real, 5 > { return {{ 0, 0, 0, 0, 0 }}; };
+      return []( real, real, real, real ) -> State { return {{ 0, 0, 0, 0, 0 }}; };
     if (p == "poiseuille") { const real mu = cfg.mu;                           // poiseuille::ic :999-1026
-      return [mu]( real, real y, real, real ) -> std::array< real, 5 > {
+      return [mu]( real, real y, real, real ) -> State {
         auto dpdx = -0.12;
         return {{ -dpdx * y * (1.0 - y) / 2.0 / mu, 0, 0, 0, 0 }}; }; }
     throw std::runtime_error( "problem type ic not hooked up: " + p );
   }
+  if (cfg.problem == "slot_cyl")                // slot_cyl::ic, Problems.cpp:513-634: solid-body rotation about
+    return [g]( real x, real y, real, real t ) -> State {        // (0.5,0.5) carrying a cone, a hump and a slotted cylinder
+      using std::sin; using std::cos; using std::sqrt;
+      State u{};
+      const real p0 = 1.0;
+      u[0] = 1.0; u[1] = u[0] * (0.5 - y); u[2] = u[0] * (x - 0.5); u[3] = 0.0;
+      u[4] = totalenergy( g, u[0], u[1]/u[0], u[2]/u[0], u[3]/u[0], p0 );
+      const real R0 = 0.15;
+      auto axdist = []( real x0, real y0 ){ return sqrt( (x0-0.5)*(x0-0.5) + (y0-0.5)*(y0-0.5) ); };
+      real r = axdist( 0.5, 0.25 );                    // cone
+      real kx = 0.5 + r*sin( t ), ky = 0.5 - r*cos( t );
+      r = axdist( 0.25, 0.5 );                         // hump
+      real hx = 0.5 + r*sin( t-M_PI/2.0 ), hy = 0.5 - r*cos( t-M_PI/2.0 );
+      r = axdist( 0.5, 0.75 );                         // slotted cylinder
+      real cx = 0.5 + r*sin( t+M_PI ), cy = 0.5 - r*cos( t+M_PI );
+      // corner points of the slot, rotated with the flow
+      real ax = 0.525, ay = cy - r*cos( std::asin( 0.025/r ) ), bx = 0.525, by = 0.8, gx = 0.475, gy = 0.8;
+      auto rotx = [t]( real px, real py ){ return 0.5 + cos(t)*(px-0.5) - sin(t)*(py-0.5); };
+      auto roty = [t]( real px, real py ){ return 0.5 + sin(t)*(px-0.5) + cos(t)*(py-0.5); };
+      real rax = rotx( ax, ay ), ray = roty( ax, ay ), rbx = rotx( bx, by ), rby = roty( bx, by ),
+           rgx = rotx( gx, gy ), rgy = roty( gx, gy );
+      real v1x = rbx-rax, v1y = rby-ray, v2x = rgx-rbx, v2y = rgy-rby;
+      real v1 = sqrt( v1x*v1x + v1y*v1y ), v2 = sqrt( v2x*v2x + v2y*v2y );
+      r = sqrt( (x-kx)*(x-kx) + (y-ky)*(y-ky) ) / R0;
+      if (r < 1.0) u[5] = 0.6*(1.0-r);
+      r = sqrt( (x-hx)*(x-hx) + (y-hy)*(y-hy) ) / R0;
+      if (r < 1.0) u[5] = 0.2*(1.0 + cos( M_PI*std::min( r, 1.0 ) ));
+      r = sqrt( (x-cx)*(x-cx) + (y-cy)*(y-cy) ) / R0;
+      real d1 = (v1x*(y-ray) - (x-rax)*v1y) / v1;      // signed distances from the two slot sides
+      real d2 = (v2x*(y-rby) - (x-rbx)*v2y) / v2;
+      if (r < 1.0 && (d1 > 0.05 || d1 < 0.0 || d2 < 0.0)) u[5] = 0.6;
+      return u; };
   if (cfg.problem == "sedov") {
     const real p0 = cfg.p0;
-    return [g,p0]( real x, real y, real z, real ) -> std::array< real, 5 > {
+    return [g,p0]( real x, real y, real z, real ) -> State {
       auto eps = std::numeric_limits< real >::epsilon();
       real p = (std::abs(x) < eps && std::abs(y) < eps && std::abs(z) < eps) ? p0 : 0.67e-4;
       real r = 1.0, u = 0.0, v = 0.0, w = 0.0;
       return {{ r, r*u, r*v, r*w, totalenergy( g, r, u, v, w, p ) }}; };
   }
   if (cfg.problem == "sod")
-    return [g]( real x, real, real, real ) -> std::array< real, 5 > {
+    return [g]( real x, real, real, real ) -> State {
       real r, p;
       if (x < 0.5) { r = 1.0; p = 1.0; } else { r = 0.125; p = 0.1; }
       real u = 0.0, v = 0.0, w = 0.0;
       return {{ r, r*u, r*v, r*w, totalenergy( g, r, u, v, w, p ) }}; };
   if (cfg.problem == "taylor_green")
-    return [g]( real x, real y, real, real ) -> std::array< real, 5 > {
+    return [g]( real x, real y, real, real ) -> State {
       real r = 1.0;
       real p = 10.0 + r/4.0*(std::cos(2.0*M_PI*x) + std::cos(2.0*M_PI*y));
       real u =  std::sin(M_PI*x) * std::cos(M_PI*y);
@@ -67,7 +101,7 @@ inline Fn IC( const Config& cfg ) {
       return {{ r, r*u, r*v, r*w, totalenergy( g, r, u, v, w, p ) }}; };
   if (cfg.problem == "vortical_flow") {         // vortical_flow::ic :454-478
     const real a = cfg.alpha, k = cfg.kappa, p0 = cfg.p0;
-    return [g,a,k,p0]( real x, real y, real z, real ) -> std::array< real, 5 > {
+    return [g,a,k,p0]( real x, real y, real z, real ) -> State {
       real ru = a*x - k*y;
       real rv = k*x + a*y;
       real rw = -2.0*a*z;
@@ -76,7 +110,7 @@ inline Fn IC( const Config& cfg ) {
   }
   if (cfg.problem == "nonlinear_energy_growth") {   // nonlinear_energy_growth::ic :126-160
     const real ce = cfg.ce, r0 = cfg.r0, a = cfg.alpha, k = cfg.kappa; const auto b = cfg.beta;
-    return [ce,r0,a,k,b]( real x, real y, real z, real t ) -> std::array< real, 5 > {
+    return [ce,r0,a,k,b]( real x, real y, real z, real t ) -> State {
       auto hx = std::cos(b[0]*M_PI*x) * std::cos(b[1]*M_PI*y) * std::cos(b[2]*M_PI*z);
       auto r = r0 + std::exp(-a*t) * (1.0 - x*x - y*y - z*z);
       auto re = r * std::pow( -3.0*(ce + k*hx*hx*t), -1.0/3.0 );
@@ -84,7 +118,7 @@ inline Fn IC( const Config& cfg ) {
   }
   if (cfg.problem == "rayleigh_taylor") {       // rayleigh_taylor::ic :225-258
     const real a = cfg.alpha, p0 = cfg.p0, r0 = cfg.r0, k = cfg.kappa; const auto b = cfg.beta;
-    return [g,a,p0,r0,k,b]( real x, real y, real z, real t ) -> std::array< real, 5 > {
+    return [g,a,p0,r0,k,b]( real x, real y, real z, real t ) -> State {
       real gx = b[0]*x*x + b[1]*y*y + b[2]*z*z;
       real r = r0 - gx;
       real ft = std::cos(k*M_PI*t);
@@ -96,7 +130,7 @@ inline Fn IC( const Config& cfg ) {
   if (cfg.problem == "userdef") {               // userdef::ic :28-115, density + velocity + pressure
     const real r = cfg.ic_density, p = cfg.ic_pressure;
     const auto vel = cfg.ic_velocity;
-    return [g,r,p,vel]( real, real, real, real ) -> std::array< real, 5 > {
+    return [g,r,p,vel]( real, real, real, real ) -> State {
       real ru = r*vel[0], rv = r*vel[1], rw = r*vel[2];
       return {{ r, ru, rv, rw, totalenergy( g, r, ru/r, rv/r, rw/r, p ) }}; };
   }
@@ -111,13 +145,18 @@ inline Fn SOL( const Config& cfg ) {
 
 //! IC (= Dirichlet values, analytic solution) or source term change in time
 inline bool timeDependent( const Config& cfg ) {
-  return cfg.problem == "nonlinear_energy_growth" || cfg.problem == "rayleigh_taylor";
+  return cfg.problem == "nonlinear_energy_growth" || cfg.problem == "rayleigh_taylor" || cfg.problem == "slot_cyl";
 }
 
 inline Fn SRC( const Config& cfg ) {
+  if (cfg.problem == "slot_cyl") {                 // slot_cyl::src :636-670: centripetal momentum source
+    auto ic = IC( cfg );
+    return [ic]( real x, real y, real z, real t ) -> State {
+      auto u = ic( x, y, z, t ); State s{}; s[1] = -u[2]; s[2] = u[1]; return s; };
+  }
   if (cfg.problem == "nonlinear_energy_growth") {   // nonlinear_energy_growth::src :162-219
     const real a = cfg.alpha, ce = cfg.ce, kappa = cfg.kappa, r0 = cfg.r0, g = cfg.gamma; const auto b = cfg.beta;
-    return [a,ce,kappa,r0,g,b]( real x, real y, real z, real t ) -> std::array< real, 5 > {
+    return [a,ce,kappa,r0,g,b]( real x, real y, real z, real t ) -> State {
       using std::sin; using std::cos; using std::pow;
       auto gx = 1.0 - x*x - y*y - z*z;
       std::array< real, 3 > dg{{ -2.0*x, -2.0*y, -2.0*z }};
@@ -136,7 +175,7 @@ inline Fn SRC( const Config& cfg ) {
                                    2.0 * pow(ie,4.0) * kappa * h * dh[1] * t,
                                    2.0 * pow(ie,4.0) * kappa * h * dh[2] * t }};
       const auto dedt = kappa * h * h * pow(ie,4.0);
-      std::array< real, 5 > s{{ 0, 0, 0, 0, 0 }};
+      State s{{ 0, 0, 0, 0, 0 }};
       s[0] = drdt;
       s[1] = (g-1.0)*(rho*dedx[0] + ie*drdx[0]);
       s[2] = (g-1.0)*(rho*dedx[1] + ie*drdx[1]);
@@ -147,7 +186,7 @@ inline Fn SRC( const Config& cfg ) {
   if (cfg.problem == "rayleigh_taylor") {       // rayleigh_taylor::src :260-332
     const real a = cfg.alpha, k = cfg.kappa, p0 = cfg.p0, g = cfg.gamma; const auto b = cfg.beta;
     auto ic = IC( cfg );
-    return [a,k,p0,g,b,ic]( real x, real y, real z, real t ) -> std::array< real, 5 > {
+    return [a,k,p0,g,b,ic]( real x, real y, real z, real t ) -> State {
       using std::sin; using std::cos;
       auto U = ic( x, y, z, t );
       auto rho = U[0];
@@ -175,7 +214,7 @@ inline Fn SRC( const Config& cfg ) {
       auto dvdt = -k*M_PI*sin(k*M_PI*t)*z*cos(M_PI*y);
       auto dwdt =  k*M_PI*sin(k*M_PI*t)/2*M_PI*z*z*(cos(M_PI*x) - sin(M_PI*y));
       auto dedt = u*dudt + v*dvdt + w*dwdt;
-      std::array< real, 5 > s{{ 0, 0, 0, 0, 0 }};
+      State s{{ 0, 0, 0, 0, 0 }};
       s[0] = u*drdx[0] + v*drdx[1] + w*drdx[2];
       s[1] = rho*dudt+u*s[0]+dpdx[0] + U[1]*dudx[0]+U[2]*dudx[1]+U[3]*dudx[2];
       s[2] = rho*dvdt+v*s[0]+dpdx[1] + U[1]*dvdx[0]+U[2]*dvdx[1]+U[3]*dvdx[2];
@@ -187,17 +226,17 @@ inline Fn SRC( const Config& cfg ) {
   if (cfg.problem == "vortical_flow") {         // vortical_flow::src :480-507
     const real a = cfg.alpha, k = cfg.kappa, g = cfg.gamma;
     auto ic = IC( cfg );
-    return [a,k,g,ic]( real x, real y, real z, real ) -> std::array< real, 5 > {
+    return [a,k,g,ic]( real x, real y, real z, real ) -> State {
       auto u = ic( x, y, z, 0.0 );
-      std::array< real, 5 > s{{ 0, 0, 0, 0, 0 }};
+      State s{{ 0, 0, 0, 0, 0 }};
       s[1] = a*u[1]/u[0] - k*u[2]/u[0];
       s[2] = k*u[1]/u[0] + a*u[2]/u[0];
       s[4] = (s[1]*u[1] + s[2]*u[2])/u[0] + 8.0*a*a*a*z*z/(g-1.0);
       return s; };
   }
   if (cfg.problem == "taylor_green")
-    return []( real x, real y, real, real ) -> std::array< real, 5 > {
-      std::array< real, 5 > s{{ 0, 0, 0, 0, 0 }};
+    return []( real x, real y, real, real ) -> State {
+      State s{{ 0, 0, 0, 0, 0 }};
       s[4] = 3.0*M_PI/8.0*( std::cos(3.0*M_PI*x)*std::cos(M_PI*y)
                           - std::cos(3.0*M_PI*y)*std::cos(M_PI*x) );
       return s; };

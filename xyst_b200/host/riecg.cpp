@@ -130,7 +130,9 @@ RieCG::RieCG( Discretization& disc, const TetMesh& chunk, const Config& cfg )
   m_cho = cfg.solver == "chocg"; if (m_cho) m_stride = 5;      // ChoCG::domint, ChoCG.cpp:399-446
   m_loh = cfg.solver == "lohcg"; if (m_loh) m_stride = 4;      // LohCG::domint, LohCG.cpp:407-453
   if (m_loh) { if (cfg.ncomp != 4) throw std::runtime_error( "LohCG: only ncomp = 4 (p,u,v,w) is supported" ); }
-  else if (cfg.ncomp != (m_cho ? 3u : 5u)) throw std::runtime_error( m_cho ? "ChoCG: only ncomp = 3 (velocity) is supported" : "only ncomp = 5 is supported" );
+  else if (m_cho ? cfg.ncomp != 3u : (cfg.ncomp < 5u || cfg.ncomp > 13u))
+    throw std::runtime_error( m_cho ? "ChoCG: only ncomp = 3 (velocity) is supported" : "ncomp must be 5 (+ at most 8 transported scalars)" );
+  if (cfg.ncomp > 5u && !m_cho && !m_loh && cfg.solver != "riecg") throw std::runtime_error( "transported scalars are implemented for RieCG only" );
   // Transporter::matchsets as the reference executes it (Transporter.cpp:125-187 with the
   // short-circuit at :347-348): with at least one side set named in the configuration the
   // faces of ALL side sets of the mesh keep their boundary integrals; with none, no face does.

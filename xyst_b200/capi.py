@@ -42,7 +42,7 @@ SYMBOLS = [
     "xyst_last_error", "xyst_device_count", "xyst_ctx_create", "xyst_ctx_set_stream",
     "xyst_ctx_destroy", "xyst_sync", "xyst_mesh_upload", "xyst_bc_upload", "xyst_dirbc_values",
     "xyst_src_upload", "xyst_state_set", "xyst_state_get", "xyst_riecg_grad", "xyst_grad_get",
-    "xyst_riecg_rhs", "xyst_rhs_get", "xyst_rk_update", "xyst_apply_bc", "xyst_dt_min", "xyst_dt_min_all", "xyst_grad_set", "xyst_besym_upload", "xyst_v_upload",
+    "xyst_riecg_rhs", "xyst_rhs_get", "xyst_rk_update", "xyst_apply_bc", "xyst_dt_min", "xyst_dt_min_all", "xyst_grad_set", "xyst_besym_upload", "xyst_v_upload", "xyst_scalar_pin",
     "xyst_riecg_stage", "xyst_riecg_step", "xyst_diag", "xyst_comm_unique_id", "xyst_comm_init",
     "xyst_halo_upload", "xyst_halo_sum", "xyst_allreduce_min", "xyst_allreduce_sum", "xyst_launch_count",
     "xyst_nedge", "xyst_kernel_time", "xyst_csr_upload", "xyst_csr_mult", "xyst_cg_setup",

@@ -145,6 +145,14 @@ __global__ void k_scal_update( size_t npoin, int ns, size_t NP, const double* __
   for (int c=0; c<ns; ++c) sU[(size_t)c*NP + p] = sUn[(size_t)c*NP + p] - f*R[p*(size_t)ncomp + 5 + c];
 }
 
+// problems::point_src (Problems.cpp:764-823; applied by RieCG::solve, RieCG.cpp:1023-1025): the first
+// scalar is set to 1 at the listed nodes after every stage update, before the BCs
+__global__ void k_scal_pin( int n, size_t NP, const int* __restrict__ node, double value, double* __restrict__ sU )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) sU[(size_t)node[i]] = value;
+}
+
 // physics::dirbc for the scalar components (BC.cpp:29-63)
 __global__ void k_scal_bc( int nbc, int ns, size_t NP, const int* __restrict__ node, const int* __restrict__ dir,
                            const int* __restrict__ smask, const double* __restrict__ sval, double* __restrict__ sU )

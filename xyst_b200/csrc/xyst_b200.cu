@@ -249,7 +249,8 @@ struct xyst_ctx : CgState {
   // transported scalars (riecg_scalar.cuh): ncomp = 5 + ns
   int ncomp = NC, ns = 0;
   DevBuf< double > sU, sUn, sG, sF, EV, sGb, sRb, sS, sdir_val;   // [ns][NP] x2, [3ns][NP], [ns][nslot], [3][nslot], ...
-  DevBuf< int > sdir_mask;
+  DevBuf< int > sdir_mask, spin;         // scalar Dirichlet masks; nodes of the point source
+  size_t nspin = 0; double spin_val = 1.0;
   bool s_src = false;
   // owner's share of the nodal flux sums (k_flux_own) and the incoming-edge lists of k_update_in
   DevBuf< double > Racc; DevBuf< long long > in_base; DevBuf< int > in_e;
@@ -536,6 +537,9 @@ void scal_flux_nodes( xyst_ctx* c, bool fused, int stage, double dt )
 
 void do_bc( xyst_ctx* c )
 {
+  if (c->ns && c->nspin) {        // the point source acts on the updated solution, then the BCs (RieCG.cpp:1023-1028)
+    k_scal_pin<<< nblk( c->nspin, 128 ), 128, 0, c->stream >>>( (int)c->nspin, c->NP, c->spin.p, c->spin_val, c->sU.p ); ++c->launches;
+  }
   if (c->ns && c->nbc && c->ndir) {
     k_scal_bc<<< nblk( c->nbc, 128 ), 128, 0, c->stream >>>( (int)c->nbc, c->ns, c->NP, c->bc_node.p, c->bc_dir.p,
       c->sdir_mask.p, c->sdir_val.p, c->sU.p ); ++c->launches;
@@ -919,6 +923,18 @@ int xyst_src_upload( xyst_ctx* c, const double* S )
   c->S.upload( f, c->stream );
   c->src_mask = mask;
   if (ns) { c->sS.upload( sc, c->stream ); c->s_src = any; }
+  API_END
+}
+
+int xyst_scalar_pin( xyst_ctx* c, size_t n, const size_t* nodes, double value )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  need_mesh( c );
+  if (!c->ns) throw std::runtime_error( "xyst_scalar_pin: no transported scalar in this context" );
+  std::vector< int > h( n );
+  for (size_t i=0; i<n; ++i) h[i] = (int)to_new( c, nodes[i], "point-source node id" );
+  c->spin.upload( h, c->stream ); c->nspin = n; c->spin_val = value;
   API_END
 }
 

@@ -67,6 +67,8 @@ Config to_cfg( const xyst_host_cfg* c ) {
   k.ic_density = c->ic_density; k.ic_pressure = c->ic_pressure;
   k.ic_velocity = {{ c->ic_velocity[0], c->ic_velocity[1], c->ic_velocity[2] }};
   if (c->soundspeed != 0.0) k.soundspeed = c->soundspeed;
+  k.src_location = {{ c->src_location[0], c->src_location[1], c->src_location[2] }};
+  k.src_radius = c->src_radius; k.src_release_time = c->src_release_time;
   if (k.solver == "chocg" || k.solver == "lohcg") {
     k.mu = c->mu; k.dif = c->dif; k.stab = c->stab != 0; k.rk = c->rk ? c->rk : 1;
     for (int i=0; i<c->nnoslip; ++i) k.bc_noslip.push_back( c->noslip[i] );

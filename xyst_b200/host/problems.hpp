@@ -127,7 +127,7 @@ inline Fn IC( const Config& cfg ) {
       real w = ft * ( -0.5*M_PI*z*z*(std::cos(M_PI*x) - std::sin(M_PI*y)) );
       return {{ r, r*u, r*v, r*w, totalenergy( g, r, u, v, w, p0 + a*gx ) }}; };
   }
-  if (cfg.problem == "userdef") {               // userdef::ic :28-115, density + velocity + pressure
+  if (cfg.problem == "userdef" || cfg.problem == "point_src") {     // userdef::ic :28-115, density + velocity + pressure (scalars 0)
     const real r = cfg.ic_density, p = cfg.ic_pressure;
     const auto vel = cfg.ic_velocity;
     return [g,r,p,vel]( real, real, real, real ) -> State {

@@ -671,6 +671,18 @@ bool RieCG::step( std::vector< real >* diagrow )
   if (m_cho) return choStep( diagrow );
   if (m_loh) return lohStep( diagrow );
   if (m_finished) return false;
+  // problems::point_src: active for all stages of a step that starts at or after the release time
+  if (m_cfg.problem == "point_src" && m_cfg.ncomp > 5 && m_cfg.src_radius >= 0.0 && !m_pinned &&
+      !(m_disc.T() < m_cfg.src_release_time)) {
+    const auto& co = m_disc.Coord();
+    std::vector< std::size_t > nodes;
+    for (std::size_t i=0; i<co[0].size(); ++i) {
+      auto rx = m_cfg.src_location[0] - co[0][i], ry = m_cfg.src_location[1] - co[1][i], rz = m_cfg.src_location[2] - co[2][i];
+      if (rx*rx + ry*ry + rz*rz < m_cfg.src_radius*m_cfg.src_radius) nodes.push_back( i );
+    }
+    ck( xyst_scalar_pin( m_ctx, nodes.size(), nodes.data(), 1.0 ) );
+    m_pinned = true;
+  }
   advance( dt() );
   if (m_zal) ck( xyst_zalcg_step( m_ctx, m_disc.Dt() ) );      // ZalCG.cpp:973-1607
   else if (m_koz) {                                            // KozCG.cpp:691-1197

@@ -84,6 +84,7 @@ struct Config {
   //! LohCG (solver = "lohcg", ncomp = 4 unknowns p,u,v,w): artificial compressibility
   //! (src/Inciter/LohCG.cpp); shares the ChoCG keys above, plus the artificial sound speed
   real soundspeed = 1.0;
+  std::array< real, 3 > src_location{{ 0, 0, 0 }}; real src_radius = -1.0, src_release_time = 0.0;   // problem "point_src"
 };
 
 //! Sum, over all partitions sharing them, `w` doubles per unique shared node (ascending
@@ -190,6 +191,7 @@ class RieCG {
     void evalDirvals( real t );      //!< physics::dirbc values = IC at the BC nodes at time t (BC.cpp:57-66)
     void evalSrcCentroids( real t, std::vector< real >& sc );   //!< problems::SRC at the tet centroids (kozak::rhs)
     void evalSrc( real t );          //!< problems::SRC at the nodes at time t (riemann::src, Riemann.cpp:880-907)
+    bool m_pinned = false;           //!< point-source nodes handed to the device
     bool m_timedep = false;          //!< IC / source depend on time: BC values per stage, source per step
     bool m_haloup = false;
     Discretization& m_disc;

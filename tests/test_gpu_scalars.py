@@ -110,9 +110,13 @@ def test_point_source_run_matches_oracle_and_golden(far):
     cols = [c for c in range(1, d.shape[1]) if c != 14]      # 14: increment norm of the pinned scalar, rounding noise
     for c in cols:
         assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-11 * np.abs(d[:, c]).max() + 1e-15, c
+    # pointwise after 50 steps of a pressure-driven flow: on the scale of the momentum (the cross-flow
+    # component is a small difference of large terms and carries the amplified rounding of both runs)
     U, Uo = s.get("u"), o.get("u")
+    mom = np.abs(Uo[:, 1:4]).max()
     for c in range(6):
-        assert np.abs(U[:, c] - Uo[:, c]).max() <= 1e-10 * np.abs(Uo[:, c]).max() + 1e-15, c
+        scale = mom if c in (1, 2, 3) else np.abs(Uo[:, c]).max()
+        assert np.abs(U[:, c] - Uo[:, c]).max() <= 1e-10 * scale + 1e-15, c
     if not far:
         gold = O.load_golden_diag("riecg_canyon")
         m = min(len(gold), len(rows))

@@ -27,7 +27,7 @@ def launch(mode, case, nsteps, tmp_path, world=2):
 
 
 def oracle_for(case, part, world):
-    kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.HCASES}[case]
+    kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.HCASES, **O.ZCASES}[case]
     return O.Oracle(O.load_mesh(kw.get("mesh", case)), O.make_cfg(**kw), "port", nchare=world,
                     target=np.asarray(part, np.uint64))
 
@@ -47,7 +47,7 @@ def check_setup(res, o, world):
         assert abs(r["meshvol"] - o.scalar("meshvol")) <= 1e-15 * o.scalar("meshvol")
 
 
-@pytest.mark.parametrize("case", ["riecg_sod", "riecg_taylor_green"])
+@pytest.mark.parametrize("case", ["riecg_sod", "riecg_taylor_green", "zalcg_sod"])
 def test_two_partitions_host_logic_gloo(case, tmp_path):
     res = launch("host", case, 0, tmp_path)
     o = oracle_for(case, res[0]["part"], 2)
@@ -105,6 +105,29 @@ def test_two_gpus_match_oracle_two_chares(case, tmp_path):
         U = np.asarray(res[k]["u"]); Uo = o.get("u", k)
         assert np.abs(U - Uo).max() <= 1e-12 * np.abs(Uo).max()
         assert res[k]["launches"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["zalcg_sod", "zalcg_sedov"])
+def test_two_gpus_zalcg_match_oracle_two_chares(case, tmp_path):
+    """ZalCG on 2 GPUs: after each FCT pass the shared nodes' own sums travel over NCCL -- rhs and
+    antidiffusive sums P+/- (summed; ZalCG::comrhs/comaec), allowed bounds Q+/- (max / min; comalw,
+    ZalCG.cpp:1316-1325), limited sums (summed; comlim) -- against the oracle's 2-chare run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    nsteps = 10
+    res = launch("gpu", case, nsteps, tmp_path)
+    o = oracle_for(case, res[0]["part"], 2)
+    o.step(nsteps)
+    d = o.diag()
+    rows = np.asarray(res[0]["rows"])
+    assert rows.shape == d.shape
+    for c in range(1, d.shape[1]):
+        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-12 * np.abs(d[:, c]).max() + 1e-300, c
+    for k in range(2):
+        U = np.asarray(res[k]["u"]); Uo = o.get("u", k)
+        assert np.abs(U - Uo).max() <= 1e-12 * np.abs(Uo).max()
 
 
 @pytest.mark.gpu

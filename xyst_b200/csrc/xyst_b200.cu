@@ -764,7 +764,6 @@ namespace {
 void zal_need( xyst_ctx* c ) {
   need_mesh( c );
   if (c->dstride != 4) throw std::runtime_error( "ZalCG needs stride-4 superedge integrals: use xyst_zalcg_mesh_upload" );
-  if (c->nsh > 0 && c->comm) throw std::runtime_error( "ZalCG on several partitions is not implemented yet" );
   if (!c->zP.p) { c->zP.alloc( c->NP*10 ); c->zQ.alloc( c->NP*10 ); c->zUL.alloc( c->NP*NC ); }
 }
 void zal_flux_and_bnd( xyst_ctx* c, double dt )
@@ -776,11 +775,23 @@ void zal_flux_and_bnd( xyst_ctx* c, double dt )
     k_zal_flux_edge<<< nblk( c->nslot, 128 ), 128, 0, s >>>( c->nslot, c->NP, c->ep.p, c->eq.p, c->D.p, c->U.p, c->X.p,
       dt, c->steady ? c->dtp.p : nullptr, dparams( c ), c->F.p ); ++c->launches; }
 }
+// With several partitions every pass is followed by the exchange of the shared nodes' own sums
+// (ZalCG::comrhs+comaec: sums, comalw: max/min, comlim: sums; ZalCG.cpp:1023-1053,1139-1148,1297-1333,
+// 1490-1499) and a kernel that finishes those nodes from the complete values.
+bool zal_halo( const xyst_ctx* c ) { return c->nsh > 0 && c->comm; }
 void zal_node1( xyst_ctx* c, double dt, int fct )
 {
-  k_zal_node1<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p,
+  auto s = c->stream;
+  k_zal_node1<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p,
     c->inc_eq.p, c->D.p, c->nslot, c->F.p, c->U.p, c->bslot.p, c->Rb.p, c->bcof.p, c->bc_symoff.p,
     c->sym_n.p, c->vol.p, dt, c->steady ? c->dtp.p : nullptr, c->zal.fctdif, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
+  if (!zal_halo( c )) return;
+  unsigned g = nblk( c->nsh, 128 );
+  k_zal_sh1<<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot, c->F.p,
+    c->U.p, c->bslot.p, c->Rb.p, c->zal.fctdif, c->bcof.p, c->bc_symoff.p, c->sym_n.p, c->sh_part.p ); ++c->launches;
+  exchange( c, 15 ); exchange_wait( c );
+  k_zal_fin1<<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p, c->sh_recvbuf.p,
+    c->U.p, c->vol.p, dt, c->steady ? c->dtp.p : nullptr, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
 }
 }
 
@@ -807,9 +818,25 @@ int xyst_zalcg_step( xyst_ctx* c, double dt )
     zal_node1( c, dt, 1 );
     k_zal_node2<<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_eq.p, c->U.p, c->zUL.p,
       c->zP.p, c->zal.fctclip, c->zQ.p ); ++c->launches;
+    if (zal_halo( c )) {
+      unsigned gs = nblk( c->nsh, 128 );
+      k_zal_sh2<<< gs, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sl_base.p, c->inc_eq.p, c->U.p, c->zUL.p,
+        c->zal.fctclip, c->sh_part.p ); ++c->launches;
+      exchange( c, 10 ); exchange_wait( c );
+      k_zal_fin2<<< gs, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p,
+        c->sh_recvbuf.p, c->zUL.p, c->zP.p, c->zQ.p ); ++c->launches;
+    }
     // new state into the other buffer, then swap: Un keeps the old state for the diagnostics
     k_zal_node3<<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot,
       c->U.p, c->zUL.p, c->zQ.p, c->vol.p, c->zal.fctdif, c->zal.fctsys_mask, c->Un.p, c->W.p ); ++c->launches;
+    if (zal_halo( c )) {
+      unsigned gs = nblk( c->nsh, 128 );
+      k_zal_sh3<<< gs, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot,
+        c->U.p, c->zQ.p, c->zal.fctdif, c->zal.fctsys_mask, c->sh_part.p ); ++c->launches;
+      exchange( c, NC ); exchange_wait( c );
+      k_zal_fin3<<< gs, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p,
+        c->sh_recvbuf.p, c->zUL.p, c->vol.p, c->Un.p, c->W.p ); ++c->launches;
+    }
   } else {
     zal_node1( c, dt, 0 );
     k_zal_nofct<<< nblk( c->npoin, 256 ), 256, 0, s >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->U.p, dt, c->steady ? c->dtp.p : nullptr, c->Un.p, c->W.p ); ++c->launches;

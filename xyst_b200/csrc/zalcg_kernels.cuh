@@ -57,21 +57,12 @@ k_zal_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int*
 // pass 1 (aec + first half of alw): R = sum +-F + boundary; P+/- from the antidiffusive edge
 // contributions aec = -dif*ctau*(u_first - u_second) (ZalCG.cpp:1071-1115), symmetry BC on P
 // (:1117-1133), then P /= vol and the low-order solution ul = u - dt R/vol - P+ - P- (:1195-1204)
-__global__ void __launch_bounds__(NODE_THREADS, 3)
-k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot,
-             const double* __restrict__ F, const double* __restrict__ U, const int* __restrict__ bslot,
-             const double* __restrict__ Rb, const int* __restrict__ bcof, const int* __restrict__ symoff,
-             const double* __restrict__ sym_n, const double* __restrict__ vol, double dt, const double* __restrict__ dtp,
-             double ctau, int fct, double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
+// raw sums of pass 1 at node p: r = sum +-F (+ boundary), P+/- before the symmetry BC and the division by vol
+__device__ __forceinline__ void zal_sum1( size_t p, int lane, long long base, int kmax, size_t NP,
+    const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot, const double* __restrict__ F,
+    const double* __restrict__ U, const int* __restrict__ bslot, const double* __restrict__ Rb, double ctau,
+    double up[NC], double r[NC], double pp[NC], double pn[NC] )
 {
-  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  size_t p = slice*32 + lane;
-  if (p >= npoin) return;
-  if (dtp) dt = dtp[p];                     // steady state (ZalCG.cpp:1195)
-  long long base = sl_base[slice];
-  int kmax = (int)((sl_base[slice+1] - base) >> 5);
-  double up[NC], r[NC], pp[NC], pn[NC];
   #pragma unroll
   for (int c=0; c<NC; ++c) { up[c] = U[c*NP+p]; r[c] = 0.0; pp[c] = 0.0; pn[c] = 0.0; }
   // padding entries (se = 0) point at the node itself and at slot 0 with weight 0: no branch
@@ -105,11 +96,12 @@ k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
     #pragma unroll
     for (int c=0; c<NC; ++c) r[c] += Rb[(size_t)b*NC+c];
   }
-  if (!fct) {
-    #pragma unroll
-    for (int c=0; c<NC; ++c) R[p*NC+c] = r[c];
-    return;
-  }
+}
+
+// symmetry BC on the (own) antidiffusive sums P (:1117-1133)
+__device__ __forceinline__ void zal_symp( size_t p, double pp[NC], double pn[NC], const int* __restrict__ bcof,
+    const int* __restrict__ symoff, const double* __restrict__ sym_n )
+{
   int bc = bcof[p];
   if (bc >= 0)
     for (int s=symoff[bc]; s<symoff[bc+1]; ++s) {
@@ -120,6 +112,12 @@ k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
       pp[2] -= rvnp * n[1]; pn[2] -= rvnn * n[1];
       pp[3] -= rvnp * n[2]; pn[3] -= rvnn * n[2];
     }
+}
+
+// P /= vol, low-order solution ul = u - dt R/vol - P+ - P- (:1195-1204)
+__device__ __forceinline__ void zal_fin1( size_t p, size_t NP, const double up[NC], const double r[NC], double pp[NC], double pn[NC],
+    const double* __restrict__ vol, double dt, double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
+{
   double vp = vol[p];
   #pragma unroll
   for (int c=0; c<NC; ++c) {
@@ -130,24 +128,84 @@ k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
   }
 }
 
-// pass 2 (second half of alw + first half of lim): allowed bounds Q+/- over the edge
-// neighbours (:1206-1290), Q -= ul, limit coefficients C+/- (:1361-1380) -> Q
 __global__ void __launch_bounds__(NODE_THREADS, 3)
-k_zal_node2( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ U, const double* __restrict__ UL,
-             const double* __restrict__ P, int clip, double* __restrict__ Q )
+k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot,
+             const double* __restrict__ F, const double* __restrict__ U, const int* __restrict__ bslot,
+             const double* __restrict__ Rb, const int* __restrict__ bcof, const int* __restrict__ symoff,
+             const double* __restrict__ sym_n, const double* __restrict__ vol, double dt, const double* __restrict__ dtp,
+             double ctau, int fct, double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   size_t p = slice*32 + lane;
   if (p >= npoin) return;
+  if (dtp) dt = dtp[p];                     // steady state (ZalCG.cpp:1195)
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
-  double hp[NC], lp[NC], qa[NC], qb[NC], ulp[NC];
+  double up[NC], r[NC], pp[NC], pn[NC];
+  zal_sum1( p, lane, base, kmax, NP, inc_eq, D, nslot, F, U, bslot, Rb, ctau, up, r, pp, pn );
+  if (!fct) {
+    #pragma unroll
+    for (int c=0; c<NC; ++c) R[p*NC+c] = r[c];
+    return;
+  }
+  zal_symp( p, pp, pn, bcof, symoff, sym_n );
+  zal_fin1( p, NP, up, r, pp, pn, vol, dt, P, UL, R );
+}
+
+// Several partitions (ZalCG::comrhs/comaec, ZalCG.cpp:1023-1053,1139-1148): the raw sums of the nodes
+// shared with other partitions -> part[i][15] = (r, P+, P-), exchanged and summed, then finished
+__global__ void k_zal_sh1( int nsh, size_t NP, const int* __restrict__ sh_node, const long long* __restrict__ sl_base,
+             const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot, const double* __restrict__ F,
+             const double* __restrict__ U, const int* __restrict__ bslot, const double* __restrict__ Rb, double ctau,
+             const int* __restrict__ bcof, const int* __restrict__ symoff, const double* __restrict__ sym_n,
+             double* __restrict__ part )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  long long base = sl_base[p >> 5];
+  int kmax = (int)((sl_base[(p >> 5)+1] - base) >> 5);
+  double up[NC], r[NC], pp[NC], pn[NC];
+  zal_sum1( p, (int)(p & 31), base, kmax, NP, inc_eq, D, nslot, F, U, bslot, Rb, ctau, up, r, pp, pn );
+  zal_symp( p, pp, pn, bcof, symoff, sym_n );       // on the own sums, before they travel (as the reference)
+  for (int c=0; c<NC; ++c) { part[(size_t)i*15+c] = r[c]; part[(size_t)i*15+5+c] = pp[c]; part[(size_t)i*15+10+c] = pn[c]; }
+}
+
+__global__ void k_zal_fin1( int nsh, size_t NP, const int* __restrict__ sh_node, const int* __restrict__ roff,
+             const int* __restrict__ ridx, const double* __restrict__ part, const double* __restrict__ recvbuf,
+             const double* __restrict__ U, const double* __restrict__ vol, double dt, const double* __restrict__ dtp,
+             int fct, double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  double t[15];
+  for (int j=0; j<15; ++j) {
+    double a = part[(size_t)i*15+j];
+    for (int r=roff[i]; r<roff[i+1]; ++r) a += recvbuf[(size_t)ridx[r]*15+j];
+    t[j] = a;
+  }
+  double up[NC];
+  for (int c=0; c<NC; ++c) up[c] = U[c*NP+p];
+  if (!fct) { for (int c=0; c<NC; ++c) R[p*NC+c] = t[c]; return; }
+  if (dtp) dt = dtp[p];
+  zal_fin1( p, NP, up, t, t+5, t+10, vol, dt, P, UL, R );
+}
+
+// pass 2 (second half of alw + first half of lim): allowed bounds Q+/- over the edge
+// neighbours (:1206-1290), Q -= ul, limit coefficients C+/- (:1361-1380) -> Q
+// raw allowed bounds of node p over its edge neighbours
+__device__ __forceinline__ void zal_sum2( size_t p, int lane, long long base, int kmax, size_t NP,
+    const int2* __restrict__ inc_eq, const double* __restrict__ U, const double* __restrict__ UL, int clip,
+    double qa[NC], double qb[NC] )
+{
+  double hp[NC], lp[NC];
   #pragma unroll
   for (int c=0; c<NC; ++c) {
-    ulp[c] = UL[c*NP+p]; double u = U[c*NP+p];
-    hp[c] = clip ? ulp[c] : fmax( ulp[c], u );
-    lp[c] = clip ? ulp[c] : fmin( ulp[c], u );
+    double ulp = UL[c*NP+p], u = U[c*NP+p];
+    hp[c] = clip ? ulp : fmax( ulp, u );
+    lp[c] = clip ? ulp : fmin( ulp, u );
     qa[c] = -1.7976931348623157e308; qb[c] = 1.7976931348623157e308;
   }
   #pragma unroll kZalUnroll
@@ -163,23 +221,26 @@ k_zal_node2( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
       qb[c] = fmin( qb[c], fmin( lp[c], lq ) );
     }
   }
+}
+
+// Q -= ul, limit coefficients C+/- (:1361-1380) -> Q
+__device__ __forceinline__ void zal_fin2( size_t p, size_t NP, const double qa[NC], const double qb[NC],
+    const double* __restrict__ UL, const double* __restrict__ P, double* __restrict__ Q )
+{
   const double eps = 2.220446049250313e-16;
   #pragma unroll
   for (int c=0; c<NC; ++c) {
-    double a = qa[c] - ulp[c], b = qb[c] - ulp[c];
+    double ulp = UL[c*NP+p];
+    double a = qa[c] - ulp, b = qb[c] - ulp;
     double pa = P[(2*c)*NP+p], pb = P[(2*c+1)*NP+p];
     Q[(2*c)*NP+p]   = pa <  eps ? 0.0 : fmin( 1.0, a/pa );
     Q[(2*c+1)*NP+p] = pb > -eps ? 0.0 : fmin( 1.0, b/pb );
   }
 }
 
-// pass 3 (second half of lim + solve): limited antidiffusive contributions (:1382-1481) and
-// u = ul + a/vol (:1552-1557)
 __global__ void __launch_bounds__(NODE_THREADS, 3)
-k_zal_node3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot,
-             const double* __restrict__ U, const double* __restrict__ UL, const double* __restrict__ Q,
-             const double* __restrict__ vol, double ctau, int sysmask, double* __restrict__ Unew,
-             double* __restrict__ W )
+k_zal_node2( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ U, const double* __restrict__ UL,
+             const double* __restrict__ P, int clip, double* __restrict__ Q )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -187,7 +248,51 @@ k_zal_node3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
   if (p >= npoin) return;
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
-  double up[NC], cpa[NC], cpb[NC], a[NC];
+  double qa[NC], qb[NC];
+  zal_sum2( p, lane, base, kmax, NP, inc_eq, U, UL, clip, qa, qb );
+  zal_fin2( p, NP, qa, qb, UL, P, Q );
+}
+
+// several partitions (ZalCG::comalw, ZalCG.cpp:1297-1333): own bounds of the shared nodes ->
+// part[i][10] = (Q+ max, Q- min) per component, combined with max / min over the sharers
+__global__ void k_zal_sh2( int nsh, size_t NP, const int* __restrict__ sh_node, const long long* __restrict__ sl_base,
+             const int2* __restrict__ inc_eq, const double* __restrict__ U, const double* __restrict__ UL, int clip,
+             double* __restrict__ part )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  long long base = sl_base[p >> 5];
+  int kmax = (int)((sl_base[(p >> 5)+1] - base) >> 5);
+  double qa[NC], qb[NC];
+  zal_sum2( p, (int)(p & 31), base, kmax, NP, inc_eq, U, UL, clip, qa, qb );
+  for (int c=0; c<NC; ++c) { part[(size_t)i*10+2*c] = qa[c]; part[(size_t)i*10+2*c+1] = qb[c]; }
+}
+
+__global__ void k_zal_fin2( int nsh, size_t NP, const int* __restrict__ sh_node, const int* __restrict__ roff,
+             const int* __restrict__ ridx, const double* __restrict__ part, const double* __restrict__ recvbuf,
+             const double* __restrict__ UL, const double* __restrict__ P, double* __restrict__ Q )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  double qa[NC], qb[NC];
+  for (int c=0; c<NC; ++c) {
+    double a = part[(size_t)i*10+2*c], b = part[(size_t)i*10+2*c+1];
+    for (int r=roff[i]; r<roff[i+1]; ++r) { a = fmax( a, recvbuf[(size_t)ridx[r]*10+2*c] ); b = fmin( b, recvbuf[(size_t)ridx[r]*10+2*c+1] ); }
+    qa[c] = a; qb[c] = b;
+  }
+  zal_fin2( p, NP, qa, qb, UL, P, Q );
+}
+
+// pass 3 (second half of lim + solve): limited antidiffusive contributions (:1382-1481) and
+// u = ul + a/vol (:1552-1557)
+// limited antidiffusive sums of node p
+__device__ __forceinline__ void zal_sum3( size_t p, int lane, long long base, int kmax, size_t NP,
+    const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot, const double* __restrict__ U,
+    const double* __restrict__ Q, double ctau, int sysmask, double a[NC] )
+{
+  double up[NC], cpa[NC], cpb[NC];
   #pragma unroll
   for (int c=0; c<NC; ++c) { up[c] = U[c*NP+p]; cpa[c] = Q[(2*c)*NP+p]; cpb[c] = Q[(2*c+1)*NP+p]; a[c] = 0.0; }
   #pragma unroll kZalUnroll
@@ -220,11 +325,64 @@ k_zal_node3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
       if (se < 0) a[c] -= v; else a[c] += v;
     }
   }
+}
+
+__device__ __forceinline__ void zal_fin3( size_t p, size_t NP, const double a[NC], const double* __restrict__ UL,
+    const double* __restrict__ vol, double* __restrict__ Unew, double* __restrict__ W )
+{
   double vp = vol[p], u[NC], w[NC];
   #pragma unroll
   for (int c=0; c<NC; ++c) { u[c] = UL[c*NP+p] + a[c]/vp; Unew[c*NP+p] = u[c]; }
   primitive( u, w );
   store_w( W, NP, p, w );
+}
+
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_zal_node3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot,
+             const double* __restrict__ U, const double* __restrict__ UL, const double* __restrict__ Q,
+             const double* __restrict__ vol, double ctau, int sysmask, double* __restrict__ Unew,
+             double* __restrict__ W )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = sl_base[slice];
+  int kmax = (int)((sl_base[slice+1] - base) >> 5);
+  double a[NC];
+  zal_sum3( p, lane, base, kmax, NP, inc_eq, D, nslot, U, Q, ctau, sysmask, a );
+  zal_fin3( p, NP, a, UL, vol, Unew, W );
+}
+
+// several partitions (ZalCG::comlim, ZalCG.cpp:1490-1499): own limited sums of the shared nodes -> part[i][5]
+__global__ void k_zal_sh3( int nsh, size_t NP, const int* __restrict__ sh_node, const long long* __restrict__ sl_base,
+             const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot, const double* __restrict__ U,
+             const double* __restrict__ Q, double ctau, int sysmask, double* __restrict__ part )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  long long base = sl_base[p >> 5];
+  int kmax = (int)((sl_base[(p >> 5)+1] - base) >> 5);
+  double a[NC];
+  zal_sum3( p, (int)(p & 31), base, kmax, NP, inc_eq, D, nslot, U, Q, ctau, sysmask, a );
+  for (int c=0; c<NC; ++c) part[(size_t)i*NC+c] = a[c];
+}
+
+__global__ void k_zal_fin3( int nsh, size_t NP, const int* __restrict__ sh_node, const int* __restrict__ roff,
+             const int* __restrict__ ridx, const double* __restrict__ part, const double* __restrict__ recvbuf,
+             const double* __restrict__ UL, const double* __restrict__ vol, double* __restrict__ Unew, double* __restrict__ W )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  double a[NC];
+  for (int c=0; c<NC; ++c) {
+    double t = part[(size_t)i*NC+c];
+    for (int r=roff[i]; r<roff[i+1]; ++r) t += recvbuf[(size_t)ridx[r]*NC+c];
+    a[c] = t;
+  }
+  zal_fin3( p, NP, a, UL, vol, Unew, W );
 }
 
 // fct = false: u = u - dt R/vol (ZalCG.cpp:1560-1567)

@@ -112,7 +112,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     if mode == "cg":
         return cg_main(out, rank, world, local)
-    kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.HCASES, **O.ZCASES}[case]
+    kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.HCASES, **O.ZCASES, **O.KCASES}[case]
     mesh = O.load_mesh(kw.get("mesh", case))
     hm = fixture_to_host_mesh(mesh)
     part = H.rcb(hm["coord"], hm["tets"], world)

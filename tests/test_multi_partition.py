@@ -27,7 +27,7 @@ def launch(mode, case, nsteps, tmp_path, world=2):
 
 
 def oracle_for(case, part, world):
-    kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.HCASES, **O.ZCASES}[case]
+    kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.HCASES, **O.ZCASES, **O.KCASES}[case]
     return O.Oracle(O.load_mesh(kw.get("mesh", case)), O.make_cfg(**kw), "port", nchare=world,
                     target=np.asarray(part, np.uint64))
 
@@ -108,9 +108,9 @@ def test_two_gpus_match_oracle_two_chares(case, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["zalcg_sod", "zalcg_sedov"])
+@pytest.mark.parametrize("case", ["zalcg_sod", "zalcg_sedov", "kozcg_sod", "kozcg_taylor_green"])
 def test_two_gpus_zalcg_match_oracle_two_chares(case, tmp_path):
-    """ZalCG on 2 GPUs: after each FCT pass the shared nodes' own sums travel over NCCL -- rhs and
+    """ZalCG and KozCG on 2 GPUs: after each FCT pass the shared nodes' own sums travel over NCCL -- rhs and
     antidiffusive sums P+/- (summed; ZalCG::comrhs/comaec), allowed bounds Q+/- (max / min; comalw,
     ZalCG.cpp:1316-1325), limited sums (summed; comlim) -- against the oracle's 2-chare run."""
     import torch

@@ -148,12 +148,13 @@ k_koz_node1( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__
       pp[2] -= rvnp * n[1]; pn[2] -= rvnn * n[1];
       pp[3] -= rvnp * n[2]; pn[3] -= rvnn * n[2];
     }
-  double vp = vol[p];
+  // one quotient per node, then products (the reference divides each component: same values up to one rounding)
+  double ivp = 1.0 / vol[p];
   #pragma unroll
   for (int c=0; c<NC; ++c) {
-    pp[c] /= vp; pn[c] /= vp;
+    pp[c] *= ivp; pn[c] *= ivp;
     P[(2*c)*NP+p] = pp[c]; P[(2*c+1)*NP+p] = pn[c];
-    UL[c*NP+p] = U[c*NP+p] + dt*r[c]/vp - pp[c] - pn[c];
+    UL[c*NP+p] = U[c*NP+p] + dt*r[c]*ivp - pp[c] - pn[c];
   }
 }
 
@@ -274,11 +275,92 @@ k_koz_node3( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__
     #pragma unroll
     for (int c=0; c<NC; ++c) a_[c] += __ldg( T + (size_t)(a*NC+c)*ntet + e );
   }
-  double vp = vol[p], u[NC], w[NC];
+  double ivp = 1.0 / vol[p], u[NC], w[NC];
   #pragma unroll
-  for (int c=0; c<NC; ++c) { u[c] = UL[c*NP+p] + a_[c]/vp; Unew[c*NP+p] = u[c]; }
+  for (int c=0; c<NC; ++c) { u[c] = UL[c*NP+p] + a_[c]*ivp; Unew[c*NP+p] = u[c]; }
   primitive( u, w );
   store_w( W, NP, p, w );
+}
+
+// ---- several partitions (KozCG::comrhs/comaec :728,:839, comalw :944, comlim :1093) -------------------
+// The full-mesh node passes above leave partial values at the nodes shared with other partitions. For
+// those nodes the OWN sums of a pass are recomputed into the exchange buffer (mode 1: r, P+, P- with the
+// symmetry BC on the own P as in the reference; mode 2: own bounds; mode 3: own limited sums), travel
+// (sum, max/min, sum), and the nodes are finished from the complete values.
+__global__ void k_koz_sh( int mode, int nsh, size_t NP, size_t ntet, const int* __restrict__ sh_node,
+             const long long* __restrict__ kbase, const int* __restrict__ kinc, const double* __restrict__ T,
+             const int* __restrict__ bcof, const int* __restrict__ symoff, const double* __restrict__ sym_n,
+             double* __restrict__ part )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  int lane = (int)(p & 31);
+  long long base = kbase[p >> 5];
+  int kmax = (int)((kbase[(p >> 5)+1] - base) >> 5);
+  if (mode == 1) {
+    double r[NC], pp[NC], pn[NC];
+    for (int c=0; c<NC; ++c) { r[c] = 0.0; pp[c] = 0.0; pn[c] = 0.0; }
+    for (int k=0; k<kmax; ++k) {
+      int ta = __ldg( kinc + base + (long long)k*32 + lane );
+      if (ta < 0) continue;
+      size_t e = (size_t)(ta >> 2); int a = ta & 3;
+      for (int c=0; c<NC; ++c) {
+        r[c] += __ldg( T + (size_t)(a*NC+c)*ntet + e );
+        double aec = __ldg( T + (size_t)(20+c*4+a)*ntet + e ); pp[c] += fmax( 0.0, aec ); pn[c] += fmin( 0.0, aec );
+      }
+    }
+    zal_symp( p, pp, pn, bcof, symoff, sym_n );
+    for (int c=0; c<NC; ++c) { part[(size_t)i*15+c] = r[c]; part[(size_t)i*15+5+c] = pp[c]; part[(size_t)i*15+10+c] = pn[c]; }
+  } else if (mode == 2) {
+    double qa[NC], qb[NC];
+    for (int c=0; c<NC; ++c) { qa[c] = -1.7976931348623157e308; qb[c] = 1.7976931348623157e308; }
+    for (int k=0; k<kmax; ++k) {
+      int ta = __ldg( kinc + base + (long long)k*32 + lane );
+      if (ta < 0) continue;
+      size_t e = (size_t)(ta >> 2);
+      for (int c=0; c<NC; ++c) {
+        qa[c] = fmax( qa[c], __ldg( T + (size_t)(2*c)*ntet + e ) );
+        qb[c] = fmin( qb[c], __ldg( T + (size_t)(2*c+1)*ntet + e ) );
+      }
+    }
+    for (int c=0; c<NC; ++c) { part[(size_t)i*10+2*c] = qa[c]; part[(size_t)i*10+2*c+1] = qb[c]; }
+  } else {
+    double a_[NC];
+    for (int c=0; c<NC; ++c) a_[c] = 0.0;
+    for (int k=0; k<kmax; ++k) {
+      int ta = __ldg( kinc + base + (long long)k*32 + lane );
+      if (ta < 0) continue;
+      size_t e = (size_t)(ta >> 2); int a = ta & 3;
+      for (int c=0; c<NC; ++c) a_[c] += __ldg( T + (size_t)(a*NC+c)*ntet + e );
+    }
+    for (int c=0; c<NC; ++c) part[(size_t)i*NC+c] = a_[c];
+  }
+}
+
+// finish of pass 1 at the shared nodes: R, P /= vol, ul = u + dt R/vol - P+ - P- (KozCG's sign, :897)
+__global__ void k_koz_fin1( int nsh, size_t NP, const int* __restrict__ sh_node, const int* __restrict__ roff,
+             const int* __restrict__ ridx, const double* __restrict__ part, const double* __restrict__ recvbuf,
+             const double* __restrict__ U, const double* __restrict__ vol, double dt, int fct,
+             double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  double t[15];
+  for (int j=0; j<15; ++j) {
+    double a = part[(size_t)i*15+j];
+    for (int r=roff[i]; r<roff[i+1]; ++r) a += recvbuf[(size_t)ridx[r]*15+j];
+    t[j] = a;
+  }
+  for (int c=0; c<NC; ++c) R[p*NC+c] = t[c];
+  if (!fct) return;
+  double ivp = 1.0 / vol[p];
+  for (int c=0; c<NC; ++c) {
+    double pp = t[5+c]*ivp, pn = t[10+c]*ivp;
+    P[(2*c)*NP+p] = pp; P[(2*c+1)*NP+p] = pn;
+    UL[c*NP+p] = U[c*NP+p] + dt*t[c]*ivp - pp - pn;
+  }
 }
 
 // fct = false: u = u + dt R/vol (KozCG.cpp:1150-1157)
@@ -287,9 +369,9 @@ __global__ void k_koz_nofct( size_t npoin, size_t NP, const double* __restrict__
 {
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= npoin) return;
-  double vp = vol[p], u[NC], w[NC];
+  double ivp = 1.0 / vol[p], u[NC], w[NC];
   #pragma unroll
-  for (int c=0; c<NC; ++c) { u[c] = U[c*NP+p] + dt*R[p*NC+c]/vp; Unew[c*NP+p] = u[c]; }
+  for (int c=0; c<NC; ++c) { u[c] = U[c*NP+p] + dt*R[p*NC+c]*ivp; Unew[c*NP+p] = u[c]; }
   primitive( u, w );
   store_w( W, NP, p, w );
 }

@@ -1400,7 +1400,6 @@ namespace {
 void koz_need( xyst_ctx* c ) {
   need_mesh( c );
   if (!c->ntet) throw std::runtime_error( "KozCG needs xyst_kozcg_mesh_upload" );
-  if (c->nsh > 0 && c->comm) throw std::runtime_error( "KozCG on several partitions is not implemented yet" );
 }
 void koz_pass1( xyst_ctx* c, double dt, int fct )
 {
@@ -1410,6 +1409,14 @@ void koz_pass1( xyst_ctx* c, double dt, int fct )
       c->ksrc ? c->S.p : nullptr, c->kSc.p, dt, c->prm.gamma, c->zal.fctdif, fct, c->kT.p ); ++c->launches; }
   k_koz_node1<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->ntet, c->kbase.p, c->kinc.p,
     c->kT.p, c->U.p, c->bcof.p, c->bc_symoff.p, c->sym_n.p, c->vol.p, dt, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
+  if (zal_halo( c )) {          // comrhs + comaec
+    unsigned g = nblk( c->nsh, 128 );
+    k_koz_sh<<< g, 128, 0, s >>>( 1, (int)c->nsh, c->NP, c->ntet, c->sh_node.p, c->kbase.p, c->kinc.p, c->kT.p,
+      c->bcof.p, c->bc_symoff.p, c->sym_n.p, c->sh_part.p ); ++c->launches;
+    exchange( c, 15 ); exchange_wait( c );
+    k_koz_fin1<<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p, c->sh_recvbuf.p,
+      c->U.p, c->vol.p, dt, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
+  }
 }
 }
 
@@ -1434,8 +1441,24 @@ int xyst_kozcg_step( xyst_ctx* c, double dt )
     koz_pass1( c, dt, 1 );
     k_koz_elem2<<< ge, 128, 0, s >>>( c->ntet, c->NP, c->ktet.p, c->U.p, c->zUL.p, c->zal.fctclip, c->kT.p ); ++c->launches;
     k_koz_node2<<< gn, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->ntet, c->kbase.p, c->kinc.p, c->kT.p, c->zUL.p, c->zP.p, c->zQ.p ); ++c->launches;
+    if (zal_halo( c )) {        // comalw: max / min over the sharers, then the limit coefficients as in ZalCG
+      unsigned gs = nblk( c->nsh, 128 );
+      k_koz_sh<<< gs, 128, 0, s >>>( 2, (int)c->nsh, c->NP, c->ntet, c->sh_node.p, c->kbase.p, c->kinc.p, c->kT.p,
+        c->bcof.p, c->bc_symoff.p, c->sym_n.p, c->sh_part.p ); ++c->launches;
+      exchange( c, 10 ); exchange_wait( c );
+      k_zal_fin2<<< gs, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p,
+        c->sh_recvbuf.p, c->zUL.p, c->zP.p, c->zQ.p ); ++c->launches;
+    }
     k_koz_elem3<<< ge, 128, 0, s >>>( c->ntet, c->NP, c->ktet.p, c->U.p, c->X.p, c->zQ.p, c->zal.fctdif, c->zal.fctsys_mask, c->kT.p ); ++c->launches;
     k_koz_node3<<< gn, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->ntet, c->kbase.p, c->kinc.p, c->kT.p, c->zUL.p, c->vol.p, c->Un.p, c->W.p ); ++c->launches;
+    if (zal_halo( c )) {        // comlim
+      unsigned gs = nblk( c->nsh, 128 );
+      k_koz_sh<<< gs, 128, 0, s >>>( 3, (int)c->nsh, c->NP, c->ntet, c->sh_node.p, c->kbase.p, c->kinc.p, c->kT.p,
+        c->bcof.p, c->bc_symoff.p, c->sym_n.p, c->sh_part.p ); ++c->launches;
+      exchange( c, NC ); exchange_wait( c );
+      k_zal_fin3<<< gs, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p,
+        c->sh_recvbuf.p, c->zUL.p, c->vol.p, c->Un.p, c->W.p ); ++c->launches;
+    }
   } else {
     koz_pass1( c, dt, 0 );
     k_koz_nofct<<< nblk( c->npoin, 256 ), 256, 0, s >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->U.p, dt, c->Un.p, c->W.p ); ++c->launches;

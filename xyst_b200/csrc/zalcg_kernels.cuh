@@ -118,12 +118,13 @@ __device__ __forceinline__ void zal_symp( size_t p, double pp[NC], double pn[NC]
 __device__ __forceinline__ void zal_fin1( size_t p, size_t NP, const double up[NC], const double r[NC], double pp[NC], double pn[NC],
     const double* __restrict__ vol, double dt, double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
 {
-  double vp = vol[p];
+  // one quotient per node, then products (the reference divides each component: same values up to one rounding)
+  double ivp = 1.0 / vol[p];
   #pragma unroll
   for (int c=0; c<NC; ++c) {
-    pp[c] /= vp; pn[c] /= vp;
+    pp[c] *= ivp; pn[c] *= ivp;
     P[(2*c)*NP+p] = pp[c]; P[(2*c+1)*NP+p] = pn[c];
-    UL[c*NP+p] = up[c] - dt*r[c]/vp - pp[c] - pn[c];
+    UL[c*NP+p] = up[c] - dt*r[c]*ivp - pp[c] - pn[c];
     R[p*NC+c] = r[c];
   }
 }
@@ -330,9 +331,9 @@ __device__ __forceinline__ void zal_sum3( size_t p, int lane, long long base, in
 __device__ __forceinline__ void zal_fin3( size_t p, size_t NP, const double a[NC], const double* __restrict__ UL,
     const double* __restrict__ vol, double* __restrict__ Unew, double* __restrict__ W )
 {
-  double vp = vol[p], u[NC], w[NC];
+  double ivp = 1.0 / vol[p], u[NC], w[NC];
   #pragma unroll
-  for (int c=0; c<NC; ++c) { u[c] = UL[c*NP+p] + a[c]/vp; Unew[c*NP+p] = u[c]; }
+  for (int c=0; c<NC; ++c) { u[c] = UL[c*NP+p] + a[c]*ivp; Unew[c*NP+p] = u[c]; }
   primitive( u, w );
   store_w( W, NP, p, w );
 }
@@ -393,9 +394,9 @@ __global__ void k_zal_nofct( size_t npoin, size_t NP, const double* __restrict__
   size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (p >= npoin) return;
   if (dtp) dt = dtp[p];                     // steady state (:1563)
-  double vp = vol[p], u[NC], w[NC];
+  double ivp = 1.0 / vol[p], u[NC], w[NC];
   #pragma unroll
-  for (int c=0; c<NC; ++c) { u[c] = U[c*NP+p] - dt*R[p*NC+c]/vp; Unew[c*NP+p] = u[c]; }
+  for (int c=0; c<NC; ++c) { u[c] = U[c*NP+p] - dt*R[p*NC+c]*ivp; Unew[c*NP+p] = u[c]; }
   primitive( u, w );
   store_w( W, NP, p, w );
 }

@@ -251,8 +251,8 @@ TCASES = {
 }
 # Scalar transport (slotted cylinder, cone and hump in a rotating flow, problems::slot_cyl): one transported
 # scalar next to the flow variables -- {RieCG,ZalCG,KozCG,ChoCG,LohCG}/SlotCyl/*.q on unitsquare_01_3.6k.exo.
-# The device path carries the flow variables only so far: these cases pin the ORACLE (port and reference
-# objects) for the scalar rows of SURVEY section 8 (a5).
+# The RieCG ones also run on the device (tests/test_gpu_scalars.py); the ZalCG/KozCG/ChoCG/LohCG ones pin the
+# ORACLE (port and reference objects) for the scalar rows of SURVEY section 8 (a5).
 _SC6 = dict(problem="slot_cyl", ncomp=6, gamma=5.0 / 3.0, nstep=20, dir_=((1, 1, 1, 1, 1, 1, 1), (2, 1, 1, 1, 1, 1, 0)),
             mesh="unitsquare_3_6k")
 _SCCHO = dict(solver="chocg", problem="slot_cyl", ncomp=4, gamma=5.0 / 3.0, cfl=0.9, nstep=20, flux="damp2", rk=3,

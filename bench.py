@@ -183,6 +183,10 @@ class ClockSampler:
                                        "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+            t0 = time.perf_counter()                      # nvidia-smi needs up to a second or two to start on an
+            while not self.rows and time.perf_counter() - t0 < 8.0:      # 8-GPU box: wait for its first sample
+                time.sleep(0.02)
+            self.n0 = len(self.rows)
         except Exception:
             self.p = None
 
@@ -193,6 +197,9 @@ class ClockSampler:
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        t0 = time.perf_counter()                          # a short timed region: make sure a sample under load is in
+        while len(self.rows) <= getattr(self, "n0", 0) and time.perf_counter() - t0 < 0.2:
+            time.sleep(0.005)
         self.p.terminate()
         try:
             self.p.wait(timeout=2)
@@ -468,12 +475,13 @@ def timed_run(rig, a, wl, n, dims, want_e2e):
     npoin = int(s.scalar("npoin")); nedge_local = ctx.nedge()
     E = box_edges(nx, ny, nz)                              # unique edges of the whole box
     stream = rig.stream
+    clocks = ClockSampler(rig.local); clocks.start()       # (running before the warm-up: its start-up is slow)
     for _ in range(a.warmup):
         s.step(1, want_diag=False)
     for k in ("grad", "flux", "update"):
         ctx.kernel_time(k, reset=True)                     # switches per-kernel events on
     rig.barrier()
-    clocks = ClockSampler(rig.local); clocks.start()
+    clocks.rows.clear(); clocks.n0 = 0                     # samples of the timed region only
     l0 = ctx.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)

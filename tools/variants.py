@@ -16,11 +16,13 @@ LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib")
 # name -> (defines, environment)
 VAR = {
     "default": ([], {}),
+    "chunks2": ([], {"XYST_CHUNKS": "2"}),
+    "chunks4": ([], {"XYST_CHUNKS": "4"}),
+    "chunks8": ([], {"XYST_CHUNKS": "8"}),
+    "chunks4_r128": (["NODE_THREADS=128", "RHS_MINB=8"], {"XYST_CHUNKS": "4"}),
+    "chunks8_r128": (["NODE_THREADS=128", "RHS_MINB=8"], {"XYST_CHUNKS": "8"}),
+    "chunks4_m3": (["OWN_MINB=3"], {"XYST_CHUNKS": "4"}),
     "grad_oneshot": ([], {"XYST_GRAD_MODE": "0"}),
-    "tile_order": ([], {"XYST_REORDER": "1"}),
-    "tile_order_rows": ([], {"XYST_REORDER": "1", "XYST_TILE_WX": "0.03"}),
-    "own_regs": (["OWN_GSMEM=0", "OWN_MINB=3"], {}),
-    "own_sint": (["MUSCL_SIGN_INT=1"], {}),
 }
 
 

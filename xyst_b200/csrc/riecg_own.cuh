@@ -110,13 +110,13 @@ __device__ __forceinline__ void edge_flux_owner( const double wo[NC], const doub
 
 template< bool EXACT, int FLUX >
 __global__ void __launch_bounds__(OWN_THREADS, OWN_MINB)
-k_flux_own( size_t nslice, size_t NP, size_t nslot, const long long* __restrict__ ebase, const int* __restrict__ eo,
+k_flux_own( size_t slice0, size_t nslice, size_t NP, size_t nslot, const long long* __restrict__ ebase, const int* __restrict__ eo,
             const double* __restrict__ D, const double* __restrict__ W, const double* __restrict__ G,
             double* __restrict__ F, double* __restrict__ Racc, DParams P, double* __restrict__ EV )
 {
   // EV (null without transported scalars): per edge, reference-oriented, the normal velocities of the
   // reconstructed states and the scalar dissipation speed (riecg_scalar.cuh)
-  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  size_t slice = slice0 + ((blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5);     // slices [slice0, nslice)
   int lane = threadIdx.x & 31;
   if (slice >= nslice) return;
   size_t p = slice*32 + lane;
@@ -187,12 +187,13 @@ k_update_in( size_t npoin, size_t NP, const long long* __restrict__ in_base, con
              const int* __restrict__ bslot, const double* __restrict__ Rb, const double* __restrict__ S, int src_mask,
              const double* __restrict__ v, const double* __restrict__ vol, const double* __restrict__ Un,
              StageArgs A, double* __restrict__ U, double* __restrict__ W, double* __restrict__ R,
-             double* __restrict__ Wn, double* __restrict__ UnOut, const unsigned char* __restrict__ skip, int rstride )
+             double* __restrict__ Wn, double* __restrict__ UnOut, const unsigned char* __restrict__ skip, int rstride,
+             size_t slice0, size_t slice1 )
 {
-  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  size_t slice = slice0 + ((blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5);     // slices [slice0, slice1)
   int lane = threadIdx.x & 31;
   size_t p = slice*32 + lane;
-  if (p >= npoin) return;
+  if (slice >= slice1 || p >= npoin) return;
   if (FUSED && skip && skip[p]) return;
   long long base = in_base[slice];
   int kmax = (int)((in_base[slice+1] - base) >> 5);

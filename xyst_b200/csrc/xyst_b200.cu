@@ -255,6 +255,8 @@ struct xyst_ctx : CgState {
   // owner's share of the nodal flux sums (k_flux_own) and the incoming-edge lists of k_update_in
   DevBuf< double > Racc; DevBuf< long long > in_base; DevBuf< int > in_e;
   bool gradp_attr = false;
+  int chunks = 1;                        // > 1: flux and update of slice ranges pipelined on two streams
+  cudaEvent_t ev_chunk[16] = {};
   int grad_mode = 1, grad_waves = 1;     // 1: persistent gradient kernel with incidence prefetch, 0: one warp per slice
   // profiling
   bool prof_on = false;
@@ -430,7 +432,7 @@ void launch_rhs_node( xyst_ctx* c, bool fused, const StageArgs& A, const double*
   // the owner's own share was summed by the flux kernel: gather the incoming edges only
   #define UPD_IN( FU, LX ) k_update_in< FU, LX ><<< g, NODE_THREADS, 0, st >>>( c->npoin, c->NP, c->in_base.p, c->in_e.p, \
       c->Racc.p, c->F.p, c->nslot, c->bslot.p, c->Rb.p, c->S.p, c->src_mask, c->v.p, c->vol.p, Un, A, Uout, c->W.p, c->R.p, \
-      c->Wn.p, c->Un.p, skip, c->ncomp )
+      c->Wn.p, c->Un.p, skip, c->ncomp, s0, s1 )
   if (fused && c->lax) UPD_IN( true, true ); else if (fused) UPD_IN( true, false ); else UPD_IN( false, false );
   #undef UPD_IN
   ++c->launches;
@@ -479,13 +481,12 @@ void do_rhs_nodes( xyst_ctx* c, bool fused, int stage, double dt, const double* 
 }
 
 // thread-per-owner flux kernel: per-edge fluxes F and the owners' own shares Racc
-void do_flux( xyst_ctx* c )
+void launch_flux( xyst_ctx* c, size_t s0, size_t s1, cudaStream_t s )
 {
-  auto s = c->stream;
+  if (s1 <= s0) return;
   auto P = dparams( c );
-  ProfScope ps( c, "flux" );
-  unsigned g = nblk( c->nslice*32, OWN_THREADS );
-  #define LAUNCH_OWN( EX, FL ) k_flux_own< EX, FL ><<< g, OWN_THREADS, 0, s >>>( c->nslice, c->NP, c->nslot, \
+  unsigned g = nblk( (s1-s0)*32, OWN_THREADS );
+  #define LAUNCH_OWN( EX, FL ) k_flux_own< EX, FL ><<< g, OWN_THREADS, 0, s >>>( s0, s1, c->NP, c->nslot, \
       c->ebase.p, c->eo.p, c->D.p, c->W.p, c->G.p, c->F.p, c->Racc.p, P, c->ns ? c->EV.p : nullptr )
   int fl = P.flux + (c->lax ? 2 : 0);
   if (P.exact) { if (fl == 0) LAUNCH_OWN( true, 0 ); else if (fl == 1) LAUNCH_OWN( true, 1 );
@@ -494,6 +495,11 @@ void do_flux( xyst_ctx* c )
                  else if (fl == 2) LAUNCH_OWN( false, 2 ); else LAUNCH_OWN( false, 3 ); }
   #undef LAUNCH_OWN
   ++c->launches;
+}
+void do_flux( xyst_ctx* c )
+{
+  ProfScope ps( c, "flux" );
+  launch_flux( c, 0, c->nslice, c->stream );
 }
 
 // ---- transported scalars (riecg_scalar.cuh) -------------------------------------------
@@ -594,6 +600,7 @@ int xyst_ctx_create( int device, const xyst_params* params, xyst_ctx** out )
   CK( cudaEventCreateWithFlags( &c->ev_e, cudaEventDisableTiming ) );
   CK( cudaEventCreateWithFlags( &c->ev_a, cudaEventDisableTiming ) );
   CK( cudaEventCreateWithFlags( &c->ev_b, cudaEventDisableTiming ) );
+  for (auto& e : c->ev_chunk) CK( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) );
   c->red.alloc( (size_t)RED_BLOCKS*NDIAG + NDIAG );
   CK( cudaMallocHost( &c->red_host, NDIAG*sizeof(double) ) );
   *out = c;
@@ -623,6 +630,7 @@ int xyst_ctx_destroy( xyst_ctx* c )
   for (auto e : { c->ev_c, c->ev_d, c->ev_e }) if (e) cudaEventDestroy( e );
   if (c->ev_a) cudaEventDestroy( c->ev_a );
   if (c->ev_b) cudaEventDestroy( c->ev_b );
+  for (auto e : c->ev_chunk) if (e) cudaEventDestroy( e );
   if (c->red_host) cudaFreeHost( c->red_host );
   delete c;
   API_END
@@ -650,6 +658,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   opt.reorder = false;
   { const char* e = getenv( "XYST_REORDER" ); if (e && e[0] == '1') opt.reorder = allow_reorder;
     e = getenv( "XYST_TILE" ); if (e && atoi( e ) >= 32) c->tile_nodes = std::min( 256, atoi( e ) / 32 * 32 );
+    e = getenv( "XYST_CHUNKS" ); if (e && atoi( e ) >= 1) c->chunks = std::min( 16, atoi( e ) );
     e = getenv( "XYST_GRAD_MODE" ); if (e) c->grad_mode = atoi( e );
     e = getenv( "XYST_GRAD_WAVES" ); if (e && atoi( e ) > 0) c->grad_waves = atoi( e ); }
   opt.tile_nodes = (size_t)c->tile_nodes;
@@ -1137,9 +1146,34 @@ int xyst_riecg_stage( xyst_ctx* c, int stage, double dt )
   if (stage < 0 || stage > 2) throw std::runtime_error( "stage must be 0, 1 or 2" );
   do_grad( c );
   if (c->ns) scal_grad( c );
-  do_flux( c );
+  const bool chunked = c->chunks > 1 && !(c->nsh > 0 && c->comm) && !c->ns;
+  if (!chunked) do_flux( c );
   if (c->ns) scal_flux_nodes( c, true, stage, dt );
-  auto nodes = [&]( const double* Un, double* Uout ) { do_rhs_nodes( c, true, stage, dt, c->U.p, Un, Uout ); };
+  // An edge is owned by its LOWER end: the incoming edges of a node come from lower nodes, the other ends
+  // of a node's own edges are higher nodes. So the nodal sums + update of the nodes of a slice range need
+  // the fluxes of that range and of lower ones only, and the flux kernel of the next range reads none of
+  // the nodes the update overwrites: the (HBM-bound) update of chunk k runs on a side stream under the
+  // (latency-bound) flux kernel of chunk k+1.
+  auto nodes_chunked = [&]( const double* Un, double* Uout ) {
+    auto s = c->stream; auto us = c->aux_stream;
+    if (c->rb_pending) { CK( cudaStreamWaitEvent( s, c->ev_e, 0 ) ); c->rb_pending = false; }
+    StageArgs A{ rkcoef[stage], dt, c->steady ? c->dtp.p : nullptr, stage, mode( c ) };
+    size_t per = (c->nslice + (size_t)c->chunks - 1) / (size_t)c->chunks;
+    ProfScope ps( c, "flux" );
+    for (int k=0; k<c->chunks; ++k) {
+      size_t a = (size_t)k*per, b = std::min( c->nslice, a + per );
+      if (b <= a) break;
+      launch_flux( c, a, b, s );
+      CK( cudaEventRecord( c->ev_chunk[k], s ) );
+      CK( cudaStreamWaitEvent( us, c->ev_chunk[k], 0 ) );
+      launch_rhs_node( c, true, A, Un, Uout, a, b, us );
+    }
+    CK( cudaEventRecord( c->ev_d, us ) );
+    CK( cudaStreamWaitEvent( s, c->ev_d, 0 ) );
+    CK( cudaGetLastError() );
+  };
+  auto nodes = [&]( const double* Un, double* Uout ) {
+    if (chunked) nodes_chunked( Un, Uout ); else do_rhs_nodes( c, true, stage, dt, c->U.p, Un, Uout ); };
   if (c->lax)           // time level n is kept in (p,u,v,w,T) form (Wn); Un is refreshed at stage 2
     nodes( c->Un.p, c->U.p );
   else if (stage == 0) { // un = u (RieCG.cpp:1011) without a copy: write the new state into the

@@ -16,13 +16,11 @@ LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib")
 # name -> (defines, environment)
 VAR = {
     "default": ([], {}),
-    "chunks2": ([], {"XYST_CHUNKS": "2"}),
-    "chunks4": ([], {"XYST_CHUNKS": "4"}),
-    "chunks8": ([], {"XYST_CHUNKS": "8"}),
-    "chunks4_r128": (["NODE_THREADS=128", "RHS_MINB=8"], {"XYST_CHUNKS": "4"}),
-    "chunks8_r128": (["NODE_THREADS=128", "RHS_MINB=8"], {"XYST_CHUNKS": "8"}),
-    "chunks4_m3": (["OWN_MINB=3"], {"XYST_CHUNKS": "4"}),
     "grad_oneshot": ([], {"XYST_GRAD_MODE": "0"}),
+    "tile_order": ([], {"XYST_REORDER": "1"}),
+    "tile_order_rows": ([], {"XYST_REORDER": "1", "XYST_TILE_WX": "0.03"}),
+    "own_regs": (["OWN_GSMEM=0", "OWN_MINB=3"], {}),
+    "own_sint": (["MUSCL_SIGN_INT=1"], {}),
 }
 
 
@@ -47,7 +45,7 @@ def main():
     for k in names:
         env = dict(os.environ, XYST_B200_LIB=os.path.join(LIBDIR, "lib_%s.so" % k), **VAR[k][1])
         r = subprocess.run([sys.executable, "bench.py", "--steps", "8", "--warmup", "3", "--no-cpu-baseline",
-                            "--no-e2e", "--n", n], env=env, capture_output=True, text=True)
+                            "--no-e2e", "--no-strong-base", "--reforder", "0", "--n", n], env=env, capture_output=True, text=True)
         try:
             j = json.loads(r.stdout.strip().splitlines()[-1])
             print(k, "ms/step %.3f" % j["ms_per_step"], "finite", j["finite"],

@@ -255,8 +255,6 @@ struct xyst_ctx : CgState {
   // owner's share of the nodal flux sums (k_flux_own) and the incoming-edge lists of k_update_in
   DevBuf< double > Racc; DevBuf< long long > in_base; DevBuf< int > in_e;
   bool gradp_attr = false;
-  int chunks = 1;                        // > 1: flux and update of slice ranges pipelined on two streams
-  cudaEvent_t ev_chunk[16] = {};
   int grad_mode = 1, grad_waves = 1;     // 1: persistent gradient kernel with incidence prefetch, 0: one warp per slice
   // profiling
   bool prof_on = false;
@@ -600,7 +598,6 @@ int xyst_ctx_create( int device, const xyst_params* params, xyst_ctx** out )
   CK( cudaEventCreateWithFlags( &c->ev_e, cudaEventDisableTiming ) );
   CK( cudaEventCreateWithFlags( &c->ev_a, cudaEventDisableTiming ) );
   CK( cudaEventCreateWithFlags( &c->ev_b, cudaEventDisableTiming ) );
-  for (auto& e : c->ev_chunk) CK( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) );
   c->red.alloc( (size_t)RED_BLOCKS*NDIAG + NDIAG );
   CK( cudaMallocHost( &c->red_host, NDIAG*sizeof(double) ) );
   *out = c;
@@ -630,7 +627,6 @@ int xyst_ctx_destroy( xyst_ctx* c )
   for (auto e : { c->ev_c, c->ev_d, c->ev_e }) if (e) cudaEventDestroy( e );
   if (c->ev_a) cudaEventDestroy( c->ev_a );
   if (c->ev_b) cudaEventDestroy( c->ev_b );
-  for (auto e : c->ev_chunk) if (e) cudaEventDestroy( e );
   if (c->red_host) cudaFreeHost( c->red_host );
   delete c;
   API_END
@@ -658,7 +654,6 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   opt.reorder = false;
   { const char* e = getenv( "XYST_REORDER" ); if (e && e[0] == '1') opt.reorder = allow_reorder;
     e = getenv( "XYST_TILE" ); if (e && atoi( e ) >= 32) c->tile_nodes = std::min( 256, atoi( e ) / 32 * 32 );
-    e = getenv( "XYST_CHUNKS" ); if (e && atoi( e ) >= 1) c->chunks = std::min( 16, atoi( e ) );
     e = getenv( "XYST_GRAD_MODE" ); if (e) c->grad_mode = atoi( e );
     e = getenv( "XYST_GRAD_WAVES" ); if (e && atoi( e ) > 0) c->grad_waves = atoi( e ); }
   opt.tile_nodes = (size_t)c->tile_nodes;
@@ -1146,34 +1141,9 @@ int xyst_riecg_stage( xyst_ctx* c, int stage, double dt )
   if (stage < 0 || stage > 2) throw std::runtime_error( "stage must be 0, 1 or 2" );
   do_grad( c );
   if (c->ns) scal_grad( c );
-  const bool chunked = c->chunks > 1 && !(c->nsh > 0 && c->comm) && !c->ns;
-  if (!chunked) do_flux( c );
+  do_flux( c );
   if (c->ns) scal_flux_nodes( c, true, stage, dt );
-  // An edge is owned by its LOWER end: the incoming edges of a node come from lower nodes, the other ends
-  // of a node's own edges are higher nodes. So the nodal sums + update of the nodes of a slice range need
-  // the fluxes of that range and of lower ones only, and the flux kernel of the next range reads none of
-  // the nodes the update overwrites: the (HBM-bound) update of chunk k runs on a side stream under the
-  // (latency-bound) flux kernel of chunk k+1.
-  auto nodes_chunked = [&]( const double* Un, double* Uout ) {
-    auto s = c->stream; auto us = c->aux_stream;
-    if (c->rb_pending) { CK( cudaStreamWaitEvent( s, c->ev_e, 0 ) ); c->rb_pending = false; }
-    StageArgs A{ rkcoef[stage], dt, c->steady ? c->dtp.p : nullptr, stage, mode( c ) };
-    size_t per = (c->nslice + (size_t)c->chunks - 1) / (size_t)c->chunks;
-    ProfScope ps( c, "flux" );
-    for (int k=0; k<c->chunks; ++k) {
-      size_t a = (size_t)k*per, b = std::min( c->nslice, a + per );
-      if (b <= a) break;
-      launch_flux( c, a, b, s );
-      CK( cudaEventRecord( c->ev_chunk[k], s ) );
-      CK( cudaStreamWaitEvent( us, c->ev_chunk[k], 0 ) );
-      launch_rhs_node( c, true, A, Un, Uout, a, b, us );
-    }
-    CK( cudaEventRecord( c->ev_d, us ) );
-    CK( cudaStreamWaitEvent( s, c->ev_d, 0 ) );
-    CK( cudaGetLastError() );
-  };
-  auto nodes = [&]( const double* Un, double* Uout ) {
-    if (chunked) nodes_chunked( Un, Uout ); else do_rhs_nodes( c, true, stage, dt, c->U.p, Un, Uout ); };
+  auto nodes = [&]( const double* Un, double* Uout ) { do_rhs_nodes( c, true, stage, dt, c->U.p, Un, Uout ); };
   if (c->lax)           // time level n is kept in (p,u,v,w,T) form (Wn); Un is refreshed at stage 2
     nodes( c->Un.p, c->U.p );
   else if (stage == 0) { // un = u (RieCG.cpp:1011) without a copy: write the new state into the

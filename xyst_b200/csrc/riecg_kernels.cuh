@@ -562,41 +562,7 @@ __device__ __forceinline__ void muscl( const double* gp, int gsp, const double* 
   }
 }
 
-__device__ __forceinline__ void rusanov( double l[NC], double r[NC], const double n[3],
-                                         const DParams& P, double f[NC] )
-{
-  double g = P.gamma;
-  double pL = (l[0]*l[4]) * (g-1.0);
-  double pR = (r[0]*r[4]) * (g-1.0);
-  const double gg1 = g*(g-1.0), eL = l[4], eR = r[4];
-  double nx = n[0], ny = n[1], nz = n[2];
-  double vnL = l[1]*nx + l[2]*ny + l[3]*nz;
-  double vnR = r[1]*nx + r[2]*ny + r[3]*nz;
-  l[4] = (l[4] + 0.5*(l[1]*l[1] + l[2]*l[2] + l[3]*l[3])) * l[0];
-  l[1] *= l[0]; l[2] *= l[0]; l[3] *= l[0];
-  r[4] = (r[4] + 0.5*(r[1]*r[1] + r[2]*r[2] + r[3]*r[3])) * r[0];
-  r[1] *= r[0]; r[2] *= r[0]; r[3] *= r[0];
-  double len = sqrt( nx*nx + ny*ny + nz*nz );
-#if MUSCL_V2
-  double sl, sr;
-  if (P.exact) { sl = fabs(vnL) + sqrt( g * pL / l[0] )*len; sr = fabs(vnR) + sqrt( g * pR / r[0] )*len; }
-  else { sl = fabs(vnL) + sqrt( gg1 * eL )*len; sr = fabs(vnR) + sqrt( gg1 * eR )*len; }   // g p / rho = g (g-1) e
-#else
-  double sl = fabs(vnL) + sqrt( g * pL / l[0] )*len;
-  double sr = fabs(vnR) + sqrt( g * pR / r[0] )*len;
-#endif
-  double fw = fmax( sl, sr );
-  f[0] = l[0]*vnL + r[0]*vnR + fw*(r[0] - l[0]);
-  f[1] = l[1]*vnL + r[1]*vnR + (pL + pR)*nx + fw*(r[1] - l[1]);
-  f[2] = l[2]*vnL + r[2]*vnR + (pL + pR)*ny + fw*(r[2] - l[2]);
-  f[3] = l[3]*vnL + r[3]*vnR + (pL + pR)*nz + fw*(r[3] - l[3]);
-  f[4] = (l[4] + pL)*vnL + (r[4] + pR)*vnR + fw*(r[4] - l[4]);
-  if (P.stab2) {
-    double fws = P.stab2coef * fw;
-    #pragma unroll
-    for (int c=0; c<NC; ++c) f[c] -= fws*(l[c] - r[c]);
-  }
-}
+// (Rusanov, Riemann.cpp:369-478: rusanov_len in riecg_own.cuh, which takes the edge normal's length as an argument)
 
 // ev (optional): what the scalar flux of the same edge needs (riecg_scalar.cuh), Riemann.cpp:636-643
 __device__ __forceinline__ void hllc( double l[NC], double r[NC], const double n[3],

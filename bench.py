@@ -252,7 +252,14 @@ def cpu_arm(n, steps, cores):
     sec = time.perf_counter() - t0
     E = box_edges(nx, ny, nz)
     assert np.isfinite(o.get("u")).all()
+    same = None
+    try:                                                  # the FULL 20M-tet box, one partition, one core: measured once
+        same = json.load(open(os.path.join(ROOT, "profiles", "r2_cpu_full_n150.json")))      # (tools/cpu_full_n150.py)
+        same["note"] = "stored measurement from the build container, not taken in this run"
+    except Exception:
+        pass
     return {"value": E * 3 * steps / sec, "unit": "edge-updates/s", "cores": p2, "kind": flavour,
+            "same_config_record": same,
             "sample": "RieCG Sedov, %dx%dx%d-cell box (%d tets, %d edges) as %d partitions of %d^3 cells, one per "
                       "core (OpenMP over the partitions, shared-node partial sums exchanged after every sweep), "
                       "1 warm + %d timed steps" % (nx, ny, nz, 6 * nx * ny * nz, E, p2, n, steps),

@@ -33,3 +33,37 @@ def test_workload_selection():
     assert bench.workload_of(a, 8) == ("tg_strong", 322, (322, 322, 322))
     a.workload = "sedov_weak"
     assert bench.workload_of(a, 4) == ("sedov_weak", 150, (300, 300, 150))
+
+
+@pytest.mark.parametrize("nparts", [2, 4, 8])
+def test_parity_check_partition_equals_the_oracles_chares(nparts):
+    """bench.py's multi-GPU parity check feeds the oracle the tet -> partition map of the box bisection:
+    every rank's host-mirror partition must then hold exactly the nodes of the oracle's chare of the
+    same number (CPU only: partitions built one after the other, no device, no communication)."""
+    import oraclelib as O
+    n = 4
+    nx, ny, nz = bench.box_dims(n, nparts)
+    h = 1.2 / 150.0
+    kw = bench.sedov_kw(h)
+    o = O.Oracle(bench.kuhn_box(nx, ny, nz, nx * h, ny * h, nz * h), O.make_cfg(**kw), "port", nchare=nparts,
+                 target=bench.box_target(nx, ny, nz, nparts))
+    assert o.scalar("nchare") == nparts
+    for r in range(nparts):
+        s = H.Solver.box(H.make_cfg(reforder=1, **kw), nx, ny, nz, nx * h, ny * h, nz * h, nparts=nparts, part=r)
+        s.prepare()
+        assert np.array_equal(s.get("gid").astype(np.uint64), o.get("gid", r)), r
+
+
+def test_reference_flavour_holds_the_compiled_shim_and_it_refuses_to_run_without_a_gpu():
+    """include/xyst_shim.hpp is compiled against the reference's headers into oracle/_ref; on a CPU-only
+    machine the wrappers must fail loudly (no fallback), not compute."""
+    import oraclelib as O
+    import torch
+    if O.lib("reference") is None:
+        pytest.skip("oracle/_ref not built")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by tests/test_gpu_shim.py")
+    kw = O.CASES["riecg_sod"]
+    o = O.Oracle(O.load_mesh("riecg_sod"), O.make_cfg(**kw), "reference")
+    with pytest.raises(RuntimeError, match="no CUDA device|not implemented|unknown"):
+        o.kernel("shim_grad")

@@ -11,8 +11,8 @@
 
 extern "C" int layout_check( size_t npoin, const double* x, const double* y, const double* z,
                              const size_t nsup[3], const size_t* const dsupedge[3], const double* const dsupint[3],
-                             size_t stride, int reorder, size_t tile_nodes, size_t /*unused*/,
-                             size_t* stats /* [10] */, char* msg, size_t msglen )
+                             size_t stride, int reorder, size_t tile_nodes,
+                             size_t* stats /* [6] */, char* msg, size_t msglen )
 {
   auto fail = [&]( const std::string& m ){ std::snprintf( msg, msglen, "%s", m.c_str() ); return 1; };
   try {
@@ -93,9 +93,8 @@ extern "C" int layout_check( size_t npoin, const double* x, const double* y, con
           if (nv) { sec += (double)S.size()*32.0/nv; lin += (double)L.size()*32.0/nv; cnt += 1; }
         }
       }
-      stats[8] = (size_t)(1000.0*sec/cnt); stats[9] = (size_t)(1000.0*lin/cnt); }
-    stats[0] = M.ne; stats[1] = M.nslot; stats[2] = 0; stats[3] = 0; stats[4] = 0;
-    stats[5] = 0; stats[6] = M.nent; stats[7] = (size_t)M.maxdeg;
+      stats[4] = (size_t)(1000.0*sec/cnt); stats[5] = (size_t)(1000.0*lin/cnt); }
+    stats[0] = M.ne; stats[1] = M.nslot; stats[2] = M.nent; stats[3] = (size_t)M.maxdeg;
   } catch (std::exception& e) { return fail( e.what() ); }
   return 0;
 }

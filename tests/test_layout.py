@@ -23,7 +23,7 @@ def _lib():
     return C.CDLL(SO)
 
 
-def _check(s, reorder, tile=256, cap=2048):
+def _check(s, reorder, tile=256):
     s.prepare(); s.host_setup()
     co = np.array([s.get("x"), s.get("y"), s.get("z")])
     npoin = co.shape[1]
@@ -31,13 +31,13 @@ def _check(s, reorder, tile=256, cap=2048):
     si = [np.ascontiguousarray(s.get("dsupint%d" % k), np.float64) for k in range(3)]
     nsup = (C.c_size_t * 3)(len(se[0]) // 4, len(se[1]) // 3, len(se[2]) // 2)
     pe = (C.c_void_p * 3)(*[a.ctypes.data for a in se]); pi = (C.c_void_p * 3)(*[a.ctypes.data for a in si])
-    stats = (C.c_size_t * 10)(); msg = C.create_string_buffer(256)
+    stats = (C.c_size_t * 6)(); msg = C.create_string_buffer(256)
     x, y, z = (np.ascontiguousarray(co[i]) for i in range(3))
     rc = _lib().layout_check(C.c_size_t(npoin), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
                              z.ctypes.data_as(C.c_void_p), nsup, pe, pi, C.c_size_t(3), reorder,
-                             C.c_size_t(tile), C.c_size_t(cap), stats, msg, C.c_size_t(256))
+                             C.c_size_t(tile), stats, msg, C.c_size_t(256))
     assert rc == 0, msg.value.decode()
-    return dict(zip(("ne", "nslot", "ntile", "nforeign", "fstride", "maxtn", "nent", "maxdeg", "sectors_x1000", "lines_x1000"), list(stats)))
+    return dict(zip(("ne", "nslot", "nent", "maxdeg", "sectors_x1000", "lines_x1000"), list(stats)))
 
 
 @pytest.mark.parametrize("n,reorder,tile", [(6, 0, 256), (6, 1, 256), (17, 1, 256), (17, 1, 128), (24, 0, 256), (24, 1, 256)])

@@ -106,12 +106,61 @@ def cg_main(out, rank, world, local):
     dist.destroy_process_group()
 
 
+def nccl_id(rank):
+    idb = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        import ctypes as C
+        buf = (C.c_char * 128)()
+        assert capi.lib().xyst_comm_unique_id(buf) == 0
+        idb = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+    dist.broadcast(idb, 0)
+    return bytes(idb.cpu().numpy().tobytes())
+
+
+def proj_main(cases, nsteps, out, rank, world, local):
+    """ChoCG / LohCG on one GPU per partition: several cases in one launch (one NCCL communicator each). Per
+    case and rank an .npz with the state after the start-up projection and after the last step, the
+    diagnostics rows and the iteration counts of the linear solves of every step."""
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tab = {**O.CCASES, **O.ICASES, **O.HCASES}
+    for case in cases.split(","):
+        kw = tab[case]
+        hm = fixture_to_host_mesh(O.load_mesh(kw.get("mesh", case)))
+        part = H.rcb(hm["coord"], hm["tets"], world)
+        s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"],
+                          hm["set_tri"], nparts=world, part=rank, tetpart=part)
+        s.prepare()
+        s.attach(local, world, rank, nccl_id(rank))
+        s.setup()
+        cho = kw["solver"] == "chocg"
+        res = {"part": np.asarray(part), "gid": s.get("gid"), "u0": s.get("u")}
+        if cho:
+            res["pr0"] = s.get("pr")
+        rows, its = [], []
+        for _ in range(nsteps if nsteps > 0 else int(kw["nstep"])):
+            r = s.step(1)
+            if len(r):
+                rows.append(r[0])
+            its.append([s.scalar("pit"), s.scalar("mit")])
+        res["rows"] = np.asarray(rows); res["its"] = np.asarray(its); res["u"] = s.get("u")
+        if cho:
+            res["pr"] = s.get("pr")
+        res["launches"] = np.asarray(s.ctx().launch_count())
+        np.savez("%s.%s.%d.npz" % (out, case, rank), **res)
+        del s
+        dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     mode, case, nsteps, out = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     if mode == "cg":
         return cg_main(out, rank, world, local)
+    if mode == "proj":
+        return proj_main(case, nsteps, out, rank, world, local)
     kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.HCASES, **O.ZCASES, **O.KCASES}[case]
     mesh = O.load_mesh(kw.get("mesh", case))
     hm = fixture_to_host_mesh(mesh)
@@ -148,6 +197,10 @@ def main():
         for n in ("dsupint2", "dsupedge2", "dirbcmasks", "dirbcval", "dirbcmaskp", "dirbcvalp", "noslipbcnodes",
                   "plhs_ia", "plhs_ja", "plhs_a"):
             res[n] = s.get(n).tolist()
+        if mode == "host":       # Dirichlet rows of the two linear solvers after the union over the sharers
+            res["pbc"] = s.get("pbc").tolist()
+            if kw.get("solver") == "chocg":
+                res["mbcrows"] = s.get("mbcrows").tolist()
     res["meshvol"] = s.scalar("meshvol")
     res["part"] = part.tolist() if rank == 0 else None
     json.dump(res, open("%s.%d.json" % (out, rank), "w"))

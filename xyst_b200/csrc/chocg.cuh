@@ -478,6 +478,49 @@ __global__ void k_cg_bc_scatter( int nbc, const int* __restrict__ node, const do
   if (i < nbc) bcval[ node[i] ] = v[i];
 }
 
+// ---- several partitions: the node gathers above are this partition's own sums at the nodes it
+// shares (ChoCG::div/velgrad/flux/sgrad/pgrad/rhs send m_div[...] etc. of the chare-boundary
+// nodes, ChoCG.cpp:889-898,936-945,989-998,1157-1167,1269-1279,1492-1501). The shared nodes'
+// values of a [m][NP] field go to the exchange buffer, and come back as own + the sharers' in
+// the fixed neighbour order (comdiv :903-920 and its siblings)
+__global__ void k_soa_shared_get( int nsh, int m, size_t NP, const int* __restrict__ sh_node,
+                                  const double* __restrict__ S, double* __restrict__ part )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)nsh*m) return;
+  part[i] = S[(i%m)*NP + (size_t)sh_node[i/m]];
+}
+__global__ void k_soa_shared_put( int nsh, int m, size_t NP, const int* __restrict__ sh_node,
+                                  const int* __restrict__ roff, const int* __restrict__ ridx,
+                                  const double* __restrict__ part, const double* __restrict__ recvbuf,
+                                  double* __restrict__ S )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)nsh*m) return;
+  size_t s = i / m, k = i % m;
+  double a = part[i];
+  for (int r=roff[s]; r<roff[s+1]; ++r) a += recvbuf[(size_t)ridx[r]*m + k];
+  S[k*NP + (size_t)sh_node[s]] = a;
+}
+// the same for the right-hand side of a Runge-Kutta stage, followed by the update of the shared
+// nodes the gather kernel could not finish: u = un - rk dt (sum of the rhs parts) / vol
+// (ChoCG::solve :1529-1545 after comrhs, LohCG::solve likewise)
+__global__ void k_soa_shared_update( int nsh, int m, size_t NP, const int* __restrict__ sh_node,
+                                     const int* __restrict__ roff, const int* __restrict__ ridx,
+                                     const double* __restrict__ part, const double* __restrict__ recvbuf,
+                                     const double* __restrict__ vol, const double* __restrict__ Un, double sdt,
+                                     double* __restrict__ Uout, double* __restrict__ R )
+{
+  size_t i = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (i >= (size_t)nsh*m) return;
+  size_t s = i / m, k = i % m;
+  double a = part[i];
+  for (int r=roff[s]; r<roff[s+1]; ++r) a += recvbuf[(size_t)ridx[r]*m + k];
+  size_t p = (size_t)sh_node[s];
+  R[k*NP+p] = a;
+  Uout[k*NP+p] = Un[k*NP+p] - sdt*a/vol[p];
+}
+
 // reference layout [node][m] <-> structure of arrays with stride NP
 __global__ void k_aos_to_soa( size_t n, size_t NP, int m, const double* __restrict__ A, double* __restrict__ S )
 {
@@ -504,9 +547,30 @@ namespace {
 void cho_need( xyst_ctx* c ) {
   need_mesh( c );
   if (!c->cho) throw std::runtime_error( "ChoCG needs stride-5 superedge integrals: use xyst_chocg_mesh_upload" );
-  // the node gathers and the rhs column sums of the pressure solve have no halo sums yet: partial results
-  // would be silently wrong on a partitioned mesh
-  if (c->nsh > 0 && c->comm) throw std::runtime_error( "ChoCG/LohCG on several partitions is not implemented yet" );
+}
+// several partitions: every node gather is followed by the sum over the partitions sharing a node
+bool cho_parts( const xyst_ctx* c ) { return c->nsh > 0 && c->comm; }
+void soa_halo( xyst_ctx* c, double* S, int m ) {
+  if (!cho_parts( c )) return;
+  if ((size_t)m*c->nsh > c->sh_part.n) throw std::runtime_error( "shared-node buffer too small" );
+  unsigned g = nblk( c->nsh*(size_t)m, 256 );
+  k_soa_shared_get<<< g, 256, 0, c->stream >>>( (int)c->nsh, m, c->NP, c->sh_node.p, S, c->sh_part.p ); ++c->launches;
+  exchange( c, m );
+  exchange_wait( c );
+  k_soa_shared_put<<< g, 256, 0, c->stream >>>( (int)c->nsh, m, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
+    c->sh_part.p, c->sh_recvbuf.p, S ); ++c->launches;
+  CK( cudaGetLastError() );
+}
+// the stage update of the shared nodes from the summed right-hand side parts (R, Un, Uout: [m][NP])
+void soa_halo_update( xyst_ctx* c, double* R, int m, const double* Un, double sdt, double* Uout ) {
+  if (!cho_parts( c )) return;
+  unsigned g = nblk( c->nsh*(size_t)m, 256 );
+  k_soa_shared_get<<< g, 256, 0, c->stream >>>( (int)c->nsh, m, c->NP, c->sh_node.p, R, c->sh_part.p ); ++c->launches;
+  exchange( c, m );
+  exchange_wait( c );
+  k_soa_shared_update<<< g, 256, 0, c->stream >>>( (int)c->nsh, m, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
+    c->sh_part.p, c->sh_recvbuf.p, c->vol.p, Un, sdt, Uout, R ); ++c->launches;
+  CK( cudaGetLastError() );
 }
 void cho_need_cg( xyst_ctx* c ) {
   cho_need( c );
@@ -542,11 +606,13 @@ void cho_vgrad( xyst_ctx* c ) {
   k_cho_grad< 3 ><<< cho_grid( c ), NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p,
     c->D.p, c->nslot, c->cU, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p, c->cVg.p ); ++c->launches;
   CK( cudaGetLastError() );
+  soa_halo( c, c->cVg.p, 9 );                       // comvgrad :949-970 (each part already over the full volume)
 }
 void cho_rhs( xyst_ctx* c, const double* Un, double sdt, double* Uout, double* R ) {
   if (c->loh) throw std::runtime_error( "context holds a LohCG mesh: use xyst_lohcg_rhs / xyst_lohcg_stage" );
   ProfScope ps( c, "cho_rhs" );
   auto g = cho_grid( c );
+  if (cho_parts( c ) && !R) R = c->cR.p;            // the shared nodes' parts travel before they are used
   if (c->chp.flux == 1)
     k_cho_rhs< true ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p,
       c->nslot, c->cU, c->cP.p, c->cVg.p, c->X.p, chop( c ), c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p,
@@ -557,6 +623,7 @@ void cho_rhs( xyst_ctx* c, const double* Un, double sdt, double* Uout, double* R
       c->cS.p, c->v.p, c->vol.p, Un, sdt, Uout, R );
   ++c->launches;
   CK( cudaGetLastError() );
+  if (Uout) soa_halo_update( c, R, 3, Un, sdt, Uout ); else soa_halo( c, R, 3 );      // comrhs :1505-1527
 }
 // ConjugateGradients::init :336-428 + apply :451-505 + r :508-556 for one partition: Dirichlet rows
 // (scalar row ids of the selected solver) with values, optional Neumann vector, applied to cg_b and,
@@ -587,6 +654,10 @@ void cho_cg_bc( xyst_ctx* c, size_t nbc, const size_t* bcnodes, const double* bc
   if (neubc) { c->cg_neu.upload( std::vector< double >( neubc, neubc+n ), s ); neu = c->cg_neu.p; }
   k_cg_bc_colsum<<< nblk( c->cg_nslice*32, 256 ), 256, 0, s >>>( n, c->cg_base.p, c->cg_col.p, c->cg_val.p, c->cg_bc.p,
     c->cg_bcval.p, c->cg_q.p ); ++c->launches;
+  // several partitions: the Neumann vector and the column sums are this partition's parts
+  // (ConjugateGradients::combc :407-428 sums qc, comr :508-525 sums rc at the shared rows)
+  if (neu) cg_halo( c, c->cg_neu.p, 0 );
+  cg_halo( c, c->cg_q.p, 0 );
   k_cg_bc_rhs<<< nblk( n, 256 ), 256, 0, s >>>( n, c->cg_bc.p, c->cg_bcval.p, neu, c->cg_q.p, c->cg_b.p ); ++c->launches;
   CK( cudaGetLastError() );
 }
@@ -695,6 +766,7 @@ int xyst_chocg_div( xyst_ctx* c, int which, double dt, int stab )
       c->nslot, V, c->X.p, c->cP.p, c->cPg.p, dt, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->cDiv.p );
   ++c->launches;
   CK( cudaGetLastError() );
+  soa_halo( c, c->cDiv.p, 1 );                      // comdiv :902-921
   API_END
 }
 
@@ -709,6 +781,7 @@ int xyst_chocg_flux( xyst_ctx* c )
   k_cho_flux<<< cho_grid( c ), NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p,
     c->nslot, c->cU, c->cVg.p, c->chp.mu, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->cFl.p ); ++c->launches;
   CK( cudaGetLastError() );
+  soa_halo( c, c->cFl.p, 3 );                       // comflux :1002-1023
   API_END
 }
 
@@ -725,6 +798,7 @@ int xyst_chocg_grad( xyst_ctx* c, int which )
   k_cho_grad< 1 ><<< cho_grid( c ), NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p,
     c->D.p, c->nslot, S, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p, G ); ++c->launches;
   CK( cudaGetLastError() );
+  soa_halo( c, G, 3 );                              // comsgrad :1171-1192, compgrad :1283-1304
   API_END
 }
 

@@ -222,7 +222,6 @@ namespace {
 void loh_need( xyst_ctx* c ) {
   need_mesh( c );
   if (!c->loh) throw std::runtime_error( "LohCG needs stride-4 superedge integrals with the Laplacian term: use xyst_lohcg_mesh_upload" );
-  if (c->nsh > 0 && c->comm) throw std::runtime_error( "ChoCG/LohCG on several partitions is not implemented yet" );
 }
 LohP lohp( const xyst_ctx* c ) { return LohP{ c->chp.stab, c->chp.stab2, c->chp.stab2coef, c->chp.mu, c->loh_s }; }
 // [4][NP] state behind the velocity pointer of the ChoCG machinery
@@ -232,10 +231,12 @@ void loh_rhs( xyst_ctx* c, const double* Un, double sdt, double* Uout, double* R
   ProfScope ps( c, "loh_rhs" );
   auto g = cho_grid( c );
   const double* U = loh_state( c->cU, c->NP );
+  if (cho_parts( c ) && !R) R = c->cR.p;            // the shared nodes' parts travel before they are used
   if (c->chp.flux == 1) {
     { ProfScope pg( c, "loh_grad" );
       k_cho_grad< 4 ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p,
         c->D.p, c->nslot, U, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p, c->lG.p ); ++c->launches; }
+    soa_halo( c, c->lG.p, 12 );                     // LohCG::comgrad, LohCG.cpp:1511-1533
     k_loh_rhs< true ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p,
       c->nslot, U, c->lG.p, c->X.p, lohp( c ), c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p,
       Un, sdt, Uout, R );
@@ -245,6 +246,7 @@ void loh_rhs( xyst_ctx* c, const double* Un, double sdt, double* Uout, double* R
       Un, sdt, Uout, R );
   ++c->launches;
   CK( cudaGetLastError() );
+  if (Uout) soa_halo_update( c, R, 4, Un, sdt, Uout ); else soa_halo( c, R, 4 );      // LohCG::comrhs, LohCG.cpp:1563-1585
 }
 // LohCG::solve/solved BCs: dirbc, dirbcp, symbc (pos 1), noslipbc (pos 1)
 void loh_bc( xyst_ctx* c, bool pressure ) {

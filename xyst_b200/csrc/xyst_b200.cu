@@ -197,6 +197,8 @@ struct xyst_ctx : CgState {
   std::vector< int > neigh; std::vector< size_t > neigh_off;
   DevBuf< int > sh_node;                 // unique shared nodes
   std::vector< int > sh_old_h;           // the unique shared nodes in the caller's numbering (ascending)
+  std::vector< double > sh_cnt_h;        // per shared node: partitions contributing to it (own included)
+  std::vector< uint8_t > sh_slave_h;     // per shared node: counted by a higher rank in global dot products
   std::vector< int > sh_node_h; DevBuf< unsigned char > sh_flag;   // host copy (library numbering); [npoin] 1 = shared (built on first use)
   DevBuf< int > sh_send;                 // [nsend] index into unique list, per neighbour segment
   DevBuf< int > sh_roff, sh_ridx;        // CSR unique node -> positions in recv buffer
@@ -1248,6 +1250,14 @@ int xyst_halo_upload( xyst_ctx* c, int nneigh, const int* neigh_rank, const size
   for (size_t i=0; i<uniq.size(); ++i) roff[i+1] += roff[i];
   { std::vector< int > f( roff.begin(), roff.end()-1 );
     for (size_t i=0; i<nsend; ++i) ridx[ f[send[i]]++ ] = (int)i; }   // ascending recv position = fixed neighbour order
+  // per shared node: number of partitions contributing (tk::count, Reorder.cpp:379-390) and whether a
+  // sharer with a higher rank counts it in the dot products (tk::slave, :392-416)
+  c->sh_cnt_h.assign( uniq.size(), 1.0 ); c->sh_slave_h.assign( uniq.size(), 0 );
+  for (int k=0; k<nneigh; ++k)
+    for (size_t i=neigh_off[k]; i<neigh_off[k+1]; ++i) {
+      c->sh_cnt_h[ send[i] ] += 1.0;
+      if (neigh_rank[k] > c->rank) c->sh_slave_h[ send[i] ] = 1;
+    }
   auto s = c->stream;
   c->nsh = uniq.size(); c->nsend = nsend; c->sh_old_h = uniq;
   refresh_shared( c );
@@ -1572,7 +1582,14 @@ int xyst_csr_upload( xyst_ctx* c, size_t nrow, size_t ncomp, const size_t* ia, c
   for (auto* v : { &c->cg_x, &c->cg_b, &c->cg_r, &c->cg_p, &c->cg_q, &c->cg_z, &c->cg_d, &c->cg_mask, &c->cg_cnt }) v->alloc( nrow );
   c->cg_scal.alloc( 16 );
   // one partition until xyst_cg_setup says otherwise: every row counted once; x = 0
-  c->cg_mask.upload( std::vector< double >( nrow, 1.0 ), s ); c->cg_cnt.upload( std::vector< double >( nrow, 1.0 ), s );
+  { std::vector< double > mask( nrow, 1.0 ), cnt( nrow, 1.0 );
+    if (c->nsh && c->comm && c->sh_cnt_h.size() == c->nsh)     // partitioned mesh with one row block per node
+      for (size_t i=0; i<c->nsh; ++i) {
+        size_t p = (size_t)c->sh_old_h[i];
+        if ((p+1)*ncomp > nrow) continue;
+        for (size_t k=0; k<ncomp; ++k) { cnt[p*ncomp+k] = c->sh_cnt_h[i]; if (c->sh_slave_h[i]) mask[p*ncomp+k] = 0.0; }
+      }
+    c->cg_mask.upload( mask, s ); c->cg_cnt.upload( cnt, s ); }
   CK( cudaMemsetAsync( c->cg_x.p, 0, nrow*sizeof(double), s ) );
   c->cg_hasbc = false;
   if (c->nsh) {           // halo buffers wide enough for ncomp values per shared node

@@ -335,6 +335,8 @@ size_t xyst_solver_get( xyst_solver* s, const char* name, void* out, size_t cap 
     if (n == "pgrad") return put( r.choGet( "pgrad", 3 ), out, cap );
     if (n == "u0") return put( r.m_u0, out, cap );
     if (n == "u") return put( r.solution(), out, cap );
+    if (n == "pbc") return put( r.pressureBC(), out, cap );
+    if (n == "mbcrows") return put( r.momentumBCRows(), out, cap );
     if (n == "shared") return put( d.sharedNodes(), out, cap );
     if (n == "bface") {
       std::vector< std::uint64_t > f;

@@ -1,5 +1,7 @@
 // xyst_b200/host/chocg.cpp -- the ChoCG members of the host mirror (solver = "chocg"):
-// projection method for constant-density flow, src/Inciter/ChoCG.cpp + chocg.ci, one partition.
+// projection method for constant-density flow, src/Inciter/ChoCG.cpp + chocg.ci, on one or several
+// partitions (the device library sums the shared nodes' parts after every operator; here: the global
+// reductions and the union of the solvers' Dirichlet rows over the partitions sharing a node).
 // Setup pieces the other solvers do not have: Dirichlet BCs with values and pressure BCs
 // (ChoCG::setupDirBC :210-300), no-slip nodes (:655-682), the pressure Poisson matrix
 // (ChoCG::prelhs :146-188 on tk::CSR, src/LinearSolver/CSR.cpp:19-84). The time step sequences
@@ -137,6 +139,20 @@ void RieCG::choPressureSetup()
     for (std::size_t p=0; p<np; ++p)
       if (gid[p] == m_cfg.p_hydrostat) { if (!m_pbc.count( p )) m_pbc[p] = pic( x[p], y[p], z[p] ); break; }
   }
+  // several partitions: a shared node may lie on a pressure-BC face of only some of its partitions; every
+  // sharer must treat its row as a Dirichlet row (ConjugateGradients::init :391-417 sends the BCs of the
+  // shared nodes to the fellow chares, apply :446-449 merges them)
+  if (m_nranks > 1) {
+    auto shared = m_disc.sharedNodes();
+    std::vector< real > vals( shared.size()*2, 0.0 );
+    for (std::size_t i=0; i<shared.size(); ++i) {
+      auto k = m_pbc.find( shared[i] );
+      if (k != m_pbc.end()) { vals[i*2] = 1.0; vals[i*2+1] = k->second; }
+    }
+    m_halosum( 2, vals );
+    for (std::size_t i=0; i<shared.size(); ++i)
+      if (vals[i*2] > 0.5 && !m_pbc.count( shared[i] )) m_pbc[ shared[i] ] = vals[i*2+1] / vals[i*2];
+  }
   m_neubc.clear();
   if (auto pg = problems::PRESSURE_GRAD( m_cfg )) {
     std::vector< std::uint8_t > besym( m_triinpoel.size()/3, 0 );
@@ -159,6 +175,26 @@ void RieCG::choPressureSetup()
   }
 }
 
+//! Dirichlet rows of the momentum solve (ChoCG::solve :1580-1599): masked Dirichlet components and
+//! no-slip nodes, value 0; scalar row = node*3 + component
+void RieCG::choMomRows()
+{
+  std::set< std::size_t > rows;
+  for (std::size_t i=0; i<m_dirbcmasks.size()/4; ++i)
+    for (std::size_t c=0; c<3; ++c) if (m_dirbcmasks[i*4+1+c]) rows.insert( m_dirbcmasks[i*4]*3+c );
+  for (auto p : m_noslipbcnodes) for (std::size_t c=0; c<3; ++c) rows.insert( p*3+c );
+  if (m_nranks > 1) {                     // union over the partitions sharing a node, as for the pressure rows
+    auto shared = m_disc.sharedNodes();
+    std::vector< real > vals( shared.size()*3, 0.0 );
+    for (std::size_t i=0; i<shared.size(); ++i)
+      for (std::size_t c=0; c<3; ++c) if (rows.count( shared[i]*3+c )) vals[i*3+c] = 1.0;
+    m_halosum( 3, vals );
+    for (std::size_t i=0; i<shared.size(); ++i)
+      for (std::size_t c=0; c<3; ++c) if (vals[i*3+c] > 0.5) rows.insert( shared[i]*3+c );
+  }
+  m_mbcrows.assign( rows.begin(), rows.end() );
+}
+
 //! Momentum matrix of the semi-implicit solve, ChoCG::lhs :1433-1477: per tetrahedron
 //! A(a,b,c) -= J/dt/120 (2 if a == b else 1) + theta mu grad N_a . grad N_b / (6J), the same for the
 //! three components, in tk::CSR( ncomp, psup ) block form (momlhs :190-208): scalar row i*3+c holds
@@ -179,12 +215,7 @@ void RieCG::choLhs()
     for (std::size_t e=0; e<ntet; ++e) for (std::size_t k=0; k<4; ++k) m_esup[ fill[ inpoel[e*4+k] ]++ ] = e*4+k;
     m_mlhs_ia.assign( np*3+1, 1 );
     for (std::size_t i=0; i<np; ++i) for (std::size_t c=0; c<3; ++c) m_mlhs_ia[i*3+c+1] = m_mlhs_ia[i*3+c] + (ia[i+1]-ia[i]);
-    // momentum BC rows (ChoCG::solve :1580-1599): masked Dirichlet components and no-slip nodes, value 0
-    std::set< std::size_t > rows;
-    for (std::size_t i=0; i<m_dirbcmasks.size()/4; ++i)
-      for (std::size_t c=0; c<3; ++c) if (m_dirbcmasks[i*4+1+c]) rows.insert( m_dirbcmasks[i*4]*3+c );
-    for (auto p : m_noslipbcnodes) for (std::size_t c=0; c<3; ++c) rows.insert( p*3+c );
-    m_mbcrows.assign( rows.begin(), rows.end() );
+    choMomRows();
   }
   const auto& X = m_disc.Coord()[0]; const auto& Y = m_disc.Coord()[1]; const auto& Z = m_disc.Coord()[2];
   const auto dt = m_disc.Dt(); const auto theta = m_cfg.theta, mu = m_cfg.mu;
@@ -232,7 +263,6 @@ void RieCG::choLhs()
 //! velocity divergence-free and compute the initial pressure
 void RieCG::choSetup()
 {
-  if (m_nranks > 1) throw std::runtime_error( "ChoCG on several partitions is not implemented yet" );
   if (m_cfg.rk < 1 || m_cfg.rk > 4) throw std::runtime_error( "ChoCG: rk must be 1..4" );
   auto np = m_disc.Gid().size();
   const auto& co = m_disc.Coord();
@@ -331,7 +361,10 @@ bool RieCG::choStep( std::vector< real >* diagrow )
   auto eps = std::numeric_limits< real >::epsilon();
   real mindt;
   if (std::abs( m_cfg.dt ) > eps) mindt = m_cfg.dt;
-  else ck( xyst_chocg_dt_min( m_ctx, m_cfg.cfl, m_cfg.dif, &mindt ) );
+  else {
+    ck( xyst_chocg_dt_min( m_ctx, m_cfg.cfl, m_cfg.dif, &mindt ) );
+    if (m_nranks > 1) { std::vector< real > t{ mindt }; m_allreduce( 1, t ); mindt = t[0]; }   // contribute(min_double) :1407-1410
+  }
   if (mindt < eps) m_finished = true;
   m_disc.setdt( mindt );
   const bool implicit = m_cfg.theta > eps;
@@ -374,6 +407,7 @@ std::vector< real > RieCG::choDiag()
   }
   real d[16];
   ck( xyst_chocg_diag( m_ctx, psol ? m_psol.data() : nullptr, anu.empty() ? nullptr : anu.data(), d ) );
+  if (m_nranks > 1) { std::vector< real > t( d, d+16 ); m_allreduce( 0, t ); std::copy( t.begin(), t.end(), d ); }
   std::size_t ncomp = psol ? 0 : 3;
   auto mv = m_disc.MeshVol();
   std::vector< real > row{ static_cast< real >( m_disc.It() ), m_disc.T(), m_disc.Dt() };

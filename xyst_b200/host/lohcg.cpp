@@ -1,6 +1,6 @@
 // xyst_b200/host/lohcg.cpp -- the LohCG members of the host mirror (solver = "lohcg"):
 // artificial-compressibility solver for constant-density flow, src/Inciter/LohCG.cpp + lohcg.ci,
-// one partition. Unknowns (p,u,v,w). Setup shares ChoCG's pieces (Dirichlet masks with values,
+// on one or several partitions. Unknowns (p,u,v,w). Setup shares ChoCG's pieces (Dirichlet masks with values,
 // pressure BCs, no-slip nodes, the pressure Poisson matrix: LohCG::setupDirBC :215-296 and
 // prelhs :140-181 are the ChoCG members of the same names); the start-up makes the initial
 // velocity divergence-free with two pressure solves (LohCG::merge :909-931 onwards) and the time
@@ -22,7 +22,6 @@ const real rkcoef[4][4] = { { 1.0, 0, 0, 0 }, { 1.0/2.0, 1.0, 0, 0 }, { 1.0/3.0,
 
 void RieCG::lohSetup()
 {
-  if (m_nranks > 1) throw std::runtime_error( "LohCG on several partitions is not implemented yet" );
   if (m_cfg.rk < 1 || m_cfg.rk > 4) throw std::runtime_error( "LohCG: rk must be 1..4" );
   if (problems::SRC( m_cfg )) throw std::runtime_error( "LohCG: source terms are not hooked up" );
   auto np = m_disc.Gid().size();
@@ -117,7 +116,10 @@ bool RieCG::lohStep( std::vector< real >* diagrow )
   auto eps = std::numeric_limits< real >::epsilon();
   real mindt;
   if (std::abs( m_cfg.dt ) > eps) mindt = m_cfg.dt;
-  else ck( xyst_lohcg_dt_min( m_ctx, m_cfg.cfl, m_cfg.dif, &mindt ) );
+  else {
+    ck( xyst_lohcg_dt_min( m_ctx, m_cfg.cfl, m_cfg.dif, &mindt ) );
+    if (m_nranks > 1) { std::vector< real > t{ mindt }; m_allreduce( 1, t ); mindt = t[0]; }   // contribute(min_double) :1445-1446
+  }
   if (mindt < eps) m_finished = true;
   m_disc.setdt( mindt );
   for (std::uint64_t s=0; s<m_cfg.rk; ++s)
@@ -144,6 +146,7 @@ std::vector< real > RieCG::lohDiag()
   }
   real d[16];
   ck( xyst_lohcg_diag( m_ctx, an.empty() ? nullptr : an.data(), d ) );
+  if (m_nranks > 1) { std::vector< real > t( d, d+16 ); m_allreduce( 0, t ); std::copy( t.begin(), t.end(), d ); }
   auto mv = m_disc.MeshVol();
   std::vector< real > row{ static_cast< real >( m_disc.It() ), m_disc.T(), m_disc.Dt() };
   for (std::size_t i=0; i<4; ++i) row.push_back( std::sqrt( d[i] / mv ) );

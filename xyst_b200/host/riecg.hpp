@@ -176,6 +176,12 @@ class RieCG {
     std::size_t m_pit = 0;           //!< iterations of the last pressure solve
     std::size_t m_mit = 0;           //!< iterations of the last momentum solve (theta > 0)
     std::vector< real > choGet( const char* what, std::size_t width );
+    //! host-side views for the tests: pressure Dirichlet (local node, value) pairs and the momentum
+    //! solve's Dirichlet rows after the union over the partitions sharing a node
+    //! (computed at the first call: the union is a collective operation, the getter is called twice per array)
+    std::vector< real > pressureBC() { if (!m_pbcview) { choPressureSetup(); m_pbcview = true; } std::vector< real > r;
+      for (const auto& [p,v] : m_pbc) { r.push_back( static_cast< real >( p ) ); r.push_back( v ); } return r; }
+    std::vector< std::size_t > momentumBCRows() { if (!m_mrowview) { choMomRows(); m_mrowview = true; } return m_mbcrows; }
     bool pendingDiag() const { return !m_lastdiag.empty(); }   //!< row of a run that ended during setup (nstep = 1)
     std::vector< real > m_u0;        //!< initial condition (npoin x ncomp)
     std::vector< double > timings;   //!< seconds spent in the setup phases (for reporting)
@@ -191,6 +197,7 @@ class RieCG {
     void evalDirvals( real t );      //!< physics::dirbc values = IC at the BC nodes at time t (BC.cpp:57-66)
     void evalSrcCentroids( real t, std::vector< real >& sc );   //!< problems::SRC at the tet centroids (kozak::rhs)
     void evalSrc( real t );          //!< problems::SRC at the nodes at time t (riemann::src, Riemann.cpp:880-907)
+    bool m_pbcview = false, m_mrowview = false;
     bool m_pinned = false;           //!< point-source nodes handed to the device
     bool m_timedep = false;          //!< IC / source depend on time: BC values per stage, source per step
     bool m_haloup = false;
@@ -221,6 +228,7 @@ class RieCG {
     std::vector< std::uint64_t > m_esup;
     bool m_mlhsup = false;
     void choPressureSetup();               //!< pressure BC values, Neumann vector, rhs override of pinit
+    void choMomRows();                     //!< Dirichlet rows of the momentum solve (theta > 0)
     void choSetup();                       //!< device upload + ChoCG::merge :816-837 onwards
     bool choStep( std::vector< real >* diagrow );
     void choPinit();                       //!< :1025-1125

@@ -165,7 +165,7 @@ _DT = {"gid": np.uint64, "inpoel": np.uint64, "triinpoel": np.uint64, "besym": n
        "dsupedge0": np.uint64, "dsupedge1": np.uint64, "dsupedge2": np.uint64,
        "dirbcmasks": np.uint64, "symbcnodes": np.uint64, "bface": np.uint64, "commmap": np.uint64,
        "shared": np.uint64, "plhs_ia": np.uint64, "plhs_ja": np.uint64, "dirbcmaskp": np.uint64,
-       "noslipbcnodes": np.uint64}
+       "noslipbcnodes": np.uint64, "mbcrows": np.uint64}
 
 
 def box_mesh(nx, ny, nz, Lx=1.0, Ly=1.0, Lz=1.0):

@@ -216,8 +216,15 @@ int xyst_kozcg_step(xyst_ctx* ctx, double dt);
  * integrals of stride 5 (normal, J/120, grad_p.grad_q/(6J); ChoCG::domint, ChoCG.cpp:399-446) and
  * the solver steps of src/Inciter/ChoCG.cpp that call them. The state (velocity u, pressure, their
  * gradients, divergence) stays on the device; the pressure Poisson matrix (ChoCG::prelhs :146-188)
- * is given with xyst_csr_upload and solved with the xyst_cg_* entries below. One partition per
- * context for now (no halo exchange on this path yet). */
+ * is given with xyst_csr_upload and solved with the xyst_cg_* entries below. With a communicator
+ * and the shared-node lists (xyst_comm_init, xyst_halo_upload BEFORE the matrix upload) every
+ * operator is followed by the sum of the sharing partitions' parts at the shared nodes
+ * (ChoCG::comdiv/comvgrad/comflux/comsgrad/compgrad/comrhs, ChoCG.cpp:902-1527), the stage update
+ * of those nodes is done from the summed rhs, and the linear solves are partitioned (row counts and
+ * slave flags from the halo lists; Neumann and Dirichlet column-sum parts summed,
+ * ConjugateGradients.cpp:407-428,508-525). The caller passes the UNION of the sharers' Dirichlet
+ * rows for shared nodes (ConjugateGradients::init/apply :391-449); dt_min and diag return this
+ * partition's values, to be reduced with xyst_allreduce_min/_sum. */
 typedef struct xyst_chocg_params {
   int flux;          /* 0 = damp2, 1 = damp4 (Chorin.cpp:640-829) */
   int stab;          /* tag::stab */
@@ -285,7 +292,8 @@ int xyst_chocg_diag(xyst_ctx* ctx, const double* an_p, const double* an_u, doubl
  * and the solver steps of src/Inciter/LohCG.cpp. div/grad/vgrad/flux are the Chorin operators on the
  * velocity: after xyst_lohcg_mesh_upload the entries xyst_chocg_div (stab 0), _vgrad, _flux, _grad(0),
  * _pinit (divisor 1), _get and xyst_cg_* serve this context too; the entries below are LohCG's own.
- * One partition per context for now. */
+ * Several partitions as for ChoCG (LohCG::comgrad/comrhs, LohCG.cpp:1511-1585, besides the shared
+ * Chorin entries' exchanges). */
 typedef struct xyst_lohcg_params {
   int flux;          /* 0 = damp2, 1 = damp4 (Lohner.cpp:724-914) */
   int stab;          /* tag::stab */

@@ -242,7 +242,20 @@ int xyst_chocg_mesh_upload(xyst_ctx* ctx, size_t npoin, const double* x, const d
 int xyst_chocg_bc_upload(xyst_ctx* ctx, size_t ndir, const size_t* dirnodes, const int* dirmask,
                          const double* dirval, size_t nsym, const size_t* symbcnodes,
                          const double* symbcnorms, size_t nnoslip, const size_t* noslipbcnodes);
-int xyst_chocg_set_u(xyst_ctx* ctx, const double* u /* [npoin][3] */);
+/* Transported scalars next to the velocity (ChoCG::m_u with problem_ncomp = 3 + ns; the scalar rows of
+ * chorin::vgrad / adv_damp2 / adv_damp4 / the boundary integral / src, Chorin.cpp:230,698-708,817-824,
+ * 947-981,1003-1007): call after the mesh upload, before any state or BC upload. From then on u, un, rhs
+ * rows have 3+ns entries, vgrad rows 3(3+ns), Dirichlet masks and values 3+ns per node, xyst_chocg_src
+ * takes 3+ns columns, xyst_chocg_diag takes an_u with 3+ns columns and returns 16 + 4 ns sums
+ * (per scalar: L2 solution, L2 increment, L2 error, L1 error). ns <= 4. */
+int xyst_chocg_scalars(xyst_ctx* ctx, int ns, double diffusivity /* tag::mat_dyn_diffusivity */);
+/* time-dependent Dirichlet values (physics::dirbc evaluates the IC at the BC time, BC.cpp:57-66):
+ * new values [ndir][3+ns] for the nodes of the last bc_upload (LohCG: [ndir][4]) */
+int xyst_chocg_dirbc_values(xyst_ctx* ctx, const double* dirval);
+/* problems::point_src (Problems.cpp:764-823; ChoCG::pred :1655-1657): the first scalar of the listed
+ * nodes is set to value after every stage update, before the BCs */
+int xyst_chocg_pin(xyst_ctx* ctx, size_t n, const size_t* nodes, double value);
+int xyst_chocg_set_u(xyst_ctx* ctx, const double* u /* [npoin][3 (+ns)] */);
 int xyst_chocg_get_u(xyst_ctx* ctx, double* u);
 int xyst_chocg_set_p(xyst_ctx* ctx, const double* p /* [npoin] */);
 int xyst_chocg_get(xyst_ctx* ctx, const char* what, double* out);   /* "pr","div" [npoin]; "sgrad","pgrad","flux","rhs" [npoin][3]; "vgrad" [npoin][9]; "un" [npoin][3] */

@@ -13,6 +13,7 @@
 // TestConjugateGradients.cpp:216-217,290-291,457-458,531-532) in tests/test_oracle_cg.py.
 #pragma once
 #include <vector>
+#include <cstdlib>
 #include <map>
 #include <unordered_map>
 #include <unordered_set>
@@ -163,14 +164,20 @@ class Solver {
     }
 
     //! ConjugateGradients::dot :128-151 summed over all partitions (contribute(sum_double))
+    //! ORACLE_DOT_REVERSE=1 (tests only): the same sum taken from the last node to the first -- a
+    //! rounding-level perturbation of every dot product, to measure how far the iteration carries it
     real dot( std::vector< real > Part::*a, std::vector< real > Part::*b ) const {
+      static const bool reverse = [](){ const char* e = std::getenv( "ORACLE_DOT_REVERSE" ); return e && e[0] == '1'; }();
       real D = 0.0;
       for (const auto& pp : parts) {
         const auto& P = *pp; auto ncomp = P.A.Ncomp();
         real d = 0.0;
-        for (std::size_t i=0; i<(P.*a).size()/ncomp; ++i)
+        auto n = (P.*a).size()/ncomp;
+        for (std::size_t k=0; k<n; ++k) {
+          auto i = reverse ? n-1-k : k;
           if (!slave( P.nodeCommMap, P.gid[i], P.index ))
             for (std::size_t c=0; c<ncomp; ++c) d += (P.*a)[i*ncomp+c] * (P.*b)[i*ncomp+c];
+        }
         D += d;
       }
       return D;

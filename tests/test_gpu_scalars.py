@@ -128,3 +128,71 @@ def test_scalar_configurations_that_are_not_implemented_fail_loudly():
         xyst_b200.Context(device=0, ncomp=4)
     with pytest.raises(xyst_b200.XystError):
         xyst_b200.Context(device=0, ncomp=14)
+
+
+# ---- ChoCG with a transported scalar (chorin::vgrad / adv_damp2 / adv_damp4 / boundary integral for the
+# ---- scalar rows, time-dependent Dirichlet values, problems::point_src) ----------------------------------
+PCASES = {"chocg_slot_cyl": O.SCASES["chocg_slot_cyl"], "chocg_slot_cyl_damp4": O.SCASES["chocg_slot_cyl_damp4"],
+          "chocg_sphere_point_src": O.SPHERE_SRC}
+
+
+@pytest.mark.parametrize("case", list(PCASES))
+def test_chocg_with_a_transported_scalar_matches_oracle_and_golden(case):
+    """{ChoCG/SlotCyl/slot_cyl.q, slot_cyl_damp4.q, ChoCG/Sphere/sphere_point_src.q}: 3 velocities + 1 scalar
+    through the C++ host mirror and the device: scalar rows of the advection flux with the flow flux's normal
+    velocities and stabilisation (damp2; damp4 with the limited reconstruction on the scalar's own nodal
+    gradient), boundary integral, RK update, Dirichlet values of the rotating scalar field re-evaluated at every
+    BC time (t + rk dt in the stages, t + dt after the projection), analytic-solution error norms of all
+    four components, the point source pinned after every stage. Free-running against the oracle: same
+    iteration count of every pressure solve, diagnostics and fields 1e-9 (CG bound of the ChoCG tests),
+    then the reference's golden rows."""
+    from xyst_b200 import hostapi as H
+    from host_common import fixture_to_host_mesh
+    kw = PCASES[case]
+    hm = fixture_to_host_mesh(O.load_mesh(kw["mesh"]))
+    s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"], hm["set_tri"])
+    s.prepare(); s.attach(0); s.setup()
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    gold = O.load_golden_diag(case)
+    n = int(gold[-1, 0]) + (1 if "point_src" in case else 0)
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    assert s.get("u").shape == o.get("u").shape == (hm["coord"].shape[1], 4)
+    assert rel(s.get("u"), o.get("u")) < 1e-9, "after the start-up projection"
+    rows = []
+    for it in range(n):
+        r = s.step(1); o.step(1)
+        if len(r):
+            rows.append(r[0])
+        # (slot_cyl: the rotation is divergence-free, the Poisson right-hand side is rounding noise of 1e-16 and
+        # so is the iteration at which its residual falls below p_tol times its norm: 154 vs 155)
+        assert "slot_cyl" in case or int(s.scalar("pit")) == int(o.scalar("pit")), it
+        U, Uo = s.get("u"), o.get("u")
+        assert rel(U[:, :3], Uo[:, :3]) < 1e-9, ("velocity", it)
+        assert np.abs(U[:, 3] - Uo[:, 3]).max() < 1e-9 * max(np.abs(Uo[:, 3]).max(), 1e-3), ("scalar", it)
+    rows = np.asarray(rows); ro = o.diag()
+    assert rows.shape == ro.shape == gold.shape
+    assert (np.abs(rows[:, :3] - ro[:, :3]) <= TOL * np.abs(ro[:, :3])).all()
+    vs = np.abs(ro[:, 3:]).max(axis=1, keepdims=True)
+    err = np.abs(rows - ro) / (np.abs(ro) + 1e-11 * vs)
+    if "slot_cyl" in case:
+        # Every node of this one-cell-thick mesh is a velocity Dirichlet node, so the velocity is prescribed
+        # (it equals the oracle's to the last bit) and nothing depends on the pressure -- which the case solves
+        # with p_tol = 1e-2 and a single pinned node. That pressure is ill-determined in the reference
+        # itself: summing the oracle's dot products from the last node to the first (ORACLE_DOT_REVERSE=1,
+        # test_oracle_cg_sensitivity.py) moves the norm of its pressure by up to 1.3e-3 (step 19), the increment norm
+        # by 9e-2 and the iteration count of 12 of the 20 solves by one. Columns 3 and 8 (norms of p and of its
+        # increment) get those bounds.
+        rest = [c for c in range(rows.shape[1]) if c not in (3, 8)]
+        assert (err[:, rest] <= 1e-9).all()
+        assert (err[:, 3] <= 5e-3).all() and (err[:, 8] <= 0.3).all()
+        assert rel(s.get("pr"), o.get("pr")) < 5e-3
+        # the reference's own acceptance test of these goldens (SlotCyl/diag.ndiff.cfg)
+        assert O.numdiff_ok(rows[:, 1:8], gold[:, 1:8], 1.0e-5, 2.0e-3).all()
+        assert O.numdiff_ok(rows[:, 8:13], gold[:, 8:13], 3.0e-3, 1.0e-6).all()
+        if case == "chocg_slot_cyl_damp4":   # (the damp2 golden's scalar columns differ from the reference's own objects)
+            assert (np.abs(rows[:, rest] - gold[:, rest]) <= 2e-8 * np.abs(gold[:, rest]) + 1e-11 * vs).all()
+    else:
+        assert (err <= 1e-9).all()
+        assert rel(s.get("pr"), o.get("pr")) < 1e-8
+        assert (np.abs(rows - gold) <= 2e-8 * np.abs(gold) + 1e-11 * vs).all()
+    print(case, "max rel diag diff vs oracle", err.max())

@@ -348,16 +348,164 @@ k_cho_rhs( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const
   }
 }
 
+// ---- transported scalars (U rows 3.., G rows 9.. of the same buffers): the scalar rows of the
+// advection flux (adv_damp2 Chorin.cpp:698-708, adv_damp4 :817-824), of the boundary integral
+// (:947-981) and of the source (:1003-1007), and the explicit update of those rows. The normal
+// velocities and the stabilisation speed are the flow flux's, recomputed here from the same inputs
+// by the same expressions, so that the velocity kernel stays as it is.
+constexpr int CHO_NSMAX = 4;
+template< bool DAMP4 >
+__device__ __forceinline__ void cho_vn( const double d[3], const double ua[3], const double ub[3],
+    const double ga[9], const double gb[9], const double dx[3], const ChoP& C, double& vnL, double& vnR, double& aw )
+{
+  double uL[3] = { ua[0], ua[1], ua[2] }, uR[3] = { ub[0], ub[1], ub[2] };
+  if (DAMP4) {
+    #pragma unroll
+    for (int c=0; c<3; ++c) {
+      double g1 = ga[c*3+0]*dx[0] + ga[c*3+1]*dx[1] + ga[c*3+2]*dx[2];
+      double g2 = gb[c*3+0]*dx[0] + gb[c*3+1]*dx[1] + gb[c*3+2]*dx[2];
+      double delta2 = uR[c] - uL[c];
+      double delta1 = 2.0 * g1 - delta2;
+      double delta3 = 2.0 * g2 - delta2;
+      double incL, incR;
+      vanleer< false >( delta1, delta2, delta3, incL, incR );
+      uL[c] += incL;
+      uR[c] -= incR;
+    }
+  }
+  vnL = uL[0]*d[0] + uL[1]*d[1] + uL[2]*d[2];
+  vnR = uR[0]*d[0] + uR[1]*d[1] + uR[2]*d[2];
+  aw = 0.0;
+  if (C.stab) aw = fabs( vnL + vnR ) / 2.0;
+  if (C.stab2) aw += C.stab2coef * fmax( fabs(vnL), fabs(vnR) );
+}
+
+// U, Un, Uout, R, S: velocity rows 0..2, scalar rows 3..3+ns-1 (stride NP); G: rows 9+3k.. hold the
+// gradient of scalar k (damp4). LAPROW: row of the Laplacian term in D (4: ChoCG, 3: LohCG).
+template< bool DAMP4, int LAPROW >
+__global__ void __launch_bounds__(NODE_THREADS)
+k_cho_srhs( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
+            const int* __restrict__ inc_q, const double* __restrict__ D, size_t nslot,
+            const double* __restrict__ U, const double* __restrict__ G, const double* __restrict__ SG,
+            const double* __restrict__ X, ChoP C, double dif, int ns,
+            const int* __restrict__ bslot, const int* __restrict__ bn_off,
+            const int* __restrict__ bn_face, const int* __restrict__ tri, const double* __restrict__ fn,
+            const double* __restrict__ S, const double* __restrict__ v, const double* __restrict__ vol,
+            const double* __restrict__ Un, double sdt, double* __restrict__ Uout, double* __restrict__ R )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = sl_base[slice];
+  int kmax = (int)((sl_base[slice+1] - base) >> 5);
+  double acc[CHO_NSMAX], sm[CHO_NSMAX], um[3], gm[9], xm[3];
+  #pragma unroll
+  for (int k=0; k<CHO_NSMAX; ++k) { acc[k] = 0.0; sm[k] = k < ns ? U[(3+k)*NP+p] : 0.0; }
+  #pragma unroll
+  for (int i=0; i<3; ++i) { um[i] = U[i*NP+p]; xm[i] = DAMP4 ? X[i*NP+p] : 0.0; }
+  #pragma unroll
+  for (int i=0; i<9; ++i) gm[i] = DAMP4 ? G[i*NP+p] : 0.0;
+  CHO_EDGE_LOOP_BEGIN
+    (void)a; (void)b;
+    double d[3] = { __ldg( D + sl ), __ldg( D + nslot + sl ), __ldg( D + 2*nslot + sl ) };
+    double df = __ldg( D + LAPROW*nslot + sl ) * dif;
+    double uo[3], go[9], xo[3];
+    #pragma unroll
+    for (int i=0; i<3; ++i) { uo[i] = __ldg( U + i*NP + nb ); xo[i] = DAMP4 ? __ldg( X + i*NP + nb ) : 0.0; }
+    #pragma unroll
+    for (int i=0; i<9; ++i) go[i] = DAMP4 ? __ldg( G + i*NP + nb ) : 0.0;
+    // end states in the edge's orientation (a = first node)
+    double ua[3], ub[3], ga[9], gb[9], dx[3], vnL, vnR, aw;
+    #pragma unroll
+    for (int i=0; i<3; ++i) { ua[i] = first ? um[i] : uo[i]; ub[i] = first ? uo[i] : um[i]; }
+    #pragma unroll
+    for (int i=0; i<9; ++i) { ga[i] = first ? gm[i] : go[i]; gb[i] = first ? go[i] : gm[i]; }
+    #pragma unroll
+    for (int i=0; i<3; ++i) dx[i] = first ? xo[i]-xm[i] : xm[i]-xo[i];
+    cho_vn< DAMP4 >( d, ua, ub, ga, gb, dx, C, vnL, vnR, aw );
+    #pragma unroll
+    for (int k=0; k<CHO_NSMAX; ++k) if (k < ns) {
+      double so = __ldg( U + (3+k)*NP + nb );
+      double sa = first ? sm[k] : so, sb = first ? so : sm[k];
+      double f;
+      if (DAMP4) {
+        double gsm[3], gso[3];
+        #pragma unroll
+        for (int j=0; j<3; ++j) { gsm[j] = SG[(3*k+j)*NP+p]; gso[j] = __ldg( SG + (3*k+j)*NP + nb ); }
+        double g1 = (first ? gsm[0] : gso[0])*dx[0] + (first ? gsm[1] : gso[1])*dx[1] + (first ? gsm[2] : gso[2])*dx[2];
+        double g2 = (first ? gso[0] : gsm[0])*dx[0] + (first ? gso[1] : gsm[1])*dx[1] + (first ? gso[2] : gsm[2])*dx[2];
+        double delta2 = sb - sa;
+        double delta1 = 2.0 * g1 - delta2;
+        double delta3 = 2.0 * g2 - delta2;
+        double incL, incR;
+        vanleer< false >( delta1, delta2, delta3, incL, incR );
+        double sL = sa + incL, sR = sb - incR;
+        f = sL*vnL + sR*vnR + aw*(sR-sL) - df*(sb-sa);
+      } else
+        f = sa*vnL + sb*vnR + (aw-df)*(sb-sa);
+      acc[k] = first ? acc[k] - f : acc[k] + f;
+    }
+  CHO_EDGE_LOOP_END
+  int bs = bslot[p];
+  if (bs >= 0)
+    for (int i=bn_off[bs]; i<bn_off[bs+1]; ++i) {
+      int f = bn_face[i] >> 2, kk = bn_face[i] & 3, N[3]; double n[3], vn[3];
+      cho_face( tri, fn, f, N, n );
+      #pragma unroll
+      for (int m=0; m<3; ++m) vn[m] = n[0]*U[N[m]] + n[1]*U[NP+N[m]] + n[2]*U[2*NP+N[m]];
+      #pragma unroll
+      for (int k=0; k<CHO_NSMAX; ++k) if (k < ns)
+        acc[k] += cho_w8( U[(3+k)*NP+N[0]]*vn[0], U[(3+k)*NP+N[1]]*vn[1], U[(3+k)*NP+N[2]]*vn[2], kk );
+    }
+  double vp = vol[p], vo = v[p];
+  #pragma unroll
+  for (int k=0; k<CHO_NSMAX; ++k) if (k < ns) {
+    double r = acc[k];
+    if (S) r -= S[(3+k)*NP+p] * vo;
+    if (R) R[(3+k)*NP+p] = r;
+    if (Uout) Uout[(3+k)*NP+p] = Un[(3+k)*NP+p] - sdt*r/vp;
+  }
+}
+
+// problems::point_src (Problems.cpp:764-823): the scalar of the listed nodes is held at a value
+__global__ void k_cho_pin( int n, const int* __restrict__ node, double val, double* __restrict__ s )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) s[ node[i] ] = val;
+}
+
+// NodeDiagnostics::precompute sums of the scalar rows: per scalar k [4k..4k+3] = L2 of the solution,
+// of the increment, and with an analytic solution the L2 and L1 error sums
+__global__ void __launch_bounds__(RED_THREADS)
+k_cho_sdiag( size_t npoin, size_t NP, int ns, int ncomp, const double* __restrict__ U, const double* __restrict__ Un,
+             const double* __restrict__ v, const double* __restrict__ an, double* __restrict__ part )
+{
+  double a[4*CHO_NSMAX];
+  #pragma unroll
+  for (int i=0; i<4*CHO_NSMAX; ++i) a[i] = 0.0;
+  for (size_t p = blockIdx.x*(size_t)blockDim.x + threadIdx.x; p < npoin; p += (size_t)gridDim.x*blockDim.x) {
+    double vp = v[p];
+    #pragma unroll
+    for (int k=0; k<CHO_NSMAX; ++k) if (k < ns) {
+      double u = U[(3+k)*NP+p], du = u - Un[(3+k)*NP+p];
+      a[4*k] += u*u*vp;
+      a[4*k+1] += du*du*vp;
+      if (an) { double e = u - an[p*ncomp+(ncomp-ns)+k]; a[4*k+2] += e*e*vp; a[4*k+3] += fabs(e)*vp; }
+    }
+  }
+  block_reduce< 4*CHO_NSMAX, false >( a, part );
+}
+
 // ---- BCs, ChoCG::BC (ChoCG.cpp:1340-1353) -> physics::dirbc (BC.cpp:29-72), symbc (:110-136),
 // noslipbc (:138-150), applied in this order by three launches on the same stream
-__global__ void k_cho_dirbc( int nd, size_t NP, const int* __restrict__ node, const int* __restrict__ mask,
+__global__ void k_cho_dirbc( int nd, size_t NP, int m, const int* __restrict__ node, const int* __restrict__ mask,
                              const double* __restrict__ val, double* __restrict__ U )
 {
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= nd) return;
   size_t p = node[i];
-  #pragma unroll
-  for (int c=0; c<3; ++c) if (mask[i*3+c]) U[c*NP+p] = val[i*3+c];
+  for (int c=0; c<m; ++c) if (mask[i*m+c]) U[c*NP+p] = val[i*m+c];
 }
 // one thread per distinct node: its side sets' normals are applied one after the other
 __global__ void k_cho_symbc( int ns, size_t NP, const int* __restrict__ node, const int* __restrict__ off,
@@ -434,7 +582,7 @@ constexpr int NCHODIAG = 16;
 __global__ void __launch_bounds__(RED_THREADS)
 k_cho_diag( size_t npoin, size_t NP, const double* __restrict__ U, const double* __restrict__ Un,
             const double* __restrict__ P, const double* __restrict__ dp, const double* __restrict__ v,
-            const double* __restrict__ anp, const double* __restrict__ anu, double* __restrict__ part )
+            const double* __restrict__ anp, const double* __restrict__ anu, int anstride, double* __restrict__ part )
 {
   double a[NCHODIAG];
   #pragma unroll
@@ -448,7 +596,7 @@ k_cho_diag( size_t npoin, size_t NP, const double* __restrict__ U, const double*
       double u = U[c*NP+p], du = u - Un[c*NP+p];
       a[1+c] += u*u*vp;
       a[5+c] += du*du*vp;
-      if (anu) { double e = u - anu[p*3+c]; a[10+c] += e*e*vp; a[13+c] += fabs(e)*vp; }
+      if (anu) { double e = u - anu[p*anstride+c]; a[10+c] += e*e*vp; a[13+c] += fabs(e)*vp; }
     }
     if (anp) { double e = pr - anp[p]; a[8] += e*e*vp; a[9] += fabs(e)*vp; }
   }
@@ -577,6 +725,8 @@ void cho_need_cg( xyst_ctx* c ) {
   if (c->cg_nrow != c->npoin) throw std::runtime_error( "ChoCG: upload the pressure Poisson matrix (one row per node) with xyst_csr_upload first" );
 }
 unsigned cho_grid( xyst_ctx* c ) { return nblk( c->nslice*32, NODE_THREADS ); }
+// rows of the velocity-like buffers: 3 velocities + transported scalars (ChoCG::m_u.nprop())
+int cho_rows( const xyst_ctx* c ) { return 3 + c->cns; }
 ChoP chop( const xyst_ctx* c ) { return ChoP{ c->chp.stab, c->chp.stab2, c->chp.stab2coef, c->chp.mu }; }
 
 void cho_set( xyst_ctx* c, const double* host, int m, double* soa ) {
@@ -596,7 +746,7 @@ void cho_get( xyst_ctx* c, const double* soa, int m, double* host ) {
 // ChoCG::BC on a velocity-like field: dirbc (only on the velocity itself), symbc, noslipbc
 void cho_bc( xyst_ctx* c, double* U, bool dir, bool noslip ) {
   auto s = c->stream;
-  if (dir && c->cb_nd) { k_cho_dirbc<<< nblk( c->cb_nd, 128 ), 128, 0, s >>>( (int)c->cb_nd, c->NP, c->cb_dnode.p, c->cb_dmask.p, c->cb_dval.p, U ); ++c->launches; }
+  if (dir && c->cb_nd) { k_cho_dirbc<<< nblk( c->cb_nd, 128 ), 128, 0, s >>>( (int)c->cb_nd, c->NP, cho_rows( c ), c->cb_dnode.p, c->cb_dmask.p, c->cb_dval.p, U ); ++c->launches; }
   if (c->cb_ns) { k_cho_symbc<<< nblk( c->cb_ns, 128 ), 128, 0, s >>>( (int)c->cb_ns, c->NP, c->cb_snode.p, c->cb_soff.p, c->cb_snorm.p, U ); ++c->launches; }
   if (noslip && c->cb_nn) { k_cho_noslip<<< nblk( c->cb_nn, 128 ), 128, 0, s >>>( (int)c->cb_nn, c->NP, c->cb_nnode.p, U ); ++c->launches; }
   CK( cudaGetLastError() );
@@ -605,8 +755,14 @@ void cho_vgrad( xyst_ctx* c ) {
   ProfScope ps( c, "cho_vgrad" );
   k_cho_grad< 3 ><<< cho_grid( c ), NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p,
     c->D.p, c->nslot, c->cU, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p, c->cVg.p ); ++c->launches;
+  for (int k=0; k<c->cns; ++k) {                    // chorin::vgrad covers the transported scalars (Chorin.cpp:230)
+    k_cho_grad< 1 ><<< cho_grid( c ), NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p,
+      c->D.p, c->nslot, c->cU + (3+k)*c->NP, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p,
+      c->cVg.p + (size_t)(9+3*k)*c->NP ); ++c->launches;
+  }
   CK( cudaGetLastError() );
   soa_halo( c, c->cVg.p, 9 );                       // comvgrad :949-970 (each part already over the full volume)
+  for (int k=0; k<c->cns; ++k) soa_halo( c, c->cVg.p + (size_t)(9+3*k)*c->NP, 3 );
 }
 void cho_rhs( xyst_ctx* c, const double* Un, double sdt, double* Uout, double* R ) {
   if (c->loh) throw std::runtime_error( "context holds a LohCG mesh: use xyst_lohcg_rhs / xyst_lohcg_stage" );
@@ -622,8 +778,24 @@ void cho_rhs( xyst_ctx* c, const double* Un, double sdt, double* Uout, double* R
       c->nslot, c->cU, c->cP.p, c->cVg.p, c->X.p, chop( c ), c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p,
       c->cS.p, c->v.p, c->vol.p, Un, sdt, Uout, R );
   ++c->launches;
+  if (c->cns) {
+    if (c->chp.flux == 1)
+      k_cho_srhs< true, 4 ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p,
+        c->nslot, c->cU, c->cVg.p, c->cVg.p + 9*c->NP, c->X.p, chop( c ), c->cdif, c->cns, c->bslot.p, c->bn_off.p,
+        c->bn_face.p, c->tri.p, c->fn.p, c->cS.p, c->v.p, c->vol.p, Un, sdt, Uout, R );
+    else
+      k_cho_srhs< false, 4 ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p,
+        c->nslot, c->cU, c->cVg.p, c->cVg.p + 9*c->NP, c->X.p, chop( c ), c->cdif, c->cns, c->bslot.p, c->bn_off.p,
+        c->bn_face.p, c->tri.p, c->fn.p, c->cS.p, c->v.p, c->vol.p, Un, sdt, Uout, R );
+    ++c->launches;
+  }
   CK( cudaGetLastError() );
-  if (Uout) soa_halo_update( c, R, 3, Un, sdt, Uout ); else soa_halo( c, R, 3 );      // comrhs :1505-1527
+  if (Uout) soa_halo_update( c, R, cho_rows( c ), Un, sdt, Uout ); else soa_halo( c, R, cho_rows( c ) );      // comrhs :1505-1527
+}
+// problems::point_src through ChoCG::pred :1655-1657 / LohCG::pred :1615-1617: first scalar row
+void cho_pin( xyst_ctx* c ) {
+  if (!c->ncpin) return;
+  k_cho_pin<<< nblk( c->ncpin, 128 ), 128, 0, c->stream >>>( (int)c->ncpin, c->cpin.p, c->cpin_val, c->cU + 3*c->NP ); ++c->launches;
 }
 // ConjugateGradients::init :336-428 + apply :451-505 + r :508-556 for one partition: Dirichlet rows
 // (scalar row ids of the selected solver) with values, optional Neumann vector, applied to cg_b and,
@@ -682,6 +854,7 @@ int xyst_chocg_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const do
   c->cVg.alloc( 9*NP ); CK( cudaMemsetAsync( c->cVg.p, 0, 9*NP*sizeof(double), c->stream ) );
   c->cS.release();
   c->cU = c->cUa.p; c->cUn = c->cUb.p; c->cUx = c->cUc.p;
+  c->cns = 0; c->cdif = 0.0; c->ncpin = 0;
   c->cb_nd = c->cb_ns = c->cb_nn = 0;
   CK( cudaStreamSynchronize( c->stream ) );
   API_END
@@ -696,10 +869,11 @@ int xyst_chocg_bc_upload( xyst_ctx* c, size_t ndir, const size_t* dirnodes, cons
   cho_need( c );
   auto s = c->stream;
   auto chk = [&]( size_t id ){ if (id >= c->npoin) throw std::runtime_error( "BC node id out of range" ); return (int)id; };
-  { std::vector< int > nd( ndir ), mk( ndir*3 ); std::vector< double > vl( ndir*3 );
+  { size_t m = (size_t)cho_rows( c );
+    std::vector< int > nd( ndir ), mk( ndir*m ); std::vector< double > vl( ndir*m );
     for (size_t i=0; i<ndir; ++i) { nd[i] = chk( dirnodes[i] );
-      for (int k=0; k<3; ++k) { mk[i*3+k] = dirmask[i*3+k]; vl[i*3+k] = dirval ? dirval[i*3+k] : 0.0;
-        if (mk[i*3+k] == 2 && !dirval) mk[i*3+k] = 0; } }             // BC.cpp:66: mask 2 needs a value list
+      for (size_t k=0; k<m; ++k) { mk[i*m+k] = dirmask[i*m+k]; vl[i*m+k] = dirval ? dirval[i*m+k] : 0.0;
+        if (mk[i*m+k] == 2 && !dirval) mk[i*m+k] = 0; } }             // BC.cpp:66: mask 2 needs a value list
     c->cb_dnode.upload( nd, s ); c->cb_dmask.upload( mk, s ); c->cb_dval.upload( vl, s ); c->cb_nd = ndir; }
   { // group the (node, normal) pairs by node, keeping the order in which a node's pairs arrive
     std::vector< int > first( c->npoin, -1 ), nodes, cnt;
@@ -719,8 +893,55 @@ int xyst_chocg_bc_upload( xyst_ctx* c, size_t ndir, const size_t* dirnodes, cons
   API_END
 }
 
-int xyst_chocg_set_u( xyst_ctx* c, const double* u ) { API_BEGIN CK( cudaSetDevice( c->device ) ); cho_need( c ); cho_set( c, u, 3, c->cU ); API_END }
-int xyst_chocg_get_u( xyst_ctx* c, double* u ) { API_BEGIN CK( cudaSetDevice( c->device ) ); cho_need( c ); cho_get( c, c->cU, 3, u ); API_END }
+int xyst_chocg_set_u( xyst_ctx* c, const double* u ) { API_BEGIN CK( cudaSetDevice( c->device ) ); cho_need( c ); cho_set( c, u, cho_rows( c ), c->cU ); API_END }
+int xyst_chocg_get_u( xyst_ctx* c, double* u ) { API_BEGIN CK( cudaSetDevice( c->device ) ); cho_need( c ); cho_get( c, c->cU, cho_rows( c ), u ); API_END }
+
+// Transported scalars next to the three velocity components (ChoCG::m_u with problem_ncomp > 3): call after
+// the mesh upload and before any state / BC upload. The velocity-like buffers get ns more rows.
+int xyst_chocg_scalars( xyst_ctx* c, int ns, double diffusivity )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  cho_need( c );
+  if (c->loh) throw std::runtime_error( "context holds a LohCG mesh: use xyst_lohcg_scalars" );
+  if (ns < 0 || ns > CHO_NSMAX) throw std::runtime_error( "xyst_chocg_scalars: 0..4 transported scalars" );
+  size_t NP = c->NP, m = 3 + (size_t)ns;
+  for (auto* b : { &c->cUa, &c->cUb, &c->cUc, &c->cR }) { b->alloc( m*NP ); CK( cudaMemsetAsync( b->p, 0, m*NP*sizeof(double), c->stream ) ); }
+  c->cVg.alloc( 3*m*NP ); CK( cudaMemsetAsync( c->cVg.p, 0, 3*m*NP*sizeof(double), c->stream ) );
+  c->cS.release();
+  c->cU = c->cUa.p; c->cUn = c->cUb.p; c->cUx = c->cUc.p;
+  c->cns = ns; c->cdif = diffusivity; c->ncpin = 0;
+  c->cb_nd = 0;
+  CK( cudaStreamSynchronize( c->stream ) );
+  API_END
+}
+
+// new values for the Dirichlet nodes of the last xyst_chocg_bc_upload / xyst_lohcg_bc_upload
+// (time-dependent physics::dirbc, BC.cpp:57-66): [ndir][rows]
+int xyst_chocg_dirbc_values( xyst_ctx* c, const double* dirval )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  cho_need( c );
+  if (!dirval) throw std::runtime_error( "null argument" );
+  if (c->loh) { if (c->lb_nd) CK( cudaMemcpyAsync( c->lb_dval.p, dirval, c->lb_nd*(size_t)(4+c->cns)*sizeof(double), cudaMemcpyHostToDevice, c->stream ) ); }
+  else if (c->cb_nd) CK( cudaMemcpyAsync( c->cb_dval.p, dirval, c->cb_nd*(size_t)cho_rows( c )*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+  CK( cudaStreamSynchronize( c->stream ) );
+  API_END
+}
+
+// problems::point_src: nodes whose (first) transported scalar is set to value after every stage's update
+int xyst_chocg_pin( xyst_ctx* c, size_t n, const size_t* nodes, double value )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  cho_need( c );
+  if (!c->cns) throw std::runtime_error( "xyst_chocg_pin: no transported scalar in this context" );
+  std::vector< int > h( n );
+  for (size_t i=0; i<n; ++i) { if (nodes[i] >= c->npoin) throw std::runtime_error( "point-source node id out of range" ); h[i] = (int)nodes[i]; }
+  c->cpin.upload( h, c->stream ); c->ncpin = n; c->cpin_val = value;
+  API_END
+}
 int xyst_chocg_set_p( xyst_ctx* c, const double* p ) { API_BEGIN CK( cudaSetDevice( c->device ) ); cho_need( c ); cho_set( c, p, 1, c->cP.p ); API_END }
 
 int xyst_chocg_get( xyst_ctx* c, const char* what, double* out )
@@ -734,10 +955,10 @@ int xyst_chocg_get( xyst_ctx* c, const char* what, double* out )
   else if (w == "sgrad") cho_get( c, c->cSg.p, 3, out );
   else if (w == "pgrad") cho_get( c, c->cPg.p, 3, out );
   else if (w == "flux") cho_get( c, c->cFl.p, 3, out );
-  else if (w == "rhs") cho_get( c, c->cR.p, 3, out );
-  else if (w == "vgrad") cho_get( c, c->cVg.p, 9, out );
-  else if (w == "un") cho_get( c, c->cUn, 3, out );
-  else if (w == "u") cho_get( c, c->cU, 3, out );
+  else if (w == "rhs") cho_get( c, c->cR.p, cho_rows( c ), out );
+  else if (w == "vgrad") cho_get( c, c->cVg.p, 3*cho_rows( c ), out );
+  else if (w == "un") cho_get( c, c->cUn, cho_rows( c ), out );
+  else if (w == "u") cho_get( c, c->cU, cho_rows( c ), out );
   else if (w == "dp") { cho_need_cg( c ); CK( cudaMemcpyAsync( out, c->cg_x.p, c->npoin*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) ); CK( cudaStreamSynchronize( c->stream ) ); }
   else throw std::runtime_error( "xyst_chocg_get: unknown field " + w );
   API_END
@@ -808,9 +1029,9 @@ int xyst_chocg_src( xyst_ctx* c, const double* S )
   CK( cudaSetDevice( c->device ) );
   cho_need( c );
   if (!S) { c->cS.release(); return 0; }
-  c->cS.alloc( 3*c->NP );
-  CK( cudaMemsetAsync( c->cS.p, 0, 3*c->NP*sizeof(double), c->stream ) );
-  cho_set( c, S, 3, c->cS.p );
+  size_t m = (size_t)cho_rows( c );
+  if (c->cS.n != m*c->NP) { c->cS.alloc( m*c->NP ); CK( cudaMemsetAsync( c->cS.p, 0, m*c->NP*sizeof(double), c->stream ) ); }
+  cho_set( c, S, (int)m, c->cS.p );
   API_END
 }
 
@@ -832,6 +1053,7 @@ int xyst_chocg_stage( xyst_ctx* c, int stage, double rkcoef_, double dt )
   // un = u at stage 0 without a copy: the three velocity buffers rotate
   if (stage == 0) { double* old_un = c->cUn; c->cUn = c->cU; cho_rhs( c, c->cUn, rkcoef_*dt, c->cUx, nullptr ); c->cU = c->cUx; c->cUx = old_un; }
   else { cho_rhs( c, c->cUn, rkcoef_*dt, c->cUx, nullptr ); std::swap( c->cU, c->cUx ); }
+  cho_pin( c );
   cho_bc( c, c->cU, true, true );
   if (c->chp.flux == 1) cho_vgrad( c );            // ChoCG::corr :1677
   API_END
@@ -862,6 +1084,7 @@ int xyst_chocg_minit( xyst_ctx* c, size_t nbc, const size_t* bcrows, int pc )
   CK( cudaSetDevice( c->device ) );
   cho_need( c );
   if (c->loh) throw std::runtime_error( "context holds a LohCG mesh" );
+  if (c->cns) throw std::runtime_error( "ChoCG: the semi-implicit momentum solve with transported scalars is not implemented" );
   if (c->cg_nrow != c->npoin*3 || c->cg_ncomp != 3)
     throw std::runtime_error( "ChoCG: select the momentum matrix (3 scalar rows per node) with xyst_cg_select / xyst_csr_upload first" );
   k_cho_mrhs<<< nblk( c->npoin*3, 256 ), 256, 0, c->stream >>>( c->npoin, c->NP, c->cR.p, c->cg_b.p ); ++c->launches;
@@ -933,15 +1156,23 @@ int xyst_chocg_diag( xyst_ctx* c, const double* an_p, const double* an_u, double
   static_assert( NCHODIAG <= NDIAG, "reduction scratch too small" );
   DevBuf< double > dp, du;
   if (an_p) dp.upload( std::vector< double >( an_p, an_p + c->npoin ), c->stream );
-  if (an_u) du.upload( std::vector< double >( an_u, an_u + c->npoin*3 ), c->stream );
+  if (an_u) du.upload( std::vector< double >( an_u, an_u + c->npoin*(size_t)cho_rows( c ) ), c->stream );
   int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( c->npoin, RED_THREADS ) );
   double* fin = c->red.p + (size_t)RED_BLOCKS*NDIAG;
-  k_cho_diag<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->cU, c->cUn, c->cP.p, c->cg_x.p, c->v.p, dp.p, du.p, c->red.p );
+  k_cho_diag<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->cU, c->cUn, c->cP.p, c->cg_x.p, c->v.p, dp.p, du.p, cho_rows( c ), c->red.p );
   k_reduce_final< NCHODIAG, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, fin );
   c->launches += 2;
   CK( cudaMemcpyAsync( c->red_host, fin, NCHODIAG*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
   CK( cudaStreamSynchronize( c->stream ) );
   for (int i=0; i<NCHODIAG; ++i) out[i] = c->red_host[i];
+  if (c->cns) {            // scalar rows: out[16+4k..] = L2 solution, L2 increment, L2 error, L1 error sums of scalar k
+    k_cho_sdiag<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->cns, cho_rows( c ), c->cU, c->cUn, c->v.p, du.p, c->red.p );
+    k_reduce_final< 4*CHO_NSMAX, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, fin );
+    c->launches += 2;
+    CK( cudaMemcpyAsync( c->red_host, fin, 4*CHO_NSMAX*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+    CK( cudaStreamSynchronize( c->stream ) );
+    for (int i=0; i<4*c->cns; ++i) out[NCHODIAG+i] = c->red_host[i];
+  }
   API_END
 }
 

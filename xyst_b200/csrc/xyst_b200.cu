@@ -230,6 +230,8 @@ struct xyst_ctx : CgState {
   xyst_chocg_params chp{};
   DevBuf< double > cUa, cUb, cUc, cP, cDiv, cSg, cPg, cVg, cFl, cR, cS;
   double *cU = nullptr, *cUn = nullptr, *cUx = nullptr;   // current, time level n, scratch (point into cUa/b/c)
+  int cns = 0; double cdif = 0.0;          // transported scalars of ChoCG/LohCG: rows after the velocity rows; diffusivity
+  DevBuf< int > cpin; size_t ncpin = 0; double cpin_val = 1.0;   // point-source nodes (problems::point_src)
   DevBuf< int > cb_dnode, cb_dmask, cb_snode, cb_soff, cb_nnode;
   DevBuf< double > cb_dval, cb_snorm;
   size_t cb_nd = 0, cb_ns = 0, cb_nn = 0;

@@ -180,8 +180,9 @@ void RieCG::choPressureSetup()
 void RieCG::choMomRows()
 {
   std::set< std::size_t > rows;
-  for (std::size_t i=0; i<m_dirbcmasks.size()/4; ++i)
-    for (std::size_t c=0; c<3; ++c) if (m_dirbcmasks[i*4+1+c]) rows.insert( m_dirbcmasks[i*4]*3+c );
+  const auto nm = m_cfg.ncomp + 1;
+  for (std::size_t i=0; i<m_dirbcmasks.size()/nm; ++i)
+    for (std::size_t c=0; c<3; ++c) if (m_dirbcmasks[i*nm+1+c]) rows.insert( m_dirbcmasks[i*nm]*3+c );
   for (auto p : m_noslipbcnodes) for (std::size_t c=0; c<3; ++c) rows.insert( p*3+c );
   if (m_nranks > 1) {                     // union over the partitions sharing a node, as for the pressure rows
     auto shared = m_disc.sharedNodes();
@@ -259,6 +260,35 @@ void RieCG::choLhs()
   ck( xyst_cg_select( m_ctx, 0 ) );
 }
 
+//! Values of physics::dirbc (BC.cpp:29-72) at time t for the nodes of m_dirbcmasks: mask 1 = the initial
+//! condition evaluated at the BC time, mask 2 = the configured value; [node][ncomp]
+void RieCG::choDirvals( real t, std::vector< real >& dv ) const
+{
+  const auto ncomp = m_cfg.ncomp;
+  const auto& co = m_disc.Coord();
+  auto nd = m_dirbcmasks.size()/(ncomp+1);
+  dv.assign( nd*ncomp, 0.0 );
+  auto ic = problems::IC( m_cfg );
+  for (std::size_t i=0; i<nd; ++i) {
+    auto p = m_dirbcmasks[i*(ncomp+1)];
+    auto u = ic( co[0][p], co[1][p], co[2][p], t );
+    for (std::size_t c=0; c<ncomp; ++c) {
+      auto mask = m_dirbcmasks[i*(ncomp+1)+1+c];
+      if (mask == 1) dv[i*ncomp+c] = u[c];
+      else if (mask == 2 && !m_dirbcval.empty()) dv[i*ncomp+c] = m_dirbcval[i*(ncomp+1)+1+c];
+    }
+  }
+}
+
+//! Dirichlet values of the next BC application on the device (time-dependent initial conditions)
+void RieCG::choBCtime( real t )
+{
+  if (m_dirbcmasks.empty()) return;
+  std::vector< real > dv;
+  choDirvals( t, dv );
+  ck( xyst_chocg_dirbc_values( m_ctx, dv.data() ) );
+}
+
 //! Device upload and the start-up sequence of ChoCG::merge :816-837 onwards: make the initial
 //! velocity divergence-free and compute the initial pressure
 void RieCG::choSetup()
@@ -276,21 +306,26 @@ void RieCG::choSetup()
   prm.stab = m_cfg.stab; prm.stab2 = m_cfg.stab2; prm.stab2coef = m_cfg.stab2coef; prm.mu = m_cfg.mu;
   ck( xyst_chocg_mesh_upload( m_ctx, np, x.data(), y.data(), z.data(), nsup, se, si, m_triinpoel.size()/3,
                               m_triinpoel.data(), m_disc.Vol().data(), m_disc.V().data(), &prm ) );
+  const auto ncomp = m_cfg.ncomp;
+  if (ncomp < 3 || ncomp > 7) throw std::runtime_error( "ChoCG: three velocity components + up to four transported scalars" );
+  if (ncomp > 3) {
+    if (m_cfg.theta > std::numeric_limits< real >::epsilon())
+      throw std::runtime_error( "ChoCG: the semi-implicit momentum solve with transported scalars is not implemented" );
+    ck( xyst_chocg_scalars( m_ctx, static_cast< int >( ncomp-3 ), m_cfg.dif ) );
+  }
   // physics::dirbc (BC.cpp:29-72): mask 1 = value of the initial condition, 2 = configured value
-  auto nd = m_dirbcmasks.size()/4;
-  std::vector< std::size_t > dn( nd ); std::vector< int > dm( nd*3 ); std::vector< real > dv( nd*3, 0.0 );
-  auto ic = problems::IC( m_cfg );
+  auto nd = m_dirbcmasks.size()/(ncomp+1);
+  std::vector< std::size_t > dn( nd ); std::vector< int > dm( nd*ncomp ); std::vector< real > dv;
   for (std::size_t i=0; i<nd; ++i) {
-    auto p = dn[i] = m_dirbcmasks[i*4];
-    auto u = ic( x[p], y[p], z[p], m_disc.T() );
-    for (std::size_t c=0; c<3; ++c) {
-      auto mask = static_cast< int >( m_dirbcmasks[i*4+1+c] );
-      if (mask == 1) dv[i*3+c] = u[c];
-      else if (mask == 2 && !m_dirbcval.empty()) dv[i*3+c] = m_dirbcval[i*4+1+c];
-      else mask = 0;
-      dm[i*3+c] = mask;
+    dn[i] = m_dirbcmasks[i*(ncomp+1)];
+    for (std::size_t c=0; c<ncomp; ++c) {
+      auto mask = static_cast< int >( m_dirbcmasks[i*(ncomp+1)+1+c] );
+      if (mask == 2 && m_dirbcval.empty()) mask = 0;
+      if (mask != 1 && mask != 2) mask = 0;
+      dm[i*ncomp+c] = mask;
     }
   }
+  choDirvals( m_disc.T(), dv );
   ck( xyst_chocg_bc_upload( m_ctx, nd, dn.data(), dm.data(), dv.data(), m_symbcnodes.size(), m_symbcnodes.data(),
                             m_symbcnorms.data(), m_noslipbcnodes.size(), m_noslipbcnodes.data() ) );
   ck( xyst_csr_upload( m_ctx, np, 1, m_plhs_ia.data(), m_plhs_ja.data(), m_plhs_a.data() ) );
@@ -325,7 +360,10 @@ void RieCG::choPsolve()
 
 void RieCG::choPsolved( std::vector< real >* diagrow )
 {
-  if (m_np != 1) ck( xyst_chocg_project( m_ctx, m_np > 1 ? m_disc.Dt() : 1.0 ) );
+  if (m_np != 1) {
+    if (m_timedep) choBCtime( m_disc.T() + m_disc.Dt() );          // BC( m_u, d->T() + d->Dt() ) :1215
+    ck( xyst_chocg_project( m_ctx, m_np > 1 ? m_disc.Dt() : 1.0 ) );
+  }
   if (m_initial) {
     if (m_cfg.nstep == 1) {                  // test first Poisson solve only (:1223-1229)
       ck( xyst_chocg_pressure_update( m_ctx, 0 ) );
@@ -369,10 +407,28 @@ bool RieCG::choStep( std::vector< real >* diagrow )
   m_disc.setdt( mindt );
   const bool implicit = m_cfg.theta > eps;
   if (implicit) choLhs();                    // advance :1414-1431
+  // problems::point_src (ChoCG::pred :1655-1657): active for all stages of a step that starts at or after
+  // the release time
+  if (m_cfg.problem == "point_src" && m_cfg.ncomp > 3 && m_cfg.src_radius >= 0.0 && !m_pinned &&
+      !(m_disc.T() < m_cfg.src_release_time)) {
+    const auto& co = m_disc.Coord();
+    std::vector< std::size_t > nodes;
+    for (std::size_t i=0; i<co[0].size(); ++i) {
+      auto rx = m_cfg.src_location[0] - co[0][i], ry = m_cfg.src_location[1] - co[1][i], rz = m_cfg.src_location[2] - co[2][i];
+      if (rx*rx + ry*ry + rz*rz < m_cfg.src_radius*m_cfg.src_radius) nodes.push_back( i );
+    }
+    ck( xyst_chocg_pin( m_ctx, nodes.size(), nodes.data(), 1.0 ) );
+    m_pinned = true;
+  }
+  if (m_timedep) {                           // chorin::rhs( ..., d->T(), ... ) :1489: the source at the step's time level
+    evalSrc( m_disc.T() );
+    if (!m_src.empty()) ck( xyst_chocg_src( m_ctx, m_src.data() ) );
+  }
   for (std::uint64_t s=0; s<m_cfg.rk; ++s)
-    if (!implicit || s+1 < m_cfg.rk)         // solve :1555-1572
+    if (!implicit || s+1 < m_cfg.rk) {       // solve :1555-1572
+      if (m_timedep) choBCtime( m_disc.T() + rkcoef[m_cfg.rk-1][s] * m_disc.Dt() );    // pred :1660
       ck( xyst_chocg_stage( m_ctx, static_cast< int >( s ), rkcoef[m_cfg.rk-1][s], m_disc.Dt() ) );
-    else {                                   // semi-implicit momentum solve at the last stage, :1574-1645
+    } else {                                   // semi-implicit momentum solve at the last stage, :1574-1645
       ck( xyst_chocg_rhs( m_ctx ) );
       ck( xyst_cg_select( m_ctx, 1 ) );
       ck( xyst_chocg_minit( m_ctx, m_mbcrows.size(), m_mbcrows.data(), m_cfg.mom_pc == "jacobi" ? 1 : 0 ) );
@@ -397,26 +453,32 @@ std::vector< real > RieCG::choDiag()
   if ((m_disc.It()+1) % m_cfg.diag_iter) return {};
   const auto& co = m_disc.Coord();
   auto np = co[0].size();
+  const auto nc = m_cfg.ncomp;
   std::vector< real > anu;
   bool psol = !m_psol.empty();
   auto sol = problems::SOL( m_cfg );
   if (sol && !psol) {
-    anu.resize( np*3 );
+    anu.resize( np*nc );
     for (std::size_t i=0; i<np; ++i) { auto s = sol( co[0][i], co[1][i], co[2][i], m_disc.T()+m_disc.Dt() );
-      for (std::size_t c=0; c<3; ++c) anu[i*3+c] = s[c]; }
+      for (std::size_t c=0; c<nc; ++c) anu[i*nc+c] = s[c]; }
   }
-  real d[16];
+  real d[32];
   ck( xyst_chocg_diag( m_ctx, psol ? m_psol.data() : nullptr, anu.empty() ? nullptr : anu.data(), d ) );
-  if (m_nranks > 1) { std::vector< real > t( d, d+16 ); m_allreduce( 0, t ); std::copy( t.begin(), t.end(), d ); }
-  std::size_t ncomp = psol ? 0 : 3;
+  if (m_nranks > 1) for (std::size_t o=0; o<16+4*(nc-3); o+=16) {
+    std::vector< real > t( d+o, d+std::min< std::size_t >( o+16, 16+4*(nc-3) ) ); m_allreduce( 0, t ); std::copy( t.begin(), t.end(), d+o ); }
+  // sums of component c (0 = pressure, 1..3 velocity, 4.. scalars): [0] L2 solution [1] L2 increment [2] L2 error [3] L1 error
+  auto sum = [&]( std::size_t k, std::size_t c ) -> real {
+    if (c > 3) return d[16 + 4*(c-4) + k];
+    return k == 0 ? d[c] : k == 1 ? d[4+c] : k == 2 ? d[9+c] : d[12+c]; };
+  std::size_t ncomp = psol ? 0 : nc;
   auto mv = m_disc.MeshVol();
   std::vector< real > row{ static_cast< real >( m_disc.It() ), m_disc.T(), m_disc.Dt() };
-  for (std::size_t i=0; i<=ncomp; ++i) row.push_back( std::sqrt( d[i] / mv ) );
-  for (std::size_t i=0; i<=ncomp; ++i) row.push_back( std::sqrt( d[4+i] / mv ) );
+  for (std::size_t i=0; i<=ncomp; ++i) row.push_back( std::sqrt( sum( 0, i ) / mv ) );
+  for (std::size_t i=0; i<=ncomp; ++i) row.push_back( std::sqrt( sum( 1, i ) / mv ) );
   if (psol) { row.push_back( std::sqrt( d[8] / mv ) ); row.push_back( d[9] / mv ); }
   if (!anu.empty()) {
-    for (std::size_t i=0; i<3; ++i) row.push_back( std::sqrt( d[10+i] / mv ) );
-    for (std::size_t i=0; i<3; ++i) row.push_back( d[13+i] / mv );
+    for (std::size_t i=1; i<=ncomp; ++i) row.push_back( std::sqrt( sum( 2, i ) / mv ) );
+    for (std::size_t i=1; i<=ncomp; ++i) row.push_back( sum( 3, i ) / mv );
   }
   return row;
 }

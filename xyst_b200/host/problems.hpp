@@ -23,6 +23,38 @@ inline real totalenergy( real g, real r, real u, real v, real w, real p ) {
   return p / (g-1.0) + 0.5 * r * (u*u + v*v + w*w);
 }
 
+//! scalar of problems::slot_cyl (Problems.cpp:549-629): a cone, a hump and a slotted cylinder carried by the
+//! solid-body rotation about (0.5,0.5); 0 elsewhere
+inline real slot_cyl_scalar( real x, real y, real t ) {
+  using std::sin; using std::cos; using std::sqrt;
+  real s = 0.0;
+  const real R0 = 0.15;
+  auto axdist = []( real x0, real y0 ){ return sqrt( (x0-0.5)*(x0-0.5) + (y0-0.5)*(y0-0.5) ); };
+  real r = axdist( 0.5, 0.25 );                    // cone
+  real kx = 0.5 + r*sin( t ), ky = 0.5 - r*cos( t );
+  r = axdist( 0.25, 0.5 );                         // hump
+  real hx = 0.5 + r*sin( t-M_PI/2.0 ), hy = 0.5 - r*cos( t-M_PI/2.0 );
+  r = axdist( 0.5, 0.75 );                         // slotted cylinder
+  real cx = 0.5 + r*sin( t+M_PI ), cy = 0.5 - r*cos( t+M_PI );
+  // corner points of the slot, rotated with the flow
+  real ax = 0.525, ay = cy - r*cos( std::asin( 0.025/r ) ), bx = 0.525, by = 0.8, gx = 0.475, gy = 0.8;
+  auto rotx = [t]( real px, real py ){ return 0.5 + cos(t)*(px-0.5) - sin(t)*(py-0.5); };
+  auto roty = [t]( real px, real py ){ return 0.5 + sin(t)*(px-0.5) + cos(t)*(py-0.5); };
+  real rax = rotx( ax, ay ), ray = roty( ax, ay ), rbx = rotx( bx, by ), rby = roty( bx, by ),
+       rgx = rotx( gx, gy ), rgy = roty( gx, gy );
+  real v1x = rbx-rax, v1y = rby-ray, v2x = rgx-rbx, v2y = rgy-rby;
+  real v1 = sqrt( v1x*v1x + v1y*v1y ), v2 = sqrt( v2x*v2x + v2y*v2y );
+  r = sqrt( (x-kx)*(x-kx) + (y-ky)*(y-ky) ) / R0;
+  if (r < 1.0) s = 0.6*(1.0-r);
+  r = sqrt( (x-hx)*(x-hx) + (y-hy)*(y-hy) ) / R0;
+  if (r < 1.0) s = 0.2*(1.0 + cos( M_PI*std::min( r, 1.0 ) ));
+  r = sqrt( (x-cx)*(x-cx) + (y-cy)*(y-cy) ) / R0;
+  real d1 = (v1x*(y-ray) - (x-rax)*v1y) / v1;      // signed distances from the two slot sides
+  real d2 = (v2x*(y-rby) - (x-rbx)*v2y) / v2;
+  if (r < 1.0 && (d1 > 0.05 || d1 < 0.0 || d2 < 0.0)) s = 0.6;
+  return s;
+}
+
 inline Fn IC( const Config& cfg ) {
   const real g = cfg.gamma;
   if (cfg.solver == "lohcg") {                  // unknowns (p,u,v,w): entries 0..3
@@ -39,6 +71,10 @@ inline Fn IC( const Config& cfg ) {
       return [vel]( real, real, real, real ) -> State { return {{ vel[0], vel[1], vel[2], 0, 0 }}; }; }
     if (p.find( "poisson" ) != std::string::npos)
       return []( real, real, real, real ) -> State { return {{ 0, 0, 0, 0, 0 }}; };
+    if (p == "point_src") { const auto vel = cfg.ic_velocity;                  // userdef::ic :44-52 (+ scalar 0)
+      return [vel]( real, real, real, real ) -> State { return {{ vel[0], vel[1], vel[2], 0, 0 }}; }; }
+    if (p == "slot_cyl")                                                       // slot_cyl::ic :531-537: (u,v,w,s)
+      return []( real x, real y, real, real t ) -> State { return {{ 0.5 - y, x - 0.5, 0.0, slot_cyl_scalar( x, y, t ), 0 }}; };
     if (p == "poiseuille") { const real mu = cfg.mu;                           // poiseuille::ic :999-1026
       return [mu]( real, real y, real, real ) -> State {
         auto dpdx = -0.12;
@@ -47,35 +83,11 @@ inline Fn IC( const Config& cfg ) {
   }
   if (cfg.problem == "slot_cyl")                // slot_cyl::ic, Problems.cpp:513-634: solid-body rotation about
     return [g]( real x, real y, real, real t ) -> State {        // (0.5,0.5) carrying a cone, a hump and a slotted cylinder
-      using std::sin; using std::cos; using std::sqrt;
       State u{};
       const real p0 = 1.0;
       u[0] = 1.0; u[1] = u[0] * (0.5 - y); u[2] = u[0] * (x - 0.5); u[3] = 0.0;
       u[4] = totalenergy( g, u[0], u[1]/u[0], u[2]/u[0], u[3]/u[0], p0 );
-      const real R0 = 0.15;
-      auto axdist = []( real x0, real y0 ){ return sqrt( (x0-0.5)*(x0-0.5) + (y0-0.5)*(y0-0.5) ); };
-      real r = axdist( 0.5, 0.25 );                    // cone
-      real kx = 0.5 + r*sin( t ), ky = 0.5 - r*cos( t );
-      r = axdist( 0.25, 0.5 );                         // hump
-      real hx = 0.5 + r*sin( t-M_PI/2.0 ), hy = 0.5 - r*cos( t-M_PI/2.0 );
-      r = axdist( 0.5, 0.75 );                         // slotted cylinder
-      real cx = 0.5 + r*sin( t+M_PI ), cy = 0.5 - r*cos( t+M_PI );
-      // corner points of the slot, rotated with the flow
-      real ax = 0.525, ay = cy - r*cos( std::asin( 0.025/r ) ), bx = 0.525, by = 0.8, gx = 0.475, gy = 0.8;
-      auto rotx = [t]( real px, real py ){ return 0.5 + cos(t)*(px-0.5) - sin(t)*(py-0.5); };
-      auto roty = [t]( real px, real py ){ return 0.5 + sin(t)*(px-0.5) + cos(t)*(py-0.5); };
-      real rax = rotx( ax, ay ), ray = roty( ax, ay ), rbx = rotx( bx, by ), rby = roty( bx, by ),
-           rgx = rotx( gx, gy ), rgy = roty( gx, gy );
-      real v1x = rbx-rax, v1y = rby-ray, v2x = rgx-rbx, v2y = rgy-rby;
-      real v1 = sqrt( v1x*v1x + v1y*v1y ), v2 = sqrt( v2x*v2x + v2y*v2y );
-      r = sqrt( (x-kx)*(x-kx) + (y-ky)*(y-ky) ) / R0;
-      if (r < 1.0) u[5] = 0.6*(1.0-r);
-      r = sqrt( (x-hx)*(x-hx) + (y-hy)*(y-hy) ) / R0;
-      if (r < 1.0) u[5] = 0.2*(1.0 + cos( M_PI*std::min( r, 1.0 ) ));
-      r = sqrt( (x-cx)*(x-cx) + (y-cy)*(y-cy) ) / R0;
-      real d1 = (v1x*(y-ray) - (x-rax)*v1y) / v1;      // signed distances from the two slot sides
-      real d2 = (v2x*(y-rby) - (x-rbx)*v2y) / v2;
-      if (r < 1.0 && (d1 > 0.05 || d1 < 0.0 || d2 < 0.0)) u[5] = 0.6;
+      u[5] = slot_cyl_scalar( x, y, t );
       return u; };
   if (cfg.problem == "sedov") {
     const real p0 = cfg.p0;
@@ -149,6 +161,11 @@ inline bool timeDependent( const Config& cfg ) {
 }
 
 inline Fn SRC( const Config& cfg ) {
+  if (cfg.problem == "slot_cyl" && cfg.solver == "chocg") {      // slot_cyl::src :655-658: (u,v,w,s) unknowns
+    auto ic = IC( cfg );
+    return [ic]( real x, real y, real z, real t ) -> State {
+      auto u = ic( x, y, z, t ); State s{}; s[0] = -u[1]; s[1] = u[0]; return s; };
+  }
   if (cfg.problem == "slot_cyl") {                 // slot_cyl::src :636-670: centripetal momentum source
     auto ic = IC( cfg );
     return [ic]( real x, real y, real z, real t ) -> State {

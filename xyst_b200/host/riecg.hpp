@@ -229,6 +229,8 @@ class RieCG {
     bool m_mlhsup = false;
     void choPressureSetup();               //!< pressure BC values, Neumann vector, rhs override of pinit
     void choMomRows();                     //!< Dirichlet rows of the momentum solve (theta > 0)
+    void choDirvals( real t, std::vector< real >& dv ) const;   //!< physics::dirbc values at time t
+    void choBCtime( real t );              //!< ... handed to the device for the next BC application
     void choSetup();                       //!< device upload + ChoCG::merge :816-837 onwards
     bool choStep( std::vector< real >* diagrow );
     void choPinit();                       //!< :1025-1125

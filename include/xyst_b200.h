@@ -326,6 +326,14 @@ int xyst_lohcg_bc_upload(xyst_ctx* ctx, size_t ndir, const size_t* dirnodes, con
                          const double* dirval, size_t npdir, const size_t* pdirnodes, const double* pdirval,
                          size_t nsym, const size_t* symbcnodes, const double* symbcnorms,
                          size_t nnoslip, const size_t* noslipbcnodes);
+/* Transported scalars after (p,u,v,w) (LohCG::m_u with problem_ncomp = 4 + ns; scalar rows of lohner::grad /
+ * adv_damp2 / adv_damp4 / the boundary integral / src, Lohner.cpp:787-793,906-911,1030-1056,1073-1087): call after
+ * the mesh upload, before any state or BC upload; then u, rhs rows have 4+ns entries, Dirichlet masks and
+ * values 4+ns per node, xyst_lohcg_diag takes `an` with 4+ns columns and returns 16 + 4 ns sums.
+ * xyst_chocg_dirbc_values ([ndir][4+ns]) and xyst_chocg_pin serve this context too. */
+int xyst_lohcg_scalars(xyst_ctx* ctx, int ns, double diffusivity);
+/* source term values at the nodes [npoin][4+ns] (lohner::src), or NULL for none */
+int xyst_lohcg_src(xyst_ctx* ctx, const double* S);
 int xyst_lohcg_set_u(xyst_ctx* ctx, const double* u /* [npoin][4] */);
 int xyst_lohcg_get_u(xyst_ctx* ctx, double* u);
 int xyst_lohcg_get_rhs(xyst_ctx* ctx, double* rhs /* [npoin][4] */);

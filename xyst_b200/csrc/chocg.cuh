@@ -215,7 +215,7 @@ k_cho_flux( size_t npoin, size_t NP, const long long* __restrict__ sl_base, cons
   for (int i=0; i<3; ++i) F[i*NP+p] = acc[i];
 }
 
-struct ChoP { int stab, stab2; double stab2coef, mu; };
+struct ChoP { int stab, stab2; double stab2coef, mu, s; };      // s: LohCG's artificial sound speed (scalar kernel only)
 
 // advection edge flux: second-order damping (Chorin.cpp:640-709) or fourth-order damping with
 // the limited reconstruction (:711-829); velocity components only
@@ -354,7 +354,7 @@ k_cho_rhs( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const
 // velocities and the stabilisation speed are the flow flux's, recomputed here from the same inputs
 // by the same expressions, so that the velocity kernel stays as it is.
 constexpr int CHO_NSMAX = 4;
-template< bool DAMP4 >
+template< bool DAMP4, bool LOH >
 __device__ __forceinline__ void cho_vn( const double d[3], const double ua[3], const double ub[3],
     const double ga[9], const double gb[9], const double dx[3], const ChoP& C, double& vnL, double& vnR, double& aw )
 {
@@ -377,11 +377,19 @@ __device__ __forceinline__ void cho_vn( const double d[3], const double ua[3], c
   vnR = uR[0]*d[0] + uR[1]*d[1] + uR[2]*d[2];
   aw = 0.0;
   if (C.stab) aw = fabs( vnL + vnR ) / 2.0;
-  if (C.stab2) aw += C.stab2coef * fmax( fabs(vnL), fabs(vnR) );
+  if (C.stab2) {
+    double sl = fabs(vnL), sr = fabs(vnR);
+    if (LOH) {                                  // Lohner.cpp:772-777,888-893
+      double len = sqrt( d[0]*d[0] + d[1]*d[1] + d[2]*d[2] );
+      sl += C.s*len; sr += C.s*len;
+    }
+    aw += C.stab2coef * fmax( sl, sr );
+  }
 }
 
 // U, Un, Uout, R, S: velocity rows 0..2, scalar rows 3..3+ns-1 (stride NP); G: rows 9+3k.. hold the
-// gradient of scalar k (damp4). LAPROW: row of the Laplacian term in D (4: ChoCG, 3: LohCG).
+// gradient of scalar k (damp4). LAPROW: row of the Laplacian term in D (4: ChoCG, 3: LohCG; LohCG also has its
+// own stab2 speed and the same scalar flux, Lohner.cpp:787-793,906-911, boundary term :1030-1056).
 template< bool DAMP4, int LAPROW >
 __global__ void __launch_bounds__(NODE_THREADS)
 k_cho_srhs( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int* __restrict__ inc_e,
@@ -423,7 +431,7 @@ k_cho_srhs( size_t npoin, size_t NP, const long long* __restrict__ sl_base, cons
     for (int i=0; i<9; ++i) { ga[i] = first ? gm[i] : go[i]; gb[i] = first ? go[i] : gm[i]; }
     #pragma unroll
     for (int i=0; i<3; ++i) dx[i] = first ? xo[i]-xm[i] : xm[i]-xo[i];
-    cho_vn< DAMP4 >( d, ua, ub, ga, gb, dx, C, vnL, vnR, aw );
+    cho_vn< DAMP4, LAPROW == 3 >( d, ua, ub, ga, gb, dx, C, vnL, vnR, aw );
     #pragma unroll
     for (int k=0; k<CHO_NSMAX; ++k) if (k < ns) {
       double so = __ldg( U + (3+k)*NP + nb );
@@ -755,14 +763,15 @@ void cho_vgrad( xyst_ctx* c ) {
   ProfScope ps( c, "cho_vgrad" );
   k_cho_grad< 3 ><<< cho_grid( c ), NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p,
     c->D.p, c->nslot, c->cU, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p, c->cVg.p ); ++c->launches;
-  for (int k=0; k<c->cns; ++k) {                    // chorin::vgrad covers the transported scalars (Chorin.cpp:230)
+  const int nsg = c->loh ? 0 : c->cns;              // (LohCG keeps its scalars' gradients in lG: loh_rhs)
+  for (int k=0; k<nsg; ++k) {                       // chorin::vgrad covers the transported scalars (Chorin.cpp:230)
     k_cho_grad< 1 ><<< cho_grid( c ), NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p,
       c->D.p, c->nslot, c->cU + (3+k)*c->NP, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p,
       c->cVg.p + (size_t)(9+3*k)*c->NP ); ++c->launches;
   }
   CK( cudaGetLastError() );
   soa_halo( c, c->cVg.p, 9 );                       // comvgrad :949-970 (each part already over the full volume)
-  for (int k=0; k<c->cns; ++k) soa_halo( c, c->cVg.p + (size_t)(9+3*k)*c->NP, 3 );
+  for (int k=0; k<nsg; ++k) soa_halo( c, c->cVg.p + (size_t)(9+3*k)*c->NP, 3 );
 }
 void cho_rhs( xyst_ctx* c, const double* Un, double sdt, double* Uout, double* R ) {
   if (c->loh) throw std::runtime_error( "context holds a LohCG mesh: use xyst_lohcg_rhs / xyst_lohcg_stage" );

@@ -70,7 +70,8 @@ k_loh_rhs( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const
            const int* __restrict__ inc_q, const double* __restrict__ D, size_t nslot,
            const double* __restrict__ U, const double* __restrict__ G, const double* __restrict__ X, LohP C,
            const int* __restrict__ bslot, const int* __restrict__ bn_off, const int* __restrict__ bn_face,
-           const int* __restrict__ tri, const double* __restrict__ fn, const double* __restrict__ vol,
+           const int* __restrict__ tri, const double* __restrict__ fn, const double* __restrict__ S,
+           const double* __restrict__ v, const double* __restrict__ vol,
            const double* __restrict__ Un, double sdt, double* __restrict__ Uout, double* __restrict__ R )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
@@ -148,6 +149,11 @@ k_loh_rhs( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const
       for (int c=0; c<4; ++c) acc[c] += cho_w8( fl[c][0], fl[c][1], fl[c][2], kk );
     }
   }
+  if (S) {                                      // lohner::src, Lohner.cpp:1073-1087
+    double vo = v[p];
+    #pragma unroll
+    for (int c=0; c<4; ++c) acc[c] -= S[c*NP+p] * vo;
+  }
   if (R) {
     #pragma unroll
     for (int c=0; c<4; ++c) R[c*NP+p] = acc[c];
@@ -160,14 +166,13 @@ k_loh_rhs( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const
 }
 
 // physics::dirbc (BC.cpp:29-72) on all four unknowns; U: [4][NP]
-__global__ void k_loh_dirbc( int nd, size_t NP, const int* __restrict__ node, const int* __restrict__ mask,
+__global__ void k_loh_dirbc( int nd, size_t NP, int m, const int* __restrict__ node, const int* __restrict__ mask,
                              const double* __restrict__ val, double* __restrict__ U )
 {
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= nd) return;
   size_t p = node[i];
-  #pragma unroll
-  for (int c=0; c<4; ++c) if (mask[i*4+c]) U[c*NP+p] = val[i*4+c];
+  for (int c=0; c<m; ++c) if (mask[i*m+c]) U[c*NP+p] = val[i*m+c];
 }
 // physics::dirbcp (BC.cpp:74-108): pressure Dirichlet values
 __global__ void k_loh_pdir( int n, const int* __restrict__ node, const double* __restrict__ val, double* __restrict__ P )
@@ -196,7 +201,7 @@ k_loh_dt( size_t npoin, size_t NP, const double* __restrict__ V, const double* _
 // with an analytic solution [8..11] L2 and [12..15] L1 error sums (component 0 unused)
 __global__ void __launch_bounds__(RED_THREADS)
 k_loh_diag( size_t npoin, size_t NP, const double* __restrict__ U, const double* __restrict__ Un,
-            const double* __restrict__ v, const double* __restrict__ an, double* __restrict__ part )
+            const double* __restrict__ v, const double* __restrict__ an, int anstride, double* __restrict__ part )
 {
   double a[16];
   #pragma unroll
@@ -208,7 +213,7 @@ k_loh_diag( size_t npoin, size_t NP, const double* __restrict__ U, const double*
       double u = U[c*NP+p], du = u - Un[c*NP+p];
       a[c] += u*u*vp;
       a[4+c] += du*du*vp;
-      if (an && c > 0) { double e = u - an[p*4+c]; a[8+c] += e*e*vp; a[12+c] += fabs(e)*vp; }
+      if (an && c > 0) { double e = u - an[p*anstride+c]; a[8+c] += e*e*vp; a[12+c] += fabs(e)*vp; }
     }
   }
   block_reduce< 16, false >( a, part );
@@ -227,31 +232,53 @@ LohP lohp( const xyst_ctx* c ) { return LohP{ c->chp.stab, c->chp.stab2, c->chp.
 // [4][NP] state behind the velocity pointer of the ChoCG machinery
 double* loh_state( double* vel, size_t NP ) { return vel - NP; }
 
+int loh_rows( const xyst_ctx* c ) { return 4 + c->cns; }
 void loh_rhs( xyst_ctx* c, const double* Un, double sdt, double* Uout, double* R ) {
   ProfScope ps( c, "loh_rhs" );
   auto g = cho_grid( c );
-  const double* U = loh_state( c->cU, c->NP );
-  if (cho_parts( c ) && !R) R = c->cR.p;            // the shared nodes' parts travel before they are used
+  size_t NP = c->NP;
+  const double* U = loh_state( c->cU, NP );
+  if ((cho_parts( c ) || c->cns) && !R) R = c->cR.p;            // the shared nodes' parts travel before they are used
+  const double* S = c->cS.p;                                     // [4+ns][NP] or null
   if (c->chp.flux == 1) {
     { ProfScope pg( c, "loh_grad" );
-      k_cho_grad< 4 ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p,
-        c->D.p, c->nslot, U, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p, c->lG.p ); ++c->launches; }
+      k_cho_grad< 4 ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, NP, c->sl_base.p, c->inc_e.p, c->inc_q.p,
+        c->D.p, c->nslot, U, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p, c->lG.p ); ++c->launches;
+      for (int k=0; k<c->cns; ++k) {             // lohner::grad covers the transported scalars
+        k_cho_grad< 1 ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, NP, c->sl_base.p, c->inc_e.p, c->inc_q.p,
+          c->D.p, c->nslot, U + (4+k)*NP, c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p,
+          c->lG.p + (size_t)(12+3*k)*NP ); ++c->launches;
+      } }
     soa_halo( c, c->lG.p, 12 );                     // LohCG::comgrad, LohCG.cpp:1511-1533
-    k_loh_rhs< true ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p,
-      c->nslot, U, c->lG.p, c->X.p, lohp( c ), c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p,
+    for (int k=0; k<c->cns; ++k) soa_halo( c, c->lG.p + (size_t)(12+3*k)*NP, 3 );
+    k_loh_rhs< true ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p,
+      c->nslot, U, c->lG.p, c->X.p, lohp( c ), c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, S, c->v.p, c->vol.p,
       Un, sdt, Uout, R );
   } else
-    k_loh_rhs< false ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p,
-      c->nslot, U, c->lG.p, c->X.p, lohp( c ), c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, c->vol.p,
+    k_loh_rhs< false ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p,
+      c->nslot, U, c->lG.p, c->X.p, lohp( c ), c->bslot.p, c->bn_off.p, c->bn_face.p, c->tri.p, c->fn.p, S, c->v.p, c->vol.p,
       Un, sdt, Uout, R );
   ++c->launches;
+  if (c->cns) {        // scalar rows: the Chorin scalar kernel on the velocity-relative rows (velocity rows 0..2, scalars 3..)
+    ChoP P{ c->chp.stab, c->chp.stab2, c->chp.stab2coef, c->chp.mu, c->loh_s };
+    const double* Sv = S ? S + NP : nullptr;
+    if (c->chp.flux == 1)
+      k_cho_srhs< true, 3 ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p,
+        c->nslot, c->cU, c->lG.p + 3*NP, c->lG.p + 12*NP, c->X.p, P, c->cdif, c->cns, c->bslot.p, c->bn_off.p,
+        c->bn_face.p, c->tri.p, c->fn.p, Sv, c->v.p, c->vol.p, Un ? Un + NP : nullptr, sdt, Uout ? Uout + NP : nullptr, R + NP );
+    else
+      k_cho_srhs< false, 3 ><<< g, NODE_THREADS, 0, c->stream >>>( c->npoin, NP, c->sl_base.p, c->inc_e.p, c->inc_q.p, c->D.p,
+        c->nslot, c->cU, c->lG.p + 3*NP, c->lG.p + 12*NP, c->X.p, P, c->cdif, c->cns, c->bslot.p, c->bn_off.p,
+        c->bn_face.p, c->tri.p, c->fn.p, Sv, c->v.p, c->vol.p, Un ? Un + NP : nullptr, sdt, Uout ? Uout + NP : nullptr, R + NP );
+    ++c->launches;
+  }
   CK( cudaGetLastError() );
-  if (Uout) soa_halo_update( c, R, 4, Un, sdt, Uout ); else soa_halo( c, R, 4 );      // LohCG::comrhs, LohCG.cpp:1563-1585
+  if (Uout) soa_halo_update( c, R, loh_rows( c ), Un, sdt, Uout ); else soa_halo( c, R, loh_rows( c ) );      // LohCG::comrhs, LohCG.cpp:1563-1585
 }
 // LohCG::solve/solved BCs: dirbc, dirbcp, symbc (pos 1), noslipbc (pos 1)
 void loh_bc( xyst_ctx* c, bool pressure ) {
   auto s = c->stream;
-  if (c->lb_nd) { k_loh_dirbc<<< nblk( c->lb_nd, 128 ), 128, 0, s >>>( (int)c->lb_nd, c->NP, c->lb_dnode.p, c->lb_dmask.p, c->lb_dval.p, loh_state( c->cU, c->NP ) ); ++c->launches; }
+  if (c->lb_nd) { k_loh_dirbc<<< nblk( c->lb_nd, 128 ), 128, 0, s >>>( (int)c->lb_nd, c->NP, loh_rows( c ), c->lb_dnode.p, c->lb_dmask.p, c->lb_dval.p, loh_state( c->cU, c->NP ) ); ++c->launches; }
   if (pressure && c->lp_n) { k_loh_pdir<<< nblk( c->lp_n, 128 ), 128, 0, s >>>( (int)c->lp_n, c->lp_node.p, c->lp_val.p, loh_state( c->cU, c->NP ) ); ++c->launches; }
   if (c->cb_ns) { k_cho_symbc<<< nblk( c->cb_ns, 128 ), 128, 0, s >>>( (int)c->cb_ns, c->NP, c->cb_snode.p, c->cb_soff.p, c->cb_snorm.p, c->cU ); ++c->launches; }
   if (c->cb_nn) { k_cho_noslip<<< nblk( c->cb_nn, 128 ), 128, 0, s >>>( (int)c->cb_nn, c->NP, c->cb_nnode.p, c->cU ); ++c->launches; }
@@ -280,6 +307,7 @@ int xyst_lohcg_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const do
   c->lG.alloc( 12*NP ); CK( cudaMemsetAsync( c->lG.p, 0, 12*NP*sizeof(double), c->stream ) );
   c->cS.release();
   c->cU = c->cUa.p + NP; c->cUn = c->cUb.p + NP; c->cUx = c->cUc.p + NP;     // velocity rows of the (p,u,v,w) buffers
+  c->cns = 0; c->cdif = 0.0; c->ncpin = 0;
   c->cb_nd = c->cb_ns = c->cb_nn = 0; c->lp_n = c->lb_nd = 0;
   CK( cudaStreamSynchronize( c->stream ) );
   API_END
@@ -297,10 +325,11 @@ int xyst_lohcg_bc_upload( xyst_ctx* c, size_t ndir, const size_t* dirnodes, cons
   API_BEGIN
   auto s = c->stream;
   auto chk = [&]( size_t id ){ if (id >= c->npoin) throw std::runtime_error( "BC node id out of range" ); return (int)id; };
-  std::vector< int > nd( ndir ), mk( ndir*4 ); std::vector< double > vl( ndir*4 );
+  size_t m = (size_t)loh_rows( c );
+  std::vector< int > nd( ndir ), mk( ndir*m ); std::vector< double > vl( ndir*m );
   for (size_t i=0; i<ndir; ++i) { nd[i] = chk( dirnodes[i] );
-    for (int k=0; k<4; ++k) { mk[i*4+k] = dirmask[i*4+k]; vl[i*4+k] = dirval ? dirval[i*4+k] : 0.0;
-      if (mk[i*4+k] == 2 && !dirval) mk[i*4+k] = 0; } }
+    for (size_t k=0; k<m; ++k) { mk[i*m+k] = dirmask[i*m+k]; vl[i*m+k] = dirval ? dirval[i*m+k] : 0.0;
+      if (mk[i*m+k] == 2 && !dirval) mk[i*m+k] = 0; } }
   c->lb_dnode.upload( nd, s ); c->lb_dmask.upload( mk, s ); c->lb_dval.upload( vl, s ); c->lb_nd = ndir;
   std::vector< int > pn( npdir ); std::vector< double > pv( npdir );
   for (size_t i=0; i<npdir; ++i) { pn[i] = chk( pdirnodes[i] ); pv[i] = pdirval[i]; }
@@ -308,9 +337,41 @@ int xyst_lohcg_bc_upload( xyst_ctx* c, size_t ndir, const size_t* dirnodes, cons
   API_END
 }
 
-int xyst_lohcg_set_u( xyst_ctx* c, const double* u ) { API_BEGIN CK( cudaSetDevice( c->device ) ); loh_need( c ); cho_set( c, u, 4, loh_state( c->cU, c->NP ) ); API_END }
-int xyst_lohcg_get_u( xyst_ctx* c, double* u ) { API_BEGIN CK( cudaSetDevice( c->device ) ); loh_need( c ); cho_get( c, loh_state( c->cU, c->NP ), 4, u ); API_END }
-int xyst_lohcg_get_rhs( xyst_ctx* c, double* r ) { API_BEGIN CK( cudaSetDevice( c->device ) ); loh_need( c ); cho_get( c, c->cR.p, 4, r ); API_END }
+int xyst_lohcg_set_u( xyst_ctx* c, const double* u ) { API_BEGIN CK( cudaSetDevice( c->device ) ); loh_need( c ); cho_set( c, u, loh_rows( c ), loh_state( c->cU, c->NP ) ); API_END }
+int xyst_lohcg_get_u( xyst_ctx* c, double* u ) { API_BEGIN CK( cudaSetDevice( c->device ) ); loh_need( c ); cho_get( c, loh_state( c->cU, c->NP ), loh_rows( c ), u ); API_END }
+int xyst_lohcg_get_rhs( xyst_ctx* c, double* r ) { API_BEGIN CK( cudaSetDevice( c->device ) ); loh_need( c ); cho_get( c, c->cR.p, loh_rows( c ), r ); API_END }
+
+// Transported scalars after (p,u,v,w) (LohCG::m_u with problem_ncomp = 4 + ns): call after the mesh upload and
+// before any state / BC upload. The state-like buffers get ns more rows, the gradient buffer 3 ns.
+int xyst_lohcg_scalars( xyst_ctx* c, int ns, double diffusivity )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  loh_need( c );
+  if (ns < 0 || ns > CHO_NSMAX) throw std::runtime_error( "xyst_lohcg_scalars: 0..4 transported scalars" );
+  size_t NP = c->NP, m = 4 + (size_t)ns;
+  for (auto* b : { &c->cUa, &c->cUb, &c->cUc, &c->cR }) { b->alloc( m*NP ); CK( cudaMemsetAsync( b->p, 0, m*NP*sizeof(double), c->stream ) ); }
+  c->lG.alloc( 3*m*NP ); CK( cudaMemsetAsync( c->lG.p, 0, 3*m*NP*sizeof(double), c->stream ) );
+  c->cS.release();
+  c->cU = c->cUa.p + NP; c->cUn = c->cUb.p + NP; c->cUx = c->cUc.p + NP;
+  c->cns = ns; c->cdif = diffusivity; c->ncpin = 0;
+  c->lb_nd = 0;
+  CK( cudaStreamSynchronize( c->stream ) );
+  API_END
+}
+
+// source term values at the nodes, [npoin][4+ns] (lohner::src, Lohner.cpp:1073-1087), or NULL for none
+int xyst_lohcg_src( xyst_ctx* c, const double* S )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  loh_need( c );
+  if (!S) { c->cS.release(); return 0; }
+  size_t m = (size_t)loh_rows( c );
+  if (c->cS.n != m*c->NP) { c->cS.alloc( m*c->NP ); CK( cudaMemsetAsync( c->cS.p, 0, m*c->NP*sizeof(double), c->stream ) ); }
+  cho_set( c, S, (int)m, c->cS.p );
+  API_END
+}
 int xyst_lohcg_apply_bc( xyst_ctx* c, int pressure ) { API_BEGIN CK( cudaSetDevice( c->device ) ); loh_need( c ); loh_bc( c, pressure != 0 ); API_END }
 
 int xyst_lohcg_rhs( xyst_ctx* c )
@@ -333,6 +394,7 @@ int xyst_lohcg_stage( xyst_ctx* c, int stage, double rkcoef_, double dt )
   if (stage == 0) { double* old_un = c->cUn; c->cUn = c->cU;
     loh_rhs( c, loh_state( c->cUn, NP ), rkcoef_*dt, loh_state( c->cUx, NP ), nullptr ); c->cU = c->cUx; c->cUx = old_un; }
   else { loh_rhs( c, loh_state( c->cUn, NP ), rkcoef_*dt, loh_state( c->cUx, NP ), nullptr ); std::swap( c->cU, c->cUx ); }
+  cho_pin( c );                                     // problems::point_src, LohCG::solve :1615-1617
   loh_bc( c, true );
   API_END
 }
@@ -381,16 +443,24 @@ int xyst_lohcg_diag( xyst_ctx* c, const double* an, double* out )
   CK( cudaSetDevice( c->device ) );
   loh_need( c );
   DevBuf< double > da;
-  if (an) da.upload( std::vector< double >( an, an + c->npoin*4 ), c->stream );
+  if (an) da.upload( std::vector< double >( an, an + c->npoin*(size_t)loh_rows( c ) ), c->stream );
   int nb = (int)std::min< size_t >( RED_BLOCKS, nblk( c->npoin, RED_THREADS ) );
   double* fin = c->red.p + (size_t)RED_BLOCKS*NDIAG;
   k_loh_diag<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, loh_state( c->cU, c->NP ), loh_state( c->cUn, c->NP ),
-    c->v.p, da.p, c->red.p );
+    c->v.p, da.p, loh_rows( c ), c->red.p );
   k_reduce_final< 16, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, fin );
   c->launches += 2;
   CK( cudaMemcpyAsync( c->red_host, fin, 16*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
   CK( cudaStreamSynchronize( c->stream ) );
   for (int i=0; i<16; ++i) out[i] = c->red_host[i];
+  if (c->cns) {            // scalar rows: out[16+4k..] = L2 solution, L2 increment, L2 error, L1 error sums of scalar k
+    k_cho_sdiag<<< nb, RED_THREADS, 0, c->stream >>>( c->npoin, c->NP, c->cns, loh_rows( c ), c->cU, c->cUn, c->v.p, da.p, c->red.p );
+    k_reduce_final< 4*CHO_NSMAX, false ><<< 1, RED_THREADS, 0, c->stream >>>( nb, c->red.p, fin );
+    c->launches += 2;
+    CK( cudaMemcpyAsync( c->red_host, fin, 4*CHO_NSMAX*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+    CK( cudaStreamSynchronize( c->stream ) );
+    for (int i=0; i<4*c->cns; ++i) out[16+i] = c->red_host[i];
+  }
   API_END
 }
 

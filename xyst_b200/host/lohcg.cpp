@@ -23,7 +23,6 @@ const real rkcoef[4][4] = { { 1.0, 0, 0, 0 }, { 1.0/2.0, 1.0, 0, 0 }, { 1.0/3.0,
 void RieCG::lohSetup()
 {
   if (m_cfg.rk < 1 || m_cfg.rk > 4) throw std::runtime_error( "LohCG: rk must be 1..4" );
-  if (problems::SRC( m_cfg )) throw std::runtime_error( "LohCG: source terms are not hooked up" );
   auto np = m_disc.Gid().size();
   const auto& co = m_disc.Coord();
   const auto& x = co[0]; const auto& y = co[1]; const auto& z = co[2];
@@ -37,21 +36,22 @@ void RieCG::lohSetup()
   prm.soundspeed = m_cfg.soundspeed;
   ck( xyst_lohcg_mesh_upload( m_ctx, np, x.data(), y.data(), z.data(), nsup, se, si, m_triinpoel.size()/3,
                               m_triinpoel.data(), m_disc.Vol().data(), m_disc.V().data(), &prm ) );
-  // physics::dirbc (BC.cpp:29-72): mask 1 = value of the initial condition, 2 = configured value
-  auto nd = m_dirbcmasks.size()/5;
-  std::vector< std::size_t > dn( nd ); std::vector< int > dm( nd*4 ); std::vector< real > dv( nd*4, 0.0 );
-  auto ic = problems::IC( m_cfg );
+  const auto ncomp = m_cfg.ncomp;
+  if (ncomp > 4) ck( xyst_lohcg_scalars( m_ctx, static_cast< int >( ncomp-4 ), m_cfg.dif ) );
+  // physics::dirbc (BC.cpp:29-72): mask 1 = value of the initial condition at the BC time (LohCG::merge :923:
+  // t + dt), 2 = configured value
+  auto nd = m_dirbcmasks.size()/(ncomp+1);
+  std::vector< std::size_t > dn( nd ); std::vector< int > dm( nd*ncomp ); std::vector< real > dv;
   for (std::size_t i=0; i<nd; ++i) {
-    auto p = dn[i] = m_dirbcmasks[i*5];
-    auto u = ic( x[p], y[p], z[p], m_disc.T() );
-    for (std::size_t c=0; c<4; ++c) {
-      auto mask = static_cast< int >( m_dirbcmasks[i*5+1+c] );
-      if (mask == 1) dv[i*4+c] = u[c];
-      else if (mask == 2 && !m_dirbcval.empty()) dv[i*4+c] = m_dirbcval[i*5+1+c];
-      else mask = 0;
-      dm[i*4+c] = mask;
+    dn[i] = m_dirbcmasks[i*(ncomp+1)];
+    for (std::size_t c=0; c<ncomp; ++c) {
+      auto mask = static_cast< int >( m_dirbcmasks[i*(ncomp+1)+1+c] );
+      if (mask == 2 && m_dirbcval.empty()) mask = 0;
+      if (mask != 1 && mask != 2) mask = 0;
+      dm[i*ncomp+c] = mask;
     }
   }
+  choDirvals( m_disc.T() + m_disc.Dt(), dv );
   // physics::dirbcp (BC.cpp:74-108)
   std::vector< std::size_t > pn; std::vector< real > pv;
   auto pic = problems::PRESSURE_IC( m_cfg );
@@ -65,6 +65,7 @@ void RieCG::lohSetup()
                             m_noslipbcnodes.size(), m_noslipbcnodes.data() ) );
   ck( xyst_csr_upload( m_ctx, np, 1, m_plhs_ia.data(), m_plhs_ja.data(), m_plhs_a.data() ) );
   choPressureSetup();
+  if (!m_src.empty()) ck( xyst_lohcg_src( m_ctx, m_src.data() ) );
   ck( xyst_lohcg_set_u( m_ctx, m_u0.data() ) );
   // LohCG::merge :917-931: velocity BCs, divergence of the velocity, first pressure solve
   ck( xyst_lohcg_apply_bc( m_ctx, 0 ) );
@@ -88,7 +89,10 @@ void RieCG::lohPinit()
 
 void RieCG::lohPsolved()
 {
-  if (m_np != 1) ck( xyst_lohcg_project( m_ctx ) );
+  if (m_np != 1) {
+    if (m_timedep) choBCtime( m_disc.T() + m_disc.Dt() );          // LohCG::psolved :1311
+    ck( xyst_lohcg_project( m_ctx ) );
+  }
   if (m_cfg.nstep == 1) {                    // test first Poisson solve only (:1330-1337)
     ck( xyst_lohcg_pressure_set( m_ctx ) );
     m_lastdiag = lohDiag();
@@ -122,8 +126,27 @@ bool RieCG::lohStep( std::vector< real >* diagrow )
   }
   if (mindt < eps) m_finished = true;
   m_disc.setdt( mindt );
-  for (std::uint64_t s=0; s<m_cfg.rk; ++s)
+  // problems::point_src (LohCG::solve :1615-1617): active for all stages of a step that starts at or after the
+  // release time
+  if (m_cfg.problem == "point_src" && m_cfg.ncomp > 4 && m_cfg.src_radius >= 0.0 && !m_pinned &&
+      !(m_disc.T() < m_cfg.src_release_time)) {
+    const auto& co = m_disc.Coord();
+    std::vector< std::size_t > nodes;
+    for (std::size_t i=0; i<co[0].size(); ++i) {
+      auto rx = m_cfg.src_location[0] - co[0][i], ry = m_cfg.src_location[1] - co[1][i], rz = m_cfg.src_location[2] - co[2][i];
+      if (rx*rx + ry*ry + rz*rz < m_cfg.src_radius*m_cfg.src_radius) nodes.push_back( i );
+    }
+    ck( xyst_chocg_pin( m_ctx, nodes.size(), nodes.data(), 1.0 ) );
+    m_pinned = true;
+  }
+  if (m_timedep) {                           // lohner::rhs( ..., d->T(), ... ) :1546: the source at the step's time level
+    evalSrc( m_disc.T() );
+    if (!m_src.empty()) ck( xyst_lohcg_src( m_ctx, m_src.data() ) );
+  }
+  for (std::uint64_t s=0; s<m_cfg.rk; ++s) {
+    if (m_timedep) choBCtime( m_disc.T() + rkcoef[m_cfg.rk-1][s] * m_disc.Dt() );      // solve :1620, solved :1640
     ck( xyst_lohcg_stage( m_ctx, static_cast< int >( s ), rkcoef[m_cfg.rk-1][s], m_disc.Dt() ) );
+  }
   auto row = lohDiag();
   if (diagrow) *diagrow = row;
   if (m_disc.finished()) m_finished = true;
@@ -138,22 +161,26 @@ std::vector< real > RieCG::lohDiag()
   if ((m_disc.It()+1) % m_cfg.diag_iter) return {};
   const auto& co = m_disc.Coord();
   auto np = co[0].size();
+  const auto nc = m_cfg.ncomp;
   std::vector< real > an;
   if (auto sol = problems::SOL( m_cfg )) {
-    an.resize( np*4 );
+    an.resize( np*nc );
     for (std::size_t i=0; i<np; ++i) { auto s = sol( co[0][i], co[1][i], co[2][i], m_disc.T()+m_disc.Dt() );
-      for (std::size_t c=0; c<4; ++c) an[i*4+c] = s[c]; }
+      for (std::size_t c=0; c<nc; ++c) an[i*nc+c] = s[c]; }
   }
-  real d[16];
+  real d[32];
   ck( xyst_lohcg_diag( m_ctx, an.empty() ? nullptr : an.data(), d ) );
-  if (m_nranks > 1) { std::vector< real > t( d, d+16 ); m_allreduce( 0, t ); std::copy( t.begin(), t.end(), d ); }
+  if (m_nranks > 1) for (std::size_t o=0; o<16+4*(nc-4); o+=16) {
+    std::vector< real > t( d+o, d+std::min< std::size_t >( o+16, 16+4*(nc-4) ) ); m_allreduce( 0, t ); std::copy( t.begin(), t.end(), d+o ); }
+  // sums of component c (0 = p, 1..3 velocity, 4.. scalars): [0] L2 solution [1] L2 increment [2] L2 error [3] L1 error
+  auto sum = [&]( std::size_t k, std::size_t c ) -> real { return c > 3 ? d[16 + 4*(c-4) + k] : d[4*k + c]; };
   auto mv = m_disc.MeshVol();
   std::vector< real > row{ static_cast< real >( m_disc.It() ), m_disc.T(), m_disc.Dt() };
-  for (std::size_t i=0; i<4; ++i) row.push_back( std::sqrt( d[i] / mv ) );
-  for (std::size_t i=0; i<4; ++i) row.push_back( std::sqrt( d[4+i] / mv ) );
+  for (std::size_t i=0; i<nc; ++i) row.push_back( std::sqrt( sum( 0, i ) / mv ) );
+  for (std::size_t i=0; i<nc; ++i) row.push_back( std::sqrt( sum( 1, i ) / mv ) );
   if (!an.empty()) {
-    for (std::size_t i=1; i<4; ++i) row.push_back( std::sqrt( d[8+i] / mv ) );
-    for (std::size_t i=1; i<4; ++i) row.push_back( d[12+i] / mv );
+    for (std::size_t i=1; i<nc; ++i) row.push_back( std::sqrt( sum( 2, i ) / mv ) );
+    for (std::size_t i=1; i<nc; ++i) row.push_back( sum( 3, i ) / mv );
   }
   return row;
 }

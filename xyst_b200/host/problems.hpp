@@ -61,6 +61,10 @@ inline Fn IC( const Config& cfg ) {
     const auto& p = cfg.problem;
     if (p == "userdef") { const auto vel = cfg.ic_velocity;                    // userdef::ic :53-65
       return [vel]( real, real, real, real ) -> State { return {{ 0, vel[0], vel[1], vel[2], 0 }}; }; }
+    if (p == "point_src") { const auto vel = cfg.ic_velocity;                  // userdef::ic :53-65 (+ scalar 0)
+      return [vel]( real, real, real, real ) -> State { return {{ 0, vel[0], vel[1], vel[2], 0 }}; }; }
+    if (p == "slot_cyl")                                                       // slot_cyl::ic :538-544: (p,u,v,w,s)
+      return []( real x, real y, real, real t ) -> State { return {{ 0.0, 0.5 - y, x - 0.5, 0.0, slot_cyl_scalar( x, y, t ) }}; };
     if (p == "poiseuille")                                                     // poiseuille::ic :1017-1019
       return []( real, real, real, real ) -> State { return {{ 0, 0, 0, 0, 0 }}; };
     throw std::runtime_error( "problem type ic not hooked up: " + p );

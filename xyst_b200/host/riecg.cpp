@@ -129,7 +129,7 @@ RieCG::RieCG( Discretization& disc, const TetMesh& chunk, const Config& cfg )
   m_zal = cfg.solver == "zalcg"; m_stride = m_zal ? 4 : 3; m_koz = cfg.solver == "kozcg"; m_lax = cfg.solver == "laxcg";
   m_cho = cfg.solver == "chocg"; if (m_cho) m_stride = 5;      // ChoCG::domint, ChoCG.cpp:399-446
   m_loh = cfg.solver == "lohcg"; if (m_loh) m_stride = 4;      // LohCG::domint, LohCG.cpp:407-453
-  if (m_loh) { if (cfg.ncomp != 4) throw std::runtime_error( "LohCG: only ncomp = 4 (p,u,v,w) is supported" ); }
+  if (m_loh) { if (cfg.ncomp < 4u || cfg.ncomp > 8u) throw std::runtime_error( "LohCG: ncomp must be 4 (p,u,v,w) + at most 4 transported scalars" ); }
   else if (m_cho ? (cfg.ncomp < 3u || cfg.ncomp > 7u) : (cfg.ncomp < 5u || cfg.ncomp > 13u))
     throw std::runtime_error( m_cho ? "ChoCG: ncomp must be 3 (velocity) + at most 4 transported scalars" : "ncomp must be 5 (+ at most 8 transported scalars)" );
   if (cfg.ncomp > 5u && !m_cho && !m_loh && cfg.solver != "riecg") throw std::runtime_error( "transported scalars are implemented for RieCG only" );
@@ -521,8 +521,8 @@ void RieCG::hostSetup()
     }
   }
   m_timedep = problems::timeDependent( m_cfg );
-  if (m_timedep && (m_zal || m_loh || m_lax || m_cfg.steady))
-    throw std::runtime_error( "time-dependent problems are hooked up for RieCG, KozCG and ChoCG only" );
+  if (m_timedep && (m_zal || m_lax || m_cfg.steady))
+    throw std::runtime_error( "time-dependent problems are hooked up for RieCG, KozCG, ChoCG and LohCG only" );
   evalDirvals( m_disc.T() );
   evalSrc( m_disc.T() );
   if (m_cho || m_loh) choPrelhs();           // LohCG::prelhs :140-181 is ChoCG's
@@ -756,7 +756,7 @@ std::vector< real > RieCG::diagnostics()
 std::vector< real > RieCG::solution()
 {
   if (m_cho) return choGet( "u", m_cfg.ncomp );
-  if (m_loh) { std::vector< real > r( m_disc.Gid().size()*4 ); ck( xyst_lohcg_get_u( m_ctx, r.data() ) ); return r; }
+  if (m_loh) { std::vector< real > r( m_disc.Gid().size()*m_cfg.ncomp ); ck( xyst_lohcg_get_u( m_ctx, r.data() ) ); return r; }
   std::vector< real > u( m_disc.Gid().size()*m_cfg.ncomp );
   ck( xyst_state_get( m_ctx, u.data() ) );
   return u;

@@ -123,7 +123,7 @@ def proj_main(cases, nsteps, out, rank, world, local):
     diagnostics rows and the iteration counts of the linear solves of every step."""
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    tab = {**O.CCASES, **O.ICASES, **O.HCASES}
+    tab = {**O.CCASES, **O.ICASES, **O.HCASES, **O.SCASES, "chocg_sphere_point_src": O.SPHERE_SRC}
     for case in cases.split(","):
         kw = tab[case]
         hm = fixture_to_host_mesh(O.load_mesh(kw.get("mesh", case)))

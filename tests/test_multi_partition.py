@@ -27,7 +27,7 @@ def launch(mode, case, nsteps, tmp_path, world=2):
 
 
 def oracle_for(case, part, world):
-    kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.ICASES, **O.HCASES, **O.ZCASES, **O.KCASES}[case]
+    kw = {**O.CASES, **O.LCASES, **O.ZCASES, **O.KCASES, **PTAB}[case]
     return O.Oracle(O.load_mesh(kw.get("mesh", case)), O.make_cfg(**kw), "port", nchare=world,
                     target=np.asarray(part, np.uint64))
 
@@ -150,7 +150,8 @@ def test_two_gpus_zalcg_match_oracle_two_chares(case, tmp_path):
 
 
 PROJ = ["chocg_poisson_neumann", "chocg_poiseuille_damp2", "chocg_ldc", "chocg_poiseuille_theta",
-        "lohcg_poiseuille_damp4", "lohcg_ldc"]
+        "lohcg_poiseuille_damp4", "lohcg_ldc", "chocg_sphere_point_src", "lohcg_slot_cyl_damp4"]
+PTAB = {**O.CCASES, **O.ICASES, **O.HCASES, **O.SCASES, "chocg_sphere_point_src": O.SPHERE_SRC}
 
 
 @pytest.mark.gpu
@@ -176,7 +177,7 @@ def test_two_gpus_projection_solvers_match_oracle_two_chares(tmp_path):
     bad = []
     for case in PROJ:
         res = [np.load("%s.%s.%d.npz" % (out, case, k)) for k in range(2)]
-        kw = {**O.CCASES, **O.ICASES, **O.HCASES}[case]
+        kw = PTAB[case]
         cho = kw["solver"] == "chocg"
         o = oracle_for(case, res[0]["part"], 2)
         rel = lambda a, b: float(np.abs(np.asarray(a).ravel() - np.asarray(b).ravel()).max() / max(np.abs(b).max(), 1e-300))
@@ -184,7 +185,8 @@ def test_two_gpus_projection_solvers_match_oracle_two_chares(tmp_path):
         for k in range(2):
             assert np.array_equal(res[k]["gid"].astype(np.uint64), o.get("gid", k))
             if kw.get("nstep") != 1:
-                msg.append(("u0", k, rel(res[k]["u0"], o.get("u", k))))
+                u0 = 1 if "slot_cyl" in case else 0
+                msg.append(("u0", k, rel(res[k]["u0"][:, u0:], o.get("u", k)[:, u0:])))
                 if cho:
                     msg.append(("pr0", k, rel(res[k]["pr0"], o.get("pr", k))))
         n = len(res[0]["its"])
@@ -200,14 +202,18 @@ def test_two_gpus_projection_solvers_match_oracle_two_chares(tmp_path):
         assert np.array_equal(res[1]["rows"], rows), case            # all ranks see the same reductions
         tol = 2e-6 if case == "chocg_poisson_neumann" else 1e-9
         vs = np.abs(ro[:, 3:]).max(axis=1, keepdims=True)
+        # slot_cyl: the start-up pressure is ill-determined in the reference itself (test_gpu_scalars.py,
+        # test_oracle_cg_sensitivity.py) and nothing else depends on it: its two norm columns and u[:, 0] are left out
+        cols = [c for c in range(rows.shape[1]) if not ("slot_cyl" in case and c in (3, 8))]
         ok = (np.abs(rows[:, :3] - ro[:, :3]) <= 1e-12 * np.abs(ro[:, :3])).all() and \
-             (np.abs(rows - ro) <= tol * np.abs(ro) + 1e-11 * vs).all()
-        msg.append(("rows", float((np.abs(rows - ro) / (np.abs(ro) + 1e-11 * vs + 1e-300)).max())))
+             (np.abs(rows - ro) <= tol * np.abs(ro) + 1e-11 * vs)[:, cols].all()
+        msg.append(("rows", float((np.abs(rows - ro) / (np.abs(ro) + 1e-11 * vs + 1e-300))[:, cols].max())))
         if kw.get("nstep") != 1:
             ok = ok and np.array_equal(its, np.asarray(pit))
             msg.append(("its", its[:, 0].tolist(), np.asarray(pit)[:, 0].tolist()))
+        u0 = 1 if "slot_cyl" in case else 0
         for k in range(2):
-            e = rel(res[k]["u"], o.get("u", k)); msg.append(("u", k, e))
+            e = rel(res[k]["u"][:, u0:], o.get("u", k)[:, u0:]); msg.append(("u", k, e))
             ok = ok and (e < tol or np.abs(o.get("u", k)).max() < 1e-10)
             if cho:
                 e = rel(res[k]["pr"], o.get("pr", k)); msg.append(("pr", k, e))

@@ -255,6 +255,8 @@ int xyst_chocg_dirbc_values(xyst_ctx* ctx, const double* dirval);
 /* problems::point_src (Problems.cpp:764-823; ChoCG::pred :1655-1657): the first scalar of the listed
  * nodes is set to value after every stage update, before the BCs */
 int xyst_chocg_pin(xyst_ctx* ctx, size_t n, const size_t* nodes, double value);
+/* frozen flow (tag::freezeflow; ChoCG::solve :1550-1552,1564-1570): velocity rows = those of time level n */
+int xyst_chocg_restore_velocity(xyst_ctx* ctx);
 int xyst_chocg_set_u(xyst_ctx* ctx, const double* u /* [npoin][3 (+ns)] */);
 int xyst_chocg_get_u(xyst_ctx* ctx, double* u);
 int xyst_chocg_set_p(xyst_ctx* ctx, const double* p /* [npoin] */);

@@ -61,6 +61,9 @@ typedef struct xyst_host_cfg {
   /* problem "point_src" (problems::point_src, src/Physics/Problems.cpp:764-823): the first transported scalar is
      set to 1 inside a sphere from the release time on, after every stage. src_radius < 0: no source. */
   double src_location[3], src_radius, src_release_time;
+  /* frozen flow (tag::freezeflow / freezetime; ChoCG::dt :1396-1399, solve :1550-1570): once t > freezetime the
+     time step is multiplied by freezeflow (> 1) and only the transported scalars advance. 0 = off (1.0). */
+  double freezeflow, freezetime;
 } xyst_host_cfg;
 
 typedef struct xyst_solver xyst_solver;

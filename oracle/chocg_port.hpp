@@ -330,7 +330,7 @@ class ChoRun : public Run {
     }
 
     //! ChoCG::dt :1356-1411 (local minimum)
-    real chodt( const Chare& c_ ) const {
+    real chodt( const Chare& c_ ) {
       auto eps = std::numeric_limits< real >::epsilon();
       if (std::abs( cfg.dt ) > eps) return cfg.dt;
       real mindt = std::numeric_limits< real >::max();
@@ -345,8 +345,11 @@ class ChoRun : public Run {
         auto dif_dt = dif > eps ? L * L / dif : large;
         mindt = std::min( mindt, dif_dt );
       }
-      return mindt * cfg.cfl;
+      mindt *= cfg.cfl;
+      if (t > cfg.freezetime) freezeflow = cfg.freezeflow;               // :1396-1399
+      return mindt * freezeflow;
     }
+    real freezeflow = 1.0;                // ChoCG::m_freezeflow
 
     //! one time step: dt :1356, advance :1414, rhs :1479, solve :1529, pred :1647, corr :1671,
     //! div :868, pinit, psolve, sgrad, psolved, pgrad, diag :1697
@@ -365,6 +368,12 @@ class ChoRun : public Run {
           be::chorin_rhs( c_.dsupedge, c_.dsupint, c_.coord, c_.triinpoel, c_.v, t, c_.pr, c_.u, c_.grad, c_.rhs ); }
         sumShared( []( Chare& c_ ) -> be::Fields& { return c_.rhs; } );
         for (auto& cp : ch) if (stage == 0) cp->un = cp->u;
+        // frozen flow (:1550-1552,1564-1570): the velocity of before the update comes back once pred() has
+        // returned. In a serial run pred() runs through corr() (and, at the last stage, div()) inline, so those
+        // see the updated velocity; the restored one enters the next rhs and the projection.
+        const bool frozen = freezeflow > 1.0 && (!implicit || stage+1 < rk.size());
+        std::vector< be::Fields > ufrozen;
+        if (frozen) for (auto& cp : ch) ufrozen.push_back( cp->u );
         if (!implicit || stage+1 < rk.size()) {                            // solve :1555-1572
           for (auto& cp : ch) { auto& c_ = *cp;
             auto sdt = rk[stage] * dt;
@@ -374,8 +383,12 @@ class ChoRun : public Run {
         for (auto& cp : ch) { be::phys_src( cp->coord, t, cp->u );         // pred :1647-1668
           cp->BC( t + rk[stage] * dt ); }
         if (cfg.flux == "damp4") { velgrad(); for (auto& cp : ch) fingrad( *cp, cp->grad ); }   // corr :1677
+        if (stage+1 == rk.size()) div_u();
+        if (frozen)
+          for (std::size_t k=0; k<ch.size(); ++k)
+            for (std::size_t i=0; i<ch[k]->u.nunk(); ++i)
+              for (std::size_t c=0; c<3; ++c) ch[k]->u(i,c) = ufrozen[k](i,c);
       }
-      div_u();
       pinit(); psolve();
       sgrad(); psolved();
       if (done()) finished = true;

@@ -71,7 +71,8 @@ EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "chocg_slot_cyl": "ChoCG/SlotCyl/diag.std",
               "chocg_slot_cyl_damp4": "ChoCG/SlotCyl/diag_damp4.std",
               "lohcg_slot_cyl": "LohCG/SlotCyl/diag.std",
-              "lohcg_slot_cyl_damp4": "LohCG/SlotCyl/diag_damp4.std"}
+              "lohcg_slot_cyl_damp4": "LohCG/SlotCyl/diag_damp4.std",
+              "chocg_slot_cyl_damp4_freeze": "ChoCG/SlotCyl/diag_damp4_freeze.std"}
 
 
 def flatten(exo):

@@ -278,6 +278,8 @@ SCASES = {
     "kozcg_slot_cyl": dict(_SC6, solver="kozcg", cfl=0.5, freezeflow=3.0, freezetime=0.0),
     "chocg_slot_cyl": dict(_SCCHO),
     "chocg_slot_cyl_damp4": dict(_SCCHO, flux="damp4", rk=4),
+    # ChoCG/SlotCyl/slot_cyl_damp4_freeze.q: after t = 0.1 the flow is frozen and the scalar advances with 2 dt
+    "chocg_slot_cyl_damp4_freeze": dict(_SCCHO, flux="damp4", rk=4, freezeflow=2.0, freezetime=1.0e-1),
     "lohcg_slot_cyl": dict(_SCLOH),
     "lohcg_slot_cyl_damp4": dict(_SCLOH, flux="damp4", rk=4),
 }

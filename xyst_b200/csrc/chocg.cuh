@@ -939,6 +939,18 @@ int xyst_chocg_dirbc_values( xyst_ctx* c, const double* dirval )
   API_END
 }
 
+// frozen flow (ChoCG::solve :1550-1552,1564-1570): the velocity rows of the time level n come back
+// (the velocity of before the stage's update: with the flow frozen for the whole step that is un)
+int xyst_chocg_restore_velocity( xyst_ctx* c )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  cho_need( c );
+  if (c->loh) throw std::runtime_error( "context holds a LohCG mesh" );
+  CK( cudaMemcpyAsync( c->cU, c->cUn, 3*c->NP*sizeof(double), cudaMemcpyDeviceToDevice, c->stream ) );
+  API_END
+}
+
 // problems::point_src: nodes whose (first) transported scalar is set to value after every stage's update
 int xyst_chocg_pin( xyst_ctx* c, size_t n, const size_t* nodes, double value )
 {

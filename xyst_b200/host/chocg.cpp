@@ -401,11 +401,17 @@ bool RieCG::choStep( std::vector< real >* diagrow )
   if (std::abs( m_cfg.dt ) > eps) mindt = m_cfg.dt;
   else {
     ck( xyst_chocg_dt_min( m_ctx, m_cfg.cfl, m_cfg.dif, &mindt ) );
+    if (m_disc.T() > m_cfg.freezetime) m_freezeflow = m_cfg.freezeflow;        // :1396-1399
+    mindt *= m_freezeflow;
     if (m_nranks > 1) { std::vector< real > t{ mindt }; m_allreduce( 1, t ); mindt = t[0]; }   // contribute(min_double) :1407-1410
   }
   if (mindt < eps) m_finished = true;
   m_disc.setdt( mindt );
   const bool implicit = m_cfg.theta > eps;
+  // frozen flow (solve :1550-1552,1564-1570): the velocity of before the update comes back once pred() has
+  // returned -- after the stage's BCs and velocity gradient and, at the last stage of a serial run, after div()
+  const bool frozen = m_freezeflow > 1.0;
+  if (frozen && implicit) throw std::runtime_error( "ChoCG: freezeflow with the semi-implicit momentum solve is not implemented" );
   if (implicit) choLhs();                    // advance :1414-1431
   // problems::point_src (ChoCG::pred :1655-1657): active for all stages of a step that starts at or after
   // the release time
@@ -428,6 +434,7 @@ bool RieCG::choStep( std::vector< real >* diagrow )
     if (!implicit || s+1 < m_cfg.rk) {       // solve :1555-1572
       if (m_timedep) choBCtime( m_disc.T() + rkcoef[m_cfg.rk-1][s] * m_disc.Dt() );    // pred :1660
       ck( xyst_chocg_stage( m_ctx, static_cast< int >( s ), rkcoef[m_cfg.rk-1][s], m_disc.Dt() ) );
+      if (frozen && s+1 < m_cfg.rk) ck( xyst_chocg_restore_velocity( m_ctx ) );
     } else {                                   // semi-implicit momentum solve at the last stage, :1574-1645
       ck( xyst_chocg_rhs( m_ctx ) );
       ck( xyst_cg_select( m_ctx, 1 ) );
@@ -438,6 +445,7 @@ bool RieCG::choStep( std::vector< real >* diagrow )
       ck( xyst_cg_select( m_ctx, 0 ) );
     }
   ck( xyst_chocg_div( m_ctx, 0, m_disc.Dt(), m_np > 1 ) );
+  if (frozen) ck( xyst_chocg_restore_velocity( m_ctx ) );
   choPinit(); choPsolve();
   ck( xyst_chocg_grad( m_ctx, 0 ) );
   choPsolved( diagrow );

@@ -85,6 +85,7 @@ struct Config {
   //! (src/Inciter/LohCG.cpp); shares the ChoCG keys above, plus the artificial sound speed
   real soundspeed = 1.0;
   std::array< real, 3 > src_location{{ 0, 0, 0 }}; real src_radius = -1.0, src_release_time = 0.0;   // problem "point_src"
+  real freezeflow = 1.0, freezetime = 0.0;      // frozen flow: dt multiplier (> 1) once t > freezetime (ChoCG)
 };
 
 //! Sum, over all partitions sharing them, `w` doubles per unique shared node (ascending
@@ -218,6 +219,7 @@ class RieCG {
     bool m_koz = false;                    //!< KozCG: element-based, no edge integrals
     bool m_cho = false;                    //!< ChoCG: stride-5 integrals, projection steps (chocg.cpp)
     int m_np = 0;                          //!< ChoCG::m_np
+    real m_freezeflow = 1.0;               //!< ChoCG::m_freezeflow
     bool m_initial = true;                 //!< Discretization::Initial()
     std::map< std::size_t, real > m_pbc;   //!< pressure Dirichlet node -> value of the first solves
     std::vector< real > m_neubc, m_prhs, m_psol, m_lastdiag;

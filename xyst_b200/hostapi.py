@@ -39,6 +39,7 @@ class HostCfg(C.Structure):
         ("theta", C.c_double), ("mom_iter", C.c_uint64), ("mom_tol", C.c_double), ("mom_pc", C.c_char * 16),
         ("soundspeed", C.c_double),
         ("src_location", C.c_double * 3), ("src_radius", C.c_double), ("src_release_time", C.c_double),
+        ("freezeflow", C.c_double), ("freezetime", C.c_double),
     ]
 
 
@@ -54,12 +55,13 @@ def make_cfg(problem, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=0.0, t0=0.0
              noslip=(), dirval=(), p_iter=10, p_tol=1.0e-3, p_pc="none", p_dir=(), p_dirval=(), p_sym=(),
              p_hydrostat=None, alpha=0.0, kappa=0.0, r0=0.0, ce=0.0, beta=(0.0, 0.0, 0.0), pre=(),
              soundspeed=1.0, theta=0.0, mom_iter=10, mom_tol=1.0e-3, mom_pc="none", src_location=(0.0, 0.0, 0.0),
-             src_radius=-1.0, src_release_time=0.0, **_ignored):
+             src_radius=-1.0, src_release_time=0.0, freezeflow=1.0, freezetime=0.0, **_ignored):
     c = HostCfg()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term; c.alpha = alpha; c.kappa = kappa
     c.r0 = r0; c.ce = ce; c.soundspeed = soundspeed
     c.src_radius = src_radius; c.src_release_time = src_release_time
+    c.freezeflow = freezeflow; c.freezetime = freezetime
     for i in range(3):
         c.src_location[i] = src_location[i]
     c.theta = theta; c.mom_iter = mom_iter; c.mom_tol = mom_tol; c.mom_pc = mom_pc.encode()

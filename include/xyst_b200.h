@@ -209,6 +209,9 @@ int xyst_kozcg_src(xyst_ctx* ctx, const double* Ssrc_nodes, const double* Ssrc_c
 /* kozak::rhs -> R (xyst_rhs_get) */
 int xyst_kozcg_rhs(xyst_ctx* ctx, double dt);
 /* one KozCG time step: rhs, aec, alw, lim, solve, BC; un keeps the old state */
+/* frozen flow (tag::freezeflow; KozCG::dt :669-674, solve :1140-1176): while on, xyst_kozcg_step advances only
+ * the transported scalars (contexts with ncomp > 5: kozak::rhs scalar rows + FCT per scalar, one partition) */
+int xyst_kozcg_freeze(xyst_ctx* ctx, int on);
 int xyst_kozcg_step(xyst_ctx* ctx, double dt);
 
 /* ---- ChoCG: projection method for constant-density flow -----------------------------------

@@ -26,7 +26,7 @@ __device__ __forceinline__ double koz_geom( const double* __restrict__ X, size_t
 __global__ void __launch_bounds__(128)
 k_koz_elem1( size_t ntet, size_t NP, const int* __restrict__ tet, const double* __restrict__ U,
              const double* __restrict__ X, const double* __restrict__ S, const double* __restrict__ Sc,
-             double dt, double gamma, double ctau, int fct, double* __restrict__ T )
+             double dt, double gamma, double ctau, int fct, double* __restrict__ T, double* __restrict__ UE )
 {
   size_t e = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (e >= ntet) return;
@@ -63,6 +63,10 @@ k_koz_elem1( size_t ntet, size_t NP, const int* __restrict__ tet, const double* 
     for (int a=0; a<4; ++a)
       #pragma unroll
       for (int c=0; c<NC; ++c) ue[c] += coef * S[(size_t)N[a]*NC+c];
+  }
+  if (UE) {                       // half-step density and momentum of the element for the transported scalars
+    #pragma unroll
+    for (int c=0; c<4; ++c) UE[(size_t)c*ntet+e] = ue[c];
   }
   double pr = (ue[4] - 0.5*(ue[1]*ue[1] + ue[2]*ue[2] + ue[3]*ue[3])/ue[0]) * (gamma-1.0);
   double R[4][NC];
@@ -159,6 +163,8 @@ k_koz_node1( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__
 }
 
 // pass 2: per-tet allowed bounds over its 4 nodes -> T[c*2], T[c*2+1]
+// (M components: the flow's NC, or one transported scalar at a time with U, UL, T pointing at its rows)
+template< int M >
 __global__ void __launch_bounds__(128)
 k_koz_elem2( size_t ntet, size_t NP, const int* __restrict__ tet, const double* __restrict__ U,
              const double* __restrict__ UL, int clip, double* __restrict__ T )
@@ -167,7 +173,7 @@ k_koz_elem2( size_t ntet, size_t NP, const int* __restrict__ tet, const double* 
   if (e >= ntet) return;
   int N[4] = { tet[e], tet[ntet+e], tet[2*ntet+e], tet[3*ntet+e] };
   #pragma unroll
-  for (int c=0; c<NC; ++c) {
+  for (int c=0; c<M; ++c) {
     double alwp = -1.7976931348623157e308, alwn = 1.7976931348623157e308;
     #pragma unroll
     for (int a=0; a<4; ++a) {
@@ -180,6 +186,7 @@ k_koz_elem2( size_t ntet, size_t NP, const int* __restrict__ tet, const double* 
 }
 
 // node pass 2: Q+/- = max/min over incident tets, minus ul, limit coefficients C+/-
+template< int M >
 __global__ void __launch_bounds__(NODE_THREADS, 3)
 k_koz_node2( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__ kbase, const int* __restrict__ kinc,
              const double* __restrict__ T, const double* __restrict__ UL, const double* __restrict__ P,
@@ -191,22 +198,22 @@ k_koz_node2( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__
   if (p >= npoin) return;
   long long base = kbase[slice];
   int kmax = (int)((kbase[slice+1] - base) >> 5);
-  double qa[NC], qb[NC];
+  double qa[M], qb[M];
   #pragma unroll
-  for (int c=0; c<NC; ++c) { qa[c] = -1.7976931348623157e308; qb[c] = 1.7976931348623157e308; }
+  for (int c=0; c<M; ++c) { qa[c] = -1.7976931348623157e308; qb[c] = 1.7976931348623157e308; }
   for (int k=0; k<kmax; ++k) {
     int ta = __ldg( kinc + base + (long long)k*32 + lane );
     if (ta < 0) continue;
     size_t e = (size_t)(ta >> 2);
     #pragma unroll
-    for (int c=0; c<NC; ++c) {
+    for (int c=0; c<M; ++c) {
       qa[c] = fmax( qa[c], __ldg( T + (size_t)(2*c)*ntet + e ) );
       qb[c] = fmin( qb[c], __ldg( T + (size_t)(2*c+1)*ntet + e ) );
     }
   }
   const double eps = 2.220446049250313e-16;
   #pragma unroll
-  for (int c=0; c<NC; ++c) {
+  for (int c=0; c<M; ++c) {
     double ul = UL[c*NP+p];
     double a = qa[c] - ul, b = qb[c] - ul;
     double pa = P[(2*c)*NP+p], pb = P[(2*c+1)*NP+p];
@@ -215,7 +222,8 @@ k_koz_node2( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__
   }
 }
 
-// pass 3: limited antidiffusive element contributions coef[c]*aec[c][a] -> T[a*5+c]
+// pass 3: limited antidiffusive element contributions coef[c]*aec[c][a] -> T[a*M+c]
+template< int M >
 __global__ void __launch_bounds__(128)
 k_koz_elem3( size_t ntet, size_t NP, const int* __restrict__ tet, const double* __restrict__ U,
              const double* __restrict__ X, const double* __restrict__ Q, double ctau, int sysmask,
@@ -226,9 +234,9 @@ k_koz_elem3( size_t ntet, size_t NP, const int* __restrict__ tet, const double* 
   int N[4] = { tet[e], tet[ntet+e], tet[2*ntet+e], tet[3*ntet+e] };
   double grad[4][3];
   double J = koz_geom( X, NP, N, grad );
-  double coef[NC], aec[NC][4];
+  double coef[M], aec[M][4];
   #pragma unroll
-  for (int c=0; c<NC; ++c) {
+  for (int c=0; c<M; ++c) {
     double u[4];
     #pragma unroll
     for (int a=0; a<4; ++a) u[a] = U[c*NP+N[a]];
@@ -244,16 +252,17 @@ k_koz_elem3( size_t ntet, size_t NP, const int* __restrict__ tet, const double* 
   }
   double cs = 1.0;
   #pragma unroll
-  for (int c=0; c<NC; ++c) if (sysmask & (1<<c)) cs = fmin( cs, coef[c] );
+  for (int c=0; c<M; ++c) if (sysmask & (1<<c)) cs = fmin( cs, coef[c] );
   #pragma unroll
-  for (int c=0; c<NC; ++c) {
+  for (int c=0; c<M; ++c) {
     if (sysmask & (1<<c)) coef[c] = cs;
     #pragma unroll
-    for (int a=0; a<4; ++a) T[(size_t)(a*NC+c)*ntet+e] = coef[c] * aec[c][a];
+    for (int a=0; a<4; ++a) T[(size_t)(a*M+c)*ntet+e] = coef[c] * aec[c][a];
   }
 }
 
 // node pass 3: a = sum of limited contributions, u = ul + a/vol (KozCG.cpp:1140-1146)
+template< int M, bool FLOW >
 __global__ void __launch_bounds__(NODE_THREADS, 3)
 k_koz_node3( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__ kbase, const int* __restrict__ kinc,
              const double* __restrict__ T, const double* __restrict__ UL, const double* __restrict__ vol,
@@ -265,21 +274,101 @@ k_koz_node3( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__
   if (p >= npoin) return;
   long long base = kbase[slice];
   int kmax = (int)((kbase[slice+1] - base) >> 5);
-  double a_[NC];
+  double a_[M];
   #pragma unroll
-  for (int c=0; c<NC; ++c) a_[c] = 0.0;
+  for (int c=0; c<M; ++c) a_[c] = 0.0;
   for (int k=0; k<kmax; ++k) {
     int ta = __ldg( kinc + base + (long long)k*32 + lane );
     if (ta < 0) continue;
     size_t e = (size_t)(ta >> 2); int a = ta & 3;
     #pragma unroll
-    for (int c=0; c<NC; ++c) a_[c] += __ldg( T + (size_t)(a*NC+c)*ntet + e );
+    for (int c=0; c<M; ++c) a_[c] += __ldg( T + (size_t)(a*M+c)*ntet + e );
   }
-  double ivp = 1.0 / vol[p], u[NC], w[NC];
+  double ivp = 1.0 / vol[p], u[M];
   #pragma unroll
-  for (int c=0; c<NC; ++c) { u[c] = UL[c*NP+p] + a_[c]*ivp; Unew[c*NP+p] = u[c]; }
-  primitive( u, w );
-  store_w( W, NP, p, w );
+  for (int c=0; c<M; ++c) { u[c] = UL[c*NP+p] + a_[c]*ivp; Unew[c*NP+p] = u[c]; }
+  if (FLOW) {
+    double uu[NC], w[NC];
+    #pragma unroll
+    for (int c=0; c<NC; ++c) uu[c] = u[c < M ? c : 0];
+    primitive( uu, w );
+    store_w( W, NP, p, w );
+  }
+}
+
+// ---- transported scalars (kozak::rhs scalar rows, Kozak.cpp:84-86,133-135; FCT as for the flow, no symmetry
+// BC on scalars): one scalar at a time. s: the scalar's nodal values [NP]; UE: the element's half-step density
+// and momentum left by k_koz_elem1; T rows: [a] rhs contributions, [4+a] antidiffusive element contributions
+__global__ void __launch_bounds__(128)
+k_koz_selem1( size_t ntet, size_t NP, const int* __restrict__ tet, const double* __restrict__ U,
+              const double* __restrict__ sv, const double* __restrict__ X, const double* __restrict__ UE,
+              double dt, double ctau, int fct, double* __restrict__ T )
+{
+  size_t e = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
+  if (e >= ntet) return;
+  int N[4] = { tet[e], tet[ntet+e], tet[2*ntet+e], tet[3*ntet+e] };
+  double grad[4][3];
+  double J = koz_geom( X, NP, N, grad );
+  double u[4];
+  #pragma unroll
+  for (int a=0; a<4; ++a) u[a] = sv[N[a]];
+  double ue = (u[0] + u[1] + u[2] + u[3])/4.0;
+  double coef = dt/J/2.0;
+  #pragma unroll
+  for (int j=0; j<3; ++j)
+    #pragma unroll
+    for (int a=0; a<4; ++a) {
+      double cg = coef * grad[a][j];
+      double uj = U[(j+1)*NP+N[a]] / U[N[a]];
+      ue -= cg * u[a] * uj;
+    }
+  double R[4] = { 0.0, 0.0, 0.0, 0.0 };
+  double r0 = UE[e];
+  coef = 1.0/6.0;
+  #pragma unroll
+  for (int j=0; j<3; ++j) {
+    double uj = UE[(size_t)(j+1)*ntet+e] / r0;
+    #pragma unroll
+    for (int a=0; a<4; ++a) R[a] += coef * grad[a][j] * ue * uj;
+  }
+  #pragma unroll
+  for (int a=0; a<4; ++a) T[(size_t)a*ntet+e] = R[a];
+  if (fct) {
+    #pragma unroll
+    for (int a=0; a<4; ++a) {
+      double aec = 0.0;
+      #pragma unroll
+      for (int b=0; b<4; ++b) { double m = J/120.0 * ((a == b) ? 3.0 : -1.0); aec += m * ctau * u[b]; }
+      T[(size_t)(4+a)*ntet+e] = aec;
+    }
+  }
+}
+
+// node pass 1 of one scalar: P+/-, low-order solution ul = s + dt r/vol - P+ - P-; without FCT s_new = s + dt r/vol
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_koz_snode1( size_t npoin, size_t NP, size_t ntet, const long long* __restrict__ kbase, const int* __restrict__ kinc,
+              const double* __restrict__ T, const double* __restrict__ sv, const double* __restrict__ vol,
+              double dt, int fct, double* __restrict__ P, double* __restrict__ UL )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = kbase[slice];
+  int kmax = (int)((kbase[slice+1] - base) >> 5);
+  double r = 0.0, pp = 0.0, pn = 0.0;
+  for (int k=0; k<kmax; ++k) {
+    int ta = __ldg( kinc + base + (long long)k*32 + lane );
+    if (ta < 0) continue;
+    size_t e = (size_t)(ta >> 2); int a = ta & 3;
+    r += __ldg( T + (size_t)a*ntet + e );
+    if (fct) { double aec = __ldg( T + (size_t)(4+a)*ntet + e ); pp += fmax( 0.0, aec ); pn += fmin( 0.0, aec ); }
+  }
+  double ivp = 1.0 / vol[p];
+  if (!fct) { UL[p] = sv[p] + dt*r*ivp; return; }
+  pp *= ivp; pn *= ivp;
+  P[p] = pp; P[NP+p] = pn;
+  UL[p] = sv[p] + dt*r*ivp - pp - pn;
 }
 
 // ---- several partitions (KozCG::comrhs/comaec :728,:839, comalw :944, comlim :1093) -------------------

@@ -222,6 +222,8 @@ struct xyst_ctx : CgState {
   DevBuf< long long > kbase;             // [nslice+1]
   DevBuf< int > kinc;                    // tet*4+a, -1 = padding
   DevBuf< double > kT, kSc;              // [40][ntet] per-tet contributions; [ntet][5] centroid source
+  DevBuf< double > kUE, ksUL, ksP, ksQ;  // transported scalars in KozCG: element half-step flow [4][ntet], per scalar ul, P+/-, Q+/-
+  bool koz_frozen = false;               // KozCG::m_freezeflow > 1: only the scalars advance
   bool ksrc = false;
   std::vector< int > kperm;              // device tet order -> caller's tet index
   // ChoCG: velocity (3 rotating buffers: time level n, current, next), pressure, divergence,
@@ -543,7 +545,7 @@ void scal_flux_nodes( xyst_ctx* c, bool fused, int stage, double dt )
   CK( cudaGetLastError() );
 }
 
-void do_bc( xyst_ctx* c )
+void do_bc( xyst_ctx* c, bool flow = true )
 {
   if (c->ns && c->nspin) {        // the point source acts on the updated solution, then the BCs (RieCG.cpp:1023-1028)
     k_scal_pin<<< nblk( c->nspin, 128 ), 128, 0, c->stream >>>( (int)c->nspin, c->NP, c->spin.p, c->spin_val, c->sU.p ); ++c->launches;
@@ -552,7 +554,7 @@ void do_bc( xyst_ctx* c )
     k_scal_bc<<< nblk( c->nbc, 128 ), 128, 0, c->stream >>>( (int)c->nbc, c->ns, c->NP, c->bc_node.p, c->bc_dir.p,
       c->sdir_mask.p, c->sdir_val.p, c->sU.p ); ++c->launches;
   }
-  if (!c->nbc) return;
+  if (!c->nbc || !flow) return;
   FarState fs{ c->far_r, c->far_p, c->far_u[0], c->far_u[1], c->far_u[2] };
   k_bc<<< nblk( c->nbc, 128 ), 128, 0, c->stream >>>( (int)c->nbc, c->NP, c->bc_node.p, c->bc_dir.p,
     c->dir_mask.p, c->dir_val.p, c->bc_symoff.p, c->sym_n.p, c->bc_faroff.p, c->far_n.p, fs,
@@ -1339,6 +1341,22 @@ int xyst_steady( xyst_ctx* c, int on )
 }
 
 // ---- KozCG -----------------------------------------------------------------------------
+// flow columns of the nodal [npoin][ncomp] and centroid [ntet][ncomp] source values (centroids in the device's
+// element order); the transported scalars' source columns must be zero (kozak::rhs adds s[c] for every c:
+// a non-zero scalar source is not implemented)
+static void koz_src_split( xyst_ctx* c, size_t npoin, size_t ntet, const std::vector< int >& perm, const double* Sn,
+                           const double* Sc, std::vector< double >& sn, std::vector< double >& sc )
+{
+  size_t m = (size_t)c->ncomp;
+  sn.resize( npoin*NC ); sc.resize( ntet*NC );
+  for (size_t i=0; i<npoin; ++i) for (size_t k=0; k<m; ++k) {
+    if (k < NC) sn[i*NC+k] = Sn[i*m+k];
+    else if (Sn[i*m+k] != 0.0) throw std::runtime_error( "KozCG: a source term of a transported scalar is not implemented" ); }
+  for (size_t i=0; i<ntet; ++i) for (size_t k=0; k<m; ++k) {
+    if (k < NC) sc[i*NC+k] = Sc[(size_t)perm[i]*m+k];
+    else if (Sc[(size_t)perm[i]*m+k] != 0.0) throw std::runtime_error( "KozCG: a source term of a transported scalar is not implemented" ); }
+}
+
 int xyst_kozcg_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const double* y, const double* z,
                             size_t ntet, const size_t* inpoel, const double* vol, const double* v,
                             const double* Sn, const double* Sc )
@@ -1382,12 +1400,16 @@ int xyst_kozcg_mesh_upload( xyst_ctx* c, size_t npoin, const double* x, const do
   c->kperm = perm;
   c->ksrc = Sn && Sc;
   if (c->ksrc) {
-    c->S.upload( std::vector< double >( Sn, Sn + npoin*NC ), s );
-    std::vector< double > sc( ntet*NC );
-    for (size_t i=0; i<ntet; ++i) for (size_t k=0; k<NC; ++k) sc[i*NC+k] = Sc[(size_t)perm[i]*NC+k];
-    c->kSc.upload( sc, s );
+    std::vector< double > sn, sc;
+    koz_src_split( c, npoin, ntet, perm, Sn, Sc, sn, sc );
+    c->S.upload( sn, s ); c->kSc.upload( sc, s );
   }
   c->zP.alloc( c->NP*10 ); c->zQ.alloc( c->NP*10 ); c->zUL.alloc( c->NP*NC );
+  c->koz_frozen = false;
+  if (c->ns) {
+    size_t ns = (size_t)c->ns;
+    c->kUE.alloc( 4*ntet ); c->ksUL.alloc( ns*c->NP ); c->ksP.alloc( 2*ns*c->NP ); c->ksQ.alloc( 2*ns*c->NP );
+  }
   API_END
 }
 
@@ -1403,9 +1425,9 @@ int xyst_kozcg_src( xyst_ctx* c, const double* Sn, const double* Sc )
   size_t ntet = c->ntet;
   if (c->S.n != c->npoin*NC) c->S.alloc( c->npoin*NC );
   if (c->kSc.n != ntet*NC) c->kSc.alloc( ntet*NC );
-  std::vector< double > sc( ntet*NC );
-  for (size_t i=0; i<ntet; ++i) for (size_t k=0; k<NC; ++k) sc[i*NC+k] = Sc[(size_t)c->kperm[i]*NC+k];
-  CK( cudaMemcpyAsync( c->S.p, Sn, c->npoin*NC*sizeof(double), cudaMemcpyHostToDevice, s ) );
+  std::vector< double > sn, sc;
+  koz_src_split( c, c->npoin, ntet, c->kperm, Sn, Sc, sn, sc );
+  CK( cudaMemcpyAsync( c->S.p, sn.data(), c->npoin*NC*sizeof(double), cudaMemcpyHostToDevice, s ) );
   CK( cudaMemcpyAsync( c->kSc.p, sc.data(), ntet*NC*sizeof(double), cudaMemcpyHostToDevice, s ) );
   CK( cudaStreamSynchronize( s ) );
   c->ksrc = true;
@@ -1422,7 +1444,7 @@ void koz_pass1( xyst_ctx* c, double dt, int fct )
   auto s = c->stream;
   { ProfScope ps( c, "kozelem" );
     k_koz_elem1<<< nblk( c->ntet, 128 ), 128, 0, s >>>( c->ntet, c->NP, c->ktet.p, c->U.p, c->X.p,
-      c->ksrc ? c->S.p : nullptr, c->kSc.p, dt, c->prm.gamma, c->zal.fctdif, fct, c->kT.p ); ++c->launches; }
+      c->ksrc ? c->S.p : nullptr, c->kSc.p, dt, c->prm.gamma, c->zal.fctdif, fct, c->kT.p, c->ns ? c->kUE.p : nullptr ); ++c->launches; }
   k_koz_node1<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->ntet, c->kbase.p, c->kinc.p,
     c->kT.p, c->U.p, c->bcof.p, c->bc_symoff.p, c->sym_n.p, c->vol.p, dt, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
   if (zal_halo( c )) {          // comrhs + comaec
@@ -1446,6 +1468,36 @@ int xyst_kozcg_rhs( xyst_ctx* c, double dt )
   API_END
 }
 
+// transported scalars of KozCG, one at a time through the same passes as the flow (kozak::rhs scalar rows,
+// KozCG::aec/alw/lim/solve per component); results in sUn
+static void koz_scalars( xyst_ctx* c, double dt, int fct )
+{
+  auto s = c->stream;
+  size_t NP = c->NP, ntet = c->ntet;
+  unsigned gn = nblk( c->nslice*32, NODE_THREADS ), ge = nblk( ntet, 128 );
+  for (int k=0; k<c->ns; ++k) {
+    const double* sv = c->sU.p + (size_t)k*NP;
+    double *sn = c->sUn.p + (size_t)k*NP, *ul = c->ksUL.p + (size_t)k*NP, *P = c->ksP.p + (size_t)2*k*NP, *Q = c->ksQ.p + (size_t)2*k*NP;
+    k_koz_selem1<<< ge, 128, 0, s >>>( ntet, NP, c->ktet.p, c->U.p, sv, c->X.p, c->kUE.p, dt, c->zal.fctdif, fct, c->kT.p ); ++c->launches;
+    k_koz_snode1<<< gn, NODE_THREADS, 0, s >>>( c->npoin, NP, ntet, c->kbase.p, c->kinc.p, c->kT.p, sv, c->vol.p, dt, fct, P, fct ? ul : sn ); ++c->launches;
+    if (!fct) continue;
+    k_koz_elem2< 1 ><<< ge, 128, 0, s >>>( ntet, NP, c->ktet.p, sv, ul, c->zal.fctclip, c->kT.p ); ++c->launches;
+    k_koz_node2< 1 ><<< gn, NODE_THREADS, 0, s >>>( c->npoin, NP, ntet, c->kbase.p, c->kinc.p, c->kT.p, ul, P, Q ); ++c->launches;
+    k_koz_elem3< 1 ><<< ge, 128, 0, s >>>( ntet, NP, c->ktet.p, sv, c->X.p, Q, c->zal.fctdif, 0, c->kT.p ); ++c->launches;
+    k_koz_node3< 1, false ><<< gn, NODE_THREADS, 0, s >>>( c->npoin, NP, ntet, c->kbase.p, c->kinc.p, c->kT.p, ul, c->vol.p, sn, nullptr ); ++c->launches;
+  }
+}
+
+// frozen flow (KozCG::dt :669-674, solve :1140-1176): only the transported scalars advance
+int xyst_kozcg_freeze( xyst_ctx* c, int on )
+{
+  API_BEGIN
+  koz_need( c );
+  if (on && !c->ns) throw std::runtime_error( "xyst_kozcg_freeze: no transported scalar in this context" );
+  c->koz_frozen = on != 0;
+  API_END
+}
+
 int xyst_kozcg_step( xyst_ctx* c, double dt )
 {
   API_BEGIN
@@ -1453,10 +1505,15 @@ int xyst_kozcg_step( xyst_ctx* c, double dt )
   koz_need( c );
   auto s = c->stream;
   unsigned gn = nblk( c->nslice*32, NODE_THREADS ), ge = nblk( c->ntet, 128 );
+  if (c->ns && zal_halo( c )) throw std::runtime_error( "KozCG: transported scalars on several partitions are not implemented" );
+  if (c->ns && (c->zal.fctsys_mask >> NC)) throw std::runtime_error( "KozCG: fctsys over transported scalars is not implemented" );
+  const bool frozen = c->koz_frozen;
   if (c->zal.fct) {
     koz_pass1( c, dt, 1 );
-    k_koz_elem2<<< ge, 128, 0, s >>>( c->ntet, c->NP, c->ktet.p, c->U.p, c->zUL.p, c->zal.fctclip, c->kT.p ); ++c->launches;
-    k_koz_node2<<< gn, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->ntet, c->kbase.p, c->kinc.p, c->kT.p, c->zUL.p, c->zP.p, c->zQ.p ); ++c->launches;
+    if (c->ns) koz_scalars( c, dt, 1 );              // (the per-tet buffer is free again after the flow's node pass 1)
+    if (!frozen) {
+    k_koz_elem2< NC ><<< ge, 128, 0, s >>>( c->ntet, c->NP, c->ktet.p, c->U.p, c->zUL.p, c->zal.fctclip, c->kT.p ); ++c->launches;
+    k_koz_node2< NC ><<< gn, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->ntet, c->kbase.p, c->kinc.p, c->kT.p, c->zUL.p, c->zP.p, c->zQ.p ); ++c->launches;
     if (zal_halo( c )) {        // comalw: max / min over the sharers, then the limit coefficients as in ZalCG
       unsigned gs = nblk( c->nsh, 128 );
       k_koz_sh<<< gs, 128, 0, s >>>( 2, (int)c->nsh, c->NP, c->ntet, c->sh_node.p, c->kbase.p, c->kinc.p, c->kT.p,
@@ -1465,8 +1522,8 @@ int xyst_kozcg_step( xyst_ctx* c, double dt )
       k_zal_fin2<<< gs, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p,
         c->sh_recvbuf.p, c->zUL.p, c->zP.p, c->zQ.p ); ++c->launches;
     }
-    k_koz_elem3<<< ge, 128, 0, s >>>( c->ntet, c->NP, c->ktet.p, c->U.p, c->X.p, c->zQ.p, c->zal.fctdif, c->zal.fctsys_mask, c->kT.p ); ++c->launches;
-    k_koz_node3<<< gn, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->ntet, c->kbase.p, c->kinc.p, c->kT.p, c->zUL.p, c->vol.p, c->Un.p, c->W.p ); ++c->launches;
+    k_koz_elem3< NC ><<< ge, 128, 0, s >>>( c->ntet, c->NP, c->ktet.p, c->U.p, c->X.p, c->zQ.p, c->zal.fctdif, c->zal.fctsys_mask, c->kT.p ); ++c->launches;
+    k_koz_node3< NC, true ><<< gn, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->ntet, c->kbase.p, c->kinc.p, c->kT.p, c->zUL.p, c->vol.p, c->Un.p, c->W.p ); ++c->launches;
     if (zal_halo( c )) {        // comlim
       unsigned gs = nblk( c->nsh, 128 );
       k_koz_sh<<< gs, 128, 0, s >>>( 3, (int)c->nsh, c->NP, c->ntet, c->sh_node.p, c->kbase.p, c->kinc.p, c->kT.p,
@@ -1475,12 +1532,18 @@ int xyst_kozcg_step( xyst_ctx* c, double dt )
       k_zal_fin3<<< gs, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p,
         c->sh_recvbuf.p, c->zUL.p, c->vol.p, c->Un.p, c->W.p ); ++c->launches;
     }
+    }
   } else {
     koz_pass1( c, dt, 0 );
-    k_koz_nofct<<< nblk( c->npoin, 256 ), 256, 0, s >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->U.p, dt, c->Un.p, c->W.p ); ++c->launches;
+    if (c->ns) koz_scalars( c, dt, 0 );
+    if (!frozen) { k_koz_nofct<<< nblk( c->npoin, 256 ), 256, 0, s >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->U.p, dt, c->Un.p, c->W.p ); ++c->launches; }
   }
-  std::swap( c->U.p, c->Un.p );
-  do_bc( c );
+  if (frozen)          // the flow of time level n stays (and is its own previous state for the diagnostics)
+    CK( cudaMemcpyAsync( c->Un.p, c->U.p, c->NP*NC*sizeof(double), cudaMemcpyDeviceToDevice, s ) );
+  else
+    std::swap( c->U.p, c->Un.p );
+  if (c->ns) std::swap( c->sU.p, c->sUn.p );
+  do_bc( c, !frozen );
   CK( cudaGetLastError() );
   API_END
 }

@@ -132,7 +132,8 @@ RieCG::RieCG( Discretization& disc, const TetMesh& chunk, const Config& cfg )
   if (m_loh) { if (cfg.ncomp < 4u || cfg.ncomp > 8u) throw std::runtime_error( "LohCG: ncomp must be 4 (p,u,v,w) + at most 4 transported scalars" ); }
   else if (m_cho ? (cfg.ncomp < 3u || cfg.ncomp > 7u) : (cfg.ncomp < 5u || cfg.ncomp > 13u))
     throw std::runtime_error( m_cho ? "ChoCG: ncomp must be 3 (velocity) + at most 4 transported scalars" : "ncomp must be 5 (+ at most 8 transported scalars)" );
-  if (cfg.ncomp > 5u && !m_cho && !m_loh && cfg.solver != "riecg") throw std::runtime_error( "transported scalars are implemented for RieCG only" );
+  if (cfg.ncomp > 5u && !m_cho && !m_loh && cfg.solver != "riecg" && cfg.solver != "kozcg")
+    throw std::runtime_error( "transported scalars are implemented for RieCG, KozCG, ChoCG and LohCG only" );
   // Transporter::matchsets as the reference executes it (Transporter.cpp:125-187 with the
   // short-circuit at :347-348): with at least one side set named in the configuration the
   // faces of ALL side sets of the mesh keep their boundary integrals; with none, no face does.
@@ -645,6 +646,13 @@ real RieCG::dt()
   if (std::abs( m_cfg.dt ) > eps) mindt = m_cfg.dt;
   else if (m_nranks > 1 && m_nccl_reduce) { ck( xyst_dt_min_all( m_ctx, m_cfg.cfl, &mindt ) ); return mindt; }   // contribute(min_double) :850
   else ck( xyst_dt_min( m_ctx, m_cfg.cfl, &mindt ) );
+  if (m_koz && !(std::abs( m_cfg.dt ) > eps)) {      // KozCG::dt :669-674: frozen flow, the scalars advance with freezeflow x dt
+    if (m_disc.T() > m_cfg.freezetime && m_cfg.freezeflow > 1.0 && m_freezeflow <= 1.0) {
+      m_freezeflow = m_cfg.freezeflow;
+      ck( xyst_kozcg_freeze( m_ctx, 1 ) );
+    }
+    mindt *= m_freezeflow;
+  }
   if (m_nranks > 1) { std::vector< real > t{ mindt }; m_allreduce( 1, t ); mindt = t[0]; }
   return mindt;
 }

@@ -175,6 +175,15 @@ int xyst_zalcg_rhs(xyst_ctx* ctx, double dt);
 /* one ZalCG time step: rhs, aec (P+/-), alw (low-order solution, Q+/-), lim (C+/-, limited
  * antidiffusive contributions), solve, BC (ZalCG.cpp:990-1607); un keeps the old state */
 int xyst_zalcg_step(xyst_ctx* ctx, double dt);
+/* Transported scalars in ZalCG (contexts with ncomp > 5; scalar rows of zalesak::rhs, Zalesak.cpp:113-116,
+ * 146-149,193-196, boundary term :380-403, and the FCT passes per scalar; one partition) need nothing extra.
+ * Source term of zalesak::rhs (Zalesak.cpp:118-128,152-163): the caller evaluates problems::SRC at the nodes
+ * (time t) and at the midpoints of the device's edge slots (time t + dt/2): */
+size_t xyst_nslot(xyst_ctx* ctx);
+int xyst_edge_list(xyst_ctx* ctx, size_t* p /* [nslot] */, size_t* q /* [nslot]; SIZE_MAX = padding slot */);
+int xyst_zalcg_src(xyst_ctx* ctx, const double* Sn /* [npoin][ncomp] */, const double* Se /* [nslot][ncomp] */);
+/* frozen flow (tag::freezeflow; ZalCG::dt :948-952, solve :1549,1577-1584): only the scalars advance */
+int xyst_zalcg_freeze(xyst_ctx* ctx, int on);
 
 /* ---- LaxCG: time-derivative preconditioning for all Mach numbers ------------------------
  * (src/Physics/Lax.cpp:216-1018, src/Inciter/LaxCG.cpp:115-259,940-1214). Same superedge data

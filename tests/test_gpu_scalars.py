@@ -301,3 +301,35 @@ def test_kozcg_with_a_transported_scalar_and_frozen_flow_matches_oracle_and_gold
     assert (np.abs(rows - ro) <= TOL * np.maximum(np.abs(ro), 1e-3 * sc) + 1e-15).all()
     assert (np.abs(rows - gold) <= 2e-11 * np.maximum(np.abs(gold), 1e-3 * sc) + 1e-15).all()
     print(case, "fields max rel diff vs oracle over the run", worst)
+
+
+def test_zalcg_with_a_transported_scalar_source_and_frozen_flow_matches_oracle_and_golden():
+    """ZalCG/SlotCyl/slot_cyl.q: Taylor-Galerkin edge flux + FCT of one transported scalar next to the flow
+    (zalesak::rhs scalar rows Zalesak.cpp:113-116,146-149, boundary term, the three FCT node passes per scalar),
+    the source term of zalesak::rhs (momentum source at the end nodes into the half step and at the edge
+    midpoints to both nodes, :118-128,152-163, evaluated by the host mirror on the device's edge list),
+    time-dependent Dirichlet values, and freezeflow = 3 from the second step on (ZalCG::dt :948-952, solve
+    :1549,1577-1584). Every step against the oracle at 1e-12, then the golden rows."""
+    case = "zalcg_slot_cyl"
+    kw = O.SCASES[case]
+    hm = fixture_to_host_mesh(O.load_mesh(kw["mesh"]))
+    s = H.Solver.mesh(H.make_cfg(**kw), hm["coord"], hm["tets"], hm["set_id"], hm["set_off"], hm["set_tri"])
+    s.prepare(); s.attach(0); s.setup()
+    o = O.Oracle(O.load_mesh(kw["mesh"]), O.make_cfg(**kw), "port")
+    gold = O.load_golden_diag(case)
+    n = int(gold[-1, 0])
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    rows = []; worst = 0.0
+    for it in range(n):
+        r = s.step(1); o.step(1)
+        rows.append(r[0])
+        U, Uo = s.get("u"), o.get("u")
+        worst = max(worst, rel(U[:, :5], Uo[:, :5]), float(np.abs(U[:, 5] - Uo[:, 5]).max() / 0.6))
+        assert worst < TOL, it
+    rows = np.asarray(rows); ro = o.diag()
+    assert rows.shape == ro.shape == gold.shape
+    assert rows[1, 2] > 2.9 * rows[0, 2]                 # dt tripled from the second step on
+    sc = np.abs(ro).max(axis=0)
+    assert (np.abs(rows - ro) <= TOL * np.maximum(np.abs(ro), 1e-3 * sc) + 1e-15).all()
+    assert (np.abs(rows - gold) <= 2e-11 * np.maximum(np.abs(gold), 1e-3 * sc) + 1e-15).all()
+    print(case, "fields max rel diff vs oracle over the run", worst)

@@ -57,6 +57,7 @@ SYMBOLS = [
     "xyst_lohcg_apply_bc", "xyst_lohcg_rhs", "xyst_lohcg_stage", "xyst_lohcg_project", "xyst_lohcg_pressure_set",
     "xyst_lohcg_dt_min", "xyst_lohcg_diag", "xyst_chocg_scalars", "xyst_chocg_dirbc_values", "xyst_chocg_pin",
     "xyst_lohcg_scalars", "xyst_lohcg_src", "xyst_chocg_restore_velocity", "xyst_kozcg_freeze",
+    "xyst_zalcg_freeze", "xyst_nslot", "xyst_edge_list", "xyst_zalcg_src",
 ]
 
 
@@ -128,6 +129,10 @@ def lib():
     for f in (L.xyst_chocg_set_u, L.xyst_chocg_get_u, L.xyst_chocg_set_p, L.xyst_chocg_src):
         f.argtypes = [C.c_void_p, C.c_void_p]
     L.xyst_kozcg_freeze.argtypes = [C.c_void_p, C.c_int]
+    L.xyst_zalcg_freeze.argtypes = [C.c_void_p, C.c_int]
+    L.xyst_nslot.argtypes = [C.c_void_p]; L.xyst_nslot.restype = C.c_size_t
+    L.xyst_edge_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.xyst_zalcg_src.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.xyst_chocg_scalars.argtypes = [C.c_void_p, C.c_int, C.c_double]
     L.xyst_chocg_dirbc_values.argtypes = [C.c_void_p, C.c_void_p]
     L.xyst_lohcg_scalars.argtypes = [C.c_void_p, C.c_int, C.c_double]

@@ -222,7 +222,9 @@ struct xyst_ctx : CgState {
   DevBuf< long long > kbase;             // [nslice+1]
   DevBuf< int > kinc;                    // tet*4+a, -1 = padding
   DevBuf< double > kT, kSc;              // [40][ntet] per-tet contributions; [ntet][5] centroid source
-  DevBuf< double > kUE, ksUL, ksP, ksQ;  // transported scalars in KozCG: element half-step flow [4][ntet], per scalar ul, P+/-, Q+/-
+  DevBuf< double > kUE, ksUL, ksP, ksQ;  // transported scalars in KozCG / ZalCG: element half-step flow [4][ntet], per scalar ul, P+/-, Q+/-
+  DevBuf< double > zSn, zSe;             // ZalCG source term: at the nodes [npoin][5], at the edge midpoints [5][nslot]
+  bool zsrc = false;
   bool koz_frozen = false;               // KozCG::m_freezeflow > 1: only the scalars advance
   bool ksrc = false;
   std::vector< int > kperm;              // device tet order -> caller's tet index
@@ -729,7 +731,7 @@ static int mesh_upload_impl( xyst_ctx* c, size_t npoin, const double* x, const d
   c->U.alloc( NP*NC ); c->Un.alloc( NP*NC ); c->G.alloc( NP*2*NGP ); c->Racc.alloc( NP*NC );
   c->R.alloc( npoin*(size_t)c->ncomp ); c->stage.alloc( npoin*(size_t)c->ncomp ); c->F.alloc( std::max< size_t >( nslot, 1 )*NC );
   if (c->ns) {
-    if (stride != 3) throw std::runtime_error( "transported scalars are implemented for RieCG only" );
+    if (stride != 3 && stride != 4) throw std::runtime_error( "transported scalars are implemented for RieCG, ZalCG and KozCG only" );
     size_t ns = (size_t)c->ns;
     c->sU.upload( std::vector< double >( ns*NP, 0.0 ), s ); c->sUn.upload( std::vector< double >( ns*NP, 0.0 ), s );
     c->sG.upload( std::vector< double >( 3*ns*NP, 0.0 ), s );
@@ -774,16 +776,40 @@ namespace {
 void zal_need( xyst_ctx* c ) {
   need_mesh( c );
   if (c->dstride != 4) throw std::runtime_error( "ZalCG needs stride-4 superedge integrals: use xyst_zalcg_mesh_upload" );
-  if (!c->zP.p) { c->zP.alloc( c->NP*10 ); c->zQ.alloc( c->NP*10 ); c->zUL.alloc( c->NP*NC ); }
+  if (!c->zP.p) { c->zP.alloc( c->NP*10 ); c->zQ.alloc( c->NP*10 ); c->zUL.alloc( c->NP*NC ); c->zsrc = false; c->koz_frozen = false; }
+  if (c->ns && c->ksUL.n != (size_t)c->ns*c->NP) {
+    size_t ns = (size_t)c->ns;
+    c->ksUL.alloc( ns*c->NP ); c->ksP.alloc( 2*ns*c->NP ); c->ksQ.alloc( 2*ns*c->NP );
+  }
 }
 void zal_flux_and_bnd( xyst_ctx* c, double dt )
 {
   auto s = c->stream;
   if (c->nbn) { k_bnd_rhs<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->NP, c->bn_off.p, c->bn_face.p,
                   c->tri.p, c->besym.p, c->fn.p, c->U.p, c->Rb.p, c->prm.gamma, c->W.p, c->rgas ); ++c->launches; }
+  if (c->ns && c->nbn) { k_scal_bnd<<< nblk( c->nbn, 128 ), 128, 0, s >>>( (int)c->nbn, c->ns, c->NP, c->bn_off.p, c->bn_face.p,
+                  c->tri.p, c->besym.p, c->fn.p, c->U.p, c->sU.p, c->sGb.p, c->sRb.p ); ++c->launches; }
   { ProfScope ps( c, "zalflux" );
     k_zal_flux_edge<<< nblk( c->nslot, 128 ), 128, 0, s >>>( c->nslot, c->NP, c->ep.p, c->eq.p, c->D.p, c->U.p, c->X.p,
-      dt, c->steady ? c->dtp.p : nullptr, dparams( c ), c->F.p ); ++c->launches; }
+      dt, c->steady ? c->dtp.p : nullptr, dparams( c ), c->F.p, c->zsrc ? c->zSn.p : nullptr, c->ns, c->sU.p, c->sF.p ); ++c->launches; }
+}
+// transported scalars of ZalCG, one at a time through the three node passes; results in sUn
+void zal_scalars( xyst_ctx* c, double dt, int fct )
+{
+  auto s = c->stream;
+  size_t NP = c->NP;
+  unsigned g = nblk( c->nslice*32, NODE_THREADS );
+  const double* dtp = c->steady ? c->dtp.p : nullptr;
+  for (int k=0; k<c->ns; ++k) {
+    const double* sv = c->sU.p + (size_t)k*NP; const double* sf = c->sF.p + (size_t)k*c->nslot;
+    double *sn = c->sUn.p + (size_t)k*NP, *ul = c->ksUL.p + (size_t)k*NP, *P = c->ksP.p + (size_t)2*k*NP, *Q = c->ksQ.p + (size_t)2*k*NP;
+    k_zal_snode1<<< g, NODE_THREADS, 0, s >>>( c->npoin, NP, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot, sf, sv, c->bslot.p,
+      c->sRb.p, c->ns, k, c->vol.p, dt, dtp, c->zal.fctdif, fct, P, fct ? ul : sn ); ++c->launches;
+    if (!fct) continue;
+    k_zal_snode2<<< g, NODE_THREADS, 0, s >>>( c->npoin, NP, c->sl_base.p, c->inc_eq.p, sv, ul, P, c->zal.fctclip, Q ); ++c->launches;
+    k_zal_snode3<<< g, NODE_THREADS, 0, s >>>( c->npoin, NP, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot, sv, ul, Q, c->vol.p,
+      c->zal.fctdif, sn ); ++c->launches;
+  }
 }
 // With several partitions every pass is followed by the exchange of the shared nodes' own sums
 // (ZalCG::comrhs+comaec: sums, comalw: max/min, comlim: sums; ZalCG.cpp:1023-1053,1139-1148,1297-1333,
@@ -794,11 +820,13 @@ void zal_node1( xyst_ctx* c, double dt, int fct )
   auto s = c->stream;
   k_zal_node1<<< nblk( c->nslice*32, NODE_THREADS ), NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p,
     c->inc_eq.p, c->D.p, c->nslot, c->F.p, c->U.p, c->bslot.p, c->Rb.p, c->bcof.p, c->bc_symoff.p,
-    c->sym_n.p, c->vol.p, dt, c->steady ? c->dtp.p : nullptr, c->zal.fctdif, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
+    c->sym_n.p, c->vol.p, dt, c->steady ? c->dtp.p : nullptr, c->zal.fctdif, fct, c->zP.p, c->zUL.p, c->R.p,
+    c->zsrc ? c->zSe.p : nullptr ); ++c->launches;
   if (!zal_halo( c )) return;
   unsigned g = nblk( c->nsh, 128 );
   k_zal_sh1<<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot, c->F.p,
-    c->U.p, c->bslot.p, c->Rb.p, c->zal.fctdif, c->bcof.p, c->bc_symoff.p, c->sym_n.p, c->sh_part.p ); ++c->launches;
+    c->U.p, c->bslot.p, c->Rb.p, c->zal.fctdif, c->bcof.p, c->bc_symoff.p, c->sym_n.p, c->sh_part.p,
+    c->zsrc ? c->zSe.p : nullptr ); ++c->launches;
   exchange( c, 15 ); exchange_wait( c );
   k_zal_fin1<<< g, 128, 0, s >>>( (int)c->nsh, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p, c->sh_recvbuf.p,
     c->U.p, c->vol.p, dt, c->steady ? c->dtp.p : nullptr, fct, c->zP.p, c->zUL.p, c->R.p ); ++c->launches;
@@ -823,7 +851,18 @@ int xyst_zalcg_step( xyst_ctx* c, double dt )
   zal_need( c );
   auto s = c->stream;
   unsigned g = nblk( c->nslice*32, NODE_THREADS );
+  if (c->ns && zal_halo( c )) throw std::runtime_error( "ZalCG: transported scalars on several partitions are not implemented" );
+  if (c->ns && (c->zal.fctsys_mask >> NC)) throw std::runtime_error( "ZalCG: fctsys over transported scalars is not implemented" );
+  const bool frozen = c->koz_frozen;            // ZalCG::m_freezeflow > 1 (ZalCG.cpp:948-952, 1549, 1577-1584)
   zal_flux_and_bnd( c, dt );
+  if (c->ns) zal_scalars( c, dt, c->zal.fct ? 1 : 0 );
+  if (frozen) {                                 // only the scalars advance; the flow of time level n stays
+    CK( cudaMemcpyAsync( c->Un.p, c->U.p, c->NP*NC*sizeof(double), cudaMemcpyDeviceToDevice, s ) );
+    std::swap( c->sU.p, c->sUn.p );
+    do_bc( c, false );
+    CK( cudaGetLastError() );
+    return 0;
+  }
   if (c->zal.fct) {
     zal_node1( c, dt, 1 );
     k_zal_node2<<< g, NODE_THREADS, 0, s >>>( c->npoin, c->NP, c->sl_base.p, c->inc_eq.p, c->U.p, c->zUL.p,
@@ -852,8 +891,66 @@ int xyst_zalcg_step( xyst_ctx* c, double dt )
     k_zal_nofct<<< nblk( c->npoin, 256 ), 256, 0, s >>>( c->npoin, c->NP, c->R.p, c->vol.p, c->U.p, dt, c->steady ? c->dtp.p : nullptr, c->Un.p, c->W.p ); ++c->launches;
   }
   std::swap( c->U.p, c->Un.p );
+  if (c->ns) std::swap( c->sU.p, c->sUn.p );
   do_bc( c );
   CK( cudaGetLastError() );
+  API_END
+}
+
+// frozen flow in ZalCG (tag::freezeflow; ZalCG::dt :948-952, solve :1549,1577-1584): as xyst_kozcg_freeze
+int xyst_zalcg_freeze( xyst_ctx* c, int on )
+{
+  API_BEGIN
+  zal_need( c );
+  if (on && !c->ns) throw std::runtime_error( "xyst_zalcg_freeze: no transported scalar in this context" );
+  c->koz_frozen = on != 0;
+  API_END
+}
+
+// End nodes of the device's edge slots (caller's numbering; slots of padding: SIZE_MAX both), for callers that
+// evaluate something per edge (the ZalCG source term at the edge midpoints). nslot from xyst_nslot.
+size_t xyst_nslot( xyst_ctx* c ) { return c ? c->nslot : 0; }
+int xyst_edge_list( xyst_ctx* c, size_t* p, size_t* q )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  need_mesh( c );
+  std::vector< int > ep( c->nslot ), eq( c->nslot );
+  CK( cudaMemcpyAsync( ep.data(), c->ep.p, c->nslot*sizeof(int), cudaMemcpyDeviceToHost, c->stream ) );
+  CK( cudaMemcpyAsync( eq.data(), c->eq.p, c->nslot*sizeof(int), cudaMemcpyDeviceToHost, c->stream ) );
+  CK( cudaStreamSynchronize( c->stream ) );
+  for (size_t i=0; i<c->nslot; ++i) {
+    if (ep[i] < 0) { p[i] = q[i] = (size_t)-1; continue; }
+    p[i] = reordered( c ) ? (size_t)c->new2old_h[ (size_t)ep[i] ] : (size_t)ep[i];
+    q[i] = reordered( c ) ? (size_t)c->new2old_h[ (size_t)eq[i] ] : (size_t)eq[i];
+  }
+  API_END
+}
+
+// ZalCG source term (problems::SRC through zalesak::rhs, Zalesak.cpp:118-128,152-163): values at the nodes at t
+// [npoin][ncomp] and at the midpoints of the edge slots at t + dt/2 [nslot][ncomp] (xyst_edge_list; padding
+// slots ignored); NULL, NULL switches it off. Source columns of transported scalars must be zero.
+int xyst_zalcg_src( xyst_ctx* c, const double* Sn, const double* Se )
+{
+  API_BEGIN
+  CK( cudaSetDevice( c->device ) );
+  zal_need( c );
+  if (!Sn && !Se) { c->zsrc = false; return 0; }
+  if (!Sn || !Se) throw std::runtime_error( "xyst_zalcg_src: null argument" );
+  size_t m = (size_t)c->ncomp, np = c->npoin, nslot = c->nslot;
+  std::vector< double > sn( np*NC ), se( std::max< size_t >( nslot, 1 )*NC, 0.0 );
+  for (size_t i=0; i<np; ++i) {
+    size_t j = reordered( c ) ? to_new( c, i, "node id" ) : i;
+    for (size_t k=0; k<m; ++k) {
+      if (k < NC) sn[j*NC+k] = Sn[i*m+k];
+      else if (Sn[i*m+k] != 0.0) throw std::runtime_error( "ZalCG: a source term of a transported scalar is not implemented" ); }
+  }
+  for (size_t i=0; i<nslot; ++i) for (size_t k=0; k<m; ++k) {
+    if (k < NC) se[k*nslot+i] = Se[i*m+k];
+    else if (Se[i*m+k] != 0.0 && std::isfinite( Se[i*m+k] )) throw std::runtime_error( "ZalCG: a source term of a transported scalar is not implemented" ); }
+  c->zSn.upload( sn, c->stream ); c->zSe.upload( se, c->stream );
+  CK( cudaStreamSynchronize( c->stream ) );
+  c->zsrc = true;
   API_END
 }
 

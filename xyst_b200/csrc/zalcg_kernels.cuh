@@ -8,7 +8,8 @@
 __global__ void __launch_bounds__(128)
 k_zal_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int* __restrict__ eq,
                  const double* __restrict__ D, const double* __restrict__ U, const double* __restrict__ X,
-                 double dt, const double* __restrict__ dtp, DParams P, double* __restrict__ F )
+                 double dt, const double* __restrict__ dtp, DParams P, double* __restrict__ F,
+                 const double* __restrict__ Sn, int ns, const double* __restrict__ sU, double* __restrict__ sF )
 {
   size_t e = blockIdx.x*(size_t)blockDim.x + threadIdx.x;
   if (e >= nslot) return;
@@ -33,6 +34,14 @@ k_zal_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int*
   double rvh = 0.5*(rvL + rvR - dt*(rvL*dnL - rvR*dnR + dp*dy));
   double rwh = 0.5*(rwL + rwR - dt*(rwL*dnL - rwR*dnR + dp*dz));
   double reh = 0.5*(reL + reR - dt*((reL+pL)*dnL - (reR+pR)*dnR));
+  if (Sn) {                                 // source at the end nodes into the half step (Zalesak.cpp:118-128)
+    double coef = dt/4.0;
+    rh  += coef*(Sn[p*NC+0] + Sn[q*NC+0]);
+    ruh += coef*(Sn[p*NC+1] + Sn[q*NC+1]);
+    rvh += coef*(Sn[p*NC+2] + Sn[q*NC+2]);
+    rwh += coef*(Sn[p*NC+3] + Sn[q*NC+3]);
+    reh += coef*(Sn[p*NC+4] + Sn[q*NC+4]);
+  }
   double ph = (reh - 0.5*(ruh*ruh + rvh*rvh + rwh*rwh)/rh) * (g-1.0);
   double vn = (ruh*nx + rvh*ny + rwh*nz)/rh;
   double f[NC];
@@ -41,17 +50,26 @@ k_zal_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int*
   f[2] = 2.0*(rvh*vn + ph*ny);
   f[3] = 2.0*(rwh*vn + ph*nz);
   f[4] = 2.0*(reh + ph)*vn;
+  double fw = 0.0;
   if (P.stab2) {
     double vnL = (ruL*nx + rvL*ny + rwL*nz)/rL;
     double vnR = (ruR*nx + rvR*ny + rwR*nz)/rR;
     double len = sqrt( nx*nx + ny*ny + nz*nz );
     double cL = sqrt( g * fmax(pL,0.0) / fmax(rL,1.0e-8) );
     double cR = sqrt( g * fmax(pR,0.0) / fmax(rR,1.0e-8) );
-    double fw = P.stab2coef * fmax( fabs(vnL) + cL*len, fabs(vnR) + cR*len );
+    fw = P.stab2coef * fmax( fabs(vnL) + cL*len, fabs(vnR) + cR*len );
     f[0] -= fw*(rL - rR); f[1] -= fw*(ruL - ruR); f[2] -= fw*(rvL - rvR);
     f[3] -= fw*(rwL - rwR); f[4] -= fw*(reL - reR);
   }
   store_f( F, nslot, e, f );
+  // transported scalars (:113-116,146-149,193-196; their source columns are zero): sF[k][e]
+  for (int k=0; k<ns; ++k) {
+    double sL = sU[(size_t)k*NP+p], sR = sU[(size_t)k*NP+q];
+    double ue = 0.5*(sL + sR - dt*(sL*dnL - sR*dnR));
+    double fs = 2.0*ue*vn;
+    if (P.stab2) fs -= fw*(sL - sR);
+    sF[(size_t)k*nslot+e] = fs;
+  }
 }
 
 // pass 1 (aec + first half of alw): R = sum +-F + boundary; P+/- from the antidiffusive edge
@@ -61,7 +79,7 @@ k_zal_flux_edge( size_t nslot, size_t NP, const int* __restrict__ ep, const int*
 __device__ __forceinline__ void zal_sum1( size_t p, int lane, long long base, int kmax, size_t NP,
     const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot, const double* __restrict__ F,
     const double* __restrict__ U, const int* __restrict__ bslot, const double* __restrict__ Rb, double ctau,
-    double up[NC], double r[NC], double pp[NC], double pn[NC] )
+    double up[NC], double r[NC], double pp[NC], double pn[NC], const double* __restrict__ Se = nullptr )
 {
   #pragma unroll
   for (int c=0; c<NC; ++c) { up[c] = U[c*NP+p]; r[c] = 0.0; pp[c] = 0.0; pn[c] = 0.0; }
@@ -89,6 +107,8 @@ __device__ __forceinline__ void zal_sum1( size_t p, int lane, long long base, in
         double aec = -dif * ctau * (uq - up[c]);
         if (aec > 0.0) pp[c] += aec; else pn[c] += aec;
       }
+      // source at the edge's midpoint, to both of its nodes (Zalesak.cpp:152-163, advdom :243-249,...)
+      if (Se && se != 0) r[c] += (-5.0/3.0*dif) * __ldg( Se + (size_t)c*nslot + sl );
     }
   }
   int b = bslot[p];
@@ -134,7 +154,8 @@ k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
              const double* __restrict__ F, const double* __restrict__ U, const int* __restrict__ bslot,
              const double* __restrict__ Rb, const int* __restrict__ bcof, const int* __restrict__ symoff,
              const double* __restrict__ sym_n, const double* __restrict__ vol, double dt, const double* __restrict__ dtp,
-             double ctau, int fct, double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R )
+             double ctau, int fct, double* __restrict__ P, double* __restrict__ UL, double* __restrict__ R,
+             const double* __restrict__ Se )
 {
   size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -144,7 +165,7 @@ k_zal_node1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, con
   long long base = sl_base[slice];
   int kmax = (int)((sl_base[slice+1] - base) >> 5);
   double up[NC], r[NC], pp[NC], pn[NC];
-  zal_sum1( p, lane, base, kmax, NP, inc_eq, D, nslot, F, U, bslot, Rb, ctau, up, r, pp, pn );
+  zal_sum1( p, lane, base, kmax, NP, inc_eq, D, nslot, F, U, bslot, Rb, ctau, up, r, pp, pn, Se );
   if (!fct) {
     #pragma unroll
     for (int c=0; c<NC; ++c) R[p*NC+c] = r[c];
@@ -160,7 +181,7 @@ __global__ void k_zal_sh1( int nsh, size_t NP, const int* __restrict__ sh_node, 
              const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot, const double* __restrict__ F,
              const double* __restrict__ U, const int* __restrict__ bslot, const double* __restrict__ Rb, double ctau,
              const int* __restrict__ bcof, const int* __restrict__ symoff, const double* __restrict__ sym_n,
-             double* __restrict__ part )
+             double* __restrict__ part, const double* __restrict__ Se )
 {
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= nsh) return;
@@ -168,7 +189,7 @@ __global__ void k_zal_sh1( int nsh, size_t NP, const int* __restrict__ sh_node, 
   long long base = sl_base[p >> 5];
   int kmax = (int)((sl_base[(p >> 5)+1] - base) >> 5);
   double up[NC], r[NC], pp[NC], pn[NC];
-  zal_sum1( p, (int)(p & 31), base, kmax, NP, inc_eq, D, nslot, F, U, bslot, Rb, ctau, up, r, pp, pn );
+  zal_sum1( p, (int)(p & 31), base, kmax, NP, inc_eq, D, nslot, F, U, bslot, Rb, ctau, up, r, pp, pn, Se );
   zal_symp( p, pp, pn, bcof, symoff, sym_n );       // on the own sums, before they travel (as the reference)
   for (int c=0; c<NC; ++c) { part[(size_t)i*15+c] = r[c]; part[(size_t)i*15+5+c] = pp[c]; part[(size_t)i*15+10+c] = pn[c]; }
 }
@@ -399,4 +420,108 @@ __global__ void k_zal_nofct( size_t npoin, size_t NP, const double* __restrict__
   for (int c=0; c<NC; ++c) { u[c] = U[c*NP+p] - dt*R[p*NC+c]*ivp; Unew[c*NP+p] = u[c]; }
   primitive( u, w );
   store_w( W, NP, p, w );
+}
+
+
+// ---- transported scalars in ZalCG: the three FCT node passes for ONE scalar (rows sv, UL, P[2], Q[2] of that
+// ---- scalar; sF its edge fluxes). Same arithmetic as a flow component, no symmetry BC.
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_zal_snode1( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq,
+              const double* __restrict__ D, size_t nslot, const double* __restrict__ sF, const double* __restrict__ sv,
+              const int* __restrict__ bslot, const double* __restrict__ sRb, int ns, int ks,
+              const double* __restrict__ vol, double dt, const double* __restrict__ dtp, double ctau, int fct,
+              double* __restrict__ P, double* __restrict__ UL )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  if (dtp) dt = dtp[p];
+  long long base = sl_base[slice];
+  int kmax = (int)((sl_base[slice+1] - base) >> 5);
+  double up = sv[p], r = 0.0, pp = 0.0, pn = 0.0;
+  for (int k=0; k<kmax; ++k) {
+    int2 eq = __ldg( inc_eq + base + (long long)k*32 + lane );
+    const int se = eq.x;
+    if (se == 0) continue;
+    size_t q = (size_t)eq.y, sl = (size_t)(abs(se)-1);
+    double dif = __ldg( D + 3*nslot + sl ), f = __ldg( sF + sl ), uq = __ldg( sv + q );
+    if (se < 0) {
+      r -= f;
+      double aec = -dif * ctau * (up - uq);
+      if (aec > 0.0) pn -= aec; else pp -= aec;
+    } else {
+      r += f;
+      double aec = -dif * ctau * (uq - up);
+      if (aec > 0.0) pp += aec; else pn += aec;
+    }
+  }
+  int b = bslot[p];
+  if (b >= 0) r += sRb[(size_t)b*ns + ks];
+  double ivp = 1.0 / vol[p];
+  if (!fct) { UL[p] = up - dt*r*ivp; return; }          // u = u - dt R/vol (ZalCG.cpp:1560-1567)
+  pp *= ivp; pn *= ivp;
+  P[p] = pp; P[NP+p] = pn;
+  UL[p] = up - dt*r*ivp - pp - pn;
+}
+
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_zal_snode2( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq,
+              const double* __restrict__ sv, const double* __restrict__ UL, const double* __restrict__ P, int clip,
+              double* __restrict__ Q )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = sl_base[slice];
+  int kmax = (int)((sl_base[slice+1] - base) >> 5);
+  double ulp = UL[p], u = sv[p];
+  double hp = clip ? ulp : fmax( ulp, u ), lp = clip ? ulp : fmin( ulp, u );
+  double qa = -1.7976931348623157e308, qb = 1.7976931348623157e308;
+  for (int k=0; k<kmax; ++k) {                 // padding entries point at the node itself: no effect on the bounds
+    size_t q = (size_t)__ldg( inc_eq + base + (long long)k*32 + lane ).y;
+    double ulq = __ldg( UL + q );
+    double hq = ulq, lq = ulq;
+    if (!clip) { double uq = __ldg( sv + q ); hq = fmax( ulq, uq ); lq = fmin( ulq, uq ); }
+    qa = fmax( qa, fmax( hp, hq ) );
+    qb = fmin( qb, fmin( lp, lq ) );
+  }
+  const double eps = 2.220446049250313e-16;
+  double a = qa - ulp, b = qb - ulp;
+  double pa = P[p], pb = P[NP+p];
+  Q[p]    = pa <  eps ? 0.0 : fmin( 1.0, a/pa );
+  Q[NP+p] = pb > -eps ? 0.0 : fmin( 1.0, b/pb );
+}
+
+__global__ void __launch_bounds__(NODE_THREADS, 3)
+k_zal_snode3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, const int2* __restrict__ inc_eq,
+              const double* __restrict__ D, size_t nslot, const double* __restrict__ sv, const double* __restrict__ UL,
+              const double* __restrict__ Q, const double* __restrict__ vol, double ctau, double* __restrict__ Unew )
+{
+  size_t slice = (blockIdx.x*(size_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  size_t p = slice*32 + lane;
+  if (p >= npoin) return;
+  long long base = sl_base[slice];
+  int kmax = (int)((sl_base[slice+1] - base) >> 5);
+  double up = sv[p], cpa = Q[p], cpb = Q[NP+p], a = 0.0;
+  for (int k=0; k<kmax; ++k) {
+    int2 eq = __ldg( inc_eq + base + (long long)k*32 + lane );
+    const int se = eq.x;
+    if (se == 0) continue;
+    size_t q = (size_t)eq.y;
+    double dif = __ldg( D + 3*nslot + (size_t)(abs(se)-1) );
+    double uq = __ldg( sv + q ), cqa = __ldg( Q + q ), cqb = __ldg( Q + NP + q );
+    if (se < 0) {      // first = this node, second = q
+      double aec = -dif * ctau * (up - uq);
+      double coef = fmin( aec < 0.0 ? cpa : cpb, aec > 0.0 ? cqa : cqb );
+      a -= aec * coef;
+    } else {           // first = q, second = this node
+      double aec = -dif * ctau * (uq - up);
+      double coef = fmin( aec < 0.0 ? cqa : cqb, aec > 0.0 ? cpa : cpb );
+      a += aec * coef;
+    }
+  }
+  Unew[p] = UL[p] + a / vol[p];
 }

@@ -71,7 +71,8 @@ Config to_cfg( const xyst_host_cfg* c ) {
   k.src_radius = c->src_radius; k.src_release_time = c->src_release_time;
   if (c->freezeflow != 0.0) k.freezeflow = c->freezeflow;
   k.freezetime = c->freezetime;
-  if (k.freezeflow > 1.0 && k.solver != "chocg" && k.solver != "kozcg") throw std::runtime_error( "freezeflow is implemented for ChoCG and KozCG only" );
+  if (k.freezeflow > 1.0 && k.solver != "chocg" && k.solver != "kozcg" && k.solver != "zalcg")
+    throw std::runtime_error( "freezeflow is implemented for ZalCG, KozCG and ChoCG only" );
   if (k.solver == "chocg" || k.solver == "lohcg") {
     k.mu = c->mu; k.dif = c->dif; k.stab = c->stab != 0; k.rk = c->rk ? c->rk : 1;
     for (int i=0; i<c->nnoslip; ++i) k.bc_noslip.push_back( c->noslip[i] );

@@ -132,8 +132,8 @@ RieCG::RieCG( Discretization& disc, const TetMesh& chunk, const Config& cfg )
   if (m_loh) { if (cfg.ncomp < 4u || cfg.ncomp > 8u) throw std::runtime_error( "LohCG: ncomp must be 4 (p,u,v,w) + at most 4 transported scalars" ); }
   else if (m_cho ? (cfg.ncomp < 3u || cfg.ncomp > 7u) : (cfg.ncomp < 5u || cfg.ncomp > 13u))
     throw std::runtime_error( m_cho ? "ChoCG: ncomp must be 3 (velocity) + at most 4 transported scalars" : "ncomp must be 5 (+ at most 8 transported scalars)" );
-  if (cfg.ncomp > 5u && !m_cho && !m_loh && cfg.solver != "riecg" && cfg.solver != "kozcg")
-    throw std::runtime_error( "transported scalars are implemented for RieCG, KozCG, ChoCG and LohCG only" );
+  if (cfg.ncomp > 5u && !m_cho && !m_loh && cfg.solver != "riecg" && cfg.solver != "kozcg" && cfg.solver != "zalcg")
+    throw std::runtime_error( "transported scalars are implemented for RieCG, ZalCG, KozCG, ChoCG and LohCG only" );
   // Transporter::matchsets as the reference executes it (Transporter.cpp:125-187 with the
   // short-circuit at :347-348): with at least one side set named in the configuration the
   // faces of ALL side sets of the mesh keep their boundary integrals; with none, no face does.
@@ -522,8 +522,8 @@ void RieCG::hostSetup()
     }
   }
   m_timedep = problems::timeDependent( m_cfg );
-  if (m_timedep && (m_zal || m_lax || m_cfg.steady))
-    throw std::runtime_error( "time-dependent problems are hooked up for RieCG, KozCG, ChoCG and LohCG only" );
+  if (m_timedep && (m_lax || m_cfg.steady))
+    throw std::runtime_error( "time-dependent problems are not hooked up for LaxCG and steady-state runs" );
   evalDirvals( m_disc.T() );
   evalSrc( m_disc.T() );
   if (m_cho || m_loh) choPrelhs();           // LohCG::prelhs :140-181 is ChoCG's
@@ -632,7 +632,7 @@ void RieCG::setup()
                       m_farbcnodes.size(), m_farbcnodes.data(), m_farbcnorms.data(),
                       m_cfg.far_density, m_cfg.far_pressure, m_cfg.far_velocity.data(),
                       m_prebcnodes.size(), m_prebcnodes.data(), m_prebcvals.data() ) );
-  if (!m_src.empty() && !m_koz) ck( xyst_src_upload( m_ctx, m_src.data() ) );
+  if (!m_src.empty() && !m_koz && !m_zal) ck( xyst_src_upload( m_ctx, m_src.data() ) );      // (ZalCG, KozCG: per step, with the edge / centroid part)
   ck( xyst_state_set( m_ctx, m_u0.data() ) );
   BC();                                            // RieCG::merge :754
   ck( xyst_sync( m_ctx ) );
@@ -646,10 +646,10 @@ real RieCG::dt()
   if (std::abs( m_cfg.dt ) > eps) mindt = m_cfg.dt;
   else if (m_nranks > 1 && m_nccl_reduce) { ck( xyst_dt_min_all( m_ctx, m_cfg.cfl, &mindt ) ); return mindt; }   // contribute(min_double) :850
   else ck( xyst_dt_min( m_ctx, m_cfg.cfl, &mindt ) );
-  if (m_koz && !(std::abs( m_cfg.dt ) > eps)) {      // KozCG::dt :669-674: frozen flow, the scalars advance with freezeflow x dt
-    if (m_disc.T() > m_cfg.freezetime && m_cfg.freezeflow > 1.0 && m_freezeflow <= 1.0) {
+  if ((m_koz || m_zal) && !(std::abs( m_cfg.dt ) > eps)) {      // KozCG::dt :669-674, ZalCG::dt :948-952: frozen flow,
+    if (m_disc.T() > m_cfg.freezetime && m_cfg.freezeflow > 1.0 && m_freezeflow <= 1.0) {      // the scalars advance with freezeflow x dt
       m_freezeflow = m_cfg.freezeflow;
-      ck( xyst_kozcg_freeze( m_ctx, 1 ) );
+      ck( (m_koz ? xyst_kozcg_freeze : xyst_zalcg_freeze)( m_ctx, 1 ) );
     }
     mindt *= m_freezeflow;
   }
@@ -692,7 +692,35 @@ bool RieCG::step( std::vector< real >* diagrow )
     m_pinned = true;
   }
   advance( dt() );
-  if (m_zal) ck( xyst_zalcg_step( m_ctx, m_disc.Dt() ) );      // ZalCG.cpp:973-1607
+  if (m_zal) {                                                  // ZalCG.cpp:973-1607
+    if (problems::SRC( m_cfg ) && (m_timedep || m_zedge[0].empty())) {
+      // zalesak::rhs source term: at the nodes at t, at the edge midpoints at t + dt/2 (Zalesak.cpp:118-128,152-163)
+      if (m_zedge[0].empty()) {
+        auto ns = xyst_nslot( m_ctx );
+        m_zedge[0].resize( ns ); m_zedge[1].resize( ns );
+        ck( xyst_edge_list( m_ctx, m_zedge[0].data(), m_zedge[1].data() ) );
+      }
+      evalSrc( m_disc.T() );
+      auto src = problems::SRC( m_cfg );
+      const auto& co = m_disc.Coord();
+      const auto ncomp = m_cfg.ncomp, ns = m_zedge[0].size();
+      const auto te = m_disc.T() + m_disc.Dt()/2.0;
+      std::vector< real > se( ns*ncomp, 0.0 );
+      #pragma omp parallel for schedule(static)
+      for (std::size_t e=0; e<ns; ++e) {
+        auto p = m_zedge[0][e], q = m_zedge[1][e];
+        if (p == static_cast< std::size_t >( -1 )) continue;
+        auto sv = src( (co[0][p] + co[0][q])/2.0, (co[1][p] + co[1][q])/2.0, (co[2][p] + co[2][q])/2.0, te );
+        for (std::size_t c=0; c<ncomp; ++c) se[e*ncomp+c] = sv[c];
+      }
+      ck( xyst_zalcg_src( m_ctx, m_src.data(), se.data() ) );
+    }
+    if (m_timedep) {                                            // BC( m_a, d->T() + d->Dt() ) :1575
+      evalDirvals( m_disc.T() + m_disc.Dt() );
+      if (!m_dirvals.empty()) ck( xyst_dirbc_values( m_ctx, m_dirvals.data() ) );
+    }
+    ck( xyst_zalcg_step( m_ctx, m_disc.Dt() ) );
+  }
   else if (m_koz) {                                            // KozCG.cpp:691-1197
     if (m_timedep) {
       // sources at the nodes at t and at the centroids at t + dt/2 (Kozak.cpp:104,163), Dirichlet

@@ -219,7 +219,8 @@ class RieCG {
     bool m_koz = false;                    //!< KozCG: element-based, no edge integrals
     bool m_cho = false;                    //!< ChoCG: stride-5 integrals, projection steps (chocg.cpp)
     int m_np = 0;                          //!< ChoCG::m_np
-    real m_freezeflow = 1.0;               //!< ChoCG::m_freezeflow
+    real m_freezeflow = 1.0;               //!< ChoCG / KozCG / ZalCG::m_freezeflow
+    std::array< std::vector< std::size_t >, 2 > m_zedge;   //!< end nodes of the device's edge slots (ZalCG source term)
     bool m_initial = true;                 //!< Discretization::Initial()
     std::map< std::size_t, real > m_pbc;   //!< pressure Dirichlet node -> value of the first solves
     std::vector< real > m_neubc, m_prhs, m_psol, m_lastdiag;

@@ -161,7 +161,7 @@ def main():
         return cg_main(out, rank, world, local)
     if mode == "proj":
         return proj_main(case, nsteps, out, rank, world, local)
-    kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.HCASES, **O.ZCASES, **O.KCASES}[case]
+    kw = {**O.CASES, **O.LCASES, **O.CCASES, **O.HCASES, **O.ZCASES, **O.KCASES, **O.SCASES}[case]
     mesh = O.load_mesh(kw.get("mesh", case))
     hm = fixture_to_host_mesh(mesh)
     part = H.rcb(hm["coord"], hm["tets"], world)

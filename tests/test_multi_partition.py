@@ -127,11 +127,14 @@ def test_two_gpus_match_oracle_two_chares(case, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["zalcg_sod", "zalcg_sedov", "kozcg_sod", "kozcg_taylor_green"])
+@pytest.mark.parametrize("case", ["zalcg_sod", "zalcg_sedov", "kozcg_sod", "kozcg_taylor_green", "zalcg_slot_cyl",
+                                  "kozcg_slot_cyl"])
 def test_two_gpus_zalcg_match_oracle_two_chares(case, tmp_path):
     """ZalCG and KozCG on 2 GPUs: after each FCT pass the shared nodes' own sums travel over NCCL -- rhs and
     antidiffusive sums P+/- (summed; ZalCG::comrhs/comaec), allowed bounds Q+/- (max / min; comalw,
-    ZalCG.cpp:1316-1325), limited sums (summed; comlim) -- against the oracle's 2-chare run."""
+    ZalCG.cpp:1316-1325), limited sums (summed; comlim) -- against the oracle's 2-chare run. The slot_cyl cases
+    add a transported scalar (the same three exchanges per scalar), the source term (each partition evaluates
+    it on its own edges / elements) and the frozen flow."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -143,10 +146,12 @@ def test_two_gpus_zalcg_match_oracle_two_chares(case, tmp_path):
     rows = np.asarray(res[0]["rows"])
     assert rows.shape == d.shape
     for c in range(1, d.shape[1]):
-        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-12 * np.abs(d[:, c]).max() + 1e-300, c
+        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-12 * np.abs(d[:, c]).max() + (1e-15 if "slot_cyl" in case else 1e-300), c
     for k in range(2):
         U = np.asarray(res[k]["u"]); Uo = o.get("u", k)
-        assert np.abs(U - Uo).max() <= 1e-12 * np.abs(Uo).max()
+        assert np.abs(U[:, :5] - Uo[:, :5]).max() <= 1e-12 * np.abs(Uo[:, :5]).max()
+        if U.shape[1] > 5:
+            assert np.abs(U[:, 5:] - Uo[:, 5:]).max() <= 1e-12 * max(np.abs(Uo[:, 5:]).max(), 0.6)
 
 
 PROJ = ["chocg_poisson_neumann", "chocg_poiseuille_damp2", "chocg_ldc", "chocg_poiseuille_theta",

@@ -464,3 +464,34 @@ __global__ void k_koz_nofct( size_t npoin, size_t NP, const double* __restrict__
   primitive( u, w );
   store_w( W, NP, p, w );
 }
+
+// one scalar on several partitions: the shared nodes' own sums of a pass from the per-tet buffer (T rows as
+// written by k_koz_selem1 / k_koz_elem2<1> / k_koz_elem3<1>) -> part[i][3|2|1]; finished by k_fct_sfin
+__global__ void k_koz_ssh( int mode, int nsh, size_t ntet, const int* __restrict__ sh_node,
+              const long long* __restrict__ kbase, const int* __restrict__ kinc, const double* __restrict__ T,
+              double* __restrict__ part )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  int lane = (int)(p & 31);
+  long long base = kbase[p >> 5];
+  int kmax = (int)((kbase[(p >> 5)+1] - base) >> 5);
+  double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+  if (mode == 2) { v0 = -1.7976931348623157e308; v1 = 1.7976931348623157e308; }
+  for (int k=0; k<kmax; ++k) {
+    int ta = __ldg( kinc + base + (long long)k*32 + lane );
+    if (ta < 0) continue;
+    size_t e = (size_t)(ta >> 2); int a = ta & 3;
+    if (mode == 1) {
+      v0 += __ldg( T + (size_t)a*ntet + e );
+      double aec = __ldg( T + (size_t)(4+a)*ntet + e ); v1 += fmax( 0.0, aec ); v2 += fmin( 0.0, aec );
+    } else if (mode == 2) {
+      v0 = fmax( v0, __ldg( T + e ) ); v1 = fmin( v1, __ldg( T + ntet + e ) );
+    } else
+      v0 += __ldg( T + (size_t)a*ntet + e );
+  }
+  if (mode == 1) { part[(size_t)i*3] = v0; part[(size_t)i*3+1] = v1; part[(size_t)i*3+2] = v2; }
+  else if (mode == 2) { part[(size_t)i*2] = v0; part[(size_t)i*2+1] = v1; }
+  else part[i] = v0;
+}

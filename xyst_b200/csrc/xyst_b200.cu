@@ -782,6 +782,7 @@ void zal_need( xyst_ctx* c ) {
     c->ksUL.alloc( ns*c->NP ); c->ksP.alloc( 2*ns*c->NP ); c->ksQ.alloc( 2*ns*c->NP );
   }
 }
+bool zal_halo( const xyst_ctx* c ) { return c->nsh > 0 && c->comm; }
 void zal_flux_and_bnd( xyst_ctx* c, double dt )
 {
   auto s = c->stream;
@@ -803,18 +804,30 @@ void zal_scalars( xyst_ctx* c, double dt, int fct )
   for (int k=0; k<c->ns; ++k) {
     const double* sv = c->sU.p + (size_t)k*NP; const double* sf = c->sF.p + (size_t)k*c->nslot;
     double *sn = c->sUn.p + (size_t)k*NP, *ul = c->ksUL.p + (size_t)k*NP, *P = c->ksP.p + (size_t)2*k*NP, *Q = c->ksQ.p + (size_t)2*k*NP;
+    // with several partitions each pass is followed by: own sums of the shared nodes -> exchange -> finish
+    auto shared = [&]( int mode, int w ) {
+      if (!zal_halo( c )) return;
+      unsigned gs = nblk( c->nsh, 128 );
+      k_zal_ssh<<< gs, 128, 0, s >>>( mode, (int)c->nsh, NP, c->sh_node.p, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot, sf, sv,
+        ul, Q, c->bslot.p, c->sRb.p, c->ns, k, c->zal.fctdif, c->zal.fctclip, c->sh_part.p ); ++c->launches;
+      exchange( c, w ); exchange_wait( c );
+      k_fct_sfin<<< gs, 128, 0, s >>>( mode, (int)c->nsh, NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p,
+        c->sh_recvbuf.p, sv, c->vol.p, -dt, dtp, fct, P, fct ? ul : sn, Q, sn ); ++c->launches;
+    };
     k_zal_snode1<<< g, NODE_THREADS, 0, s >>>( c->npoin, NP, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot, sf, sv, c->bslot.p,
       c->sRb.p, c->ns, k, c->vol.p, dt, dtp, c->zal.fctdif, fct, P, fct ? ul : sn ); ++c->launches;
+    shared( 1, 3 );
     if (!fct) continue;
     k_zal_snode2<<< g, NODE_THREADS, 0, s >>>( c->npoin, NP, c->sl_base.p, c->inc_eq.p, sv, ul, P, c->zal.fctclip, Q ); ++c->launches;
+    shared( 2, 2 );
     k_zal_snode3<<< g, NODE_THREADS, 0, s >>>( c->npoin, NP, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot, sv, ul, Q, c->vol.p,
       c->zal.fctdif, sn ); ++c->launches;
+    shared( 3, 1 );
   }
 }
 // With several partitions every pass is followed by the exchange of the shared nodes' own sums
 // (ZalCG::comrhs+comaec: sums, comalw: max/min, comlim: sums; ZalCG.cpp:1023-1053,1139-1148,1297-1333,
 // 1490-1499) and a kernel that finishes those nodes from the complete values.
-bool zal_halo( const xyst_ctx* c ) { return c->nsh > 0 && c->comm; }
 void zal_node1( xyst_ctx* c, double dt, int fct )
 {
   auto s = c->stream;
@@ -851,7 +864,6 @@ int xyst_zalcg_step( xyst_ctx* c, double dt )
   zal_need( c );
   auto s = c->stream;
   unsigned g = nblk( c->nslice*32, NODE_THREADS );
-  if (c->ns && zal_halo( c )) throw std::runtime_error( "ZalCG: transported scalars on several partitions are not implemented" );
   if (c->ns && (c->zal.fctsys_mask >> NC)) throw std::runtime_error( "ZalCG: fctsys over transported scalars is not implemented" );
   const bool frozen = c->koz_frozen;            // ZalCG::m_freezeflow > 1 (ZalCG.cpp:948-952, 1549, 1577-1584)
   zal_flux_and_bnd( c, dt );
@@ -1400,13 +1412,15 @@ static int allreduce( xyst_ctx* c, double* v, int n, int op )
   API_BEGIN
   CK( cudaSetDevice( c->device ) );
   if (!c->comm) return 0;                       // single partition: nothing to do
-  if (n > NDIAG) throw std::runtime_error( "allreduce: too many values" );
   double* d = c->red.p + (size_t)RED_BLOCKS*NDIAG;
-  CK( cudaMemcpyAsync( d, v, n*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
-  NK( g_nccl.AllReduce( d, d, (size_t)n, NCCL_FLOAT64, op, c->comm, c->stream ) );
-  CK( cudaMemcpyAsync( c->red_host, d, n*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
-  CK( cudaStreamSynchronize( c->stream ) );
-  for (int i=0; i<n; ++i) v[i] = c->red_host[i];
+  for (int o=0; o<n; o+=NDIAG) {                // in pieces of the scratch size (diagnostics with transported scalars)
+    int m = std::min( NDIAG, n-o );
+    CK( cudaMemcpyAsync( d, v+o, m*sizeof(double), cudaMemcpyHostToDevice, c->stream ) );
+    NK( g_nccl.AllReduce( d, d, (size_t)m, NCCL_FLOAT64, op, c->comm, c->stream ) );
+    CK( cudaMemcpyAsync( c->red_host, d, m*sizeof(double), cudaMemcpyDeviceToHost, c->stream ) );
+    CK( cudaStreamSynchronize( c->stream ) );
+    for (int i=0; i<m; ++i) v[o+i] = c->red_host[i];
+  }
   API_END
 }
 int xyst_allreduce_min( xyst_ctx* c, double* v, int n ) { return allreduce( c, v, n, NCCL_MIN ); }
@@ -1575,13 +1589,24 @@ static void koz_scalars( xyst_ctx* c, double dt, int fct )
   for (int k=0; k<c->ns; ++k) {
     const double* sv = c->sU.p + (size_t)k*NP;
     double *sn = c->sUn.p + (size_t)k*NP, *ul = c->ksUL.p + (size_t)k*NP, *P = c->ksP.p + (size_t)2*k*NP, *Q = c->ksQ.p + (size_t)2*k*NP;
+    auto shared = [&]( int mode, int w ) {          // several partitions: own sums of the shared nodes -> exchange -> finish
+      if (!zal_halo( c )) return;
+      unsigned gs = nblk( c->nsh, 128 );
+      k_koz_ssh<<< gs, 128, 0, s >>>( mode, (int)c->nsh, ntet, c->sh_node.p, c->kbase.p, c->kinc.p, c->kT.p, c->sh_part.p ); ++c->launches;
+      exchange( c, w ); exchange_wait( c );
+      k_fct_sfin<<< gs, 128, 0, s >>>( mode, (int)c->nsh, NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p,
+        c->sh_recvbuf.p, sv, c->vol.p, dt, nullptr, fct, P, fct ? ul : sn, Q, sn ); ++c->launches;
+    };
     k_koz_selem1<<< ge, 128, 0, s >>>( ntet, NP, c->ktet.p, c->U.p, sv, c->X.p, c->kUE.p, dt, c->zal.fctdif, fct, c->kT.p ); ++c->launches;
     k_koz_snode1<<< gn, NODE_THREADS, 0, s >>>( c->npoin, NP, ntet, c->kbase.p, c->kinc.p, c->kT.p, sv, c->vol.p, dt, fct, P, fct ? ul : sn ); ++c->launches;
+    shared( 1, 3 );
     if (!fct) continue;
     k_koz_elem2< 1 ><<< ge, 128, 0, s >>>( ntet, NP, c->ktet.p, sv, ul, c->zal.fctclip, c->kT.p ); ++c->launches;
     k_koz_node2< 1 ><<< gn, NODE_THREADS, 0, s >>>( c->npoin, NP, ntet, c->kbase.p, c->kinc.p, c->kT.p, ul, P, Q ); ++c->launches;
+    shared( 2, 2 );
     k_koz_elem3< 1 ><<< ge, 128, 0, s >>>( ntet, NP, c->ktet.p, sv, c->X.p, Q, c->zal.fctdif, 0, c->kT.p ); ++c->launches;
     k_koz_node3< 1, false ><<< gn, NODE_THREADS, 0, s >>>( c->npoin, NP, ntet, c->kbase.p, c->kinc.p, c->kT.p, ul, c->vol.p, sn, nullptr ); ++c->launches;
+    shared( 3, 1 );
   }
 }
 
@@ -1602,7 +1627,6 @@ int xyst_kozcg_step( xyst_ctx* c, double dt )
   koz_need( c );
   auto s = c->stream;
   unsigned gn = nblk( c->nslice*32, NODE_THREADS ), ge = nblk( c->ntet, 128 );
-  if (c->ns && zal_halo( c )) throw std::runtime_error( "KozCG: transported scalars on several partitions are not implemented" );
   if (c->ns && (c->zal.fctsys_mask >> NC)) throw std::runtime_error( "KozCG: fctsys over transported scalars is not implemented" );
   const bool frozen = c->koz_frozen;
   if (c->zal.fct) {

@@ -525,3 +525,97 @@ k_zal_snode3( size_t npoin, size_t NP, const long long* __restrict__ sl_base, co
   }
   Unew[p] = UL[p] + a / vol[p];
 }
+
+// ---- one scalar on several partitions (ZalCG::comrhs/comaec, comalw, comlim per component): the shared nodes'
+// ---- OWN sums of a pass (mode 1: r, P+, P-; 2: bounds; 3: limited sum) -> part[i][3|2|1]; after the exchange
+// ---- the nodes are finished from the complete values by k_fct_sfin (shared with KozCG)
+__global__ void k_zal_ssh( int mode, int nsh, size_t NP, const int* __restrict__ sh_node, const long long* __restrict__ sl_base,
+              const int2* __restrict__ inc_eq, const double* __restrict__ D, size_t nslot, const double* __restrict__ sF,
+              const double* __restrict__ sv, const double* __restrict__ UL, const double* __restrict__ Q,
+              const int* __restrict__ bslot, const double* __restrict__ sRb, int ns, int ks, double ctau, int clip,
+              double* __restrict__ part )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  int lane = (int)(p & 31);
+  long long base = sl_base[p >> 5];
+  int kmax = (int)((sl_base[(p >> 5)+1] - base) >> 5);
+  double up = sv[p];
+  if (mode == 1) {
+    double r = 0.0, pp = 0.0, pn = 0.0;
+    for (int k=0; k<kmax; ++k) {
+      int2 eq = __ldg( inc_eq + base + (long long)k*32 + lane );
+      const int se = eq.x;
+      if (se == 0) continue;
+      size_t q = (size_t)eq.y, sl = (size_t)(abs(se)-1);
+      double dif = __ldg( D + 3*nslot + sl ), f = __ldg( sF + sl ), uq = __ldg( sv + q );
+      if (se < 0) { r -= f; double aec = -dif * ctau * (up - uq); if (aec > 0.0) pn -= aec; else pp -= aec; }
+      else        { r += f; double aec = -dif * ctau * (uq - up); if (aec > 0.0) pp += aec; else pn += aec; }
+    }
+    int b = bslot[p];
+    if (b >= 0) r += sRb[(size_t)b*ns + ks];
+    part[(size_t)i*3] = r; part[(size_t)i*3+1] = pp; part[(size_t)i*3+2] = pn;
+  } else if (mode == 2) {
+    double ulp = UL[p];
+    double hp = clip ? ulp : fmax( ulp, up ), lp = clip ? ulp : fmin( ulp, up );
+    double qa = -1.7976931348623157e308, qb = 1.7976931348623157e308;
+    for (int k=0; k<kmax; ++k) {
+      size_t q = (size_t)__ldg( inc_eq + base + (long long)k*32 + lane ).y;
+      double ulq = __ldg( UL + q );
+      double hq = ulq, lq = ulq;
+      if (!clip) { double uq = __ldg( sv + q ); hq = fmax( ulq, uq ); lq = fmin( ulq, uq ); }
+      qa = fmax( qa, fmax( hp, hq ) );
+      qb = fmin( qb, fmin( lp, lq ) );
+    }
+    part[(size_t)i*2] = qa; part[(size_t)i*2+1] = qb;
+  } else {
+    double cpa = Q[p], cpb = Q[NP+p], a = 0.0;
+    for (int k=0; k<kmax; ++k) {
+      int2 eq = __ldg( inc_eq + base + (long long)k*32 + lane );
+      const int se = eq.x;
+      if (se == 0) continue;
+      size_t q = (size_t)eq.y;
+      double dif = __ldg( D + 3*nslot + (size_t)(abs(se)-1) );
+      double uq = __ldg( sv + q ), cqa = __ldg( Q + q ), cqb = __ldg( Q + NP + q );
+      if (se < 0) { double aec = -dif * ctau * (up - uq); a -= aec * fmin( aec < 0.0 ? cpa : cpb, aec > 0.0 ? cqa : cqb ); }
+      else        { double aec = -dif * ctau * (uq - up); a += aec * fmin( aec < 0.0 ? cqa : cqb, aec > 0.0 ? cpa : cpb ); }
+    }
+    part[i] = a;
+  }
+}
+
+// finish of a pass of one scalar at the shared nodes from own + received parts; sign = -1 (ZalCG: ul = u - dt r/vol)
+// or +1 (KozCG: ul = u + dt r/vol). mode 1 writes P, UL (or, without FCT, the new value into UL); 2: Q; 3: Unew.
+__global__ void k_fct_sfin( int mode, int nsh, size_t NP, const int* __restrict__ sh_node, const int* __restrict__ roff,
+              const int* __restrict__ ridx, const double* __restrict__ part, const double* __restrict__ recvbuf,
+              const double* __restrict__ sv, const double* __restrict__ vol, double sdt, const double* __restrict__ dtp,
+              int fct, double* __restrict__ P, double* __restrict__ UL, double* __restrict__ Q, double* __restrict__ Unew )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  if (mode == 1) {
+    double t[3];
+    for (int j=0; j<3; ++j) { double a = part[(size_t)i*3+j]; for (int r=roff[i]; r<roff[i+1]; ++r) a += recvbuf[(size_t)ridx[r]*3+j]; t[j] = a; }
+    if (dtp) sdt = sdt < 0.0 ? -dtp[p] : dtp[p];
+    double ivp = 1.0 / vol[p];
+    if (!fct) { UL[p] = sv[p] + sdt*t[0]*ivp; return; }
+    double pp = t[1]*ivp, pn = t[2]*ivp;
+    P[p] = pp; P[NP+p] = pn;
+    UL[p] = sv[p] + sdt*t[0]*ivp - pp - pn;
+  } else if (mode == 2) {
+    double a = part[(size_t)i*2], b = part[(size_t)i*2+1];
+    for (int r=roff[i]; r<roff[i+1]; ++r) { a = fmax( a, recvbuf[(size_t)ridx[r]*2] ); b = fmin( b, recvbuf[(size_t)ridx[r]*2+1] ); }
+    const double eps = 2.220446049250313e-16;
+    double ulp = UL[p];
+    a -= ulp; b -= ulp;
+    double pa = P[p], pb = P[NP+p];
+    Q[p]    = pa <  eps ? 0.0 : fmin( 1.0, a/pa );
+    Q[NP+p] = pb > -eps ? 0.0 : fmin( 1.0, b/pb );
+  } else {
+    double a = part[i];
+    for (int r=roff[i]; r<roff[i+1]; ++r) a += recvbuf[ridx[r]];
+    Unew[p] = UL[p] + a / vol[p];
+  }
+}

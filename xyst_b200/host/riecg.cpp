@@ -643,8 +643,9 @@ real RieCG::dt()
 {
   real mindt;
   auto eps = std::numeric_limits< real >::epsilon();
+  bool reduced = false;
   if (std::abs( m_cfg.dt ) > eps) mindt = m_cfg.dt;
-  else if (m_nranks > 1 && m_nccl_reduce) { ck( xyst_dt_min_all( m_ctx, m_cfg.cfl, &mindt ) ); return mindt; }   // contribute(min_double) :850
+  else if (m_nranks > 1 && m_nccl_reduce) { ck( xyst_dt_min_all( m_ctx, m_cfg.cfl, &mindt ) ); reduced = true; }   // contribute(min_double) :850
   else ck( xyst_dt_min( m_ctx, m_cfg.cfl, &mindt ) );
   if ((m_koz || m_zal) && !(std::abs( m_cfg.dt ) > eps)) {      // KozCG::dt :669-674, ZalCG::dt :948-952: frozen flow,
     if (m_disc.T() > m_cfg.freezetime && m_cfg.freezeflow > 1.0 && m_freezeflow <= 1.0) {      // the scalars advance with freezeflow x dt
@@ -653,7 +654,7 @@ real RieCG::dt()
     }
     mindt *= m_freezeflow;
   }
-  if (m_nranks > 1) { std::vector< real > t{ mindt }; m_allreduce( 1, t ); mindt = t[0]; }
+  if (m_nranks > 1 && !reduced) { std::vector< real > t{ mindt }; m_allreduce( 1, t ); mindt = t[0]; }
   return mindt;
 }
 

@@ -104,7 +104,7 @@ def test_two_partitions_projection_solver_setup_gloo(case, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["riecg_sod", "riecg_sedov", "riecg_taylor_green"])
+@pytest.mark.parametrize("case", ["riecg_sod", "riecg_sedov", "riecg_taylor_green", "riecg_slot_cyl"])
 def test_two_gpus_match_oracle_two_chares(case, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
@@ -117,8 +117,8 @@ def test_two_gpus_match_oracle_two_chares(case, tmp_path):
     d = o.diag()
     rows = np.asarray(res[0]["rows"])
     assert rows.shape == d.shape
-    for c in range(1, d.shape[1]):
-        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-12 * np.abs(d[:, c]).max(), c
+    for c in range(1, d.shape[1]):      # (+ 1e-15: the z-momentum columns of the planar slot_cyl rotation are zero up to rounding)
+        assert np.abs(rows[:, c] - d[:, c]).max() <= 1e-12 * np.abs(d[:, c]).max() + (1e-15 if "slot_cyl" in case else 0.0), c
     assert np.array_equal(np.asarray(res[1]["rows"]), rows)      # all ranks see the same reductions
     for k in range(2):
         U = np.asarray(res[k]["u"]); Uo = o.get("u", k)

@@ -134,6 +134,53 @@ __global__ void k_scal_node( size_t npoin, int ns, size_t NP, const long long* _
   }
 }
 
+// several partitions (RieCG::comrhs for the scalar columns): the own nodal sums of the shared nodes ->
+// part[i][ns]; after the exchange the shared nodes are finished from the complete sums
+__global__ void k_scal_sh( int nsh, int ns, const int* __restrict__ sh_node, const long long* __restrict__ sl_base,
+                           const int* __restrict__ inc_e, const double* __restrict__ sF, size_t nslot,
+                           const int* __restrict__ bslot, const double* __restrict__ sRb, const double* __restrict__ sS,
+                           const double* __restrict__ v, double* __restrict__ part )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  int lane = (int)(p & 31);
+  long long base = sl_base[p >> 5];
+  int kmax = (int)((sl_base[(p >> 5)+1] - base) >> 5);
+  int b = bslot[p];
+  for (int c=0; c<ns; ++c) {
+    double acc = 0.0;
+    for (int k=0; k<kmax; ++k) {
+      int se = __ldg( inc_e + base + (long long)k*32 + lane );
+      if (se == 0) continue;
+      double f = sF[(size_t)c*nslot + (size_t)(abs(se)-1)];
+      acc = se > 0 ? acc + f : acc - f;
+    }
+    if (b >= 0) acc += sRb[(size_t)b*ns + c];
+    if (sS) acc -= sS[p*(size_t)ns + c] * v[p];
+    part[(size_t)i*ns + c] = acc;
+  }
+}
+template< bool FUSED >
+__global__ void k_scal_shfin( int nsh, int ns, size_t NP, const int* __restrict__ sh_node, const int* __restrict__ roff,
+                              const int* __restrict__ ridx, const double* __restrict__ part, const double* __restrict__ recvbuf,
+                              const double* __restrict__ vol, const double* __restrict__ sUn, double rkdt,
+                              const double* __restrict__ dtp, double rk, double* __restrict__ sUo, double* __restrict__ R, int ncomp )
+{
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= nsh) return;
+  size_t p = sh_node[i];
+  for (int c=0; c<ns; ++c) {
+    double acc = part[(size_t)i*ns + c];
+    for (int r=roff[i]; r<roff[i+1]; ++r) acc += recvbuf[(size_t)ridx[r]*ns + c];
+    if (FUSED) {
+      double f = (dtp ? rk*dtp[p] : rkdt) / vol[p];
+      sUo[(size_t)c*NP + p] = sUn[(size_t)c*NP + p] - f*acc;
+    } else
+      R[p*(size_t)ncomp + 5 + c] = acc;
+  }
+}
+
 // RieCG::solve for the scalar columns of a materialised R (xyst_rk_update)
 __global__ void k_scal_update( size_t npoin, int ns, size_t NP, const double* __restrict__ R, int ncomp,
                                const double* __restrict__ vol, const double* __restrict__ sUn, double rkdt,

@@ -511,7 +511,6 @@ void do_flux( xyst_ctx* c )
 // ---- transported scalars (riecg_scalar.cuh) -------------------------------------------
 void scal_need( xyst_ctx* c ) {
   if (c->lax) throw std::runtime_error( "transported scalars are not implemented for LaxCG" );
-  if (c->nsh > 0 && c->comm) throw std::runtime_error( "transported scalars on several partitions are not implemented yet" );
 }
 // boundary parts + gradients of the scalars; needs the state at stage start
 void scal_grad( xyst_ctx* c )
@@ -523,6 +522,15 @@ void scal_grad( xyst_ctx* c )
   k_scal_grad<<< nblk( c->nslice*32, 128 ), 128, 0, s >>>( c->npoin, c->ns, c->NP, c->sl_base.p, c->inc_eq.p, c->D.p, c->nslot,
     c->sU.p, c->bslot.p, c->sGb.p, c->vol.p, c->sG.p ); ++c->launches;
   CK( cudaGetLastError() );
+  if (c->nsh > 0 && c->comm)              // several partitions (RieCG::comgrad): each part is already over the full nodal volume
+    for (int k=0; k<c->ns; ++k) {
+      double* G = c->sG.p + (size_t)3*k*c->NP;
+      unsigned g = nblk( c->nsh*(size_t)3, 256 );
+      k_soa_shared_get<<< g, 256, 0, s >>>( (int)c->nsh, 3, c->NP, c->sh_node.p, G, c->sh_part.p ); ++c->launches;
+      exchange( c, 3 ); exchange_wait( c );
+      k_soa_shared_put<<< g, 256, 0, s >>>( (int)c->nsh, 3, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p,
+        c->sh_part.p, c->sh_recvbuf.p, G ); ++c->launches;
+    }
 }
 // scalar edge fluxes (after the flow's k_flux_own, which leaves EV) and nodal sums / update
 void scal_flux_nodes( xyst_ctx* c, bool fused, int stage, double dt )
@@ -539,10 +547,27 @@ void scal_flux_nodes( xyst_ctx* c, bool fused, int stage, double dt )
     double* out = stage == 0 ? c->sUn.p : c->sU.p;
     k_scal_node< true ><<< g, 128, 0, s >>>( c->npoin, c->ns, c->NP, c->sl_base.p, c->inc_e.p, c->sF.p, c->nslot, c->bslot.p,
       c->sRb.p, S, c->v.p, c->vol.p, un, rkcoef[stage]*dt, c->steady ? c->dtp.p : nullptr, rkcoef[stage], out, c->R.p, c->ncomp );
+    if (c->nsh > 0 && c->comm) {          // several partitions (RieCG::comrhs): the shared nodes from the complete sums
+      unsigned gs = nblk( c->nsh, 128 );
+      k_scal_sh<<< gs, 128, 0, s >>>( (int)c->nsh, c->ns, c->sh_node.p, c->sl_base.p, c->inc_e.p, c->sF.p, c->nslot, c->bslot.p,
+        c->sRb.p, S, c->v.p, c->sh_part.p ); ++c->launches;
+      exchange( c, c->ns ); exchange_wait( c );
+      k_scal_shfin< true ><<< gs, 128, 0, s >>>( (int)c->nsh, c->ns, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p,
+        c->sh_recvbuf.p, c->vol.p, un, rkcoef[stage]*dt, c->steady ? c->dtp.p : nullptr, rkcoef[stage], out, c->R.p, c->ncomp ); ++c->launches;
+    }
     if (stage == 0) std::swap( c->sU.p, c->sUn.p );
-  } else
+  } else {
     k_scal_node< false ><<< g, 128, 0, s >>>( c->npoin, c->ns, c->NP, c->sl_base.p, c->inc_e.p, c->sF.p, c->nslot, c->bslot.p,
       c->sRb.p, S, c->v.p, c->vol.p, c->sUn.p, 0.0, nullptr, 0.0, c->sU.p, c->R.p, c->ncomp );
+    if (c->nsh > 0 && c->comm) {
+      unsigned gs = nblk( c->nsh, 128 );
+      k_scal_sh<<< gs, 128, 0, s >>>( (int)c->nsh, c->ns, c->sh_node.p, c->sl_base.p, c->inc_e.p, c->sF.p, c->nslot, c->bslot.p,
+        c->sRb.p, S, c->v.p, c->sh_part.p ); ++c->launches;
+      exchange( c, c->ns ); exchange_wait( c );
+      k_scal_shfin< false ><<< gs, 128, 0, s >>>( (int)c->nsh, c->ns, c->NP, c->sh_node.p, c->sh_roff.p, c->sh_ridx.p, c->sh_part.p,
+        c->sh_recvbuf.p, c->vol.p, c->sUn.p, 0.0, nullptr, 0.0, c->sU.p, c->R.p, c->ncomp ); ++c->launches;
+    }
+  }
   ++c->launches;
   CK( cudaGetLastError() );
 }

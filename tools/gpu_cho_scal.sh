@@ -1,6 +1,8 @@
 #!/bin/bash
-# single-GPU check of the projection solvers incl. the transported-scalar cases
+# single-GPU run of the transported-scalar / frozen-flow tests with the regression tests of one solver family:
+#   tools/gpu_cho_scal.sh [pytest -k expression] [extra test files...]
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests/test_gpu_scalars.py tests/test_gpu_zalcg.py -q -s -k "zalcg" > gpurun_out/r2n_cho.log 2>&1
+K="${1:-chocg or lohcg or zalcg or kozcg}"; shift
+timeout 500 python -m pytest tests/test_gpu_scalars.py "$@" -q -s -k "$K" > gpurun_out/r2n_cho.log 2>&1
 echo "rc=$?" >> gpurun_out/r2n_cho.log
 grep -v "^$" gpurun_out/r2n_cho.log | tail -60

@@ -56,19 +56,20 @@ def test_two_partitions_host_logic_gloo(case, tmp_path):
     check_setup(res, o, 2)
 
 
-@pytest.mark.parametrize("case", ["chocg_poiseuille_damp2", "chocg_ldc", "lohcg_poiseuille_damp4"])
-def test_two_partitions_projection_solver_setup_gloo(case, tmp_path):
-    """The partition-level setup of the projection solvers (groundwork for their multi-GPU path; the device
-    time loop of ChoCG/LohCG is single-partition so far): per-partition stride-5 / stride-4 edge integrals
-    incl. the Laplacian term (partial sums on shared edges), Dirichlet masks and values of velocity and
-    pressure, no-slip nodes and the partition's part of the pressure Poisson matrix -- bitwise equal to the
-    oracle's chares on the same element partition."""
-    res = launch("host", case, 0, tmp_path)
-    o = oracle_for(case, res[0]["part"], 2)
-    assert o.scalar("nchare") == 2 and len(o.get("commmap", 0)) > 2
-    check_setup(res, o, 2)
+@pytest.mark.parametrize("case,world", [("chocg_poiseuille_damp2", 2), ("chocg_ldc", 2), ("lohcg_poiseuille_damp4", 2),
+                                        ("chocg_ldc", 4), ("chocg_viscous_sphere", 4)])
+def test_partitions_projection_solver_setup_gloo(case, world, tmp_path):
+    """The partition-level setup of the projection solvers on 2 and 4 partitions (nodes shared by more than two
+    of them included): per-partition stride-5 / stride-4 edge integrals incl. the Laplacian term (partial sums
+    on shared edges), Dirichlet masks and values of velocity and pressure, no-slip nodes and the partition's
+    part of the pressure Poisson matrix -- bitwise equal to the oracle's chares on the same element partition --
+    and the union of the linear solvers' Dirichlet rows over the partitions sharing a node."""
+    res = launch("host", case, 0, tmp_path, world=world)
+    o = oracle_for(case, res[0]["part"], world)
+    assert o.scalar("nchare") == world and len(o.get("commmap", 0)) > 2
+    check_setup(res, o, world)
     st = 4 if case.startswith("lohcg") else 5
-    for k in range(2):
+    for k in range(world):
         r = res[k]
         def singles(e, d):
             e = np.asarray(e).reshape(-1, 2); d = np.asarray(d).reshape(-1, st)
@@ -82,25 +83,38 @@ def test_two_partitions_projection_solver_setup_gloo(case, tmp_path):
             assert np.array_equal(mo[np.argsort(mo[:, 0])], ms[np.argsort(ms[:, 0])]), masks
             vo, vs = o.get(vals, k).reshape(-1, w), np.asarray(r[vals]).reshape(-1, w)
             assert np.array_equal(vo[np.argsort(vo[:, 0])], vs[np.argsort(vs[:, 0])]), vals
-    # Dirichlet rows of the linear solvers: a node shared by the partitions is a BC row on all of them or on
-    # none, with one value (ConjugateGradients::init/combc/apply :391-449 merge the sharers' lists); nodes
-    # that are not shared keep exactly the partition's own list
-    gids = [np.asarray(res[k]["gid"], np.int64) for k in range(2)]
-    pbc = [dict(zip(gids[k][np.asarray(res[k]["pbc"][0::2], np.int64)].tolist(), res[k]["pbc"][1::2])) for k in range(2)]
-    common = set(gids[0].tolist()) & set(gids[1].tolist())
-    assert len(common) > 2
-    for g in common:
-        assert (g in pbc[0]) == (g in pbc[1]) and pbc[0].get(g) == pbc[1].get(g), g
-    for k in range(2):
+    # Dirichlet rows of the linear solvers: a node shared by partitions is a BC row on all of them or on none,
+    # with one value (ConjugateGradients::init/combc/apply :391-449 merge the sharers' lists); nodes that are
+    # not shared keep exactly the partition's own list
+    gids = [np.asarray(res[k]["gid"], np.int64) for k in range(world)]
+    pbc = [dict(zip(gids[k][np.asarray(res[k]["pbc"][0::2], np.int64)].tolist(), res[k]["pbc"][1::2])) for k in range(world)]
+    rows = None
+    if not case.startswith("lohcg"):
+        rows = [set((int(gids[k][r // 3]), int(r % 3)) for r in res[k]["mbcrows"]) for k in range(world)]
+        assert len(rows[0]) > 0
+    allshared = set(); three = 0
+    for a in range(world):
+        for b in range(a+1, world):
+            common = set(gids[a].tolist()) & set(gids[b].tolist())
+            allshared |= common
+            for g in common:
+                assert (g in pbc[a]) == (g in pbc[b]), g
+                if g in pbc[a]:      # one value: exact for two sharers, to rounding where three or more average theirs
+                    assert abs(pbc[a][g] - pbc[b][g]) <= 4e-16 * max(abs(pbc[a][g]), 1.0), g
+                if rows:
+                    for c in range(3):
+                        assert ((g, c) in rows[a]) == ((g, c) in rows[b]), (g, c)
+    if world > 2:
+        cnt = {}
+        for k in range(world):
+            for g in gids[k].tolist():
+                cnt[g] = cnt.get(g, 0) + 1
+        three = sum(1 for v in cnt.values() if v > 2)
+        assert three > 0                                   # the case does have nodes shared by 3+ partitions
+    for k in range(world):
         own = o.get("dirbcmaskp", k).reshape(-1, 2)
         own = set(gids[k][own[own[:, 1] > 0, 0].astype(np.int64)].tolist())
-        assert own <= set(pbc[k]) and set(pbc[k]) - own <= common | ({0} if "ldc" in case else set())
-    if not case.startswith("lohcg"):
-        rows = [set((int(gids[k][r // 3]), int(r % 3)) for r in res[k]["mbcrows"]) for k in range(2)]
-        for g in common:
-            for c in range(3):
-                assert ((g, c) in rows[0]) == ((g, c) in rows[1]), (g, c)
-        assert len(rows[0]) > 0
+        assert own <= set(pbc[k]) and set(pbc[k]) - own <= allshared | ({0} if "ldc" in case else set())
 
 
 @pytest.mark.gpu

@@ -47,13 +47,14 @@ def check_setup(res, o, world):
         assert abs(r["meshvol"] - o.scalar("meshvol")) <= 1e-15 * o.scalar("meshvol")
 
 
-@pytest.mark.parametrize("case", ["riecg_sod", "riecg_taylor_green", "zalcg_sod"])
-def test_two_partitions_host_logic_gloo(case, tmp_path):
-    res = launch("host", case, 0, tmp_path)
-    o = oracle_for(case, res[0]["part"], 2)
-    assert o.scalar("nchare") == 2
+@pytest.mark.parametrize("case,world", [("riecg_sod", 2), ("riecg_taylor_green", 2), ("zalcg_sod", 2),
+                                        ("riecg_taylor_green", 4), ("riecg_slot_cyl", 4)])
+def test_partitions_host_logic_gloo(case, world, tmp_path):
+    res = launch("host", case, 0, tmp_path, world=world)
+    o = oracle_for(case, res[0]["part"], world)
+    assert o.scalar("nchare") == world
     assert len(o.get("commmap", 0)) > 2           # the partitions do share nodes
-    check_setup(res, o, 2)
+    check_setup(res, o, world)
 
 
 @pytest.mark.parametrize("case,world", [("chocg_poiseuille_damp2", 2), ("chocg_ldc", 2), ("lohcg_poiseuille_damp4", 2),

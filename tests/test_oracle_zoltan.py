@@ -1,0 +1,51 @@
+"""The partitioner, pinned to the reference's own: oracle/_ref/libzoltan_ref.so is the reference's vendored Zoltan
+3.901 (src/zoltan, compiled where it lies against a one-rank MPI stub, oracle/stub/mpi) behind a restatement of the
+reference's call into it (inciter::geomPartMesh, src/Partition/ZoltanGeom.cpp:139-244; oracle/zoltan_geom.c). The
+host mirror's rcb() (xyst_b200/host/mesh.cpp: Zoltan's serial_rcb / find_median / average-cut restated) must give
+every element the part Zoltan gives it -- on every regression mesh and on box meshes, for 2..8 parts, powers of
+two or not. CPU only; skipped where the reference tree (and with it the library) is absent."""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+import oraclelib as O
+from xyst_b200 import hostapi as H
+from host_common import fixture_to_host_mesh
+
+LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "libzoltan_ref.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libzoltan_ref.so not built (needs /root/reference)")
+
+MESHES = ["riecg_sod", "riecg_sedov", "riecg_taylor_green", "laxcg_bump", "chocg_unitcube", "chocg_pidiv4",
+          "chocg_poiseuille", "sphere2_5k", "unitsquare_3_6k", "riecg_canyon"]
+
+
+def zoltan(alg, coord, tets, n):
+    L = C.CDLL(LIB)
+    L.orc_zoltan_geom.argtypes = [C.c_char_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
+    t = tets.astype(np.int64)
+    cen = [np.ascontiguousarray((c[t[:, 0]] + c[t[:, 1]] + c[t[:, 2]] + c[t[:, 3]]) / 4.0) for c in coord]   # ZoltanGeom.cpp:133-135
+    out = np.full(len(t), -1, np.int32)
+    rc = L.orc_zoltan_geom(alg.encode(), len(t), cen[0].ctypes.data, cen[1].ctypes.data, cen[2].ctypes.data, n,
+                           out.ctypes.data)
+    assert rc == 0, rc
+    return out
+
+
+@pytest.mark.parametrize("name", MESHES)
+def test_own_rcb_is_zoltans_rcb_on_the_regression_meshes(name):
+    hm = fixture_to_host_mesh(O.load_mesh(name))
+    for n in (2, 3, 4, 5, 7, 8):
+        z = zoltan("RCB", hm["coord"], hm["tets"], n)
+        m = H.rcb(hm["coord"], hm["tets"], n)
+        assert z.min() == 0 and z.max() == n - 1
+        assert np.array_equal(z, m), (name, n, int((z != m).sum()))
+
+
+@pytest.mark.parametrize("dims", [(8, 8, 8), (12, 6, 4), (5, 7, 9)])
+def test_own_rcb_is_zoltans_rcb_on_box_meshes(dims):
+    """Structured meshes: many centroids share a coordinate, so the cuts go through Zoltan's tie handling (dots on
+    the median are moved one by one in list order until the target weight is met, par_median.c:373-412)."""
+    m = H.box_mesh(*dims)
+    for n in (2, 3, 4, 6, 8):
+        z = zoltan("RCB", m["coord"], m["tets"], n)
+        assert np.array_equal(z, H.rcb(m["coord"], m["tets"], n)), (dims, n)

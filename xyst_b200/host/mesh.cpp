@@ -1,6 +1,7 @@
 // xyst_b200/host/mesh.cpp -- see mesh.hpp
 #include "mesh.hpp"
 #include <algorithm>
+#include <limits>
 #include <numeric>
 #include <stdexcept>
 #include <cmath>
@@ -104,38 +105,177 @@ TetMesh boxMesh( std::size_t nx, std::size_t ny, std::size_t nz, real Lx, real L
   return m;
 }
 
+// ---- recursive coordinate bisection as the reference gets it from Zoltan ---------------------------------
+// inciter::geomPartMesh (src/Partition/ZoltanGeom.cpp:139-244) hands the element centroids to Zoltan 3.901
+// (vendored under src/zoltan) with LB_METHOD RCB, LB_APPROACH PARTITION, no weights, AVERAGE_CUTS 1. What follows
+// restates the algorithm Zoltan runs for that: serial_rcb (src/zoltan/src/rcb/rcb.c:1516-1860) with cut_dimension
+// (:1380-1413), Zoltan_Divide_Parts (ha/divide_machine.c), Zoltan_RB_find_median (par/par_median.c:88-560) and
+// Zoltan_RB_Average_Cut (par/par_average.c), for unit weights on one process. tests/test_oracle_zoltan.py compares
+// it element by element with the reference's own Zoltan sources compiled into oracle/_ref.
+namespace {
+
+struct RcbBox { real lo[3], hi[3]; };
+
+// Zoltan_RB_find_median for unit weights: marks every dot 0 (lower set) or 1; returns the cut after averaging
+real zoltanMedian( const std::vector< real >& dots, real fractionlo, real valuemin, real valuemax, real weight,
+                   std::vector< int >& dotmark, real& wlo, real& whi )
+{
+  const real TINY = 1.0e-6, DMAX = std::numeric_limits< real >::max();
+  const auto dotnum = dots.size();
+  std::vector< std::size_t > dotlist( dotnum );
+  std::iota( dotlist.begin(), dotlist.end(), 0 );
+  auto numlist = dotnum;
+  const real tolerance = 1.0 * (0.5 + TINY);
+  const real targetlo = fractionlo * weight, targethi = weight - targetlo;
+  real weightlo = 0.0, weighthi = 0.0, tmp_half = 0.0;
+  std::size_t indexlo = 0, indexhi = 0;
+  while (true) {
+    if (weight != 0.0)
+      tmp_half = valuemin + (targetlo - weightlo) / (weight - weightlo - weighthi) * (valuemax - valuemin);
+    else
+      tmp_half = 0.5 * (valuemin + valuemax);
+    real totallo = 0.0, totalhi = 0.0, valuelo = -DMAX, valuehi = DMAX, wtlo = 0.0, wthi = 0.0;
+    int countlo = 0, counthi = 0;
+    for (std::size_t j=0; j<numlist; ++j) {
+      auto i = dotlist[j];
+      if (dots[i] <= tmp_half) {
+        totallo += 1.0; dotmark[i] = 0;
+        if (dots[i] > valuelo) { valuelo = dots[i]; wtlo = 1.0; countlo = 1; indexlo = i; }
+        else if (dots[i] == valuelo) { wtlo += 1.0; ++countlo; }
+      } else {
+        totalhi += 1.0; dotmark[i] = 1;
+        if (dots[i] < valuehi) { valuehi = dots[i]; wthi = 1.0; counthi = 1; indexhi = i; }
+        else if (dots[i] == valuehi) { wthi += 1.0; ++counthi; }
+      }
+    }
+    int markactive;
+    if (weightlo + totallo < targetlo) {                 // lower half too small
+      weightlo += totallo;
+      tmp_half = valuehi;
+      if (counthi == 1) {
+        if (weightlo + wthi < targetlo) dotmark[indexhi] = 0;
+        else {
+          if (weightlo + wthi - targetlo < targetlo - weightlo) { dotmark[indexhi] = 0; weightlo += wthi; }
+          weighthi = weight - weightlo;
+          break;
+        }
+      } else {
+        bool done = false;
+        real wtok = wthi;                                // one process: all dots at valuehi are mine
+        if (weightlo + wthi >= targetlo) {
+          real wtmax = targetlo - weightlo;
+          if (wtok > wtmax) wtok = wtok - (wtok - wtmax);
+          done = true;
+        }
+        real wtsum = 0.0;
+        for (std::size_t j=0; j<numlist; ++j) {
+          auto i = dotlist[j];
+          if (dots[i] == valuehi && (wtsum + 1.0 - wtok < wtok - wtsum)) { dotmark[i] = 0; wtsum += 1.0; }
+        }
+        if (done) { weightlo += wtsum; weighthi = weight - weightlo; break; }
+      }
+      weightlo += wthi;
+      if (targetlo - weightlo <= tolerance) { weighthi = weight - weightlo; break; }
+      valuemin = valuehi;
+      markactive = 1;
+    }
+    else if (weighthi + totalhi < targethi) {            // upper half too small
+      weighthi += totalhi;
+      tmp_half = valuelo;
+      if (countlo == 1) {
+        if (weighthi + wtlo < targethi) dotmark[indexlo] = 1;
+        else {
+          if (weighthi + wtlo - targethi < targethi - weighthi) { dotmark[indexlo] = 1; weighthi += wtlo; }
+          weightlo = weight - weighthi;
+          break;
+        }
+      } else {
+        bool done = false;
+        real wtok = wtlo;
+        if (weighthi + wtlo >= targethi) {
+          real wtmax = targethi - weighthi;
+          if (wtok > wtmax) wtok = wtok - (wtok - wtmax);
+          done = true;
+        }
+        real wtsum = 0.0;
+        for (std::size_t j=0; j<numlist; ++j) {
+          auto i = dotlist[j];
+          if (dots[i] == valuelo && (wtsum + 1.0 - wtok < wtok - wtsum)) { dotmark[i] = 1; wtsum += 1.0; }
+        }
+        if (done) { weighthi += wtsum; weightlo = weight - weighthi; break; }
+      }
+      weighthi += wtlo;
+      if (targethi - weighthi <= tolerance) { weightlo = weight - weighthi; break; }
+      valuemax = valuelo;
+      markactive = 0;
+    }
+    else { weightlo += totallo; weighthi += totalhi; break; }
+    std::size_t k = 0;
+    for (std::size_t j=0; j<numlist; ++j) { auto i = dotlist[j]; if (dotmark[i] == markactive) dotlist[k++] = i; }
+    numlist = k;
+  }
+  // Zoltan_RB_Average_Cut: halfway between the closest dots of the two sets
+  real v0 = -DMAX, v1 = DMAX;
+  for (std::size_t i=0; i<dotnum; ++i) { if (dotmark[i] == 0) { if (dots[i] > v0) v0 = dots[i]; } else if (dots[i] < v1) v1 = dots[i]; }
+  wlo = weightlo; whi = weighthi;
+  return 0.5 * (v0 + v1);
+}
+
+void zoltanSerialRcb( const std::array< std::vector< real >, 3 >& cen, RcbBox box, real weight, std::size_t* dindx,
+                      std::size_t* tmpdindx, std::size_t dotnum, int num_parts, int partlower, std::vector< int >& part )
+{
+  if (num_parts == 1) { for (std::size_t i=0; i<dotnum; ++i) part[dindx[i]] = partlower; return; }
+  // Zoltan_Divide_Parts with uniform part sizes
+  int partmid = partlower + (num_parts - 1)/2 + 1;
+  real fractionlo = 0.0, sum = 0.0;
+  for (int i=0; i<num_parts; ++i) { if (partlower + i < partmid) fractionlo += 1.0; sum += 1.0; }
+  fractionlo /= sum;
+  // cut_dimension: the longest side of the (cut, not recomputed) box; ties go to the lower dimension
+  int dim = 0;
+  if (box.hi[1] - box.lo[1] > box.hi[0] - box.lo[0]) dim = 1;
+  if (dim == 0 && box.hi[2] - box.lo[2] > box.hi[0] - box.lo[0]) dim = 2;
+  if (dim == 1 && box.hi[2] - box.lo[2] > box.hi[1] - box.lo[1]) dim = 2;
+  std::vector< real > coord( dotnum );
+  for (std::size_t i=0; i<dotnum; ++i) coord[i] = cen[static_cast< std::size_t >( dim )][dindx[i]];
+  std::vector< int > dotmark( dotnum, 0 );
+  real wlo, whi;
+  auto D = static_cast< std::size_t >( dim );
+  real valuehalf = zoltanMedian( coord, fractionlo, box.lo[D], box.hi[D], weight, dotmark, wlo, whi );
+  // set 0 dots in order at the front, set 1 dots from the back (rcb.c:1797-1803)
+  std::size_t set0 = 0, set1 = dotnum;
+  for (std::size_t i=0; i<dotnum; ++i) { if (dotmark[i] == 0) tmpdindx[set0++] = dindx[i]; else tmpdindx[--set1] = dindx[i]; }
+  std::copy( tmpdindx, tmpdindx + dotnum, dindx );
+  int nlo = partmid - partlower;
+  if (nlo > 0 && set1 != 0) { auto b = box; b.hi[D] = valuehalf;
+    zoltanSerialRcb( cen, b, wlo, dindx, tmpdindx, set0, nlo, partlower, part ); }
+  int nhi = partlower + num_parts - partmid;
+  if (nhi > 0 && set0 != dotnum) { auto b = box; b.lo[D] = valuehalf;
+    zoltanSerialRcb( cen, b, whi, dindx + set1, tmpdindx + set1, dotnum - set1, nhi, partmid, part ); }
+}
+
+} // namespace
+
 std::vector< int > rcb( const Coords& coord, const std::vector< std::size_t >& ginpoel, int nparts )
 {
-  if (nparts < 1 || (nparts & (nparts-1))) throw std::runtime_error( "rcb: nparts must be a power of two" );
+  if (nparts < 1) throw std::runtime_error( "rcb: nparts must be positive" );
   std::size_t nel = ginpoel.size()/4;
-  std::vector< std::array< real, 3 > > cen( nel );
+  std::array< std::vector< real >, 3 > cen;
+  for (auto& c : cen) c.resize( nel );
   for (std::size_t e=0; e<nel; ++e)
     for (std::size_t d=0; d<3; ++d) {
       const auto N = ginpoel.data() + e*4;
-      cen[e][d] = (coord[d][N[0]] + coord[d][N[1]] + coord[d][N[2]] + coord[d][N[3]]) / 4.0;
+      cen[d][e] = (coord[d][N[0]] + coord[d][N[1]] + coord[d][N[2]] + coord[d][N[3]]) / 4.0;     // ZoltanGeom.cpp:133-135
     }
   std::vector< int > part( nel, 0 );
-  std::vector< std::size_t > idx( nel );
-  std::iota( idx.begin(), idx.end(), 0 );
-  // recursive bisection on index ranges of idx
-  struct Job { std::size_t b, e; int p0, np; };
-  std::vector< Job > jobs{ { 0, nel, 0, nparts } };
-  while (!jobs.empty()) {
-    auto jb = jobs.back(); jobs.pop_back();
-    if (jb.np == 1) { for (std::size_t i=jb.b; i<jb.e; ++i) part[idx[i]] = jb.p0; continue; }
-    real lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
-    for (std::size_t i=jb.b; i<jb.e; ++i) for (int d=0; d<3; ++d) {
-      lo[d] = std::min( lo[d], cen[idx[i]][static_cast<std::size_t>(d)] ); hi[d] = std::max( hi[d], cen[idx[i]][static_cast<std::size_t>(d)] ); }
-    int dim = 0;
-    for (int d=1; d<3; ++d) if (hi[d]-lo[d] > (hi[dim]-lo[dim])*(1.0+1e-12)) dim = d;
-    std::size_t mid = jb.b + (jb.e-jb.b)/2;
-    auto D = static_cast< std::size_t >( dim );
-    std::nth_element( idx.begin()+static_cast<std::ptrdiff_t>(jb.b), idx.begin()+static_cast<std::ptrdiff_t>(mid),
-                      idx.begin()+static_cast<std::ptrdiff_t>(jb.e),
-      [&]( std::size_t a, std::size_t b ){ return cen[a][D] < cen[b][D] || (cen[a][D] == cen[b][D] && a < b); } );
-    jobs.push_back( { jb.b, mid, jb.p0, jb.np/2 } );
-    jobs.push_back( { mid, jb.e, jb.p0 + jb.np/2, jb.np/2 } );
+  if (nel == 0 || nparts == 1) return part;
+  RcbBox box;
+  for (std::size_t d=0; d<3; ++d) {
+    box.lo[d] = *std::min_element( cen[d].begin(), cen[d].end() );
+    box.hi[d] = *std::max_element( cen[d].begin(), cen[d].end() );
   }
+  std::vector< std::size_t > dindx( 2*nel );
+  std::iota( dindx.begin(), dindx.begin() + static_cast< std::ptrdiff_t >( nel ), 0 );
+  zoltanSerialRcb( cen, box, static_cast< real >( nel ), dindx.data(), dindx.data() + nel, nel, nparts, 0, part );
   return part;
 }
 

@@ -125,6 +125,12 @@ int xyst_box_counts(size_t nx, size_t ny, size_t nz, size_t* npoin, size_t* ntet
 int xyst_box_mesh(size_t nx, size_t ny, size_t nz, double Lx, double Ly, double Lz,
                   double* x, double* y, double* z, uint64_t* tets,
                   int32_t set_id[6], uint64_t set_off[7], uint64_t* set_tri);
+/* Number of partitions ("chares") the reference creates on npe processing elements with virtualization u in [0,1]
+ * (command-line -u; 0 = one per PE): tk::linearLoadDistributor, src/Base/LoadDistributor.cpp:24-97, with load = the
+ * number of mesh elements. Returns the count; chunksize/remainder as the reference computes them (may be NULL). */
+int xyst_chare_count(double virtualization, uint64_t load, int npe, uint64_t* chunksize, uint64_t* remainder, uint64_t* nchare);
+/* Element partition as the reference gets it from Zoltan's RCB (Partition/ZoltanGeom.cpp:139-244 with Zoltan 3.901's
+ * serial_rcb / find_median restated; any number of parts): part[e] for every tetrahedron */
 int xyst_rcb(size_t npoin, const double* x, const double* y, const double* z, size_t ntet,
              const uint64_t* tets, int nparts, int32_t* part);
 int xyst_test_faceset_order(size_t nface, const uint64_t* faces, size_t nerase, const uint64_t* erase,

@@ -212,8 +212,7 @@ def test_vortical_flow_oracle_reproduces_reference_golden_diag(case):
         from xyst_b200 import hostapi as H
         from host_common import fixture_to_host_mesh
         hm = fixture_to_host_mesh(mesh)
-        ntet = hm["tets"].shape[0]; n = ntet / 4
-        nchare = ntet // int((1.0 - n) * 0.5 + n)
+        nchare = H.chare_count(0.5, hm["tets"].shape[0], 4)[0]
         assert nchare == 8
         part = H.rcb(hm["coord"], hm["tets"], nchare).astype(np.uint64)
     o = O.Oracle(mesh, O.make_cfg(**kw), "port", nchare=nchare, target=part)

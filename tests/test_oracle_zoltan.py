@@ -49,3 +49,19 @@ def test_own_rcb_is_zoltans_rcb_on_box_meshes(dims):
     for n in (2, 3, 4, 6, 8):
         z = zoltan("RCB", m["coord"], m["tets"], n)
         assert np.array_equal(z, H.rcb(m["coord"], m["tets"], n)), (dims, n)
+
+
+def test_chare_count_of_the_references_over_decomposition():
+    """tk::linearLoadDistributor (Base/LoadDistributor.cpp:24-97; the -u command-line argument): the assertions of the
+    reference's unit test (tests/unit/Base/TestLoadDistributor.cpp:57-160) and the values behind its -u goldens."""
+    n, chunk, rem = H.chare_count(0.5, 1234, 2)
+    assert n < 1235 and chunk < 1235 and rem < chunk and n * chunk + rem == 1234
+    n0, chunk0, rem0 = H.chare_count(0.0, 1234, 2)
+    assert (n0, chunk0, rem0) == (2, 617, 0)                       # no virtualization: one chare per PE
+    n1, chunk1, rem1 = H.chare_count(1.0, 1234, 2)
+    assert (n1, chunk1, rem1) == (1234, 1, 0)                      # full virtualization: one chare per element
+    from xyst_b200 import capi
+    for bad in ((-0.5, 1234, 2), (1.5, 1234, 2), (0.5, 1234, 0)):
+        with pytest.raises(capi.XystError):
+            H.chare_count(*bad)
+    assert H.chare_count(0.5, 730, 4)[0] == 8                      # VorticalFlow -u 0.5 on 4 PEs (the HLLC goldens)

@@ -4,6 +4,7 @@
 #include <string>
 #include <algorithm>
 #include <stdexcept>
+#include <limits>
 #include <cmath>
 #include "riecg.hpp"
 #include "refhashset.hpp"
@@ -382,6 +383,26 @@ int xyst_box_mesh( size_t nx, size_t ny, size_t nz, double Lx, double Ly, double
     set_off[i+1] = set_off[i] + t.size()/3;
     ++i;
   }
+  API_END
+}
+
+int xyst_chare_count( double virtualization, uint64_t load, int npe, uint64_t* chunksize, uint64_t* remainder, uint64_t* nchare )
+{
+  API_BEGIN
+  auto eps = std::numeric_limits< double >::epsilon();
+  if (!(virtualization > -eps && virtualization < 1.0+eps)) throw std::runtime_error( "Virtualization parameter must be between [0.0...1.0]" );
+  if (npe <= 0) throw std::runtime_error( "Number of processing elements must be larger than zero" );
+  if (!nchare) throw std::runtime_error( "null argument" );
+  const auto n = static_cast< double >( load ) / npe;                          // LoadDistributor.cpp:71
+  auto chunk = static_cast< uint64_t >( (1.0 - n) * virtualization + n );       // :74
+  if (chunk == 0 || load < chunk) throw std::runtime_error( "Load must be larger than chunksize" );
+  uint64_t nc = load / chunk;                                                    // :79
+  uint64_t rem = load - nc * chunk;                                              // :82
+  chunk += rem / nc;                                                             // :85
+  rem = load - nc * chunk;                                                       // :88
+  if (chunksize) *chunksize = chunk;
+  if (remainder) *remainder = rem;
+  *nchare = nc;
   API_END
 }
 

@@ -149,6 +149,7 @@ def lib():
     L.xyst_box_counts.argtypes = [C.c_size_t] * 3 + [C.POINTER(C.c_size_t)] * 3
     L.xyst_box_mesh.argtypes = [C.c_size_t] * 3 + [C.c_double] * 3 + [vp] * 7
     L.xyst_rcb.argtypes = [C.c_size_t, vp, vp, vp, C.c_size_t, vp, C.c_int, vp]
+    L.xyst_chare_count.argtypes = [C.c_double, C.c_uint64, C.c_int, vp, vp, vp]
     L.xyst_box_part_range.argtypes = [C.c_size_t] * 3 + [C.c_int, C.c_int, vp]
     _lib = L
     return L
@@ -200,6 +201,14 @@ def rcb(coord, tets, nparts):
     part = np.zeros(len(t), np.int32)
     _ck(L.xyst_rcb(co.shape[1], _p(co[0]), _p(co[1]), _p(co[2]), len(t), _p(t), nparts, _p(part)))
     return part
+
+
+def chare_count(virtualization, load, npe):
+    """(nchare, chunksize, remainder) of tk::linearLoadDistributor (the reference's -u over-decomposition)."""
+    v = (C.c_uint64 * 3)()
+    a = C.addressof(v)
+    _ck(lib().xyst_chare_count(virtualization, load, npe, a, a + 8, a + 16))
+    return int(v[2]), int(v[0]), int(v[1])
 
 
 def box_part_range(nx, ny, nz, nparts, part):

@@ -133,6 +133,9 @@ int xyst_chare_count(double virtualization, uint64_t load, int npe, uint64_t* ch
  * serial_rcb / find_median restated; any number of parts): part[e] for every tetrahedron */
 int xyst_rcb(size_t npoin, const double* x, const double* y, const double* z, size_t ntet,
              const uint64_t* tets, int nparts, int32_t* part);
+/* ... and from Zoltan's RIB (part = "rib": serial_rib + Zoltan_RIB_inertial3d restated) */
+int xyst_rib(size_t npoin, const double* x, const double* y, const double* z, size_t ntet,
+             const uint64_t* tets, int nparts, int32_t* part);
 int xyst_test_faceset_order(size_t nface, const uint64_t* faces, size_t nerase, const uint64_t* erase,
                             uint64_t* out_std, uint64_t* out_emu, size_t* nout);
 int xyst_box_part_range(size_t nx, size_t ny, size_t nz, int nparts, int part, uint64_t range[6]);

@@ -1,8 +1,8 @@
 """The partitioner, pinned to the reference's own: oracle/_ref/libzoltan_ref.so is the reference's vendored Zoltan
 3.901 (src/zoltan, compiled where it lies against a one-rank MPI stub, oracle/stub/mpi) behind a restatement of the
 reference's call into it (inciter::geomPartMesh, src/Partition/ZoltanGeom.cpp:139-244; oracle/zoltan_geom.c). The
-host mirror's rcb() (xyst_b200/host/mesh.cpp: Zoltan's serial_rcb / find_median / average-cut restated) must give
-every element the part Zoltan gives it -- on every regression mesh and on box meshes, for 2..8 parts, powers of
+host mirror's rcb() and rib() (xyst_b200/host/mesh.cpp: Zoltan's serial_rcb / serial_rib / inertial3d / find_median /
+average-cut restated) must give every element the part Zoltan gives it -- on every regression mesh and on box meshes, for 2..8 parts, powers of
 two or not. CPU only; skipped where the reference tree (and with it the library) is absent."""
 import ctypes as C
 import os
@@ -41,6 +41,16 @@ def test_own_rcb_is_zoltans_rcb_on_the_regression_meshes(name):
         assert np.array_equal(z, m), (name, n, int((z != m).sum()))
 
 
+@pytest.mark.parametrize("name", MESHES)
+def test_own_rib_is_zoltans_rib_on_the_regression_meshes(name):
+    """part = "rib" (ZalCG/Bump/*.q): recursive inertial bisection -- centre of mass, inertia tensor, eigenvector of
+    the largest eigenvalue (cubic roots + pivoted elimination, rcb/inertial3d.c), projections, the same median."""
+    hm = fixture_to_host_mesh(O.load_mesh(name))
+    for n in (2, 3, 4, 5, 7, 8):
+        z = zoltan("RIB", hm["coord"], hm["tets"], n)
+        assert np.array_equal(z, H.rib(hm["coord"], hm["tets"], n)), (name, n)
+
+
 @pytest.mark.parametrize("dims", [(8, 8, 8), (12, 6, 4), (5, 7, 9)])
 def test_own_rcb_is_zoltans_rcb_on_box_meshes(dims):
     """Structured meshes: many centroids share a coordinate, so the cuts go through Zoltan's tie handling (dots on
@@ -49,6 +59,7 @@ def test_own_rcb_is_zoltans_rcb_on_box_meshes(dims):
     for n in (2, 3, 4, 6, 8):
         z = zoltan("RCB", m["coord"], m["tets"], n)
         assert np.array_equal(z, H.rcb(m["coord"], m["tets"], n)), (dims, n)
+        assert np.array_equal(zoltan("RIB", m["coord"], m["tets"], n), H.rib(m["coord"], m["tets"], n)), (dims, n)
 
 
 def test_chare_count_of_the_references_over_decomposition():

@@ -418,6 +418,18 @@ int xyst_rcb( size_t npoin, const double* x, const double* y, const double* z, s
   API_END
 }
 
+int xyst_rib( size_t npoin, const double* x, const double* y, const double* z, size_t ntet,
+              const uint64_t* tets, int nparts, int32_t* part )
+{
+  API_BEGIN
+  Coords co;
+  co[0].assign( x, x+npoin ); co[1].assign( y, y+npoin ); co[2].assign( z, z+npoin );
+  std::vector< std::size_t > g( tets, tets+ntet*4 );
+  auto p = rib( co, g, nparts );
+  std::copy( p.begin(), p.end(), part );
+  API_END
+}
+
 // test hook: iteration order of the real std::unordered_set vs RefOrderFaceSet after
 // inserting nface faces and erasing nerase of them; writes surviving faces (3 ids each)
 int xyst_test_faceset_order( size_t nface, const uint64_t* faces, size_t nerase, const uint64_t* erase,

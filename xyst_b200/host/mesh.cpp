@@ -253,7 +253,149 @@ void zoltanSerialRcb( const std::array< std::vector< real >, 3 >& cen, RcbBox bo
     zoltanSerialRcb( cen, b, whi, dindx + set1, tmpdindx + set1, dotnum - set1, nhi, partmid, part ); }
 }
 
+// ---- recursive inertial bisection (part = "rib"): Zoltan's serial_rib (src/zoltan/src/rcb/rib.c:1060-1215) with the
+// direction of Zoltan_RIB_inertial3d (rcb/inertial3d.c:69-218): centre of mass, inertia tensor, eigenvector of its
+// largest eigenvalue (roots of the characteristic cubic :221-313, eigenvector by pivoted elimination :329-455), the dots
+// projected on it, then the same median search, set ordering and recursion as RCB.
+
+// largest root of the characteristic polynomial of a symmetric 3x3 matrix (Zoltan_evals3)
+real ribLargestEigenvalue( const real H[3][3] )
+{
+  real xmax = 0.0;
+  for (int i=0; i<3; ++i) for (int j=i; j<3; ++j) xmax = std::max( xmax, std::abs( H[i][j] ) );
+  real m[3][3];
+  for (int i=0; i<3; ++i) for (int j=0; j<3; ++j) m[i][j] = xmax != 0.0 ? H[i][j] / xmax : H[i][j];
+  const real a1 = -(m[0][0] + m[1][1] + m[2][2]);
+  const real a2 = (m[0][0]*m[1][1] - m[0][1]*m[1][0]) + (m[0][0]*m[2][2] - m[0][2]*m[2][0]) + (m[1][1]*m[2][2] - m[1][2]*m[2][1]);
+  const real det = m[0][0]*m[1][1]*m[2][2] + m[0][1]*m[1][2]*m[2][0] + m[0][2]*m[1][0]*m[2][1]
+                 - m[0][1]*m[1][0]*m[2][2] - m[0][0]*m[1][2]*m[2][1] - m[0][2]*m[1][1]*m[2][0];
+  const real a3 = -det;
+  auto sgn = []( real x ){ return x >= 0 ? 1.0 : -1.0; };
+  real r1, r2, r3;
+  if (a3 == 0) {                                     // one root is zero: the quadratic
+    r1 = 0;
+    real q = -.5 * (a1 + sgn(a1) * std::sqrt( std::max( 0.0, a1*a1 - 4*a2 ) ));
+    r2 = q; r3 = a2 / q;
+  } else {
+    real q = (a1*a1 - 3*a2) / 9;
+    real r = (2*a1*a1*a1 - 9*a1*a2 + 27*a3) / 54;
+    real q3 = q*q*q, rr = r*r;
+    const real tol = 1.0e-6, HALFPI = 1.570796327, TWOPI = 6.283185307;       // (the constants as Zoltan has them)
+    if (q3 < rr && std::abs( q3 - rr ) < tol * (std::abs( q3 ) + std::abs( rr ))) q3 = rr;
+    if (q3 >= rr) {                                  // three real roots
+      real theta;
+      if (r == 0) theta = HALFPI;
+      else { q3 = std::sqrt( q3 ); if (q3 < std::abs( r )) q3 = std::abs( r ); theta = std::acos( r / q3 ); }
+      q = -2 * std::sqrt( q );
+      r1 = q * std::cos( theta / 3 ) - a1 / 3;
+      r2 = q * std::cos( (theta + TWOPI) / 3 ) - a1 / 3;
+      r3 = q * std::cos( (theta + 2 * TWOPI) / 3 ) - a1 / 3;
+    } else {                                         // one real root
+      real theta = std::sqrt( rr - q3 ) + std::abs( r );
+      theta = std::pow( theta, 1.0 / 3.0 );
+      r1 = r2 = r3 = -sgn(r) * (theta + q / theta) - a1 / 3;
+    }
+  }
+  r1 *= xmax; r2 *= xmax; r3 *= xmax;
+  return std::max( std::max( r1, r2 ), r3 );
+}
+
+// eigenvector of A for the eigenvalue ev by fully pivoted elimination (Zoltan_eigenvec3), normalised
+void ribEigenvector( const real A[3][3], real ev, real evec[3] )
+{
+  real m[3][3];
+  for (int i=0; i<3; ++i) for (int j=0; j<3; ++j) m[i][j] = A[i][j];
+  for (int i=0; i<3; ++i) m[i][i] -= ev;
+  int ind[3] = { 0, 1, 2 }, imax = 0, jmax = 0;
+  real xmax = 0.0;
+  for (int i=0; i<3; ++i) for (int j=i; j<3; ++j) if (std::abs( m[i][j] ) > xmax) { imax = i; jmax = j; xmax = std::abs( m[i][j] ); }
+  if (xmax == 0.0) { evec[0] = 1.0; evec[1] = evec[2] = 0.0; }
+  else {
+    for (int i=0; i<3; ++i) for (int j=0; j<3; ++j) m[i][j] /= xmax;
+    if (imax != 0) for (int j=0; j<3; ++j) std::swap( m[0][j], m[imax][j] );
+    if (jmax != 0) { for (int i=0; i<3; ++i) std::swap( m[i][0], m[i][jmax] ); ind[0] = jmax; ind[jmax] = 0; }
+    for (int i=1; i<3; ++i) for (int j=1; j<3; ++j) m[i][j] = m[0][0] * m[i][j] - m[i][0] * m[0][j];
+    xmax = 0.0;
+    for (int i=1; i<3; ++i) for (int j=i; j<3; ++j) if (std::abs( m[i][j] ) > xmax) { imax = i; jmax = j; xmax = std::abs( m[i][j] ); }
+    real ex, ey, ez;
+    if (xmax < 1.0e-6) { ey = 1.0; ex = ez = 0; }                              // two-fold degenerate
+    else {
+      if (imax != 1) for (int j=0; j<3; ++j) std::swap( m[1][j], m[imax][j] );
+      if (jmax != 1) { for (int i=0; i<3; ++i) std::swap( m[i][1], m[i][2] ); std::swap( ind[1], ind[2] ); }
+      ez = m[0][0] * m[1][1];
+      ey = -m[1][2] * m[0][0];
+      ex = m[0][1] * m[1][2] - m[0][2] * m[1][1];
+    }
+    evec[ind[0]] = ex; evec[ind[1]] = ey; evec[ind[2]] = ez;
+  }
+  real norm = std::sqrt( evec[0]*evec[0] + evec[1]*evec[1] + evec[2]*evec[2] );
+  for (int i=0; i<3; ++i) evec[i] /= norm;
+}
+
+void zoltanSerialRib( const std::array< std::vector< real >, 3 >& cen, real weight, std::size_t* dindx, std::size_t* tmpdindx,
+                      std::size_t dotnum, int num_parts, int partlower, std::vector< int >& part )
+{
+  if (num_parts == 1) { for (std::size_t i=0; i<dotnum; ++i) part[dindx[i]] = partlower; return; }
+  int partmid = partlower + (num_parts - 1)/2 + 1;
+  real fractionlo = 0.0, sum = 0.0;
+  for (int i=0; i<num_parts; ++i) { if (partlower + i < partmid) fractionlo += 1.0; sum += 1.0; }
+  fractionlo /= sum;
+  // centre of mass, inertia tensor, principal direction, projections (unit weights)
+  real cm[3] = { 0.0, 0.0, 0.0 };
+  for (std::size_t j=0; j<dotnum; ++j) { auto i = dindx[j]; cm[0] += cen[0][i]; cm[1] += cen[1][i]; cm[2] += cen[2][i]; }
+  const real wsum = static_cast< real >( dotnum );
+  for (auto& c : cm) c /= wsum;
+  real xx = 0, yy = 0, zz = 0, xy = 0, xz = 0, yz = 0;
+  for (std::size_t j=0; j<dotnum; ++j) { auto i = dindx[j];
+    real dx = cen[0][i] - cm[0], dy = cen[1][i] - cm[1], dz = cen[2][i] - cm[2];
+    xx += dx*dx; yy += dy*dy; zz += dz*dz; xy += dx*dy; xz += dx*dz; yz += dy*dz; }
+  real T[3][3] = { { xx, xy, xz }, { xy, yy, yz }, { xz, yz, zz } };
+  real evec[3];
+  ribEigenvector( T, ribLargestEigenvalue( T ), evec );
+  std::vector< real > value( dotnum );
+  real vlo = std::numeric_limits< real >::max(), vhi = -std::numeric_limits< real >::max();
+  for (std::size_t j=0; j<dotnum; ++j) { auto i = dindx[j];
+    value[j] = (cen[0][i] - cm[0])*evec[0] + (cen[1][i] - cm[1])*evec[1] + (cen[2][i] - cm[2])*evec[2];
+    vlo = std::min( vlo, value[j] ); vhi = std::max( vhi, value[j] ); }
+  std::vector< int > dotmark( dotnum, 0 );
+  real wlo, whi;
+  zoltanMedian( value, fractionlo, vlo, vhi, weight, dotmark, wlo, whi );
+  std::size_t set0 = 0, set1 = dotnum;
+  for (std::size_t i=0; i<dotnum; ++i) { if (dotmark[i] == 0) tmpdindx[set0++] = dindx[i]; else tmpdindx[--set1] = dindx[i]; }
+  std::copy( tmpdindx, tmpdindx + dotnum, dindx );
+  int nlo = partmid - partlower;
+  if (nlo > 0 && set1 != 0) zoltanSerialRib( cen, wlo, dindx, tmpdindx, set0, nlo, partlower, part );
+  int nhi = partlower + num_parts - partmid;
+  if (nhi > 0 && set0 != dotnum) zoltanSerialRib( cen, whi, dindx + set1, tmpdindx + set1, dotnum - set0, nhi, partmid, part );
+}
+
+std::array< std::vector< real >, 3 > centroidsOf( const Coords& coord, const std::vector< std::size_t >& ginpoel )
+{
+  std::size_t nel = ginpoel.size()/4;
+  std::array< std::vector< real >, 3 > cen;
+  for (auto& c : cen) c.resize( nel );
+  for (std::size_t e=0; e<nel; ++e)
+    for (std::size_t d=0; d<3; ++d) {
+      const auto N = ginpoel.data() + e*4;
+      cen[d][e] = (coord[d][N[0]] + coord[d][N[1]] + coord[d][N[2]] + coord[d][N[3]]) / 4.0;     // ZoltanGeom.cpp:133-135
+    }
+  return cen;
+}
+
 } // namespace
+
+std::vector< int > rib( const Coords& coord, const std::vector< std::size_t >& ginpoel, int nparts )
+{
+  if (nparts < 1) throw std::runtime_error( "rib: nparts must be positive" );
+  auto cen = centroidsOf( coord, ginpoel );
+  std::size_t nel = ginpoel.size()/4;
+  std::vector< int > part( nel, 0 );
+  if (nel == 0 || nparts == 1) return part;
+  std::vector< std::size_t > dindx( 2*nel );
+  std::iota( dindx.begin(), dindx.begin() + static_cast< std::ptrdiff_t >( nel ), 0 );
+  zoltanSerialRib( cen, static_cast< real >( nel ), dindx.data(), dindx.data() + nel, nel, nparts, 0, part );
+  return part;
+}
 
 std::vector< int > rcb( const Coords& coord, const std::vector< std::size_t >& ginpoel, int nparts )
 {

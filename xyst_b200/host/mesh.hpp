@@ -39,6 +39,8 @@ TetMesh boxMesh( std::size_t nx, std::size_t ny, std::size_t nz, real Lx, real L
 //! Recursive coordinate bisection of tet centroids into nparts (power of two) parts,
 //! cutting the longest extent at the median; deterministic. Returns part id per tet.
 std::vector< int > rcb( const Coords& coord, const std::vector< std::size_t >& ginpoel, int nparts );
+//! the same for part = "rib" (Zoltan's recursive inertial bisection, serial_rib + inertial3d restated)
+std::vector< int > rib( const Coords& coord, const std::vector< std::size_t >& ginpoel, int nparts );
 
 //! Hex-index ranges of the `part`-th of nparts (1,2,4,8) RCB parts of a uniform box: what
 //! rcb() yields for boxMesh (verified in tests), without building the full mesh.

@@ -150,6 +150,7 @@ def lib():
     L.xyst_box_mesh.argtypes = [C.c_size_t] * 3 + [C.c_double] * 3 + [vp] * 7
     L.xyst_rcb.argtypes = [C.c_size_t, vp, vp, vp, C.c_size_t, vp, C.c_int, vp]
     L.xyst_chare_count.argtypes = [C.c_double, C.c_uint64, C.c_int, vp, vp, vp]
+    L.xyst_rib.argtypes = [C.c_size_t, vp, vp, vp, C.c_size_t, vp, C.c_int, vp]
     L.xyst_box_part_range.argtypes = [C.c_size_t] * 3 + [C.c_int, C.c_int, vp]
     _lib = L
     return L
@@ -200,6 +201,14 @@ def rcb(coord, tets, nparts):
     co = np.ascontiguousarray(coord, np.float64); t = np.ascontiguousarray(tets, np.uint64)
     part = np.zeros(len(t), np.int32)
     _ck(L.xyst_rcb(co.shape[1], _p(co[0]), _p(co[1]), _p(co[2]), len(t), _p(t), nparts, _p(part)))
+    return part
+
+
+def rib(coord, tets, nparts):
+    L = lib()
+    co = np.ascontiguousarray(coord, np.float64); t = np.ascontiguousarray(tets, np.uint64)
+    part = np.zeros(len(t), np.int32)
+    _ck(L.xyst_rib(co.shape[1], _p(co[0]), _p(co[1]), _p(co[2]), len(t), _p(t), nparts, _p(part)))
     return part
 
 

@@ -401,13 +401,7 @@ std::vector< int > rcb( const Coords& coord, const std::vector< std::size_t >& g
 {
   if (nparts < 1) throw std::runtime_error( "rcb: nparts must be positive" );
   std::size_t nel = ginpoel.size()/4;
-  std::array< std::vector< real >, 3 > cen;
-  for (auto& c : cen) c.resize( nel );
-  for (std::size_t e=0; e<nel; ++e)
-    for (std::size_t d=0; d<3; ++d) {
-      const auto N = ginpoel.data() + e*4;
-      cen[d][e] = (coord[d][N[0]] + coord[d][N[1]] + coord[d][N[2]] + coord[d][N[3]]) / 4.0;     // ZoltanGeom.cpp:133-135
-    }
+  auto cen = centroidsOf( coord, ginpoel );
   std::vector< int > part( nel, 0 );
   if (nel == 0 || nparts == 1) return part;
   RcbBox box;

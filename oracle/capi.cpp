@@ -23,6 +23,7 @@ Cfg to_cfg( const orc_cfg* c ) {
     k.src_radius = c->src_radius; k.src_release_time = c->src_release_time; }
   if (c->freezeflow != 0.0) k.freezeflow = c->freezeflow;
   k.freezetime = c->freezetime;
+  if (c->fctfreeze != 0.0) k.fctfreeze = c->fctfreeze;
   k.theta = c->theta; k.mom_iter = c->mom_iter ? c->mom_iter : 10; k.mom_tol = c->mom_tol; if (c->mom_pc[0]) k.mom_pc = c->mom_pc;
   k.alpha = c->alpha; k.kappa = c->kappa; k.r0 = c->r0; k.ce = c->ce; k.beta = {{ c->beta[0], c->beta[1], c->beta[2] }};
   k.gamma = c->gamma; k.p0 = c->p0; k.cfl = c->cfl; k.dt = c->dt; k.t0 = c->t0; k.term = c->term;

@@ -944,11 +944,21 @@ class Chare {
       a.fill( 0.0 );
       auto fctsys = cfg.fctsys;
       for (auto& c : fctsys) --c;
-      std::vector< real > aec( ncomp ), coef( ncomp );
-      foredge( [&]( std::size_t P, std::size_t Q, const real* D ){
+      // The limit coefficients live in per-superedge arrays (m_dsuplim, ZalCG.cpp:754-759; [0] is sized with
+      // dsupedge[0].size() = 4 ids per tetrahedron, i.e. four times what the tetrahedra need) and stay there once
+      // the FCT is frozen (fctfreeze, :1411,1441,1469: the coefficient is then not recomputed). The triangle loop
+      // addresses m_dsuplim[0], not [1] (:1433): triangle edge j overwrites what tetrahedron edge j left, and in
+      // the frozen state the tetrahedron edges j < 3 ntri use the triangles' coefficients. Restated as is.
+      if (dsuplim[0].empty() && dsuplim[2].empty()) {
+        dsuplim[0].assign( std::max( dsupedge[0].size()*6, dsupedge[1].size() ) * ncomp, 0.0 );
+        dsuplim[2].assign( dsupedge[2].size()/2 * ncomp, 0.0 );
+      }
+      std::vector< real > aec( ncomp );
+      auto edge = [&]( std::size_t P, std::size_t Q, const real* D, real* coef ){
         auto dif = D[3];
         for (std::size_t c=0; c<ncomp; ++c) {
           aec[c] = -dif * ctau * (u(P,c) - u(Q,c));
+          if (fctfrozen) continue;
           auto A = c*2; auto B = A+1;
           coef[c] = min( aec[c] < 0.0 ? q(P,A) : q(P,B), aec[c] > 0.0 ? q(Q,A) : q(Q,B) );
         }
@@ -956,8 +966,16 @@ class Chare {
         for (auto c : fctsys) cs = min( cs, coef[c] );
         for (auto c : fctsys) coef[c] = cs;
         for (std::size_t c=0; c<ncomp; ++c) { aec[c] *= coef[c]; a(P,c) -= aec[c]; a(Q,c) += aec[c]; }
-      } );
+      };
+      for (std::size_t e=0; e<dsupedge[0].size()/4; ++e) { const auto N = dsupedge[0].data() + e*4; std::size_t i = 0;
+        for (const auto& pq : lpoed) { edge( N[pq[0]], N[pq[1]], dsupint[0].data() + (e*6+i)*4, dsuplim[0].data() + (e*6+i)*ncomp ); ++i; } }
+      for (std::size_t e=0; e<dsupedge[1].size()/3; ++e) { const auto N = dsupedge[1].data() + e*3; std::size_t i = 0;
+        for (const auto& pq : lpoet) { edge( N[pq[0]], N[pq[1]], dsupint[1].data() + (e*3+i)*4, dsuplim[0].data() + (e*3+i)*ncomp ); ++i; } }
+      for (std::size_t e=0; e<dsupedge[2].size()/2; ++e) { const auto N = dsupedge[2].data() + e*2;
+        edge( N[0], N[1], dsupint[2].data() + e*4, dsuplim[2].data() + e*ncomp ); }
     }
+    std::array< std::vector< real >, 3 > dsuplim;   // ZalCG::m_dsuplim
+    bool fctfrozen = false;                          // ZalCG::m_fctfreeze
 
     //! ZalCG::solve :1524-1607: merge A, apply to the low-order solution, BCs; un/u for diagnostics
     void zsolve( real t, real dt, real freezeflow = 1.0 ) {
@@ -1306,6 +1324,8 @@ class Run {
       for (std::size_t i=0; i<ncomp; ++i) row.push_back( std::sqrt( d[1][i] / meshvol ) );
       row.push_back( d[2][0] );
       if (cfg.steady) res = std::sqrt( d[1][cfg.rescomp-1] / meshvol );   // evalres: RieCG.cpp:1062-1075, Discretization.cpp:1267-1283
+      if (cfg.steady && cfg.solver == "zalcg" && res < cfg.fctfreeze)     // ZalCG::evalres :1619-1623
+        for (auto& c_ : ch) c_->fctfrozen = true;
       if (sol) {
         for (std::size_t i=0; i<ncomp; ++i) row.push_back( std::sqrt( d[3][i] / meshvol ) );
         for (std::size_t i=0; i<ncomp; ++i) row.push_back( d[4][i] / meshvol );

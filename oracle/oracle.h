@@ -60,6 +60,7 @@ typedef struct orc_cfg {
   double freezeflow, freezetime;   /* ZalCG/KozCG scalar transport in a frozen flow; freezeflow 0 = 1.0 */
   /* ChoCG semi-implicit momentum solve: theta > 0 turns it on; iterations (0 = 10), tolerance, preconditioner */
   double theta; uint64_t mom_iter; double mom_tol; char mom_pc[16];
+  double fctfreeze;           /* ZalCG steady state: freeze the FCT limit coefficients below this residual; 0 = never */
 } orc_cfg;
 
 const char* orc_backend(void);      /* "port" or "reference" */

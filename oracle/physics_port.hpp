@@ -91,6 +91,7 @@ struct Cfg {
   real src_radius = -1.0, src_release_time = 0.0;
   // ZalCG/KozCG: freeze the flow after freezetime and advance the scalars with freezeflow x dt
   real freezeflow = 1.0, freezetime = 0.0;
+  real fctfreeze = -1.0e300;     // ZalCG steady state: freeze the FCT limit coefficients once the residual is below this (default: never)
   // semi-implicit momentum solve of ChoCG (tag::theta, mom_iter, mom_tol, mom_pc)
   real theta = 0.0;
   std::uint64_t mom_iter = 10;

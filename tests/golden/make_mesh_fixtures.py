@@ -73,7 +73,8 @@ EXTRA_DIAG = {"laxcg_bump_hllc": "LaxCG/Bump/diag_hllc.std",
               "lohcg_slot_cyl": "LohCG/SlotCyl/diag.std",
               "lohcg_slot_cyl_damp4": "LohCG/SlotCyl/diag_damp4.std",
               "chocg_slot_cyl_damp4_freeze": "ChoCG/SlotCyl/diag_damp4_freeze.std",
-              "riecg_sod_hist_range": "RieCG/Sod/diag_hist_range.std"}
+              "riecg_sod_hist_range": "RieCG/Sod/diag_hist_range.std",
+              "zalcg_bump_fctfreeze": "ZalCG/Bump/diag_fctfreeze.std"}
 
 
 def flatten(exo):

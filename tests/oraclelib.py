@@ -49,6 +49,7 @@ class Cfg(C.Structure):
         ("src_location", C.c_double * 3), ("src_radius", C.c_double), ("src_release_time", C.c_double),
         ("freezeflow", C.c_double), ("freezetime", C.c_double),
         ("theta", C.c_double), ("mom_iter", C.c_uint64), ("mom_tol", C.c_double), ("mom_pc", C.c_char * 16),
+        ("fctfreeze", C.c_double),
     ]
 
 
@@ -60,14 +61,14 @@ def make_cfg(problem, mesh=None, flux="rusanov", gamma=1.4, p0=0.0, cfl=0.0, dt=
              ic_density=0.0, ic_pressure=0.0, ic_velocity=(0.0, 0.0, 0.0),
              mu=0.0, dif=0.0, stab=True, rk=1, noslip=(), dirval=(), p_iter=10, p_tol=1.0e-3, p_pc="none",
              p_dir=(), p_dirval=(), p_sym=(), p_hydrostat=None, alpha=0.0, kappa=0.0, r0=0.0, ce=0.0, beta=(0.0, 0.0, 0.0), pre=(), soundspeed=1.0,
-             theta=0.0, mom_iter=10, mom_tol=1.0e-3, mom_pc="none", freezeflow=1.0, freezetime=0.0,
+             theta=0.0, mom_iter=10, mom_tol=1.0e-3, mom_pc="none", freezeflow=1.0, freezetime=0.0, fctfreeze=0.0,
              src_location=(0.0, 0.0, 0.0), src_radius=0.0, src_release_time=0.0, cls=Cfg):
     """Control-file equivalent; defaults are the reference's (InciterConfig.cpp:1707-1757)."""
     c = cls()
     c.problem = problem.encode(); c.flux = flux.encode(); c.ncomp = ncomp
     c.gamma = gamma; c.p0 = p0; c.cfl = cfl; c.dt = dt; c.t0 = t0; c.term = term; c.alpha = alpha; c.kappa = kappa
     c.r0 = r0; c.ce = ce; c.soundspeed = soundspeed
-    c.freezeflow = freezeflow; c.freezetime = freezetime
+    c.freezeflow = freezeflow; c.freezetime = freezetime; c.fctfreeze = fctfreeze
     c.src_radius = src_radius; c.src_release_time = src_release_time
     for i in range(3):
         c.src_location[i] = src_location[i]
